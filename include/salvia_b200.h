@@ -1,0 +1,279 @@
+/* salvia_b200.h — the C-ABI drop-in boundary of the B200-native SALVIA draw pipeline.
+ *
+ * One flat `extern "C"` surface with opaque handles, POD descriptors and int32 status codes equal to
+ * `salvia::result` (reference: salvia/include/salvia/common/constants.h:9).  It is what a third
+ * subclass of the reference's `renderer_impl` (next to sync_renderer / async_renderer) binds in its
+ * `commit_state_and_command()` override (reference: salvia/include/salvia/core/renderer_impl.h:111,
+ * salvia/src/core/sync_renderer.cpp:26-29): every piece of state the reference snapshots into
+ * `render_state` (salvia/include/salvia/core/render_state.h:46-94) for one draw/clear command is a
+ * field of `slv_draw_desc` / an argument of `slv_clear_*`.  See INTEGRATION.md for the binding stub.
+ *
+ * Three shared libraries export this same table:
+ *   libsalvia_b200.so   (salviarenderer_b200/csrc)  the product: hand-written sm_100a CUDA, no CPU path
+ *   libsalvia_oracle.so (oracle/)                   CPU restatement — test infrastructure only
+ *   libsalvia_ref.so    (oracle/_ref/)              the unmodified reference behind this ABI — ditto
+ * so the parity tests drive all three with identical calls.
+ *
+ * No torch types, no C++ types: plain pointers and sizes only.
+ */
+#ifndef SALVIA_B200_H
+#define SALVIA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLV_ABI_VERSION 1
+
+/* ---- status codes == salvia::result (constants.h:9) -------------------------------------------- */
+typedef int32_t slv_result;
+enum { SLV_OK = 0, SLV_FAILED = 1, SLV_OUT_OF_MEMORY = 2, SLV_INVALID_PARAMETER = 3 };
+
+/* ---- capacities (renderer_capacity.h:7-15) ------------------------------------------------------ */
+enum {
+  SLV_MAX_VS_INPUT_ATTRS = 8,
+  SLV_MAX_VS_OUTPUT_ATTRS = 5, /* vs_output_ops is only populated for N = 0..5 (shader.cpp:45-52) */
+  SLV_MAX_RENDER_TARGETS = 8,
+  SLV_MAX_INPUT_SLOTS = 32,
+  SLV_MAX_RENDER_TARGET_SIZE = 8192,
+  SLV_MAX_SAMPLE_COUNT = 4,    /* sample patterns exist for 1, 2, 4 (rasterizer.cpp:1087-1103) */
+  SLV_MAX_SAMPLERS = 4,
+  SLV_MAX_UNIFORM_BYTES = 256,
+  SLV_TILE_SIZE = 64           /* rasterizer.cpp:32 */
+};
+
+/* ---- enums with the reference's numeric values (constants.h) ------------------------------------ */
+enum { SLV_TOPO_TRIANGLE_LIST = 2, SLV_TOPO_TRIANGLE_STRIP = 4 };          /* primitive_topology   */
+enum { SLV_CULL_NONE = 0, SLV_CULL_FRONT = 1, SLV_CULL_BACK = 2 };         /* cull_mode            */
+enum { SLV_ADDR_WRAP = 0, SLV_ADDR_MIRROR = 1, SLV_ADDR_CLAMP = 2, SLV_ADDR_BORDER = 3 };
+enum { SLV_FILTER_POINT = 0, SLV_FILTER_LINEAR = 1, SLV_FILTER_ANISOTROPIC = 2 };
+enum { SLV_MIP_LO_QUALITY = 0, SLV_MIP_MI_QUALITY = 1, SLV_MIP_HI_QUALITY = 2 };
+enum {                                                                     /* compare_function     */
+  SLV_CMP_NEVER = 0, SLV_CMP_LESS = 1, SLV_CMP_EQUAL = 2, SLV_CMP_LESS_EQUAL = 3,
+  SLV_CMP_GREATER = 4, SLV_CMP_NOT_EQUAL = 5, SLV_CMP_GREATER_EQUAL = 6, SLV_CMP_ALWAYS = 7
+};
+enum {                                                                     /* stencil_op           */
+  SLV_SOP_KEEP = 1, SLV_SOP_ZERO = 2, SLV_SOP_REPLACE = 3, SLV_SOP_INCR_SAT = 4,
+  SLV_SOP_DECR_SAT = 5, SLV_SOP_INVERT = 6, SLV_SOP_INCR_WRAP = 7, SLV_SOP_DECR_WRAP = 8
+};
+enum { SLV_CLEAR_DEPTH = 1, SLV_CLEAR_STENCIL = 2 };                       /* clear_flag           */
+enum { SLV_INDEX_NONE = 0, SLV_INDEX_R16_UINT = 57, SLV_INDEX_R32_UINT = 42 }; /* format.h         */
+enum {                                                                     /* vertex element format */
+  SLV_FMT_R32_FLOAT = 41, SLV_FMT_R32G32_FLOAT = 16, SLV_FMT_R32G32B32_FLOAT = 6,
+  SLV_FMT_R32G32B32A32_FLOAT = 2
+};
+/* pixel formats of surfaces/textures, numeric values of the reference's pixel_format codes
+ * (salvia/include/salvia/common/colors_convertors.h:40-47) */
+enum { SLV_PF_RGBA32F = 0, SLV_PF_BGRA8 = 2, SLV_PF_RGBA8 = 3, SLV_PF_RG32F = 5 };
+/* vs_output::attrib_modifier_type (shader_regs.h:53-59) */
+enum { SLV_AM_LINEAR = 1, SLV_AM_CENTROID = 2, SLV_AM_NOINTERPOLATION = 4, SLV_AM_NOPERSPECTIVE = 8 };
+
+/* ---- device shader programs ----------------------------------------------------------------------
+ * cpp_vertex_shader / cpp_pixel_shader / cpp_blend_shader subclasses cannot run on the GPU, so a
+ * host shader object names a registered __device__ program and carries its uniforms as a POD block
+ * (layout documented per program; all floats, mat44 row-major as eflib::mat44, vec4 = 4 floats). */
+enum {
+  /* pos = in[0]·wvp; attr[i] = in[src[i]].   uniforms: mat44 wvp; u32 n_attrs; u32 src[5]          */
+  SLV_VS_MVP_PASSTHROUGH = 1,
+  /* pos = in[0]·wvp; attr0 = (in0.x, in0.z, 0, 0)  (TextureAndBlending.cpp:121-143) uniforms: wvp  */
+  SLV_VS_PLANE_XZ = 2,
+  /* pos = in[0]·wvp; attr0 = in[1]; attr1..3 = lightPos_k − in[0]
+   * (ColorizedTriangle.cpp:29-53).  uniforms: mat44 wvp; vec4 lightPos[3]                          */
+  SLV_VS_LIGHTS3 = 3,
+  /* pos = in[0]·wvp; attr0 = in[1] (uv); attr1 = in[2] (normal); attr2 = lightPos − in[0];
+   * attr3 = eyePos − in[0]  (Sponza.cpp:64-97).  uniforms: mat44 wvp; vec4 lightPos; vec4 eyePos   */
+  SLV_VS_SPONZA = 4
+};
+enum {
+  SLV_PS_ATTR0_COLOR = 1,   /* color0 = attr0                                    no uniforms        */
+  SLV_PS_LIGHTS3 = 2,       /* ColorizedTriangle.cpp:55-92                       no uniforms        */
+  /* color0 = tex2d(sampler0, attr[reg]); color0.a = alpha (TextureAndBlending.cpp:96-166)
+   * uniforms: u32 reg; f32 alpha                                                                   */
+  SLV_PS_TEX_ALPHA = 3,
+  /* diffuse texture × clamp(N·L) (Sponza.cpp:99-141).  uniforms: u32 has_sampler                   */
+  SLV_PS_SPONZA = 4,
+  /* color0 = sample_2d_grad(sampler0, attr[reg].xy, ddx, ddy, 0); a = alpha — the SASL tex2D path,
+   * required for anisotropic filtering.  uniforms: u32 reg; f32 alpha       */
+  SLV_PS_TEX_GRAD_ALPHA = 5,
+  SLV_PS_DISCARD_ALL = 6    /* returns false for every pixel (early-Z quirk probe, App. B #3)       */
+};
+enum {
+  SLV_BS_REPLACE = 1,        /* inout.color(0,s) = src              (ColorizedTriangle.cpp:94-106)  */
+  SLV_BS_LERP_SRC_ALPHA = 2, /* dst + (src − dst)·src.a             (TextureAndBlending.cpp:168-180)*/
+  SLV_BS_REPLACE_AND_COUNT = 3 /* REPLACE on target 0, and target1(s) = target1(s) + 1 (coverage probe,
+                                  SURVEY §8c "Extracting coverage from the oracle")                 */
+};
+
+/* uniform blocks of the programs above (mat44 = eflib::mat44, row-major data_[row][col]) */
+typedef struct slv_vs_mvp_passthrough_uniforms { float wvp[16]; uint32_t n_attrs; uint32_t src[5]; } slv_vs_mvp_passthrough_uniforms;
+typedef struct slv_vs_plane_xz_uniforms { float wvp[16]; } slv_vs_plane_xz_uniforms;
+typedef struct slv_vs_lights3_uniforms { float wvp[16]; float light_pos[3][4]; } slv_vs_lights3_uniforms;
+typedef struct slv_vs_sponza_uniforms { float wvp[16]; float light_pos[4]; float eye_pos[4]; } slv_vs_sponza_uniforms;
+typedef struct slv_ps_tex_alpha_uniforms { uint32_t reg; float alpha; } slv_ps_tex_alpha_uniforms;
+typedef struct slv_ps_sponza_uniforms { uint32_t has_sampler; } slv_ps_sponza_uniforms;
+
+/* ---- handles ---------------------------------------------------------------------------------- */
+typedef struct slv_device_t* slv_device;
+typedef uint32_t slv_handle;  /* 0 = null. buffers, textures and samplers share one id space        */
+
+/* ---- descriptors ------------------------------------------------------------------------------ */
+typedef struct slv_sampler_desc {      /* sampler_desc (sampler.h:16-45) */
+  uint32_t min_filter, mag_filter, mip_filter;
+  uint32_t mip_qual;
+  uint32_t addr_mode_u, addr_mode_v, addr_mode_w;
+  float mip_lod_bias;
+  uint32_t max_anisotropy;
+  uint32_t comparison_func;
+  float border_color[4];
+  float min_lod, max_lod;
+} slv_sampler_desc;
+
+typedef struct slv_viewport {          /* viewport (viewport.h:5-12) */
+  float x, y, w, h, minz, maxz;
+} slv_viewport;
+
+typedef struct slv_stencil_op_desc {   /* depth_stencil_op_desc (framebuffer.h:20-32) */
+  uint32_t stencil_fail_op, stencil_depth_fail_op, stencil_pass_op, stencil_func;
+} slv_stencil_op_desc;
+
+typedef struct slv_depth_stencil_desc { /* depth_stencil_desc (framebuffer.h:34-50) */
+  uint32_t depth_enable, depth_write_mask, depth_func;
+  uint32_t stencil_enable, stencil_read_mask, stencil_write_mask;
+  slv_stencil_op_desc front_face, back_face;
+} slv_depth_stencil_desc;
+
+typedef struct slv_raster_desc {       /* the fields of raster_desc that are read (raster_state.h:17-40) */
+  uint32_t cull_mode;
+  uint32_t front_ccw;
+} slv_raster_desc;
+
+typedef struct slv_vertex_stream {     /* set_vertex_buffers(slot, buf, stride, offset) */
+  slv_handle buffer;
+  uint32_t stride;
+  uint32_t offset;
+} slv_vertex_stream;
+
+typedef struct slv_input_element {     /* input_element_desc resolved against the VS register map
+                                          (stream_assembler.cpp:52-86): register <- slot/offset/fmt */
+  uint32_t reg;                        /* vs_input register index 0..7                              */
+  uint32_t format;                     /* SLV_FMT_*                                                 */
+  uint32_t slot;                       /* index into slv_draw_desc.streams                          */
+  uint32_t aligned_byte_offset;
+  float default_w;                     /* 1 for POSITION semantics, else 0 (shader/constants.h:119) */
+} slv_input_element;
+
+typedef struct slv_shader_binding {
+  uint32_t program;                    /* SLV_VS_* / SLV_PS_* / SLV_BS_*                            */
+  uint32_t uniform_bytes;
+  uint8_t uniforms[SLV_MAX_UNIFORM_BYTES];
+  slv_handle samplers[SLV_MAX_SAMPLERS];
+} slv_shader_binding;
+
+typedef struct slv_draw_desc {
+  /* input assembler */
+  uint32_t n_streams;
+  slv_vertex_stream streams[8];
+  uint32_t n_elements;
+  slv_input_element elements[SLV_MAX_VS_INPUT_ATTRS];
+  slv_handle index_buffer;             /* 0 for draw(), else draw_index()                           */
+  uint32_t index_format;               /* SLV_INDEX_*                                               */
+  uint32_t topology;                   /* SLV_TOPO_*                                                */
+  uint32_t start;                      /* start index (draw_index) / start vertex (draw)            */
+  uint32_t prim_count;
+  int32_t base_vertex;
+  /* shaders */
+  slv_shader_binding vs, ps, bs;
+  uint32_t vs_attr_modifiers[SLV_MAX_VS_OUTPUT_ATTRS]; /* output_attribute_modifiers(i); 0 => linear */
+  /* fixed-function state */
+  slv_raster_desc raster;
+  slv_depth_stencil_desc ds;
+  int32_t stencil_ref;
+  slv_viewport viewport;
+  /* output merger targets: surfaces = mip 0 of textures */
+  uint32_t n_color_targets;
+  slv_handle color_targets[SLV_MAX_RENDER_TARGETS];
+  slv_handle ds_target;
+} slv_draw_desc;
+
+typedef struct slv_pipeline_statistics { /* pipeline_statistics + internal_statistics (async_object.h:90-175) */
+  uint64_t ia_vertices, ia_primitives, vs_invocations, gs_invocations, gs_primitives;
+  uint64_t cinvocations, cprimitives, ps_invocations;
+  uint64_t backend_input_pixels;
+} slv_pipeline_statistics;
+
+typedef struct slv_pipeline_profiles {   /* pipeline_profiles, nanoseconds (async_object.h:177-233) */
+  uint64_t gather_vtx, vtx_proc, clipping, compact_clip, vp_trans, tri_dispatch, ras;
+} slv_pipeline_profiles;
+
+/* ---- entry points ----------------------------------------------------------------------------- */
+/* replaces create_software_renderer()/create_benchmark_renderer() (renderer.h:133-134).
+ * `ordinal` = CUDA device index (ignored by the CPU checkers).  Product: fails with SLV_FAILED when
+ * no CUDA device is usable — there is no CPU fallback. */
+slv_result slv_device_create(int32_t ordinal, slv_device* out);
+void slv_device_destroy(slv_device dev);
+/* name of the implementation: "cuda-sm100a" | "oracle" | "reference" */
+const char* slv_backend_name(void);
+uint32_t slv_abi_version(void);
+
+/* renderer::create_buffer + map(write)/unmap (renderer.h:45,60-62; buffer.h:16) */
+slv_result slv_buffer_create(slv_device dev, size_t bytes, slv_handle* out);
+slv_result slv_buffer_upload(slv_device dev, slv_handle buf, size_t offset, const void* src, size_t bytes);
+slv_result slv_buffer_readback(slv_device dev, slv_handle buf, size_t offset, void* dst, size_t bytes);
+
+/* renderer::create_tex2d (renderer.h:46-47); level 0 is also the render-target `surface`.
+ * Storage layout of a level is the reference's linear one: ((y*W + x)*S + s)*bpp (surface.cpp:277-295). */
+slv_result slv_texture_create(slv_device dev, uint32_t width, uint32_t height, uint32_t samples,
+                              uint32_t pixel_format, slv_handle* out);
+/* texture_2d::gen_mipmap(filter, auto_gen=true) (texture2d.cpp:25-36, surface.cpp:53-92) */
+slv_result slv_texture_gen_mipmap(slv_device dev, slv_handle tex, uint32_t filter);
+slv_result slv_texture_level_count(slv_device dev, slv_handle tex, uint32_t* out_levels);
+slv_result slv_texture_level_size(slv_device dev, slv_handle tex, uint32_t level, uint32_t* w, uint32_t* h);
+/* map(surface, map_write) + memcpy / map(surface, map_read) (resource_manager.cpp:8-54) */
+slv_result slv_texture_upload(slv_device dev, slv_handle tex, uint32_t level, const void* src, size_t bytes);
+slv_result slv_texture_readback(slv_device dev, slv_handle tex, uint32_t level, void* dst, size_t bytes);
+/* renderer::create_sampler (renderer.h:50) */
+slv_result slv_sampler_create(slv_device dev, const slv_sampler_desc* desc, slv_handle tex, slv_handle* out);
+slv_result slv_resource_release(slv_device dev, slv_handle h);
+
+/* renderer::draw / draw_index -> commit_state_and_command() (renderer_impl.cpp:337-353) */
+slv_result slv_draw(slv_device dev, const slv_draw_desc* desc);
+/* renderer::clear_color (render_core.cpp:96-99) */
+slv_result slv_clear_color(slv_device dev, slv_handle surface_tex, const float rgba[4]);
+/* renderer::clear_depth_stencil (render_core.cpp:101-111, framebuffer.cpp:616-644) */
+slv_result slv_clear_depth_stencil(slv_device dev, slv_handle surface_tex, uint32_t flags, float depth,
+                                   uint32_t stencil);
+/* surface::resolve (surface.cpp:123-140) — src multi-sampled, dst single-sampled */
+slv_result slv_resolve(slv_device dev, slv_handle src_tex, slv_handle dst_tex);
+/* renderer::flush (renderer.h:128): returns when every queued command has finished */
+slv_result slv_flush(slv_device dev);
+
+/* queries: begin/end/get_data of pipeline_statistics + internal_statistics (renderer.h:116-119).
+ * begin zeroes the counters; get flushes and copies them. */
+slv_result slv_query_begin(slv_device dev);
+slv_result slv_query_get(slv_device dev, slv_pipeline_statistics* out);
+
+/* per-stage time accumulated since slv_query_begin (pipeline_profiles query, rasterizer.cpp:1128-1195).
+ * Product: CUDA-event time of the kernels of each stage; only collected while SLV_PROFILE=1 is set in
+ * the environment at device creation (it serialises the stream), otherwise all zeros. */
+slv_result slv_profile_get(slv_device dev, slv_pipeline_profiles* out);
+
+/* sort-first multi-GPU split (new; the reference is single-process): this device renders only the
+ * 64x64 screen tiles t=(tx,ty) with (tx + 3*ty) % nranks == rank; geometry stages run for all
+ * primitives.  (0,1) = everything (default).  Not supported by the reference backend. */
+slv_result slv_set_tile_shard(slv_device dev, uint32_t rank, uint32_t nranks);
+
+/* sampler probe used by the sampler parity tests: evaluates sampler::sample_2d_grad
+ * (sampler.cpp:854-873) [use_lod = 0] or sample_2d_lod (:850-852) [use_lod = 1] for n coordinates.
+ * coords: n×2 floats; ddx, ddy: n×2 floats (ignored for lod); lod: n floats; out: n×4 floats.
+ * All pointers are HOST pointers. */
+slv_result slv_sampler_probe(slv_device dev, slv_handle sampler, uint32_t n, const float* coords,
+                             const float* ddx, const float* ddy, const float* lod, uint32_t use_lod,
+                             float* out_rgba);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SALVIA_B200_H */

@@ -1,0 +1,322 @@
+"""Frozen synthetic workloads of SURVEY.md §8d, expressed as slv_* command streams.
+
+Every scene is a pure function of its parameters: float32 inputs are produced here once (numpy, fixed
+seeds) and the SAME bytes are handed to whichever backend renders them — the CUDA product, the CPU
+restatement or the unmodified reference — so results are comparable bit for bit.
+
+Scene sources in the reference (what each restates):
+  colorized_triangle : samples/ColorizedTriangle/ColorizedTriangle.cpp:108-205
+  texture_and_blending: samples/TextureAndBlending/TextureAndBlending.cpp:196-347
+  anisotropic_filter : samples/AnisotropicFilter/AnisotropicFilter.cpp
+  sponza_like        : samples/Sponza/Sponza.cpp:143-278 (assets are Git-LFS pointers -> procedural atrium)
+  grid_stress        : SURVEY §6 smoke probe (jittered height-field, one draw)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import struct
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import abi as A
+
+f32 = np.float32
+
+
+# ---- eflib-style float32 math (row-vector convention, eflib/src/math.cpp:142-154,418-570) ------------
+def mat_identity():
+    return np.eye(4, dtype=f32)
+
+
+def mat_translate(x, y, z):
+    m = np.eye(4, dtype=f32)
+    m[3, :3] = (x, y, z)
+    return m
+
+
+def mat_scale(x, y, z):
+    return np.diag(np.array([x, y, z, 1], dtype=f32)).astype(f32)
+
+
+def mat_rotate_y(a):
+    c, s = f32(math.cos(a)), f32(math.sin(a))
+    m = np.eye(4, dtype=f32)
+    m[0, 0], m[0, 2], m[2, 0], m[2, 2] = c, -s, s, c
+    return m
+
+
+def mat_mul(a, b):
+    return (a.astype(f32) @ b.astype(f32)).astype(f32)
+
+
+def _normalize(v):
+    v = np.asarray(v, dtype=f32)
+    return (v / f32(np.sqrt(np.sum(v * v, dtype=f32)))).astype(f32)
+
+
+def mat_lookat(eye, target, up):
+    eye, target, up = (np.asarray(v, dtype=f32) for v in (eye, target, up))
+    z = _normalize(target - eye)
+    x = _normalize(np.cross(up, z).astype(f32))
+    y = np.cross(z, x).astype(f32)
+    m = np.zeros((4, 4), dtype=f32)
+    m[:3, 0], m[:3, 1], m[:3, 2] = x, y, z
+    m[3, 0], m[3, 1], m[3, 2], m[3, 3] = -np.dot(x, eye), -np.dot(y, eye), -np.dot(z, eye), 1
+    return m
+
+
+def mat_perspective_fov(fovy, aspect, n, f):
+    ys = f32(1.0 / math.tan(fovy / 2))
+    xs = f32(ys / f32(aspect))
+    m = np.zeros((4, 4), dtype=f32)
+    m[0, 0], m[1, 1] = xs, ys
+    m[2, 2], m[2, 3] = f32(f / (f - n)), 1
+    m[3, 2] = f32(-n * f / (f - n))
+    return m
+
+
+def mat_ortho(l, r, b, t, n, f):
+    m = np.zeros((4, 4), dtype=f32)
+    m[0, 0], m[1, 1], m[2, 2] = 2 / (r - l), 2 / (t - b), 1 / (f - n)
+    m[3, 0], m[3, 1], m[3, 2], m[3, 3] = (l + r) / (l - r), (t + b) / (b - t), n / (n - f), 1
+    return m.astype(f32)
+
+
+# ---- geometry ----------------------------------------------------------------------------------------
+@dataclass
+class Mesh:
+    """Host-side mesh: vertex streams (each an (n, k) float32 array), elements, index array."""
+    streams: list            # list[np.ndarray float32 (nverts, comps)]
+    elements: list           # list[(reg, fmt, slot, byte_offset, default_w)]
+    indices: np.ndarray      # uint16 / uint32
+    prim_count: int
+    topology: int = A.TOPO_TRIANGLE_LIST
+    handles: dict = field(default_factory=dict)
+
+    def upload(self, be: A.Backend):
+        key = id(be)
+        if key not in self.handles:
+            vb = [be.create_buffer(np.ascontiguousarray(s, dtype=f32)) for s in self.streams]
+            ib = be.create_buffer(np.ascontiguousarray(self.indices)) if self.indices is not None else 0
+            self.handles[key] = (vb, ib)
+        return self.handles[key]
+
+    def fill_desc(self, be: A.Backend, d: A.DrawDesc, start=0, prim_count=None, base_vertex=0):
+        vb, ib = self.upload(be)
+        d.n_streams = len(vb)
+        for i, (h, s) in enumerate(zip(vb, self.streams)):
+            d.streams[i].buffer, d.streams[i].stride, d.streams[i].offset = h, s.shape[1] * 4, 0
+        d.n_elements = len(self.elements)
+        for i, (reg, fmt, slot, off, dw) in enumerate(self.elements):
+            e = d.elements[i]
+            e.reg, e.format, e.slot, e.aligned_byte_offset, e.default_w = reg, fmt, slot, off, dw
+        d.index_buffer = ib
+        if self.indices is None:
+            d.index_format = A.INDEX_NONE
+        else:
+            d.index_format = A.INDEX_R16_UINT if self.indices.dtype == np.uint16 else A.INDEX_R32_UINT
+        d.topology = self.topology
+        d.start, d.prim_count, d.base_vertex = start, self.prim_count if prim_count is None else prim_count, base_vertex
+
+
+_V4 = A.FMT_R32G32B32A32_FLOAT
+
+
+def create_planar(start, xdir, ydir, rx, ry, positive_normal=False, index_dtype=np.uint16) -> Mesh:
+    """salvia/src/ext/resource/mesh/mesh_io.cpp:182-265: 3 vec4 streams (pos w=1, normal, uv)."""
+    start, xdir, ydir = (np.asarray(v, dtype=f32) for v in (start, xdir, ydir))
+    n = _normalize(np.cross(xdir, ydir).astype(f32))
+    if not positive_normal:
+        n = -n
+    pos, nor, uv = [], [], []
+    line = np.array([*start, 1], dtype=f32)
+    x4, y4 = np.array([*xdir, 0], dtype=f32), np.array([*ydir, 0], dtype=f32)
+    for i in range(rx + 1):
+        p = line.copy()
+        for j in range(ry + 1):
+            pos.append(p.copy())
+            nor.append(np.array([*n, 0], dtype=f32))
+            uv.append(np.array([f32(i) / f32(rx), f32(j) / f32(ry), 0, 0], dtype=f32))
+            p = (p + y4).astype(f32)
+        line = (line + x4).astype(f32)
+    idx = []
+    for i in range(rx):
+        for j in range(ry):
+            q0 = i * (ry + 1) + j
+            q2 = q0 + ry + 2
+            idx += [q0, q0 + 1, q2, q2, q2 - 1, q0]
+    return Mesh([np.array(pos, f32), np.array(nor, f32), np.array(uv, f32)],
+                [(0, _V4, 0, 0, 1.0), (1, _V4, 1, 0, 0.0), (2, _V4, 2, 0, 0.0)],
+                np.array(idx, dtype=index_dtype), rx * ry * 2)
+
+
+def create_box() -> Mesh:
+    """mesh_io.cpp:35-180: unit box, 24 verts / 12 tris, streams pos/normal/uv as vec4, u16 indices."""
+    faces = [  # (normal, 4 corner positions)
+        ((1, 0, 0), [(1, 0, 0), (1, 1, 0), (1, 1, 1), (1, 0, 1)]),
+        ((-1, 0, 0), [(0, 0, 0), (0, 0, 1), (0, 1, 1), (0, 1, 0)]),
+        ((0, 1, 0), [(0, 1, 0), (0, 1, 1), (1, 1, 1), (1, 1, 0)]),
+        ((0, -1, 0), [(0, 0, 0), (1, 0, 0), (1, 0, 1), (0, 0, 1)]),
+        ((0, 0, 1), [(0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]),
+        ((0, 0, -1), [(0, 0, 0), (0, 1, 0), (1, 1, 0), (1, 0, 0)]),
+    ]
+    uvs4 = [(0, 0), (1, 0), (1, 1), (0, 1)]
+    pos, nor, uv, idx = [], [], [], []
+    for f, (n, corners) in enumerate(faces):
+        for k, c in enumerate(corners):
+            pos.append((*c, 1))
+            nor.append((*n, 0))
+            uv.append((*uvs4[k], 0, 0))
+        b = f * 4
+        idx += [b, b + 1, b + 2, b + 2, b + 3, b]
+    return Mesh([np.array(pos, f32), np.array(nor, f32), np.array(uv, f32)],
+                [(0, _V4, 0, 0, 1.0), (1, _V4, 1, 0, 0.0), (2, _V4, 2, 0, 0.0)],
+                np.array(idx, dtype=np.uint16), 12)
+
+
+# ---- uniform packing -----------------------------------------------------------------------------------
+def u_mvp_passthrough(wvp, src):
+    src = list(src) + [0] * (5 - len(src))
+    return wvp.astype(f32).tobytes() + struct.pack("<I5I", len([s for s in src[:5]]) if False else 0, *src[:5])
+
+
+def pack_vs_mvp_passthrough(wvp, src):
+    n = len(src)
+    src = list(src) + [0] * (5 - n)
+    return np.asarray(wvp, f32).tobytes() + struct.pack("<6I", n, *src)
+
+
+def pack_vs_plane_xz(wvp):
+    return np.asarray(wvp, f32).tobytes()
+
+
+def pack_vs_lights3(wvp, lights):
+    return np.asarray(wvp, f32).tobytes() + np.asarray(lights, f32).reshape(3, 4).tobytes()
+
+
+def pack_vs_sponza(wvp, light, eye):
+    return np.asarray(wvp, f32).tobytes() + np.asarray(light, f32).tobytes() + np.asarray(eye, f32).tobytes()
+
+
+def pack_ps_tex_alpha(reg, alpha):
+    return struct.pack("<If", reg, alpha)
+
+
+def pack_ps_sponza(has_sampler):
+    return struct.pack("<I", int(has_sampler))
+
+
+# ---- frame targets ---------------------------------------------------------------------------------------
+@dataclass
+class Targets:
+    color: A.Texture
+    ds: A.Texture
+    resolved: A.Texture | None
+    count: A.Texture | None = None   # rgba32f coverage counter (MRT 1), optional
+
+
+def create_targets(be: A.Backend, w, h, samples, color_fmt, with_count=False) -> Targets:
+    color = be.create_texture(w, h, samples, color_fmt)
+    ds = be.create_texture(w, h, samples, A.PF_RG32F)
+    resolved = be.create_texture(w, h, 1, color_fmt) if samples > 1 else None
+    count = be.create_texture(w, h, samples, A.PF_RGBA32F) if with_count else None
+    return Targets(color, ds, resolved, count)
+
+
+def base_desc(t: Targets, w, h, cull=A.CULL_BACK, ds=None) -> A.DrawDesc:
+    d = A.DrawDesc()
+    d.raster.cull_mode, d.raster.front_ccw = cull, 0
+    d.ds = ds if ds is not None else A.depth_stencil_desc()
+    d.stencil_ref = 0
+    d.viewport.x, d.viewport.y, d.viewport.w, d.viewport.h = 0, 0, w, h
+    d.viewport.minz, d.viewport.maxz = 0.0, 1.0
+    if t.count is not None:
+        d.n_color_targets = 2
+        d.color_targets[0], d.color_targets[1] = t.color.handle, t.count.handle
+    else:
+        d.n_color_targets = 1
+        d.color_targets[0] = t.color.handle
+    d.ds_target = t.ds.handle
+    return d
+
+
+@dataclass
+class FrameResult:
+    color: np.ndarray                 # uint8 [h, w, S, 4]
+    depth: np.ndarray                 # float32 [h, w, S]
+    stencil: np.ndarray               # uint32 [h, w, S]
+    resolved: np.ndarray | None       # uint8 [h, w, 1, 4]
+    count: np.ndarray | None          # float32 [h, w, S] coverage counter
+    stats: dict
+
+
+def read_frame(be: A.Backend, t: Targets, stats=None) -> FrameResult:
+    color = be.read_texture(t.color)
+    ds = be.read_texture(t.ds)
+    dsf = ds.view(np.float32).reshape(ds.shape[0], ds.shape[1], ds.shape[2], 2)
+    depth = dsf[..., 0].copy()
+    stencil = dsf[..., 1].copy().view(np.uint32)
+    resolved = be.read_texture(t.resolved) if t.resolved is not None else None
+    count = None
+    if t.count is not None:
+        c = be.read_texture(t.count)
+        count = c.view(np.float32).reshape(c.shape[0], c.shape[1], c.shape[2], 4)[..., 0].copy()
+    return FrameResult(color, depth, stencil, resolved, count, stats or {})
+
+
+# ===========================================================================================================
+# C1 / C3a: ColorizedTriangle (and AntiAliasing = same scene with 4x MSAA + resolve)
+# ===========================================================================================================
+class ColorizedTriangle:
+    """samples/ColorizedTriangle/ColorizedTriangle.cpp:108-205; test-mode camera: angle -= 0.55f per frame
+    accumulated in float32 BEFORE use (:166-175)."""
+
+    def __init__(self, w=800, h=600, samples=1, with_count=False):
+        self.w, self.h, self.samples, self.with_count = w, h, samples, with_count
+        self.mesh = create_planar((-3.0, -1.0, -3.0), (6, 0, 0), (0, 0, 6), 1, 1, False)
+        self.n_frames = 5
+
+    def setup(self, be: A.Backend):
+        self.t = create_targets(be, self.w, self.h, self.samples, A.PF_RGBA8, self.with_count)
+        self.mesh.upload(be)
+
+    def frame_uniforms(self, frame):
+        ang = f32(0.0)
+        for _ in range(frame + 1):
+            ang = f32(ang - f32(0.55))
+        ang = float(ang)
+        camera = (math.cos(ang) * 2.3, 2.5, math.sin(ang) * 2.3)
+        view = mat_lookat(camera, (0, 0, 0), (0, 1, 0))
+        proj = mat_perspective_fov(math.pi / 2, f32(self.w) / f32(self.h), 0.1, 100.0)
+        world = mat_translate(-0.5, 0, -0.5)
+        wvp = mat_mul(world, mat_mul(view, proj))
+        lights = [
+            (math.sin(-ang * 1.5) * 2.2, 0.15, math.cos(ang * 0.9) * 1.8, 0.0),
+            (math.sin(ang * 0.7) * 1.9, 0.15, math.cos(-ang * 0.4) * 2.5, 0.0),
+            (math.sin(ang * 2.6) * 2.3, 0.15, math.cos(ang * 0.6) * 1.7, 0.0),
+        ]
+        return wvp, lights
+
+    def render(self, be: A.Backend, frame: int):
+        t = self.t
+        be.clear_color(t.color, (0.2, 0.2, 0.5, 1.0))
+        if t.count is not None:
+            be.clear_color(t.count, (0, 0, 0, 0))
+        be.clear_depth_stencil(t.ds, A.CLEAR_DEPTH | A.CLEAR_STENCIL, 1.0, 0)
+        wvp, lights = self.frame_uniforms(frame)
+        d = base_desc(t, self.w, self.h, cull=A.CULL_BACK)
+        self.mesh.fill_desc(be, d)
+        d.vs = A.shader_binding(A.VS_LIGHTS3, pack_vs_lights3(wvp, lights))
+        d.ps = A.shader_binding(A.PS_LIGHTS3)
+        d.bs = A.shader_binding(A.BS_REPLACE_AND_COUNT if t.count is not None else A.BS_REPLACE)
+        be.draw(d)
+        if t.resolved is not None:
+            be.resolve(t.color, t.resolved)
+
+    def run(self, be: A.Backend, frame: int) -> FrameResult:
+        be.query_begin()
+        self.render(be, frame)
+        stats = be.query_get()
+        return read_frame(be, self.t, stats)
