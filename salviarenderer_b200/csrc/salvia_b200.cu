@@ -1,0 +1,722 @@
+// salvia_b200.cu — the C ABI of include/salvia_b200.h over the sm_100a kernels in slv_kernels.cuh.
+//
+// Host side of the product: resource table (buffers / textures / samplers in HBM), per-draw resolution of
+// the reference's render_state (render_state.h:46-94) into POD kernel parameter blocks, and the kernel
+// graph of one draw:   k_geometry -> k_scan_tiles -> k_bin_fill -> k_sort_lists -> k_raster.
+// There is NO CPU implementation behind these entry points: without a usable CUDA device
+// slv_device_create fails and nothing else can be called.
+//
+// Build (see __graft_entry__.build): nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo
+//        -fmad=false -prec-div=true -prec-sqrt=true -ftz=false -shared -Xcompiler -fPIC
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "salvia_b200.h"
+#include "slv_kernels.cuh"
+
+using namespace slv;
+
+namespace {
+
+struct Resource {
+  enum Kind { NONE, BUFFER, TEXTURE, SAMPLER } kind = NONE;
+  uint8_t* dptr = nullptr;  // buffers
+  size_t bytes = 0;
+  TextureRef tex{};         // textures: every level is its own allocation
+  uint32_t fmt = 0, samples = 1;
+  slv_sampler_desc sd{};    // samplers
+  slv_handle sampler_tex = 0;
+};
+
+uint32_t bpp_of(uint32_t fmt) {
+  switch (fmt) {
+  case SLV_PF_RGBA32F: return 16;
+  case SLV_PF_RG32F: return 8;
+  case SLV_PF_RGBA8:
+  case SLV_PF_BGRA8: return 4;
+  }
+  return 0;
+}
+
+uint8_t host_unorm8(float x) {  // colors.h:182-192
+  float m = x * 255.0f;
+  m = (m > 0.0f) ? m : 0.0f;
+  m = (m < 255.0f) ? m : 255.0f;
+  return (uint8_t)lrintf(m);
+}
+
+}  // namespace
+
+struct slv_device_t {
+  int ordinal = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<Resource> res;
+  // scratch arenas in HBM (grown on demand, never shrunk)
+  float4* tris = nullptr;
+  size_t tris_cap = 0;  // float4 units
+  uint32_t *tile_count = nullptr, *tile_offset = nullptr, *tile_cursor = nullptr;
+  uint32_t tiles_cap = 0;
+  uint32_t* list = nullptr;
+  uint32_t list_cap = 0;
+  uint32_t* overflow_flag = nullptr;
+  unsigned long long* d_stats = nullptr;
+  slv_pipeline_statistics host_stats{};  // counters that are pure functions of the draw arguments
+  uint32_t shard_rank = 0, shard_n = 1;
+  bool failed = false;  // sticky CUDA error
+  // profiling (SLV_PROFILE=1)
+  bool profile = false;
+  cudaEvent_t ev[5] = {};
+  double prof_ms[4] = {0, 0, 0, 0};  // geometry, binning, sort, raster
+  unsigned long long n_launches = 0;
+
+  Resource* get(slv_handle h, Resource::Kind k) {
+    if (h == 0 || h >= res.size() || res[h].kind != k) return nullptr;
+    return &res[h];
+  }
+};
+
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess) {                                                                            \
+      fprintf(stderr, "[salvia_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e__), __FILE__,     \
+              __LINE__, cudaGetErrorString(e__));                                                        \
+      return SLV_FAILED;                                                                                 \
+    }                                                                                                    \
+  } while (0)
+
+namespace {
+
+slv_result ensure_scratch(slv_device dev, size_t tris_needed, uint32_t n_tiles, uint32_t list_needed) {
+  if (tris_needed > dev->tris_cap) {
+    CU(cudaStreamSynchronize(dev->stream));
+    if (dev->tris) CU(cudaFree(dev->tris));
+    size_t cap = std::max(tris_needed, dev->tris_cap * 2);
+    CU(cudaMalloc(&dev->tris, cap * sizeof(float4)));
+    dev->tris_cap = cap;
+  }
+  if (n_tiles + 1 > dev->tiles_cap) {
+    CU(cudaStreamSynchronize(dev->stream));
+    if (dev->tile_count) { CU(cudaFree(dev->tile_count)); CU(cudaFree(dev->tile_offset)); CU(cudaFree(dev->tile_cursor)); }
+    uint32_t cap = std::max(n_tiles + 1, 4096u);
+    CU(cudaMalloc(&dev->tile_count, cap * sizeof(uint32_t)));
+    CU(cudaMalloc(&dev->tile_offset, cap * sizeof(uint32_t)));
+    CU(cudaMalloc(&dev->tile_cursor, cap * sizeof(uint32_t)));
+    CU(cudaMemsetAsync(dev->tile_count, 0, cap * sizeof(uint32_t), dev->stream));
+    CU(cudaMemsetAsync(dev->tile_offset, 0, cap * sizeof(uint32_t), dev->stream));
+    CU(cudaMemsetAsync(dev->tile_cursor, 0, cap * sizeof(uint32_t), dev->stream));
+    dev->tiles_cap = cap;
+  }
+  if (list_needed > dev->list_cap) {
+    CU(cudaStreamSynchronize(dev->stream));
+    if (dev->list) CU(cudaFree(dev->list));
+    uint32_t cap = std::max(list_needed, dev->list_cap * 2);
+    CU(cudaMalloc(&dev->list, (size_t)cap * sizeof(uint32_t)));
+    dev->list_cap = cap;
+  }
+  return SLV_OK;
+}
+
+SurfaceRef surface_of(slv_device dev, slv_handle h) {
+  SurfaceRef s{};
+  auto r = dev->get(h, Resource::TEXTURE);
+  if (r) s = r->tex.level[0];
+  return s;
+}
+
+uint32_t vs_num_attrs(const slv_shader_binding& vs) {
+  switch (vs.program) {
+  case SLV_VS_MVP_PASSTHROUGH: return reinterpret_cast<const slv_vs_mvp_passthrough_uniforms*>(vs.uniforms)->n_attrs;
+  case SLV_VS_PLANE_XZ: return 1;
+  case SLV_VS_LIGHTS3: return 4;
+  case SLV_VS_SPONZA: return 4;
+  }
+  return 0xFFFFFFFFu;
+}
+
+template <int R>
+void launch_geometry(const GeomParams& gp, cudaStream_t st) {
+  uint32_t blocks = (gp.prim_count + 127) / 128;
+  k_geometry<R><<<blocks, 128, 0, st>>>(gp);
+}
+
+template <int S>
+bool launch_raster_s(const RasterParams& rp, uint32_t blocks, cudaStream_t st) {
+  switch (rp.ps_program) {
+  case SLV_PS_ATTR0_COLOR: k_raster<S, SLV_PS_ATTR0_COLOR><<<blocks, RASTER_THREADS, 0, st>>>(rp); return true;
+  case SLV_PS_LIGHTS3: k_raster<S, SLV_PS_LIGHTS3><<<blocks, RASTER_THREADS, 0, st>>>(rp); return true;
+  case SLV_PS_TEX_ALPHA: k_raster<S, SLV_PS_TEX_ALPHA><<<blocks, RASTER_THREADS, 0, st>>>(rp); return true;
+  case SLV_PS_SPONZA: k_raster<S, SLV_PS_SPONZA><<<blocks, RASTER_THREADS, 0, st>>>(rp); return true;
+  case SLV_PS_TEX_GRAD_ALPHA: k_raster<S, SLV_PS_TEX_GRAD_ALPHA><<<blocks, RASTER_THREADS, 0, st>>>(rp); return true;
+  case SLV_PS_DISCARD_ALL: k_raster<S, SLV_PS_DISCARD_ALL><<<blocks, RASTER_THREADS, 0, st>>>(rp); return true;
+  }
+  return false;
+}
+
+slv_result check_overflow(slv_device dev) {
+  uint32_t flag = 0;
+  CU(cudaMemcpyAsync(&flag, dev->overflow_flag, sizeof(flag), cudaMemcpyDeviceToHost, dev->stream));
+  CU(cudaStreamSynchronize(dev->stream));
+  if (flag) {
+    fprintf(stderr, "[salvia_b200] per-tile triangle lists overflowed the %u-entry arena\n", dev->list_cap);
+    dev->failed = true;
+    return SLV_OUT_OF_MEMORY;
+  }
+  return dev->failed ? SLV_FAILED : SLV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* slv_backend_name(void) { return "cuda-sm100a"; }
+uint32_t slv_abi_version(void) { return SLV_ABI_VERSION; }
+
+slv_result slv_device_create(int32_t ordinal, slv_device* out) {
+  if (!out) return SLV_INVALID_PARAMETER;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    fprintf(stderr, "[salvia_b200] no CUDA device available (%s); this library has no CPU fallback\n",
+            e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return SLV_FAILED;
+  }
+  if (ordinal < 0 || ordinal >= n) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(ordinal));
+  auto dev = new slv_device_t;
+  dev->ordinal = ordinal;
+  dev->res.resize(1);
+  CU(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
+  CU(cudaMalloc(&dev->overflow_flag, sizeof(uint32_t)));
+  CU(cudaMemsetAsync(dev->overflow_flag, 0, sizeof(uint32_t), dev->stream));
+  CU(cudaMalloc(&dev->d_stats, 9 * sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(dev->d_stats, 0, 9 * sizeof(unsigned long long), dev->stream));
+  const char* prof = getenv("SLV_PROFILE");
+  dev->profile = prof && prof[0] == '1';
+  if (dev->profile)
+    for (auto& ev : dev->ev) CU(cudaEventCreate(&ev));
+  *out = dev;
+  return SLV_OK;
+}
+
+void slv_device_destroy(slv_device dev) {
+  if (!dev) return;
+  cudaSetDevice(dev->ordinal);
+  cudaStreamSynchronize(dev->stream);
+  for (auto& r : dev->res) {
+    if (r.kind == Resource::BUFFER) cudaFree(r.dptr);
+    if (r.kind == Resource::TEXTURE)
+      for (uint32_t l = 0; l < r.tex.n_levels; ++l) cudaFree(r.tex.level[l].data);
+  }
+  cudaFree(dev->tris);
+  cudaFree(dev->tile_count);
+  cudaFree(dev->tile_offset);
+  cudaFree(dev->tile_cursor);
+  cudaFree(dev->list);
+  cudaFree(dev->overflow_flag);
+  cudaFree(dev->d_stats);
+  if (dev->profile)
+    for (auto& ev : dev->ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(dev->stream);
+  delete dev;
+}
+
+slv_result slv_buffer_create(slv_device dev, size_t bytes, slv_handle* out) {
+  if (!dev || !out) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  Resource r;
+  r.kind = Resource::BUFFER;
+  r.bytes = bytes;
+  if (cudaMalloc(&r.dptr, std::max<size_t>(bytes, 16)) != cudaSuccess) return SLV_OUT_OF_MEMORY;
+  dev->res.push_back(r);
+  *out = (slv_handle)(dev->res.size() - 1);
+  return SLV_OK;
+}
+
+slv_result slv_buffer_upload(slv_device dev, slv_handle h, size_t off, const void* src, size_t bytes) {
+  auto r = dev ? dev->get(h, Resource::BUFFER) : nullptr;
+  if (!r || off + bytes > r->bytes) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  CU(cudaMemcpyAsync(r->dptr + off, src, bytes, cudaMemcpyHostToDevice, dev->stream));
+  return SLV_OK;
+}
+
+slv_result slv_buffer_readback(slv_device dev, slv_handle h, size_t off, void* dst, size_t bytes) {
+  auto r = dev ? dev->get(h, Resource::BUFFER) : nullptr;
+  if (!r || off + bytes > r->bytes) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  CU(cudaMemcpyAsync(dst, r->dptr + off, bytes, cudaMemcpyDeviceToHost, dev->stream));
+  CU(cudaStreamSynchronize(dev->stream));
+  return SLV_OK;
+}
+
+static slv_result alloc_level(SurfaceRef& s, uint32_t w, uint32_t h, uint32_t samples, uint32_t fmt) {
+  s.w = w; s.h = h; s.samples = samples; s.fmt = fmt; s.bpp = bpp_of(fmt);
+  s.bytes = (size_t)w * h * samples * s.bpp;
+  if (cudaMalloc(&s.data, std::max<size_t>(s.bytes, 16)) != cudaSuccess) return SLV_OUT_OF_MEMORY;
+  return SLV_OK;
+}
+
+slv_result slv_texture_create(slv_device dev, uint32_t w, uint32_t h, uint32_t samples, uint32_t fmt, slv_handle* out) {
+  if (!dev || !out || !bpp_of(fmt) || !w || !h || !samples) return SLV_INVALID_PARAMETER;
+  if (w > SLV_MAX_RENDER_TARGET_SIZE || h > SLV_MAX_RENDER_TARGET_SIZE) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  Resource r;
+  r.kind = Resource::TEXTURE;
+  r.fmt = fmt;
+  r.samples = samples;
+  r.tex.n_levels = 1;
+  slv_result rc = alloc_level(r.tex.level[0], w, h, samples, fmt);
+  if (rc != SLV_OK) return rc;
+  CU(cudaMemsetAsync(r.tex.level[0].data, 0, r.tex.level[0].bytes, dev->stream));
+  dev->res.push_back(r);
+  *out = (slv_handle)(dev->res.size() - 1);
+  return SLV_OK;
+}
+
+slv_result slv_texture_gen_mipmap(slv_device dev, slv_handle h, uint32_t filter) {
+  auto r = dev ? dev->get(h, Resource::TEXTURE) : nullptr;
+  if (!r || (filter != SLV_FILTER_POINT && filter != SLV_FILTER_LINEAR)) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  CU(cudaStreamSynchronize(dev->stream));
+  for (uint32_t l = 1; l < r->tex.n_levels; ++l) CU(cudaFree(r->tex.level[l].data));
+  r->tex.n_levels = 1;
+  uint32_t m = std::max(r->tex.level[0].w, r->tex.level[0].h);
+  uint32_t limit = 0;  // texture::calc_lod_limit (texture.h:26-35)
+  while (m > 0) { m >>= 1; ++limit; }
+  for (uint32_t l = 0; l + 1 < limit && l + 1 < (uint32_t)MAX_LEVELS; ++l) {
+    const SurfaceRef src = r->tex.level[l];
+    SurfaceRef& dst = r->tex.level[l + 1];
+    slv_result rc = alloc_level(dst, (src.w + 1) / 2, (src.h + 1) / 2, src.samples, src.fmt);
+    if (rc != SLV_OK) return rc;
+    dim3 blk(16, 16), grd((dst.w + 15) / 16, (dst.h + 15) / 16);
+    k_mipgen<<<grd, blk, 0, dev->stream>>>(src, dst, filter);
+    ++dev->n_launches;
+    r->tex.n_levels = l + 2;
+  }
+  CU(cudaGetLastError());
+  return SLV_OK;
+}
+
+slv_result slv_texture_level_count(slv_device dev, slv_handle h, uint32_t* out) {
+  auto r = dev ? dev->get(h, Resource::TEXTURE) : nullptr;
+  if (!r || !out) return SLV_INVALID_PARAMETER;
+  *out = r->tex.n_levels;
+  return SLV_OK;
+}
+
+slv_result slv_texture_level_size(slv_device dev, slv_handle h, uint32_t level, uint32_t* w, uint32_t* hh) {
+  auto r = dev ? dev->get(h, Resource::TEXTURE) : nullptr;
+  if (!r || level >= r->tex.n_levels) return SLV_INVALID_PARAMETER;
+  *w = r->tex.level[level].w;
+  *hh = r->tex.level[level].h;
+  return SLV_OK;
+}
+
+slv_result slv_texture_upload(slv_device dev, slv_handle h, uint32_t level, const void* src, size_t bytes) {
+  auto r = dev ? dev->get(h, Resource::TEXTURE) : nullptr;
+  if (!r || level >= r->tex.n_levels || bytes != r->tex.level[level].bytes) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  CU(cudaMemcpyAsync(r->tex.level[level].data, src, bytes, cudaMemcpyHostToDevice, dev->stream));
+  return SLV_OK;
+}
+
+slv_result slv_texture_readback(slv_device dev, slv_handle h, uint32_t level, void* dst, size_t bytes) {
+  auto r = dev ? dev->get(h, Resource::TEXTURE) : nullptr;
+  if (!r || level >= r->tex.n_levels || bytes != r->tex.level[level].bytes) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  CU(cudaMemcpyAsync(dst, r->tex.level[level].data, bytes, cudaMemcpyDeviceToHost, dev->stream));
+  CU(cudaStreamSynchronize(dev->stream));
+  return check_overflow(dev);
+}
+
+slv_result slv_sampler_create(slv_device dev, const slv_sampler_desc* d, slv_handle tex, slv_handle* out) {
+  if (!dev || !d || !out || !dev->get(tex, Resource::TEXTURE)) return SLV_INVALID_PARAMETER;
+  if (d->min_filter > SLV_FILTER_LINEAR || d->mag_filter > SLV_FILTER_LINEAR || d->mip_filter > SLV_FILTER_ANISOTROPIC ||
+      d->addr_mode_u > SLV_ADDR_BORDER || d->addr_mode_v > SLV_ADDR_BORDER || d->mip_qual > SLV_MIP_HI_QUALITY)
+    return SLV_INVALID_PARAMETER;
+  Resource r;
+  r.kind = Resource::SAMPLER;
+  r.sd = *d;
+  r.sampler_tex = tex;
+  dev->res.push_back(r);
+  *out = (slv_handle)(dev->res.size() - 1);
+  return SLV_OK;
+}
+
+slv_result slv_resource_release(slv_device dev, slv_handle h) {
+  if (!dev || h == 0 || h >= dev->res.size()) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  CU(cudaStreamSynchronize(dev->stream));
+  Resource& r = dev->res[h];
+  if (r.kind == Resource::BUFFER) CU(cudaFree(r.dptr));
+  if (r.kind == Resource::TEXTURE)
+    for (uint32_t l = 0; l < r.tex.n_levels; ++l) CU(cudaFree(r.tex.level[l].data));
+  r = Resource();
+  return SLV_OK;
+}
+
+static bool fill_sampler(slv_device dev, slv_handle h, SamplerRef& out) {
+  auto r = dev->get(h, Resource::SAMPLER);
+  if (!r) return false;
+  auto t = dev->get(r->sampler_tex, Resource::TEXTURE);
+  if (!t) return false;
+  out.d = r->sd;
+  out.tex = t->tex;
+  return true;
+}
+
+slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
+  if (!dev || !d) return SLV_INVALID_PARAMETER;
+  if (dev->failed) return SLV_FAILED;
+  CU(cudaSetDevice(dev->ordinal));
+  // ---- validation that the reference performs (renderer_impl.cpp:49-54,71-78,145-152,159-238)
+  if (d->topology != SLV_TOPO_TRIANGLE_LIST && d->topology != SLV_TOPO_TRIANGLE_STRIP) return SLV_FAILED;
+  if (d->index_buffer && d->index_format != SLV_INDEX_R16_UINT && d->index_format != SLV_INDEX_R32_UINT) return SLV_FAILED;
+  const slv_viewport& vp = d->viewport;
+  if (vp.x < 0 || vp.y < 0 || vp.w >= SLV_MAX_RENDER_TARGET_SIZE || vp.h >= SLV_MAX_RENDER_TARGET_SIZE) return SLV_FAILED;
+  if (d->n_color_targets >= SLV_MAX_RENDER_TARGETS) return SLV_FAILED;
+  if (d->n_streams > 8 || d->n_elements > SLV_MAX_VS_INPUT_ATTRS) return SLV_INVALID_PARAMETER;
+  uint32_t n_attrs = vs_num_attrs(d->vs);
+  if (n_attrs > SLV_MAX_VS_OUTPUT_ATTRS) return SLV_INVALID_PARAMETER;
+
+  RasterParams rp{};
+  float tw = FLT_MAX, th = FLT_MAX;
+  uint32_t S = 0;
+  for (uint32_t i = 0; i < d->n_color_targets; ++i) {
+    SurfaceRef s = surface_of(dev, d->color_targets[i]);
+    if (i == 0) rp.color0 = s;
+    if (i == 1) rp.color1 = s;
+    if (s.data) {
+      tw = std::min((float)s.w, tw);
+      th = std::min((float)s.h, th);
+      if (S == 0) S = s.samples;
+      else if (S != s.samples) return SLV_FAILED;
+    }
+  }
+  if (d->ds_target) {
+    auto r = dev->get(d->ds_target, Resource::TEXTURE);
+    if (!r || r->fmt != SLV_PF_RG32F) return SLV_FAILED;
+    rp.ds = r->tex.level[0];
+    if (d->n_color_targets == 0) { S = rp.ds.samples; tw = (float)rp.ds.w; th = (float)rp.ds.h; }
+    if ((float)rp.ds.w < tw || (float)rp.ds.h < th || rp.ds.samples != S) return SLV_FAILED;
+  }
+  if ((d->n_color_targets == 0 || !rp.color0.data) && !rp.ds.data) return SLV_FAILED;
+  if (S != 1 && S != 2 && S != 4) return SLV_INVALID_PARAMETER;
+  if (rp.color1.data && (rp.color1.w != rp.color0.w || rp.color1.h != rp.color0.h)) return SLV_INVALID_PARAMETER;
+  rp.target_w = (uint32_t)tw;
+  rp.target_h = (uint32_t)th;
+
+  // ---- geometry parameters
+  GeomParams gp{};
+  for (uint32_t i = 0; i < d->n_streams; ++i) {
+    auto r = dev->get(d->streams[i].buffer, Resource::BUFFER);
+    if (!r) return SLV_INVALID_PARAMETER;
+    gp.streams[i].data = r->dptr;
+    gp.streams[i].stride = d->streams[i].stride;
+    gp.streams[i].offset = d->streams[i].offset;
+  }
+  gp.n_elements = d->n_elements;
+  for (uint32_t i = 0; i < d->n_elements; ++i) {
+    gp.elements[i] = d->elements[i];
+    if (d->elements[i].slot >= d->n_streams || d->elements[i].reg >= SLV_MAX_VS_INPUT_ATTRS) return SLV_INVALID_PARAMETER;
+  }
+  if (d->index_buffer) {
+    auto r = dev->get(d->index_buffer, Resource::BUFFER);
+    if (!r) return SLV_INVALID_PARAMETER;
+    gp.indices = r->dptr;
+    gp.index_stride = d->index_format == SLV_INDEX_R16_UINT ? 2 : 4;
+  }
+  gp.topology = d->topology;
+  gp.start = d->start;
+  gp.prim_count = d->prim_count;
+  gp.base_vertex = d->base_vertex;
+  gp.vs_program = d->vs.program;
+  memcpy(gp.vs_uniforms, d->vs.uniforms, sizeof(gp.vs_uniforms));
+  gp.n_attrs = n_attrs;
+  rp.has_centroid = 0;
+  for (uint32_t i = 0; i < SLV_MAX_VS_OUTPUT_ATTRS; ++i) {
+    gp.mods[i] = rp.mods[i] = d->vs_attr_modifiers[i] ? d->vs_attr_modifiers[i] : (uint32_t)SLV_AM_LINEAR;
+    if (i < n_attrs && (gp.mods[i] & SLV_AM_CENTROID)) rp.has_centroid = 1;
+  }
+  gp.cull_mode = d->raster.cull_mode;
+  gp.front_ccw = d->raster.front_ccw;
+  gp.vp = vp;
+  // tile grid (rasterizer.cpp:1106-1108)
+  gp.tiles_x = (uint32_t)(static_cast<size_t>(vp.w + SLV_TILE_SIZE - 1) / SLV_TILE_SIZE);
+  gp.tiles_y = (uint32_t)(static_cast<size_t>(vp.h + SLV_TILE_SIZE - 1) / SLV_TILE_SIZE);
+  const uint32_t n_tiles = gp.tiles_x * gp.tiles_y;
+  gp.shard_rank = dev->shard_rank;
+  gp.shard_n = dev->shard_n;
+
+  // counters that are pure functions of the arguments (default_vertex_cache.cpp:354-364,
+  // geom_setup_engine.cpp:103, rasterizer.cpp:1137)
+  dev->host_stats.ia_vertices += 3ull * d->prim_count;
+  dev->host_stats.ia_primitives += d->prim_count;
+  dev->host_stats.vs_invocations += 3ull * d->prim_count;  // no post-transform cache: VS recomputed per corner
+  dev->host_stats.cinvocations += d->prim_count;
+  if (d->prim_count == 0 || n_tiles == 0) return SLV_OK;
+
+  const uint32_t R = 1 + n_attrs;
+  const uint32_t tri_stride = TRI_HEADER + 3 * R;
+  const uint64_t n_slots64 = 3ull * d->prim_count;
+  if (n_slots64 >= (1ull << 30)) return SLV_INVALID_PARAMETER;
+  const uint32_t n_slots = (uint32_t)n_slots64;
+  uint32_t list_needed = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(8ull * n_slots, 1u << 22), 1ull << 30);
+  slv_result rc = ensure_scratch(dev, (size_t)n_slots * tri_stride, n_tiles, list_needed);
+  if (rc != SLV_OK) return rc;
+  gp.tris = dev->tris;
+  gp.tri_stride = tri_stride;
+  gp.tile_count = dev->tile_count;
+  gp.stats = dev->d_stats;
+
+  // ---- depth/stencil function selection (framebuffer.cpp:325-425)
+  const slv_depth_stencil_desc& ds = d->ds;
+  rp.depth_enable = ds.depth_enable != 0;
+  rp.depth_func = ds.depth_func;
+  rp.stencil_enable = ds.stencil_enable != 0;
+  rp.read_depth = rp.write_depth = 0;
+  if (rp.ds.data && ds.depth_enable) {
+    if (ds.depth_func != SLV_CMP_NEVER && ds.depth_func != SLV_CMP_ALWAYS) rp.read_depth = 1;
+    if (ds.depth_write_mask && ds.depth_func != SLV_CMP_NEVER) rp.write_depth = 1;
+  }
+  if (!rp.ds.data) rp.stencil_enable = 0;
+  rp.early_z = !ds.stencil_enable;
+  rp.read_mask = ds.stencil_read_mask & 0xFF;
+  rp.write_mask = ds.stencil_write_mask & 0xFF;
+  rp.stencil_ref = ds.stencil_enable ? ((uint32_t)d->stencil_ref & rp.read_mask) : 0;
+  rp.front_face = ds.front_face;
+  rp.back_face = ds.back_face;
+  rp.ps_program = d->ps.program;
+  rp.bs_program = d->bs.program;
+  if (rp.bs_program < SLV_BS_REPLACE || rp.bs_program > SLV_BS_REPLACE_AND_COUNT) return SLV_INVALID_PARAMETER;
+  memcpy(rp.ps_uniforms, d->ps.uniforms, sizeof(rp.ps_uniforms));
+  bool needs_sampler = rp.ps_program == SLV_PS_TEX_ALPHA || rp.ps_program == SLV_PS_TEX_GRAD_ALPHA ||
+                       (rp.ps_program == SLV_PS_SPONZA &&
+                        reinterpret_cast<const slv_ps_sponza_uniforms*>(d->ps.uniforms)->has_sampler);
+  if (needs_sampler && !fill_sampler(dev, d->ps.samplers[0], rp.sampler0)) return SLV_INVALID_PARAMETER;
+  if (rp.ps_program == SLV_PS_TEX_ALPHA || rp.ps_program == SLV_PS_TEX_GRAD_ALPHA) {
+    if (reinterpret_cast<const slv_ps_tex_alpha_uniforms*>(d->ps.uniforms)->reg >= n_attrs) return SLV_INVALID_PARAMETER;
+  }
+  if ((rp.ps_program == SLV_PS_LIGHTS3 || rp.ps_program == SLV_PS_SPONZA) && n_attrs < 4) return SLV_INVALID_PARAMETER;
+  if ((rp.ps_program == SLV_PS_ATTR0_COLOR || rp.ps_program == SLV_PS_DISCARD_ALL) && n_attrs < 1) return SLV_INVALID_PARAMETER;
+  rp.tris = dev->tris;
+  rp.tri_stride = tri_stride;
+  rp.tiles_x = gp.tiles_x;
+  rp.tiles_y = gp.tiles_y;
+  rp.shard_rank = dev->shard_rank;
+  rp.shard_n = dev->shard_n;
+  rp.tile_offset = dev->tile_offset;
+  rp.list = dev->list;
+  rp.list_capacity = dev->list_cap;
+  rp.n_attrs = n_attrs;
+  rp.stats = dev->d_stats;
+
+  BinParams bp{};
+  bp.tris = dev->tris;
+  bp.tri_stride = tri_stride;
+  bp.n_slots = n_slots;
+  bp.tiles_x = gp.tiles_x;
+  bp.tiles_y = gp.tiles_y;
+  bp.shard_rank = dev->shard_rank;
+  bp.shard_n = dev->shard_n;
+  bp.tile_offset = dev->tile_offset;
+  bp.tile_cursor = dev->tile_cursor;
+  bp.list = dev->list;
+  bp.list_capacity = dev->list_cap;
+  bp.overflow_flag = dev->overflow_flag;
+
+  // ---- the kernel graph of one draw
+  cudaStream_t st = dev->stream;
+  if (dev->profile) CU(cudaEventRecord(dev->ev[0], st));
+  switch (R) {
+  case 1: launch_geometry<1>(gp, st); break;
+  case 2: launch_geometry<2>(gp, st); break;
+  case 3: launch_geometry<3>(gp, st); break;
+  case 4: launch_geometry<4>(gp, st); break;
+  case 5: launch_geometry<5>(gp, st); break;
+  default: launch_geometry<6>(gp, st); break;
+  }
+  if (dev->profile) CU(cudaEventRecord(dev->ev[1], st));
+  k_scan_tiles<<<1, 1024, 0, st>>>(dev->tile_count, dev->tile_offset, dev->tile_cursor, n_tiles);
+  k_bin_fill<<<(n_slots + 255) / 256, 256, 0, st>>>(bp);
+  if (dev->profile) CU(cudaEventRecord(dev->ev[2], st));
+  k_sort_lists<<<n_tiles, 256, 0, st>>>(dev->tile_offset, dev->list, dev->list_cap);
+  if (dev->profile) CU(cudaEventRecord(dev->ev[3], st));
+  bool ok = false;
+  const uint32_t blocks = n_tiles * 16;
+  switch (S) {
+  case 1: ok = launch_raster_s<1>(rp, blocks, st); break;
+  case 2: ok = launch_raster_s<2>(rp, blocks, st); break;
+  case 4: ok = launch_raster_s<4>(rp, blocks, st); break;
+  }
+  if (!ok) return SLV_INVALID_PARAMETER;
+  dev->n_launches += 5;
+  CU(cudaGetLastError());
+  if (dev->profile) {
+    CU(cudaEventRecord(dev->ev[4], st));
+    CU(cudaEventSynchronize(dev->ev[4]));
+    for (int i = 0; i < 4; ++i) {
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, dev->ev[i], dev->ev[i + 1]));
+      dev->prof_ms[i] += ms;
+    }
+  }
+  return SLV_OK;
+}
+
+static slv_result fill_surface(slv_device dev, const SurfaceRef& s, uint4 pattern) {
+  size_t n_vec = s.bytes / 16, n_words = s.bytes / 4;
+  if (n_vec) {
+    uint32_t blocks = (uint32_t)std::min<size_t>((n_vec + 255) / 256, 148 * 16);
+    k_fill<<<blocks, 256, 0, dev->stream>>>(reinterpret_cast<uint4*>(s.data), n_vec, pattern);
+    ++dev->n_launches;
+  }
+  if (n_words > n_vec * 4) {
+    k_fill_words<<<1, 32, 0, dev->stream>>>(reinterpret_cast<uint32_t*>(s.data), n_vec * 4, n_words, pattern);
+    ++dev->n_launches;
+  }
+  CU(cudaGetLastError());
+  return SLV_OK;
+}
+
+slv_result slv_clear_color(slv_device dev, slv_handle h, const float rgba[4]) {
+  auto r = dev ? dev->get(h, Resource::TEXTURE) : nullptr;
+  if (!r || !rgba) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  const SurfaceRef& s = r->tex.level[0];
+  uint32_t w[4];
+  switch (s.fmt) {  // from_rgba32 conversion done once (surface.cpp:170-173)
+  case SLV_PF_RGBA32F: memcpy(w, rgba, 16); break;
+  case SLV_PF_RG32F: memcpy(w, rgba, 8); w[2] = w[0]; w[3] = w[1]; break;
+  case SLV_PF_RGBA8: {
+    uint32_t p = host_unorm8(rgba[0]) | (host_unorm8(rgba[1]) << 8) | (host_unorm8(rgba[2]) << 16) | ((uint32_t)host_unorm8(rgba[3]) << 24);
+    w[0] = w[1] = w[2] = w[3] = p;
+  } break;
+  default: {
+    uint32_t p = host_unorm8(rgba[2]) | (host_unorm8(rgba[1]) << 8) | (host_unorm8(rgba[0]) << 16) | ((uint32_t)host_unorm8(rgba[3]) << 24);
+    w[0] = w[1] = w[2] = w[3] = p;
+  } break;
+  }
+  return fill_surface(dev, s, make_uint4(w[0], w[1], w[2], w[3]));
+}
+
+slv_result slv_clear_depth_stencil(slv_device dev, slv_handle h, uint32_t flags, float depth, uint32_t stencil) {
+  auto r = dev ? dev->get(h, Resource::TEXTURE) : nullptr;
+  if (!r || r->fmt != SLV_PF_RG32F) return SLV_INVALID_PARAMETER;
+  if (!(flags & (SLV_CLEAR_DEPTH | SLV_CLEAR_STENCIL))) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  const SurfaceRef& s = r->tex.level[0];
+  if ((flags & 3) == 3) {
+    uint32_t dbits;
+    memcpy(&dbits, &depth, 4);
+    return fill_surface(dev, s, make_uint4(dbits, stencil, dbits, stencil));
+  }
+  size_t n = s.bytes / 8;
+  uint32_t blocks = (uint32_t)std::min<size_t>((n + 255) / 256, 148 * 16);
+  k_clear_ds_partial<<<blocks, 256, 0, dev->stream>>>(reinterpret_cast<float2*>(s.data), n, flags, depth, stencil);
+  ++dev->n_launches;
+  CU(cudaGetLastError());
+  return SLV_OK;
+}
+
+slv_result slv_resolve(slv_device dev, slv_handle src, slv_handle dst) {
+  auto rs = dev ? dev->get(src, Resource::TEXTURE) : nullptr;
+  auto rd = dev ? dev->get(dst, Resource::TEXTURE) : nullptr;
+  if (!rs || !rd) return SLV_INVALID_PARAMETER;
+  const SurfaceRef& s = rs->tex.level[0];
+  const SurfaceRef& t = rd->tex.level[0];
+  if (t.samples != 1 || t.w < s.w || t.h < s.h) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  dim3 blk(32, 8), grd((s.w + 31) / 32, (s.h + 7) / 8);
+  k_resolve<<<grd, blk, 0, dev->stream>>>(s, t);
+  ++dev->n_launches;
+  CU(cudaGetLastError());
+  return SLV_OK;
+}
+
+slv_result slv_flush(slv_device dev) {
+  if (!dev) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  CU(cudaStreamSynchronize(dev->stream));
+  return check_overflow(dev);
+}
+
+slv_result slv_query_begin(slv_device dev) {
+  if (!dev) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  dev->host_stats = slv_pipeline_statistics{};
+  CU(cudaMemsetAsync(dev->d_stats, 0, 9 * sizeof(unsigned long long), dev->stream));
+  for (auto& m : dev->prof_ms) m = 0;
+  dev->n_launches = 0;
+  return SLV_OK;
+}
+
+slv_result slv_query_get(slv_device dev, slv_pipeline_statistics* out) {
+  if (!dev || !out) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  unsigned long long h[9];
+  CU(cudaMemcpyAsync(h, dev->d_stats, sizeof(h), cudaMemcpyDeviceToHost, dev->stream));
+  CU(cudaStreamSynchronize(dev->stream));
+  *out = dev->host_stats;
+  out->cprimitives = h[6];
+  out->ps_invocations = h[7];
+  out->backend_input_pixels = h[8];
+  out->gs_invocations = dev->n_launches;  // no geometry shader stage exists: repurposed as "kernels launched"
+  return check_overflow(dev);
+}
+
+slv_result slv_profile_get(slv_device dev, slv_pipeline_profiles* out) {
+  if (!dev || !out) return SLV_INVALID_PARAMETER;
+  memset(out, 0, sizeof(*out));
+  out->clipping = (uint64_t)(dev->prof_ms[0] * 1e6);      // VS + clip + viewport + setup are one kernel
+  out->tri_dispatch = (uint64_t)((dev->prof_ms[1] + dev->prof_ms[2]) * 1e6);
+  out->ras = (uint64_t)(dev->prof_ms[3] * 1e6);
+  return SLV_OK;
+}
+
+slv_result slv_set_tile_shard(slv_device dev, uint32_t rank, uint32_t nranks) {
+  if (!dev || nranks == 0 || rank >= nranks) return SLV_INVALID_PARAMETER;
+  dev->shard_rank = rank;
+  dev->shard_n = nranks;
+  return SLV_OK;
+}
+
+slv_result slv_sampler_probe(slv_device dev, slv_handle sh, uint32_t n, const float* coords, const float* ddx,
+                             const float* ddy, const float* lod, uint32_t use_lod, float* out) {
+  if (!dev || !coords || !out) return SLV_INVALID_PARAMETER;
+  SamplerRef sm{};
+  if (!fill_sampler(dev, sh, sm)) return SLV_INVALID_PARAMETER;
+  if (n == 0) return SLV_OK;
+  CU(cudaSetDevice(dev->ordinal));
+  float *d_c = nullptr, *d_dx = nullptr, *d_dy = nullptr, *d_l = nullptr;
+  float4* d_o = nullptr;
+  CU(cudaMalloc(&d_c, n * 8));
+  CU(cudaMalloc(&d_dx, n * 8));
+  CU(cudaMalloc(&d_dy, n * 8));
+  CU(cudaMalloc(&d_l, n * 4));
+  CU(cudaMalloc(&d_o, n * 16));
+  cudaStream_t st = dev->stream;
+  CU(cudaMemcpyAsync(d_c, coords, n * 8, cudaMemcpyHostToDevice, st));
+  if (ddx) CU(cudaMemcpyAsync(d_dx, ddx, n * 8, cudaMemcpyHostToDevice, st));
+  if (ddy) CU(cudaMemcpyAsync(d_dy, ddy, n * 8, cudaMemcpyHostToDevice, st));
+  if (lod) CU(cudaMemcpyAsync(d_l, lod, n * 4, cudaMemcpyHostToDevice, st));
+  k_sampler_probe<<<(n + 127) / 128, 128, 0, st>>>(sm, n, d_c, d_dx, d_dy, d_l, use_lod, d_o);
+  ++dev->n_launches;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, d_o, n * 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  cudaFree(d_c); cudaFree(d_dx); cudaFree(d_dy); cudaFree(d_l); cudaFree(d_o);
+  return SLV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,214 @@
+// slv_common.cuh — device-side data layout and exact-arithmetic helpers of the B200 SALVIA pipeline.
+//
+// Numerics contract: every float op is issued un-fused and in the reference's
+// association order.  This translation unit is compiled with
+//   -fmad=false -prec-div=true -prec-sqrt=true -ftz=false
+// so `a*b + c` is a rounded multiply followed by a rounded add, `/` and sqrtf are IEEE-correct and
+// denormals are kept — the same results as the reference's x86-64 SSE2 build (no FMA).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "salvia_b200.h"
+
+namespace slv {
+
+constexpr int MAX_REGS = 1 + SLV_MAX_VS_OUTPUT_ATTRS;  // position + attributes of a vs_output
+constexpr int TILE = SLV_TILE_SIZE;                    // reference tile, 64x64 px (rasterizer.cpp:32)
+constexpr int REGION = 16;                             // one raster CTA = one level-16 child of a tile
+constexpr int RASTER_THREADS = REGION * REGION;        // thread == pixel
+constexpr int MAX_LEVELS = 14;                         // 8192 -> 1
+
+// ---- resources -------------------------------------------------------------------------------------
+struct SurfaceRef {  // reference layout: ((y*W + x)*S + s)*bpp (surface.cpp:277-295)
+  uint8_t* data;
+  uint32_t w, h, samples, fmt, bpp;
+  size_t bytes;
+};
+
+struct TextureRef {
+  SurfaceRef level[MAX_LEVELS];
+  uint32_t n_levels;
+};
+
+struct SamplerRef {
+  slv_sampler_desc d;
+  TextureRef tex;
+};
+
+// ---- per-draw parameter block (passed by value to the kernels; < 4 KB) ------------------------------
+struct StreamRef {
+  const uint8_t* data;
+  uint32_t stride, offset;
+};
+
+struct GeomParams {
+  StreamRef streams[8];
+  slv_input_element elements[SLV_MAX_VS_INPUT_ATTRS];
+  uint32_t n_elements;
+  const uint8_t* indices;  // nullptr for draw()
+  uint32_t index_stride;   // 2 or 4
+  uint32_t topology, start, prim_count;
+  int32_t base_vertex;
+  uint32_t vs_program;
+  uint8_t vs_uniforms[128];  // the largest VS uniform block is slv_vs_lights3_uniforms (112 B)
+  uint32_t n_attrs;
+  uint32_t mods[SLV_MAX_VS_OUTPUT_ATTRS];
+  uint32_t cull_mode, front_ccw;
+  slv_viewport vp;
+  uint32_t tiles_x, tiles_y;
+  uint32_t shard_rank, shard_n;
+  // outputs
+  float4* tris;            // triangle records, slot = prim*3 + k, stride tri_stride float4
+  uint32_t tri_stride;
+  uint32_t* tile_count;    // [tiles]
+  unsigned long long* stats;  // slv_pipeline_statistics as 9 x u64
+};
+
+// triangle record (float4 units): [0..2] edge A,B,C,0  [3] bbox xmin,xmax,ymin,ymax
+// [4] misc: x = as_uint(valid | front<<1), y = sx | ex<<16, z = sy | ey<<16 (tile range)
+// [5 .. 5+R) v0 regs   [5+R .. 5+2R) ddx regs   [5+2R .. 5+3R) ddy regs, R = 1 + n_attrs
+constexpr int TRI_HEADER = 5;
+
+struct BinParams {
+  const float4* tris;
+  uint32_t tri_stride, n_slots;  // n_slots = prim_count * 3
+  uint32_t tiles_x, tiles_y;
+  uint32_t shard_rank, shard_n;
+  const uint32_t* tile_offset;  // [tiles + 1]
+  uint32_t* tile_cursor;        // [tiles]
+  uint32_t* list;               // entries (slot << 1) | accept
+  uint32_t list_capacity;
+  uint32_t* overflow_flag;
+};
+
+struct RasterParams {
+  const float4* tris;
+  uint32_t tri_stride;
+  uint32_t tiles_x, tiles_y;
+  uint32_t shard_rank, shard_n;
+  const uint32_t* tile_offset;
+  const uint32_t* list;
+  uint32_t list_capacity;
+  uint32_t n_attrs;
+  uint32_t mods[SLV_MAX_VS_OUTPUT_ATTRS];
+  uint32_t has_centroid;
+  // targets
+  SurfaceRef color0, color1, ds;  // data == nullptr when unbound
+  uint32_t target_w, target_h;    // min over colour targets (renderer_impl.cpp:159-238)
+  // depth-stencil state (framebuffer.cpp:358-425 resolved on the host)
+  uint32_t depth_enable, depth_func, read_depth, write_depth, stencil_enable, early_z;
+  uint32_t stencil_ref, read_mask, write_mask;
+  slv_stencil_op_desc front_face, back_face;
+  // shaders
+  uint32_t ps_program, bs_program;
+  uint8_t ps_uniforms[16];
+  SamplerRef sampler0;
+  unsigned long long* stats;
+};
+
+// ---- exact float helpers (eflib/include/eflib/math/math.h:89-164) ------------------------------------
+__device__ __forceinline__ float fast_log2(float val) {
+  int x = __float_as_int(val);
+  int log_2 = ((x >> 23) & 255) - 128;
+  x &= ~(255 << 23);
+  x += 127 << 23;
+  float f = __int_as_float(x);
+  f = ((-1.0f / 3) * f + 2) * f - 2.0f / 3;
+  return f + (float)log_2;
+}
+
+__device__ __forceinline__ float fast_round(float val) {
+  int n = __float_as_int(val);
+  float bias = __int_as_float(((23 + 127) << 23) + (n & 0x80000000));
+  float t = __fadd_rn(val, bias);
+  return __fsub_rn(t, bias);
+}
+
+__device__ __forceinline__ float fast_floor(float val) {
+  float f = fast_round(val);
+  return (f > val) ? f - 1 : f;
+}
+
+__device__ __forceinline__ int fast_roundi(double d) { return (int)floor(d + 0.5); }
+#define SLV_MAGIC_EPS ((double)0.5f - 1.5e-8)
+__device__ __forceinline__ int fast_ceili(double d) { return fast_roundi(d + SLV_MAGIC_EPS); }
+__device__ __forceinline__ int fast_floori(double d) { return fast_roundi(d - SLV_MAGIC_EPS); }
+
+__device__ __forceinline__ bool eq_eps(float a, float b) { return fabsf(a - b) <= 1.1920928955078125e-7f; }
+
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+  return ax * bx + ay * by + az * bz;
+}
+__device__ __forceinline__ float length3(float x, float y, float z) {
+  float t = 0.0f;
+  t += x * x;
+  t += y * y;
+  t += z * z;
+  return sqrtf(t);
+}
+__device__ __forceinline__ float length2(float x, float y) {
+  float t = 0.0f;
+  t += x * x;
+  t += y * y;
+  return sqrtf(t);
+}
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (hi < v ? hi : v); }
+__device__ __forceinline__ float std_min(float a, float b) { return (b < a) ? b : a; }
+__device__ __forceinline__ float std_max(float a, float b) { return (a < b) ? b : a; }
+
+__device__ __forceinline__ float4 f4_sub(float4 a, float4 b) {
+  return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+}
+__device__ __forceinline__ float f4_get(const float4& v, int i) {
+  return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+
+// float -> unorm8: mul 255, max 0, min 255, cvtps2dq (round-to-nearest-even)  (colors.h:182-192)
+__device__ __forceinline__ uint32_t unorm8_rne(float x) {
+  float m = x * 255.0f;
+  m = (m > 0.0f) ? m : 0.0f;
+  m = (m < 255.0f) ? m : 255.0f;
+  return (uint32_t)__float2int_rn(m);
+}
+
+__device__ __forceinline__ uint32_t pack_color(uint32_t fmt, float4 c) {
+  uint32_t r = unorm8_rne(c.x), g = unorm8_rne(c.y), b = unorm8_rne(c.z), a = unorm8_rne(c.w);
+  return fmt == SLV_PF_RGBA8 ? (r | (g << 8) | (b << 16) | (a << 24)) : (b | (g << 8) | (r << 16) | (a << 24));
+}
+
+__device__ __forceinline__ float4 unpack_color(uint32_t fmt, uint32_t p) {
+  const float inv_255 = 1.0f / 255;
+  float b0 = (float)(p & 0xFF) * inv_255, b1 = (float)((p >> 8) & 0xFF) * inv_255;
+  float b2 = (float)((p >> 16) & 0xFF) * inv_255, b3 = (float)(p >> 24) * inv_255;
+  return fmt == SLV_PF_RGBA8 ? make_float4(b0, b1, b2, b3) : make_float4(b2, b1, b0, b3);
+}
+
+// generic texel <-> rgba32f (colors.h:148-267)
+__device__ __forceinline__ float4 load_texel_rgba32f(uint32_t fmt, const uint8_t* p) {
+  switch (fmt) {
+  case SLV_PF_RGBA32F: return *reinterpret_cast<const float4*>(p);
+  case SLV_PF_RG32F: {
+    float2 v = *reinterpret_cast<const float2*>(p);
+    return make_float4(v.x, v.y, 0.0f, 0.0f);
+  }
+  default: return unpack_color(fmt, *reinterpret_cast<const uint32_t*>(p));
+  }
+}
+
+__device__ __forceinline__ void store_texel_rgba32f(uint32_t fmt, uint8_t* p, float4 c) {
+  switch (fmt) {
+  case SLV_PF_RGBA32F: *reinterpret_cast<float4*>(p) = c; break;
+  case SLV_PF_RG32F: *reinterpret_cast<float2*>(p) = make_float2(c.x, c.y); break;
+  default: *reinterpret_cast<uint32_t*>(p) = pack_color(fmt, c); break;
+  }
+}
+
+}  // namespace slv
+
+static_assert(sizeof(slv_vs_lights3_uniforms) <= 128 && sizeof(slv_vs_sponza_uniforms) <= 128 &&
+                  sizeof(slv_vs_mvp_passthrough_uniforms) <= 128 && sizeof(slv_vs_plane_xz_uniforms) <= 128,
+              "GeomParams::vs_uniforms too small");
+static_assert(sizeof(slv_ps_tex_alpha_uniforms) <= 16 && sizeof(slv_ps_sponza_uniforms) <= 16, "ps_uniforms too small");

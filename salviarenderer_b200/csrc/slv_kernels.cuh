@@ -1,0 +1,1109 @@
+// slv_kernels.cuh — the sm_100a kernels of the draw pipeline.
+//
+//   k_geometry      one thread per input primitive: index fetch, vertex fetch, vertex shader, near/far
+//                   clip, cull, fan, viewport+project, triangle setup, 64x64 tile coverage count.
+//                   (reference phases 1-4: geom_setup_engine.cpp:43-124, clipper.cpp:43-228,
+//                   shader.cpp:499-511, rasterizer.cpp:864-945, 775-862)
+//   k_scan_tiles    exclusive scan of the per-tile counts -> per-tile list offsets
+//   k_bin_fill      one thread per triangle slot: scatter (slot<<1 | accept) into the tile lists
+//   k_sort_lists    one CTA per tile: restore API order (the reference's std::sort, rasterizer.cpp:976)
+//   k_raster<S,PS>  one CTA per 16x16-pixel region (= one level-16 child of the reference's tile
+//                   hierarchy), thread == pixel, all S samples of depth/stencil/colour live in registers
+//                   for the whole draw; triangles are streamed through shared memory in API order.
+//                   (reference phase 5: rasterizer.cpp:617-773, 298-439, 1245-1421, framebuffer.cpp:445-614)
+#pragma once
+
+#include "slv_common.cuh"
+#include "slv_sampler.cuh"
+
+namespace slv {
+
+// =====================================================================================================
+// geometry
+// =====================================================================================================
+template <int R>
+struct VsOut {
+  float4 r[R];
+};
+
+__device__ __forceinline__ float4 fetch_element(const GeomParams& p, const slv_input_element& el, uint32_t index) {
+  const StreamRef& st = p.streams[el.slot];
+  const float* f = reinterpret_cast<const float*>(st.data + el.aligned_byte_offset + (size_t)st.stride * index + st.offset);
+  switch (el.format) {  // get_vec4 (stream_assembler.cpp:26-45)
+  case SLV_FMT_R32_FLOAT: return make_float4(__ldg(f), 0.0f, 0.0f, el.default_w);
+  case SLV_FMT_R32G32_FLOAT: return make_float4(__ldg(f), __ldg(f + 1), 0.0f, el.default_w);
+  case SLV_FMT_R32G32B32_FLOAT: return make_float4(__ldg(f), __ldg(f + 1), __ldg(f + 2), el.default_w);
+  default:
+    if ((reinterpret_cast<uintptr_t>(f) & 15) == 0) return __ldg(reinterpret_cast<const float4*>(f));
+    return make_float4(__ldg(f), __ldg(f + 1), __ldg(f + 2), __ldg(f + 3));
+  }
+}
+
+// pos = v · M (row vector × matrix; eflib/src/math.cpp:142-154)
+__device__ __forceinline__ float4 transform(float4 v, const float* m) {
+  float4 o;
+  o.x = v.x * m[0] + v.y * m[4] + v.z * m[8] + v.w * m[12];
+  o.y = v.x * m[1] + v.y * m[5] + v.z * m[9] + v.w * m[13];
+  o.z = v.x * m[2] + v.y * m[6] + v.z * m[10] + v.w * m[14];
+  o.w = v.x * m[3] + v.y * m[7] + v.z * m[11] + v.w * m[15];
+  return o;
+}
+
+template <int R>
+__device__ __forceinline__ void run_vs(const GeomParams& p, uint32_t index, VsOut<R>& out) {
+  float4 in[SLV_MAX_VS_INPUT_ATTRS];
+#pragma unroll
+  for (int i = 0; i < SLV_MAX_VS_INPUT_ATTRS; ++i) in[i] = make_float4(0, 0, 0, 0);
+  for (uint32_t e = 0; e < p.n_elements; ++e) {
+    float4 v = fetch_element(p, p.elements[e], index);
+    uint32_t reg = p.elements[e].reg;
+#pragma unroll
+    for (int i = 0; i < SLV_MAX_VS_INPUT_ATTRS; ++i)
+      if (reg == (uint32_t)i) in[i] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < R; ++i) out.r[i] = make_float4(0, 0, 0, 0);
+  switch (p.vs_program) {
+  case SLV_VS_MVP_PASSTHROUGH: {
+    auto u = reinterpret_cast<const slv_vs_mvp_passthrough_uniforms*>(p.vs_uniforms);
+    out.r[0] = transform(in[0], u->wvp);
+#pragma unroll
+    for (int i = 1; i < R; ++i) {
+      uint32_t s = u->src[i - 1];
+      float4 v = in[0];
+#pragma unroll
+      for (int k = 1; k < SLV_MAX_VS_INPUT_ATTRS; ++k)
+        if (s == (uint32_t)k) v = in[k];
+      out.r[i] = v;
+    }
+  } break;
+  case SLV_VS_PLANE_XZ: {
+    auto u = reinterpret_cast<const slv_vs_plane_xz_uniforms*>(p.vs_uniforms);
+    out.r[0] = transform(in[0], u->wvp);
+    if (R > 1) out.r[R > 1 ? 1 : 0] = make_float4(in[0].x, in[0].z, 0.0f, 0.0f);
+  } break;
+  case SLV_VS_LIGHTS3: {
+    auto u = reinterpret_cast<const slv_vs_lights3_uniforms*>(p.vs_uniforms);
+    out.r[0] = transform(in[0], u->wvp);
+    if (R == 5) {
+      out.r[R > 1 ? 1 : 0] = in[1];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float4 l = make_float4(u->light_pos[k][0], u->light_pos[k][1], u->light_pos[k][2], u->light_pos[k][3]);
+        out.r[R > 4 ? 2 + k : 0] = f4_sub(l, in[0]);
+      }
+    }
+  } break;
+  case SLV_VS_SPONZA: {
+    auto u = reinterpret_cast<const slv_vs_sponza_uniforms*>(p.vs_uniforms);
+    out.r[0] = transform(in[0], u->wvp);
+    if (R == 5) {
+      out.r[R > 4 ? 1 : 0] = in[1];
+      out.r[R > 4 ? 2 : 0] = in[2];
+      out.r[R > 4 ? 3 : 0] = f4_sub(make_float4(u->light_pos[0], u->light_pos[1], u->light_pos[2], u->light_pos[3]), in[0]);
+      out.r[R > 4 ? 4 : 0] = f4_sub(make_float4(u->eye_pos[0], u->eye_pos[1], u->eye_pos[2], u->eye_pos[3]), in[0]);
+    }
+  } break;
+  }
+}
+
+__device__ __forceinline__ bool cull_tri(uint32_t cull_mode, uint32_t front_ccw, float area) {  // raster_state.cpp:10-31
+  switch (cull_mode) {
+  case SLV_CULL_FRONT: return front_ccw ? (area <= 0) : (area >= 0);
+  case SLV_CULL_BACK: return front_ccw ? (area >= 0) : (area <= 0);
+  default: return false;
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void lerp_vso(const GeomParams& p, VsOut<R>& out, const VsOut<R>& a, const VsOut<R>& b, float t) {
+  // shader.cpp:170-180: start + (end - start) * step; nointerpolation attributes copied from start
+  out.r[0] = make_float4(a.r[0].x + (b.r[0].x - a.r[0].x) * t, a.r[0].y + (b.r[0].y - a.r[0].y) * t,
+                         a.r[0].z + (b.r[0].z - a.r[0].z) * t, a.r[0].w + (b.r[0].w - a.r[0].w) * t);
+#pragma unroll
+  for (int i = 1; i < R; ++i) {
+    float4 s = a.r[i];
+    if (!(p.mods[i - 1] & SLV_AM_NOINTERPOLATION)) {
+      s.x += (b.r[i].x - a.r[i].x) * t;
+      s.y += (b.r[i].y - a.r[i].y) * t;
+      s.z += (b.r[i].z - a.r[i].z) * t;
+      s.w += (b.r[i].w - a.r[i].w) * t;
+    }
+    out.r[i] = s;
+  }
+}
+
+__device__ __forceinline__ float plane_dist(int plane, float4 pos) {
+  // dot_prod4 with (0,0,1,0) / (0,0,-1,1), zero terms included (clipper.cpp:21-27,111)
+  return plane == 0 ? (0.0f * pos.x + 0.0f * pos.y + 1.0f * pos.z + 0.0f * pos.w)
+                    : (0.0f * pos.x + 0.0f * pos.y + -1.0f * pos.z + 1.0f * pos.w);
+}
+
+// viewport_transform + project_n (shader.cpp:499-511, 116-134)
+template <int R>
+__device__ __forceinline__ void viewport_project(const GeomParams& p, VsOut<R>& v) {
+  const slv_viewport& vp = p.vp;
+  float w = v.r[0].w;
+  float invw = eq_eps(w, 0.0f) ? 1.0f : 1.0f / w;
+  float px = v.r[0].x * invw, py = v.r[0].y * invw, pz = v.r[0].z * invw;
+  float ox = (vp.x + vp.w) * 0.5f;
+  float oy = (vp.y + vp.h) * 0.5f;
+  v.r[0].x = (vp.w * 0.5f) * px + ox;
+  v.r[0].y = (vp.h * 0.5f) * -py + oy;
+  v.r[0].z = (vp.maxz - vp.minz) * pz + vp.minz;
+  v.r[0].w = invw;
+#pragma unroll
+  for (int i = 1; i < R; ++i)
+    if (!(p.mods[i - 1] & SLV_AM_NOPERSPECTIVE)) {
+      v.r[i].x *= invw; v.r[i].y *= invw; v.r[i].z *= invw; v.r[i].w *= invw;
+    }
+}
+
+// the reference's tile-level test (rasterizer.cpp:831-848): returns 0 = rejected, 1 = partial, 3 = accepted
+__device__ __forceinline__ int tile_test(const float4 edge[3], int x, int y) {
+  int rejection = 0, acceptance = 1;
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {
+    float A = edge[e].x, B = edge[e].y, C = edge[e].z;
+    int mark_x = A > 0, mark_y = B > 0;
+    float step_x = TILE * A, step_y = TILE * B;
+    float rej_to_acc = -fabsf(step_x) - fabsf(step_y);
+    float ev = C - ((float)(x + mark_x) * TILE * A + (float)(y + mark_y) * TILE * B);
+    rejection |= (0 < ev);
+    acceptance &= (rej_to_acc >= ev);
+  }
+  return rejection ? 0 : (acceptance ? 3 : 1);
+}
+
+struct TileRange { int sx, sy, ex, ey; };
+
+__device__ __forceinline__ TileRange tile_range(const float bbox[4], uint32_t tiles_x, uint32_t tiles_y) {
+  // rasterizer.cpp:800-807 (fast_floori / fast_ceili evaluated in double)
+  TileRange r;
+  r.sx = min(fast_floori((double)(std_max(0.0f, bbox[0]) / TILE)), (int)tiles_x);
+  r.sy = min(fast_floori((double)(std_max(0.0f, bbox[2]) / TILE)), (int)tiles_y);
+  r.ex = min(fast_ceili((double)(std_max(0.0f, bbox[1]) / TILE)) + 1, (int)tiles_x);
+  r.ey = min(fast_ceili((double)(std_max(0.0f, bbox[3]) / TILE)) + 1, (int)tiles_y);
+  return r;
+}
+
+__device__ __forceinline__ bool tile_owned(uint32_t tx, uint32_t ty, uint32_t rank, uint32_t n) {
+  return n <= 1 || ((tx + 3 * ty) % n) == rank;
+}
+
+// rasterizer::compute_triangle_info (rasterizer.cpp:864-945) + record store + tile coverage count
+template <int R>
+__device__ __forceinline__ void setup_triangle(const GeomParams& p, const VsOut<R> v[3], float4* rec) {
+  float4 misc = make_float4(0, 0, 0, 0);
+  double d0 = (double)fabsf(v[0].r[0].x) + (double)fabsf(v[0].r[0].y);
+  double d1 = (double)fabsf(v[1].r[0].x) + (double)fabsf(v[1].r[0].y);
+  double d2 = (double)fabsf(v[2].r[0].x) + (double)fabsf(v[2].r[0].y);
+  int r0;
+  if (d0 < d1) r0 = (d0 < d2) ? 0 : 2;
+  else r0 = (d1 < d2) ? 1 : 2;
+  // rotate (v[r0], v[r0+1], v[r0+2]) without dynamic indexing
+  float4 a[R], b[R], c[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    a[i] = r0 == 0 ? v[0].r[i] : (r0 == 1 ? v[1].r[i] : v[2].r[i]);
+    b[i] = r0 == 0 ? v[1].r[i] : (r0 == 1 ? v[2].r[i] : v[0].r[i]);
+    c[i] = r0 == 0 ? v[2].r[i] : (r0 == 1 ? v[0].r[i] : v[1].r[i]);
+  }
+  float e01x = b[0].x - a[0].x, e01y = b[0].y - a[0].y;
+  float e02x = c[0].x - a[0].x, e02y = c[0].y - a[0].y;
+  float area = e02x * e01y - e02y * e01x;  // cross_prod2(e02.xy, e01.xy)
+  if (eq_eps(area, 0.0f)) {
+    rec[4] = misc;  // invalid (v0 == nullptr upstream)
+    return;
+  }
+  bool front = area > 0.0f;
+  float inv_area = 1.0f / area;
+  float bbox[4];
+  bbox[0] = std_min(std_min(v[0].r[0].x, v[1].r[0].x), v[2].r[0].x);
+  bbox[1] = std_max(std_max(v[0].r[0].x, v[1].r[0].x), v[2].r[0].x);
+  bbox[2] = std_min(std_min(v[0].r[0].y, v[1].r[0].y), v[2].r[0].y);
+  bbox[3] = std_max(std_max(v[0].r[0].y, v[1].r[0].y), v[2].r[0].y);
+  float4 edge[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {  // original vertex order (rasterizer.cpp:928-939)
+    float4 s = v[i].r[0], e = v[(i + 1) % 3].r[0];
+    edge[i] = make_float4(s.y - e.y, e.x - s.x, e.x * s.y - e.y * s.x, 0.0f);
+  }
+  rec[0] = edge[0];
+  rec[1] = edge[1];
+  rec[2] = edge[2];
+  rec[3] = make_float4(bbox[0], bbox[1], bbox[2], bbox[3]);
+  // compute_derivative_n (shader.cpp:413-449)
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    float4 e01 = f4_sub(b[i], a[i]), e02 = f4_sub(c[i], a[i]);
+    float4 ddx, ddy;
+    ddx.x = (e02.x * e01y - e01.x * e02y) * inv_area;
+    ddx.y = (e02.y * e01y - e01.y * e02y) * inv_area;
+    ddx.z = (e02.z * e01y - e01.z * e02y) * inv_area;
+    ddx.w = (e02.w * e01y - e01.w * e02y) * inv_area;
+    ddy.x = (e01.x * e02x - e02.x * e01x) * inv_area;
+    ddy.y = (e01.y * e02x - e02.y * e01x) * inv_area;
+    ddy.z = (e01.z * e02x - e02.z * e01x) * inv_area;
+    ddy.w = (e01.w * e02x - e02.w * e01x) * inv_area;
+    rec[TRI_HEADER + i] = a[i];
+    rec[TRI_HEADER + R + i] = ddx;
+    rec[TRI_HEADER + 2 * R + i] = ddy;
+  }
+  TileRange tr = tile_range(bbox, p.tiles_x, p.tiles_y);
+  misc.x = __uint_as_float(1u | (front ? 2u : 0u));
+  misc.y = __uint_as_float((uint32_t)tr.sx | ((uint32_t)tr.ex << 16));
+  misc.z = __uint_as_float((uint32_t)tr.sy | ((uint32_t)tr.ey << 16));
+  rec[4] = misc;
+  // tile coverage count (rasterizer.cpp:809-857)
+  if ((tr.sx + 1 == tr.ex) && (tr.sy + 1 == tr.ey)) {
+    if (tile_owned(tr.sx, tr.sy, p.shard_rank, p.shard_n)) atomicAdd(&p.tile_count[tr.sy * p.tiles_x + tr.sx], 1u);
+  } else {
+    for (int y = tr.sy; y < tr.ey; ++y)
+      for (int x = tr.sx; x < tr.ex; ++x)
+        if (tile_owned(x, y, p.shard_rank, p.shard_n) && tile_test(edge, x, y))
+          atomicAdd(&p.tile_count[y * p.tiles_x + x], 1u);
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(128) k_geometry(GeomParams p) {
+  uint32_t prim = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t n_out = 0;
+  if (prim < p.prim_count) {
+    // ---- index fetch (index_fetcher.cpp:26-115)
+    uint32_t ids[3];
+    if (p.topology == SLV_TOPO_TRIANGLE_LIST) {
+      ids[0] = prim * 3; ids[1] = prim * 3 + 1; ids[2] = prim * 3 + 2;
+    } else {
+      ids[0] = prim; ids[1] = prim + 1; ids[2] = prim + 2;
+      if (prim & 1) { uint32_t t = ids[0]; ids[0] = ids[2]; ids[2] = t; }
+    }
+    uint32_t idx[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      uint32_t v = ids[i];
+      if (p.indices) {
+        const uint8_t* base = p.indices + (size_t)p.start * p.index_stride;
+        v = p.index_stride == 2 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(base) + ids[i])
+                                : __ldg(reinterpret_cast<const uint32_t*>(base) + ids[i]);
+      }
+      idx[i] = v + (uint32_t)p.base_vertex;
+    }
+    // ---- vertex fetch + vertex shader, recomputed per corner (VS is pure, so this equals the
+    //      reference's post-transform cache hit: default_vertex_cache.cpp:354-390)
+    VsOut<R> tri[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) run_vs<R>(p, idx[i], tri[i]);
+
+    float4* rec = p.tris + (size_t)prim * 3 * p.tri_stride;
+    // ---- clip (clipper.cpp:103-228)
+    bool in_frustum = true;
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+      for (int v = 0; v < 3; ++v)
+        if (plane_dist(pl, tri[v].r[0]) < 0) in_frustum = false;
+
+    if (in_frustum) {
+      float px[3], py[3];
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        float iw = 1.0f / tri[v].r[0].w;
+        px[v] = tri[v].r[0].x * iw;
+        py[v] = tri[v].r[0].y * iw;
+      }
+      float area = (px[2] - px[0]) * (py[1] - py[0]) - (py[2] - py[0]) * (px[1] - px[0]);
+      bool front = area > 0.0f;
+      if (!cull_tri(p.cull_mode, p.front_ccw, front ? 1.0f : -1.0f)) {
+        VsOut<R> o[3];
+        o[0] = tri[0];
+        o[1] = front ? tri[1] : tri[2];  // un-clipped back faces get v1 <-> v2 swapped (clipper.cpp:59-65)
+        o[2] = front ? tri[2] : tri[1];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) viewport_project<R>(p, o[k]);
+        setup_triangle<R>(p, o, rec);
+        n_out = 1;
+      }
+    } else {
+      VsOut<R> pool[2][5];
+      int n[2] = {3, 0};
+      pool[0][0] = tri[0]; pool[0][1] = tri[1]; pool[0][2] = tri[2];
+      int src = 0, dst = 1;
+      bool is_front = false, culled = false;
+      for (int pl = 0; pl < 2 && !culled; ++pl) {
+        n[dst] = 0;
+        float dd0 = 0.0f, dd1;
+        if (n[src] != 0) dd0 = plane_dist(pl, pool[src][0].r[0]);
+        for (int i = 0, j = 1; i < n[src]; ++i, ++j) {
+          j %= n[src];
+          dd1 = plane_dist(pl, pool[src][j].r[0]);
+          if (dd0 >= 0.0f) {
+            pool[dst][n[dst]++] = pool[src][i];
+            if (dd1 < 0.0f) {
+              lerp_vso<R>(p, pool[dst][n[dst]], pool[src][i], pool[src][j], dd0 / (dd0 - dd1));
+              ++n[dst];
+            }
+          } else if (dd1 >= 0.0f) {
+            lerp_vso<R>(p, pool[dst][n[dst]], pool[src][j], pool[src][i], dd1 / (dd1 - dd0));
+            ++n[dst];
+          }
+          dd0 = dd1;
+        }
+        if (pl == 0 && n[dst] >= 3) {  // facing after the near plane (clipper.cpp:191-211)
+          float px[3], py[3];
+          for (int i = 0; i < 3; ++i) {
+            float inv_abs_w = 1 / fabsf(pool[dst][i].r[0].w);
+            px[i] = pool[dst][i].r[0].x * inv_abs_w;
+            py[i] = pool[dst][i].r[0].y * inv_abs_w;
+          }
+          float area = (px[2] - px[0]) * (py[1] - py[0]) - (py[2] - py[0]) * (px[1] - px[0]);
+          is_front = area > 0.0f;
+          if (cull_tri(p.cull_mode, p.front_ccw, area)) culled = true;
+        }
+        src ^= 1;
+        dst ^= 1;
+      }
+      int nv = culled ? 0 : n[src];
+      if (nv >= 3) {
+        for (int t = 1; t <= nv - 2; ++t) {  // fan (0, t, t+1); back faces reversed (clipper.cpp:75-89)
+          VsOut<R> o[3];
+          o[0] = pool[src][0];
+          o[1] = is_front ? pool[src][t] : pool[src][t + 1];
+          o[2] = is_front ? pool[src][t + 1] : pool[src][t];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) viewport_project<R>(p, o[k]);
+          setup_triangle<R>(p, o, rec + (size_t)(t - 1) * p.tri_stride);
+        }
+        n_out = nv - 2;
+      }
+    }
+    for (uint32_t k = n_out; k < 3; ++k) rec[(size_t)k * p.tri_stride + 4] = make_float4(0, 0, 0, 0);
+  }
+  // cprimitives (rasterizer.cpp:1138): warp-aggregated
+  uint32_t total = n_out;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+  if ((threadIdx.x & 31) == 0 && total) atomicAdd(&p.stats[6], (unsigned long long)total);
+}
+
+// =====================================================================================================
+// binning
+// =====================================================================================================
+// single CTA, 1024 threads: exclusive scan of tile_count -> tile_offset[0..n]; zeroes count and cursor
+__global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint32_t* tile_offset, uint32_t* tile_cursor,
+                                                     uint32_t n_tiles) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_tiles; base += 1024) {
+    const uint32_t i = base + tid;
+    const uint32_t v = i < n_tiles ? tile_count[i] : 0;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const uint32_t w = s_warp[lane];
+      uint32_t wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+        if (lane >= (uint32_t)o) wi += t;
+      }
+      s_warp[lane] = wi - w;  // exclusive offset of each warp
+    }
+    __syncthreads();
+    const uint32_t excl = s_carry + s_warp[warp] + incl - v;
+    if (i < n_tiles) {
+      tile_offset[i] = excl;
+      tile_cursor[i] = 0;
+      tile_count[i] = 0;
+    }
+    __syncthreads();
+    if (tid == 1023) s_carry = excl + v;
+    __syncthreads();
+  }
+  if (tid == 0) tile_offset[n_tiles] = s_carry;
+}
+
+__global__ void __launch_bounds__(256) k_bin_fill(BinParams p) {
+  uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= p.n_slots) return;
+  const float4* rec = p.tris + (size_t)slot * p.tri_stride;
+  float4 misc = __ldg(rec + 4);
+  uint32_t flags = __float_as_uint(misc.x);
+  if (!(flags & 1)) return;
+  uint32_t xr = __float_as_uint(misc.y), yr = __float_as_uint(misc.z);
+  int sx = xr & 0xFFFF, ex = xr >> 16, sy = yr & 0xFFFF, ey = yr >> 16;
+  if ((sx + 1 == ex) && (sy + 1 == ey)) {
+    if (tile_owned(sx, sy, p.shard_rank, p.shard_n)) {
+      uint32_t t = sy * p.tiles_x + sx;
+      uint32_t at = p.tile_offset[t] + atomicAdd(&p.tile_cursor[t], 1u);
+      if (at < p.list_capacity) p.list[at] = slot << 1;
+      else *p.overflow_flag = 1;
+    }
+    return;
+  }
+  float4 edge[3] = {__ldg(rec), __ldg(rec + 1), __ldg(rec + 2)};
+  for (int y = sy; y < ey; ++y)
+    for (int x = sx; x < ex; ++x) {
+      if (!tile_owned(x, y, p.shard_rank, p.shard_n)) continue;
+      int st = tile_test(edge, x, y);
+      if (!st) continue;
+      uint32_t t = y * p.tiles_x + x;
+      uint32_t at = p.tile_offset[t] + atomicAdd(&p.tile_cursor[t], 1u);
+      if (at < p.list_capacity) p.list[at] = (slot << 1) | (st == 3 ? 1u : 0u);
+      else *p.overflow_flag = 1;
+    }
+}
+
+// one CTA per tile; normalized bitonic network (every compare-exchange puts the minimum at the lower
+// index), so virtual +inf padding past n works in place for any n.
+constexpr int SORT_SMEM = 4096;
+__global__ void __launch_bounds__(256) k_sort_lists(const uint32_t* tile_offset, uint32_t* list, uint32_t capacity) {
+  __shared__ uint32_t s[SORT_SMEM];
+  uint32_t beg = tile_offset[blockIdx.x], end = tile_offset[blockIdx.x + 1];
+  if (end > capacity) end = capacity;
+  if (beg >= end) return;
+  uint32_t n = end - beg;
+  if (n < 2) return;
+  uint32_t* a = list + beg;
+  uint32_t N = 1;
+  while (N < n) N <<= 1;
+  bool use_smem = n <= SORT_SMEM;
+  uint32_t* buf = use_smem ? s : a;
+  if (use_smem) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s[i] = a[i];
+    __syncthreads();
+  }
+  for (uint32_t k = 2; k <= N; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      bool first = (j == (k >> 1));
+      for (uint32_t t = threadIdx.x; t < (N >> 1); t += blockDim.x) {
+        // t-th compare-exchange of this step: i = index with bit j clear
+        uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        uint32_t l = first ? (i ^ (k - 1)) : (i | j);
+        if (first && l < i) { uint32_t tmp = i; i = l; l = tmp; }
+        if (l < n && i < n) {
+          uint32_t x = buf[i], y = buf[l];
+          if (x > y) { buf[i] = y; buf[l] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (use_smem) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) a[i] = s[i];
+  }
+}
+
+// =====================================================================================================
+// raster + shade + merge
+// =====================================================================================================
+__device__ __forceinline__ bool compare_f(uint32_t fn, float l, float r) {  // framebuffer.cpp:96-134
+  switch (fn) {
+  case SLV_CMP_NEVER: return false;
+  case SLV_CMP_LESS: return l < r;
+  case SLV_CMP_EQUAL: return l == r;
+  case SLV_CMP_LESS_EQUAL: return l <= r;
+  case SLV_CMP_GREATER: return l > r;
+  case SLV_CMP_NOT_EQUAL: return l != r;
+  case SLV_CMP_GREATER_EQUAL: return l >= r;
+  default: return true;
+  }
+}
+__device__ __forceinline__ bool compare_u(uint32_t fn, uint32_t l, uint32_t r) {
+  switch (fn) {
+  case SLV_CMP_NEVER: return false;
+  case SLV_CMP_LESS: return l < r;
+  case SLV_CMP_EQUAL: return l == r;
+  case SLV_CMP_LESS_EQUAL: return l <= r;
+  case SLV_CMP_GREATER: return l > r;
+  case SLV_CMP_NOT_EQUAL: return l != r;
+  case SLV_CMP_GREATER_EQUAL: return l >= r;
+  default: return true;
+  }
+}
+__device__ __forceinline__ uint32_t stencil_op_apply(uint32_t op, uint32_t ref, uint32_t cur) {  // framebuffer.cpp:136-166
+  switch (op) {
+  case SLV_SOP_ZERO: return 0;
+  case SLV_SOP_REPLACE: return ref;
+  case SLV_SOP_INCR_SAT: return min(0xFFu, cur + 1);
+  case SLV_SOP_DECR_SAT: return cur - 1;  // max<uint32>(0, cur-1): underflows (Appendix B #5)
+  case SLV_SOP_INVERT: return ~cur;
+  case SLV_SOP_INCR_WRAP: return (cur + 1) & 0xFF;
+  case SLV_SOP_DECR_WRAP: return (cur - 1 + 256) & 0xFF;
+  default: return cur;
+  }
+}
+
+struct TriEntry {  // one surviving triangle of the current chunk, staged in shared memory
+  float A[3], B[3], C[3];
+  float bbox[4];
+  uint32_t slot_flags;  // slot << 2 | full16 << 1 | front
+  uint32_t pad[2];
+};
+
+template <int S>
+struct SamplePattern;
+template <>
+struct SamplePattern<1> {
+  __device__ static float x(int) { return 0.5f; }
+  __device__ static float y(int) { return 0.5f; }
+};
+template <>
+struct SamplePattern<2> {
+  __device__ static float x(int s) { return s == 0 ? 0.25f : 0.75f; }
+  __device__ static float y(int s) { return s == 0 ? 0.25f : 0.75f; }
+};
+template <>
+struct SamplePattern<4> {  // rasterizer.cpp:1095-1100
+  __device__ static float x(int s) { return s == 0 ? 0.375f : (s == 1 ? 0.875f : (s == 2 ? 0.125f : 0.625f)); }
+  __device__ static float y(int s) { return s == 0 ? 0.125f : (s == 1 ? 0.375f : (s == 2 ? 0.625f : 0.875f)); }
+};
+
+// interpolated attribute register of this pixel: quad stepping (shader.cpp:289-367) or the centroid
+// variant (rasterizer.cpp:1366-1397 + shader.cpp:208-255)
+__device__ __forceinline__ float4 interp_attr(const float4* rec, int R, int reg, uint32_t mod, float dx, float dy, bool odd_x,
+                                              bool odd_y, bool centroid_path, float pdx, float pdy, float inv_w) {
+  float4 a0 = __ldg(rec + TRI_HEADER + reg);
+  float4 r;
+  if (mod & SLV_AM_NOINTERPOLATION) {
+    r = a0;
+  } else {
+    float4 gx = __ldg(rec + TRI_HEADER + R + reg), gy = __ldg(rec + TRI_HEADER + 2 * R + reg);
+    if (centroid_path) {
+      r = make_float4(a0.x + (gx.x * pdx + gy.x * pdy), a0.y + (gx.y * pdx + gy.y * pdy),
+                      a0.z + (gx.z * pdx + gy.z * pdy), a0.w + (gx.w * pdx + gy.w * pdy));
+    } else {
+      r = make_float4(a0.x + (gx.x * dx + gy.x * dy), a0.y + (gx.y * dx + gy.y * dy), a0.z + (gx.z * dx + gy.z * dy),
+                      a0.w + (gx.w * dx + gy.w * dy));
+      if (odd_x) { r.x += gx.x; r.y += gx.y; r.z += gx.z; r.w += gx.w; }
+      if (odd_y) { r.x += gy.x; r.y += gy.y; r.z += gy.z; r.w += gy.w; }
+    }
+  }
+  if (!(mod & SLV_AM_NOPERSPECTIVE)) { r.x *= inv_w; r.y *= inv_w; r.z *= inv_w; r.w *= inv_w; }
+  return r;
+}
+
+struct PixelCtx {  // what a pixel shader may read
+  const float4* rec;
+  int R;
+  const uint32_t* mods;
+  float dx, dy, pdx, pdy, inv_w;
+  bool odd_x, odd_y, centroid_path;
+  uint32_t quad_base;  // lane of pixel 0 of this quad
+  __device__ __forceinline__ float4 attr(int i) const {
+    return interp_attr(rec, R, 1 + i, mods[i], dx, dy, odd_x, odd_y, centroid_path, pdx, pdy, inv_w);
+  }
+};
+
+// cpp_pixel_shader::tex2d (cpp_pixel_shader.cpp:13-31): ddx = q1 - q0, ddy = q2 - q0 for the whole quad,
+// LOD once per quad; computed redundantly by the four lanes from shuffled values (all 32 lanes converge here)
+__device__ __forceinline__ float4 ps_tex2d(const SamplerRef& sm, const PixelCtx& px, float4 a) {
+  float u0 = __shfl_sync(0xFFFFFFFFu, a.x, px.quad_base), v0 = __shfl_sync(0xFFFFFFFFu, a.y, px.quad_base);
+  float u1 = __shfl_sync(0xFFFFFFFFu, a.x, px.quad_base + 1), v1 = __shfl_sync(0xFFFFFFFFu, a.y, px.quad_base + 1);
+  float u2 = __shfl_sync(0xFFFFFFFFu, a.x, px.quad_base + 2), v2 = __shfl_sync(0xFFFFFFFFu, a.y, px.quad_base + 2);
+  float lod = calc_lod_2d(sm, u1 - u0, v1 - v0, u2 - u0, v2 - v0);
+  return sample_impl(sm, a.x, a.y, lod, nullptr);
+}
+
+template <int PS>
+__device__ __forceinline__ bool run_ps(const RasterParams& p, const PixelCtx& px, float4& color) {
+  if (PS == SLV_PS_ATTR0_COLOR) {
+    color = px.attr(0);
+    return true;
+  }
+  if (PS == SLV_PS_DISCARD_ALL) {
+    color = px.attr(0);
+    return false;
+  }
+  if (PS == SLV_PS_LIGHTS3) {  // ColorizedTriangle.cpp:55-92
+    float4 nrm = px.attr(0), l0 = px.attr(1), l1 = px.attr(2), l2 = px.attr(3);
+    float i0 = 1.0f / length3(l0.x, l0.y, l0.z);
+    float i1 = 1.0f / length3(l1.x, l1.y, l1.z);
+    float i2 = 1.0f / length3(l2.x, l2.y, l2.z);
+    float nl = length3(nrm.x, nrm.y, nrm.z);
+    if (eq_eps(nl, 0.0f)) nl = 1.0f;
+    float ninv = 1.0f / nl;
+    float nx = nrm.x * ninv, ny = nrm.y * ninv, nz = nrm.z * ninv;
+    float r0 = dot3(nx, ny, nz, l0.x * i0, l0.y * i0, l0.z * i0);
+    float r1 = dot3(nx, ny, nz, l1.x * i1, l1.y * i1, l1.z * i1);
+    float r2 = dot3(nx, ny, nz, l2.x * i2, l2.y * i2, l2.z * i2);
+    const float A[4] = {0.7f, 0.1f, 0.3f, 1.0f}, B[4] = {0.1f, 0.3f, 0.7f, 1.0f}, Cc[4] = {0.3f, 0.7f, 0.1f, 1.0f};
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float a = ((A[k] * r0) * i0) * i0;
+      float b = ((B[k] * r1) * i1) * i1;
+      float c = ((Cc[k] * r2) * i2) * i2;
+      o[k] = clampf((a + b) + c, 0.0f, 1.0f);
+    }
+    color = make_float4(o[0], o[1], o[2], 1.0f);
+    return true;
+  }
+  if (PS == SLV_PS_TEX_ALPHA) {  // TextureAndBlending.cpp:96-166
+    auto u = reinterpret_cast<const slv_ps_tex_alpha_uniforms*>(p.ps_uniforms);
+    float4 a = px.attr((int)u->reg);
+    color = ps_tex2d(p.sampler0, px, a);
+    color.w = u->alpha;
+    return true;
+  }
+  if (PS == SLV_PS_TEX_GRAD_ALPHA) {  // SASL tex2D == sample_2d_grad with the quad derivatives
+    auto u = reinterpret_cast<const slv_ps_tex_alpha_uniforms*>(p.ps_uniforms);
+    float4 a = px.attr((int)u->reg);
+    float u0 = __shfl_sync(0xFFFFFFFFu, a.x, px.quad_base), v0 = __shfl_sync(0xFFFFFFFFu, a.y, px.quad_base);
+    float u1 = __shfl_sync(0xFFFFFFFFu, a.x, px.quad_base + 1), v1 = __shfl_sync(0xFFFFFFFFu, a.y, px.quad_base + 1);
+    float u2 = __shfl_sync(0xFFFFFFFFu, a.x, px.quad_base + 2), v2 = __shfl_sync(0xFFFFFFFFu, a.y, px.quad_base + 2);
+    color = sample_2d_grad(p.sampler0, a.x, a.y, u1 - u0, v1 - v0, u2 - u0, v2 - v0, 0.0f);
+    color.w = u->alpha;
+    return true;
+  }
+  if (PS == SLV_PS_SPONZA) {  // Sponza.cpp:117-136
+    auto u = reinterpret_cast<const slv_ps_sponza_uniforms*>(p.ps_uniforms);
+    float4 diff = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    float4 uv = px.attr(0);
+    if (u->has_sampler) diff = ps_tex2d(p.sampler0, px, uv);
+    float4 n = px.attr(1), l = px.attr(2);
+    float nl = length3(n.x, n.y, n.z);
+    if (eq_eps(nl, 0.0f)) nl = 1.0f;
+    float ninv = 1.0f / nl;
+    float ll = length3(l.x, l.y, l.z);
+    if (eq_eps(ll, 0.0f)) ll = 1.0f;
+    float linv = 1.0f / ll;
+    float illum = clampf(dot3(l.x * linv, l.y * linv, l.z * linv, n.x * ninv, n.y * ninv, n.z * ninv), 0.0f, 1.0f);
+    color = make_float4(diff.x * illum, diff.y * illum, diff.z * illum, 1.0f);
+    return true;
+  }
+  color = make_float4(0, 0, 0, 0);
+  return true;
+}
+
+template <int S, int PS>
+__global__ void __launch_bounds__(RASTER_THREADS) k_raster(RasterParams p) {
+  __shared__ TriEntry s_tri[RASTER_THREADS];
+  __shared__ uint32_t s_warp_cnt[RASTER_THREADS / 32];
+
+  const uint32_t tile = blockIdx.x >> 4, sub = blockIdx.x & 15;
+  const uint32_t list_beg = p.tile_offset[tile];
+  uint32_t list_end = p.tile_offset[tile + 1];
+  if (list_end > p.list_capacity) list_end = p.list_capacity;
+  if (list_beg >= list_end) return;
+  const uint32_t tile_x = tile % p.tiles_x, tile_y = tile / p.tiles_x;
+  const int X16 = (sub & 3) * REGION, Y16 = (sub >> 2) * REGION;  // tile-relative origin of this region
+  const int gx0 = tile_x * TILE + X16, gy0 = tile_y * TILE + Y16;
+  // "Sub tile is out of screen" (rasterizer.cpp:721-724)
+  if ((float)gx0 >= (float)p.target_w || (float)gy0 >= (float)p.target_h) return;
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // warp = 8x4 pixels = two 4x4 blocks; lanes 4q..4q+3 form the 2x2 quad q
+  const int wx = (warp & 1) * 8, wy = (warp >> 1) * 4;
+  const int q = lane >> 2, pi = lane & 3;
+  const int lx = wx + (q & 3) * 2 + (pi & 1), ly = wy + (q >> 2) * 2 + (pi >> 1);  // region-relative
+  const int x = gx0 + lx, y = gy0 + ly;
+  const int bx = lx >> 2, by = ly >> 2;  // 4x4 block inside the region
+  const int ix = lx & 3, iy = ly & 3;    // pixel inside the block
+  const bool odd_x = x & 1, odd_y = y & 1;
+  const uint32_t quad_base = lane & ~3u;
+  const bool in_target = (uint32_t)x < p.target_w && (uint32_t)y < p.target_h;
+  const uint32_t fullmask = (1u << S) - 1;
+
+  // ---- per-pixel framebuffer state in registers ----
+  float zbuf[S];
+  uint32_t sbuf[S], cbuf[S];
+  bool dirty_ds = false, dirty_c = false;
+  const bool c0_packed = p.color0.data && p.color0.bpp == 4;
+  uint8_t* ds_ptr = nullptr;
+  uint8_t* c_ptr = nullptr;
+#pragma unroll
+  for (int s = 0; s < S; ++s) { zbuf[s] = 0.0f; sbuf[s] = 0; cbuf[s] = 0; }
+  if (in_target) {
+    if (p.ds.data) {
+      ds_ptr = p.ds.data + ((size_t)y * p.ds.w + x) * S * 8;
+      if (S == 4) {
+        float4 a = *reinterpret_cast<const float4*>(ds_ptr), b = *reinterpret_cast<const float4*>(ds_ptr + 16);
+        zbuf[0] = a.x; sbuf[0] = __float_as_uint(a.y); zbuf[1 % S] = a.z; sbuf[1 % S] = __float_as_uint(a.w);
+        zbuf[2 % S] = b.x; sbuf[2 % S] = __float_as_uint(b.y); zbuf[3 % S] = b.z; sbuf[3 % S] = __float_as_uint(b.w);
+      } else if (S == 2) {
+        float4 a = *reinterpret_cast<const float4*>(ds_ptr);
+        zbuf[0] = a.x; sbuf[0] = __float_as_uint(a.y); zbuf[1 % S] = a.z; sbuf[1 % S] = __float_as_uint(a.w);
+      } else {
+        float2 a = *reinterpret_cast<const float2*>(ds_ptr);
+        zbuf[0] = a.x; sbuf[0] = __float_as_uint(a.y);
+      }
+    }
+    if (c0_packed) {
+      c_ptr = p.color0.data + ((size_t)y * p.color0.w + x) * S * 4;
+      if (S == 4) {
+        uint4 a = *reinterpret_cast<const uint4*>(c_ptr);
+        cbuf[0] = a.x; cbuf[1 % S] = a.y; cbuf[2 % S] = a.z; cbuf[3 % S] = a.w;
+      } else if (S == 2) {
+        uint2 a = *reinterpret_cast<const uint2*>(c_ptr);
+        cbuf[0] = a.x; cbuf[1 % S] = a.y;
+      } else {
+        cbuf[0] = *reinterpret_cast<const uint32_t*>(c_ptr);
+      }
+    }
+  }
+
+  uint32_t n_ps_quads = 0, n_backend_quads = 0;
+  const int R = 1 + (int)p.n_attrs;
+  const float vpx = (float)(tile_x * TILE), vpy = (float)(tile_y * TILE);
+
+  for (uint32_t chunk = list_beg; chunk < list_end; chunk += RASTER_THREADS) {
+    // ================= filter: the reference's level-16 decision for this region =================
+    uint32_t ei = chunk + tid;
+    bool keep = false;
+    TriEntry ent;
+    if (ei < list_end) {
+      uint32_t e = __ldg(p.list + ei);
+      uint32_t slot = e >> 1;
+      const float4* rec = p.tris + (size_t)slot * p.tri_stride;
+      float4 e0 = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2), bb = __ldg(rec + 3);
+      uint32_t flags = __float_as_uint(__ldg(rec + 4).x);
+      ent.A[0] = e0.x; ent.B[0] = e0.y; ent.C[0] = e0.z;
+      ent.A[1] = e1.x; ent.B[1] = e1.y; ent.C[1] = e1.z;
+      ent.A[2] = e2.x; ent.B[2] = e2.y; ent.C[2] = e2.z;
+      ent.bbox[0] = bb.x; ent.bbox[1] = bb.y; ent.bbox[2] = bb.z; ent.bbox[3] = bb.w;
+      uint32_t full16;
+      if (e & 1) {  // the whole 64x64 tile is inside the triangle (rasterizer.cpp:736-743)
+        keep = true;
+        full16 = 1;
+      } else {
+        // subdivide_tile at the 16-px level (rasterizer.cpp:441-602, 698-772)
+        float x_min = bb.x - vpx, x_max = bb.y - vpx, y_min = bb.z - vpy, y_max = bb.w - vpy;
+        bool rej = (x_min >= (float)(X16 + REGION)) || (x_max < (float)X16) || (y_min >= (float)(Y16 + REGION)) ||
+                   (y_max < (float)Y16);
+        bool acc = true;
+        const float ftx = (float)(X16 / REGION), fty = (float)(Y16 / REGION);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          float A = ent.A[k], B = ent.B[k], C = ent.C[k];
+          float step_x = TILE * A, step_y = TILE * B;
+          float r2a = -fabsf(step_x) - fabsf(step_y);
+          float part = (float)((A > 0) * TILE) * A + (float)((B > 0) * TILE) * B;
+          step_x *= 0.25f; step_y *= 0.25f; r2a *= 0.25f; part *= 0.25f;
+          float ev = C - part;
+          float ev1 = ev - (vpx * A + vpy * B);
+          float step = step_x * ftx + step_y * fty;
+          rej |= (step < ev1);
+          acc &= !((step + r2a) < ev1);
+        }
+        keep = !rej;
+        full16 = acc ? 1 : 0;
+      }
+      ent.slot_flags = (slot << 2) | (full16 << 1) | ((flags >> 1) & 1);
+    }
+    // order-preserving compaction of the survivors into shared memory
+    uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+    if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t base = 0, n_surv = 0;
+#pragma unroll
+    for (int w = 0; w < RASTER_THREADS / 32; ++w) {
+      const uint32_t c = s_warp_cnt[w];
+      if ((uint32_t)w < warp) base += c;
+      n_surv += c;
+    }
+    if (keep) s_tri[base + __popc(bal & ((1u << lane) - 1))] = ent;
+    __syncthreads();
+
+    // ================= main loop: triangles of this chunk in API order =================
+    for (uint32_t ti = 0; ti < n_surv; ++ti) {
+      const TriEntry& t = s_tri[ti];
+      const uint32_t sf = t.slot_flags;
+      // ---- level-4 decision for my 4x4 block (half-warp uniform) ----
+      int blk;  // 0 rejected, 1 partial, 2 full
+      if (sf & 2) {
+        blk = 2;
+      } else {
+        float x_min = t.bbox[0] - vpx, x_max = t.bbox[1] - vpx, y_min = t.bbox[2] - vpy, y_max = t.bbox[3] - vpy;
+        const int rx = X16 + bx * 4, ry = Y16 + by * 4;  // tile-relative block origin
+        bool rej = (x_min >= (float)(rx + 4)) || (x_max < (float)rx) || (y_min >= (float)(ry + 4)) || (y_max < (float)ry);
+        bool acc = true;
+        const float left_f = (float)gx0, top_f = (float)gy0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          float A = t.A[k], B = t.B[k], C = t.C[k];
+          float step_x = TILE * A, step_y = TILE * B;
+          float r2a = -fabsf(step_x) - fabsf(step_y);
+          float part = (float)((A > 0) * TILE) * A + (float)((B > 0) * TILE) * B;
+          step_x *= 0.25f; step_y *= 0.25f; r2a *= 0.25f; part *= 0.25f;
+          step_x *= 0.25f; step_y *= 0.25f; r2a *= 0.25f; part *= 0.25f;
+          float ev = C - part;
+          float ev1 = ev - (left_f * A + top_f * B);
+          float step = step_x * (float)bx + step_y * (float)by;
+          rej |= (step < ev1);
+          acc &= !((step + r2a) < ev1);
+        }
+        blk = rej ? 0 : (acc ? 2 : 1);
+      }
+      // ---- per-sample coverage (draw_partial_tile, rasterizer.cpp:298-439) ----
+      uint32_t pm = 0;
+      if (in_target) {
+        if (blk == 2) {
+          pm = fullmask;
+        } else if (blk == 1) {
+          const float left_f = (float)(gx0 + bx * 4), top_f = (float)(gy0 + by * 4);
+          float ev[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) ev[k] = t.C[k] - (left_f * t.A[k] + top_f * t.B[k]);
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            float fx = SamplePattern<S>::x(s) + (float)ix, fy = SamplePattern<S>::y(s) + (float)iy;
+            bool rj = false;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) rj |= (fx * t.A[k] + fy * t.B[k]) < ev[k];
+            if (!rj) pm |= 1u << s;
+          }
+        }
+      }
+      if (!__any_sync(0xFFFFFFFFu, pm != 0)) continue;
+
+      // ---- quad assembly ----
+      uint32_t m0 = __shfl_sync(0xFFFFFFFFu, pm, quad_base), m1 = __shfl_sync(0xFFFFFFFFu, pm, quad_base + 1);
+      uint32_t m2 = __shfl_sync(0xFFFFFFFFu, pm, quad_base + 2), m3 = __shfl_sync(0xFFFFFFFFu, pm, quad_base + 3);
+      const bool quad_alive = (m0 | m1 | m2 | m3) != 0;
+      const bool quad_full = (m0 & m1 & m2 & m3) == fullmask;
+
+      const float4* rec = p.tris + (size_t)(sf >> 2) * p.tri_stride;
+      const bool front = sf & 1;
+      // step_2d_unproj_pos_quad (shader.cpp:257-287): only z and w are consumed downstream
+      float4 v0p = __ldg(rec + TRI_HEADER), gxp = __ldg(rec + TRI_HEADER + R), gyp = __ldg(rec + TRI_HEADER + 2 * R);
+      const float dx = 0.5f + (float)(uint32_t)(x & ~1) - v0p.x;
+      const float dy = 0.5f + (float)(uint32_t)(y & ~1) - v0p.y;
+      float pz = v0p.z + (gxp.z * dx + gyp.z * dy);
+      float pw = v0p.w + (gxp.w * dx + gyp.w * dy);
+      if (odd_x) { pz += gxp.z; pw += gxp.w; }
+      if (odd_y) { pz += gyp.z; pw += gyp.w; }
+      const float depth = pz;
+      float aa[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s)
+        aa[s] = (S > 1) ? (SamplePattern<S>::x(s) - 0.5f) * gxp.z + (SamplePattern<S>::y(s) - 0.5f) * gyp.z : 0.0f;
+
+      // ---- early-Z: test and WRITE depth now (framebuffer.cpp:522-614; Appendix B #3) ----
+      uint32_t tested = pm;
+      if (p.early_z && pm) {
+        tested = 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          if (pm & (1u << s)) {
+            float nd = (S == 1) ? depth : aa[s] + depth;
+            float od = p.read_depth ? zbuf[s] : 0.0f;
+            bool pass = p.depth_enable ? compare_f(p.depth_func, nd, od) : true;
+            if (pass) {
+              tested |= 1u << s;
+              if (p.write_depth) { zbuf[s] = nd; dirty_ds = true; }
+            }
+          }
+        }
+      }
+      uint32_t t0 = __shfl_sync(0xFFFFFFFFu, tested, quad_base), t1 = __shfl_sync(0xFFFFFFFFu, tested, quad_base + 1);
+      uint32_t t2 = __shfl_sync(0xFFFFFFFFu, tested, quad_base + 2), t3 = __shfl_sync(0xFFFFFFFFu, tested, quad_base + 3);
+      const bool quad_shade = quad_alive && ((t0 | t1 | t2 | t3) != 0);
+      if (!__any_sync(0xFFFFFFFFu, quad_shade)) continue;
+      if (quad_shade && pi == 0) ++n_ps_quads;
+
+      // ---- attribute interpolation + pixel shader on 32-pixel quad batches ----
+      PixelCtx px;
+      px.rec = rec; px.R = R; px.mods = p.mods;
+      px.dx = dx; px.dy = dy; px.odd_x = odd_x; px.odd_y = odd_y;
+      px.inv_w = 1.0f / pw;
+      px.quad_base = quad_base;
+      px.centroid_path = p.has_centroid && !quad_full;
+      px.pdx = dx + (float)(int)odd_x;
+      px.pdy = dy + (float)(int)odd_y;
+      if (px.centroid_path && pm != fullmask && pm != 0) {
+        float cx = 0.0f, cy = 0.0f;
+        int n = 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+          if (pm & (1u << s)) { cx += SamplePattern<S>::x(s); cy += SamplePattern<S>::y(s); ++n; }
+        float inv = 1 / (float)n;
+        cx *= inv; cy *= inv;
+        px.pdx += cx - 0.5f;
+        px.pdy += cy - 0.5f;
+      }
+      float4 color;
+      bool keep_px = run_ps<PS>(p, px, color);
+      uint32_t fin = keep_px ? tested : 0u;
+      uint32_t f0 = __shfl_sync(0xFFFFFFFFu, fin, quad_base), f1 = __shfl_sync(0xFFFFFFFFu, fin, quad_base + 1);
+      uint32_t f2 = __shfl_sync(0xFFFFFFFFu, fin, quad_base + 2), f3 = __shfl_sync(0xFFFFFFFFu, fin, quad_base + 3);
+      // draw_full_quad tests the post-PS mask, draw_quad the pre-Z mask (rasterizer.cpp:1311,1409)
+      const bool to_backend = quad_shade && (quad_full ? ((f0 | f1 | f2 | f3) != 0) : true);
+      if (to_backend && pi == 0) ++n_backend_quads;
+      if (!to_backend) fin = 0;
+
+      // ---- output merger (framebuffer.cpp:445-520) ----
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        if (!(fin & (1u << s))) continue;
+        if (!p.early_z) {
+          float sd = (S == 1) ? depth : depth + aa[s];
+          float od = p.read_depth ? zbuf[s] : 0.0f;
+          uint32_t os = p.stencil_enable ? (sbuf[s] & p.read_mask) : 0u;
+          bool dp = p.depth_enable ? compare_f(p.depth_func, sd, od) : true;
+          const slv_stencil_op_desc& face = front ? p.front_face : p.back_face;
+          bool sp = p.stencil_enable ? compare_u(face.stencil_func, p.stencil_ref, os) : true;
+          if (!(dp && sp)) continue;
+          uint32_t ns = p.stencil_enable ? stencil_op_apply(face.stencil_pass_op, p.stencil_ref, os) : os;
+          if (p.write_depth) { zbuf[s] = sd; dirty_ds = true; }
+          if (p.stencil_enable) { sbuf[s] = ns & p.write_mask; dirty_ds = true; }
+        }
+        // blend shader
+        if (p.color0.data) {
+          if (c0_packed) {
+            if (p.bs_program == SLV_BS_LERP_SRC_ALPHA) {
+              float4 d = unpack_color(p.color0.fmt, cbuf[s]);
+              float4 r = make_float4(d.x + (color.x - d.x) * color.w, d.y + (color.y - d.y) * color.w,
+                                     d.z + (color.z - d.z) * color.w, d.w + (color.w - d.w) * color.w);
+              cbuf[s] = pack_color(p.color0.fmt, r);
+            } else {
+              cbuf[s] = pack_color(p.color0.fmt, color);
+            }
+            dirty_c = true;
+          } else {
+            uint8_t* cp = p.color0.data + (((size_t)y * p.color0.w + x) * S + s) * p.color0.bpp;
+            if (p.bs_program == SLV_BS_LERP_SRC_ALPHA) {
+              float4 d = load_texel_rgba32f(p.color0.fmt, cp);
+              float4 r = make_float4(d.x + (color.x - d.x) * color.w, d.y + (color.y - d.y) * color.w,
+                                     d.z + (color.z - d.z) * color.w, d.w + (color.w - d.w) * color.w);
+              store_texel_rgba32f(p.color0.fmt, cp, r);
+            } else {
+              store_texel_rgba32f(p.color0.fmt, cp, color);
+            }
+          }
+        }
+        if (p.bs_program == SLV_BS_REPLACE_AND_COUNT && p.color1.data) {
+          uint8_t* cp = p.color1.data + (((size_t)y * p.color1.w + x) * S + s) * p.color1.bpp;
+          float4 v = load_texel_rgba32f(p.color1.fmt, cp);
+          v.x += 1.0f;
+          store_texel_rgba32f(p.color1.fmt, cp, v);
+        }
+      }
+    }
+    __syncthreads();  // s_tri is rewritten by the next chunk
+  }
+
+  // ---- write the pixel back once, 128-bit stores at 4x MSAA ----
+  if (in_target) {
+    if (dirty_ds && ds_ptr) {
+      if (S == 4) {
+        *reinterpret_cast<float4*>(ds_ptr) =
+            make_float4(zbuf[0], __uint_as_float(sbuf[0]), zbuf[1 % S], __uint_as_float(sbuf[1 % S]));
+        *reinterpret_cast<float4*>(ds_ptr + 16) =
+            make_float4(zbuf[2 % S], __uint_as_float(sbuf[2 % S]), zbuf[3 % S], __uint_as_float(sbuf[3 % S]));
+      } else if (S == 2) {
+        *reinterpret_cast<float4*>(ds_ptr) =
+            make_float4(zbuf[0], __uint_as_float(sbuf[0]), zbuf[1 % S], __uint_as_float(sbuf[1 % S]));
+      } else {
+        *reinterpret_cast<float2*>(ds_ptr) = make_float2(zbuf[0], __uint_as_float(sbuf[0]));
+      }
+    }
+    if (dirty_c && c_ptr) {
+      if (S == 4) *reinterpret_cast<uint4*>(c_ptr) = make_uint4(cbuf[0], cbuf[1 % S], cbuf[2 % S], cbuf[3 % S]);
+      else if (S == 2) *reinterpret_cast<uint2*>(c_ptr) = make_uint2(cbuf[0], cbuf[1 % S]);
+      else *reinterpret_cast<uint32_t*>(c_ptr) = cbuf[0];
+    }
+  }
+  // ---- statistics: ps_invocations / backend_input_pixels count 4 per quad ----
+  uint32_t a = n_ps_quads, b = n_backend_quads;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+    b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+  }
+  if (lane == 0) {
+    if (a) atomicAdd(&p.stats[7], (unsigned long long)a * 4ull);
+    if (b) atomicAdd(&p.stats[8], (unsigned long long)b * 4ull);
+  }
+}
+
+// =====================================================================================================
+// clears / resolve / mip generation / sampler probe
+// =====================================================================================================
+// surface::fill (surface.cpp:170-271): every texel = one converted pattern; 128-bit stores
+__global__ void k_fill(uint4* dst, size_t n_vec, uint4 pattern) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n_vec; i += stride) dst[i] = pattern;
+}
+__global__ void k_fill_words(uint32_t* dst, size_t first_word, size_t n_words, uint4 pattern) {
+  size_t i = first_word + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_words) dst[i] = (i & 3) == 0 ? pattern.x : ((i & 3) == 1 ? pattern.y : ((i & 3) == 2 ? pattern.z : pattern.w));
+}
+// framebuffer::clear_depth_stencil with a single flag (framebuffer.cpp:616-644)
+__global__ void k_clear_ds_partial(float2* dst, size_t n, uint32_t flags, float depth, uint32_t stencil) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float2 v = dst[i];
+    if (flags & SLV_CLEAR_DEPTH) v.x = depth;
+    if (flags & SLV_CLEAR_STENCIL) v.y = __uint_as_float(stencil);
+    dst[i] = v;
+  }
+}
+
+// surface::resolve (surface.cpp:123-140)
+__global__ void k_resolve(SurfaceRef src, SurfaceRef dst) {
+  uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= src.w || y >= src.h) return;
+  float4 clr = make_float4(0, 0, 0, 0);
+  const uint8_t* sp = src.data + ((size_t)y * src.w + x) * src.samples * src.bpp;
+  for (uint32_t s = 0; s < src.samples; ++s) {
+    float4 t = load_texel_rgba32f(src.fmt, sp + (size_t)s * src.bpp);
+    clr.x += t.x; clr.y += t.y; clr.z += t.z; clr.w += t.w;
+  }
+  float inv = 1 / (float)src.samples;
+  clr.x *= inv; clr.y *= inv; clr.z *= inv; clr.w *= inv;
+  store_texel_rgba32f(dst.fmt, dst.data + ((size_t)y * dst.w + x) * dst.bpp, clr);
+}
+
+// surface::make_mip_surface (surface.cpp:53-92): box filter ((c0+c1)+c2)+c3 then *0.25; reads of texel
+// 2x+1 / 2y+1 are not bounds-checked upstream: an x overflow wraps into the next row (mirrored), a read
+// past the allocation is undefined upstream and returns zeros here.
+__global__ void k_mipgen(SurfaceRef src, SurfaceRef dst, uint32_t filter) {
+  uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= dst.w || y >= dst.h) return;
+  for (uint32_t s = 0; s < src.samples; ++s) {
+    auto rd = [&](uint32_t xx, uint32_t yy) {
+      size_t off = (((size_t)yy * src.w + xx) * src.samples + s) * src.bpp;
+      if (off + src.bpp > src.bytes) return make_float4(0, 0, 0, 0);
+      return load_texel_rgba32f(src.fmt, src.data + off);
+    };
+    float4 o;
+    if (filter == SLV_FILTER_POINT) {
+      o = rd(x * 2, y * 2);
+    } else {
+      float4 c0 = rd(x * 2, y * 2), c1 = rd(x * 2 + 1, y * 2), c2 = rd(x * 2, y * 2 + 1), c3 = rd(x * 2 + 1, y * 2 + 1);
+      o = make_float4((((c0.x + c1.x) + c2.x) + c3.x) * 0.25f, (((c0.y + c1.y) + c2.y) + c3.y) * 0.25f,
+                      (((c0.z + c1.z) + c2.z) + c3.z) * 0.25f, (((c0.w + c1.w) + c2.w) + c3.w) * 0.25f);
+    }
+    store_texel_rgba32f(dst.fmt, dst.data + (((size_t)y * dst.w + x) * dst.samples + s) * dst.bpp, o);
+  }
+}
+
+__global__ void k_sampler_probe(SamplerRef sm, uint32_t n, const float* coords, const float* ddx, const float* ddy,
+                                const float* lod, uint32_t use_lod, float4* out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 c;
+  if (use_lod) {
+    bool aniso = sm.d.mip_filter == SLV_FILTER_ANISOTROPIC;
+    AfInfo af = {0, 1, 0, 0, 0};
+    c = sample_impl(sm, coords[2 * i], coords[2 * i + 1], lod[i], aniso ? &af : nullptr);
+  } else {
+    c = sample_2d_grad(sm, coords[2 * i], coords[2 * i + 1], ddx[2 * i], ddx[2 * i + 1], ddy[2 * i], ddy[2 * i + 1], 0.0f);
+  }
+  out[i] = c;
+}
+
+}  // namespace slv

@@ -1,0 +1,374 @@
+// slv_sampler.cuh — the texture sampler on the device: address modes, point / bilinear in the native texel
+// format, mip selection (three LOD qualities) kept in registers, trilinear and anisotropic (EWA) probes.
+// Follows salvia/src/resource/sampler.cpp op for op; rgba8 texels of a
+// bilinear footprint are fetched as 32-bit words and expanded in registers, float formats with 64/128-bit
+// vector loads.
+#pragma once
+
+#include "slv_common.cuh"
+
+namespace slv {
+
+__constant__ float c_ewa_wts[256] = {
+#include "ewa_weights.inc"
+};
+
+__device__ __forceinline__ float trunc_f(float x) { return (float)(int)x; }  // cvttps2dq ; cvtdq2ps
+__device__ __forceinline__ float floor_fix(float x) {                          // sampler.cpp:36-40
+  float ip = trunc_f(x);
+  if (ip > x) ip = ip - 1.0f;
+  return ip;
+}
+__device__ __forceinline__ int wrap_index(float ipart_plus, float fsize) {  // sampler.cpp:42-44, 90-92
+  float v = ipart_plus + fsize * 8192.0f;
+  float dv = trunc_f(v / fsize);
+  return (int)(v - dv * fsize);
+}
+__device__ __forceinline__ float clamp01_idx(float v, float hi) {  // _mm_min_ps(_mm_max_ps(v, 0), hi)
+  float m = v > 0.0f ? v : 0.0f;
+  return m < hi ? m : hi;
+}
+
+// same addresser on u and v: the SIMD branches of addresser::*::do_coordi_point_2d
+__device__ inline int point_coord_2d(uint32_t mode, float c, int size) {
+  float fs = (float)size;
+  switch (mode) {
+  case SLV_ADDR_WRAP: {
+    float f = c - trunc_f(c);
+    f = fs * f;
+    return wrap_index(floor_fix(f), fs);
+  }
+  case SLV_ADDR_MIRROR: {
+    int sel = fast_floori((double)c);
+    float o = ((sel & 1) ? (float)(1 + sel) - c : c - (float)sel) * fs;
+    return (int)clamp01_idx(floor_fix(o), fs - 1.0f);
+  }
+  case SLV_ADDR_CLAMP: {
+    float o = c * fs;
+    o = o > 0.5f ? o : 0.5f;
+    float hi = fs - 0.5f;
+    o = o < hi ? o : hi;
+    return (int)clamp01_idx(floor_fix(o), fs - 1.0f);
+  }
+  default: {  // border
+    float o = c * fs;
+    o = o > -0.5f ? o : -0.5f;
+    float hi = fs - (-0.5f);
+    o = o < hi ? o : hi;
+    int ip = (int)floor_fix(o);
+    return ip >= size ? -1 : ip;
+  }
+  }
+}
+
+__device__ inline void linear_coord_2d(uint32_t mode, float c, int size, int& lo, int& up, float& frac) {
+  float fs = (float)size;
+  switch (mode) {
+  case SLV_ADDR_WRAP: {
+    float f = c - trunc_f(c);
+    f = fs * f;
+    f = f - 0.5f;
+    float ip = floor_fix(f);
+    frac = f - ip;
+    lo = wrap_index(ip + 0.0f, fs);
+    up = wrap_index(ip + 1.0f, fs);
+    return;
+  }
+  case SLV_ADDR_MIRROR: {
+    int sel = fast_floori((double)c);
+    float o = ((sel & 1) ? (float)(1 + sel) - c : c - (float)sel) * fs - 0.5f;
+    float ip = floor_fix(o);
+    frac = o - ip;
+    lo = (int)clamp01_idx(ip + 0.0f, fs - 1.0f);
+    up = (int)clamp01_idx(ip + 1.0f, fs - 1.0f);
+    return;
+  }
+  case SLV_ADDR_CLAMP: {
+    float o = c * fs;
+    o = o > 0.5f ? o : 0.5f;
+    float hi = fs - 0.5f;
+    o = o < hi ? o : hi;
+    o = o - 0.5f;
+    float ip = floor_fix(o);
+    frac = o - ip;
+    lo = (int)clamp01_idx(ip + 0.0f, fs - 1.0f);
+    up = (int)clamp01_idx(ip + 1.0f, fs - 1.0f);
+    return;
+  }
+  default: {  // border: the reference reads texel -1 (undefined); indices are clamped at the fetch
+    float o = c * fs;
+    o = o > -0.5f ? o : -0.5f;
+    float hi = fs - (-0.5f);
+    o = o < hi ? o : hi;
+    o = o + (-0.5f);
+    float ip = floor_fix(o);
+    frac = o - ip;
+    int i = (int)ip;
+    lo = i >= size ? -1 : i;
+    up = i + 1 >= size ? -1 : i + 1;
+    return;
+  }
+  }
+}
+
+// mixed addressers: the scalar coord_calculator path (sampler.cpp:396-410)
+__device__ inline float do_coordf(uint32_t mode, float coord, int size) {
+  float fs = (float)size;
+  switch (mode) {
+  case SLV_ADDR_WRAP: return (coord - fast_floor(coord)) * fs - 0.5f;
+  case SLV_ADDR_MIRROR: {
+    int sel = fast_floori((double)coord);
+    return ((sel & 1) ? (float)(1 + sel) - coord : coord - (float)sel) * fs - 0.5f;
+  }
+  case SLV_ADDR_CLAMP: return clampf(coord * fs, 0.5f, fs - 0.5f) - 0.5f;
+  default: return clampf(coord * fs, -0.5f, fs + 0.5f) - 0.5f;
+  }
+}
+__device__ inline int do_coordi_point_1d(uint32_t mode, int coord, int size) {
+  switch (mode) {
+  case SLV_ADDR_WRAP: return (size * 8192 + coord) % size;
+  case SLV_ADDR_MIRROR:
+  case SLV_ADDR_CLAMP: return min(max(coord, 0), size - 1);
+  default: return coord >= size ? -1 : coord;
+  }
+}
+
+__device__ __forceinline__ const uint8_t* texel_ptr(const SurfaceRef& s, int x, int y) {
+  x = min(max(x, 0), (int)s.w - 1);
+  y = min(max(y, 0), (int)s.h - 1);
+  return s.data + ((size_t)y * s.w + x) * s.bpp;  // textures are single-sampled
+}
+
+__device__ __forceinline__ float lerp1(float a, float b, float t) { return a + (b - a) * t; }
+
+// surface::get_texel(x0,y0,x1,y1,tx,ty): bilinear in the NATIVE format (colors.h:341-488)
+__device__ inline float4 bilinear(const SurfaceRef& s, int x0, int y0, int x1, int y1, float tx, float ty) {
+  const uint8_t* p0 = texel_ptr(s, x0, y0);
+  const uint8_t* p1 = texel_ptr(s, x1, y0);
+  const uint8_t* p2 = texel_ptr(s, x0, y1);
+  const uint8_t* p3 = texel_ptr(s, x1, y1);
+  if (s.fmt == SLV_PF_RGBA8) {
+    uint32_t t0 = __ldg(reinterpret_cast<const uint32_t*>(p0)), t1 = __ldg(reinterpret_cast<const uint32_t*>(p1));
+    uint32_t t2 = __ldg(reinterpret_cast<const uint32_t*>(p2)), t3 = __ldg(reinterpret_cast<const uint32_t*>(p3));
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float c0 = (float)((t0 >> (8 * j)) & 0xFF), c1 = (float)((t1 >> (8 * j)) & 0xFF);
+      float c2 = (float)((t2 >> (8 * j)) & 0xFF), c3 = (float)((t3 >> (8 * j)) & 0xFF);
+      float c01 = lerp1(c0, c1, tx), c23 = lerp1(c2, c3, tx);
+      o[j] = lerp1(c01, c23, ty) * (1.0f / 255);
+    }
+    return make_float4(o[0], o[1], o[2], o[3]);
+  }
+  if (s.fmt == SLV_PF_RGBA32F) {
+    float4 c0 = __ldg(reinterpret_cast<const float4*>(p0)), c1 = __ldg(reinterpret_cast<const float4*>(p1));
+    float4 c2 = __ldg(reinterpret_cast<const float4*>(p2)), c3 = __ldg(reinterpret_cast<const float4*>(p3));
+    return make_float4(lerp1(lerp1(c0.x, c1.x, tx), lerp1(c2.x, c3.x, tx), ty),
+                       lerp1(lerp1(c0.y, c1.y, tx), lerp1(c2.y, c3.y, tx), ty),
+                       lerp1(lerp1(c0.z, c1.z, tx), lerp1(c2.z, c3.z, tx), ty),
+                       lerp1(lerp1(c0.w, c1.w, tx), lerp1(c2.w, c3.w, tx), ty));
+  }
+  if (s.fmt == SLV_PF_RG32F) {  // upstream bases every channel on c0.r (Appendix B #10) — mirrored
+    float2 c0 = __ldg(reinterpret_cast<const float2*>(p0)), c1 = __ldg(reinterpret_cast<const float2*>(p1));
+    float2 c2 = __ldg(reinterpret_cast<const float2*>(p2)), c3 = __ldg(reinterpret_cast<const float2*>(p3));
+    float c01r = c0.x + (c1.x - c0.x) * tx, c01g = c0.x + (c1.y - c0.y) * tx;
+    float c23r = c2.x + (c3.x - c2.x) * tx, c23g = c2.x + (c3.y - c2.y) * tx;
+    return make_float4(c01r + (c23r - c01r) * ty, c01r + (c23g - c01g) * ty, 0.0f, 0.0f);
+  }
+  // bgra8 textures: upstream loads from byte offset 2 of the texel (Appendix B #10) — mirrored
+  const uint8_t* end = s.data + s.bytes;
+  const uint8_t* ps[4] = {p0, p1, p2, p3};
+  float c[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint8_t* q = ps[k] + 2;
+    uint32_t b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = (q + j < end) ? q[j] : 0;
+    c[k][0] = (float)b[2]; c[k][1] = (float)b[1]; c[k][2] = (float)b[0]; c[k][3] = (float)b[3];
+  }
+  float o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = lerp1(lerp1(c[0][j], c[1][j], tx), lerp1(c[2][j], c[3][j], tx), ty) * (1.0f / 255);
+  return make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// surface_sampler::point / linear ::op (sampler.cpp:423-483)
+__device__ inline float4 sample_surface(const SurfaceRef& s, const slv_sampler_desc& d, uint32_t filter, float x, float y) {
+  int W = (int)s.w, H = (int)s.h;
+  bool same = d.addr_mode_u == d.addr_mode_v;
+  if (filter == SLV_FILTER_POINT) {
+    int ix, iy;
+    bool inside;
+    if (same) {
+      ix = point_coord_2d(d.addr_mode_u, x, W);
+      iy = point_coord_2d(d.addr_mode_v, y, H);
+      inside = (0 <= ix && ix < W && 0 <= iy && iy < H);
+    } else {
+      ix = do_coordi_point_1d(d.addr_mode_u, fast_floori((double)(do_coordf(d.addr_mode_u, x, W) + 0.5f)), W);
+      iy = do_coordi_point_1d(d.addr_mode_v, fast_floori((double)(do_coordf(d.addr_mode_v, y, H) + 0.5f)), H);
+      inside = !(ix < 0 || iy < 0);
+    }
+    if (!inside) return make_float4(d.border_color[0], d.border_color[1], d.border_color[2], d.border_color[3]);
+    return load_texel_rgba32f(s.fmt, texel_ptr(s, ix, iy));
+  }
+  int x0, x1, y0, y1;
+  float tx, ty;
+  if (same) {
+    linear_coord_2d(d.addr_mode_u, x, W, x0, x1, tx);
+    linear_coord_2d(d.addr_mode_v, y, H, y0, y1, ty);
+  } else {
+    float ox = do_coordf(d.addr_mode_u, x, W);
+    int ipx = fast_floori((double)ox);
+    x0 = do_coordi_point_1d(d.addr_mode_u, ipx, W);
+    x1 = do_coordi_point_1d(d.addr_mode_u, ipx + 1, W);
+    tx = ox - (float)ipx;
+    float oy = do_coordf(d.addr_mode_v, y, H);
+    int ipy = fast_floori((double)oy);
+    y0 = do_coordi_point_1d(d.addr_mode_v, ipy, H);
+    y1 = do_coordi_point_1d(d.addr_mode_v, ipy + 1, H);
+    ty = oy - (float)ipy;
+  }
+  return bilinear(s, x0, y0, x1, y1, tx, ty);
+}
+
+struct AfInfo { float lod, probe_count, weight_D, du, dv; };
+
+// sampler::calc_lod (sampler.cpp:521-603)
+__device__ inline float calc_lod(const slv_sampler_desc& d, float sw, float sh, float ddx0, float ddx1, float ddy0,
+                                 float ddy1, float bias) {
+  if (d.mip_qual == SLV_MIP_LO_QUALITY) {
+    float m0 = std_max(fabsf(ddx0), fabsf(ddy0));
+    float m1 = std_max(fabsf(ddx1), fabsf(ddy1));
+    float m2 = 0.0f;
+    m0 *= sw; m1 *= sh; m2 *= 1.0f;
+    float rho = std_max(std_max(m0, m1), m2);
+    return fast_log2(rho) + bias;
+  }
+  float dxs0 = ddx0 * sw, dxs1 = ddx1 * sh, dxs2 = 0.0f;
+  float dys0 = ddy0 * sw, dys1 = ddy1 * sh, dys2 = 0.0f;
+  float rho;
+  if (d.mip_qual == SLV_MIP_HI_QUALITY) {
+    float A = dxs0 * dxs0 + dys0 * dys0;
+    float B = -2.0f * (dxs0 * dxs1 + dys0 * dys1);
+    float Cc = dxs1 * dxs1 + dys1 * dys1;
+    float F = A * Cc - B * B * 0.25f;
+    float invF = 1.0f / F;
+    A *= invF; B *= invF; Cc *= invF;
+    float AsubC = A - Cc;
+    float R = sqrtf(AsubC * AsubC + B * B);
+    rho = sqrtf(2.0f / (A + Cc - R));
+  } else {
+    rho = std_max(length3(dxs0, dxs1, dxs2), length3(dys0, dys1, dys2));
+  }
+  if (rho == 0.0f) rho = 0.000001f;
+  return fast_log2(rho) + bias;
+}
+
+// sampler::calc_anisotropic_info (sampler.cpp:875-958)
+__device__ inline void calc_af(const slv_sampler_desc& d, float sw, float sh, float ddx0, float ddx1, float ddy0,
+                               float ddy1, float bias, AfInfo& o) {
+  float dxs0 = ddx0 * sw, dxs1 = ddx1 * sh;
+  float dys0 = ddy0 * sw, dys1 = ddy1 * sh;
+  float ddx_len = length2(dxs0, dxs1);
+  float ddy_len = length2(dys0, dys1);
+  float diag0 = length2(dxs0 - dys0, dxs1 - dys1);
+  float diag1 = length2(dxs0 + dys0, dxs1 + dys1);
+  float minor = std_min(std_min(diag0, diag1), std_min(ddx_len, ddy_len));
+  if (minor == 0.0f) minor = 0.000001f;
+  float la0, la1, la_len;
+  if (ddx_len > ddy_len) { la_len = ddx_len; la0 = dxs0; la1 = dxs1; } else { la_len = ddy_len; la0 = dys0; la1 = dys1; }
+  float probe = (2.0f * la_len / minor) - 1.0f;
+  float rp = fast_round(probe);
+  rp = std_min((float)d.max_anisotropy, rp);
+  if (rp < probe) minor = 2.0f * la_len / (rp + 1.0f);
+  o.lod = fast_log2(minor) + bias;
+  o.probe_count = rp;
+  if (rp <= 1.0f) {
+    o.du = o.dv = 0.0f;
+    o.weight_D = 0.0f;
+  } else {
+    float r = minor / la_len;
+    float k0 = (1.0f - r), k2 = (1.0f / (rp - 1.0f));
+    float dx = ((la0 * k0) * 2.0f) * k2, dy = ((la1 * k0) * 2.0f) * k2;
+    float dz = ((0.0f * k0) * 2.0f) * k2;
+    float lsq = 0.0f;
+    lsq += dx * dx; lsq += dy * dy; lsq += dz * dz; lsq += dz * dz;
+    o.weight_D = 256.0f * lsq * 0.25f / (la_len * la_len);
+    o.du = dx / sw;
+    o.dv = dy / sh;
+  }
+}
+
+// sampler::sample_impl<false> (sampler.cpp:680-764)
+__device__ inline float4 sample_impl(const SamplerRef& sm, float cx, float cy, float miplevel, const AfInfo* af) {
+  const slv_sampler_desc& d = sm.d;
+  const TextureRef& t = sm.tex;
+  int max_lod = 0, min_lod = (int)t.n_levels - 1;
+  bool is_mag = (d.mip_filter == SLV_FILTER_POINT) ? (miplevel < 0.5f) : (miplevel < 0.0f);
+  if (is_mag) return sample_surface(t.level[max_lod], d, d.mag_filter, cx, cy);
+  if (d.mip_filter == SLV_FILTER_POINT) {
+    int ml = fast_floori(0.5 + (double)miplevel);
+    ml = min(max(ml, max_lod), min_lod);
+    return sample_surface(t.level[ml], d, d.min_filter, cx, cy);
+  }
+  if (d.mip_filter == SLV_FILTER_LINEAR) {
+    int lo = fast_floori((double)miplevel);
+    int hi = lo + 1;
+    float frac = miplevel - (float)lo;
+    int lo_sz = min(max(lo, max_lod), min_lod);
+    int hi_sz = min(max(hi, max_lod), min_lod);
+    float4 c0 = sample_surface(t.level[lo_sz], d, d.min_filter, cx, cy);
+    float4 c1 = sample_surface(t.level[hi_sz], d, d.min_filter, cx, cy);
+    return make_float4(lerp1(c0.x, c1.x, frac), lerp1(c0.y, c1.y, frac), lerp1(c0.z, c1.z, frac),
+                       lerp1(c0.w, c1.w, frac));
+  }
+  // anisotropic: N probes along the major axis, EWA weights (sampler.cpp:730-760)
+  float start = -0.5f * (af->probe_count - 1.0f);
+  float sx = cx + af->du * start;
+  float sy = cy + af->dv * start;
+  int lo = fast_roundi((double)miplevel);
+  int lo_sz = lo < 0 ? min_lod : min(max(lo, max_lod), min_lod);  // size_t cast of a negative int clamps to min_lod
+  float4 color = make_float4(0, 0, 0, 0);
+  float w_sum = 0.0f;
+  int pc = (int)af->probe_count;
+  for (int i = -pc + 1; i < pc; i += 2) {
+    float4 c0 = sample_surface(t.level[lo_sz], d, d.min_filter, sx, sy);
+    int wi = (int)((float)(i * i) * af->weight_D);
+    float w = c_ewa_wts[min(max(wi, 0), 255)];
+    color.x += c0.x * w; color.y += c0.y * w; color.z += c0.z * w; color.w += c0.w * w;
+    w_sum += w;
+    sx += af->du;
+    sy += af->dv;
+  }
+  float inv = 1 / w_sum;
+  return make_float4(color.x * inv, color.y * inv, color.z * inv, color.w * inv);
+}
+
+// sampler::calc_lod_2d (sampler.cpp:831-848)
+__device__ inline float calc_lod_2d(const SamplerRef& sm, float ddx0, float ddx1, float ddy0, float ddy1) {
+  float sw = (float)sm.tex.level[0].w, sh = (float)sm.tex.level[0].h;
+  if (sm.d.mip_filter == SLV_FILTER_ANISOTROPIC && sm.d.max_anisotropy > 1) {
+    AfInfo af;
+    calc_af(sm.d, sw, sh, ddx0, ddx1, ddy0, ddy1, 0.0f, af);
+    return af.lod;
+  }
+  return calc_lod(sm.d, sw, sh, ddx0, ddx1, ddy0, ddy1, 0.0f);
+}
+
+// sampler::sample_2d_grad (sampler.cpp:854-873)
+__device__ inline float4 sample_2d_grad(const SamplerRef& sm, float u, float v, float ddx0, float ddx1, float ddy0,
+                                        float ddy1, float bias) {
+  float sw = (float)sm.tex.level[0].w, sh = (float)sm.tex.level[0].h;
+  AfInfo af = {0, 0, 0, 0, 0};
+  float lod;
+  if (sm.d.mip_filter == SLV_FILTER_ANISOTROPIC && sm.d.max_anisotropy > 1) {
+    calc_af(sm.d, sw, sh, ddx0, ddx1, ddy0, ddy1, bias, af);
+    lod = af.lod;
+  } else {
+    lod = calc_lod(sm.d, sw, sh, ddx0, ddx1, ddy0, ddy1, bias);
+  }
+  return sample_impl(sm, u, v, lod, &af);
+}
+
+}  // namespace slv

@@ -320,3 +320,195 @@ class ColorizedTriangle:
         self.render(be, frame)
         stats = be.query_get()
         return read_frame(be, self.t, stats)
+
+
+# ---- textures ----------------------------------------------------------------------------------------------
+def chessboard_texture(n=32, cell=4) -> np.ndarray:
+    """Procedural stand-in for resources/texture_and_blending/chessboard.png (32x32 RGBA)."""
+    y, x = np.mgrid[0:n, 0:n]
+    on = ((x // cell + y // cell) & 1).astype(np.uint8)
+    img = np.empty((n, n, 4), dtype=np.uint8)
+    img[..., 0] = 40 + on * 200
+    img[..., 1] = 40 + on * 190
+    img[..., 2] = 50 + on * 170
+    img[..., 3] = 255
+    return img
+
+
+def noise_texture(size=512, seed=20240607) -> np.ndarray:
+    """Seeded value-noise RGBA8 (stand-in for Dirt.jpg): uniform bytes + 3x3 box blur."""
+    rng = np.random.default_rng(seed)
+    raw = rng.integers(0, 256, size=(size, size, 4), dtype=np.uint8).astype(np.uint32)
+    acc = np.zeros_like(raw)
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            acc += np.roll(np.roll(raw, dy, 0), dx, 1)
+    img = (acc // 9).astype(np.uint8)
+    img[..., 3] = 255
+    return img
+
+
+def brick_texture(size=1024, seed=1) -> np.ndarray:
+    """Seeded brick/noise RGBA8 used by the Sponza-like atrium materials."""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(60, 200, size=3)
+    y, x = np.mgrid[0:size, 0:size]
+    bh, bw = size // 16, size // 8
+    row = y // bh
+    xs = x + (row & 1) * (bw // 2)
+    mortar = ((y % bh) < max(2, bh // 10)) | ((xs % bw) < max(2, bw // 16))
+    grain = rng.integers(0, 48, size=(size, size), dtype=np.int32)
+    brick_id = (row * 131 + xs // bw * 71) % 29
+    img = np.empty((size, size, 4), dtype=np.uint8)
+    for c in range(3):
+        v = base[c] + (brick_id - 14) * 2 + grain - 24
+        v = np.where(mortar, 200 + grain // 4, v)
+        img[..., c] = np.clip(v, 0, 255).astype(np.uint8)
+    img[..., 3] = 255
+    return img
+
+
+def make_texture(be: A.Backend, img: np.ndarray, fmt=A.PF_RGBA8, mips=True) -> A.Texture:
+    h, w = img.shape[:2]
+    t = be.create_texture(w, h, 1, fmt)
+    be.upload_texture(t, img)
+    if mips:
+        be.gen_mipmap(t, A.FILTER_LINEAR)
+    return t
+
+
+# ===========================================================================================================
+# C2: TextureAndBlending
+# ===========================================================================================================
+class TextureAndBlending:
+    """samples/TextureAndBlending/TextureAndBlending.cpp:196-347: plane (wrap chessboard, replace) then the
+    box twice (cull front, cull back) with lerp(dst, src, 0.5); color target bgra8; trilinear samplers."""
+
+    def __init__(self, w=1920, h=1080, samples=1, ps_program=A.PS_TEX_ALPHA, mip_filter=A.FILTER_LINEAR,
+                 max_aniso=0):
+        self.w, self.h, self.samples = w, h, samples
+        self.ps_program, self.mip_filter, self.max_aniso = ps_program, mip_filter, max_aniso
+        self.plane = create_planar((-3.0, -1.0, -3.0), (6, 0, 0), (0, 0, 6), 1, 1, True)
+        box = create_box()
+        # vs_box binds POSITION -> reg0 and TEXCOORD -> reg1 (the uv stream, slot 2)
+        box.elements = [(0, _V4, 0, 0, 1.0), (1, _V4, 2, 0, 0.0)]
+        self.box = box
+        self.plane.elements = [(0, _V4, 0, 0, 1.0)]
+        self.n_frames = 5
+        self.chess = chessboard_texture()
+        self.noise = noise_texture()
+
+    def setup(self, be: A.Backend):
+        self.t = create_targets(be, self.w, self.h, self.samples, A.PF_BGRA8)
+        self.plane.upload(be)
+        self.box.upload(be)
+        self.plane_tex = make_texture(be, self.chess)
+        self.box_tex = make_texture(be, self.noise)
+        self.plane_samp = be.create_sampler(
+            A.sampler_desc(A.FILTER_LINEAR, A.FILTER_LINEAR, self.mip_filter, addr_u=A.ADDR_WRAP, addr_v=A.ADDR_WRAP,
+                           max_anisotropy=self.max_aniso), self.plane_tex)
+        self.box_samp = be.create_sampler(
+            A.sampler_desc(A.FILTER_LINEAR, A.FILTER_LINEAR, self.mip_filter, addr_u=A.ADDR_CLAMP, addr_v=A.ADDR_CLAMP,
+                           max_anisotropy=self.max_aniso), self.box_tex)
+
+    def render(self, be: A.Backend, frame: int):
+        t = self.t
+        be.clear_color(t.color, (0.2, 0.2, 0.5, 1.0))
+        be.clear_depth_stencil(t.ds, A.CLEAR_DEPTH | A.CLEAR_STENCIL, 1.0, 0)
+        scene_sec = float(f32(frame * 6) / f32(self.n_frames - 1))
+        angle = -scene_sec * 60.0 * (2 * math.pi / 360.0)
+        camera = (math.cos(angle) * 1.5, 1.5, math.sin(angle) * 1.5)
+        view = mat_lookat(camera, (0, 0, 0), (0, 1, 0))
+        proj = mat_perspective_fov(math.pi / 2, f32(self.w) / f32(self.h), 0.1, 100.0)
+        wvp = mat_mul(mat_translate(-0.5, 0, -0.5), mat_mul(view, proj))
+
+        d = base_desc(t, self.w, self.h, cull=A.CULL_BACK)
+        self.plane.fill_desc(be, d)
+        d.vs = A.shader_binding(A.VS_PLANE_XZ, pack_vs_plane_xz(wvp))
+        d.ps = A.shader_binding(self.ps_program, pack_ps_tex_alpha(0, 1.0), [self.plane_samp])
+        d.bs = A.shader_binding(A.BS_REPLACE)
+        be.draw(d)
+
+        for cull in (A.CULL_FRONT, A.CULL_BACK):
+            d = base_desc(t, self.w, self.h, cull=cull)
+            self.box.fill_desc(be, d)
+            d.vs = A.shader_binding(A.VS_MVP_PASSTHROUGH, pack_vs_mvp_passthrough(wvp, [0, 1]))
+            d.ps = A.shader_binding(self.ps_program, pack_ps_tex_alpha(1, 0.5), [self.box_samp])
+            d.bs = A.shader_binding(A.BS_LERP_SRC_ALPHA)
+            be.draw(d)
+        if t.resolved is not None:
+            be.resolve(t.color, t.resolved)
+
+    def run(self, be: A.Backend, frame: int) -> FrameResult:
+        be.query_begin()
+        self.render(be, frame)
+        stats = be.query_get()
+        return read_frame(be, self.t, stats)
+
+
+# ===========================================================================================================
+# triangle soup: seeded random triangles that cross the near/far planes, every cull/depth/stencil variant
+# ===========================================================================================================
+class TriangleSoup:
+    """Parity torture scene (no reference twin): `n` random triangles in clip space, a good share of which
+    straddle z=0 / z=w, drawn with PS_ATTR0_COLOR.  Exercises clipper.cpp:103-228, cull modes, depth
+    functions, the stencil path and the coverage counter."""
+
+    def __init__(self, w=256, h=192, samples=1, n=300, seed=7, cull=A.CULL_NONE, ds=None, stencil_ref=0,
+                 bs=A.BS_REPLACE_AND_COUNT, index_dtype=np.uint16, modifiers=None, strip=False, size=1.0,
+                 color_fmt=A.PF_RGBA8, ps=A.PS_ATTR0_COLOR):
+        self.w, self.h, self.samples, self.n = w, h, samples, n
+        self.cull, self.ds, self.stencil_ref, self.bs, self.modifiers = cull, ds, stencil_ref, bs, modifiers
+        self.color_fmt, self.ps = color_fmt, ps
+        rng = np.random.default_rng(seed)
+        nv = n + 2 if strip else n * 3
+        c = rng.uniform(-1.2, 1.2, size=(nv, 2)).astype(f32)
+        if strip:
+            pos_xy = c + rng.uniform(-0.1, 0.1, size=(nv, 2)).astype(f32)
+        else:
+            ctr = np.repeat(rng.uniform(-1.1, 1.1, size=(n, 2)), 3, axis=0)
+            pos_xy = (ctr + rng.normal(0, 0.25 * size, size=(nv, 2))).astype(f32)
+        wv = rng.uniform(0.2, 3.0, size=(nv, 1)).astype(f32)
+        z = (rng.uniform(-0.3, 1.3, size=(nv, 1)) * wv).astype(f32)
+        # a few exactly-degenerate and w<=0 vertices
+        neg = rng.random(nv) < 0.05
+        wv[neg] *= -1
+        pos = np.concatenate([pos_xy * wv, z, wv], axis=1).astype(f32)
+        col = rng.uniform(0, 1, size=(nv, 4)).astype(f32)
+        if strip:
+            idx = np.arange(nv, dtype=index_dtype)
+            self.mesh = Mesh([pos, col], [(0, _V4, 0, 0, 1.0), (1, _V4, 1, 0, 0.0)], idx, n, A.TOPO_TRIANGLE_STRIP)
+        else:
+            idx = rng.permutation(nv).astype(index_dtype)
+            self.mesh = Mesh([pos, col], [(0, _V4, 0, 0, 1.0), (1, _V4, 1, 0, 0.0)], idx, n)
+        self.n_frames = 1
+
+    def setup(self, be: A.Backend):
+        self.t = create_targets(be, self.w, self.h, self.samples, self.color_fmt,
+                                with_count=self.bs == A.BS_REPLACE_AND_COUNT)
+        self.mesh.upload(be)
+
+    def render(self, be: A.Backend, frame: int = 0):
+        t = self.t
+        be.clear_color(t.color, (0.1, 0.2, 0.3, 1.0))
+        if t.count is not None:
+            be.clear_color(t.count, (0, 0, 0, 0))
+        be.clear_depth_stencil(t.ds, A.CLEAR_DEPTH | A.CLEAR_STENCIL, 0.6, 3)
+        d = base_desc(t, self.w, self.h, cull=self.cull, ds=self.ds)
+        d.stencil_ref = self.stencil_ref
+        self.mesh.fill_desc(be, d)
+        if self.modifiers:
+            for i, m in enumerate(self.modifiers):
+                d.vs_attr_modifiers[i] = m
+        d.vs = A.shader_binding(A.VS_MVP_PASSTHROUGH, pack_vs_mvp_passthrough(mat_identity(), [1]))
+        d.ps = A.shader_binding(self.ps)
+        d.bs = A.shader_binding(self.bs)
+        be.draw(d)
+        if t.resolved is not None:
+            be.resolve(t.color, t.resolved)
+
+    def run(self, be: A.Backend, frame: int = 0) -> FrameResult:
+        be.query_begin()
+        self.render(be, frame)
+        stats = be.query_get()
+        return read_frame(be, self.t, stats)
