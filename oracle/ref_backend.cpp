@@ -292,6 +292,11 @@ struct slv_device_t {
   renderer_ptr r;
   std::vector<resource_entry> res;  // index = handle; [0] unused
   async_object_ptr q_stat, q_internal, q_prof;
+  // State objects are kept alive and re-used per distinct descriptor, like an application does: the
+  // reference caches on the POINTER identity of the depth-stencil state (framebuffer.cpp:326,361-363), so
+  // re-allocating a state object per draw could alias a stale one at a recycled address.
+  std::vector<std::pair<slv_depth_stencil_desc, depth_stencil_state_ptr>> ds_states;
+  std::vector<std::pair<slv_raster_desc, raster_state_ptr>> rs_states;
   bool q_active = false;
 
   resource_entry* get(slv_handle h) {
@@ -512,7 +517,16 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   raster_desc rd;
   rd.cm = (cull_mode)d->raster.cull_mode;
   rd.front_ccw = d->raster.front_ccw != 0;
-  r->set_rasterizer_state(raster_state_ptr(new raster_state(rd)));
+  {
+    raster_state_ptr rs;
+    for (auto& kv : dev->rs_states)
+      if (memcmp(&kv.first, &d->raster, sizeof(slv_raster_desc)) == 0) rs = kv.second;
+    if (!rs) {
+      rs.reset(new raster_state(rd));
+      dev->rs_states.emplace_back(d->raster, rs);
+    }
+    r->set_rasterizer_state(rs);
+  }
 
   depth_stencil_desc dd;
   dd.depth_enable = d->ds.depth_enable != 0;
@@ -531,7 +545,16 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   };
   dd.front_face = cvt(d->ds.front_face);
   dd.back_face = cvt(d->ds.back_face);
-  r->set_depth_stencil_state(depth_stencil_state_ptr(new depth_stencil_state(dd)), d->stencil_ref);
+  {
+    depth_stencil_state_ptr dss;
+    for (auto& kv : dev->ds_states)
+      if (memcmp(&kv.first, &d->ds, sizeof(slv_depth_stencil_desc)) == 0) dss = kv.second;
+    if (!dss) {
+      dss.reset(new depth_stencil_state(dd));
+      dev->ds_states.emplace_back(d->ds, dss);
+    }
+    r->set_depth_stencil_state(dss, d->stencil_ref);
+  }
 
   std::vector<surface_ptr> colors;
   for (uint32_t i = 0; i < d->n_color_targets; ++i) colors.push_back(dev->surface_of(d->color_targets[i]));

@@ -512,3 +512,220 @@ class TriangleSoup:
         self.render(be, frame)
         stats = be.query_get()
         return read_frame(be, self.t, stats)
+
+
+# ===========================================================================================================
+# C4: Sponza-like atrium (procedural stand-in for resources/sponza_lq/sponza.obj, a Git-LFS pointer upstream)
+# ===========================================================================================================
+def _grid(fn, nu, nv, flip=False):
+    """Samples a parametric surface fn(u, v) -> (pos[...,3], normal[...,3], uv[...,2]) on an (nu x nv) quad grid.
+    Returns interleaved 48-byte vertices (pos.xyz1, uv00, normal.xyz0 — mesh_io_obj.cpp:398-431 layout) and
+    a (2*nu*nv, 3) index array."""
+    u, v = np.meshgrid(np.linspace(0, 1, nu + 1, dtype=np.float64), np.linspace(0, 1, nv + 1, dtype=np.float64), indexing="ij")
+    pos, nrm, uv = fn(u, v)
+    n = (nu + 1) * (nv + 1)
+    vb = np.zeros((n, 12), dtype=f32)
+    vb[:, 0:3] = pos.reshape(n, 3)
+    vb[:, 3] = 1.0
+    vb[:, 4:6] = uv.reshape(n, 2)
+    nn = nrm.reshape(n, 3)
+    nn = nn / np.maximum(np.linalg.norm(nn, axis=1, keepdims=True), 1e-12)
+    vb[:, 8:11] = nn
+    i, j = np.meshgrid(np.arange(nu), np.arange(nv), indexing="ij")
+    q0 = (i * (nv + 1) + j).reshape(-1)
+    q1, q2, q3 = q0 + 1, q0 + nv + 2, q0 + nv + 1
+    tri = np.stack([np.stack([q0, q1, q2], 1), np.stack([q2, q3, q0], 1)], 1).reshape(-1, 3)
+    if flip:
+        tri = tri[:, ::-1]
+    return vb, tri.astype(np.uint32)
+
+
+def _plane(origin, du, dv, uvscale, nu, nv, flip=False, bump=0.0, seed=0):
+    origin, du, dv = (np.asarray(a, dtype=np.float64) for a in (origin, du, dv))
+    # with index order (q0, q0+v, q0+u+v) the front (un-culled) side is the one dv x du points to
+    nrm0 = np.cross(du, dv) if flip else np.cross(dv, du)
+    nrm0 = nrm0 / np.linalg.norm(nrm0)
+
+    def fn(u, v):
+        pos = origin + u[..., None] * du + v[..., None] * dv
+        nrm = np.broadcast_to(nrm0, pos.shape).copy()
+        if bump:
+            h = bump * (np.sin(u * 37.0 + seed) * np.cos(v * 29.0 + seed * 0.7) + 0.5 * np.sin(u * 91.0) * np.sin(v * 83.0))
+            pos = pos + h[..., None] * nrm0
+            nrm = nrm + 0.3 * np.stack([np.cos(u * 37.0 + seed), np.sin(v * 29.0), np.zeros_like(u)], -1)
+        uv = np.stack([u * uvscale[0], v * uvscale[1]], -1)
+        return pos, nrm, uv
+
+    return _grid(fn, nu, nv, flip)
+
+
+def _cylinder(base, radius, height, nu, nv, uvscale=(4, 4), bulge=0.0):
+    base = np.asarray(base, dtype=np.float64)
+
+    def fn(u, v):
+        a = u * 2 * np.pi
+        r = radius * (1.0 + bulge * np.sin(v * np.pi))
+        pos = base + np.stack([r * np.cos(a), v * height, r * np.sin(a)], -1)
+        nrm = np.stack([np.cos(a), np.zeros_like(a), np.sin(a)], -1)
+        return pos, nrm, np.stack([u * uvscale[0], v * uvscale[1]], -1)
+
+    return _grid(fn, nu, nv, flip=True)
+
+
+def _sphere(center, radius, nu, nv, squash=1.0):
+    center = np.asarray(center, dtype=np.float64)
+
+    def fn(u, v):
+        a, b = u * 2 * np.pi, (v - 0.5) * np.pi
+        d = np.stack([np.cos(b) * np.cos(a), squash * np.sin(b), np.cos(b) * np.sin(a)], -1)
+        return center + radius * d, d, np.stack([u * 2, v * 2], -1)
+
+    return _grid(fn, nu, nv, flip=True)
+
+
+def _arch(center, span, rise, depth, nu, nv):
+    """Half-ring (arch) in the xy plane extruded along z, between two columns."""
+    center = np.asarray(center, dtype=np.float64)
+
+    def fn(u, v):
+        a = u * np.pi
+        ring = np.stack([0.5 * span * np.cos(a), rise * np.sin(a), np.zeros_like(a)], -1)
+        b = v * 2 * np.pi
+        tube = 0.6 * np.stack([np.cos(a) * np.cos(b), np.sin(a) * np.cos(b), (depth / 0.6) * 0.5 * np.sin(b)], -1)
+        pos = center + ring + tube
+        return pos, tube, np.stack([u * 6, v * 2], -1)
+
+    return _grid(fn, nu, nv, flip=True)
+
+
+def _drape(origin, width, height, nu, nv, seed, flip=False):
+    origin = np.asarray(origin, dtype=np.float64)
+    sgn = -1.0 if flip else 1.0
+
+    def fn(u, v):
+        wave = 0.6 * np.sin(u * 14.0 + seed) * (0.3 + v) + 0.25 * np.sin(v * 9.0 + 2 * seed)
+        pos = origin + np.stack([u * width, -v * height, wave], -1)
+        nrm = sgn * np.stack([-0.6 * 14.0 / width * np.cos(u * 14.0 + seed) * (0.3 + v), np.zeros_like(u), np.ones_like(u)], -1)
+        return pos, nrm, np.stack([u * 3, v * 3], -1)
+
+    return _grid(fn, nu, nv, flip=flip)
+
+
+class SponzaLike:
+    """Deterministic 262,249-triangle atrium in 24 material groups, one shared 48-byte-stride vertex buffer and
+    one u32 index buffer, one draw per material, trilinear wrap samplers, PS = diffuse x clamp(N.L)
+    (samples/Sponza/Sponza.cpp:143-278; counters to match: benchmark.db.txt ia_primitives 262,249)."""
+
+    N_TRIS = 262249
+    N_MATERIALS = 24
+
+    def __init__(self, w=3840, h=2160, samples=4, tex_size=1024, max_aniso=0, color_fmt=A.PF_BGRA8):
+        self.w, self.h, self.samples, self.tex_size, self.max_aniso = w, h, samples, tex_size, max_aniso
+        self.color_fmt = color_fmt
+        self.n_frames = 8
+        self._build()
+
+    def _build(self):
+        parts = []  # (material, vb, tris)
+        add = lambda m, g: parts.append((m, g[0], g[1]))  # noqa: E731
+        X0, X1, Y1, Z = -45.0, 45.0, 32.0, 14.0
+        add(0, _plane((X0, 0, -Z), (X1 - X0, 0, 0), (0, 0, 2 * Z), (12, 4), 128, 48, flip=False))          # floor
+        add(1, _plane((X0, Y1, -Z), (X1 - X0, 0, 0), (0, 0, 2 * Z), (6, 2), 64, 24, flip=True))            # ceiling
+        add(2, _plane((X0, 0, -Z), (X1 - X0, 0, 0), (0, Y1, 0), (10, 4), 128, 32, flip=True, bump=0.05))   # wall -z
+        add(3, _plane((X0, 0, Z), (X1 - X0, 0, 0), (0, Y1, 0), (10, 4), 128, 32, flip=False, bump=0.05, seed=3))
+        add(4, _plane((X0, 0, -Z), (0, 0, 2 * Z), (0, Y1, 0), (4, 4), 32, 32, flip=False))                 # end wall
+        add(5, _plane((X1, 0, -Z), (0, 0, 2 * Z), (0, Y1, 0), (4, 4), 32, 32, flip=True))
+        xs = np.linspace(-40, 40, 12)
+        for k, x in enumerate(xs):
+            for side in (-1, 1):
+                add(6 + (k % 2), _cylinder((x, 0, side * 8.0), 0.9, 12.0, 32, 24, bulge=0.08))
+                add(8, _sphere((x, 12.4, side * 8.0), 1.3, 24, 12, squash=0.5))
+        for k in range(11):
+            xc = 0.5 * (xs[k] + xs[k + 1])
+            for side in (-1, 1):
+                add(9 + (k % 2), _arch((xc, 12.0, side * 8.0), xs[1] - xs[0] - 1.8, 3.0, 1.2, 32, 16))
+                add(11 + (k % 2), _arch((xc, 22.0, side * 8.0), xs[1] - xs[0] - 1.8, 2.5, 1.0, 32, 16))
+        add(13, _plane((X0, 16.0, -Z), (X1 - X0, 0, 0), (0, 0, Z - 8.0), (12, 1), 128, 8, flip=False))     # balconies
+        add(14, _plane((X0, 16.0, 8.0), (X1 - X0, 0, 0), (0, 0, Z - 8.0), (12, 1), 128, 8, flip=False))
+        for k in range(8):
+            add(15 + (k % 3), _drape((-38 + k * 10.0, 15.5, (-1) ** k * 7.0), 6.0, 9.0, 64, 64, seed=k, flip=(k % 2 == 0)))
+        for k in range(16):
+            add(18 + (k % 2), _sphere((-37.5 + k * 5.0, 1.2, (-1) ** k * 4.5), 1.2, 48, 24))
+        add(20, _plane((-30, 4.0, -Z + 0.2), (20, 0, 0), (0, 12, 0), (2, 2), 64, 64, flip=True, bump=0.35, seed=5))
+        add(21, _plane((10, 4.0, Z - 0.2), (20, 0, 0), (0, 12, 0), (2, 2), 64, 64, flip=False, bump=0.35, seed=6))
+        add(22, _plane((-35, 0.02, -2.0), (70, 0, 0), (0, 0, 4.0), (20, 1), 139, 28, flip=False, bump=0.02, seed=8))  # carpet
+        n = sum(p[2].shape[0] for p in parts)
+        assert n == self.N_TRIS - 1, n
+        vb1 = np.zeros((3, 12), dtype=f32)  # one lone triangle (banner) completes the published count
+        vb1[:, 0:3] = [(-1, 26, 0), (1, 26, 0), (0, 28, 0)]
+        vb1[:, 3] = 1
+        vb1[:, 4:6] = [(0, 0), (1, 0), (0.5, 1)]
+        vb1[:, 8:11] = (0, 0, -1)
+        parts.append((23, vb1, np.array([[0, 1, 2]], dtype=np.uint32)))
+        # concatenate by material
+        parts.sort(key=lambda p: p[0])
+        vbs, ibs, self.groups = [], [], []
+        base = 0
+        tri_cursor = 0
+        cur_m, cur_start = None, 0
+        for m, vb, tri in parts:
+            if m != cur_m:
+                if cur_m is not None:
+                    self.groups.append((cur_m, cur_start, tri_cursor - cur_start))
+                cur_m, cur_start = m, tri_cursor
+            vbs.append(vb)
+            ibs.append(tri + base)
+            base += vb.shape[0]
+            tri_cursor += tri.shape[0]
+        self.groups.append((cur_m, cur_start, tri_cursor - cur_start))
+        vb = np.concatenate(vbs).astype(f32)
+        ib = np.concatenate(ibs).astype(np.uint32).reshape(-1)
+        assert ib.size == self.N_TRIS * 3 and len(self.groups) == self.N_MATERIALS
+        self.mesh = Mesh([vb], [(0, _V4, 0, 0, 1.0), (1, _V4, 0, 16, 0.0), (2, _V4, 0, 32, 0.0)], ib, self.N_TRIS)
+
+    def setup(self, be: A.Backend):
+        self.t = create_targets(be, self.w, self.h, self.samples, self.color_fmt)
+        self.mesh.upload(be)
+        self.textures, self.samplers = [], []
+        mipf = A.FILTER_ANISOTROPIC if self.max_aniso > 1 else A.FILTER_LINEAR
+        for m in range(self.N_MATERIALS):
+            tex = make_texture(be, brick_texture(self.tex_size, seed=100 + m))
+            self.textures.append(tex)
+            self.samplers.append(be.create_sampler(
+                A.sampler_desc(A.FILTER_LINEAR, A.FILTER_LINEAR, mipf, addr_u=A.ADDR_WRAP, addr_v=A.ADDR_WRAP,
+                               max_anisotropy=self.max_aniso), tex))
+
+    def frame_uniforms(self, frame):
+        scene_sec = float(f32(frame * 18) / f32(self.n_frames - 1))
+        xpos = -36.0 + math.fmod(3.0 * scene_sec, 66.0)
+        camera = (xpos, 8.0, 0.0)
+        view = mat_lookat(camera, (40.0, 15.0, 0.0), (0, 1, 0))
+        proj = mat_perspective_fov(math.pi / 2, f32(self.w) / f32(self.h), 0.1, 1000.0)
+        wvp = mat_mul(mat_translate(-0.5, 0, -0.5), mat_mul(view, proj))
+        ypos = 10.0 + math.fmod(8.0 * scene_sec, 40.0)
+        return wvp, (0.0, ypos, 0.0, 1.0), (*camera, 1.0)
+
+    def render(self, be: A.Backend, frame: int):
+        t = self.t
+        be.clear_color(t.color, (0.2, 0.2, 0.5, 1.0))
+        be.clear_depth_stencil(t.ds, A.CLEAR_DEPTH | A.CLEAR_STENCIL, 1.0, 0)
+        wvp, light, eye = self.frame_uniforms(frame)
+        vs = A.shader_binding(A.VS_SPONZA, pack_vs_sponza(wvp, light, eye))
+        bs = A.shader_binding(A.BS_REPLACE)
+        # the SASL tex2D path is required for anisotropic filtering (SURVEY Appendix B #6); the cpp tex2d path
+        # (LOD once per quad) is what samples/Sponza uses for trilinear
+        for m, start, count in self.groups:
+            d = base_desc(t, self.w, self.h, cull=A.CULL_BACK)
+            self.mesh.fill_desc(be, d, start=start * 3, prim_count=count)
+            d.vs = vs
+            d.ps = A.shader_binding(A.PS_SPONZA, pack_ps_sponza(True), [self.samplers[m]])
+            d.bs = bs
+            be.draw(d)
+        if t.resolved is not None:
+            be.resolve(t.color, t.resolved)
+
+    def run(self, be: A.Backend, frame: int) -> FrameResult:
+        be.query_begin()
+        self.render(be, frame)
+        stats = be.query_get()
+        return read_frame(be, self.t, stats)

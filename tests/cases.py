@@ -1,0 +1,99 @@
+"""The parity cases shared by the golden generator, the oracle tests (CPU) and the CUDA tests (GPU)."""
+import hashlib
+
+import numpy as np
+
+from salviarenderer_b200 import abi as A, scenes as S
+
+GATED_COUNTERS = ("ia_vertices", "ia_primitives", "cinvocations", "cprimitives", "ps_invocations", "backend_input_pixels")
+
+
+def _stencil_ds(sop, fn):
+    return A.depth_stencil_desc(stencil_enable=True, read_mask=0x0F, write_mask=0x3F,
+                                front=(A.SOP_KEEP, A.SOP_KEEP, sop, fn),
+                                back=(A.SOP_ZERO, A.SOP_INVERT, (sop % 8) + 1, A.CMP_GREATER_EQUAL))
+
+
+# name -> (constructor, frames)
+CASES = {
+    # BASELINE.json configs[0]: ColorizedTriangle 800x600, no MSAA
+    "c1_colorized_triangle_800x600": (lambda: S.ColorizedTriangle(800, 600, 1, with_count=True), (0, 1, 2, 3, 4)),
+    # configs[2] (AntiAliasing): same scene, 4x MSAA + resolve (reduced size for the CPU suite; full size on GPU)
+    "c3a_antialiasing_800x600x4": (lambda: S.ColorizedTriangle(800, 600, 4, with_count=True), (0, 3)),
+    "c3a_antialiasing_400x300x2": (lambda: S.ColorizedTriangle(400, 300, 2, with_count=True), (1,)),
+    # configs[1]: TextureAndBlending (trilinear + alpha blending + depth), bgra8 target
+    "c2_texture_and_blending_640x360": (lambda: S.TextureAndBlending(640, 360), (0, 1, 2, 3, 4)),
+    "c2_texture_and_blending_1920x1080": (lambda: S.TextureAndBlending(1920, 1080), (2,)),
+    # configs[2] (AnisotropicFilter): 16x AF through the sample_2d_grad path, 4x MSAA
+    "c3b_aniso16_640x360x4": (lambda: S.TextureAndBlending(640, 360, samples=4, ps_program=A.PS_TEX_GRAD_ALPHA,
+                                                           mip_filter=A.FILTER_ANISOTROPIC, max_aniso=16), (0, 2)),
+    "c3b_pointmip_320x180": (lambda: S.TextureAndBlending(320, 180, mip_filter=A.FILTER_POINT), (1,)),
+    # configs[3]: Sponza-like atrium, reduced size (full 4K 4x is covered by property tests on the GPU)
+    "c4_sponza_like_480x272x4": (lambda: S.SponzaLike(480, 272, 4, tex_size=128), (0, 5)),
+    "c4_sponza_like_960x540x1": (lambda: S.SponzaLike(960, 540, 1, tex_size=256), (3,)),
+    # clipping / culling / topology torture
+    "soup_s1_cull_none": (lambda: S.TriangleSoup(samples=1, cull=A.CULL_NONE, seed=8), (0,)),
+    "soup_s2_cull_back": (lambda: S.TriangleSoup(samples=2, cull=A.CULL_BACK, seed=9), (0,)),
+    "soup_s4_cull_front": (lambda: S.TriangleSoup(samples=4, cull=A.CULL_FRONT, seed=11), (0,)),
+    "soup_strip_s4": (lambda: S.TriangleSoup(samples=4, strip=True, n=500), (0,)),
+    "soup_small_tris_u32": (lambda: S.TriangleSoup(samples=1, index_dtype=np.uint32, n=2000, size=0.2, w=512, h=512), (0,)),
+    "soup_target_not_multiple_of_16": (lambda: S.TriangleSoup(samples=1, n=3000, size=0.1, w=1000, h=600), (0,)),
+    "soup_centroid_s4": (lambda: S.TriangleSoup(samples=4, modifiers=[A.AM_CENTROID | A.AM_LINEAR]), (0,)),
+    "soup_noperspective_s4": (lambda: S.TriangleSoup(samples=4, modifiers=[A.AM_NOPERSPECTIVE]), (0,)),
+    "soup_nointerpolation_s2": (lambda: S.TriangleSoup(samples=2, modifiers=[A.AM_NOINTERPOLATION]), (0,)),
+    "soup_nodepth_s4": (lambda: S.TriangleSoup(samples=4, ds=A.depth_stencil_desc(depth_enable=False)), (0,)),
+    "soup_nodepthwrite_s4": (lambda: S.TriangleSoup(samples=4, ds=A.depth_stencil_desc(depth_write=False)), (0,)),
+    "soup_blend_s4": (lambda: S.TriangleSoup(samples=4, bs=A.BS_LERP_SRC_ALPHA), (0,)),
+    "soup_blend_bgra8": (lambda: S.TriangleSoup(samples=1, bs=A.BS_LERP_SRC_ALPHA, color_fmt=A.PF_BGRA8), (0,)),
+    "soup_blend_rgba32f": (lambda: S.TriangleSoup(samples=1, bs=A.BS_LERP_SRC_ALPHA, color_fmt=A.PF_RGBA32F), (0,)),
+    # early-Z writes depth before a PS discard
+    "soup_discard_all_s4": (lambda: S.TriangleSoup(samples=4, ps=A.PS_DISCARD_ALL), (0,)),
+}
+for _fn in range(8):
+    CASES[f"soup_depthfunc{_fn}_s4"] = (lambda fn=_fn: S.TriangleSoup(samples=4, ds=A.depth_stencil_desc(depth_func=fn)), (0,))
+for _sop in range(1, 9):
+    _f = (A.CMP_ALWAYS, A.CMP_LESS_EQUAL, A.CMP_NOT_EQUAL)[_sop % 3]
+    CASES[f"soup_stencil_op{_sop}_fn{_f}_s2"] = (
+        lambda sop=_sop, f=_f: S.TriangleSoup(samples=2, ds=_stencil_ds(sop, f), stencil_ref=5), (0,))
+
+# cases small enough for the CPU suite to run against the reference / oracle in seconds
+CPU_CASES = [k for k in CASES if "1920x1080" not in k]
+
+
+def digest(arr) -> str:
+    return hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest()[:24]
+
+
+def summarize(res) -> dict:
+    """Compact, exact fingerprint of one frame (the golden fixture format)."""
+    out = {"stats": {k: res.stats[k] for k in GATED_COUNTERS}, "shape": list(res.color.shape)}
+    for k in ("color", "depth", "stencil", "resolved", "count"):
+        a = getattr(res, k)
+        if a is not None:
+            out[k] = digest(a)
+    out["color_sum"] = [int(v) for v in res.color.reshape(-1, res.color.shape[-1]).astype(np.uint64).sum(0)] \
+        if res.color.dtype == np.uint8 else None
+    return out
+
+
+def compare_frames(ra, rb, color_tol=0):
+    """Returns a list of human-readable mismatch descriptions (empty == parity)."""
+    msgs = []
+    for k in ("depth", "stencil", "count", "color", "resolved"):
+        a, b = getattr(ra, k), getattr(rb, k)
+        if a is None and b is None:
+            continue
+        if k == "depth":
+            a, b = a.view(np.uint32), b.view(np.uint32)
+        if k in ("color", "resolved") and color_tol and a.dtype == np.uint8:
+            diff = np.abs(a.astype(np.int32) - b.astype(np.int32))
+            npx = int((diff > 0).any(axis=-1).sum())
+            if diff.max() > color_tol or npx > 1e-4 * diff[..., 0].size:
+                msgs.append(f"{k}: max |d|={int(diff.max())} LSB, {npx} samples differ (tol {color_tol} LSB, <0.01%)")
+        elif not np.array_equal(a, b):
+            idx = np.argwhere(a != b)
+            msgs.append(f"{k}: {len(idx)} values differ, first at {idx[0].tolist()}: {a[tuple(idx[0])]} vs {b[tuple(idx[0])]}")
+    for c in GATED_COUNTERS:
+        if ra.stats[c] != rb.stats[c]:
+            msgs.append(f"counter {c}: {ra.stats[c]} vs {rb.stats[c]}")
+    return msgs
