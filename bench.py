@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — frames/s (and shaded Mpix/s) of the Sponza-class scene at 3840x2160, 4x MSAA (BASELINE.json
+configs[3]) on N B200s, through the C ABI of the CUDA product.
+
+    python bench.py --gpus N --steps K --warmup W            # the product (torchrun launches N ranks for N>1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU renderer (rank 0 only)
+
+A "step" is one frame: clear colour + clear depth/stencil + 24 draws (one per material group) + MSAA resolve
+(+ for N>1 the sort-first gather of the owned tiles to rank 0 over NCCL).  All inputs are resident in HBM when the
+timed region starts (`value`); `e2e` repeats the measurement with the frame's geometry uploaded from pinned host
+memory and the resolved frame read back to pinned host memory inside the timed region, every step.
+
+Timing: CUDA events recorded on the stream the kernels run on, barrier + synchronize on both sides, max over
+ranks.  Inputs are larger than L2 (the 4K 4xMSAA colour + depth/stencil targets alone are 398 MB vs 126 MB of L2).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = "Sponza-like atrium (262,249 tris, 24 material draws, trilinear), 3840x2160, 4x MSAA + resolve"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--width", type=int, default=3840)
+    ap.add_argument("--height", type=int, default=2160)
+    ap.add_argument("--samples", type=int, default=4)
+    ap.add_argument("--tex-size", type=int, default=1024)
+    ap.add_argument("--aniso", type=int, default=0, help="max anisotropy (0 = trilinear, as samples/Sponza)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-frames", type=int, default=2)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy kernel)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max((float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()), default=None),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the path (oracle/_ref = the unmodified reference compiled in
+    place; falls back to the oracle port when that library did not travel), all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    from salviarenderer_b200 import abi, scenes
+    ref_lib = os.path.join(ROOT, "oracle", "_ref", "libsalvia_ref.so")
+    kind = "reference"
+    if not os.path.exists(ref_lib):
+        import __graft_entry__ as g
+        ref_lib, kind = g.build_oracle(), "port"
+    be = abi.Backend(ref_lib)
+    sc = scenes.SponzaLike(args.width, args.height, args.samples, tex_size=args.tex_size, max_aniso=args.aniso)
+    sc.setup(be)
+    budget_s = 150.0
+    t0 = time.perf_counter()
+    sc.render(be, 0)
+    be.flush()
+    first = time.perf_counter() - t0
+    warm = max(0, min(args.warmup, int(20.0 / max(first, 1e-3))) - 1)
+    for i in range(warm):
+        sc.render(be, (i + 1) % sc.n_frames)
+    be.flush()
+    steps = max(1, min(args.steps, int(budget_s / max(first, 1e-3))))
+    be.query_begin()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        sc.render(be, i % sc.n_frames)
+    be.flush()
+    dt = time.perf_counter() - t0
+    stats = be.query_get()
+    fps = steps / dt
+    cores = os.cpu_count() if kind == "reference" else 1
+    line = {
+        "impl": "reference", "metric": "frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm + 1, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "shaded_mpix_per_s": stats["ps_invocations"] / dt / 1e6,
+        "config": config_dict(args, 1),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+                         "sample": f"{steps} full frames of the same workload (requested {args.steps})"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, n):
+    return {"workload": WORKLOAD if (args.width, args.height, args.samples) == (3840, 2160, 4) else
+            f"Sponza-like atrium {args.width}x{args.height}x{args.samples}",
+            "width": args.width, "height": args.height, "msaa": args.samples, "triangles": 262249, "draws_per_frame": 24,
+            "texture": f"24 x {args.tex_size}^2 rgba8 + mips, wrap, " + (f"{args.aniso}x anisotropic" if args.aniso > 1 else "trilinear"),
+            "color_format": "bgra8", "depth_stencil_format": "rg32f",
+            "parallelism": "single GPU" if n == 1 else f"sort-first: 64x64 screen tiles interleaved over {n} GPUs, geometry replicated, NCCL gather to rank 0",
+            "l2_policy": "inputs larger than L2 (398 MB of render targets per frame vs 126 MB L2); no explicit flush"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import salviarenderer_b200 as pkg
+    from salviarenderer_b200 import scenes
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = world
+    be = pkg.load(local)
+    stream = torch.cuda.Stream()  # a real (non-legacy) stream shared by the library, torch and NCCL
+    torch.cuda.set_stream(stream)
+    be.set_stream(stream.cuda_stream)  # kernels, copies and NCCL all order on torch's current stream
+    be.set_tile_shard(rank, n)
+    sc = scenes.SponzaLike(args.width, args.height, args.samples, tex_size=args.tex_size, max_aniso=args.aniso)
+    sc.setup(be)
+    resolved = sc.t.resolved if sc.t.resolved is not None else sc.t.color
+
+    # ---- sort-first gather plumbing (N > 1) ----
+    stage = gather_list = None
+    if n > 1:
+        sizes = [be.packed_tiles_bytes(resolved, r, n) for r in range(n)]
+        mx = max(sizes)
+        stage = torch.empty(mx, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            gather_list = [torch.empty(mx, dtype=torch.uint8, device="cuda") for _ in range(n)]
+
+    def gather():
+        be.pack_tiles(resolved, rank, n, stage.data_ptr())
+        dist.gather(stage, gather_list, dst=0)
+        if rank == 0:
+            for r in range(1, n):
+                be.unpack_tiles(resolved, r, n, gather_list[r].data_ptr())
+
+    def frame(i):
+        sc.render(be, i % sc.n_frames)
+        if n > 1:
+            gather()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if n > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            fn(i)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if n > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    # ---- warm-up, then the headline: inputs resident in HBM ----
+    for i in range(max(args.warmup, 3)):
+        frame(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    be.query_begin()
+    ms_total = timed(frame, args.steps)
+    launches = be.launch_count()
+    stats = be.query_get()
+    clocks = sampler.stop() if rank == 0 else None
+    ps_all = torch.tensor([float(stats["ps_invocations"])], device="cuda", dtype=torch.float64)
+    if n > 1:
+        dist.all_reduce(ps_all)
+    ms_per_step = ms_total / args.steps
+    fps = 1e3 / ms_per_step
+
+    # ---- e2e: the frame's geometry comes from pinned host memory, the resolved frame goes back to the host ----
+    vb_np, ib_np = sc.mesh.streams[0], sc.mesh.indices
+    vb_host = torch.from_numpy(np.ascontiguousarray(vb_np)).pin_memory()
+    ib_host = torch.from_numpy(np.ascontiguousarray(ib_np).view(np.int32)).pin_memory()
+    vb_h, ib_h = sc.mesh.upload(be)[0][0], sc.mesh.upload(be)[1]
+    out_bytes = args.width * args.height * 4
+    out_host = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
+    h2d = vb_host.numel() * 4 + ib_host.numel() * 4
+    d2h = out_bytes if rank == 0 else 0
+
+    def frame_e2e(i):
+        be.upload_from_ptr(vb_h, vb_host.data_ptr(), vb_host.numel() * 4)
+        be.upload_from_ptr(ib_h, ib_host.data_ptr(), ib_host.numel() * 4)
+        frame(i)
+        if rank == 0:
+            be.read_texture_into(resolved, out_host.data_ptr(), out_bytes)  # synchronises: the app now owns the pixels
+
+    for i in range(3):
+        frame_e2e(i)
+    e2e_ms = timed(frame_e2e, args.steps) / args.steps
+
+    # ---- roofline of the dominant kernel (k_raster): per-stage CUDA events on the launching stream ----
+    be.profile_enable(True)
+    be.query_begin()
+    for i in range(args.steps):
+        frame(i)
+    be.flush()
+    prof = be.profile_get()
+    traffic = be.traffic()
+    st2 = be.query_get()
+    be.profile_enable(False)
+    raster_ms = prof["ras"] / 1e6 / args.steps
+    geom_ms = prof["clipping"] / 1e6 / args.steps
+    bin_ms = prof["tri_dispatch"] / 1e6 / args.steps
+    R = 5  # position + 4 attributes (VS_SPONZA)
+    b_frag = 8 * traffic["z_tested"] + 8 * traffic["z_written"] + 4 * traffic["c_written"] + 4 * traffic["c_read"]
+    b_setup = st2["cprimitives"] * 3 * 16 * R
+    b_tex = 24 * sum((args.tex_size >> l) ** 2 * 4 for l in range(args.tex_size.bit_length())) * args.steps
+    b_alg_raster = (b_frag + b_setup + b_tex) / args.steps  # bytes per frame, over the 24 k_raster launches
+    peak, peak_src = peaks()
+    achieved = b_alg_raster / (raster_ms * 1e-3) / 1e9 if raster_ms > 0 else 0.0
+    traffic_measured = None
+    tpath = os.path.join(ROOT, "profiles", "r01_raster_dram_bytes.json")
+    if os.path.exists(tpath):
+        traffic_measured = json.load(open(tpath)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "k_raster<4, PS_SPONZA>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic_measured, "peak_source": peak_src,
+                "algorithmic_bytes_per_frame": b_alg_raster, "algorithmic_bytes_per_launch": b_alg_raster / 24,
+                "launches_per_frame": 24, "kernel_ms_per_frame": raster_ms, "kernel_ms_per_launch": raster_ms / 24,
+                "kernel_share_of_step": raster_ms / max(raster_ms + geom_ms + bin_ms, 1e-9),
+                "stage_ms_per_frame": {"geometry": geom_ms, "binning+sort": bin_ms, "raster": raster_ms},
+                "note": "per-stage times from CUDA events around each kernel in a separate profiling pass of the same "
+                        "K frames (events force a sync per draw, so they are not taken inside the headline region)"}
+
+    # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample (rank 0, N == 1) ----
+    cpu_baseline = None
+    if rank == 0 and n == 1 and not args.no_cpu_baseline:
+        cpu_baseline = run_cpu_baseline(args)
+
+    if rank == 0:
+        line = {
+            "metric": "frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": n, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "shaded_mpix_per_s": float(ps_all.item()) / (ms_total * 1e-3) / 1e6,
+            "ps_invocations_per_frame": float(ps_all.item()) / args.steps,
+            "config": config_dict(args, n),
+            "clocks": clocks,
+            "e2e": {"value": 1e3 / e2e_ms, "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h,
+                    "what": "slv_buffer_upload of the vertex+index buffers from pinned host memory, the full frame, and "
+                            "slv_texture_readback of the resolved 4K frame into pinned host memory, every step"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if n > 1:
+        dist.destroy_process_group()
+
+
+def run_cpu_baseline(args):
+    """Times the reference CPU renderer on a bounded sample, in a subprocess (so that its thread pool and any
+    crash stay out of this process)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(args.cpu_baseline_frames),
+           "--warmup", "1", "--width", str(args.width), "--height", str(args.height), "--samples", str(args.samples),
+           "--tex-size", str(args.tex_size), "--aniso", str(args.aniso)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        for ln in out.stdout.splitlines():
+            if ln.startswith("{"):
+                d = json.loads(ln)
+                cb = d["cpu_baseline"]
+                cb["shaded_mpix_per_s"] = d.get("shaded_mpix_per_s")
+                cb["ms_per_frame"] = d.get("ms_per_step")
+                return cb
+        return {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "reference",
+                "sample": "failed: " + (out.stderr or out.stdout)[-300:]}
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+
+
+if __name__ == "__main__":
+    main()

@@ -265,6 +265,36 @@ slv_result slv_profile_get(slv_device dev, slv_pipeline_profiles* out);
  * primitives.  (0,1) = everything (default).  Not supported by the reference backend. */
 slv_result slv_set_tile_shard(slv_device dev, uint32_t rank, uint32_t nranks);
 
+/* ---- measurement and multi-GPU plumbing (no reference twin; used by bench.py and the sharded path) ------ */
+/* Algorithmic framebuffer traffic counters since slv_query_begin (B_frag): samples depth-tested,
+ * samples whose depth/stencil was written, samples blended into colour, samples whose destination colour
+ * was read by the blend shader. Exact integers; the oracle produces the same numbers. */
+typedef struct slv_traffic_counters {
+  uint64_t z_tested, z_written, c_written, c_read;
+} slv_traffic_counters;
+slv_result slv_traffic_get(slv_device dev, slv_traffic_counters* out);
+/* number of kernels this library launched since slv_query_begin (0 for the CPU checkers) */
+slv_result slv_kernel_launch_count(slv_device dev, uint64_t* out);
+/* CUDA events on the stream the kernels are launched on: record event `slot` (0..15) now; elapsed
+ * milliseconds between two recorded slots (synchronises on `b`).  CPU checkers use a steady clock. */
+slv_result slv_event_record(slv_device dev, uint32_t slot);
+slv_result slv_event_elapsed_ms(slv_device dev, uint32_t a, uint32_t b, float* ms);
+/* make the library enqueue all its work on a caller-owned CUDA stream (e.g. torch's current stream) so that
+ * host plumbing such as NCCL collectives orders against the kernels on the device, without host syncs.
+ * `cuda_stream` is a cudaStream_t; NULL restores the device's own stream.  CPU checkers ignore it. */
+slv_result slv_set_stream(slv_device dev, void* cuda_stream);
+/* per-kernel-stage event timing on/off at run time (same data as SLV_PROFILE=1; read with slv_profile_get) */
+slv_result slv_profile_enable(slv_device dev, uint32_t on);
+/* raw device address of a texture level (product only; CPU checkers return their host address) so the
+ * host plumbing (torch.distributed / NCCL) can exchange it without a copy */
+slv_result slv_texture_device_ptr(slv_device dev, slv_handle tex, uint32_t level, void** out, size_t* bytes);
+/* sort-first gather helpers: copy the 64x64 tiles owned by (rank, nranks) — see slv_set_tile_shard — of a
+ * single-sampled surface into / out of a dense staging buffer (tiles in row-major tile order, each tile
+ * 64 rows x 64 texels, clipped tiles padded).  `staging` is a DEVICE pointer for the product, a host pointer
+ * for the CPU checkers; *bytes receives the packed size (call with staging == NULL to query it). */
+slv_result slv_pack_tiles(slv_device dev, slv_handle tex, uint32_t rank, uint32_t nranks, void* staging, size_t* bytes);
+slv_result slv_unpack_tiles(slv_device dev, slv_handle tex, uint32_t rank, uint32_t nranks, const void* staging);
+
 /* sampler probe used by the sampler parity tests: evaluates sampler::sample_2d_grad
  * (sampler.cpp:854-873) [use_lod = 0] or sample_2d_lod (:850-852) [use_lod = 1] for n coordinates.
  * coords: n×2 floats; ddx, ddy: n×2 floats (ignored for lod); lod: n floats; out: n×4 floats.

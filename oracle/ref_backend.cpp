@@ -27,6 +27,7 @@
 
 #include <eflib/math/math.h>
 
+#include <chrono>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -298,6 +299,7 @@ struct slv_device_t {
   std::vector<std::pair<slv_depth_stencil_desc, depth_stencil_state_ptr>> ds_states;
   std::vector<std::pair<slv_raster_desc, raster_state_ptr>> rs_states;
   bool q_active = false;
+  std::chrono::steady_clock::time_point events[16];
 
   resource_entry* get(slv_handle h) {
     if (h == 0 || h >= res.size()) return nullptr;
@@ -654,6 +656,34 @@ slv_result slv_query_get(slv_device dev, slv_pipeline_statistics* out) {
   out->backend_input_pixels = is.backend_input_pixels;
   return SLV_OK;
 }
+
+// measurement / multi-GPU plumbing: the reference has no such facilities; timers use the host clock
+slv_result slv_traffic_get(slv_device, slv_traffic_counters*) { return SLV_FAILED; }
+slv_result slv_kernel_launch_count(slv_device, uint64_t* out) { *out = 0; return SLV_OK; }
+slv_result slv_event_record(slv_device dev, uint32_t slot) {
+  if (slot >= 16) return SLV_INVALID_PARAMETER;
+  dev->r->flush();
+  dev->events[slot] = std::chrono::steady_clock::now();
+  return SLV_OK;
+}
+slv_result slv_event_elapsed_ms(slv_device dev, uint32_t a, uint32_t b, float* ms) {
+  if (a >= 16 || b >= 16) return SLV_INVALID_PARAMETER;
+  *ms = std::chrono::duration<float, std::milli>(dev->events[b] - dev->events[a]).count();
+  return SLV_OK;
+}
+slv_result slv_profile_enable(slv_device, uint32_t) { return SLV_OK; }
+slv_result slv_set_stream(slv_device, void*) { return SLV_OK; }
+slv_result slv_texture_device_ptr(slv_device dev, slv_handle h, uint32_t level, void** out, size_t* bytes) {
+  auto e = dev->get(h);
+  if (!e || !e->tex) return SLV_INVALID_PARAMETER;
+  auto s = e->tex->subresource(level);
+  if (!s) return SLV_INVALID_PARAMETER;
+  *out = s->texel_address(0, 0, 0);
+  if (bytes) *bytes = s->pitch() * s->height();
+  return SLV_OK;
+}
+slv_result slv_pack_tiles(slv_device, slv_handle, uint32_t, uint32_t, void*, size_t*) { return SLV_FAILED; }
+slv_result slv_unpack_tiles(slv_device, slv_handle, uint32_t, uint32_t, const void*) { return SLV_FAILED; }
 
 slv_result slv_sampler_probe(slv_device dev, slv_handle sh, uint32_t n, const float* coords, const float* ddx,
                              const float* ddy, const float* lod, uint32_t use_lod, float* out) {

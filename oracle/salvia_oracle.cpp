@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -563,6 +564,8 @@ V4 sample_2d_grad(Texture const& t, slv_sampler_desc const& d, float u, float v,
 struct Device {
   std::vector<Resource> res;
   slv_pipeline_statistics stats{};
+  slv_traffic_counters traffic{};
+  std::chrono::steady_clock::time_point events[16];
   uint32_t shard_rank = 0, shard_n = 1;
   Resource* get(slv_handle h, Resource::Kind k) {
     if (h == 0 || h >= res.size() || res[h].kind != k) return nullptr;
@@ -930,7 +933,8 @@ uint32_t early_z_test(DrawCtx& c, uint32_t x, uint32_t y, uint32_t px_mask, floa
     uint8_t* p = c.ds->addr(x, y, 0);
     float od; uint32_t os;
     read_ds(c, p, od, os);
-    if (depth_test(c, depth, od)) { write_ds(c, p, depth, 0, 0); return 1; }
+    c.dev->traffic.z_tested += c.read_depth;
+    if (depth_test(c, depth, od)) { write_ds(c, p, depth, 0, 0); c.dev->traffic.z_written += c.write_depth; return 1; }
     return 0;
   }
   for (uint32_t s = 0; s < c.S; ++s) {
@@ -939,7 +943,8 @@ uint32_t early_z_test(DrawCtx& c, uint32_t x, uint32_t y, uint32_t px_mask, floa
     float od; uint32_t os;
     read_ds(c, p, od, os);
     float nd = aa[s] + depth;
-    if (depth_test(c, nd, od)) { mask |= 1u << s; write_ds(c, p, nd, 0, 0); }
+    c.dev->traffic.z_tested += c.read_depth;
+    if (depth_test(c, nd, od)) { mask |= 1u << s; write_ds(c, p, nd, 0, 0); c.dev->traffic.z_written += c.write_depth; }
   }
   return mask;
 }
@@ -1027,6 +1032,10 @@ bool run_ps(DrawCtx& c, PsQuad& q, int pix, V4& color) {
 // ---- output merger (framebuffer.cpp:445-520) ----------------------------------------------------------
 void blend(DrawCtx& c, uint32_t x, uint32_t y, uint32_t s, V4 const& src) {
   Surface* t0 = c.colors.size() > 0 ? c.colors[0] : nullptr;
+  if (t0) {
+    ++c.dev->traffic.c_written;
+    if (c.d->bs.program == SLV_BS_LERP_SRC_ALPHA) ++c.dev->traffic.c_read;
+  }
   switch (c.d->bs.program) {
   case SLV_BS_REPLACE:
     if (t0) from_rgba32f(t0->fmt, t0->addr(x, y, s), src);
@@ -1057,6 +1066,7 @@ void render_sample(DrawCtx& c, uint32_t x, uint32_t y, uint32_t s, V4 const& col
   float od; uint32_t os;
   read_ds(c, p, od, os);
   bool dp = depth_test(c, depth, od);
+  c.dev->traffic.z_tested += (c.read_depth || c.read_stencil) ? 1 : 0;
   auto const& ds = c.d->ds;
   auto const& face = front ? ds.front_face : ds.back_face;
   bool sp = ds.stencil_enable ? compare_u(face.stencil_func, c.stencil_ref, os) : true;
@@ -1065,6 +1075,7 @@ void render_sample(DrawCtx& c, uint32_t x, uint32_t y, uint32_t s, V4 const& col
     uint32_t ns = ds.stencil_enable ? stencil_op(face.stencil_pass_op, c.stencil_ref, os) : os;
     blend(c, x, y, s, color);
     write_ds(c, p, depth, ns, c.write_mask);
+    c.dev->traffic.z_written += (c.write_depth || c.write_stencil) ? 1 : 0;
   }
 }
 
@@ -1631,7 +1642,62 @@ slv_result slv_resolve(slv_device dev, slv_handle src, slv_handle dst) {
 }
 
 slv_result slv_flush(slv_device) { return SLV_OK; }
-slv_result slv_query_begin(slv_device dev) { dev->stats = slv_pipeline_statistics{}; return SLV_OK; }
+slv_result slv_query_begin(slv_device dev) {
+  dev->stats = slv_pipeline_statistics{};
+  dev->traffic = slv_traffic_counters{};
+  return SLV_OK;
+}
+slv_result slv_traffic_get(slv_device dev, slv_traffic_counters* out) { *out = dev->traffic; return SLV_OK; }
+slv_result slv_kernel_launch_count(slv_device, uint64_t* out) { *out = 0; return SLV_OK; }
+slv_result slv_event_record(slv_device dev, uint32_t slot) {
+  if (slot >= 16) return SLV_INVALID_PARAMETER;
+  dev->events[slot] = std::chrono::steady_clock::now();
+  return SLV_OK;
+}
+slv_result slv_event_elapsed_ms(slv_device dev, uint32_t a, uint32_t b, float* ms) {
+  if (a >= 16 || b >= 16) return SLV_INVALID_PARAMETER;
+  *ms = std::chrono::duration<float, std::milli>(dev->events[b] - dev->events[a]).count();
+  return SLV_OK;
+}
+slv_result slv_profile_enable(slv_device, uint32_t) { return SLV_OK; }
+slv_result slv_set_stream(slv_device, void*) { return SLV_OK; }
+slv_result slv_texture_device_ptr(slv_device dev, slv_handle h, uint32_t level, void** out, size_t* bytes) {
+  auto r = dev->get(h, Resource::TEXTURE);
+  if (!r || level >= r->tex.levels.size()) return SLV_INVALID_PARAMETER;
+  *out = r->tex.levels[level].data.data();
+  if (bytes) *bytes = r->tex.levels[level].data.size();
+  return SLV_OK;
+}
+static slv_result pack_common(slv_device dev, slv_handle h, uint32_t rank, uint32_t n, uint8_t* staging, size_t* bytes, bool unpack) {
+  auto r = dev->get(h, Resource::TEXTURE);
+  if (!r || n == 0 || rank >= n || r->tex.samples != 1) return SLV_INVALID_PARAMETER;
+  Surface& s = r->tex.levels[0];
+  const uint32_t T = SLV_TILE_SIZE;
+  uint32_t tiles_x = (s.w + T - 1) / T, tiles_y = (s.h + T - 1) / T, slot = 0;
+  for (uint32_t ty = 0; ty < tiles_y; ++ty)
+    for (uint32_t tx = 0; tx < tiles_x; ++tx) {
+      if (n > 1 && (tx + 3 * ty) % n != rank) continue;
+      if (staging)
+        for (uint32_t row = 0; row < T; ++row) {
+          uint32_t y = ty * T + row;
+          if (y >= s.h) break;
+          uint32_t x0 = tx * T, cnt = std::min(T, s.w - x0);
+          uint8_t* g = s.addr(x0, y, 0);
+          uint8_t* st = staging + ((size_t)slot * T * T + (size_t)row * T) * s.bpp;
+          if (unpack) memcpy(g, st, (size_t)cnt * s.bpp); else memcpy(st, g, (size_t)cnt * s.bpp);
+        }
+      ++slot;
+    }
+  if (bytes) *bytes = (size_t)slot * T * T * s.bpp;
+  return SLV_OK;
+}
+slv_result slv_pack_tiles(slv_device dev, slv_handle h, uint32_t rank, uint32_t n, void* staging, size_t* bytes) {
+  return pack_common(dev, h, rank, n, (uint8_t*)staging, bytes, false);
+}
+slv_result slv_unpack_tiles(slv_device dev, slv_handle h, uint32_t rank, uint32_t n, const void* staging) {
+  if (!staging) return SLV_INVALID_PARAMETER;
+  return pack_common(dev, h, rank, n, (uint8_t*)staging, nullptr, true);
+}
 slv_result slv_query_get(slv_device dev, slv_pipeline_statistics* out) { *out = dev->stats; return SLV_OK; }
 slv_result slv_profile_get(slv_device, slv_pipeline_profiles* out) { memset(out, 0, sizeof(*out)); return SLV_OK; }
 slv_result slv_set_tile_shard(slv_device dev, uint32_t rank, uint32_t nranks) {

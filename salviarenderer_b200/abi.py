@@ -107,6 +107,21 @@ class PipelineStatistics(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class PipelineProfiles(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("gather_vtx", "vtx_proc", "clipping", "compact_clip", "vp_trans",
+                                          "tri_dispatch", "ras")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class TrafficCounters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("z_tested", "z_written", "c_written", "c_read")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
 # every symbol include/salvia_b200.h declares (the CPU test-suite checks each library exports them all)
 ENTRY_POINTS = [
     "slv_device_create", "slv_device_destroy", "slv_backend_name", "slv_abi_version",
@@ -116,6 +131,8 @@ ENTRY_POINTS = [
     "slv_draw", "slv_clear_color", "slv_clear_depth_stencil", "slv_resolve", "slv_flush",
     "slv_query_begin", "slv_query_get", "slv_sampler_probe",
     "slv_set_tile_shard", "slv_profile_get",
+    "slv_traffic_get", "slv_kernel_launch_count", "slv_event_record", "slv_event_elapsed_ms", "slv_profile_enable",
+    "slv_texture_device_ptr", "slv_pack_tiles", "slv_unpack_tiles", "slv_set_stream",
 ]
 
 
@@ -211,7 +228,16 @@ class Backend:
         L.slv_sampler_probe.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_uint32, C.c_void_p]
         L.slv_set_tile_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
-        L.slv_profile_get.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.slv_profile_get.argtypes = [C.c_void_p, C.POINTER(PipelineProfiles)]
+        L.slv_traffic_get.argtypes = [C.c_void_p, C.POINTER(TrafficCounters)]
+        L.slv_kernel_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.slv_event_record.argtypes = [C.c_void_p, C.c_uint32]
+        L.slv_event_elapsed_ms.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
+        L.slv_profile_enable.argtypes = [C.c_void_p, C.c_uint32]
+        L.slv_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.slv_texture_device_ptr.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.slv_pack_tiles.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_size_t)]
+        L.slv_unpack_tiles.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         self.name = L.slv_backend_name().decode()
         if L.slv_abi_version() != 1:
             raise SlvError("ABI version mismatch")
@@ -324,3 +350,58 @@ class Backend:
 
     def set_tile_shard(self, rank: int, nranks: int):
         _chk(self.lib.slv_set_tile_shard(self.dev, rank, nranks), "slv_set_tile_shard")
+
+    # ---- measurement / multi-GPU plumbing -------------------------------------------------------------
+    def traffic(self) -> dict:
+        t = TrafficCounters()
+        _chk(self.lib.slv_traffic_get(self.dev, C.byref(t)), "slv_traffic_get")
+        return t.as_dict()
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        _chk(self.lib.slv_kernel_launch_count(self.dev, C.byref(n)), "slv_kernel_launch_count")
+        return n.value
+
+    def event_record(self, slot: int):
+        _chk(self.lib.slv_event_record(self.dev, slot), "slv_event_record")
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        _chk(self.lib.slv_event_elapsed_ms(self.dev, a, b, C.byref(ms)), "slv_event_elapsed_ms")
+        return ms.value
+
+    def set_stream(self, cuda_stream: int | None):
+        _chk(self.lib.slv_set_stream(self.dev, C.c_void_p(cuda_stream or 0)), "slv_set_stream")
+
+    def profile_enable(self, on: bool):
+        _chk(self.lib.slv_profile_enable(self.dev, int(on)), "slv_profile_enable")
+
+    def profile_get(self) -> dict:
+        p = PipelineProfiles()
+        _chk(self.lib.slv_profile_get(self.dev, C.byref(p)), "slv_profile_get")
+        return p.as_dict()
+
+    def texture_ptr(self, tex: Texture, level: int = 0):
+        p, n = C.c_void_p(), C.c_size_t()
+        _chk(self.lib.slv_texture_device_ptr(self.dev, tex.handle, level, C.byref(p), C.byref(n)), "slv_texture_device_ptr")
+        return p.value, n.value
+
+    def packed_tiles_bytes(self, tex: Texture, rank: int, nranks: int) -> int:
+        n = C.c_size_t()
+        _chk(self.lib.slv_pack_tiles(self.dev, tex.handle, rank, nranks, None, C.byref(n)), "slv_pack_tiles(size)")
+        return n.value
+
+    def pack_tiles(self, tex: Texture, rank: int, nranks: int, staging_ptr: int) -> int:
+        n = C.c_size_t()
+        _chk(self.lib.slv_pack_tiles(self.dev, tex.handle, rank, nranks, C.c_void_p(staging_ptr), C.byref(n)), "slv_pack_tiles")
+        return n.value
+
+    def unpack_tiles(self, tex: Texture, rank: int, nranks: int, staging_ptr: int):
+        _chk(self.lib.slv_unpack_tiles(self.dev, tex.handle, rank, nranks, C.c_void_p(staging_ptr)), "slv_unpack_tiles")
+
+    def upload_from_ptr(self, handle: int, host_ptr: int, nbytes: int, offset: int = 0):
+        """slv_buffer_upload from a raw host address (e.g. pinned memory) — no intermediate copy."""
+        _chk(self.lib.slv_buffer_upload(self.dev, handle, offset, C.c_void_p(host_ptr), nbytes), "slv_buffer_upload")
+
+    def read_texture_into(self, tex: Texture, host_ptr: int, nbytes: int, level: int = 0):
+        _chk(self.lib.slv_texture_readback(self.dev, tex.handle, level, C.c_void_p(host_ptr), nbytes), "slv_texture_readback")

@@ -57,7 +57,8 @@ uint8_t host_unorm8(float x) {  // colors.h:182-192
 
 struct slv_device_t {
   int ordinal = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // the stream every kernel / copy is enqueued on
+  cudaStream_t own_stream = nullptr;  // created with the device; `stream` may point at a caller-owned one
   std::vector<Resource> res;
   // scratch arenas in HBM (grown on demand, never shrunk)
   float4* tris = nullptr;
@@ -74,6 +75,9 @@ struct slv_device_t {
   // profiling (SLV_PROFILE=1)
   bool profile = false;
   cudaEvent_t ev[5] = {};
+  cudaEvent_t user_ev[16] = {};
+  uint32_t* tile_slot = nullptr;  // pack/unpack: dense slot of every owned tile
+  uint32_t tile_slot_cap = 0;
   double prof_ms[4] = {0, 0, 0, 0};  // geometry, binning, sort, raster
   unsigned long long n_launches = 0;
 
@@ -195,15 +199,16 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   auto dev = new slv_device_t;
   dev->ordinal = ordinal;
   dev->res.resize(1);
-  CU(cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&dev->own_stream, cudaStreamNonBlocking));
+  dev->stream = dev->own_stream;
   CU(cudaMalloc(&dev->overflow_flag, sizeof(uint32_t)));
   CU(cudaMemsetAsync(dev->overflow_flag, 0, sizeof(uint32_t), dev->stream));
-  CU(cudaMalloc(&dev->d_stats, 9 * sizeof(unsigned long long)));
-  CU(cudaMemsetAsync(dev->d_stats, 0, 9 * sizeof(unsigned long long), dev->stream));
+  CU(cudaMalloc(&dev->d_stats, 13 * sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(dev->d_stats, 0, 13 * sizeof(unsigned long long), dev->stream));
   const char* prof = getenv("SLV_PROFILE");
   dev->profile = prof && prof[0] == '1';
-  if (dev->profile)
-    for (auto& ev : dev->ev) CU(cudaEventCreate(&ev));
+  for (auto& ev : dev->ev) CU(cudaEventCreate(&ev));
+  for (auto& ev : dev->user_ev) CU(cudaEventCreate(&ev));
   *out = dev;
   return SLV_OK;
 }
@@ -224,9 +229,10 @@ void slv_device_destroy(slv_device dev) {
   cudaFree(dev->list);
   cudaFree(dev->overflow_flag);
   cudaFree(dev->d_stats);
-  if (dev->profile)
-    for (auto& ev : dev->ev) cudaEventDestroy(ev);
-  cudaStreamDestroy(dev->stream);
+  for (auto& ev : dev->ev) cudaEventDestroy(ev);
+  for (auto& ev : dev->user_ev) cudaEventDestroy(ev);
+  cudaFree(dev->tile_slot);
+  cudaStreamDestroy(dev->own_stream);
   delete dev;
 }
 
@@ -655,7 +661,7 @@ slv_result slv_query_begin(slv_device dev) {
   if (!dev) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
   dev->host_stats = slv_pipeline_statistics{};
-  CU(cudaMemsetAsync(dev->d_stats, 0, 9 * sizeof(unsigned long long), dev->stream));
+  CU(cudaMemsetAsync(dev->d_stats, 0, 13 * sizeof(unsigned long long), dev->stream));
   for (auto& m : dev->prof_ms) m = 0;
   dev->n_launches = 0;
   return SLV_OK;
@@ -671,7 +677,6 @@ slv_result slv_query_get(slv_device dev, slv_pipeline_statistics* out) {
   out->cprimitives = h[6];
   out->ps_invocations = h[7];
   out->backend_input_pixels = h[8];
-  out->gs_invocations = dev->n_launches;  // no geometry shader stage exists: repurposed as "kernels launched"
   return check_overflow(dev);
 }
 
@@ -682,6 +687,99 @@ slv_result slv_profile_get(slv_device dev, slv_pipeline_profiles* out) {
   out->tri_dispatch = (uint64_t)((dev->prof_ms[1] + dev->prof_ms[2]) * 1e6);
   out->ras = (uint64_t)(dev->prof_ms[3] * 1e6);
   return SLV_OK;
+}
+
+slv_result slv_traffic_get(slv_device dev, slv_traffic_counters* out) {
+  if (!dev || !out) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  unsigned long long h[13];
+  CU(cudaMemcpyAsync(h, dev->d_stats, sizeof(h), cudaMemcpyDeviceToHost, dev->stream));
+  CU(cudaStreamSynchronize(dev->stream));
+  out->z_tested = h[9];
+  out->z_written = h[10];
+  out->c_written = h[11];
+  out->c_read = h[12];
+  return SLV_OK;
+}
+
+slv_result slv_kernel_launch_count(slv_device dev, uint64_t* out) {
+  if (!dev || !out) return SLV_INVALID_PARAMETER;
+  *out = dev->n_launches;
+  return SLV_OK;
+}
+
+slv_result slv_event_record(slv_device dev, uint32_t slot) {
+  if (!dev || slot >= 16) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  CU(cudaEventRecord(dev->user_ev[slot], dev->stream));
+  return SLV_OK;
+}
+
+slv_result slv_event_elapsed_ms(slv_device dev, uint32_t a, uint32_t b, float* ms) {
+  if (!dev || a >= 16 || b >= 16 || !ms) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  CU(cudaEventSynchronize(dev->user_ev[b]));
+  CU(cudaEventElapsedTime(ms, dev->user_ev[a], dev->user_ev[b]));
+  return SLV_OK;
+}
+
+slv_result slv_set_stream(slv_device dev, void* cuda_stream) {
+  if (!dev) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  CU(cudaStreamSynchronize(dev->stream));
+  dev->stream = cuda_stream ? (cudaStream_t)cuda_stream : dev->own_stream;
+  return SLV_OK;
+}
+
+slv_result slv_profile_enable(slv_device dev, uint32_t on) {
+  if (!dev) return SLV_INVALID_PARAMETER;
+  dev->profile = on != 0;
+  return SLV_OK;
+}
+
+slv_result slv_texture_device_ptr(slv_device dev, slv_handle tex, uint32_t level, void** out, size_t* bytes) {
+  auto r = dev ? dev->get(tex, Resource::TEXTURE) : nullptr;
+  if (!r || level >= r->tex.n_levels || !out) return SLV_INVALID_PARAMETER;
+  *out = r->tex.level[level].data;
+  if (bytes) *bytes = r->tex.level[level].bytes;
+  return SLV_OK;
+}
+
+static slv_result pack_common(slv_device dev, slv_handle tex, uint32_t rank, uint32_t nranks, void* staging, size_t* bytes,
+                              int unpack) {
+  auto r = dev ? dev->get(tex, Resource::TEXTURE) : nullptr;
+  if (!r || nranks == 0 || rank >= nranks) return SLV_INVALID_PARAMETER;
+  const SurfaceRef& s = r->tex.level[0];
+  if (s.samples != 1) return SLV_INVALID_PARAMETER;
+  uint32_t tiles_x = (s.w + TILE - 1) / TILE, tiles_y = (s.h + TILE - 1) / TILE, n_tiles = tiles_x * tiles_y;
+  std::vector<uint32_t> slot(n_tiles, 0);
+  uint32_t owned = 0;
+  for (uint32_t t = 0; t < n_tiles; ++t)
+    if (nranks <= 1 || ((t % tiles_x) + 3 * (t / tiles_x)) % nranks == rank) slot[t] = owned++;
+  if (bytes) *bytes = (size_t)owned * TILE * TILE * s.bpp;
+  if (!staging) return SLV_OK;
+  CU(cudaSetDevice(dev->ordinal));
+  if (n_tiles > dev->tile_slot_cap) {
+    CU(cudaStreamSynchronize(dev->stream));
+    if (dev->tile_slot) CU(cudaFree(dev->tile_slot));
+    CU(cudaMalloc(&dev->tile_slot, n_tiles * sizeof(uint32_t)));
+    dev->tile_slot_cap = n_tiles;
+  }
+  CU(cudaMemcpyAsync(dev->tile_slot, slot.data(), n_tiles * sizeof(uint32_t), cudaMemcpyHostToDevice, dev->stream));
+  CU(cudaStreamSynchronize(dev->stream));  // `slot` is pageable host memory
+  k_pack_tiles<<<n_tiles, 256, 0, dev->stream>>>(s, tiles_x, tiles_y, rank, nranks, (uint8_t*)staging, dev->tile_slot, unpack);
+  ++dev->n_launches;
+  CU(cudaGetLastError());
+  return SLV_OK;
+}
+
+slv_result slv_pack_tiles(slv_device dev, slv_handle tex, uint32_t rank, uint32_t nranks, void* staging, size_t* bytes) {
+  return pack_common(dev, tex, rank, nranks, staging, bytes, 0);
+}
+
+slv_result slv_unpack_tiles(slv_device dev, slv_handle tex, uint32_t rank, uint32_t nranks, const void* staging) {
+  if (!staging) return SLV_INVALID_PARAMETER;
+  return pack_common(dev, tex, rank, nranks, const_cast<void*>(staging), nullptr, 1);
 }
 
 slv_result slv_set_tile_shard(slv_device dev, uint32_t rank, uint32_t nranks) {

@@ -754,6 +754,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster(RasterParams p) {
   }
 
   uint32_t n_ps_quads = 0, n_backend_quads = 0;
+  uint32_t n_ztest = 0, n_zwrite = 0, n_cwrite = 0, n_cread = 0;  // algorithmic traffic (SURVEY §8d B_frag)
   const int R = 1 + (int)p.n_attrs;
   const float vpx = (float)(tile_x * TILE), vpy = (float)(tile_y * TILE);
 
@@ -899,9 +900,10 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster(RasterParams p) {
             float nd = (S == 1) ? depth : aa[s] + depth;
             float od = p.read_depth ? zbuf[s] : 0.0f;
             bool pass = p.depth_enable ? compare_f(p.depth_func, nd, od) : true;
+            n_ztest += p.read_depth;
             if (pass) {
               tested |= 1u << s;
-              if (p.write_depth) { zbuf[s] = nd; dirty_ds = true; }
+              if (p.write_depth) { zbuf[s] = nd; dirty_ds = true; ++n_zwrite; }
             }
           }
         }
@@ -951,15 +953,19 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster(RasterParams p) {
           float od = p.read_depth ? zbuf[s] : 0.0f;
           uint32_t os = p.stencil_enable ? (sbuf[s] & p.read_mask) : 0u;
           bool dp = p.depth_enable ? compare_f(p.depth_func, sd, od) : true;
+          n_ztest += (p.read_depth | p.stencil_enable) ? 1u : 0u;
           const slv_stencil_op_desc& face = front ? p.front_face : p.back_face;
           bool sp = p.stencil_enable ? compare_u(face.stencil_func, p.stencil_ref, os) : true;
           if (!(dp && sp)) continue;
           uint32_t ns = p.stencil_enable ? stencil_op_apply(face.stencil_pass_op, p.stencil_ref, os) : os;
           if (p.write_depth) { zbuf[s] = sd; dirty_ds = true; }
           if (p.stencil_enable) { sbuf[s] = ns & p.write_mask; dirty_ds = true; }
+          n_zwrite += (p.write_depth | p.stencil_enable) ? 1u : 0u;
         }
         // blend shader
         if (p.color0.data) {
+          ++n_cwrite;
+          n_cread += (p.bs_program == SLV_BS_LERP_SRC_ALPHA) ? 1u : 0u;
           if (c0_packed) {
             if (p.bs_program == SLV_BS_LERP_SRC_ALPHA) {
               float4 d = unpack_color(p.color0.fmt, cbuf[s]);
@@ -1020,10 +1026,18 @@ __global__ void __launch_bounds__(RASTER_THREADS) k_raster(RasterParams p) {
   for (int o = 16; o > 0; o >>= 1) {
     a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
     b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+    n_ztest += __shfl_xor_sync(0xFFFFFFFFu, n_ztest, o);
+    n_zwrite += __shfl_xor_sync(0xFFFFFFFFu, n_zwrite, o);
+    n_cwrite += __shfl_xor_sync(0xFFFFFFFFu, n_cwrite, o);
+    n_cread += __shfl_xor_sync(0xFFFFFFFFu, n_cread, o);
   }
   if (lane == 0) {
     if (a) atomicAdd(&p.stats[7], (unsigned long long)a * 4ull);
     if (b) atomicAdd(&p.stats[8], (unsigned long long)b * 4ull);
+    if (n_ztest) atomicAdd(&p.stats[9], (unsigned long long)n_ztest);
+    if (n_zwrite) atomicAdd(&p.stats[10], (unsigned long long)n_zwrite);
+    if (n_cwrite) atomicAdd(&p.stats[11], (unsigned long long)n_cwrite);
+    if (n_cread) atomicAdd(&p.stats[12], (unsigned long long)n_cread);
   }
 }
 
@@ -1088,6 +1102,25 @@ __global__ void k_mipgen(SurfaceRef src, SurfaceRef dst, uint32_t filter) {
                       (((c0.z + c1.z) + c2.z) + c3.z) * 0.25f, (((c0.w + c1.w) + c2.w) + c3.w) * 0.25f);
     }
     store_texel_rgba32f(dst.fmt, dst.data + (((size_t)y * dst.w + x) * dst.samples + s) * dst.bpp, o);
+  }
+}
+
+// sort-first gather helpers: owned 64x64 tiles of a single-sampled surface <-> dense staging buffer
+__global__ void k_pack_tiles(SurfaceRef s, uint32_t tiles_x, uint32_t tiles_y, uint32_t rank, uint32_t n, uint8_t* staging,
+                             const uint32_t* tile_slot, int unpack) {
+  uint32_t tile = blockIdx.x;
+  uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+  if (!tile_owned(tx, ty, rank, n)) return;
+  uint32_t slot = tile_slot[tile];
+  uint32_t words_per_texel = s.bpp / 4;
+  uint32_t row_words = TILE * words_per_texel;
+  for (uint32_t i = threadIdx.x; i < TILE * row_words; i += blockDim.x) {
+    uint32_t row = i / row_words, w = i % row_words;
+    uint32_t x = tx * TILE + w / words_per_texel, y = ty * TILE + row;
+    if (x >= s.w || y >= s.h) continue;
+    uint32_t* g = reinterpret_cast<uint32_t*>(s.data + ((size_t)y * s.w + x) * s.bpp) + (w % words_per_texel);
+    uint32_t* st = reinterpret_cast<uint32_t*>(staging) + (size_t)slot * TILE * row_words + i;
+    if (unpack) *g = *st; else *st = *g;
   }
 }
 
