@@ -63,7 +63,9 @@ struct slv_device_t {
   // scratch arenas in HBM (grown on demand, never shrunk)
   float4* tris = nullptr;
   size_t tris_cap = 0;  // float4 units
-  uint32_t *tile_count = nullptr, *tile_offset = nullptr, *tile_cursor = nullptr;
+  uint32_t *tile_count = nullptr, *tile_offset = nullptr, *tile_cursor = nullptr, *active_tiles = nullptr;
+  uint32_t* work_counter = nullptr;
+  int raster_grid = 0;  // persistent raster CTAs (SM count x resident CTAs per SM)
   uint32_t tiles_cap = 0;
   uint32_t* list = nullptr;
   uint32_t list_cap = 0;
@@ -109,11 +111,12 @@ slv_result ensure_scratch(slv_device dev, size_t tris_needed, uint32_t n_tiles, 
   }
   if (n_tiles + 1 > dev->tiles_cap) {
     CU(cudaStreamSynchronize(dev->stream));
-    if (dev->tile_count) { CU(cudaFree(dev->tile_count)); CU(cudaFree(dev->tile_offset)); CU(cudaFree(dev->tile_cursor)); }
+    if (dev->tile_count) { CU(cudaFree(dev->tile_count)); CU(cudaFree(dev->tile_offset)); CU(cudaFree(dev->tile_cursor)); CU(cudaFree(dev->active_tiles)); }
     uint32_t cap = std::max(n_tiles + 1, 4096u);
     CU(cudaMalloc(&dev->tile_count, cap * sizeof(uint32_t)));
     CU(cudaMalloc(&dev->tile_offset, cap * sizeof(uint32_t)));
     CU(cudaMalloc(&dev->tile_cursor, cap * sizeof(uint32_t)));
+    CU(cudaMalloc(&dev->active_tiles, (cap + 1) * sizeof(uint32_t)));
     CU(cudaMemsetAsync(dev->tile_count, 0, cap * sizeof(uint32_t), dev->stream));
     CU(cudaMemsetAsync(dev->tile_offset, 0, cap * sizeof(uint32_t), dev->stream));
     CU(cudaMemsetAsync(dev->tile_cursor, 0, cap * sizeof(uint32_t), dev->stream));
@@ -202,6 +205,12 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   CU(cudaStreamCreateWithFlags(&dev->own_stream, cudaStreamNonBlocking));
   dev->stream = dev->own_stream;
   CU(cudaMalloc(&dev->overflow_flag, sizeof(uint32_t)));
+  CU(cudaMalloc(&dev->work_counter, sizeof(uint32_t)));
+  {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, ordinal));
+    dev->raster_grid = prop.multiProcessorCount * 2;  // k_raster is built for 2 resident CTAs per SM
+  }
   CU(cudaMemsetAsync(dev->overflow_flag, 0, sizeof(uint32_t), dev->stream));
   CU(cudaMalloc(&dev->d_stats, 13 * sizeof(unsigned long long)));
   CU(cudaMemsetAsync(dev->d_stats, 0, 13 * sizeof(unsigned long long), dev->stream));
@@ -226,6 +235,8 @@ void slv_device_destroy(slv_device dev) {
   cudaFree(dev->tile_count);
   cudaFree(dev->tile_offset);
   cudaFree(dev->tile_cursor);
+  cudaFree(dev->active_tiles);
+  cudaFree(dev->work_counter);
   cudaFree(dev->list);
   cudaFree(dev->overflow_flag);
   cudaFree(dev->d_stats);
@@ -522,6 +533,8 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   rp.shard_rank = dev->shard_rank;
   rp.shard_n = dev->shard_n;
   rp.tile_offset = dev->tile_offset;
+  rp.active_tiles = dev->active_tiles;
+  rp.work_counter = dev->work_counter;
   rp.list = dev->list;
   rp.list_capacity = dev->list_cap;
   rp.n_attrs = n_attrs;
@@ -553,13 +566,14 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   default: launch_geometry<6>(gp, st); break;
   }
   if (dev->profile) CU(cudaEventRecord(dev->ev[1], st));
-  k_scan_tiles<<<1, 1024, 0, st>>>(dev->tile_count, dev->tile_offset, dev->tile_cursor, n_tiles);
+  k_scan_tiles<<<1, 1024, 0, st>>>(dev->tile_count, dev->tile_offset, dev->tile_cursor, n_tiles, dev->active_tiles,
+                                    dev->work_counter);
   k_bin_fill<<<(n_slots + 255) / 256, 256, 0, st>>>(bp);
   if (dev->profile) CU(cudaEventRecord(dev->ev[2], st));
   k_sort_lists<<<n_tiles, 256, 0, st>>>(dev->tile_offset, dev->list, dev->list_cap);
   if (dev->profile) CU(cudaEventRecord(dev->ev[3], st));
   bool ok = false;
-  const uint32_t blocks = n_tiles * 16;
+  const uint32_t blocks = std::min<uint32_t>(n_tiles * 16, (uint32_t)dev->raster_grid);
   switch (S) {
   case 1: ok = launch_raster_s<1>(rp, blocks, st); break;
   case 2: ok = launch_raster_s<2>(rp, blocks, st); break;

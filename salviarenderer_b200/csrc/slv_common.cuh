@@ -89,6 +89,8 @@ struct RasterParams {
   uint32_t tiles_x, tiles_y;
   uint32_t shard_rank, shard_n;
   const uint32_t* tile_offset;
+  const uint32_t* active_tiles;  // [0] = count, [1..] = ids of the non-empty tiles of this draw
+  uint32_t* work_counter;        // persistent-CTA work queue head (reset by k_scan_tiles)
   const uint32_t* list;
   uint32_t list_capacity;
   uint32_t n_attrs;

@@ -391,16 +391,26 @@ __global__ void __launch_bounds__(128) k_geometry(GeomParams p) {
 // binning
 // =====================================================================================================
 // single CTA, 1024 threads: exclusive scan of tile_count -> tile_offset[0..n]; zeroes count and cursor
+// also compacts the ids of the non-empty tiles into active_tiles[1..] (count in active_tiles[0]) and resets the
+// raster work counter.
 __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint32_t* tile_offset, uint32_t* tile_cursor,
-                                                     uint32_t n_tiles) {
+                                                     uint32_t n_tiles, uint32_t* active_tiles, uint32_t* work_counter) {
+  __shared__ uint32_t s_active;
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_carry = 0;
+  if (tid == 0) { s_carry = 0; s_active = 0; *work_counter = 0; }
   __syncthreads();
   for (uint32_t base = 0; base < n_tiles; base += 1024) {
     const uint32_t i = base + tid;
     const uint32_t v = i < n_tiles ? tile_count[i] : 0;
+    {  // active-tile compaction (order across warps is irrelevant)
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, v != 0);
+      uint32_t wbase = 0;
+      if (lane == 0 && bal) wbase = atomicAdd(&s_active, (uint32_t)__popc(bal));
+      wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+      if (v != 0) active_tiles[1 + wbase + __popc(bal & ((1u << lane) - 1))] = i;
+    }
     uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -430,7 +440,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint3
     if (tid == 1023) s_carry = excl + v;
     __syncthreads();
   }
-  if (tid == 0) tile_offset[n_tiles] = s_carry;
+  if (tid == 0) { tile_offset[n_tiles] = s_carry; active_tiles[0] = s_active; }
 }
 
 __global__ void __launch_bounds__(256) k_bin_fill(BinParams p) {
@@ -547,7 +557,7 @@ __device__ __forceinline__ uint32_t stencil_op_apply(uint32_t op, uint32_t ref, 
 struct TriEntry {  // one surviving triangle of the current chunk, staged in shared memory
   float A[3], B[3], C[3];
   float bbox[4];
-  uint32_t slot_flags;  // slot << 2 | full16 << 1 | front
+  uint32_t slot_flags;  // slot << 2 | front
   uint32_t pad[2];
 };
 
@@ -686,340 +696,486 @@ __device__ __forceinline__ bool run_ps(const RasterParams& p, const PixelCtx& px
   return true;
 }
 
-template <int S, int PS>
-__global__ void __launch_bounds__(RASTER_THREADS) k_raster(RasterParams p) {
-  __shared__ TriEntry s_tri[RASTER_THREADS];
-  __shared__ uint32_t s_warp_cnt[RASTER_THREADS / 32];
+// level-4 decision of the reference hierarchy for one 4x4 block of a region (subdivide_tile at the 4-px
+// level, rasterizer.cpp:441-602): 0 rejected, 1 partial, 2 full.  (rx, ry) = tile-relative block origin,
+// (left_f, top_f) = origin of the 16-px region the block belongs to, (bx, by) = block index inside it.
+__device__ __forceinline__ int block_test(const TriEntry& t, float x_min, float x_max, float y_min, float y_max, int rx,
+                                          int ry, float left_f, float top_f, int bx, int by) {
+  bool rej = (x_min >= (float)(rx + 4)) || (x_max < (float)rx) || (y_min >= (float)(ry + 4)) || (y_max < (float)ry);
+  bool acc = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float A = t.A[k], B = t.B[k], C = t.C[k];
+    float step_x = TILE * A, step_y = TILE * B;
+    float r2a = -fabsf(step_x) - fabsf(step_y);
+    float part = (float)((A > 0) * TILE) * A + (float)((B > 0) * TILE) * B;
+    step_x *= 0.25f; step_y *= 0.25f; r2a *= 0.25f; part *= 0.25f;
+    step_x *= 0.25f; step_y *= 0.25f; r2a *= 0.25f; part *= 0.25f;
+    float ev = C - part;
+    float ev1 = ev - (left_f * A + top_f * B);
+    float step = step_x * (float)bx + step_y * (float)by;
+    rej |= (step < ev1);
+    acc &= !((step + r2a) < ev1);
+  }
+  return rej ? 0 : (acc ? 2 : 1);
+}
 
-  const uint32_t tile = blockIdx.x >> 4, sub = blockIdx.x & 15;
-  const uint32_t list_beg = p.tile_offset[tile];
-  uint32_t list_end = p.tile_offset[tile + 1];
-  if (list_end > p.list_capacity) list_end = p.list_capacity;
-  if (list_beg >= list_end) return;
-  const uint32_t tile_x = tile % p.tiles_x, tile_y = tile / p.tiles_x;
-  const int X16 = (sub & 3) * REGION, Y16 = (sub >> 2) * REGION;  // tile-relative origin of this region
-  const int gx0 = tile_x * TILE + X16, gy0 = tile_y * TILE + Y16;
-  // "Sub tile is out of screen" (rasterizer.cpp:721-724)
-  if ((float)gx0 >= (float)p.target_w || (float)gy0 >= (float)p.target_h) return;
+constexpr int RASTER_WARPS = RASTER_THREADS / 32;
+constexpr int QCAP = 32;  // quads a warp may queue per round (a triangle adds at most 8)
+
+// Persistent CTAs: work item = (active tile, 16x16 region).  Per item the tile's sorted triangle list is
+// filtered in chunks of 256 entries: one thread per entry evaluates the reference's level-16 decision for the
+// region and the level-4 decision of all 16 blocks ONCE, and the survivors are compacted (order preserving) into
+// one shared-memory triangle array plus one ordered work list per warp holding only the triangles that touch
+// that warp's two 4x4 blocks.  Each warp then walks its own list: thread == pixel, all S samples of
+// depth / stencil / colour stay in registers until the item is finished.
+template <int S, int PS>
+__global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams p) {
+  __shared__ TriEntry s_tri[RASTER_THREADS];
+  __shared__ uint16_t s_wlist[RASTER_WARPS][RASTER_THREADS];
+  __shared__ uint16_t s_cnt[RASTER_WARPS + 1][RASTER_WARPS];  // [list][filter warp]; list RASTER_WARPS = survivors
+  __shared__ uint2 s_items[RASTER_WARPS][QCAP];                // quad queue of each warp (phase A -> B, C)
+  __shared__ uint32_t s_qcnt[RASTER_WARPS];
+  __shared__ float4 s_color[RASTER_WARPS * QCAP * 4];          // shaded colour of every queued pixel (phase B -> C)
+  __shared__ uint32_t s_fin[RASTER_WARPS * QCAP];              // final 4x4-bit sample masks of every queued quad
+  __shared__ uint32_t s_item;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // warp = 8x4 pixels = two 4x4 blocks; lanes 4q..4q+3 form the 2x2 quad q
   const int wx = (warp & 1) * 8, wy = (warp >> 1) * 4;
   const int q = lane >> 2, pi = lane & 3;
   const int lx = wx + (q & 3) * 2 + (pi & 1), ly = wy + (q >> 2) * 2 + (pi >> 1);  // region-relative
-  const int x = gx0 + lx, y = gy0 + ly;
   const int bx = lx >> 2, by = ly >> 2;  // 4x4 block inside the region
   const int ix = lx & 3, iy = ly & 3;    // pixel inside the block
-  const bool odd_x = x & 1, odd_y = y & 1;
   const uint32_t quad_base = lane & ~3u;
-  const bool in_target = (uint32_t)x < p.target_w && (uint32_t)y < p.target_h;
   const uint32_t fullmask = (1u << S) - 1;
-
-  // ---- per-pixel framebuffer state in registers ----
-  float zbuf[S];
-  uint32_t sbuf[S], cbuf[S];
-  bool dirty_ds = false, dirty_c = false;
+  const int R = 1 + (int)p.n_attrs;
   const bool c0_packed = p.color0.data && p.color0.bpp == 4;
-  uint8_t* ds_ptr = nullptr;
-  uint8_t* c_ptr = nullptr;
-#pragma unroll
-  for (int s = 0; s < S; ++s) { zbuf[s] = 0.0f; sbuf[s] = 0; cbuf[s] = 0; }
-  if (in_target) {
-    if (p.ds.data) {
-      ds_ptr = p.ds.data + ((size_t)y * p.ds.w + x) * S * 8;
-      if (S == 4) {
-        float4 a = *reinterpret_cast<const float4*>(ds_ptr), b = *reinterpret_cast<const float4*>(ds_ptr + 16);
-        zbuf[0] = a.x; sbuf[0] = __float_as_uint(a.y); zbuf[1 % S] = a.z; sbuf[1 % S] = __float_as_uint(a.w);
-        zbuf[2 % S] = b.x; sbuf[2 % S] = __float_as_uint(b.y); zbuf[3 % S] = b.z; sbuf[3 % S] = __float_as_uint(b.w);
-      } else if (S == 2) {
-        float4 a = *reinterpret_cast<const float4*>(ds_ptr);
-        zbuf[0] = a.x; sbuf[0] = __float_as_uint(a.y); zbuf[1 % S] = a.z; sbuf[1 % S] = __float_as_uint(a.w);
-      } else {
-        float2 a = *reinterpret_cast<const float2*>(ds_ptr);
-        zbuf[0] = a.x; sbuf[0] = __float_as_uint(a.y);
-      }
-    }
-    if (c0_packed) {
-      c_ptr = p.color0.data + ((size_t)y * p.color0.w + x) * S * 4;
-      if (S == 4) {
-        uint4 a = *reinterpret_cast<const uint4*>(c_ptr);
-        cbuf[0] = a.x; cbuf[1 % S] = a.y; cbuf[2 % S] = a.z; cbuf[3 % S] = a.w;
-      } else if (S == 2) {
-        uint2 a = *reinterpret_cast<const uint2*>(c_ptr);
-        cbuf[0] = a.x; cbuf[1 % S] = a.y;
-      } else {
-        cbuf[0] = *reinterpret_cast<const uint32_t*>(c_ptr);
-      }
-    }
-  }
 
   uint32_t n_ps_quads = 0, n_backend_quads = 0;
   uint32_t n_ztest = 0, n_zwrite = 0, n_cwrite = 0, n_cread = 0;  // algorithmic traffic (SURVEY §8d B_frag)
-  const int R = 1 + (int)p.n_attrs;
-  const float vpx = (float)(tile_x * TILE), vpy = (float)(tile_y * TILE);
 
-  for (uint32_t chunk = list_beg; chunk < list_end; chunk += RASTER_THREADS) {
-    // ================= filter: the reference's level-16 decision for this region =================
-    uint32_t ei = chunk + tid;
-    bool keep = false;
-    TriEntry ent;
-    if (ei < list_end) {
-      uint32_t e = __ldg(p.list + ei);
-      uint32_t slot = e >> 1;
-      const float4* rec = p.tris + (size_t)slot * p.tri_stride;
-      float4 e0 = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2), bb = __ldg(rec + 3);
-      uint32_t flags = __float_as_uint(__ldg(rec + 4).x);
-      ent.A[0] = e0.x; ent.B[0] = e0.y; ent.C[0] = e0.z;
-      ent.A[1] = e1.x; ent.B[1] = e1.y; ent.C[1] = e1.z;
-      ent.A[2] = e2.x; ent.B[2] = e2.y; ent.C[2] = e2.z;
-      ent.bbox[0] = bb.x; ent.bbox[1] = bb.y; ent.bbox[2] = bb.z; ent.bbox[3] = bb.w;
-      uint32_t full16;
-      if (e & 1) {  // the whole 64x64 tile is inside the triangle (rasterizer.cpp:736-743)
-        keep = true;
-        full16 = 1;
-      } else {
-        // subdivide_tile at the 16-px level (rasterizer.cpp:441-602, 698-772)
-        float x_min = bb.x - vpx, x_max = bb.y - vpx, y_min = bb.z - vpy, y_max = bb.w - vpy;
-        bool rej = (x_min >= (float)(X16 + REGION)) || (x_max < (float)X16) || (y_min >= (float)(Y16 + REGION)) ||
-                   (y_max < (float)Y16);
-        bool acc = true;
-        const float ftx = (float)(X16 / REGION), fty = (float)(Y16 / REGION);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          float A = ent.A[k], B = ent.B[k], C = ent.C[k];
-          float step_x = TILE * A, step_y = TILE * B;
-          float r2a = -fabsf(step_x) - fabsf(step_y);
-          float part = (float)((A > 0) * TILE) * A + (float)((B > 0) * TILE) * B;
-          step_x *= 0.25f; step_y *= 0.25f; r2a *= 0.25f; part *= 0.25f;
-          float ev = C - part;
-          float ev1 = ev - (vpx * A + vpy * B);
-          float step = step_x * ftx + step_y * fty;
-          rej |= (step < ev1);
-          acc &= !((step + r2a) < ev1);
-        }
-        keep = !rej;
-        full16 = acc ? 1 : 0;
-      }
-      ent.slot_flags = (slot << 2) | (full16 << 1) | ((flags >> 1) & 1);
-    }
-    // order-preserving compaction of the survivors into shared memory
-    uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
-    if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+  const uint32_t n_items = p.active_tiles[0] * 16u;
+  for (;;) {
     __syncthreads();
-    uint32_t base = 0, n_surv = 0;
-#pragma unroll
-    for (int w = 0; w < RASTER_THREADS / 32; ++w) {
-      const uint32_t c = s_warp_cnt[w];
-      if ((uint32_t)w < warp) base += c;
-      n_surv += c;
-    }
-    if (keep) s_tri[base + __popc(bal & ((1u << lane) - 1))] = ent;
+    if (tid == 0) s_item = atomicAdd(p.work_counter, 1u);
     __syncthreads();
+    const uint32_t item = s_item;
+    if (item >= n_items) break;
+    const uint32_t tile = p.active_tiles[1 + (item >> 4)], sub = item & 15;
+    const uint32_t list_beg = p.tile_offset[tile];
+    uint32_t list_end = p.tile_offset[tile + 1];
+    if (list_end > p.list_capacity) list_end = p.list_capacity;
+    const uint32_t tile_x = tile % p.tiles_x, tile_y = tile / p.tiles_x;
+    const int X16 = (sub & 3) * REGION, Y16 = (sub >> 2) * REGION;  // tile-relative origin of this region
+    const int gx0 = tile_x * TILE + X16, gy0 = tile_y * TILE + Y16;
+    // "Sub tile is out of screen" (rasterizer.cpp:721-724)
+    if ((float)gx0 >= (float)p.target_w || (float)gy0 >= (float)p.target_h) continue;
+    const int x = gx0 + lx, y = gy0 + ly;
+    const bool odd_x = x & 1, odd_y = y & 1;
+    const bool in_target = (uint32_t)x < p.target_w && (uint32_t)y < p.target_h;
+    const float vpx = (float)(tile_x * TILE), vpy = (float)(tile_y * TILE);
 
-    // ================= main loop: triangles of this chunk in API order =================
-    for (uint32_t ti = 0; ti < n_surv; ++ti) {
-      const TriEntry& t = s_tri[ti];
-      const uint32_t sf = t.slot_flags;
-      // ---- level-4 decision for my 4x4 block (half-warp uniform) ----
-      int blk;  // 0 rejected, 1 partial, 2 full
-      if (sf & 2) {
-        blk = 2;
-      } else {
-        float x_min = t.bbox[0] - vpx, x_max = t.bbox[1] - vpx, y_min = t.bbox[2] - vpy, y_max = t.bbox[3] - vpy;
-        const int rx = X16 + bx * 4, ry = Y16 + by * 4;  // tile-relative block origin
-        bool rej = (x_min >= (float)(rx + 4)) || (x_max < (float)rx) || (y_min >= (float)(ry + 4)) || (y_max < (float)ry);
-        bool acc = true;
-        const float left_f = (float)gx0, top_f = (float)gy0;
+    // ---- per-pixel framebuffer state in registers (loaded when the first triangle reaches this warp) ----
+    float zbuf[S];
+    uint32_t sbuf[S], cbuf[S];
+    bool dirty_ds = false, dirty_c = false, fb_loaded = false;
+    uint8_t* ds_ptr = nullptr;
+    uint8_t* c_ptr = nullptr;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          float A = t.A[k], B = t.B[k], C = t.C[k];
-          float step_x = TILE * A, step_y = TILE * B;
-          float r2a = -fabsf(step_x) - fabsf(step_y);
-          float part = (float)((A > 0) * TILE) * A + (float)((B > 0) * TILE) * B;
-          step_x *= 0.25f; step_y *= 0.25f; r2a *= 0.25f; part *= 0.25f;
-          step_x *= 0.25f; step_y *= 0.25f; r2a *= 0.25f; part *= 0.25f;
-          float ev = C - part;
-          float ev1 = ev - (left_f * A + top_f * B);
-          float step = step_x * (float)bx + step_y * (float)by;
-          rej |= (step < ev1);
-          acc &= !((step + r2a) < ev1);
+    for (int s = 0; s < S; ++s) { zbuf[s] = 0.0f; sbuf[s] = 0; cbuf[s] = 0; }
+
+    for (uint32_t chunk = list_beg; chunk < list_end; chunk += RASTER_THREADS) {
+      // ================= filter: level-16 decision for the region + level-4 decision of its 16 blocks =================
+      const uint32_t ei = chunk + tid;
+      bool keep = false;
+      uint32_t st_bits = 0;  // 2 bits per block: 0 rejected, 1 partial, 2 full
+      TriEntry ent;
+      if (ei < list_end) {
+        const uint32_t e = __ldg(p.list + ei);
+        const uint32_t slot = e >> 1;
+        const float4* rec = p.tris + (size_t)slot * p.tri_stride;
+        const float4 e0 = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2), bb = __ldg(rec + 3);
+        const uint32_t flags = __float_as_uint(__ldg(rec + 4).x);
+        ent.A[0] = e0.x; ent.B[0] = e0.y; ent.C[0] = e0.z;
+        ent.A[1] = e1.x; ent.B[1] = e1.y; ent.C[1] = e1.z;
+        ent.A[2] = e2.x; ent.B[2] = e2.y; ent.C[2] = e2.z;
+        ent.bbox[0] = bb.x; ent.bbox[1] = bb.y; ent.bbox[2] = bb.z; ent.bbox[3] = bb.w;
+        uint32_t full16;
+        const float x_min = bb.x - vpx, x_max = bb.y - vpx, y_min = bb.z - vpy, y_max = bb.w - vpy;
+        if (e & 1) {  // the whole 64x64 tile is inside the triangle (rasterizer.cpp:736-743)
+          keep = true;
+          full16 = 1;
+        } else {
+          // subdivide_tile at the 16-px level (rasterizer.cpp:441-602, 698-772)
+          bool rej = (x_min >= (float)(X16 + REGION)) || (x_max < (float)X16) || (y_min >= (float)(Y16 + REGION)) ||
+                     (y_max < (float)Y16);
+          bool acc = true;
+          const float ftx = (float)(X16 / REGION), fty = (float)(Y16 / REGION);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            float A = ent.A[k], B = ent.B[k], C = ent.C[k];
+            float step_x = TILE * A, step_y = TILE * B;
+            float r2a = -fabsf(step_x) - fabsf(step_y);
+            float part = (float)((A > 0) * TILE) * A + (float)((B > 0) * TILE) * B;
+            step_x *= 0.25f; step_y *= 0.25f; r2a *= 0.25f; part *= 0.25f;
+            float ev = C - part;
+            float ev1 = ev - (vpx * A + vpy * B);
+            float step = step_x * ftx + step_y * fty;
+            rej |= (step < ev1);
+            acc &= !((step + r2a) < ev1);
+          }
+          keep = !rej;
+          full16 = acc ? 1 : 0;
         }
-        blk = rej ? 0 : (acc ? 2 : 1);
+        if (keep) {
+          if (full16) {
+            st_bits = 0xAAAAAAAAu;  // every block full
+          } else {
+            const float left_f = (float)gx0, top_f = (float)gy0;
+            for (int b = 0; b < 16; ++b) {
+              const int bbx = b & 3, bby = b >> 2;
+              st_bits |= (uint32_t)block_test(ent, x_min, x_max, y_min, y_max, X16 + bbx * 4, Y16 + bby * 4, left_f, top_f,
+                                              bbx, bby) << (2 * b);
+            }
+            keep = st_bits != 0;
+          }
+        }
+        ent.slot_flags = (slot << 2) | ((flags >> 1) & 1);
       }
-      // ---- per-sample coverage (draw_partial_tile, rasterizer.cpp:298-439) ----
-      uint32_t pm = 0;
-      if (in_target) {
-        if (blk == 2) {
-          pm = fullmask;
-        } else if (blk == 1) {
-          const float left_f = (float)(gx0 + bx * 4), top_f = (float)(gy0 + by * 4);
-          float ev[3];
+      // ---- order-preserving compaction: survivors -> s_tri, and per target warp -> s_wlist[w] ----
+      // target warp w owns blocks (by = w >> 1, bx = (w & 1) * 2 + {0, 1}): 4 status bits at 2 * (by * 4 + bx)
+      uint32_t hit = 0;  // bit w: this triangle touches warp w
 #pragma unroll
-          for (int k = 0; k < 3; ++k) ev[k] = t.C[k] - (left_f * t.A[k] + top_f * t.B[k]);
+      for (int w = 0; w < RASTER_WARPS; ++w) {
+        const uint32_t four = (st_bits >> (2 * ((w >> 1) * 4 + (w & 1) * 2))) & 0xFu;
+        hit |= (keep && four) ? (1u << w) : 0u;
+      }
+      uint32_t bal[RASTER_WARPS + 1];
+#pragma unroll
+      for (int w = 0; w < RASTER_WARPS; ++w) bal[w] = __ballot_sync(0xFFFFFFFFu, (hit >> w) & 1u);
+      bal[RASTER_WARPS] = __ballot_sync(0xFFFFFFFFu, keep);
+      if (lane <= RASTER_WARPS) {
+        uint32_t mine = bal[0];
+#pragma unroll
+        for (int w = 1; w <= RASTER_WARPS; ++w) mine = (lane == (uint32_t)w) ? bal[w] : mine;
+        s_cnt[lane][warp] = (uint16_t)__popc(mine);
+      }
+      __syncthreads();
+      uint32_t my_cnt = 0;  // entries in this warp's list
+      {
+        const uint32_t below = (1u << lane) - 1;
+        uint32_t sbase = 0;
+#pragma unroll
+        for (int fw = 0; fw < RASTER_WARPS; ++fw) {
+          if ((uint32_t)fw < warp) sbase += s_cnt[RASTER_WARPS][fw];
+          my_cnt += s_cnt[warp][fw];
+        }
+        if (keep) {
+          const uint32_t sidx = sbase + __popc(bal[RASTER_WARPS] & below);
+          s_tri[sidx] = ent;
+#pragma unroll
+          for (int w = 0; w < RASTER_WARPS; ++w) {
+            if ((hit >> w) & 1u) {
+              uint32_t wbase = 0;
+#pragma unroll
+              for (int fw = 0; fw < RASTER_WARPS; ++fw)
+                if ((uint32_t)fw < warp) wbase += s_cnt[w][fw];
+              const uint32_t four = (st_bits >> (2 * ((w >> 1) * 4 + (w & 1) * 2))) & 0xFu;
+              s_wlist[w][wbase + __popc(bal[w] & below)] = (uint16_t)(sidx | (four << 8));
+            }
+          }
+        }
+      }
+      __syncthreads();
+
+      // ================= rounds: (A) coverage + early-Z by the pixel owners -> quad queue,
+      //                         (B) dense shading of every queued quad by all threads,
+      //                         (C) ordered output merge by the pixel owners =================
+      if (my_cnt && !fb_loaded) {
+        fb_loaded = true;
+        if (in_target) {
+          if (p.ds.data) {
+            ds_ptr = p.ds.data + ((size_t)y * p.ds.w + x) * S * 8;
+            if (S == 4) {
+              float4 a = *reinterpret_cast<const float4*>(ds_ptr), b = *reinterpret_cast<const float4*>(ds_ptr + 16);
+              zbuf[0] = a.x; sbuf[0] = __float_as_uint(a.y); zbuf[1 % S] = a.z; sbuf[1 % S] = __float_as_uint(a.w);
+              zbuf[2 % S] = b.x; sbuf[2 % S] = __float_as_uint(b.y); zbuf[3 % S] = b.z; sbuf[3 % S] = __float_as_uint(b.w);
+            } else if (S == 2) {
+              float4 a = *reinterpret_cast<const float4*>(ds_ptr);
+              zbuf[0] = a.x; sbuf[0] = __float_as_uint(a.y); zbuf[1 % S] = a.z; sbuf[1 % S] = __float_as_uint(a.w);
+            } else {
+              float2 a = *reinterpret_cast<const float2*>(ds_ptr);
+              zbuf[0] = a.x; sbuf[0] = __float_as_uint(a.y);
+            }
+          }
+          if (c0_packed) {
+            c_ptr = p.color0.data + ((size_t)y * p.color0.w + x) * S * 4;
+            if (S == 4) {
+              uint4 a = *reinterpret_cast<const uint4*>(c_ptr);
+              cbuf[0] = a.x; cbuf[1 % S] = a.y; cbuf[2 % S] = a.z; cbuf[3 % S] = a.w;
+            } else if (S == 2) {
+              uint2 a = *reinterpret_cast<const uint2*>(c_ptr);
+              cbuf[0] = a.x; cbuf[1 % S] = a.y;
+            } else {
+              cbuf[0] = *reinterpret_cast<const uint32_t*>(c_ptr);
+            }
+          }
+        }
+      }
+      uint32_t wi = 0;
+      for (;;) {
+        // ---------------- phase A: this warp's triangles, in API order, until its queue is full ----------------
+        uint32_t qn = 0;
+        while (wi < my_cnt && qn + 8 <= (uint32_t)QCAP) {
+          const uint32_t we = s_wlist[warp][wi];
+          ++wi;
+          const TriEntry& t = s_tri[we & 0xFF];
+          const int blk = (we >> (8 + 2 * (bx & 1))) & 3;  // 0 rejected, 1 partial, 2 full
+          // per-sample coverage (draw_partial_tile, rasterizer.cpp:298-439)
+          uint32_t pm = 0;
+          if (in_target) {
+            if (blk == 2) {
+              pm = fullmask;
+            } else if (blk == 1) {
+              const float left_f = (float)(gx0 + bx * 4), top_f = (float)(gy0 + by * 4);
+              float ev[3];
+#pragma unroll
+              for (int k = 0; k < 3; ++k) ev[k] = t.C[k] - (left_f * t.A[k] + top_f * t.B[k]);
+#pragma unroll
+              for (int s = 0; s < S; ++s) {
+                float fx = SamplePattern<S>::x(s) + (float)ix, fy = SamplePattern<S>::y(s) + (float)iy;
+                bool rj = false;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) rj |= (fx * t.A[k] + fy * t.B[k]) < ev[k];
+                if (!rj) pm |= 1u << s;
+              }
+            }
+          }
+          if (!__any_sync(0xFFFFFFFFu, pm != 0)) continue;
+          // early-Z: test and WRITE depth now (framebuffer.cpp:522-614; Appendix B #3)
+          uint32_t tested = pm;
+          if (p.early_z) {
+            tested = 0;
+            if (pm) {
+              const float4* rec = p.tris + (size_t)(t.slot_flags >> 2) * p.tri_stride;
+              const float4 v0p = __ldg(rec + TRI_HEADER), gxp = __ldg(rec + TRI_HEADER + R), gyp = __ldg(rec + TRI_HEADER + 2 * R);
+              const float dx = 0.5f + (float)(uint32_t)(x & ~1) - v0p.x;
+              const float dy = 0.5f + (float)(uint32_t)(y & ~1) - v0p.y;
+              float depth = v0p.z + (gxp.z * dx + gyp.z * dy);
+              if (odd_x) depth += gxp.z;
+              if (odd_y) depth += gyp.z;
+#pragma unroll
+              for (int s = 0; s < S; ++s) {
+                if (pm & (1u << s)) {
+                  const float aa = (S > 1) ? (SamplePattern<S>::x(s) - 0.5f) * gxp.z + (SamplePattern<S>::y(s) - 0.5f) * gyp.z : 0.0f;
+                  const float nd = (S == 1) ? depth : aa + depth;
+                  const float od = p.read_depth ? zbuf[s] : 0.0f;
+                  const bool pass = p.depth_enable ? compare_f(p.depth_func, nd, od) : true;
+                  n_ztest += p.read_depth;
+                  if (pass) {
+                    tested |= 1u << s;
+                    if (p.write_depth) { zbuf[s] = nd; dirty_ds = true; ++n_zwrite; }
+                  }
+                }
+              }
+            }
+          }
+          // quad assembly: one queue item per quad that still has a live sample
+          const uint32_t m0 = __shfl_sync(0xFFFFFFFFu, pm, quad_base), m1 = __shfl_sync(0xFFFFFFFFu, pm, quad_base + 1);
+          const uint32_t m2 = __shfl_sync(0xFFFFFFFFu, pm, quad_base + 2), m3 = __shfl_sync(0xFFFFFFFFu, pm, quad_base + 3);
+          const uint32_t t0 = __shfl_sync(0xFFFFFFFFu, tested, quad_base), t1 = __shfl_sync(0xFFFFFFFFu, tested, quad_base + 1);
+          const uint32_t t2 = __shfl_sync(0xFFFFFFFFu, tested, quad_base + 2), t3 = __shfl_sync(0xFFFFFFFFu, tested, quad_base + 3);
+          const bool quad_shade = ((m0 | m1 | m2 | m3) != 0) && ((t0 | t1 | t2 | t3) != 0);
+          const uint32_t qbal = __ballot_sync(0xFFFFFFFFu, quad_shade && pi == 0);
+          if (quad_shade && pi == 0) {
+            const uint32_t quad_full = ((m0 & m1 & m2 & m3) == fullmask) ? 1u : 0u;
+            uint2 it;
+            it.x = (we & 0xFF) | ((uint32_t)q << 8) | (quad_full << 11) | ((m0 | (m1 << 4) | (m2 << 8) | (m3 << 12)) << 16);
+            it.y = t0 | (t1 << 4) | (t2 << 8) | (t3 << 12);
+            s_items[warp][qn + __popc(qbal & ((1u << lane) - 1))] = it;
+          }
+          qn += __popc(qbal);
+        }
+        if (lane == 0) {
+          s_qcnt[warp] = qn;
+          n_ps_quads += qn;
+        }
+        const int any_more = __syncthreads_or(wi < my_cnt);
+
+        // ---------------- phase B: shade all queued quads, 64 quads (256 pixels) per pass ----------------
+        uint32_t qbase[RASTER_WARPS + 1];
+        qbase[0] = 0;
+#pragma unroll
+        for (int w = 0; w < RASTER_WARPS; ++w) qbase[w + 1] = qbase[w] + s_qcnt[w];
+        const uint32_t q_total = qbase[RASTER_WARPS];
+        for (uint32_t jb = 0; jb < q_total; jb += RASTER_THREADS / 4) {
+          const uint32_t j_raw = jb + (tid >> 2);
+          const bool valid = j_raw < q_total;
+          const uint32_t j = valid ? j_raw : q_total - 1;
+          uint32_t ow = 0;  // owner warp of item j
+#pragma unroll
+          for (int w = 1; w < RASTER_WARPS; ++w) ow += (j >= qbase[w]) ? 1u : 0u;
+          uint32_t ob = 0;
+#pragma unroll
+          for (int w = 1; w < RASTER_WARPS; ++w) ob = (ow == (uint32_t)w) ? qbase[w] : ob;
+          const uint2 it = s_items[ow][j - ob];
+          const TriEntry& t = s_tri[it.x & 0xFF];
+          const uint32_t oq = (it.x >> 8) & 7;
+          const bool quad_full = (it.x >> 11) & 1;
+          const uint32_t pm = (it.x >> (16 + 4 * pi)) & 0xF;
+          const uint32_t tested = (it.y >> (4 * pi)) & 0xF;
+          // pixel handled by this thread: pixel pi of quad oq of warp ow
+          const int plx = (int)(ow & 1) * 8 + (int)(oq & 3) * 2 + (pi & 1), ply = (int)(ow >> 1) * 4 + (int)(oq >> 2) * 2 + (pi >> 1);
+          const int sx_ = gx0 + plx, sy_ = gy0 + ply;
+          const float4* rec = p.tris + (size_t)(t.slot_flags >> 2) * p.tri_stride;
+          // step_2d_unproj_pos_quad (shader.cpp:257-287): only w is needed here
+          const float4 v0p = __ldg(rec + TRI_HEADER), gxp = __ldg(rec + TRI_HEADER + R), gyp = __ldg(rec + TRI_HEADER + 2 * R);
+          PixelCtx px;
+          px.rec = rec; px.R = R; px.mods = p.mods;
+          px.dx = 0.5f + (float)(uint32_t)(sx_ & ~1) - v0p.x;
+          px.dy = 0.5f + (float)(uint32_t)(sy_ & ~1) - v0p.y;
+          px.odd_x = sx_ & 1; px.odd_y = sy_ & 1;
+          float pw = v0p.w + (gxp.w * px.dx + gyp.w * px.dy);
+          if (px.odd_x) pw += gxp.w;
+          if (px.odd_y) pw += gyp.w;
+          px.inv_w = 1.0f / pw;
+          px.quad_base = quad_base;
+          px.centroid_path = p.has_centroid && !quad_full;
+          px.pdx = px.dx + (float)(int)px.odd_x;
+          px.pdy = px.dy + (float)(int)px.odd_y;
+          if (px.centroid_path && pm != fullmask && pm != 0) {
+            float cx = 0.0f, cy = 0.0f;
+            int n = 0;
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+              if (pm & (1u << s)) { cx += SamplePattern<S>::x(s); cy += SamplePattern<S>::y(s); ++n; }
+            float inv = 1 / (float)n;
+            cx *= inv; cy *= inv;
+            px.pdx += cx - 0.5f;
+            px.pdy += cy - 0.5f;
+          }
+          float4 color;
+          const bool keep_px = run_ps<PS>(p, px, color);
+          uint32_t fin = keep_px ? tested : 0u;
+          const uint32_t f0 = __shfl_sync(0xFFFFFFFFu, fin, quad_base), f1 = __shfl_sync(0xFFFFFFFFu, fin, quad_base + 1);
+          const uint32_t f2 = __shfl_sync(0xFFFFFFFFu, fin, quad_base + 2), f3 = __shfl_sync(0xFFFFFFFFu, fin, quad_base + 3);
+          // draw_full_quad tests the post-PS mask, draw_quad the pre-Z mask (rasterizer.cpp:1311,1409)
+          const bool to_backend = quad_full ? ((f0 | f1 | f2 | f3) != 0) : true;
+          if (valid) {
+            s_color[j * 4 + pi] = color;
+            if (pi == 0) {
+              s_fin[j] = to_backend ? (f0 | (f1 << 4) | (f2 << 8) | (f3 << 12)) : 0u;
+              n_backend_quads += to_backend ? 1u : 0u;
+            }
+          }
+        }
+        __syncthreads();
+
+        // ---------------- phase C: output merger by the pixel owners, in queue (= API) order ----------------
+        for (uint32_t i = 0; i < qn; ++i) {
+          const uint2 it = s_items[warp][i];
+          if ((uint32_t)q != ((it.x >> 8) & 7)) continue;
+          uint32_t flat = i;
+#pragma unroll
+          for (int w = 1; w < RASTER_WARPS; ++w) flat = (warp == (uint32_t)w) ? qbase[w] + i : flat;
+          const uint32_t fin = (s_fin[flat] >> (4 * pi)) & 0xF;
+          if (!fin) continue;
+          const float4 color = s_color[flat * 4 + pi];
+          const TriEntry& t = s_tri[it.x & 0xFF];
+          const bool front = t.slot_flags & 1;
+          float depth = 0.0f, gz_x = 0.0f, gz_y = 0.0f;
+          if (!p.early_z) {  // late depth/stencil needs the sample depths again
+            const float4* rec = p.tris + (size_t)(t.slot_flags >> 2) * p.tri_stride;
+            const float4 v0p = __ldg(rec + TRI_HEADER), gxp = __ldg(rec + TRI_HEADER + R), gyp = __ldg(rec + TRI_HEADER + 2 * R);
+            const float dx = 0.5f + (float)(uint32_t)(x & ~1) - v0p.x;
+            const float dy = 0.5f + (float)(uint32_t)(y & ~1) - v0p.y;
+            depth = v0p.z + (gxp.z * dx + gyp.z * dy);
+            if (odd_x) depth += gxp.z;
+            if (odd_y) depth += gyp.z;
+            gz_x = gxp.z; gz_y = gyp.z;
+          }
 #pragma unroll
           for (int s = 0; s < S; ++s) {
-            float fx = SamplePattern<S>::x(s) + (float)ix, fy = SamplePattern<S>::y(s) + (float)iy;
-            bool rj = false;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) rj |= (fx * t.A[k] + fy * t.B[k]) < ev[k];
-            if (!rj) pm |= 1u << s;
-          }
-        }
-      }
-      if (!__any_sync(0xFFFFFFFFu, pm != 0)) continue;
-
-      // ---- quad assembly ----
-      uint32_t m0 = __shfl_sync(0xFFFFFFFFu, pm, quad_base), m1 = __shfl_sync(0xFFFFFFFFu, pm, quad_base + 1);
-      uint32_t m2 = __shfl_sync(0xFFFFFFFFu, pm, quad_base + 2), m3 = __shfl_sync(0xFFFFFFFFu, pm, quad_base + 3);
-      const bool quad_alive = (m0 | m1 | m2 | m3) != 0;
-      const bool quad_full = (m0 & m1 & m2 & m3) == fullmask;
-
-      const float4* rec = p.tris + (size_t)(sf >> 2) * p.tri_stride;
-      const bool front = sf & 1;
-      // step_2d_unproj_pos_quad (shader.cpp:257-287): only z and w are consumed downstream
-      float4 v0p = __ldg(rec + TRI_HEADER), gxp = __ldg(rec + TRI_HEADER + R), gyp = __ldg(rec + TRI_HEADER + 2 * R);
-      const float dx = 0.5f + (float)(uint32_t)(x & ~1) - v0p.x;
-      const float dy = 0.5f + (float)(uint32_t)(y & ~1) - v0p.y;
-      float pz = v0p.z + (gxp.z * dx + gyp.z * dy);
-      float pw = v0p.w + (gxp.w * dx + gyp.w * dy);
-      if (odd_x) { pz += gxp.z; pw += gxp.w; }
-      if (odd_y) { pz += gyp.z; pw += gyp.w; }
-      const float depth = pz;
-      float aa[S];
-#pragma unroll
-      for (int s = 0; s < S; ++s)
-        aa[s] = (S > 1) ? (SamplePattern<S>::x(s) - 0.5f) * gxp.z + (SamplePattern<S>::y(s) - 0.5f) * gyp.z : 0.0f;
-
-      // ---- early-Z: test and WRITE depth now (framebuffer.cpp:522-614; Appendix B #3) ----
-      uint32_t tested = pm;
-      if (p.early_z && pm) {
-        tested = 0;
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          if (pm & (1u << s)) {
-            float nd = (S == 1) ? depth : aa[s] + depth;
-            float od = p.read_depth ? zbuf[s] : 0.0f;
-            bool pass = p.depth_enable ? compare_f(p.depth_func, nd, od) : true;
-            n_ztest += p.read_depth;
-            if (pass) {
-              tested |= 1u << s;
-              if (p.write_depth) { zbuf[s] = nd; dirty_ds = true; ++n_zwrite; }
+            if (!(fin & (1u << s))) continue;
+            if (!p.early_z) {
+              const float aa = (S > 1) ? (SamplePattern<S>::x(s) - 0.5f) * gz_x + (SamplePattern<S>::y(s) - 0.5f) * gz_y : 0.0f;
+              float sd = (S == 1) ? depth : depth + aa;
+              float od = p.read_depth ? zbuf[s] : 0.0f;
+              uint32_t os = p.stencil_enable ? (sbuf[s] & p.read_mask) : 0u;
+              bool dp = p.depth_enable ? compare_f(p.depth_func, sd, od) : true;
+              n_ztest += (p.read_depth | p.stencil_enable) ? 1u : 0u;
+              const slv_stencil_op_desc& face = front ? p.front_face : p.back_face;
+              bool sp = p.stencil_enable ? compare_u(face.stencil_func, p.stencil_ref, os) : true;
+              if (!(dp && sp)) continue;
+              uint32_t ns = p.stencil_enable ? stencil_op_apply(face.stencil_pass_op, p.stencil_ref, os) : os;
+              if (p.write_depth) { zbuf[s] = sd; dirty_ds = true; }
+              if (p.stencil_enable) { sbuf[s] = ns & p.write_mask; dirty_ds = true; }
+              n_zwrite += (p.write_depth | p.stencil_enable) ? 1u : 0u;
+            }
+            // blend shader
+            if (p.color0.data) {
+              ++n_cwrite;
+              n_cread += (p.bs_program == SLV_BS_LERP_SRC_ALPHA) ? 1u : 0u;
+              if (c0_packed) {
+                if (p.bs_program == SLV_BS_LERP_SRC_ALPHA) {
+                  float4 d = unpack_color(p.color0.fmt, cbuf[s]);
+                  float4 r = make_float4(d.x + (color.x - d.x) * color.w, d.y + (color.y - d.y) * color.w,
+                                         d.z + (color.z - d.z) * color.w, d.w + (color.w - d.w) * color.w);
+                  cbuf[s] = pack_color(p.color0.fmt, r);
+                } else {
+                  cbuf[s] = pack_color(p.color0.fmt, color);
+                }
+                dirty_c = true;
+              } else {
+                uint8_t* cp = p.color0.data + (((size_t)y * p.color0.w + x) * S + s) * p.color0.bpp;
+                if (p.bs_program == SLV_BS_LERP_SRC_ALPHA) {
+                  float4 d = load_texel_rgba32f(p.color0.fmt, cp);
+                  float4 r = make_float4(d.x + (color.x - d.x) * color.w, d.y + (color.y - d.y) * color.w,
+                                         d.z + (color.z - d.z) * color.w, d.w + (color.w - d.w) * color.w);
+                  store_texel_rgba32f(p.color0.fmt, cp, r);
+                } else {
+                  store_texel_rgba32f(p.color0.fmt, cp, color);
+                }
+              }
+            }
+            if (p.bs_program == SLV_BS_REPLACE_AND_COUNT && p.color1.data) {
+              uint8_t* cp = p.color1.data + (((size_t)y * p.color1.w + x) * S + s) * p.color1.bpp;
+              float4 v = load_texel_rgba32f(p.color1.fmt, cp);
+              v.x += 1.0f;
+              store_texel_rgba32f(p.color1.fmt, cp, v);
             }
           }
         }
+        if (!any_more) break;
       }
-      uint32_t t0 = __shfl_sync(0xFFFFFFFFu, tested, quad_base), t1 = __shfl_sync(0xFFFFFFFFu, tested, quad_base + 1);
-      uint32_t t2 = __shfl_sync(0xFFFFFFFFu, tested, quad_base + 2), t3 = __shfl_sync(0xFFFFFFFFu, tested, quad_base + 3);
-      const bool quad_shade = quad_alive && ((t0 | t1 | t2 | t3) != 0);
-      if (!__any_sync(0xFFFFFFFFu, quad_shade)) continue;
-      if (quad_shade && pi == 0) ++n_ps_quads;
-
-      // ---- attribute interpolation + pixel shader on 32-pixel quad batches ----
-      PixelCtx px;
-      px.rec = rec; px.R = R; px.mods = p.mods;
-      px.dx = dx; px.dy = dy; px.odd_x = odd_x; px.odd_y = odd_y;
-      px.inv_w = 1.0f / pw;
-      px.quad_base = quad_base;
-      px.centroid_path = p.has_centroid && !quad_full;
-      px.pdx = dx + (float)(int)odd_x;
-      px.pdy = dy + (float)(int)odd_y;
-      if (px.centroid_path && pm != fullmask && pm != 0) {
-        float cx = 0.0f, cy = 0.0f;
-        int n = 0;
-#pragma unroll
-        for (int s = 0; s < S; ++s)
-          if (pm & (1u << s)) { cx += SamplePattern<S>::x(s); cy += SamplePattern<S>::y(s); ++n; }
-        float inv = 1 / (float)n;
-        cx *= inv; cy *= inv;
-        px.pdx += cx - 0.5f;
-        px.pdy += cy - 0.5f;
-      }
-      float4 color;
-      bool keep_px = run_ps<PS>(p, px, color);
-      uint32_t fin = keep_px ? tested : 0u;
-      uint32_t f0 = __shfl_sync(0xFFFFFFFFu, fin, quad_base), f1 = __shfl_sync(0xFFFFFFFFu, fin, quad_base + 1);
-      uint32_t f2 = __shfl_sync(0xFFFFFFFFu, fin, quad_base + 2), f3 = __shfl_sync(0xFFFFFFFFu, fin, quad_base + 3);
-      // draw_full_quad tests the post-PS mask, draw_quad the pre-Z mask (rasterizer.cpp:1311,1409)
-      const bool to_backend = quad_shade && (quad_full ? ((f0 | f1 | f2 | f3) != 0) : true);
-      if (to_backend && pi == 0) ++n_backend_quads;
-      if (!to_backend) fin = 0;
-
-      // ---- output merger (framebuffer.cpp:445-520) ----
-#pragma unroll
-      for (int s = 0; s < S; ++s) {
-        if (!(fin & (1u << s))) continue;
-        if (!p.early_z) {
-          float sd = (S == 1) ? depth : depth + aa[s];
-          float od = p.read_depth ? zbuf[s] : 0.0f;
-          uint32_t os = p.stencil_enable ? (sbuf[s] & p.read_mask) : 0u;
-          bool dp = p.depth_enable ? compare_f(p.depth_func, sd, od) : true;
-          n_ztest += (p.read_depth | p.stencil_enable) ? 1u : 0u;
-          const slv_stencil_op_desc& face = front ? p.front_face : p.back_face;
-          bool sp = p.stencil_enable ? compare_u(face.stencil_func, p.stencil_ref, os) : true;
-          if (!(dp && sp)) continue;
-          uint32_t ns = p.stencil_enable ? stencil_op_apply(face.stencil_pass_op, p.stencil_ref, os) : os;
-          if (p.write_depth) { zbuf[s] = sd; dirty_ds = true; }
-          if (p.stencil_enable) { sbuf[s] = ns & p.write_mask; dirty_ds = true; }
-          n_zwrite += (p.write_depth | p.stencil_enable) ? 1u : 0u;
-        }
-        // blend shader
-        if (p.color0.data) {
-          ++n_cwrite;
-          n_cread += (p.bs_program == SLV_BS_LERP_SRC_ALPHA) ? 1u : 0u;
-          if (c0_packed) {
-            if (p.bs_program == SLV_BS_LERP_SRC_ALPHA) {
-              float4 d = unpack_color(p.color0.fmt, cbuf[s]);
-              float4 r = make_float4(d.x + (color.x - d.x) * color.w, d.y + (color.y - d.y) * color.w,
-                                     d.z + (color.z - d.z) * color.w, d.w + (color.w - d.w) * color.w);
-              cbuf[s] = pack_color(p.color0.fmt, r);
-            } else {
-              cbuf[s] = pack_color(p.color0.fmt, color);
-            }
-            dirty_c = true;
-          } else {
-            uint8_t* cp = p.color0.data + (((size_t)y * p.color0.w + x) * S + s) * p.color0.bpp;
-            if (p.bs_program == SLV_BS_LERP_SRC_ALPHA) {
-              float4 d = load_texel_rgba32f(p.color0.fmt, cp);
-              float4 r = make_float4(d.x + (color.x - d.x) * color.w, d.y + (color.y - d.y) * color.w,
-                                     d.z + (color.z - d.z) * color.w, d.w + (color.w - d.w) * color.w);
-              store_texel_rgba32f(p.color0.fmt, cp, r);
-            } else {
-              store_texel_rgba32f(p.color0.fmt, cp, color);
-            }
-          }
-        }
-        if (p.bs_program == SLV_BS_REPLACE_AND_COUNT && p.color1.data) {
-          uint8_t* cp = p.color1.data + (((size_t)y * p.color1.w + x) * S + s) * p.color1.bpp;
-          float4 v = load_texel_rgba32f(p.color1.fmt, cp);
-          v.x += 1.0f;
-          store_texel_rgba32f(p.color1.fmt, cp, v);
-        }
-      }
+      // (the barrier at the top of the next chunk / item protects s_tri, s_wlist and s_cnt)
+      __syncthreads();
     }
-    __syncthreads();  // s_tri is rewritten by the next chunk
-  }
 
-  // ---- write the pixel back once, 128-bit stores at 4x MSAA ----
-  if (in_target) {
-    if (dirty_ds && ds_ptr) {
-      if (S == 4) {
-        *reinterpret_cast<float4*>(ds_ptr) =
-            make_float4(zbuf[0], __uint_as_float(sbuf[0]), zbuf[1 % S], __uint_as_float(sbuf[1 % S]));
-        *reinterpret_cast<float4*>(ds_ptr + 16) =
-            make_float4(zbuf[2 % S], __uint_as_float(sbuf[2 % S]), zbuf[3 % S], __uint_as_float(sbuf[3 % S]));
-      } else if (S == 2) {
-        *reinterpret_cast<float4*>(ds_ptr) =
-            make_float4(zbuf[0], __uint_as_float(sbuf[0]), zbuf[1 % S], __uint_as_float(sbuf[1 % S]));
-      } else {
-        *reinterpret_cast<float2*>(ds_ptr) = make_float2(zbuf[0], __uint_as_float(sbuf[0]));
+    // ---- write the pixel back once, 128-bit stores at 4x MSAA ----
+    if (in_target) {
+      if (dirty_ds && ds_ptr) {
+        if (S == 4) {
+          *reinterpret_cast<float4*>(ds_ptr) =
+              make_float4(zbuf[0], __uint_as_float(sbuf[0]), zbuf[1 % S], __uint_as_float(sbuf[1 % S]));
+          *reinterpret_cast<float4*>(ds_ptr + 16) =
+              make_float4(zbuf[2 % S], __uint_as_float(sbuf[2 % S]), zbuf[3 % S], __uint_as_float(sbuf[3 % S]));
+        } else if (S == 2) {
+          *reinterpret_cast<float4*>(ds_ptr) =
+              make_float4(zbuf[0], __uint_as_float(sbuf[0]), zbuf[1 % S], __uint_as_float(sbuf[1 % S]));
+        } else {
+          *reinterpret_cast<float2*>(ds_ptr) = make_float2(zbuf[0], __uint_as_float(sbuf[0]));
+        }
       }
-    }
-    if (dirty_c && c_ptr) {
-      if (S == 4) *reinterpret_cast<uint4*>(c_ptr) = make_uint4(cbuf[0], cbuf[1 % S], cbuf[2 % S], cbuf[3 % S]);
-      else if (S == 2) *reinterpret_cast<uint2*>(c_ptr) = make_uint2(cbuf[0], cbuf[1 % S]);
-      else *reinterpret_cast<uint32_t*>(c_ptr) = cbuf[0];
+      if (dirty_c && c_ptr) {
+        if (S == 4) *reinterpret_cast<uint4*>(c_ptr) = make_uint4(cbuf[0], cbuf[1 % S], cbuf[2 % S], cbuf[3 % S]);
+        else if (S == 2) *reinterpret_cast<uint2*>(c_ptr) = make_uint2(cbuf[0], cbuf[1 % S]);
+        else *reinterpret_cast<uint32_t*>(c_ptr) = cbuf[0];
+      }
     }
   }
+
   // ---- statistics: ps_invocations / backend_input_pixels count 4 per quad ----
   uint32_t a = n_ps_quads, b = n_backend_quads;
 #pragma unroll
