@@ -66,6 +66,21 @@ struct slv_device_t {
   uint32_t *tile_count = nullptr, *tile_offset = nullptr, *tile_cursor = nullptr, *active_tiles = nullptr;
   uint32_t* work_counter = nullptr;
   int raster_grid = 0;  // persistent raster CTAs (SM count x resident CTAs per SM)
+  // ---- draw batching: geometry + binning run at slv_draw time, the raster pass of all queued draws of a
+  // frame runs at the next flush point (readback, clear, resolve, state that changes the targets ...), so each
+  // pixel's depth/stencil/colour is loaded once and stored once per batch instead of once per draw.
+  std::vector<RasterParams> pending;
+  RasterParams* d_batch = nullptr;
+  uint32_t* tile_any = nullptr;
+  uint32_t* list_bump = nullptr;
+  size_t tris_used = 0;      // float4 units used by the queued draws
+  uint64_t slots_queued = 0; // triangle slots of the queued draws (sizes the list arena)
+  uint32_t batch_S = 0;
+  // profiling event pool
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span { size_t a, b; int stage; };
+  std::vector<Span> spans;
   uint32_t tiles_cap = 0;
   uint32_t* list = nullptr;
   uint32_t list_cap = 0;
@@ -76,7 +91,6 @@ struct slv_device_t {
   bool failed = false;  // sticky CUDA error
   // profiling (SLV_PROFILE=1)
   bool profile = false;
-  cudaEvent_t ev[5] = {};
   cudaEvent_t user_ev[16] = {};
   uint32_t* tile_slot = nullptr;  // pack/unpack: dense slot of every owned tile
   uint32_t tile_slot_cap = 0;
@@ -101,35 +115,66 @@ struct slv_device_t {
 
 namespace {
 
-slv_result ensure_scratch(slv_device dev, size_t tris_needed, uint32_t n_tiles, uint32_t list_needed) {
-  if (tris_needed > dev->tris_cap) {
+constexpr uint32_t MAX_BATCH = 64;  // draws whose raster pass is fused into one k_raster launch
+
+slv_result flush_batch(slv_device dev);
+
+// Arenas are shared by the queued draws of a batch; growing one needs the batch flushed first.
+slv_result ensure_scratch(slv_device dev, size_t tris_needed_total, uint32_t n_tiles, uint64_t list_needed_total) {
+  if (tris_needed_total > dev->tris_cap) {
+    slv_result rc = flush_batch(dev);
+    if (rc != SLV_OK) return rc;
     CU(cudaStreamSynchronize(dev->stream));
+    size_t need = tris_needed_total;  // after the flush only the new draw remains; callers pass used + new
     if (dev->tris) CU(cudaFree(dev->tris));
-    size_t cap = std::max(tris_needed, dev->tris_cap * 2);
+    size_t cap = std::max(need, dev->tris_cap * 2);
     CU(cudaMalloc(&dev->tris, cap * sizeof(float4)));
     dev->tris_cap = cap;
   }
   if (n_tiles + 1 > dev->tiles_cap) {
+    slv_result rc = flush_batch(dev);
+    if (rc != SLV_OK) return rc;
     CU(cudaStreamSynchronize(dev->stream));
-    if (dev->tile_count) { CU(cudaFree(dev->tile_count)); CU(cudaFree(dev->tile_offset)); CU(cudaFree(dev->tile_cursor)); CU(cudaFree(dev->active_tiles)); }
+    if (dev->tile_count) {
+      CU(cudaFree(dev->tile_count)); CU(cudaFree(dev->tile_offset)); CU(cudaFree(dev->tile_cursor));
+      CU(cudaFree(dev->active_tiles)); CU(cudaFree(dev->tile_any));
+    }
     uint32_t cap = std::max(n_tiles + 1, 4096u);
     CU(cudaMalloc(&dev->tile_count, cap * sizeof(uint32_t)));
-    CU(cudaMalloc(&dev->tile_offset, cap * sizeof(uint32_t)));
+    CU(cudaMalloc(&dev->tile_offset, (size_t)MAX_BATCH * cap * sizeof(uint32_t)));  // one offset table per queued draw
     CU(cudaMalloc(&dev->tile_cursor, cap * sizeof(uint32_t)));
     CU(cudaMalloc(&dev->active_tiles, (cap + 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&dev->tile_any, cap * sizeof(uint32_t)));
     CU(cudaMemsetAsync(dev->tile_count, 0, cap * sizeof(uint32_t), dev->stream));
-    CU(cudaMemsetAsync(dev->tile_offset, 0, cap * sizeof(uint32_t), dev->stream));
     CU(cudaMemsetAsync(dev->tile_cursor, 0, cap * sizeof(uint32_t), dev->stream));
+    CU(cudaMemsetAsync(dev->tile_any, 0, cap * sizeof(uint32_t), dev->stream));
     dev->tiles_cap = cap;
   }
-  if (list_needed > dev->list_cap) {
+  if (list_needed_total > dev->list_cap) {
+    slv_result rc = flush_batch(dev);
+    if (rc != SLV_OK) return rc;
     CU(cudaStreamSynchronize(dev->stream));
     if (dev->list) CU(cudaFree(dev->list));
-    uint32_t cap = std::max(list_needed, dev->list_cap * 2);
+    uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(list_needed_total, 2ull * dev->list_cap), 1ull << 31);
     CU(cudaMalloc(&dev->list, (size_t)cap * sizeof(uint32_t)));
-    dev->list_cap = cap;
+    dev->list_cap = (uint32_t)cap;
   }
   return SLV_OK;
+}
+
+cudaEvent_t next_event(slv_device dev) {
+  if (dev->ev_used == dev->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    dev->ev_pool.push_back(e);
+  }
+  cudaEvent_t e = dev->ev_pool[dev->ev_used++];
+  cudaEventRecord(e, dev->stream);
+  return e;
+}
+size_t mark(slv_device dev) {  // records an event on the stream, returns its index
+  next_event(dev);
+  return dev->ev_used - 1;
 }
 
 SurfaceRef surface_of(slv_device dev, slv_handle h) {
@@ -156,16 +201,43 @@ void launch_geometry(const GeomParams& gp, cudaStream_t st) {
 }
 
 template <int S>
-bool launch_raster_s(const RasterParams& rp, uint32_t blocks, cudaStream_t st) {
+bool launch_raster_s(const RasterParams& rp, const RasterParams* batch, uint32_t n, uint32_t blocks, cudaStream_t st) {
   switch (rp.ps_program) {
-  case SLV_PS_ATTR0_COLOR: k_raster<S, SLV_PS_ATTR0_COLOR><<<blocks, RASTER_THREADS, 0, st>>>(rp); return true;
-  case SLV_PS_LIGHTS3: k_raster<S, SLV_PS_LIGHTS3><<<blocks, RASTER_THREADS, 0, st>>>(rp); return true;
-  case SLV_PS_TEX_ALPHA: k_raster<S, SLV_PS_TEX_ALPHA><<<blocks, RASTER_THREADS, 0, st>>>(rp); return true;
-  case SLV_PS_SPONZA: k_raster<S, SLV_PS_SPONZA><<<blocks, RASTER_THREADS, 0, st>>>(rp); return true;
-  case SLV_PS_TEX_GRAD_ALPHA: k_raster<S, SLV_PS_TEX_GRAD_ALPHA><<<blocks, RASTER_THREADS, 0, st>>>(rp); return true;
-  case SLV_PS_DISCARD_ALL: k_raster<S, SLV_PS_DISCARD_ALL><<<blocks, RASTER_THREADS, 0, st>>>(rp); return true;
+  case SLV_PS_ATTR0_COLOR: k_raster<S, SLV_PS_ATTR0_COLOR><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, n); return true;
+  case SLV_PS_LIGHTS3: k_raster<S, SLV_PS_LIGHTS3><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, n); return true;
+  case SLV_PS_TEX_ALPHA: k_raster<S, SLV_PS_TEX_ALPHA><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, n); return true;
+  case SLV_PS_SPONZA: k_raster<S, SLV_PS_SPONZA><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, n); return true;
+  case SLV_PS_TEX_GRAD_ALPHA: k_raster<S, SLV_PS_TEX_GRAD_ALPHA><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, n); return true;
+  case SLV_PS_DISCARD_ALL: k_raster<S, SLV_PS_DISCARD_ALL><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, n); return true;
   }
   return false;
+}
+
+// the raster pass of every queued draw, in submission order, as ONE kernel
+slv_result flush_batch(slv_device dev) {
+  if (dev->pending.empty()) return SLV_OK;
+  cudaStream_t st = dev->stream;
+  const RasterParams& first = dev->pending[0];
+  const uint32_t n = (uint32_t)dev->pending.size();
+  const uint32_t n_tiles = first.tiles_x * first.tiles_y;
+  CU(cudaMemcpyAsync(dev->d_batch, dev->pending.data(), n * sizeof(RasterParams), cudaMemcpyHostToDevice, st));
+  size_t e0 = dev->profile ? mark(dev) : 0;
+  k_compact_active<<<1, 1024, 0, st>>>(dev->tile_any, n_tiles, dev->active_tiles, dev->work_counter, dev->list_bump);
+  const uint32_t blocks = std::min<uint32_t>(n_tiles * 16, (uint32_t)dev->raster_grid);
+  bool ok = false;
+  switch (dev->batch_S) {
+  case 1: ok = launch_raster_s<1>(first, dev->d_batch, n, blocks, st); break;
+  case 2: ok = launch_raster_s<2>(first, dev->d_batch, n, blocks, st); break;
+  case 4: ok = launch_raster_s<4>(first, dev->d_batch, n, blocks, st); break;
+  }
+  dev->n_launches += 2;
+  if (dev->profile) dev->spans.push_back({e0, mark(dev), 3});
+  dev->pending.clear();
+  dev->tris_used = 0;
+  dev->slots_queued = 0;
+  if (!ok) return SLV_INVALID_PARAMETER;
+  CU(cudaGetLastError());
+  return SLV_OK;
 }
 
 slv_result check_overflow(slv_device dev) {
@@ -216,8 +288,10 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   CU(cudaMemsetAsync(dev->d_stats, 0, 13 * sizeof(unsigned long long), dev->stream));
   const char* prof = getenv("SLV_PROFILE");
   dev->profile = prof && prof[0] == '1';
-  for (auto& ev : dev->ev) CU(cudaEventCreate(&ev));
   for (auto& ev : dev->user_ev) CU(cudaEventCreate(&ev));
+  CU(cudaMalloc(&dev->d_batch, MAX_BATCH * sizeof(RasterParams)));
+  CU(cudaMalloc(&dev->list_bump, sizeof(uint32_t)));
+  CU(cudaMemsetAsync(dev->list_bump, 0, sizeof(uint32_t), dev->stream));
   *out = dev;
   return SLV_OK;
 }
@@ -225,6 +299,7 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
 void slv_device_destroy(slv_device dev) {
   if (!dev) return;
   cudaSetDevice(dev->ordinal);
+  flush_batch(dev);
   cudaStreamSynchronize(dev->stream);
   for (auto& r : dev->res) {
     if (r.kind == Resource::BUFFER) cudaFree(r.dptr);
@@ -240,8 +315,11 @@ void slv_device_destroy(slv_device dev) {
   cudaFree(dev->list);
   cudaFree(dev->overflow_flag);
   cudaFree(dev->d_stats);
-  for (auto& ev : dev->ev) cudaEventDestroy(ev);
+  for (auto& ev : dev->ev_pool) cudaEventDestroy(ev);
   for (auto& ev : dev->user_ev) cudaEventDestroy(ev);
+  cudaFree(dev->d_batch);
+  cudaFree(dev->tile_any);
+  cudaFree(dev->list_bump);
   cudaFree(dev->tile_slot);
   cudaStreamDestroy(dev->own_stream);
   delete dev;
@@ -263,6 +341,7 @@ slv_result slv_buffer_upload(slv_device dev, slv_handle h, size_t off, const voi
   auto r = dev ? dev->get(h, Resource::BUFFER) : nullptr;
   if (!r || off + bytes > r->bytes) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   CU(cudaMemcpyAsync(r->dptr + off, src, bytes, cudaMemcpyHostToDevice, dev->stream));
   return SLV_OK;
 }
@@ -271,6 +350,7 @@ slv_result slv_buffer_readback(slv_device dev, slv_handle h, size_t off, void* d
   auto r = dev ? dev->get(h, Resource::BUFFER) : nullptr;
   if (!r || off + bytes > r->bytes) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   CU(cudaMemcpyAsync(dst, r->dptr + off, bytes, cudaMemcpyDeviceToHost, dev->stream));
   CU(cudaStreamSynchronize(dev->stream));
   return SLV_OK;
@@ -304,6 +384,7 @@ slv_result slv_texture_gen_mipmap(slv_device dev, slv_handle h, uint32_t filter)
   auto r = dev ? dev->get(h, Resource::TEXTURE) : nullptr;
   if (!r || (filter != SLV_FILTER_POINT && filter != SLV_FILTER_LINEAR)) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   CU(cudaStreamSynchronize(dev->stream));
   for (uint32_t l = 1; l < r->tex.n_levels; ++l) CU(cudaFree(r->tex.level[l].data));
   r->tex.n_levels = 1;
@@ -343,6 +424,7 @@ slv_result slv_texture_upload(slv_device dev, slv_handle h, uint32_t level, cons
   auto r = dev ? dev->get(h, Resource::TEXTURE) : nullptr;
   if (!r || level >= r->tex.n_levels || bytes != r->tex.level[level].bytes) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   CU(cudaMemcpyAsync(r->tex.level[level].data, src, bytes, cudaMemcpyHostToDevice, dev->stream));
   return SLV_OK;
 }
@@ -351,6 +433,7 @@ slv_result slv_texture_readback(slv_device dev, slv_handle h, uint32_t level, vo
   auto r = dev ? dev->get(h, Resource::TEXTURE) : nullptr;
   if (!r || level >= r->tex.n_levels || bytes != r->tex.level[level].bytes) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   CU(cudaMemcpyAsync(dst, r->tex.level[level].data, bytes, cudaMemcpyDeviceToHost, dev->stream));
   CU(cudaStreamSynchronize(dev->stream));
   return check_overflow(dev);
@@ -373,6 +456,7 @@ slv_result slv_sampler_create(slv_device dev, const slv_sampler_desc* d, slv_han
 slv_result slv_resource_release(slv_device dev, slv_handle h) {
   if (!dev || h == 0 || h >= dev->res.size()) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   CU(cudaStreamSynchronize(dev->stream));
   Resource& r = dev->res[h];
   if (r.kind == Resource::BUFFER) CU(cudaFree(r.dptr));
@@ -488,10 +572,25 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   const uint64_t n_slots64 = 3ull * d->prim_count;
   if (n_slots64 >= (1ull << 30)) return SLV_INVALID_PARAMETER;
   const uint32_t n_slots = (uint32_t)n_slots64;
-  uint32_t list_needed = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(8ull * n_slots, 1u << 22), 1ull << 30);
-  slv_result rc = ensure_scratch(dev, (size_t)n_slots * tri_stride, n_tiles, list_needed);
+  // ---- can this draw join the queued batch? (same targets, sample count, pixel-shader program, tile grid)
+  if (!dev->pending.empty()) {
+    const RasterParams& f = dev->pending[0];
+    bool same = f.color0.data == rp.color0.data && f.color1.data == rp.color1.data && f.ds.data == rp.ds.data &&
+                f.ps_program == d->ps.program && dev->batch_S == S && f.tiles_x == gp.tiles_x && f.tiles_y == gp.tiles_y &&
+                f.target_w == rp.target_w && f.target_h == rp.target_h && dev->pending.size() < MAX_BATCH;
+    if (!same) {
+      slv_result rcf = flush_batch(dev);
+      if (rcf != SLV_OK) return rcf;
+    }
+  }
+  const size_t tris_need = (size_t)n_slots * tri_stride;
+  const uint64_t list_need = std::max<uint64_t>(8ull * (dev->slots_queued + n_slots), 1u << 22);
+  slv_result rc = ensure_scratch(dev, dev->tris_used + tris_need, n_tiles, list_need);
   if (rc != SLV_OK) return rc;
-  gp.tris = dev->tris;
+  if (dev->tris_used + tris_need > dev->tris_cap) return SLV_OUT_OF_MEMORY;
+  float4* tris_base = dev->tris + dev->tris_used;
+  uint32_t* tile_offset = dev->tile_offset + (size_t)dev->pending.size() * dev->tiles_cap;
+  gp.tris = tris_base;
   gp.tri_stride = tri_stride;
   gp.tile_count = dev->tile_count;
   gp.stats = dev->d_stats;
@@ -526,13 +625,13 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   }
   if ((rp.ps_program == SLV_PS_LIGHTS3 || rp.ps_program == SLV_PS_SPONZA) && n_attrs < 4) return SLV_INVALID_PARAMETER;
   if ((rp.ps_program == SLV_PS_ATTR0_COLOR || rp.ps_program == SLV_PS_DISCARD_ALL) && n_attrs < 1) return SLV_INVALID_PARAMETER;
-  rp.tris = dev->tris;
+  rp.tris = tris_base;
   rp.tri_stride = tri_stride;
   rp.tiles_x = gp.tiles_x;
   rp.tiles_y = gp.tiles_y;
   rp.shard_rank = dev->shard_rank;
   rp.shard_n = dev->shard_n;
-  rp.tile_offset = dev->tile_offset;
+  rp.tile_offset = tile_offset;
   rp.active_tiles = dev->active_tiles;
   rp.work_counter = dev->work_counter;
   rp.list = dev->list;
@@ -541,22 +640,39 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   rp.stats = dev->d_stats;
 
   BinParams bp{};
-  bp.tris = dev->tris;
+  bp.tris = tris_base;
   bp.tri_stride = tri_stride;
   bp.n_slots = n_slots;
   bp.tiles_x = gp.tiles_x;
   bp.tiles_y = gp.tiles_y;
   bp.shard_rank = dev->shard_rank;
   bp.shard_n = dev->shard_n;
-  bp.tile_offset = dev->tile_offset;
+  bp.tile_offset = tile_offset;
   bp.tile_cursor = dev->tile_cursor;
   bp.list = dev->list;
   bp.list_capacity = dev->list_cap;
   bp.overflow_flag = dev->overflow_flag;
 
-  // ---- the kernel graph of one draw
+  // sampling a texture that is a target of the queued batch: the earlier draws must land first
+  if (needs_sampler && !dev->pending.empty()) {
+    const uint8_t* t0 = rp.sampler0.tex.level[0].data;
+    if (t0 == rp.color0.data || t0 == rp.color1.data || t0 == rp.ds.data) {
+      slv_result rcf = flush_batch(dev);
+      if (rcf != SLV_OK) return rcf;
+      // the flush reset the arenas: re-point this draw at the start of them
+      tris_base = dev->tris;
+      tile_offset = dev->tile_offset;
+      gp.tris = tris_base;
+      rp.tris = tris_base;
+      bp.tris = tris_base;
+      rp.tile_offset = tile_offset;
+      bp.tile_offset = tile_offset;
+    }
+  }
+
+  // ---- geometry + binning of this draw now; its raster pass is queued
   cudaStream_t st = dev->stream;
-  if (dev->profile) CU(cudaEventRecord(dev->ev[0], st));
+  size_t e0 = dev->profile ? mark(dev) : 0;
   switch (R) {
   case 1: launch_geometry<1>(gp, st); break;
   case 2: launch_geometry<2>(gp, st); break;
@@ -565,32 +681,23 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   case 5: launch_geometry<5>(gp, st); break;
   default: launch_geometry<6>(gp, st); break;
   }
-  if (dev->profile) CU(cudaEventRecord(dev->ev[1], st));
-  k_scan_tiles<<<1, 1024, 0, st>>>(dev->tile_count, dev->tile_offset, dev->tile_cursor, n_tiles, dev->active_tiles,
-                                    dev->work_counter);
+  size_t e1 = dev->profile ? mark(dev) : 0;
+  k_scan_tiles<<<1, 1024, 0, st>>>(dev->tile_count, tile_offset, dev->tile_cursor, n_tiles, dev->tile_any, dev->list_bump);
   k_bin_fill<<<(n_slots + 255) / 256, 256, 0, st>>>(bp);
-  if (dev->profile) CU(cudaEventRecord(dev->ev[2], st));
-  k_sort_lists<<<n_tiles, 256, 0, st>>>(dev->tile_offset, dev->list, dev->list_cap);
-  if (dev->profile) CU(cudaEventRecord(dev->ev[3], st));
-  bool ok = false;
-  const uint32_t blocks = std::min<uint32_t>(n_tiles * 16, (uint32_t)dev->raster_grid);
-  switch (S) {
-  case 1: ok = launch_raster_s<1>(rp, blocks, st); break;
-  case 2: ok = launch_raster_s<2>(rp, blocks, st); break;
-  case 4: ok = launch_raster_s<4>(rp, blocks, st); break;
-  }
-  if (!ok) return SLV_INVALID_PARAMETER;
-  dev->n_launches += 5;
-  CU(cudaGetLastError());
+  size_t e2 = dev->profile ? mark(dev) : 0;
+  k_sort_lists<<<n_tiles, 256, 0, st>>>(tile_offset, dev->list, dev->list_cap);
   if (dev->profile) {
-    CU(cudaEventRecord(dev->ev[4], st));
-    CU(cudaEventSynchronize(dev->ev[4]));
-    for (int i = 0; i < 4; ++i) {
-      float ms = 0;
-      CU(cudaEventElapsedTime(&ms, dev->ev[i], dev->ev[i + 1]));
-      dev->prof_ms[i] += ms;
-    }
+    size_t e3 = mark(dev);
+    dev->spans.push_back({e0, e1, 0});
+    dev->spans.push_back({e1, e2, 1});
+    dev->spans.push_back({e2, e3, 2});
   }
+  dev->n_launches += 4;
+  CU(cudaGetLastError());
+  dev->pending.push_back(rp);
+  dev->batch_S = S;
+  dev->tris_used += tris_need;
+  dev->slots_queued += n_slots;
   return SLV_OK;
 }
 
@@ -613,6 +720,7 @@ slv_result slv_clear_color(slv_device dev, slv_handle h, const float rgba[4]) {
   auto r = dev ? dev->get(h, Resource::TEXTURE) : nullptr;
   if (!r || !rgba) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   const SurfaceRef& s = r->tex.level[0];
   uint32_t w[4];
   switch (s.fmt) {  // from_rgba32 conversion done once (surface.cpp:170-173)
@@ -635,6 +743,7 @@ slv_result slv_clear_depth_stencil(slv_device dev, slv_handle h, uint32_t flags,
   if (!r || r->fmt != SLV_PF_RG32F) return SLV_INVALID_PARAMETER;
   if (!(flags & (SLV_CLEAR_DEPTH | SLV_CLEAR_STENCIL))) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   const SurfaceRef& s = r->tex.level[0];
   if ((flags & 3) == 3) {
     uint32_t dbits;
@@ -657,6 +766,7 @@ slv_result slv_resolve(slv_device dev, slv_handle src, slv_handle dst) {
   const SurfaceRef& t = rd->tex.level[0];
   if (t.samples != 1 || t.w < s.w || t.h < s.h) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   dim3 blk(32, 8), grd((s.w + 31) / 32, (s.h + 7) / 8);
   k_resolve<<<grd, blk, 0, dev->stream>>>(s, t);
   ++dev->n_launches;
@@ -667,6 +777,7 @@ slv_result slv_resolve(slv_device dev, slv_handle src, slv_handle dst) {
 slv_result slv_flush(slv_device dev) {
   if (!dev) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   CU(cudaStreamSynchronize(dev->stream));
   return check_overflow(dev);
 }
@@ -674,9 +785,13 @@ slv_result slv_flush(slv_device dev) {
 slv_result slv_query_begin(slv_device dev) {
   if (!dev) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   dev->host_stats = slv_pipeline_statistics{};
   CU(cudaMemsetAsync(dev->d_stats, 0, 13 * sizeof(unsigned long long), dev->stream));
   for (auto& m : dev->prof_ms) m = 0;
+  if (!dev->spans.empty()) CU(cudaStreamSynchronize(dev->stream));
+  dev->spans.clear();
+  dev->ev_used = 0;
   dev->n_launches = 0;
   return SLV_OK;
 }
@@ -684,6 +799,7 @@ slv_result slv_query_begin(slv_device dev) {
 slv_result slv_query_get(slv_device dev, slv_pipeline_statistics* out) {
   if (!dev || !out) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   unsigned long long h[9];
   CU(cudaMemcpyAsync(h, dev->d_stats, sizeof(h), cudaMemcpyDeviceToHost, dev->stream));
   CU(cudaStreamSynchronize(dev->stream));
@@ -696,6 +812,16 @@ slv_result slv_query_get(slv_device dev, slv_pipeline_statistics* out) {
 
 slv_result slv_profile_get(slv_device dev, slv_pipeline_profiles* out) {
   if (!dev || !out) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  CU(cudaStreamSynchronize(dev->stream));
+  for (auto& sp : dev->spans) {  // fold the recorded event spans into the per-stage sums
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, dev->ev_pool[sp.a], dev->ev_pool[sp.b]));
+    dev->prof_ms[sp.stage] += ms;
+  }
+  dev->spans.clear();
+  dev->ev_used = 0;
   memset(out, 0, sizeof(*out));
   out->clipping = (uint64_t)(dev->prof_ms[0] * 1e6);      // VS + clip + viewport + setup are one kernel
   out->tri_dispatch = (uint64_t)((dev->prof_ms[1] + dev->prof_ms[2]) * 1e6);
@@ -706,6 +832,7 @@ slv_result slv_profile_get(slv_device dev, slv_pipeline_profiles* out) {
 slv_result slv_traffic_get(slv_device dev, slv_traffic_counters* out) {
   if (!dev || !out) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   unsigned long long h[13];
   CU(cudaMemcpyAsync(h, dev->d_stats, sizeof(h), cudaMemcpyDeviceToHost, dev->stream));
   CU(cudaStreamSynchronize(dev->stream));
@@ -725,6 +852,7 @@ slv_result slv_kernel_launch_count(slv_device dev, uint64_t* out) {
 slv_result slv_event_record(slv_device dev, uint32_t slot) {
   if (!dev || slot >= 16) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   CU(cudaEventRecord(dev->user_ev[slot], dev->stream));
   return SLV_OK;
 }
@@ -740,6 +868,7 @@ slv_result slv_event_elapsed_ms(slv_device dev, uint32_t a, uint32_t b, float* m
 slv_result slv_set_stream(slv_device dev, void* cuda_stream) {
   if (!dev) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   CU(cudaStreamSynchronize(dev->stream));
   dev->stream = cuda_stream ? (cudaStream_t)cuda_stream : dev->own_stream;
   return SLV_OK;
@@ -773,6 +902,7 @@ static slv_result pack_common(slv_device dev, slv_handle tex, uint32_t rank, uin
   if (bytes) *bytes = (size_t)owned * TILE * TILE * s.bpp;
   if (!staging) return SLV_OK;
   CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   if (n_tiles > dev->tile_slot_cap) {
     CU(cudaStreamSynchronize(dev->stream));
     if (dev->tile_slot) CU(cudaFree(dev->tile_slot));
@@ -798,6 +928,8 @@ slv_result slv_unpack_tiles(slv_device dev, slv_handle tex, uint32_t rank, uint3
 
 slv_result slv_set_tile_shard(slv_device dev, uint32_t rank, uint32_t nranks) {
   if (!dev || nranks == 0 || rank >= nranks) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   dev->shard_rank = rank;
   dev->shard_n = nranks;
   return SLV_OK;
@@ -810,6 +942,7 @@ slv_result slv_sampler_probe(slv_device dev, slv_handle sh, uint32_t n, const fl
   if (!fill_sampler(dev, sh, sm)) return SLV_INVALID_PARAMETER;
   if (n == 0) return SLV_OK;
   CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   float *d_c = nullptr, *d_dx = nullptr, *d_dy = nullptr, *d_l = nullptr;
   float4* d_o = nullptr;
   CU(cudaMalloc(&d_c, n * 8));

@@ -393,24 +393,20 @@ __global__ void __launch_bounds__(128) k_geometry(GeomParams p) {
 // single CTA, 1024 threads: exclusive scan of tile_count -> tile_offset[0..n]; zeroes count and cursor
 // also compacts the ids of the non-empty tiles into active_tiles[1..] (count in active_tiles[0]) and resets the
 // raster work counter.
+// Offsets are absolute positions in the batch-wide list arena: the draw's segment starts at *list_bump, which is
+// advanced by the draw's total (device-side bump allocation, no host round trip).  tile_any[i] is set for every
+// tile that received a triangle from any draw of the batch.
 __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint32_t* tile_offset, uint32_t* tile_cursor,
-                                                     uint32_t n_tiles, uint32_t* active_tiles, uint32_t* work_counter) {
-  __shared__ uint32_t s_active;
+                                                     uint32_t n_tiles, uint32_t* tile_any, uint32_t* list_bump) {
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { s_carry = 0; s_active = 0; *work_counter = 0; }
+  if (tid == 0) s_carry = *list_bump;
   __syncthreads();
   for (uint32_t base = 0; base < n_tiles; base += 1024) {
     const uint32_t i = base + tid;
     const uint32_t v = i < n_tiles ? tile_count[i] : 0;
-    {  // active-tile compaction (order across warps is irrelevant)
-      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, v != 0);
-      uint32_t wbase = 0;
-      if (lane == 0 && bal) wbase = atomicAdd(&s_active, (uint32_t)__popc(bal));
-      wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-      if (v != 0) active_tiles[1 + wbase + __popc(bal & ((1u << lane) - 1))] = i;
-    }
+    if (v != 0) tile_any[i] = 1;
     uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -440,7 +436,29 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint3
     if (tid == 1023) s_carry = excl + v;
     __syncthreads();
   }
-  if (tid == 0) { tile_offset[n_tiles] = s_carry; active_tiles[0] = s_active; }
+  if (tid == 0) { tile_offset[n_tiles] = s_carry; *list_bump = s_carry; }
+}
+
+// batch flush: compacts the ids of the tiles touched by any draw of the batch into active_tiles[1..] (count in
+// [0]), clears the flags and resets the raster work-queue head and the list bump allocator for the next batch.
+__global__ void __launch_bounds__(1024) k_compact_active(uint32_t* tile_any, uint32_t n_tiles, uint32_t* active_tiles,
+                                                         uint32_t* work_counter, uint32_t* list_bump) {
+  __shared__ uint32_t s_active;
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) { s_active = 0; *work_counter = 0; *list_bump = 0; }
+  __syncthreads();
+  for (uint32_t base = 0; base < n_tiles; base += 1024) {
+    const uint32_t i = base + tid;
+    const bool on = i < n_tiles && tile_any[i] != 0;
+    if (i < n_tiles) tile_any[i] = 0;
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, on);
+    uint32_t wbase = 0;
+    if (lane == 0 && bal) wbase = atomicAdd(&s_active, (uint32_t)__popc(bal));
+    wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+    if (on) active_tiles[1 + wbase + __popc(bal & ((1u << lane) - 1))] = i;
+  }
+  __syncthreads();
+  if (tid == 0) active_tiles[0] = s_active;
 }
 
 __global__ void __launch_bounds__(256) k_bin_fill(BinParams p) {
@@ -730,7 +748,8 @@ constexpr int QCAP = 32;  // quads a warp may queue per round (a triangle adds a
 // that warp's two 4x4 blocks.  Each warp then walks its own list: thread == pixel, all S samples of
 // depth / stencil / colour stay in registers until the item is finished.
 template <int S, int PS>
-__global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams p) {
+__global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, const RasterParams* __restrict__ batch,
+                                                               uint32_t n_draws) {
   __shared__ TriEntry s_tri[RASTER_THREADS];
   __shared__ uint16_t s_wlist[RASTER_WARPS][RASTER_THREADS];
   __shared__ uint16_t s_cnt[RASTER_WARPS + 1][RASTER_WARPS];  // [list][filter warp]; list RASTER_WARPS = survivors
@@ -749,31 +768,27 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams p) {
   const int ix = lx & 3, iy = ly & 3;    // pixel inside the block
   const uint32_t quad_base = lane & ~3u;
   const uint32_t fullmask = (1u << S) - 1;
-  const int R = 1 + (int)p.n_attrs;
-  const bool c0_packed = p.color0.data && p.color0.bpp == 4;
+  const bool c0_packed = c.color0.data && c.color0.bpp == 4;
 
   uint32_t n_ps_quads = 0, n_backend_quads = 0;
   uint32_t n_ztest = 0, n_zwrite = 0, n_cwrite = 0, n_cread = 0;  // algorithmic traffic (SURVEY §8d B_frag)
 
-  const uint32_t n_items = p.active_tiles[0] * 16u;
+  const uint32_t n_items = c.active_tiles[0] * 16u;
   for (;;) {
     __syncthreads();
-    if (tid == 0) s_item = atomicAdd(p.work_counter, 1u);
+    if (tid == 0) s_item = atomicAdd(c.work_counter, 1u);
     __syncthreads();
     const uint32_t item = s_item;
     if (item >= n_items) break;
-    const uint32_t tile = p.active_tiles[1 + (item >> 4)], sub = item & 15;
-    const uint32_t list_beg = p.tile_offset[tile];
-    uint32_t list_end = p.tile_offset[tile + 1];
-    if (list_end > p.list_capacity) list_end = p.list_capacity;
-    const uint32_t tile_x = tile % p.tiles_x, tile_y = tile / p.tiles_x;
+    const uint32_t tile = c.active_tiles[1 + (item >> 4)], sub = item & 15;
+    const uint32_t tile_x = tile % c.tiles_x, tile_y = tile / c.tiles_x;
     const int X16 = (sub & 3) * REGION, Y16 = (sub >> 2) * REGION;  // tile-relative origin of this region
     const int gx0 = tile_x * TILE + X16, gy0 = tile_y * TILE + Y16;
     // "Sub tile is out of screen" (rasterizer.cpp:721-724)
-    if ((float)gx0 >= (float)p.target_w || (float)gy0 >= (float)p.target_h) continue;
+    if ((float)gx0 >= (float)c.target_w || (float)gy0 >= (float)c.target_h) continue;
     const int x = gx0 + lx, y = gy0 + ly;
     const bool odd_x = x & 1, odd_y = y & 1;
-    const bool in_target = (uint32_t)x < p.target_w && (uint32_t)y < p.target_h;
+    const bool in_target = (uint32_t)x < c.target_w && (uint32_t)y < c.target_h;
     const float vpx = (float)(tile_x * TILE), vpy = (float)(tile_y * TILE);
 
     // ---- per-pixel framebuffer state in registers (loaded when the first triangle reaches this warp) ----
@@ -785,6 +800,14 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams p) {
 #pragma unroll
     for (int s = 0; s < S; ++s) { zbuf[s] = 0.0f; sbuf[s] = 0; cbuf[s] = 0; }
 
+    // the draws of the batch, in submission order; the pixel's framebuffer state stays in registers throughout
+    for (uint32_t di = 0; di < n_draws; ++di) {
+    const RasterParams& p = batch[di];
+    const uint32_t list_beg = p.tile_offset[tile];
+    uint32_t list_end = p.tile_offset[tile + 1];
+    if (list_end > p.list_capacity) list_end = p.list_capacity;
+    if (list_beg >= list_end) continue;
+    const int R = 1 + (int)p.n_attrs;
     for (uint32_t chunk = list_beg; chunk < list_end; chunk += RASTER_THREADS) {
       // ================= filter: level-16 decision for the region + level-4 decision of its 16 blocks =================
       const uint32_t ei = chunk + tid;
@@ -895,8 +918,8 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams p) {
       if (my_cnt && !fb_loaded) {
         fb_loaded = true;
         if (in_target) {
-          if (p.ds.data) {
-            ds_ptr = p.ds.data + ((size_t)y * p.ds.w + x) * S * 8;
+          if (c.ds.data) {
+            ds_ptr = c.ds.data + ((size_t)y * c.ds.w + x) * S * 8;
             if (S == 4) {
               float4 a = *reinterpret_cast<const float4*>(ds_ptr), b = *reinterpret_cast<const float4*>(ds_ptr + 16);
               zbuf[0] = a.x; sbuf[0] = __float_as_uint(a.y); zbuf[1 % S] = a.z; sbuf[1 % S] = __float_as_uint(a.w);
@@ -910,7 +933,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams p) {
             }
           }
           if (c0_packed) {
-            c_ptr = p.color0.data + ((size_t)y * p.color0.w + x) * S * 4;
+            c_ptr = c.color0.data + ((size_t)y * c.color0.w + x) * S * 4;
             if (S == 4) {
               uint4 a = *reinterpret_cast<const uint4*>(c_ptr);
               cbuf[0] = a.x; cbuf[1 % S] = a.y; cbuf[2 % S] = a.z; cbuf[3 % S] = a.w;
@@ -1114,36 +1137,36 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams p) {
               n_zwrite += (p.write_depth | p.stencil_enable) ? 1u : 0u;
             }
             // blend shader
-            if (p.color0.data) {
+            if (c.color0.data) {
               ++n_cwrite;
               n_cread += (p.bs_program == SLV_BS_LERP_SRC_ALPHA) ? 1u : 0u;
               if (c0_packed) {
                 if (p.bs_program == SLV_BS_LERP_SRC_ALPHA) {
-                  float4 d = unpack_color(p.color0.fmt, cbuf[s]);
+                  float4 d = unpack_color(c.color0.fmt, cbuf[s]);
                   float4 r = make_float4(d.x + (color.x - d.x) * color.w, d.y + (color.y - d.y) * color.w,
                                          d.z + (color.z - d.z) * color.w, d.w + (color.w - d.w) * color.w);
-                  cbuf[s] = pack_color(p.color0.fmt, r);
+                  cbuf[s] = pack_color(c.color0.fmt, r);
                 } else {
-                  cbuf[s] = pack_color(p.color0.fmt, color);
+                  cbuf[s] = pack_color(c.color0.fmt, color);
                 }
                 dirty_c = true;
               } else {
-                uint8_t* cp = p.color0.data + (((size_t)y * p.color0.w + x) * S + s) * p.color0.bpp;
+                uint8_t* cp = c.color0.data + (((size_t)y * c.color0.w + x) * S + s) * c.color0.bpp;
                 if (p.bs_program == SLV_BS_LERP_SRC_ALPHA) {
-                  float4 d = load_texel_rgba32f(p.color0.fmt, cp);
+                  float4 d = load_texel_rgba32f(c.color0.fmt, cp);
                   float4 r = make_float4(d.x + (color.x - d.x) * color.w, d.y + (color.y - d.y) * color.w,
                                          d.z + (color.z - d.z) * color.w, d.w + (color.w - d.w) * color.w);
-                  store_texel_rgba32f(p.color0.fmt, cp, r);
+                  store_texel_rgba32f(c.color0.fmt, cp, r);
                 } else {
-                  store_texel_rgba32f(p.color0.fmt, cp, color);
+                  store_texel_rgba32f(c.color0.fmt, cp, color);
                 }
               }
             }
-            if (p.bs_program == SLV_BS_REPLACE_AND_COUNT && p.color1.data) {
-              uint8_t* cp = p.color1.data + (((size_t)y * p.color1.w + x) * S + s) * p.color1.bpp;
-              float4 v = load_texel_rgba32f(p.color1.fmt, cp);
+            if (p.bs_program == SLV_BS_REPLACE_AND_COUNT && c.color1.data) {
+              uint8_t* cp = c.color1.data + (((size_t)y * c.color1.w + x) * S + s) * c.color1.bpp;
+              float4 v = load_texel_rgba32f(c.color1.fmt, cp);
               v.x += 1.0f;
-              store_texel_rgba32f(p.color1.fmt, cp, v);
+              store_texel_rgba32f(c.color1.fmt, cp, v);
             }
           }
         }
@@ -1152,6 +1175,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams p) {
       // (the barrier at the top of the next chunk / item protects s_tri, s_wlist and s_cnt)
       __syncthreads();
     }
+    }  // draws
 
     // ---- write the pixel back once, 128-bit stores at 4x MSAA ----
     if (in_target) {
@@ -1188,12 +1212,12 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams p) {
     n_cread += __shfl_xor_sync(0xFFFFFFFFu, n_cread, o);
   }
   if (lane == 0) {
-    if (a) atomicAdd(&p.stats[7], (unsigned long long)a * 4ull);
-    if (b) atomicAdd(&p.stats[8], (unsigned long long)b * 4ull);
-    if (n_ztest) atomicAdd(&p.stats[9], (unsigned long long)n_ztest);
-    if (n_zwrite) atomicAdd(&p.stats[10], (unsigned long long)n_zwrite);
-    if (n_cwrite) atomicAdd(&p.stats[11], (unsigned long long)n_cwrite);
-    if (n_cread) atomicAdd(&p.stats[12], (unsigned long long)n_cread);
+    if (a) atomicAdd(&c.stats[7], (unsigned long long)a * 4ull);
+    if (b) atomicAdd(&c.stats[8], (unsigned long long)b * 4ull);
+    if (n_ztest) atomicAdd(&c.stats[9], (unsigned long long)n_ztest);
+    if (n_zwrite) atomicAdd(&c.stats[10], (unsigned long long)n_zwrite);
+    if (n_cwrite) atomicAdd(&c.stats[11], (unsigned long long)n_cwrite);
+    if (n_cread) atomicAdd(&c.stats[12], (unsigned long long)n_cread);
   }
 }
 

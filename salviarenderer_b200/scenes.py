@@ -619,9 +619,10 @@ class SponzaLike:
     N_TRIS = 262249
     N_MATERIALS = 24
 
-    def __init__(self, w=3840, h=2160, samples=4, tex_size=1024, max_aniso=0, color_fmt=A.PF_BGRA8):
+    def __init__(self, w=3840, h=2160, samples=4, tex_size=1024, max_aniso=0, color_fmt=A.PF_BGRA8, ps_program=A.PS_SPONZA,
+                 textured=True):
         self.w, self.h, self.samples, self.tex_size, self.max_aniso = w, h, samples, tex_size, max_aniso
-        self.color_fmt = color_fmt
+        self.color_fmt, self.ps_program, self.textured = color_fmt, ps_program, textured
         self.n_frames = 8
         self._build()
 
@@ -718,7 +719,10 @@ class SponzaLike:
             d = base_desc(t, self.w, self.h, cull=A.CULL_BACK)
             self.mesh.fill_desc(be, d, start=start * 3, prim_count=count)
             d.vs = vs
-            d.ps = A.shader_binding(A.PS_SPONZA, pack_ps_sponza(True), [self.samplers[m]])
+            if self.ps_program == A.PS_SPONZA:
+                d.ps = A.shader_binding(A.PS_SPONZA, pack_ps_sponza(self.textured), [self.samplers[m]])
+            else:
+                d.ps = A.shader_binding(self.ps_program)
             d.bs = bs
             be.draw(d)
         if t.resolved is not None:
