@@ -71,8 +71,6 @@ struct slv_device_t {
   // pixel's depth/stencil/colour is loaded once and stored once per batch instead of once per draw.
   std::vector<RasterParams> pending;
   RasterParams* d_batch = nullptr;
-  uint32_t* tile_any = nullptr;
-  uint32_t* list_bump = nullptr;
   size_t tris_used = 0;      // float4 units used by the queued draws
   uint64_t slots_queued = 0; // triangle slots of the queued draws (sizes the list arena)
   uint32_t batch_S = 0;
@@ -137,28 +135,18 @@ slv_result ensure_scratch(slv_device dev, size_t tris_needed_total, uint32_t n_t
     CU(cudaStreamSynchronize(dev->stream));
     if (dev->tile_count) {
       CU(cudaFree(dev->tile_count)); CU(cudaFree(dev->tile_offset)); CU(cudaFree(dev->tile_cursor));
-      CU(cudaFree(dev->active_tiles)); CU(cudaFree(dev->tile_any));
+      CU(cudaFree(dev->active_tiles));
     }
     uint32_t cap = std::max(n_tiles + 1, 4096u);
     CU(cudaMalloc(&dev->tile_count, cap * sizeof(uint32_t)));
-    CU(cudaMalloc(&dev->tile_offset, (size_t)MAX_BATCH * cap * sizeof(uint32_t)));  // one offset table per queued draw
+    CU(cudaMalloc(&dev->tile_offset, cap * sizeof(uint32_t)));
     CU(cudaMalloc(&dev->tile_cursor, cap * sizeof(uint32_t)));
     CU(cudaMalloc(&dev->active_tiles, (cap + 1) * sizeof(uint32_t)));
-    CU(cudaMalloc(&dev->tile_any, cap * sizeof(uint32_t)));
     CU(cudaMemsetAsync(dev->tile_count, 0, cap * sizeof(uint32_t), dev->stream));
     CU(cudaMemsetAsync(dev->tile_cursor, 0, cap * sizeof(uint32_t), dev->stream));
-    CU(cudaMemsetAsync(dev->tile_any, 0, cap * sizeof(uint32_t), dev->stream));
     dev->tiles_cap = cap;
   }
-  if (list_needed_total > dev->list_cap) {
-    slv_result rc = flush_batch(dev);
-    if (rc != SLV_OK) return rc;
-    CU(cudaStreamSynchronize(dev->stream));
-    if (dev->list) CU(cudaFree(dev->list));
-    uint64_t cap = std::min<uint64_t>(std::max<uint64_t>(list_needed_total, 2ull * dev->list_cap), 1ull << 31);
-    CU(cudaMalloc(&dev->list, (size_t)cap * sizeof(uint32_t)));
-    dev->list_cap = (uint32_t)cap;
-  }
+  (void)list_needed_total;
   return SLV_OK;
 }
 
@@ -213,16 +201,46 @@ bool launch_raster_s(const RasterParams& rp, const RasterParams* batch, uint32_t
   return false;
 }
 
-// the raster pass of every queued draw, in submission order, as ONE kernel
+// Batch flush: binning (scan, fill, sort) over the triangles of every queued draw, then the raster pass of all of
+// them, in submission order, as ONE kernel.
 slv_result flush_batch(slv_device dev) {
   if (dev->pending.empty()) return SLV_OK;
   cudaStream_t st = dev->stream;
-  const RasterParams& first = dev->pending[0];
+  RasterParams& first = dev->pending[0];
   const uint32_t n = (uint32_t)dev->pending.size();
   const uint32_t n_tiles = first.tiles_x * first.tiles_y;
+  const uint32_t n_slots = (uint32_t)dev->slots_queued;
+  // list arena: heuristic bound, checked on the device (overflow flag -> SLV_OUT_OF_MEMORY at the next flush point)
+  const uint64_t list_need = std::min<uint64_t>(std::max<uint64_t>(8ull * n_slots, 1u << 22), 1ull << 31);
+  if (list_need > dev->list_cap) {
+    CU(cudaStreamSynchronize(st));
+    if (dev->list) CU(cudaFree(dev->list));
+    CU(cudaMalloc(&dev->list, (size_t)list_need * sizeof(uint32_t)));
+    dev->list_cap = (uint32_t)list_need;
+  }
+  first.list = dev->list;
+  first.list_capacity = dev->list_cap;
   CU(cudaMemcpyAsync(dev->d_batch, dev->pending.data(), n * sizeof(RasterParams), cudaMemcpyHostToDevice, st));
+  BinParams bp{};
+  bp.tris = dev->tris;
+  bp.tri_stride = first.tri_stride;
+  bp.n_slots = n_slots;
+  bp.tiles_x = first.tiles_x;
+  bp.tiles_y = first.tiles_y;
+  bp.shard_rank = dev->shard_rank;
+  bp.shard_n = dev->shard_n;
+  bp.tile_offset = dev->tile_offset;
+  bp.tile_cursor = dev->tile_cursor;
+  bp.list = dev->list;
+  bp.list_capacity = dev->list_cap;
+  bp.overflow_flag = dev->overflow_flag;
   size_t e0 = dev->profile ? mark(dev) : 0;
-  k_compact_active<<<1, 1024, 0, st>>>(dev->tile_any, n_tiles, dev->active_tiles, dev->work_counter, dev->list_bump);
+  k_scan_tiles<<<1, 1024, 0, st>>>(dev->tile_count, dev->tile_offset, dev->tile_cursor, n_tiles, dev->active_tiles,
+                                    dev->work_counter);
+  k_bin_fill<<<(n_slots + 255) / 256, 256, 0, st>>>(bp);
+  size_t e1 = dev->profile ? mark(dev) : 0;
+  k_sort_lists<<<n_tiles, 256, 0, st>>>(dev->tile_offset, dev->list, dev->list_cap);
+  size_t e2 = dev->profile ? mark(dev) : 0;
   const uint32_t blocks = std::min<uint32_t>(n_tiles * 16, (uint32_t)dev->raster_grid);
   bool ok = false;
   switch (dev->batch_S) {
@@ -230,8 +248,13 @@ slv_result flush_batch(slv_device dev) {
   case 2: ok = launch_raster_s<2>(first, dev->d_batch, n, blocks, st); break;
   case 4: ok = launch_raster_s<4>(first, dev->d_batch, n, blocks, st); break;
   }
-  dev->n_launches += 2;
-  if (dev->profile) dev->spans.push_back({e0, mark(dev), 3});
+  dev->n_launches += 4;
+  if (dev->profile) {
+    size_t e3 = mark(dev);
+    dev->spans.push_back({e0, e1, 1});
+    dev->spans.push_back({e1, e2, 2});
+    dev->spans.push_back({e2, e3, 3});
+  }
   dev->pending.clear();
   dev->tris_used = 0;
   dev->slots_queued = 0;
@@ -290,8 +313,7 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   dev->profile = prof && prof[0] == '1';
   for (auto& ev : dev->user_ev) CU(cudaEventCreate(&ev));
   CU(cudaMalloc(&dev->d_batch, MAX_BATCH * sizeof(RasterParams)));
-  CU(cudaMalloc(&dev->list_bump, sizeof(uint32_t)));
-  CU(cudaMemsetAsync(dev->list_bump, 0, sizeof(uint32_t), dev->stream));
+
   *out = dev;
   return SLV_OK;
 }
@@ -318,8 +340,7 @@ void slv_device_destroy(slv_device dev) {
   for (auto& ev : dev->ev_pool) cudaEventDestroy(ev);
   for (auto& ev : dev->user_ev) cudaEventDestroy(ev);
   cudaFree(dev->d_batch);
-  cudaFree(dev->tile_any);
-  cudaFree(dev->list_bump);
+
   cudaFree(dev->tile_slot);
   cudaStreamDestroy(dev->own_stream);
   delete dev;
@@ -568,7 +589,7 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   if (d->prim_count == 0 || n_tiles == 0) return SLV_OK;
 
   const uint32_t R = 1 + n_attrs;
-  const uint32_t tri_stride = TRI_HEADER + 3 * R;
+  const uint32_t tri_stride = TRI_HEADER + 3 * MAX_REGS;  // uniform across the batch: slot -> record address
   const uint64_t n_slots64 = 3ull * d->prim_count;
   if (n_slots64 >= (1ull << 30)) return SLV_INVALID_PARAMETER;
   const uint32_t n_slots = (uint32_t)n_slots64;
@@ -588,10 +609,16 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   slv_result rc = ensure_scratch(dev, dev->tris_used + tris_need, n_tiles, list_need);
   if (rc != SLV_OK) return rc;
   if (dev->tris_used + tris_need > dev->tris_cap) return SLV_OUT_OF_MEMORY;
-  float4* tris_base = dev->tris + dev->tris_used;
-  uint32_t* tile_offset = dev->tile_offset + (size_t)dev->pending.size() * dev->tiles_cap;
+  if (dev->slots_queued + n_slots >= (1ull << 30)) {  // 31-bit list entries: (slot << 1) | accept
+    slv_result rcf = flush_batch(dev);
+    if (rcf != SLV_OK) return rcf;
+  }
+  float4* tris_base = dev->tris;
+  uint32_t* tile_offset = dev->tile_offset;
   gp.tris = tris_base;
   gp.tri_stride = tri_stride;
+  gp.slot_base = (uint32_t)dev->slots_queued;
+  gp.draw_id = (uint32_t)dev->pending.size();
   gp.tile_count = dev->tile_count;
   gp.stats = dev->d_stats;
 
@@ -639,20 +666,6 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   rp.n_attrs = n_attrs;
   rp.stats = dev->d_stats;
 
-  BinParams bp{};
-  bp.tris = tris_base;
-  bp.tri_stride = tri_stride;
-  bp.n_slots = n_slots;
-  bp.tiles_x = gp.tiles_x;
-  bp.tiles_y = gp.tiles_y;
-  bp.shard_rank = dev->shard_rank;
-  bp.shard_n = dev->shard_n;
-  bp.tile_offset = tile_offset;
-  bp.tile_cursor = dev->tile_cursor;
-  bp.list = dev->list;
-  bp.list_capacity = dev->list_cap;
-  bp.overflow_flag = dev->overflow_flag;
-
   // sampling a texture that is a target of the queued batch: the earlier draws must land first
   if (needs_sampler && !dev->pending.empty()) {
     const uint8_t* t0 = rp.sampler0.tex.level[0].data;
@@ -660,17 +673,12 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
       slv_result rcf = flush_batch(dev);
       if (rcf != SLV_OK) return rcf;
       // the flush reset the arenas: re-point this draw at the start of them
-      tris_base = dev->tris;
-      tile_offset = dev->tile_offset;
-      gp.tris = tris_base;
-      rp.tris = tris_base;
-      bp.tris = tris_base;
-      rp.tile_offset = tile_offset;
-      bp.tile_offset = tile_offset;
+      gp.slot_base = 0;
+      gp.draw_id = 0;
     }
   }
 
-  // ---- geometry + binning of this draw now; its raster pass is queued
+  // ---- geometry of this draw now (it also accumulates the per-tile counts); binning + raster at the flush
   cudaStream_t st = dev->stream;
   size_t e0 = dev->profile ? mark(dev) : 0;
   switch (R) {
@@ -681,18 +689,8 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   case 5: launch_geometry<5>(gp, st); break;
   default: launch_geometry<6>(gp, st); break;
   }
-  size_t e1 = dev->profile ? mark(dev) : 0;
-  k_scan_tiles<<<1, 1024, 0, st>>>(dev->tile_count, tile_offset, dev->tile_cursor, n_tiles, dev->tile_any, dev->list_bump);
-  k_bin_fill<<<(n_slots + 255) / 256, 256, 0, st>>>(bp);
-  size_t e2 = dev->profile ? mark(dev) : 0;
-  k_sort_lists<<<n_tiles, 256, 0, st>>>(tile_offset, dev->list, dev->list_cap);
-  if (dev->profile) {
-    size_t e3 = mark(dev);
-    dev->spans.push_back({e0, e1, 0});
-    dev->spans.push_back({e1, e2, 1});
-    dev->spans.push_back({e2, e3, 2});
-  }
-  dev->n_launches += 4;
+  if (dev->profile) dev->spans.push_back({e0, mark(dev), 0});
+  dev->n_launches += 1;
   CU(cudaGetLastError());
   dev->pending.push_back(rp);
   dev->batch_S = S;

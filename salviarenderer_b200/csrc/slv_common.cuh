@@ -59,15 +59,17 @@ struct GeomParams {
   slv_viewport vp;
   uint32_t tiles_x, tiles_y;
   uint32_t shard_rank, shard_n;
+  uint32_t slot_base;      // first global triangle slot of this draw inside the batch
+  uint32_t draw_id;        // index of this draw inside the batch
   // outputs
-  float4* tris;            // triangle records, slot = prim*3 + k, stride tri_stride float4
+  float4* tris;            // triangle records, slot = slot_base + prim*3 + k, stride tri_stride float4
   uint32_t tri_stride;
   uint32_t* tile_count;    // [tiles]
   unsigned long long* stats;  // slv_pipeline_statistics as 9 x u64
 };
 
 // triangle record (float4 units): [0..2] edge A,B,C,0  [3] bbox xmin,xmax,ymin,ymax
-// [4] misc: x = as_uint(valid | front<<1), y = sx | ex<<16, z = sy | ey<<16 (tile range)
+// [4] misc: x = as_uint(valid | front<<1), y = sx | ex<<16, z = sy | ey<<16 (tile range), w = draw id in the batch
 // [5 .. 5+R) v0 regs   [5+R .. 5+2R) ddx regs   [5+2R .. 5+3R) ddy regs, R = 1 + n_attrs
 constexpr int TRI_HEADER = 5;
 

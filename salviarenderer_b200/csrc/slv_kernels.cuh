@@ -254,6 +254,7 @@ __device__ __forceinline__ void setup_triangle(const GeomParams& p, const VsOut<
   misc.x = __uint_as_float(1u | (front ? 2u : 0u));
   misc.y = __uint_as_float((uint32_t)tr.sx | ((uint32_t)tr.ex << 16));
   misc.z = __uint_as_float((uint32_t)tr.sy | ((uint32_t)tr.ey << 16));
+  misc.w = __uint_as_float(p.draw_id);
   rec[4] = misc;
   // tile coverage count (rasterizer.cpp:809-857)
   if ((tr.sx + 1 == tr.ex) && (tr.sy + 1 == tr.ey)) {
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(128) k_geometry(GeomParams p) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) run_vs<R>(p, idx[i], tri[i]);
 
-    float4* rec = p.tris + (size_t)prim * 3 * p.tri_stride;
+    float4* rec = p.tris + ((size_t)p.slot_base + (size_t)prim * 3) * p.tri_stride;
     // ---- clip (clipper.cpp:103-228)
     bool in_frustum = true;
 #pragma unroll
@@ -393,20 +394,26 @@ __global__ void __launch_bounds__(128) k_geometry(GeomParams p) {
 // single CTA, 1024 threads: exclusive scan of tile_count -> tile_offset[0..n]; zeroes count and cursor
 // also compacts the ids of the non-empty tiles into active_tiles[1..] (count in active_tiles[0]) and resets the
 // raster work counter.
-// Offsets are absolute positions in the batch-wide list arena: the draw's segment starts at *list_bump, which is
-// advanced by the draw's total (device-side bump allocation, no host round trip).  tile_any[i] is set for every
-// tile that received a triangle from any draw of the batch.
+// Runs once per batch over the counts accumulated by every queued draw's k_geometry.  Also compacts the ids of the
+// non-empty tiles into active_tiles[1..] (count in [0]) and resets the raster work-queue head.
 __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint32_t* tile_offset, uint32_t* tile_cursor,
-                                                     uint32_t n_tiles, uint32_t* tile_any, uint32_t* list_bump) {
+                                                     uint32_t n_tiles, uint32_t* active_tiles, uint32_t* work_counter) {
+  __shared__ uint32_t s_active;
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_carry = *list_bump;
+  if (tid == 0) { s_carry = 0; s_active = 0; *work_counter = 0; }
   __syncthreads();
   for (uint32_t base = 0; base < n_tiles; base += 1024) {
     const uint32_t i = base + tid;
     const uint32_t v = i < n_tiles ? tile_count[i] : 0;
-    if (v != 0) tile_any[i] = 1;
+    {  // active-tile compaction (order across warps is irrelevant)
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, v != 0);
+      uint32_t wbase = 0;
+      if (lane == 0 && bal) wbase = atomicAdd(&s_active, (uint32_t)__popc(bal));
+      wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+      if (v != 0) active_tiles[1 + wbase + __popc(bal & ((1u << lane) - 1))] = i;
+    }
     uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -436,29 +443,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint3
     if (tid == 1023) s_carry = excl + v;
     __syncthreads();
   }
-  if (tid == 0) { tile_offset[n_tiles] = s_carry; *list_bump = s_carry; }
-}
-
-// batch flush: compacts the ids of the tiles touched by any draw of the batch into active_tiles[1..] (count in
-// [0]), clears the flags and resets the raster work-queue head and the list bump allocator for the next batch.
-__global__ void __launch_bounds__(1024) k_compact_active(uint32_t* tile_any, uint32_t n_tiles, uint32_t* active_tiles,
-                                                         uint32_t* work_counter, uint32_t* list_bump) {
-  __shared__ uint32_t s_active;
-  const uint32_t tid = threadIdx.x, lane = tid & 31;
-  if (tid == 0) { s_active = 0; *work_counter = 0; *list_bump = 0; }
-  __syncthreads();
-  for (uint32_t base = 0; base < n_tiles; base += 1024) {
-    const uint32_t i = base + tid;
-    const bool on = i < n_tiles && tile_any[i] != 0;
-    if (i < n_tiles) tile_any[i] = 0;
-    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, on);
-    uint32_t wbase = 0;
-    if (lane == 0 && bal) wbase = atomicAdd(&s_active, (uint32_t)__popc(bal));
-    wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-    if (on) active_tiles[1 + wbase + __popc(bal & ((1u << lane) - 1))] = i;
-  }
-  __syncthreads();
-  if (tid == 0) active_tiles[0] = s_active;
+  if (tid == 0) { tile_offset[n_tiles] = s_carry; active_tiles[0] = s_active; }
 }
 
 __global__ void __launch_bounds__(256) k_bin_fill(BinParams p) {
@@ -575,8 +560,9 @@ __device__ __forceinline__ uint32_t stencil_op_apply(uint32_t op, uint32_t ref, 
 struct TriEntry {  // one surviving triangle of the current chunk, staged in shared memory
   float A[3], B[3], C[3];
   float bbox[4];
-  uint32_t slot_flags;  // slot << 2 | front
-  uint32_t pad[2];
+  uint32_t slot_flags;  // global slot << 2 | front
+  uint32_t draw;        // index of the triangle's draw in the batch
+  uint32_t pad;
 };
 
 template <int S>
@@ -800,14 +786,11 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, co
 #pragma unroll
     for (int s = 0; s < S; ++s) { zbuf[s] = 0.0f; sbuf[s] = 0; cbuf[s] = 0; }
 
-    // the draws of the batch, in submission order; the pixel's framebuffer state stays in registers throughout
-    for (uint32_t di = 0; di < n_draws; ++di) {
-    const RasterParams& p = batch[di];
-    const uint32_t list_beg = p.tile_offset[tile];
-    uint32_t list_end = p.tile_offset[tile + 1];
-    if (list_end > p.list_capacity) list_end = p.list_capacity;
-    if (list_beg >= list_end) continue;
-    const int R = 1 + (int)p.n_attrs;
+    // ONE list per tile for the whole batch: entries are global triangle slots, sorted = submission order of the
+    // draws and API order inside each draw; the per-draw state is looked up through the triangle's draw id.
+    const uint32_t list_beg = c.tile_offset[tile];
+    uint32_t list_end = c.tile_offset[tile + 1];
+    if (list_end > c.list_capacity) list_end = c.list_capacity;
     for (uint32_t chunk = list_beg; chunk < list_end; chunk += RASTER_THREADS) {
       // ================= filter: level-16 decision for the region + level-4 decision of its 16 blocks =================
       const uint32_t ei = chunk + tid;
@@ -815,11 +798,13 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, co
       uint32_t st_bits = 0;  // 2 bits per block: 0 rejected, 1 partial, 2 full
       TriEntry ent;
       if (ei < list_end) {
-        const uint32_t e = __ldg(p.list + ei);
+        const uint32_t e = __ldg(c.list + ei);
         const uint32_t slot = e >> 1;
-        const float4* rec = p.tris + (size_t)slot * p.tri_stride;
+        const float4* rec = c.tris + (size_t)slot * c.tri_stride;
         const float4 e0 = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2), bb = __ldg(rec + 3);
-        const uint32_t flags = __float_as_uint(__ldg(rec + 4).x);
+        const float4 misc = __ldg(rec + 4);
+        const uint32_t flags = __float_as_uint(misc.x);
+        ent.draw = __float_as_uint(misc.w);
         ent.A[0] = e0.x; ent.B[0] = e0.y; ent.C[0] = e0.z;
         ent.A[1] = e1.x; ent.B[1] = e1.y; ent.C[1] = e1.z;
         ent.A[2] = e2.x; ent.B[2] = e2.y; ent.C[2] = e2.z;
@@ -954,6 +939,8 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, co
           const uint32_t we = s_wlist[warp][wi];
           ++wi;
           const TriEntry& t = s_tri[we & 0xFF];
+          const RasterParams& p = batch[t.draw];
+          const int R = 1 + (int)p.n_attrs;
           const int blk = (we >> (8 + 2 * (bx & 1))) & 3;  // 0 rejected, 1 partial, 2 full
           // per-sample coverage (draw_partial_tile, rasterizer.cpp:298-439)
           uint32_t pm = 0;
@@ -981,7 +968,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, co
           if (p.early_z) {
             tested = 0;
             if (pm) {
-              const float4* rec = p.tris + (size_t)(t.slot_flags >> 2) * p.tri_stride;
+              const float4* rec = c.tris + (size_t)(t.slot_flags >> 2) * c.tri_stride;
               const float4 v0p = __ldg(rec + TRI_HEADER), gxp = __ldg(rec + TRI_HEADER + R), gyp = __ldg(rec + TRI_HEADER + 2 * R);
               const float dx = 0.5f + (float)(uint32_t)(x & ~1) - v0p.x;
               const float dy = 0.5f + (float)(uint32_t)(y & ~1) - v0p.y;
@@ -1044,6 +1031,8 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, co
           for (int w = 1; w < RASTER_WARPS; ++w) ob = (ow == (uint32_t)w) ? qbase[w] : ob;
           const uint2 it = s_items[ow][j - ob];
           const TriEntry& t = s_tri[it.x & 0xFF];
+          const RasterParams& p = batch[t.draw];
+          const int R = 1 + (int)p.n_attrs;
           const uint32_t oq = (it.x >> 8) & 7;
           const bool quad_full = (it.x >> 11) & 1;
           const uint32_t pm = (it.x >> (16 + 4 * pi)) & 0xF;
@@ -1051,7 +1040,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, co
           // pixel handled by this thread: pixel pi of quad oq of warp ow
           const int plx = (int)(ow & 1) * 8 + (int)(oq & 3) * 2 + (pi & 1), ply = (int)(ow >> 1) * 4 + (int)(oq >> 2) * 2 + (pi >> 1);
           const int sx_ = gx0 + plx, sy_ = gy0 + ply;
-          const float4* rec = p.tris + (size_t)(t.slot_flags >> 2) * p.tri_stride;
+          const float4* rec = c.tris + (size_t)(t.slot_flags >> 2) * c.tri_stride;
           // step_2d_unproj_pos_quad (shader.cpp:257-287): only w is needed here
           const float4 v0p = __ldg(rec + TRI_HEADER), gxp = __ldg(rec + TRI_HEADER + R), gyp = __ldg(rec + TRI_HEADER + 2 * R);
           PixelCtx px;
@@ -1106,10 +1095,12 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, co
           if (!fin) continue;
           const float4 color = s_color[flat * 4 + pi];
           const TriEntry& t = s_tri[it.x & 0xFF];
+          const RasterParams& p = batch[t.draw];
+          const int R = 1 + (int)p.n_attrs;
           const bool front = t.slot_flags & 1;
           float depth = 0.0f, gz_x = 0.0f, gz_y = 0.0f;
           if (!p.early_z) {  // late depth/stencil needs the sample depths again
-            const float4* rec = p.tris + (size_t)(t.slot_flags >> 2) * p.tri_stride;
+            const float4* rec = c.tris + (size_t)(t.slot_flags >> 2) * c.tri_stride;
             const float4 v0p = __ldg(rec + TRI_HEADER), gxp = __ldg(rec + TRI_HEADER + R), gyp = __ldg(rec + TRI_HEADER + 2 * R);
             const float dx = 0.5f + (float)(uint32_t)(x & ~1) - v0p.x;
             const float dy = 0.5f + (float)(uint32_t)(y & ~1) - v0p.y;
@@ -1175,7 +1166,6 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, co
       // (the barrier at the top of the next chunk / item protects s_tri, s_wlist and s_cnt)
       __syncthreads();
     }
-    }  // draws
 
     // ---- write the pixel back once, 128-bit stores at 4x MSAA ----
     if (in_target) {
