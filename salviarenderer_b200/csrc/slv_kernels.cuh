@@ -532,6 +532,23 @@ __device__ __forceinline__ bool compare_f(uint32_t fn, float l, float r) {  // f
   default: return true;
   }
 }
+// branch-free form for the hot early-Z loop: bit 0 = result when l < r, 1 = l == r, 2 = l > r, 3 = unordered
+__device__ __forceinline__ uint32_t compare_lut(uint32_t fn) {
+  switch (fn) {
+  case SLV_CMP_NEVER: return 0x0u;
+  case SLV_CMP_LESS: return 0x1u;
+  case SLV_CMP_EQUAL: return 0x2u;
+  case SLV_CMP_LESS_EQUAL: return 0x3u;
+  case SLV_CMP_GREATER: return 0x4u;
+  case SLV_CMP_NOT_EQUAL: return 0xDu;
+  case SLV_CMP_GREATER_EQUAL: return 0x6u;
+  default: return 0xFu;
+  }
+}
+__device__ __forceinline__ bool compare_with_lut(uint32_t lut, float l, float r) {
+  const uint32_t idx = (l < r) ? 0u : ((l == r) ? 1u : ((l > r) ? 2u : 3u));
+  return (lut >> idx) & 1u;
+}
 __device__ __forceinline__ bool compare_u(uint32_t fn, uint32_t l, uint32_t r) {
   switch (fn) {
   case SLV_CMP_NEVER: return false;
@@ -739,10 +756,12 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, co
   __shared__ TriEntry s_tri[RASTER_THREADS];
   __shared__ uint16_t s_wlist[RASTER_WARPS][RASTER_THREADS];
   __shared__ uint16_t s_cnt[RASTER_WARPS + 1][RASTER_WARPS];  // [list][filter warp]; list RASTER_WARPS = survivors
-  __shared__ uint2 s_items[RASTER_WARPS][QCAP];                // quad queue of each warp (phase A -> B, C)
-  __shared__ uint32_t s_qcnt[RASTER_WARPS];
-  __shared__ float4 s_color[RASTER_WARPS * QCAP * 4];          // shaded colour of every queued pixel (phase B -> C)
-  __shared__ uint32_t s_fin[RASTER_WARPS * QCAP];              // final 4x4-bit sample masks of every queued quad
+  __shared__ uint2 s_items[RASTER_WARPS][QCAP];                // quad queue of each warp
+  // the warp's 8x4-pixel framebuffer tile, [sample][pixel == owner lane]: loaded once per work item, merged into by
+  // whichever lane shades the pixel, stored once
+  __shared__ float s_z[RASTER_WARPS][S][32];
+  __shared__ uint32_t s_st[RASTER_WARPS][S][32];
+  __shared__ uint32_t s_c[RASTER_WARPS][S][32];
   __shared__ uint32_t s_item;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -777,14 +796,9 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, co
     const bool in_target = (uint32_t)x < c.target_w && (uint32_t)y < c.target_h;
     const float vpx = (float)(tile_x * TILE), vpy = (float)(tile_y * TILE);
 
-    // ---- per-pixel framebuffer state in registers (loaded when the first triangle reaches this warp) ----
-    float zbuf[S];
-    uint32_t sbuf[S], cbuf[S];
-    bool dirty_ds = false, dirty_c = false, fb_loaded = false;
-    uint8_t* ds_ptr = nullptr;
-    uint8_t* c_ptr = nullptr;
-#pragma unroll
-    for (int s = 0; s < S; ++s) { zbuf[s] = 0.0f; sbuf[s] = 0; cbuf[s] = 0; }
+    // ---- the warp's framebuffer tile lives in shared memory (loaded when the first triangle reaches the warp) ----
+    bool fb_loaded = false;
+    uint32_t wdirty = 0;  // bit 0: depth/stencil modified, bit 1: colour modified (by this lane, for any pixel)
 
     // ONE list per tile for the whole batch: entries are global triangle slots, sorted = submission order of the
     // draws and API order inside each draw; the per-draw state is looked up through the triangle's draw id.
@@ -897,296 +911,280 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, co
       }
       __syncthreads();
 
-      // ================= rounds: (A) coverage + early-Z by the pixel owners -> quad queue,
-      //                         (B) dense shading of every queued quad by all threads,
-      //                         (C) ordered output merge by the pixel owners =================
+      // ================= per-warp loop over this warp's triangles of the chunk, in API order =================
+      // (A) coverage (+ early-Z) by the pixel owners -> quads are pushed to the warp's queue;
+      // (B) when the queue is full (or the list ends) 8 queued quads at a time are shaded DENSELY, whatever
+      //     triangles they come from, and merged into the warp's depth/stencil/colour tile in shared memory in
+      //     queue (= API) order.  No CTA-wide barrier inside this loop.
       if (my_cnt && !fb_loaded) {
         fb_loaded = true;
         if (in_target) {
           if (c.ds.data) {
-            ds_ptr = c.ds.data + ((size_t)y * c.ds.w + x) * S * 8;
-            if (S == 4) {
-              float4 a = *reinterpret_cast<const float4*>(ds_ptr), b = *reinterpret_cast<const float4*>(ds_ptr + 16);
-              zbuf[0] = a.x; sbuf[0] = __float_as_uint(a.y); zbuf[1 % S] = a.z; sbuf[1 % S] = __float_as_uint(a.w);
-              zbuf[2 % S] = b.x; sbuf[2 % S] = __float_as_uint(b.y); zbuf[3 % S] = b.z; sbuf[3 % S] = __float_as_uint(b.w);
-            } else if (S == 2) {
-              float4 a = *reinterpret_cast<const float4*>(ds_ptr);
-              zbuf[0] = a.x; sbuf[0] = __float_as_uint(a.y); zbuf[1 % S] = a.z; sbuf[1 % S] = __float_as_uint(a.w);
-            } else {
-              float2 a = *reinterpret_cast<const float2*>(ds_ptr);
-              zbuf[0] = a.x; sbuf[0] = __float_as_uint(a.y);
+            const float2* dp = reinterpret_cast<const float2*>(c.ds.data + ((size_t)y * c.ds.w + x) * S * 8);
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              const float2 v = dp[s];
+              s_z[warp][s][lane] = v.x;
+              s_st[warp][s][lane] = __float_as_uint(v.y);
             }
           }
           if (c0_packed) {
-            c_ptr = c.color0.data + ((size_t)y * c.color0.w + x) * S * 4;
-            if (S == 4) {
-              uint4 a = *reinterpret_cast<const uint4*>(c_ptr);
-              cbuf[0] = a.x; cbuf[1 % S] = a.y; cbuf[2 % S] = a.z; cbuf[3 % S] = a.w;
-            } else if (S == 2) {
-              uint2 a = *reinterpret_cast<const uint2*>(c_ptr);
-              cbuf[0] = a.x; cbuf[1 % S] = a.y;
-            } else {
-              cbuf[0] = *reinterpret_cast<const uint32_t*>(c_ptr);
-            }
+            const uint32_t* cp = reinterpret_cast<const uint32_t*>(c.color0.data + ((size_t)y * c.color0.w + x) * S * 4);
+#pragma unroll
+            for (int s = 0; s < S; ++s) s_c[warp][s][lane] = cp[s];
           }
         }
+        __syncwarp();
       }
-      uint32_t wi = 0;
+      uint32_t wi = 0, qn = 0;
+      bool queue_has_late = false;
       for (;;) {
-        // ---------------- phase A: this warp's triangles, in API order, until its queue is full ----------------
-        uint32_t qn = 0;
-        while (wi < my_cnt && qn + 8 <= (uint32_t)QCAP) {
-          const uint32_t we = s_wlist[warp][wi];
-          ++wi;
-          const TriEntry& t = s_tri[we & 0xFF];
-          const RasterParams& p = batch[t.draw];
-          const int R = 1 + (int)p.n_attrs;
-          const int blk = (we >> (8 + 2 * (bx & 1))) & 3;  // 0 rejected, 1 partial, 2 full
-          // per-sample coverage (draw_partial_tile, rasterizer.cpp:298-439)
-          uint32_t pm = 0;
-          if (in_target) {
-            if (blk == 2) {
-              pm = fullmask;
-            } else if (blk == 1) {
-              const float left_f = (float)(gx0 + bx * 4), top_f = (float)(gy0 + by * 4);
-              float ev[3];
+        const bool have_entry = wi < my_cnt;
+        uint32_t we = 0;
+        bool entry_early_z = true;
+        if (have_entry) {
+          we = s_wlist[warp][wi];
+          entry_early_z = batch[s_tri[we & 0xFF].draw].early_z != 0;
+        }
+        const bool need_flush = qn > 0 && (!have_entry || qn + 8 > (uint32_t)QCAP || (entry_early_z && queue_has_late));
+        if (need_flush) {
+          // ---------------- (B) dense shading + ordered merge of the queued quads ----------------
+          for (uint32_t jb = 0; jb < qn; jb += 8) {
+            const uint32_t j_raw = jb + (lane >> 2);
+            const bool valid = j_raw < qn;
+            const uint2 it = s_items[warp][valid ? j_raw : qn - 1];
+            const TriEntry& t = s_tri[it.x & 0xFF];
+            const RasterParams& p = batch[t.draw];
+            const int R = 1 + (int)p.n_attrs;
+            const uint32_t oq = (it.x >> 8) & 7;
+            const bool quad_full = (it.x >> 11) & 1;
+            const uint32_t pm = (it.x >> (16 + 4 * pi)) & 0xF;
+            const uint32_t tested = (it.y >> (4 * pi)) & 0xF;
+            // the pixel this lane shades: pixel pi of quad oq of this warp (its owner is lane oq*4 + pi)
+            const uint32_t own = oq * 4 + pi;
+            const int plx = wx + (int)(oq & 3) * 2 + (pi & 1), ply = wy + (int)(oq >> 2) * 2 + (pi >> 1);
+            const int sx_ = gx0 + plx, sy_ = gy0 + ply;
+            const float4* rec = c.tris + (size_t)(t.slot_flags >> 2) * c.tri_stride;
+            // step_2d_unproj_pos_quad (shader.cpp:257-287)
+            const float4 v0p = __ldg(rec + TRI_HEADER), gxp = __ldg(rec + TRI_HEADER + R), gyp = __ldg(rec + TRI_HEADER + 2 * R);
+            PixelCtx px;
+            px.rec = rec; px.R = R; px.mods = p.mods;
+            px.dx = 0.5f + (float)(uint32_t)(sx_ & ~1) - v0p.x;
+            px.dy = 0.5f + (float)(uint32_t)(sy_ & ~1) - v0p.y;
+            px.odd_x = sx_ & 1; px.odd_y = sy_ & 1;
+            float pz = v0p.z + (gxp.z * px.dx + gyp.z * px.dy);
+            float pw = v0p.w + (gxp.w * px.dx + gyp.w * px.dy);
+            if (px.odd_x) { pz += gxp.z; pw += gxp.w; }
+            if (px.odd_y) { pz += gyp.z; pw += gyp.w; }
+            px.inv_w = 1.0f / pw;
+            px.quad_base = quad_base;
+            px.centroid_path = p.has_centroid && !quad_full;
+            px.pdx = px.dx + (float)(int)px.odd_x;
+            px.pdy = px.dy + (float)(int)px.odd_y;
+            if (px.centroid_path && pm != fullmask && pm != 0) {
+              float cx = 0.0f, cy = 0.0f;
+              int n = 0;
 #pragma unroll
-              for (int k = 0; k < 3; ++k) ev[k] = t.C[k] - (left_f * t.A[k] + top_f * t.B[k]);
-#pragma unroll
-              for (int s = 0; s < S; ++s) {
-                float fx = SamplePattern<S>::x(s) + (float)ix, fy = SamplePattern<S>::y(s) + (float)iy;
-                bool rj = false;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) rj |= (fx * t.A[k] + fy * t.B[k]) < ev[k];
-                if (!rj) pm |= 1u << s;
-              }
+              for (int s = 0; s < S; ++s)
+                if (pm & (1u << s)) { cx += SamplePattern<S>::x(s); cy += SamplePattern<S>::y(s); ++n; }
+              float inv = 1 / (float)n;
+              cx *= inv; cy *= inv;
+              px.pdx += cx - 0.5f;
+              px.pdy += cy - 0.5f;
             }
-          }
-          if (!__any_sync(0xFFFFFFFFu, pm != 0)) continue;
-          // early-Z: test and WRITE depth now (framebuffer.cpp:522-614; Appendix B #3)
-          uint32_t tested = pm;
-          if (p.early_z) {
-            tested = 0;
-            if (pm) {
-              const float4* rec = c.tris + (size_t)(t.slot_flags >> 2) * c.tri_stride;
-              const float4 v0p = __ldg(rec + TRI_HEADER), gxp = __ldg(rec + TRI_HEADER + R), gyp = __ldg(rec + TRI_HEADER + 2 * R);
-              const float dx = 0.5f + (float)(uint32_t)(x & ~1) - v0p.x;
-              const float dy = 0.5f + (float)(uint32_t)(y & ~1) - v0p.y;
-              float depth = v0p.z + (gxp.z * dx + gyp.z * dy);
-              if (odd_x) depth += gxp.z;
-              if (odd_y) depth += gyp.z;
+            float4 color;
+            const bool keep_px = run_ps<PS>(p, px, color);
+            uint32_t fin = (keep_px && valid) ? tested : 0u;
+            const uint32_t f0 = __shfl_sync(0xFFFFFFFFu, fin, quad_base), f1 = __shfl_sync(0xFFFFFFFFu, fin, quad_base + 1);
+            const uint32_t f2 = __shfl_sync(0xFFFFFFFFu, fin, quad_base + 2), f3 = __shfl_sync(0xFFFFFFFFu, fin, quad_base + 3);
+            // draw_full_quad tests the post-PS mask, draw_quad the pre-Z mask (rasterizer.cpp:1311,1409)
+            const bool to_backend = valid && (quad_full ? ((f0 | f1 | f2 | f3) != 0) : true);
+            if (to_backend && pi == 0) ++n_backend_quads;
+            if (!to_backend) fin = 0;
+            // two queued quads of this group may be the same screen quad (different triangles): merge those in
+            // queue order -> rank = number of earlier group members with the same quad
+            uint32_t rank = 0;
 #pragma unroll
-              for (int s = 0; s < S; ++s) {
-                if (pm & (1u << s)) {
-                  const float aa = (S > 1) ? (SamplePattern<S>::x(s) - 0.5f) * gxp.z + (SamplePattern<S>::y(s) - 0.5f) * gyp.z : 0.0f;
-                  const float nd = (S == 1) ? depth : aa + depth;
-                  const float od = p.read_depth ? zbuf[s] : 0.0f;
-                  const bool pass = p.depth_enable ? compare_f(p.depth_func, nd, od) : true;
-                  n_ztest += p.read_depth;
-                  if (pass) {
-                    tested |= 1u << s;
-                    if (p.write_depth) { zbuf[s] = nd; dirty_ds = true; ++n_zwrite; }
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t oq_k = __shfl_sync(0xFFFFFFFFu, oq, k * 4);
+              const bool valid_k = (jb + k) < qn;
+              if (valid_k && oq_k == oq && (uint32_t)k < (lane >> 2)) ++rank;
+            }
+            uint32_t max_rank = rank;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) max_rank = max(max_rank, __shfl_xor_sync(0xFFFFFFFFu, max_rank, o));
+            const bool front = t.slot_flags & 1;
+            const bool sx_in = (uint32_t)sx_ < c.target_w && (uint32_t)sy_ < c.target_h;
+            for (uint32_t r = 0; r <= max_rank; ++r) {
+              if (rank == r && fin && sx_in) {
+                // ---- output merger (framebuffer.cpp:445-520) ----
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                  if (!(fin & (1u << s))) continue;
+                  if (!p.early_z) {
+                    const float aa = (S > 1) ? (SamplePattern<S>::x(s) - 0.5f) * gxp.z + (SamplePattern<S>::y(s) - 0.5f) * gyp.z : 0.0f;
+                    const float sd = (S == 1) ? pz : pz + aa;
+                    const float od = p.read_depth ? s_z[warp][s][own] : 0.0f;
+                    const uint32_t os = p.stencil_enable ? (s_st[warp][s][own] & p.read_mask) : 0u;
+                    const bool dp = p.depth_enable ? compare_f(p.depth_func, sd, od) : true;
+                    n_ztest += (p.read_depth | p.stencil_enable) ? 1u : 0u;
+                    const slv_stencil_op_desc& face = front ? p.front_face : p.back_face;
+                    const bool sp = p.stencil_enable ? compare_u(face.stencil_func, p.stencil_ref, os) : true;
+                    if (!(dp && sp)) continue;
+                    const uint32_t ns = p.stencil_enable ? stencil_op_apply(face.stencil_pass_op, p.stencil_ref, os) : os;
+                    if (p.write_depth) s_z[warp][s][own] = sd;
+                    if (p.stencil_enable) s_st[warp][s][own] = ns & p.write_mask;
+                    if (p.write_depth | p.stencil_enable) { ++n_zwrite; wdirty |= 1u; }
+                  }
+                  // blend shader
+                  if (c.color0.data) {
+                    ++n_cwrite;
+                    n_cread += (p.bs_program == SLV_BS_LERP_SRC_ALPHA) ? 1u : 0u;
+                    if (c0_packed) {
+                      if (p.bs_program == SLV_BS_LERP_SRC_ALPHA) {
+                        const float4 d = unpack_color(c.color0.fmt, s_c[warp][s][own]);
+                        const float4 rr = make_float4(d.x + (color.x - d.x) * color.w, d.y + (color.y - d.y) * color.w,
+                                                      d.z + (color.z - d.z) * color.w, d.w + (color.w - d.w) * color.w);
+                        s_c[warp][s][own] = pack_color(c.color0.fmt, rr);
+                      } else {
+                        s_c[warp][s][own] = pack_color(c.color0.fmt, color);
+                      }
+                      wdirty |= 2u;
+                    } else {
+                      uint8_t* cp = c.color0.data + (((size_t)sy_ * c.color0.w + sx_) * S + s) * c.color0.bpp;
+                      if (p.bs_program == SLV_BS_LERP_SRC_ALPHA) {
+                        const float4 d = load_texel_rgba32f(c.color0.fmt, cp);
+                        const float4 rr = make_float4(d.x + (color.x - d.x) * color.w, d.y + (color.y - d.y) * color.w,
+                                                      d.z + (color.z - d.z) * color.w, d.w + (color.w - d.w) * color.w);
+                        store_texel_rgba32f(c.color0.fmt, cp, rr);
+                      } else {
+                        store_texel_rgba32f(c.color0.fmt, cp, color);
+                      }
+                    }
+                  }
+                  if (p.bs_program == SLV_BS_REPLACE_AND_COUNT && c.color1.data) {
+                    uint8_t* cp = c.color1.data + (((size_t)sy_ * c.color1.w + sx_) * S + s) * c.color1.bpp;
+                    float4 v = load_texel_rgba32f(c.color1.fmt, cp);
+                    v.x += 1.0f;
+                    store_texel_rgba32f(c.color1.fmt, cp, v);
                   }
                 }
               }
+              __syncwarp();
             }
           }
-          // quad assembly: one queue item per quad that still has a live sample
-          const uint32_t m0 = __shfl_sync(0xFFFFFFFFu, pm, quad_base), m1 = __shfl_sync(0xFFFFFFFFu, pm, quad_base + 1);
-          const uint32_t m2 = __shfl_sync(0xFFFFFFFFu, pm, quad_base + 2), m3 = __shfl_sync(0xFFFFFFFFu, pm, quad_base + 3);
-          const uint32_t t0 = __shfl_sync(0xFFFFFFFFu, tested, quad_base), t1 = __shfl_sync(0xFFFFFFFFu, tested, quad_base + 1);
-          const uint32_t t2 = __shfl_sync(0xFFFFFFFFu, tested, quad_base + 2), t3 = __shfl_sync(0xFFFFFFFFu, tested, quad_base + 3);
-          const bool quad_shade = ((m0 | m1 | m2 | m3) != 0) && ((t0 | t1 | t2 | t3) != 0);
-          const uint32_t qbal = __ballot_sync(0xFFFFFFFFu, quad_shade && pi == 0);
-          if (quad_shade && pi == 0) {
-            const uint32_t quad_full = ((m0 & m1 & m2 & m3) == fullmask) ? 1u : 0u;
-            uint2 it;
-            it.x = (we & 0xFF) | ((uint32_t)q << 8) | (quad_full << 11) | ((m0 | (m1 << 4) | (m2 << 8) | (m3 << 12)) << 16);
-            it.y = t0 | (t1 << 4) | (t2 << 8) | (t3 << 12);
-            s_items[warp][qn + __popc(qbal & ((1u << lane) - 1))] = it;
-          }
-          qn += __popc(qbal);
+          qn = 0;
+          queue_has_late = false;
+          continue;
         }
-        if (lane == 0) {
-          s_qcnt[warp] = qn;
-          n_ps_quads += qn;
-        }
-        const int any_more = __syncthreads_or(wi < my_cnt);
-
-        // ---------------- phase B: shade all queued quads, 64 quads (256 pixels) per pass ----------------
-        uint32_t qbase[RASTER_WARPS + 1];
-        qbase[0] = 0;
+        if (!have_entry) break;
+        ++wi;
+        // ---------------- (A) coverage + early-Z of the next triangle of this warp's list ----------------
+        const TriEntry& t = s_tri[we & 0xFF];
+        const RasterParams& p = batch[t.draw];
+        const int R = 1 + (int)p.n_attrs;
+        const int blk = (we >> (8 + 2 * (bx & 1))) & 3;  // 0 rejected, 1 partial, 2 full
+        // per-sample coverage (draw_partial_tile, rasterizer.cpp:298-439)
+        uint32_t pm = 0;
+        if (in_target) {
+          if (blk == 2) {
+            pm = fullmask;
+          } else if (blk == 1) {
+            const float left_f = (float)(gx0 + bx * 4), top_f = (float)(gy0 + by * 4);
+            float ev[3];
 #pragma unroll
-        for (int w = 0; w < RASTER_WARPS; ++w) qbase[w + 1] = qbase[w] + s_qcnt[w];
-        const uint32_t q_total = qbase[RASTER_WARPS];
-        for (uint32_t jb = 0; jb < q_total; jb += RASTER_THREADS / 4) {
-          const uint32_t j_raw = jb + (tid >> 2);
-          const bool valid = j_raw < q_total;
-          const uint32_t j = valid ? j_raw : q_total - 1;
-          uint32_t ow = 0;  // owner warp of item j
+            for (int k = 0; k < 3; ++k) ev[k] = t.C[k] - (left_f * t.A[k] + top_f * t.B[k]);
 #pragma unroll
-          for (int w = 1; w < RASTER_WARPS; ++w) ow += (j >= qbase[w]) ? 1u : 0u;
-          uint32_t ob = 0;
+            for (int s = 0; s < S; ++s) {
+              float fx = SamplePattern<S>::x(s) + (float)ix, fy = SamplePattern<S>::y(s) + (float)iy;
+              bool rj = false;
 #pragma unroll
-          for (int w = 1; w < RASTER_WARPS; ++w) ob = (ow == (uint32_t)w) ? qbase[w] : ob;
-          const uint2 it = s_items[ow][j - ob];
-          const TriEntry& t = s_tri[it.x & 0xFF];
-          const RasterParams& p = batch[t.draw];
-          const int R = 1 + (int)p.n_attrs;
-          const uint32_t oq = (it.x >> 8) & 7;
-          const bool quad_full = (it.x >> 11) & 1;
-          const uint32_t pm = (it.x >> (16 + 4 * pi)) & 0xF;
-          const uint32_t tested = (it.y >> (4 * pi)) & 0xF;
-          // pixel handled by this thread: pixel pi of quad oq of warp ow
-          const int plx = (int)(ow & 1) * 8 + (int)(oq & 3) * 2 + (pi & 1), ply = (int)(ow >> 1) * 4 + (int)(oq >> 2) * 2 + (pi >> 1);
-          const int sx_ = gx0 + plx, sy_ = gy0 + ply;
-          const float4* rec = c.tris + (size_t)(t.slot_flags >> 2) * c.tri_stride;
-          // step_2d_unproj_pos_quad (shader.cpp:257-287): only w is needed here
-          const float4 v0p = __ldg(rec + TRI_HEADER), gxp = __ldg(rec + TRI_HEADER + R), gyp = __ldg(rec + TRI_HEADER + 2 * R);
-          PixelCtx px;
-          px.rec = rec; px.R = R; px.mods = p.mods;
-          px.dx = 0.5f + (float)(uint32_t)(sx_ & ~1) - v0p.x;
-          px.dy = 0.5f + (float)(uint32_t)(sy_ & ~1) - v0p.y;
-          px.odd_x = sx_ & 1; px.odd_y = sy_ & 1;
-          float pw = v0p.w + (gxp.w * px.dx + gyp.w * px.dy);
-          if (px.odd_x) pw += gxp.w;
-          if (px.odd_y) pw += gyp.w;
-          px.inv_w = 1.0f / pw;
-          px.quad_base = quad_base;
-          px.centroid_path = p.has_centroid && !quad_full;
-          px.pdx = px.dx + (float)(int)px.odd_x;
-          px.pdy = px.dy + (float)(int)px.odd_y;
-          if (px.centroid_path && pm != fullmask && pm != 0) {
-            float cx = 0.0f, cy = 0.0f;
-            int n = 0;
-#pragma unroll
-            for (int s = 0; s < S; ++s)
-              if (pm & (1u << s)) { cx += SamplePattern<S>::x(s); cy += SamplePattern<S>::y(s); ++n; }
-            float inv = 1 / (float)n;
-            cx *= inv; cy *= inv;
-            px.pdx += cx - 0.5f;
-            px.pdy += cy - 0.5f;
-          }
-          float4 color;
-          const bool keep_px = run_ps<PS>(p, px, color);
-          uint32_t fin = keep_px ? tested : 0u;
-          const uint32_t f0 = __shfl_sync(0xFFFFFFFFu, fin, quad_base), f1 = __shfl_sync(0xFFFFFFFFu, fin, quad_base + 1);
-          const uint32_t f2 = __shfl_sync(0xFFFFFFFFu, fin, quad_base + 2), f3 = __shfl_sync(0xFFFFFFFFu, fin, quad_base + 3);
-          // draw_full_quad tests the post-PS mask, draw_quad the pre-Z mask (rasterizer.cpp:1311,1409)
-          const bool to_backend = quad_full ? ((f0 | f1 | f2 | f3) != 0) : true;
-          if (valid) {
-            s_color[j * 4 + pi] = color;
-            if (pi == 0) {
-              s_fin[j] = to_backend ? (f0 | (f1 << 4) | (f2 << 8) | (f3 << 12)) : 0u;
-              n_backend_quads += to_backend ? 1u : 0u;
+              for (int k = 0; k < 3; ++k) rj |= (fx * t.A[k] + fy * t.B[k]) < ev[k];
+              if (!rj) pm |= 1u << s;
             }
           }
         }
-        __syncthreads();
-
-        // ---------------- phase C: output merger by the pixel owners, in queue (= API) order ----------------
-        for (uint32_t i = 0; i < qn; ++i) {
-          const uint2 it = s_items[warp][i];
-          if ((uint32_t)q != ((it.x >> 8) & 7)) continue;
-          uint32_t flat = i;
-#pragma unroll
-          for (int w = 1; w < RASTER_WARPS; ++w) flat = (warp == (uint32_t)w) ? qbase[w] + i : flat;
-          const uint32_t fin = (s_fin[flat] >> (4 * pi)) & 0xF;
-          if (!fin) continue;
-          const float4 color = s_color[flat * 4 + pi];
-          const TriEntry& t = s_tri[it.x & 0xFF];
-          const RasterParams& p = batch[t.draw];
-          const int R = 1 + (int)p.n_attrs;
-          const bool front = t.slot_flags & 1;
-          float depth = 0.0f, gz_x = 0.0f, gz_y = 0.0f;
-          if (!p.early_z) {  // late depth/stencil needs the sample depths again
+        if (!__any_sync(0xFFFFFFFFu, pm != 0)) continue;
+        // early-Z: test and WRITE depth now (framebuffer.cpp:522-614; Appendix B #3)
+        uint32_t tested = pm;
+        if (entry_early_z) {
+          tested = 0;
+          if (pm) {
             const float4* rec = c.tris + (size_t)(t.slot_flags >> 2) * c.tri_stride;
             const float4 v0p = __ldg(rec + TRI_HEADER), gxp = __ldg(rec + TRI_HEADER + R), gyp = __ldg(rec + TRI_HEADER + 2 * R);
             const float dx = 0.5f + (float)(uint32_t)(x & ~1) - v0p.x;
             const float dy = 0.5f + (float)(uint32_t)(y & ~1) - v0p.y;
-            depth = v0p.z + (gxp.z * dx + gyp.z * dy);
+            float depth = v0p.z + (gxp.z * dx + gyp.z * dy);
             if (odd_x) depth += gxp.z;
             if (odd_y) depth += gyp.z;
-            gz_x = gxp.z; gz_y = gyp.z;
-          }
+            const uint32_t cmp_lut = p.depth_enable ? compare_lut(p.depth_func) : 0xFu;
 #pragma unroll
-          for (int s = 0; s < S; ++s) {
-            if (!(fin & (1u << s))) continue;
-            if (!p.early_z) {
-              const float aa = (S > 1) ? (SamplePattern<S>::x(s) - 0.5f) * gz_x + (SamplePattern<S>::y(s) - 0.5f) * gz_y : 0.0f;
-              float sd = (S == 1) ? depth : depth + aa;
-              float od = p.read_depth ? zbuf[s] : 0.0f;
-              uint32_t os = p.stencil_enable ? (sbuf[s] & p.read_mask) : 0u;
-              bool dp = p.depth_enable ? compare_f(p.depth_func, sd, od) : true;
-              n_ztest += (p.read_depth | p.stencil_enable) ? 1u : 0u;
-              const slv_stencil_op_desc& face = front ? p.front_face : p.back_face;
-              bool sp = p.stencil_enable ? compare_u(face.stencil_func, p.stencil_ref, os) : true;
-              if (!(dp && sp)) continue;
-              uint32_t ns = p.stencil_enable ? stencil_op_apply(face.stencil_pass_op, p.stencil_ref, os) : os;
-              if (p.write_depth) { zbuf[s] = sd; dirty_ds = true; }
-              if (p.stencil_enable) { sbuf[s] = ns & p.write_mask; dirty_ds = true; }
-              n_zwrite += (p.write_depth | p.stencil_enable) ? 1u : 0u;
-            }
-            // blend shader
-            if (c.color0.data) {
-              ++n_cwrite;
-              n_cread += (p.bs_program == SLV_BS_LERP_SRC_ALPHA) ? 1u : 0u;
-              if (c0_packed) {
-                if (p.bs_program == SLV_BS_LERP_SRC_ALPHA) {
-                  float4 d = unpack_color(c.color0.fmt, cbuf[s]);
-                  float4 r = make_float4(d.x + (color.x - d.x) * color.w, d.y + (color.y - d.y) * color.w,
-                                         d.z + (color.z - d.z) * color.w, d.w + (color.w - d.w) * color.w);
-                  cbuf[s] = pack_color(c.color0.fmt, r);
-                } else {
-                  cbuf[s] = pack_color(c.color0.fmt, color);
-                }
-                dirty_c = true;
-              } else {
-                uint8_t* cp = c.color0.data + (((size_t)y * c.color0.w + x) * S + s) * c.color0.bpp;
-                if (p.bs_program == SLV_BS_LERP_SRC_ALPHA) {
-                  float4 d = load_texel_rgba32f(c.color0.fmt, cp);
-                  float4 r = make_float4(d.x + (color.x - d.x) * color.w, d.y + (color.y - d.y) * color.w,
-                                         d.z + (color.z - d.z) * color.w, d.w + (color.w - d.w) * color.w);
-                  store_texel_rgba32f(c.color0.fmt, cp, r);
-                } else {
-                  store_texel_rgba32f(c.color0.fmt, cp, color);
+            for (int s = 0; s < S; ++s) {
+              if (pm & (1u << s)) {
+                const float aa = (S > 1) ? (SamplePattern<S>::x(s) - 0.5f) * gxp.z + (SamplePattern<S>::y(s) - 0.5f) * gyp.z : 0.0f;
+                const float nd = (S == 1) ? depth : aa + depth;
+                const float od = p.read_depth ? s_z[warp][s][lane] : 0.0f;
+                const bool pass = compare_with_lut(cmp_lut, nd, od);
+                n_ztest += p.read_depth;
+                if (pass) {
+                  tested |= 1u << s;
+                  if (p.write_depth) { s_z[warp][s][lane] = nd; wdirty |= 1u; ++n_zwrite; }
                 }
               }
             }
-            if (p.bs_program == SLV_BS_REPLACE_AND_COUNT && c.color1.data) {
-              uint8_t* cp = c.color1.data + (((size_t)y * c.color1.w + x) * S + s) * c.color1.bpp;
-              float4 v = load_texel_rgba32f(c.color1.fmt, cp);
-              v.x += 1.0f;
-              store_texel_rgba32f(c.color1.fmt, cp, v);
-            }
           }
         }
-        if (!any_more) break;
+        // quad assembly: one queue item per quad that still has a live sample
+        const uint32_t m0 = __shfl_sync(0xFFFFFFFFu, pm, quad_base), m1 = __shfl_sync(0xFFFFFFFFu, pm, quad_base + 1);
+        const uint32_t m2 = __shfl_sync(0xFFFFFFFFu, pm, quad_base + 2), m3 = __shfl_sync(0xFFFFFFFFu, pm, quad_base + 3);
+        const uint32_t t0 = __shfl_sync(0xFFFFFFFFu, tested, quad_base), t1 = __shfl_sync(0xFFFFFFFFu, tested, quad_base + 1);
+        const uint32_t t2 = __shfl_sync(0xFFFFFFFFu, tested, quad_base + 2), t3 = __shfl_sync(0xFFFFFFFFu, tested, quad_base + 3);
+        const bool quad_shade = ((m0 | m1 | m2 | m3) != 0) && ((t0 | t1 | t2 | t3) != 0);
+        const uint32_t qbal = __ballot_sync(0xFFFFFFFFu, quad_shade && pi == 0);
+        if (quad_shade && pi == 0) {
+          const uint32_t quad_full = ((m0 & m1 & m2 & m3) == fullmask) ? 1u : 0u;
+          uint2 it;
+          it.x = (we & 0xFF) | ((uint32_t)q << 8) | (quad_full << 11) | ((m0 | (m1 << 4) | (m2 << 8) | (m3 << 12)) << 16);
+          it.y = t0 | (t1 << 4) | (t2 << 8) | (t3 << 12);
+          s_items[warp][qn + __popc(qbal & ((1u << lane) - 1))] = it;
+        }
+        const uint32_t pushed = __popc(qbal);
+        if (lane == 0) n_ps_quads += pushed;
+        qn += pushed;
+        if (pushed && !entry_early_z) queue_has_late = true;
+        __syncwarp();
       }
       // (the barrier at the top of the next chunk / item protects s_tri, s_wlist and s_cnt)
       __syncthreads();
     }
 
-    // ---- write the pixel back once, 128-bit stores at 4x MSAA ----
-    if (in_target) {
-      if (dirty_ds && ds_ptr) {
-        if (S == 4) {
-          *reinterpret_cast<float4*>(ds_ptr) =
-              make_float4(zbuf[0], __uint_as_float(sbuf[0]), zbuf[1 % S], __uint_as_float(sbuf[1 % S]));
-          *reinterpret_cast<float4*>(ds_ptr + 16) =
-              make_float4(zbuf[2 % S], __uint_as_float(sbuf[2 % S]), zbuf[3 % S], __uint_as_float(sbuf[3 % S]));
-        } else if (S == 2) {
-          *reinterpret_cast<float4*>(ds_ptr) =
-              make_float4(zbuf[0], __uint_as_float(sbuf[0]), zbuf[1 % S], __uint_as_float(sbuf[1 % S]));
-        } else {
-          *reinterpret_cast<float2*>(ds_ptr) = make_float2(zbuf[0], __uint_as_float(sbuf[0]));
+    // ---- write the warp's tile back once, 128-bit stores at 4x MSAA ----
+    if (fb_loaded) {
+      __syncwarp();
+      const bool any_ds = __any_sync(0xFFFFFFFFu, (wdirty & 1u) != 0), any_c = __any_sync(0xFFFFFFFFu, (wdirty & 2u) != 0);
+      if (in_target) {
+        if (any_ds && c.ds.data) {
+          uint8_t* ds_ptr = c.ds.data + ((size_t)y * c.ds.w + x) * S * 8;
+          if (S == 4) {
+            *reinterpret_cast<float4*>(ds_ptr) = make_float4(s_z[warp][0][lane], __uint_as_float(s_st[warp][0][lane]),
+                                                             s_z[warp][1 % S][lane], __uint_as_float(s_st[warp][1 % S][lane]));
+            *reinterpret_cast<float4*>(ds_ptr + 16) = make_float4(s_z[warp][2 % S][lane], __uint_as_float(s_st[warp][2 % S][lane]),
+                                                                  s_z[warp][3 % S][lane], __uint_as_float(s_st[warp][3 % S][lane]));
+          } else if (S == 2) {
+            *reinterpret_cast<float4*>(ds_ptr) = make_float4(s_z[warp][0][lane], __uint_as_float(s_st[warp][0][lane]),
+                                                             s_z[warp][1 % S][lane], __uint_as_float(s_st[warp][1 % S][lane]));
+          } else {
+            *reinterpret_cast<float2*>(ds_ptr) = make_float2(s_z[warp][0][lane], __uint_as_float(s_st[warp][0][lane]));
+          }
+        }
+        if (any_c && c0_packed) {
+          uint8_t* c_ptr = c.color0.data + ((size_t)y * c.color0.w + x) * S * 4;
+          if (S == 4) *reinterpret_cast<uint4*>(c_ptr) = make_uint4(s_c[warp][0][lane], s_c[warp][1 % S][lane], s_c[warp][2 % S][lane], s_c[warp][3 % S][lane]);
+          else if (S == 2) *reinterpret_cast<uint2*>(c_ptr) = make_uint2(s_c[warp][0][lane], s_c[warp][1 % S][lane]);
+          else *reinterpret_cast<uint32_t*>(c_ptr) = s_c[warp][0][lane];
         }
       }
-      if (dirty_c && c_ptr) {
-        if (S == 4) *reinterpret_cast<uint4*>(c_ptr) = make_uint4(cbuf[0], cbuf[1 % S], cbuf[2 % S], cbuf[3 % S]);
-        else if (S == 2) *reinterpret_cast<uint2*>(c_ptr) = make_uint2(cbuf[0], cbuf[1 % S]);
-        else *reinterpret_cast<uint32_t*>(c_ptr) = cbuf[0];
-      }
+      __syncwarp();
     }
   }
 

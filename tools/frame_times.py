@@ -1,0 +1,25 @@
+"""Developer tool: per-frame GPU time and counters of the Sponza-like scene (frames 0..7)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import salviarenderer_b200 as pkg
+from salviarenderer_b200 import abi as A, scenes as S
+be = pkg.load(0)
+sc = S.SponzaLike(3840, 2160, 4)
+sc.setup(be)
+for f in range(8):
+    sc.render(be, f)
+be.flush()
+for f in range(8):
+    be.profile_enable(True)
+    be.query_begin()
+    sc.render(be, f)
+    be.flush()
+    pr = be.profile_get(); st = be.query_get(); tr = be.traffic()
+    be.profile_enable(False)
+    be.event_record(0)
+    for _ in range(3):
+        sc.render(be, f)
+    be.event_record(1)
+    ms = be.event_elapsed_ms(0, 1) / 3
+    print(f"frame {f}: {ms:6.3f} ms | geom {pr['clipping']/1e6:5.3f} bin {pr['tri_dispatch']/1e6:5.3f} raster {pr['ras']/1e6:6.3f} | ps {st['ps_invocations']/1e6:6.2f}M cprims {st['cprimitives']:7d} ztest {tr['z_tested']/1e6:6.1f}M cwr {tr['c_written']/1e6:6.1f}M", flush=True)
