@@ -271,6 +271,9 @@ slv_result slv_set_tile_shard(slv_device dev, uint32_t rank, uint32_t nranks);
  * was read by the blend shader. Exact integers; the oracle produces the same numbers. */
 typedef struct slv_traffic_counters {
   uint64_t z_tested, z_written, c_written, c_read;
+  /* work counters of the product's raster kernel (0 for the CPU checkers): tile-list entries examined by the
+   * region filters, (triangle, 16x16 region) survivors, (triangle, warp) pairs walked, quads shaded */
+  uint64_t list_entries_scanned, region_survivors, warp_pairs, quads_shaded;
 } slv_traffic_counters;
 slv_result slv_traffic_get(slv_device dev, slv_traffic_counters* out);
 /* number of kernels this library launched since slv_query_begin (0 for the CPU checkers) */

@@ -304,11 +304,11 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, ordinal));
-    dev->raster_grid = prop.multiProcessorCount * 2;  // k_raster is built for 2 resident CTAs per SM
+    dev->raster_grid = prop.multiProcessorCount * RASTER_CTAS_PER_SM;
   }
   CU(cudaMemsetAsync(dev->overflow_flag, 0, sizeof(uint32_t), dev->stream));
-  CU(cudaMalloc(&dev->d_stats, 13 * sizeof(unsigned long long)));
-  CU(cudaMemsetAsync(dev->d_stats, 0, 13 * sizeof(unsigned long long), dev->stream));
+  CU(cudaMalloc(&dev->d_stats, 16 * sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(dev->d_stats, 0, 16 * sizeof(unsigned long long), dev->stream));
   const char* prof = getenv("SLV_PROFILE");
   dev->profile = prof && prof[0] == '1';
   for (auto& ev : dev->user_ev) CU(cudaEventCreate(&ev));
@@ -379,6 +379,8 @@ slv_result slv_buffer_readback(slv_device dev, slv_handle h, size_t off, void* d
 
 static slv_result alloc_level(SurfaceRef& s, uint32_t w, uint32_t h, uint32_t samples, uint32_t fmt) {
   s.w = w; s.h = h; s.samples = samples; s.fmt = fmt; s.bpp = bpp_of(fmt);
+  s.wmask = (w <= 1024 && (w & (w - 1)) == 0) ? w - 1 : 0;
+  s.hmask = (h <= 1024 && (h & (h - 1)) == 0) ? h - 1 : 0;
   s.bytes = (size_t)w * h * samples * s.bpp;
   if (cudaMalloc(&s.data, std::max<size_t>(s.bytes, 16)) != cudaSuccess) return SLV_OUT_OF_MEMORY;
   return SLV_OK;
@@ -785,7 +787,7 @@ slv_result slv_query_begin(slv_device dev) {
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   dev->host_stats = slv_pipeline_statistics{};
-  CU(cudaMemsetAsync(dev->d_stats, 0, 13 * sizeof(unsigned long long), dev->stream));
+  CU(cudaMemsetAsync(dev->d_stats, 0, 16 * sizeof(unsigned long long), dev->stream));
   for (auto& m : dev->prof_ms) m = 0;
   if (!dev->spans.empty()) CU(cudaStreamSynchronize(dev->stream));
   dev->spans.clear();
@@ -831,9 +833,13 @@ slv_result slv_traffic_get(slv_device dev, slv_traffic_counters* out) {
   if (!dev || !out) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
-  unsigned long long h[13];
+  unsigned long long h[16];
   CU(cudaMemcpyAsync(h, dev->d_stats, sizeof(h), cudaMemcpyDeviceToHost, dev->stream));
   CU(cudaStreamSynchronize(dev->stream));
+  out->list_entries_scanned = h[13];
+  out->region_survivors = h[14];
+  out->warp_pairs = h[15];
+  out->quads_shaded = h[7] / 4;
   out->z_tested = h[9];
   out->z_written = h[10];
   out->c_written = h[11];

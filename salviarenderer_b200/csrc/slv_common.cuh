@@ -24,6 +24,7 @@ constexpr int MAX_LEVELS = 14;                         // 8192 -> 1
 struct SurfaceRef {  // reference layout: ((y*W + x)*S + s)*bpp (surface.cpp:277-295)
   uint8_t* data;
   uint32_t w, h, samples, fmt, bpp;
+  uint32_t wmask, hmask;  // size-1 when the size is a power of two <= 1024 (exact integer wrap), else 0
   size_t bytes;
 };
 

@@ -742,6 +742,10 @@ __device__ __forceinline__ int block_test(const TriEntry& t, float x_min, float 
 }
 
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
+#ifndef SLV_RASTER_CTAS_PER_SM
+#define SLV_RASTER_CTAS_PER_SM 3
+#endif
+constexpr int RASTER_CTAS_PER_SM = SLV_RASTER_CTAS_PER_SM;  // resident CTAs per SM the kernel is compiled for
 constexpr int QCAP = 32;  // quads a warp may queue per round (a triangle adds at most 8)
 
 // Persistent CTAs: work item = (active tile, 16x16 region).  Per item the tile's sorted triangle list is
@@ -751,7 +755,7 @@ constexpr int QCAP = 32;  // quads a warp may queue per round (a triangle adds a
 // that warp's two 4x4 blocks.  Each warp then walks its own list: thread == pixel, all S samples of
 // depth / stencil / colour stay in registers until the item is finished.
 template <int S, int PS>
-__global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, const RasterParams* __restrict__ batch,
+__global__ void __launch_bounds__(RASTER_THREADS, RASTER_CTAS_PER_SM) k_raster(RasterParams c, const RasterParams* __restrict__ batch,
                                                                uint32_t n_draws) {
   __shared__ TriEntry s_tri[RASTER_THREADS];
   __shared__ uint16_t s_wlist[RASTER_WARPS][RASTER_THREADS];
@@ -777,6 +781,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, co
 
   uint32_t n_ps_quads = 0, n_backend_quads = 0;
   uint32_t n_ztest = 0, n_zwrite = 0, n_cwrite = 0, n_cread = 0;  // algorithmic traffic (SURVEY §8d B_frag)
+  uint32_t n_scanned = 0, n_surv = 0, n_pairs = 0;                 // work counters
 
   const uint32_t n_items = c.active_tiles[0] * 16u;
   for (;;) {
@@ -812,6 +817,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, co
       uint32_t st_bits = 0;  // 2 bits per block: 0 rejected, 1 partial, 2 full
       TriEntry ent;
       if (ei < list_end) {
+        ++n_scanned;
         const uint32_t e = __ldg(c.list + ei);
         const uint32_t slot = e >> 1;
         const float4* rec = c.tris + (size_t)slot * c.tri_stride;
@@ -894,6 +900,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, co
           my_cnt += s_cnt[warp][fw];
         }
         if (keep) {
+          ++n_surv;
           const uint32_t sidx = sbase + __popc(bal[RASTER_WARPS] & below);
           s_tri[sidx] = ent;
 #pragma unroll
@@ -938,6 +945,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, co
       }
       uint32_t wi = 0, qn = 0;
       bool queue_has_late = false;
+      if (lane == 0) n_pairs += my_cnt;
       for (;;) {
         const bool have_entry = wi < my_cnt;
         uint32_t we = 0;
@@ -1018,6 +1026,14 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, co
             for (uint32_t r = 0; r <= max_rank; ++r) {
               if (rank == r && fin && sx_in) {
                 // ---- output merger (framebuffer.cpp:445-520) ----
+                if (p.early_z && c0_packed && p.bs_program == SLV_BS_REPLACE) {  // the common case, hoisted
+                  const uint32_t packed = pack_color(c.color0.fmt, color);
+#pragma unroll
+                  for (int s = 0; s < S; ++s)
+                    if (fin & (1u << s)) s_c[warp][s][own] = packed;
+                  n_cwrite += __popc(fin);
+                  wdirty |= 2u;
+                } else
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
                   if (!(fin & (1u << s))) continue;
@@ -1198,6 +1214,9 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, co
     n_zwrite += __shfl_xor_sync(0xFFFFFFFFu, n_zwrite, o);
     n_cwrite += __shfl_xor_sync(0xFFFFFFFFu, n_cwrite, o);
     n_cread += __shfl_xor_sync(0xFFFFFFFFu, n_cread, o);
+    n_scanned += __shfl_xor_sync(0xFFFFFFFFu, n_scanned, o);
+    n_surv += __shfl_xor_sync(0xFFFFFFFFu, n_surv, o);
+    n_pairs += __shfl_xor_sync(0xFFFFFFFFu, n_pairs, o);
   }
   if (lane == 0) {
     if (a) atomicAdd(&c.stats[7], (unsigned long long)a * 4ull);
@@ -1206,6 +1225,9 @@ __global__ void __launch_bounds__(RASTER_THREADS, 2) k_raster(RasterParams c, co
     if (n_zwrite) atomicAdd(&c.stats[10], (unsigned long long)n_zwrite);
     if (n_cwrite) atomicAdd(&c.stats[11], (unsigned long long)n_cwrite);
     if (n_cread) atomicAdd(&c.stats[12], (unsigned long long)n_cread);
+    if (n_scanned) atomicAdd(&c.stats[13], (unsigned long long)n_scanned);
+    if (n_surv) atomicAdd(&c.stats[14], (unsigned long long)n_surv);
+    if (n_pairs) atomicAdd(&c.stats[15], (unsigned long long)n_pairs);
   }
 }
 

@@ -61,7 +61,9 @@ __device__ inline int point_coord_2d(uint32_t mode, float c, int size) {
   }
 }
 
-__device__ inline void linear_coord_2d(uint32_t mode, float c, int size, int& lo, int& up, float& frac) {
+// `mask` = size-1 when size is a power of two <= 1024: then ip + size*8192 < 2^24 and every step of the reference's
+// float modulo (sampler.cpp:88-92) is exact, so it equals the integer (ip + k) & mask bit for bit.
+__device__ inline void linear_coord_2d(uint32_t mode, float c, int size, uint32_t mask, int& lo, int& up, float& frac) {
   float fs = (float)size;
   switch (mode) {
   case SLV_ADDR_WRAP: {
@@ -70,8 +72,14 @@ __device__ inline void linear_coord_2d(uint32_t mode, float c, int size, int& lo
     f = f - 0.5f;
     float ip = floor_fix(f);
     frac = f - ip;
-    lo = wrap_index(ip + 0.0f, fs);
-    up = wrap_index(ip + 1.0f, fs);
+    if (mask) {
+      const int i = (int)ip;
+      lo = i & (int)mask;
+      up = (i + 1) & (int)mask;
+    } else {
+      lo = wrap_index(ip + 0.0f, fs);
+      up = wrap_index(ip + 1.0f, fs);
+    }
     return;
   }
   case SLV_ADDR_MIRROR: {
@@ -215,8 +223,8 @@ __device__ inline float4 sample_surface(const SurfaceRef& s, const slv_sampler_d
   int x0, x1, y0, y1;
   float tx, ty;
   if (same) {
-    linear_coord_2d(d.addr_mode_u, x, W, x0, x1, tx);
-    linear_coord_2d(d.addr_mode_v, y, H, y0, y1, ty);
+    linear_coord_2d(d.addr_mode_u, x, W, s.wmask, x0, x1, tx);
+    linear_coord_2d(d.addr_mode_v, y, H, s.hmask, y0, y1, ty);
   } else {
     float ox = do_coordf(d.addr_mode_u, x, W);
     int ipx = fast_floori((double)ox);
@@ -313,7 +321,9 @@ __device__ inline float4 sample_impl(const SamplerRef& sm, float cx, float cy, f
     return sample_surface(t.level[ml], d, d.min_filter, cx, cy);
   }
   if (d.mip_filter == SLV_FILTER_LINEAR) {
-    int lo = fast_floori((double)miplevel);
+    // miplevel >= 0 here (the mag case returned above): for non-negative floats the reference's double-precision
+    // fast_floori(d) = floor(d + 1.5e-8) equals floorf(d) exactly (no float lies within 1.5e-8 below an integer >= 1)
+    int lo = (int)floorf(miplevel);
     int hi = lo + 1;
     float frac = miplevel - (float)lo;
     int lo_sz = min(max(lo, max_lod), min_lod);

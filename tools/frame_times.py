@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import salviarenderer_b200 as pkg
 from salviarenderer_b200 import abi as A, scenes as S
-be = pkg.load(0)
+be = A.Backend(os.environ['SLV_LIB']) if os.environ.get('SLV_LIB') else pkg.load(0)
 sc = S.SponzaLike(3840, 2160, 4)
 sc.setup(be)
 for f in range(8):
@@ -22,4 +22,4 @@ for f in range(8):
         sc.render(be, f)
     be.event_record(1)
     ms = be.event_elapsed_ms(0, 1) / 3
-    print(f"frame {f}: {ms:6.3f} ms | geom {pr['clipping']/1e6:5.3f} bin {pr['tri_dispatch']/1e6:5.3f} raster {pr['ras']/1e6:6.3f} | ps {st['ps_invocations']/1e6:6.2f}M cprims {st['cprimitives']:7d} ztest {tr['z_tested']/1e6:6.1f}M cwr {tr['c_written']/1e6:6.1f}M", flush=True)
+    print(f"frame {f}: {ms:6.3f} ms | geom {pr['clipping']/1e6:5.3f} bin {pr['tri_dispatch']/1e6:5.3f} raster {pr['ras']/1e6:6.3f} | ps {st['ps_invocations']/1e6:6.2f}M cprims {st['cprimitives']:7d} ztest {tr['z_tested']/1e6:6.1f}M cwr {tr['c_written']/1e6:6.1f}M | scanned {tr['list_entries_scanned']/1e6:6.2f}M surv {tr['region_survivors']/1e6:6.2f}M pairs {tr['warp_pairs']/1e6:6.2f}M quads {tr['quads_shaded']/1e6:6.2f}M", flush=True)
