@@ -165,7 +165,7 @@ def main():
     import torch
     import torch.distributed as dist
     import salviarenderer_b200 as pkg
-    from salviarenderer_b200 import scenes
+    from salviarenderer_b200 import scenes, sortfirst
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product has no CPU path")
@@ -178,31 +178,16 @@ def main():
     stream = torch.cuda.Stream()  # a real (non-legacy) stream shared by the library, torch and NCCL
     torch.cuda.set_stream(stream)
     be.set_stream(stream.cuda_stream)  # kernels, copies and NCCL all order on torch's current stream
-    be.set_tile_shard(rank, n)
     sc = scenes.SponzaLike(args.width, args.height, args.samples, tex_size=args.tex_size, max_aniso=args.aniso)
     sc.setup(be)
     resolved = sc.t.resolved if sc.t.resolved is not None else sc.t.color
 
-    # ---- sort-first gather plumbing (N > 1) ----
-    stage = gather_list = None
-    if n > 1:
-        sizes = [be.packed_tiles_bytes(resolved, r, n) for r in range(n)]
-        mx = max(sizes)
-        stage = torch.empty(mx, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            gather_list = [torch.empty(mx, dtype=torch.uint8, device="cuda") for _ in range(n)]
-
-    def gather():
-        be.pack_tiles(resolved, rank, n, stage.data_ptr())
-        dist.gather(stage, gather_list, dst=0)
-        if rank == 0:
-            for r in range(1, n):
-                be.unpack_tiles(resolved, r, n, gather_list[r].data_ptr())
+    # ---- sort-first gather plumbing (N > 1): salviarenderer_b200/sortfirst.py ----
+    fg = sortfirst.FrameGather(be, resolved, rank, n, "cuda")
 
     def frame(i):
         sc.render(be, i % sc.n_frames)
-        if n > 1:
-            gather()
+        fg.gather()
 
     def barrier():
         torch.cuda.synchronize()
