@@ -21,6 +21,7 @@
 
 #include "salvia_b200.h"
 #include "slv_kernels.cuh"
+#include "slv_deferred.cuh"
 
 using namespace slv;
 
@@ -64,7 +65,11 @@ struct slv_device_t {
   float4* tris = nullptr;
   size_t tris_cap = 0;  // float4 units
   uint32_t *tile_count = nullptr, *tile_offset = nullptr, *tile_cursor = nullptr, *active_tiles = nullptr;
-  uint32_t* work_counter = nullptr;
+  uint32_t* work_counter = nullptr;  // [0] k_raster / k_cover queue head, [1] k_shade queue head
+  uint32_t* vis = nullptr;           // visibility buffer of the deferred path: owner slot per sample
+  size_t vis_cap = 0;                // in uint32 units
+  bool force_immediate = false;      // SLV_FORCE_IMMEDIATE=1: always use k_raster (tests compare both paths)
+  int cover_grid = 0, shade_grid = 0;
   int raster_grid = 0;  // persistent raster CTAs (SM count x resident CTAs per SM)
   // ---- draw batching: geometry + binning run at slv_draw time, the raster pass of all queued draws of a
   // frame runs at the next flush point (readback, clear, resolve, state that changes the targets ...), so each
@@ -201,6 +206,20 @@ bool launch_raster_s(const RasterParams& rp, const RasterParams* batch, uint32_t
   return false;
 }
 
+template <int S>
+bool launch_shade_s(const RasterParams& rp, const RasterParams* batch, const uint32_t* vis, uint32_t* counter, uint32_t blocks,
+                    cudaStream_t st) {
+  const uint32_t pitch = rp.color0.w;
+  switch (rp.ps_program) {
+  case SLV_PS_ATTR0_COLOR: k_shade<S, SLV_PS_ATTR0_COLOR><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, vis, pitch, counter); return true;
+  case SLV_PS_LIGHTS3: k_shade<S, SLV_PS_LIGHTS3><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, vis, pitch, counter); return true;
+  case SLV_PS_TEX_ALPHA: k_shade<S, SLV_PS_TEX_ALPHA><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, vis, pitch, counter); return true;
+  case SLV_PS_SPONZA: k_shade<S, SLV_PS_SPONZA><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, vis, pitch, counter); return true;
+  case SLV_PS_TEX_GRAD_ALPHA: k_shade<S, SLV_PS_TEX_GRAD_ALPHA><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, vis, pitch, counter); return true;
+  }
+  return false;
+}
+
 // Batch flush: binning (scan, fill, sort) over the triangles of every queued draw, then the raster pass of all of
 // them, in submission order, as ONE kernel.
 slv_result flush_batch(slv_device dev) {
@@ -241,12 +260,46 @@ slv_result flush_batch(slv_device dev) {
   size_t e1 = dev->profile ? mark(dev) : 0;
   k_sort_lists<<<n_tiles, 256, 0, st>>>(dev->tile_offset, dev->list, dev->list_cap);
   size_t e2 = dev->profile ? mark(dev) : 0;
-  const uint32_t blocks = std::min<uint32_t>(n_tiles * 16, (uint32_t)dev->raster_grid);
+  // ---- phase 5: visibility-first (k_cover + k_shade) when every queued draw qualifies, else the immediate k_raster
+  bool deferred = !dev->force_immediate;
+  for (const RasterParams& r : dev->pending)
+    deferred = deferred && r.early_z && r.bs_program == SLV_BS_REPLACE && !r.has_centroid && r.ps_program != SLV_PS_DISCARD_ALL &&
+               !r.color1.data && (!r.color0.data || r.color0.bpp == 4);
   bool ok = false;
-  switch (dev->batch_S) {
-  case 1: ok = launch_raster_s<1>(first, dev->d_batch, n, blocks, st); break;
-  case 2: ok = launch_raster_s<2>(first, dev->d_batch, n, blocks, st); break;
-  case 4: ok = launch_raster_s<4>(first, dev->d_batch, n, blocks, st); break;
+  if (deferred) {
+    const bool shade = first.color0.data != nullptr;
+    if (shade) {
+      const size_t need = (size_t)first.color0.w * first.color0.h * dev->batch_S;
+      if (need > dev->vis_cap) {
+        CU(cudaStreamSynchronize(st));
+        if (dev->vis) CU(cudaFree(dev->vis));
+        CU(cudaMalloc(&dev->vis, need * sizeof(uint32_t)));
+        dev->vis_cap = need;
+      }
+    }
+    uint32_t* vis = shade ? dev->vis : nullptr;
+    const uint32_t cblocks = std::min<uint32_t>(n_tiles * 16, (uint32_t)dev->cover_grid);
+    const uint32_t sblocks = std::min<uint32_t>(n_tiles * 16, (uint32_t)dev->shade_grid);
+    switch (dev->batch_S) {
+    case 1: k_cover<1><<<cblocks, RASTER_THREADS, 0, st>>>(first, dev->d_batch, vis, first.color0.w); ok = true; break;
+    case 2: k_cover<2><<<cblocks, RASTER_THREADS, 0, st>>>(first, dev->d_batch, vis, first.color0.w); ok = true; break;
+    case 4: k_cover<4><<<cblocks, RASTER_THREADS, 0, st>>>(first, dev->d_batch, vis, first.color0.w); ok = true; break;
+    }
+    if (ok && shade) {
+      switch (dev->batch_S) {
+      case 1: ok = launch_shade_s<1>(first, dev->d_batch, vis, dev->work_counter + 1, sblocks, st); break;
+      case 2: ok = launch_shade_s<2>(first, dev->d_batch, vis, dev->work_counter + 1, sblocks, st); break;
+      case 4: ok = launch_shade_s<4>(first, dev->d_batch, vis, dev->work_counter + 1, sblocks, st); break;
+      }
+      dev->n_launches += 1;
+    }
+  } else {
+    const uint32_t blocks = std::min<uint32_t>(n_tiles * 16, (uint32_t)dev->raster_grid);
+    switch (dev->batch_S) {
+    case 1: ok = launch_raster_s<1>(first, dev->d_batch, n, blocks, st); break;
+    case 2: ok = launch_raster_s<2>(first, dev->d_batch, n, blocks, st); break;
+    case 4: ok = launch_raster_s<4>(first, dev->d_batch, n, blocks, st); break;
+    }
   }
   dev->n_launches += 4;
   if (dev->profile) {
@@ -300,17 +353,21 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   CU(cudaStreamCreateWithFlags(&dev->own_stream, cudaStreamNonBlocking));
   dev->stream = dev->own_stream;
   CU(cudaMalloc(&dev->overflow_flag, sizeof(uint32_t)));
-  CU(cudaMalloc(&dev->work_counter, sizeof(uint32_t)));
+  CU(cudaMalloc(&dev->work_counter, 2 * sizeof(uint32_t)));
   {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, ordinal));
     dev->raster_grid = prop.multiProcessorCount * RASTER_CTAS_PER_SM;
+    dev->cover_grid = prop.multiProcessorCount * SLV_COVER_CTAS_PER_SM;
+    dev->shade_grid = prop.multiProcessorCount * SLV_SHADE_CTAS_PER_SM;
   }
   CU(cudaMemsetAsync(dev->overflow_flag, 0, sizeof(uint32_t), dev->stream));
   CU(cudaMalloc(&dev->d_stats, 16 * sizeof(unsigned long long)));
   CU(cudaMemsetAsync(dev->d_stats, 0, 16 * sizeof(unsigned long long), dev->stream));
   const char* prof = getenv("SLV_PROFILE");
   dev->profile = prof && prof[0] == '1';
+  const char* fi = getenv("SLV_FORCE_IMMEDIATE");
+  dev->force_immediate = fi && fi[0] == '1';
   for (auto& ev : dev->user_ev) CU(cudaEventCreate(&ev));
   CU(cudaMalloc(&dev->d_batch, MAX_BATCH * sizeof(RasterParams)));
 
@@ -334,6 +391,7 @@ void slv_device_destroy(slv_device dev) {
   cudaFree(dev->tile_cursor);
   cudaFree(dev->active_tiles);
   cudaFree(dev->work_counter);
+  cudaFree(dev->vis);
   cudaFree(dev->list);
   cudaFree(dev->overflow_flag);
   cudaFree(dev->d_stats);

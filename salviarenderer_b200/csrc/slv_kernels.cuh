@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint3
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { s_carry = 0; s_active = 0; *work_counter = 0; }
+  if (tid == 0) { s_carry = 0; s_active = 0; work_counter[0] = 0; work_counter[1] = 0; }
   __syncthreads();
   for (uint32_t base = 0; base < n_tiles; base += 1024) {
     const uint32_t i = base + tid;
@@ -624,7 +624,7 @@ __device__ __forceinline__ float4 interp_attr(const float4* rec, int R, int reg,
   return r;
 }
 
-struct PixelCtx {  // what a pixel shader may read
+struct PixelCtx {  // what a pixel shader may read (immediate path: the four lanes of a quad run together)
   const float4* rec;
   int R;
   const uint32_t* mods;
@@ -634,20 +634,27 @@ struct PixelCtx {  // what a pixel shader may read
   __device__ __forceinline__ float4 attr(int i) const {
     return interp_attr(rec, R, 1 + i, mods[i], dx, dy, odd_x, odd_y, centroid_path, pdx, pdy, inv_w);
   }
+  // .xy of attribute register i (value `a` on this lane) at pixels 0, 1, 2 of the quad: shuffled from the quad's lanes
+  // (all 32 lanes converge here)
+  __device__ __forceinline__ void quad_xy(int, float4 a, float& u0, float& v0, float& u1, float& v1, float& u2, float& v2) const {
+    u0 = __shfl_sync(0xFFFFFFFFu, a.x, quad_base); v0 = __shfl_sync(0xFFFFFFFFu, a.y, quad_base);
+    u1 = __shfl_sync(0xFFFFFFFFu, a.x, quad_base + 1); v1 = __shfl_sync(0xFFFFFFFFu, a.y, quad_base + 1);
+    u2 = __shfl_sync(0xFFFFFFFFu, a.x, quad_base + 2); v2 = __shfl_sync(0xFFFFFFFFu, a.y, quad_base + 2);
+  }
 };
 
 // cpp_pixel_shader::tex2d (cpp_pixel_shader.cpp:13-31): ddx = q1 - q0, ddy = q2 - q0 for the whole quad,
-// LOD once per quad; computed redundantly by the four lanes from shuffled values (all 32 lanes converge here)
-__device__ __forceinline__ float4 ps_tex2d(const SamplerRef& sm, const PixelCtx& px, float4 a) {
-  float u0 = __shfl_sync(0xFFFFFFFFu, a.x, px.quad_base), v0 = __shfl_sync(0xFFFFFFFFu, a.y, px.quad_base);
-  float u1 = __shfl_sync(0xFFFFFFFFu, a.x, px.quad_base + 1), v1 = __shfl_sync(0xFFFFFFFFu, a.y, px.quad_base + 1);
-  float u2 = __shfl_sync(0xFFFFFFFFu, a.x, px.quad_base + 2), v2 = __shfl_sync(0xFFFFFFFFu, a.y, px.quad_base + 2);
+// LOD once per quad (computed redundantly by the lanes of the quad)
+template <class Ctx>
+__device__ __forceinline__ float4 ps_tex2d(const SamplerRef& sm, const Ctx& px, int reg, float4 a) {
+  float u0, v0, u1, v1, u2, v2;
+  px.quad_xy(reg, a, u0, v0, u1, v1, u2, v2);
   float lod = calc_lod_2d(sm, u1 - u0, v1 - v0, u2 - u0, v2 - v0);
   return sample_impl(sm, a.x, a.y, lod, nullptr);
 }
 
-template <int PS>
-__device__ __forceinline__ bool run_ps(const RasterParams& p, const PixelCtx& px, float4& color) {
+template <int PS, class Ctx>
+__device__ __forceinline__ bool run_ps(const RasterParams& p, const Ctx& px, float4& color) {
   if (PS == SLV_PS_ATTR0_COLOR) {
     color = px.attr(0);
     return true;
@@ -683,16 +690,15 @@ __device__ __forceinline__ bool run_ps(const RasterParams& p, const PixelCtx& px
   if (PS == SLV_PS_TEX_ALPHA) {  // TextureAndBlending.cpp:96-166
     auto u = reinterpret_cast<const slv_ps_tex_alpha_uniforms*>(p.ps_uniforms);
     float4 a = px.attr((int)u->reg);
-    color = ps_tex2d(p.sampler0, px, a);
+    color = ps_tex2d(p.sampler0, px, (int)u->reg, a);
     color.w = u->alpha;
     return true;
   }
   if (PS == SLV_PS_TEX_GRAD_ALPHA) {  // SASL tex2D == sample_2d_grad with the quad derivatives
     auto u = reinterpret_cast<const slv_ps_tex_alpha_uniforms*>(p.ps_uniforms);
     float4 a = px.attr((int)u->reg);
-    float u0 = __shfl_sync(0xFFFFFFFFu, a.x, px.quad_base), v0 = __shfl_sync(0xFFFFFFFFu, a.y, px.quad_base);
-    float u1 = __shfl_sync(0xFFFFFFFFu, a.x, px.quad_base + 1), v1 = __shfl_sync(0xFFFFFFFFu, a.y, px.quad_base + 1);
-    float u2 = __shfl_sync(0xFFFFFFFFu, a.x, px.quad_base + 2), v2 = __shfl_sync(0xFFFFFFFFu, a.y, px.quad_base + 2);
+    float u0, v0, u1, v1, u2, v2;
+    px.quad_xy((int)u->reg, a, u0, v0, u1, v1, u2, v2);
     color = sample_2d_grad(p.sampler0, a.x, a.y, u1 - u0, v1 - v0, u2 - u0, v2 - v0, 0.0f);
     color.w = u->alpha;
     return true;
@@ -701,7 +707,7 @@ __device__ __forceinline__ bool run_ps(const RasterParams& p, const PixelCtx& px
     auto u = reinterpret_cast<const slv_ps_sponza_uniforms*>(p.ps_uniforms);
     float4 diff = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
     float4 uv = px.attr(0);
-    if (u->has_sampler) diff = ps_tex2d(p.sampler0, px, uv);
+    if (u->has_sampler) diff = ps_tex2d(p.sampler0, px, 0, uv);
     float4 n = px.attr(1), l = px.attr(2);
     float nl = length3(n.x, n.y, n.z);
     if (eq_eps(nl, 0.0f)) nl = 1.0f;

@@ -385,8 +385,8 @@ class TextureAndBlending:
     box twice (cull front, cull back) with lerp(dst, src, 0.5); color target bgra8; trilinear samplers."""
 
     def __init__(self, w=1920, h=1080, samples=1, ps_program=A.PS_TEX_ALPHA, mip_filter=A.FILTER_LINEAR,
-                 max_aniso=0):
-        self.w, self.h, self.samples = w, h, samples
+                 max_aniso=0, boxes=True):
+        self.w, self.h, self.samples, self.boxes = w, h, samples, boxes
         self.ps_program, self.mip_filter, self.max_aniso = ps_program, mip_filter, max_aniso
         self.plane = create_planar((-3.0, -1.0, -3.0), (6, 0, 0), (0, 0, 6), 1, 1, True)
         box = create_box()
@@ -429,7 +429,7 @@ class TextureAndBlending:
         d.bs = A.shader_binding(A.BS_REPLACE)
         be.draw(d)
 
-        for cull in (A.CULL_FRONT, A.CULL_BACK):
+        for cull in ((A.CULL_FRONT, A.CULL_BACK) if self.boxes else ()):
             d = base_desc(t, self.w, self.h, cull=cull)
             self.box.fill_desc(be, d)
             d.vs = A.shader_binding(A.VS_MVP_PASSTHROUGH, pack_vs_mvp_passthrough(wvp, [0, 1]))

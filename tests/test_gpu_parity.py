@@ -142,3 +142,75 @@ def test_full_size_antialiasing_1080p_msaa4(cuda, oracle):
     a.setup(cuda)
     b.setup(oracle)
     assert not cases.compare_frames(a.run(cuda, 2), b.run(oracle, 2), color_tol=COLOR_TOL_LSB)
+
+
+@pytest.fixture(scope="module")
+def cuda_immediate(built):
+    """A second device of the product with the visibility-first path disabled (k_raster for every batch)."""
+    import salviarenderer_b200 as pkg
+    os.environ["SLV_FORCE_IMMEDIATE"] = "1"
+    try:
+        be = pkg.load(0)
+    finally:
+        del os.environ["SLV_FORCE_IMMEDIATE"]
+    return be
+
+
+def _soup(**kw):
+    return lambda: S.TriangleSoup(bs=A.BS_REPLACE, **kw)
+
+
+# batches that qualify for the visibility-first path (early-Z, REPLACE blend, no discard, no centroid)
+DEFERRED_CASES = {
+    "c1_800x600": (lambda: S.ColorizedTriangle(800, 600, 1), (0, 3)),
+    "c3a_800x600x4": (lambda: S.ColorizedTriangle(800, 600, 4), (1, 4)),
+    "c3a_402x300x2": (lambda: S.ColorizedTriangle(404, 300, 2), (2,)),
+    "c4_480x272x4": (lambda: S.SponzaLike(480, 272, 4, tex_size=128), (0, 5)),
+    "c4_960x540x1": (lambda: S.SponzaLike(960, 540, 1, tex_size=256), (3,)),
+    "c4_1280x720x2": (lambda: S.SponzaLike(1280, 720, 2, tex_size=64), (7,)),
+    "soup_s1": (_soup(samples=1, seed=8), (0,)),
+    "soup_s2_back": (_soup(samples=2, cull=A.CULL_BACK, seed=9), (0,)),
+    "soup_s4_front": (_soup(samples=4, cull=A.CULL_FRONT, seed=11), (0,)),
+    "soup_strip_s4": (_soup(samples=4, strip=True, n=500), (0,)),
+    "soup_small_u32": (_soup(samples=1, index_dtype=np.uint32, n=2000, size=0.2, w=512, h=512), (0,)),
+    "soup_small_s4": (_soup(samples=4, n=4000, size=0.05, w=640, h=448, seed=21), (0,)),
+    "soup_odd_target": (_soup(samples=1, n=3000, size=0.1, w=1000, h=600), (0,)),
+    "soup_odd_target_s4": (_soup(samples=4, n=1500, size=0.3, w=1000, h=600, seed=5), (0,)),
+    "soup_noperspective_s4": (_soup(samples=4, modifiers=[A.AM_NOPERSPECTIVE]), (0,)),
+    "soup_nointerpolation_s2": (_soup(samples=2, modifiers=[A.AM_NOINTERPOLATION]), (0,)),
+    "soup_nodepth_s4": (_soup(samples=4, ds=A.depth_stencil_desc(depth_enable=False)), (0,)),
+    "soup_nodepthwrite_s4": (_soup(samples=4, ds=A.depth_stencil_desc(depth_write=False)), (0,)),
+    "soup_bgra8_s2": (_soup(samples=2, color_fmt=A.PF_BGRA8, seed=13), (0,)),
+    "tex_plane_only": (lambda: S.TextureAndBlending(640, 360, boxes=False), (0, 2)),
+    "tex_plane_only_aniso16_s4": (lambda: S.TextureAndBlending(640, 360, samples=4, boxes=False, ps_program=A.PS_TEX_GRAD_ALPHA,
+                                                                mip_filter=A.FILTER_ANISOTROPIC, max_aniso=16), (1,)),
+    "tex_plane_only_pointmip": (lambda: S.TextureAndBlending(320, 180, boxes=False, mip_filter=A.FILTER_POINT), (3,)),
+}
+for _fn in range(8):
+    DEFERRED_CASES[f"soup_depthfunc{_fn}_s4"] = (_soup(samples=4, ds=A.depth_stencil_desc(depth_func=_fn)), (0,))
+
+
+@pytest.mark.parametrize("name", list(DEFERRED_CASES))
+def test_deferred_equals_immediate(cuda, cuda_immediate, name):
+    """k_cover + k_shade (visibility-first) against k_raster (immediate) on batches that qualify for both:
+    every buffer, the pipeline counters and the algorithmic traffic counters must be identical."""
+    mk, frames = DEFERRED_CASES[name]
+    a, b = mk(), mk()
+    a.setup(cuda)
+    b.setup(cuda_immediate)
+    for f in frames:
+        ra, rb = a.run(cuda, f), b.run(cuda_immediate, f)
+        msgs = cases.compare_frames(ra, rb)
+        assert not msgs, f"{name} frame {f}: {msgs}"
+        ta, tb = cuda.traffic(), cuda_immediate.traffic()
+        for k in ("z_tested", "z_written", "c_written", "c_read"):
+            assert ta[k] == tb[k], f"{name} frame {f}: traffic counter {k}: {ta[k]} vs {tb[k]}"
+        assert ra.stats["ps_invocations"] > 0 or "depthfunc0" in name
+
+
+def test_deferred_full_size_sponza_equals_immediate(cuda, cuda_immediate):
+    a, b = S.SponzaLike(3840, 2160, 4, tex_size=256), S.SponzaLike(3840, 2160, 4, tex_size=256)
+    a.setup(cuda)
+    b.setup(cuda_immediate)
+    for f in (0, 6):
+        assert not cases.compare_frames(a.run(cuda, f), b.run(cuda_immediate, f))
