@@ -634,6 +634,11 @@ slv_result slv_profile_get(slv_device dev, slv_pipeline_profiles* out) {
   return SLV_OK;
 }
 
+slv_result slv_profile_get_stages(slv_device, double* ms, uint32_t n) {
+  if (!ms || n < 5) return SLV_INVALID_PARAMETER;
+  for (uint32_t i = 0; i < n; ++i) ms[i] = 0.0;
+  return SLV_OK;
+}
 slv_result slv_set_tile_shard(slv_device, uint32_t rank, uint32_t nranks) {
   return (rank == 0 && nranks == 1) ? SLV_OK : SLV_FAILED;  // the reference is single-process
 }

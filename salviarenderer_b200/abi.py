@@ -133,7 +133,7 @@ ENTRY_POINTS = [
     "slv_query_begin", "slv_query_get", "slv_sampler_probe",
     "slv_set_tile_shard", "slv_profile_get",
     "slv_traffic_get", "slv_kernel_launch_count", "slv_event_record", "slv_event_elapsed_ms", "slv_profile_enable",
-    "slv_texture_device_ptr", "slv_pack_tiles", "slv_unpack_tiles", "slv_set_stream",
+    "slv_texture_device_ptr", "slv_pack_tiles", "slv_unpack_tiles", "slv_set_stream", "slv_profile_get_stages",
 ]
 
 
@@ -239,6 +239,7 @@ class Backend:
         L.slv_texture_device_ptr.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.slv_pack_tiles.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_size_t)]
         L.slv_unpack_tiles.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.slv_profile_get_stages.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_uint32]
         self.name = L.slv_backend_name().decode()
         if L.slv_abi_version() != 1:
             raise SlvError("ABI version mismatch")
@@ -381,6 +382,12 @@ class Backend:
         p = PipelineProfiles()
         _chk(self.lib.slv_profile_get(self.dev, C.byref(p)), "slv_profile_get")
         return p.as_dict()
+
+    def profile_stages(self) -> dict:
+        """Event time per kernel stage of the product since query_begin, in milliseconds."""
+        ms = (C.c_double * 5)()
+        _chk(self.lib.slv_profile_get_stages(self.dev, ms, 5), "slv_profile_get_stages")
+        return dict(zip(("geometry", "bin", "sort", "raster_or_cover", "shade"), (float(v) for v in ms)))
 
     def texture_ptr(self, tex: Texture, level: int = 0):
         p, n = C.c_void_p(), C.c_size_t()

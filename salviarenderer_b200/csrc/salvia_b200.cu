@@ -75,7 +75,9 @@ struct slv_device_t {
   // frame runs at the next flush point (readback, clear, resolve, state that changes the targets ...), so each
   // pixel's depth/stencil/colour is loaded once and stored once per batch instead of once per draw.
   std::vector<RasterParams> pending;
+  std::vector<GeomParams> pending_geom;  // geometry parameters of the queued draws (same index as `pending`)
   RasterParams* d_batch = nullptr;
+  GeomParams* d_geom = nullptr;
   size_t tris_used = 0;      // float4 units used by the queued draws
   uint64_t slots_queued = 0; // triangle slots of the queued draws (sizes the list arena)
   uint32_t batch_S = 0;
@@ -97,7 +99,7 @@ struct slv_device_t {
   cudaEvent_t user_ev[16] = {};
   uint32_t* tile_slot = nullptr;  // pack/unpack: dense slot of every owned tile
   uint32_t tile_slot_cap = 0;
-  double prof_ms[4] = {0, 0, 0, 0};  // geometry, binning, sort, raster
+  double prof_ms[5] = {0, 0, 0, 0, 0};  // geometry, binning, sort, raster (k_raster or k_cover), shade (k_shade)
   unsigned long long n_launches = 0;
 
   Resource* get(slv_handle h, Resource::Kind k) {
@@ -118,7 +120,7 @@ struct slv_device_t {
 
 namespace {
 
-constexpr uint32_t MAX_BATCH = 64;  // draws whose raster pass is fused into one k_raster launch
+constexpr uint32_t MAX_BATCH = MAX_BATCH_DRAWS;  // draws whose geometry / raster passes are fused into one launch each
 
 slv_result flush_batch(slv_device dev);
 
@@ -188,9 +190,8 @@ uint32_t vs_num_attrs(const slv_shader_binding& vs) {
 }
 
 template <int R>
-void launch_geometry(const GeomParams& gp, cudaStream_t st) {
-  uint32_t blocks = (gp.prim_count + 127) / 128;
-  k_geometry<R><<<blocks, 128, 0, st>>>(gp);
+void launch_geometry(const GeomParams* d_draws, const GeomBatch& hb, cudaStream_t st) {
+  k_geometry<R><<<hb.cta_prefix[hb.n], 128, 0, st>>>(d_draws, hb);
 }
 
 template <int S>
@@ -253,6 +254,29 @@ slv_result flush_batch(slv_device dev) {
   bp.list = dev->list;
   bp.list_capacity = dev->list_cap;
   bp.overflow_flag = dev->overflow_flag;
+  // ---- geometry of every queued draw: one launch per distinct register count (normally one)
+  CU(cudaMemcpyAsync(dev->d_geom, dev->pending_geom.data(), n * sizeof(GeomParams), cudaMemcpyHostToDevice, st));
+  size_t eg0 = dev->profile ? mark(dev) : 0;
+  for (uint32_t R = 1; R <= (uint32_t)MAX_REGS; ++R) {
+    GeomBatch hb{};
+    for (uint32_t i = 0; i < n; ++i) {
+      if (1 + dev->pending_geom[i].n_attrs != R) continue;
+      hb.draw_of[hb.n] = i;
+      hb.cta_prefix[hb.n + 1] = hb.cta_prefix[hb.n] + (dev->pending_geom[i].prim_count + 127) / 128;
+      ++hb.n;
+    }
+    if (!hb.n) continue;
+    switch (R) {
+    case 1: launch_geometry<1>(dev->d_geom, hb, st); break;
+    case 2: launch_geometry<2>(dev->d_geom, hb, st); break;
+    case 3: launch_geometry<3>(dev->d_geom, hb, st); break;
+    case 4: launch_geometry<4>(dev->d_geom, hb, st); break;
+    case 5: launch_geometry<5>(dev->d_geom, hb, st); break;
+    default: launch_geometry<6>(dev->d_geom, hb, st); break;
+    }
+    dev->n_launches += 1;
+  }
+  if (dev->profile) dev->spans.push_back({eg0, mark(dev), 0});
   size_t e0 = dev->profile ? mark(dev) : 0;
   k_scan_tiles<<<1, 1024, 0, st>>>(dev->tile_count, dev->tile_offset, dev->tile_cursor, n_tiles, dev->active_tiles,
                                     dev->work_counter);
@@ -266,6 +290,7 @@ slv_result flush_batch(slv_device dev) {
     deferred = deferred && r.early_z && r.bs_program == SLV_BS_REPLACE && !r.has_centroid && r.ps_program != SLV_PS_DISCARD_ALL &&
                !r.color1.data && (!r.color0.data || r.color0.bpp == 4);
   bool ok = false;
+  size_t e_mid = (size_t)-1;
   if (deferred) {
     const bool shade = first.color0.data != nullptr;
     if (shade) {
@@ -286,6 +311,7 @@ slv_result flush_batch(slv_device dev) {
     case 4: k_cover<4><<<cblocks, RASTER_THREADS, 0, st>>>(first, dev->d_batch, vis, first.color0.w); ok = true; break;
     }
     if (ok && shade) {
+      if (dev->profile) e_mid = mark(dev);
       switch (dev->batch_S) {
       case 1: ok = launch_shade_s<1>(first, dev->d_batch, vis, dev->work_counter + 1, sblocks, st); break;
       case 2: ok = launch_shade_s<2>(first, dev->d_batch, vis, dev->work_counter + 1, sblocks, st); break;
@@ -306,9 +332,15 @@ slv_result flush_batch(slv_device dev) {
     size_t e3 = mark(dev);
     dev->spans.push_back({e0, e1, 1});
     dev->spans.push_back({e1, e2, 2});
-    dev->spans.push_back({e2, e3, 3});
+    if (e_mid != (size_t)-1) {
+      dev->spans.push_back({e2, e_mid, 3});
+      dev->spans.push_back({e_mid, e3, 4});
+    } else {
+      dev->spans.push_back({e2, e3, 3});
+    }
   }
   dev->pending.clear();
+  dev->pending_geom.clear();
   dev->tris_used = 0;
   dev->slots_queued = 0;
   if (!ok) return SLV_INVALID_PARAMETER;
@@ -370,6 +402,7 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   dev->force_immediate = fi && fi[0] == '1';
   for (auto& ev : dev->user_ev) CU(cudaEventCreate(&ev));
   CU(cudaMalloc(&dev->d_batch, MAX_BATCH * sizeof(RasterParams)));
+  CU(cudaMalloc(&dev->d_geom, MAX_BATCH * sizeof(GeomParams)));
 
   *out = dev;
   return SLV_OK;
@@ -398,6 +431,7 @@ void slv_device_destroy(slv_device dev) {
   for (auto& ev : dev->ev_pool) cudaEventDestroy(ev);
   for (auto& ev : dev->user_ev) cudaEventDestroy(ev);
   cudaFree(dev->d_batch);
+  cudaFree(dev->d_geom);
 
   cudaFree(dev->tile_slot);
   cudaStreamDestroy(dev->own_stream);
@@ -738,21 +772,9 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
     }
   }
 
-  // ---- geometry of this draw now (it also accumulates the per-tile counts); binning + raster at the flush
-  cudaStream_t st = dev->stream;
-  size_t e0 = dev->profile ? mark(dev) : 0;
-  switch (R) {
-  case 1: launch_geometry<1>(gp, st); break;
-  case 2: launch_geometry<2>(gp, st); break;
-  case 3: launch_geometry<3>(gp, st); break;
-  case 4: launch_geometry<4>(gp, st); break;
-  case 5: launch_geometry<5>(gp, st); break;
-  default: launch_geometry<6>(gp, st); break;
-  }
-  if (dev->profile) dev->spans.push_back({e0, mark(dev), 0});
-  dev->n_launches += 1;
-  CU(cudaGetLastError());
+  // ---- queue the draw: geometry, binning and the raster pass all run at the next flush point
   dev->pending.push_back(rp);
+  dev->pending_geom.push_back(gp);
   dev->batch_S = S;
   dev->tris_used += tris_need;
   dev->slots_queued += n_slots;
@@ -883,7 +905,16 @@ slv_result slv_profile_get(slv_device dev, slv_pipeline_profiles* out) {
   memset(out, 0, sizeof(*out));
   out->clipping = (uint64_t)(dev->prof_ms[0] * 1e6);      // VS + clip + viewport + setup are one kernel
   out->tri_dispatch = (uint64_t)((dev->prof_ms[1] + dev->prof_ms[2]) * 1e6);
-  out->ras = (uint64_t)(dev->prof_ms[3] * 1e6);
+  out->ras = (uint64_t)((dev->prof_ms[3] + dev->prof_ms[4]) * 1e6);
+  return SLV_OK;
+}
+
+slv_result slv_profile_get_stages(slv_device dev, double* ms, uint32_t n) {
+  if (!dev || !ms || n < 5) return SLV_INVALID_PARAMETER;
+  slv_pipeline_profiles tmp;
+  slv_result rc = slv_profile_get(dev, &tmp);  // folds the pending event spans
+  if (rc != SLV_OK) return rc;
+  for (uint32_t i = 0; i < 5; ++i) ms[i] = dev->prof_ms[i];
   return SLV_OK;
 }
 

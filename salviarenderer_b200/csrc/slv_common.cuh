@@ -69,6 +69,14 @@ struct GeomParams {
   unsigned long long* stats;  // slv_pipeline_statistics as 9 x u64
 };
 
+// geometry of all queued draws in ONE launch: CTA b works on draw draw_of[g] where cta_prefix[g] <= b < cta_prefix[g+1]
+constexpr uint32_t MAX_BATCH_DRAWS = 64;
+struct GeomBatch {
+  uint32_t n;
+  uint32_t cta_prefix[MAX_BATCH_DRAWS + 1];
+  uint32_t draw_of[MAX_BATCH_DRAWS];
+};
+
 // triangle record (float4 units): [0..2] edge A,B,C,0  [3] bbox xmin,xmax,ymin,ymax
 // [4] misc: x = as_uint(valid | front<<1), y = sx | ex<<16, z = sy | ey<<16 (tile range), w = draw id in the batch
 // [5 .. 5+R) v0 regs   [5+R .. 5+2R) ddx regs   [5+2R .. 5+3R) ddy regs, R = 1 + n_attrs

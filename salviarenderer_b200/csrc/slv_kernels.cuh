@@ -1,6 +1,6 @@
 // slv_kernels.cuh — the sm_100a kernels of the draw pipeline.
 //
-//   k_geometry      one thread per input primitive: index fetch, vertex fetch, vertex shader, near/far
+//   k_geometry      one launch per batch (all queued draws), one thread per input primitive: index fetch, vertex fetch, vertex shader, near/far
 //                   clip, cull, fan, viewport+project, triangle setup, 64x64 tile coverage count.
 //                   (reference phases 1-4: geom_setup_engine.cpp:43-124, clipper.cpp:43-228,
 //                   shader.cpp:499-511, rasterizer.cpp:864-945, 775-862)
@@ -268,8 +268,15 @@ __device__ __forceinline__ void setup_triangle(const GeomParams& p, const VsOut<
 }
 
 template <int R>
-__global__ void __launch_bounds__(128) k_geometry(GeomParams p) {
-  uint32_t prim = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_geometry(const GeomParams* __restrict__ draws, GeomBatch hb) {
+  // every queued draw with R registers shares this launch; a CTA belongs to exactly one draw
+  uint32_t lo = 0, hi = hb.n;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (blockIdx.x >= hb.cta_prefix[mid]) lo = mid; else hi = mid;
+  }
+  const GeomParams& p = draws[hb.draw_of[lo]];
+  uint32_t prim = (blockIdx.x - hb.cta_prefix[lo]) * blockDim.x + threadIdx.x;
   uint32_t n_out = 0;
   if (prim < p.prim_count) {
     // ---- index fetch (index_fetcher.cpp:26-115)
