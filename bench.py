@@ -250,38 +250,61 @@ def main():
         frame_e2e(i)
     e2e_ms = timed(frame_e2e, args.steps) / args.steps
 
-    # ---- roofline of the dominant kernel (k_raster): per-stage CUDA events on the launching stream ----
+    # ---- roofline: per-stage CUDA events on the launching stream, algorithmic bytes from exact counters ----
     be.profile_enable(True)
     be.query_begin()
     for i in range(args.steps):
         frame(i)
     be.flush()
-    prof = be.profile_get()
+    stages = be.profile_stages()
     traffic = be.traffic()
     st2 = be.query_get()
     be.profile_enable(False)
-    raster_ms = prof["ras"] / 1e6 / args.steps
-    geom_ms = prof["clipping"] / 1e6 / args.steps
-    bin_ms = prof["tri_dispatch"] / 1e6 / args.steps
+    K = args.steps
+    cover_ms, shade_ms = stages["raster_or_cover"] / K, stages["shade"] / K
+    geom_ms, bin_ms, sort_ms = stages["geometry"] / K, stages["bin"] / K, stages["sort"] / K
     R = 5  # position + 4 attributes (VS_SPONZA)
-    b_frag = 8 * traffic["z_tested"] + 8 * traffic["z_written"] + 4 * traffic["c_written"] + 4 * traffic["c_read"]
-    b_setup = st2["cprimitives"] * 3 * 16 * R
-    b_tex = 24 * sum((args.tex_size >> l) ** 2 * 4 for l in range(args.tex_size.bit_length())) * args.steps
-    b_alg_raster = (b_frag + b_setup + b_tex) / args.steps  # bytes per frame, over the 24 k_raster launches
+    S, W, H = args.samples, args.width, args.height
+    vstride, n_prims = 48, 262249
+    n_unique = len(np.unique(ib_np))
+    # B_alg = B_clear + B_geom + B_frag + B_tex + B_resolve (per frame)
+    b_clear = W * H * S * (4 + 8)
+    b_geom = n_prims * 3 * 4 + n_unique * vstride + n_unique * 16 * R
+    b_setup = st2["cprimitives"] / K * 3 * 16 * R
+    b_depth = (8 * traffic["z_tested"] + 8 * traffic["z_written"]) / K
+    b_color = (4 * traffic["c_written"] + 4 * traffic["c_read"]) / K
+    b_tex = 24 * sum(max(args.tex_size >> l, 1) ** 2 * 4 for l in range(args.tex_size.bit_length()))
+    b_resolve = W * H * 4 * (S + 1) if S > 1 else 0
+    b_frame = b_clear + b_geom + b_setup + b_depth + b_color + b_tex + b_resolve
     peak, peak_src = peaks()
-    achieved = b_alg_raster / (raster_ms * 1e-3) / 1e9 if raster_ms > 0 else 0.0
+    kernels = {  # algorithmic bytes per launch (one launch per frame) and measured launch time
+        "k_cover": {"bytes": b_depth + b_setup, "ms": cover_ms,
+                    "what": "8 B per depth-tested sample + 8 B per depth-written sample + one read of every emitted triangle's setup"},
+        "k_shade": {"bytes": b_color + b_tex, "ms": shade_ms,
+                    "what": "4 B per colour-written sample (+4 B per blended read) + the bound textures' mip chains once"},
+    }
+    for v in kernels.values():
+        v["achieved_gbs"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0
+        v["frac"] = v["achieved_gbs"] / peak
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])
     traffic_measured = None
-    tpath = os.path.join(ROOT, "profiles", "r01_raster_dram_bytes.json")
+    tpath = os.path.join(ROOT, "profiles", "dram_bytes.json")
     if os.path.exists(tpath):
-        traffic_measured = json.load(open(tpath)).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "k_raster<4, PS_SPONZA>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic_measured, "peak_source": peak_src,
-                "algorithmic_bytes_per_frame": b_alg_raster, "algorithmic_bytes_per_launch": b_alg_raster / 24,
-                "launches_per_frame": 24, "kernel_ms_per_frame": raster_ms, "kernel_ms_per_launch": raster_ms / 24,
-                "kernel_share_of_step": raster_ms / max(raster_ms + geom_ms + bin_ms, 1e-9),
-                "stage_ms_per_frame": {"geometry": geom_ms, "binning+sort": bin_ms, "raster": raster_ms},
-                "note": "per-stage times from CUDA events around each kernel in a separate profiling pass of the same "
-                        "K frames (events force a sync per draw, so they are not taken inside the headline region)"}
+        traffic_measured = json.load(open(tpath)).get(dom, {}).get("dram_bytes_per_launch")
+    stage_sum = geom_ms + bin_ms + sort_ms + cover_ms + shade_ms
+    roofline = {"bound": "hbm", "kernel": dom + f"<{S}>" if dom == "k_cover" else dom + f"<{S}, PS_SPONZA>",
+                "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac"],
+                "traffic": traffic_measured, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": kernels[dom]["bytes"], "launches_per_frame": 1,
+                "kernel_ms_per_launch": kernels[dom]["ms"], "kernel_share_of_step": kernels[dom]["ms"] / max(stage_sum, 1e-9),
+                "kernels": kernels,
+                "stage_ms_per_frame": {"geometry": geom_ms, "scan+bin_fill": bin_ms, "sort": sort_ms, "cover": cover_ms, "shade": shade_ms},
+                "frame": {"algorithmic_bytes": b_frame, "achieved_gbs": b_frame / (ms_per_step * 1e-3) / 1e9,
+                          "frac": b_frame / (ms_per_step * 1e-3) / 1e9 / peak,
+                          "terms": {"clear": b_clear, "geometry": b_geom, "setup": b_setup, "depth": b_depth, "colour": b_color,
+                                    "texture": b_tex, "resolve": b_resolve}},
+                "note": "kernel times from CUDA events around each kernel (slv_profile_get_stages) in a separate pass over the same "
+                        "K frames; `frame` divides the whole frame's algorithmic bytes (SURVEY 8d) by the headline ms_per_step"}
 
     # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample (rank 0, N == 1) ----
     cpu_baseline = None

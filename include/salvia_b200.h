@@ -289,7 +289,7 @@ slv_result slv_set_stream(slv_device dev, void* cuda_stream);
 /* per-kernel-stage event timing on/off at run time (same data as SLV_PROFILE=1; read with slv_profile_get) */
 slv_result slv_profile_enable(slv_device dev, uint32_t on);
 /* the same event times split by kernel stage of the product, milliseconds since slv_query_begin:
- * ms[0] k_geometry, [1] k_scan_tiles + k_bin_fill, [2] k_sort_lists, [3] k_raster or k_cover, [4] k_shade.  n >= 5.
+ * ms[0] k_geometry, [1] k_scan_tiles + k_bin_fill, [2] k_sort_lists, [3] k_raster or k_cover, [4] k_shade, [5] k_region_bin.  n >= 6.
  * CPU checkers return zeros. */
 slv_result slv_profile_get_stages(slv_device dev, double* ms, uint32_t n);
 /* raw device address of a texture level (product only; CPU checkers return their host address) so the

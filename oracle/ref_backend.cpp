@@ -635,7 +635,7 @@ slv_result slv_profile_get(slv_device dev, slv_pipeline_profiles* out) {
 }
 
 slv_result slv_profile_get_stages(slv_device, double* ms, uint32_t n) {
-  if (!ms || n < 5) return SLV_INVALID_PARAMETER;
+  if (!ms || n < 6) return SLV_INVALID_PARAMETER;
   for (uint32_t i = 0; i < n; ++i) ms[i] = 0.0;
   return SLV_OK;
 }

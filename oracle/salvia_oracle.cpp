@@ -1701,7 +1701,7 @@ slv_result slv_unpack_tiles(slv_device dev, slv_handle h, uint32_t rank, uint32_
 slv_result slv_query_get(slv_device dev, slv_pipeline_statistics* out) { *out = dev->stats; return SLV_OK; }
 slv_result slv_profile_get(slv_device, slv_pipeline_profiles* out) { memset(out, 0, sizeof(*out)); return SLV_OK; }
 slv_result slv_profile_get_stages(slv_device, double* ms, uint32_t n) {
-  if (!ms || n < 5) return SLV_INVALID_PARAMETER;
+  if (!ms || n < 6) return SLV_INVALID_PARAMETER;
   for (uint32_t i = 0; i < n; ++i) ms[i] = 0.0;
   return SLV_OK;
 }

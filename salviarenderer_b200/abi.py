@@ -385,9 +385,9 @@ class Backend:
 
     def profile_stages(self) -> dict:
         """Event time per kernel stage of the product since query_begin, in milliseconds."""
-        ms = (C.c_double * 5)()
-        _chk(self.lib.slv_profile_get_stages(self.dev, ms, 5), "slv_profile_get_stages")
-        return dict(zip(("geometry", "bin", "sort", "raster_or_cover", "shade"), (float(v) for v in ms)))
+        ms = (C.c_double * 6)()
+        _chk(self.lib.slv_profile_get_stages(self.dev, ms, 6), "slv_profile_get_stages")
+        return dict(zip(("geometry", "bin", "sort", "raster_or_cover", "shade", "region_bin"), (float(v) for v in ms)))
 
     def texture_ptr(self, tex: Texture, level: int = 0):
         p, n = C.c_void_p(), C.c_size_t()

@@ -64,12 +64,16 @@ struct slv_device_t {
   // scratch arenas in HBM (grown on demand, never shrunk)
   float4* tris = nullptr;
   size_t tris_cap = 0;  // float4 units
-  uint32_t *tile_count = nullptr, *tile_offset = nullptr, *tile_cursor = nullptr, *active_tiles = nullptr;
-  uint32_t* work_counter = nullptr;  // [0] k_raster / k_cover queue head, [1] k_shade queue head
+  uint32_t *tile_count = nullptr, *tile_offset = nullptr, *tile_cursor = nullptr, *active_tiles = nullptr, *large_tiles = nullptr;
+  uint32_t* work_counter = nullptr;  // [0] k_raster / k_cover queue head, [1] k_shade queue head, [2] region-list cursor
+  uint32_t *region_list = nullptr, *region_offset = nullptr, *region_count = nullptr;  // deferred path: per-region lists
+  uint32_t region_cap = 0;
+  uint32_t* region_mask = nullptr;  // one word per tile-list entry
+  uint8_t* item_flag = nullptr;
   uint32_t* vis = nullptr;           // visibility buffer of the deferred path: owner slot per sample
   size_t vis_cap = 0;                // in uint32 units
   bool force_immediate = false;      // SLV_FORCE_IMMEDIATE=1: always use k_raster (tests compare both paths)
-  int cover_grid = 0, shade_grid = 0;
+  int cover_grid = 0, shade_grid = 0, sm_count = 0;
   int raster_grid = 0;  // persistent raster CTAs (SM count x resident CTAs per SM)
   // ---- draw batching: geometry + binning run at slv_draw time, the raster pass of all queued draws of a
   // frame runs at the next flush point (readback, clear, resolve, state that changes the targets ...), so each
@@ -97,9 +101,9 @@ struct slv_device_t {
   // profiling (SLV_PROFILE=1)
   bool profile = false;
   cudaEvent_t user_ev[16] = {};
-  uint32_t* tile_slot = nullptr;  // pack/unpack: dense slot of every owned tile
-  uint32_t tile_slot_cap = 0;
-  double prof_ms[5] = {0, 0, 0, 0, 0};  // geometry, binning, sort, raster (k_raster or k_cover), shade (k_shade)
+  struct SlotTable { uint32_t tiles_x, tiles_y, rank, nranks, owned; uint32_t* d_slot; };
+  std::vector<SlotTable> slot_tables;  // pack/unpack: dense slot of every owned tile, per (grid, rank, nranks)
+  double prof_ms[6] = {0, 0, 0, 0, 0, 0};  // geometry, binning, sort, raster (k_raster or k_cover), shade, region bin
   unsigned long long n_launches = 0;
 
   Resource* get(slv_handle h, Resource::Kind k) {
@@ -142,13 +146,18 @@ slv_result ensure_scratch(slv_device dev, size_t tris_needed_total, uint32_t n_t
     CU(cudaStreamSynchronize(dev->stream));
     if (dev->tile_count) {
       CU(cudaFree(dev->tile_count)); CU(cudaFree(dev->tile_offset)); CU(cudaFree(dev->tile_cursor));
-      CU(cudaFree(dev->active_tiles));
+      CU(cudaFree(dev->active_tiles)); CU(cudaFree(dev->large_tiles));
+      CU(cudaFree(dev->region_offset)); CU(cudaFree(dev->region_count)); CU(cudaFree(dev->item_flag));
     }
     uint32_t cap = std::max(n_tiles + 1, 4096u);
     CU(cudaMalloc(&dev->tile_count, cap * sizeof(uint32_t)));
     CU(cudaMalloc(&dev->tile_offset, cap * sizeof(uint32_t)));
     CU(cudaMalloc(&dev->tile_cursor, cap * sizeof(uint32_t)));
     CU(cudaMalloc(&dev->active_tiles, (cap + 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&dev->large_tiles, (cap + 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&dev->region_offset, (size_t)cap * 16 * sizeof(uint32_t)));
+    CU(cudaMalloc(&dev->region_count, (size_t)cap * 16 * sizeof(uint32_t)));
+    CU(cudaMalloc(&dev->item_flag, (size_t)cap * 128));
     CU(cudaMemsetAsync(dev->tile_count, 0, cap * sizeof(uint32_t), dev->stream));
     CU(cudaMemsetAsync(dev->tile_cursor, 0, cap * sizeof(uint32_t), dev->stream));
     dev->tiles_cap = cap;
@@ -208,15 +217,13 @@ bool launch_raster_s(const RasterParams& rp, const RasterParams* batch, uint32_t
 }
 
 template <int S>
-bool launch_shade_s(const RasterParams& rp, const RasterParams* batch, const uint32_t* vis, uint32_t* counter, uint32_t blocks,
-                    cudaStream_t st) {
-  const uint32_t pitch = rp.color0.w;
+bool launch_shade_s(const RasterParams& rp, const RasterParams* batch, const DeferredBufs& db, uint32_t blocks, cudaStream_t st) {
   switch (rp.ps_program) {
-  case SLV_PS_ATTR0_COLOR: k_shade<S, SLV_PS_ATTR0_COLOR><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, vis, pitch, counter); return true;
-  case SLV_PS_LIGHTS3: k_shade<S, SLV_PS_LIGHTS3><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, vis, pitch, counter); return true;
-  case SLV_PS_TEX_ALPHA: k_shade<S, SLV_PS_TEX_ALPHA><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, vis, pitch, counter); return true;
-  case SLV_PS_SPONZA: k_shade<S, SLV_PS_SPONZA><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, vis, pitch, counter); return true;
-  case SLV_PS_TEX_GRAD_ALPHA: k_shade<S, SLV_PS_TEX_GRAD_ALPHA><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, vis, pitch, counter); return true;
+  case SLV_PS_ATTR0_COLOR: k_shade<S, SLV_PS_ATTR0_COLOR><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, db); return true;
+  case SLV_PS_LIGHTS3: k_shade<S, SLV_PS_LIGHTS3><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, db); return true;
+  case SLV_PS_TEX_ALPHA: k_shade<S, SLV_PS_TEX_ALPHA><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, db); return true;
+  case SLV_PS_SPONZA: k_shade<S, SLV_PS_SPONZA><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, db); return true;
+  case SLV_PS_TEX_GRAD_ALPHA: k_shade<S, SLV_PS_TEX_GRAD_ALPHA><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, db); return true;
   }
   return false;
 }
@@ -237,6 +244,14 @@ slv_result flush_batch(slv_device dev) {
     if (dev->list) CU(cudaFree(dev->list));
     CU(cudaMalloc(&dev->list, (size_t)list_need * sizeof(uint32_t)));
     dev->list_cap = (uint32_t)list_need;
+    // per-region lists of the deferred path: exact two-pass allocation on the device inside this arena; a triangle
+    // list entry survives in 1..16 regions (about 1.5 on the Sponza-like scene)
+    if (dev->region_list) CU(cudaFree(dev->region_list));
+    const uint64_t rcap = std::min<uint64_t>(2ull * list_need, 0xFFFFFFF0ull);
+    CU(cudaMalloc(&dev->region_list, (size_t)rcap * sizeof(uint32_t)));
+    dev->region_cap = (uint32_t)rcap;
+    if (dev->region_mask) CU(cudaFree(dev->region_mask));
+    CU(cudaMalloc(&dev->region_mask, (size_t)list_need * sizeof(uint32_t)));
   }
   first.list = dev->list;
   first.list_capacity = dev->list_cap;
@@ -279,10 +294,12 @@ slv_result flush_batch(slv_device dev) {
   if (dev->profile) dev->spans.push_back({eg0, mark(dev), 0});
   size_t e0 = dev->profile ? mark(dev) : 0;
   k_scan_tiles<<<1, 1024, 0, st>>>(dev->tile_count, dev->tile_offset, dev->tile_cursor, n_tiles, dev->active_tiles,
-                                    dev->work_counter);
+                                    dev->work_counter, dev->large_tiles);
   k_bin_fill<<<(n_slots + 255) / 256, 256, 0, st>>>(bp);
   size_t e1 = dev->profile ? mark(dev) : 0;
   k_sort_lists<<<n_tiles, 256, 0, st>>>(dev->tile_offset, dev->list, dev->list_cap);
+  k_sort_lists_large<<<dev->sm_count, 1024, SORT_LARGE_SMEM * sizeof(uint32_t), st>>>(dev->tile_offset, dev->list, dev->list_cap,
+                                                                                      dev->large_tiles);
   size_t e2 = dev->profile ? mark(dev) : 0;
   // ---- phase 5: visibility-first (k_cover + k_shade) when every queued draw qualifies, else the immediate k_raster
   bool deferred = !dev->force_immediate;
@@ -290,7 +307,7 @@ slv_result flush_batch(slv_device dev) {
     deferred = deferred && r.early_z && r.bs_program == SLV_BS_REPLACE && !r.has_centroid && r.ps_program != SLV_PS_DISCARD_ALL &&
                !r.color1.data && (!r.color0.data || r.color0.bpp == 4);
   bool ok = false;
-  size_t e_mid = (size_t)-1;
+  size_t e_mid = (size_t)-1, e_rbin = (size_t)-1;
   if (deferred) {
     const bool shade = first.color0.data != nullptr;
     if (shade) {
@@ -302,20 +319,33 @@ slv_result flush_batch(slv_device dev) {
         dev->vis_cap = need;
       }
     }
-    uint32_t* vis = shade ? dev->vis : nullptr;
-    const uint32_t cblocks = std::min<uint32_t>(n_tiles * 16, (uint32_t)dev->cover_grid);
-    const uint32_t sblocks = std::min<uint32_t>(n_tiles * 16, (uint32_t)dev->shade_grid);
+    DeferredBufs db{};
+    db.region_list = dev->region_list;
+    db.region_cap = dev->region_cap;
+    db.region_mask = dev->region_mask;
+    db.region_offset = dev->region_offset;
+    db.region_count = dev->region_count;
+    db.cursor = dev->work_counter + 2;
+    db.overflow_flag = dev->overflow_flag;
+    db.item_flag = dev->item_flag;
+    db.vis = shade ? dev->vis : nullptr;
+    db.vis_pitch = first.color0.w;
+    db.cover_counter = dev->work_counter;
+    db.shade_counter = dev->work_counter + 1;
+    k_region_bin<<<n_tiles, RBIN_THREADS, 0, st>>>(first, db);
+    dev->n_launches += 1;
+    if (dev->profile) e_rbin = mark(dev);
     switch (dev->batch_S) {
-    case 1: k_cover<1><<<cblocks, RASTER_THREADS, 0, st>>>(first, dev->d_batch, vis, first.color0.w); ok = true; break;
-    case 2: k_cover<2><<<cblocks, RASTER_THREADS, 0, st>>>(first, dev->d_batch, vis, first.color0.w); ok = true; break;
-    case 4: k_cover<4><<<cblocks, RASTER_THREADS, 0, st>>>(first, dev->d_batch, vis, first.color0.w); ok = true; break;
+    case 1: k_cover<1><<<dev->cover_grid, DEF_THREADS, 0, st>>>(first, dev->d_batch, db); ok = true; break;
+    case 2: k_cover<2><<<dev->cover_grid, DEF_THREADS, 0, st>>>(first, dev->d_batch, db); ok = true; break;
+    case 4: k_cover<4><<<dev->cover_grid, DEF_THREADS, 0, st>>>(first, dev->d_batch, db); ok = true; break;
     }
     if (ok && shade) {
       if (dev->profile) e_mid = mark(dev);
       switch (dev->batch_S) {
-      case 1: ok = launch_shade_s<1>(first, dev->d_batch, vis, dev->work_counter + 1, sblocks, st); break;
-      case 2: ok = launch_shade_s<2>(first, dev->d_batch, vis, dev->work_counter + 1, sblocks, st); break;
-      case 4: ok = launch_shade_s<4>(first, dev->d_batch, vis, dev->work_counter + 1, sblocks, st); break;
+      case 1: ok = launch_shade_s<1>(first, dev->d_batch, db, dev->shade_grid, st); break;
+      case 2: ok = launch_shade_s<2>(first, dev->d_batch, db, dev->shade_grid, st); break;
+      case 4: ok = launch_shade_s<4>(first, dev->d_batch, db, dev->shade_grid, st); break;
       }
       dev->n_launches += 1;
     }
@@ -327,14 +357,18 @@ slv_result flush_batch(slv_device dev) {
     case 4: ok = launch_raster_s<4>(first, dev->d_batch, n, blocks, st); break;
     }
   }
-  dev->n_launches += 4;
+  dev->n_launches += 5;
   if (dev->profile) {
     size_t e3 = mark(dev);
     dev->spans.push_back({e0, e1, 1});
     dev->spans.push_back({e1, e2, 2});
-    if (e_mid != (size_t)-1) {
-      dev->spans.push_back({e2, e_mid, 3});
+    if (e_rbin != (size_t)-1 && e_mid != (size_t)-1) {
+      dev->spans.push_back({e2, e_rbin, 5});
+      dev->spans.push_back({e_rbin, e_mid, 3});
       dev->spans.push_back({e_mid, e3, 4});
+    } else if (e_rbin != (size_t)-1) {
+      dev->spans.push_back({e2, e_rbin, 5});
+      dev->spans.push_back({e_rbin, e3, 3});
     } else {
       dev->spans.push_back({e2, e3, 3});
     }
@@ -385,11 +419,13 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   CU(cudaStreamCreateWithFlags(&dev->own_stream, cudaStreamNonBlocking));
   dev->stream = dev->own_stream;
   CU(cudaMalloc(&dev->overflow_flag, sizeof(uint32_t)));
-  CU(cudaMalloc(&dev->work_counter, 2 * sizeof(uint32_t)));
+  CU(cudaMalloc(&dev->work_counter, 4 * sizeof(uint32_t)));
   {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, ordinal));
     dev->raster_grid = prop.multiProcessorCount * RASTER_CTAS_PER_SM;
+    dev->sm_count = prop.multiProcessorCount;
+    CU(cudaFuncSetAttribute(k_sort_lists_large, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_LARGE_SMEM * (int)sizeof(uint32_t)));
     dev->cover_grid = prop.multiProcessorCount * SLV_COVER_CTAS_PER_SM;
     dev->shade_grid = prop.multiProcessorCount * SLV_SHADE_CTAS_PER_SM;
   }
@@ -423,8 +459,14 @@ void slv_device_destroy(slv_device dev) {
   cudaFree(dev->tile_offset);
   cudaFree(dev->tile_cursor);
   cudaFree(dev->active_tiles);
+  cudaFree(dev->large_tiles);
   cudaFree(dev->work_counter);
   cudaFree(dev->vis);
+  cudaFree(dev->region_list);
+  cudaFree(dev->region_mask);
+  cudaFree(dev->region_offset);
+  cudaFree(dev->region_count);
+  cudaFree(dev->item_flag);
   cudaFree(dev->list);
   cudaFree(dev->overflow_flag);
   cudaFree(dev->d_stats);
@@ -433,7 +475,7 @@ void slv_device_destroy(slv_device dev) {
   cudaFree(dev->d_batch);
   cudaFree(dev->d_geom);
 
-  cudaFree(dev->tile_slot);
+  for (auto& t : dev->slot_tables) cudaFree(t.d_slot);
   cudaStreamDestroy(dev->own_stream);
   delete dev;
 }
@@ -904,17 +946,17 @@ slv_result slv_profile_get(slv_device dev, slv_pipeline_profiles* out) {
   dev->ev_used = 0;
   memset(out, 0, sizeof(*out));
   out->clipping = (uint64_t)(dev->prof_ms[0] * 1e6);      // VS + clip + viewport + setup are one kernel
-  out->tri_dispatch = (uint64_t)((dev->prof_ms[1] + dev->prof_ms[2]) * 1e6);
+  out->tri_dispatch = (uint64_t)((dev->prof_ms[1] + dev->prof_ms[2] + dev->prof_ms[5]) * 1e6);
   out->ras = (uint64_t)((dev->prof_ms[3] + dev->prof_ms[4]) * 1e6);
   return SLV_OK;
 }
 
 slv_result slv_profile_get_stages(slv_device dev, double* ms, uint32_t n) {
-  if (!dev || !ms || n < 5) return SLV_INVALID_PARAMETER;
+  if (!dev || !ms || n < 6) return SLV_INVALID_PARAMETER;
   slv_pipeline_profiles tmp;
   slv_result rc = slv_profile_get(dev, &tmp);  // folds the pending event spans
   if (rc != SLV_OK) return rc;
-  for (uint32_t i = 0; i < 5; ++i) ms[i] = dev->prof_ms[i];
+  for (uint32_t i = 0; i < 6; ++i) ms[i] = dev->prof_ms[i];
   return SLV_OK;
 }
 
@@ -988,23 +1030,28 @@ static slv_result pack_common(slv_device dev, slv_handle tex, uint32_t rank, uin
   const SurfaceRef& s = r->tex.level[0];
   if (s.samples != 1) return SLV_INVALID_PARAMETER;
   uint32_t tiles_x = (s.w + TILE - 1) / TILE, tiles_y = (s.h + TILE - 1) / TILE, n_tiles = tiles_x * tiles_y;
-  std::vector<uint32_t> slot(n_tiles, 0);
-  uint32_t owned = 0;
-  for (uint32_t t = 0; t < n_tiles; ++t)
-    if (nranks <= 1 || ((t % tiles_x) + 3 * (t / tiles_x)) % nranks == rank) slot[t] = owned++;
-  if (bytes) *bytes = (size_t)owned * TILE * TILE * s.bpp;
+  // dense slot of every owned tile: built once per (grid, rank, nranks) and kept on the device, so the per-frame
+  // pack / unpack calls enqueue one kernel and never synchronise the host
+  slv_device_t::SlotTable* tab = nullptr;
+  for (auto& t : dev->slot_tables)
+    if (t.tiles_x == tiles_x && t.tiles_y == tiles_y && t.rank == rank && t.nranks == nranks) tab = &t;
+  if (!tab) {
+    std::vector<uint32_t> slot(n_tiles, 0);
+    uint32_t owned = 0;
+    for (uint32_t t = 0; t < n_tiles; ++t)
+      if (nranks <= 1 || ((t % tiles_x) + 3 * (t / tiles_x)) % nranks == rank) slot[t] = owned++;
+    slv_device_t::SlotTable nt{tiles_x, tiles_y, rank, nranks, owned, nullptr};
+    CU(cudaSetDevice(dev->ordinal));
+    CU(cudaMalloc(&nt.d_slot, n_tiles * sizeof(uint32_t)));
+    CU(cudaMemcpy(nt.d_slot, slot.data(), n_tiles * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    dev->slot_tables.push_back(nt);
+    tab = &dev->slot_tables.back();
+  }
+  if (bytes) *bytes = (size_t)tab->owned * TILE * TILE * s.bpp;
   if (!staging) return SLV_OK;
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
-  if (n_tiles > dev->tile_slot_cap) {
-    CU(cudaStreamSynchronize(dev->stream));
-    if (dev->tile_slot) CU(cudaFree(dev->tile_slot));
-    CU(cudaMalloc(&dev->tile_slot, n_tiles * sizeof(uint32_t)));
-    dev->tile_slot_cap = n_tiles;
-  }
-  CU(cudaMemcpyAsync(dev->tile_slot, slot.data(), n_tiles * sizeof(uint32_t), cudaMemcpyHostToDevice, dev->stream));
-  CU(cudaStreamSynchronize(dev->stream));  // `slot` is pageable host memory
-  k_pack_tiles<<<n_tiles, 256, 0, dev->stream>>>(s, tiles_x, tiles_y, rank, nranks, (uint8_t*)staging, dev->tile_slot, unpack);
+  k_pack_tiles<<<n_tiles, 256, 0, dev->stream>>>(s, tiles_x, tiles_y, rank, nranks, (uint8_t*)staging, tab->d_slot, unpack);
   ++dev->n_launches;
   CU(cudaGetLastError());
   return SLV_OK;

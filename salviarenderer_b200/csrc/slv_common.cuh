@@ -79,8 +79,10 @@ struct GeomBatch {
 
 // triangle record (float4 units): [0..2] edge A,B,C,0  [3] bbox xmin,xmax,ymin,ymax
 // [4] misc: x = as_uint(valid | front<<1), y = sx | ex<<16, z = sy | ey<<16 (tile range), w = draw id in the batch
-// [5 .. 5+R) v0 regs   [5+R .. 5+2R) ddx regs   [5+2R .. 5+3R) ddy regs, R = 1 + n_attrs
+// then one (v0, ddx, ddy) triple per register r (0 = position, 1.. = attributes) at TRI_HEADER + 3r: the layout does
+// not depend on the draw's register count, so readers need no per-draw state to address it
 constexpr int TRI_HEADER = 5;
+constexpr int REC_V0 = TRI_HEADER, REC_DDX = TRI_HEADER + 1, REC_DDY = TRI_HEADER + 2;  // + 3 * reg
 
 struct BinParams {
   const float4* tris;

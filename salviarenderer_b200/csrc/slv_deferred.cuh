@@ -4,17 +4,21 @@
 // discards and no centroid attributes, the colour of a sample at the end of the batch is the pixel-shader colour of
 // the LAST fragment that passed the in-order early depth test at that sample (framebuffer.cpp:522-614 writes depth at
 // test time; render_sample_quad, framebuffer.cpp:481-520, then lets the blend shader overwrite the sample).  So the
-// pass is split:
+// pass is split into three kernels, none of which has a CTA-wide barrier:
 //
-//   k_cover<S>     in-order coverage + early-Z (+ the pipeline counters) exactly as k_raster does it, but instead of
-//                  shading it records, per sample, the triangle slot of the last passing fragment ("visibility").
-//                  Depth and owner live in REGISTERS (thread == pixel); nothing is shaded, no quad queue.
-//   k_shade<S,PS>  runs the pixel shader once per (pixel, distinct owner): dense, order-free, no warp coupling.  The quad
+//   k_region_bin   one CTA per non-empty 64x64 tile, one warp per 16x16 region: the reference's level-16 decision
+//                  (subdivide_tile, rasterizer.cpp:441-602) for every entry of the tile's sorted list, compacted IN ORDER
+//                  into one list per region.
+//   k_cover<S>     work item = (region, 8x4-pixel warp block), one WARP per item, warps fully independent: level-4
+//                  decisions of the warp's two 4x4 blocks, per-sample coverage, in-order early-Z (+ the pipeline
+//                  counters) exactly as k_raster does them, but instead of shading it records, per sample, the triangle
+//                  slot of the last passing fragment ("visibility").  Depth and owner live in REGISTERS (lane == pixel).
+//   k_shade<S,PS>  same items: runs the pixel shader once per (pixel, distinct owner): dense, order-free.  The quad
 //                  derivatives a cpp_pixel_shader sees (ddx = q1 - q0, ddy = q2 - q0 over the 2x2 quad evaluated with
 //                  the SAME triangle, cpp_pixel_shader.cpp:13-19) are recomputed by the lane itself from the triangle's
-//                  plane equations with the reference's stepping order (shader.cpp:289-367), so the lanes are
-//                  independent.  Pixels whose samples belong to several triangles push their extra owners to a
-//                  shared-memory queue that the CTA drains densely.
+//                  plane equations with the reference's stepping order (shader.cpp:289-367), so lanes are independent.
+//                  Pixels whose samples belong to several triangles push their extra owners to the warp's queue,
+//                  which the warp drains densely.
 //
 // The results (colour, depth, counters) are bit-identical to k_raster; tests/test_gpu_parity.py runs every case
 // through whichever path the batch qualifies for, and test_deferred_equals_immediate forces both.
@@ -25,295 +29,355 @@
 namespace slv {
 
 constexpr uint32_t VIS_NONE = 0xFFFFFFFFu;
+constexpr int DEF_WARPS = 4;                 // warps per CTA of k_cover / k_shade (independent of each other)
+constexpr int DEF_THREADS = DEF_WARPS * 32;
+constexpr uint32_t ITEMS_PER_TILE = 128;     // 16 regions x 8 warp blocks
+constexpr uint32_t FETCH = 4;                // items a warp takes from the queue at a time
 
-struct CovTri {  // one surviving triangle of the current chunk, staged in shared memory (80 B, 128-bit loads)
+struct CovTri {  // one surviving triangle of the warp's current chunk, staged in shared memory (80 B, 128-bit loads)
   float4 e0;     // A0 B0 C0 A1
   float4 e1;     // B1 C1 A2 B2
   float4 e2;     // C2 v0.x v0.y v0.z
   float4 e3;     // ddx.z ddy.z as_float(slot) as_float(bits)
   float4 aa;     // per-sample depth offsets (rasterizer.cpp:678-687)
 };
-// CovTri bits: 0 read_depth, 1 write_depth, 4..7 compare LUT (compare_lut)
+// CovTri bits: 0 read_depth, 1 write_depth, 4..7 compare LUT (compare_lut), 8..11 status of the warp's two blocks
+// (2 bits each: 0 rejected, 1 partial, 2 full)
+
+struct DeferredBufs {
+  uint32_t* region_list;      // entries (slot << 1) | region_fully_inside, in API order per region
+  uint32_t* region_mask;      // scratch, one word per tile-list entry: regions survived | regions fully inside << 16
+  uint32_t region_cap;
+  uint32_t* region_offset;    // [active tile index * 16 + region]
+  uint32_t* region_count;
+  uint32_t* cursor;           // region_list allocation cursor (reset by k_scan_tiles)
+  uint32_t* overflow_flag;
+  uint8_t* item_flag;         // [item] 1 when k_cover recorded an owner in the warp block
+  uint32_t* vis;              // owner slot per sample, layout ((y * vis_pitch + x) * S + s); nullptr = depth-only batch
+  uint32_t vis_pitch;
+  uint32_t* cover_counter;    // work-queue heads (reset by k_scan_tiles)
+  uint32_t* shade_counter;
+};
 
 #ifndef SLV_COVER_CTAS_PER_SM
-#define SLV_COVER_CTAS_PER_SM 4
+#define SLV_COVER_CTAS_PER_SM 10
 #endif
 #ifndef SLV_SHADE_CTAS_PER_SM
-#define SLV_SHADE_CTAS_PER_SM 3
+#define SLV_SHADE_CTAS_PER_SM 6
 #endif
 
-template <int S>
-__global__ void __launch_bounds__(RASTER_THREADS, SLV_COVER_CTAS_PER_SM)
-    k_cover(RasterParams c, const RasterParams* __restrict__ batch, uint32_t* __restrict__ vis, uint32_t vis_pitch) {
-  __shared__ CovTri s_tri[RASTER_THREADS];
-  __shared__ uint16_t s_wlist[RASTER_WARPS][RASTER_THREADS];
-  __shared__ uint16_t s_cnt[RASTER_WARPS + 1][RASTER_WARPS];
-  __shared__ uint32_t s_item;
+constexpr int RBIN_THREADS = 512;  // 16 warps == the 16 regions of a tile
 
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wx = (warp & 1) * 8, wy = (warp >> 1) * 4;
+// Phase 1: one thread per tile-list entry evaluates the reference's level-16 decision (subdivide_tile at the 16-px
+// level, rasterizer.cpp:441-602, 698-772) for all 16 regions of the tile and stores survive | accept << 16.
+// Phase 2: warp r compacts, IN ORDER, the entries surviving in region r into the region's list (two streaming passes
+// over the masks: count, then fill; allocation = one atomicAdd per tile).
+__global__ void __launch_bounds__(RBIN_THREADS) k_region_bin(RasterParams c, DeferredBufs d) {
+  __shared__ uint32_t s_cnt[16], s_base[16];
+  const uint32_t b = blockIdx.x;
+  if (b >= c.active_tiles[0]) return;
+  const uint32_t tile = c.active_tiles[1 + b];
+  const uint32_t lane = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const uint32_t tile_x = tile % c.tiles_x, tile_y = tile / c.tiles_x;
+  const float vpx = (float)(tile_x * TILE), vpy = (float)(tile_y * TILE);
+  const uint32_t beg = c.tile_offset[tile];
+  uint32_t end = c.tile_offset[tile + 1];
+  if (end > c.list_capacity) end = c.list_capacity;
+  // regions that start outside the target: "Sub tile is out of screen" (rasterizer.cpp:721-724)
+  uint32_t on_screen = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    if (!((float)(tile_x * TILE + (k & 3) * REGION) >= (float)c.target_w || (float)(tile_y * TILE + (k >> 2) * REGION) >= (float)c.target_h))
+      on_screen |= 1u << k;
+
+  for (uint32_t i = beg + threadIdx.x; i < end; i += RBIN_THREADS) {
+    const uint32_t e = __ldg(c.list + i);
+    uint32_t survive = 0xFFFFu, accept = 0xFFFFu;  // e & 1: the whole 64x64 tile is inside (rasterizer.cpp:736-743)
+    if (!(e & 1)) {
+      const float4* rec = c.tris + (size_t)(e >> 1) * c.tri_stride;
+      const float4 e0 = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2), bb = __ldg(rec + 3);
+      const float x_min = bb.x - vpx, x_max = bb.y - vpx, y_min = bb.z - vpy, y_max = bb.w - vpy;
+      const float A3[3] = {e0.x, e1.x, e2.x}, B3[3] = {e0.y, e1.y, e2.y}, C3[3] = {e0.z, e1.z, e2.z};
+      float sx[3], sy[3], r2a[3], ev1[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float A = A3[k], B = B3[k], C = C3[k];
+        float step_x = TILE * A, step_y = TILE * B;
+        float ra = -fabsf(step_x) - fabsf(step_y);
+        float part = (float)((A > 0) * TILE) * A + (float)((B > 0) * TILE) * B;
+        step_x *= 0.25f; step_y *= 0.25f; ra *= 0.25f; part *= 0.25f;
+        const float ev = C - part;
+        sx[k] = step_x; sy[k] = step_y; r2a[k] = ra;
+        ev1[k] = ev - (vpx * A + vpy * B);
+      }
+      survive = 0; accept = 0;
+#pragma unroll
+      for (int reg = 0; reg < 16; ++reg) {
+        const int X16 = (reg & 3) * REGION, Y16 = (reg >> 2) * REGION;
+        bool rej = (x_min >= (float)(X16 + REGION)) || (x_max < (float)X16) || (y_min >= (float)(Y16 + REGION)) || (y_max < (float)Y16);
+        bool acc = true;
+        const float ftx = (float)(reg & 3), fty = (float)(reg >> 2);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float step = sx[k] * ftx + sy[k] * fty;
+          rej |= (step < ev1[k]);
+          acc &= !((step + r2a[k]) < ev1[k]);
+        }
+        survive |= rej ? 0u : (1u << reg);
+        accept |= (!rej && acc) ? (1u << reg) : 0u;
+      }
+    }
+    survive &= on_screen;
+    d.region_mask[i] = survive | ((accept & survive) << 16);
+  }
+  __syncthreads();
+
+  uint32_t cnt = 0;
+  for (uint32_t i = beg; i < end; i += 32) {
+    const uint32_t ei = i + lane;
+    const uint32_t m = ei < end ? d.region_mask[ei] : 0u;
+    cnt += __popc(__ballot_sync(0xFFFFFFFFu, (m >> r) & 1u));
+  }
+  if (lane == 0) s_cnt[r] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+    for (int k = 0; k < 16; ++k) total += s_cnt[k];
+    uint32_t base = total ? atomicAdd(d.cursor, total) : 0u;
+    const bool fits = base + total <= d.region_cap;
+    if (!fits) *d.overflow_flag = 1;
+    for (int k = 0; k < 16; ++k) {
+      s_base[k] = base;
+      d.region_offset[b * 16 + k] = base;
+      d.region_count[b * 16 + k] = fits ? s_cnt[k] : 0u;
+      base += s_cnt[k];
+    }
+    if (!fits) s_base[0] = 0xFFFFFFFFu;
+    if (total) {
+      atomicAdd(&c.stats[13], (unsigned long long)(end - beg) * 16ull);  // (entry, region) decisions evaluated
+      atomicAdd(&c.stats[14], (unsigned long long)total);                 // region-list entries
+    }
+  }
+  __syncthreads();
+  if (s_base[0] == 0xFFFFFFFFu || !cnt) return;
+  uint32_t at = s_base[r];
+  for (uint32_t i = beg; i < end; i += 32) {
+    const uint32_t ei = i + lane;
+    const uint32_t m = ei < end ? d.region_mask[ei] : 0u;
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, (m >> r) & 1u);
+    if ((m >> r) & 1u) d.region_list[at + __popc(bal & ((1u << lane) - 1))] = (__ldg(c.list + ei) & ~1u) | ((m >> (16 + r)) & 1u);
+    at += __popc(bal);
+  }
+}
+
+// work-queue fetch: lane 0 takes FETCH consecutive items; the result is consumed one fetch later (latency hidden)
+__device__ __forceinline__ uint32_t fetch_items(uint32_t* counter, uint32_t lane) {
+  uint32_t v = 0;
+  if (lane == 0) v = atomicAdd(counter, FETCH);
+  return v;
+}
+
+template <int S>
+__global__ void __launch_bounds__(DEF_THREADS, SLV_COVER_CTAS_PER_SM)
+    k_cover(RasterParams c, const RasterParams* __restrict__ batch, DeferredBufs d) {
+  __shared__ CovTri s_tri_all[DEF_WARPS][32];
+
+  const uint32_t lane = threadIdx.x & 31;
+  CovTri* s_tri = s_tri_all[threadIdx.x >> 5];
   const int q = lane >> 2, pi = lane & 3;
-  const int lx = wx + (q & 3) * 2 + (pi & 1), ly = wy + (q >> 2) * 2 + (pi >> 1);
-  const int bx = lx >> 2, by = ly >> 2;
-  const int ix = lx & 3, iy = ly & 3;
+  const int wlx = (q & 3) * 2 + (pi & 1), wly = (q >> 2) * 2 + (pi >> 1);  // pixel inside the 8x4 warp block
+  const int ix = wlx & 3, iy = wly & 3;                                    // pixel inside its 4x4 block
+  const int bsel = wlx >> 2;                                               // which of the warp's two blocks
   const uint32_t fullmask = (1u << S) - 1;
 
   uint32_t n_ps_quads = 0;
-  uint32_t n_ztest = 0, n_zwrite = 0, n_cwrite = 0;
-  uint32_t n_scanned = 0, n_surv = 0, n_pairs = 0;
+  uint32_t n_ztest = 0, n_zwrite = 0, n_cwrite = 0, n_pairs = 0;
 
-  const uint32_t n_items = c.active_tiles[0] * 16u;
+  const uint32_t n_items = c.active_tiles[0] * ITEMS_PER_TILE;
+  uint32_t next_raw = fetch_items(d.cover_counter, lane);
   for (;;) {
-    __syncthreads();
-    if (tid == 0) s_item = atomicAdd(c.work_counter, 1u);
-    __syncthreads();
-    const uint32_t item = s_item;
-    if (item >= n_items) break;
-    const uint32_t tile = c.active_tiles[1 + (item >> 4)], sub = item & 15;
-    const uint32_t tile_x = tile % c.tiles_x, tile_y = tile / c.tiles_x;
-    const int X16 = (sub & 3) * REGION, Y16 = (sub >> 2) * REGION;
-    const int gx0 = tile_x * TILE + X16, gy0 = tile_y * TILE + Y16;
-    if ((float)gx0 >= (float)c.target_w || (float)gy0 >= (float)c.target_h) continue;  // rasterizer.cpp:721-724
-    const int x = gx0 + lx, y = gy0 + ly;
-    const bool odd_x = x & 1, odd_y = y & 1;
-    const bool in_target = (uint32_t)x < c.target_w && (uint32_t)y < c.target_h;
-    const float vpx = (float)(tile_x * TILE), vpy = (float)(tile_y * TILE);
-    const float hx = 0.5f + (float)(uint32_t)(x & ~1), hy = 0.5f + (float)(uint32_t)(y & ~1);
-    const float left_f = (float)(gx0 + bx * 4), top_f = (float)(gy0 + by * 4);
+    const uint32_t base_item = __shfl_sync(0xFFFFFFFFu, next_raw, 0);
+    if (base_item >= n_items) break;
+    next_raw = fetch_items(d.cover_counter, lane);
+    for (uint32_t item = base_item; item < base_item + FETCH && item < n_items; ++item) {
+      const uint32_t b = item >> 7, sub = (item >> 3) & 15, w = item & 7;
+      const uint32_t rcnt = d.region_count[b * 16 + sub];
+      if (rcnt == 0) {
+        if (lane == 0) d.item_flag[item] = 0;
+        continue;
+      }
+      const uint32_t rbeg = d.region_offset[b * 16 + sub];
+      const uint32_t tile = c.active_tiles[1 + b];
+      const uint32_t tile_x = tile % c.tiles_x, tile_y = tile / c.tiles_x;
+      const int X16 = (sub & 3) * REGION, Y16 = (sub >> 2) * REGION;
+      const int gx0 = tile_x * TILE + X16, gy0 = tile_y * TILE + Y16;
+      const int wx = (w & 1) * 8, wy = (w >> 1) * 4;
+      const int x = gx0 + wx + wlx, y = gy0 + wy + wly;
+      const bool odd_x = x & 1, odd_y = y & 1;
+      const bool in_target = (uint32_t)x < c.target_w && (uint32_t)y < c.target_h;
+      const float vpx = (float)(tile_x * TILE), vpy = (float)(tile_y * TILE);
+      const float hx = 0.5f + (float)(uint32_t)(x & ~1), hy = 0.5f + (float)(uint32_t)(y & ~1);
+      const int bxA = wx >> 2, by = wy >> 2;  // block A of the warp inside the region; block B = bxA + 1
+      const float left_f = (float)(gx0 + (bxA + bsel) * 4), top_f = (float)(gy0 + by * 4);
 
-    float z[S];
-    uint32_t st[S], own[S];
+      float z[S];
+      uint32_t st[S], own[S];
 #pragma unroll
-    for (int s = 0; s < S; ++s) { z[s] = 0.0f; st[s] = 0u; own[s] = VIS_NONE; }
-    bool fb_loaded = false, dirty = false;
+      for (int s = 0; s < S; ++s) { z[s] = 0.0f; st[s] = 0u; own[s] = VIS_NONE; }
+      bool fb_loaded = false, dirty = false;
 
-    const uint32_t list_beg = c.tile_offset[tile];
-    uint32_t list_end = c.tile_offset[tile + 1];
-    if (list_end > c.list_capacity) list_end = c.list_capacity;
-    for (uint32_t chunk = list_beg; chunk < list_end; chunk += RASTER_THREADS) {
-      // ================= filter: level-16 decision for the region + level-4 decision of its 16 blocks =================
-      const uint32_t ei = chunk + tid;
-      bool keep = false;
-      uint32_t st_bits = 0;  // 2 bits per block: 0 rejected, 1 partial, 2 full
-      CovTri ent;
-      if (ei < list_end) {
-        ++n_scanned;
-        const uint32_t e = __ldg(c.list + ei);
-        const uint32_t slot = e >> 1;
-        const float4* rec = c.tris + (size_t)slot * c.tri_stride;
-        const float4 e0 = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2), bb = __ldg(rec + 3);
-        TriEntry te;
-        te.A[0] = e0.x; te.B[0] = e0.y; te.C[0] = e0.z;
-        te.A[1] = e1.x; te.B[1] = e1.y; te.C[1] = e1.z;
-        te.A[2] = e2.x; te.B[2] = e2.y; te.C[2] = e2.z;
-        uint32_t full16;
-        const float x_min = bb.x - vpx, x_max = bb.y - vpx, y_min = bb.z - vpy, y_max = bb.w - vpy;
-        if (e & 1) {  // the whole 64x64 tile is inside the triangle (rasterizer.cpp:736-743)
-          keep = true;
-          full16 = 1;
-        } else {  // subdivide_tile at the 16-px level (rasterizer.cpp:441-602, 698-772)
-          bool rej = (x_min >= (float)(X16 + REGION)) || (x_max < (float)X16) || (y_min >= (float)(Y16 + REGION)) ||
-                     (y_max < (float)Y16);
-          bool acc = true;
-          const float ftx = (float)(X16 / REGION), fty = (float)(Y16 / REGION);
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            float A = te.A[k], B = te.B[k], C = te.C[k];
-            float step_x = TILE * A, step_y = TILE * B;
-            float r2a = -fabsf(step_x) - fabsf(step_y);
-            float part = (float)((A > 0) * TILE) * A + (float)((B > 0) * TILE) * B;
-            step_x *= 0.25f; step_y *= 0.25f; r2a *= 0.25f; part *= 0.25f;
-            float ev = C - part;
-            float ev1 = ev - (vpx * A + vpy * B);
-            float step = step_x * ftx + step_y * fty;
-            rej |= (step < ev1);
-            acc &= !((step + r2a) < ev1);
-          }
-          keep = !rej;
-          full16 = acc ? 1 : 0;
-        }
-        if (keep) {
-          if (full16) {
-            st_bits = 0xAAAAAAAAu;
+      for (uint32_t chunk = 0; chunk < rcnt; chunk += 32) {
+        // ---- filter: level-4 decision of the warp's two blocks, one lane per region-list entry ----
+        const uint32_t ei = chunk + lane;
+        uint32_t st4 = 0;
+        if (ei < rcnt) {
+          const uint32_t e = __ldg(d.region_list + rbeg + ei);
+          const uint32_t slot = e >> 1;
+          const float4* rec = c.tris + (size_t)slot * c.tri_stride;
+          const float4 e0 = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2);
+          if (e & 1) {
+            st4 = 0xAu;  // region fully inside: both blocks full
           } else {
+            const float4 bb = __ldg(rec + 3);
+            TriEntry te;
+            te.A[0] = e0.x; te.B[0] = e0.y; te.C[0] = e0.z;
+            te.A[1] = e1.x; te.B[1] = e1.y; te.C[1] = e1.z;
+            te.A[2] = e2.x; te.B[2] = e2.y; te.C[2] = e2.z;
+            const float x_min = bb.x - vpx, x_max = bb.y - vpx, y_min = bb.z - vpy, y_max = bb.w - vpy;
             const float rl = (float)gx0, rt = (float)gy0;
-            for (int b = 0; b < 16; ++b) {
-              const int bbx = b & 3, bby = b >> 2;
-              st_bits |= (uint32_t)block_test(te, x_min, x_max, y_min, y_max, X16 + bbx * 4, Y16 + bby * 4, rl, rt, bbx, bby)
-                         << (2 * b);
-            }
-            keep = st_bits != 0;
+            st4 = (uint32_t)block_test(te, x_min, x_max, y_min, y_max, X16 + bxA * 4, Y16 + by * 4, rl, rt, bxA, by) |
+                  ((uint32_t)block_test(te, x_min, x_max, y_min, y_max, X16 + (bxA + 1) * 4, Y16 + by * 4, rl, rt, bxA + 1, by) << 2);
+          }
+          if (st4) {
+            const RasterParams& p = batch[__float_as_uint(__ldg(rec + 4).w)];
+            const float4 v0p = __ldg(rec + REC_V0), gxp = __ldg(rec + REC_DDX), gyp = __ldg(rec + REC_DDY);
+            const uint32_t bits = (p.read_depth ? 1u : 0u) | (p.write_depth ? 2u : 0u) |
+                                  ((p.depth_enable ? compare_lut(p.depth_func) : 0xFu) << 4) | (st4 << 8);
+            CovTri ent;
+            ent.e0 = make_float4(e0.x, e0.y, e0.z, e1.x);
+            ent.e1 = make_float4(e1.y, e1.z, e2.x, e2.y);
+            ent.e2 = make_float4(e2.z, v0p.x, v0p.y, v0p.z);
+            ent.e3 = make_float4(gxp.z, gyp.z, __uint_as_float(slot), __uint_as_float(bits));
+            float aa[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+              aa[s] = (s < S && S > 1) ? (SamplePattern<S>::x(s) - 0.5f) * gxp.z + (SamplePattern<S>::y(s) - 0.5f) * gyp.z : 0.0f;
+            ent.aa = make_float4(aa[0], aa[1], aa[2], aa[3]);
+            s_tri[lane] = ent;
           }
         }
-        if (keep) {
-          const float4 misc = __ldg(rec + 4);
-          const RasterParams& p = batch[__float_as_uint(misc.w)];
-          const int R = 1 + (int)p.n_attrs;
-          const float4 v0p = __ldg(rec + TRI_HEADER), gxp = __ldg(rec + TRI_HEADER + R), gyp = __ldg(rec + TRI_HEADER + 2 * R);
-          const uint32_t bits = (p.read_depth ? 1u : 0u) | (p.write_depth ? 2u : 0u) |
-                                ((p.depth_enable ? compare_lut(p.depth_func) : 0xFu) << 4);
-          ent.e0 = make_float4(e0.x, e0.y, e0.z, e1.x);
-          ent.e1 = make_float4(e1.y, e1.z, e2.x, e2.y);
-          ent.e2 = make_float4(e2.z, v0p.x, v0p.y, v0p.z);
-          ent.e3 = make_float4(gxp.z, gyp.z, __uint_as_float(slot), __uint_as_float(bits));
-          float aa[4];
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, st4 != 0);
+        __syncwarp();  // orders the shared-memory writes above before the reads below
+        if (todo && !fb_loaded) {
+          fb_loaded = true;
+          if (in_target && c.ds.data) {
+            const float2* dp = reinterpret_cast<const float2*>(c.ds.data + ((size_t)y * c.ds.w + x) * S * 8);
+            if (S == 4) {
+              const float4 a = *reinterpret_cast<const float4*>(dp), b2 = *reinterpret_cast<const float4*>(dp + 2);
+              z[0] = a.x; st[0] = __float_as_uint(a.y); z[1 % S] = a.z; st[1 % S] = __float_as_uint(a.w);
+              z[2 % S] = b2.x; st[2 % S] = __float_as_uint(b2.y); z[3 % S] = b2.z; st[3 % S] = __float_as_uint(b2.w);
+            } else {
 #pragma unroll
-          for (int s = 0; s < 4; ++s)
-            aa[s] = (s < S && S > 1) ? (SamplePattern<S>::x(s) - 0.5f) * gxp.z + (SamplePattern<S>::y(s) - 0.5f) * gyp.z : 0.0f;
-          ent.aa = make_float4(aa[0], aa[1], aa[2], aa[3]);
-        }
-      }
-      // ---- order-preserving compaction: survivors -> s_tri, and per target warp -> s_wlist[w] ----
-      uint32_t hit = 0;
-#pragma unroll
-      for (int w = 0; w < RASTER_WARPS; ++w) {
-        const uint32_t four = (st_bits >> (2 * ((w >> 1) * 4 + (w & 1) * 2))) & 0xFu;
-        hit |= (keep && four) ? (1u << w) : 0u;
-      }
-      uint32_t bal[RASTER_WARPS + 1];
-#pragma unroll
-      for (int w = 0; w < RASTER_WARPS; ++w) bal[w] = __ballot_sync(0xFFFFFFFFu, (hit >> w) & 1u);
-      bal[RASTER_WARPS] = __ballot_sync(0xFFFFFFFFu, keep);
-      if (lane <= RASTER_WARPS) {
-        uint32_t mine = bal[0];
-#pragma unroll
-        for (int w = 1; w <= RASTER_WARPS; ++w) mine = (lane == (uint32_t)w) ? bal[w] : mine;
-        s_cnt[lane][warp] = (uint16_t)__popc(mine);
-      }
-      __syncthreads();
-      uint32_t my_cnt = 0;
-      {
-        const uint32_t below = (1u << lane) - 1;
-        uint32_t sbase = 0;
-#pragma unroll
-        for (int fw = 0; fw < RASTER_WARPS; ++fw) {
-          if ((uint32_t)fw < warp) sbase += s_cnt[RASTER_WARPS][fw];
-          my_cnt += s_cnt[warp][fw];
-        }
-        if (keep) {
-          ++n_surv;
-          const uint32_t sidx = sbase + __popc(bal[RASTER_WARPS] & below);
-          s_tri[sidx] = ent;
-#pragma unroll
-          for (int w = 0; w < RASTER_WARPS; ++w) {
-            if ((hit >> w) & 1u) {
-              uint32_t wbase = 0;
-#pragma unroll
-              for (int fw = 0; fw < RASTER_WARPS; ++fw)
-                if ((uint32_t)fw < warp) wbase += s_cnt[w][fw];
-              const uint32_t four = (st_bits >> (2 * ((w >> 1) * 4 + (w & 1) * 2))) & 0xFu;
-              s_wlist[w][wbase + __popc(bal[w] & below)] = (uint16_t)(sidx | (four << 8));
-            }
-          }
-        }
-      }
-      __syncthreads();
-
-      // ================= per-warp loop over this warp's triangles of the chunk, in API order =================
-      if (my_cnt && !fb_loaded) {
-        fb_loaded = true;
-        if (in_target && c.ds.data) {
-          const float2* dp = reinterpret_cast<const float2*>(c.ds.data + ((size_t)y * c.ds.w + x) * S * 8);
-          if (S == 4) {
-            const float4 a = *reinterpret_cast<const float4*>(dp), b = *reinterpret_cast<const float4*>(dp + 2);
-            z[0] = a.x; st[0] = __float_as_uint(a.y); z[1 % S] = a.z; st[1 % S] = __float_as_uint(a.w);
-            z[2 % S] = b.x; st[2 % S] = __float_as_uint(b.y); z[3 % S] = b.z; st[3 % S] = __float_as_uint(b.w);
-          } else {
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              const float2 v = dp[s];
-              z[s] = v.x;
-              st[s] = __float_as_uint(v.y);
-            }
-          }
-        }
-      }
-      if (lane == 0) n_pairs += my_cnt;
-      for (uint32_t wi = 0; wi < my_cnt; ++wi) {
-        const uint32_t we = s_wlist[warp][wi];
-        const CovTri& t = s_tri[we & 0xFF];
-        const int blk = (we >> (8 + 2 * (bx & 1))) & 3;  // 0 rejected, 1 partial, 2 full
-        // per-sample coverage (draw_partial_tile, rasterizer.cpp:298-439)
-        uint32_t pm = 0;
-        if (in_target) {
-          if (blk == 2) {
-            pm = fullmask;
-          } else if (blk == 1) {
-            const float4 e0 = t.e0, e1 = t.e1;
-            const float C2 = t.e2.x;
-            const float A[3] = {e0.x, e0.w, e1.z}, B[3] = {e0.y, e1.x, e1.w}, Cc[3] = {e0.z, e1.y, C2};
-            float ev[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) ev[k] = Cc[k] - (left_f * A[k] + top_f * B[k]);
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-              const float fx = SamplePattern<S>::x(s) + (float)ix, fy = SamplePattern<S>::y(s) + (float)iy;
-              bool rj = false;
-#pragma unroll
-              for (int k = 0; k < 3; ++k) rj |= (fx * A[k] + fy * B[k]) < ev[k];
-              if (!rj) pm |= 1u << s;
-            }
-          }
-        }
-        if (!__any_sync(0xFFFFFFFFu, pm != 0)) continue;
-        // early-Z: test and WRITE depth now (framebuffer.cpp:522-614; Appendix B #3); record the owner
-        uint32_t tested = 0;
-        if (pm) {
-          const float4 e2 = t.e2, e3 = t.e3, aa4 = t.aa;
-          const uint32_t bits = __float_as_uint(e3.w), slot = __float_as_uint(e3.z);
-          const float dx = hx - e2.y, dy = hy - e2.z;
-          float depth = e2.w + (e3.x * dx + e3.y * dy);
-          if (odd_x) depth += e3.x;
-          if (odd_y) depth += e3.y;
-          const uint32_t lut = bits >> 4;
-          const bool rd = bits & 1u, wr = bits & 2u;
-          const float aa[4] = {aa4.x, aa4.y, aa4.z, aa4.w};
-#pragma unroll
-          for (int s = 0; s < S; ++s) {
-            if (pm & (1u << s)) {
-              const float nd = (S == 1) ? depth : aa[s] + depth;
-              const float od = rd ? z[s] : 0.0f;
-              if (compare_with_lut(lut, nd, od)) {
-                tested |= 1u << s;
-                own[s] = slot;
-                if (wr) z[s] = nd;
+              for (int s = 0; s < S; ++s) {
+                const float2 v = dp[s];
+                z[s] = v.x;
+                st[s] = __float_as_uint(v.y);
               }
             }
           }
-          const uint32_t np = __popc(pm), nt = __popc(tested);
-          n_ztest += rd ? np : 0u;
-          n_zwrite += wr ? nt : 0u;
-          n_cwrite += vis ? nt : 0u;
-          dirty |= wr && nt;
         }
-        // ps_invocations: one quad per 2x2 with a live sample after early-Z (rasterizer.cpp:1274-1321)
-        const uint32_t tb = __ballot_sync(0xFFFFFFFFu, tested != 0);
-        if (lane == 0) n_ps_quads += __popc((tb | (tb >> 1) | (tb >> 2) | (tb >> 3)) & 0x11111111u);
+        if (lane == 0) n_pairs += __popc(todo);
+        // ---- the chunk's surviving triangles, in API order ----
+        while (todo) {
+          const int j = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const CovTri& t = s_tri[j];
+          const float4 e3 = t.e3;
+          const uint32_t bits = __float_as_uint(e3.w), slot = __float_as_uint(e3.z);
+          const int blk = (bits >> (8 + 2 * bsel)) & 3;  // 0 rejected, 1 partial, 2 full
+          // per-sample coverage (draw_partial_tile, rasterizer.cpp:298-439)
+          uint32_t pm = 0;
+          if (in_target) {
+            if (blk == 2) {
+              pm = fullmask;
+            } else if (blk == 1) {
+              const float4 e0 = t.e0, e1 = t.e1;
+              const float C2 = t.e2.x;
+              const float A[3] = {e0.x, e0.w, e1.z}, B[3] = {e0.y, e1.x, e1.w}, Cc[3] = {e0.z, e1.y, C2};
+              float ev[3];
+#pragma unroll
+              for (int k = 0; k < 3; ++k) ev[k] = Cc[k] - (left_f * A[k] + top_f * B[k]);
+#pragma unroll
+              for (int s = 0; s < S; ++s) {
+                const float fx = SamplePattern<S>::x(s) + (float)ix, fy = SamplePattern<S>::y(s) + (float)iy;
+                bool rj = false;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) rj |= (fx * A[k] + fy * B[k]) < ev[k];
+                if (!rj) pm |= 1u << s;
+              }
+            }
+          }
+          if (!__any_sync(0xFFFFFFFFu, pm != 0)) continue;
+          // early-Z: test and WRITE depth now (framebuffer.cpp:522-614; Appendix B #3); record the owner
+          uint32_t tested = 0;
+          if (pm) {
+            const float4 e2 = t.e2, aa4 = t.aa;
+            const float dx = hx - e2.y, dy = hy - e2.z;
+            float depth = e2.w + (e3.x * dx + e3.y * dy);
+            if (odd_x) depth += e3.x;
+            if (odd_y) depth += e3.y;
+            const uint32_t lut = (bits >> 4) & 0xFu;
+            const bool rd = bits & 1u, wr = bits & 2u;
+            const float aa[4] = {aa4.x, aa4.y, aa4.z, aa4.w};
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              if (pm & (1u << s)) {
+                const float nd = (S == 1) ? depth : aa[s] + depth;
+                const float od = rd ? z[s] : 0.0f;
+                if (compare_with_lut(lut, nd, od)) {
+                  tested |= 1u << s;
+                  own[s] = slot;
+                  if (wr) z[s] = nd;
+                }
+              }
+            }
+            const uint32_t np = __popc(pm), nt = __popc(tested);
+            n_ztest += rd ? np : 0u;
+            n_zwrite += wr ? nt : 0u;
+            n_cwrite += d.vis ? nt : 0u;
+            dirty |= wr && nt;
+          }
+          // ps_invocations: one quad per 2x2 with a live sample after early-Z (rasterizer.cpp:1274-1321)
+          const uint32_t tb = __ballot_sync(0xFFFFFFFFu, tested != 0);
+          if (lane == 0) n_ps_quads += __popc((tb | (tb >> 1) | (tb >> 2) | (tb >> 3)) & 0x11111111u);
+        }
+        __syncwarp();  // s_tri is overwritten by the next chunk
       }
-      // (the barrier at the top of the next chunk / item protects s_tri, s_wlist and s_cnt)
-      __syncthreads();
-    }
 
-    // ---- write back: owners always (k_shade reads every pixel of a processed region), depth when modified ----
-    if (in_target) {
-      if (vis) {
-        uint32_t* vp = vis + ((size_t)y * vis_pitch + x) * S;
+      // ---- write back: owners when any were recorded (k_shade skips unflagged items), depth when modified ----
+      bool any_own = false;
+#pragma unroll
+      for (int s = 0; s < S; ++s) any_own |= own[s] != VIS_NONE;
+      const bool flag = __any_sync(0xFFFFFFFFu, any_own);
+      if (lane == 0) d.item_flag[item] = flag ? 1 : 0;
+      if (flag && in_target && d.vis) {
+        uint32_t* vp = d.vis + ((size_t)y * d.vis_pitch + x) * S;
         if (S == 4) *reinterpret_cast<uint4*>(vp) = make_uint4(own[0], own[1 % S], own[2 % S], own[3 % S]);
         else if (S == 2) *reinterpret_cast<uint2*>(vp) = make_uint2(own[0], own[1 % S]);
         else *vp = own[0];
       }
-    }
-    if (fb_loaded) {
-      const bool any_ds = __any_sync(0xFFFFFFFFu, dirty);
-      if (in_target && any_ds && c.ds.data) {
-        uint8_t* ds_ptr = c.ds.data + ((size_t)y * c.ds.w + x) * S * 8;
-        if (S == 4) {
-          *reinterpret_cast<float4*>(ds_ptr) = make_float4(z[0], __uint_as_float(st[0]), z[1 % S], __uint_as_float(st[1 % S]));
-          *reinterpret_cast<float4*>(ds_ptr + 16) = make_float4(z[2 % S], __uint_as_float(st[2 % S]), z[3 % S], __uint_as_float(st[3 % S]));
-        } else if (S == 2) {
-          *reinterpret_cast<float4*>(ds_ptr) = make_float4(z[0], __uint_as_float(st[0]), z[1 % S], __uint_as_float(st[1 % S]));
-        } else {
-          *reinterpret_cast<float2*>(ds_ptr) = make_float2(z[0], __uint_as_float(st[0]));
+      if (fb_loaded) {
+        const bool any_ds = __any_sync(0xFFFFFFFFu, dirty);
+        if (in_target && any_ds && c.ds.data) {
+          uint8_t* ds_ptr = c.ds.data + ((size_t)y * c.ds.w + x) * S * 8;
+          if (S == 4) {
+            *reinterpret_cast<float4*>(ds_ptr) = make_float4(z[0], __uint_as_float(st[0]), z[1 % S], __uint_as_float(st[1 % S]));
+            *reinterpret_cast<float4*>(ds_ptr + 16) = make_float4(z[2 % S], __uint_as_float(st[2 % S]), z[3 % S], __uint_as_float(st[3 % S]));
+          } else if (S == 2) {
+            *reinterpret_cast<float4*>(ds_ptr) = make_float4(z[0], __uint_as_float(st[0]), z[1 % S], __uint_as_float(st[1 % S]));
+          } else {
+            *reinterpret_cast<float2*>(ds_ptr) = make_float2(z[0], __uint_as_float(st[0]));
+          }
         }
       }
     }
@@ -326,8 +390,6 @@ __global__ void __launch_bounds__(RASTER_THREADS, SLV_COVER_CTAS_PER_SM)
     n_ztest += __shfl_xor_sync(0xFFFFFFFFu, n_ztest, o);
     n_zwrite += __shfl_xor_sync(0xFFFFFFFFu, n_zwrite, o);
     n_cwrite += __shfl_xor_sync(0xFFFFFFFFu, n_cwrite, o);
-    n_scanned += __shfl_xor_sync(0xFFFFFFFFu, n_scanned, o);
-    n_surv += __shfl_xor_sync(0xFFFFFFFFu, n_surv, o);
     n_pairs += __shfl_xor_sync(0xFFFFFFFFu, n_pairs, o);
   }
   if (lane == 0) {
@@ -338,8 +400,6 @@ __global__ void __launch_bounds__(RASTER_THREADS, SLV_COVER_CTAS_PER_SM)
     if (n_ztest) atomicAdd(&c.stats[9], (unsigned long long)n_ztest);
     if (n_zwrite) atomicAdd(&c.stats[10], (unsigned long long)n_zwrite);
     if (n_cwrite) atomicAdd(&c.stats[11], (unsigned long long)n_cwrite);
-    if (n_scanned) atomicAdd(&c.stats[13], (unsigned long long)n_scanned);
-    if (n_surv) atomicAdd(&c.stats[14], (unsigned long long)n_surv);
     if (n_pairs) atomicAdd(&c.stats[15], (unsigned long long)n_pairs);
   }
 }
@@ -361,10 +421,10 @@ struct DeferredCtx {  // what a pixel shader may read when a lane shades its pix
   //  each times 1/pos.w of its pixel unless noperspective)
   __device__ __forceinline__ void quad_xy(int i, float4, float& u0, float& v0, float& u1, float& v1, float& u2, float& v2) const {
     const uint32_t mod = mods[i];
-    const float4 a0 = __ldg(rec + TRI_HEADER + 1 + i);
+    const float4 a0 = __ldg(rec + REC_V0 + 3 * (1 + i));
     float x00 = a0.x, y00 = a0.y, x01 = a0.x, y01 = a0.y, x10 = a0.x, y10 = a0.y;
     if (!(mod & SLV_AM_NOINTERPOLATION)) {
-      const float4 gx = __ldg(rec + TRI_HEADER + R + 1 + i), gy = __ldg(rec + TRI_HEADER + 2 * R + 1 + i);
+      const float4 gx = __ldg(rec + REC_DDX + 3 * (1 + i)), gy = __ldg(rec + REC_DDY + 3 * (1 + i));
       x00 = a0.x + (gx.x * dx + gy.x * dy);
       y00 = a0.y + (gx.y * dx + gy.y * dy);
       x01 = x00 + gx.x; y01 = y00 + gx.y;
@@ -383,7 +443,7 @@ __device__ __forceinline__ uint32_t shade_sample_owner(const RasterParams& c, co
   const float4* rec = c.tris + (size_t)slot * c.tri_stride;
   const RasterParams& p = batch[__float_as_uint(__ldg(rec + 4).w)];
   const int R = 1 + (int)p.n_attrs;
-  const float4 v0p = __ldg(rec + TRI_HEADER), gxp = __ldg(rec + TRI_HEADER + R), gyp = __ldg(rec + TRI_HEADER + 2 * R);
+  const float4 v0p = __ldg(rec + REC_V0), gxp = __ldg(rec + REC_DDX), gyp = __ldg(rec + REC_DDY);
   DeferredCtx px;
   px.rec = rec; px.R = R; px.mods = p.mods;
   px.dx = 0.5f + (float)(uint32_t)(x & ~1) - v0p.x;
@@ -399,70 +459,74 @@ __device__ __forceinline__ uint32_t shade_sample_owner(const RasterParams& c, co
   return pack_color(c.color0.fmt, color);
 }
 
-constexpr int SHADE_QCAP = RASTER_THREADS * 3;  // a pixel has at most S - 1 extra owners
+constexpr int SHADE_QCAP = 96;  // a pixel has at most S - 1 = 3 extra owners
 
 template <int S, int PS>
-__global__ void __launch_bounds__(RASTER_THREADS, SLV_SHADE_CTAS_PER_SM)
-    k_shade(RasterParams c, const RasterParams* __restrict__ batch, const uint32_t* __restrict__ vis, uint32_t vis_pitch,
-            uint32_t* __restrict__ work_counter) {
-  __shared__ uint32_t s_color[RASTER_THREADS][S];
-  __shared__ uint2 s_q[SHADE_QCAP];  // x = pixel (tid) | sample mask << 8, y = owner slot
-  __shared__ uint32_t s_qn, s_item;
+__global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
+    k_shade(RasterParams c, const RasterParams* __restrict__ batch, DeferredBufs d) {
+  __shared__ uint32_t s_color_all[DEF_WARPS][32][S];
+  __shared__ uint2 s_q_all[DEF_WARPS][SHADE_QCAP];  // x = pixel (lane) | sample mask << 8, y = owner slot
 
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wx = (warp & 1) * 8, wy = (warp >> 1) * 4;
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t (*s_color)[S] = s_color_all[threadIdx.x >> 5];
+  uint2* s_q = s_q_all[threadIdx.x >> 5];
   const int q = lane >> 2, pi = lane & 3;
-  const int lx = wx + (q & 3) * 2 + (pi & 1), ly = wy + (q >> 2) * 2 + (pi >> 1);  // same pixel <-> thread map as k_cover
+  const int wlx = (q & 3) * 2 + (pi & 1), wly = (q >> 2) * 2 + (pi >> 1);  // same pixel <-> lane map as k_cover
   const uint32_t fullmask = (1u << S) - 1;
+  const uint32_t below = (1u << lane) - 1;
 
-  const uint32_t n_items = c.active_tiles[0] * 16u;
+  const uint32_t n_items = c.active_tiles[0] * ITEMS_PER_TILE;
+  uint32_t next_raw = fetch_items(d.shade_counter, lane);
   for (;;) {
-    __syncthreads();
-    if (tid == 0) { s_item = atomicAdd(work_counter, 1u); s_qn = 0; }
-    __syncthreads();
-    const uint32_t item = s_item;
-    if (item >= n_items) break;
-    const uint32_t tile = c.active_tiles[1 + (item >> 4)], sub = item & 15;
-    const uint32_t tile_x = tile % c.tiles_x, tile_y = tile / c.tiles_x;
-    const int gx0 = tile_x * TILE + (sub & 3) * REGION, gy0 = tile_y * TILE + (sub >> 2) * REGION;
-    if ((float)gx0 >= (float)c.target_w || (float)gy0 >= (float)c.target_h) continue;
-    const int x = gx0 + lx, y = gy0 + ly;
-    const bool in_target = (uint32_t)x < c.target_w && (uint32_t)y < c.target_h;
+    const uint32_t base_item = __shfl_sync(0xFFFFFFFFu, next_raw, 0);
+    if (base_item >= n_items) break;
+    next_raw = fetch_items(d.shade_counter, lane);
+    for (uint32_t item = base_item; item < base_item + FETCH && item < n_items; ++item) {
+      if (!d.item_flag[item]) continue;
+      const uint32_t b = item >> 7, sub = (item >> 3) & 15, w = item & 7;
+      const uint32_t tile = c.active_tiles[1 + b];
+      const uint32_t tile_x = tile % c.tiles_x, tile_y = tile / c.tiles_x;
+      const int gx0 = tile_x * TILE + (sub & 3) * REGION + (w & 1) * 8, gy0 = tile_y * TILE + (sub >> 2) * REGION + (w >> 1) * 4;
+      const int x = gx0 + wlx, y = gy0 + wly;
+      const bool in_target = (uint32_t)x < c.target_w && (uint32_t)y < c.target_h;
 
-    uint32_t own[S];
+      uint32_t own[S];
 #pragma unroll
-    for (int s = 0; s < S; ++s) own[s] = VIS_NONE;
-    if (in_target) {
-      const uint32_t* vp = vis + ((size_t)y * vis_pitch + x) * S;
-      if (S == 4) {
-        const uint4 v = *reinterpret_cast<const uint4*>(vp);
-        own[0] = v.x; own[1 % S] = v.y; own[2 % S] = v.z; own[3 % S] = v.w;
-      } else if (S == 2) {
-        const uint2 v = *reinterpret_cast<const uint2*>(vp);
-        own[0] = v.x; own[1 % S] = v.y;
-      } else {
-        own[0] = *vp;
+      for (int s = 0; s < S; ++s) own[s] = VIS_NONE;
+      if (in_target) {
+        const uint32_t* vp = d.vis + ((size_t)y * d.vis_pitch + x) * S;
+        if (S == 4) {
+          const uint4 v = *reinterpret_cast<const uint4*>(vp);
+          own[0] = v.x; own[1 % S] = v.y; own[2 % S] = v.z; own[3 % S] = v.w;
+        } else if (S == 2) {
+          const uint2 v = *reinterpret_cast<const uint2*>(vp);
+          own[0] = v.x; own[1 % S] = v.y;
+        } else {
+          own[0] = *vp;
+        }
       }
-    }
-    uint32_t rem = 0;
+      uint32_t rem = 0;
 #pragma unroll
-    for (int s = 0; s < S; ++s) rem |= (own[s] != VIS_NONE) ? (1u << s) : 0u;
-    const uint32_t touched = rem;
-    uint32_t* cptr = reinterpret_cast<uint32_t*>(c.color0.data + ((size_t)y * c.color0.w + x) * S * 4);
-    if (touched && touched != fullmask) {  // some samples keep their colour: fetch it for the 128-bit store
+      for (int s = 0; s < S; ++s) rem |= (own[s] != VIS_NONE) ? (1u << s) : 0u;
+      const uint32_t touched = rem;
+      uint32_t* cptr = reinterpret_cast<uint32_t*>(c.color0.data + ((size_t)y * c.color0.w + x) * S * 4);
+      if (touched && touched != fullmask) {  // some samples keep their colour: fetch it for the 128-bit store
 #pragma unroll
-      for (int s = 0; s < S; ++s) s_color[tid][s] = cptr[s];
-    }
-    uint32_t first_slot = VIS_NONE, first_mask = 0;
-    if (rem) {
+        for (int s = 0; s < S; ++s) s_color[lane][s] = cptr[s];
+      }
+      // first owner of this pixel
+      uint32_t first_slot = VIS_NONE, first_mask = 0;
 #pragma unroll
       for (int s = S - 1; s >= 0; --s)
         if (rem & (1u << s)) first_slot = own[s];
 #pragma unroll
       for (int s = 0; s < S; ++s)
-        if (own[s] == first_slot) first_mask |= 1u << s;
+        if (rem & (1u << s) && own[s] == first_slot) first_mask |= 1u << s;
       rem &= ~first_mask;
-      while (rem) {  // further distinct owners of this pixel -> the CTA's queue
+      // further distinct owners -> the warp's queue (order irrelevant: every (pixel, sample) has exactly one writer)
+      uint32_t qn = 0;
+#pragma unroll
+      for (int round = 0; round < S - 1; ++round) {
         uint32_t sl = VIS_NONE, m = 0;
 #pragma unroll
         for (int s = S - 1; s >= 0; --s)
@@ -471,30 +535,34 @@ __global__ void __launch_bounds__(RASTER_THREADS, SLV_SHADE_CTAS_PER_SM)
         for (int s = 0; s < S; ++s)
           if ((rem & (1u << s)) && own[s] == sl) m |= 1u << s;
         rem &= ~m;
-        s_q[atomicAdd(&s_qn, 1u)] = make_uint2(tid | (m << 8), sl);
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, m != 0);
+        if (m) s_q[qn + __popc(bal & below)] = make_uint2(lane | (m << 8), sl);
+        qn += __popc(bal);
       }
-      const uint32_t packed = shade_sample_owner<PS>(c, batch, first_slot, x, y);
+      if (first_mask) {
+        const uint32_t packed = shade_sample_owner<PS>(c, batch, first_slot, x, y);
 #pragma unroll
-      for (int s = 0; s < S; ++s)
-        if (first_mask & (1u << s)) s_color[tid][s] = packed;
-    }
-    __syncthreads();
-    const uint32_t qn = s_qn;
-    for (uint32_t j = tid; j < qn; j += RASTER_THREADS) {
-      const uint2 it = s_q[j];
-      const uint32_t pt = it.x & 0xFF, m = it.x >> 8;
-      const uint32_t pl = pt & 31, pw = pt >> 5, pq = pl >> 2, pp = pl & 3;
-      const int px_ = gx0 + (int)((pw & 1) * 8 + (pq & 3) * 2 + (pp & 1)), py_ = gy0 + (int)((pw >> 1) * 4 + (pq >> 2) * 2 + (pp >> 1));
-      const uint32_t packed = shade_sample_owner<PS>(c, batch, it.y, px_, py_);
+        for (int s = 0; s < S; ++s)
+          if (first_mask & (1u << s)) s_color[lane][s] = packed;
+      }
+      __syncwarp();
+      for (uint32_t j = lane; j < qn; j += 32) {
+        const uint2 it = s_q[j];
+        const uint32_t pl = it.x & 0xFF, m = it.x >> 8;
+        const uint32_t pq = pl >> 2, pp = pl & 3;
+        const int px_ = gx0 + (int)((pq & 3) * 2 + (pp & 1)), py_ = gy0 + (int)((pq >> 2) * 2 + (pp >> 1));
+        const uint32_t packed = shade_sample_owner<PS>(c, batch, it.y, px_, py_);
 #pragma unroll
-      for (int s = 0; s < S; ++s)
-        if (m & (1u << s)) s_color[pt][s] = packed;
-    }
-    __syncthreads();
-    if (touched) {
-      if (S == 4) *reinterpret_cast<uint4*>(cptr) = make_uint4(s_color[tid][0], s_color[tid][1 % S], s_color[tid][2 % S], s_color[tid][3 % S]);
-      else if (S == 2) *reinterpret_cast<uint2*>(cptr) = make_uint2(s_color[tid][0], s_color[tid][1 % S]);
-      else *cptr = s_color[tid][0];
+        for (int s = 0; s < S; ++s)
+          if (m & (1u << s)) s_color[pl][s] = packed;
+      }
+      __syncwarp();
+      if (touched) {
+        if (S == 4) *reinterpret_cast<uint4*>(cptr) = make_uint4(s_color[lane][0], s_color[lane][1 % S], s_color[lane][2 % S], s_color[lane][3 % S]);
+        else if (S == 2) *reinterpret_cast<uint2*>(cptr) = make_uint2(s_color[lane][0], s_color[lane][1 % S]);
+        else *cptr = s_color[lane][0];
+      }
+      __syncwarp();
     }
   }
 }

@@ -246,9 +246,9 @@ __device__ __forceinline__ void setup_triangle(const GeomParams& p, const VsOut<
     ddy.y = (e01.y * e02x - e02.y * e01x) * inv_area;
     ddy.z = (e01.z * e02x - e02.z * e01x) * inv_area;
     ddy.w = (e01.w * e02x - e02.w * e01x) * inv_area;
-    rec[TRI_HEADER + i] = a[i];
-    rec[TRI_HEADER + R + i] = ddx;
-    rec[TRI_HEADER + 2 * R + i] = ddy;
+    rec[REC_V0 + 3 * i] = a[i];
+    rec[REC_DDX + 3 * i] = ddx;
+    rec[REC_DDY + 3 * i] = ddy;
   }
   TileRange tr = tile_range(bbox, p.tiles_x, p.tiles_y);
   misc.x = __uint_as_float(1u | (front ? 2u : 0u));
@@ -398,18 +398,22 @@ __global__ void __launch_bounds__(128) k_geometry(const GeomParams* __restrict__
 // =====================================================================================================
 // binning
 // =====================================================================================================
+constexpr int SORT_SMEM = 4096;         // list length k_sort_lists sorts in static shared memory
+constexpr int SORT_LARGE_SMEM = 49152;  // list length k_sort_lists_large sorts in dynamic shared memory (192 KB)
+
 // single CTA, 1024 threads: exclusive scan of tile_count -> tile_offset[0..n]; zeroes count and cursor
 // also compacts the ids of the non-empty tiles into active_tiles[1..] (count in active_tiles[0]) and resets the
 // raster work counter.
 // Runs once per batch over the counts accumulated by every queued draw's k_geometry.  Also compacts the ids of the
 // non-empty tiles into active_tiles[1..] (count in [0]) and resets the raster work-queue head.
 __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint32_t* tile_offset, uint32_t* tile_cursor,
-                                                     uint32_t n_tiles, uint32_t* active_tiles, uint32_t* work_counter) {
-  __shared__ uint32_t s_active;
+                                                     uint32_t n_tiles, uint32_t* active_tiles, uint32_t* work_counter,
+                                                     uint32_t* large_tiles) {
+  __shared__ uint32_t s_active, s_large;
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { s_carry = 0; s_active = 0; work_counter[0] = 0; work_counter[1] = 0; }
+  if (tid == 0) { s_carry = 0; s_active = 0; s_large = 0; work_counter[0] = 0; work_counter[1] = 0; work_counter[2] = 0; work_counter[3] = 0; }
   __syncthreads();
   for (uint32_t base = 0; base < n_tiles; base += 1024) {
     const uint32_t i = base + tid;
@@ -420,6 +424,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint3
       if (lane == 0 && bal) wbase = atomicAdd(&s_active, (uint32_t)__popc(bal));
       wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
       if (v != 0) active_tiles[1 + wbase + __popc(bal & ((1u << lane) - 1))] = i;
+      if (v > (uint32_t)SORT_SMEM) large_tiles[1 + atomicAdd(&s_large, 1u)] = i;  // sorted by k_sort_lists_large
     }
     uint32_t incl = v;
 #pragma unroll
@@ -450,7 +455,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint3
     if (tid == 1023) s_carry = excl + v;
     __syncthreads();
   }
-  if (tid == 0) { tile_offset[n_tiles] = s_carry; active_tiles[0] = s_active; }
+  if (tid == 0) { tile_offset[n_tiles] = s_carry; active_tiles[0] = s_active; large_tiles[0] = s_large; }
 }
 
 __global__ void __launch_bounds__(256) k_bin_fill(BinParams p) {
@@ -486,26 +491,12 @@ __global__ void __launch_bounds__(256) k_bin_fill(BinParams p) {
 
 // one CTA per tile; normalized bitonic network (every compare-exchange puts the minimum at the lower
 // index), so virtual +inf padding past n works in place for any n.
-constexpr int SORT_SMEM = 4096;
-__global__ void __launch_bounds__(256) k_sort_lists(const uint32_t* tile_offset, uint32_t* list, uint32_t capacity) {
-  __shared__ uint32_t s[SORT_SMEM];
-  uint32_t beg = tile_offset[blockIdx.x], end = tile_offset[blockIdx.x + 1];
-  if (end > capacity) end = capacity;
-  if (beg >= end) return;
-  uint32_t n = end - beg;
-  if (n < 2) return;
-  uint32_t* a = list + beg;
+__device__ __forceinline__ void bitonic_sort_block(uint32_t* buf, uint32_t n) {
   uint32_t N = 1;
   while (N < n) N <<= 1;
-  bool use_smem = n <= SORT_SMEM;
-  uint32_t* buf = use_smem ? s : a;
-  if (use_smem) {
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s[i] = a[i];
-    __syncthreads();
-  }
   for (uint32_t k = 2; k <= N; k <<= 1) {
     for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      bool first = (j == (k >> 1));
+      const bool first = (j == (k >> 1));
       for (uint32_t t = threadIdx.x; t < (N >> 1); t += blockDim.x) {
         // t-th compare-exchange of this step: i = index with bit j clear
         uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
@@ -519,8 +510,43 @@ __global__ void __launch_bounds__(256) k_sort_lists(const uint32_t* tile_offset,
       __syncthreads();
     }
   }
-  if (use_smem) {
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) a[i] = s[i];
+}
+
+__global__ void __launch_bounds__(256) k_sort_lists(const uint32_t* tile_offset, uint32_t* list, uint32_t capacity) {
+  __shared__ uint32_t s[SORT_SMEM];
+  uint32_t beg = tile_offset[blockIdx.x], end = tile_offset[blockIdx.x + 1];
+  if (end > capacity) end = capacity;
+  if (beg >= end) return;
+  const uint32_t n = end - beg;
+  if (n < 2 || n > (uint32_t)SORT_SMEM) return;  // longer lists: k_sort_lists_large
+  uint32_t* a = list + beg;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s[i] = a[i];
+  __syncthreads();
+  bitonic_sort_block(s, n);
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) a[i] = s[i];
+}
+
+// the few tiles whose list exceeds SORT_SMEM entries (ids compacted by k_scan_tiles): 1024 threads, dynamic shared memory
+__global__ void __launch_bounds__(1024) k_sort_lists_large(const uint32_t* tile_offset, uint32_t* list, uint32_t capacity,
+                                                           const uint32_t* large_tiles) {
+  extern __shared__ uint32_t s_dyn[];
+  const uint32_t n_large = large_tiles[0];
+  for (uint32_t k = blockIdx.x; k < n_large; k += gridDim.x) {
+    const uint32_t tile = large_tiles[1 + k];
+    uint32_t beg = tile_offset[tile], end = tile_offset[tile + 1];
+    if (end > capacity) end = capacity;
+    if (beg >= end) continue;
+    const uint32_t n = end - beg;
+    uint32_t* a = list + beg;
+    if (n <= (uint32_t)SORT_LARGE_SMEM) {
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_dyn[i] = a[i];
+      __syncthreads();
+      bitonic_sort_block(s_dyn, n);
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) a[i] = s_dyn[i];
+      __syncthreads();
+    } else {
+      bitonic_sort_block(a, n);  // in place in global memory
+    }
   }
 }
 
@@ -611,12 +637,12 @@ struct SamplePattern<4> {  // rasterizer.cpp:1095-1100
 // variant (rasterizer.cpp:1366-1397 + shader.cpp:208-255)
 __device__ __forceinline__ float4 interp_attr(const float4* rec, int R, int reg, uint32_t mod, float dx, float dy, bool odd_x,
                                               bool odd_y, bool centroid_path, float pdx, float pdy, float inv_w) {
-  float4 a0 = __ldg(rec + TRI_HEADER + reg);
+  float4 a0 = __ldg(rec + REC_V0 + 3 * reg);
   float4 r;
   if (mod & SLV_AM_NOINTERPOLATION) {
     r = a0;
   } else {
-    float4 gx = __ldg(rec + TRI_HEADER + R + reg), gy = __ldg(rec + TRI_HEADER + 2 * R + reg);
+    float4 gx = __ldg(rec + REC_DDX + 3 * reg), gy = __ldg(rec + REC_DDY + 3 * reg);
     if (centroid_path) {
       r = make_float4(a0.x + (gx.x * pdx + gy.x * pdy), a0.y + (gx.y * pdx + gy.y * pdy),
                       a0.z + (gx.z * pdx + gy.z * pdy), a0.w + (gx.w * pdx + gy.w * pdy));
@@ -987,7 +1013,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, RASTER_CTAS_PER_SM) k_raster(R
             const int sx_ = gx0 + plx, sy_ = gy0 + ply;
             const float4* rec = c.tris + (size_t)(t.slot_flags >> 2) * c.tri_stride;
             // step_2d_unproj_pos_quad (shader.cpp:257-287)
-            const float4 v0p = __ldg(rec + TRI_HEADER), gxp = __ldg(rec + TRI_HEADER + R), gyp = __ldg(rec + TRI_HEADER + 2 * R);
+            const float4 v0p = __ldg(rec + REC_V0), gxp = __ldg(rec + REC_DDX), gyp = __ldg(rec + REC_DDY);
             PixelCtx px;
             px.rec = rec; px.R = R; px.mods = p.mods;
             px.dx = 0.5f + (float)(uint32_t)(sx_ & ~1) - v0p.x;
@@ -1140,7 +1166,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, RASTER_CTAS_PER_SM) k_raster(R
           tested = 0;
           if (pm) {
             const float4* rec = c.tris + (size_t)(t.slot_flags >> 2) * c.tri_stride;
-            const float4 v0p = __ldg(rec + TRI_HEADER), gxp = __ldg(rec + TRI_HEADER + R), gyp = __ldg(rec + TRI_HEADER + 2 * R);
+            const float4 v0p = __ldg(rec + REC_V0), gxp = __ldg(rec + REC_DDX), gyp = __ldg(rec + REC_DDY);
             const float dx = 0.5f + (float)(uint32_t)(x & ~1) - v0p.x;
             const float dy = 0.5f + (float)(uint32_t)(y & ~1) - v0p.y;
             float depth = v0p.z + (gxp.z * dx + gyp.z * dy);

@@ -84,7 +84,7 @@ def main():
         if name in seen:
             continue
         seen.add(name)
-        short = name.split("(")[0].split("::")[-1].strip().split(" ")[-1]
+        short = name.split("(")[0].replace("void ", "").split("::")[-1].strip()
         hdr, agg = source_page(rep, f"regex:{short.split('<')[0]}")
         if not agg:
             continue
