@@ -60,7 +60,7 @@ struct DeferredBufs {
 };
 
 #ifndef SLV_COVER_CTAS_PER_SM
-#define SLV_COVER_CTAS_PER_SM 10
+#define SLV_COVER_CTAS_PER_SM 8
 #endif
 #ifndef SLV_SHADE_CTAS_PER_SM
 #define SLV_SHADE_CTAS_PER_SM 6
@@ -329,15 +329,27 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_COVER_CTAS_PER_SM)
             const uint32_t lut = (bits >> 4) & 0xFu;
             const bool rd = bits & 1u, wr = bits & 2u;
             const float aa[4] = {aa4.x, aa4.y, aa4.z, aa4.w};
+            if (lut == 0x1u && rd && wr) {  // compare_less, depth read + write: the common state, one FSETP per sample
 #pragma unroll
-            for (int s = 0; s < S; ++s) {
-              if (pm & (1u << s)) {
+              for (int s = 0; s < S; ++s) {
                 const float nd = (S == 1) ? depth : aa[s] + depth;
-                const float od = rd ? z[s] : 0.0f;
-                if (compare_with_lut(lut, nd, od)) {
+                if ((pm & (1u << s)) && nd < z[s]) {
                   tested |= 1u << s;
                   own[s] = slot;
-                  if (wr) z[s] = nd;
+                  z[s] = nd;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int s = 0; s < S; ++s) {
+                if (pm & (1u << s)) {
+                  const float nd = (S == 1) ? depth : aa[s] + depth;
+                  const float od = rd ? z[s] : 0.0f;
+                  if (compare_with_lut(lut, nd, od)) {
+                    tested |= 1u << s;
+                    own[s] = slot;
+                    if (wr) z[s] = nd;
+                  }
                 }
               }
             }
@@ -539,22 +551,23 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
         if (m) s_q[qn + __popc(bal & below)] = make_uint2(lane | (m << 8), sl);
         qn += __popc(bal);
       }
-      if (first_mask) {
-        const uint32_t packed = shade_sample_owner<PS>(c, batch, first_slot, x, y);
-#pragma unroll
-        for (int s = 0; s < S; ++s)
-          if (first_mask & (1u << s)) s_color[lane][s] = packed;
-      }
+      // ONE shading call site: round 0 = every lane's own first owner, then the queued extras, 32 at a time
       __syncwarp();
-      for (uint32_t j = lane; j < qn; j += 32) {
-        const uint2 it = s_q[j];
-        const uint32_t pl = it.x & 0xFF, m = it.x >> 8;
-        const uint32_t pq = pl >> 2, pp = pl & 3;
-        const int px_ = gx0 + (int)((pq & 3) * 2 + (pp & 1)), py_ = gy0 + (int)((pq >> 2) * 2 + (pp >> 1));
-        const uint32_t packed = shade_sample_owner<PS>(c, batch, it.y, px_, py_);
+#pragma unroll 1
+      for (uint32_t j = lane; j < 32 + qn; j += 32) {
+        uint32_t pl = lane, m = first_mask, slot = first_slot;
+        if (j >= 32) {
+          const uint2 it = s_q[j - 32];
+          pl = it.x & 0xFF; m = it.x >> 8; slot = it.y;
+        }
+        if (m) {
+          const uint32_t pq = pl >> 2, pp = pl & 3;
+          const int px_ = gx0 + (int)((pq & 3) * 2 + (pp & 1)), py_ = gy0 + (int)((pq >> 2) * 2 + (pp >> 1));
+          const uint32_t packed = shade_sample_owner<PS>(c, batch, slot, px_, py_);
 #pragma unroll
-        for (int s = 0; s < S; ++s)
-          if (m & (1u << s)) s_color[pl][s] = packed;
+          for (int s = 0; s < S; ++s)
+            if (m & (1u << s)) s_color[pl][s] = packed;
+        }
       }
       __syncwarp();
       if (touched) {

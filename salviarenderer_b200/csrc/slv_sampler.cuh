@@ -308,51 +308,70 @@ __device__ inline void calc_af(const slv_sampler_desc& d, float sw, float sh, fl
   }
 }
 
-// sampler::sample_impl<false> (sampler.cpp:680-764)
+// sampler::sample_impl<false> (sampler.cpp:680-764).  The magnification / point-mip / linear-mip cases differ only in
+// which level(s) and which filter are used, so they share ONE sample_surface call site (a 1- or 2-trip loop) and the
+// anisotropic probes another: the sampler is the bulk of the shading kernels' code and must stay inside the
+// instruction cache.
 __device__ inline float4 sample_impl(const SamplerRef& sm, float cx, float cy, float miplevel, const AfInfo* af) {
   const slv_sampler_desc& d = sm.d;
   const TextureRef& t = sm.tex;
-  int max_lod = 0, min_lod = (int)t.n_levels - 1;
-  bool is_mag = (d.mip_filter == SLV_FILTER_POINT) ? (miplevel < 0.5f) : (miplevel < 0.0f);
-  if (is_mag) return sample_surface(t.level[max_lod], d, d.mag_filter, cx, cy);
-  if (d.mip_filter == SLV_FILTER_POINT) {
-    int ml = fast_floori(0.5 + (double)miplevel);
-    ml = min(max(ml, max_lod), min_lod);
-    return sample_surface(t.level[ml], d, d.min_filter, cx, cy);
+  const int max_lod = 0, min_lod = (int)t.n_levels - 1;
+  const bool is_mag = (d.mip_filter == SLV_FILTER_POINT) ? (miplevel < 0.5f) : (miplevel < 0.0f);
+  const bool aniso = !is_mag && d.mip_filter == SLV_FILTER_ANISOTROPIC;
+  int lv0 = max_lod, lv1 = max_lod, n = 1;
+  uint32_t filter = d.mag_filter;
+  float frac = 0.0f, sx = cx, sy = cy, du = 0.0f, dv = 0.0f, weight_D = 0.0f;
+  int tap_i = 0;  // anisotropic: i = -N+1, -N+3, ... (sampler.cpp:741)
+  if (!is_mag) {
+    filter = d.min_filter;
+    if (d.mip_filter == SLV_FILTER_POINT) {
+      const int ml = fast_floori(0.5 + (double)miplevel);
+      lv0 = min(max(ml, max_lod), min_lod);
+    } else if (d.mip_filter == SLV_FILTER_LINEAR) {
+      // miplevel >= 0 here (the mag case is handled above): for non-negative floats the reference's double-precision
+      // fast_floori(d) = floor(d + 1.5e-8) equals floorf(d) exactly (no float lies within 1.5e-8 below an integer >= 1)
+      const int lo = (int)floorf(miplevel);
+      frac = miplevel - (float)lo;
+      lv0 = min(max(lo, max_lod), min_lod);
+      lv1 = min(max(lo + 1, max_lod), min_lod);
+      n = 2;
+    } else {  // anisotropic: N probes along the major axis, EWA weights (sampler.cpp:730-760)
+      const float start = -0.5f * (af->probe_count - 1.0f);
+      du = af->du; dv = af->dv; weight_D = af->weight_D;
+      sx = cx + du * start;
+      sy = cy + dv * start;
+      const int lo = fast_roundi((double)miplevel);
+      lv0 = lv1 = lo < 0 ? min_lod : min(max(lo, max_lod), min_lod);  // size_t cast of a negative int clamps to min_lod
+      const int pc = (int)af->probe_count;
+      n = pc > 0 ? pc : 0;  // taps i = -pc+1, -pc+3, ..., pc-1
+      tap_i = -pc + 1;
+    }
   }
-  if (d.mip_filter == SLV_FILTER_LINEAR) {
-    // miplevel >= 0 here (the mag case returned above): for non-negative floats the reference's double-precision
-    // fast_floori(d) = floor(d + 1.5e-8) equals floorf(d) exactly (no float lies within 1.5e-8 below an integer >= 1)
-    int lo = (int)floorf(miplevel);
-    int hi = lo + 1;
-    float frac = miplevel - (float)lo;
-    int lo_sz = min(max(lo, max_lod), min_lod);
-    int hi_sz = min(max(hi, max_lod), min_lod);
-    float4 c0 = sample_surface(t.level[lo_sz], d, d.min_filter, cx, cy);
-    float4 c1 = sample_surface(t.level[hi_sz], d, d.min_filter, cx, cy);
-    return make_float4(lerp1(c0.x, c1.x, frac), lerp1(c0.y, c1.y, frac), lerp1(c0.z, c1.z, frac),
-                       lerp1(c0.w, c1.w, frac));
-  }
-  // anisotropic: N probes along the major axis, EWA weights (sampler.cpp:730-760)
-  float start = -0.5f * (af->probe_count - 1.0f);
-  float sx = cx + af->du * start;
-  float sy = cy + af->dv * start;
-  int lo = fast_roundi((double)miplevel);
-  int lo_sz = lo < 0 ? min_lod : min(max(lo, max_lod), min_lod);  // size_t cast of a negative int clamps to min_lod
-  float4 color = make_float4(0, 0, 0, 0);
+  float4 c0 = make_float4(0, 0, 0, 0), c1 = c0;  // aniso: c0 accumulates the weighted colour
   float w_sum = 0.0f;
-  int pc = (int)af->probe_count;
-  for (int i = -pc + 1; i < pc; i += 2) {
-    float4 c0 = sample_surface(t.level[lo_sz], d, d.min_filter, sx, sy);
-    int wi = (int)((float)(i * i) * af->weight_D);
-    float w = c_ewa_wts[min(max(wi, 0), 255)];
-    color.x += c0.x * w; color.y += c0.y * w; color.z += c0.z * w; color.w += c0.w * w;
-    w_sum += w;
-    sx += af->du;
-    sy += af->dv;
+#pragma unroll 1
+  for (int k = 0; k < n; ++k) {
+    const float4 v = sample_surface(t.level[k ? lv1 : lv0], d, filter, sx, sy);
+    if (aniso) {
+      const int wi = (int)((float)(tap_i * tap_i) * weight_D);
+      const float w = c_ewa_wts[min(max(wi, 0), 255)];
+      c0.x += v.x * w; c0.y += v.y * w; c0.z += v.z * w; c0.w += v.w * w;
+      w_sum += w;
+      sx += du;
+      sy += dv;
+      tap_i += 2;
+    } else if (k) {
+      c1 = v;
+    } else {
+      c0 = v;
+    }
   }
-  float inv = 1 / w_sum;
-  return make_float4(color.x * inv, color.y * inv, color.z * inv, color.w * inv);
+  if (aniso) {
+    const float inv = 1 / w_sum;
+    return make_float4(c0.x * inv, c0.y * inv, c0.z * inv, c0.w * inv);
+  }
+  if (n == 1) return c0;
+  return make_float4(lerp1(c0.x, c1.x, frac), lerp1(c0.y, c1.y, frac), lerp1(c0.z, c1.z, frac), lerp1(c0.w, c1.w, frac));
 }
 
 // sampler::calc_lod_2d (sampler.cpp:831-848)

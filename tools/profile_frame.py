@@ -1,0 +1,36 @@
+"""Developer tool: renders warm-up frames, then ONE frame of the bench workload between cudaProfilerStart/Stop, so that
+`ncu --profile-from-start off ...` captures exactly the kernels of one steady-state frame.
+
+    ncu --set full --import-source on --clock-control none --profile-from-start off -o gpurun_out/prof -f \
+        python tools/profile_frame.py [--frame 3] [--width 3840 --height 2160 --samples 4]
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import salviarenderer_b200 as pkg  # noqa: E402
+from salviarenderer_b200 import scenes as S  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--frame", type=int, default=3)
+ap.add_argument("--width", type=int, default=3840)
+ap.add_argument("--height", type=int, default=2160)
+ap.add_argument("--samples", type=int, default=4)
+ap.add_argument("--tex-size", type=int, default=1024)
+ap.add_argument("--aniso", type=int, default=0)
+a = ap.parse_args()
+be = pkg.load(0)
+sc = S.SponzaLike(a.width, a.height, a.samples, tex_size=a.tex_size, max_aniso=a.aniso)
+sc.setup(be)
+for f in range(4):
+    sc.render(be, f)
+be.flush()
+rt = torch.cuda.cudart()
+rt.cudaProfilerStart()
+sc.render(be, a.frame)
+be.flush()
+rt.cudaProfilerStop()
+print("profiled frame", a.frame, be.query_get())
