@@ -274,6 +274,9 @@ typedef struct slv_traffic_counters {
   /* work counters of the product's raster kernel (0 for the CPU checkers): tile-list entries examined by the
    * region filters, (triangle, 16x16 region) survivors, (triangle, warp) pairs walked, quads shaded */
   uint64_t list_entries_scanned, region_survivors, warp_pairs, quads_shaded;
+  /* pixel-shader executions the product actually performed (the visibility-first path shades a pixel once per
+   * distinct final owner, so this is <= ps_invocations, which still counts what the reference would shade) */
+  uint64_t ps_executed;
 } slv_traffic_counters;
 slv_result slv_traffic_get(slv_device dev, slv_traffic_counters* out);
 /* number of kernels this library launched since slv_query_begin (0 for the CPU checkers) */

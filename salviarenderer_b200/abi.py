@@ -117,7 +117,7 @@ class PipelineProfiles(C.Structure):
 
 class TrafficCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("z_tested", "z_written", "c_written", "c_read", "list_entries_scanned",
-                                          "region_survivors", "warp_pairs", "quads_shaded")]
+                                          "region_survivors", "warp_pairs", "quads_shaded", "ps_executed")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -430,8 +430,8 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
     dev->shade_grid = prop.multiProcessorCount * SLV_SHADE_CTAS_PER_SM;
   }
   CU(cudaMemsetAsync(dev->overflow_flag, 0, sizeof(uint32_t), dev->stream));
-  CU(cudaMalloc(&dev->d_stats, 16 * sizeof(unsigned long long)));
-  CU(cudaMemsetAsync(dev->d_stats, 0, 16 * sizeof(unsigned long long), dev->stream));
+  CU(cudaMalloc(&dev->d_stats, 20 * sizeof(unsigned long long)));
+  CU(cudaMemsetAsync(dev->d_stats, 0, 20 * sizeof(unsigned long long), dev->stream));
   const char* prof = getenv("SLV_PROFILE");
   dev->profile = prof && prof[0] == '1';
   const char* fi = getenv("SLV_FORCE_IMMEDIATE");
@@ -630,6 +630,13 @@ static bool fill_sampler(slv_device dev, slv_handle h, SamplerRef& out) {
   if (!t) return false;
   out.d = r->sd;
   out.tex = t->tex;
+  bool fast = r->sd.min_filter == SLV_FILTER_LINEAR && r->sd.mag_filter == SLV_FILTER_LINEAR &&
+              r->sd.addr_mode_u == SLV_ADDR_WRAP && r->sd.addr_mode_v == SLV_ADDR_WRAP && t->fmt == SLV_PF_RGBA8;
+  for (uint32_t l = 0; l < t->tex.n_levels; ++l) {  // size 1 has mask 0 and index 0 for every coordinate: also exact
+    const SurfaceRef& lv = t->tex.level[l];
+    fast = fast && lv.w <= 1024 && lv.h <= 1024 && (lv.w & (lv.w - 1)) == 0 && (lv.h & (lv.h - 1)) == 0;
+  }
+  out.fast_wrap_rgba8 = fast ? 1u : 0u;
   return true;
 }
 
@@ -909,7 +916,7 @@ slv_result slv_query_begin(slv_device dev) {
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   dev->host_stats = slv_pipeline_statistics{};
-  CU(cudaMemsetAsync(dev->d_stats, 0, 16 * sizeof(unsigned long long), dev->stream));
+  CU(cudaMemsetAsync(dev->d_stats, 0, 20 * sizeof(unsigned long long), dev->stream));
   for (auto& m : dev->prof_ms) m = 0;
   if (!dev->spans.empty()) CU(cudaStreamSynchronize(dev->stream));
   dev->spans.clear();
@@ -964,9 +971,10 @@ slv_result slv_traffic_get(slv_device dev, slv_traffic_counters* out) {
   if (!dev || !out) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
-  unsigned long long h[16];
+  unsigned long long h[20];
   CU(cudaMemcpyAsync(h, dev->d_stats, sizeof(h), cudaMemcpyDeviceToHost, dev->stream));
   CU(cudaStreamSynchronize(dev->stream));
+  out->ps_executed = h[16];
   out->list_entries_scanned = h[13];
   out->region_survivors = h[14];
   out->warp_pairs = h[15];

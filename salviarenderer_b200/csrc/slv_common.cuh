@@ -36,6 +36,9 @@ struct TextureRef {
 struct SamplerRef {
   slv_sampler_desc d;
   TextureRef tex;
+  // 1 when min = mag = linear, u and v both wrap, texels are rgba8 and every level is a power of two <= 1024 (exact
+  // integer wrap): the specialised tap sample_wrap_rgba8_linear applies (same arithmetic, no mode / format dispatch)
+  uint32_t fast_wrap_rgba8;
 };
 
 // ---- per-draw parameter block (passed by value to the kernels; < 4 KB) ------------------------------

@@ -471,113 +471,138 @@ __device__ __forceinline__ uint32_t shade_sample_owner(const RasterParams& c, co
   return pack_color(c.color0.fmt, color);
 }
 
-constexpr int SHADE_QCAP = 96;  // a pixel has at most S - 1 = 3 extra owners
+constexpr uint32_t SHADE_GROUP = 8;   // items a warp of k_shade takes at a time; all their (pixel, owner) pairs share one pool
+constexpr int SHADE_POOL = 512;       // pool entries per warp (an item adds at most 32 * S = 128)
+
+__device__ __forceinline__ uint32_t fetch_group(uint32_t* counter, uint32_t lane) {
+  uint32_t v = 0;
+  if (lane == 0) v = atomicAdd(counter, SHADE_GROUP);
+  return v;
+}
 
 template <int S, int PS>
 __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
     k_shade(RasterParams c, const RasterParams* __restrict__ batch, DeferredBufs d) {
-  __shared__ uint32_t s_color_all[DEF_WARPS][32][S];
-  __shared__ uint2 s_q_all[DEF_WARPS][SHADE_QCAP];  // x = pixel (lane) | sample mask << 8, y = owner slot
+  // per warp: the colour rows of the group's items, the pool of (pixel, owner) pairs, per-item origin / touched masks
+  __shared__ uint32_t s_color_all[DEF_WARPS][SHADE_GROUP][32][S];
+  __shared__ uint2 s_pool_all[DEF_WARPS][SHADE_POOL];  // x = lane | mask << 5 | item-in-group << 9, y = owner slot
+  __shared__ uint32_t s_org_all[DEF_WARPS][SHADE_GROUP];  // gx0 | gy0 << 16 of the item's 8x4 block
+  __shared__ uint8_t s_touched_all[DEF_WARPS][SHADE_GROUP][32];
 
-  const uint32_t lane = threadIdx.x & 31;
-  uint32_t (*s_color)[S] = s_color_all[threadIdx.x >> 5];
-  uint2* s_q = s_q_all[threadIdx.x >> 5];
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t (*s_color)[32][S] = s_color_all[wid];
+  uint2* s_pool = s_pool_all[wid];
+  uint32_t* s_org = s_org_all[wid];
+  uint8_t (*s_touched)[32] = s_touched_all[wid];
   const int q = lane >> 2, pi = lane & 3;
   const int wlx = (q & 3) * 2 + (pi & 1), wly = (q >> 2) * 2 + (pi >> 1);  // same pixel <-> lane map as k_cover
   const uint32_t fullmask = (1u << S) - 1;
   const uint32_t below = (1u << lane) - 1;
 
+  uint32_t n_exec = 0;
   const uint32_t n_items = c.active_tiles[0] * ITEMS_PER_TILE;
-  uint32_t next_raw = fetch_items(d.shade_counter, lane);
+  uint32_t next_raw = fetch_group(d.shade_counter, lane);
   for (;;) {
     const uint32_t base_item = __shfl_sync(0xFFFFFFFFu, next_raw, 0);
     if (base_item >= n_items) break;
-    next_raw = fetch_items(d.shade_counter, lane);
-    for (uint32_t item = base_item; item < base_item + FETCH && item < n_items; ++item) {
-      if (!d.item_flag[item]) continue;
-      const uint32_t b = item >> 7, sub = (item >> 3) & 15, w = item & 7;
-      const uint32_t tile = c.active_tiles[1 + b];
-      const uint32_t tile_x = tile % c.tiles_x, tile_y = tile / c.tiles_x;
-      const int gx0 = tile_x * TILE + (sub & 3) * REGION + (w & 1) * 8, gy0 = tile_y * TILE + (sub >> 2) * REGION + (w >> 1) * 4;
-      const int x = gx0 + wlx, y = gy0 + wly;
-      const bool in_target = (uint32_t)x < c.target_w && (uint32_t)y < c.target_h;
-
-      uint32_t own[S];
-#pragma unroll
-      for (int s = 0; s < S; ++s) own[s] = VIS_NONE;
-      if (in_target) {
-        const uint32_t* vp = d.vis + ((size_t)y * d.vis_pitch + x) * S;
-        if (S == 4) {
-          const uint4 v = *reinterpret_cast<const uint4*>(vp);
-          own[0] = v.x; own[1 % S] = v.y; own[2 % S] = v.z; own[3 % S] = v.w;
-        } else if (S == 2) {
-          const uint2 v = *reinterpret_cast<const uint2*>(vp);
-          own[0] = v.x; own[1 % S] = v.y;
-        } else {
-          own[0] = *vp;
-        }
-      }
-      uint32_t rem = 0;
-#pragma unroll
-      for (int s = 0; s < S; ++s) rem |= (own[s] != VIS_NONE) ? (1u << s) : 0u;
-      const uint32_t touched = rem;
-      uint32_t* cptr = reinterpret_cast<uint32_t*>(c.color0.data + ((size_t)y * c.color0.w + x) * S * 4);
-      if (touched && touched != fullmask) {  // some samples keep their colour: fetch it for the 128-bit store
-#pragma unroll
-        for (int s = 0; s < S; ++s) s_color[lane][s] = cptr[s];
-      }
-      // first owner of this pixel
-      uint32_t first_slot = VIS_NONE, first_mask = 0;
-#pragma unroll
-      for (int s = S - 1; s >= 0; --s)
-        if (rem & (1u << s)) first_slot = own[s];
-#pragma unroll
-      for (int s = 0; s < S; ++s)
-        if (rem & (1u << s) && own[s] == first_slot) first_mask |= 1u << s;
-      rem &= ~first_mask;
-      // further distinct owners -> the warp's queue (order irrelevant: every (pixel, sample) has exactly one writer)
-      uint32_t qn = 0;
-#pragma unroll
-      for (int round = 0; round < S - 1; ++round) {
-        uint32_t sl = VIS_NONE, m = 0;
-#pragma unroll
-        for (int s = S - 1; s >= 0; --s)
-          if (rem & (1u << s)) sl = own[s];
-#pragma unroll
-        for (int s = 0; s < S; ++s)
-          if ((rem & (1u << s)) && own[s] == sl) m |= 1u << s;
-        rem &= ~m;
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, m != 0);
-        if (m) s_q[qn + __popc(bal & below)] = make_uint2(lane | (m << 8), sl);
-        qn += __popc(bal);
-      }
-      // ONE shading call site: round 0 = every lane's own first owner, then the queued extras, 32 at a time
-      __syncwarp();
+    next_raw = fetch_group(d.shade_counter, lane);
+    uint32_t pool_n = 0, k = 0;
+    for (;;) {
+      // ---- fill: analyse items while the pool has room for a whole item ----
 #pragma unroll 1
-      for (uint32_t j = lane; j < 32 + qn; j += 32) {
-        uint32_t pl = lane, m = first_mask, slot = first_slot;
-        if (j >= 32) {
-          const uint2 it = s_q[j - 32];
-          pl = it.x & 0xFF; m = it.x >> 8; slot = it.y;
+      for (; k < SHADE_GROUP && pool_n + 32 * S <= (uint32_t)SHADE_POOL; ++k) {
+        const uint32_t item = base_item + k;
+        const bool live = item < n_items && d.item_flag[item];
+        if (lane == 0) s_org[k] = 0xFFFFFFFFu;
+        if (!live) continue;
+        const uint32_t b = item >> 7, sub = (item >> 3) & 15, w = item & 7;
+        const uint32_t tile = c.active_tiles[1 + b];
+        const uint32_t tile_x = tile % c.tiles_x, tile_y = tile / c.tiles_x;
+        const int gx0 = tile_x * TILE + (sub & 3) * REGION + (w & 1) * 8, gy0 = tile_y * TILE + (sub >> 2) * REGION + (w >> 1) * 4;
+        const int x = gx0 + wlx, y = gy0 + wly;
+        const bool in_target = (uint32_t)x < c.target_w && (uint32_t)y < c.target_h;
+        if (lane == 0) s_org[k] = (uint32_t)gx0 | ((uint32_t)gy0 << 16);
+
+        uint32_t own[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) own[s] = VIS_NONE;
+        if (in_target) {
+          const uint32_t* vp = d.vis + ((size_t)y * d.vis_pitch + x) * S;
+          if (S == 4) {
+            const uint4 v = *reinterpret_cast<const uint4*>(vp);
+            own[0] = v.x; own[1 % S] = v.y; own[2 % S] = v.z; own[3 % S] = v.w;
+          } else if (S == 2) {
+            const uint2 v = *reinterpret_cast<const uint2*>(vp);
+            own[0] = v.x; own[1 % S] = v.y;
+          } else {
+            own[0] = *vp;
+          }
         }
-        if (m) {
-          const uint32_t pq = pl >> 2, pp = pl & 3;
-          const int px_ = gx0 + (int)((pq & 3) * 2 + (pp & 1)), py_ = gy0 + (int)((pq >> 2) * 2 + (pp >> 1));
-          const uint32_t packed = shade_sample_owner<PS>(c, batch, slot, px_, py_);
+        uint32_t rem = 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) rem |= (own[s] != VIS_NONE) ? (1u << s) : 0u;
+        const uint32_t touched = rem;
+        s_touched[k][lane] = (uint8_t)touched;
+        if (touched && touched != fullmask) {  // some samples keep their colour: fetch it for the 128-bit store
+          const uint32_t* cptr = reinterpret_cast<const uint32_t*>(c.color0.data + ((size_t)y * c.color0.w + x) * S * 4);
+#pragma unroll
+          for (int s = 0; s < S; ++s) s_color[k][lane][s] = cptr[s];
+        }
+        // the pixel's distinct owners -> the pool, one ballot-compacted round per owner rank (order irrelevant:
+        // every (pixel, sample) has exactly one writer); round 0 = everybody's first owner, dense for covered blocks
+#pragma unroll
+        for (int round = 0; round < S; ++round) {
+          if (round > 0 && !__any_sync(0xFFFFFFFFu, rem != 0)) break;
+          uint32_t sl = VIS_NONE, m = 0;
+#pragma unroll
+          for (int s = S - 1; s >= 0; --s)
+            if (rem & (1u << s)) sl = own[s];
 #pragma unroll
           for (int s = 0; s < S; ++s)
-            if (m & (1u << s)) s_color[pl][s] = packed;
+            if ((rem & (1u << s)) && own[s] == sl) m |= 1u << s;
+          rem &= ~m;
+          const uint32_t bal = __ballot_sync(0xFFFFFFFFu, m != 0);
+          if (m) s_pool[pool_n + __popc(bal & below)] = make_uint2(lane | (m << 5) | (k << 9), sl);
+          pool_n += __popc(bal);
         }
       }
+      // ---- drain (the ONE shading call site): 32 (pixel, owner) pairs per round, whatever items they come from ----
       __syncwarp();
-      if (touched) {
-        if (S == 4) *reinterpret_cast<uint4*>(cptr) = make_uint4(s_color[lane][0], s_color[lane][1 % S], s_color[lane][2 % S], s_color[lane][3 % S]);
-        else if (S == 2) *reinterpret_cast<uint2*>(cptr) = make_uint2(s_color[lane][0], s_color[lane][1 % S]);
-        else *cptr = s_color[lane][0];
+#pragma unroll 1
+      for (uint32_t j = lane; j < pool_n; j += 32) {
+        const uint2 it = s_pool[j];
+        const uint32_t pl = it.x & 31, m = (it.x >> 5) & 0xF, kk = it.x >> 9;
+        const uint32_t org = s_org[kk];
+        const uint32_t pq = pl >> 2, pp = pl & 3;
+        const int px_ = (int)(org & 0xFFFF) + (int)((pq & 3) * 2 + (pp & 1)), py_ = (int)(org >> 16) + (int)((pq >> 2) * 2 + (pp >> 1));
+        const uint32_t packed = shade_sample_owner<PS>(c, batch, it.y, px_, py_);
+        ++n_exec;
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+          if (m & (1u << s)) s_color[kk][pl][s] = packed;
       }
       __syncwarp();
+      pool_n = 0;
+      if (k >= SHADE_GROUP) break;
     }
+    // ---- store the group's items, one 128-bit store per touched pixel at 4x ----
+#pragma unroll 1
+    for (uint32_t kk = 0; kk < SHADE_GROUP; ++kk) {
+      const uint32_t org = s_org[kk];
+      if (org == 0xFFFFFFFFu) continue;
+      if (s_touched[kk][lane]) {
+        const int x = (int)(org & 0xFFFF) + wlx, y = (int)(org >> 16) + wly;
+        uint32_t* cptr = reinterpret_cast<uint32_t*>(c.color0.data + ((size_t)y * c.color0.w + x) * S * 4);
+        if (S == 4) *reinterpret_cast<uint4*>(cptr) = make_uint4(s_color[kk][lane][0], s_color[kk][lane][1 % S], s_color[kk][lane][2 % S], s_color[kk][lane][3 % S]);
+        else if (S == 2) *reinterpret_cast<uint2*>(cptr) = make_uint2(s_color[kk][lane][0], s_color[kk][lane][1 % S]);
+        else *cptr = s_color[kk][lane][0];
+      }
+    }
+    __syncwarp();
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_exec += __shfl_xor_sync(0xFFFFFFFFu, n_exec, o);
+  if (lane == 0 && n_exec) atomicAdd(&c.stats[16], (unsigned long long)n_exec);
 }
 
 }  // namespace slv

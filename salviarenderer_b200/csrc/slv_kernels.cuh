@@ -1259,6 +1259,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, RASTER_CTAS_PER_SM) k_raster(R
   }
   if (lane == 0) {
     if (a) atomicAdd(&c.stats[7], (unsigned long long)a * 4ull);
+    if (a) atomicAdd(&c.stats[16], (unsigned long long)a * 4ull);  // the immediate path shades every quad it counts
     if (b) atomicAdd(&c.stats[8], (unsigned long long)b * 4ull);
     if (n_ztest) atomicAdd(&c.stats[9], (unsigned long long)n_ztest);
     if (n_zwrite) atomicAdd(&c.stats[10], (unsigned long long)n_zwrite);
@@ -1295,17 +1296,27 @@ __global__ void k_clear_ds_partial(float2* dst, size_t n, uint32_t flags, float 
   }
 }
 
-// surface::resolve (surface.cpp:123-140)
+// surface::resolve (surface.cpp:123-140): sum of to_rgba32f(sample) in sample order, * (1/S), convert (RNE)
 __global__ void k_resolve(SurfaceRef src, SurfaceRef dst) {
   uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= src.w || y >= src.h) return;
   float4 clr = make_float4(0, 0, 0, 0);
   const uint8_t* sp = src.data + ((size_t)y * src.w + x) * src.samples * src.bpp;
-  for (uint32_t s = 0; s < src.samples; ++s) {
-    float4 t = load_texel_rgba32f(src.fmt, sp + (size_t)s * src.bpp);
-    clr.x += t.x; clr.y += t.y; clr.z += t.z; clr.w += t.w;
+  const float inv = 1 / (float)src.samples;
+  if (src.bpp == 4 && src.samples == 4) {  // one 128-bit load per pixel
+    const uint4 v = *reinterpret_cast<const uint4*>(sp);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const float4 t = unpack_color(src.fmt, w[s]);
+      clr.x += t.x; clr.y += t.y; clr.z += t.z; clr.w += t.w;
+    }
+  } else {
+    for (uint32_t s = 0; s < src.samples; ++s) {
+      float4 t = load_texel_rgba32f(src.fmt, sp + (size_t)s * src.bpp);
+      clr.x += t.x; clr.y += t.y; clr.z += t.z; clr.w += t.w;
+    }
   }
-  float inv = 1 / (float)src.samples;
   clr.x *= inv; clr.y *= inv; clr.z *= inv; clr.w *= inv;
   store_texel_rgba32f(dst.fmt, dst.data + ((size_t)y * dst.w + x) * dst.bpp, clr);
 }

@@ -150,14 +150,17 @@ __device__ __forceinline__ const uint8_t* texel_ptr(const SurfaceRef& s, int x, 
 __device__ __forceinline__ float lerp1(float a, float b, float t) { return a + (b - a) * t; }
 
 // surface::get_texel(x0,y0,x1,y1,tx,ty): bilinear in the NATIVE format (colors.h:341-488)
-__device__ inline float4 bilinear(const SurfaceRef& s, int x0, int y0, int x1, int y1, float tx, float ty) {
-  const uint8_t* p0 = texel_ptr(s, x0, y0);
-  const uint8_t* p1 = texel_ptr(s, x1, y0);
-  const uint8_t* p2 = texel_ptr(s, x0, y1);
-  const uint8_t* p3 = texel_ptr(s, x1, y1);
+__device__ inline float4 bilinear(const SurfaceRef& s, int x0, int y0, int x1, int y1, float tx, float ty, bool in_range) {
   if (s.fmt == SLV_PF_RGBA8) {
-    uint32_t t0 = __ldg(reinterpret_cast<const uint32_t*>(p0)), t1 = __ldg(reinterpret_cast<const uint32_t*>(p1));
-    uint32_t t2 = __ldg(reinterpret_cast<const uint32_t*>(p2)), t3 = __ldg(reinterpret_cast<const uint32_t*>(p3));
+    // `in_range`: the addresser guarantees 0 <= index < size (every mode but border): 32-bit index arithmetic, no clamps
+    if (!in_range) {
+      x0 = min(max(x0, 0), (int)s.w - 1); x1 = min(max(x1, 0), (int)s.w - 1);
+      y0 = min(max(y0, 0), (int)s.h - 1); y1 = min(max(y1, 0), (int)s.h - 1);
+    }
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(s.data);
+    const uint32_t r0 = (uint32_t)y0 * s.w, r1 = (uint32_t)y1 * s.w;
+    uint32_t t0 = __ldg(base + (r0 + (uint32_t)x0)), t1 = __ldg(base + (r0 + (uint32_t)x1));
+    uint32_t t2 = __ldg(base + (r1 + (uint32_t)x0)), t3 = __ldg(base + (r1 + (uint32_t)x1));
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -168,6 +171,10 @@ __device__ inline float4 bilinear(const SurfaceRef& s, int x0, int y0, int x1, i
     }
     return make_float4(o[0], o[1], o[2], o[3]);
   }
+  const uint8_t* p0 = texel_ptr(s, x0, y0);
+  const uint8_t* p1 = texel_ptr(s, x1, y0);
+  const uint8_t* p2 = texel_ptr(s, x0, y1);
+  const uint8_t* p3 = texel_ptr(s, x1, y1);
   if (s.fmt == SLV_PF_RGBA32F) {
     float4 c0 = __ldg(reinterpret_cast<const float4*>(p0)), c1 = __ldg(reinterpret_cast<const float4*>(p1));
     float4 c2 = __ldg(reinterpret_cast<const float4*>(p2)), c3 = __ldg(reinterpret_cast<const float4*>(p3));
@@ -237,7 +244,44 @@ __device__ inline float4 sample_surface(const SurfaceRef& s, const slv_sampler_d
     y1 = do_coordi_point_1d(d.addr_mode_v, ipy + 1, H);
     ty = oy - (float)ipy;
   }
-  return bilinear(s, x0, y0, x1, y1, tx, ty);
+  // indices are provably inside the level for clamp / mirror, and for wrap when the exact integer wrap is used; the
+  // reference's float modulo (other sizes) and border addressing can step outside: those keep the clamped fetch
+  const bool safe_u = d.addr_mode_u == SLV_ADDR_CLAMP || d.addr_mode_u == SLV_ADDR_MIRROR || (d.addr_mode_u == SLV_ADDR_WRAP && s.wmask);
+  const bool safe_v = d.addr_mode_v == SLV_ADDR_CLAMP || d.addr_mode_v == SLV_ADDR_MIRROR || (d.addr_mode_v == SLV_ADDR_WRAP && s.hmask);
+  return bilinear(s, x0, y0, x1, y1, tx, ty, safe_u && safe_v);
+}
+
+// One bilinear tap for the commonest sampler state (SamplerRef::fast_wrap_rgba8): wrap addressing with the exact
+// integer modulo, rgba8 texels.  Operation for operation the WRAP branch of linear_coord_2d + the rgba8 branch of
+// bilinear above, minus the per-tap mode / format dispatch.
+__device__ __forceinline__ float4 sample_wrap_rgba8_linear(const SurfaceRef& s, float x, float y) {
+  const float fw = (float)(int)s.w, fh = (float)(int)s.h;
+  float fx = x - trunc_f(x);
+  fx = fw * fx;
+  fx = fx - 0.5f;
+  const float ipx = floor_fix(fx);
+  const float tx = fx - ipx;
+  float fy = y - trunc_f(y);
+  fy = fh * fy;
+  fy = fy - 0.5f;
+  const float ipy = floor_fix(fy);
+  const float ty = fy - ipy;
+  const int ix = (int)ipx, iy = (int)ipy;
+  const uint32_t wm = s.w - 1, hm = s.h - 1;
+  const uint32_t x0 = (uint32_t)ix & wm, x1 = (uint32_t)(ix + 1) & wm;
+  const uint32_t r0 = ((uint32_t)iy & hm) * s.w, r1 = ((uint32_t)(iy + 1) & hm) * s.w;
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(s.data);
+  const uint32_t t0 = __ldg(base + (r0 + x0)), t1 = __ldg(base + (r0 + x1));
+  const uint32_t t2 = __ldg(base + (r1 + x0)), t3 = __ldg(base + (r1 + x1));
+  float o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float c0 = (float)((t0 >> (8 * j)) & 0xFF), c1 = (float)((t1 >> (8 * j)) & 0xFF);
+    const float c2 = (float)((t2 >> (8 * j)) & 0xFF), c3 = (float)((t3 >> (8 * j)) & 0xFF);
+    const float c01 = lerp1(c0, c1, tx), c23 = lerp1(c2, c3, tx);
+    o[j] = lerp1(c01, c23, ty) * (1.0f / 255);
+  }
+  return make_float4(o[0], o[1], o[2], o[3]);
 }
 
 struct AfInfo { float lod, probe_count, weight_D, du, dv; };
@@ -351,7 +395,8 @@ __device__ inline float4 sample_impl(const SamplerRef& sm, float cx, float cy, f
   float w_sum = 0.0f;
 #pragma unroll 1
   for (int k = 0; k < n; ++k) {
-    const float4 v = sample_surface(t.level[k ? lv1 : lv0], d, filter, sx, sy);
+    const SurfaceRef& lvl = t.level[k ? lv1 : lv0];
+    const float4 v = sm.fast_wrap_rgba8 ? sample_wrap_rgba8_linear(lvl, sx, sy) : sample_surface(lvl, d, filter, sx, sy);
     if (aniso) {
       const int wi = (int)((float)(tap_i * tap_i) * weight_D);
       const float w = c_ewa_wts[min(max(wi, 0), 255)];

@@ -22,4 +22,4 @@ for f in range(8):
         sc.render(be, f)
     be.event_record(1)
     ms = be.event_elapsed_ms(0, 1) / 3
-    print(f"frame {f}: {ms:6.3f} ms | geom {pr['clipping']/1e6:5.3f} bin {pr['tri_dispatch']/1e6:5.3f} raster {pr['ras']/1e6:6.3f} (cover {sg['raster_or_cover']:5.3f} shade {sg['shade']:5.3f} sort {sg['sort']:5.3f} rbin {sg['region_bin']:5.3f}) | ps {st['ps_invocations']/1e6:6.2f}M cprims {st['cprimitives']:7d} ztest {tr['z_tested']/1e6:6.1f}M cwr {tr['c_written']/1e6:6.1f}M | scanned {tr['list_entries_scanned']/1e6:6.2f}M surv {tr['region_survivors']/1e6:6.2f}M pairs {tr['warp_pairs']/1e6:6.2f}M quads {tr['quads_shaded']/1e6:6.2f}M", flush=True)
+    print(f"frame {f}: {ms:6.3f} ms | geom {pr['clipping']/1e6:5.3f} bin {pr['tri_dispatch']/1e6:5.3f} raster {pr['ras']/1e6:6.3f} (cover {sg['raster_or_cover']:5.3f} shade {sg['shade']:5.3f} sort {sg['sort']:5.3f} rbin {sg['region_bin']:5.3f}) | ps {st['ps_invocations']/1e6:6.2f}M cprims {st['cprimitives']:7d} ztest {tr['z_tested']/1e6:6.1f}M cwr {tr['c_written']/1e6:6.1f}M | scanned {tr['list_entries_scanned']/1e6:6.2f}M surv {tr['region_survivors']/1e6:6.2f}M pairs {tr['warp_pairs']/1e6:6.2f}M quads {tr['quads_shaded']/1e6:6.2f}M ps_exec {tr['ps_executed']/1e6:6.2f}M", flush=True)
