@@ -70,6 +70,7 @@ struct slv_device_t {
   uint32_t region_cap = 0;
   uint32_t* region_mask = nullptr;  // one word per tile-list entry
   uint8_t* item_flag = nullptr;
+  uint32_t* block_count = nullptr;  // entries in each (region, warp block) sub-list
   uint32_t* vis = nullptr;           // visibility buffer of the deferred path: owner slot per sample
   size_t vis_cap = 0;                // in uint32 units
   bool force_immediate = false;      // SLV_FORCE_IMMEDIATE=1: always use k_raster (tests compare both paths)
@@ -147,7 +148,7 @@ slv_result ensure_scratch(slv_device dev, size_t tris_needed_total, uint32_t n_t
     if (dev->tile_count) {
       CU(cudaFree(dev->tile_count)); CU(cudaFree(dev->tile_offset)); CU(cudaFree(dev->tile_cursor));
       CU(cudaFree(dev->active_tiles)); CU(cudaFree(dev->large_tiles));
-      CU(cudaFree(dev->region_offset)); CU(cudaFree(dev->region_count)); CU(cudaFree(dev->item_flag));
+      CU(cudaFree(dev->region_offset)); CU(cudaFree(dev->region_count)); CU(cudaFree(dev->item_flag)); CU(cudaFree(dev->block_count));
     }
     uint32_t cap = std::max(n_tiles + 1, 4096u);
     CU(cudaMalloc(&dev->tile_count, cap * sizeof(uint32_t)));
@@ -158,6 +159,7 @@ slv_result ensure_scratch(slv_device dev, size_t tris_needed_total, uint32_t n_t
     CU(cudaMalloc(&dev->region_offset, (size_t)cap * 16 * sizeof(uint32_t)));
     CU(cudaMalloc(&dev->region_count, (size_t)cap * 16 * sizeof(uint32_t)));
     CU(cudaMalloc(&dev->item_flag, (size_t)cap * 128));
+    CU(cudaMalloc(&dev->block_count, (size_t)cap * 128 * sizeof(uint32_t)));
     CU(cudaMemsetAsync(dev->tile_count, 0, cap * sizeof(uint32_t), dev->stream));
     CU(cudaMemsetAsync(dev->tile_cursor, 0, cap * sizeof(uint32_t), dev->stream));
     dev->tiles_cap = cap;
@@ -238,20 +240,21 @@ slv_result flush_batch(slv_device dev) {
   const uint32_t n_tiles = first.tiles_x * first.tiles_y;
   const uint32_t n_slots = (uint32_t)dev->slots_queued;
   // list arena: heuristic bound, checked on the device (overflow flag -> SLV_OUT_OF_MEMORY at the next flush point)
-  const uint64_t list_need = std::min<uint64_t>(std::max<uint64_t>(8ull * n_slots, 1u << 22), 1ull << 31);
+  const uint64_t list_need = std::min<uint64_t>(std::max<uint64_t>(4ull * n_slots, 1u << 22), 1ull << 31);
   if (list_need > dev->list_cap) {
     CU(cudaStreamSynchronize(st));
     if (dev->list) CU(cudaFree(dev->list));
     CU(cudaMalloc(&dev->list, (size_t)list_need * sizeof(uint32_t)));
     dev->list_cap = (uint32_t)list_need;
-    // per-region lists of the deferred path: exact two-pass allocation on the device inside this arena; a triangle
-    // list entry survives in 1..16 regions (about 1.5 on the Sponza-like scene)
+    // (region, warp block) sub-lists of the deferred path, allocated on the device inside this arena: 8 sub-lists of
+    // capacity n per region with n surviving entries; a tile-list entry survives in 1..16 regions (about 1.5 on the
+    // Sponza-like scene, i.e. ~12 words per tile-list entry; overflow raises the sticky out-of-memory error)
     if (dev->region_list) CU(cudaFree(dev->region_list));
-    const uint64_t rcap = std::min<uint64_t>(2ull * list_need, 0xFFFFFFF0ull);
+    const uint64_t rcap = std::min<uint64_t>(std::max<uint64_t>(2ull * list_need, 1ull << 24), 0xFFFFFFF0ull);
     CU(cudaMalloc(&dev->region_list, (size_t)rcap * sizeof(uint32_t)));
     dev->region_cap = (uint32_t)rcap;
     if (dev->region_mask) CU(cudaFree(dev->region_mask));
-    CU(cudaMalloc(&dev->region_mask, (size_t)list_need * sizeof(uint32_t)));
+    CU(cudaMalloc(&dev->region_mask, (size_t)list_need * RMASK_STRIDE * sizeof(uint32_t)));
   }
   first.list = dev->list;
   first.list_capacity = dev->list_cap;
@@ -297,7 +300,7 @@ slv_result flush_batch(slv_device dev) {
                                     dev->work_counter, dev->large_tiles);
   k_bin_fill<<<(n_slots + 255) / 256, 256, 0, st>>>(bp);
   size_t e1 = dev->profile ? mark(dev) : 0;
-  k_sort_lists<<<n_tiles, 256, 0, st>>>(dev->tile_offset, dev->list, dev->list_cap);
+  k_sort_lists<<<n_tiles, 256, 0, st>>>(dev->tile_offset, dev->list, dev->list_cap, dev->active_tiles);
   k_sort_lists_large<<<dev->sm_count, 1024, SORT_LARGE_SMEM * sizeof(uint32_t), st>>>(dev->tile_offset, dev->list, dev->list_cap,
                                                                                       dev->large_tiles);
   size_t e2 = dev->profile ? mark(dev) : 0;
@@ -328,6 +331,7 @@ slv_result flush_batch(slv_device dev) {
     db.cursor = dev->work_counter + 2;
     db.overflow_flag = dev->overflow_flag;
     db.item_flag = dev->item_flag;
+    db.block_count = dev->block_count;
     db.vis = shade ? dev->vis : nullptr;
     db.vis_pitch = first.color0.w;
     db.cover_counter = dev->work_counter;
@@ -467,6 +471,7 @@ void slv_device_destroy(slv_device dev) {
   cudaFree(dev->region_offset);
   cudaFree(dev->region_count);
   cudaFree(dev->item_flag);
+  cudaFree(dev->block_count);
   cudaFree(dev->list);
   cudaFree(dev->overflow_flag);
   cudaFree(dev->d_stats);
@@ -734,7 +739,7 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   const uint32_t R = 1 + n_attrs;
   const uint32_t tri_stride = TRI_HEADER + 3 * MAX_REGS;  // uniform across the batch: slot -> record address
   const uint64_t n_slots64 = 3ull * d->prim_count;
-  if (n_slots64 >= (1ull << 30)) return SLV_INVALID_PARAMETER;
+  if (n_slots64 >= (1ull << 28)) return SLV_INVALID_PARAMETER;  // sub-list entries are (slot << 4) | block status
   const uint32_t n_slots = (uint32_t)n_slots64;
   // ---- can this draw join the queued batch? (same targets, sample count, pixel-shader program, tile grid)
   if (!dev->pending.empty()) {
@@ -752,7 +757,7 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   slv_result rc = ensure_scratch(dev, dev->tris_used + tris_need, n_tiles, list_need);
   if (rc != SLV_OK) return rc;
   if (dev->tris_used + tris_need > dev->tris_cap) return SLV_OUT_OF_MEMORY;
-  if (dev->slots_queued + n_slots >= (1ull << 30)) {  // 31-bit list entries: (slot << 1) | accept
+  if (dev->slots_queued + n_slots >= (1ull << 28)) {  // 28-bit slots: sub-list entries are (slot << 4) | block status
     slv_result rcf = flush_batch(dev);
     if (rcf != SLV_OK) return rcf;
   }

@@ -45,7 +45,9 @@ struct CovTri {  // one surviving triangle of the warp's current chunk, staged i
 // (2 bits each: 0 rejected, 1 partial, 2 full)
 
 struct DeferredBufs {
-  uint32_t* region_list;      // entries (slot << 1) | region_fully_inside, in API order per region
+  uint32_t* region_list;      // per region 8 sub-lists (one per 8x4 warp block) of capacity region_count, entries
+                              // (slot << 4) | status of the warp's two 4x4 blocks, in API order
+  uint32_t* block_count;      // [(active tile index * 16 + region) * 8 + warp block] entries in the sub-list
   uint32_t* region_mask;      // scratch, one word per tile-list entry: regions survived | regions fully inside << 16
   uint32_t region_cap;
   uint32_t* region_offset;    // [active tile index * 16 + region]
@@ -67,12 +69,26 @@ struct DeferredBufs {
 #endif
 
 constexpr int RBIN_THREADS = 512;  // 16 warps == the 16 regions of a tile
+constexpr int RMASK_STRIDE = 5;    // scratch words per tile-list entry: region masks + block bits of up to 4 partial regions
+
+// level-4 decision of the 16 blocks of region `reg` of tile (tile_x, tile_y): 2 bits per block, 0 rejected, 1 partial, 2 full
+__device__ __forceinline__ uint32_t region_block_bits(const TriEntry& te, float x_min, float x_max, float y_min, float y_max,
+                                                      uint32_t tile_x, uint32_t tile_y, int reg) {
+  const int X16 = (reg & 3) * REGION, Y16 = (reg >> 2) * REGION;
+  const float rl = (float)(tile_x * TILE + X16), rt = (float)(tile_y * TILE + Y16);
+  uint32_t st_bits = 0;
+  for (int blk = 0; blk < 16; ++blk) {
+    const int bbx = blk & 3, bby = blk >> 2;
+    st_bits |= (uint32_t)block_test(te, x_min, x_max, y_min, y_max, X16 + bbx * 4, Y16 + bby * 4, rl, rt, bbx, bby) << (2 * blk);
+  }
+  return st_bits;
+}
 
 // Phase 1: one thread per tile-list entry evaluates the reference's level-16 decision (subdivide_tile at the 16-px
 // level, rasterizer.cpp:441-602, 698-772) for all 16 regions of the tile and stores survive | accept << 16.
 // Phase 2: warp r compacts, IN ORDER, the entries surviving in region r into the region's list (two streaming passes
 // over the masks: count, then fill; allocation = one atomicAdd per tile).
-__global__ void __launch_bounds__(RBIN_THREADS) k_region_bin(RasterParams c, DeferredBufs d) {
+__global__ void __launch_bounds__(RBIN_THREADS, 2) k_region_bin(RasterParams c, DeferredBufs d) {
   __shared__ uint32_t s_cnt[16], s_base[16];
   const uint32_t b = blockIdx.x;
   if (b >= c.active_tiles[0]) return;
@@ -128,14 +144,32 @@ __global__ void __launch_bounds__(RBIN_THREADS) k_region_bin(RasterParams c, Def
       }
     }
     survive &= on_screen;
-    d.region_mask[i] = survive | ((accept & survive) << 16);
+    accept &= survive;
+    d.region_mask[(size_t)i * RMASK_STRIDE] = survive | (accept << 16);
+    // level-4 decisions (subdivide_tile at the 4-px level) of the first RMASK_STRIDE - 1 partially covered regions,
+    // 2 bits per 4x4 block: evaluated here, with one thread per entry, so that the ordered compaction below is cheap
+    uint32_t partial = survive & ~accept;
+    if (partial) {
+      const float4* rec = c.tris + (size_t)(e >> 1) * c.tri_stride;
+      const float4 e0 = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2), bb = __ldg(rec + 3);
+      TriEntry te;
+      te.A[0] = e0.x; te.B[0] = e0.y; te.C[0] = e0.z;
+      te.A[1] = e1.x; te.B[1] = e1.y; te.C[1] = e1.z;
+      te.A[2] = e2.x; te.B[2] = e2.y; te.C[2] = e2.z;
+      const float x_min = bb.x - vpx, x_max = bb.y - vpx, y_min = bb.z - vpy, y_max = bb.w - vpy;
+      for (int k = 1; k < RMASK_STRIDE && partial; ++k) {
+        const int reg = __ffs(partial) - 1;
+        partial &= partial - 1;
+        d.region_mask[(size_t)i * RMASK_STRIDE + k] = region_block_bits(te, x_min, x_max, y_min, y_max, tile_x, tile_y, reg);
+      }
+    }
   }
   __syncthreads();
 
   uint32_t cnt = 0;
   for (uint32_t i = beg; i < end; i += 32) {
     const uint32_t ei = i + lane;
-    const uint32_t m = ei < end ? d.region_mask[ei] : 0u;
+    const uint32_t m = ei < end ? d.region_mask[(size_t)ei * RMASK_STRIDE] : 0u;
     cnt += __popc(__ballot_sync(0xFFFFFFFFu, (m >> r) & 1u));
   }
   if (lane == 0) s_cnt[r] = cnt;
@@ -143,30 +177,71 @@ __global__ void __launch_bounds__(RBIN_THREADS) k_region_bin(RasterParams c, Def
   if (threadIdx.x == 0) {
     uint32_t total = 0;
     for (int k = 0; k < 16; ++k) total += s_cnt[k];
-    uint32_t base = total ? atomicAdd(d.cursor, total) : 0u;
-    const bool fits = base + total <= d.region_cap;
+    // every region gets 8 sub-lists (one per 8x4 warp block) of capacity cnt each
+    uint32_t base = total ? atomicAdd(d.cursor, total * 8u) : 0u;
+    const bool fits = (uint64_t)base + (uint64_t)total * 8u <= (uint64_t)d.region_cap;
     if (!fits) *d.overflow_flag = 1;
     for (int k = 0; k < 16; ++k) {
       s_base[k] = base;
       d.region_offset[b * 16 + k] = base;
       d.region_count[b * 16 + k] = fits ? s_cnt[k] : 0u;
-      base += s_cnt[k];
+      base += s_cnt[k] * 8u;
     }
     if (!fits) s_base[0] = 0xFFFFFFFFu;
     if (total) {
       atomicAdd(&c.stats[13], (unsigned long long)(end - beg) * 16ull);  // (entry, region) decisions evaluated
-      atomicAdd(&c.stats[14], (unsigned long long)total);                 // region-list entries
+      atomicAdd(&c.stats[14], (unsigned long long)total);                 // (entry, region) survivors
     }
   }
   __syncthreads();
-  if (s_base[0] == 0xFFFFFFFFu || !cnt) return;
-  uint32_t at = s_base[r];
-  for (uint32_t i = beg; i < end; i += 32) {
-    const uint32_t ei = i + lane;
-    const uint32_t m = ei < end ? d.region_mask[ei] : 0u;
-    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, (m >> r) & 1u);
-    if ((m >> r) & 1u) d.region_list[at + __popc(bal & ((1u << lane) - 1))] = (__ldg(c.list + ei) & ~1u) | ((m >> (16 + r)) & 1u);
-    at += __popc(bal);
+  const bool ok = s_base[0] != 0xFFFFFFFFu;
+  // Phase 3: warp r walks the tile list once more; the lane of a surviving entry evaluates the level-4 decision of
+  // the region's 16 blocks (subdivide_tile at the 4-px level) and the entry is appended, IN ORDER, to the sub-list of
+  // every 8x4 warp block it touches, as (slot << 4) | status of the block pair (2 bits each: 1 partial, 2 full).
+  uint32_t pos[8];
+#pragma unroll
+  for (int w = 0; w < 8; ++w) pos[w] = 0;
+  if (ok && cnt) {
+    const uint32_t rbase = s_base[r];
+    const uint32_t below = (1u << lane) - 1;
+    for (uint32_t i = beg; i < end; i += 32) {
+      const uint32_t ei = i + lane;
+      const uint32_t m = ei < end ? d.region_mask[(size_t)ei * RMASK_STRIDE] : 0u;
+      uint32_t st_bits = 0, slot = 0;
+      if ((m >> r) & 1u) {
+        slot = __ldg(c.list + ei) >> 1;
+        if ((m >> (16 + r)) & 1u) {
+          st_bits = 0xAAAAAAAAu;  // region fully inside: every block full
+        } else {
+          const uint32_t partial = (m & 0xFFFFu) & ~(m >> 16);
+          const uint32_t k = __popc(partial & ((1u << r) - 1));  // rank of this region among the entry's partial ones
+          if (k < (uint32_t)RMASK_STRIDE - 1) {
+            st_bits = d.region_mask[(size_t)ei * RMASK_STRIDE + 1 + k];
+          } else {  // an entry with more partially covered regions than phase 1 stores: evaluate here
+            const float4* rec = c.tris + (size_t)slot * c.tri_stride;
+            const float4 e0 = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2), bb = __ldg(rec + 3);
+            TriEntry te;
+            te.A[0] = e0.x; te.B[0] = e0.y; te.C[0] = e0.z;
+            te.A[1] = e1.x; te.B[1] = e1.y; te.C[1] = e1.z;
+            te.A[2] = e2.x; te.B[2] = e2.y; te.C[2] = e2.z;
+            st_bits = region_block_bits(te, bb.x - vpx, bb.y - vpx, bb.z - vpy, bb.w - vpy, tile_x, tile_y, (int)r);
+          }
+        }
+      }
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {  // warp block w owns blocks (by = w >> 1, bx = (w & 1) * 2 + {0, 1})
+        const uint32_t four = (st_bits >> (2 * ((w >> 1) * 4 + (w & 1) * 2))) & 0xFu;
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, four != 0);
+        if (four) d.region_list[rbase + (uint32_t)w * cnt + pos[w] + __popc(bal & below)] = (slot << 4) | four;
+        pos[w] += __popc(bal);
+      }
+    }
+  }
+  if (lane < 8) {
+    uint32_t mine = pos[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mine = (lane == (uint32_t)w) ? pos[w] : mine;
+    d.block_count[(b * 16 + r) * 8 + lane] = mine;
   }
 }
 
@@ -201,12 +276,12 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_COVER_CTAS_PER_SM)
     next_raw = fetch_items(d.cover_counter, lane);
     for (uint32_t item = base_item; item < base_item + FETCH && item < n_items; ++item) {
       const uint32_t b = item >> 7, sub = (item >> 3) & 15, w = item & 7;
-      const uint32_t rcnt = d.region_count[b * 16 + sub];
+      const uint32_t rcnt = d.block_count[item];  // item == (b * 16 + sub) * 8 + w
       if (rcnt == 0) {
         if (lane == 0) d.item_flag[item] = 0;
         continue;
       }
-      const uint32_t rbeg = d.region_offset[b * 16 + sub];
+      const uint32_t rbeg = d.region_offset[b * 16 + sub] + w * d.region_count[b * 16 + sub];
       const uint32_t tile = c.active_tiles[1 + b];
       const uint32_t tile_x = tile % c.tiles_x, tile_y = tile / c.tiles_x;
       const int X16 = (sub & 3) * REGION, Y16 = (sub >> 2) * REGION;
@@ -215,7 +290,6 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_COVER_CTAS_PER_SM)
       const int x = gx0 + wx + wlx, y = gy0 + wy + wly;
       const bool odd_x = x & 1, odd_y = y & 1;
       const bool in_target = (uint32_t)x < c.target_w && (uint32_t)y < c.target_h;
-      const float vpx = (float)(tile_x * TILE), vpy = (float)(tile_y * TILE);
       const float hx = 0.5f + (float)(uint32_t)(x & ~1), hy = 0.5f + (float)(uint32_t)(y & ~1);
       const int bxA = wx >> 2, by = wy >> 2;  // block A of the warp inside the region; block B = bxA + 1
       const float left_f = (float)(gx0 + (bxA + bsel) * 4), top_f = (float)(gy0 + by * 4);
@@ -224,68 +298,49 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_COVER_CTAS_PER_SM)
       uint32_t st[S], own[S];
 #pragma unroll
       for (int s = 0; s < S; ++s) { z[s] = 0.0f; st[s] = 0u; own[s] = VIS_NONE; }
-      bool fb_loaded = false, dirty = false;
+      bool dirty = false;
+      if (in_target && c.ds.data) {
+        const float2* dp = reinterpret_cast<const float2*>(c.ds.data + ((size_t)y * c.ds.w + x) * S * 8);
+        if (S == 4) {
+          const float4 a = *reinterpret_cast<const float4*>(dp), b2 = *reinterpret_cast<const float4*>(dp + 2);
+          z[0] = a.x; st[0] = __float_as_uint(a.y); z[1 % S] = a.z; st[1 % S] = __float_as_uint(a.w);
+          z[2 % S] = b2.x; st[2 % S] = __float_as_uint(b2.y); z[3 % S] = b2.z; st[3 % S] = __float_as_uint(b2.w);
+        } else {
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            const float2 v = dp[s];
+            z[s] = v.x;
+            st[s] = __float_as_uint(v.y);
+          }
+        }
+      }
 
       for (uint32_t chunk = 0; chunk < rcnt; chunk += 32) {
-        // ---- filter: level-4 decision of the warp's two blocks, one lane per region-list entry ----
+        // ---- stage the chunk's triangles in shared memory, one lane per list entry (every entry touches this warp) ----
         const uint32_t ei = chunk + lane;
-        uint32_t st4 = 0;
         if (ei < rcnt) {
           const uint32_t e = __ldg(d.region_list + rbeg + ei);
-          const uint32_t slot = e >> 1;
+          const uint32_t slot = e >> 4, st4 = e & 0xFu;
           const float4* rec = c.tris + (size_t)slot * c.tri_stride;
           const float4 e0 = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2);
-          if (e & 1) {
-            st4 = 0xAu;  // region fully inside: both blocks full
-          } else {
-            const float4 bb = __ldg(rec + 3);
-            TriEntry te;
-            te.A[0] = e0.x; te.B[0] = e0.y; te.C[0] = e0.z;
-            te.A[1] = e1.x; te.B[1] = e1.y; te.C[1] = e1.z;
-            te.A[2] = e2.x; te.B[2] = e2.y; te.C[2] = e2.z;
-            const float x_min = bb.x - vpx, x_max = bb.y - vpx, y_min = bb.z - vpy, y_max = bb.w - vpy;
-            const float rl = (float)gx0, rt = (float)gy0;
-            st4 = (uint32_t)block_test(te, x_min, x_max, y_min, y_max, X16 + bxA * 4, Y16 + by * 4, rl, rt, bxA, by) |
-                  ((uint32_t)block_test(te, x_min, x_max, y_min, y_max, X16 + (bxA + 1) * 4, Y16 + by * 4, rl, rt, bxA + 1, by) << 2);
-          }
-          if (st4) {
-            const RasterParams& p = batch[__float_as_uint(__ldg(rec + 4).w)];
-            const float4 v0p = __ldg(rec + REC_V0), gxp = __ldg(rec + REC_DDX), gyp = __ldg(rec + REC_DDY);
-            const uint32_t bits = (p.read_depth ? 1u : 0u) | (p.write_depth ? 2u : 0u) |
-                                  ((p.depth_enable ? compare_lut(p.depth_func) : 0xFu) << 4) | (st4 << 8);
-            CovTri ent;
-            ent.e0 = make_float4(e0.x, e0.y, e0.z, e1.x);
-            ent.e1 = make_float4(e1.y, e1.z, e2.x, e2.y);
-            ent.e2 = make_float4(e2.z, v0p.x, v0p.y, v0p.z);
-            ent.e3 = make_float4(gxp.z, gyp.z, __uint_as_float(slot), __uint_as_float(bits));
-            float aa[4];
+          const RasterParams& p = batch[__float_as_uint(__ldg(rec + 4).w)];
+          const float4 v0p = __ldg(rec + REC_V0), gxp = __ldg(rec + REC_DDX), gyp = __ldg(rec + REC_DDY);
+          const uint32_t bits = (p.read_depth ? 1u : 0u) | (p.write_depth ? 2u : 0u) |
+                                ((p.depth_enable ? compare_lut(p.depth_func) : 0xFu) << 4) | (st4 << 8);
+          CovTri ent;
+          ent.e0 = make_float4(e0.x, e0.y, e0.z, e1.x);
+          ent.e1 = make_float4(e1.y, e1.z, e2.x, e2.y);
+          ent.e2 = make_float4(e2.z, v0p.x, v0p.y, v0p.z);
+          ent.e3 = make_float4(gxp.z, gyp.z, __uint_as_float(slot), __uint_as_float(bits));
+          float aa[4];
 #pragma unroll
-            for (int s = 0; s < 4; ++s)
-              aa[s] = (s < S && S > 1) ? (SamplePattern<S>::x(s) - 0.5f) * gxp.z + (SamplePattern<S>::y(s) - 0.5f) * gyp.z : 0.0f;
-            ent.aa = make_float4(aa[0], aa[1], aa[2], aa[3]);
-            s_tri[lane] = ent;
-          }
+          for (int s = 0; s < 4; ++s)
+            aa[s] = (s < S && S > 1) ? (SamplePattern<S>::x(s) - 0.5f) * gxp.z + (SamplePattern<S>::y(s) - 0.5f) * gyp.z : 0.0f;
+          ent.aa = make_float4(aa[0], aa[1], aa[2], aa[3]);
+          s_tri[lane] = ent;
         }
-        uint32_t todo = __ballot_sync(0xFFFFFFFFu, st4 != 0);
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, ei < rcnt);
         __syncwarp();  // orders the shared-memory writes above before the reads below
-        if (todo && !fb_loaded) {
-          fb_loaded = true;
-          if (in_target && c.ds.data) {
-            const float2* dp = reinterpret_cast<const float2*>(c.ds.data + ((size_t)y * c.ds.w + x) * S * 8);
-            if (S == 4) {
-              const float4 a = *reinterpret_cast<const float4*>(dp), b2 = *reinterpret_cast<const float4*>(dp + 2);
-              z[0] = a.x; st[0] = __float_as_uint(a.y); z[1 % S] = a.z; st[1 % S] = __float_as_uint(a.w);
-              z[2 % S] = b2.x; st[2 % S] = __float_as_uint(b2.y); z[3 % S] = b2.z; st[3 % S] = __float_as_uint(b2.w);
-            } else {
-#pragma unroll
-              for (int s = 0; s < S; ++s) {
-                const float2 v = dp[s];
-                z[s] = v.x;
-                st[s] = __float_as_uint(v.y);
-              }
-            }
-          }
-        }
         if (lane == 0) n_pairs += __popc(todo);
         // ---- the chunk's surviving triangles, in API order ----
         while (todo) {
@@ -378,7 +433,7 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_COVER_CTAS_PER_SM)
         else if (S == 2) *reinterpret_cast<uint2*>(vp) = make_uint2(own[0], own[1 % S]);
         else *vp = own[0];
       }
-      if (fb_loaded) {
+      {
         const bool any_ds = __any_sync(0xFFFFFFFFu, dirty);
         if (in_target && any_ds && c.ds.data) {
           uint8_t* ds_ptr = c.ds.data + ((size_t)y * c.ds.w + x) * S * 8;

@@ -415,17 +415,27 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint3
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) { s_carry = 0; s_active = 0; s_large = 0; work_counter[0] = 0; work_counter[1] = 0; work_counter[2] = 0; work_counter[3] = 0; }
   __syncthreads();
-  for (uint32_t base = 0; base < n_tiles; base += 1024) {
-    const uint32_t i = base + tid;
-    const uint32_t v = i < n_tiles ? tile_count[i] : 0;
-    {  // active-tile compaction (order across warps is irrelevant)
-      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, v != 0);
+  // active-tile compaction, longest lists first (classes >= 2048, >= 512, >= 128, rest): the raster work queue hands
+  // items out in this order, so the few very long in-order chains start early instead of forming the kernel's tail
+  for (int cls = 0; cls < 4; ++cls) {
+    const uint32_t lo = cls == 0 ? 2048u : (cls == 1 ? 512u : (cls == 2 ? 128u : 1u));
+    const uint32_t hi = cls == 0 ? 0xFFFFFFFFu : (cls == 1 ? 2048u : (cls == 2 ? 512u : 128u));
+    for (uint32_t base = 0; base < n_tiles; base += 1024) {
+      const uint32_t i = base + tid;
+      const uint32_t v = i < n_tiles ? tile_count[i] : 0;
+      const bool in_cls = v >= lo && v < hi;
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, in_cls);
       uint32_t wbase = 0;
       if (lane == 0 && bal) wbase = atomicAdd(&s_active, (uint32_t)__popc(bal));
       wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-      if (v != 0) active_tiles[1 + wbase + __popc(bal & ((1u << lane) - 1))] = i;
-      if (v > (uint32_t)SORT_SMEM) large_tiles[1 + atomicAdd(&s_large, 1u)] = i;  // sorted by k_sort_lists_large
+      if (in_cls) active_tiles[1 + wbase + __popc(bal & ((1u << lane) - 1))] = i;
+      if (cls == 0 && v > (uint32_t)SORT_SMEM) large_tiles[1 + atomicAdd(&s_large, 1u)] = i;  // sorted by k_sort_lists_large
     }
+    __syncthreads();  // classes must not interleave in active_tiles
+  }
+  for (uint32_t base = 0; base < n_tiles; base += 1024) {
+    const uint32_t i = base + tid;
+    const uint32_t v = i < n_tiles ? tile_count[i] : 0;
     uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -512,9 +522,12 @@ __device__ __forceinline__ void bitonic_sort_block(uint32_t* buf, uint32_t n) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_sort_lists(const uint32_t* tile_offset, uint32_t* list, uint32_t capacity) {
+__global__ void __launch_bounds__(256) k_sort_lists(const uint32_t* tile_offset, uint32_t* list, uint32_t capacity,
+                                                    const uint32_t* active_tiles) {
   __shared__ uint32_t s[SORT_SMEM];
-  uint32_t beg = tile_offset[blockIdx.x], end = tile_offset[blockIdx.x + 1];
+  if (blockIdx.x >= active_tiles[0]) return;
+  const uint32_t tile = active_tiles[1 + blockIdx.x];  // longest lists first
+  uint32_t beg = tile_offset[tile], end = tile_offset[tile + 1];
   if (end > capacity) end = capacity;
   if (beg >= end) return;
   const uint32_t n = end - beg;
