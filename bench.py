@@ -262,7 +262,7 @@ def main():
     be.profile_enable(False)
     K = args.steps
     cover_ms, shade_ms = stages["raster_or_cover"] / K, stages["shade"] / K
-    geom_ms, bin_ms, sort_ms = stages["geometry"] / K, stages["bin"] / K, stages["sort"] / K
+    geom_ms, bin_ms, sort_ms, rbin_ms = stages["geometry"] / K, stages["bin"] / K, stages["sort"] / K, stages["region_bin"] / K
     R = 5  # position + 4 attributes (VS_SPONZA)
     S, W, H = args.samples, args.width, args.height
     vstride, n_prims = 48, 262249
@@ -291,14 +291,14 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "dram_bytes.json")
     if os.path.exists(tpath):
         traffic_measured = json.load(open(tpath)).get(dom, {}).get("dram_bytes_per_launch")
-    stage_sum = geom_ms + bin_ms + sort_ms + cover_ms + shade_ms
+    stage_sum = geom_ms + bin_ms + sort_ms + rbin_ms + cover_ms + shade_ms
     roofline = {"bound": "hbm", "kernel": dom + f"<{S}>" if dom == "k_cover" else dom + f"<{S}, PS_SPONZA>",
                 "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac"],
                 "traffic": traffic_measured, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kernels[dom]["bytes"], "launches_per_frame": 1,
                 "kernel_ms_per_launch": kernels[dom]["ms"], "kernel_share_of_step": kernels[dom]["ms"] / max(stage_sum, 1e-9),
                 "kernels": kernels,
-                "stage_ms_per_frame": {"geometry": geom_ms, "scan+bin_fill": bin_ms, "sort": sort_ms, "cover": cover_ms, "shade": shade_ms},
+                "stage_ms_per_frame": {"geometry": geom_ms, "scan+bin_fill": bin_ms, "sort": sort_ms, "region_bin": rbin_ms, "cover": cover_ms, "shade": shade_ms},
                 "frame": {"algorithmic_bytes": b_frame, "achieved_gbs": b_frame / (ms_per_step * 1e-3) / 1e9,
                           "frac": b_frame / (ms_per_step * 1e-3) / 1e9 / peak,
                           "terms": {"clear": b_clear, "geometry": b_geom, "setup": b_setup, "depth": b_depth, "colour": b_color,

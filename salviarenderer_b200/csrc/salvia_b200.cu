@@ -64,13 +64,15 @@ struct slv_device_t {
   // scratch arenas in HBM (grown on demand, never shrunk)
   float4* tris = nullptr;
   size_t tris_cap = 0;  // float4 units
+  uint32_t* valid_slots = nullptr;  // one entry per slot of the tris arena
+  uint32_t* valid_count = nullptr;
   uint32_t *tile_count = nullptr, *tile_offset = nullptr, *tile_cursor = nullptr, *active_tiles = nullptr, *large_tiles = nullptr;
   uint32_t* work_counter = nullptr;  // [0] k_raster / k_cover queue head, [1] k_shade queue head, [2] region-list cursor
   uint32_t *region_list = nullptr, *region_offset = nullptr, *region_count = nullptr;  // deferred path: per-region lists
   uint32_t region_cap = 0;
   uint32_t* region_mask = nullptr;  // one word per tile-list entry
   uint8_t* item_flag = nullptr;
-  uint32_t* block_count = nullptr;  // entries in each (region, warp block) sub-list
+  uint2* block_desc = nullptr;  // (first entry, entries) of each (region, warp block) sub-list
   uint32_t* vis = nullptr;           // visibility buffer of the deferred path: owner slot per sample
   size_t vis_cap = 0;                // in uint32 units
   bool force_immediate = false;      // SLV_FORCE_IMMEDIATE=1: always use k_raster (tests compare both paths)
@@ -137,8 +139,10 @@ slv_result ensure_scratch(slv_device dev, size_t tris_needed_total, uint32_t n_t
     CU(cudaStreamSynchronize(dev->stream));
     size_t need = tris_needed_total;  // after the flush only the new draw remains; callers pass used + new
     if (dev->tris) CU(cudaFree(dev->tris));
+    if (dev->valid_slots) CU(cudaFree(dev->valid_slots));
     size_t cap = std::max(need, dev->tris_cap * 2);
     CU(cudaMalloc(&dev->tris, cap * sizeof(float4)));
+    CU(cudaMalloc(&dev->valid_slots, (cap / (TRI_HEADER + 3 * MAX_REGS) + 1) * sizeof(uint32_t)));
     dev->tris_cap = cap;
   }
   if (n_tiles + 1 > dev->tiles_cap) {
@@ -148,7 +152,7 @@ slv_result ensure_scratch(slv_device dev, size_t tris_needed_total, uint32_t n_t
     if (dev->tile_count) {
       CU(cudaFree(dev->tile_count)); CU(cudaFree(dev->tile_offset)); CU(cudaFree(dev->tile_cursor));
       CU(cudaFree(dev->active_tiles)); CU(cudaFree(dev->large_tiles));
-      CU(cudaFree(dev->region_offset)); CU(cudaFree(dev->region_count)); CU(cudaFree(dev->item_flag)); CU(cudaFree(dev->block_count));
+      CU(cudaFree(dev->region_offset)); CU(cudaFree(dev->region_count)); CU(cudaFree(dev->item_flag)); CU(cudaFree(dev->block_desc));
     }
     uint32_t cap = std::max(n_tiles + 1, 4096u);
     CU(cudaMalloc(&dev->tile_count, cap * sizeof(uint32_t)));
@@ -159,7 +163,7 @@ slv_result ensure_scratch(slv_device dev, size_t tris_needed_total, uint32_t n_t
     CU(cudaMalloc(&dev->region_offset, (size_t)cap * 16 * sizeof(uint32_t)));
     CU(cudaMalloc(&dev->region_count, (size_t)cap * 16 * sizeof(uint32_t)));
     CU(cudaMalloc(&dev->item_flag, (size_t)cap * 128));
-    CU(cudaMalloc(&dev->block_count, (size_t)cap * 128 * sizeof(uint32_t)));
+    CU(cudaMalloc(&dev->block_desc, (size_t)cap * 128 * sizeof(uint2)));
     CU(cudaMemsetAsync(dev->tile_count, 0, cap * sizeof(uint32_t), dev->stream));
     CU(cudaMemsetAsync(dev->tile_cursor, 0, cap * sizeof(uint32_t), dev->stream));
     dev->tiles_cap = cap;
@@ -219,13 +223,14 @@ bool launch_raster_s(const RasterParams& rp, const RasterParams* batch, uint32_t
 }
 
 template <int S>
-bool launch_shade_s(const RasterParams& rp, const RasterParams* batch, const DeferredBufs& db, uint32_t blocks, cudaStream_t st) {
+bool launch_shade_s(const RasterParams& rp, const RasterParams* batch, uint32_t n_draws, const DeferredBufs& db, uint32_t blocks,
+                    cudaStream_t st) {
   switch (rp.ps_program) {
-  case SLV_PS_ATTR0_COLOR: k_shade<S, SLV_PS_ATTR0_COLOR><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, db); return true;
-  case SLV_PS_LIGHTS3: k_shade<S, SLV_PS_LIGHTS3><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, db); return true;
-  case SLV_PS_TEX_ALPHA: k_shade<S, SLV_PS_TEX_ALPHA><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, db); return true;
-  case SLV_PS_SPONZA: k_shade<S, SLV_PS_SPONZA><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, db); return true;
-  case SLV_PS_TEX_GRAD_ALPHA: k_shade<S, SLV_PS_TEX_GRAD_ALPHA><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, db); return true;
+  case SLV_PS_ATTR0_COLOR: k_shade<S, SLV_PS_ATTR0_COLOR><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, n_draws, db); return true;
+  case SLV_PS_LIGHTS3: k_shade<S, SLV_PS_LIGHTS3><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, n_draws, db); return true;
+  case SLV_PS_TEX_ALPHA: k_shade<S, SLV_PS_TEX_ALPHA><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, n_draws, db); return true;
+  case SLV_PS_SPONZA: k_shade<S, SLV_PS_SPONZA><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, n_draws, db); return true;
+  case SLV_PS_TEX_GRAD_ALPHA: k_shade<S, SLV_PS_TEX_GRAD_ALPHA><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, n_draws, db); return true;
   }
   return false;
 }
@@ -272,7 +277,10 @@ slv_result flush_batch(slv_device dev) {
   bp.list = dev->list;
   bp.list_capacity = dev->list_cap;
   bp.overflow_flag = dev->overflow_flag;
+  bp.valid_slots = dev->valid_slots;
+  bp.valid_count = dev->valid_count;
   // ---- geometry of every queued draw: one launch per distinct register count (normally one)
+  CU(cudaMemsetAsync(dev->valid_count, 0, sizeof(uint32_t), st));
   CU(cudaMemcpyAsync(dev->d_geom, dev->pending_geom.data(), n * sizeof(GeomParams), cudaMemcpyHostToDevice, st));
   size_t eg0 = dev->profile ? mark(dev) : 0;
   for (uint32_t R = 1; R <= (uint32_t)MAX_REGS; ++R) {
@@ -331,7 +339,7 @@ slv_result flush_batch(slv_device dev) {
     db.cursor = dev->work_counter + 2;
     db.overflow_flag = dev->overflow_flag;
     db.item_flag = dev->item_flag;
-    db.block_count = dev->block_count;
+    db.block_desc = dev->block_desc;
     db.vis = shade ? dev->vis : nullptr;
     db.vis_pitch = first.color0.w;
     db.cover_counter = dev->work_counter;
@@ -340,16 +348,16 @@ slv_result flush_batch(slv_device dev) {
     dev->n_launches += 1;
     if (dev->profile) e_rbin = mark(dev);
     switch (dev->batch_S) {
-    case 1: k_cover<1><<<dev->cover_grid, DEF_THREADS, 0, st>>>(first, dev->d_batch, db); ok = true; break;
-    case 2: k_cover<2><<<dev->cover_grid, DEF_THREADS, 0, st>>>(first, dev->d_batch, db); ok = true; break;
-    case 4: k_cover<4><<<dev->cover_grid, DEF_THREADS, 0, st>>>(first, dev->d_batch, db); ok = true; break;
+    case 1: k_cover<1><<<dev->cover_grid, DEF_THREADS, 0, st>>>(first, dev->d_batch, n, db); ok = true; break;
+    case 2: k_cover<2><<<dev->cover_grid, DEF_THREADS, 0, st>>>(first, dev->d_batch, n, db); ok = true; break;
+    case 4: k_cover<4><<<dev->cover_grid, DEF_THREADS, 0, st>>>(first, dev->d_batch, n, db); ok = true; break;
     }
     if (ok && shade) {
       if (dev->profile) e_mid = mark(dev);
       switch (dev->batch_S) {
-      case 1: ok = launch_shade_s<1>(first, dev->d_batch, db, dev->shade_grid, st); break;
-      case 2: ok = launch_shade_s<2>(first, dev->d_batch, db, dev->shade_grid, st); break;
-      case 4: ok = launch_shade_s<4>(first, dev->d_batch, db, dev->shade_grid, st); break;
+      case 1: ok = launch_shade_s<1>(first, dev->d_batch, n, db, dev->shade_grid, st); break;
+      case 2: ok = launch_shade_s<2>(first, dev->d_batch, n, db, dev->shade_grid, st); break;
+      case 4: ok = launch_shade_s<4>(first, dev->d_batch, n, db, dev->shade_grid, st); break;
       }
       dev->n_launches += 1;
     }
@@ -424,6 +432,7 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   dev->stream = dev->own_stream;
   CU(cudaMalloc(&dev->overflow_flag, sizeof(uint32_t)));
   CU(cudaMalloc(&dev->work_counter, 4 * sizeof(uint32_t)));
+  CU(cudaMalloc(&dev->valid_count, sizeof(uint32_t)));
   {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, ordinal));
@@ -459,6 +468,8 @@ void slv_device_destroy(slv_device dev) {
       for (uint32_t l = 0; l < r.tex.n_levels; ++l) cudaFree(r.tex.level[l].data);
   }
   cudaFree(dev->tris);
+  cudaFree(dev->valid_slots);
+  cudaFree(dev->valid_count);
   cudaFree(dev->tile_count);
   cudaFree(dev->tile_offset);
   cudaFree(dev->tile_cursor);
@@ -471,7 +482,7 @@ void slv_device_destroy(slv_device dev) {
   cudaFree(dev->region_offset);
   cudaFree(dev->region_count);
   cudaFree(dev->item_flag);
-  cudaFree(dev->block_count);
+  cudaFree(dev->block_desc);
   cudaFree(dev->list);
   cudaFree(dev->overflow_flag);
   cudaFree(dev->d_stats);
@@ -769,6 +780,8 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   gp.draw_id = (uint32_t)dev->pending.size();
   gp.tile_count = dev->tile_count;
   gp.stats = dev->d_stats;
+  gp.valid_slots = dev->valid_slots;
+  gp.valid_count = dev->valid_count;
 
   // ---- depth/stencil function selection (framebuffer.cpp:325-425)
   const slv_depth_stencil_desc& ds = d->ds;
@@ -813,6 +826,7 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   rp.list_capacity = dev->list_cap;
   rp.n_attrs = n_attrs;
   rp.stats = dev->d_stats;
+  rp.slot_base = gp.slot_base;
 
   // sampling a texture that is a target of the queued batch: the earlier draws must land first
   if (needs_sampler && !dev->pending.empty()) {
@@ -823,6 +837,7 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
       // the flush reset the arenas: re-point this draw at the start of them
       gp.slot_base = 0;
       gp.draw_id = 0;
+      rp.slot_base = 0;
     }
   }
 
@@ -836,6 +851,13 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
 }
 
 static slv_result fill_surface(slv_device dev, const SurfaceRef& s, uint4 pattern) {
+  if (dev->shard_n > 1) {  // sort-first: clear the owned tiles only
+    const uint32_t tiles_x = (s.w + SLV_TILE_SIZE - 1) / SLV_TILE_SIZE, tiles_y = (s.h + SLV_TILE_SIZE - 1) / SLV_TILE_SIZE;
+    k_fill_tiles<<<tiles_x * tiles_y, 256, 0, dev->stream>>>(s, pattern, tiles_x, dev->shard_rank, dev->shard_n);
+    ++dev->n_launches;
+    CU(cudaGetLastError());
+    return SLV_OK;
+  }
   size_t n_vec = s.bytes / 16, n_words = s.bytes / 4;
   if (n_vec) {
     uint32_t blocks = (uint32_t)std::min<size_t>((n_vec + 255) / 256, 148 * 16);
@@ -902,7 +924,7 @@ slv_result slv_resolve(slv_device dev, slv_handle src, slv_handle dst) {
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   dim3 blk(32, 8), grd((s.w + 31) / 32, (s.h + 7) / 8);
-  k_resolve<<<grd, blk, 0, dev->stream>>>(s, t);
+  k_resolve<<<grd, blk, 0, dev->stream>>>(s, t, dev->shard_rank, dev->shard_n);
   ++dev->n_launches;
   CU(cudaGetLastError());
   return SLV_OK;
@@ -960,6 +982,20 @@ slv_result slv_profile_get(slv_device dev, slv_pipeline_profiles* out) {
   out->clipping = (uint64_t)(dev->prof_ms[0] * 1e6);      // VS + clip + viewport + setup are one kernel
   out->tri_dispatch = (uint64_t)((dev->prof_ms[1] + dev->prof_ms[2] + dev->prof_ms[5]) * 1e6);
   out->ras = (uint64_t)((dev->prof_ms[3] + dev->prof_ms[4]) * 1e6);
+  return SLV_OK;
+}
+
+// Developer aid (not part of the reference surface): copies internal work-list sizes of the LAST flushed batch to the
+// host.  which = 0: active tile ids ([0] = count), 1: tile_offset[tiles + 1], 2: block_desc[active tiles * 128] as (first entry, entries) pairs.
+slv_result slv_debug_read(slv_device dev, uint32_t which, void* dst, size_t bytes) {
+  if (!dev || !dst) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  const void* src = which == 0 ? (const void*)dev->active_tiles : which == 1 ? (const void*)dev->tile_offset : (const void*)dev->block_desc;
+  const size_t cap = which == 0 ? ((size_t)dev->tiles_cap + 1) * 4 : which == 1 ? (size_t)dev->tiles_cap * 4 : (size_t)dev->tiles_cap * 128 * 8;
+  if (!src || bytes > cap) return SLV_INVALID_PARAMETER;
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, dev->stream));
+  CU(cudaStreamSynchronize(dev->stream));
   return SLV_OK;
 }
 

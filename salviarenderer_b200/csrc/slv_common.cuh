@@ -70,6 +70,8 @@ struct GeomParams {
   uint32_t tri_stride;
   uint32_t* tile_count;    // [tiles]
   unsigned long long* stats;  // slv_pipeline_statistics as 9 x u64
+  uint32_t* valid_slots;      // compact list of the slots that hold a triangle binned on this rank
+  uint32_t* valid_count;
 };
 
 // geometry of all queued draws in ONE launch: CTA b works on draw draw_of[g] where cta_prefix[g] <= b < cta_prefix[g+1]
@@ -97,6 +99,8 @@ struct BinParams {
   uint32_t* list;               // entries (slot << 1) | accept
   uint32_t list_capacity;
   uint32_t* overflow_flag;
+  const uint32_t* valid_slots;
+  const uint32_t* valid_count;
 };
 
 struct RasterParams {
@@ -112,6 +116,7 @@ struct RasterParams {
   uint32_t n_attrs;
   uint32_t mods[SLV_MAX_VS_OUTPUT_ATTRS];
   uint32_t has_centroid;
+  uint32_t slot_base;             // first global triangle slot of this draw inside the batch (slots are draw-ordered)
   // targets
   SurfaceRef color0, color1, ds;  // data == nullptr when unbound
   uint32_t target_w, target_h;    // min over colour targets (renderer_impl.cpp:159-238)

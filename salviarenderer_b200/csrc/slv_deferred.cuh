@@ -32,7 +32,7 @@ constexpr uint32_t VIS_NONE = 0xFFFFFFFFu;
 constexpr int DEF_WARPS = 4;                 // warps per CTA of k_cover / k_shade (independent of each other)
 constexpr int DEF_THREADS = DEF_WARPS * 32;
 constexpr uint32_t ITEMS_PER_TILE = 128;     // 16 regions x 8 warp blocks
-constexpr uint32_t FETCH = 4;                // items a warp takes from the queue at a time
+constexpr uint32_t FETCH = 2;               // items a warp of k_cover takes from the queue at a time
 
 struct CovTri {  // one surviving triangle of the warp's current chunk, staged in shared memory (80 B, 128-bit loads)
   float4 e0;     // A0 B0 C0 A1
@@ -47,7 +47,7 @@ struct CovTri {  // one surviving triangle of the warp's current chunk, staged i
 struct DeferredBufs {
   uint32_t* region_list;      // per region 8 sub-lists (one per 8x4 warp block) of capacity region_count, entries
                               // (slot << 4) | status of the warp's two 4x4 blocks, in API order
-  uint32_t* block_count;      // [(active tile index * 16 + region) * 8 + warp block] entries in the sub-list
+  uint2* block_desc;          // [item = (active tile index * 16 + region) * 8 + warp block]: (first entry, entries)
   uint32_t* region_mask;      // scratch, one word per tile-list entry: regions survived | regions fully inside << 16
   uint32_t region_cap;
   uint32_t* region_offset;    // [active tile index * 16 + region]
@@ -65,7 +65,7 @@ struct DeferredBufs {
 #define SLV_COVER_CTAS_PER_SM 8
 #endif
 #ifndef SLV_SHADE_CTAS_PER_SM
-#define SLV_SHADE_CTAS_PER_SM 6
+#define SLV_SHADE_CTAS_PER_SM 8
 #endif
 
 constexpr int RBIN_THREADS = 512;  // 16 warps == the 16 regions of a tile
@@ -241,8 +241,19 @@ __global__ void __launch_bounds__(RBIN_THREADS, 2) k_region_bin(RasterParams c, 
     uint32_t mine = pos[0];
 #pragma unroll
     for (int w = 1; w < 8; ++w) mine = (lane == (uint32_t)w) ? pos[w] : mine;
-    d.block_count[(b * 16 + r) * 8 + lane] = mine;
+    d.block_desc[(b * 16 + r) * 8 + lane] = make_uint2((ok && cnt) ? s_base[r] + lane * cnt : 0u, mine);
   }
+}
+
+// the draw a triangle slot belongs to: slots are allocated draw by draw, so it is the last draw whose first slot is <=
+// `slot` (binary search over <= 64 bases kept in shared memory: no global load on the kernels' dependent chains)
+__device__ __forceinline__ uint32_t draw_of_slot(const uint32_t* s_slot_base, uint32_t n_draws, uint32_t slot) {
+  uint32_t lo = 0, hi = n_draws;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (slot >= s_slot_base[mid]) lo = mid; else hi = mid;
+  }
+  return lo;
 }
 
 // work-queue fetch: lane 0 takes FETCH consecutive items; the result is consumed one fetch later (latency hidden)
@@ -254,8 +265,11 @@ __device__ __forceinline__ uint32_t fetch_items(uint32_t* counter, uint32_t lane
 
 template <int S>
 __global__ void __launch_bounds__(DEF_THREADS, SLV_COVER_CTAS_PER_SM)
-    k_cover(RasterParams c, const RasterParams* __restrict__ batch, DeferredBufs d) {
+    k_cover(RasterParams c, const RasterParams* __restrict__ batch, uint32_t n_draws, DeferredBufs d) {
   __shared__ CovTri s_tri_all[DEF_WARPS][32];
+  __shared__ uint32_t s_slot_base[MAX_BATCH_DRAWS];
+  if (threadIdx.x < n_draws) s_slot_base[threadIdx.x] = batch[threadIdx.x].slot_base;
+  __syncthreads();
 
   const uint32_t lane = threadIdx.x & 31;
   CovTri* s_tri = s_tri_all[threadIdx.x >> 5];
@@ -276,12 +290,12 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_COVER_CTAS_PER_SM)
     next_raw = fetch_items(d.cover_counter, lane);
     for (uint32_t item = base_item; item < base_item + FETCH && item < n_items; ++item) {
       const uint32_t b = item >> 7, sub = (item >> 3) & 15, w = item & 7;
-      const uint32_t rcnt = d.block_count[item];  // item == (b * 16 + sub) * 8 + w
+      const uint2 desc = d.block_desc[item];  // item == (b * 16 + sub) * 8 + w
+      const uint32_t rbeg = desc.x, rcnt = desc.y;
       if (rcnt == 0) {
         if (lane == 0) d.item_flag[item] = 0;
         continue;
       }
-      const uint32_t rbeg = d.region_offset[b * 16 + sub] + w * d.region_count[b * 16 + sub];
       const uint32_t tile = c.active_tiles[1 + b];
       const uint32_t tile_x = tile % c.tiles_x, tile_y = tile / c.tiles_x;
       const int X16 = (sub & 3) * REGION, Y16 = (sub >> 2) * REGION;
@@ -323,7 +337,7 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_COVER_CTAS_PER_SM)
           const uint32_t slot = e >> 4, st4 = e & 0xFu;
           const float4* rec = c.tris + (size_t)slot * c.tri_stride;
           const float4 e0 = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2);
-          const RasterParams& p = batch[__float_as_uint(__ldg(rec + 4).w)];
+          const RasterParams& p = batch[draw_of_slot(s_slot_base, n_draws, slot)];
           const float4 v0p = __ldg(rec + REC_V0), gxp = __ldg(rec + REC_DDX), gyp = __ldg(rec + REC_DDY);
           const uint32_t bits = (p.read_depth ? 1u : 0u) | (p.write_depth ? 2u : 0u) |
                                 ((p.depth_enable ? compare_lut(p.depth_func) : 0xFu) << 4) | (st4 << 8);
@@ -505,10 +519,10 @@ struct DeferredCtx {  // what a pixel shader may read when a lane shades its pix
 };
 
 template <int PS>
-__device__ __forceinline__ uint32_t shade_sample_owner(const RasterParams& c, const RasterParams* __restrict__ batch, uint32_t slot,
-                                                       int x, int y) {
+__device__ __forceinline__ uint32_t shade_sample_owner(const RasterParams& c, const RasterParams* __restrict__ batch, uint32_t draw,
+                                                       uint32_t slot, int x, int y) {
   const float4* rec = c.tris + (size_t)slot * c.tri_stride;
-  const RasterParams& p = batch[__float_as_uint(__ldg(rec + 4).w)];
+  const RasterParams& p = batch[draw];
   const int R = 1 + (int)p.n_attrs;
   const float4 v0p = __ldg(rec + REC_V0), gxp = __ldg(rec + REC_DDX), gyp = __ldg(rec + REC_DDY);
   DeferredCtx px;
@@ -527,7 +541,7 @@ __device__ __forceinline__ uint32_t shade_sample_owner(const RasterParams& c, co
 }
 
 constexpr uint32_t SHADE_GROUP = 8;   // items a warp of k_shade takes at a time; all their (pixel, owner) pairs share one pool
-constexpr int SHADE_POOL = 512;       // pool entries per warp (an item adds at most 32 * S = 128)
+constexpr int SHADE_POOL = 256;       // pool entries per warp (an item adds at most 32 * S = 128)
 
 __device__ __forceinline__ uint32_t fetch_group(uint32_t* counter, uint32_t lane) {
   uint32_t v = 0;
@@ -537,7 +551,10 @@ __device__ __forceinline__ uint32_t fetch_group(uint32_t* counter, uint32_t lane
 
 template <int S, int PS>
 __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
-    k_shade(RasterParams c, const RasterParams* __restrict__ batch, DeferredBufs d) {
+    k_shade(RasterParams c, const RasterParams* __restrict__ batch, uint32_t n_draws, DeferredBufs d) {
+  __shared__ uint32_t s_slot_base[MAX_BATCH_DRAWS];
+  if (threadIdx.x < n_draws) s_slot_base[threadIdx.x] = batch[threadIdx.x].slot_base;
+  __syncthreads();
   // per warp: the colour rows of the group's items, the pool of (pixel, owner) pairs, per-item origin / touched masks
   __shared__ uint32_t s_color_all[DEF_WARPS][SHADE_GROUP][32][S];
   __shared__ uint2 s_pool_all[DEF_WARPS][SHADE_POOL];  // x = lane | mask << 5 | item-in-group << 9, y = owner slot
@@ -630,7 +647,7 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
         const uint32_t org = s_org[kk];
         const uint32_t pq = pl >> 2, pp = pl & 3;
         const int px_ = (int)(org & 0xFFFF) + (int)((pq & 3) * 2 + (pp & 1)), py_ = (int)(org >> 16) + (int)((pq >> 2) * 2 + (pp >> 1));
-        const uint32_t packed = shade_sample_owner<PS>(c, batch, it.y, px_, py_);
+        const uint32_t packed = shade_sample_owner<PS>(c, batch, draw_of_slot(s_slot_base, n_draws, it.y), it.y, px_, py_);
         ++n_exec;
 #pragma unroll
         for (int s = 0; s < S; ++s)

@@ -193,7 +193,7 @@ __device__ __forceinline__ bool tile_owned(uint32_t tx, uint32_t ty, uint32_t ra
 
 // rasterizer::compute_triangle_info (rasterizer.cpp:864-945) + record store + tile coverage count
 template <int R>
-__device__ __forceinline__ void setup_triangle(const GeomParams& p, const VsOut<R> v[3], float4* rec) {
+__device__ __forceinline__ bool setup_triangle(const GeomParams& p, const VsOut<R> v[3], float4* rec) {  // true: binned somewhere
   float4 misc = make_float4(0, 0, 0, 0);
   double d0 = (double)fabsf(v[0].r[0].x) + (double)fabsf(v[0].r[0].y);
   double d1 = (double)fabsf(v[1].r[0].x) + (double)fabsf(v[1].r[0].y);
@@ -214,7 +214,7 @@ __device__ __forceinline__ void setup_triangle(const GeomParams& p, const VsOut<
   float area = e02x * e01y - e02y * e01x;  // cross_prod2(e02.xy, e01.xy)
   if (eq_eps(area, 0.0f)) {
     rec[4] = misc;  // invalid (v0 == nullptr upstream)
-    return;
+    return false;
   }
   bool front = area > 0.0f;
   float inv_area = 1.0f / area;
@@ -228,6 +228,27 @@ __device__ __forceinline__ void setup_triangle(const GeomParams& p, const VsOut<
   for (int i = 0; i < 3; ++i) {  // original vertex order (rasterizer.cpp:928-939)
     float4 s = v[i].r[0], e = v[(i + 1) % 3].r[0];
     edge[i] = make_float4(s.y - e.y, e.x - s.x, e.x * s.y - e.y * s.x, 0.0f);
+  }
+  // tile coverage count (rasterizer.cpp:809-857), done first: under sort-first sharding a triangle that reaches none
+  // of this rank's tiles is dropped here, before its 23-float4 record is written
+  TileRange tr = tile_range(bbox, p.tiles_x, p.tiles_y);
+  bool any_owned = false;
+  if ((tr.sx + 1 == tr.ex) && (tr.sy + 1 == tr.ey)) {
+    if (tile_owned(tr.sx, tr.sy, p.shard_rank, p.shard_n)) {
+      atomicAdd(&p.tile_count[tr.sy * p.tiles_x + tr.sx], 1u);
+      any_owned = true;
+    }
+  } else {
+    for (int y = tr.sy; y < tr.ey; ++y)
+      for (int x = tr.sx; x < tr.ex; ++x)
+        if (tile_owned(x, y, p.shard_rank, p.shard_n) && tile_test(edge, x, y)) {
+          atomicAdd(&p.tile_count[y * p.tiles_x + x], 1u);
+          any_owned = true;
+        }
+  }
+  if (!any_owned) {
+    rec[4] = misc;  // not binned anywhere on this rank
+    return false;
   }
   rec[0] = edge[0];
   rec[1] = edge[1];
@@ -250,21 +271,12 @@ __device__ __forceinline__ void setup_triangle(const GeomParams& p, const VsOut<
     rec[REC_DDX + 3 * i] = ddx;
     rec[REC_DDY + 3 * i] = ddy;
   }
-  TileRange tr = tile_range(bbox, p.tiles_x, p.tiles_y);
   misc.x = __uint_as_float(1u | (front ? 2u : 0u));
   misc.y = __uint_as_float((uint32_t)tr.sx | ((uint32_t)tr.ex << 16));
   misc.z = __uint_as_float((uint32_t)tr.sy | ((uint32_t)tr.ey << 16));
   misc.w = __uint_as_float(p.draw_id);
   rec[4] = misc;
-  // tile coverage count (rasterizer.cpp:809-857)
-  if ((tr.sx + 1 == tr.ex) && (tr.sy + 1 == tr.ey)) {
-    if (tile_owned(tr.sx, tr.sy, p.shard_rank, p.shard_n)) atomicAdd(&p.tile_count[tr.sy * p.tiles_x + tr.sx], 1u);
-  } else {
-    for (int y = tr.sy; y < tr.ey; ++y)
-      for (int x = tr.sx; x < tr.ex; ++x)
-        if (tile_owned(x, y, p.shard_rank, p.shard_n) && tile_test(edge, x, y))
-          atomicAdd(&p.tile_count[y * p.tiles_x + x], 1u);
-  }
+  return true;
 }
 
 template <int R>
@@ -277,7 +289,7 @@ __global__ void __launch_bounds__(128) k_geometry(const GeomParams* __restrict__
   }
   const GeomParams& p = draws[hb.draw_of[lo]];
   uint32_t prim = (blockIdx.x - hb.cta_prefix[lo]) * blockDim.x + threadIdx.x;
-  uint32_t n_out = 0;
+  uint32_t n_out = 0, valid_mask = 0;  // valid_mask bit k: slot prim*3+k holds a triangle binned on this rank
   if (prim < p.prim_count) {
     // ---- index fetch (index_fetcher.cpp:26-115)
     uint32_t ids[3];
@@ -330,7 +342,7 @@ __global__ void __launch_bounds__(128) k_geometry(const GeomParams* __restrict__
         o[2] = front ? tri[2] : tri[1];
 #pragma unroll
         for (int k = 0; k < 3; ++k) viewport_project<R>(p, o[k]);
-        setup_triangle<R>(p, o, rec);
+        valid_mask = setup_triangle<R>(p, o, rec) ? 1u : 0u;
         n_out = 1;
       }
     } else {
@@ -381,12 +393,31 @@ __global__ void __launch_bounds__(128) k_geometry(const GeomParams* __restrict__
           o[2] = is_front ? pool[src][t + 1] : pool[src][t];
 #pragma unroll
           for (int k = 0; k < 3; ++k) viewport_project<R>(p, o[k]);
-          setup_triangle<R>(p, o, rec + (size_t)(t - 1) * p.tri_stride);
+          if (setup_triangle<R>(p, o, rec + (size_t)(t - 1) * p.tri_stride)) valid_mask |= 1u << (t - 1);
         }
         n_out = nv - 2;
       }
     }
     for (uint32_t k = n_out; k < 3; ++k) rec[(size_t)k * p.tri_stride + 4] = make_float4(0, 0, 0, 0);
+  }
+  // compact list of the slots k_bin_fill has to look at (order is irrelevant: the tile lists are sorted afterwards);
+  // one atomicAdd per warp
+  {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t nv = __popc(valid_mask), incl = nv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    const uint32_t warp_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    uint32_t base = 0;
+    if (lane == 31 && warp_total) base = atomicAdd(p.valid_count, warp_total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - nv;
+    const uint32_t slot0 = p.slot_base + prim * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      if (valid_mask & (1u << k)) p.valid_slots[base++] = slot0 + k;
   }
   // cprimitives (rasterizer.cpp:1138): warp-aggregated
   uint32_t total = n_out;
@@ -469,8 +500,9 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint3
 }
 
 __global__ void __launch_bounds__(256) k_bin_fill(BinParams p) {
-  uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= p.n_slots) return;
+  const uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (vi >= *p.valid_count) return;  // the grid is sized for the worst case (every slot valid)
+  const uint32_t slot = p.valid_slots[vi];
   const float4* rec = p.tris + (size_t)slot * p.tri_stride;
   float4 misc = __ldg(rec + 4);
   uint32_t flags = __float_as_uint(misc.x);
@@ -1297,6 +1329,28 @@ __global__ void k_fill_words(uint32_t* dst, size_t first_word, size_t n_words, u
   size_t i = first_word + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_words) dst[i] = (i & 3) == 0 ? pattern.x : ((i & 3) == 1 ? pattern.y : ((i & 3) == 2 ? pattern.z : pattern.w));
 }
+// sort-first: a rank only ever reads and writes its own 64x64 tiles, so it only clears those (CTA per owned tile,
+// 128-bit stores along the tile's rows)
+__global__ void __launch_bounds__(256) k_fill_tiles(SurfaceRef s, uint4 pattern, uint32_t tiles_x, uint32_t rank, uint32_t n) {
+  const uint32_t tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  if (!tile_owned(tx, ty, rank, n)) return;
+  const uint32_t texel = s.samples * s.bpp;                      // bytes per pixel (all samples)
+  const uint32_t x0 = tx * TILE, y0 = ty * TILE;
+  const uint32_t cols = min((uint32_t)TILE, s.w - x0), rows = min((uint32_t)TILE, s.h - y0);
+  const uint32_t row_bytes = cols * texel;                       // multiple of 4; 16-byte aligned when texel*x0 is
+  for (uint32_t r = 0; r < rows; ++r) {
+    uint8_t* row = s.data + ((size_t)(y0 + r) * s.w + x0) * texel;
+    if (((reinterpret_cast<uintptr_t>(row) | row_bytes) & 15) == 0) {
+      for (uint32_t i = threadIdx.x; i < row_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(row)[i] = pattern;
+    } else {  // rows that are not 16-byte aligned: word stores, pattern word chosen by absolute position
+      for (uint32_t i = threadIdx.x; i < row_bytes / 4; i += blockDim.x) {
+        const uint32_t wabs = (uint32_t)(((row - s.data) / 4 + i) & 3);
+        reinterpret_cast<uint32_t*>(row)[i] = wabs == 0 ? pattern.x : (wabs == 1 ? pattern.y : (wabs == 2 ? pattern.z : pattern.w));
+      }
+    }
+  }
+}
+
 // framebuffer::clear_depth_stencil with a single flag (framebuffer.cpp:616-644)
 __global__ void k_clear_ds_partial(float2* dst, size_t n, uint32_t flags, float depth, uint32_t stencil) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1310,9 +1364,10 @@ __global__ void k_clear_ds_partial(float2* dst, size_t n, uint32_t flags, float 
 }
 
 // surface::resolve (surface.cpp:123-140): sum of to_rgba32f(sample) in sample order, * (1/S), convert (RNE)
-__global__ void k_resolve(SurfaceRef src, SurfaceRef dst) {
+__global__ void k_resolve(SurfaceRef src, SurfaceRef dst, uint32_t rank, uint32_t n) {
   uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= src.w || y >= src.h) return;
+  if (!tile_owned(x / TILE, y / TILE, rank, n)) return;  // sort-first: other ranks resolve their own tiles
   float4 clr = make_float4(0, 0, 0, 0);
   const uint8_t* sp = src.data + ((size_t)y * src.w + x) * src.samples * src.bpp;
   const float inv = 1 / (float)src.samples;

@@ -393,6 +393,14 @@ __device__ inline float4 sample_impl(const SamplerRef& sm, float cx, float cy, f
   }
   float4 c0 = make_float4(0, 0, 0, 0), c1 = c0;  // aniso: c0 accumulates the weighted colour
   float w_sum = 0.0f;
+  if (sm.fast_wrap_rgba8 && !aniso) {
+    // straight-line: the texel loads of both mip levels are in flight together (the tap is ~100 instructions, so
+    // duplicating it costs little code; the generic loop below keeps ONE copy of the big mode/format dispatch)
+    c0 = sample_wrap_rgba8_linear(t.level[lv0], sx, sy);
+    if (n == 1) return c0;
+    c1 = sample_wrap_rgba8_linear(t.level[lv1], sx, sy);
+    return make_float4(lerp1(c0.x, c1.x, frac), lerp1(c0.y, c1.y, frac), lerp1(c0.z, c1.z, frac), lerp1(c0.w, c1.w, frac));
+  }
 #pragma unroll 1
   for (int k = 0; k < n; ++k) {
     const SurfaceRef& lvl = t.level[k ? lv1 : lv0];

@@ -7,6 +7,10 @@ from salviarenderer_b200 import abi as A, scenes as S
 be = A.Backend(os.environ['SLV_LIB']) if os.environ.get('SLV_LIB') else pkg.load(0)
 sc = S.SponzaLike(3840, 2160, 4)
 sc.setup(be)
+if os.environ.get('SHARD'):
+    r, n = map(int, os.environ['SHARD'].split(','))
+    be.set_tile_shard(r, n)
+    print('tile shard', r, 'of', n)
 for f in range(8):
     sc.render(be, f)
 be.flush()
