@@ -61,18 +61,36 @@ struct slv_device_t {
   cudaStream_t stream = nullptr;      // the stream every kernel / copy is enqueued on
   cudaStream_t own_stream = nullptr;  // created with the device; `stream` may point at a caller-owned one
   std::vector<Resource> res;
-  // scratch arenas in HBM (grown on demand, never shrunk)
-  float4* tris = nullptr;
-  size_t tris_cap = 0;  // float4 units
-  uint32_t* valid_slots = nullptr;  // one entry per slot of the tris arena
-  uint32_t* valid_count = nullptr;
-  uint32_t *tile_count = nullptr, *tile_offset = nullptr, *tile_cursor = nullptr, *active_tiles = nullptr, *large_tiles = nullptr;
-  uint32_t* work_counter = nullptr;  // [0] k_raster / k_cover queue head, [1] k_shade queue head, [2] region-list cursor
-  uint32_t *region_list = nullptr, *region_offset = nullptr, *region_count = nullptr;  // deferred path: per-region lists
+  // scratch written by the front half of a batch (geometry, binning, region lists) and read by its back half (coverage,
+  // shading).  Two sets: the front half of batch k+1 runs on `front_stream` while the back half of batch k is still
+  // running on `stream` (frame pipelining); a set is reused for batch k+2 once ev_back_done of batch k has fired.
+  struct Scratch {
+    float4* tris = nullptr;           // triangle records (grown on demand, never shrunk)
+    uint32_t* valid_slots = nullptr;  // one entry per slot of the tris arena
+    uint32_t* valid_count = nullptr;
+    uint32_t *tile_count = nullptr, *tile_offset = nullptr, *tile_cursor = nullptr, *active_tiles = nullptr, *large_tiles = nullptr;
+    uint32_t* work_counter = nullptr;  // [0] k_raster / k_cover queue head, [1] k_shade queue head, [2] region-list cursor, [3] long lists
+    uint32_t *region_list = nullptr, *region_offset = nullptr, *region_count = nullptr;  // deferred path: per-region lists
+    uint32_t* region_mask = nullptr;  // one word per tile-list entry
+    uint8_t* item_flag = nullptr;
+    uint2* block_desc = nullptr;  // (first entry, entries) of each (region, warp block) sub-list
+    uint32_t* list = nullptr;
+    RasterParams* d_batch = nullptr;
+    GeomParams* d_geom = nullptr;
+    RasterParams* h_batch = nullptr;  // pinned staging of d_batch / d_geom: the uploads never synchronise a stream
+    GeomParams* h_geom = nullptr;
+    cudaEvent_t ev_front_done = nullptr, ev_back_done = nullptr;
+    bool in_flight = false;           // ev_back_done has been recorded and not yet waited for
+  };
+  Scratch sc[2];
+  int cur = 0;                        // the set the queued draws point at
+  Scratch& S() { return sc[cur]; }
+  size_t tris_cap = 0;  // float4 units (both sets)
   uint32_t region_cap = 0;
-  uint32_t* region_mask = nullptr;  // one word per tile-list entry
-  uint8_t* item_flag = nullptr;
-  uint2* block_desc = nullptr;  // (first entry, entries) of each (region, warp block) sub-list
+  cudaStream_t front_stream = nullptr;  // front halves run here when pipelining
+  cudaEvent_t ev_sync = nullptr;        // scratch event: orders front_stream after buffer uploads on `stream`
+  bool buffers_dirty = false;           // a vertex / index buffer was written on `stream` since the last front half
+  bool pipeline = true;                 // SLV_PIPELINE=0: everything on `stream`
   uint32_t* vis = nullptr;           // visibility buffer of the deferred path: owner slot per sample
   size_t vis_cap = 0;                // in uint32 units
   bool force_immediate = false;      // SLV_FORCE_IMMEDIATE=1: always use k_raster (tests compare both paths)
@@ -83,8 +101,6 @@ struct slv_device_t {
   // pixel's depth/stencil/colour is loaded once and stored once per batch instead of once per draw.
   std::vector<RasterParams> pending;
   std::vector<GeomParams> pending_geom;  // geometry parameters of the queued draws (same index as `pending`)
-  RasterParams* d_batch = nullptr;
-  GeomParams* d_geom = nullptr;
   size_t tris_used = 0;      // float4 units used by the queued draws
   uint64_t slots_queued = 0; // triangle slots of the queued draws (sizes the list arena)
   uint32_t batch_S = 0;
@@ -94,7 +110,6 @@ struct slv_device_t {
   struct Span { size_t a, b; int stage; };
   std::vector<Span> spans;
   uint32_t tiles_cap = 0;
-  uint32_t* list = nullptr;
   uint32_t list_cap = 0;
   uint32_t* overflow_flag = nullptr;
   unsigned long long* d_stats = nullptr;
@@ -131,41 +146,55 @@ constexpr uint32_t MAX_BATCH = MAX_BATCH_DRAWS;  // draws whose geometry / raste
 
 slv_result flush_batch(slv_device dev);
 
+slv_result sync_all(slv_device dev) {  // both streams idle
+  CU(cudaStreamSynchronize(dev->front_stream));
+  CU(cudaStreamSynchronize(dev->stream));
+  for (auto& S : dev->sc) S.in_flight = false;
+  return SLV_OK;
+}
+
 // Arenas are shared by the queued draws of a batch; growing one needs the batch flushed first.
 slv_result ensure_scratch(slv_device dev, size_t tris_needed_total, uint32_t n_tiles, uint64_t list_needed_total) {
   if (tris_needed_total > dev->tris_cap) {
     slv_result rc = flush_batch(dev);
     if (rc != SLV_OK) return rc;
-    CU(cudaStreamSynchronize(dev->stream));
+    rc = sync_all(dev);
+    if (rc != SLV_OK) return rc;
     size_t need = tris_needed_total;  // after the flush only the new draw remains; callers pass used + new
-    if (dev->tris) CU(cudaFree(dev->tris));
-    if (dev->valid_slots) CU(cudaFree(dev->valid_slots));
     size_t cap = std::max(need, dev->tris_cap * 2);
-    CU(cudaMalloc(&dev->tris, cap * sizeof(float4)));
-    CU(cudaMalloc(&dev->valid_slots, (cap / (TRI_HEADER + 3 * MAX_REGS) + 1) * sizeof(uint32_t)));
+    for (auto& S : dev->sc) {
+      if (S.tris) CU(cudaFree(S.tris));
+      if (S.valid_slots) CU(cudaFree(S.valid_slots));
+      CU(cudaMalloc(&S.tris, cap * sizeof(float4)));
+      CU(cudaMalloc(&S.valid_slots, (cap / (TRI_HEADER + 3 * MAX_REGS) + 1) * sizeof(uint32_t)));
+    }
     dev->tris_cap = cap;
   }
   if (n_tiles + 1 > dev->tiles_cap) {
     slv_result rc = flush_batch(dev);
     if (rc != SLV_OK) return rc;
-    CU(cudaStreamSynchronize(dev->stream));
-    if (dev->tile_count) {
-      CU(cudaFree(dev->tile_count)); CU(cudaFree(dev->tile_offset)); CU(cudaFree(dev->tile_cursor));
-      CU(cudaFree(dev->active_tiles)); CU(cudaFree(dev->large_tiles));
-      CU(cudaFree(dev->region_offset)); CU(cudaFree(dev->region_count)); CU(cudaFree(dev->item_flag)); CU(cudaFree(dev->block_desc));
-    }
+    rc = sync_all(dev);
+    if (rc != SLV_OK) return rc;
     uint32_t cap = std::max(n_tiles + 1, 4096u);
-    CU(cudaMalloc(&dev->tile_count, cap * sizeof(uint32_t)));
-    CU(cudaMalloc(&dev->tile_offset, cap * sizeof(uint32_t)));
-    CU(cudaMalloc(&dev->tile_cursor, cap * sizeof(uint32_t)));
-    CU(cudaMalloc(&dev->active_tiles, (cap + 1) * sizeof(uint32_t)));
-    CU(cudaMalloc(&dev->large_tiles, (cap + 1) * sizeof(uint32_t)));
-    CU(cudaMalloc(&dev->region_offset, (size_t)cap * 16 * sizeof(uint32_t)));
-    CU(cudaMalloc(&dev->region_count, (size_t)cap * 16 * sizeof(uint32_t)));
-    CU(cudaMalloc(&dev->item_flag, (size_t)cap * 128));
-    CU(cudaMalloc(&dev->block_desc, (size_t)cap * 128 * sizeof(uint2)));
-    CU(cudaMemsetAsync(dev->tile_count, 0, cap * sizeof(uint32_t), dev->stream));
-    CU(cudaMemsetAsync(dev->tile_cursor, 0, cap * sizeof(uint32_t), dev->stream));
+    for (auto& S : dev->sc) {
+      if (S.tile_count) {
+        CU(cudaFree(S.tile_count)); CU(cudaFree(S.tile_offset)); CU(cudaFree(S.tile_cursor));
+        CU(cudaFree(S.active_tiles)); CU(cudaFree(S.large_tiles));
+        CU(cudaFree(S.region_offset)); CU(cudaFree(S.region_count)); CU(cudaFree(S.item_flag)); CU(cudaFree(S.block_desc));
+      }
+      CU(cudaMalloc(&S.tile_count, cap * sizeof(uint32_t)));
+      CU(cudaMalloc(&S.tile_offset, cap * sizeof(uint32_t)));
+      CU(cudaMalloc(&S.tile_cursor, cap * sizeof(uint32_t)));
+      CU(cudaMalloc(&S.active_tiles, (cap + 1) * sizeof(uint32_t)));
+      CU(cudaMalloc(&S.large_tiles, (cap + 1) * sizeof(uint32_t)));
+      CU(cudaMalloc(&S.region_offset, (size_t)cap * 16 * sizeof(uint32_t)));
+      CU(cudaMalloc(&S.region_count, (size_t)cap * 16 * sizeof(uint32_t)));
+      CU(cudaMalloc(&S.item_flag, (size_t)cap * 128));
+      CU(cudaMalloc(&S.block_desc, (size_t)cap * 128 * sizeof(uint2)));
+      CU(cudaMemsetAsync(S.tile_count, 0, cap * sizeof(uint32_t), dev->stream));
+      CU(cudaMemsetAsync(S.tile_cursor, 0, cap * sizeof(uint32_t), dev->stream));
+    }
+    CU(cudaStreamSynchronize(dev->stream));
     dev->tiles_cap = cap;
   }
   (void)list_needed_total;
@@ -235,11 +264,16 @@ bool launch_shade_s(const RasterParams& rp, const RasterParams* batch, uint32_t 
   return false;
 }
 
-// Batch flush: binning (scan, fill, sort) over the triangles of every queued draw, then the raster pass of all of
-// them, in submission order, as ONE kernel.
+// Batch flush: geometry and binning (scan, fill, sort, region lists) over the triangles of every queued draw - the FRONT
+// half, which touches no render target - then the raster pass of all of them, in submission order - the BACK half.
+// When pipelining, the front half is enqueued on front_stream, so it overlaps the back half / clears / resolve of the
+// previous batch still running on the main stream; the back half waits for it with an event.
 slv_result flush_batch(slv_device dev) {
   if (dev->pending.empty()) return SLV_OK;
   cudaStream_t st = dev->stream;
+  slv_device_t::Scratch& S = dev->S();
+  const bool piped = dev->pipeline && !dev->profile;
+  cudaStream_t fs = piped ? dev->front_stream : st;
   RasterParams& first = dev->pending[0];
   const uint32_t n = (uint32_t)dev->pending.size();
   const uint32_t n_tiles = first.tiles_x * first.tiles_y;
@@ -247,41 +281,70 @@ slv_result flush_batch(slv_device dev) {
   // list arena: heuristic bound, checked on the device (overflow flag -> SLV_OUT_OF_MEMORY at the next flush point)
   const uint64_t list_need = std::min<uint64_t>(std::max<uint64_t>(4ull * n_slots, 1u << 22), 1ull << 31);
   if (list_need > dev->list_cap) {
-    CU(cudaStreamSynchronize(st));
-    if (dev->list) CU(cudaFree(dev->list));
-    CU(cudaMalloc(&dev->list, (size_t)list_need * sizeof(uint32_t)));
-    dev->list_cap = (uint32_t)list_need;
-    // (region, warp block) sub-lists of the deferred path, allocated on the device inside this arena: 8 sub-lists of
+    slv_result rcs = sync_all(dev);
+    if (rcs != SLV_OK) return rcs;
+    // (region, warp block) sub-lists of the deferred path, allocated on the device inside the region arena: 8 sub-lists of
     // capacity n per region with n surviving entries; a tile-list entry survives in 1..16 regions (about 1.5 on the
     // Sponza-like scene, i.e. ~12 words per tile-list entry; overflow raises the sticky out-of-memory error)
-    if (dev->region_list) CU(cudaFree(dev->region_list));
     const uint64_t rcap = std::min<uint64_t>(std::max<uint64_t>(2ull * list_need, 1ull << 24), 0xFFFFFFF0ull);
-    CU(cudaMalloc(&dev->region_list, (size_t)rcap * sizeof(uint32_t)));
+    for (auto& T : dev->sc) {
+      if (T.list) CU(cudaFree(T.list));
+      CU(cudaMalloc(&T.list, (size_t)list_need * sizeof(uint32_t)));
+      if (T.region_list) CU(cudaFree(T.region_list));
+      CU(cudaMalloc(&T.region_list, (size_t)rcap * sizeof(uint32_t)));
+      if (T.region_mask) CU(cudaFree(T.region_mask));
+      CU(cudaMalloc(&T.region_mask, (size_t)list_need * RMASK_STRIDE * sizeof(uint32_t)));
+    }
+    dev->list_cap = (uint32_t)list_need;
     dev->region_cap = (uint32_t)rcap;
-    if (dev->region_mask) CU(cudaFree(dev->region_mask));
-    CU(cudaMalloc(&dev->region_mask, (size_t)list_need * RMASK_STRIDE * sizeof(uint32_t)));
   }
-  first.list = dev->list;
-  first.list_capacity = dev->list_cap;
-  CU(cudaMemcpyAsync(dev->d_batch, dev->pending.data(), n * sizeof(RasterParams), cudaMemcpyHostToDevice, st));
+  for (RasterParams& r : dev->pending) {  // the list arena may have grown since the draws were queued
+    r.list = S.list;
+    r.list_capacity = dev->list_cap;
+  }
+  if (piped) {
+    // the front half reads vertex / index buffers: order it after the uploads enqueued on the main stream
+    if (dev->buffers_dirty) {
+      CU(cudaEventRecord(dev->ev_sync, st));
+      CU(cudaStreamWaitEvent(fs, dev->ev_sync, 0));
+    }
+    // this scratch set was last read by the back half of the batch before the previous one
+    if (S.in_flight) {
+      CU(cudaEventSynchronize(S.ev_front_done));  // host: the pinned parameter staging of that batch has been consumed
+      CU(cudaStreamWaitEvent(fs, S.ev_back_done, 0));
+      S.in_flight = false;
+    }
+  }
+  dev->buffers_dirty = false;
+  // parameter upload: through this set's pinned staging when pipelining (no stream synchronisation; the staging is free
+  // again once ev_front_done has fired, checked above), else straight from pageable memory (the driver stages it)
+  const RasterParams* src_batch = dev->pending.data();
+  const GeomParams* src_geom = dev->pending_geom.data();
+  if (piped) {
+    memcpy(S.h_batch, src_batch, n * sizeof(RasterParams));
+    memcpy(S.h_geom, src_geom, n * sizeof(GeomParams));
+    src_batch = S.h_batch;
+    src_geom = S.h_geom;
+  }
+  CU(cudaMemcpyAsync(S.d_batch, src_batch, n * sizeof(RasterParams), cudaMemcpyHostToDevice, fs));
   BinParams bp{};
-  bp.tris = dev->tris;
+  bp.tris = S.tris;
   bp.tri_stride = first.tri_stride;
   bp.n_slots = n_slots;
   bp.tiles_x = first.tiles_x;
   bp.tiles_y = first.tiles_y;
   bp.shard_rank = dev->shard_rank;
   bp.shard_n = dev->shard_n;
-  bp.tile_offset = dev->tile_offset;
-  bp.tile_cursor = dev->tile_cursor;
-  bp.list = dev->list;
+  bp.tile_offset = S.tile_offset;
+  bp.tile_cursor = S.tile_cursor;
+  bp.list = S.list;
   bp.list_capacity = dev->list_cap;
   bp.overflow_flag = dev->overflow_flag;
-  bp.valid_slots = dev->valid_slots;
-  bp.valid_count = dev->valid_count;
+  bp.valid_slots = S.valid_slots;
+  bp.valid_count = S.valid_count;
   // ---- geometry of every queued draw: one launch per distinct register count (normally one)
-  CU(cudaMemsetAsync(dev->valid_count, 0, sizeof(uint32_t), st));
-  CU(cudaMemcpyAsync(dev->d_geom, dev->pending_geom.data(), n * sizeof(GeomParams), cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(S.valid_count, 0, sizeof(uint32_t), fs));
+  CU(cudaMemcpyAsync(S.d_geom, src_geom, n * sizeof(GeomParams), cudaMemcpyHostToDevice, fs));
   size_t eg0 = dev->profile ? mark(dev) : 0;
   for (uint32_t R = 1; R <= (uint32_t)MAX_REGS; ++R) {
     GeomBatch hb{};
@@ -293,24 +356,22 @@ slv_result flush_batch(slv_device dev) {
     }
     if (!hb.n) continue;
     switch (R) {
-    case 1: launch_geometry<1>(dev->d_geom, hb, st); break;
-    case 2: launch_geometry<2>(dev->d_geom, hb, st); break;
-    case 3: launch_geometry<3>(dev->d_geom, hb, st); break;
-    case 4: launch_geometry<4>(dev->d_geom, hb, st); break;
-    case 5: launch_geometry<5>(dev->d_geom, hb, st); break;
-    default: launch_geometry<6>(dev->d_geom, hb, st); break;
+    case 1: launch_geometry<1>(S.d_geom, hb, fs); break;
+    case 2: launch_geometry<2>(S.d_geom, hb, fs); break;
+    case 3: launch_geometry<3>(S.d_geom, hb, fs); break;
+    case 4: launch_geometry<4>(S.d_geom, hb, fs); break;
+    case 5: launch_geometry<5>(S.d_geom, hb, fs); break;
+    default: launch_geometry<6>(S.d_geom, hb, fs); break;
     }
     dev->n_launches += 1;
   }
   if (dev->profile) dev->spans.push_back({eg0, mark(dev), 0});
   size_t e0 = dev->profile ? mark(dev) : 0;
-  k_scan_tiles<<<1, 1024, 0, st>>>(dev->tile_count, dev->tile_offset, dev->tile_cursor, n_tiles, dev->active_tiles,
-                                    dev->work_counter, dev->large_tiles);
-  k_bin_fill<<<(n_slots + 255) / 256, 256, 0, st>>>(bp);
+  k_scan_tiles<<<1, 1024, 0, fs>>>(S.tile_count, S.tile_offset, S.tile_cursor, n_tiles, S.active_tiles, S.work_counter, S.large_tiles);
+  k_bin_fill<<<(n_slots + 255) / 256, 256, 0, fs>>>(bp);
   size_t e1 = dev->profile ? mark(dev) : 0;
-  k_sort_lists<<<n_tiles, 256, 0, st>>>(dev->tile_offset, dev->list, dev->list_cap, dev->active_tiles);
-  k_sort_lists_large<<<dev->sm_count, 1024, SORT_LARGE_SMEM * sizeof(uint32_t), st>>>(dev->tile_offset, dev->list, dev->list_cap,
-                                                                                      dev->large_tiles);
+  k_sort_lists<<<n_tiles, SORT_THREADS, 0, fs>>>(S.tile_offset, S.list, dev->list_cap, S.active_tiles, S.work_counter + 3);
+  k_sort_lists_large<<<dev->sm_count, 1024, SORT_LARGE_SMEM * sizeof(uint32_t), fs>>>(S.tile_offset, S.list, dev->list_cap, S.large_tiles);
   size_t e2 = dev->profile ? mark(dev) : 0;
   // ---- phase 5: visibility-first (k_cover + k_shade) when every queued draw qualifies, else the immediate k_raster
   bool deferred = !dev->force_immediate;
@@ -319,8 +380,9 @@ slv_result flush_batch(slv_device dev) {
                !r.color1.data && (!r.color0.data || r.color0.bpp == 4);
   bool ok = false;
   size_t e_mid = (size_t)-1, e_rbin = (size_t)-1;
+  DeferredBufs db{};
+  const bool shade = deferred && first.color0.data != nullptr;
   if (deferred) {
-    const bool shade = first.color0.data != nullptr;
     if (shade) {
       const size_t need = (size_t)first.color0.w * first.color0.h * dev->batch_S;
       if (need > dev->vis_cap) {
@@ -330,44 +392,55 @@ slv_result flush_batch(slv_device dev) {
         dev->vis_cap = need;
       }
     }
-    DeferredBufs db{};
-    db.region_list = dev->region_list;
+    db.region_list = S.region_list;
     db.region_cap = dev->region_cap;
-    db.region_mask = dev->region_mask;
-    db.region_offset = dev->region_offset;
-    db.region_count = dev->region_count;
-    db.cursor = dev->work_counter + 2;
+    db.region_mask = S.region_mask;
+    db.region_offset = S.region_offset;
+    db.region_count = S.region_count;
+    db.cursor = S.work_counter + 2;
     db.overflow_flag = dev->overflow_flag;
-    db.item_flag = dev->item_flag;
-    db.block_desc = dev->block_desc;
+    db.item_flag = S.item_flag;
+    db.block_desc = S.block_desc;
     db.vis = shade ? dev->vis : nullptr;
     db.vis_pitch = first.color0.w;
-    db.cover_counter = dev->work_counter;
-    db.shade_counter = dev->work_counter + 1;
-    k_region_bin<<<n_tiles, RBIN_THREADS, 0, st>>>(first, db);
+    db.cover_counter = S.work_counter;
+    db.shade_counter = S.work_counter + 1;
+    k_region_bin<<<n_tiles, RBIN_THREADS, 0, fs>>>(first, db);
     dev->n_launches += 1;
     if (dev->profile) e_rbin = mark(dev);
+  }
+  // ---- back half, on the main stream
+  if (piped) {
+    CU(cudaEventRecord(S.ev_front_done, fs));
+    CU(cudaStreamWaitEvent(st, S.ev_front_done, 0));
+  }
+  if (deferred) {
     switch (dev->batch_S) {
-    case 1: k_cover<1><<<dev->cover_grid, DEF_THREADS, 0, st>>>(first, dev->d_batch, n, db); ok = true; break;
-    case 2: k_cover<2><<<dev->cover_grid, DEF_THREADS, 0, st>>>(first, dev->d_batch, n, db); ok = true; break;
-    case 4: k_cover<4><<<dev->cover_grid, DEF_THREADS, 0, st>>>(first, dev->d_batch, n, db); ok = true; break;
+    case 1: k_cover<1><<<dev->cover_grid, DEF_THREADS, 0, st>>>(first, S.d_batch, n, db); ok = true; break;
+    case 2: k_cover<2><<<dev->cover_grid, DEF_THREADS, 0, st>>>(first, S.d_batch, n, db); ok = true; break;
+    case 4: k_cover<4><<<dev->cover_grid, DEF_THREADS, 0, st>>>(first, S.d_batch, n, db); ok = true; break;
     }
     if (ok && shade) {
       if (dev->profile) e_mid = mark(dev);
       switch (dev->batch_S) {
-      case 1: ok = launch_shade_s<1>(first, dev->d_batch, n, db, dev->shade_grid, st); break;
-      case 2: ok = launch_shade_s<2>(first, dev->d_batch, n, db, dev->shade_grid, st); break;
-      case 4: ok = launch_shade_s<4>(first, dev->d_batch, n, db, dev->shade_grid, st); break;
+      case 1: ok = launch_shade_s<1>(first, S.d_batch, n, db, dev->shade_grid, st); break;
+      case 2: ok = launch_shade_s<2>(first, S.d_batch, n, db, dev->shade_grid, st); break;
+      case 4: ok = launch_shade_s<4>(first, S.d_batch, n, db, dev->shade_grid, st); break;
       }
       dev->n_launches += 1;
     }
   } else {
     const uint32_t blocks = std::min<uint32_t>(n_tiles * 16, (uint32_t)dev->raster_grid);
     switch (dev->batch_S) {
-    case 1: ok = launch_raster_s<1>(first, dev->d_batch, n, blocks, st); break;
-    case 2: ok = launch_raster_s<2>(first, dev->d_batch, n, blocks, st); break;
-    case 4: ok = launch_raster_s<4>(first, dev->d_batch, n, blocks, st); break;
+    case 1: ok = launch_raster_s<1>(first, S.d_batch, n, blocks, st); break;
+    case 2: ok = launch_raster_s<2>(first, S.d_batch, n, blocks, st); break;
+    case 4: ok = launch_raster_s<4>(first, S.d_batch, n, blocks, st); break;
     }
+  }
+  if (piped) {
+    CU(cudaEventRecord(S.ev_back_done, st));
+    S.in_flight = true;
+    dev->cur ^= 1;  // the next batch is built in the other set
   }
   dev->n_launches += 5;
   if (dev->profile) {
@@ -430,9 +503,23 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   dev->res.resize(1);
   CU(cudaStreamCreateWithFlags(&dev->own_stream, cudaStreamNonBlocking));
   dev->stream = dev->own_stream;
+  CU(cudaStreamCreateWithFlags(&dev->front_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&dev->ev_sync, cudaEventDisableTiming));
   CU(cudaMalloc(&dev->overflow_flag, sizeof(uint32_t)));
-  CU(cudaMalloc(&dev->work_counter, 4 * sizeof(uint32_t)));
-  CU(cudaMalloc(&dev->valid_count, sizeof(uint32_t)));
+  for (auto& S : dev->sc) {
+    CU(cudaMalloc(&S.work_counter, 4 * sizeof(uint32_t)));
+    CU(cudaMalloc(&S.valid_count, sizeof(uint32_t)));
+    CU(cudaMalloc(&S.d_batch, MAX_BATCH * sizeof(RasterParams)));
+    CU(cudaMalloc(&S.d_geom, MAX_BATCH * sizeof(GeomParams)));
+    CU(cudaHostAlloc(&S.h_batch, MAX_BATCH * sizeof(RasterParams), cudaHostAllocDefault));
+    CU(cudaHostAlloc(&S.h_geom, MAX_BATCH * sizeof(GeomParams), cudaHostAllocDefault));
+    CU(cudaEventCreateWithFlags(&S.ev_front_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&S.ev_back_done, cudaEventDisableTiming));
+  }
+  {
+    const char* pl = getenv("SLV_PIPELINE");
+    dev->pipeline = !(pl && pl[0] == '0');
+  }
   {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, ordinal));
@@ -450,8 +537,6 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   const char* fi = getenv("SLV_FORCE_IMMEDIATE");
   dev->force_immediate = fi && fi[0] == '1';
   for (auto& ev : dev->user_ev) CU(cudaEventCreate(&ev));
-  CU(cudaMalloc(&dev->d_batch, MAX_BATCH * sizeof(RasterParams)));
-  CU(cudaMalloc(&dev->d_geom, MAX_BATCH * sizeof(GeomParams)));
 
   *out = dev;
   return SLV_OK;
@@ -461,35 +546,28 @@ void slv_device_destroy(slv_device dev) {
   if (!dev) return;
   cudaSetDevice(dev->ordinal);
   flush_batch(dev);
+  cudaStreamSynchronize(dev->front_stream);
   cudaStreamSynchronize(dev->stream);
   for (auto& r : dev->res) {
     if (r.kind == Resource::BUFFER) cudaFree(r.dptr);
     if (r.kind == Resource::TEXTURE)
       for (uint32_t l = 0; l < r.tex.n_levels; ++l) cudaFree(r.tex.level[l].data);
   }
-  cudaFree(dev->tris);
-  cudaFree(dev->valid_slots);
-  cudaFree(dev->valid_count);
-  cudaFree(dev->tile_count);
-  cudaFree(dev->tile_offset);
-  cudaFree(dev->tile_cursor);
-  cudaFree(dev->active_tiles);
-  cudaFree(dev->large_tiles);
-  cudaFree(dev->work_counter);
+  for (auto& S : dev->sc) {
+    cudaFree(S.tris); cudaFree(S.valid_slots); cudaFree(S.valid_count);
+    cudaFree(S.tile_count); cudaFree(S.tile_offset); cudaFree(S.tile_cursor); cudaFree(S.active_tiles); cudaFree(S.large_tiles);
+    cudaFree(S.work_counter); cudaFree(S.region_list); cudaFree(S.region_mask); cudaFree(S.region_offset); cudaFree(S.region_count);
+    cudaFree(S.item_flag); cudaFree(S.block_desc); cudaFree(S.list); cudaFree(S.d_batch); cudaFree(S.d_geom);
+    cudaFreeHost(S.h_batch); cudaFreeHost(S.h_geom);
+    cudaEventDestroy(S.ev_front_done); cudaEventDestroy(S.ev_back_done);
+  }
   cudaFree(dev->vis);
-  cudaFree(dev->region_list);
-  cudaFree(dev->region_mask);
-  cudaFree(dev->region_offset);
-  cudaFree(dev->region_count);
-  cudaFree(dev->item_flag);
-  cudaFree(dev->block_desc);
-  cudaFree(dev->list);
   cudaFree(dev->overflow_flag);
   cudaFree(dev->d_stats);
   for (auto& ev : dev->ev_pool) cudaEventDestroy(ev);
   for (auto& ev : dev->user_ev) cudaEventDestroy(ev);
-  cudaFree(dev->d_batch);
-  cudaFree(dev->d_geom);
+  cudaEventDestroy(dev->ev_sync);
+  cudaStreamDestroy(dev->front_stream);
 
   for (auto& t : dev->slot_tables) cudaFree(t.d_slot);
   cudaStreamDestroy(dev->own_stream);
@@ -514,6 +592,7 @@ slv_result slv_buffer_upload(slv_device dev, slv_handle h, size_t off, const voi
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   CU(cudaMemcpyAsync(r->dptr + off, src, bytes, cudaMemcpyHostToDevice, dev->stream));
+  dev->buffers_dirty = true;  // the next front half (front_stream) must order after this copy
   return SLV_OK;
 }
 
@@ -772,16 +851,8 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
     slv_result rcf = flush_batch(dev);
     if (rcf != SLV_OK) return rcf;
   }
-  float4* tris_base = dev->tris;
-  uint32_t* tile_offset = dev->tile_offset;
-  gp.tris = tris_base;
   gp.tri_stride = tri_stride;
-  gp.slot_base = (uint32_t)dev->slots_queued;
-  gp.draw_id = (uint32_t)dev->pending.size();
-  gp.tile_count = dev->tile_count;
   gp.stats = dev->d_stats;
-  gp.valid_slots = dev->valid_slots;
-  gp.valid_count = dev->valid_count;
 
   // ---- depth/stencil function selection (framebuffer.cpp:325-425)
   const slv_depth_stencil_desc& ds = d->ds;
@@ -813,20 +884,13 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   }
   if ((rp.ps_program == SLV_PS_LIGHTS3 || rp.ps_program == SLV_PS_SPONZA) && n_attrs < 4) return SLV_INVALID_PARAMETER;
   if ((rp.ps_program == SLV_PS_ATTR0_COLOR || rp.ps_program == SLV_PS_DISCARD_ALL) && n_attrs < 1) return SLV_INVALID_PARAMETER;
-  rp.tris = tris_base;
   rp.tri_stride = tri_stride;
   rp.tiles_x = gp.tiles_x;
   rp.tiles_y = gp.tiles_y;
   rp.shard_rank = dev->shard_rank;
   rp.shard_n = dev->shard_n;
-  rp.tile_offset = tile_offset;
-  rp.active_tiles = dev->active_tiles;
-  rp.work_counter = dev->work_counter;
-  rp.list = dev->list;
-  rp.list_capacity = dev->list_cap;
   rp.n_attrs = n_attrs;
   rp.stats = dev->d_stats;
-  rp.slot_base = gp.slot_base;
 
   // sampling a texture that is a target of the queued batch: the earlier draws must land first
   if (needs_sampler && !dev->pending.empty()) {
@@ -834,11 +898,24 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
     if (t0 == rp.color0.data || t0 == rp.color1.data || t0 == rp.ds.data) {
       slv_result rcf = flush_batch(dev);
       if (rcf != SLV_OK) return rcf;
-      // the flush reset the arenas: re-point this draw at the start of them
-      gp.slot_base = 0;
-      gp.draw_id = 0;
-      rp.slot_base = 0;
     }
+  }
+
+  // ---- bind the scratch set the batch is being built in (every flush above may have switched sets)
+  {
+    slv_device_t::Scratch& S = dev->S();
+    gp.tris = S.tris;
+    rp.tris = S.tris;
+    gp.slot_base = rp.slot_base = (uint32_t)dev->slots_queued;
+    gp.draw_id = (uint32_t)dev->pending.size();
+    gp.tile_count = S.tile_count;
+    gp.valid_slots = S.valid_slots;
+    gp.valid_count = S.valid_count;
+    rp.tile_offset = S.tile_offset;
+    rp.active_tiles = S.active_tiles;
+    rp.work_counter = S.work_counter;
+    rp.list = S.list;
+    rp.list_capacity = dev->list_cap;
   }
 
   // ---- queue the draw: geometry, binning and the raster pass all run at the next flush point
@@ -991,7 +1068,8 @@ slv_result slv_debug_read(slv_device dev, uint32_t which, void* dst, size_t byte
   if (!dev || !dst) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
-  const void* src = which == 0 ? (const void*)dev->active_tiles : which == 1 ? (const void*)dev->tile_offset : (const void*)dev->block_desc;
+  const slv_device_t::Scratch& L = dev->sc[(dev->pipeline && !dev->profile) ? (dev->cur ^ 1) : dev->cur];  // the last flushed batch's set
+  const void* src = which == 0 ? (const void*)L.active_tiles : which == 1 ? (const void*)L.tile_offset : (const void*)L.block_desc;
   const size_t cap = which == 0 ? ((size_t)dev->tiles_cap + 1) * 4 : which == 1 ? (size_t)dev->tiles_cap * 4 : (size_t)dev->tiles_cap * 128 * 8;
   if (!src || bytes > cap) return SLV_INVALID_PARAMETER;
   CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, dev->stream));
@@ -1053,7 +1131,7 @@ slv_result slv_set_stream(slv_device dev, void* cuda_stream) {
   if (!dev) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
-  CU(cudaStreamSynchronize(dev->stream));
+  { slv_result rcs__ = sync_all(dev); if (rcs__ != SLV_OK) return rcs__; }
   dev->stream = cuda_stream ? (cudaStream_t)cuda_stream : dev->own_stream;
   return SLV_OK;
 }

@@ -543,9 +543,9 @@ __device__ __forceinline__ uint32_t shade_sample_owner(const RasterParams& c, co
 constexpr uint32_t SHADE_GROUP = 8;   // items a warp of k_shade takes at a time; all their (pixel, owner) pairs share one pool
 constexpr int SHADE_POOL = 256;       // pool entries per warp (an item adds at most 32 * S = 128)
 
-__device__ __forceinline__ uint32_t fetch_group(uint32_t* counter, uint32_t lane) {
+__device__ __forceinline__ uint32_t fetch_group(uint32_t* counter, uint32_t lane, uint32_t grp) {
   uint32_t v = 0;
-  if (lane == 0) v = atomicAdd(counter, SHADE_GROUP);
+  if (lane == 0) v = atomicAdd(counter, grp);
   return v;
 }
 
@@ -573,18 +573,21 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
 
   uint32_t n_exec = 0;
   const uint32_t n_items = c.active_tiles[0] * ITEMS_PER_TILE;
-  uint32_t next_raw = fetch_group(d.shade_counter, lane);
+  // items per fetch: SHADE_GROUP when there is plenty of work, fewer when the launch has only a few items per warp
+  // (sort-first shards, small targets) so that the heavy items spread over all warps
+  const uint32_t grp = min(SHADE_GROUP, max(1u, n_items / (gridDim.x * DEF_WARPS * 4u)));
+  uint32_t next_raw = fetch_group(d.shade_counter, lane, grp);
   for (;;) {
     const uint32_t base_item = __shfl_sync(0xFFFFFFFFu, next_raw, 0);
     if (base_item >= n_items) break;
-    next_raw = fetch_group(d.shade_counter, lane);
+    next_raw = fetch_group(d.shade_counter, lane, grp);
     uint32_t pool_n = 0, k = 0;
     for (;;) {
       // ---- fill: analyse items while the pool has room for a whole item ----
 #pragma unroll 1
       for (; k < SHADE_GROUP && pool_n + 32 * S <= (uint32_t)SHADE_POOL; ++k) {
         const uint32_t item = base_item + k;
-        const bool live = item < n_items && d.item_flag[item];
+        const bool live = k < grp && item < n_items && d.item_flag[item];
         if (lane == 0) s_org[k] = 0xFFFFFFFFu;
         if (!live) continue;
         const uint32_t b = item >> 7, sub = (item >> 3) & 15, w = item & 7;

@@ -49,14 +49,17 @@ __device__ __forceinline__ float4 transform(float4 v, const float* m) {
   return o;
 }
 
-template <int R>
+// POS_ONLY: only input register 0 is fetched and only out.r[0] is meaningful (every shipped vertex program derives the
+// position from in[0] alone); the attribute fetches and arithmetic are dead code in that instantiation.
+template <int R, bool POS_ONLY = false>
 __device__ __forceinline__ void run_vs(const GeomParams& p, uint32_t index, VsOut<R>& out) {
   float4 in[SLV_MAX_VS_INPUT_ATTRS];
 #pragma unroll
   for (int i = 0; i < SLV_MAX_VS_INPUT_ATTRS; ++i) in[i] = make_float4(0, 0, 0, 0);
   for (uint32_t e = 0; e < p.n_elements; ++e) {
-    float4 v = fetch_element(p, p.elements[e], index);
     uint32_t reg = p.elements[e].reg;
+    if (POS_ONLY && reg != 0) continue;
+    float4 v = fetch_element(p, p.elements[e], index);
 #pragma unroll
     for (int i = 0; i < SLV_MAX_VS_INPUT_ATTRS; ++i)
       if (reg == (uint32_t)i) in[i] = v;
@@ -139,24 +142,29 @@ __device__ __forceinline__ float plane_dist(int plane, float4 pos) {
                     : (0.0f * pos.x + 0.0f * pos.y + -1.0f * pos.z + 1.0f * pos.w);
 }
 
-// viewport_transform + project_n (shader.cpp:499-511, 116-134)
-template <int R>
-__device__ __forceinline__ void viewport_project(const GeomParams& p, VsOut<R>& v) {
+// viewport_transform + project_n (shader.cpp:499-511, 116-134), position part: returns the screen position, .w = 1/w
+__device__ __forceinline__ float4 viewport_project_pos(const GeomParams& p, float4 pos) {
   const slv_viewport& vp = p.vp;
-  float w = v.r[0].w;
+  float w = pos.w;
   float invw = eq_eps(w, 0.0f) ? 1.0f : 1.0f / w;
-  float px = v.r[0].x * invw, py = v.r[0].y * invw, pz = v.r[0].z * invw;
+  float px = pos.x * invw, py = pos.y * invw, pz = pos.z * invw;
   float ox = (vp.x + vp.w) * 0.5f;
   float oy = (vp.y + vp.h) * 0.5f;
-  v.r[0].x = (vp.w * 0.5f) * px + ox;
-  v.r[0].y = (vp.h * 0.5f) * -py + oy;
-  v.r[0].z = (vp.maxz - vp.minz) * pz + vp.minz;
-  v.r[0].w = invw;
+  return make_float4((vp.w * 0.5f) * px + ox, (vp.h * 0.5f) * -py + oy, (vp.maxz - vp.minz) * pz + vp.minz, invw);
+}
+// attribute part: attributes * (1/w) unless noperspective
+template <int R>
+__device__ __forceinline__ void project_attrs(const GeomParams& p, VsOut<R>& v, float invw) {
 #pragma unroll
   for (int i = 1; i < R; ++i)
     if (!(p.mods[i - 1] & SLV_AM_NOPERSPECTIVE)) {
       v.r[i].x *= invw; v.r[i].y *= invw; v.r[i].z *= invw; v.r[i].w *= invw;
     }
+}
+template <int R>
+__device__ __forceinline__ void viewport_project(const GeomParams& p, VsOut<R>& v) {
+  v.r[0] = viewport_project_pos(p, v.r[0]);
+  project_attrs<R>(p, v, v.r[0].w);
 }
 
 // the reference's tile-level test (rasterizer.cpp:831-848): returns 0 = rejected, 1 = partial, 3 = accepted
@@ -191,47 +199,48 @@ __device__ __forceinline__ bool tile_owned(uint32_t tx, uint32_t ty, uint32_t ra
   return n <= 1 || ((tx + 3 * ty) % n) == rank;
 }
 
-// rasterizer::compute_triangle_info (rasterizer.cpp:864-945) + record store + tile coverage count
-template <int R>
-__device__ __forceinline__ bool setup_triangle(const GeomParams& p, const VsOut<R> v[3], float4* rec) {  // true: binned somewhere
-  float4 misc = make_float4(0, 0, 0, 0);
-  double d0 = (double)fabsf(v[0].r[0].x) + (double)fabsf(v[0].r[0].y);
-  double d1 = (double)fabsf(v[1].r[0].x) + (double)fabsf(v[1].r[0].y);
-  double d2 = (double)fabsf(v[2].r[0].x) + (double)fabsf(v[2].r[0].y);
+// rasterizer::compute_triangle_info (rasterizer.cpp:864-945) + record store + tile coverage count, in two steps:
+// setup_position needs the three screen positions only (rotation, area, bounding box, edge equations, tile range, tile
+// counting); setup_store computes the derivatives of every register and writes the record.  Triangles that are
+// degenerate or reach none of this rank's tiles stop after the first step, before their attributes are even fetched.
+struct TriPos {
+  float4 edge[3];
+  float bbox[4];
+  TileRange tr;
+  int r0;                         // vertex nearest the origin: the record's v0 (rasterizer.cpp:873-890)
+  float e01x, e01y, e02x, e02y, inv_area;
+  bool front;
+};
+
+__device__ __forceinline__ bool setup_position(const GeomParams& p, const float4 v[3], TriPos& s) {  // true: binned somewhere
+  double d0 = (double)fabsf(v[0].x) + (double)fabsf(v[0].y);
+  double d1 = (double)fabsf(v[1].x) + (double)fabsf(v[1].y);
+  double d2 = (double)fabsf(v[2].x) + (double)fabsf(v[2].y);
   int r0;
   if (d0 < d1) r0 = (d0 < d2) ? 0 : 2;
   else r0 = (d1 < d2) ? 1 : 2;
-  // rotate (v[r0], v[r0+1], v[r0+2]) without dynamic indexing
-  float4 a[R], b[R], c[R];
-#pragma unroll
-  for (int i = 0; i < R; ++i) {
-    a[i] = r0 == 0 ? v[0].r[i] : (r0 == 1 ? v[1].r[i] : v[2].r[i]);
-    b[i] = r0 == 0 ? v[1].r[i] : (r0 == 1 ? v[2].r[i] : v[0].r[i]);
-    c[i] = r0 == 0 ? v[2].r[i] : (r0 == 1 ? v[0].r[i] : v[1].r[i]);
-  }
-  float e01x = b[0].x - a[0].x, e01y = b[0].y - a[0].y;
-  float e02x = c[0].x - a[0].x, e02y = c[0].y - a[0].y;
-  float area = e02x * e01y - e02y * e01x;  // cross_prod2(e02.xy, e01.xy)
-  if (eq_eps(area, 0.0f)) {
-    rec[4] = misc;  // invalid (v0 == nullptr upstream)
-    return false;
-  }
-  bool front = area > 0.0f;
-  float inv_area = 1.0f / area;
-  float bbox[4];
-  bbox[0] = std_min(std_min(v[0].r[0].x, v[1].r[0].x), v[2].r[0].x);
-  bbox[1] = std_max(std_max(v[0].r[0].x, v[1].r[0].x), v[2].r[0].x);
-  bbox[2] = std_min(std_min(v[0].r[0].y, v[1].r[0].y), v[2].r[0].y);
-  bbox[3] = std_max(std_max(v[0].r[0].y, v[1].r[0].y), v[2].r[0].y);
-  float4 edge[3];
+  s.r0 = r0;
+  const float4 a = r0 == 0 ? v[0] : (r0 == 1 ? v[1] : v[2]);
+  const float4 b = r0 == 0 ? v[1] : (r0 == 1 ? v[2] : v[0]);
+  const float4 c = r0 == 0 ? v[2] : (r0 == 1 ? v[0] : v[1]);
+  s.e01x = b.x - a.x; s.e01y = b.y - a.y;
+  s.e02x = c.x - a.x; s.e02y = c.y - a.y;
+  float area = s.e02x * s.e01y - s.e02y * s.e01x;  // cross_prod2(e02.xy, e01.xy)
+  if (eq_eps(area, 0.0f)) return false;            // invalid (v0 == nullptr upstream)
+  s.front = area > 0.0f;
+  s.inv_area = 1.0f / area;
+  s.bbox[0] = std_min(std_min(v[0].x, v[1].x), v[2].x);
+  s.bbox[1] = std_max(std_max(v[0].x, v[1].x), v[2].x);
+  s.bbox[2] = std_min(std_min(v[0].y, v[1].y), v[2].y);
+  s.bbox[3] = std_max(std_max(v[0].y, v[1].y), v[2].y);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {  // original vertex order (rasterizer.cpp:928-939)
-    float4 s = v[i].r[0], e = v[(i + 1) % 3].r[0];
-    edge[i] = make_float4(s.y - e.y, e.x - s.x, e.x * s.y - e.y * s.x, 0.0f);
+    float4 st = v[i], e = v[(i + 1) % 3];
+    s.edge[i] = make_float4(st.y - e.y, e.x - st.x, e.x * st.y - e.y * st.x, 0.0f);
   }
-  // tile coverage count (rasterizer.cpp:809-857), done first: under sort-first sharding a triangle that reaches none
-  // of this rank's tiles is dropped here, before its 23-float4 record is written
-  TileRange tr = tile_range(bbox, p.tiles_x, p.tiles_y);
+  // tile coverage count (rasterizer.cpp:809-857); under sort-first sharding only this rank's tiles count
+  s.tr = tile_range(s.bbox, p.tiles_x, p.tiles_y);
+  const TileRange& tr = s.tr;
   bool any_owned = false;
   if ((tr.sx + 1 == tr.ex) && (tr.sy + 1 == tr.ey)) {
     if (tile_owned(tr.sx, tr.sy, p.shard_rank, p.shard_n)) {
@@ -241,23 +250,35 @@ __device__ __forceinline__ bool setup_triangle(const GeomParams& p, const VsOut<
   } else {
     for (int y = tr.sy; y < tr.ey; ++y)
       for (int x = tr.sx; x < tr.ex; ++x)
-        if (tile_owned(x, y, p.shard_rank, p.shard_n) && tile_test(edge, x, y)) {
+        if (tile_owned(x, y, p.shard_rank, p.shard_n) && tile_test(s.edge, x, y)) {
           atomicAdd(&p.tile_count[y * p.tiles_x + x], 1u);
           any_owned = true;
         }
   }
-  if (!any_owned) {
-    rec[4] = misc;  // not binned anywhere on this rank
-    return false;
-  }
-  rec[0] = edge[0];
-  rec[1] = edge[1];
-  rec[2] = edge[2];
-  rec[3] = make_float4(bbox[0], bbox[1], bbox[2], bbox[3]);
-  // compute_derivative_n (shader.cpp:413-449)
+  return any_owned;
+}
+
+template <int R>
+__device__ __forceinline__ void setup_store(const GeomParams& p, const VsOut<R> v[3], const TriPos& s, float4* rec) {
+  const int r0 = s.r0;
+  const float e01x = s.e01x, e01y = s.e01y, e02x = s.e02x, e02y = s.e02y, inv_area = s.inv_area;
+  rec[0] = s.edge[0];
+  rec[1] = s.edge[1];
+  rec[2] = s.edge[2];
+  rec[3] = make_float4(s.bbox[0], s.bbox[1], s.bbox[2], s.bbox[3]);
+  float4 misc;
+  misc.x = __uint_as_float(1u | (s.front ? 2u : 0u));
+  misc.y = __uint_as_float((uint32_t)s.tr.sx | ((uint32_t)s.tr.ex << 16));
+  misc.z = __uint_as_float((uint32_t)s.tr.sy | ((uint32_t)s.tr.ey << 16));
+  misc.w = __uint_as_float(p.draw_id);
+  rec[4] = misc;
+  // compute_derivative_n (shader.cpp:413-449), registers rotated so that v0 is the vertex nearest the origin
 #pragma unroll
   for (int i = 0; i < R; ++i) {
-    float4 e01 = f4_sub(b[i], a[i]), e02 = f4_sub(c[i], a[i]);
+    const float4 a = r0 == 0 ? v[0].r[i] : (r0 == 1 ? v[1].r[i] : v[2].r[i]);
+    const float4 b = r0 == 0 ? v[1].r[i] : (r0 == 1 ? v[2].r[i] : v[0].r[i]);
+    const float4 c = r0 == 0 ? v[2].r[i] : (r0 == 1 ? v[0].r[i] : v[1].r[i]);
+    float4 e01 = f4_sub(b, a), e02 = f4_sub(c, a);
     float4 ddx, ddy;
     ddx.x = (e02.x * e01y - e01.x * e02y) * inv_area;
     ddx.y = (e02.y * e01y - e01.y * e02y) * inv_area;
@@ -267,20 +288,23 @@ __device__ __forceinline__ bool setup_triangle(const GeomParams& p, const VsOut<
     ddy.y = (e01.y * e02x - e02.y * e01x) * inv_area;
     ddy.z = (e01.z * e02x - e02.z * e01x) * inv_area;
     ddy.w = (e01.w * e02x - e02.w * e01x) * inv_area;
-    rec[REC_V0 + 3 * i] = a[i];
+    rec[REC_V0 + 3 * i] = a;
     rec[REC_DDX + 3 * i] = ddx;
     rec[REC_DDY + 3 * i] = ddy;
   }
-  misc.x = __uint_as_float(1u | (front ? 2u : 0u));
-  misc.y = __uint_as_float((uint32_t)tr.sx | ((uint32_t)tr.ex << 16));
-  misc.z = __uint_as_float((uint32_t)tr.sy | ((uint32_t)tr.ey << 16));
-  misc.w = __uint_as_float(p.draw_id);
-  rec[4] = misc;
+}
+
+template <int R>
+__device__ __forceinline__ bool setup_triangle(const GeomParams& p, const VsOut<R> v[3], float4* rec) {  // true: binned somewhere
+  const float4 pos[3] = {v[0].r[0], v[1].r[0], v[2].r[0]};
+  TriPos s;
+  if (!setup_position(p, pos, s)) return false;
+  setup_store<R>(p, v, s, rec);
   return true;
 }
 
 template <int R>
-__global__ void __launch_bounds__(128) k_geometry(const GeomParams* __restrict__ draws, GeomBatch hb) {
+__global__ void __launch_bounds__(128, 4) k_geometry(const GeomParams* __restrict__ draws, GeomBatch hb) {
   // every queued draw with R registers shares this launch; a CTA belongs to exactly one draw
   uint32_t lo = 0, hi = hb.n;
   while (hi - lo > 1) {
@@ -311,10 +335,15 @@ __global__ void __launch_bounds__(128) k_geometry(const GeomParams* __restrict__
       idx[i] = v + (uint32_t)p.base_vertex;
     }
     // ---- vertex fetch + vertex shader, recomputed per corner (VS is pure, so this equals the
-    //      reference's post-transform cache hit: default_vertex_cache.cpp:354-390)
-    VsOut<R> tri[3];
+    //      reference's post-transform cache hit: default_vertex_cache.cpp:354-390).  Positions first: most primitives
+    //      are culled, degenerate or (sort-first) outside this rank's tiles and never need their attributes.
+    float4 cpos[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) run_vs<R>(p, idx[i], tri[i]);
+    for (int i = 0; i < 3; ++i) {
+      VsOut<R> t;
+      run_vs<R, true>(p, idx[i], t);
+      cpos[i] = t.r[0];
+    }
 
     float4* rec = p.tris + ((size_t)p.slot_base + (size_t)prim * 3) * p.tri_stride;
     // ---- clip (clipper.cpp:103-228)
@@ -323,32 +352,44 @@ __global__ void __launch_bounds__(128) k_geometry(const GeomParams* __restrict__
     for (int pl = 0; pl < 2; ++pl)
 #pragma unroll
       for (int v = 0; v < 3; ++v)
-        if (plane_dist(pl, tri[v].r[0]) < 0) in_frustum = false;
+        if (plane_dist(pl, cpos[v]) < 0) in_frustum = false;
 
     if (in_frustum) {
       float px[3], py[3];
 #pragma unroll
       for (int v = 0; v < 3; ++v) {
-        float iw = 1.0f / tri[v].r[0].w;
-        px[v] = tri[v].r[0].x * iw;
-        py[v] = tri[v].r[0].y * iw;
+        float iw = 1.0f / cpos[v].w;
+        px[v] = cpos[v].x * iw;
+        py[v] = cpos[v].y * iw;
       }
       float area = (px[2] - px[0]) * (py[1] - py[0]) - (py[2] - py[0]) * (px[1] - px[0]);
       bool front = area > 0.0f;
       if (!cull_tri(p.cull_mode, p.front_ccw, front ? 1.0f : -1.0f)) {
-        VsOut<R> o[3];
-        o[0] = tri[0];
-        o[1] = front ? tri[1] : tri[2];  // un-clipped back faces get v1 <-> v2 swapped (clipper.cpp:59-65)
-        o[2] = front ? tri[2] : tri[1];
+        // un-clipped back faces get v1 <-> v2 swapped (clipper.cpp:59-65)
+        const uint32_t oi[3] = {idx[0], front ? idx[1] : idx[2], front ? idx[2] : idx[1]};
+        float4 spos[3];
+        spos[0] = viewport_project_pos(p, cpos[0]);
+        spos[1] = viewport_project_pos(p, front ? cpos[1] : cpos[2]);
+        spos[2] = viewport_project_pos(p, front ? cpos[2] : cpos[1]);
+        TriPos ts;
+        if (setup_position(p, spos, ts)) {
+          VsOut<R> o[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) viewport_project<R>(p, o[k]);
-        valid_mask = setup_triangle<R>(p, o, rec) ? 1u : 0u;
+          for (int k = 0; k < 3; ++k) {
+            run_vs<R>(p, oi[k], o[k]);
+            o[k].r[0] = spos[k];
+            project_attrs<R>(p, o[k], spos[k].w);
+          }
+          setup_store<R>(p, o, ts, rec);
+          valid_mask = 1u;
+        }
         n_out = 1;
       }
     } else {
       VsOut<R> pool[2][5];
       int n[2] = {3, 0};
-      pool[0][0] = tri[0]; pool[0][1] = tri[1]; pool[0][2] = tri[2];
+#pragma unroll 1
+      for (int i = 0; i < 3; ++i) run_vs<R>(p, idx[i], pool[0][i]);
       int src = 0, dst = 1;
       bool is_front = false, culled = false;
       for (int pl = 0; pl < 2 && !culled; ++pl) {
@@ -398,7 +439,6 @@ __global__ void __launch_bounds__(128) k_geometry(const GeomParams* __restrict__
         n_out = nv - 2;
       }
     }
-    for (uint32_t k = n_out; k < 3; ++k) rec[(size_t)k * p.tri_stride + 4] = make_float4(0, 0, 0, 0);
   }
   // compact list of the slots k_bin_fill has to look at (order is irrelevant: the tile lists are sorted afterwards);
   // one atomicAdd per warp
@@ -430,6 +470,9 @@ __global__ void __launch_bounds__(128) k_geometry(const GeomParams* __restrict__
 // binning
 // =====================================================================================================
 constexpr int SORT_SMEM = 4096;         // list length k_sort_lists sorts in static shared memory
+constexpr int SORT_THREADS = 1024;      // CTA of k_sort_lists: one long list, or four short ones (one per SORT_GROUP threads)
+constexpr int SORT_GROUP = 256;
+constexpr int SORT_LONG = SORT_SMEM / (SORT_THREADS / SORT_GROUP);  // lists longer than this (1024) get a whole CTA
 constexpr int SORT_LARGE_SMEM = 49152;  // list length k_sort_lists_large sorts in dynamic shared memory (192 KB)
 
 // single CTA, 1024 threads: exclusive scan of tile_count -> tile_offset[0..n]; zeroes count and cursor
@@ -449,8 +492,8 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint3
   // active-tile compaction, longest lists first (classes >= 2048, >= 512, >= 128, rest): the raster work queue hands
   // items out in this order, so the few very long in-order chains start early instead of forming the kernel's tail
   for (int cls = 0; cls < 4; ++cls) {
-    const uint32_t lo = cls == 0 ? 2048u : (cls == 1 ? 512u : (cls == 2 ? 128u : 1u));
-    const uint32_t hi = cls == 0 ? 0xFFFFFFFFu : (cls == 1 ? 2048u : (cls == 2 ? 512u : 128u));
+    const uint32_t lo = cls == 0 ? (uint32_t)SORT_LONG + 1 : (cls == 1 ? 512u : (cls == 2 ? 128u : 1u));
+    const uint32_t hi = cls == 0 ? 0xFFFFFFFFu : (cls == 1 ? (uint32_t)SORT_LONG + 1 : (cls == 2 ? 512u : 128u));
     for (uint32_t base = 0; base < n_tiles; base += 1024) {
       const uint32_t i = base + tid;
       const uint32_t v = i < n_tiles ? tile_count[i] : 0;
@@ -463,6 +506,10 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint3
       if (cls == 0 && v > (uint32_t)SORT_SMEM) large_tiles[1 + atomicAdd(&s_large, 1u)] = i;  // sorted by k_sort_lists_large
     }
     __syncthreads();  // classes must not interleave in active_tiles
+    if (cls == 0) {  // number of long lists (k_sort_lists gives each a whole CTA)
+      if (tid == 0) work_counter[3] = s_active;
+      __syncthreads();
+    }
   }
   for (uint32_t base = 0; base < n_tiles; base += 1024) {
     const uint32_t i = base + tid;
@@ -531,8 +578,29 @@ __global__ void __launch_bounds__(256) k_bin_fill(BinParams p) {
     }
 }
 
-// one CTA per tile; normalized bitonic network (every compare-exchange puts the minimum at the lower
-// index), so virtual +inf padding past n works in place for any n.
+// Bitonic network over buf[0..N) (N a power of two, entries past the list padded with 0xFFFFFFFF) by NTH threads that
+// share named barrier `bar_id`.  Pair t of a pass sits at i = index with bit j clear; for j <= 32 both ends of every
+// pair a warp handles lie in that warp's own 64-entry blocks (the same blocks in every pass), so those passes need
+// __syncwarp() only: a 4096-entry list takes 33 CTA-wide barriers instead of 78.
+template <int NTH>
+__device__ __forceinline__ void bitonic_sort_padded(uint32_t* buf, uint32_t N, uint32_t tid, int bar_id) {
+  for (uint32_t k = 2; k <= N; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      const bool flip = (j == (k >> 1));
+      for (uint32_t t = tid; t < (N >> 1); t += NTH) {
+        const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const uint32_t l = flip ? (i ^ (k - 1)) : (i | j);
+        const uint32_t x = buf[i], y = buf[l];
+        if (x > y) { buf[i] = y; buf[l] = x; }
+      }
+      if (j > 32) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NTH) : "memory");
+      else __syncwarp();
+    }
+    if (k >= 64) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NTH) : "memory");
+  }
+}
+
+// generic in-place variant (any n, any buffer): only used for lists that do not fit shared memory
 __device__ __forceinline__ void bitonic_sort_block(uint32_t* buf, uint32_t n) {
   uint32_t N = 1;
   while (N < n) N <<= 1;
@@ -540,10 +608,8 @@ __device__ __forceinline__ void bitonic_sort_block(uint32_t* buf, uint32_t n) {
     for (uint32_t j = k >> 1; j > 0; j >>= 1) {
       const bool first = (j == (k >> 1));
       for (uint32_t t = threadIdx.x; t < (N >> 1); t += blockDim.x) {
-        // t-th compare-exchange of this step: i = index with bit j clear
         uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
         uint32_t l = first ? (i ^ (k - 1)) : (i | j);
-        if (first && l < i) { uint32_t tmp = i; i = l; l = tmp; }
         if (l < n && i < n) {
           uint32_t x = buf[i], y = buf[l];
           if (x > y) { buf[i] = y; buf[l] = x; }
@@ -554,21 +620,45 @@ __device__ __forceinline__ void bitonic_sort_block(uint32_t* buf, uint32_t n) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_sort_lists(const uint32_t* tile_offset, uint32_t* list, uint32_t capacity,
-                                                    const uint32_t* active_tiles) {
+// Restores API order in every tile list (the reference's std::sort, rasterizer.cpp:976).  1024-thread CTAs: the first
+// *n_long CTAs take one long list (1025..4096 entries, the head of active_tiles) with all their threads, the others four
+// short lists each, one per 256-thread group with its own named barrier - the few long lists no longer form the
+// kernel's tail while the short ones keep their low barrier cost.
+template <int NTH>
+__device__ __forceinline__ void sort_one_list(uint32_t* a, uint32_t n, uint32_t* s, uint32_t tid, int bar_id) {
+  uint32_t N = 2;
+  while (N < n) N <<= 1;
+  for (uint32_t i = tid; i < N; i += NTH) s[i] = i < n ? a[i] : 0xFFFFFFFFu;
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NTH) : "memory");
+  bitonic_sort_padded<NTH>(s, N, tid, bar_id);
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NTH) : "memory");
+  for (uint32_t i = tid; i < n; i += NTH) a[i] = s[i];
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_lists(const uint32_t* tile_offset, uint32_t* list, uint32_t capacity,
+                                                             const uint32_t* active_tiles, const uint32_t* n_long_ptr) {
   __shared__ uint32_t s[SORT_SMEM];
-  if (blockIdx.x >= active_tiles[0]) return;
-  const uint32_t tile = active_tiles[1 + blockIdx.x];  // longest lists first
-  uint32_t beg = tile_offset[tile], end = tile_offset[tile + 1];
-  if (end > capacity) end = capacity;
-  if (beg >= end) return;
-  const uint32_t n = end - beg;
-  if (n < 2 || n > (uint32_t)SORT_SMEM) return;  // longer lists: k_sort_lists_large
-  uint32_t* a = list + beg;
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s[i] = a[i];
-  __syncthreads();
-  bitonic_sort_block(s, n);
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) a[i] = s[i];
+  const uint32_t n_active = active_tiles[0], n_long = min(*n_long_ptr, n_active);
+  if (blockIdx.x < n_long) {
+    const uint32_t tile = active_tiles[1 + blockIdx.x];
+    uint32_t beg = tile_offset[tile], end = tile_offset[tile + 1];
+    if (end > capacity) end = capacity;
+    if (beg >= end) return;
+    const uint32_t n = end - beg;
+    if (n < 2 || n > (uint32_t)SORT_SMEM) return;  // longer lists: k_sort_lists_large
+    sort_one_list<SORT_THREADS>(list + beg, n, s, threadIdx.x, 0);
+  } else {
+    const uint32_t grp = threadIdx.x / SORT_GROUP;
+    const uint32_t idx = n_long + (blockIdx.x - n_long) * (SORT_THREADS / SORT_GROUP) + grp;
+    if (idx >= n_active) return;
+    const uint32_t tile = active_tiles[1 + idx];
+    uint32_t beg = tile_offset[tile], end = tile_offset[tile + 1];
+    if (end > capacity) end = capacity;
+    if (beg >= end) return;
+    const uint32_t n = end - beg;
+    if (n < 2 || n > (uint32_t)SORT_LONG) return;
+    sort_one_list<SORT_GROUP>(list + beg, n, s + grp * SORT_LONG, threadIdx.x % SORT_GROUP, 1 + (int)grp);
+  }
 }
 
 // the few tiles whose list exceeds SORT_SMEM entries (ids compacted by k_scan_tiles): 1024 threads, dynamic shared memory

@@ -11,9 +11,17 @@ if os.environ.get('SHARD'):
     r, n = map(int, os.environ['SHARD'].split(','))
     be.set_tile_shard(r, n)
     print('tile shard', r, 'of', n)
+import time
 for f in range(8):
     sc.render(be, f)
 be.flush()
+t0 = time.perf_counter()
+for f in range(40):
+    sc.render(be, f % 8)
+t1 = time.perf_counter()
+be.flush()
+t2 = time.perf_counter()
+print(f"host enqueue {1e3 * (t1 - t0) / 40:.3f} ms/frame, with the final sync {1e3 * (t2 - t0) / 40:.3f} ms/frame (40 frames)", flush=True)
 for f in range(8):
     be.profile_enable(True)
     be.query_begin()
