@@ -149,7 +149,8 @@ def config_dict(args, n):
             "width": args.width, "height": args.height, "msaa": args.samples, "triangles": 262249, "draws_per_frame": 24,
             "texture": f"24 x {args.tex_size}^2 rgba8 + mips, wrap, " + (f"{args.aniso}x anisotropic" if args.aniso > 1 else "trilinear"),
             "color_format": "bgra8", "depth_stencil_format": "rg32f",
-            "parallelism": "single GPU" if n == 1 else f"sort-first: 64x64 screen tiles interleaved over {n} GPUs, geometry replicated, NCCL gather to rank 0",
+            "parallelism": "single GPU" if n == 1 else f"sort-first: 64x64 screen tiles interleaved over {n} GPUs, geometry replicated, "
+                           "finished tiles resolved straight into rank 0's surface over NVLink peer memory (fallback: NCCL gather)",
             "l2_policy": "inputs larger than L2 (398 MB of render targets per frame vs 126 MB L2); no explicit flush"}
 
 
@@ -186,7 +187,8 @@ def main():
     fg = sortfirst.FrameGather(be, resolved, rank, n, "cuda")
 
     def frame(i):
-        sc.render(be, i % sc.n_frames)
+        fg.begin_frame()
+        sc.render(be, i % sc.n_frames, before_resolve=fg.before_resolve)
         fg.gather()
 
     def barrier():
@@ -318,7 +320,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "shaded_mpix_per_s": float(ps_all.item()) / (ms_total * 1e-3) / 1e6,
             "ps_invocations_per_frame": float(ps_all.item()) / args.steps,
-            "config": config_dict(args, n),
+            "config": dict(config_dict(args, n), sortfirst_transport=fg.transport),
             "clocks": clocks,
             "e2e": {"value": 1e3 / e2e_ms, "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
@@ -330,6 +332,7 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if n > 1:
+        fg.close()
         dist.destroy_process_group()
 
 

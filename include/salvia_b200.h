@@ -305,6 +305,24 @@ slv_result slv_texture_device_ptr(slv_device dev, slv_handle tex, uint32_t level
 slv_result slv_pack_tiles(slv_device dev, slv_handle tex, uint32_t rank, uint32_t nranks, void* staging, size_t* bytes);
 slv_result slv_unpack_tiles(slv_device dev, slv_handle tex, uint32_t rank, uint32_t nranks, const void* staging);
 
+/* sort-first frame assembly over peer memory (NVLink / NVSwitch; new, the reference is single-process).  One process
+ * per GPU: the root rank exports its resolved surface and its flag block as CUDA IPC handles, every other rank opens
+ * them and redirects slv_resolve into the root's surface (only its own tiles are written, see slv_set_tile_shard), so
+ * the MSAA resolve and the gather of the finished tiles are ONE kernel writing over NVLink.  Flags order the ranks'
+ * streams on the device: slv_peer_signal raises flags[index] = value in `peer_flags` (NULL = this device's own block)
+ * after all earlier work of this device's stream; slv_flags_wait blocks this device's stream until
+ * flags[first .. first+count) of `flags` (NULL = this device's own block, else an opened peer block polled over
+ * NVLink) have all reached `value` (wrap-safe comparison; gives up after ~10 s and makes the next flush point fail).  The CPU checkers return SLV_FAILED from all of these. */
+#define SLV_PEER_HANDLE_BYTES 64
+#define SLV_PEER_FLAGS 64
+slv_result slv_peer_export_texture(slv_device dev, slv_handle tex, uint32_t level, uint8_t handle_out[SLV_PEER_HANDLE_BYTES]);
+slv_result slv_peer_export_flags(slv_device dev, uint8_t handle_out[SLV_PEER_HANDLE_BYTES]);
+slv_result slv_peer_open(slv_device dev, const uint8_t handle[SLV_PEER_HANDLE_BYTES], void** dptr_out);
+slv_result slv_peer_close(slv_device dev, void* dptr);
+slv_result slv_resolve_target_peer(slv_device dev, slv_handle dst, void* peer_surface);
+slv_result slv_peer_signal(slv_device dev, void* peer_flags, uint32_t index, uint32_t value);
+slv_result slv_flags_wait(slv_device dev, const void* flags, uint32_t first, uint32_t count, uint32_t value);
+
 /* sampler probe used by the sampler parity tests: evaluates sampler::sample_2d_grad
  * (sampler.cpp:854-873) [use_lod = 0] or sample_2d_lod (:850-852) [use_lod = 1] for n coordinates.
  * coords: n×2 floats; ddx, ddy: n×2 floats (ignored for lod); lod: n floats; out: n×4 floats.

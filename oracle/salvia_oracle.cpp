@@ -1661,6 +1661,15 @@ slv_result slv_event_elapsed_ms(slv_device dev, uint32_t a, uint32_t b, float* m
 }
 slv_result slv_profile_enable(slv_device, uint32_t) { return SLV_OK; }
 slv_result slv_set_stream(slv_device, void*) { return SLV_OK; }
+// peer-memory frame assembly is a property of the CUDA product (NVLink); the CPU checkers do not implement it
+slv_result slv_peer_export_texture(slv_device, slv_handle, uint32_t, uint8_t*) { return SLV_FAILED; }
+slv_result slv_peer_export_flags(slv_device, uint8_t*) { return SLV_FAILED; }
+slv_result slv_peer_open(slv_device, const uint8_t*, void**) { return SLV_FAILED; }
+slv_result slv_peer_close(slv_device, void*) { return SLV_FAILED; }
+slv_result slv_resolve_target_peer(slv_device, slv_handle, void*) { return SLV_FAILED; }
+slv_result slv_peer_signal(slv_device, void*, uint32_t, uint32_t) { return SLV_FAILED; }
+slv_result slv_flags_wait(slv_device, const void*, uint32_t, uint32_t, uint32_t) { return SLV_FAILED; }
+
 slv_result slv_texture_device_ptr(slv_device dev, slv_handle h, uint32_t level, void** out, size_t* bytes) {
   auto r = dev->get(h, Resource::TEXTURE);
   if (!r || level >= r->tex.levels.size()) return SLV_INVALID_PARAMETER;

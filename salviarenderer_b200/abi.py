@@ -134,6 +134,8 @@ ENTRY_POINTS = [
     "slv_set_tile_shard", "slv_profile_get",
     "slv_traffic_get", "slv_kernel_launch_count", "slv_event_record", "slv_event_elapsed_ms", "slv_profile_enable",
     "slv_texture_device_ptr", "slv_pack_tiles", "slv_unpack_tiles", "slv_set_stream", "slv_profile_get_stages",
+    "slv_peer_export_texture", "slv_peer_export_flags", "slv_peer_open", "slv_peer_close", "slv_resolve_target_peer",
+    "slv_peer_signal", "slv_flags_wait",
 ]
 
 
@@ -240,6 +242,13 @@ class Backend:
         L.slv_pack_tiles.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_size_t)]
         L.slv_unpack_tiles.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         L.slv_profile_get_stages.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_uint32]
+        L.slv_peer_export_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.slv_peer_export_flags.argtypes = [C.c_void_p, C.c_void_p]
+        L.slv_peer_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.slv_peer_close.argtypes = [C.c_void_p, C.c_void_p]
+        L.slv_resolve_target_peer.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.slv_peer_signal.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.slv_flags_wait.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
         self.name = L.slv_backend_name().decode()
         if L.slv_abi_version() != 1:
             raise SlvError("ABI version mismatch")
@@ -393,6 +402,35 @@ class Backend:
         p, n = C.c_void_p(), C.c_size_t()
         _chk(self.lib.slv_texture_device_ptr(self.dev, tex.handle, level, C.byref(p), C.byref(n)), "slv_texture_device_ptr")
         return p.value, n.value
+
+    # ---- peer-memory frame assembly (CUDA IPC; product only) ----
+    def peer_export_texture(self, tex: Texture, level: int = 0) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        _chk(self.lib.slv_peer_export_texture(self.dev, tex.handle, level, buf), "slv_peer_export_texture")
+        return bytes(buf)
+
+    def peer_export_flags(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        _chk(self.lib.slv_peer_export_flags(self.dev, buf), "slv_peer_export_flags")
+        return bytes(buf)
+
+    def peer_open(self, handle: bytes) -> int:
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        out = C.c_void_p()
+        _chk(self.lib.slv_peer_open(self.dev, buf, C.byref(out)), "slv_peer_open")
+        return out.value
+
+    def peer_close(self, dptr: int):
+        _chk(self.lib.slv_peer_close(self.dev, C.c_void_p(dptr)), "slv_peer_close")
+
+    def resolve_target_peer(self, dst: Texture, peer_surface: int | None):
+        _chk(self.lib.slv_resolve_target_peer(self.dev, dst.handle, C.c_void_p(peer_surface or 0)), "slv_resolve_target_peer")
+
+    def peer_signal(self, peer_flags: int | None, index: int, value: int):
+        _chk(self.lib.slv_peer_signal(self.dev, C.c_void_p(peer_flags or 0), index, value & 0xFFFFFFFF), "slv_peer_signal")
+
+    def flags_wait(self, flags: int | None, first: int, count: int, value: int):
+        _chk(self.lib.slv_flags_wait(self.dev, C.c_void_p(flags or 0), first, count, value & 0xFFFFFFFF), "slv_flags_wait")
 
     def packed_tiles_bytes(self, tex: Texture, rank: int, nranks: int) -> int:
         n = C.c_size_t()

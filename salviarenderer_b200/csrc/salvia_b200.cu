@@ -35,6 +35,7 @@ struct Resource {
   uint32_t fmt = 0, samples = 1;
   slv_sampler_desc sd{};    // samplers
   slv_handle sampler_tex = 0;
+  uint8_t* resolve_peer = nullptr;  // textures: slv_resolve into this texture writes the owned tiles here instead (peer memory)
 };
 
 uint32_t bpp_of(uint32_t fmt) {
@@ -91,6 +92,7 @@ struct slv_device_t {
   cudaEvent_t ev_sync = nullptr;        // scratch event: orders front_stream after buffer uploads on `stream`
   bool buffers_dirty = false;           // a vertex / index buffer was written on `stream` since the last front half
   bool pipeline = true;                 // SLV_PIPELINE=0: everything on `stream`
+  uint32_t* peer_flags = nullptr;       // SLV_PEER_FLAGS words other ranks raise over NVLink (slv_peer_signal / slv_flags_wait)
   uint32_t* vis = nullptr;           // visibility buffer of the deferred path: owner slot per sample
   size_t vis_cap = 0;                // in uint32 units
   bool force_immediate = false;      // SLV_FORCE_IMMEDIATE=1: always use k_raster (tests compare both paths)
@@ -471,6 +473,11 @@ slv_result check_overflow(slv_device dev) {
   uint32_t flag = 0;
   CU(cudaMemcpyAsync(&flag, dev->overflow_flag, sizeof(flag), cudaMemcpyDeviceToHost, dev->stream));
   CU(cudaStreamSynchronize(dev->stream));
+  if (flag == 2) {
+    fprintf(stderr, "[salvia_b200] slv_flags_wait timed out: a peer rank never raised its flag\n");
+    dev->failed = true;
+    return SLV_FAILED;
+  }
   if (flag) {
     fprintf(stderr, "[salvia_b200] per-tile triangle lists overflowed the %u-entry arena\n", dev->list_cap);
     dev->failed = true;
@@ -506,6 +513,8 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   CU(cudaStreamCreateWithFlags(&dev->front_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&dev->ev_sync, cudaEventDisableTiming));
   CU(cudaMalloc(&dev->overflow_flag, sizeof(uint32_t)));
+  CU(cudaMalloc(&dev->peer_flags, SLV_PEER_FLAGS * sizeof(uint32_t)));
+  CU(cudaMemset(dev->peer_flags, 0, SLV_PEER_FLAGS * sizeof(uint32_t)));
   for (auto& S : dev->sc) {
     CU(cudaMalloc(&S.work_counter, 4 * sizeof(uint32_t)));
     CU(cudaMalloc(&S.valid_count, sizeof(uint32_t)));
@@ -563,6 +572,7 @@ void slv_device_destroy(slv_device dev) {
   }
   cudaFree(dev->vis);
   cudaFree(dev->overflow_flag);
+  cudaFree(dev->peer_flags);
   cudaFree(dev->d_stats);
   for (auto& ev : dev->ev_pool) cudaEventDestroy(ev);
   for (auto& ev : dev->user_ev) cudaEventDestroy(ev);
@@ -790,6 +800,12 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
     gp.elements[i] = d->elements[i];
     if (d->elements[i].slot >= d->n_streams || d->elements[i].reg >= SLV_MAX_VS_INPUT_ATTRS) return SLV_INVALID_PARAMETER;
   }
+  gp.fast_layout = 1;
+  for (uint32_t i = 0; i < d->n_elements; ++i) {
+    const slv_input_element& e = d->elements[i];
+    const slv_vertex_stream& vs = d->streams[e.slot];
+    if (e.reg != i || e.format != SLV_FMT_R32G32B32A32_FLOAT || ((vs.offset + e.aligned_byte_offset) & 15) || (vs.stride & 15)) gp.fast_layout = 0;
+  }
   if (d->index_buffer) {
     auto r = dev->get(d->index_buffer, Resource::BUFFER);
     if (!r) return SLV_INVALID_PARAMETER;
@@ -1001,7 +1017,9 @@ slv_result slv_resolve(slv_device dev, slv_handle src, slv_handle dst) {
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   dim3 blk(32, 8), grd((s.w + 31) / 32, (s.h + 7) / 8);
-  k_resolve<<<grd, blk, 0, dev->stream>>>(s, t, dev->shard_rank, dev->shard_n);
+  SurfaceRef t2 = t;
+  if (rd->resolve_peer && dev->shard_n > 1) t2.data = rd->resolve_peer;  // owned tiles go straight to the root's surface
+  k_resolve<<<grd, blk, 0, dev->stream>>>(s, t2, dev->shard_rank, dev->shard_n);
   ++dev->n_launches;
   CU(cudaGetLastError());
   return SLV_OK;
@@ -1191,6 +1209,80 @@ slv_result slv_pack_tiles(slv_device dev, slv_handle tex, uint32_t rank, uint32_
 slv_result slv_unpack_tiles(slv_device dev, slv_handle tex, uint32_t rank, uint32_t nranks, const void* staging) {
   if (!staging) return SLV_INVALID_PARAMETER;
   return pack_common(dev, tex, rank, nranks, const_cast<void*>(staging), nullptr, 1);
+}
+
+// ---- sort-first frame assembly over peer memory (CUDA IPC between the one-process-per-GPU ranks) -------------------
+slv_result slv_peer_export_texture(slv_device dev, slv_handle tex, uint32_t level, uint8_t handle_out[SLV_PEER_HANDLE_BYTES]) {
+  auto r = dev ? dev->get(tex, Resource::TEXTURE) : nullptr;
+  if (!r || level >= r->tex.n_levels || !handle_out) return SLV_INVALID_PARAMETER;
+  static_assert(sizeof(cudaIpcMemHandle_t) <= SLV_PEER_HANDLE_BYTES, "IPC handle does not fit");
+  CU(cudaSetDevice(dev->ordinal));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, r->tex.level[level].data));
+  memset(handle_out, 0, SLV_PEER_HANDLE_BYTES);
+  memcpy(handle_out, &h, sizeof(h));
+  return SLV_OK;
+}
+
+slv_result slv_peer_export_flags(slv_device dev, uint8_t handle_out[SLV_PEER_HANDLE_BYTES]) {
+  if (!dev || !handle_out) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, dev->peer_flags));
+  memset(handle_out, 0, SLV_PEER_HANDLE_BYTES);
+  memcpy(handle_out, &h, sizeof(h));
+  return SLV_OK;
+}
+
+slv_result slv_peer_open(slv_device dev, const uint8_t handle[SLV_PEER_HANDLE_BYTES], void** dptr_out) {
+  if (!dev || !handle || !dptr_out) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  CU(cudaIpcOpenMemHandle(dptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return SLV_OK;
+}
+
+slv_result slv_peer_close(slv_device dev, void* dptr) {
+  if (!dev || !dptr) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  { slv_result rcs__ = sync_all(dev); if (rcs__ != SLV_OK) return rcs__; }
+  for (auto& r : dev->res)
+    if (r.kind == Resource::TEXTURE && r.resolve_peer == dptr) r.resolve_peer = nullptr;
+  CU(cudaIpcCloseMemHandle(dptr));
+  return SLV_OK;
+}
+
+slv_result slv_resolve_target_peer(slv_device dev, slv_handle dst, void* peer_surface) {
+  auto r = dev ? dev->get(dst, Resource::TEXTURE) : nullptr;
+  if (!r) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  r->resolve_peer = (uint8_t*)peer_surface;
+  return SLV_OK;
+}
+
+slv_result slv_peer_signal(slv_device dev, void* peer_flags, uint32_t index, uint32_t value) {
+  if (!dev || index >= SLV_PEER_FLAGS) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  uint32_t* base = peer_flags ? (uint32_t*)peer_flags : dev->peer_flags;
+  k_peer_signal<<<1, 1, 0, dev->stream>>>(base + index, value);
+  ++dev->n_launches;
+  CU(cudaGetLastError());
+  return SLV_OK;
+}
+
+slv_result slv_flags_wait(slv_device dev, const void* flags, uint32_t first, uint32_t count, uint32_t value) {
+  if (!dev || first + count > SLV_PEER_FLAGS) return SLV_INVALID_PARAMETER;
+  if (count == 0) return SLV_OK;
+  CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  k_flags_wait<<<1, 32, 0, dev->stream>>>(flags ? (const uint32_t*)flags : dev->peer_flags, first, count, value, dev->overflow_flag);
+  ++dev->n_launches;
+  CU(cudaGetLastError());
+  return SLV_OK;
 }
 
 slv_result slv_set_tile_shard(slv_device dev, uint32_t rank, uint32_t nranks) {

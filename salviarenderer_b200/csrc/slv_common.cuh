@@ -51,6 +51,7 @@ struct GeomParams {
   StreamRef streams[8];
   slv_input_element elements[SLV_MAX_VS_INPUT_ATTRS];
   uint32_t n_elements;
+  uint32_t fast_layout;    // every element is a 16-byte aligned rgba32f feeding register == element index: direct 128-bit loads
   const uint8_t* indices;  // nullptr for draw()
   uint32_t index_stride;   // 2 or 4
   uint32_t topology, start, prim_count;

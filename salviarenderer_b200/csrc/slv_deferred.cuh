@@ -245,17 +245,6 @@ __global__ void __launch_bounds__(RBIN_THREADS, 2) k_region_bin(RasterParams c, 
   }
 }
 
-// the draw a triangle slot belongs to: slots are allocated draw by draw, so it is the last draw whose first slot is <=
-// `slot` (binary search over <= 64 bases kept in shared memory: no global load on the kernels' dependent chains)
-__device__ __forceinline__ uint32_t draw_of_slot(const uint32_t* s_slot_base, uint32_t n_draws, uint32_t slot) {
-  uint32_t lo = 0, hi = n_draws;
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (slot >= s_slot_base[mid]) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-
 // work-queue fetch: lane 0 takes FETCH consecutive items; the result is consumed one fetch later (latency hidden)
 __device__ __forceinline__ uint32_t fetch_items(uint32_t* counter, uint32_t lane) {
   uint32_t v = 0;
@@ -267,9 +256,6 @@ template <int S>
 __global__ void __launch_bounds__(DEF_THREADS, SLV_COVER_CTAS_PER_SM)
     k_cover(RasterParams c, const RasterParams* __restrict__ batch, uint32_t n_draws, DeferredBufs d) {
   __shared__ CovTri s_tri_all[DEF_WARPS][32];
-  __shared__ uint32_t s_slot_base[MAX_BATCH_DRAWS];
-  if (threadIdx.x < n_draws) s_slot_base[threadIdx.x] = batch[threadIdx.x].slot_base;
-  __syncthreads();
 
   const uint32_t lane = threadIdx.x & 31;
   CovTri* s_tri = s_tri_all[threadIdx.x >> 5];
@@ -337,8 +323,8 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_COVER_CTAS_PER_SM)
           const uint32_t slot = e >> 4, st4 = e & 0xFu;
           const float4* rec = c.tris + (size_t)slot * c.tri_stride;
           const float4 e0 = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2);
-          const RasterParams& p = batch[draw_of_slot(s_slot_base, n_draws, slot)];
           const float4 v0p = __ldg(rec + REC_V0), gxp = __ldg(rec + REC_DDX), gyp = __ldg(rec + REC_DDY);
+          const RasterParams& p = batch[min(__float_as_uint(gxp.x), n_draws - 1)];  // draw id rides in the unused d(pos.x)/dx
           const uint32_t bits = (p.read_depth ? 1u : 0u) | (p.write_depth ? 2u : 0u) |
                                 ((p.depth_enable ? compare_lut(p.depth_func) : 0xFu) << 4) | (st4 << 8);
           CovTri ent;
@@ -519,12 +505,12 @@ struct DeferredCtx {  // what a pixel shader may read when a lane shades its pix
 };
 
 template <int PS>
-__device__ __forceinline__ uint32_t shade_sample_owner(const RasterParams& c, const RasterParams* __restrict__ batch, uint32_t draw,
+__device__ __forceinline__ uint32_t shade_sample_owner(const RasterParams& c, const RasterParams* __restrict__ batch, uint32_t n_draws,
                                                        uint32_t slot, int x, int y) {
   const float4* rec = c.tris + (size_t)slot * c.tri_stride;
-  const RasterParams& p = batch[draw];
-  const int R = 1 + (int)p.n_attrs;
   const float4 v0p = __ldg(rec + REC_V0), gxp = __ldg(rec + REC_DDX), gyp = __ldg(rec + REC_DDY);
+  const RasterParams& p = batch[min(__float_as_uint(gxp.x), n_draws - 1)];  // draw id rides in the unused d(pos.x)/dx
+  const int R = 1 + (int)p.n_attrs;
   DeferredCtx px;
   px.rec = rec; px.R = R; px.mods = p.mods;
   px.dx = 0.5f + (float)(uint32_t)(x & ~1) - v0p.x;
@@ -552,9 +538,6 @@ __device__ __forceinline__ uint32_t fetch_group(uint32_t* counter, uint32_t lane
 template <int S, int PS>
 __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
     k_shade(RasterParams c, const RasterParams* __restrict__ batch, uint32_t n_draws, DeferredBufs d) {
-  __shared__ uint32_t s_slot_base[MAX_BATCH_DRAWS];
-  if (threadIdx.x < n_draws) s_slot_base[threadIdx.x] = batch[threadIdx.x].slot_base;
-  __syncthreads();
   // per warp: the colour rows of the group's items, the pool of (pixel, owner) pairs, per-item origin / touched masks
   __shared__ uint32_t s_color_all[DEF_WARPS][SHADE_GROUP][32][S];
   __shared__ uint2 s_pool_all[DEF_WARPS][SHADE_POOL];  // x = lane | mask << 5 | item-in-group << 9, y = owner slot
@@ -650,7 +633,7 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
         const uint32_t org = s_org[kk];
         const uint32_t pq = pl >> 2, pp = pl & 3;
         const int px_ = (int)(org & 0xFFFF) + (int)((pq & 3) * 2 + (pp & 1)), py_ = (int)(org >> 16) + (int)((pq >> 2) * 2 + (pp >> 1));
-        const uint32_t packed = shade_sample_owner<PS>(c, batch, draw_of_slot(s_slot_base, n_draws, it.y), it.y, px_, py_);
+        const uint32_t packed = shade_sample_owner<PS>(c, batch, n_draws, it.y, px_, py_);
         ++n_exec;
 #pragma unroll
         for (int s = 0; s < S; ++s)

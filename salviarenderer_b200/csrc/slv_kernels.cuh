@@ -56,13 +56,23 @@ __device__ __forceinline__ void run_vs(const GeomParams& p, uint32_t index, VsOu
   float4 in[SLV_MAX_VS_INPUT_ATTRS];
 #pragma unroll
   for (int i = 0; i < SLV_MAX_VS_INPUT_ATTRS; ++i) in[i] = make_float4(0, 0, 0, 0);
-  for (uint32_t e = 0; e < p.n_elements; ++e) {
-    uint32_t reg = p.elements[e].reg;
-    if (POS_ONLY && reg != 0) continue;
-    float4 v = fetch_element(p, p.elements[e], index);
+  if (p.fast_layout) {  // element e -> register e, one aligned 128-bit load each (the interleaved layouts of the samples)
 #pragma unroll
-    for (int i = 0; i < SLV_MAX_VS_INPUT_ATTRS; ++i)
-      if (reg == (uint32_t)i) in[i] = v;
+    for (int e = 0; e < (POS_ONLY ? 1 : SLV_MAX_VS_INPUT_ATTRS); ++e)
+      if ((uint32_t)e < p.n_elements) {
+        const slv_input_element& el = p.elements[e];
+        const StreamRef& st = p.streams[el.slot];
+        in[e] = __ldg(reinterpret_cast<const float4*>(st.data + el.aligned_byte_offset + (size_t)st.stride * index + st.offset));
+      }
+  } else {
+    for (uint32_t e = 0; e < p.n_elements; ++e) {
+      uint32_t reg = p.elements[e].reg;
+      if (POS_ONLY && reg != 0) continue;
+      float4 v = fetch_element(p, p.elements[e], index);
+#pragma unroll
+      for (int i = 0; i < SLV_MAX_VS_INPUT_ATTRS; ++i)
+        if (reg == (uint32_t)i) in[i] = v;
+    }
   }
 #pragma unroll
   for (int i = 0; i < R; ++i) out.r[i] = make_float4(0, 0, 0, 0);
@@ -288,6 +298,9 @@ __device__ __forceinline__ void setup_store(const GeomParams& p, const VsOut<R> 
     ddy.y = (e01.y * e02x - e02.y * e01x) * inv_area;
     ddy.z = (e01.z * e02x - e02.z * e01x) * inv_area;
     ddy.w = (e01.w * e02x - e02.w * e01x) * inv_area;
+    // the x / y derivatives of the screen position itself are never read (they are 1 / 0): the slot carries the draw id,
+    // which k_cover / k_shade pick up with the depth / w derivatives they load anyway
+    if (i == 0) ddx.x = __uint_as_float(p.draw_id);
     rec[REC_V0 + 3 * i] = a;
     rec[REC_DDX + 3 * i] = ddx;
     rec[REC_DDY + 3 * i] = ddy;
@@ -311,7 +324,15 @@ __global__ void __launch_bounds__(128, 4) k_geometry(const GeomParams* __restric
     const uint32_t mid = (lo + hi) >> 1;
     if (blockIdx.x >= hb.cta_prefix[mid]) lo = mid; else hi = mid;
   }
-  const GeomParams& p = draws[hb.draw_of[lo]];
+  // the draw's parameter block, staged once per CTA: every later field access is a shared-memory broadcast
+  __shared__ GeomParams s_params;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(draws + hb.draw_of[lo]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&s_params);
+    for (uint32_t i = threadIdx.x; i < sizeof(GeomParams) / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const GeomParams& p = s_params;
   uint32_t prim = (blockIdx.x - hb.cta_prefix[lo]) * blockDim.x + threadIdx.x;
   uint32_t n_out = 0, valid_mask = 0;  // valid_mask bit k: slot prim*3+k holds a triangle binned on this rank
   if (prim < p.prim_count) {
@@ -1451,6 +1472,32 @@ __global__ void k_clear_ds_partial(float2* dst, size_t n, uint32_t flags, float 
     if (flags & SLV_CLEAR_STENCIL) v.y = __uint_as_float(stencil);
     dst[i] = v;
   }
+}
+
+// ---- sort-first frame assembly over peer memory (NVLink / NVSwitch): flags that order one rank's stream after
+// another rank's, without the host.  A rank resolves its tiles straight into the root's surface (k_resolve with a peer
+// destination), then raises its flag there; the root's stream waits for every rank's flag.
+__global__ void k_peer_signal(uint32_t* flag, uint32_t value) {
+  __threadfence_system();  // the preceding kernels' peer stores are performed before the flag becomes visible
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+// one warp; lane i polls flags[first + i] until it reaches `value`.  Gives up after ~10 s (a peer died): *err = 2, which the
+// next flush point reports, instead of hanging the stream forever.
+__global__ void __launch_bounds__(32) k_flags_wait(const uint32_t* flags, uint32_t first, uint32_t count, uint32_t value, uint32_t* err) {
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (uint32_t i = threadIdx.x; i < count; i += 32) {
+    for (;;) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + first + i) : "memory");
+      if ((int32_t)(v - value) >= 0) break;
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 10000000000ull) { *err = 2; break; }
+      __nanosleep(200);
+    }
+  }
+  __threadfence_system();
 }
 
 // surface::resolve (surface.cpp:123-140): sum of to_rgba32f(sample) in sample order, * (1/S), convert (RNE)

@@ -736,12 +736,15 @@ class SponzaLike:
         self._draw_cache[key] = draws
         return draws
 
-    def render(self, be: A.Backend, frame: int):
+    def render(self, be: A.Backend, frame: int, before_resolve=None):
+        """`before_resolve`: hook of the sort-first frame assembly (sortfirst.FrameGather.before_resolve)."""
         t = self.t
         be.clear_color(t.color, (0.2, 0.2, 0.5, 1.0))
         be.clear_depth_stencil(t.ds, A.CLEAR_DEPTH | A.CLEAR_STENCIL, 1.0, 0)
         for d in self.frame_draws(be, frame):
             be.draw(d)
+        if before_resolve is not None:
+            before_resolve()
         if t.resolved is not None:
             be.resolve(t.color, t.resolved)
 

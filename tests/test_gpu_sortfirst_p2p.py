@@ -1,0 +1,80 @@
+"""GPU suite: sort-first frame assembly over peer memory (salviarenderer_b200/sortfirst.py, transport "p2p").
+
+Two processes (one per GPU when the box has two, else both on cuda:0 — CUDA IPC works either way) render the same
+Sponza-like frames with interleaved tile ownership; rank 1 resolves its tiles straight into rank 0's surface and the
+ranks' streams are ordered by device-side flags only.  Rank 0's assembled frames must equal an unsharded render of the
+same frames on the same device, bit for bit, for several frames in a row (so the release / wait handshake is used)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+FRAMES = (0, 3, 5, 7, 2)
+W, H, S = 576, 320, 4
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_path, transport):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import salviarenderer_b200 as pkg
+    from salviarenderer_b200 import scenes, sortfirst
+    ordinal = rank % torch.cuda.device_count()
+    be = pkg.load(ordinal)
+    # as bench.py does: the library, torch and the collective backend all order on one stream
+    torch.cuda.set_device(ordinal)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    be.set_stream(stream.cuda_stream)
+    sc = scenes.SponzaLike(W, H, S, tex_size=64)
+    sc.setup(be)
+    fg = sortfirst.FrameGather(be, sc.t.resolved, rank, world, f"cuda:{ordinal}", transport=transport)
+    frames = []
+    for f in FRAMES:
+        fg.begin_frame()
+        sc.render(be, f, before_resolve=fg.before_resolve)
+        fg.gather()
+        if rank == 0:
+            frames.append(be.read_texture(sc.t.resolved).copy())  # synchronous: the app owns frame f now
+    be.flush()
+    if rank == 0:
+        np.save(out_path, np.stack(frames))
+        open(out_path + ".transport", "w").write(fg.transport)
+    dist.barrier()
+    fg.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("transport", ["p2p", "gather"])
+def test_world2_assembled_frames_equal_unsharded(cuda, tmp_path, transport):
+    from salviarenderer_b200 import scenes
+    out = str(tmp_path / "frames.npy")
+    mp.spawn(_worker, args=(2, _free_port(), out, transport), nprocs=2, join=True)
+    got = np.load(out)
+    assert open(out + ".transport").read() == transport
+    sc = scenes.SponzaLike(W, H, S, tex_size=64)
+    sc.setup(cuda)
+    cuda.set_tile_shard(0, 1)
+    for i, f in enumerate(FRAMES):
+        sc.render(cuda, f)
+        want = cuda.read_texture(sc.t.resolved)
+        assert np.array_equal(got[i], want), f"frame {f} ({transport})"
