@@ -85,7 +85,8 @@ enum {
   SLV_VS_LIGHTS3 = 3,
   /* pos = in[0]·wvp; attr0 = in[1] (uv); attr1 = in[2] (normal); attr2 = lightPos − in[0];
    * attr3 = eyePos − in[0]  (Sponza.cpp:64-97).  uniforms: mat44 wvp; vec4 lightPos; vec4 eyePos   */
-  SLV_VS_SPONZA = 4
+  SLV_VS_SPONZA = 4,
+  SLV_VS_JIT = 255          /* a SASL vertex shader compiled at run time; select it with SLV_PROGRAM_JIT(module) */
 };
 enum {
   SLV_PS_ATTR0_COLOR = 1,   /* color0 = attr0                                    no uniforms        */
@@ -98,7 +99,8 @@ enum {
   /* color0 = sample_2d_grad(sampler0, attr[reg].xy, ddx, ddy, 0); a = alpha — the SASL tex2D path,
    * required for anisotropic filtering.  uniforms: u32 reg; f32 alpha       */
   SLV_PS_TEX_GRAD_ALPHA = 5,
-  SLV_PS_DISCARD_ALL = 6    /* returns false for every pixel (early-Z quirk probe, App. B #3)       */
+  SLV_PS_DISCARD_ALL = 6,   /* returns false for every pixel (early-Z quirk probe, App. B #3)       */
+  SLV_PS_JIT = 255          /* a SASL pixel shader compiled at run time; select it with SLV_PROGRAM_JIT(module) */
 };
 enum {
   SLV_BS_REPLACE = 1,        /* inout.color(0,s) = src              (ColorizedTriangle.cpp:94-106)  */
@@ -236,6 +238,19 @@ slv_result slv_texture_upload(slv_device dev, slv_handle tex, uint32_t level, co
 slv_result slv_texture_readback(slv_device dev, slv_handle tex, uint32_t level, void* dst, size_t bytes);
 /* renderer::create_sampler (renderer.h:50) */
 slv_result slv_sampler_create(slv_device dev, const slv_sampler_desc* desc, slv_handle tex, slv_handle* out);
+/* SASL shaders compiled at run time.  The reference's compile(code, profile) + set_vertex_shader_code /
+ * set_pixel_shader_code (salvia/include/salvia/core/renderer.h:75-82,136-147) JIT the shader to host code with LLVM; here
+ * salviarenderer_b200/sasl lowers it to device code and the CUDA toolchain (NVVM's NVPTX backend) produces a cubin for
+ * sm_100a holding the pipeline kernel with the shader inlined (k_geometry for a vertex shader, k_raster for a pixel
+ * shader).  slv_shader_module_load hands that image to the device; a draw selects it with
+ * vs.program / ps.program = SLV_PROGRAM_JIT(module) and passes the shader's globals, packed as the reflection says, in
+ * `uniforms` (<= SLV_MAX_UNIFORM_BYTES).  n_vs_output_attrs: the vertex shader's outputs besides SV_Position.
+ * Released with slv_resource_release.  The CPU checkers return SLV_FAILED. */
+#define SLV_STAGE_VS 0u
+#define SLV_STAGE_PS 1u
+#define SLV_PROGRAM_JIT(module) (0x80000000u | (uint32_t)(module))
+slv_result slv_shader_module_load(slv_device dev, uint32_t stage, const void* image, size_t bytes, uint32_t n_vs_output_attrs,
+                                  slv_handle* out);
 slv_result slv_resource_release(slv_device dev, slv_handle h);
 
 /* renderer::draw / draw_index -> commit_state_and_command() (renderer_impl.cpp:337-353) */

@@ -1664,6 +1664,7 @@ slv_result slv_set_stream(slv_device, void*) { return SLV_OK; }
 // peer-memory frame assembly is a property of the CUDA product (NVLink); the CPU checkers do not implement it
 slv_result slv_peer_export_texture(slv_device, slv_handle, uint32_t, uint8_t*) { return SLV_FAILED; }
 slv_result slv_peer_export_flags(slv_device, uint8_t*) { return SLV_FAILED; }
+slv_result slv_shader_module_load(slv_device, uint32_t, const void*, size_t, uint32_t, slv_handle*) { return SLV_FAILED; }
 slv_result slv_peer_open(slv_device, const uint8_t*, void**) { return SLV_FAILED; }
 slv_result slv_peer_close(slv_device, void*) { return SLV_FAILED; }
 slv_result slv_resolve_target_peer(slv_device, slv_handle, void*) { return SLV_FAILED; }

@@ -135,7 +135,7 @@ ENTRY_POINTS = [
     "slv_traffic_get", "slv_kernel_launch_count", "slv_event_record", "slv_event_elapsed_ms", "slv_profile_enable",
     "slv_texture_device_ptr", "slv_pack_tiles", "slv_unpack_tiles", "slv_set_stream", "slv_profile_get_stages",
     "slv_peer_export_texture", "slv_peer_export_flags", "slv_peer_open", "slv_peer_close", "slv_resolve_target_peer",
-    "slv_peer_signal", "slv_flags_wait",
+    "slv_peer_signal", "slv_flags_wait", "slv_shader_module_load",
 ]
 
 
@@ -146,6 +146,11 @@ class SlvError(RuntimeError):
 def _chk(rc, what):
     if rc != OK:
         raise SlvError(f"{what} failed with slv_result={rc}")
+
+
+def program_jit(module: int) -> int:
+    """SLV_PROGRAM_JIT(module): the program id that selects a loaded run-time shader module."""
+    return 0x80000000 | int(module)
 
 
 def shader_binding(program: int, uniforms: bytes = b"", samplers=()) -> ShaderBinding:
@@ -242,6 +247,7 @@ class Backend:
         L.slv_pack_tiles.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_size_t)]
         L.slv_unpack_tiles.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         L.slv_profile_get_stages.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_uint32]
+        L.slv_shader_module_load.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_uint32)]
         L.slv_peer_export_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.slv_peer_export_flags.argtypes = [C.c_void_p, C.c_void_p]
         L.slv_peer_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
@@ -402,6 +408,13 @@ class Backend:
         p, n = C.c_void_p(), C.c_size_t()
         _chk(self.lib.slv_texture_device_ptr(self.dev, tex.handle, level, C.byref(p), C.byref(n)), "slv_texture_device_ptr")
         return p.value, n.value
+
+    # ---- SASL shaders compiled at run time (product only; see salviarenderer_b200/sasl) ----
+    def shader_module_load(self, stage: str, image: bytes, n_vs_output_attrs: int = 0) -> int:
+        h = C.c_uint32()
+        _chk(self.lib.slv_shader_module_load(self.dev, 0 if stage == "vs" else 1, image, len(image), n_vs_output_attrs, C.byref(h)),
+             "slv_shader_module_load")
+        return h.value
 
     # ---- peer-memory frame assembly (CUDA IPC; product only) ----
     def peer_export_texture(self, tex: Texture, level: int = 0) -> bytes:

@@ -9,7 +9,9 @@
 // Build (see __graft_entry__.build): nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo
 //        -fmad=false -prec-div=true -prec-sqrt=true -ftz=false -shared -Xcompiler -fPIC
 
+#include <cuda.h>  // types only: the driver entry points are bound with dlsym (no link-time dependency on libcuda)
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cfloat>
@@ -28,7 +30,7 @@ using namespace slv;
 namespace {
 
 struct Resource {
-  enum Kind { NONE, BUFFER, TEXTURE, SAMPLER } kind = NONE;
+  enum Kind { NONE, BUFFER, TEXTURE, SAMPLER, MODULE } kind = NONE;
   uint8_t* dptr = nullptr;  // buffers
   size_t bytes = 0;
   TextureRef tex{};         // textures: every level is its own allocation
@@ -36,7 +38,38 @@ struct Resource {
   slv_sampler_desc sd{};    // samplers
   slv_handle sampler_tex = 0;
   uint8_t* resolve_peer = nullptr;  // textures: slv_resolve into this texture writes the owned tiles here instead (peer memory)
+  // shader modules (SASL shaders compiled at run time, salviarenderer_b200/sasl): the pipeline kernels with the shader inlined
+  CUmodule module = nullptr;
+  uint32_t module_stage = 0;        // SLV_STAGE_VS / SLV_STAGE_PS
+  uint32_t module_attrs = 0;        // VS: output attributes
+  CUfunction fn_geometry = nullptr; // VS: slv_jit_k_geometry
+  CUfunction fn_raster[3] = {};     // PS: slv_jit_k_raster_s1 / _s2 / _s4
 };
+
+// the four driver-API entry points run-time modules need, bound on first use
+struct DriverApi {
+  CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+  CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*ModuleUnload)(CUmodule) = nullptr;
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+  bool ok = false;
+};
+DriverApi& driver_api() {
+  static DriverApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      api.ModuleLoadData = (decltype(api.ModuleLoadData))dlsym(h, "cuModuleLoadData");
+      api.ModuleGetFunction = (decltype(api.ModuleGetFunction))dlsym(h, "cuModuleGetFunction");
+      api.ModuleUnload = (decltype(api.ModuleUnload))dlsym(h, "cuModuleUnload");
+      api.LaunchKernel = (decltype(api.LaunchKernel))dlsym(h, "cuLaunchKernel");
+      api.ok = api.ModuleLoadData && api.ModuleGetFunction && api.ModuleUnload && api.LaunchKernel;
+    }
+  }
+  return api;
+}
 
 uint32_t bpp_of(uint32_t fmt) {
   switch (fmt) {
@@ -103,6 +136,8 @@ struct slv_device_t {
   // pixel's depth/stencil/colour is loaded once and stored once per batch instead of once per draw.
   std::vector<RasterParams> pending;
   std::vector<GeomParams> pending_geom;  // geometry parameters of the queued draws (same index as `pending`)
+  std::vector<slv_handle> pending_vs_module;  // run-time vertex-shader module of each queued draw (0 = built-in program)
+  slv_handle batch_ps_module = 0;             // run-time pixel-shader module of the batch (0 = built-in program)
   size_t tris_used = 0;      // float4 units used by the queued draws
   uint64_t slots_queued = 0; // triangle slots of the queued draws (sizes the list arena)
   uint32_t batch_S = 0;
@@ -348,24 +383,37 @@ slv_result flush_batch(slv_device dev) {
   CU(cudaMemsetAsync(S.valid_count, 0, sizeof(uint32_t), fs));
   CU(cudaMemcpyAsync(S.d_geom, src_geom, n * sizeof(GeomParams), cudaMemcpyHostToDevice, fs));
   size_t eg0 = dev->profile ? mark(dev) : 0;
-  for (uint32_t R = 1; R <= (uint32_t)MAX_REGS; ++R) {
-    GeomBatch hb{};
-    for (uint32_t i = 0; i < n; ++i) {
-      if (1 + dev->pending_geom[i].n_attrs != R) continue;
-      hb.draw_of[hb.n] = i;
-      hb.cta_prefix[hb.n + 1] = hb.cta_prefix[hb.n] + (dev->pending_geom[i].prim_count + 127) / 128;
-      ++hb.n;
-    }
-    if (!hb.n) continue;
-    switch (R) {
-    case 1: launch_geometry<1>(S.d_geom, hb, fs); break;
-    case 2: launch_geometry<2>(S.d_geom, hb, fs); break;
-    case 3: launch_geometry<3>(S.d_geom, hb, fs); break;
-    case 4: launch_geometry<4>(S.d_geom, hb, fs); break;
-    case 5: launch_geometry<5>(S.d_geom, hb, fs); break;
-    default: launch_geometry<6>(S.d_geom, hb, fs); break;
-    }
-    dev->n_launches += 1;
+  {
+    std::vector<slv_handle> mods;  // distinct vertex-shader modules of the batch (0 = the built-in programs)
+    for (slv_handle m : dev->pending_vs_module)
+      if (std::find(mods.begin(), mods.end(), m) == mods.end()) mods.push_back(m);
+    for (slv_handle m : mods)
+      for (uint32_t R = 1; R <= (uint32_t)MAX_REGS; ++R) {
+        GeomBatch hb{};
+        for (uint32_t i = 0; i < n; ++i) {
+          if (1 + dev->pending_geom[i].n_attrs != R || dev->pending_vs_module[i] != m) continue;
+          hb.draw_of[hb.n] = i;
+          hb.cta_prefix[hb.n + 1] = hb.cta_prefix[hb.n] + (dev->pending_geom[i].prim_count + 127) / 128;
+          ++hb.n;
+        }
+        if (!hb.n) continue;
+        if (m) {  // SASL vertex shader: the module's own k_geometry instance
+          const GeomParams* d_geom = S.d_geom;
+          void* args[] = {(void*)&d_geom, (void*)&hb};
+          if (driver_api().LaunchKernel(dev->res[m].fn_geometry, hb.cta_prefix[hb.n], 1, 1, 128, 1, 1, 0, (CUstream)fs, args, nullptr) != CUDA_SUCCESS)
+            return SLV_FAILED;
+        } else {
+          switch (R) {
+          case 1: launch_geometry<1>(S.d_geom, hb, fs); break;
+          case 2: launch_geometry<2>(S.d_geom, hb, fs); break;
+          case 3: launch_geometry<3>(S.d_geom, hb, fs); break;
+          case 4: launch_geometry<4>(S.d_geom, hb, fs); break;
+          case 5: launch_geometry<5>(S.d_geom, hb, fs); break;
+          default: launch_geometry<6>(S.d_geom, hb, fs); break;
+          }
+        }
+        dev->n_launches += 1;
+      }
   }
   if (dev->profile) dev->spans.push_back({eg0, mark(dev), 0});
   size_t e0 = dev->profile ? mark(dev) : 0;
@@ -379,6 +427,7 @@ slv_result flush_batch(slv_device dev) {
   bool deferred = !dev->force_immediate;
   for (const RasterParams& r : dev->pending)
     deferred = deferred && r.early_z && r.bs_program == SLV_BS_REPLACE && !r.has_centroid && r.ps_program != SLV_PS_DISCARD_ALL &&
+               r.ps_program != SLV_PS_JIT &&  // SASL pixel shaders take derivatives across the quad: k_raster shades whole quads
                !r.color1.data && (!r.color0.data || r.color0.bpp == 4);
   bool ok = false;
   size_t e_mid = (size_t)-1, e_rbin = (size_t)-1;
@@ -433,6 +482,14 @@ slv_result flush_batch(slv_device dev) {
     }
   } else {
     const uint32_t blocks = std::min<uint32_t>(n_tiles * 16, (uint32_t)dev->raster_grid);
+    if (first.ps_program == SLV_PS_JIT) {  // SASL pixel shader: the module's own k_raster instance
+      const Resource& m = dev->res[dev->batch_ps_module];
+      CUfunction fn = m.fn_raster[dev->batch_S == 1 ? 0 : (dev->batch_S == 2 ? 1 : 2)];
+      const RasterParams* d_batch = S.d_batch;
+      uint32_t nd = n;
+      void* args[] = {(void*)&first, (void*)&d_batch, (void*)&nd};
+      ok = driver_api().LaunchKernel(fn, blocks, 1, 1, RASTER_THREADS, 1, 1, 0, (CUstream)st, args, nullptr) == CUDA_SUCCESS;
+    } else
     switch (dev->batch_S) {
     case 1: ok = launch_raster_s<1>(first, S.d_batch, n, blocks, st); break;
     case 2: ok = launch_raster_s<2>(first, S.d_batch, n, blocks, st); break;
@@ -462,6 +519,7 @@ slv_result flush_batch(slv_device dev) {
   }
   dev->pending.clear();
   dev->pending_geom.clear();
+  dev->pending_vs_module.clear();
   dev->tris_used = 0;
   dev->slots_queued = 0;
   if (!ok) return SLV_INVALID_PARAMETER;
@@ -561,6 +619,7 @@ void slv_device_destroy(slv_device dev) {
     if (r.kind == Resource::BUFFER) cudaFree(r.dptr);
     if (r.kind == Resource::TEXTURE)
       for (uint32_t l = 0; l < r.tex.n_levels; ++l) cudaFree(r.tex.level[l].data);
+    if (r.kind == Resource::MODULE && r.module) driver_api().ModuleUnload(r.module);
   }
   for (auto& S : dev->sc) {
     cudaFree(S.tris); cudaFree(S.valid_slots); cudaFree(S.valid_count);
@@ -715,6 +774,40 @@ slv_result slv_sampler_create(slv_device dev, const slv_sampler_desc* d, slv_han
   return SLV_OK;
 }
 
+// compile(code, profile) of the reference (salvia/include/salvia/core/renderer.h:136-147) ends in a host function pointer
+// from LLVM's JIT; here it ends in a cubin (salviarenderer_b200/sasl/jit.py) that is loaded into the device's context.
+slv_result slv_shader_module_load(slv_device dev, uint32_t stage, const void* image, size_t bytes, uint32_t n_vs_output_attrs,
+                                  slv_handle* out) {
+  if (!dev || !image || !bytes || !out || (stage != SLV_STAGE_VS && stage != SLV_STAGE_PS)) return SLV_INVALID_PARAMETER;
+  if (stage == SLV_STAGE_VS && n_vs_output_attrs > SLV_MAX_VS_OUTPUT_ATTRS) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  CU(cudaFree(nullptr));  // the primary context exists and is current
+  DriverApi& api = driver_api();
+  if (!api.ok) {
+    fprintf(stderr, "[salvia_b200] libcuda.so.1 is not available: cannot load run-time shader modules\n");
+    return SLV_FAILED;
+  }
+  Resource r;
+  r.kind = Resource::MODULE;
+  r.module_stage = stage;
+  r.module_attrs = n_vs_output_attrs;
+  if (api.ModuleLoadData(&r.module, image) != CUDA_SUCCESS) return SLV_FAILED;
+  bool ok = true;
+  if (stage == SLV_STAGE_VS) {
+    ok = api.ModuleGetFunction(&r.fn_geometry, r.module, "slv_jit_k_geometry") == CUDA_SUCCESS;
+  } else {
+    const char* names[3] = {"slv_jit_k_raster_s1", "slv_jit_k_raster_s2", "slv_jit_k_raster_s4"};
+    for (int i = 0; i < 3; ++i) ok = ok && api.ModuleGetFunction(&r.fn_raster[i], r.module, names[i]) == CUDA_SUCCESS;
+  }
+  if (!ok) {
+    api.ModuleUnload(r.module);
+    return SLV_INVALID_PARAMETER;
+  }
+  dev->res.push_back(r);
+  *out = (slv_handle)(dev->res.size() - 1);
+  return SLV_OK;
+}
+
 slv_result slv_resource_release(slv_device dev, slv_handle h) {
   if (!dev || h == 0 || h >= dev->res.size()) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
@@ -724,6 +817,7 @@ slv_result slv_resource_release(slv_device dev, slv_handle h) {
   if (r.kind == Resource::BUFFER) CU(cudaFree(r.dptr));
   if (r.kind == Resource::TEXTURE)
     for (uint32_t l = 0; l < r.tex.n_levels; ++l) CU(cudaFree(r.tex.level[l].data));
+  if (r.kind == Resource::MODULE && r.module) driver_api().ModuleUnload(r.module);
   r = Resource();
   return SLV_OK;
 }
@@ -756,7 +850,22 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   if (vp.x < 0 || vp.y < 0 || vp.w >= SLV_MAX_RENDER_TARGET_SIZE || vp.h >= SLV_MAX_RENDER_TARGET_SIZE) return SLV_FAILED;
   if (d->n_color_targets >= SLV_MAX_RENDER_TARGETS) return SLV_FAILED;
   if (d->n_streams > 8 || d->n_elements > SLV_MAX_VS_INPUT_ATTRS) return SLV_INVALID_PARAMETER;
-  uint32_t n_attrs = vs_num_attrs(d->vs);
+  // SASL shaders compiled at run time: SLV_PROGRAM_JIT(module) names a loaded shader module
+  slv_handle vs_module = 0, ps_module = 0;
+  uint32_t vs_program = d->vs.program, ps_program = d->ps.program;
+  if (vs_program & 0x80000000u) {
+    vs_module = vs_program & 0x7FFFFFFFu;
+    auto m = dev->get(vs_module, Resource::MODULE);
+    if (!m || m->module_stage != SLV_STAGE_VS) return SLV_INVALID_PARAMETER;
+    vs_program = SLV_VS_JIT;
+  }
+  if (ps_program & 0x80000000u) {
+    ps_module = ps_program & 0x7FFFFFFFu;
+    auto m = dev->get(ps_module, Resource::MODULE);
+    if (!m || m->module_stage != SLV_STAGE_PS) return SLV_INVALID_PARAMETER;
+    ps_program = SLV_PS_JIT;
+  }
+  uint32_t n_attrs = vs_module ? dev->res[vs_module].module_attrs : vs_num_attrs(d->vs);
   if (n_attrs > SLV_MAX_VS_OUTPUT_ATTRS) return SLV_INVALID_PARAMETER;
 
   RasterParams rp{};
@@ -816,7 +925,7 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   gp.start = d->start;
   gp.prim_count = d->prim_count;
   gp.base_vertex = d->base_vertex;
-  gp.vs_program = d->vs.program;
+  gp.vs_program = vs_program;
   memcpy(gp.vs_uniforms, d->vs.uniforms, sizeof(gp.vs_uniforms));
   gp.n_attrs = n_attrs;
   rp.has_centroid = 0;
@@ -851,7 +960,7 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   if (!dev->pending.empty()) {
     const RasterParams& f = dev->pending[0];
     bool same = f.color0.data == rp.color0.data && f.color1.data == rp.color1.data && f.ds.data == rp.ds.data &&
-                f.ps_program == d->ps.program && dev->batch_S == S && f.tiles_x == gp.tiles_x && f.tiles_y == gp.tiles_y &&
+                f.ps_program == ps_program && dev->batch_ps_module == ps_module && dev->batch_S == S && f.tiles_x == gp.tiles_x && f.tiles_y == gp.tiles_y &&
                 f.target_w == rp.target_w && f.target_h == rp.target_h && dev->pending.size() < MAX_BATCH;
     if (!same) {
       slv_result rcf = flush_batch(dev);
@@ -887,11 +996,12 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   rp.stencil_ref = ds.stencil_enable ? ((uint32_t)d->stencil_ref & rp.read_mask) : 0;
   rp.front_face = ds.front_face;
   rp.back_face = ds.back_face;
-  rp.ps_program = d->ps.program;
+  rp.ps_program = ps_program;
   rp.bs_program = d->bs.program;
   if (rp.bs_program < SLV_BS_REPLACE || rp.bs_program > SLV_BS_REPLACE_AND_COUNT) return SLV_INVALID_PARAMETER;
   memcpy(rp.ps_uniforms, d->ps.uniforms, sizeof(rp.ps_uniforms));
-  bool needs_sampler = rp.ps_program == SLV_PS_TEX_ALPHA || rp.ps_program == SLV_PS_TEX_GRAD_ALPHA ||
+  bool needs_sampler = (rp.ps_program == SLV_PS_JIT && d->ps.samplers[0] != 0) ||
+                       rp.ps_program == SLV_PS_TEX_ALPHA || rp.ps_program == SLV_PS_TEX_GRAD_ALPHA ||
                        (rp.ps_program == SLV_PS_SPONZA &&
                         reinterpret_cast<const slv_ps_sponza_uniforms*>(d->ps.uniforms)->has_sampler);
   if (needs_sampler && !fill_sampler(dev, d->ps.samplers[0], rp.sampler0)) return SLV_INVALID_PARAMETER;
@@ -937,6 +1047,8 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   // ---- queue the draw: geometry, binning and the raster pass all run at the next flush point
   dev->pending.push_back(rp);
   dev->pending_geom.push_back(gp);
+  dev->pending_vs_module.push_back(vs_module);
+  dev->batch_ps_module = ps_module;
   dev->batch_S = S;
   dev->tris_used += tris_need;
   dev->slots_queued += n_slots;

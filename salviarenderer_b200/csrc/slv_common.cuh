@@ -57,7 +57,7 @@ struct GeomParams {
   uint32_t topology, start, prim_count;
   int32_t base_vertex;
   uint32_t vs_program;
-  uint8_t vs_uniforms[128];  // the largest VS uniform block is slv_vs_lights3_uniforms (112 B)
+  alignas(16) uint8_t vs_uniforms[SLV_MAX_UNIFORM_BYTES];  // built-in programs: their slv_vs_*_uniforms; SASL: the packed globals
   uint32_t n_attrs;
   uint32_t mods[SLV_MAX_VS_OUTPUT_ATTRS];
   uint32_t cull_mode, front_ccw;
@@ -127,7 +127,7 @@ struct RasterParams {
   slv_stencil_op_desc front_face, back_face;
   // shaders
   uint32_t ps_program, bs_program;
-  uint8_t ps_uniforms[16];
+  alignas(16) uint8_t ps_uniforms[SLV_MAX_UNIFORM_BYTES];
   SamplerRef sampler0;
   unsigned long long* stats;
 };
@@ -232,7 +232,7 @@ __device__ __forceinline__ void store_texel_rgba32f(uint32_t fmt, uint8_t* p, fl
 
 }  // namespace slv
 
-static_assert(sizeof(slv_vs_lights3_uniforms) <= 128 && sizeof(slv_vs_sponza_uniforms) <= 128 &&
-                  sizeof(slv_vs_mvp_passthrough_uniforms) <= 128 && sizeof(slv_vs_plane_xz_uniforms) <= 128,
+static_assert(sizeof(slv_vs_lights3_uniforms) <= SLV_MAX_UNIFORM_BYTES && sizeof(slv_vs_sponza_uniforms) <= SLV_MAX_UNIFORM_BYTES &&
+                  sizeof(slv_vs_mvp_passthrough_uniforms) <= SLV_MAX_UNIFORM_BYTES && sizeof(slv_vs_plane_xz_uniforms) <= SLV_MAX_UNIFORM_BYTES,
               "GeomParams::vs_uniforms too small");
-static_assert(sizeof(slv_ps_tex_alpha_uniforms) <= 16 && sizeof(slv_ps_sponza_uniforms) <= 16, "ps_uniforms too small");
+static_assert(sizeof(slv_ps_tex_alpha_uniforms) <= SLV_MAX_UNIFORM_BYTES && sizeof(slv_ps_sponza_uniforms) <= SLV_MAX_UNIFORM_BYTES, "ps_uniforms too small");

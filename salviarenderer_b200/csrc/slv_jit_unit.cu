@@ -1,0 +1,31 @@
+// slv_jit_unit.cu — the translation unit salviarenderer_b200/sasl/jit.py compiles at run time, one per SASL shader.
+// NOT part of libsalvia_b200.so.  nvcc flags (the library's, so every float operation keeps the numerics contract):
+//   -cubin -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -prec-div=true -prec-sqrt=true -ftz=false
+//   -DSLV_JIT_VS=1 -DSLV_JIT_R=<registers>        a vertex shader   -> slv_jit_k_geometry
+//   -DSLV_JIT_PS=1 [-DSLV_JIT_DERIV_CPP=1]        a pixel shader    -> slv_jit_k_raster_s1 / _s2 / _s4
+//   -DSLV_JIT_GENERATED="<path of the generated .cuh>"
+// The pipeline kernels are the library's own code (slv_kernels.cuh); the shader is inlined into them.
+#include <cuda_runtime.h>
+
+#include "salvia_b200.h"
+#include "slv_kernels.cuh"
+#include "sasl_rt.h"
+#include SLV_JIT_GENERATED
+
+#ifdef SLV_JIT_VS
+static_assert(SLV_JIT_R == SLV_JIT_VS_OUTPUT_ATTRS + 1, "register count does not match the shader's outputs");
+extern "C" __global__ void __launch_bounds__(128, 4) slv_jit_k_geometry(const slv::GeomParams* __restrict__ draws, slv::GeomBatch hb) {
+  slv::geometry_main<SLV_JIT_R>(draws, hb);
+}
+#endif
+
+#ifdef SLV_JIT_PS
+#define SLV_JIT_RASTER(S)                                                                                              \
+  extern "C" __global__ void __launch_bounds__(slv::RASTER_THREADS, slv::RASTER_CTAS_PER_SM)                           \
+      slv_jit_k_raster_s##S(slv::RasterParams c, const slv::RasterParams* __restrict__ batch, uint32_t n_draws) {      \
+    slv::raster_main<S, SLV_PS_JIT>(c, batch, n_draws);                                                               \
+  }
+SLV_JIT_RASTER(1)
+SLV_JIT_RASTER(2)
+SLV_JIT_RASTER(4)
+#endif

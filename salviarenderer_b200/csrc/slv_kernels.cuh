@@ -16,6 +16,18 @@
 #include "slv_common.cuh"
 #include "slv_sampler.cuh"
 
+// SASL shaders compiled at run time (salviarenderer_b200/sasl): the JIT translation unit csrc/slv_jit_unit.cu includes
+// this header with SLV_JIT_VS / SLV_JIT_PS defined and the generated entry points below defined after it, so the shader is
+// inlined into k_geometry / k_raster like the built-in programs.  The library build knows nothing about them.
+#ifdef SLV_JIT_VS
+__device__ void slv_jit_vs(const float4* in, const unsigned char* uniforms, float4* out);
+#endif
+#ifdef SLV_JIT_PS
+namespace slv { struct RasterParams; }
+template <class Ctx>
+__device__ bool slv_jit_ps(const slv::RasterParams& p, const Ctx& px, float4& color);
+#endif
+
 namespace slv {
 
 // =====================================================================================================
@@ -107,6 +119,11 @@ __device__ __forceinline__ void run_vs(const GeomParams& p, uint32_t index, VsOu
       }
     }
   } break;
+#ifdef SLV_JIT_VS
+  case SLV_VS_JIT:
+    if (R == SLV_JIT_R) slv_jit_vs(in, p.vs_uniforms, out.r);
+    break;
+#endif
   case SLV_VS_SPONZA: {
     auto u = reinterpret_cast<const slv_vs_sponza_uniforms*>(p.vs_uniforms);
     out.r[0] = transform(in[0], u->wvp);
@@ -317,7 +334,7 @@ __device__ __forceinline__ bool setup_triangle(const GeomParams& p, const VsOut<
 }
 
 template <int R>
-__global__ void __launch_bounds__(128, 4) k_geometry(const GeomParams* __restrict__ draws, GeomBatch hb) {
+__device__ __forceinline__ void geometry_main(const GeomParams* __restrict__ draws, const GeomBatch& hb) {
   // every queued draw with R registers shares this launch; a CTA belongs to exactly one draw
   uint32_t lo = 0, hi = hb.n;
   while (hi - lo > 1) {
@@ -485,6 +502,11 @@ __global__ void __launch_bounds__(128, 4) k_geometry(const GeomParams* __restric
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
   if ((threadIdx.x & 31) == 0 && total) atomicAdd(&p.stats[6], (unsigned long long)total);
+}
+
+template <int R>
+__global__ void __launch_bounds__(128, 4) k_geometry(const GeomParams* __restrict__ draws, GeomBatch hb) {
+  geometry_main<R>(draws, hb);
 }
 
 // =====================================================================================================
@@ -844,6 +866,9 @@ __device__ __forceinline__ float4 ps_tex2d(const SamplerRef& sm, const Ctx& px, 
 
 template <int PS, class Ctx>
 __device__ __forceinline__ bool run_ps(const RasterParams& p, const Ctx& px, float4& color) {
+#ifdef SLV_JIT_PS
+  if (PS == SLV_PS_JIT) return slv_jit_ps(p, px, color);
+#endif
   if (PS == SLV_PS_ATTR0_COLOR) {
     color = px.attr(0);
     return true;
@@ -950,8 +975,7 @@ constexpr int QCAP = 32;  // quads a warp may queue per round (a triangle adds a
 // that warp's two 4x4 blocks.  Each warp then walks its own list: thread == pixel, all S samples of
 // depth / stencil / colour stay in registers until the item is finished.
 template <int S, int PS>
-__global__ void __launch_bounds__(RASTER_THREADS, RASTER_CTAS_PER_SM) k_raster(RasterParams c, const RasterParams* __restrict__ batch,
-                                                               uint32_t n_draws) {
+__device__ __forceinline__ void raster_main(const RasterParams& c, const RasterParams* __restrict__ batch, uint32_t n_draws) {
   __shared__ TriEntry s_tri[RASTER_THREADS];
   __shared__ uint16_t s_wlist[RASTER_WARPS][RASTER_THREADS];
   __shared__ uint16_t s_cnt[RASTER_WARPS + 1][RASTER_WARPS];  // [list][filter warp]; list RASTER_WARPS = survivors
@@ -1425,6 +1449,12 @@ __global__ void __launch_bounds__(RASTER_THREADS, RASTER_CTAS_PER_SM) k_raster(R
     if (n_surv) atomicAdd(&c.stats[14], (unsigned long long)n_surv);
     if (n_pairs) atomicAdd(&c.stats[15], (unsigned long long)n_pairs);
   }
+}
+
+template <int S, int PS>
+__global__ void __launch_bounds__(RASTER_THREADS, RASTER_CTAS_PER_SM) k_raster(RasterParams c, const RasterParams* __restrict__ batch,
+                                                               uint32_t n_draws) {
+  raster_main<S, PS>(c, batch, n_draws);
 }
 
 // =====================================================================================================

@@ -1,0 +1,97 @@
+// sasl_rt.h — runtime support of the code salviarenderer_b200/sasl/frontend.py generates.
+//
+// Two builds: (1) CUDA, inside csrc/slv_jit_unit.cu, after slv_kernels.cuh: derivatives are quad shuffles, texture
+// sampling is the product's sampler (slv_sampler.cuh); (2) host C++ (no CUDA), used by the CPU test-suite to execute
+// generated shaders without a GPU: the arithmetic is the same scalar code, derivatives / sampling are not available.
+#pragma once
+
+#if defined(__CUDACC__)
+#define SASL_FN __device__ __forceinline__
+#else
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#define SASL_FN static inline
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+namespace slv { struct RasterParams { unsigned char ps_uniforms[256]; }; }
+#endif
+
+SASL_FN float sasl_clamp(float v, float lo, float hi) { return v < lo ? lo : (hi < v ? hi : v); }  // eflib::clamp
+SASL_FN bool sasl_eq_eps(float a, float b) { return fabsf(a - b) <= 1.1920928955078125e-7f; }      // eflib equal<float>
+SASL_FN float sasl_smoothstep(float lo, float hi, float x) {
+  const float t = sasl_clamp((x - lo) / (hi - lo), 0.0f, 1.0f);
+  return (t * t) * (3.0f - (2.0f * t));
+}
+SASL_FN float sasl_asfloat(int v) { float f; memcpy(&f, &v, 4); return f; }
+SASL_FN float sasl_asfloat(unsigned v) { float f; memcpy(&f, &v, 4); return f; }
+SASL_FN float sasl_asfloat(float v) { return v; }
+SASL_FN int sasl_asint(float v) { int i; memcpy(&i, &v, 4); return i; }
+SASL_FN int sasl_asint(unsigned v) { return (int)v; }
+SASL_FN int sasl_asint(int v) { return v; }
+SASL_FN unsigned sasl_asuint(float v) { unsigned i; memcpy(&i, &v, 4); return i; }
+SASL_FN unsigned sasl_asuint(int v) { return (unsigned)v; }
+SASL_FN unsigned sasl_asuint(unsigned v) { return v; }
+SASL_FN unsigned sasl_countbits(unsigned v) {
+#if defined(__CUDACC__)
+  return (unsigned)__popc(v);
+#else
+  return (unsigned)__builtin_popcount(v);
+#endif
+}
+
+#if defined(__CUDACC__)
+// Screen-space derivatives: the four pixels of a quad sit in four consecutive lanes (pixel i of the quad in lane
+// quad_base + i, k_raster's shading phases; helper pixels run too).  SLV_JIT_DERIV_CPP selects the cpp_pixel_shader
+// convention (ddx = q1 - q0, ddy = q2 - q0 for all four pixels, cpp_pixel_shader.cpp:13-19), the default is the SASL one
+// (per row / per column, sasl/src/codegen/cgs_simd.cpp:275-313).  All lanes of the warp must call these together.
+template <class Ctx>
+SASL_FN float sasl_ddx(const Ctx& px, float v) {
+  const unsigned pi = (threadIdx.x & 31u) - px.quad_base;
+#ifdef SLV_JIT_DERIV_CPP
+  const unsigned hi = 1, lo = 0;
+  (void)pi;
+#else
+  const unsigned hi = pi | 1u, lo = pi & ~1u;
+#endif
+  const float a = __shfl_sync(0xFFFFFFFFu, v, px.quad_base + hi), b = __shfl_sync(0xFFFFFFFFu, v, px.quad_base + lo);
+  return a - b;
+}
+template <class Ctx>
+SASL_FN float sasl_ddy(const Ctx& px, float v) {
+  const unsigned pi = (threadIdx.x & 31u) - px.quad_base;
+#ifdef SLV_JIT_DERIV_CPP
+  const unsigned hi = 2, lo = 0;
+  (void)pi;
+#else
+  const unsigned hi = pi | 2u, lo = pi & ~2u;
+#endif
+  const float a = __shfl_sync(0xFFFFFFFFu, v, px.quad_base + hi), b = __shfl_sync(0xFFFFFFFFu, v, px.quad_base + lo);
+  return a - b;
+}
+// sasl.ps.tex2d.grad -> sampler::sample_2d_grad (sampler_api.h:9-30, sampler.cpp:854-873)
+template <class Ctx>
+SASL_FN void sasl_tex2d_grad(const slv::RasterParams& p, const Ctx&, int slot, float u, float v, float dudx, float dvdx, float dudy,
+                             float dvdy, float bias, float& r, float& g, float& b, float& a) {
+  (void)slot;  // one sampler per pixel shader (slot 0)
+  const float4 c = slv::sample_2d_grad(p.sampler0, u, v, dudx, dvdx, dudy, dvdy, bias);
+  r = c.x; g = c.y; b = c.z; a = c.w;
+}
+template <class Ctx>
+SASL_FN void sasl_tex2d_lod(const slv::RasterParams& p, const Ctx&, int slot, float u, float v, float lod, float& r, float& g, float& b,
+                            float& a) {
+  (void)slot;
+  const float4 c = slv::sample_impl(p.sampler0, u, v, lod, nullptr);
+  r = c.x; g = c.y; b = c.z; a = c.w;
+}
+#else
+template <class Ctx> SASL_FN float sasl_ddx(const Ctx&, float) { return 0.0f; }
+template <class Ctx> SASL_FN float sasl_ddy(const Ctx&, float) { return 0.0f; }
+template <class Ctx>
+SASL_FN void sasl_tex2d_grad(const slv::RasterParams&, const Ctx&, int, float, float, float, float, float, float, float, float& r, float& g,
+                             float& b, float& a) { r = g = b = a = 0.0f; }
+template <class Ctx>
+SASL_FN void sasl_tex2d_lod(const slv::RasterParams&, const Ctx&, int, float, float, float, float& r, float& g, float& b, float& a) {
+  r = g = b = a = 0.0f;
+}
+#endif

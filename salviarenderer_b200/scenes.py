@@ -388,6 +388,8 @@ class TextureAndBlending:
                  max_aniso=0, boxes=True):
         self.w, self.h, self.samples, self.boxes = w, h, samples, boxes
         self.ps_program, self.mip_filter, self.max_aniso = ps_program, mip_filter, max_aniso
+        # optional override (tests of run-time compiled SASL shaders): (reg, alpha, sampler) -> ShaderBinding
+        self.ps_binding = None
         self.plane = create_planar((-3.0, -1.0, -3.0), (6, 0, 0), (0, 0, 6), 1, 1, True)
         box = create_box()
         # vs_box binds POSITION -> reg0 and TEXCOORD -> reg1 (the uv stream, slot 2)
@@ -425,7 +427,8 @@ class TextureAndBlending:
         d = base_desc(t, self.w, self.h, cull=A.CULL_BACK)
         self.plane.fill_desc(be, d)
         d.vs = A.shader_binding(A.VS_PLANE_XZ, pack_vs_plane_xz(wvp))
-        d.ps = A.shader_binding(self.ps_program, pack_ps_tex_alpha(0, 1.0), [self.plane_samp])
+        d.ps = self.ps_binding(0, 1.0, self.plane_samp) if self.ps_binding else \
+            A.shader_binding(self.ps_program, pack_ps_tex_alpha(0, 1.0), [self.plane_samp])
         d.bs = A.shader_binding(A.BS_REPLACE)
         be.draw(d)
 
@@ -433,7 +436,8 @@ class TextureAndBlending:
             d = base_desc(t, self.w, self.h, cull=cull)
             self.box.fill_desc(be, d)
             d.vs = A.shader_binding(A.VS_MVP_PASSTHROUGH, pack_vs_mvp_passthrough(wvp, [0, 1]))
-            d.ps = A.shader_binding(self.ps_program, pack_ps_tex_alpha(1, 0.5), [self.box_samp])
+            d.ps = self.ps_binding(1, 0.5, self.box_samp) if self.ps_binding else \
+                A.shader_binding(self.ps_program, pack_ps_tex_alpha(1, 0.5), [self.box_samp])
             d.bs = A.shader_binding(A.BS_LERP_SRC_ALPHA)
             be.draw(d)
         if t.resolved is not None:
@@ -625,6 +629,8 @@ class SponzaLike:
         self.color_fmt, self.ps_program, self.textured = color_fmt, ps_program, textured
         self.n_frames = 8
         self._draw_cache = {}
+        # optional override (tests of run-time compiled SASL shaders): (wvp, light, eye) -> ShaderBinding
+        self.vs_binding = None
         self._build()
 
     def _build(self):
@@ -718,7 +724,7 @@ class SponzaLike:
             return cached
         t = self.t
         wvp, light, eye = self.frame_uniforms(frame)
-        vs = A.shader_binding(A.VS_SPONZA, pack_vs_sponza(wvp, light, eye))
+        vs = self.vs_binding(wvp, light, eye) if self.vs_binding else A.shader_binding(A.VS_SPONZA, pack_vs_sponza(wvp, light, eye))
         bs = A.shader_binding(A.BS_REPLACE)
         draws = []
         # the SASL tex2D path is required for anisotropic filtering; the cpp tex2d path

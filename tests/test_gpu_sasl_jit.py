@@ -1,0 +1,121 @@
+"""GPU suite: SASL shaders compiled at run time (salviarenderer_b200/sasl: front end -> CUDA toolchain -> cubin ->
+slv_shader_module_load) against the built-in device programs that are themselves pinned to the reference.
+
+* the Sponza vertex shader written in SASL (the sample ships the same shader as SASL text and as a cpp twin,
+  samples/Sponza/Sponza.cpp:39-97) must give bit-identical frames and counters to SLV_VS_SPONZA;
+* `tex2D` + constant alpha written in SASL (TextureAndBlending.cpp:79-94) with the cpp derivative convention must equal
+  SLV_PS_TEX_GRAD_ALPHA (sample_2d_grad with the quad's derivatives), trilinear and 16x anisotropic, with blending;
+* the SASL derivative convention (per row / per column) is checked through ddx / ddy of a linear function.
+"""
+import numpy as np
+import pytest
+
+import cases
+from salviarenderer_b200 import abi as A, scenes as S
+from salviarenderer_b200.sasl import jit
+
+pytestmark = pytest.mark.gpu
+
+VS_SPONZA = """
+float4x4 wvpMatrix;
+float4   lightPos;
+float4   eyePos;
+struct VSIn  { float4 pos: POSITION; float4 tex: TEXCOORD0; float4 norm: NORMAL; };
+struct VSOut { float4 pos: sv_position; float4 tex: TEXCOORD0; float4 norm: TEXCOORD1; float4 lightDir: TEXCOORD2; float4 eyeDir: TEXCOORD3; };
+VSOut vs_main(VSIn in) {
+    VSOut o;
+    o.norm = in.norm;
+    o.pos = mul(in.pos, wvpMatrix);
+    o.lightDir = lightPos - in.pos;
+    o.eyeDir = eyePos - in.pos;
+    o.tex = in.tex;
+    return o;
+}
+"""
+
+PS_TEX_ALPHA = """
+sampler texSamp;
+float   alpha;
+struct PSIn {{ {decls} }};
+float4 ps_main(PSIn in): COLOR {{
+    float4 c = tex2D(texSamp, in.uv.xy);
+    c.w = alpha;
+    return c;
+}}
+"""
+
+
+@pytest.mark.parametrize("samples,size", [(4, (480, 272)), (1, (640, 360))])
+def test_sasl_sponza_vertex_shader_equals_builtin(cuda, samples, size):
+    sh = jit.compile(VS_SPONZA, "vs")
+    mod = jit.load(cuda, sh)
+    w, h = size
+    ref = S.SponzaLike(w, h, samples, tex_size=128)
+    ref.setup(cuda)
+    got = S.SponzaLike(w, h, samples, tex_size=128)
+    got.setup(cuda)
+    got.vs_binding = lambda wvp, light, eye: A.shader_binding(
+        A.program_jit(mod), sh.unit.pack_uniforms({"wvpMatrix": np.asarray(wvp, np.float32).reshape(4, 4), "lightPos": light, "eyePos": eye}))
+    for f in (0, 5):
+        a, b = ref.run(cuda, f), got.run(cuda, f)
+        assert cases.compare_frames(a, b) == [], f"frame {f}"
+        assert a.stats["cprimitives"] > 1000
+
+
+@pytest.mark.parametrize("mip_filter,aniso,samples", [(A.FILTER_LINEAR, 0, 1), (A.FILTER_ANISOTROPIC, 16, 4)])
+def test_sasl_tex2d_pixel_shader_equals_builtin_grad_path(cuda, mip_filter, aniso, samples):
+    # the plane draw reads attribute 0, the box draws attribute 1: two shaders (a SASL pixel shader's k-th input is attribute k)
+    sh = [jit.compile(PS_TEX_ALPHA.format(decls=d), "ps", derivatives="cpp")
+          for d in ("float4 uv: TEXCOORD0;", "float4 pad: TEXCOORD0; float4 uv: TEXCOORD1;")]
+    mods = [jit.load(cuda, s) for s in sh]
+    ref = S.TextureAndBlending(640, 360, samples=samples, ps_program=A.PS_TEX_GRAD_ALPHA, mip_filter=mip_filter, max_aniso=aniso)
+    ref.setup(cuda)
+    got = S.TextureAndBlending(640, 360, samples=samples, ps_program=A.PS_TEX_GRAD_ALPHA, mip_filter=mip_filter, max_aniso=aniso)
+    got.setup(cuda)
+    got.ps_binding = lambda reg, alpha, samp: A.shader_binding(A.program_jit(mods[reg]), sh[reg].unit.pack_uniforms({"alpha": alpha}), [samp])
+    for f in (0, 2):
+        a, b = ref.run(cuda, f), got.run(cuda, f)
+        assert cases.compare_frames(a, b) == [], f"frame {f}"
+
+
+def test_sasl_derivative_convention(cuda):
+    """ddx / ddy of attribute values: the SASL convention differences pixel pairs per row / per column, the cpp one uses
+    q1 - q0 / q2 - q0 for the whole quad; for a noperspective linear attribute both must give the constant gradient, and for
+    a perspective one they must agree exactly on pixel 0 of every quad."""
+    src = """
+    struct PSIn { float4 c: TEXCOORD0; };
+    float4 ps_main(PSIn in): COLOR { return float4(ddx(in.c.x) * 8.0f + 0.5f, ddy(in.c.z) * 8.0f + 0.5f, in.c.z, 1.0f); }
+    """
+    out = {}
+    for conv in ("sasl", "cpp"):
+        sh = jit.compile(src, "ps", derivatives=conv)
+        mod = jit.load(cuda, sh)
+        t = S.create_targets(cuda, 256, 256, 1, A.PF_RGBA8)
+        # one large triangle pair with attribute = position (varies linearly on screen)
+        mesh = S.create_planar((-3.0, -1.0, -3.0), (6, 0, 0), (0, 0, 6), 1, 1, True)
+        mesh.elements = [(0, S._V4, 0, 0, 1.0)]
+        mesh.upload(cuda)
+        cuda.clear_color(t.color, (0, 0, 0, 0))
+        cuda.clear_depth_stencil(t.ds, A.CLEAR_DEPTH | A.CLEAR_STENCIL, 1.0, 0)
+        view = S.mat_lookat((0.4, 2.5, 0.7), (0, 0, 0), (0, 1, 0))
+        proj = S.mat_perspective_fov(np.pi / 2, 1.0, 0.1, 100.0)
+        wvp = S.mat_mul(view, proj)
+        d = S.base_desc(t, 256, 256, cull=A.CULL_NONE)
+        mesh.fill_desc(cuda, d, prim_count=1)  # ONE triangle: every fully covered quad lies inside it
+        d.vs = A.shader_binding(A.VS_MVP_PASSTHROUGH, S.pack_vs_mvp_passthrough(wvp, [0]))
+        d.ps = A.shader_binding(A.program_jit(mod))
+        d.bs = A.shader_binding(A.BS_REPLACE)
+        cuda.draw(d)
+        out[conv] = cuda.read_texture(t.color).reshape(256, 256, 4).astype(np.int32)
+    a, b = out["sasl"], out["cpp"]
+    covered = (a[..., 3] == 255) & (b[..., 3] == 255)
+    assert covered.sum() > 5000
+    # pixel 0 of every quad (even x, even y): identical in both conventions
+    q0 = covered[0::2, 0::2]
+    assert np.array_equal(a[0::2, 0::2][q0], b[0::2, 0::2][q0])
+    # fully covered quads: the cpp convention gives all four pixels pixel 0's derivatives, the SASL one does not
+    full = covered[0::2, 0::2] & covered[0::2, 1::2] & covered[1::2, 0::2] & covered[1::2, 1::2]
+    assert full.sum() > 1000
+    for dy, dx in ((0, 1), (1, 0), (1, 1)):
+        assert np.array_equal(b[dy::2, dx::2, :2][full], b[0::2, 0::2, :2][full])
+    assert np.any(a[1::2, 1::2, :2][full] != a[0::2, 0::2, :2][full])

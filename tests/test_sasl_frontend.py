@@ -1,0 +1,247 @@
+"""CPU suite: the SASL front end (salviarenderer_b200/sasl/frontend.py).  Generated code is compiled for the host and
+executed (tests/sasl_host.py); expected values are restated in numpy float32 with the same operation order.  The
+shaders are written for these tests; the features are the ones sasl/test/repo/*.svs|*.sps and the samples' shaders use
+(struct semantics, swizzles and write masks, branches, loops, intrinsics, constructors, casts, functions)."""
+import numpy as np
+import pytest
+
+from salviarenderer_b200.sasl import CompileError, compile_shader
+from sasl_host import HostShader
+
+f32 = np.float32
+
+VS_SPONZA = """
+float4x4 wvpMatrix;
+float4   eyePos;
+float4   lightPos;
+struct VSIn  { float4 pos: POSITION; float4 tex: TEXCOORD0; float4 norm: NORMAL; };
+struct VSOut { float4 pos: sv_position; float4 tex: TEXCOORD0; float4 norm: TEXCOORD1; float4 lightDir: TEXCOORD2; float4 eyeDir: TEXCOORD3; };
+VSOut vs_main(VSIn in) {
+    VSOut o;
+    o.norm = in.norm;
+    o.pos = mul(in.pos, wvpMatrix);
+    o.lightDir = lightPos - in.pos;
+    o.eyeDir = eyePos - in.pos;
+    o.tex = in.tex;
+    return o;
+}
+"""
+
+
+def mul_row(v, m):
+    """eflib transform: out[j] = ((v0*m0j + v1*m1j) + v2*m2j) + v3*m3j in float32."""
+    v, m = np.asarray(v, f32), np.asarray(m, f32).reshape(4, 4)
+    out = np.zeros(4, f32)
+    for j in range(4):
+        acc = f32(v[0] * m[0, j])
+        for i in range(1, 4):
+            acc = f32(acc + f32(v[i] * m[i, j]))
+        out[j] = acc
+    return out
+
+
+def test_vertex_shader_reflection_and_values():
+    unit = compile_shader(VS_SPONZA, "vs")
+    r = unit.reflection
+    assert r.entry == "vs_main"
+    assert [(u[0], u[1], u[2], u[3]) for u in r.uniforms] == [("wvpMatrix", "float4x4", 0, 64), ("eyePos", "float4", 64, 16), ("lightPos", "float4", 80, 16)]
+    assert r.uniform_bytes == 96
+    assert [(s, i) for s, i, _ in r.inputs] == [("POSITION", 0), ("TEXCOORD", 0), ("NORMAL", 0)]
+    assert [(s, i) for s, i, _ in r.outputs] == [("TEXCOORD", 0), ("TEXCOORD", 1), ("TEXCOORD", 2), ("TEXCOORD", 3)]
+    assert r.n_vs_output_attrs == 4
+    rng = np.random.default_rng(5)
+    m = rng.standard_normal((4, 4)).astype(f32)
+    eye, light = rng.standard_normal(4).astype(f32), rng.standard_normal(4).astype(f32)
+    ub = unit.pack_uniforms({"wvpMatrix": m, "eyePos": eye, "lightPos": light})
+    hs = HostShader(unit)
+    for _ in range(16):
+        pos, tex, nrm = (rng.standard_normal(4).astype(f32) for _ in range(3))
+        o = hs.vs([pos, tex, nrm], ub)
+        assert np.array_equal(o[0], mul_row(pos, m))
+        assert np.array_equal(o[1], tex) and np.array_equal(o[2], nrm)
+        assert np.array_equal(o[3], light - pos) and np.array_equal(o[4], eye - pos)
+    with pytest.raises(KeyError):
+        unit.pack_uniforms({"Shininess": 1.0})  # unknown names fail, as set_constant does upstream
+
+
+PS_MISC = """
+float4 tint;
+int    steps;
+struct PSIn  { float4 a: TEXCOORD0; float3 b: TEXCOORD1; float s: TEXCOORD2; };
+struct PSOut { float4 c: COLOR0; };
+
+float3 shade(float3 n, float3 l, float k) {
+    float3 nn = normalize(n);
+    float d = clamp(dot(normalize(l), nn), 0.0f, 1.0f);
+    return lerp(float3(0.0f, 0.0f, 0.0f), nn, d) * k;
+}
+
+PSOut fn(PSIn in) {
+    PSOut o;
+    float3 x, y;
+    x = (in.a).xyz;
+    y = (in.a).wxy;
+    o.c.yzx = x + y;              // write mask with a permutation
+    o.c.w = 88.3f;
+    if (in.s > 0.0f) { o.c.w = in.s; }
+    if (in.s > 1.0f) { o.c.w = in.b.x; } else if (in.s > 0.5f) { o.c.w = o.c.w + 2.0f; }
+    float acc = in.s;
+    for (int i = 0; i < steps; i = i + 1) {
+        if (i == 1) { continue; }
+        acc = acc * 2.0f;
+        if (acc > 5000.0f) { break; }
+    }
+    int n = 0;
+    do { n += 2; } while (n < 5);
+    float3 r = reflect(in.b, normalize(x));
+    float3 sh = shade(in.b, x, tint.y);
+    float3 cr = cross(in.b, x);
+    o.c.x += acc + (float)n + r.z + sh.x + cr.y;
+    o.c.y = (in.a.x > in.a.y ? in.a.x : in.a.y) * tint.x;
+    o.c.z *= -tint.z;
+    return o;
+}
+"""
+
+
+def np_normalize(v):
+    v = np.asarray(v, f32)
+    acc = f32(v[0] * v[0])
+    for c in v[1:]:
+        acc = f32(acc + f32(c * c))
+    ln = f32(np.sqrt(acc))
+    if abs(ln) <= f32(1.1920928955078125e-7):
+        ln = f32(1)
+    return (v * f32(f32(1) / ln)).astype(f32)
+
+
+def np_dot(a, b):
+    acc = f32(a[0] * b[0])
+    for x, y in zip(a[1:], b[1:]):
+        acc = f32(acc + f32(x * y))
+    return acc
+
+
+def ps_misc_expected(a, b, s, tint, steps):
+    a, b, tint = (np.asarray(v, f32) for v in (a, b, tint))
+    s = f32(s)
+    x, y = a[[0, 1, 2]], a[[3, 0, 1]]
+    c = np.zeros(4, f32)
+    t = (x + y).astype(f32)
+    c[1], c[2], c[0] = t[0], t[1], t[2]
+    c[3] = f32(88.3)
+    if s > 0:
+        c[3] = s
+    if s > 1:
+        c[3] = b[0]
+    elif s > f32(0.5):
+        c[3] = f32(c[3] + f32(2))
+    acc = s
+    for i in range(steps):
+        if i == 1:
+            continue
+        acc = f32(acc * f32(2))
+        if acc > f32(5000):
+            break
+    n = 6
+    nx = np_normalize(x)
+    d2 = f32(f32(2) * np_dot(b, nx))
+    r = (b - (d2 * nx).astype(f32)).astype(f32)
+    nn = np_normalize(b)
+    d = np_dot(np_normalize(x), nn)
+    d = f32(0) if d < 0 else (f32(1) if d > 1 else d)
+    sh = ((np.zeros(3, f32) + ((nn - np.zeros(3, f32)).astype(f32) * d).astype(f32)).astype(f32) * tint[1]).astype(f32)
+    cr_y = f32(f32(b[2] * x[0]) - f32(b[0] * x[2]))
+    add = f32(f32(f32(f32(acc + f32(n)) + r[2]) + sh[0]) + cr_y)
+    c[0] = f32(c[0] + add)
+    c[1] = f32((a[0] if a[0] > a[1] else a[1]) * tint[0])
+    c[2] = f32(c[2] * f32(-tint[2]))
+    return c
+
+
+def test_pixel_shader_control_flow_and_intrinsics():
+    unit = compile_shader(PS_MISC, "ps")
+    assert unit.reflection.entry == "fn"
+    assert [(s, i, t) for s, i, t in unit.reflection.inputs] == [("TEXCOORD", 0, "float4"), ("TEXCOORD", 1, "float3"), ("TEXCOORD", 2, "float")]
+    hs = HostShader(unit)
+    rng = np.random.default_rng(11)
+    for k in range(40):
+        a, b = rng.standard_normal(4).astype(f32), rng.standard_normal(3).astype(f32)
+        s = f32(rng.uniform(-1, 3))
+        tint = rng.standard_normal(4).astype(f32)
+        steps = int(rng.integers(0, 14))
+        got, keep = hs.ps([a, list(b) + [0], [s, 0, 0, 0]], unit.pack_uniforms({"tint": tint, "steps": steps}))
+        assert keep
+        assert np.array_equal(got, ps_misc_expected(a, b, s, tint, steps)), (k, got, ps_misc_expected(a, b, s, tint, steps))
+
+
+def test_matrix_ops_constructors_and_casts():
+    src = """
+    float4x4 M;
+    float3x3 N;
+    struct I { float4 v: TEXCOORD0; };
+    float4 main(I i): COLOR {
+        float4 a = mul(M, i.v);            // matrix x column vector
+        float4 b = mul(i.v, transpose(M)); // == a, by the other path
+        float3 c = mul(i.v.xyz, N);
+        int k = (int)(i.v.x * 10.0f);
+        uint u = (uint)abs(k);
+        float4 r = float4(a.x - b.x, c.yz, float(k) + (float)(u & 3u));
+        r.y += float2(1.0f, 2.0f).y + M[1].z + M._m23;
+        bool big = any(i.v > float4(1.0f, 1.0f, 1.0f, 1.0f)) && !all(i.v > float4(0.0f, 0.0f, 0.0f, 0.0f));
+        r.z = big ? r.z : -r.z;
+        return r;
+    }
+    """
+    unit = compile_shader(src, "ps")
+    hs = HostShader(unit)
+    rng = np.random.default_rng(3)
+    M, N = rng.standard_normal((4, 4)).astype(f32), rng.standard_normal((3, 3)).astype(f32)
+    ub = unit.pack_uniforms({"M": M, "N": N})
+    assert unit.reflection.uniform("N")[2] == 64 and unit.reflection.uniform_bytes == 112
+    for _ in range(20):
+        v = rng.standard_normal(4).astype(f32)
+        got, _ = hs.ps([v], ub)
+        a0 = f32(M[0, 0] * v[0])
+        for j in range(1, 4):
+            a0 = f32(a0 + f32(M[0, j] * v[j]))
+        c = np.zeros(3, f32)
+        for j in range(3):
+            acc = f32(v[0] * N[0, j])
+            for i in range(1, 3):
+                acc = f32(acc + f32(v[i] * N[i, j]))
+            c[j] = acc
+        k = int(f32(v[0] * f32(10)))
+        u = abs(k)
+        want = np.array([f32(a0 - a0), f32(c[1] + f32(f32(f32(2) + M[1, 2]) + M[2, 3])), c[2], f32(f32(k) + f32(u & 3))], f32)
+        big = bool((v > 1).any()) and not bool((v > 0).all())
+        if not big:
+            want[2] = -want[2]
+        assert np.array_equal(got, want), (got, want)
+
+
+@pytest.mark.parametrize("src,stage,needle", [
+    ("float4 main(float4 p: POSITION): SV_Position { return q; }", "vs", "undeclared"),
+    ("float4 main(float4 p: POSITION): SV_Position { return ddx(p); }", "vs", "pixel shaders"),
+    ("sampler s; float4 main(float4 t: TEXCOORD0): COLOR { float4 c = t; if (t.x > 0.0f) { c = tex2D(s, t.xy); } return c; }", "ps", "divergent"),
+    ("float4 main(float4 p): SV_Position { return p; }", "vs", "semantic"),
+    ("float4 main(float4 p: POSITION): TEXCOORD0 { return p; }", "vs", "SV_Position"),
+    ("float4 main(float4 p: POSITION): SV_Position { return p.xyzq; }", "vs", "cannot take"),
+    ("sampler a; sampler b; float4 main(float4 t: TEXCOORD0): COLOR { return tex2D(a, t.xy) + tex2D(b, t.xy); }", "ps", "one sampler"),
+    ("float4 main(float4 p: POSITION): SV_Position { return p @ p; }", "vs", "unexpected character"),
+])
+def test_compile_errors(src, stage, needle):
+    with pytest.raises(CompileError) as e:
+        compile_shader(src, stage)
+    assert needle in str(e.value)
+
+
+def test_texture_shader_reflection():
+    unit = compile_shader("""
+        sampler texSamp;
+        float alpha;
+        float4 ps_main(float4 uv: TEXCOORD0): COLOR { float4 c = tex2D(texSamp, uv.xy); c.w = alpha; return c; }
+    """, "ps")
+    r = unit.reflection
+    assert r.samplers == ["texSamp"] and r.uses_derivatives and r.uniform("alpha")[2:] == (0, 4)
+    assert "sasl_tex2d_grad" in unit.code and "sasl_ddx" in unit.code
