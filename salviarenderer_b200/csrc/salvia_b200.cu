@@ -38,6 +38,10 @@ struct Resource {
   slv_sampler_desc sd{};    // samplers
   slv_handle sampler_tex = 0;
   uint8_t* resolve_peer = nullptr;  // textures: slv_resolve into this texture writes the owned tiles here instead (peer memory)
+  // textures: a whole-surface clear that has been recorded but not executed (lazy clear).  The next visibility-first batch
+  // that renders to the surface starts from this value without reading or pre-filling it; anything else materialises it.
+  bool clear_pending = false;
+  uint4 clear_pattern{};
   // shader modules (SASL shaders compiled at run time, salviarenderer_b200/sasl): the pipeline kernels with the shader inlined
   CUmodule module = nullptr;
   uint32_t module_stage = 0;        // SLV_STAGE_VS / SLV_STAGE_PS
@@ -138,6 +142,8 @@ struct slv_device_t {
   std::vector<GeomParams> pending_geom;  // geometry parameters of the queued draws (same index as `pending`)
   std::vector<slv_handle> pending_vs_module;  // run-time vertex-shader module of each queued draw (0 = built-in program)
   slv_handle batch_ps_module = 0;             // run-time pixel-shader module of the batch (0 = built-in program)
+  slv_handle batch_color = 0, batch_ds = 0;   // texture handles of the batch's colour target 0 and depth/stencil target
+  bool lazy_clear = true;                     // SLV_LAZY_CLEAR=0: clears always execute immediately
   size_t tris_used = 0;      // float4 units used by the queued draws
   uint64_t slots_queued = 0; // triangle slots of the queued draws (sizes the list arena)
   uint32_t batch_S = 0;
@@ -182,6 +188,7 @@ namespace {
 constexpr uint32_t MAX_BATCH = MAX_BATCH_DRAWS;  // draws whose geometry / raster passes are fused into one launch each
 
 slv_result flush_batch(slv_device dev);
+slv_result materialize_clear(slv_device dev, Resource* r);
 
 slv_result sync_all(slv_device dev) {  // both streams idle
   CU(cudaStreamSynchronize(dev->front_stream));
@@ -299,6 +306,50 @@ bool launch_shade_s(const RasterParams& rp, const RasterParams* batch, uint32_t 
   case SLV_PS_TEX_GRAD_ALPHA: k_shade<S, SLV_PS_TEX_GRAD_ALPHA><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, n_draws, db); return true;
   }
   return false;
+}
+
+slv_result fill_surface(slv_device dev, const SurfaceRef& s, uint4 pattern) {
+  if (dev->shard_n > 1) {  // sort-first: clear the owned tiles only
+    const uint32_t tiles_x = (s.w + SLV_TILE_SIZE - 1) / SLV_TILE_SIZE, tiles_y = (s.h + SLV_TILE_SIZE - 1) / SLV_TILE_SIZE;
+    k_fill_tiles<<<tiles_x * tiles_y, 256, 0, dev->stream>>>(s, pattern, tiles_x, dev->shard_rank, dev->shard_n);
+    ++dev->n_launches;
+    CU(cudaGetLastError());
+    return SLV_OK;
+  }
+  size_t n_vec = s.bytes / 16, n_words = s.bytes / 4;
+  if (n_vec) {
+    uint32_t blocks = (uint32_t)std::min<size_t>((n_vec + 255) / 256, 148 * 16);
+    k_fill<<<blocks, 256, 0, dev->stream>>>(reinterpret_cast<uint4*>(s.data), n_vec, pattern);
+    ++dev->n_launches;
+  }
+  if (n_words > n_vec * 4) {
+    k_fill_words<<<1, 32, 0, dev->stream>>>(reinterpret_cast<uint32_t*>(s.data), n_vec * 4, n_words, pattern);
+    ++dev->n_launches;
+  }
+  CU(cudaGetLastError());
+  return SLV_OK;
+}
+
+
+// executes a recorded whole-surface clear (see Resource::clear_pending)
+slv_result materialize_clear(slv_device dev, Resource* r) {
+  if (!r || !r->clear_pending) return SLV_OK;
+  r->clear_pending = false;
+  return fill_surface(dev, r->tex.level[0], r->clear_pattern);
+}
+slv_result materialize_all(slv_device dev) {
+  for (auto& r : dev->res)
+    if (r.kind == Resource::TEXTURE && r.clear_pending) {
+      slv_result rc = materialize_clear(dev, &r);
+      if (rc != SLV_OK) return rc;
+    }
+  return SLV_OK;
+}
+Resource* texture_of_data(slv_device dev, const uint8_t* data) {
+  if (!data) return nullptr;
+  for (auto& r : dev->res)
+    if (r.kind == Resource::TEXTURE && r.tex.level[0].data == data) return &r;
+  return nullptr;
 }
 
 // Batch flush: geometry and binning (scan, fill, sort, region lists) over the triangles of every queued draw - the FRONT
@@ -433,6 +484,16 @@ slv_result flush_batch(slv_device dev) {
   size_t e_mid = (size_t)-1, e_rbin = (size_t)-1;
   DeferredBufs db{};
   const bool shade = deferred && first.color0.data != nullptr;
+  // ---- lazy clears of the batch's targets: consumed by the visibility-first path when the tile grid covers the whole
+  // surface, executed now (on the main stream, ahead of the back half) otherwise
+  Resource* rcol = dev->get(dev->batch_color, Resource::TEXTURE);
+  Resource* rds = dev->get(dev->batch_ds, Resource::TEXTURE);
+  const bool grid_covers = first.tiles_x * SLV_TILE_SIZE >= first.target_w && first.tiles_y * SLV_TILE_SIZE >= first.target_h;
+  const bool lazy_c = shade && rcol && rcol->clear_pending && grid_covers && first.color0.w == first.target_w && first.color0.h == first.target_h;
+  const bool lazy_d = deferred && rds && rds->clear_pending && first.ds.data && grid_covers && first.ds.w == first.target_w &&
+                      first.ds.h == first.target_h;
+  if (!lazy_c) { slv_result rcm = materialize_clear(dev, rcol); if (rcm != SLV_OK) return rcm; }
+  if (!lazy_d) { slv_result rcm = materialize_clear(dev, rds); if (rcm != SLV_OK) return rcm; }
   if (deferred) {
     if (shade) {
       const size_t need = (size_t)first.color0.w * first.color0.h * dev->batch_S;
@@ -456,6 +517,13 @@ slv_result flush_batch(slv_device dev) {
     db.vis_pitch = first.color0.w;
     db.cover_counter = S.work_counter;
     db.shade_counter = S.work_counter + 1;
+    db.lazy_depth = lazy_d ? 1u : 0u;
+    db.lazy_color = lazy_c ? 1u : 0u;
+    if (lazy_d) {
+      memcpy(&db.clear_z, &rds->clear_pattern.x, 4);
+      db.clear_st = rds->clear_pattern.y;
+    }
+    if (lazy_c) db.clear_color = rcol->clear_pattern.x;
     k_region_bin<<<n_tiles, RBIN_THREADS, 0, fs>>>(first, db);
     dev->n_launches += 1;
     if (dev->profile) e_rbin = mark(dev);
@@ -464,6 +532,15 @@ slv_result flush_batch(slv_device dev) {
   if (piped) {
     CU(cudaEventRecord(S.ev_front_done, fs));
     CU(cudaStreamWaitEvent(st, S.ev_front_done, 0));
+  }
+  if (lazy_c || lazy_d) {  // tiles without triangles get the clear values (k_cover / k_shade never visit them)
+    SurfaceRef none{};
+    k_fill_inactive_tiles<<<n_tiles, 256, 0, st>>>(lazy_c ? first.color0 : none, lazy_c ? rcol->clear_pattern : make_uint4(0, 0, 0, 0),
+                                                    lazy_d ? first.ds : none, lazy_d ? rds->clear_pattern : make_uint4(0, 0, 0, 0),
+                                                    S.tile_offset, first.tiles_x, dev->shard_rank, dev->shard_n);
+    dev->n_launches += 1;
+    if (lazy_c) rcol->clear_pending = false;
+    if (lazy_d) rds->clear_pending = false;
   }
   if (deferred) {
     switch (dev->batch_S) {
@@ -586,6 +663,8 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   {
     const char* pl = getenv("SLV_PIPELINE");
     dev->pipeline = !(pl && pl[0] == '0');
+    const char* lc = getenv("SLV_LAZY_CLEAR");
+    dev->lazy_clear = !(lc && lc[0] == '0');
   }
   {
     cudaDeviceProp prop;
@@ -706,6 +785,7 @@ slv_result slv_texture_gen_mipmap(slv_device dev, slv_handle h, uint32_t filter)
   if (!r || (filter != SLV_FILTER_POINT && filter != SLV_FILTER_LINEAR)) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  { slv_result rcm__ = materialize_clear(dev, r); if (rcm__ != SLV_OK) return rcm__; }
   CU(cudaStreamSynchronize(dev->stream));
   for (uint32_t l = 1; l < r->tex.n_levels; ++l) CU(cudaFree(r->tex.level[l].data));
   r->tex.n_levels = 1;
@@ -746,6 +826,7 @@ slv_result slv_texture_upload(slv_device dev, slv_handle h, uint32_t level, cons
   if (!r || level >= r->tex.n_levels || bytes != r->tex.level[level].bytes) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  if (level == 0) r->clear_pending = false;  // the whole level is overwritten
   CU(cudaMemcpyAsync(r->tex.level[level].data, src, bytes, cudaMemcpyHostToDevice, dev->stream));
   return SLV_OK;
 }
@@ -755,6 +836,7 @@ slv_result slv_texture_readback(slv_device dev, slv_handle h, uint32_t level, vo
   if (!r || level >= r->tex.n_levels || bytes != r->tex.level[level].bytes) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  { slv_result rcm__ = materialize_clear(dev, r); if (rcm__ != SLV_OK) return rcm__; }
   CU(cudaMemcpyAsync(dst, r->tex.level[level].data, bytes, cudaMemcpyDeviceToHost, dev->stream));
   CU(cudaStreamSynchronize(dev->stream));
   return check_overflow(dev);
@@ -1027,6 +1109,12 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
     }
   }
 
+  // lazy clears: a texture this draw SAMPLES, and the second colour target, must hold their cleared contents for real
+  if (needs_sampler) { slv_result rcm__ = materialize_clear(dev, texture_of_data(dev, rp.sampler0.tex.level[0].data)); if (rcm__ != SLV_OK) return rcm__; }
+  if (rp.color1.data) { slv_result rcm__ = materialize_clear(dev, texture_of_data(dev, rp.color1.data)); if (rcm__ != SLV_OK) return rcm__; }
+  dev->batch_color = d->n_color_targets ? d->color_targets[0] : 0;
+  dev->batch_ds = d->ds_target;
+
   // ---- bind the scratch set the batch is being built in (every flush above may have switched sets)
   {
     slv_device_t::Scratch& S = dev->S();
@@ -1055,28 +1143,6 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   return SLV_OK;
 }
 
-static slv_result fill_surface(slv_device dev, const SurfaceRef& s, uint4 pattern) {
-  if (dev->shard_n > 1) {  // sort-first: clear the owned tiles only
-    const uint32_t tiles_x = (s.w + SLV_TILE_SIZE - 1) / SLV_TILE_SIZE, tiles_y = (s.h + SLV_TILE_SIZE - 1) / SLV_TILE_SIZE;
-    k_fill_tiles<<<tiles_x * tiles_y, 256, 0, dev->stream>>>(s, pattern, tiles_x, dev->shard_rank, dev->shard_n);
-    ++dev->n_launches;
-    CU(cudaGetLastError());
-    return SLV_OK;
-  }
-  size_t n_vec = s.bytes / 16, n_words = s.bytes / 4;
-  if (n_vec) {
-    uint32_t blocks = (uint32_t)std::min<size_t>((n_vec + 255) / 256, 148 * 16);
-    k_fill<<<blocks, 256, 0, dev->stream>>>(reinterpret_cast<uint4*>(s.data), n_vec, pattern);
-    ++dev->n_launches;
-  }
-  if (n_words > n_vec * 4) {
-    k_fill_words<<<1, 32, 0, dev->stream>>>(reinterpret_cast<uint32_t*>(s.data), n_vec * 4, n_words, pattern);
-    ++dev->n_launches;
-  }
-  CU(cudaGetLastError());
-  return SLV_OK;
-}
-
 slv_result slv_clear_color(slv_device dev, slv_handle h, const float rgba[4]) {
   auto r = dev ? dev->get(h, Resource::TEXTURE) : nullptr;
   if (!r || !rgba) return SLV_INVALID_PARAMETER;
@@ -1096,6 +1162,11 @@ slv_result slv_clear_color(slv_device dev, slv_handle h, const float rgba[4]) {
     w[0] = w[1] = w[2] = w[3] = p;
   } break;
   }
+  if (dev->lazy_clear) {
+    r->clear_pending = true;
+    r->clear_pattern = make_uint4(w[0], w[1], w[2], w[3]);
+    return SLV_OK;
+  }
   return fill_surface(dev, s, make_uint4(w[0], w[1], w[2], w[3]));
 }
 
@@ -1109,8 +1180,14 @@ slv_result slv_clear_depth_stencil(slv_device dev, slv_handle h, uint32_t flags,
   if ((flags & 3) == 3) {
     uint32_t dbits;
     memcpy(&dbits, &depth, 4);
+    if (dev->lazy_clear) {
+      r->clear_pending = true;
+      r->clear_pattern = make_uint4(dbits, stencil, dbits, stencil);
+      return SLV_OK;
+    }
     return fill_surface(dev, s, make_uint4(dbits, stencil, dbits, stencil));
   }
+  { slv_result rcm__ = materialize_clear(dev, r); if (rcm__ != SLV_OK) return rcm__; }
   size_t n = s.bytes / 8;
   uint32_t blocks = (uint32_t)std::min<size_t>((n + 255) / 256, 148 * 16);
   k_clear_ds_partial<<<blocks, 256, 0, dev->stream>>>(reinterpret_cast<float2*>(s.data), n, flags, depth, stencil);
@@ -1128,6 +1205,8 @@ slv_result slv_resolve(slv_device dev, slv_handle src, slv_handle dst) {
   if (t.samples != 1 || t.w < s.w || t.h < s.h) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  { slv_result rcm__ = materialize_clear(dev, rs); if (rcm__ != SLV_OK) return rcm__; }
+  { slv_result rcm__ = materialize_clear(dev, rd); if (rcm__ != SLV_OK) return rcm__; }
   dim3 blk(32, 8), grd((s.w + 31) / 32, (s.h + 7) / 8);
   SurfaceRef t2 = t;
   if (rd->resolve_peer && dev->shard_n > 1) t2.data = rd->resolve_peer;  // owned tiles go straight to the root's surface
@@ -1141,6 +1220,7 @@ slv_result slv_flush(slv_device dev) {
   if (!dev) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  { slv_result rcm__ = materialize_all(dev); if (rcm__ != SLV_OK) return rcm__; }
   CU(cudaStreamSynchronize(dev->stream));
   return check_overflow(dev);
 }
@@ -1261,6 +1341,7 @@ slv_result slv_set_stream(slv_device dev, void* cuda_stream) {
   if (!dev) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  { slv_result rcm__ = materialize_all(dev); if (rcm__ != SLV_OK) return rcm__; }
   { slv_result rcs__ = sync_all(dev); if (rcs__ != SLV_OK) return rcs__; }
   dev->stream = cuda_stream ? (cudaStream_t)cuda_stream : dev->own_stream;
   return SLV_OK;
@@ -1275,6 +1356,7 @@ slv_result slv_profile_enable(slv_device dev, uint32_t on) {
 slv_result slv_texture_device_ptr(slv_device dev, slv_handle tex, uint32_t level, void** out, size_t* bytes) {
   auto r = dev ? dev->get(tex, Resource::TEXTURE) : nullptr;
   if (!r || level >= r->tex.n_levels || !out) return SLV_INVALID_PARAMETER;
+  { slv_result rcm__ = materialize_clear(dev, r); if (rcm__ != SLV_OK) return rcm__; }  // the caller will touch the memory itself
   *out = r->tex.level[level].data;
   if (bytes) *bytes = r->tex.level[level].bytes;
   return SLV_OK;
@@ -1308,6 +1390,7 @@ static slv_result pack_common(slv_device dev, slv_handle tex, uint32_t rank, uin
   if (!staging) return SLV_OK;
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  { slv_result rcm__ = materialize_clear(dev, r); if (rcm__ != SLV_OK) return rcm__; }
   k_pack_tiles<<<n_tiles, 256, 0, dev->stream>>>(s, tiles_x, tiles_y, rank, nranks, (uint8_t*)staging, tab->d_slot, unpack);
   ++dev->n_launches;
   CU(cudaGetLastError());
@@ -1329,6 +1412,7 @@ slv_result slv_peer_export_texture(slv_device dev, slv_handle tex, uint32_t leve
   if (!r || level >= r->tex.n_levels || !handle_out) return SLV_INVALID_PARAMETER;
   static_assert(sizeof(cudaIpcMemHandle_t) <= SLV_PEER_HANDLE_BYTES, "IPC handle does not fit");
   CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcm__ = materialize_clear(dev, r); if (rcm__ != SLV_OK) return rcm__; }
   cudaIpcMemHandle_t h;
   CU(cudaIpcGetMemHandle(&h, r->tex.level[level].data));
   memset(handle_out, 0, SLV_PEER_HANDLE_BYTES);
@@ -1414,6 +1498,7 @@ slv_result slv_sampler_probe(slv_device dev, slv_handle sh, uint32_t n, const fl
   if (n == 0) return SLV_OK;
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  { slv_result rcm__ = materialize_clear(dev, texture_of_data(dev, sm.tex.level[0].data)); if (rcm__ != SLV_OK) return rcm__; }
   float *d_c = nullptr, *d_dx = nullptr, *d_dy = nullptr, *d_l = nullptr;
   float4* d_o = nullptr;
   CU(cudaMalloc(&d_c, n * 8));

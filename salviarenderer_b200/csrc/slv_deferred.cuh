@@ -45,6 +45,12 @@ struct CovTri {  // one surviving triangle of the warp's current chunk, staged i
 // (2 bits each: 0 rejected, 1 partial, 2 full)
 
 struct DeferredBufs {
+  // lazy clears: the whole-surface clear that preceded the batch was not executed; k_cover / k_shade start from the clear
+  // value instead of loading, and write every pixel of every item of the active tiles (tiles without triangles are
+  // filled by k_fill_inactive_tiles), so depth / colour are written ONCE per frame and depth is never read
+  uint32_t lazy_depth, lazy_color;
+  float clear_z;
+  uint32_t clear_st, clear_color;
   uint32_t* region_list;      // per region 8 sub-lists (one per 8x4 warp block) of capacity region_count, entries
                               // (slot << 4) | status of the warp's two 4x4 blocks, in API order
   uint2* block_desc;          // [item = (active tile index * 16 + region) * 8 + warp block]: (first entry, entries)
@@ -278,7 +284,7 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_COVER_CTAS_PER_SM)
       const uint32_t b = item >> 7, sub = (item >> 3) & 15, w = item & 7;
       const uint2 desc = d.block_desc[item];  // item == (b * 16 + sub) * 8 + w
       const uint32_t rbeg = desc.x, rcnt = desc.y;
-      if (rcnt == 0) {
+      if (rcnt == 0 && !d.lazy_depth) {
         if (lane == 0) d.item_flag[item] = 0;
         continue;
       }
@@ -290,6 +296,17 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_COVER_CTAS_PER_SM)
       const int x = gx0 + wx + wlx, y = gy0 + wy + wly;
       const bool odd_x = x & 1, odd_y = y & 1;
       const bool in_target = (uint32_t)x < c.target_w && (uint32_t)y < c.target_h;
+      if (rcnt == 0) {  // lazy depth clear: nothing lands here, the block just receives the clear value
+        if (lane == 0) d.item_flag[item] = 0;
+        if (in_target) {
+          float4* ds_ptr = reinterpret_cast<float4*>(c.ds.data + ((size_t)y * c.ds.w + x) * S * 8);
+          const float4 cv = make_float4(d.clear_z, __uint_as_float(d.clear_st), d.clear_z, __uint_as_float(d.clear_st));
+          if (S == 4) { ds_ptr[0] = cv; ds_ptr[1] = cv; }
+          else if (S == 2) ds_ptr[0] = cv;
+          else *reinterpret_cast<float2*>(ds_ptr) = make_float2(cv.x, cv.y);
+        }
+        continue;
+      }
       const float hx = 0.5f + (float)(uint32_t)(x & ~1), hy = 0.5f + (float)(uint32_t)(y & ~1);
       const int bxA = wx >> 2, by = wy >> 2;  // block A of the warp inside the region; block B = bxA + 1
       const float left_f = (float)(gx0 + (bxA + bsel) * 4), top_f = (float)(gy0 + by * 4);
@@ -297,9 +314,9 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_COVER_CTAS_PER_SM)
       float z[S];
       uint32_t st[S], own[S];
 #pragma unroll
-      for (int s = 0; s < S; ++s) { z[s] = 0.0f; st[s] = 0u; own[s] = VIS_NONE; }
-      bool dirty = false;
-      if (in_target && c.ds.data) {
+      for (int s = 0; s < S; ++s) { z[s] = d.clear_z; st[s] = d.clear_st; own[s] = VIS_NONE; }
+      bool dirty = d.lazy_depth != 0;
+      if (in_target && c.ds.data && !d.lazy_depth) {
         const float2* dp = reinterpret_cast<const float2*>(c.ds.data + ((size_t)y * c.ds.w + x) * S * 8);
         if (S == 4) {
           const float4 a = *reinterpret_cast<const float4*>(dp), b2 = *reinterpret_cast<const float4*>(dp + 2);
@@ -570,7 +587,8 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
 #pragma unroll 1
       for (; k < SHADE_GROUP && pool_n + 32 * S <= (uint32_t)SHADE_POOL; ++k) {
         const uint32_t item = base_item + k;
-        const bool live = k < grp && item < n_items && d.item_flag[item];
+        const bool flagged = k < grp && item < n_items && d.item_flag[item];
+        const bool live = flagged || (d.lazy_color && k < grp && item < n_items);  // lazy colour clear: every item is written
         if (lane == 0) s_org[k] = 0xFFFFFFFFu;
         if (!live) continue;
         const uint32_t b = item >> 7, sub = (item >> 3) & 15, w = item & 7;
@@ -584,7 +602,7 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
         uint32_t own[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) own[s] = VIS_NONE;
-        if (in_target) {
+        if (in_target && flagged) {  // unflagged items hold stale owners from an earlier batch
           const uint32_t* vp = d.vis + ((size_t)y * d.vis_pitch + x) * S;
           if (S == 4) {
             const uint4 v = *reinterpret_cast<const uint4*>(vp);
@@ -600,8 +618,14 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
 #pragma unroll
         for (int s = 0; s < S; ++s) rem |= (own[s] != VIS_NONE) ? (1u << s) : 0u;
         const uint32_t touched = rem;
-        s_touched[k][lane] = (uint8_t)touched;
-        if (touched && touched != fullmask) {  // some samples keep their colour: fetch it for the 128-bit store
+        // bit 7: the pixel is written even when no sample was touched (lazy colour clear, pixels inside the target)
+        s_touched[k][lane] = (uint8_t)(touched | ((d.lazy_color && in_target) ? 0x80u : 0u));
+        if (d.lazy_color) {
+          if (touched != fullmask) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) s_color[k][lane][s] = d.clear_color;
+          }
+        } else if (touched && touched != fullmask) {  // some samples keep their colour: fetch it for the 128-bit store
           const uint32_t* cptr = reinterpret_cast<const uint32_t*>(c.color0.data + ((size_t)y * c.color0.w + x) * S * 4);
 #pragma unroll
           for (int s = 0; s < S; ++s) s_color[k][lane][s] = cptr[s];

@@ -1470,13 +1470,11 @@ __global__ void k_fill_words(uint32_t* dst, size_t first_word, size_t n_words, u
   size_t i = first_word + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_words) dst[i] = (i & 3) == 0 ? pattern.x : ((i & 3) == 1 ? pattern.y : ((i & 3) == 2 ? pattern.z : pattern.w));
 }
-// sort-first: a rank only ever reads and writes its own 64x64 tiles, so it only clears those (CTA per owned tile,
-// 128-bit stores along the tile's rows)
-__global__ void __launch_bounds__(256) k_fill_tiles(SurfaceRef s, uint4 pattern, uint32_t tiles_x, uint32_t rank, uint32_t n) {
-  const uint32_t tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-  if (!tile_owned(tx, ty, rank, n)) return;
+// one 64x64 tile of a surface <- pattern (all threads of the CTA; 128-bit stores along the tile's rows)
+__device__ __forceinline__ void fill_tile(const SurfaceRef& s, uint4 pattern, uint32_t tx, uint32_t ty) {
   const uint32_t texel = s.samples * s.bpp;                      // bytes per pixel (all samples)
   const uint32_t x0 = tx * TILE, y0 = ty * TILE;
+  if (x0 >= s.w || y0 >= s.h) return;
   const uint32_t cols = min((uint32_t)TILE, s.w - x0), rows = min((uint32_t)TILE, s.h - y0);
   const uint32_t row_bytes = cols * texel;                       // multiple of 4; 16-byte aligned when texel*x0 is
   for (uint32_t r = 0; r < rows; ++r) {
@@ -1490,6 +1488,26 @@ __global__ void __launch_bounds__(256) k_fill_tiles(SurfaceRef s, uint4 pattern,
       }
     }
   }
+}
+
+// sort-first: a rank only ever reads and writes its own 64x64 tiles, so it only clears those (CTA per owned tile)
+__global__ void __launch_bounds__(256) k_fill_tiles(SurfaceRef s, uint4 pattern, uint32_t tiles_x, uint32_t rank, uint32_t n) {
+  const uint32_t tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  if (!tile_owned(tx, ty, rank, n)) return;
+  fill_tile(s, pattern, tx, ty);
+}
+
+// lazy clears: the batch's k_cover / k_shade write every pixel of the tiles that have triangles; the owned tiles WITHOUT
+// triangles (empty list: tile_offset[t + 1] == tile_offset[t]) receive the clear values here.  color / ds .data == nullptr:
+// that surface has no pending clear.
+__global__ void __launch_bounds__(256) k_fill_inactive_tiles(SurfaceRef color, uint4 color_pattern, SurfaceRef ds, uint4 ds_pattern,
+                                                             const uint32_t* __restrict__ tile_offset, uint32_t tiles_x,
+                                                             uint32_t rank, uint32_t n) {
+  const uint32_t t = blockIdx.x;
+  const uint32_t tx = t % tiles_x, ty = t / tiles_x;
+  if (!tile_owned(tx, ty, rank, n) || tile_offset[t + 1] != tile_offset[t]) return;
+  if (color.data) fill_tile(color, color_pattern, tx, ty);
+  if (ds.data) fill_tile(ds, ds_pattern, tx, ty);
 }
 
 // framebuffer::clear_depth_stencil with a single flag (framebuffer.cpp:616-644)
