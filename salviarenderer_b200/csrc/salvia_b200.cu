@@ -144,6 +144,11 @@ struct slv_device_t {
   slv_handle batch_ps_module = 0;             // run-time pixel-shader module of the batch (0 = built-in program)
   slv_handle batch_color = 0, batch_ds = 0;   // texture handles of the batch's colour target 0 and depth/stencil target
   bool lazy_clear = true;                     // SLV_LAZY_CLEAR=0: clears always execute immediately
+  // fused resolve: slv_resolve(src, dst) of the pending batch's colour target is handed to the batch flush, whose k_shade
+  // writes the resolved texels as it stores the samples (SLV_FUSE_RESOLVE=0 disables)
+  bool fuse_resolve = true;
+  bool resolve_requested = false, resolve_done = false;
+  SurfaceRef resolve_dst{};
   size_t tris_used = 0;      // float4 units used by the queued draws
   uint64_t slots_queued = 0; // triangle slots of the queued draws (sizes the list arena)
   uint32_t batch_S = 0;
@@ -524,6 +529,10 @@ slv_result flush_batch(slv_device dev) {
       db.clear_st = rds->clear_pattern.y;
     }
     if (lazy_c) db.clear_color = rcol->clear_pattern.x;
+    if (dev->resolve_requested && shade && grid_covers && first.color0.w == first.target_w && first.color0.h == first.target_h) {
+      db.resolve_dst = dev->resolve_dst;
+      dev->resolve_done = true;
+    }
     k_region_bin<<<n_tiles, RBIN_THREADS, 0, fs>>>(first, db);
     dev->n_launches += 1;
     if (dev->profile) e_rbin = mark(dev);
@@ -556,6 +565,10 @@ slv_result flush_batch(slv_device dev) {
       case 4: ok = launch_shade_s<4>(first, S.d_batch, n, db, dev->shade_grid, st); break;
       }
       dev->n_launches += 1;
+      if (db.resolve_dst.data) {  // fused resolve: the tiles k_shade never visits (no triangles) are resolved the plain way
+        k_resolve_inactive_tiles<<<n_tiles, 256, 0, st>>>(first.color0, db.resolve_dst, S.tile_offset, first.tiles_x, dev->shard_rank, dev->shard_n);
+        dev->n_launches += 1;
+      }
     }
   } else {
     const uint32_t blocks = std::min<uint32_t>(n_tiles * 16, (uint32_t)dev->raster_grid);
@@ -665,6 +678,8 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
     dev->pipeline = !(pl && pl[0] == '0');
     const char* lc = getenv("SLV_LAZY_CLEAR");
     dev->lazy_clear = !(lc && lc[0] == '0');
+    const char* fr = getenv("SLV_FUSE_RESOLVE");
+    dev->fuse_resolve = !(fr && fr[0] == '0');
   }
   {
     cudaDeviceProp prop;
@@ -1204,12 +1219,26 @@ slv_result slv_resolve(slv_device dev, slv_handle src, slv_handle dst) {
   const SurfaceRef& t = rd->tex.level[0];
   if (t.samples != 1 || t.w < s.w || t.h < s.h) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
-  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  SurfaceRef t2 = t;
+  if (rd->resolve_peer && dev->shard_n > 1) t2.data = rd->resolve_peer;  // owned tiles go straight to the root's surface
+  // the pending batch renders to `src`: its k_shade can write the resolved texels itself (fused resolve)
+  if (dev->fuse_resolve && !dev->pending.empty() && dev->pending[0].color0.data == s.data && rd != rs) {
+    { slv_result rcm__ = materialize_clear(dev, rd); if (rcm__ != SLV_OK) return rcm__; }
+    dev->resolve_requested = true;
+    dev->resolve_dst = t2;
+  }
+  dev->resolve_done = false;
+  slv_result rcf = flush_batch(dev);
+  dev->resolve_requested = false;
+  if (rcf != SLV_OK) return rcf;
+  if (dev->resolve_done) {
+    dev->resolve_done = false;
+    CU(cudaGetLastError());
+    return SLV_OK;
+  }
   { slv_result rcm__ = materialize_clear(dev, rs); if (rcm__ != SLV_OK) return rcm__; }
   { slv_result rcm__ = materialize_clear(dev, rd); if (rcm__ != SLV_OK) return rcm__; }
   dim3 blk(32, 8), grd((s.w + 31) / 32, (s.h + 7) / 8);
-  SurfaceRef t2 = t;
-  if (rd->resolve_peer && dev->shard_n > 1) t2.data = rd->resolve_peer;  // owned tiles go straight to the root's surface
   k_resolve<<<grd, blk, 0, dev->stream>>>(s, t2, dev->shard_rank, dev->shard_n);
   ++dev->n_launches;
   CU(cudaGetLastError());

@@ -51,6 +51,9 @@ struct DeferredBufs {
   uint32_t lazy_depth, lazy_color;
   float clear_z;
   uint32_t clear_st, clear_color;
+  // fused MSAA resolve: k_shade holds every pixel's final samples when it stores them, so it also writes the resolved
+  // texel (surface::resolve, surface.cpp:123-140) - into this surface, which may be another rank's memory (sort-first)
+  SurfaceRef resolve_dst;
   uint32_t* region_list;      // per region 8 sub-lists (one per 8x4 warp block) of capacity region_count, entries
                               // (slot << 4) | status of the warp's two 4x4 blocks, in API order
   uint2* block_desc;          // [item = (active tile index * 16 + region) * 8 + warp block]: (first entry, entries)
@@ -588,7 +591,8 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
       for (; k < SHADE_GROUP && pool_n + 32 * S <= (uint32_t)SHADE_POOL; ++k) {
         const uint32_t item = base_item + k;
         const bool flagged = k < grp && item < n_items && d.item_flag[item];
-        const bool live = flagged || (d.lazy_color && k < grp && item < n_items);  // lazy colour clear: every item is written
+        // lazy colour clear / fused resolve: every item of the active tiles is visited, not only those with new owners
+        const bool live = flagged || ((d.lazy_color || d.resolve_dst.data) && k < grp && item < n_items);
         if (lane == 0) s_org[k] = 0xFFFFFFFFu;
         if (!live) continue;
         const uint32_t b = item >> 7, sub = (item >> 3) & 15, w = item & 7;
@@ -619,13 +623,15 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
         for (int s = 0; s < S; ++s) rem |= (own[s] != VIS_NONE) ? (1u << s) : 0u;
         const uint32_t touched = rem;
         // bit 7: the pixel is written even when no sample was touched (lazy colour clear, pixels inside the target)
-        s_touched[k][lane] = (uint8_t)(touched | ((d.lazy_color && in_target) ? 0x80u : 0u));
+        // bit 6: the pixel lies inside the target (fused resolve)
+        s_touched[k][lane] = (uint8_t)(touched | ((d.lazy_color && in_target) ? 0x80u : 0u) | (in_target ? 0x40u : 0u));
         if (d.lazy_color) {
           if (touched != fullmask) {
 #pragma unroll
             for (int s = 0; s < S; ++s) s_color[k][lane][s] = d.clear_color;
           }
-        } else if (touched && touched != fullmask) {  // some samples keep their colour: fetch it for the 128-bit store
+        } else if (touched != fullmask && in_target && (touched || d.resolve_dst.data)) {
+          // some samples keep their colour: fetch it for the 128-bit store (and for the resolve of untouched pixels)
           const uint32_t* cptr = reinterpret_cast<const uint32_t*>(c.color0.data + ((size_t)y * c.color0.w + x) * S * 4);
 #pragma unroll
           for (int s = 0; s < S; ++s) s_color[k][lane][s] = cptr[s];
@@ -668,16 +674,52 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
       if (k >= SHADE_GROUP) break;
     }
     // ---- store the group's items, one 128-bit store per touched pixel at 4x ----
+    uint32_t n_slow = 0;
 #pragma unroll 1
     for (uint32_t kk = 0; kk < SHADE_GROUP; ++kk) {
       const uint32_t org = s_org[kk];
       if (org == 0xFFFFFFFFu) continue;
-      if (s_touched[kk][lane]) {
-        const int x = (int)(org & 0xFFFF) + wlx, y = (int)(org >> 16) + wly;
+      const uint32_t fl = s_touched[kk][lane];
+      const int x = (int)(org & 0xFFFF) + wlx, y = (int)(org >> 16) + wly;
+      if (fl & 0x8Fu) {
         uint32_t* cptr = reinterpret_cast<uint32_t*>(c.color0.data + ((size_t)y * c.color0.w + x) * S * 4);
         if (S == 4) *reinterpret_cast<uint4*>(cptr) = make_uint4(s_color[kk][lane][0], s_color[kk][lane][1 % S], s_color[kk][lane][2 % S], s_color[kk][lane][3 % S]);
         else if (S == 2) *reinterpret_cast<uint2*>(cptr) = make_uint2(s_color[kk][lane][0], s_color[kk][lane][1 % S]);
         else *cptr = s_color[kk][lane][0];
+      }
+      // fused resolve.  Pixels whose S samples are equal (the great majority) resolve to that very value: for unorm8 c,
+      // ((v+v)+v)+v with v = c/255 is off 4v by < 3 ulp, so * (1/S) * 255 lies within 1e-4 of c and rounds back to c.
+      // The others (triangle edges) are pooled over the group's items and resolved densely below.
+      bool slow = false;
+      if (d.resolve_dst.data && (fl & 0x40u)) {
+        bool same = d.resolve_dst.fmt == c.color0.fmt;
+#pragma unroll
+        for (int s = 1; s < S; ++s) same = same && s_color[kk][lane][s] == s_color[kk][lane][0];
+        if (same) *reinterpret_cast<uint32_t*>(d.resolve_dst.data + ((size_t)y * d.resolve_dst.w + x) * 4) = s_color[kk][lane][0];
+        slow = !same;
+      }
+      if (d.resolve_dst.data) {
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, slow);
+        if (slow) s_pool[n_slow + __popc(bal & below)] = make_uint2(lane | (kk << 5), 0u);
+        n_slow += __popc(bal);
+      }
+    }
+    if (n_slow) {  // sum of to_rgba32f(sample) in sample order, * (1 / S), convert (RNE)  (surface.cpp:123-140)
+      __syncwarp();
+      for (uint32_t j = lane; j < n_slow; j += 32) {
+        const uint32_t pl = s_pool[j].x & 31, k2 = s_pool[j].x >> 5;
+        const uint32_t org = s_org[k2];
+        const uint32_t pq = pl >> 2, pp = pl & 3;
+        const int x = (int)(org & 0xFFFF) + (int)((pq & 3) * 2 + (pp & 1)), y = (int)(org >> 16) + (int)((pq >> 2) * 2 + (pp >> 1));
+        float4 clr = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const float4 t = unpack_color(c.color0.fmt, s_color[k2][pl][s]);
+          clr.x += t.x; clr.y += t.y; clr.z += t.z; clr.w += t.w;
+        }
+        const float inv = 1 / (float)S;
+        clr.x *= inv; clr.y *= inv; clr.z *= inv; clr.w *= inv;
+        store_texel_rgba32f(d.resolve_dst.fmt, d.resolve_dst.data + ((size_t)y * d.resolve_dst.w + x) * d.resolve_dst.bpp, clr);
       }
     }
     __syncwarp();

@@ -1549,10 +1549,7 @@ __global__ void __launch_bounds__(32) k_flags_wait(const uint32_t* flags, uint32
 }
 
 // surface::resolve (surface.cpp:123-140): sum of to_rgba32f(sample) in sample order, * (1/S), convert (RNE)
-__global__ void k_resolve(SurfaceRef src, SurfaceRef dst, uint32_t rank, uint32_t n) {
-  uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= src.w || y >= src.h) return;
-  if (!tile_owned(x / TILE, y / TILE, rank, n)) return;  // sort-first: other ranks resolve their own tiles
+__device__ __forceinline__ void resolve_pixel(const SurfaceRef& src, const SurfaceRef& dst, uint32_t x, uint32_t y) {
   float4 clr = make_float4(0, 0, 0, 0);
   const uint8_t* sp = src.data + ((size_t)y * src.w + x) * src.samples * src.bpp;
   const float inv = 1 / (float)src.samples;
@@ -1572,6 +1569,26 @@ __global__ void k_resolve(SurfaceRef src, SurfaceRef dst, uint32_t rank, uint32_
   }
   clr.x *= inv; clr.y *= inv; clr.z *= inv; clr.w *= inv;
   store_texel_rgba32f(dst.fmt, dst.data + ((size_t)y * dst.w + x) * dst.bpp, clr);
+}
+
+__global__ void k_resolve(SurfaceRef src, SurfaceRef dst, uint32_t rank, uint32_t n) {
+  uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= src.w || y >= src.h) return;
+  if (!tile_owned(x / TILE, y / TILE, rank, n)) return;  // sort-first: other ranks resolve their own tiles
+  resolve_pixel(src, dst, x, y);
+}
+
+// fused resolve: k_shade resolved every tile it visited; the owned tiles WITHOUT triangles in the batch (empty list) are
+// resolved here, one CTA per tile (CTAs of the other tiles exit at once)
+__global__ void __launch_bounds__(256) k_resolve_inactive_tiles(SurfaceRef src, SurfaceRef dst, const uint32_t* __restrict__ tile_offset,
+                                                                uint32_t tiles_x, uint32_t rank, uint32_t n) {
+  const uint32_t t = blockIdx.x;
+  const uint32_t tx = t % tiles_x, ty = t / tiles_x;
+  if (!tile_owned(tx, ty, rank, n) || tile_offset[t + 1] != tile_offset[t]) return;
+  for (uint32_t i = threadIdx.x; i < TILE * TILE; i += blockDim.x) {
+    const uint32_t x = tx * TILE + (i % TILE), y = ty * TILE + (i / TILE);
+    if (x < src.w && y < src.h) resolve_pixel(src, dst, x, y);
+  }
 }
 
 // surface::make_mip_surface (surface.cpp:53-92): box filter ((c0+c1)+c2)+c3 then *0.25; reads of texel
