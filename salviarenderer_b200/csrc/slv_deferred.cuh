@@ -51,6 +51,10 @@ struct DeferredBufs {
   uint32_t lazy_depth, lazy_color;
   float clear_z;
   uint32_t clear_st, clear_color;
+  // work-queue budget: fetches a warp of k_cover / k_shade performs before it exits (0 = until the queue is empty, i.e. a
+  // persistent grid).  With a budget the grid is sized to cover the queue and its CTAs are short-lived, so CTAs of the NEXT
+  // frame's geometry / binning kernels (higher-priority stream) are scheduled in between instead of after the kernel.
+  uint32_t cover_budget, shade_budget, shade_grp;
   // fused MSAA resolve: k_shade holds every pixel's final samples when it stores them, so it also writes the resolved
   // texel (surface::resolve, surface.cpp:123-140) - into this surface, which may be another rank's memory (sort-first)
   SurfaceRef resolve_dst;
@@ -279,10 +283,12 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_COVER_CTAS_PER_SM)
 
   const uint32_t n_items = c.active_tiles[0] * ITEMS_PER_TILE;
   uint32_t next_raw = fetch_items(d.cover_counter, lane);
+  uint32_t fetches = 1;
   for (;;) {
     const uint32_t base_item = __shfl_sync(0xFFFFFFFFu, next_raw, 0);
     if (base_item >= n_items) break;
-    next_raw = fetch_items(d.cover_counter, lane);
+    next_raw = (d.cover_budget == 0 || fetches < d.cover_budget) ? fetch_items(d.cover_counter, lane) : 0xFFFFFFFFu;
+    ++fetches;
     for (uint32_t item = base_item; item < base_item + FETCH && item < n_items; ++item) {
       const uint32_t b = item >> 7, sub = (item >> 3) & 15, w = item & 7;
       const uint2 desc = d.block_desc[item];  // item == (b * 16 + sub) * 8 + w
@@ -578,12 +584,14 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
   const uint32_t n_items = c.active_tiles[0] * ITEMS_PER_TILE;
   // items per fetch: SHADE_GROUP when there is plenty of work, fewer when the launch has only a few items per warp
   // (sort-first shards, small targets) so that the heavy items spread over all warps
-  const uint32_t grp = min(SHADE_GROUP, max(1u, n_items / (gridDim.x * DEF_WARPS * 4u)));
+  const uint32_t grp = d.shade_grp ? d.shade_grp : min(SHADE_GROUP, max(1u, n_items / (gridDim.x * DEF_WARPS * 4u)));
   uint32_t next_raw = fetch_group(d.shade_counter, lane, grp);
+  uint32_t fetches = 1;
   for (;;) {
     const uint32_t base_item = __shfl_sync(0xFFFFFFFFu, next_raw, 0);
     if (base_item >= n_items) break;
-    next_raw = fetch_group(d.shade_counter, lane, grp);
+    next_raw = (d.shade_budget == 0 || fetches < d.shade_budget) ? fetch_group(d.shade_counter, lane, grp) : 0xFFFFFFFFu;
+    ++fetches;
     uint32_t pool_n = 0, k = 0;
     for (;;) {
       // ---- fill: analyse items while the pool has room for a whole item ----
