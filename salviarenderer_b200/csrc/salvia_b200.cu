@@ -424,6 +424,7 @@ slv_result flush_batch(slv_device dev) {
     src_geom = S.h_geom;
   }
   CU(cudaMemcpyAsync(S.d_batch, src_batch, n * sizeof(RasterParams), cudaMemcpyHostToDevice, fs));
+  CU(cudaMemcpyAsync(S.d_geom, src_geom, n * sizeof(GeomParams), cudaMemcpyHostToDevice, fs));
   BinParams bp{};
   bp.tris = S.tris;
   bp.tri_stride = first.tri_stride;
@@ -440,8 +441,6 @@ slv_result flush_batch(slv_device dev) {
   bp.valid_slots = S.valid_slots;
   bp.valid_count = S.valid_count;
   // ---- geometry of every queued draw: one launch per distinct register count (normally one)
-  CU(cudaMemsetAsync(S.valid_count, 0, sizeof(uint32_t), fs));
-  CU(cudaMemcpyAsync(S.d_geom, src_geom, n * sizeof(GeomParams), cudaMemcpyHostToDevice, fs));
   size_t eg0 = dev->profile ? mark(dev) : 0;
   {
     std::vector<slv_handle> mods;  // distinct vertex-shader modules of the batch (0 = the built-in programs)
@@ -481,7 +480,7 @@ slv_result flush_batch(slv_device dev) {
   k_bin_fill<<<(n_slots + 255) / 256, 256, 0, fs>>>(bp);
   size_t e1 = dev->profile ? mark(dev) : 0;
   k_sort_lists<<<n_tiles, SORT_THREADS, 0, fs>>>(S.tile_offset, S.list, dev->list_cap, S.active_tiles, S.work_counter + 3);
-  k_sort_lists_large<<<dev->sm_count, 1024, SORT_LARGE_SMEM * sizeof(uint32_t), fs>>>(S.tile_offset, S.list, dev->list_cap, S.large_tiles);
+  k_sort_lists_large<<<dev->sm_count, 1024, SORT_LARGE_SMEM * sizeof(uint32_t), fs>>>(S.tile_offset, S.list, dev->list_cap, S.large_tiles, S.valid_count);
   size_t e2 = dev->profile ? mark(dev) : 0;
   // ---- phase 5: visibility-first (k_cover + k_shade) when every queued draw qualifies, else the immediate k_raster
   bool deferred = !dev->force_immediate;
@@ -546,15 +545,6 @@ slv_result flush_batch(slv_device dev) {
     CU(cudaEventRecord(S.ev_front_done, fs));
     CU(cudaStreamWaitEvent(st, S.ev_front_done, 0));
   }
-  if (lazy_c || lazy_d) {  // tiles without triangles get the clear values (k_cover / k_shade never visit them)
-    SurfaceRef none{};
-    k_fill_inactive_tiles<<<n_tiles, 256, 0, st>>>(lazy_c ? first.color0 : none, lazy_c ? rcol->clear_pattern : make_uint4(0, 0, 0, 0),
-                                                    lazy_d ? first.ds : none, lazy_d ? rds->clear_pattern : make_uint4(0, 0, 0, 0),
-                                                    S.tile_offset, first.tiles_x, dev->shard_rank, dev->shard_n);
-    dev->n_launches += 1;
-    if (lazy_c) rcol->clear_pending = false;
-    if (lazy_d) rds->clear_pending = false;
-  }
   uint32_t cover_grid = (uint32_t)dev->cover_grid, shade_grid = (uint32_t)dev->shade_grid;
   const bool persistent = dev->persistent >= 0 ? dev->persistent != 0 : dev->shard_n < 4;
   if (deferred && !persistent) {
@@ -584,10 +574,16 @@ slv_result flush_batch(slv_device dev) {
       case 4: ok = launch_shade_s<4>(first, S.d_batch, n, db, shade_grid, st); break;
       }
       dev->n_launches += 1;
-      if (db.resolve_dst.data) {  // fused resolve: the tiles k_shade never visits (no triangles) are resolved the plain way
-        k_resolve_inactive_tiles<<<n_tiles, 256, 0, st>>>(first.color0, db.resolve_dst, S.tile_offset, first.tiles_x, dev->shard_rank, dev->shard_n);
-        dev->n_launches += 1;
-      }
+    }
+    if (ok && (lazy_c || lazy_d || db.resolve_dst.data)) {
+      // the tiles without triangles (never visited by k_cover / k_shade): clear values and, with a fused resolve, their resolve
+      SurfaceRef none{};
+      k_inactive_tiles<<<n_tiles, 256, 0, st>>>(first.color0, lazy_c ? 1u : 0u, lazy_c ? rcol->clear_pattern : make_uint4(0, 0, 0, 0),
+                                                 lazy_d ? first.ds : none, lazy_d ? rds->clear_pattern : make_uint4(0, 0, 0, 0),
+                                                 db.resolve_dst, S.tile_offset, first.tiles_x, dev->shard_rank, dev->shard_n);
+      dev->n_launches += 1;
+      if (lazy_c) rcol->clear_pending = false;
+      if (lazy_d) rds->clear_pending = false;
     }
   } else {
     const uint32_t blocks = std::min<uint32_t>(n_tiles * 16, (uint32_t)dev->raster_grid);
@@ -689,6 +685,7 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   for (auto& S : dev->sc) {
     CU(cudaMalloc(&S.work_counter, 4 * sizeof(uint32_t)));
     CU(cudaMalloc(&S.valid_count, sizeof(uint32_t)));
+    CU(cudaMemset(S.valid_count, 0, sizeof(uint32_t)));  // k_sort_lists_large re-zeroes it at the end of every binning chain
     CU(cudaMalloc(&S.d_batch, MAX_BATCH * sizeof(RasterParams)));
     CU(cudaMalloc(&S.d_geom, MAX_BATCH * sizeof(GeomParams)));
     CU(cudaHostAlloc(&S.h_batch, MAX_BATCH * sizeof(RasterParams), cudaHostAllocDefault));

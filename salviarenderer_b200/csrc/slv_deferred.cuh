@@ -47,7 +47,7 @@ struct CovTri {  // one surviving triangle of the warp's current chunk, staged i
 struct DeferredBufs {
   // lazy clears: the whole-surface clear that preceded the batch was not executed; k_cover / k_shade start from the clear
   // value instead of loading, and write every pixel of every item of the active tiles (tiles without triangles are
-  // filled by k_fill_inactive_tiles), so depth / colour are written ONCE per frame and depth is never read
+  // filled by k_inactive_tiles), so depth / colour are written ONCE per frame and depth is never read
   uint32_t lazy_depth, lazy_color;
   float clear_z;
   uint32_t clear_st, clear_color;

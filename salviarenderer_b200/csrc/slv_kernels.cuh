@@ -706,8 +706,11 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_lists(const uint32_t* til
 
 // the few tiles whose list exceeds SORT_SMEM entries (ids compacted by k_scan_tiles): 1024 threads, dynamic shared memory
 __global__ void __launch_bounds__(1024) k_sort_lists_large(const uint32_t* tile_offset, uint32_t* list, uint32_t capacity,
-                                                           const uint32_t* large_tiles) {
+                                                           const uint32_t* large_tiles, uint32_t* valid_count) {
   extern __shared__ uint32_t s_dyn[];
+  // last kernel of the binning chain (k_bin_fill, the only reader, is done): reset the valid-slot counter for the next batch
+  // built in this scratch set, so that no memset sits at the head of the next frame's chain
+  if (blockIdx.x == 0 && threadIdx.x == 0) *valid_count = 0;
   const uint32_t n_large = large_tiles[0];
   for (uint32_t k = blockIdx.x; k < n_large; k += gridDim.x) {
     const uint32_t tile = large_tiles[1 + k];
@@ -1497,18 +1500,7 @@ __global__ void __launch_bounds__(256) k_fill_tiles(SurfaceRef s, uint4 pattern,
   fill_tile(s, pattern, tx, ty);
 }
 
-// lazy clears: the batch's k_cover / k_shade write every pixel of the tiles that have triangles; the owned tiles WITHOUT
-// triangles (empty list: tile_offset[t + 1] == tile_offset[t]) receive the clear values here.  color / ds .data == nullptr:
-// that surface has no pending clear.
-__global__ void __launch_bounds__(256) k_fill_inactive_tiles(SurfaceRef color, uint4 color_pattern, SurfaceRef ds, uint4 ds_pattern,
-                                                             const uint32_t* __restrict__ tile_offset, uint32_t tiles_x,
-                                                             uint32_t rank, uint32_t n) {
-  const uint32_t t = blockIdx.x;
-  const uint32_t tx = t % tiles_x, ty = t / tiles_x;
-  if (!tile_owned(tx, ty, rank, n) || tile_offset[t + 1] != tile_offset[t]) return;
-  if (color.data) fill_tile(color, color_pattern, tx, ty);
-  if (ds.data) fill_tile(ds, ds_pattern, tx, ty);
-}
+// (k_inactive_tiles, after k_resolve below, handles the tiles a lazily cleared / fused-resolve batch never visits)
 
 // framebuffer::clear_depth_stencil with a single flag (framebuffer.cpp:616-644)
 __global__ void k_clear_ds_partial(float2* dst, size_t n, uint32_t flags, float depth, uint32_t stencil) {
@@ -1578,16 +1570,25 @@ __global__ void k_resolve(SurfaceRef src, SurfaceRef dst, uint32_t rank, uint32_
   resolve_pixel(src, dst, x, y);
 }
 
-// fused resolve: k_shade resolved every tile it visited; the owned tiles WITHOUT triangles in the batch (empty list) are
-// resolved here, one CTA per tile (CTAs of the other tiles exit at once)
-__global__ void __launch_bounds__(256) k_resolve_inactive_tiles(SurfaceRef src, SurfaceRef dst, const uint32_t* __restrict__ tile_offset,
-                                                                uint32_t tiles_x, uint32_t rank, uint32_t n) {
+// Lazy clears / fused resolve: the batch's k_cover / k_shade write (and resolve) every pixel of the tiles that have
+// triangles; the owned tiles WITHOUT triangles (empty list: tile_offset[t + 1] == tile_offset[t]) receive the clear values
+// and are resolved here, one CTA per tile (CTAs of the other tiles exit at once).  color / ds / resolve_dst .data ==
+// nullptr: nothing to do for that surface.  Independent of k_cover / k_shade (disjoint tiles): runs after them.
+__global__ void __launch_bounds__(256) k_inactive_tiles(SurfaceRef color, uint32_t fill_color, uint4 color_pattern, SurfaceRef ds,
+                                                        uint4 ds_pattern, SurfaceRef resolve_dst,
+                                                        const uint32_t* __restrict__ tile_offset, uint32_t tiles_x, uint32_t rank,
+                                                        uint32_t n) {
   const uint32_t t = blockIdx.x;
   const uint32_t tx = t % tiles_x, ty = t / tiles_x;
   if (!tile_owned(tx, ty, rank, n) || tile_offset[t + 1] != tile_offset[t]) return;
-  for (uint32_t i = threadIdx.x; i < TILE * TILE; i += blockDim.x) {
-    const uint32_t x = tx * TILE + (i % TILE), y = ty * TILE + (i / TILE);
-    if (x < src.w && y < src.h) resolve_pixel(src, dst, x, y);
+  if (fill_color) fill_tile(color, color_pattern, tx, ty);
+  if (ds.data) fill_tile(ds, ds_pattern, tx, ty);
+  if (resolve_dst.data) {
+    __syncthreads();  // the colour fill above is read back below (same CTA)
+    for (uint32_t i = threadIdx.x; i < TILE * TILE; i += blockDim.x) {
+      const uint32_t x = tx * TILE + (i % TILE), y = ty * TILE + (i / TILE);
+      if (x < color.w && y < color.h) resolve_pixel(color, resolve_dst, x, y);
+    }
   }
 }
 
