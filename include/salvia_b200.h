@@ -236,6 +236,13 @@ slv_result slv_texture_level_size(slv_device dev, slv_handle tex, uint32_t level
 /* map(surface, map_write) + memcpy / map(surface, map_read) (resource_manager.cpp:8-54) */
 slv_result slv_texture_upload(slv_device dev, slv_handle tex, uint32_t level, const void* src, size_t bytes);
 slv_result slv_texture_readback(slv_device dev, slv_handle tex, uint32_t level, void* dst, size_t bytes);
+/* the same copy without blocking the caller (the async_renderer keeps the application running while a frame is in flight,
+ * async_renderer.cpp:42-74): enqueued on a copy stream behind everything submitted so far; `dst` (pinned host memory for a
+ * truly asynchronous copy) is valid after slv_readback_wait or slv_flush.  The next command that WRITES the texture waits for
+ * the copy on the device, so alternating two textures overlaps the readback of frame k with the rendering of frame k+1.
+ * The CPU checkers copy synchronously. */
+slv_result slv_texture_readback_async(slv_device dev, slv_handle tex, uint32_t level, void* dst, size_t bytes);
+slv_result slv_readback_wait(slv_device dev);
 /* renderer::create_sampler (renderer.h:50) */
 slv_result slv_sampler_create(slv_device dev, const slv_sampler_desc* desc, slv_handle tex, slv_handle* out);
 /* SASL shaders compiled at run time.  The reference's compile(code, profile) + set_vertex_shader_code /

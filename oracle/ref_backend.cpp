@@ -678,6 +678,10 @@ slv_result slv_event_elapsed_ms(slv_device dev, uint32_t a, uint32_t b, float* m
 }
 slv_result slv_profile_enable(slv_device, uint32_t) { return SLV_OK; }
 slv_result slv_set_stream(slv_device, void*) { return SLV_OK; }
+slv_result slv_texture_readback_async(slv_device dev, slv_handle tex, uint32_t level, void* dst, size_t bytes) {
+  return slv_texture_readback(dev, tex, level, dst, bytes);
+}
+slv_result slv_readback_wait(slv_device) { return SLV_OK; }
 // peer-memory frame assembly is a property of the CUDA product (NVLink); the CPU checkers do not implement it
 slv_result slv_peer_export_texture(slv_device, slv_handle, uint32_t, uint8_t*) { return SLV_FAILED; }
 slv_result slv_peer_export_flags(slv_device, uint8_t*) { return SLV_FAILED; }

@@ -42,6 +42,10 @@ struct Resource {
   // that renders to the surface starts from this value without reading or pre-filling it; anything else materialises it.
   bool clear_pending = false;
   uint4 clear_pattern{};
+  // textures: an asynchronous readback (slv_texture_readback_async) still reading this texture on the copy stream; the next
+  // writer of the texture waits for it on the device
+  cudaEvent_t rb_event = nullptr;
+  bool rb_pending = false;
   // shader modules (SASL shaders compiled at run time, salviarenderer_b200/sasl): the pipeline kernels with the shader inlined
   CUmodule module = nullptr;
   uint32_t module_stage = 0;        // SLV_STAGE_VS / SLV_STAGE_PS
@@ -129,6 +133,10 @@ struct slv_device_t {
   cudaEvent_t ev_sync = nullptr;        // scratch event: orders front_stream after buffer uploads on `stream`
   bool buffers_dirty = false;           // a vertex / index buffer was written on `stream` since the last front half
   bool pipeline = true;                 // SLV_PIPELINE=0: everything on `stream`
+  cudaStream_t copy_stream = nullptr;   // asynchronous readbacks (overlap the next frame's rendering)
+  cudaEvent_t ev_copy = nullptr;        // orders the copy stream after the producer of the texture on `stream`
+  cudaEvent_t ev_upload = nullptr;      // last buffer upload enqueued on front_stream
+  bool upload_on_front = false;         // ... and not yet ordered before work on `stream`
   uint32_t* peer_flags = nullptr;       // SLV_PEER_FLAGS words other ranks raise over NVLink (slv_peer_signal / slv_flags_wait)
   uint32_t* vis = nullptr;           // visibility buffer of the deferred path: owner slot per sample
   size_t vis_cap = 0;                // in uint32 units
@@ -198,11 +206,15 @@ constexpr uint32_t MAX_BATCH = MAX_BATCH_DRAWS;  // draws whose geometry / raste
 
 slv_result flush_batch(slv_device dev);
 slv_result materialize_clear(slv_device dev, Resource* r);
+slv_result wait_readback(slv_device dev, Resource* r);
 
 slv_result sync_all(slv_device dev) {  // both streams idle
   CU(cudaStreamSynchronize(dev->front_stream));
   CU(cudaStreamSynchronize(dev->stream));
+  CU(cudaStreamSynchronize(dev->copy_stream));
   for (auto& S : dev->sc) S.in_flight = false;
+  for (auto& r : dev->res) r.rb_pending = false;
+  dev->upload_on_front = false;
   return SLV_OK;
 }
 
@@ -340,10 +352,20 @@ slv_result fill_surface(slv_device dev, const SurfaceRef& s, uint4 pattern) {
 }
 
 
+// a texture about to be WRITTEN on the main stream: order the write after an asynchronous readback still copying it out
+slv_result wait_readback(slv_device dev, Resource* r) {
+  if (r && r->rb_pending) {
+    CU(cudaStreamWaitEvent(dev->stream, r->rb_event, 0));
+    r->rb_pending = false;
+  }
+  return SLV_OK;
+}
+
 // executes a recorded whole-surface clear (see Resource::clear_pending)
 slv_result materialize_clear(slv_device dev, Resource* r) {
   if (!r || !r->clear_pending) return SLV_OK;
   r->clear_pending = false;
+  { slv_result rcw = wait_readback(dev, r); if (rcw != SLV_OK) return rcw; }
   return fill_surface(dev, r->tex.level[0], r->clear_pattern);
 }
 slv_result materialize_all(slv_device dev) {
@@ -411,6 +433,10 @@ slv_result flush_batch(slv_device dev) {
       CU(cudaStreamWaitEvent(fs, S.ev_back_done, 0));
       S.in_flight = false;
     }
+  }
+  if (!piped && dev->upload_on_front) {
+    CU(cudaStreamWaitEvent(st, dev->ev_upload, 0));
+    dev->upload_on_front = false;
   }
   dev->buffers_dirty = false;
   // parameter upload: through this set's pinned staging when pipelining (no stream synchronisation; the staging is free
@@ -500,6 +526,8 @@ slv_result flush_batch(slv_device dev) {
   const bool lazy_c = shade && rcol && rcol->clear_pending && grid_covers && first.color0.w == first.target_w && first.color0.h == first.target_h;
   const bool lazy_d = deferred && rds && rds->clear_pending && first.ds.data && grid_covers && first.ds.w == first.target_w &&
                       first.ds.h == first.target_h;
+  { slv_result rcw = wait_readback(dev, rcol); if (rcw != SLV_OK) return rcw; }
+  { slv_result rcw = wait_readback(dev, rds); if (rcw != SLV_OK) return rcw; }
   if (!lazy_c) { slv_result rcm = materialize_clear(dev, rcol); if (rcm != SLV_OK) return rcm; }
   if (!lazy_d) { slv_result rcm = materialize_clear(dev, rds); if (rcm != SLV_OK) return rcm; }
   if (deferred) {
@@ -679,6 +707,9 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
     CU(cudaStreamCreateWithPriority(&dev->front_stream, cudaStreamNonBlocking, greatest));
   }
   CU(cudaEventCreateWithFlags(&dev->ev_sync, cudaEventDisableTiming));
+  CU(cudaStreamCreateWithFlags(&dev->copy_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&dev->ev_copy, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&dev->ev_upload, cudaEventDisableTiming));
   CU(cudaMalloc(&dev->overflow_flag, sizeof(uint32_t)));
   CU(cudaMalloc(&dev->peer_flags, SLV_PEER_FLAGS * sizeof(uint32_t)));
   CU(cudaMemset(dev->peer_flags, 0, SLV_PEER_FLAGS * sizeof(uint32_t)));
@@ -731,11 +762,13 @@ void slv_device_destroy(slv_device dev) {
   flush_batch(dev);
   cudaStreamSynchronize(dev->front_stream);
   cudaStreamSynchronize(dev->stream);
+  cudaStreamSynchronize(dev->copy_stream);
   for (auto& r : dev->res) {
     if (r.kind == Resource::BUFFER) cudaFree(r.dptr);
     if (r.kind == Resource::TEXTURE)
       for (uint32_t l = 0; l < r.tex.n_levels; ++l) cudaFree(r.tex.level[l].data);
     if (r.kind == Resource::MODULE && r.module) driver_api().ModuleUnload(r.module);
+    if (r.rb_event) cudaEventDestroy(r.rb_event);
   }
   for (auto& S : dev->sc) {
     cudaFree(S.tris); cudaFree(S.valid_slots); cudaFree(S.valid_count);
@@ -752,6 +785,9 @@ void slv_device_destroy(slv_device dev) {
   for (auto& ev : dev->ev_pool) cudaEventDestroy(ev);
   for (auto& ev : dev->user_ev) cudaEventDestroy(ev);
   cudaEventDestroy(dev->ev_sync);
+  cudaEventDestroy(dev->ev_copy);
+  cudaEventDestroy(dev->ev_upload);
+  cudaStreamDestroy(dev->copy_stream);
   cudaStreamDestroy(dev->front_stream);
 
   for (auto& t : dev->slot_tables) cudaFree(t.d_slot);
@@ -776,6 +812,14 @@ slv_result slv_buffer_upload(slv_device dev, slv_handle h, size_t off, const voi
   if (!r || off + bytes > r->bytes) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  if (dev->pipeline && !dev->profile) {
+    // vertex / index data is only read by the front half: upload on its stream, so the copy (and the next frame's geometry
+    // after it) does not queue behind the previous frame's raster work on the main stream
+    CU(cudaMemcpyAsync(r->dptr + off, src, bytes, cudaMemcpyHostToDevice, dev->front_stream));
+    CU(cudaEventRecord(dev->ev_upload, dev->front_stream));
+    dev->upload_on_front = true;
+    return SLV_OK;
+  }
   CU(cudaMemcpyAsync(r->dptr + off, src, bytes, cudaMemcpyHostToDevice, dev->stream));
   dev->buffers_dirty = true;  // the next front half (front_stream) must order after this copy
   return SLV_OK;
@@ -786,6 +830,10 @@ slv_result slv_buffer_readback(slv_device dev, slv_handle h, size_t off, void* d
   if (!r || off + bytes > r->bytes) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  if (dev->upload_on_front) {
+    CU(cudaStreamWaitEvent(dev->stream, dev->ev_upload, 0));
+    dev->upload_on_front = false;
+  }
   CU(cudaMemcpyAsync(dst, r->dptr + off, bytes, cudaMemcpyDeviceToHost, dev->stream));
   CU(cudaStreamSynchronize(dev->stream));
   return SLV_OK;
@@ -864,6 +912,7 @@ slv_result slv_texture_upload(slv_device dev, slv_handle h, uint32_t level, cons
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   if (level == 0) r->clear_pending = false;  // the whole level is overwritten
+  { slv_result rcw = wait_readback(dev, r); if (rcw != SLV_OK) return rcw; }
   CU(cudaMemcpyAsync(r->tex.level[level].data, src, bytes, cudaMemcpyHostToDevice, dev->stream));
   return SLV_OK;
 }
@@ -876,6 +925,28 @@ slv_result slv_texture_readback(slv_device dev, slv_handle h, uint32_t level, vo
   { slv_result rcm__ = materialize_clear(dev, r); if (rcm__ != SLV_OK) return rcm__; }
   CU(cudaMemcpyAsync(dst, r->tex.level[level].data, bytes, cudaMemcpyDeviceToHost, dev->stream));
   CU(cudaStreamSynchronize(dev->stream));
+  return check_overflow(dev);
+}
+
+slv_result slv_texture_readback_async(slv_device dev, slv_handle h, uint32_t level, void* dst, size_t bytes) {
+  auto r = dev ? dev->get(h, Resource::TEXTURE) : nullptr;
+  if (!r || level >= r->tex.n_levels || bytes != r->tex.level[level].bytes || !dst) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  { slv_result rcm__ = materialize_clear(dev, r); if (rcm__ != SLV_OK) return rcm__; }
+  if (!r->rb_event) CU(cudaEventCreateWithFlags(&r->rb_event, cudaEventDisableTiming));
+  CU(cudaEventRecord(dev->ev_copy, dev->stream));            // the texture's producers are ahead of this point
+  CU(cudaStreamWaitEvent(dev->copy_stream, dev->ev_copy, 0));
+  CU(cudaMemcpyAsync(dst, r->tex.level[level].data, bytes, cudaMemcpyDeviceToHost, dev->copy_stream));
+  CU(cudaEventRecord(r->rb_event, dev->copy_stream));
+  r->rb_pending = true;                                      // the next writer of the texture waits for the copy
+  return SLV_OK;
+}
+
+slv_result slv_readback_wait(slv_device dev) {
+  if (!dev) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  CU(cudaStreamSynchronize(dev->copy_stream));
   return check_overflow(dev);
 }
 
@@ -937,6 +1008,7 @@ slv_result slv_resource_release(slv_device dev, slv_handle h) {
   if (r.kind == Resource::TEXTURE)
     for (uint32_t l = 0; l < r.tex.n_levels; ++l) CU(cudaFree(r.tex.level[l].data));
   if (r.kind == Resource::MODULE && r.module) driver_api().ModuleUnload(r.module);
+  if (r.rb_event) { CU(cudaStreamSynchronize(dev->copy_stream)); cudaEventDestroy(r.rb_event); }
   r = Resource();
   return SLV_OK;
 }
@@ -1204,6 +1276,7 @@ slv_result slv_clear_color(slv_device dev, slv_handle h, const float rgba[4]) {
     r->clear_pattern = make_uint4(w[0], w[1], w[2], w[3]);
     return SLV_OK;
   }
+  { slv_result rcw = wait_readback(dev, r); if (rcw != SLV_OK) return rcw; }
   return fill_surface(dev, s, make_uint4(w[0], w[1], w[2], w[3]));
 }
 
@@ -1222,9 +1295,11 @@ slv_result slv_clear_depth_stencil(slv_device dev, slv_handle h, uint32_t flags,
       r->clear_pattern = make_uint4(dbits, stencil, dbits, stencil);
       return SLV_OK;
     }
+    { slv_result rcw = wait_readback(dev, r); if (rcw != SLV_OK) return rcw; }
     return fill_surface(dev, s, make_uint4(dbits, stencil, dbits, stencil));
   }
   { slv_result rcm__ = materialize_clear(dev, r); if (rcm__ != SLV_OK) return rcm__; }
+  { slv_result rcw = wait_readback(dev, r); if (rcw != SLV_OK) return rcw; }
   size_t n = s.bytes / 8;
   uint32_t blocks = (uint32_t)std::min<size_t>((n + 255) / 256, 148 * 16);
   k_clear_ds_partial<<<blocks, 256, 0, dev->stream>>>(reinterpret_cast<float2*>(s.data), n, flags, depth, stencil);
@@ -1243,6 +1318,7 @@ slv_result slv_resolve(slv_device dev, slv_handle src, slv_handle dst) {
   CU(cudaSetDevice(dev->ordinal));
   SurfaceRef t2 = t;
   if (rd->resolve_peer && dev->shard_n > 1) t2.data = rd->resolve_peer;  // owned tiles go straight to the root's surface
+  { slv_result rcw = wait_readback(dev, rd); if (rcw != SLV_OK) return rcw; }
   // the pending batch renders to `src`: its k_shade can write the resolved texels itself (fused resolve)
   if (dev->fuse_resolve && !dev->pending.empty() && dev->pending[0].color0.data == s.data && rd != rs) {
     { slv_result rcm__ = materialize_clear(dev, rd); if (rcm__ != SLV_OK) return rcm__; }
@@ -1273,6 +1349,7 @@ slv_result slv_flush(slv_device dev) {
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   { slv_result rcm__ = materialize_all(dev); if (rcm__ != SLV_OK) return rcm__; }
   CU(cudaStreamSynchronize(dev->stream));
+  CU(cudaStreamSynchronize(dev->copy_stream));  // asynchronous readbacks have landed too
   return check_overflow(dev);
 }
 
@@ -1442,6 +1519,7 @@ static slv_result pack_common(slv_device dev, slv_handle tex, uint32_t rank, uin
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   { slv_result rcm__ = materialize_clear(dev, r); if (rcm__ != SLV_OK) return rcm__; }
+  if (unpack) { slv_result rcw = wait_readback(dev, r); if (rcw != SLV_OK) return rcw; }
   k_pack_tiles<<<n_tiles, 256, 0, dev->stream>>>(s, tiles_x, tiles_y, rank, nranks, (uint8_t*)staging, tab->d_slot, unpack);
   ++dev->n_launches;
   CU(cudaGetLastError());
