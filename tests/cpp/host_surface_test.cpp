@@ -1,0 +1,116 @@
+// Drives the C++ host surface (salviarenderer_b200/host/salvia_b200_renderer.hpp) the way samples/ColorizedTriangle does:
+// a two-triangle plane, vs_lights3 / ps_lights3 / bs_replace, 4x MSAA + resolve, one textured blended quad on top.
+// Prints FNV-1a hashes of the colour / depth / resolved buffers and the pipeline statistics, so the Python test can run the
+// same program against two libraries (CUDA product vs CPU checker) and demand identical output.
+//   usage: host_surface_test <library.so> [width height samples]
+#include <cinttypes>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "salvia_b200_renderer.hpp"
+
+using namespace salvia_b200;
+
+static uint64_t fnv(const void* p, size_t n) {
+  const uint8_t* b = static_cast<const uint8_t*>(p);
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+static mat44 mul(mat44 const& a, mat44 const& b) {
+  mat44 r;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) { float s = 0; for (int k = 0; k < 4; ++k) s += a.m[i][k] * b.m[k][j]; r.m[i][j] = s; }
+  return r;
+}
+#define CHECK(e) do { if ((e) != result::ok) { std::fprintf(stderr, "FAILED: %s (line %d)\n", #e, __LINE__); return 2; } } while (0)
+
+int main(int argc, char** argv) {
+  if (argc < 2) { std::fprintf(stderr, "usage: %s <library.so> [w h samples]\n", argv[0]); return 1; }
+  const size_t W = argc > 3 ? std::atoi(argv[2]) : 320, H = argc > 3 ? std::atoi(argv[3]) : 240, S = argc > 4 ? std::atoi(argv[4]) : 4;
+  renderer_ptr r = create_b200_renderer(argv[1]);
+  std::printf("backend %s\n", r->backend_name().c_str());
+
+  // targets (ColorizedTriangle.cpp:109-141)
+  texture_ptr color = r->create_tex2d(W, H, S, pixel_format_color_rgba8), ds = r->create_tex2d(W, H, S, pixel_format_color_rg32f);
+  texture_ptr resolved = r->create_tex2d(W, H, 1, pixel_format_color_rgba8);
+  surface_ptr cs = color->subresource(0), dss = ds->subresource(0);
+  CHECK(r->set_render_targets(1, &cs, dss));
+  CHECK(r->set_viewport(viewport{0, 0, (float)W, (float)H, 0.0f, 1.0f}));
+  if (r->set_viewport(viewport{-1, 0, 1, 1, 0, 1}) != result::failed) return 3;             // renderer_impl.cpp:145-152
+  if (r->set_index_buffer(nullptr, format_r32_float) != result::failed) return 3;           // renderer_impl.cpp:49-54
+
+  // geometry: create_planar-like quad, positions + normals in two streams, u16 indices
+  const float pos[4][4] = {{-3, -1, -3, 1}, {3, -1, -3, 1}, {-3, -1, 3, 1}, {3, -1, 3, 1}};
+  const float nrm[4][4] = {{0, 1, 0, 0}, {0, 1, 0, 0}, {0, 1, 0, 0}, {0, 1, 0, 0}};
+  const uint16_t idx[6] = {0, 2, 1, 1, 2, 3};
+  buffer_ptr vb0 = r->create_buffer(sizeof(pos)), vb1 = r->create_buffer(sizeof(nrm)), ib = r->create_buffer(sizeof(idx));
+  CHECK(vb0->transfer(0, pos, 16, 4));
+  CHECK(vb1->transfer(0, nrm, 16, 4));
+  {  // the index buffer through map / unmap
+    mapped_resource m;
+    CHECK(r->map(m, ib, map_write));
+    std::memcpy(m.data, idx, sizeof(idx));
+    CHECK(r->unmap());
+  }
+  auto vs = std::make_shared<vs_lights3>();
+  input_element_desc descs[] = {{"POSITION", 0, format_r32g32b32a32_float, 0, 0}, {"NORMAL", 0, format_r32g32b32a32_float, 1, 0},
+                                {"TEXCOORD", 0, format_r32g32b32a32_float, 2, 0}};  // the last one is not read by the shader
+  input_layout_ptr layout = r->create_input_layout(descs, 3, vs);
+  if (layout->elements.size() != 2) return 3;
+  buffer_ptr bufs[2] = {vb0, vb1};
+  size_t strides[2] = {16, 16}, offsets[2] = {0, 0};
+  CHECK(r->set_vertex_buffers(0, 2, bufs, strides, offsets));
+  CHECK(r->set_index_buffer(ib, format_r16_uint));
+  CHECK(r->set_input_layout(layout));
+  CHECK(r->set_primitive_topology(primitive_triangle_list));
+  CHECK(r->set_vertex_shader(vs));
+  CHECK(r->set_pixel_shader(std::make_shared<ps_lights3>()));
+  CHECK(r->set_blend_shader(std::make_shared<bs_replace>()));
+  CHECK(r->set_rasterizer_state(std::make_shared<raster_state>(raster_desc{cull_none, false})));
+
+  // constants by name: a wrong type or an unknown name must fail (shader_utility.h:45-74)
+  mat44 view, proj;  // look at the plane from above / front, perspective
+  view.m[3][1] = 0.2f; view.m[3][2] = 4.0f; view.m[1][1] = 0.8f; view.m[1][2] = 0.6f; view.m[2][1] = -0.6f; view.m[2][2] = 0.8f;
+  const float f = 1.0f / std::tan(0.785398163f), a = (float)W / (float)H, zn = 0.1f, zf = 100.0f;
+  proj = mat44{}; proj.m[0][0] = f / a; proj.m[1][1] = f; proj.m[2][2] = zf / (zf - zn); proj.m[2][3] = 1.0f; proj.m[3][2] = -zn * zf / (zf - zn); proj.m[3][3] = 0.0f;
+  mat44 wvp = mul(view, proj);
+  CHECK(r->set_vs_variable("wvpMatrix", &wvp));
+  vec4 l0{2, 2, 0, 1}, l1{-2, 1, 2, 1}, l2{0, 3, -2, 1};
+  CHECK(r->set_vs_variable("lightPos0", &l0));
+  CHECK(r->set_vs_variable("lightPos1", &l1));
+  CHECK(r->set_vs_variable("lightPos2", &l2));
+  float wrong = 1.0f;
+  if (r->set_vs_variable("lightPos0", &wrong) != result::failed) return 3;   // size / type mismatch
+  if (r->set_vs_variable("Shininess", &wrong) != result::failed) return 3;   // unknown name
+  if (vs->set_constant("wvpMatrix", &l0) != result::failed) return 3;        // typed by name
+
+  async_object_ptr q = r->create_query(async_object_ids::pipeline_statistics);
+  CHECK(r->begin(q));
+  CHECK(r->clear_color(cs, color_rgba32f{0.2f, 0.2f, 0.5f, 1.0f}));
+  CHECK(r->clear_depth_stencil(dss, clear_depth | clear_stencil, 1.0f, 0));
+  CHECK(r->draw_index(0, 2, 0));
+  CHECK(r->end(q));
+  pipeline_statistics st{};
+  if (r->get_data(q, &st, false) != async_status::ready) return 3;
+  CHECK(cs->resolve(*resolved->subresource(0)));
+  CHECK(r->flush());
+
+  mapped_resource m;
+  CHECK(r->map(m, cs, map_read));
+  const uint64_t hc = fnv(m.data, cs->bytes());
+  CHECK(r->unmap());
+  CHECK(r->map(m, dss, map_read));
+  const uint64_t hd = fnv(m.data, dss->bytes());
+  CHECK(r->unmap());
+  CHECK(r->map(m, resolved->subresource(0), map_read));
+  const uint64_t hr = fnv(m.data, resolved->subresource(0)->bytes());
+  CHECK(r->unmap());
+  if (r->unmap() != result::failed) return 3;  // nothing mapped
+  std::printf("color %016" PRIx64 " depth %016" PRIx64 " resolved %016" PRIx64 "\n", hc, hd, hr);
+  std::printf("stats ia_vertices %" PRIu64 " ia_primitives %" PRIu64 " cinvocations %" PRIu64 " cprimitives %" PRIu64 " ps_invocations %" PRIu64 "\n",
+              st.ia_vertices, st.ia_primitives, st.cinvocations, st.cprimitives, st.ps_invocations);
+  if (st.ia_primitives != 2 || st.cprimitives == 0 || st.ps_invocations == 0) return 4;
+  return 0;
+}

@@ -1,0 +1,46 @@
+"""The C++ host surface (salviarenderer_b200/host/salvia_b200_renderer.hpp — the mirror of salvia::core::renderer over the C
+ABI): tests/cpp/host_surface_test.cpp renders through it and prints buffer hashes and counters.  The SAME binary is run
+against different libraries and must print the same lines: CPU checkers here, the CUDA product on the GPU box."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ORACLE_LIB, PRODUCT_LIB, REF_LIB, ROOT
+
+
+@pytest.fixture(scope="module")
+def host_binary(built, tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("host") / "host_surface_test")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    "-I" + os.path.join(ROOT, "salviarenderer_b200", "host"), os.path.join(ROOT, "tests", "cpp", "host_surface_test.cpp"),
+                    "-o", exe, "-ldl"], check=True)
+    return exe
+
+
+def run(exe, lib, *size):
+    out = subprocess.run([exe, lib, *map(str, size)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.strip().splitlines()
+    return lines[0], lines[1:]
+
+
+@pytest.mark.parametrize("size", [(320, 240, 4), (200, 120, 1)])
+def test_cpp_surface_oracle_equals_reference(host_binary, size):
+    name_o, out_o = run(host_binary, ORACLE_LIB, *size)
+    assert name_o == "backend oracle"
+    if not os.path.exists(REF_LIB):
+        pytest.skip("reference library not built here")
+    name_r, out_r = run(host_binary, REF_LIB, *size)
+    assert name_r == "backend reference"
+    assert out_o == out_r
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", [(320, 240, 4), (1000, 600, 2), (200, 120, 1)])
+def test_cpp_surface_product_equals_checker(host_binary, size):
+    name_p, out_p = run(host_binary, PRODUCT_LIB, *size)
+    assert name_p == "backend cuda-sm100a"
+    checker = REF_LIB if os.path.exists(REF_LIB) else ORACLE_LIB
+    _, out_c = run(host_binary, checker, *size)
+    assert out_p == out_c
