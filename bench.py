@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--tex-size", type=int, default=1024)
     ap.add_argument("--aniso", type=int, default=0, help="max anisotropy (0 = trilinear, as samples/Sponza)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the SASL-shader variants of the workload")
     ap.add_argument("--cpu-baseline-frames", type=int, default=2)
     return ap.parse_args()
 
@@ -338,6 +339,11 @@ def main():
                 "note": "kernel times from CUDA events around each kernel (slv_profile_get_stages) in a separate pass over the same "
                         "K frames; `frame` divides the whole frame's algorithmic bytes (SURVEY 8d) by the headline ms_per_step"}
 
+    # ---- variants (N == 1): the same frames with SASL shaders compiled at run time ----
+    variants = None
+    if n == 1 and not args.no_variants:
+        variants = run_variants(args, be, sc, timed)
+
     # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample (rank 0, N == 1) ----
     cpu_baseline = None
     if rank == 0 and n == 1 and not args.no_cpu_baseline:
@@ -357,12 +363,90 @@ def main():
                     "what": e2e_how},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "variants": variants,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
     if n > 1:
         fg.close()
         dist.destroy_process_group()
+
+
+SASL_VS_SPONZA = """
+float4x4 wvpMatrix; float4 lightPos; float4 eyePos;
+struct VSIn  { float4 pos: POSITION; float4 tex: TEXCOORD0; float4 norm: NORMAL; };
+struct VSOut { float4 pos: sv_position; float4 tex: TEXCOORD0; float4 norm: TEXCOORD1; float4 lightDir: TEXCOORD2; float4 eyeDir: TEXCOORD3; };
+VSOut vs_main(VSIn in) {
+    VSOut o;
+    o.norm = in.norm; o.pos = mul(in.pos, wvpMatrix); o.lightDir = lightPos - in.pos; o.eyeDir = eyePos - in.pos; o.tex = in.tex;
+    return o;
+}
+"""
+SASL_PS_SPONZA = """
+sampler texSamp;
+struct PSIn { float4 tex: TEXCOORD0; float4 norm: TEXCOORD1; float4 lightDir: TEXCOORD2; float4 eyeDir: TEXCOORD3; };
+float4 ps_main(PSIn in): COLOR {
+    float4 diff = tex2D(texSamp, in.tex.xy);
+    float illum = clamp(dot(normalize(in.lightDir.xyz), normalize(in.norm.xyz)), 0.0f, 1.0f);
+    return float4(diff.xyz * illum, 1.0f);
+}
+"""
+
+
+def run_variants(args, be, sc, timed):
+    """The workload with SASL shaders compiled at run time (salviarenderer_b200/sasl): (1) the sample's SASL vertex shader in
+    place of its cpp twin — samples/Sponza runs exactly this pair (SASL VS + cpp PS); (2) additionally a SASL pixel shader
+    (tex2D = sample_2d_grad) with 16x anisotropic samplers — the only way the reference can filter anisotropically (SURVEY
+    App. B #6); SASL pixel shaders take the immediate k_raster path.  Reported beside the headline, never instead of it."""
+    import numpy as np
+    from salviarenderer_b200 import abi as A, scenes
+    out = {}
+    try:
+        from salviarenderer_b200.sasl import jit
+        steps = max(10, min(args.steps, 60))
+        vs = jit.compile(SASL_VS_SPONZA, "vs")
+        vs_mod = jit.load(be, vs)
+
+        def vs_binding(wvp, light, eye):
+            return A.shader_binding(A.program_jit(vs_mod), vs.unit.pack_uniforms(
+                {"wvpMatrix": np.asarray(wvp, np.float32).reshape(4, 4), "lightPos": light, "eyePos": eye}))
+
+        sc.vs_binding = vs_binding
+        sc._draw_cache = {}
+        for i in range(3):
+            sc.render(be, i)
+        ms = timed(lambda i: sc.render(be, i % sc.n_frames), steps) / steps
+        out["sasl_vertex_shader"] = {"frames_per_sec": 1e3 / ms, "ms_per_step": ms, "steps": steps,
+                                     "what": "SASL vertex shader (JIT module) + built-in pixel shader, trilinear"}
+        sc.vs_binding = None
+        sc._draw_cache = {}
+
+        ps = jit.compile(SASL_PS_SPONZA, "ps")
+        ps_mod = jit.load(be, ps)
+        sc2 = scenes.SponzaLike(args.width, args.height, args.samples, tex_size=args.tex_size, max_aniso=16)
+        sc2.setup(be)
+        sc2.vs_binding = vs_binding
+        draws = {}
+
+        def render2(i):
+            f = i % sc2.n_frames
+            if f not in draws:
+                ds = sc2.frame_draws(be, f)
+                for d, (m, _, _) in zip(ds, sc2.groups):
+                    d.ps = A.shader_binding(A.program_jit(ps_mod), b"", [sc2.samplers[m]])
+                draws[f] = ds
+            sc2.render(be, f)
+
+        for i in range(3):
+            render2(i)
+        steps2 = max(5, steps // 3)
+        ms2 = timed(render2, steps2) / steps2
+        out["sasl_vs_ps_aniso16"] = {"frames_per_sec": 1e3 / ms2, "ms_per_step": ms2, "steps": steps2,
+                                     "what": "SASL vertex + pixel shader (tex2D with per-pixel derivatives), 16x anisotropic samplers, "
+                                             "immediate k_raster path"}
+    except Exception as e:  # noqa: BLE001 - e.g. no nvcc on the box: the variants are optional
+        out["error"] = f"{type(e).__name__}: {e}"[:300]
+    return out
 
 
 def run_cpu_baseline(args):

@@ -451,6 +451,89 @@ class TextureAndBlending:
 
 
 # ===========================================================================================================
+# C5: two-pass height field (the mesh and pass structure of BASELINE configs[4]: StandardShadowMap + 10 M triangles)
+# ===========================================================================================================
+class HeightFieldTwoPass:
+    """a seeded (10000019) jittered height field of nx x nz quads (shared vertices, u32 indices; xz jitter and
+    height uniform in +-0.2 cell) — 2500 x 2000 quads = 10,000,000 triangles at full size — drawn in two passes like
+    samples/StandardShadowMap/StandardShadowMap.cpp:212-260: pass 1 depth-only from the light into an rg32f texture of the
+    screen size with NO colour target (the shadow map), pass 2 from the camera with colour + depth.  The binning / raster
+    stress of the config.  Pass 2 is lit with the ColorizedTriangle shaders: the sample's exponential-shadow pixel shader
+    (exp / log / pow on a 9-tap tex2dlod) is not part of this scene.  FrameResult.count carries the shadow map's depth."""
+
+    def __init__(self, w=7680, h=4320, samples=1, nx=2500, nz=2000, seed=10000019):
+        self.w, self.h, self.samples, self.nx, self.nz = w, h, samples, nx, nz
+        rng = np.random.default_rng(seed)
+        gx, gz = np.meshgrid(np.arange(nx + 1, dtype=np.float64), np.arange(nz + 1, dtype=np.float64))
+        jx = rng.uniform(-0.2, 0.2, size=gx.shape)
+        jz = rng.uniform(-0.2, 0.2, size=gx.shape)
+        hy = rng.uniform(-0.2, 0.2, size=gx.shape)
+        cell = 20.0 / max(nx, nz)
+        px = ((gx + jx) - nx / 2.0) * cell
+        pz = ((gz + jz) - nz / 2.0) * cell
+        py = hy * cell
+        pos = np.stack([px, py, pz, np.ones_like(px)], -1).reshape(-1, 4).astype(f32)
+        # normals from the un-jittered height differences (any fixed normal field does: it is an input, not a result)
+        ny_ = np.ones_like(px)
+        nxv = np.gradient(py, axis=1) / cell
+        nzv = np.gradient(py, axis=0) / cell
+        nrm = np.stack([-nxv, ny_, -nzv, np.zeros_like(px)], -1).reshape(-1, 4).astype(f32)
+        i0 = (np.arange(nz)[:, None] * (nx + 1) + np.arange(nx)[None, :]).reshape(-1).astype(np.uint32)
+        tri = np.stack([i0, i0 + (nx + 1), i0 + 1, i0 + 1, i0 + (nx + 1), i0 + (nx + 2)], -1).reshape(-1)
+        self.mesh = Mesh([pos, nrm], [(0, _V4, 0, 0, 1.0), (1, _V4, 1, 0, 0.0)], tri.astype(np.uint32), 2 * nx * nz)
+        self.n_frames = 3
+
+    def setup(self, be: A.Backend):
+        self.t = create_targets(be, self.w, self.h, self.samples, A.PF_BGRA8)
+        self.shadow = be.create_texture(self.w, self.h, self.samples, A.PF_RG32F)
+        self.mesh.upload(be)
+
+    def frame_uniforms(self, frame):
+        ang = 0.3 + 0.45 * frame
+        camera = (math.cos(ang) * 6.0, 4.5, math.sin(ang) * 6.0)
+        aspect = f32(self.w) / f32(self.h)
+        cam = mat_mul(mat_lookat(camera, (0, 0, 0), (0, 1, 0)), mat_perspective_fov(math.pi / 3, aspect, 0.1, 100.0))
+        light_pos = (3.0, 9.0, -2.0)
+        light = mat_mul(mat_lookat(light_pos, (0, 0, 0), (0, 0, 1)), mat_perspective_fov(math.pi / 2, aspect, 0.1, 100.0))
+        lights = [(light_pos[0], light_pos[1], light_pos[2], 0.0), (-4.0, 3.0, 4.0, 0.0), (0.0, 2.0, -6.0, 0.0)]
+        return cam, light, lights
+
+    def render(self, be: A.Backend, frame: int):
+        t = self.t
+        cam, light, lights = self.frame_uniforms(frame)
+        # ---- pass 1: depth only, from the light, into the shadow map (no colour target)
+        be.clear_depth_stencil(self.shadow, A.CLEAR_DEPTH | A.CLEAR_STENCIL, 1.0, 0)
+        d = base_desc(t, self.w, self.h, cull=A.CULL_NONE)
+        d.n_color_targets = 0
+        d.ds_target = self.shadow.handle
+        self.mesh.fill_desc(be, d)
+        d.vs = A.shader_binding(A.VS_LIGHTS3, pack_vs_lights3(light, lights))
+        d.ps = A.shader_binding(A.PS_LIGHTS3)
+        d.bs = A.shader_binding(A.BS_REPLACE)
+        be.draw(d)
+        # ---- pass 2: colour + depth from the camera
+        be.clear_color(t.color, (0.2, 0.2, 0.5, 1.0))
+        be.clear_depth_stencil(t.ds, A.CLEAR_DEPTH | A.CLEAR_STENCIL, 1.0, 0)
+        d = base_desc(t, self.w, self.h, cull=A.CULL_BACK)
+        self.mesh.fill_desc(be, d)
+        d.vs = A.shader_binding(A.VS_LIGHTS3, pack_vs_lights3(cam, lights))
+        d.ps = A.shader_binding(A.PS_LIGHTS3)
+        d.bs = A.shader_binding(A.BS_REPLACE)
+        be.draw(d)
+        if t.resolved is not None:
+            be.resolve(t.color, t.resolved)
+
+    def run(self, be: A.Backend, frame: int) -> FrameResult:
+        be.query_begin()
+        self.render(be, frame)
+        stats = be.query_get()
+        res = read_frame(be, self.t, stats)
+        sm = be.read_texture(self.shadow)
+        res.count = sm.view(np.float32).reshape(sm.shape[0], sm.shape[1], sm.shape[2], 2)[..., 0].copy()
+        return res
+
+
+# ===========================================================================================================
 # triangle soup: seeded random triangles that cross the near/far planes, every cull/depth/stencil variant
 # ===========================================================================================================
 class TriangleSoup:

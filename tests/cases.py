@@ -56,6 +56,13 @@ for _sop in range(1, 9):
     CASES[f"soup_stencil_op{_sop}_fn{_f}_s2"] = (
         lambda sop=_sop, f=_f: S.TriangleSoup(samples=2, ds=_stencil_ds(sop, f), stencil_ref=5), (0,))
 
+# configs[4]: the two-pass height-field mesh (shadow-map pass without a colour target + colour pass), reduced size.
+# Kept LAST: the reference's clipper over-runs its fan loop (clipper.cpp:75-89) and copies whatever
+# lies behind a 5-entry stack array into other primitives' result slots; which garbage that is depends on what ran before
+# in the process, and with these scenes ahead of the clipping-heavy soup cases the reference was observed to segfault.
+CASES["c5_heightfield_two_pass_640x360"] = (lambda: S.HeightFieldTwoPass(640, 360, 1, nx=125, nz=100), (0, 2))
+CASES["c5_heightfield_two_pass_320x180x4"] = (lambda: S.HeightFieldTwoPass(320, 180, 4, nx=60, nz=48), (1,))
+
 # cases small enough for the CPU suite to run against the reference / oracle in seconds
 CPU_CASES = [k for k in CASES if "1920x1080" not in k]
 
