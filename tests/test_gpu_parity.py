@@ -216,3 +216,29 @@ def test_deferred_full_size_sponza_equals_immediate(cuda, cuda_immediate):
     b.setup(cuda_immediate)
     for f in (0, 6):
         assert not cases.compare_frames(a.run(cuda, f), b.run(cuda_immediate, f))
+
+
+@pytest.mark.timeout(900)
+def test_heightfield_two_pass_large(cuda):
+    """configs[4] mesh at a size the checkers cannot render in seconds (1.6 M triangles, 3840x2160, two passes): properties
+    instead of a pixel oracle — exact counters of the input assembler, run-to-run determinism of every buffer, agreement of
+    the covered-pixel sets of depth and colour, and the shadow pass leaving the colour target untouched."""
+    import numpy as np
+    from salviarenderer_b200 import scenes as S
+    sc = S.HeightFieldTwoPass(3840, 2160, 1, nx=1000, nz=800)
+    sc.setup(cuda)
+    a = sc.run(cuda, 1)
+    b = sc.run(cuda, 1)
+    n_tri = 2 * 1000 * 800
+    assert a.stats["ia_primitives"] == 2 * n_tri and a.stats["ia_vertices"] == 6 * n_tri and a.stats["cinvocations"] == 2 * n_tri
+    assert 0 < a.stats["cprimitives"] <= 3 * 2 * n_tri and a.stats["ps_invocations"] > 1_000_000
+    for k in ("color", "depth", "stencil", "count"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert a.stats == b.stats
+    covered = a.depth[..., 0] < 1.0
+    clear = np.array([128, 51, 51, 255], np.uint8)  # bgra8 of (0.2, 0.2, 0.5, 1)
+    is_clear = (a.color[:, :, 0, :] == clear).all(-1)
+    assert covered.mean() > 0.3
+    assert not is_clear[covered].any() or is_clear[covered].mean() < 1e-3   # lit terrain is never exactly the clear colour
+    assert is_clear[~covered].all()
+    assert (a.count[..., 0] < 1.0).mean() > 0.2                             # the shadow map was written by the depth-only pass
