@@ -71,10 +71,11 @@ RANK = {"bool": 0, "int": 1, "uint": 2, "float": 3}
 
 
 def parse_type_name(s: str):
-    m = re.fullmatch(r"(float|int|uint|bool|half|double)(?:([1-4])(?:x([1-4]))?)?", s)
+    m = re.fullmatch(r"(float|int|uint|bool|half|double|int8_t|int16_t|int32_t|int64_t|uint8_t|uint16_t|uint32_t|uint64_t)(?:([1-4])(?:x([1-4]))?)?", s)
     if not m:
         return None
-    base = {"half": "float", "double": "float"}.get(m.group(1), m.group(1))
+    base = m.group(1)
+    base = {"half": "float", "double": "float"}.get(base, "uint" if base.startswith("uint") else ("int" if base.startswith("int") else base))
     if m.group(3):
         return mat(base, int(m.group(2)), int(m.group(3)))
     if m.group(2):
@@ -153,7 +154,7 @@ def norm_semantic(s: str | None):
 
 
 class Parser:
-    ASSIGN_OPS = {"=", "+=", "-=", "*=", "/=", "%="}
+    ASSIGN_OPS = {"=", "+=", "-=", "*=", "/=", "%=", "&=", "|=", "^=", "<<=", ">>="}
     BIN_PREC = [("||",), ("&&",), ("|",), ("^",), ("&",), ("==", "!="), ("<", ">", "<=", ">="), ("<<", ">>"), ("+", "-"), ("*", "/", "%")]
 
     def __init__(self, src):
@@ -519,8 +520,8 @@ class Gen:
         self.loop_depth = 0
         self.divergent = 0   # > 0 while emitting code under a data-dependent branch or loop
         self.cur_ret: Value | None = None
-        self.entry = self.pick_entry(entry)
-        self.refl.entry = self.entry.name
+        self.entry = None if stage == "lib" else self.pick_entry(entry)
+        self.refl.entry = self.entry.name if self.entry else ""
 
     # ---- helpers
     def err(self, node, msg):
@@ -1224,7 +1225,7 @@ class Gen:
             self.gen_function(f)
             if f is self.entry:
                 break
-        wrapper = self.gen_vs_wrapper() if self.stage == "vs" else self.gen_ps_wrapper()
+        wrapper = [] if self.stage == "lib" else (self.gen_vs_wrapper() if self.stage == "vs" else self.gen_ps_wrapper())
         code = "\n".join(header + self.lines + wrapper) + "\n"
         return ShaderUnit(self.stage, code, self.refl, self.src)
 
@@ -1337,8 +1338,8 @@ def _Lit(v: Value) -> Node:
 
 def compile_shader(source: str, stage: str, entry: str | None = None) -> ShaderUnit:
     """stage: 'vs' or 'ps' (the reference's compile(code, profile): salvia/include/salvia/core/renderer.h:136-147)."""
-    if stage not in ("vs", "ps"):
-        raise ValueError("stage must be 'vs' or 'ps'")
+    if stage not in ("vs", "ps", "lib"):
+        raise ValueError("stage must be 'vs', 'ps' or 'lib' (functions only, no entry point: the reference's *.ss test units)")
     g = Gen(source, stage, entry)
     unit = g.run()
     if stage == "ps" and len(unit.reflection.samplers) > 1:

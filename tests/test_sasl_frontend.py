@@ -245,3 +245,50 @@ def test_texture_shader_reflection():
     r = unit.reflection
     assert r.samplers == ["texSamp"] and r.uses_derivatives and r.uniform("alpha")[2:] == (0, 4)
     assert "sasl_tex2d_grad" in unit.code and "sasl_ddx" in unit.code
+
+
+# The reference's own SASL test units (sasl/test/repo) and the shadow-map sample's shaders: the ones inside the supported
+# subset must go through the front end AND the generated code must compile (host C++).  Read in place, never copied;
+# skipped where /root/reference does not exist (the GPU box).
+REFERENCE_UNITS_OK = [
+    "arithmetic.sps", "arithmetic.ss", "array_and_index.ss", "assigns.ss", "bit_ops.ss", "branches.sps", "casts.ss", "comments.ss",
+    "constructors.ss", "ddx_ddy.sps", "decl.ss", "deps.ss", "do_while.sps", "empty.ss", "for_loop.sps", "host_intrinsic_detection.ss",
+    "initializer.ss", "intrinsics.sps", "intrinsics.svs", "local_var.ss", "null.ss", "swizzle.ss", "swizzle_and_wm.sps", "tex.sps",
+    "unary_operators.ss", "vec_and_mat.sps", "vec_and_mat.svs", "while.sps",
+]
+REFERENCE_UNITS_REJECTED = {  # outside the subset (or erroneous on purpose upstream): must fail with CompileError, not crash
+    "incomplete.ss", "semantic_errors.ss", "preprocessors.ss", "include_main.ss", "function.ss", "scalar.sps", "tex.svs",
+}
+
+
+def _ref_unit(name):
+    import os
+    for d in ("/root/reference/sasl/test/repo", "/root/reference/resources/ssm"):
+        p = os.path.join(d, name)
+        if os.path.exists(p):
+            return open(p, errors="replace").read()
+    pytest.skip("reference tree not present")
+
+
+@pytest.mark.parametrize("name", REFERENCE_UNITS_OK + ["Draw.savs", "GenSM.savs", "GenSM.saps"])
+def test_reference_sasl_units_compile(name, tmp_path):
+    import subprocess
+    from sasl_host import RT_DIR
+    ext = name.rsplit(".", 1)[1]
+    stage = "vs" if ext in ("svs", "savs") else ("ps" if ext in ("sps", "saps") else "lib")
+    unit = compile_shader(_ref_unit(name), stage)
+    src = tmp_path / "u.cpp"
+    body = unit.code
+    if stage == "lib":  # functions only: instantiate nothing, but the code must parse and type-check
+        body = "namespace slv { struct RasterParams; }\n" + body
+    src.write_text('#include "sasl_rt.h"\n' + body + "\nint main() { return 0; }\n")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I" + RT_DIR, str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", sorted(REFERENCE_UNITS_REJECTED))
+def test_reference_sasl_units_outside_subset_fail_cleanly(name):
+    ext = name.rsplit(".", 1)[1]
+    stage = "vs" if ext == "svs" else ("ps" if ext == "sps" else "lib")
+    with pytest.raises(CompileError):
+        compile_shader(_ref_unit(name), stage)
