@@ -86,6 +86,10 @@ enum {
   /* pos = in[0]·wvp; attr0 = in[1] (uv); attr1 = in[2] (normal); attr2 = lightPos − in[0];
    * attr3 = eyePos − in[0]  (Sponza.cpp:64-97).  uniforms: mat44 wvp; vec4 lightPos; vec4 eyePos   */
   SLV_VS_SPONZA = 4,
+  /* vertex texture fetch (samples/VertexTextureFetch/VertexTextureFetch.cpp:38-61): uv = offset + in[1].xy * scale;
+   * d = tex2Dlod(samplers[0], float4(uv, 0, 0)).x = sampler::sample_2d_lod(uv, 0); pos = float4(in[0].xyz + (0, d*20, 0), 1)·wvp;
+   * attr0 = (d, 0, 0, 0).   uniforms: mat44 wvp; vec2 terrainOffset; vec2 terrainScale; vs.samplers[0] = the height map  */
+  SLV_VS_TERRAIN_VTF = 5,
   SLV_VS_JIT = 255          /* a SASL vertex shader compiled at run time; select it with SLV_PROGRAM_JIT(module) */
 };
 enum {
@@ -100,6 +104,7 @@ enum {
    * required for anisotropic filtering.  uniforms: u32 reg; f32 alpha       */
   SLV_PS_TEX_GRAD_ALPHA = 5,
   SLV_PS_DISCARD_ALL = 6,   /* returns false for every pixel (early-Z quirk probe, App. B #3)       */
+  SLV_PS_HEIGHT_COLOR = 7,  /* colour ramp over attr0.x (VertexTextureFetch.cpp:70-113)          no uniforms */
   SLV_PS_JIT = 255          /* a SASL pixel shader compiled at run time; select it with SLV_PROGRAM_JIT(module) */
 };
 enum {
@@ -114,6 +119,7 @@ typedef struct slv_vs_mvp_passthrough_uniforms { float wvp[16]; uint32_t n_attrs
 typedef struct slv_vs_plane_xz_uniforms { float wvp[16]; } slv_vs_plane_xz_uniforms;
 typedef struct slv_vs_lights3_uniforms { float wvp[16]; float light_pos[3][4]; } slv_vs_lights3_uniforms;
 typedef struct slv_vs_sponza_uniforms { float wvp[16]; float light_pos[4]; float eye_pos[4]; } slv_vs_sponza_uniforms;
+typedef struct slv_vs_terrain_vtf_uniforms { float wvp[16]; float offset[2]; float scale[2]; } slv_vs_terrain_vtf_uniforms;
 typedef struct slv_ps_tex_alpha_uniforms { uint32_t reg; float alpha; } slv_ps_tex_alpha_uniforms;
 typedef struct slv_ps_sponza_uniforms { uint32_t has_sampler; } slv_ps_sponza_uniforms;
 

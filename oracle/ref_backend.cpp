@@ -123,6 +123,27 @@ struct vs_lights3 : vs_base {
   SLV_CLONE()
 };
 
+// cpp twin of the SASL vertex shader of samples/VertexTextureFetch/VertexTextureFetch.cpp:38-61; tex2Dlod is the reference's
+// own sasl.vs.tex2d.lod implementation: sampler::sample_2d_lod(coord.xy, coord.w) (salvia/src/resource/sampler_api.cpp:50-52)
+struct vs_terrain_vtf : vs_base {
+  mat44 wvp;
+  float off[2], scale[2];
+  sampler_ptr samp;
+  vs_terrain_vtf(slv_vs_terrain_vtf_uniforms const& u, sampler_ptr const& s) : wvp(load_mat(u.wvp)), samp(s) {
+    n_attrs = 1;
+    off[0] = u.offset[0]; off[1] = u.offset[1]; scale[0] = u.scale[0]; scale[1] = u.scale[1];
+  }
+  void shader_prog(const vs_input& in, vs_output& out) override {
+    vec4 pos = in.attribute(0), uv = in.attribute(1);
+    eflib::vec2 terrain_uv(off[0] + uv.x() * scale[0], off[1] + uv.y() * scale[1]);
+    float displacement = samp->sample_2d_lod(terrain_uv, 0.0f).get_vec4().x();
+    vec4 displaced(pos.x() + 0.0f, pos.y() + displacement * 20.0f, pos.z() + 0.0f, 1.0f);
+    eflib::transform(out.position(), displaced, wvp);
+    out.attribute(0) = vec4(displacement, 0.0f, 0.0f, 0.0f);
+  }
+  SLV_CLONE()
+};
+
 // samples/Sponza/Sponza.cpp:64-97 (sponza_vs)
 struct vs_sponza : vs_base {
   mat44 wvp;
@@ -149,6 +170,30 @@ struct vs_sponza : vs_base {
 struct ps_attr0_color : cpp_pixel_shader {
   bool shader_prog(const vs_output& in, ps_output& out) override {
     out.color[0] = in.attribute(0);
+    return true;
+  }
+  SLV_CLONE()
+};
+
+// samples/VertexTextureFetch/VertexTextureFetch.cpp:70-113
+struct ps_height_color : cpp_pixel_shader {
+  bool shader_prog(const vs_output& in, ps_output& out) override {
+    float height = in.attribute(0)[0];
+    vec4 colors[] = {vec4(0.0f, 0.0f, 0.5f, 1.0f), vec4(0.7f, 0.6f, 0.0f, 1.0f), vec4(0.45f, 0.38f, 0.26f, 1.0f),
+                     vec4(0.0f, 0.7f, 0.8f, 1.0f), vec4(0.9f, 0.9f, 1.0f, 1.0f), vec4(0.9f, 0.9f, 1.0f, 1.0f)};
+    float boundary_points[] = {0.0f, 0.62f, 0.75f, 0.88f, 1.0f, 1.0f};
+    int lower_bound = -1;
+    for (int i = 0; i < 5; ++i) {
+      if (height < boundary_points[i]) break;
+      lower_bound = i;
+    }
+    if (lower_bound == -1) {
+      out.color[0] = colors[0];
+    } else {
+      float lower_value = boundary_points[lower_bound];
+      float interval = boundary_points[lower_bound + 1] - lower_value;
+      out.color[0] = eflib::lerp(colors[lower_bound], colors[lower_bound + 1], (height - lower_value) / interval);
+    }
     return true;
   }
   SLV_CLONE()
@@ -457,6 +502,11 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   case SLV_VS_PLANE_XZ: vs.reset(new vs_plane_xz(*(slv_vs_plane_xz_uniforms const*)d->vs.uniforms)); break;
   case SLV_VS_LIGHTS3: vs.reset(new vs_lights3(*(slv_vs_lights3_uniforms const*)d->vs.uniforms)); break;
   case SLV_VS_SPONZA: vs.reset(new vs_sponza(*(slv_vs_sponza_uniforms const*)d->vs.uniforms)); break;
+  case SLV_VS_TERRAIN_VTF: {
+    sampler_ptr s = sampler_of(dev, d->vs.samplers[0]);
+    if (!s) return SLV_INVALID_PARAMETER;
+    vs.reset(new vs_terrain_vtf(*(slv_vs_terrain_vtf_uniforms const*)d->vs.uniforms, s));
+  } break;
   default: return SLV_INVALID_PARAMETER;
   }
   vs->bind_regs(*d);
@@ -478,6 +528,7 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
     ps.reset(new ps_sponza(u->has_sampler ? sampler_of(dev, d->ps.samplers[0]) : sampler_ptr()));
   } break;
   case SLV_PS_DISCARD_ALL: ps.reset(new ps_discard_all()); break;
+  case SLV_PS_HEIGHT_COLOR: ps.reset(new ps_height_color()); break;
   default: return SLV_INVALID_PARAMETER;
   }
 

@@ -608,6 +608,8 @@ struct DrawCtx {
   uint32_t stencil_ref, read_mask, write_mask;
   Sampler const* samplers[SLV_MAX_SAMPLERS];
   Texture const* sampler_tex[SLV_MAX_SAMPLERS];
+  Sampler const* vs_sampler = nullptr;       // vertex texture fetch: vs.samplers[0]
+  Texture const* vs_sampler_tex = nullptr;
   uint64_t ps_invocations = 0, backend_input_pixels = 0;
 };
 
@@ -674,6 +676,7 @@ uint32_t vs_num_attrs(slv_shader_binding const& vs) {
   case SLV_VS_PLANE_XZ: return 1;
   case SLV_VS_LIGHTS3: return 4;
   case SLV_VS_SPONZA: return 4;
+  case SLV_VS_TERRAIN_VTF: return 1;
   }
   return 0;
 }
@@ -708,6 +711,14 @@ void run_vs(DrawCtx& c, V4 const in[SLV_MAX_VS_INPUT_ATTRS], VsOut& out) {
     out.r[2] = in[2];
     out.r[3] = sub4(mk4(u->light_pos[0], u->light_pos[1], u->light_pos[2], u->light_pos[3]), in[0]);
     out.r[4] = sub4(mk4(u->eye_pos[0], u->eye_pos[1], u->eye_pos[2], u->eye_pos[3]), in[0]);
+  } break;
+  case SLV_VS_TERRAIN_VTF: {  // VertexTextureFetch.cpp:38-61; tex2Dlod = sample_2d_lod (sampler_api.cpp:50-52, sampler.cpp:850-852)
+    auto u = (slv_vs_terrain_vtf_uniforms const*)vs.uniforms;
+    float tu = u->offset[0] + in[1][0] * u->scale[0], tv = u->offset[1] + in[1][1] * u->scale[1];
+    float disp = sample_impl(*c.vs_sampler_tex, c.vs_sampler->d, tu, tv, 0.0f, nullptr)[0];
+    V4 displaced = mk4(in[0][0] + 0.0f, in[0][1] + disp * 20.0f, in[0][2] + 0.0f, 1.0f);
+    out.r[0] = transform(displaced, u->wvp);
+    out.r[1] = mk4(disp, 0, 0, 0);
   } break;
   }
 }
@@ -977,6 +988,25 @@ bool run_ps(DrawCtx& c, PsQuad& q, int pix, V4& color) {
   switch (ps.program) {
   case SLV_PS_ATTR0_COLOR: color = in.r[1]; return true;
   case SLV_PS_DISCARD_ALL: color = in.r[1]; return false;
+  case SLV_PS_HEIGHT_COLOR: {  // VertexTextureFetch.cpp:70-113
+    float height = in.r[1][0];
+    static const float colors[6][4] = {{0.0f, 0.0f, 0.5f, 1.0f}, {0.7f, 0.6f, 0.0f, 1.0f}, {0.45f, 0.38f, 0.26f, 1.0f},
+                                       {0.0f, 0.7f, 0.8f, 1.0f}, {0.9f, 0.9f, 1.0f, 1.0f}, {0.9f, 0.9f, 1.0f, 1.0f}};
+    static const float boundary[6] = {0.0f, 0.62f, 0.75f, 0.88f, 1.0f, 1.0f};
+    int lower = -1;
+    for (int i = 0; i < 5; ++i) {
+      if (height < boundary[i]) break;
+      lower = i;
+    }
+    if (lower == -1) {
+      color = mk4(colors[0][0], colors[0][1], colors[0][2], colors[0][3]);
+    } else {
+      float lv = boundary[lower], interval = boundary[lower + 1] - lv;
+      float t = (height - lv) / interval;
+      for (int k = 0; k < 4; ++k) color[k] = colors[lower][k] + (colors[lower + 1][k] - colors[lower][k]) * t;  // eflib::lerp
+    }
+    return true;
+  }
   case SLV_PS_LIGHTS3: {  // ColorizedTriangle.cpp:55-92
     float const* l0 = in.r[2].v; float const* l1 = in.r[3].v; float const* l2 = in.r[4].v;
     float const* norm = in.r[1].v;
@@ -1361,6 +1391,13 @@ slv_result do_draw(Device& dev, slv_draw_desc const& d) {
       c.samplers[i] = &r->samp;
       c.sampler_tex[i] = sampler_texture(dev, r->samp);
     }
+  }
+  if (d.vs.program == SLV_VS_TERRAIN_VTF) {
+    auto r = dev.get(d.vs.samplers[0], Resource::SAMPLER);
+    if (!r) return SLV_INVALID_PARAMETER;
+    c.vs_sampler = &r->samp;
+    c.vs_sampler_tex = sampler_texture(dev, r->samp);
+    if (!c.vs_sampler_tex) return SLV_INVALID_PARAMETER;
   }
 
   auto const& vp = d.viewport;

@@ -294,6 +294,7 @@ uint32_t vs_num_attrs(const slv_shader_binding& vs) {
   case SLV_VS_PLANE_XZ: return 1;
   case SLV_VS_LIGHTS3: return 4;
   case SLV_VS_SPONZA: return 4;
+  case SLV_VS_TERRAIN_VTF: return 1;
   }
   return 0xFFFFFFFFu;
 }
@@ -312,6 +313,7 @@ bool launch_raster_s(const RasterParams& rp, const RasterParams* batch, uint32_t
   case SLV_PS_SPONZA: k_raster<S, SLV_PS_SPONZA><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, n); return true;
   case SLV_PS_TEX_GRAD_ALPHA: k_raster<S, SLV_PS_TEX_GRAD_ALPHA><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, n); return true;
   case SLV_PS_DISCARD_ALL: k_raster<S, SLV_PS_DISCARD_ALL><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, n); return true;
+  case SLV_PS_HEIGHT_COLOR: k_raster<S, SLV_PS_HEIGHT_COLOR><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, n); return true;
   }
   return false;
 }
@@ -325,6 +327,7 @@ bool launch_shade_s(const RasterParams& rp, const RasterParams* batch, uint32_t 
   case SLV_PS_TEX_ALPHA: k_shade<S, SLV_PS_TEX_ALPHA><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, n_draws, db); return true;
   case SLV_PS_SPONZA: k_shade<S, SLV_PS_SPONZA><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, n_draws, db); return true;
   case SLV_PS_TEX_GRAD_ALPHA: k_shade<S, SLV_PS_TEX_GRAD_ALPHA><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, n_draws, db); return true;
+  case SLV_PS_HEIGHT_COLOR: k_shade<S, SLV_PS_HEIGHT_COLOR><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, n_draws, db); return true;
   }
   return false;
 }
@@ -1117,6 +1120,10 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   gp.prim_count = d->prim_count;
   gp.base_vertex = d->base_vertex;
   gp.vs_program = vs_program;
+  // vertex texture fetch: vs.samplers[0] (set_vs_sampler, renderer.h:80)
+  const bool vs_needs_sampler = vs_program == SLV_VS_TERRAIN_VTF || (vs_program == SLV_VS_JIT && d->vs.samplers[0] != 0);
+  if (vs_needs_sampler && !fill_sampler(dev, d->vs.samplers[0], gp.sampler0)) return SLV_INVALID_PARAMETER;
+  if (vs_program == SLV_VS_TERRAIN_VTF && d->n_elements < 2) return SLV_INVALID_PARAMETER;
   memcpy(gp.vs_uniforms, d->vs.uniforms, sizeof(gp.vs_uniforms));
   gp.n_attrs = n_attrs;
   rp.has_centroid = 0;
@@ -1200,7 +1207,7 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
     if (reinterpret_cast<const slv_ps_tex_alpha_uniforms*>(d->ps.uniforms)->reg >= n_attrs) return SLV_INVALID_PARAMETER;
   }
   if ((rp.ps_program == SLV_PS_LIGHTS3 || rp.ps_program == SLV_PS_SPONZA) && n_attrs < 4) return SLV_INVALID_PARAMETER;
-  if ((rp.ps_program == SLV_PS_ATTR0_COLOR || rp.ps_program == SLV_PS_DISCARD_ALL) && n_attrs < 1) return SLV_INVALID_PARAMETER;
+  if ((rp.ps_program == SLV_PS_ATTR0_COLOR || rp.ps_program == SLV_PS_DISCARD_ALL || rp.ps_program == SLV_PS_HEIGHT_COLOR) && n_attrs < 1) return SLV_INVALID_PARAMETER;
   rp.tri_stride = tri_stride;
   rp.tiles_x = gp.tiles_x;
   rp.tiles_y = gp.tiles_y;
@@ -1216,6 +1223,17 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
       slv_result rcf = flush_batch(dev);
       if (rcf != SLV_OK) return rcf;
     }
+  }
+  if (vs_needs_sampler) {
+    // the vertex stage runs on the front stream: a height map written on the main stream (upload, an earlier render pass) has to
+    // be complete first - flush what is queued and let the front half order after the main stream
+    const uint8_t* t0 = gp.sampler0.tex.level[0].data;
+    if (!dev->pending.empty() && (t0 == dev->pending[0].color0.data || t0 == dev->pending[0].color1.data || t0 == dev->pending[0].ds.data)) {
+      slv_result rcf = flush_batch(dev);
+      if (rcf != SLV_OK) return rcf;
+    }
+    { slv_result rcm__ = materialize_clear(dev, texture_of_data(dev, t0)); if (rcm__ != SLV_OK) return rcm__; }
+    dev->buffers_dirty = true;
   }
 
   // lazy clears: a texture this draw SAMPLES, and the second colour target, must hold their cleared contents for real

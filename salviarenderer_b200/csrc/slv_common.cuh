@@ -73,6 +73,7 @@ struct GeomParams {
   unsigned long long* stats;  // slv_pipeline_statistics as 9 x u64
   uint32_t* valid_slots;      // compact list of the slots that hold a triangle binned on this rank
   uint32_t* valid_count;
+  SamplerRef sampler0;        // vertex texture fetch (vs.samplers[0]); tex.n_levels == 0 when the draw binds none
 };
 
 // geometry of all queued draws in ONE launch: CTA b works on draw draw_of[g] where cta_prefix[g] <= b < cta_prefix[g+1]

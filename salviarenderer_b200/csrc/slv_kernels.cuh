@@ -20,7 +20,8 @@
 // this header with SLV_JIT_VS / SLV_JIT_PS defined and the generated entry points below defined after it, so the shader is
 // inlined into k_geometry / k_raster like the built-in programs.  The library build knows nothing about them.
 #ifdef SLV_JIT_VS
-__device__ void slv_jit_vs(const float4* in, const unsigned char* uniforms, float4* out);
+namespace slv { struct SamplerRef; }
+__device__ void slv_jit_vs(const float4* in, const unsigned char* uniforms, float4* out, const slv::SamplerRef& s0);
 #endif
 #ifdef SLV_JIT_PS
 namespace slv { struct RasterParams; }
@@ -119,9 +120,16 @@ __device__ __forceinline__ void run_vs(const GeomParams& p, uint32_t index, VsOu
       }
     }
   } break;
+  case SLV_VS_TERRAIN_VTF: {  // VertexTextureFetch.cpp:38-61; tex2Dlod = sampler::sample_2d_lod (sampler_api.cpp:50-52)
+    auto u = reinterpret_cast<const slv_vs_terrain_vtf_uniforms*>(p.vs_uniforms);
+    const float tu = u->offset[0] + in[1].x * u->scale[0], tv = u->offset[1] + in[1].y * u->scale[1];
+    const float disp = sample_impl(p.sampler0, tu, tv, 0.0f, nullptr).x;
+    out.r[0] = transform(make_float4(in[0].x + 0.0f, in[0].y + disp * 20.0f, in[0].z + 0.0f, 1.0f), u->wvp);
+    if (R > 1) out.r[R > 1 ? 1 : 0] = make_float4(disp, 0.0f, 0.0f, 0.0f);
+  } break;
 #ifdef SLV_JIT_VS
   case SLV_VS_JIT:
-    if (R == SLV_JIT_R) slv_jit_vs(in, p.vs_uniforms, out.r);
+    if (R == SLV_JIT_R) slv_jit_vs(in, p.vs_uniforms, out.r, p.sampler0);
     break;
 #endif
   case SLV_VS_SPONZA: {
@@ -879,6 +887,31 @@ __device__ __forceinline__ bool run_ps(const RasterParams& p, const Ctx& px, flo
   if (PS == SLV_PS_DISCARD_ALL) {
     color = px.attr(0);
     return false;
+  }
+  if (PS == SLV_PS_HEIGHT_COLOR) {  // VertexTextureFetch.cpp:70-113
+    const float height = px.attr(0).x;
+    const float colors[6][4] = {{0.0f, 0.0f, 0.5f, 1.0f}, {0.7f, 0.6f, 0.0f, 1.0f}, {0.45f, 0.38f, 0.26f, 1.0f},
+                                {0.0f, 0.7f, 0.8f, 1.0f}, {0.9f, 0.9f, 1.0f, 1.0f}, {0.9f, 0.9f, 1.0f, 1.0f}};
+    const float boundary[6] = {0.0f, 0.62f, 0.75f, 0.88f, 1.0f, 1.0f};
+    int lower = -1;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+      if (lower == i - 1 && !(height < boundary[i])) lower = i;
+    if (lower == -1) {
+      color = make_float4(colors[0][0], colors[0][1], colors[0][2], colors[0][3]);
+    } else {
+      float c0[4], c1[4], lv = 0.0f, hv = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+        if (lower == i) {
+          lv = boundary[i]; hv = boundary[i + 1];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { c0[k] = colors[i][k]; c1[k] = colors[i + 1][k]; }
+        }
+      const float t = (height - lv) / (hv - lv);
+      color = make_float4(c0[0] + (c1[0] - c0[0]) * t, c0[1] + (c1[1] - c0[1]) * t, c0[2] + (c1[2] - c0[2]) * t, c0[3] + (c1[3] - c0[3]) * t);
+    }
+    return true;
   }
   if (PS == SLV_PS_LIGHTS3) {  // ColorizedTriangle.cpp:55-92
     float4 nrm = px.attr(0), l0 = px.attr(1), l1 = px.attr(2), l2 = px.attr(3);

@@ -832,7 +832,7 @@ class Gen:
         return Value(f.ret, rets)
 
     def ctx_args(self):
-        return ["U", "p", "px"] if self.stage == "ps" else ["U"]
+        return ["U", "p", "px"] if self.stage == "ps" else ["U", "S0"]
 
     def map1(self, args, n, fmt, base="float"):
         if len(args) != 1:
@@ -1035,8 +1035,8 @@ class Gen:
             self.err(n, "tex2Dlod(sampler, float4(uv, _, lod))")
         s = self.sampler_slot(a[0], n)
         c = self.convert(self.to_base(a[1], "float", n), vec("float", 4), n)
-        if self.stage == "vs":
-            self.err(n, "vertex texture fetch is not wired into k_geometry yet")
+        if self.stage == "vs":  # sasl.vs.tex2d.lod = sampler::sample_2d_lod(coord.xy, coord.w) (sampler_api.cpp:50-52)
+            return self.tex_result(lambda r: f"sasl_vs_tex2d_lod(S0, {s}, {c.comps[0]}, {c.comps[1]}, {c.comps[3]}, {', '.join(r)});")
         return self.tex_result(lambda r: f"sasl_tex2d_lod(p, px, {s}, {c.comps[0]}, {c.comps[1]}, {c.comps[3]}, {', '.join(r)});")
 
     def i_tex2Dproj(self, a, n):
@@ -1179,7 +1179,8 @@ class Gen:
                 ret_names.append(f"ret_{k}")
                 bases_params.append(f"{C_BASE[b]}& ret_{k}")
         self.cur_ret = Value(f.ret, ret_names, True) if ret_names else None
-        ctx = (["const SaslUniforms& U", "const slv::RasterParams& p", "const Ctx& px"] if self.stage == "ps" else ["const SaslUniforms& U"])
+        ctx = (["const SaslUniforms& U", "const slv::RasterParams& p", "const Ctx& px"] if self.stage == "ps"
+               else ["const SaslUniforms& U", "const SaslSampler& S0"])
         head = ("template <class Ctx>\n" if self.stage == "ps" else "") + f"SASL_FN void sasl_fn_{f.name}({', '.join(ctx + bases_params)}) {{"
         start = len(self.lines)
         self.indent = 1
@@ -1249,7 +1250,7 @@ class Gen:
     def gen_vs_wrapper(self):
         ins, outs = self.entry_io()
         L = ["// entry wrapper: input register k <- k-th input semantic; out[0] <- SV_Position, out[1 + k] <- k-th other output",
-             "SASL_FN void slv_jit_vs(const float4* in, const unsigned char* uniforms, float4* out) {",
+             "SASL_FN void slv_jit_vs(const float4* in, const unsigned char* uniforms, float4* out, const SaslSampler& S0) {",
              "  const SaslUniforms& U = *reinterpret_cast<const SaslUniforms*>(uniforms);"]
         args, reg = [], 0
         for _, prm, members in ins:
@@ -1287,10 +1288,11 @@ class Gen:
         if attr > 5:
             raise CompileError("more than 5 vertex-shader output attributes (vs_output_ops, shader.cpp:45-52)")
         self.refl.n_vs_output_attrs = attr
-        L.append(f"  sasl_fn_{self.entry.name}({', '.join(['U'] + args + rets)});")
+        L.append(f"  sasl_fn_{self.entry.name}({', '.join(['U', 'S0'] + args + rets)});")
         L += stores
         L.append("}")
         L.append(f"#define SLV_JIT_VS_OUTPUT_ATTRS {attr}")
+        L.append(f"#define SLV_JIT_VS_SAMPLERS {len(self.refl.samplers)}")
         return L
 
     def gen_ps_wrapper(self):
@@ -1342,6 +1344,6 @@ def compile_shader(source: str, stage: str, entry: str | None = None) -> ShaderU
         raise ValueError("stage must be 'vs', 'ps' or 'lib' (functions only, no entry point: the reference's *.ss test units)")
     g = Gen(source, stage, entry)
     unit = g.run()
-    if stage == "ps" and len(unit.reflection.samplers) > 1:
-        raise CompileError("more than one sampler per pixel shader is not supported yet")
+    if stage in ("ps", "vs") and len(unit.reflection.samplers) > 1:
+        raise CompileError("more than one sampler per shader is not supported yet")
     return unit

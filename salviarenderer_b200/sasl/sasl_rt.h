@@ -15,6 +15,7 @@
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 namespace slv { struct RasterParams { unsigned char ps_uniforms[256]; }; }
+struct SaslSampler {};  // host build: no texture sampling
 #endif
 
 SASL_FN float sasl_clamp(float v, float lo, float hi) { return v < lo ? lo : (hi < v ? hi : v); }  // eflib::clamp
@@ -41,6 +42,13 @@ SASL_FN unsigned sasl_countbits(unsigned v) {
 }
 
 #if defined(__CUDACC__)
+typedef slv::SamplerRef SaslSampler;
+// sasl.vs.tex2d.lod -> sampler::sample_2d_lod(coord.xy, coord.w) (salvia/src/resource/sampler_api.cpp:50-52)
+SASL_FN void sasl_vs_tex2d_lod(const SaslSampler& s0, int slot, float u, float v, float lod, float& r, float& g, float& b, float& a) {
+  (void)slot;  // one sampler per vertex shader (slot 0)
+  const float4 c = slv::sample_impl(s0, u, v, lod, nullptr);
+  r = c.x; g = c.y; b = c.z; a = c.w;
+}
 // Screen-space derivatives: the four pixels of a quad sit in four consecutive lanes (pixel i of the quad in lane
 // quad_base + i, k_raster's shading phases; helper pixels run too).  SLV_JIT_DERIV_CPP selects the cpp_pixel_shader
 // convention (ddx = q1 - q0, ddy = q2 - q0 for all four pixels, cpp_pixel_shader.cpp:13-19), the default is the SASL one
@@ -85,6 +93,7 @@ SASL_FN void sasl_tex2d_lod(const slv::RasterParams& p, const Ctx&, int slot, fl
   r = c.x; g = c.y; b = c.z; a = c.w;
 }
 #else
+SASL_FN void sasl_vs_tex2d_lod(const SaslSampler&, int, float, float, float, float& r, float& g, float& b, float& a) { r = g = b = a = 0.0f; }
 template <class Ctx> SASL_FN float sasl_ddx(const Ctx&, float) { return 0.0f; }
 template <class Ctx> SASL_FN float sasl_ddy(const Ctx&, float) { return 0.0f; }
 template <class Ctx>

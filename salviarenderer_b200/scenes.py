@@ -451,6 +451,68 @@ class TextureAndBlending:
 
 
 # ===========================================================================================================
+# VertexTextureFetch (scope row f-4): a plane displaced in the VERTEX shader by a height map
+# ===========================================================================================================
+class TerrainVTF:
+    """samples/VertexTextureFetch/VertexTextureFetch.cpp:128-252: create_planar grid (2B x 2B quads of 0.5), vertex shader
+    tex2Dlod of a height map (mirror addressing, linear filters, no mip chain) displacing y by 20 * height, pixel shader = colour
+    ramp over the height; camera (0, 32, -7), the terrain scrolls with the frame.  The sample's plasma terrain (r32f) is replaced
+    by a seeded smooth height field in an rg32f texture (.x = height in [0, 1])."""
+
+    def __init__(self, w=640, h=360, samples=1, block=32, tex_size=64, seed=77, vs_binding=None):
+        self.w, self.h, self.samples, self.block = w, h, samples, block
+        self.vs_binding = vs_binding   # optional override: (wvp, offset, scale, sampler) -> ShaderBinding (SASL vertex shader)
+        self.plane = create_planar((-block / 2.0, 0.0, -block / 2.0), (0.5, 0, 0), (0, 0, 0.5), block * 2, block * 2, False)
+        self.plane.elements = [(0, _V4, 0, 0, 1.0), (1, _V4, 2, 0, 0.0)]   # POSITION -> reg 0, TEXCOORD (uv stream) -> reg 1
+        rng = np.random.default_rng(seed)
+        f = rng.uniform(0, 1, size=(tex_size, tex_size))
+        for _ in range(3):  # smooth, periodic
+            f = (f + np.roll(f, 1, 0) + np.roll(f, -1, 0) + np.roll(f, 1, 1) + np.roll(f, -1, 1)) / 5.0
+        f = (f - f.min()) / (f.max() - f.min())
+        self.height = np.stack([f, np.zeros_like(f)], -1).astype(f32)
+        self.n_frames = 5
+
+    def setup(self, be: A.Backend):
+        self.t = create_targets(be, self.w, self.h, self.samples, A.PF_BGRA8)
+        self.plane.upload(be)
+        self.tex = be.create_texture(self.height.shape[1], self.height.shape[0], 1, A.PF_RG32F)
+        be.upload_texture(self.tex, self.height)
+        self.samp = be.create_sampler(A.sampler_desc(A.FILTER_LINEAR, A.FILTER_LINEAR, A.FILTER_LINEAR, addr_u=A.ADDR_MIRROR,
+                                                     addr_v=A.ADDR_MIRROR), self.tex)
+
+    def frame_uniforms(self, frame):
+        view = mat_lookat((0.0, 32.0, -7.0), (0, 0, 0), (0, 1, 0))
+        proj = mat_perspective_fov(math.pi / 2, f32(self.w) / f32(self.h), 0.1, 1000.0)
+        wvp = mat_mul(view, proj)
+        scene_sec = float(f32(frame * 161.2) / f32(self.n_frames - 1))
+        scale = 1.0 / 32
+        return wvp, (0.006 * scene_sec, 0.0088 * scene_sec), (scale, scale)
+
+    def render(self, be: A.Backend, frame: int):
+        t = self.t
+        be.clear_color(t.color, (0.2, 0.2, 0.5, 1.0))
+        be.clear_depth_stencil(t.ds, A.CLEAR_DEPTH | A.CLEAR_STENCIL, 1.0, 0)
+        wvp, off, scale = self.frame_uniforms(frame)
+        d = base_desc(t, self.w, self.h, cull=A.CULL_NONE)
+        self.plane.fill_desc(be, d)
+        if self.vs_binding is not None:
+            d.vs = self.vs_binding(wvp, off, scale, self.samp)
+        else:
+            d.vs = A.shader_binding(A.VS_TERRAIN_VTF, np.asarray(wvp, f32).tobytes() + struct.pack("<4f", *off, *scale), [self.samp])
+        d.ps = A.shader_binding(A.PS_HEIGHT_COLOR)
+        d.bs = A.shader_binding(A.BS_REPLACE)
+        be.draw(d)
+        if t.resolved is not None:
+            be.resolve(t.color, t.resolved)
+
+    def run(self, be: A.Backend, frame: int) -> FrameResult:
+        be.query_begin()
+        self.render(be, frame)
+        stats = be.query_get()
+        return read_frame(be, self.t, stats)
+
+
+# ===========================================================================================================
 # C5: two-pass height field (the mesh and pass structure of BASELINE configs[4]: StandardShadowMap + 10 M triangles)
 # ===========================================================================================================
 class HeightFieldTwoPass:

@@ -60,6 +60,9 @@ for _sop in range(1, 9):
 # Kept LAST: the reference's clipper over-runs its fan loop (clipper.cpp:75-89) and copies whatever
 # lies behind a 5-entry stack array into other primitives' result slots; which garbage that is depends on what ran before
 # in the process, and with these scenes ahead of the clipping-heavy soup cases the reference was observed to segfault.
+# VertexTextureFetch (row f-4): height-map displacement in the vertex shader, colour ramp in the pixel shader
+CASES["vtf_terrain_640x360"] = (lambda: S.TerrainVTF(640, 360, 1), (0, 2, 4))
+CASES["vtf_terrain_320x200x4"] = (lambda: S.TerrainVTF(320, 200, 4, block=16, tex_size=32), (1,))
 CASES["c5_heightfield_two_pass_640x360"] = (lambda: S.HeightFieldTwoPass(640, 360, 1, nx=125, nz=100), (0, 2))
 CASES["c5_heightfield_two_pass_320x180x4"] = (lambda: S.HeightFieldTwoPass(320, 180, 4, nx=60, nz=48), (1,))
 

@@ -119,3 +119,40 @@ def test_sasl_derivative_convention(cuda):
     for dy, dx in ((0, 1), (1, 0), (1, 1)):
         assert np.array_equal(b[dy::2, dx::2, :2][full], b[0::2, 0::2, :2][full])
     assert np.any(a[1::2, 1::2, :2][full] != a[0::2, 0::2, :2][full])
+
+
+VS_TERRAIN = """
+float4x4 wvpMatrix;
+float2   terrainOffset;
+float2   terrainScale;
+sampler  terrainSamp;
+struct VSIn  { float4 pos: POSITION; float4 uv: TEXCOORD0; };
+struct VSOut { float4 pos: sv_position; float displacement: TEXCOORD0; };
+VSOut vs_main(VSIn in) {
+    VSOut o;
+    float2 terrainUV = terrainOffset + in.uv.xy * terrainScale;
+    float displacement = tex2Dlod(terrainSamp, float4(terrainUV, 0.0f, 0.0f)).x;
+    float4 displaced_pos = float4(in.pos.xyz + float3(0.0f, displacement * 20.0f, 0.0f), 1.0f);
+    o.pos = mul(displaced_pos, wvpMatrix);
+    o.displacement = displacement;
+    return o;
+}
+"""
+
+
+def test_sasl_vertex_texture_fetch_equals_builtin(cuda):
+    """The VertexTextureFetch sample's vertex shader (tex2Dlod in the VERTEX stage) in SASL against SLV_VS_TERRAIN_VTF,
+    which is pinned to the reference's sampler::sample_2d_lod through the golden fixtures."""
+    sh = jit.compile(VS_TERRAIN, "vs")
+    assert sh.reflection.samplers == ["terrainSamp"] and sh.reflection.n_vs_output_attrs == 1
+    mod = jit.load(cuda, sh)
+    ref = S.TerrainVTF(640, 360, 1)
+    ref.setup(cuda)
+    got = S.TerrainVTF(640, 360, 1, vs_binding=lambda wvp, off, scale, samp: A.shader_binding(
+        A.program_jit(mod), sh.unit.pack_uniforms({"wvpMatrix": np.asarray(wvp, np.float32).reshape(4, 4), "terrainOffset": off,
+                                                   "terrainScale": scale}), [samp]))
+    got.setup(cuda)
+    for f in (0, 3):
+        a, b = ref.run(cuda, f), got.run(cuda, f)
+        assert cases.compare_frames(a, b) == [], f"frame {f}"
+        assert a.stats["cprimitives"] == 8192

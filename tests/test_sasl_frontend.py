@@ -257,7 +257,7 @@ REFERENCE_UNITS_OK = [
     "unary_operators.ss", "vec_and_mat.sps", "vec_and_mat.svs", "while.sps",
 ]
 REFERENCE_UNITS_REJECTED = {  # outside the subset (or erroneous on purpose upstream): must fail with CompileError, not crash
-    "incomplete.ss", "semantic_errors.ss", "preprocessors.ss", "include_main.ss", "function.ss", "scalar.sps", "tex.svs",
+    "incomplete.ss", "semantic_errors.ss", "preprocessors.ss", "include_main.ss", "function.ss", "scalar.sps",
 }
 
 
@@ -270,7 +270,7 @@ def _ref_unit(name):
     pytest.skip("reference tree not present")
 
 
-@pytest.mark.parametrize("name", REFERENCE_UNITS_OK + ["Draw.savs", "GenSM.savs", "GenSM.saps"])
+@pytest.mark.parametrize("name", REFERENCE_UNITS_OK + ["tex.svs", "Draw.savs", "GenSM.savs", "GenSM.saps"])
 def test_reference_sasl_units_compile(name, tmp_path):
     import subprocess
     from sasl_host import RT_DIR
