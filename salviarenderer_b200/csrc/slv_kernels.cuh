@@ -69,10 +69,13 @@ __device__ __forceinline__ void run_vs(const GeomParams& p, uint32_t index, VsOu
   float4 in[SLV_MAX_VS_INPUT_ATTRS];
 #pragma unroll
   for (int i = 0; i < SLV_MAX_VS_INPUT_ATTRS; ++i) in[i] = make_float4(0, 0, 0, 0);
+  // position-only pass: the built-in programs derive the position from in[0] alone, except the vertex-texture-fetch one (uv
+  // in in[1]); a SASL vertex shader may read anything
+  const bool pos_from_in0 = POS_ONLY && p.vs_program != SLV_VS_TERRAIN_VTF && p.vs_program != SLV_VS_JIT;
   if (p.fast_layout) {  // element e -> register e, one aligned 128-bit load each (the interleaved layouts of the samples)
 #pragma unroll
-    for (int e = 0; e < (POS_ONLY ? 1 : SLV_MAX_VS_INPUT_ATTRS); ++e)
-      if ((uint32_t)e < p.n_elements) {
+    for (int e = 0; e < SLV_MAX_VS_INPUT_ATTRS; ++e)
+      if ((uint32_t)e < p.n_elements && (e == 0 || !pos_from_in0)) {
         const slv_input_element& el = p.elements[e];
         const StreamRef& st = p.streams[el.slot];
         in[e] = __ldg(reinterpret_cast<const float4*>(st.data + el.aligned_byte_offset + (size_t)st.stride * index + st.offset));
@@ -80,7 +83,7 @@ __device__ __forceinline__ void run_vs(const GeomParams& p, uint32_t index, VsOu
   } else {
     for (uint32_t e = 0; e < p.n_elements; ++e) {
       uint32_t reg = p.elements[e].reg;
-      if (POS_ONLY && reg != 0) continue;
+      if (pos_from_in0 && reg != 0) continue;
       float4 v = fetch_element(p, p.elements[e], index);
 #pragma unroll
       for (int i = 0; i < SLV_MAX_VS_INPUT_ATTRS; ++i)
