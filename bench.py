@@ -184,11 +184,17 @@ def main():
     sc.setup(be)
     resolved = sc.t.resolved if sc.t.resolved is not None else sc.t.color
 
-    # ---- sort-first gather plumbing (N > 1): salviarenderer_b200/sortfirst.py ----
-    fg = sortfirst.FrameGather(be, resolved, rank, n, "cuda")
+    # ---- sort-first frame assembly (N > 1): salviarenderer_b200/sortfirst.py.  Two frame buffers on rank 0: the ranks are not
+    # in lockstep with rank 0's consumer, and the e2e readback of frame k overlaps frame k+1 ----
+    targets = [resolved]
+    if sc.t.resolved is not None:
+        targets.append(be.create_texture(args.width, args.height, 1, resolved.fmt))
+    fg = sortfirst.FrameGather(be, targets, rank, n, "cuda")
 
     def frame(i):
         fg.begin_frame()
+        if sc.t.resolved is not None:
+            sc.t.resolved = fg.target()
         sc.render(be, i % sc.n_frames, before_resolve=fg.before_resolve)
         fg.gather()
 
@@ -242,25 +248,25 @@ def main():
     out_bytes = args.width * args.height * 4
     h2d = vb_host.numel() * 4 + ib_host.numel() * 4
     d2h = out_bytes if rank == 0 else 0
-    if n == 1 and sc.t.resolved is not None:
-        # one GPU: the resolved frame goes back through slv_texture_readback_async into one of two pinned buffers while the
-        # next frame renders into the other resolve target (what an application pipelining frames does); every step's
-        # upload and readback is inside the timed region, which ends only after the last copy has landed
-        targets = [sc.t.resolved, be.create_texture(args.width, args.height, 1, sc.t.resolved.fmt)]
-        out_host = [torch.empty(out_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    if sc.t.resolved is not None:
+        # the assembled frame goes back through slv_texture_readback_async into one of two pinned buffers while the next frame
+        # renders into the other frame buffer (what an application pipelining frames does); every step's upload and readback is
+        # inside the timed region, which ends only after the last copy has landed
+        out_host = [torch.empty(out_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)] if rank == 0 else None
 
         def frame_e2e(i):
             be.upload_from_ptr(vb_h, vb_host.data_ptr(), vb_host.numel() * 4)
             be.upload_from_ptr(ib_h, ib_host.data_ptr(), ib_host.numel() * 4)
-            sc.t.resolved = targets[i % 2]
+            tgt, slot = fg.target(), fg.frame % 2
             frame(i)
-            be.read_texture_into_async(targets[i % 2], out_host[i % 2].data_ptr(), out_bytes)
+            if rank == 0:
+                be.read_texture_into_async(tgt, out_host[slot].data_ptr(), out_bytes)
 
         finish_e2e = be.readback_wait
         e2e_how = ("slv_buffer_upload of the vertex+index buffers from pinned host memory, the full frame, and "
-                   "slv_texture_readback_async of the resolved 4K frame into pinned host memory, every step; two resolve targets / host "
-                   "buffers alternate so that the readback of frame k overlaps the rendering of frame k+1; the timed region ends after "
-                   "the last readback has landed (slv_readback_wait)")
+                   "slv_texture_readback_async of the resolved 4K frame into pinned host memory (rank 0), every step; two frame buffers "
+                   "/ host buffers alternate so that the readback of frame k overlaps the rendering of frame k+1; the timed region ends "
+                   "after the last readback has landed (slv_readback_wait)")
     else:
         out_host1 = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
 
@@ -273,15 +279,13 @@ def main():
 
         finish_e2e = None
         e2e_how = ("slv_buffer_upload of the vertex+index buffers from pinned host memory, the full frame, and "
-                   "slv_texture_readback of the assembled 4K frame into pinned host memory on rank 0, every step")
+                   "slv_texture_readback of the frame into pinned host memory on rank 0, every step")
 
     for i in range(4):
         frame_e2e(i)
     if finish_e2e:
         finish_e2e()
     e2e_ms = timed(frame_e2e, args.steps, finish_e2e) / args.steps
-    if n == 1 and sc.t.resolved is not None:
-        sc.t.resolved = targets[0]
 
     # ---- roofline: per-stage CUDA events on the launching stream, algorithmic bytes from exact counters ----
     be.profile_enable(True)

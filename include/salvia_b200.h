@@ -249,6 +249,9 @@ slv_result slv_texture_readback(slv_device dev, slv_handle tex, uint32_t level, 
  * The CPU checkers copy synchronously. */
 slv_result slv_texture_readback_async(slv_device dev, slv_handle tex, uint32_t level, void* dst, size_t bytes);
 slv_result slv_readback_wait(slv_device dev);
+/* device-side: orders everything submitted after this call behind the pending asynchronous readback of `tex` (no host wait).
+ * The sort-first root uses it before it tells the other ranks that a frame buffer may be overwritten. */
+slv_result slv_readback_fence(slv_device dev, slv_handle tex);
 /* renderer::create_sampler (renderer.h:50) */
 slv_result slv_sampler_create(slv_device dev, const slv_sampler_desc* desc, slv_handle tex, slv_handle* out);
 /* SASL shaders compiled at run time.  The reference's compile(code, profile) + set_vertex_shader_code /

@@ -946,6 +946,14 @@ slv_result slv_texture_readback_async(slv_device dev, slv_handle h, uint32_t lev
   return SLV_OK;
 }
 
+slv_result slv_readback_fence(slv_device dev, slv_handle h) {
+  auto r = dev ? dev->get(h, Resource::TEXTURE) : nullptr;
+  if (!r) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  return wait_readback(dev, r);
+}
+
 slv_result slv_readback_wait(slv_device dev) {
   if (!dev) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));

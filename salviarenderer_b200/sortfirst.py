@@ -33,23 +33,31 @@ def tile_owner(tx: int, ty: int, nranks: int) -> int:
 
 
 class FrameGather:
-    """Per-frame assembly of the owned tiles of `surface` (single-sampled) on rank 0.
+    """Per-frame assembly of the owned tiles of the resolved (single-sampled) frame on rank 0.
 
-    Per frame:  begin_frame(); <clears and draws>; before_resolve(); <slv_resolve into `surface`>; gather()
+    Per frame:  begin_frame(); <clears and draws>; before_resolve(); <slv_resolve into target()>; gather()
+
+    `surface` may be a list of textures: rank 0 then assembles frame k in surfaces[k % len] (the other ranks always resolve
+    "into" surfaces[0], which the peer-memory transport redirects to rank 0's buffer of the frame).  With two buffers a rank
+    may run one frame ahead of rank 0's consumer (e.g. an asynchronous readback) instead of in lockstep with it.
     """
 
-    def __init__(self, be: abi.Backend, surface: abi.Texture, rank: int, nranks: int, device: str | torch.device,
+    def __init__(self, be: abi.Backend, surface, rank: int, nranks: int, device: str | torch.device,
                  transport: str | None = None):
         if nranks < 1 or not (0 <= rank < nranks):
             raise ValueError("bad rank / nranks")
-        if surface.samples != 1:
+        surfaces = list(surface) if isinstance(surface, (list, tuple)) else [surface]
+        if not surfaces or any(t.samples != 1 for t in surfaces):
             raise ValueError("sort-first gather works on the resolved (single-sampled) surface")
+        surface = surfaces[0]
+        self.surfaces = surfaces
         self.be, self.surface, self.rank, self.n, self.device = be, surface, rank, nranks, device
         # flag values only ever grow: a second FrameGather on the same device continues the numbering (all ranks run the
         # same frames, so they agree on it)
         self.frame = getattr(be, "_sortfirst_frame", 0)
         self.transport = "none" if nranks == 1 else "gather"
         self.root_surface = self.root_flags = None
+        self.root_surfaces = []
         be.set_tile_shard(rank, nranks)
         want = transport or os.environ.get("SLV_SORTFIRST_TRANSPORT", "p2p")
         if nranks > 1 and want == "p2p" and be.name.startswith("cuda") and nranks <= 64:
@@ -66,14 +74,15 @@ class FrameGather:
         payload = [None]
         if self.rank == 0:
             try:
-                payload = [(be.peer_export_texture(self.surface), be.peer_export_flags())]
+                payload = [([be.peer_export_texture(t) for t in self.surfaces], be.peer_export_flags())]
             except abi.SlvError:
                 payload = [None]
         dist.broadcast_object_list(payload, src=0)
         ok = 1 if payload[0] is not None else 0
         if ok and self.rank != 0:
             try:
-                self.root_surface = be.peer_open(payload[0][0])
+                self.root_surfaces = [be.peer_open(h) for h in payload[0][0]]
+                self.root_surface = self.root_surfaces[0]
                 self.root_flags = be.peer_open(payload[0][1])
                 be.resolve_target_peer(self.surface, self.root_surface)
             except abi.SlvError:
@@ -88,12 +97,15 @@ class FrameGather:
 
     def _close_p2p(self):
         be = self.be
-        if self.root_surface:
+        if self.root_surfaces:
             be.resolve_target_peer(self.surface, None)
-            be.peer_close(self.root_surface)
+            for p in self.root_surfaces:
+                be.peer_close(p)
         if self.root_flags:
             be.peer_close(self.root_flags)
         self.root_surface = self.root_flags = None
+        self.root_surfaces = []
+        self.root_surfaces = []
 
     def close(self):
         if self.transport == "p2p":
@@ -107,20 +119,37 @@ class FrameGather:
         return sum(self.be.packed_tiles_bytes(self.surface, r, self.n) for r in range(1, self.n))
 
     # ---- per frame ----
+    @property
+    def nbuf(self) -> int:
+        return len(self.surfaces)
+
+    def target(self) -> abi.Texture:
+        """The texture this rank resolves the current frame into (rank 0: the frame's buffer; others: their local stand-in)."""
+        return self.surfaces[self.frame % self.nbuf] if self.rank == 0 else self.surface
+
     def begin_frame(self):
-        """Rank 0: everything enqueued so far that reads the assembled surface is ahead in the stream, so the other
-        ranks may overwrite it with frame `self.frame`."""
-        if self.transport == "p2p" and self.rank == 0 and self.frame > 0:
-            self.be.peer_signal(None, 0, self.frame)
+        """Rank 0: frame k reuses the buffer of frame k - nbuf; everything rank 0 enqueued that reads that buffer (including an
+        asynchronous readback) is ordered ahead, then the other ranks are told they may overwrite it.  Other ranks (peer
+        memory): point this frame's resolve at rank 0's buffer."""
+        if self.transport != "p2p":
+            return
+        k = self.frame
+        if self.rank == 0:
+            if k >= self.nbuf:
+                self.be.readback_fence(self.surfaces[k % self.nbuf])
+                self.be.peer_signal(None, 0, k - self.nbuf + 1)
+        elif self.nbuf > 1:
+            self.be.resolve_target_peer(self.surface, self.root_surfaces[k % self.nbuf])
 
     def before_resolve(self):
-        """Other ranks: do not store frame k into rank 0's surface before rank 0 released frame k-1."""
-        if self.transport == "p2p" and self.rank != 0 and self.frame > 0:
-            self.be.flags_wait(self.root_flags, 0, 1, self.frame)
+        """Other ranks: do not store frame k into rank 0's buffer before rank 0 released frame k - nbuf."""
+        if self.transport == "p2p" and self.rank != 0 and self.frame >= self.nbuf:
+            self.be.flags_wait(self.root_flags, 0, 1, self.frame - self.nbuf + 1)
 
     def gather(self):
-        """Call after the frame's resolve.  On return rank 0's `surface` holds the whole frame (stream-ordered)."""
+        """Call after the frame's resolve.  On return rank 0's target() holds the whole frame (stream-ordered)."""
         if self.transport == "none":
+            self.frame += 1
             return
         if self.transport == "p2p":
             if self.rank == 0:
@@ -130,9 +159,10 @@ class FrameGather:
             self.frame += 1
             self.be._sortfirst_frame = self.frame
             return
-        self.be.pack_tiles(self.surface, self.rank, self.n, self.stage.data_ptr())
+        tgt = self.target()
+        self.be.pack_tiles(tgt, self.rank, self.n, self.stage.data_ptr())
         dist.gather(self.stage, self.gather_list, dst=0)
         if self.rank == 0:
             for r in range(1, self.n):
-                self.be.unpack_tiles(self.surface, r, self.n, self.gather_list[r].data_ptr())
+                self.be.unpack_tiles(tgt, r, self.n, self.gather_list[r].data_ptr())
         self.frame += 1

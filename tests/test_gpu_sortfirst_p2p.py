@@ -30,7 +30,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_path, transport):
+def _worker(rank, world, port, out_path, transport, nbuf=1):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -46,16 +46,25 @@ def _worker(rank, world, port, out_path, transport):
     be.set_stream(stream.cuda_stream)
     sc = scenes.SponzaLike(W, H, S, tex_size=64)
     sc.setup(be)
-    fg = sortfirst.FrameGather(be, sc.t.resolved, rank, world, f"cuda:{ordinal}", transport=transport)
+    targets = [sc.t.resolved] + [be.create_texture(W, H, 1, sc.t.resolved.fmt) for _ in range(nbuf - 1)]
+    fg = sortfirst.FrameGather(be, targets if nbuf > 1 else targets[0], rank, world, f"cuda:{ordinal}", transport=transport)
     frames = []
-    for f in FRAMES:
+    pinned = [torch.zeros(W * H * 4, dtype=torch.uint8).pin_memory() for _ in FRAMES]
+    for i, f in enumerate(FRAMES):
         fg.begin_frame()
+        sc.t.resolved = fg.target()
+        tgt = fg.target()
         sc.render(be, f, before_resolve=fg.before_resolve)
         fg.gather()
         if rank == 0:
-            frames.append(be.read_texture(sc.t.resolved).copy())  # synchronous: the app owns frame f now
+            if nbuf > 1:  # asynchronous: frame f is copied out while the ranks already render the next one into the other buffer
+                be.read_texture_into_async(tgt, pinned[i].data_ptr(), W * H * 4)
+            else:
+                frames.append(be.read_texture(tgt).copy())  # synchronous: the app owns frame f now
     be.flush()
     if rank == 0:
+        if nbuf > 1:
+            frames = [p.numpy().reshape(H, W, 1, 4).copy() for p in pinned]
         np.save(out_path, np.stack(frames))
         open(out_path + ".transport", "w").write(fg.transport)
     dist.barrier()
@@ -64,11 +73,11 @@ def _worker(rank, world, port, out_path, transport):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("transport", ["p2p", "gather"])
-def test_world2_assembled_frames_equal_unsharded(cuda, tmp_path, transport):
+@pytest.mark.parametrize("transport,nbuf", [("p2p", 1), ("gather", 1), ("p2p", 2)])
+def test_world2_assembled_frames_equal_unsharded(cuda, tmp_path, transport, nbuf):
     from salviarenderer_b200 import scenes
     out = str(tmp_path / "frames.npy")
-    mp.spawn(_worker, args=(2, _free_port(), out, transport), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, transport, nbuf), nprocs=2, join=True)
     got = np.load(out)
     assert open(out + ".transport").read() == transport
     sc = scenes.SponzaLike(W, H, S, tex_size=64)
@@ -77,4 +86,4 @@ def test_world2_assembled_frames_equal_unsharded(cuda, tmp_path, transport):
     for i, f in enumerate(FRAMES):
         sc.render(cuda, f)
         want = cuda.read_texture(sc.t.resolved)
-        assert np.array_equal(got[i], want), f"frame {f} ({transport})"
+        assert np.array_equal(got[i].reshape(want.shape), want), f"frame {f} ({transport}, {nbuf} buffers)"
