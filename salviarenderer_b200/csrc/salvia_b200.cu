@@ -155,9 +155,15 @@ struct slv_device_t {
   // fused resolve: slv_resolve(src, dst) of the pending batch's colour target is handed to the batch flush, whose k_shade
   // writes the resolved texels as it stores the samples (SLV_FUSE_RESOLVE=0 disables)
   // k_cover / k_shade grids: persistent (one CTA set per SM draining the work queue) or budgeted (short-lived CTAs, grid sized to
-  // the queue).  Measured: persistent wins when a GPU has the whole frame (0.80 vs 0.87 ms), budgeted wins by ~3 % when it has an
-  // eighth of it (CTAs of the next frame's front half slip in between).  -1 = choose by shard count; SLV_PERSISTENT=0/1 forces.
+  // the queue; SLV_PERSISTENT=0).  Measured: persistent wins when a GPU has the whole frame (0.80 vs 0.87 ms); on an eighth of the
+  // frame budgeted beat fully occupied persistent grids by ~3 %, but persistent grids that leave part of each SM free (back_ctas
+  // below) beat both, so persistent is the default everywhere.
   int persistent = -1;
+  // resident CTAs per SM of the persistent k_cover / k_shade grids (<= the 8 they are compiled for).  Leaving part of every SM
+  // free lets the NEXT frame's front half (other stream) run concurrently instead of waiting for the persistent CTAs to drain.
+  // Measured (ms/frame, 8 / 7 / 6 / 5 / 4 CTAs per SM): whole frame on one GPU 0.877 / 0.835 / 0.904 / 0.976 / 1.168; an eighth of
+  // the frame 0.284 / 0.270 / 0.250 / 0.258 / 0.252.  0 = choose by shard count; SLV_BACK_CTAS overrides.
+  int back_ctas = 0;
   bool fuse_resolve = true;
   bool resolve_requested = false, resolve_done = false;
   SurfaceRef resolve_dst{};
@@ -577,7 +583,13 @@ slv_result flush_batch(slv_device dev) {
     CU(cudaStreamWaitEvent(st, S.ev_front_done, 0));
   }
   uint32_t cover_grid = (uint32_t)dev->cover_grid, shade_grid = (uint32_t)dev->shade_grid;
-  const bool persistent = dev->persistent >= 0 ? dev->persistent != 0 : dev->shard_n < 4;
+  {
+    int k = dev->back_ctas > 0 ? dev->back_ctas : (dev->shard_n >= 4 ? 6 : 7);
+    if (!(dev->pipeline && !dev->profile)) k = SLV_COVER_CTAS_PER_SM;  // nothing to overlap with on a single stream
+    if (k >= 1 && k <= SLV_COVER_CTAS_PER_SM) cover_grid = (uint32_t)(dev->sm_count * k);
+    if (k >= 1 && k <= SLV_SHADE_CTAS_PER_SM) shade_grid = (uint32_t)(dev->sm_count * k);
+  }
+  const bool persistent = dev->persistent >= 0 ? dev->persistent != 0 : true;
   if (deferred && !persistent) {
     // short-lived CTAs: every warp performs a fixed number of queue fetches, the grid covers the worst case (every owned
     // tile active).  Items per warp: 8 (k_cover, 4 fetches of FETCH) / 2 groups (k_shade).
@@ -745,6 +757,7 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
     CU(cudaFuncSetAttribute(k_sort_lists_large, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_LARGE_SMEM * (int)sizeof(uint32_t)));
     dev->cover_grid = prop.multiProcessorCount * SLV_COVER_CTAS_PER_SM;
     dev->shade_grid = prop.multiProcessorCount * SLV_SHADE_CTAS_PER_SM;
+    if (const char* bc = getenv("SLV_BACK_CTAS")) dev->back_ctas = atoi(bc);
   }
   CU(cudaMemsetAsync(dev->overflow_flag, 0, sizeof(uint32_t), dev->stream));
   CU(cudaMalloc(&dev->d_stats, 20 * sizeof(unsigned long long)));
