@@ -62,6 +62,11 @@ __device__ __forceinline__ float4 transform(float4 v, const float* m) {
   return o;
 }
 
+// vertex texture fetch: ONE out-of-line copy of the sampler for the whole geometry kernel (run_vs is instantiated six times per
+// primitive - three corners, position-only and full - and the sampler is ~3 k instructions: inlined, it pushed the kernel out
+// of the instruction cache and cost every draw 15 % whether it sampled or not)
+__device__ __noinline__ float4 vs_sample_lod(const SamplerRef& sm, float u, float v, float lod) { return sample_impl(sm, u, v, lod, nullptr); }
+
 // POS_ONLY: only input register 0 is fetched and only out.r[0] is meaningful (every shipped vertex program derives the
 // position from in[0] alone); the attribute fetches and arithmetic are dead code in that instantiation.
 template <int R, bool POS_ONLY = false>
@@ -126,7 +131,7 @@ __device__ __forceinline__ void run_vs(const GeomParams& p, uint32_t index, VsOu
   case SLV_VS_TERRAIN_VTF: {  // VertexTextureFetch.cpp:38-61; tex2Dlod = sampler::sample_2d_lod (sampler_api.cpp:50-52)
     auto u = reinterpret_cast<const slv_vs_terrain_vtf_uniforms*>(p.vs_uniforms);
     const float tu = u->offset[0] + in[1].x * u->scale[0], tv = u->offset[1] + in[1].y * u->scale[1];
-    const float disp = sample_impl(p.sampler0, tu, tv, 0.0f, nullptr).x;
+    const float disp = vs_sample_lod(p.sampler0, tu, tv, 0.0f).x;
     out.r[0] = transform(make_float4(in[0].x + 0.0f, in[0].y + disp * 20.0f, in[0].z + 0.0f, 1.0f), u->wvp);
     if (R > 1) out.r[R > 1 ? 1 : 0] = make_float4(disp, 0.0f, 0.0f, 0.0f);
   } break;
@@ -355,9 +360,14 @@ __device__ __forceinline__ void geometry_main(const GeomParams* __restrict__ dra
   // the draw's parameter block, staged once per CTA: every later field access is a shared-memory broadcast
   __shared__ GeomParams s_params;
   {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(draws + hb.draw_of[lo]);
+    const GeomParams* gsrc = draws + hb.draw_of[lo];
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(gsrc);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&s_params);
-    for (uint32_t i = threadIdx.x; i < sizeof(GeomParams) / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    // the sampler block (vertex texture fetch) is the tail of the struct: staged only for draws that bind one
+    const bool has_sampler = gsrc->sampler0.tex.n_levels != 0;
+    const uint32_t n_words = (uint32_t)((has_sampler ? sizeof(GeomParams) : offsetof(GeomParams, sampler0)) / 4);
+    for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = __ldg(src + i);
+    if (!has_sampler && threadIdx.x == 0) s_params.sampler0.tex.n_levels = 0;
   }
   __syncthreads();
   const GeomParams& p = s_params;

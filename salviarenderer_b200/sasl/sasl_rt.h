@@ -46,7 +46,7 @@ typedef slv::SamplerRef SaslSampler;
 // sasl.vs.tex2d.lod -> sampler::sample_2d_lod(coord.xy, coord.w) (salvia/src/resource/sampler_api.cpp:50-52)
 SASL_FN void sasl_vs_tex2d_lod(const SaslSampler& s0, int slot, float u, float v, float lod, float& r, float& g, float& b, float& a) {
   (void)slot;  // one sampler per vertex shader (slot 0)
-  const float4 c = slv::sample_impl(s0, u, v, lod, nullptr);
+  const float4 c = slv::vs_sample_lod(s0, u, v, lod);
   r = c.x; g = c.y; b = c.z; a = c.w;
 }
 // Screen-space derivatives: the four pixels of a quad sit in four consecutive lanes (pixel i of the quad in lane
