@@ -400,8 +400,9 @@ float4 ps_main(PSIn in): COLOR {
 def run_variants(args, be, sc, timed):
     """The workload with SASL shaders compiled at run time (salviarenderer_b200/sasl): (1) the sample's SASL vertex shader in
     place of its cpp twin — samples/Sponza runs exactly this pair (SASL VS + cpp PS); (2) additionally a SASL pixel shader
-    (tex2D = sample_2d_grad) with 16x anisotropic samplers — the only way the reference can filter anisotropically (SURVEY
-    App. B #6); SASL pixel shaders take the immediate k_raster path.  Reported beside the headline, never instead of it."""
+    (tex2D = sample_2d_grad), with the headline's trilinear samplers and with 16x anisotropic ones — the only way the
+    reference can filter anisotropically; SASL pixel shaders run in the module's quad-granular k_shade on
+    the visibility-first path.  Reported beside the headline, never instead of it."""
     import numpy as np
     from salviarenderer_b200 import abi as A, scenes
     out = {}
@@ -427,27 +428,37 @@ def run_variants(args, be, sc, timed):
 
         ps = jit.compile(SASL_PS_SPONZA, "ps")
         ps_mod = jit.load(be, ps)
-        sc2 = scenes.SponzaLike(args.width, args.height, args.samples, tex_size=args.tex_size, max_aniso=16)
-        sc2.setup(be)
-        sc2.vs_binding = vs_binding
-        draws = {}
+        # BASELINE configs[3] literally: the headline scene with SASL vertex AND pixel shaders (trilinear), then with 16x
+        # anisotropic samplers; both on the visibility-first path (k_cover + the module's quad-granular k_shade)
+        for key, aniso, what in (
+                ("sasl_vs_ps", args.aniso, "SASL vertex + pixel shader (tex2D with per-pixel derivatives), the headline's samplers, "
+                                           "visibility-first path (quad-granular k_shade)"),
+                ("sasl_vs_ps_aniso16", 16, "SASL vertex + pixel shader (tex2D with per-pixel derivatives), 16x anisotropic samplers, "
+                                           "visibility-first path (quad-granular k_shade)")):
+            sc2 = scenes.SponzaLike(args.width, args.height, args.samples, tex_size=args.tex_size, max_aniso=aniso)
+            sc2.setup(be)
+            sc2.vs_binding = vs_binding
+            draws = {}
 
-        def render2(i):
-            f = i % sc2.n_frames
-            if f not in draws:
-                ds = sc2.frame_draws(be, f)
-                for d, (m, _, _) in zip(ds, sc2.groups):
-                    d.ps = A.shader_binding(A.program_jit(ps_mod), b"", [sc2.samplers[m]])
-                draws[f] = ds
-            sc2.render(be, f)
+            def render2(i, sc2=sc2, draws=draws):
+                f = i % sc2.n_frames
+                if f not in draws:
+                    ds = sc2.frame_draws(be, f)
+                    for d, (m, _, _) in zip(ds, sc2.groups):
+                        d.ps = A.shader_binding(A.program_jit(ps_mod), b"", [sc2.samplers[m]])
+                    draws[f] = ds
+                sc2.render(be, f)
 
-        for i in range(3):
-            render2(i)
-        steps2 = max(5, steps // 3)
-        ms2 = timed(render2, steps2) / steps2
-        out["sasl_vs_ps_aniso16"] = {"frames_per_sec": 1e3 / ms2, "ms_per_step": ms2, "steps": steps2,
-                                     "what": "SASL vertex + pixel shader (tex2D with per-pixel derivatives), 16x anisotropic samplers, "
-                                             "immediate k_raster path"}
+            for i in range(3):
+                render2(i)
+            steps2 = max(5, steps // 2)
+            be.query_begin()
+            ms2 = timed(render2, steps2) / steps2
+            st = be.query_get()
+            tr = be.traffic()
+            out[key] = {"frames_per_sec": 1e3 / ms2, "ms_per_step": ms2, "steps": steps2, "what": what,
+                        "ps_lanes_executed_per_frame": tr["ps_executed"] / steps2,
+                        "ps_invocations_per_frame": st["ps_invocations"] / steps2}
     except Exception as e:  # noqa: BLE001 - e.g. no nvcc on the box: the variants are optional
         out["error"] = f"{type(e).__name__}: {e}"[:300]
     return out

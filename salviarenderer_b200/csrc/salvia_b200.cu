@@ -52,6 +52,7 @@ struct Resource {
   uint32_t module_attrs = 0;        // VS: output attributes
   CUfunction fn_geometry = nullptr; // VS: slv_jit_k_geometry
   CUfunction fn_raster[3] = {};     // PS: slv_jit_k_raster_s1 / _s2 / _s4
+  CUfunction fn_shade[3] = {};      // PS: slv_jit_k_shade_s1 / _s2 / _s4 (visibility-first path; absent in older cubins)
 };
 
 // the four driver-API entry points run-time modules need, bound on first use
@@ -141,6 +142,7 @@ struct slv_device_t {
   uint32_t* vis = nullptr;           // visibility buffer of the deferred path: owner slot per sample
   size_t vis_cap = 0;                // in uint32 units
   bool force_immediate = false;      // SLV_FORCE_IMMEDIATE=1: always use k_raster (tests compare both paths)
+  bool jit_immediate = false;        // SLV_JIT_IMMEDIATE=1: SASL pixel shaders always take k_raster
   int cover_grid = 0, shade_grid = 0, sm_count = 0;
   int raster_grid = 0;  // persistent raster CTAs (SM count x resident CTAs per SM)
   // ---- draw batching: geometry + binning run at slv_draw time, the raster pass of all queued draws of a
@@ -519,9 +521,14 @@ slv_result flush_batch(slv_device dev) {
   size_t e2 = dev->profile ? mark(dev) : 0;
   // ---- phase 5: visibility-first (k_cover + k_shade) when every queued draw qualifies, else the immediate k_raster
   bool deferred = !dev->force_immediate;
+  CUfunction jit_shade_fn = nullptr;  // a batch has ONE pixel-shader program (a program change is a flush point)
+  if (first.ps_program == SLV_PS_JIT && !dev->jit_immediate) {
+    const Resource* m = dev->get(dev->batch_ps_module, Resource::MODULE);
+    if (m) jit_shade_fn = m->fn_shade[dev->batch_S == 1 ? 0 : (dev->batch_S == 2 ? 1 : 2)];
+  }
   for (const RasterParams& r : dev->pending)
     deferred = deferred && r.early_z && r.bs_program == SLV_BS_REPLACE && !r.has_centroid && r.ps_program != SLV_PS_DISCARD_ALL &&
-               r.ps_program != SLV_PS_JIT &&  // SASL pixel shaders take derivatives across the quad: k_raster shades whole quads
+               (r.ps_program != SLV_PS_JIT || jit_shade_fn) &&  // SASL pixel shaders: the module's quad-granular k_shade
                !r.color1.data && (!r.color0.data || r.color0.bpp == 4);
   bool ok = false;
   size_t e_mid = (size_t)-1, e_rbin = (size_t)-1;
@@ -611,6 +618,12 @@ slv_result flush_batch(slv_device dev) {
     }
     if (ok && shade) {
       if (dev->profile) e_mid = mark(dev);
+      if (first.ps_program == SLV_PS_JIT) {  // SASL pixel shader: the module's own quad-granular k_shade instance
+        const RasterParams* d_batch = S.d_batch;
+        uint32_t nd = n;
+        void* args[] = {(void*)&first, (void*)&d_batch, (void*)&nd, (void*)&db};
+        ok = driver_api().LaunchKernel(jit_shade_fn, shade_grid, 1, 1, DEF_THREADS, 1, 1, 0, (CUstream)st, args, nullptr) == CUDA_SUCCESS;
+      } else
       switch (dev->batch_S) {
       case 1: ok = launch_shade_s<1>(first, S.d_batch, n, db, shade_grid, st); break;
       case 2: ok = launch_shade_s<2>(first, S.d_batch, n, db, shade_grid, st); break;
@@ -766,6 +779,8 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   dev->profile = prof && prof[0] == '1';
   const char* fi = getenv("SLV_FORCE_IMMEDIATE");
   dev->force_immediate = fi && fi[0] == '1';
+  const char* ji = getenv("SLV_JIT_IMMEDIATE");
+  dev->jit_immediate = ji && ji[0] == '1';
   for (auto& ev : dev->user_ev) CU(cudaEventCreate(&ev));
 
   *out = dev;
@@ -1012,6 +1027,9 @@ slv_result slv_shader_module_load(slv_device dev, uint32_t stage, const void* im
   } else {
     const char* names[3] = {"slv_jit_k_raster_s1", "slv_jit_k_raster_s2", "slv_jit_k_raster_s4"};
     for (int i = 0; i < 3; ++i) ok = ok && api.ModuleGetFunction(&r.fn_raster[i], r.module, names[i]) == CUDA_SUCCESS;
+    const char* shade_names[3] = {"slv_jit_k_shade_s1", "slv_jit_k_shade_s2", "slv_jit_k_shade_s4"};
+    for (int i = 0; i < 3; ++i)
+      if (api.ModuleGetFunction(&r.fn_shade[i], r.module, shade_names[i]) != CUDA_SUCCESS) r.fn_shade[i] = nullptr;
   }
   if (!ok) {
     api.ModuleUnload(r.module);

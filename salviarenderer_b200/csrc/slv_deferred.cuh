@@ -97,6 +97,7 @@ __device__ __forceinline__ uint32_t region_block_bits(const TriEntry& te, float 
   return st_bits;
 }
 
+#ifndef SLV_JIT_PS  // k_region_bin is the library's; a JIT unit only instantiates shade_quad_main
 // Phase 1: one thread per tile-list entry evaluates the reference's level-16 decision (subdivide_tile at the 16-px
 // level, rasterizer.cpp:441-602, 698-772) for all 16 regions of the tile and stores survive | accept << 16.
 // Phase 2: warp r compacts, IN ORDER, the entries surviving in region r into the region's list (two streaming passes
@@ -257,6 +258,8 @@ __global__ void __launch_bounds__(RBIN_THREADS, 2) k_region_bin(RasterParams c, 
     d.block_desc[(b * 16 + r) * 8 + lane] = make_uint2((ok && cnt) ? s_base[r] + lane * cnt : 0u, mine);
   }
 }
+
+#endif  // SLV_JIT_PS
 
 // work-queue fetch: lane 0 takes FETCH consecutive items; the result is consumed one fetch later (latency hidden)
 __device__ __forceinline__ uint32_t fetch_items(uint32_t* counter, uint32_t lane) {
@@ -713,6 +716,214 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
       }
     }
     if (n_slow) {  // sum of to_rgba32f(sample) in sample order, * (1 / S), convert (RNE)  (surface.cpp:123-140)
+      __syncwarp();
+      for (uint32_t j = lane; j < n_slow; j += 32) {
+        const uint32_t pl = s_pool[j].x & 31, k2 = s_pool[j].x >> 5;
+        const uint32_t org = s_org[k2];
+        const uint32_t pq = pl >> 2, pp = pl & 3;
+        const int x = (int)(org & 0xFFFF) + (int)((pq & 3) * 2 + (pp & 1)), y = (int)(org >> 16) + (int)((pq >> 2) * 2 + (pp >> 1));
+        float4 clr = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const float4 t = unpack_color(c.color0.fmt, s_color[k2][pl][s]);
+          clr.x += t.x; clr.y += t.y; clr.z += t.z; clr.w += t.w;
+        }
+        const float inv = 1 / (float)S;
+        clr.x *= inv; clr.y *= inv; clr.z *= inv; clr.w *= inv;
+        store_texel_rgba32f(d.resolve_dst.fmt, d.resolve_dst.data + ((size_t)y * d.resolve_dst.w + x) * d.resolve_dst.bpp, clr);
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_exec += __shfl_xor_sync(0xFFFFFFFFu, n_exec, o);
+  if (lane == 0 && n_exec) atomicAdd(&c.stats[16], (unsigned long long)n_exec);
+}
+
+// ---- quad-granular shading: run-time compiled SASL pixel shaders on the visibility-first path -------------------------
+// A SASL pixel shader differences ARBITRARY expressions across the 2x2 quad (ddx / ddy, tex2D's implicit gradients:
+// sasl/src/codegen/cgs_simd.cpp:275-313), so its four pixels must execute together in four consecutive lanes, helper pixels
+// included, exactly as k_raster's shading phase runs them.  shade_quad_main is k_shade with the pool holding (quad,
+// distinct owner) pairs instead of (pixel, distinct owner) pairs: 8 pairs per round, lane 4e + i shades pixel i of pair e.
+// Every owner of any sample of the quad is shaded once for the whole quad (the reference shades the quad once per
+// triangle that has a live sample in it; the visibility-first argument at the top of the file applies unchanged).
+template <int PS>
+__device__ __forceinline__ uint32_t shade_quad_owner(const RasterParams& c, const RasterParams* __restrict__ batch, uint32_t n_draws,
+                                                     uint32_t slot, int x, int y, uint32_t quad_base) {
+  const float4* rec = c.tris + (size_t)slot * c.tri_stride;
+  // step_2d_unproj_pos_quad (shader.cpp:257-287), in k_raster's order of operations
+  const float4 v0p = __ldg(rec + REC_V0), gxp = __ldg(rec + REC_DDX), gyp = __ldg(rec + REC_DDY);
+  const RasterParams& p = batch[min(__float_as_uint(gxp.x), n_draws - 1)];  // draw id rides in the unused d(pos.x)/dx
+  PixelCtx px;
+  px.rec = rec; px.R = 1 + (int)p.n_attrs; px.mods = p.mods;
+  px.dx = 0.5f + (float)(uint32_t)(x & ~1) - v0p.x;
+  px.dy = 0.5f + (float)(uint32_t)(y & ~1) - v0p.y;
+  px.odd_x = x & 1; px.odd_y = y & 1;
+  float pw = v0p.w + (gxp.w * px.dx + gyp.w * px.dy);
+  if (px.odd_x) pw += gxp.w;
+  if (px.odd_y) pw += gyp.w;
+  px.inv_w = 1.0f / pw;
+  px.quad_base = quad_base;
+  px.centroid_path = false;  // batches with centroid attributes never take this path
+  px.pdx = 0.0f; px.pdy = 0.0f;
+  float4 color;
+  run_ps<PS>(p, px, color);
+  return pack_color(c.color0.fmt, color);
+}
+
+template <int S, int PS>
+__device__ __forceinline__ void shade_quad_main(const RasterParams& c, const RasterParams* __restrict__ batch, uint32_t n_draws,
+                                                const DeferredBufs& d) {
+  __shared__ uint32_t s_color_all[DEF_WARPS][SHADE_GROUP][32][S];
+  __shared__ uint2 s_pool_all[DEF_WARPS][SHADE_POOL];  // x = quad | item-in-group << 3 | 4 x S-bit sample masks << 6, y = owner slot
+  __shared__ uint32_t s_org_all[DEF_WARPS][SHADE_GROUP];
+  __shared__ uint8_t s_touched_all[DEF_WARPS][SHADE_GROUP][32];
+
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t (*s_color)[32][S] = s_color_all[wid];
+  uint2* s_pool = s_pool_all[wid];
+  uint32_t* s_org = s_org_all[wid];
+  uint8_t (*s_touched)[32] = s_touched_all[wid];
+  const uint32_t q = lane >> 2, pi = lane & 3;
+  const int wlx = (q & 3) * 2 + (pi & 1), wly = (q >> 2) * 2 + (pi >> 1);  // same pixel <-> lane map as k_cover
+  const uint32_t fullmask = (1u << S) - 1;
+  const uint32_t below = (1u << lane) - 1;
+
+  uint32_t n_exec = 0;
+  const uint32_t n_items = c.active_tiles[0] * ITEMS_PER_TILE;
+  const uint32_t grp = d.shade_grp ? d.shade_grp : min(SHADE_GROUP, max(1u, n_items / (gridDim.x * DEF_WARPS * 4u)));
+  uint32_t next_raw = fetch_group(d.shade_counter, lane, grp);
+  uint32_t fetches = 1;
+  for (;;) {
+    const uint32_t base_item = __shfl_sync(0xFFFFFFFFu, next_raw, 0);
+    if (base_item >= n_items) break;
+    next_raw = (d.shade_budget == 0 || fetches < d.shade_budget) ? fetch_group(d.shade_counter, lane, grp) : 0xFFFFFFFFu;
+    ++fetches;
+    uint32_t pool_n = 0, k = 0;
+    for (;;) {
+      // ---- fill: an item adds at most 8 quads x min(4 S, 16) owners = 32 S pairs ----
+#pragma unroll 1
+      for (; k < SHADE_GROUP && pool_n + 32 * S <= (uint32_t)SHADE_POOL; ++k) {
+        const uint32_t item = base_item + k;
+        const bool flagged = k < grp && item < n_items && d.item_flag[item];
+        const bool live = flagged || ((d.lazy_color || d.resolve_dst.data) && k < grp && item < n_items);
+        if (lane == 0) s_org[k] = 0xFFFFFFFFu;
+        if (!live) continue;
+        const uint32_t b = item >> 7, sub = (item >> 3) & 15, w = item & 7;
+        const uint32_t tile = c.active_tiles[1 + b];
+        const uint32_t tile_x = tile % c.tiles_x, tile_y = tile / c.tiles_x;
+        const int gx0 = tile_x * TILE + (sub & 3) * REGION + (w & 1) * 8, gy0 = tile_y * TILE + (sub >> 2) * REGION + (w >> 1) * 4;
+        const int x = gx0 + wlx, y = gy0 + wly;
+        const bool in_target = (uint32_t)x < c.target_w && (uint32_t)y < c.target_h;
+        if (lane == 0) s_org[k] = (uint32_t)gx0 | ((uint32_t)gy0 << 16);
+
+        uint32_t own[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) own[s] = VIS_NONE;
+        if (in_target && flagged) {
+          const uint32_t* vp = d.vis + ((size_t)y * d.vis_pitch + x) * S;
+          if (S == 4) {
+            const uint4 v = *reinterpret_cast<const uint4*>(vp);
+            own[0] = v.x; own[1 % S] = v.y; own[2 % S] = v.z; own[3 % S] = v.w;
+          } else if (S == 2) {
+            const uint2 v = *reinterpret_cast<const uint2*>(vp);
+            own[0] = v.x; own[1 % S] = v.y;
+          } else {
+            own[0] = *vp;
+          }
+        }
+        uint32_t rem = 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) rem |= (own[s] != VIS_NONE) ? (1u << s) : 0u;
+        const uint32_t touched = rem;
+        s_touched[k][lane] = (uint8_t)(touched | ((d.lazy_color && in_target) ? 0x80u : 0u) | (in_target ? 0x40u : 0u));
+        if (d.lazy_color) {
+          if (touched != fullmask) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) s_color[k][lane][s] = d.clear_color;
+          }
+        } else if (touched != fullmask && in_target && (touched || d.resolve_dst.data)) {
+          const uint32_t* cptr = reinterpret_cast<const uint32_t*>(c.color0.data + ((size_t)y * c.color0.w + x) * S * 4);
+#pragma unroll
+          for (int s = 0; s < S; ++s) s_color[k][lane][s] = cptr[s];
+        }
+        // the quad's distinct owners -> the pool.  Per round every quad with samples left elects the owner of its lowest
+        // such lane's lowest remaining sample; all four lanes hand in the samples they hold of that owner.
+        for (;;) {
+          const uint32_t bal = __ballot_sync(0xFFFFFFFFu, rem != 0);
+          if (!bal) break;
+          const uint32_t qbits = (bal >> (q * 4)) & 0xFu;
+          const uint32_t leader = q * 4 + (qbits ? (uint32_t)__ffs(qbits) - 1u : 0u);
+          uint32_t sl = VIS_NONE;
+#pragma unroll
+          for (int s = S - 1; s >= 0; --s)
+            if (rem & (1u << s)) sl = own[s];
+          const uint32_t qsl = __shfl_sync(0xFFFFFFFFu, sl, leader);
+          uint32_t m = 0;
+#pragma unroll
+          for (int s = 0; s < S; ++s)
+            if (qbits && (rem & (1u << s)) && own[s] == qsl) m |= 1u << s;
+          rem &= ~m;
+          uint32_t m16 = m << (4 * pi);
+          m16 |= __shfl_xor_sync(0xFFFFFFFFu, m16, 1);
+          m16 |= __shfl_xor_sync(0xFFFFFFFFu, m16, 2);
+          const bool writer = qbits && lane == leader;
+          const uint32_t wb = __ballot_sync(0xFFFFFFFFu, writer);
+          if (writer) s_pool[pool_n + __popc(wb & below)] = make_uint2(q | (k << 3) | (m16 << 6), qsl);
+          pool_n += __popc(wb);
+        }
+      }
+      // ---- drain (the ONE shading call site): 8 (quad, owner) pairs per round, all 32 lanes converged ----
+      __syncwarp();
+#pragma unroll 1
+      for (uint32_t j0 = 0; j0 < pool_n; j0 += 8) {
+        const uint32_t e = j0 + q;
+        const bool valid = e < pool_n;
+        const uint2 it = s_pool[valid ? e : pool_n - 1];
+        const uint32_t eq = it.x & 7, kk = (it.x >> 3) & 7;
+        const uint32_t m = valid ? (it.x >> (6 + 4 * pi)) & 0xFu : 0u;
+        const uint32_t org = s_org[kk];
+        const int px_ = (int)(org & 0xFFFF) + (int)((eq & 3) * 2 + (pi & 1)), py_ = (int)(org >> 16) + (int)((eq >> 2) * 2 + (pi >> 1));
+        const uint32_t packed = shade_quad_owner<PS>(c, batch, n_draws, it.y, px_, py_, lane & ~3u);
+        if (valid) ++n_exec;
+        const uint32_t pl = eq * 4 + pi;
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+          if (m & (1u << s)) s_color[kk][pl][s] = packed;
+      }
+      __syncwarp();
+      pool_n = 0;
+      if (k >= SHADE_GROUP) break;
+    }
+    // ---- store the group's items (identical to k_shade) ----
+    uint32_t n_slow = 0;
+#pragma unroll 1
+    for (uint32_t kk = 0; kk < SHADE_GROUP; ++kk) {
+      const uint32_t org = s_org[kk];
+      if (org == 0xFFFFFFFFu) continue;
+      const uint32_t fl = s_touched[kk][lane];
+      const int x = (int)(org & 0xFFFF) + wlx, y = (int)(org >> 16) + wly;
+      if (fl & 0x8Fu) {
+        uint32_t* cptr = reinterpret_cast<uint32_t*>(c.color0.data + ((size_t)y * c.color0.w + x) * S * 4);
+        if (S == 4) *reinterpret_cast<uint4*>(cptr) = make_uint4(s_color[kk][lane][0], s_color[kk][lane][1 % S], s_color[kk][lane][2 % S], s_color[kk][lane][3 % S]);
+        else if (S == 2) *reinterpret_cast<uint2*>(cptr) = make_uint2(s_color[kk][lane][0], s_color[kk][lane][1 % S]);
+        else *cptr = s_color[kk][lane][0];
+      }
+      bool slow = false;
+      if (d.resolve_dst.data && (fl & 0x40u)) {
+        bool same = d.resolve_dst.fmt == c.color0.fmt;
+#pragma unroll
+        for (int s = 1; s < S; ++s) same = same && s_color[kk][lane][s] == s_color[kk][lane][0];
+        if (same) *reinterpret_cast<uint32_t*>(d.resolve_dst.data + ((size_t)y * d.resolve_dst.w + x) * 4) = s_color[kk][lane][0];
+        slow = !same;
+      }
+      if (d.resolve_dst.data) {
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, slow);
+        if (slow) s_pool[n_slow + __popc(bal & below)] = make_uint2(lane | (kk << 5), 0u);
+        n_slow += __popc(bal);
+      }
+    }
+    if (n_slow) {  // surface.cpp:123-140
       __syncwarp();
       for (uint32_t j = lane; j < n_slow; j += 32) {
         const uint32_t pl = s_pool[j].x & 31, k2 = s_pool[j].x >> 5;

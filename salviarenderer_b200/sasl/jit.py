@@ -51,7 +51,8 @@ def compile(source: str, stage: str, entry: str | None = None, derivatives: str 
     if stage == "ps" and derivatives == "cpp":
         defs.append("-DSLV_JIT_DERIV_CPP=1")
     deps = b"".join(open(os.path.join(d, f), "rb").read() for d, f in
-                    ((CSRC, "slv_jit_unit.cu"), (CSRC, "slv_kernels.cuh"), (CSRC, "slv_sampler.cuh"), (CSRC, "slv_common.cuh"),
+                    ((CSRC, "slv_jit_unit.cu"), (CSRC, "slv_kernels.cuh"), (CSRC, "slv_deferred.cuh"), (CSRC, "slv_sampler.cuh"),
+                     (CSRC, "slv_common.cuh"),
                      (HERE, "sasl_rt.h"), (INCLUDE, "salvia_b200.h")))
     key = hashlib.sha256(unit.code.encode() + b"\0" + " ".join(defs + NVCC_FLAGS).encode() + b"\0" + deps).hexdigest()[:24]
     path = os.path.join(cache_dir(), key + ".cubin")
@@ -71,7 +72,8 @@ def compile(source: str, stage: str, entry: str | None = None, derivatives: str 
         finally:
             if keep_dir is None:
                 shutil.rmtree(work, ignore_errors=True)
-    names = ("slv_jit_k_geometry",) if stage == "vs" else ("slv_jit_k_raster_s1", "slv_jit_k_raster_s2", "slv_jit_k_raster_s4")
+    names = ("slv_jit_k_geometry",) if stage == "vs" else (
+        "slv_jit_k_raster_s1", "slv_jit_k_raster_s2", "slv_jit_k_raster_s4", "slv_jit_k_shade_s1", "slv_jit_k_shade_s2", "slv_jit_k_shade_s4")
     return CompiledShader(unit, open(path, "rb").read(), names)
 
 

@@ -156,3 +156,92 @@ def test_sasl_vertex_texture_fetch_equals_builtin(cuda):
         a, b = ref.run(cuda, f), got.run(cuda, f)
         assert cases.compare_frames(a, b) == [], f"frame {f}"
         assert a.stats["cprimitives"] == 8192
+
+
+# ---- SASL pixel shaders on the visibility-first path (the module's quad-granular k_shade) --------------------------------
+PS_SPONZA = """
+sampler texSamp;
+struct PSIn { float4 tex: TEXCOORD0; float4 norm: TEXCOORD1; float4 lightDir: TEXCOORD2; float4 eyeDir: TEXCOORD3; };
+float4 ps_main(PSIn in): COLOR {
+    float4 diff = tex2D(texSamp, in.tex.xy);
+    float illum = clamp(dot(normalize(in.lightDir.xyz), normalize(in.norm.xyz)), 0.0f, 1.0f);
+    return float4(diff.xyz * illum, 1.0f);
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def cuda_jit_immediate(built):
+    """A second device of the product on which SASL pixel shaders always take the immediate k_raster path."""
+    import os
+    import salviarenderer_b200 as pkg
+    os.environ["SLV_JIT_IMMEDIATE"] = "1"
+    try:
+        be = pkg.load(0)
+    finally:
+        del os.environ["SLV_JIT_IMMEDIATE"]
+    return be
+
+
+def _sponza_with_ps(be, sh, w, h, samples, tex_size, max_aniso, uniforms=None):
+    mod = jit.load(be, sh)
+    sc = S.SponzaLike(w, h, samples, tex_size=tex_size, max_aniso=max_aniso)
+    sc.setup(be)
+    base = sc.frame_draws
+
+    def frame_draws(be_, frame):
+        ds = base(be_, frame)
+        for d, (m, _, _) in zip(ds, sc.groups):
+            d.ps = A.shader_binding(A.program_jit(mod), sh.unit.pack_uniforms(uniforms or {}), [sc.samplers[m]])
+        return ds
+
+    sc.frame_draws = frame_draws
+    return sc
+
+
+@pytest.mark.parametrize("w,h,samples,aniso,conv,frames", [
+    (480, 272, 4, 0, "sasl", (0, 5)),
+    (960, 540, 1, 0, "sasl", (3,)),
+    (640, 360, 2, 16, "sasl", (7,)),
+    (1000, 600, 4, 16, "cpp", (2,)),     # target size not a multiple of the tile / quad size
+])
+def test_sasl_pixel_shader_visibility_first_equals_immediate(cuda, cuda_jit_immediate, w, h, samples, aniso, conv, frames):
+    """A SASL pixel shader (lighting + tex2D with implicit gradients) over the Sponza-like scene: the visibility-first path
+    (k_cover + the module's quad-granular k_shade, fused resolve, lazy clears) against the immediate k_raster path, which
+    test_sasl_tex2d_pixel_shader_equals_builtin_grad_path pins to the built-in program.  Every buffer and counter identical;
+    the visibility-first path must have run fewer shader lanes (it shades a quad once per DISTINCT final owner)."""
+    sh = jit.compile(PS_SPONZA, "ps", derivatives=conv)
+    a = _sponza_with_ps(cuda, sh, w, h, samples, 128, aniso)
+    b = _sponza_with_ps(cuda_jit_immediate, sh, w, h, samples, 128, aniso)
+    for f in frames:
+        ra, rb = a.run(cuda, f), b.run(cuda_jit_immediate, f)
+        assert cases.compare_frames(ra, rb) == [], f"frame {f}"
+        ta, tb = cuda.traffic(), cuda_jit_immediate.traffic()
+        for k in ("z_tested", "z_written", "c_written", "c_read"):
+            assert ta[k] == tb[k], f"frame {f}: traffic counter {k}"
+        assert ra.stats["ps_invocations"] > 1000
+        assert tb["ps_executed"] == rb.stats["ps_invocations"]  # the immediate path shades every quad it counts
+        assert 0 < ta["ps_executed"] < tb["ps_executed"], "the SASL shader did not take the visibility-first path"
+
+
+def test_sasl_pixel_shader_visibility_first_equals_builtin_twin(cuda):
+    """tex2D + constant alpha in SASL (cpp derivative convention) on every draw of the Sponza-like scene against the built-in
+    SLV_PS_TEX_GRAD_ALPHA: both take the visibility-first path (REPLACE blend), one through the pixel-granular k_shade, the
+    other through the quad-granular one; 16x anisotropic samplers, 4x MSAA."""
+    sh = jit.compile(PS_TEX_ALPHA.format(decls="float4 uv: TEXCOORD0;"), "ps", derivatives="cpp")
+    got = _sponza_with_ps(cuda, sh, 800, 448, 4, 128, 16, uniforms={"alpha": 0.75})
+    ref = S.SponzaLike(800, 448, 4, tex_size=128, max_aniso=16)
+    ref.setup(cuda)
+    base = ref.frame_draws
+
+    def frame_draws(be_, frame):
+        ds = base(be_, frame)
+        for d, (m, _, _) in zip(ds, ref.groups):
+            d.ps = A.shader_binding(A.PS_TEX_GRAD_ALPHA, S.pack_ps_tex_alpha(0, 0.75), [ref.samplers[m]])
+        return ds
+
+    ref.frame_draws = frame_draws
+    for f in (1, 6):
+        ra, rb = ref.run(cuda, f), got.run(cuda, f)
+        assert cases.compare_frames(ra, rb) == [], f"frame {f}"
+        assert ra.stats["ps_invocations"] > 1000
