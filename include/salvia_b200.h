@@ -90,6 +90,10 @@ enum {
    * d = tex2Dlod(samplers[0], float4(uv, 0, 0)).x = sampler::sample_2d_lod(uv, 0); pos = float4(in[0].xyz + (0, d*20, 0), 1)·wvp;
    * attr0 = (d, 0, 0, 0).   uniforms: mat44 wvp; vec2 terrainOffset; vec2 terrainScale; vs.samplers[0] = the height map  */
   SLV_VS_TERRAIN_VTF = 5,
+  /* the colour pass of samples/StandardShadowMap (resources/ssm/Draw.savs): in[0] = POSITION, in[1] = NORMAL, in[2] = TEXCOORD0;
+   * pos = in[0]·cameraWvp; attr0 = in[2]; attr1 = in[1]; attr2 = lightPos − in[0]; attr3 = cameraPos − in[0];
+   * attr4 = in[0]·lightWvp (the light-space position).  uniforms: slv_vs_ssm_draw_uniforms                              */
+  SLV_VS_SSM_DRAW = 6,
   SLV_VS_JIT = 255          /* a SASL vertex shader compiled at run time; select it with SLV_PROGRAM_JIT(module) */
 };
 enum {
@@ -105,6 +109,12 @@ enum {
   SLV_PS_TEX_GRAD_ALPHA = 5,
   SLV_PS_DISCARD_ALL = 6,   /* returns false for every pixel (early-Z quirk probe, App. B #3)       */
   SLV_PS_HEIGHT_COLOR = 7,  /* colour ramp over attr0.x (VertexTextureFetch.cpp:70-113)          no uniforms */
+  /* draw_cpp_ps of samples/StandardShadowMap/StandardShadowMap.cpp:62-142 — TWO samplers: samplers[0] = TexSampler (diffuse,
+   * tex2d of attr0, optional), samplers[1] = DepthSampler (the shadow map, nine tex2dlod taps at +-1/512 around the light-space
+   * position attr4.xyz / attr4.w, exponential shadow map with esm_constant 25000 and the sample's Gaussian weights);
+   * colour = tex · (ambient + (diffuse · clamp(L·N) + specular · pow(clamp(−reflect(L, N)·E), shininess)) · occlusion), a = 1.
+   * exp / log evaluate in float (expf / logf), pow in double (pow(float, int) promotes).  uniforms: slv_ps_ssm_draw_uniforms */
+  SLV_PS_SSM_DRAW = 8,
   SLV_PS_JIT = 255          /* a SASL pixel shader compiled at run time; select it with SLV_PROGRAM_JIT(module) */
 };
 enum {
@@ -122,6 +132,13 @@ typedef struct slv_vs_sponza_uniforms { float wvp[16]; float light_pos[4]; float
 typedef struct slv_vs_terrain_vtf_uniforms { float wvp[16]; float offset[2]; float scale[2]; } slv_vs_terrain_vtf_uniforms;
 typedef struct slv_ps_tex_alpha_uniforms { uint32_t reg; float alpha; } slv_ps_tex_alpha_uniforms;
 typedef struct slv_ps_sponza_uniforms { uint32_t has_sampler; } slv_ps_sponza_uniforms;
+typedef struct slv_vs_ssm_draw_uniforms { float camera_wvp[16]; float light_wvp[16]; float light_pos[4]; float camera_pos[4]; } slv_vs_ssm_draw_uniforms;
+typedef struct slv_ps_ssm_draw_uniforms {
+  float ambient[4], diffuse[4], specular[4];
+  int32_t shininess;
+  uint32_t has_tex_sampler;    /* samplers[0] bound (else the texture colour is white)    */
+  uint32_t has_depth_sampler;  /* samplers[1] bound (else occlusion = 0: ambient only)    */
+} slv_ps_ssm_draw_uniforms;
 
 /* ---- handles ---------------------------------------------------------------------------------- */
 typedef struct slv_device_t* slv_device;

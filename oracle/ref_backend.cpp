@@ -165,6 +165,29 @@ struct vs_sponza : vs_base {
   SLV_CLONE()
 };
 
+// cpp twin of resources/ssm/Draw.savs (the SASL vertex shader of samples/StandardShadowMap's colour pass)
+struct vs_ssm_draw : vs_base {
+  mat44 camera_wvp, light_wvp;
+  vec4 light_pos, camera_pos;
+  explicit vs_ssm_draw(slv_vs_ssm_draw_uniforms const& u)
+    : camera_wvp(load_mat(u.camera_wvp))
+    , light_wvp(load_mat(u.light_wvp))
+    , light_pos(u.light_pos[0], u.light_pos[1], u.light_pos[2], u.light_pos[3])
+    , camera_pos(u.camera_pos[0], u.camera_pos[1], u.camera_pos[2], u.camera_pos[3]) {
+    n_attrs = 5;
+  }
+  void shader_prog(const vs_input& in, vs_output& out) override {
+    vec4 pos = in.attribute(0);
+    out.attribute(1) = in.attribute(1);                          // norm
+    eflib::transform(out.position(), pos, camera_wvp);
+    eflib::transform(out.attribute(4), pos, light_wvp);          // lightSpacePos
+    out.attribute(2) = light_pos - pos;                          // lightDir
+    out.attribute(3) = camera_pos - pos;                         // cameraDir
+    out.attribute(0) = in.attribute(2);                          // tex
+  }
+  SLV_CLONE()
+};
+
 // ---------------------------------------------------------------------------------------------
 // pixel shaders
 struct ps_attr0_color : cpp_pixel_shader {
@@ -281,6 +304,62 @@ struct ps_sponza : cpp_pixel_shader {
     vec3 light_dir(eflib::normalize3(in.attribute(2).xyz()));
     float illum_diffuse = eflib::clamp(eflib::dot_prod3(light_dir, norm), 0.0f, 1.0f);
     out.color[0] = diff_color * illum_diffuse;
+    out.color[0][3] = 1.0f;
+    return true;
+  }
+  SLV_CLONE()
+};
+
+// draw_cpp_ps of samples/StandardShadowMap/StandardShadowMap.cpp:62-142, restated over the reference's own classes
+// (two samplers, nine tex2dlod taps of the shadow map, exponential shadow map).  The overloads the sample leaves to the
+// platform's <cmath> are pinned: exp / log in float, pow(float, int) in double (include/salvia_b200.h, SLV_PS_SSM_DRAW).
+struct ps_ssm_draw : cpp_pixel_shader {
+  sampler_ptr texsamp_, dsamp_;
+  vec4 ambient, diffuse, specular;
+  int shininess;
+  ps_ssm_draw(slv_ps_ssm_draw_uniforms const& u, sampler_ptr const& tex, sampler_ptr const& depth)
+    : texsamp_(tex), dsamp_(depth)
+    , ambient(u.ambient[0], u.ambient[1], u.ambient[2], u.ambient[3])
+    , diffuse(u.diffuse[0], u.diffuse[1], u.diffuse[2], u.diffuse[3])
+    , specular(u.specular[0], u.specular[1], u.specular[2], u.specular[3])
+    , shininess(u.shininess) {}
+  bool shader_prog(const vs_output& in, ps_output& out) override {
+    const float esm_constant = 25000.0f;
+    static const float gaussian_weights[9] = {0.027681f, 0.111014f, 0.027681f, 0.111014f, 0.445213f,
+                                              0.111014f, 0.027681f, 0.111014f, 0.027681f};
+    float occlusion = 0.0f;
+    if (dsamp_) {
+      vec3 lis_pos(in.attribute(4).xyz() / in.attribute(4).w());
+      vec2 sm_center((lis_pos.x() + 1.0f) * 0.5f, (1.0f - (lis_pos.y() + 1.0f) * 0.5f));
+      float sm_offset = 1 / 512.0f;
+      float shadow_depth[9];
+      for (int i = 0; i < 9; ++i) {
+        vec2 d(i % 3 == 0 ? -sm_offset : (i % 3 == 1 ? 0.0f : +sm_offset), i / 3 == 0 ? -sm_offset : (i / 3 == 1 ? 0.0f : +sm_offset));
+        vec2 c = sm_center + d;
+        vec4 coord_lod(c.x(), c.y(), 0.0f, 0.0f);
+        shadow_depth[i] = tex2dlod(*dsamp_, coord_lod).r;
+      }
+      float occluder = 0.0f;
+      for (int i = 1; i < 9; ++i) {
+        occluder += gaussian_weights[i] * std::exp(esm_constant * (shadow_depth[i] - shadow_depth[0]));
+      }
+      occluder += gaussian_weights[0];
+      occluder = std::log(occluder);
+      occluder += esm_constant * shadow_depth[0];
+      occlusion = eflib::clamp(std::exp(occluder - esm_constant * lis_pos[2]), 0.0f, 1.0f);
+    }
+    color_rgba32f tex_color(1.0f, 1.0f, 1.0f, 1.0f);
+    if (texsamp_) {
+      tex_color = tex2d(*texsamp_, 0);
+    }
+    vec3 norm(eflib::normalize3(in.attribute(1).xyz()));
+    vec3 light_dir(eflib::normalize3(in.attribute(2).xyz()));
+    vec3 eye_dir(eflib::normalize3(in.attribute(3).xyz()));
+    float illum_diffuse = eflib::clamp(eflib::dot_prod3(light_dir, norm), 0.0f, 1.0f);
+    float illum_specular = eflib::clamp(eflib::dot_prod3(-eflib::reflect3(light_dir, norm), eye_dir), 0.0f, 1.0f);
+    float sp = (float)std::pow((double)illum_specular, (double)shininess);
+    vec4 illum = ambient + (diffuse * illum_diffuse + specular * sp) * occlusion;
+    out.color[0] = tex_color.get_vec4() * illum;
     out.color[0][3] = 1.0f;
     return true;
   }
@@ -502,6 +581,7 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   case SLV_VS_PLANE_XZ: vs.reset(new vs_plane_xz(*(slv_vs_plane_xz_uniforms const*)d->vs.uniforms)); break;
   case SLV_VS_LIGHTS3: vs.reset(new vs_lights3(*(slv_vs_lights3_uniforms const*)d->vs.uniforms)); break;
   case SLV_VS_SPONZA: vs.reset(new vs_sponza(*(slv_vs_sponza_uniforms const*)d->vs.uniforms)); break;
+  case SLV_VS_SSM_DRAW: vs.reset(new vs_ssm_draw(*(slv_vs_ssm_draw_uniforms const*)d->vs.uniforms)); break;
   case SLV_VS_TERRAIN_VTF: {
     sampler_ptr s = sampler_of(dev, d->vs.samplers[0]);
     if (!s) return SLV_INVALID_PARAMETER;
@@ -529,6 +609,13 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   } break;
   case SLV_PS_DISCARD_ALL: ps.reset(new ps_discard_all()); break;
   case SLV_PS_HEIGHT_COLOR: ps.reset(new ps_height_color()); break;
+  case SLV_PS_SSM_DRAW: {
+    auto u = (slv_ps_ssm_draw_uniforms const*)d->ps.uniforms;
+    sampler_ptr tex = u->has_tex_sampler ? sampler_of(dev, d->ps.samplers[0]) : sampler_ptr();
+    sampler_ptr depth = u->has_depth_sampler ? sampler_of(dev, d->ps.samplers[1]) : sampler_ptr();
+    if ((u->has_tex_sampler && !tex) || (u->has_depth_sampler && !depth)) return SLV_INVALID_PARAMETER;
+    ps.reset(new ps_ssm_draw(*u, tex, depth));
+  } break;
   default: return SLV_INVALID_PARAMETER;
   }
 

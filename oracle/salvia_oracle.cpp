@@ -677,6 +677,7 @@ uint32_t vs_num_attrs(slv_shader_binding const& vs) {
   case SLV_VS_LIGHTS3: return 4;
   case SLV_VS_SPONZA: return 4;
   case SLV_VS_TERRAIN_VTF: return 1;
+  case SLV_VS_SSM_DRAW: return 5;
   }
   return 0;
 }
@@ -711,6 +712,15 @@ void run_vs(DrawCtx& c, V4 const in[SLV_MAX_VS_INPUT_ATTRS], VsOut& out) {
     out.r[2] = in[2];
     out.r[3] = sub4(mk4(u->light_pos[0], u->light_pos[1], u->light_pos[2], u->light_pos[3]), in[0]);
     out.r[4] = sub4(mk4(u->eye_pos[0], u->eye_pos[1], u->eye_pos[2], u->eye_pos[3]), in[0]);
+  } break;
+  case SLV_VS_SSM_DRAW: {  // resources/ssm/Draw.savs:25-36 (inputs: POSITION, NORMAL, TEXCOORD0)
+    auto u = (slv_vs_ssm_draw_uniforms const*)vs.uniforms;
+    out.r[0] = transform(in[0], u->camera_wvp);
+    out.r[1] = in[2];                                                                                       // tex
+    out.r[2] = in[1];                                                                                       // norm
+    out.r[3] = sub4(mk4(u->light_pos[0], u->light_pos[1], u->light_pos[2], u->light_pos[3]), in[0]);        // lightDir
+    out.r[4] = sub4(mk4(u->camera_pos[0], u->camera_pos[1], u->camera_pos[2], u->camera_pos[3]), in[0]);    // cameraDir
+    out.r[5] = transform(in[0], u->light_wvp);                                                              // lightSpacePos
   } break;
   case SLV_VS_TERRAIN_VTF: {  // VertexTextureFetch.cpp:38-61; tex2Dlod = sample_2d_lod (sampler_api.cpp:50-52, sampler.cpp:850-852)
     auto u = (slv_vs_terrain_vtf_uniforms const*)vs.uniforms;
@@ -1040,6 +1050,44 @@ bool run_ps(DrawCtx& c, PsQuad& q, int pix, V4& color) {
     color = sample_2d_grad(*c.sampler_tex[0], c.samplers[0]->d, a[0], a[1], a1[0] - a0[0], a1[1] - a0[1],
                            a2[0] - a0[0], a2[1] - a0[1], 0.0f);
     color[3] = u->alpha;
+    return true;
+  }
+  case SLV_PS_SSM_DRAW: {  // draw_cpp_ps::shader_prog, samples/StandardShadowMap/StandardShadowMap.cpp:84-137
+    auto u = (slv_ps_ssm_draw_uniforms const*)ps.uniforms;
+    const float esm_constant = 25000.0f;                                                                   // :33
+    static const float gaussian_weights[9] = {0.027681f, 0.111014f, 0.027681f, 0.111014f, 0.445213f,       // :34-42
+                                              0.111014f, 0.027681f, 0.111014f, 0.027681f};
+    float occlusion = 0.0f;
+    if (u->has_depth_sampler) {
+      V4 const& a4 = in.r[5];
+      float lis[3] = {a4[0] / a4[3], a4[1] / a4[3], a4[2] / a4[3]};   // vec3 / float: per-component division (vector_generic.h:340)
+      float cx = (lis[0] + 1.0f) * 0.5f, cy = (1.0f - (lis[1] + 1.0f) * 0.5f);
+      float sm_offset = 1 / 512.0f;
+      const float ox[3] = {-sm_offset, 0.0f, +sm_offset};
+      float shadow_depth[9];
+      for (int i = 0; i < 9; ++i)  // tex2dlod(s, coord) = s.sample(x, y, lod) (cpp_pixel_shader.cpp:33-35, sampler.cpp:767-769)
+        shadow_depth[i] = sample_impl(*c.sampler_tex[1], c.samplers[1]->d, cx + ox[i % 3], cy + ox[i / 3], 0.0f, nullptr)[0];
+      float occluder = 0.0f;
+      for (int i = 1; i < 9; ++i) occluder += gaussian_weights[i] * std::exp(esm_constant * (shadow_depth[i] - shadow_depth[0]));
+      occluder += gaussian_weights[0];
+      occluder = std::log(occluder);
+      occluder += esm_constant * shadow_depth[0];
+      occlusion = clampf(std::exp(occluder - esm_constant * lis[2]), 0.0f, 1.0f);
+    }
+    V4 tex = mk4(1, 1, 1, 1);
+    if (u->has_tex_sampler) tex = ps_tex2d(c, q, pix, 0, 0);
+    float n[3], l[3], e[3];
+    normalize3(n, in.r[2].v);
+    normalize3(l, in.r[3].v);
+    normalize3(e, in.r[4].v);
+    float illum_diffuse = clampf(dot3(l, n), 0.0f, 1.0f);
+    float k2 = 2.0f * dot3(l, n);  // reflect3(i, n) = i - n * (2 * dot(i, n))  (eflib/src/math.cpp:85-87)
+    float r[3] = {-(l[0] - n[0] * k2), -(l[1] - n[1] * k2), -(l[2] - n[2] * k2)};
+    float illum_specular = clampf(dot3(r, e), 0.0f, 1.0f);
+    float sp = (float)std::pow((double)illum_specular, (double)u->shininess);  // pow(float, int): both promoted to double
+    for (int k = 0; k < 3; ++k)
+      color[k] = tex[k] * (u->ambient[k] + (u->diffuse[k] * illum_diffuse + u->specular[k] * sp) * occlusion);
+    color[3] = 1.0f;
     return true;
   }
   case SLV_PS_SPONZA: {  // Sponza.cpp:117-136 (the dead specular/ambient terms are dropped)
@@ -1391,6 +1439,11 @@ slv_result do_draw(Device& dev, slv_draw_desc const& d) {
       c.samplers[i] = &r->samp;
       c.sampler_tex[i] = sampler_texture(dev, r->samp);
     }
+  }
+  if (d.ps.program == SLV_PS_SSM_DRAW) {
+    auto u = (slv_ps_ssm_draw_uniforms const*)d.ps.uniforms;
+    if (d.ps.uniform_bytes < sizeof(slv_ps_ssm_draw_uniforms) || vs_num_attrs(d.vs) < 5) return SLV_INVALID_PARAMETER;
+    if ((u->has_tex_sampler && !c.sampler_tex[0]) || (u->has_depth_sampler && !c.sampler_tex[1])) return SLV_INVALID_PARAMETER;
   }
   if (d.vs.program == SLV_VS_TERRAIN_VTF) {
     auto r = dev.get(d.vs.samplers[0], Resource::SAMPLER);

@@ -303,6 +303,7 @@ uint32_t vs_num_attrs(const slv_shader_binding& vs) {
   case SLV_VS_LIGHTS3: return 4;
   case SLV_VS_SPONZA: return 4;
   case SLV_VS_TERRAIN_VTF: return 1;
+  case SLV_VS_SSM_DRAW: return 5;
   }
   return 0xFFFFFFFFu;
 }
@@ -322,6 +323,7 @@ bool launch_raster_s(const RasterParams& rp, const RasterParams* batch, uint32_t
   case SLV_PS_TEX_GRAD_ALPHA: k_raster<S, SLV_PS_TEX_GRAD_ALPHA><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, n); return true;
   case SLV_PS_DISCARD_ALL: k_raster<S, SLV_PS_DISCARD_ALL><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, n); return true;
   case SLV_PS_HEIGHT_COLOR: k_raster<S, SLV_PS_HEIGHT_COLOR><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, n); return true;
+  case SLV_PS_SSM_DRAW: k_raster<S, SLV_PS_SSM_DRAW><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, n); return true;
   }
   return false;
 }
@@ -336,6 +338,7 @@ bool launch_shade_s(const RasterParams& rp, const RasterParams* batch, uint32_t 
   case SLV_PS_SPONZA: k_shade<S, SLV_PS_SPONZA><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, n_draws, db); return true;
   case SLV_PS_TEX_GRAD_ALPHA: k_shade<S, SLV_PS_TEX_GRAD_ALPHA><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, n_draws, db); return true;
   case SLV_PS_HEIGHT_COLOR: k_shade<S, SLV_PS_HEIGHT_COLOR><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, n_draws, db); return true;
+  case SLV_PS_SSM_DRAW: k_shade<S, SLV_PS_SSM_DRAW><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, n_draws, db); return true;
   }
   return false;
 }
@@ -1241,7 +1244,15 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
                        rp.ps_program == SLV_PS_TEX_ALPHA || rp.ps_program == SLV_PS_TEX_GRAD_ALPHA ||
                        (rp.ps_program == SLV_PS_SPONZA &&
                         reinterpret_cast<const slv_ps_sponza_uniforms*>(d->ps.uniforms)->has_sampler);
+  bool needs_sampler1 = false;
+  if (rp.ps_program == SLV_PS_SSM_DRAW) {
+    auto u = reinterpret_cast<const slv_ps_ssm_draw_uniforms*>(d->ps.uniforms);
+    if (d->ps.uniform_bytes < sizeof(slv_ps_ssm_draw_uniforms) || n_attrs < 5) return SLV_INVALID_PARAMETER;
+    needs_sampler = u->has_tex_sampler != 0;
+    needs_sampler1 = u->has_depth_sampler != 0;
+  }
   if (needs_sampler && !fill_sampler(dev, d->ps.samplers[0], rp.sampler0)) return SLV_INVALID_PARAMETER;
+  if (needs_sampler1 && !fill_sampler(dev, d->ps.samplers[1], rp.sampler1)) return SLV_INVALID_PARAMETER;
   if (rp.ps_program == SLV_PS_TEX_ALPHA || rp.ps_program == SLV_PS_TEX_GRAD_ALPHA) {
     if (reinterpret_cast<const slv_ps_tex_alpha_uniforms*>(d->ps.uniforms)->reg >= n_attrs) return SLV_INVALID_PARAMETER;
   }
@@ -1263,6 +1274,13 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
       if (rcf != SLV_OK) return rcf;
     }
   }
+  if (needs_sampler1 && !dev->pending.empty()) {
+    const uint8_t* t1 = rp.sampler1.tex.level[0].data;
+    if (t1 == rp.color0.data || t1 == rp.color1.data || t1 == rp.ds.data) {
+      slv_result rcf = flush_batch(dev);
+      if (rcf != SLV_OK) return rcf;
+    }
+  }
   if (vs_needs_sampler) {
     // the vertex stage runs on the front stream: a height map written on the main stream (upload, an earlier render pass) has to
     // be complete first - flush what is queued and let the front half order after the main stream
@@ -1277,6 +1295,7 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
 
   // lazy clears: a texture this draw SAMPLES, and the second colour target, must hold their cleared contents for real
   if (needs_sampler) { slv_result rcm__ = materialize_clear(dev, texture_of_data(dev, rp.sampler0.tex.level[0].data)); if (rcm__ != SLV_OK) return rcm__; }
+  if (needs_sampler1) { slv_result rcm__ = materialize_clear(dev, texture_of_data(dev, rp.sampler1.tex.level[0].data)); if (rcm__ != SLV_OK) return rcm__; }
   if (rp.color1.data) { slv_result rcm__ = materialize_clear(dev, texture_of_data(dev, rp.color1.data)); if (rcm__ != SLV_OK) return rcm__; }
   dev->batch_color = d->n_color_targets ? d->color_targets[0] : 0;
   dev->batch_ds = d->ds_target;

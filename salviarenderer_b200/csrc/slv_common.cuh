@@ -130,6 +130,7 @@ struct RasterParams {
   uint32_t ps_program, bs_program;
   alignas(16) uint8_t ps_uniforms[SLV_MAX_UNIFORM_BYTES];
   SamplerRef sampler0;
+  SamplerRef sampler1;  // second pixel-shader sampler (SLV_PS_SSM_DRAW: the shadow map); tex.n_levels == 0 when unbound
   unsigned long long* stats;
 };
 

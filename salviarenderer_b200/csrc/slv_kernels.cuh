@@ -140,6 +140,17 @@ __device__ __forceinline__ void run_vs(const GeomParams& p, uint32_t index, VsOu
     if (R == SLV_JIT_R) slv_jit_vs(in, p.vs_uniforms, out.r, p.sampler0);
     break;
 #endif
+  case SLV_VS_SSM_DRAW: {  // resources/ssm/Draw.savs (StandardShadowMap colour pass)
+    auto u = reinterpret_cast<const slv_vs_ssm_draw_uniforms*>(p.vs_uniforms);
+    out.r[0] = transform(in[0], u->camera_wvp);
+    if (R == 6) {
+      out.r[R > 5 ? 1 : 0] = in[2];
+      out.r[R > 5 ? 2 : 0] = in[1];
+      out.r[R > 5 ? 3 : 0] = f4_sub(make_float4(u->light_pos[0], u->light_pos[1], u->light_pos[2], u->light_pos[3]), in[0]);
+      out.r[R > 5 ? 4 : 0] = f4_sub(make_float4(u->camera_pos[0], u->camera_pos[1], u->camera_pos[2], u->camera_pos[3]), in[0]);
+      out.r[R > 5 ? 5 : 0] = transform(in[0], u->light_wvp);
+    }
+  } break;
   case SLV_VS_SPONZA: {
     auto u = reinterpret_cast<const slv_vs_sponza_uniforms*>(p.vs_uniforms);
     out.r[0] = transform(in[0], u->wvp);
@@ -859,6 +870,12 @@ __device__ __forceinline__ float4 interp_attr(const float4* rec, int R, int reg,
   return r;
 }
 
+// expf / logf of the host C library, on the device: evaluated in double and rounded once to float, i.e. the correctly
+// rounded result, which is what glibc's expf (<= 0.502 ULP) and logf return in all but rare last-bit cases (documented
+// tolerance of the programs that use them, tests/cases.py TRANSCENDENTAL_CASES)
+__device__ __forceinline__ float exp_f32(float x) { return (float)exp((double)x); }
+__device__ __forceinline__ float log_f32(float x) { return (float)log((double)x); }
+
 struct PixelCtx {  // what a pixel shader may read (immediate path: the four lanes of a quad run together)
   const float4* rec;
   int R;
@@ -980,6 +997,54 @@ __device__ __forceinline__ bool run_ps(const RasterParams& p, const Ctx& px, flo
     float linv = 1.0f / ll;
     float illum = clampf(dot3(l.x * linv, l.y * linv, l.z * linv, n.x * ninv, n.y * ninv, n.z * ninv), 0.0f, 1.0f);
     color = make_float4(diff.x * illum, diff.y * illum, diff.z * illum, 1.0f);
+    return true;
+  }
+  if (PS == SLV_PS_SSM_DRAW) {  // draw_cpp_ps, StandardShadowMap.cpp:62-142
+    auto u = reinterpret_cast<const slv_ps_ssm_draw_uniforms*>(p.ps_uniforms);
+    const float esm = 25000.0f;
+    float occlusion = 0.0f;
+    if (u->has_depth_sampler) {
+      const float4 a4 = px.attr(4);
+      const float lx = a4.x / a4.w, ly = a4.y / a4.w, lz = a4.z / a4.w;  // vec3 / float divides per component
+      const float cx = (lx + 1.0f) * 0.5f, cy = 1.0f - (ly + 1.0f) * 0.5f;
+      const float off = 1 / 512.0f;
+      // nine taps, row-major from (-off, -off); tap 0 is the reference depth of the exponential filter.  One out-of-line
+      // sampler (tex2dlod = sampler::sample, cpp_pixel_shader.cpp:33-35) serves all of them.
+      const float sd0 = vs_sample_lod(p.sampler1, cx + -off, cy + -off, 0.0f).x;
+      float occluder = 0.0f;
+#pragma unroll 1
+      for (int i = 1; i < 9; ++i) {
+        const int ix = i % 3, iy = i / 3;
+        const float ox = ix == 0 ? -off : (ix == 1 ? 0.0f : off), oy = iy == 0 ? -off : (iy == 1 ? 0.0f : off);
+        const float sd = vs_sample_lod(p.sampler1, cx + ox, cy + oy, 0.0f).x;
+        const float gw = i == 4 ? 0.445213f : ((i & 1) ? 0.111014f : 0.027681f);
+        occluder += gw * exp_f32(esm * (sd - sd0));
+      }
+      occluder += 0.027681f;
+      occluder = log_f32(occluder);
+      occluder += esm * sd0;
+      occlusion = clampf(exp_f32(occluder - esm * lz), 0.0f, 1.0f);
+    }
+    float4 tex = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    if (u->has_tex_sampler) tex = ps_tex2d(p.sampler0, px, 0, px.attr(0));
+    const float4 nr = px.attr(1), lr = px.attr(2), er = px.attr(3);
+    float nl = length3(nr.x, nr.y, nr.z); if (eq_eps(nl, 0.0f)) nl = 1.0f;
+    float ll = length3(lr.x, lr.y, lr.z); if (eq_eps(ll, 0.0f)) ll = 1.0f;
+    float el = length3(er.x, er.y, er.z); if (eq_eps(el, 0.0f)) el = 1.0f;
+    const float ninv = 1.0f / nl, linv = 1.0f / ll, einv = 1.0f / el;
+    const float nx = nr.x * ninv, ny = nr.y * ninv, nz = nr.z * ninv;
+    const float Lx = lr.x * linv, Ly = lr.y * linv, Lz = lr.z * linv;
+    const float ex = er.x * einv, ey = er.y * einv, ez = er.z * einv;
+    const float illum_diffuse = clampf(dot3(Lx, Ly, Lz, nx, ny, nz), 0.0f, 1.0f);
+    const float k2 = 2.0f * dot3(Lx, Ly, Lz, nx, ny, nz);  // reflect3: i - n * (2 * dot(i, n))  (eflib/src/math.cpp:85-87)
+    const float rx = -(Lx - nx * k2), ry = -(Ly - ny * k2), rz = -(Lz - nz * k2);
+    const float illum_specular = clampf(dot3(rx, ry, rz, ex, ey, ez), 0.0f, 1.0f);
+    const float sp = (float)pow((double)illum_specular, (double)u->shininess);  // pow(float, int) promotes to double
+    float o[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      o[k] = u->ambient[k] + (u->diffuse[k] * illum_diffuse + u->specular[k] * sp) * occlusion;
+    color = make_float4(tex.x * o[0], tex.y * o[1], tex.z * o[2], 1.0f);
     return true;
   }
   color = make_float4(0, 0, 0, 0);

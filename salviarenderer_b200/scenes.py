@@ -208,6 +208,15 @@ def pack_ps_sponza(has_sampler):
     return struct.pack("<I", int(has_sampler))
 
 
+def pack_vs_ssm_draw(camera_wvp, light_wvp, light_pos, camera_pos):
+    return (np.asarray(camera_wvp, f32).tobytes() + np.asarray(light_wvp, f32).tobytes() + np.asarray(light_pos, f32).tobytes() +
+            np.asarray(camera_pos, f32).tobytes())
+
+
+def pack_ps_ssm_draw(ambient, diffuse, specular, shininess, has_tex, has_depth):
+    return struct.pack("<12fiII", *ambient, *diffuse, *specular, int(shininess), int(has_tex), int(has_depth))
+
+
 # ---- frame targets ---------------------------------------------------------------------------------------
 @dataclass
 class Targets:
@@ -582,6 +591,92 @@ class HeightFieldTwoPass:
         d.ps = A.shader_binding(A.PS_LIGHTS3)
         d.bs = A.shader_binding(A.BS_REPLACE)
         be.draw(d)
+        if t.resolved is not None:
+            be.resolve(t.color, t.resolved)
+
+    def run(self, be: A.Backend, frame: int) -> FrameResult:
+        be.query_begin()
+        self.render(be, frame)
+        stats = be.query_get()
+        res = read_frame(be, self.t, stats)
+        sm = be.read_texture(self.shadow)
+        res.count = sm.view(np.float32).reshape(sm.shape[0], sm.shape[1], sm.shape[2], 2)[..., 0].copy()
+        return res
+
+
+# ===========================================================================================================
+# StandardShadowMap (BASELINE configs[4], the sample itself): shadow pass from the light + colour pass that SAMPLES the map
+# ===========================================================================================================
+class StandardShadowMap:
+    """samples/StandardShadowMap/StandardShadowMap.cpp:160-330.  Pass 1 (gen_sm): depth only from the light into an rg32f
+    texture of the screen size, no colour target, cull back.  Pass 2 (draw): Draw.savs + draw_cpp_ps — diffuse texture,
+    Phong terms and an exponential shadow map read through a SECOND sampler (point filter, border colour (1, 0, 0, 0)) with
+    nine tex2dlod taps.  The slanted ground plane, camera, light orbit and material constants are the sample's; cup.obj (an
+    asset that does not travel) is replaced by a bulged cylinder and a sphere from this file's generators, textured with the
+    seeded brick texture through a linear / clamp sampler like the sample's materials."""
+
+    def __init__(self, w=640, h=360, samples=1, tex_size=128, detail=1):
+        self.w, self.h, self.samples = w, h, samples
+        self.plane = create_planar((-3.0, 0.0, -3.0), (6.0, -1.0, 0.0), (0.0, -1.0, 6.0), 1, 1, False)   # :199-205
+        cyl_vb, cyl_ib = _cylinder((0.2, -1.0, 0.1), 0.7, 1.7, 24 * detail, 6 * detail, uvscale=(2, 1), bulge=0.25)
+        sph_vb, sph_ib = _sphere((1.5, -0.55, -1.3), 0.55, 20 * detail, 10 * detail)
+        # interleaved 48-byte vertices (pos, uv, normal): POSITION -> reg 0, NORMAL -> reg 1, TEXCOORD0 -> reg 2 (Draw.savs VSIn)
+        el = [(0, _V4, 0, 0, 1.0), (1, _V4, 0, 32, 0.0), (2, _V4, 0, 16, 0.0)]
+        self.objects = [Mesh([cyl_vb], el, cyl_ib.reshape(-1), len(cyl_ib)), Mesh([sph_vb], el, sph_ib.reshape(-1), len(sph_ib))]
+        self.brick = brick_texture(tex_size)
+        self.n_frames = 8                                                                                   # TEST_FRAME_COUNT
+
+    def setup(self, be: A.Backend):
+        self.t = create_targets(be, self.w, self.h, self.samples, A.PF_BGRA8)
+        self.shadow = be.create_texture(self.w, self.h, 1, A.PF_RG32F)                                      # :174-175
+        self.sm_samp = be.create_sampler(A.sampler_desc(A.FILTER_POINT, A.FILTER_POINT, A.FILTER_POINT, addr_u=A.ADDR_BORDER,
+                                                        addr_v=A.ADDR_BORDER, border=(1.0, 0.0, 0.0, 0.0)), self.shadow)  # :177-185
+        self.tex = make_texture(be, self.brick)
+        self.tex_samp = be.create_sampler(A.sampler_desc(A.FILTER_LINEAR, A.FILTER_LINEAR, A.FILTER_LINEAR, addr_u=A.ADDR_CLAMP,
+                                                         addr_v=A.ADDR_CLAMP), self.tex)                    # :272-278
+        self.plane.upload(be)
+        for m in self.objects:
+            m.upload(be)
+
+    def frame_uniforms(self, frame):
+        aspect = f32(self.w) / f32(self.h)
+        camera_pos = (6.0, 3.1, 3.0, 1.0)                                                                   # :305-310
+        cam = mat_mul(mat_lookat(camera_pos[:3], (0.0, 0.6, 0.0), (0, 1, 0)), mat_perspective_fov(math.pi / 4, aspect, 0.1, 100.0))
+        scene_sec = float(f32(frame * 3.3) / f32(self.n_frames - 1))                                        # :317-319
+        theta = 0.3 * scene_sec
+        light_pos = (-4.0 * math.sin(theta), 6.1, 3.5 * math.cos(theta), 1.0)                               # :323-327
+        light = mat_mul(mat_lookat(light_pos[:3], (0.0, 0.6, 0.0), (0, 1, 0)), mat_perspective_fov(math.pi / 4, aspect, 0.1, 40.0))
+        return cam, light, light_pos, camera_pos
+
+    def render(self, be: A.Backend, frame: int):
+        t = self.t
+        cam, light, light_pos, camera_pos = self.frame_uniforms(frame)
+        # ---- gen_sm (:212-239): every mesh from the light, depth only
+        be.clear_depth_stencil(self.shadow, A.CLEAR_DEPTH | A.CLEAR_STENCIL, 1.0, 0)
+        for m in [self.plane] + self.objects:
+            d = base_desc(t, self.w, self.h, cull=A.CULL_BACK)
+            d.n_color_targets = 0
+            d.ds_target = self.shadow.handle
+            m.fill_desc(be, d)
+            d.vs = A.shader_binding(A.VS_MVP_PASSTHROUGH, pack_vs_mvp_passthrough(light, [0]))
+            d.ps = A.shader_binding(A.PS_ATTR0_COLOR)
+            d.bs = A.shader_binding(A.BS_REPLACE)
+            be.draw(d)
+        # ---- draw (:241-300)
+        be.clear_color(t.color, (0.2, 0.2, 0.5, 1.0))
+        be.clear_depth_stencil(t.ds, A.CLEAR_DEPTH | A.CLEAR_STENCIL, 1.0, 0)
+        vs = A.shader_binding(A.VS_SSM_DRAW, pack_vs_ssm_draw(cam, light, light_pos, camera_pos))
+        mats = [((0.1, 0.1, 0.1, 0.1), (0.8, 0.8, 0.8, 0.1), (0.4, 0.4, 0.4, 0.1), 32, False),            # the plane (:262-270)
+                ((0.18, 0.14, 0.12, 1.0), (0.9, 0.8, 0.7, 1.0), (0.5, 0.5, 0.5, 1.0), 16, True),
+                ((0.10, 0.14, 0.20, 1.0), (0.6, 0.8, 0.95, 1.0), (0.9, 0.9, 0.9, 1.0), 48, True)]
+        for m, (amb, dif, spe, shin, textured) in zip([self.plane] + self.objects, mats):
+            d = base_desc(t, self.w, self.h, cull=A.CULL_BACK)
+            m.fill_desc(be, d)
+            d.vs = vs
+            d.ps = A.shader_binding(A.PS_SSM_DRAW, pack_ps_ssm_draw(amb, dif, spe, shin, textured, True),
+                                    [self.tex_samp if textured else 0, self.sm_samp])
+            d.bs = A.shader_binding(A.BS_REPLACE)
+            be.draw(d)
         if t.resolved is not None:
             be.resolve(t.color, t.resolved)
 

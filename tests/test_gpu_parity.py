@@ -33,6 +33,8 @@ def test_cuda_matches_reference_golden(cuda, name):
         want = GOLDEN[name][str(f)]
         for k in ("stats", "depth", "stencil", "count"):  # bit-exact class
             assert got.get(k) == want.get(k), f"{name} frame {f}: {k}"
+        if name in cases.TRANSCENDENTAL_CASES:
+            continue  # colour of these cases: per-pixel tolerance check against the oracle (test_cuda_matches_oracle)
         if got["color"] != want["color"] or got.get("resolved") != want.get("resolved"):
             pytest.fail(f"{name} frame {f}: colour hash differs from the reference fixture "
                         f"(see test_cuda_matches_oracle for the per-pixel tolerance check)")
