@@ -1244,7 +1244,7 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
                        rp.ps_program == SLV_PS_TEX_ALPHA || rp.ps_program == SLV_PS_TEX_GRAD_ALPHA ||
                        (rp.ps_program == SLV_PS_SPONZA &&
                         reinterpret_cast<const slv_ps_sponza_uniforms*>(d->ps.uniforms)->has_sampler);
-  bool needs_sampler1 = false;
+  bool needs_sampler1 = rp.ps_program == SLV_PS_JIT && d->ps.samplers[1] != 0;  // a SASL pixel shader's second sampler
   if (rp.ps_program == SLV_PS_SSM_DRAW) {
     auto u = reinterpret_cast<const slv_ps_ssm_draw_uniforms*>(d->ps.uniforms);
     if (d->ps.uniform_bytes < sizeof(slv_ps_ssm_draw_uniforms) || n_attrs < 5) return SLV_INVALID_PARAMETER;

@@ -492,10 +492,13 @@ class ShaderUnit:
 
 
 SWZ = {"x": 0, "y": 1, "z": 2, "w": 3, "r": 0, "g": 1, "b": 2, "a": 3}
-UNARY_MATH = {"sqrt": "sqrtf", "exp": "expf", "exp2": "exp2f", "log": "logf", "log2": "log2f", "log10": "log10f",
-              "sin": "sinf", "cos": "cosf", "tan": "tanf", "asin": "asinf", "acos": "acosf", "atan": "atanf",
-              "sinh": "sinhf", "cosh": "coshf", "tanh": "tanhf", "floor": "floorf", "ceil": "ceilf",
-              "trunc": "truncf", "round": "rintf"}
+# transcendental functions go through sasl_rt.h's sasl_m_* wrappers: the host C library's float function on the CPU, the
+# double-precision device function rounded ONCE to float on the GPU (= the correctly rounded result, which is what glibc's
+# float functions return but for rare last-bit cases; CUDA's own float versions are 1-2 ulp off)
+UNARY_MATH = {"sqrt": "sqrtf", "exp": "sasl_m_exp", "exp2": "sasl_m_exp2", "log": "sasl_m_log", "log2": "sasl_m_log2",
+              "log10": "sasl_m_log10", "sin": "sasl_m_sin", "cos": "sasl_m_cos", "tan": "sasl_m_tan", "asin": "sasl_m_asin",
+              "acos": "sasl_m_acos", "atan": "sasl_m_atan", "sinh": "sasl_m_sinh", "cosh": "sasl_m_cosh", "tanh": "sasl_m_tanh",
+              "floor": "floorf", "ceil": "ceilf", "trunc": "truncf", "round": "rintf"}
 INTRINSICS = sorted(list(UNARY_MATH) + ["abs", "rsqrt", "frac", "saturate", "sign", "radians", "degrees", "min", "max", "pow",
                                          "fmod", "step", "atan2", "ldexp", "clamp", "lerp", "smoothstep", "mad", "dot", "cross",
                                          "length", "distance", "normalize", "reflect", "mul", "transpose", "any", "all",
@@ -868,9 +871,9 @@ class Gen:
     def i_degrees(self, a, n): return self.map1(a, n, lambda c: f"({c} * 57.29577951308232f)")
     def i_min(self, a, n): return self.mapn(a, n, lambda x, y: f"fminf({x}, {y})", 2)
     def i_max(self, a, n): return self.mapn(a, n, lambda x, y: f"fmaxf({x}, {y})", 2)
-    def i_pow(self, a, n): return self.mapn(a, n, lambda x, y: f"powf({x}, {y})", 2)
+    def i_pow(self, a, n): return self.mapn(a, n, lambda x, y: f"sasl_m_pow({x}, {y})", 2)
     def i_fmod(self, a, n): return self.mapn(a, n, lambda x, y: f"fmodf({x}, {y})", 2)
-    def i_atan2(self, a, n): return self.mapn(a, n, lambda x, y: f"atan2f({x}, {y})", 2)
+    def i_atan2(self, a, n): return self.mapn(a, n, lambda x, y: f"sasl_m_atan2({x}, {y})", 2)
     def i_step(self, a, n): return self.mapn(a, n, lambda e, x: f"(({x} >= {e}) ? 1.0f : 0.0f)", 2)
     def i_clamp(self, a, n): return self.mapn(a, n, lambda x, lo, hi: f"sasl_clamp({x}, {lo}, {hi})", 3)
     def i_mad(self, a, n): return self.mapn(a, n, lambda x, y, z: f"(({x} * {y}) + {z})", 3)
@@ -1344,6 +1347,6 @@ def compile_shader(source: str, stage: str, entry: str | None = None) -> ShaderU
         raise ValueError("stage must be 'vs', 'ps' or 'lib' (functions only, no entry point: the reference's *.ss test units)")
     g = Gen(source, stage, entry)
     unit = g.run()
-    if stage in ("ps", "vs") and len(unit.reflection.samplers) > 1:
-        raise CompileError("more than one sampler per shader is not supported yet")
+    if len(unit.reflection.samplers) > (2 if stage == "ps" else 1):  # RasterParams.sampler0 / sampler1, GeomParams.sampler0
+        raise CompileError("at most two samplers per pixel shader and one per vertex shader are supported")
     return unit

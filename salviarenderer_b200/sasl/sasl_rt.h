@@ -41,6 +41,19 @@ SASL_FN unsigned sasl_countbits(unsigned v) {
 #endif
 }
 
+// libm (see frontend.py UNARY_MATH)
+#if defined(__CUDACC__)
+#define SASL_M1(name) SASL_FN float sasl_m_##name(float x) { return (float)name((double)x); }
+#define SASL_M2(name) SASL_FN float sasl_m_##name(float x, float y) { return (float)name((double)x, (double)y); }
+#else
+#define SASL_M1(name) SASL_FN float sasl_m_##name(float x) { return std::name(x); }
+#define SASL_M2(name) SASL_FN float sasl_m_##name(float x, float y) { return std::name(x, y); }
+#endif
+SASL_M1(exp) SASL_M1(exp2) SASL_M1(log) SASL_M1(log2) SASL_M1(log10) SASL_M1(sin) SASL_M1(cos) SASL_M1(tan) SASL_M1(asin)
+SASL_M1(acos) SASL_M1(atan) SASL_M1(sinh) SASL_M1(cosh) SASL_M1(tanh) SASL_M2(pow) SASL_M2(atan2)
+#undef SASL_M1
+#undef SASL_M2
+
 #if defined(__CUDACC__)
 typedef slv::SamplerRef SaslSampler;
 // sasl.vs.tex2d.lod -> sampler::sample_2d_lod(coord.xy, coord.w) (salvia/src/resource/sampler_api.cpp:50-52)
@@ -81,15 +94,13 @@ SASL_FN float sasl_ddy(const Ctx& px, float v) {
 template <class Ctx>
 SASL_FN void sasl_tex2d_grad(const slv::RasterParams& p, const Ctx&, int slot, float u, float v, float dudx, float dvdx, float dudy,
                              float dvdy, float bias, float& r, float& g, float& b, float& a) {
-  (void)slot;  // one sampler per pixel shader (slot 0)
-  const float4 c = slv::sample_2d_grad(p.sampler0, u, v, dudx, dvdx, dudy, dvdy, bias);
+  const float4 c = slv::sample_2d_grad(slot ? p.sampler1 : p.sampler0, u, v, dudx, dvdx, dudy, dvdy, bias);  // slots 0 and 1
   r = c.x; g = c.y; b = c.z; a = c.w;
 }
 template <class Ctx>
 SASL_FN void sasl_tex2d_lod(const slv::RasterParams& p, const Ctx&, int slot, float u, float v, float lod, float& r, float& g, float& b,
                             float& a) {
-  (void)slot;
-  const float4 c = slv::sample_impl(p.sampler0, u, v, lod, nullptr);
+  const float4 c = slv::sample_impl(slot ? p.sampler1 : p.sampler0, u, v, lod, nullptr);
   r = c.x; g = c.y; b = c.z; a = c.w;
 }
 #else

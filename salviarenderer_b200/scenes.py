@@ -615,8 +615,11 @@ class StandardShadowMap:
     asset that does not travel) is replaced by a bulged cylinder and a sphere from this file's generators, textured with the
     seeded brick texture through a linear / clamp sampler like the sample's materials."""
 
-    def __init__(self, w=640, h=360, samples=1, tex_size=128, detail=1):
+    def __init__(self, w=640, h=360, samples=1, tex_size=128, detail=1, textured_plane=False, ps_binding=None):
         self.w, self.h, self.samples = w, h, samples
+        # optional override (tests of run-time compiled SASL shaders): (ambient, diffuse, specular, shininess, tex_sampler,
+        # shadow_sampler) -> ShaderBinding; textured_plane binds the brick texture to the ground plane as well
+        self.textured_plane, self.ps_binding = textured_plane, ps_binding
         self.plane = create_planar((-3.0, 0.0, -3.0), (6.0, -1.0, 0.0), (0.0, -1.0, 6.0), 1, 1, False)   # :199-205
         cyl_vb, cyl_ib = _cylinder((0.2, -1.0, 0.1), 0.7, 1.7, 24 * detail, 6 * detail, uvscale=(2, 1), bulge=0.25)
         sph_vb, sph_ib = _sphere((1.5, -0.55, -1.3), 0.55, 20 * detail, 10 * detail)
@@ -666,15 +669,18 @@ class StandardShadowMap:
         be.clear_color(t.color, (0.2, 0.2, 0.5, 1.0))
         be.clear_depth_stencil(t.ds, A.CLEAR_DEPTH | A.CLEAR_STENCIL, 1.0, 0)
         vs = A.shader_binding(A.VS_SSM_DRAW, pack_vs_ssm_draw(cam, light, light_pos, camera_pos))
-        mats = [((0.1, 0.1, 0.1, 0.1), (0.8, 0.8, 0.8, 0.1), (0.4, 0.4, 0.4, 0.1), 32, False),            # the plane (:262-270)
+        mats = [((0.1, 0.1, 0.1, 0.1), (0.8, 0.8, 0.8, 0.1), (0.4, 0.4, 0.4, 0.1), 32, self.textured_plane),   # the plane (:262-270)
                 ((0.18, 0.14, 0.12, 1.0), (0.9, 0.8, 0.7, 1.0), (0.5, 0.5, 0.5, 1.0), 16, True),
                 ((0.10, 0.14, 0.20, 1.0), (0.6, 0.8, 0.95, 1.0), (0.9, 0.9, 0.9, 1.0), 48, True)]
         for m, (amb, dif, spe, shin, textured) in zip([self.plane] + self.objects, mats):
             d = base_desc(t, self.w, self.h, cull=A.CULL_BACK)
             m.fill_desc(be, d)
             d.vs = vs
-            d.ps = A.shader_binding(A.PS_SSM_DRAW, pack_ps_ssm_draw(amb, dif, spe, shin, textured, True),
-                                    [self.tex_samp if textured else 0, self.sm_samp])
+            if self.ps_binding is not None:
+                d.ps = self.ps_binding(amb, dif, spe, shin, self.tex_samp, self.sm_samp)
+            else:
+                d.ps = A.shader_binding(A.PS_SSM_DRAW, pack_ps_ssm_draw(amb, dif, spe, shin, textured, True),
+                                        [self.tex_samp if textured else 0, self.sm_samp])
             d.bs = A.shader_binding(A.BS_REPLACE)
             be.draw(d)
         if t.resolved is not None:

@@ -245,3 +245,70 @@ def test_sasl_pixel_shader_visibility_first_equals_builtin_twin(cuda):
         ra, rb = ref.run(cuda, f), got.run(cuda, f)
         assert cases.compare_frames(ra, rb) == [], f"frame {f}"
         assert ra.stats["ps_invocations"] > 1000
+
+
+# ---- two samplers in one SASL pixel shader: the StandardShadowMap colour pass ---------------------------------------------
+PS_SSM_DRAW = """
+sampler texSamp;
+sampler smSamp;
+float4 ambient;
+float4 diffuse;
+float4 specular;
+float  shininess;
+struct PSIn { float4 tex: TEXCOORD0; float4 norm: TEXCOORD1; float4 lightDir: TEXCOORD2; float4 eyeDir: TEXCOORD3; float4 lsp: TEXCOORD4; };
+float tap(float x, float y) { return tex2Dlod(smSamp, float4(x, y, 0.0f, 0.0f)).x; }
+float4 ps_main(PSIn in): COLOR {
+    float esm = 25000.0f;
+    float lx = in.lsp.x / in.lsp.w;
+    float ly = in.lsp.y / in.lsp.w;
+    float lz = in.lsp.z / in.lsp.w;
+    float cx = (lx + 1.0f) * 0.5f;
+    float cy = 1.0f - (ly + 1.0f) * 0.5f;
+    float off = 1.0f / 512.0f;
+    float sd0 = tap(cx + -off, cy + -off);
+    float occluder = 0.0f;
+    occluder += 0.111014f * exp(esm * (tap(cx + 0.0f, cy + -off) - sd0));
+    occluder += 0.027681f * exp(esm * (tap(cx + off, cy + -off) - sd0));
+    occluder += 0.111014f * exp(esm * (tap(cx + -off, cy + 0.0f) - sd0));
+    occluder += 0.445213f * exp(esm * (tap(cx + 0.0f, cy + 0.0f) - sd0));
+    occluder += 0.111014f * exp(esm * (tap(cx + off, cy + 0.0f) - sd0));
+    occluder += 0.027681f * exp(esm * (tap(cx + -off, cy + off) - sd0));
+    occluder += 0.111014f * exp(esm * (tap(cx + 0.0f, cy + off) - sd0));
+    occluder += 0.027681f * exp(esm * (tap(cx + off, cy + off) - sd0));
+    occluder += 0.027681f;
+    occluder = log(occluder);
+    occluder += esm * sd0;
+    float occlusion = clamp(exp(occluder - esm * lz), 0.0f, 1.0f);
+    float4 tex = tex2D(texSamp, in.tex.xy);
+    float3 n = normalize(in.norm.xyz);
+    float3 l = normalize(in.lightDir.xyz);
+    float3 e = normalize(in.eyeDir.xyz);
+    float idiff = clamp(dot(l, n), 0.0f, 1.0f);
+    float k2 = 2.0f * dot(l, n);
+    float3 r = -(l - n * k2);
+    float ispec = clamp(dot(r, e), 0.0f, 1.0f);
+    float sp = pow(ispec, shininess);
+    float3 illum = ambient.xyz + (diffuse.xyz * idiff + specular.xyz * sp) * occlusion;
+    return float4(tex.xyz * illum, 1.0f);
+}
+"""
+
+
+@pytest.mark.parametrize("w,h,samples", [(640, 360, 1), (400, 240, 4)])
+def test_sasl_two_sampler_shadow_map_shader_equals_builtin(cuda, w, h, samples):
+    """The colour pass of samples/StandardShadowMap written in SASL — TWO samplers (diffuse texture through tex2D, the shadow
+    map through nine tex2Dlod taps), exp / log / pow — against the built-in SLV_PS_SSM_DRAW, which is pinned to the reference
+    (cases c5_ssm_*).  Both run on the visibility-first path; cpp derivative convention so that tex2D's LOD equals the
+    built-in's cpp tex2d."""
+    sh = jit.compile(PS_SSM_DRAW, "ps", derivatives="cpp")
+    assert sh.reflection.samplers == ["texSamp", "smSamp"]
+    mod = jit.load(cuda, sh)
+    ref = S.StandardShadowMap(w, h, samples, tex_size=64, textured_plane=True)
+    ref.setup(cuda)
+    got = S.StandardShadowMap(w, h, samples, tex_size=64, textured_plane=True, ps_binding=lambda amb, dif, spe, shin, ts, ss: A.shader_binding(
+        A.program_jit(mod), sh.unit.pack_uniforms({"ambient": amb, "diffuse": dif, "specular": spe, "shininess": float(shin)}), [ts, ss]))
+    got.setup(cuda)
+    for f in (1, 6):
+        a, b = ref.run(cuda, f), got.run(cuda, f)
+        assert cases.compare_frames(a, b) == [], f"frame {f}"
+        assert a.stats["ps_invocations"] > 1000

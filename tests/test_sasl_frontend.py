@@ -227,7 +227,9 @@ def test_matrix_ops_constructors_and_casts():
     ("float4 main(float4 p): SV_Position { return p; }", "vs", "semantic"),
     ("float4 main(float4 p: POSITION): TEXCOORD0 { return p; }", "vs", "SV_Position"),
     ("float4 main(float4 p: POSITION): SV_Position { return p.xyzq; }", "vs", "cannot take"),
-    ("sampler a; sampler b; float4 main(float4 t: TEXCOORD0): COLOR { return tex2D(a, t.xy) + tex2D(b, t.xy); }", "ps", "one sampler"),
+    ("sampler a; sampler b; sampler c; float4 main(float4 t: TEXCOORD0): COLOR { return tex2D(a, t.xy) + tex2D(b, t.xy) + tex2D(c, t.xy); }",
+     "ps", "two samplers"),
+    ("sampler a; sampler b; float4 main(float4 p: POSITION): SV_Position { return p + tex2Dlod(a, p) + tex2Dlod(b, p); }", "vs", "one per vertex"),
     ("float4 main(float4 p: POSITION): SV_Position { return p @ p; }", "vs", "unexpected character"),
 ])
 def test_compile_errors(src, stage, needle):
