@@ -314,6 +314,22 @@ public:
     std::memcpy(dst, &u, sizeof(u)); return sizeof(u);
   }
 };
+class vs_ssm_draw : public cpp_vertex_shader {  // resources/ssm/Draw.savs (StandardShadowMap.cpp:192, colour pass)
+public:
+  mat44 camera_wvp, light_wvp; vec4 light_pos, camera_pos;
+  vs_ssm_draw() {
+    declare_constant("cameraWvp", camera_wvp); declare_constant("lightWvp", light_wvp);
+    declare_constant("lightPos", light_pos); declare_constant("cameraPos", camera_pos);
+    bind_semantic("POSITION", 0, 0); bind_semantic("NORMAL", 0, 1); bind_semantic("TEXCOORD", 0, 2);
+  }
+  uint32_t device_program() const override { return SLV_VS_SSM_DRAW; }
+  uint32_t num_output_attributes() const override { return 5; }
+  size_t pack_uniforms(uint8_t* dst, size_t) const override {
+    slv_vs_ssm_draw_uniforms u{}; std::memcpy(u.camera_wvp, camera_wvp.m, 64); std::memcpy(u.light_wvp, light_wvp.m, 64);
+    std::memcpy(u.light_pos, &light_pos, 16); std::memcpy(u.camera_pos, &camera_pos, 16);
+    std::memcpy(dst, &u, sizeof(u)); return sizeof(u);
+  }
+};
 class ps_lights3 : public cpp_pixel_shader { public: uint32_t device_program() const override { return SLV_PS_LIGHTS3; } };  // ColorizedTriangle.cpp:55-92
 class ps_attr0_color : public cpp_pixel_shader { public: uint32_t device_program() const override { return SLV_PS_ATTR0_COLOR; } };
 class ps_sponza : public cpp_pixel_shader {  // samples/Sponza/Sponza.cpp:99-146
@@ -326,6 +342,24 @@ public:
   uint32_t device_program() const override { return SLV_PS_SPONZA; }
   size_t pack_uniforms(uint8_t* dst, size_t) const override { slv_ps_sponza_uniforms u{sampler_ ? 1u : 0u}; std::memcpy(dst, &u, sizeof(u)); return sizeof(u); }
   void samplers(slv_handle (&out)[SLV_MAX_SAMPLERS]) const override { out[0] = sampler_ ? sampler_->handle() : 0; }
+};
+class ps_ssm_draw : public cpp_pixel_shader {  // draw_cpp_ps, samples/StandardShadowMap/StandardShadowMap.cpp:62-142 (two samplers)
+public:
+  vec4 ambient, diffuse, specular; int shininess = 0; sampler_ptr texsamp_, dsamp_;
+  ps_ssm_draw() {
+    declare_constant("Ambient", ambient); declare_constant("Diffuse", diffuse); declare_constant("Specular", specular);
+    declare_constant("Shininess", shininess); declare_sampler("DepthSampler", dsamp_); declare_sampler("TexSampler", texsamp_);
+  }
+  uint32_t device_program() const override { return SLV_PS_SSM_DRAW; }
+  size_t pack_uniforms(uint8_t* dst, size_t) const override {
+    slv_ps_ssm_draw_uniforms u{};
+    std::memcpy(u.ambient, &ambient, 16); std::memcpy(u.diffuse, &diffuse, 16); std::memcpy(u.specular, &specular, 16);
+    u.shininess = shininess; u.has_tex_sampler = texsamp_ ? 1u : 0u; u.has_depth_sampler = dsamp_ ? 1u : 0u;
+    std::memcpy(dst, &u, sizeof(u)); return sizeof(u);
+  }
+  void samplers(slv_handle (&out)[SLV_MAX_SAMPLERS]) const override {
+    out[0] = texsamp_ ? texsamp_->handle() : 0; out[1] = dsamp_ ? dsamp_->handle() : 0;
+  }
 };
 class ps_tex_alpha : public cpp_pixel_shader {  // samples/TextureAndBlending/TextureAndBlending.cpp:96-166
 public:

@@ -112,5 +112,90 @@ int main(int argc, char** argv) {
   std::printf("stats ia_vertices %" PRIu64 " ia_primitives %" PRIu64 " cinvocations %" PRIu64 " cprimitives %" PRIu64 " ps_invocations %" PRIu64 "\n",
               st.ia_vertices, st.ia_primitives, st.cinvocations, st.cprimitives, st.ps_invocations);
   if (st.ia_primitives != 2 || st.cprimitives == 0 || st.ps_invocations == 0) return 4;
+
+  // ---- StandardShadowMap through the surface (StandardShadowMap.cpp:212-300): depth-only pass from the light into an rg32f
+  // texture, then the colour pass whose pixel shader reads that texture through a SECOND sampler (declare_sampler by name)
+  {
+    texture_ptr sm = r->create_tex2d(W, H, 1, pixel_format_color_rg32f);
+    texture_ptr color1 = r->create_tex2d(W, H, 1, pixel_format_color_rgba8), ds1 = r->create_tex2d(W, H, 1, pixel_format_color_rg32f);
+    surface_ptr sms = sm->subresource(0), c1 = color1->subresource(0), d1 = ds1->subresource(0);
+    sampler_desc smd{};
+    smd.min_filter = smd.mag_filter = smd.mip_filter = filter_point;
+    smd.mip_qual = mip_mi_quality;
+    smd.addr_mode_u = smd.addr_mode_v = smd.addr_mode_w = address_border;
+    smd.border_color[0] = 1.0f;
+    smd.min_lod = -1e20f; smd.max_lod = 1e20f;
+    sampler_ptr sm_sampler = r->create_sampler(smd, sm);
+    if (!sm_sampler) return 5;
+    // a small occluder quad above the plane (streams 0 / 1 keep the plane, the occluder gets its own buffers)
+    const float opos[4][4] = {{-0.8f, 0.2f, -0.8f, 1}, {0.8f, 0.2f, -0.8f, 1}, {-0.8f, 0.2f, 0.8f, 1}, {0.8f, 0.2f, 0.8f, 1}};
+    const float ouv[4][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {0, 1, 0, 0}, {1, 1, 0, 0}};
+    buffer_ptr ob0 = r->create_buffer(sizeof(opos)), ob2 = r->create_buffer(sizeof(ouv));
+    CHECK(ob0->transfer(0, opos, 16, 4));
+    CHECK(ob2->transfer(0, ouv, 16, 4));
+    mat44 lview;  // the light looks straight down the -y axis from (0, 5, 0): x -> x, z -> y, depth = 5 - y
+    lview = mat44{}; lview.m[0][0] = 1; lview.m[1][1] = 0; lview.m[1][2] = -1; lview.m[2][1] = 1; lview.m[2][2] = 0; lview.m[3][2] = 5; lview.m[3][3] = 1;
+    mat44 lproj = mat44{}; lproj.m[0][0] = f / a; lproj.m[1][1] = f; lproj.m[2][2] = 40.0f / (40.0f - zn); lproj.m[2][3] = 1.0f;
+    lproj.m[3][2] = -zn * 40.0f / (40.0f - zn); lproj.m[3][3] = 0.0f;
+    mat44 light_wvp = mul(lview, lproj);
+    // pass 1: depth only
+    auto vs_sm = std::make_shared<vs_mvp_passthrough>(std::vector<uint32_t>{0});
+    vs_sm->wvp = light_wvp;
+    input_element_desc d3[] = {{"POSITION", 0, format_r32g32b32a32_float, 0, 0}, {"NORMAL", 0, format_r32g32b32a32_float, 1, 0},
+                               {"TEXCOORD", 0, format_r32g32b32a32_float, 2, 0}};
+    CHECK(r->set_render_targets(0, nullptr, sms));
+    CHECK(r->clear_depth_stencil(sms, clear_depth | clear_stencil, 1.0f, 0));
+    CHECK(r->set_input_layout(r->create_input_layout(d3, 3, vs_sm)));
+    CHECK(r->set_vertex_shader(vs_sm));
+    CHECK(r->set_pixel_shader(std::make_shared<ps_attr0_color>()));
+    buffer_ptr pb[3] = {vb0, vb1, ob2};
+    size_t st3[3] = {16, 16, 16}, of3[3] = {0, 0, 0};
+    CHECK(r->set_vertex_buffers(0, 3, pb, st3, of3));
+    CHECK(r->draw_index(0, 2, 0));
+    buffer_ptr qb[3] = {ob0, vb1, ob2};
+    CHECK(r->set_vertex_buffers(0, 3, qb, st3, of3));
+    CHECK(r->draw_index(0, 2, 0));
+    // pass 2: colour, Draw.savs twin + draw_cpp_ps twin
+    auto vs_draw = std::make_shared<vs_ssm_draw>();
+    auto ps_draw = std::make_shared<ps_ssm_draw>();
+    CHECK(r->set_render_targets(1, &c1, d1));
+    CHECK(r->clear_color(c1, color_rgba32f{0.2f, 0.2f, 0.5f, 1.0f}));
+    CHECK(r->clear_depth_stencil(d1, clear_depth | clear_stencil, 1.0f, 0));
+    CHECK(r->set_input_layout(r->create_input_layout(d3, 3, vs_draw)));
+    CHECK(r->set_vertex_shader(vs_draw));
+    CHECK(r->set_pixel_shader(ps_draw));
+    vec4 lpos{0, 5, 0, 1}, cpos{0, 3, -4, 1};
+    CHECK(r->set_vs_variable("cameraWvp", &wvp));
+    CHECK(r->set_vs_variable("lightWvp", &light_wvp));
+    CHECK(r->set_vs_variable("lightPos", &lpos));
+    CHECK(r->set_vs_variable("cameraPos", &cpos));
+    vec4 amb{0.1f, 0.1f, 0.1f, 0.1f}, dif{0.8f, 0.8f, 0.8f, 0.1f}, spe{0.4f, 0.4f, 0.4f, 0.1f};
+    int shin = 32;
+    CHECK(r->set_ps_variable("Ambient", &amb));
+    CHECK(r->set_ps_variable("Diffuse", &dif));
+    CHECK(r->set_ps_variable("Specular", &spe));
+    CHECK(r->set_ps_variable("Shininess", &shin));
+    CHECK(r->set_ps_sampler("DepthSampler", sm_sampler));
+    CHECK(r->set_ps_sampler("TexSampler", sampler_ptr()));
+    if (r->set_ps_sampler("NoSuchSampler", sm_sampler) != result::failed) return 5;
+    CHECK(r->set_vertex_buffers(0, 3, pb, st3, of3));
+    CHECK(r->draw_index(0, 2, 0));
+    CHECK(r->set_vertex_buffers(0, 3, qb, st3, of3));
+    CHECK(r->draw_index(0, 2, 0));
+    CHECK(r->flush());
+    CHECK(r->map(m, c1, map_read));
+    const uint64_t h1 = fnv(m.data, c1->bytes());
+    size_t lit = 0, dark = 0;  // the occluder must actually shadow part of the plane: both lit and shadowed grey pixels exist
+    const uint8_t* px = static_cast<const uint8_t*>(m.data);
+    for (size_t i = 0; i < W * H; ++i) {
+      if (px[4 * i] == px[4 * i + 1] && px[4 * i + 1] == px[4 * i + 2]) { if (px[4 * i] > 100) ++lit; else if (px[4 * i] > 0 && px[4 * i] < 40) ++dark; }
+    }
+    CHECK(r->unmap());
+    CHECK(r->map(m, sms, map_read));
+    const uint64_t h2 = fnv(m.data, sms->bytes());
+    CHECK(r->unmap());
+    std::printf("ssm color %016" PRIx64 " shadow map %016" PRIx64 " lit %zu shadowed %zu\n", h1, h2, lit, dark);
+    if (lit == 0 || dark == 0) return 6;
+  }
   return 0;
 }
