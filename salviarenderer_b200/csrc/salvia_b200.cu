@@ -143,6 +143,8 @@ struct slv_device_t {
   size_t vis_cap = 0;                // in uint32 units
   bool force_immediate = false;      // SLV_FORCE_IMMEDIATE=1: always use k_raster (tests compare both paths)
   bool jit_immediate = false;        // SLV_JIT_IMMEDIATE=1: SASL pixel shaders always take k_raster
+  bool front_grids = true;           // SLV_FRONT_GRIDS=0: full-size k_sort_lists / k_region_bin / k_sort_lists_large grids
+  int sort_large_grid = 0;           // SLV_SORT_LARGE_GRID: CTAs of k_sort_lists_large (0 = by tile count)
   int cover_grid = 0, shade_grid = 0, sm_count = 0;
   int raster_grid = 0;  // persistent raster CTAs (SM count x resident CTAs per SM)
   // ---- draw batching: geometry + binning run at slv_draw time, the raster pass of all queued draws of a
@@ -519,8 +521,23 @@ slv_result flush_batch(slv_device dev) {
   k_scan_tiles<<<1, 1024, 0, fs>>>(S.tile_count, S.tile_offset, S.tile_cursor, n_tiles, S.active_tiles, S.work_counter, S.large_tiles);
   k_bin_fill<<<(n_slots + 255) / 256, 256, 0, fs>>>(bp);
   size_t e1 = dev->profile ? mark(dev) : 0;
-  k_sort_lists<<<n_tiles, SORT_THREADS, 0, fs>>>(S.tile_offset, S.list, dev->list_cap, S.active_tiles, S.work_counter + 3);
-  k_sort_lists_large<<<dev->sm_count, 1024, SORT_LARGE_SMEM * sizeof(uint32_t), fs>>>(S.tile_offset, S.list, dev->list_cap, S.large_tiles, S.valid_count);
+  // k_sort_lists and k_region_bin index the COMPACTED list of non-empty tiles, which holds at most the tiles this rank owns: a
+  // sort-first rank launches an N-th of the CTAs (each empty 1024-thread CTA still has to find room on an SM next to the
+  // previous frame's back half).  k_sort_lists_large needs a whole SM's shared memory per CTA: a few CTAs, not one per SM,
+  // so that only a few SMs have to drain before the front half can go on.  SLV_FRONT_GRIDS=0: the former full-size grids.
+  uint32_t owned_tiles = n_tiles, sort_large_grid = (uint32_t)dev->sm_count;
+  if (dev->front_grids) {
+    if (dev->shard_n > 1) {
+      owned_tiles = 0;
+      for (uint32_t ty = 0; ty < first.tiles_y; ++ty)
+        for (uint32_t tx = 0; tx < first.tiles_x; ++tx) owned_tiles += ((tx + 3 * ty) % dev->shard_n == dev->shard_rank) ? 1u : 0u;
+      owned_tiles = std::max(owned_tiles, 1u);
+    }
+    sort_large_grid = std::min<uint32_t>((uint32_t)dev->sm_count, std::max<uint32_t>(4u, owned_tiles / 32u));
+    if (dev->sort_large_grid > 0) sort_large_grid = (uint32_t)dev->sort_large_grid;
+  }
+  k_sort_lists<<<owned_tiles, SORT_THREADS, 0, fs>>>(S.tile_offset, S.list, dev->list_cap, S.active_tiles, S.work_counter + 3);
+  k_sort_lists_large<<<sort_large_grid, 1024, SORT_LARGE_SMEM * sizeof(uint32_t), fs>>>(S.tile_offset, S.list, dev->list_cap, S.large_tiles, S.valid_count);
   size_t e2 = dev->profile ? mark(dev) : 0;
   // ---- phase 5: visibility-first (k_cover + k_shade) when every queued draw qualifies, else the immediate k_raster
   bool deferred = !dev->force_immediate;
@@ -583,7 +600,7 @@ slv_result flush_batch(slv_device dev) {
       db.resolve_dst = dev->resolve_dst;
       dev->resolve_done = true;
     }
-    k_region_bin<<<n_tiles, RBIN_THREADS, 0, fs>>>(first, db);
+    k_region_bin<<<owned_tiles, RBIN_THREADS, 0, fs>>>(first, db);
     dev->n_launches += 1;
     if (dev->profile) e_rbin = mark(dev);
   }
@@ -782,6 +799,9 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   dev->profile = prof && prof[0] == '1';
   const char* fi = getenv("SLV_FORCE_IMMEDIATE");
   dev->force_immediate = fi && fi[0] == '1';
+  const char* fg = getenv("SLV_FRONT_GRIDS");
+  dev->front_grids = !(fg && fg[0] == '0');
+  if (const char* sg = getenv("SLV_SORT_LARGE_GRID")) dev->sort_large_grid = atoi(sg);
   const char* ji = getenv("SLV_JIT_IMMEDIATE");
   dev->jit_immediate = ji && ji[0] == '1';
   for (auto& ev : dev->user_ev) CU(cudaEventCreate(&ev));

@@ -15,14 +15,16 @@ import time
 for f in range(8):
     sc.render(be, f)
 be.flush()
-t0 = time.perf_counter()
-for f in range(40):
-    sc.render(be, f % 8)
-t1 = time.perf_counter()
-be.flush()
-t2 = time.perf_counter()
-print(f"host enqueue {1e3 * (t1 - t0) / 40:.3f} ms/frame, with the final sync {1e3 * (t2 - t0) / 40:.3f} ms/frame (40 frames)", flush=True)
-for f in range(8):
+NF = int(os.environ.get('FRAMES', '40'))
+for rep in range(int(os.environ.get('REPS', '1'))):
+    t0 = time.perf_counter()
+    for f in range(NF):
+        sc.render(be, f % 8)
+    t1 = time.perf_counter()
+    be.flush()
+    t2 = time.perf_counter()
+    print(f"host enqueue {1e3 * (t1 - t0) / NF:.3f} ms/frame, with the final sync {1e3 * (t2 - t0) / NF:.3f} ms/frame ({NF} frames)", flush=True)
+for f in range(0 if os.environ.get('NO_STAGES') else 8):
     be.profile_enable(True)
     be.query_begin()
     sc.render(be, f)
