@@ -532,8 +532,11 @@ class HeightFieldTwoPass:
     stress of the config.  Pass 2 is lit with the ColorizedTriangle shaders: the sample's exponential-shadow pixel shader
     (exp / log / pow on a 9-tap tex2dlod) is not part of this scene.  FrameResult.count carries the shadow map's depth."""
 
-    def __init__(self, w=7680, h=4320, samples=1, nx=2500, nz=2000, seed=10000019):
+    def __init__(self, w=7680, h=4320, samples=1, nx=2500, nz=2000, seed=10000019, shadowed=False):
         self.w, self.h, self.samples, self.nx, self.nz = w, h, samples, nx, nz
+        # shadowed: pass 2 runs the StandardShadowMap sample's colour-pass shaders (SLV_VS_SSM_DRAW / SLV_PS_SSM_DRAW) and
+        # reads pass 1's depth through the sample's point / border sampler; the shadow map is then single-sample
+        self.shadowed = shadowed
         rng = np.random.default_rng(seed)
         gx, gz = np.meshgrid(np.arange(nx + 1, dtype=np.float64), np.arange(nz + 1, dtype=np.float64))
         jx = rng.uniform(-0.2, 0.2, size=gx.shape)
@@ -556,7 +559,10 @@ class HeightFieldTwoPass:
 
     def setup(self, be: A.Backend):
         self.t = create_targets(be, self.w, self.h, self.samples, A.PF_BGRA8)
-        self.shadow = be.create_texture(self.w, self.h, self.samples, A.PF_RG32F)
+        self.shadow = be.create_texture(self.w, self.h, 1 if self.shadowed else self.samples, A.PF_RG32F)
+        if self.shadowed:
+            self.sm_samp = be.create_sampler(A.sampler_desc(A.FILTER_POINT, A.FILTER_POINT, A.FILTER_POINT, addr_u=A.ADDR_BORDER,
+                                                            addr_v=A.ADDR_BORDER, border=(1.0, 0.0, 0.0, 0.0)), self.shadow)
         self.mesh.upload(be)
 
     def frame_uniforms(self, frame):
@@ -587,8 +593,15 @@ class HeightFieldTwoPass:
         be.clear_depth_stencil(t.ds, A.CLEAR_DEPTH | A.CLEAR_STENCIL, 1.0, 0)
         d = base_desc(t, self.w, self.h, cull=A.CULL_BACK)
         self.mesh.fill_desc(be, d)
-        d.vs = A.shader_binding(A.VS_LIGHTS3, pack_vs_lights3(cam, lights))
-        d.ps = A.shader_binding(A.PS_LIGHTS3)
+        if self.shadowed:
+            ang = 0.3 + 0.45 * frame
+            d.vs = A.shader_binding(A.VS_SSM_DRAW, pack_vs_ssm_draw(cam, light, (*lights[0][:3], 1.0),
+                                                                    (math.cos(ang) * 6.0, 4.5, math.sin(ang) * 6.0, 1.0)))
+            d.ps = A.shader_binding(A.PS_SSM_DRAW, pack_ps_ssm_draw((0.1, 0.1, 0.1, 0.1), (0.8, 0.8, 0.8, 0.1), (0.4, 0.4, 0.4, 0.1), 32,
+                                                                    False, True), [0, self.sm_samp])
+        else:
+            d.vs = A.shader_binding(A.VS_LIGHTS3, pack_vs_lights3(cam, lights))
+            d.ps = A.shader_binding(A.PS_LIGHTS3)
         d.bs = A.shader_binding(A.BS_REPLACE)
         be.draw(d)
         if t.resolved is not None:

@@ -70,12 +70,14 @@ CASES["c5_heightfield_two_pass_320x180x4"] = (lambda: S.HeightFieldTwoPass(320, 
 # (SLV_VS_SSM_DRAW + SLV_PS_SSM_DRAW: nine tex2dlod taps, exponential shadow map, Phong terms, diffuse texture)
 CASES["c5_ssm_640x360"] = (lambda: S.StandardShadowMap(640, 360, 1), (0, 3, 7))
 CASES["c5_ssm_400x240x4"] = (lambda: S.StandardShadowMap(400, 240, 4, tex_size=64), (5,))
+# ... and the config's stress mesh with the sample's shaders in the colour pass (what tools/stress_10m.py --shadowed runs at full size)
+CASES["c5_heightfield_shadowed_480x272"] = (lambda: S.HeightFieldTwoPass(480, 272, 1, nx=100, nz=80, shadowed=True), (0, 2))
 
 # Cases whose pixel shader calls expf / logf / pow: the device evaluates them in double and rounds once (the correctly
 # rounded float), the host C library is allowed a last-bit difference, so their COLOUR is gated by the north_star tolerance
 # (<= 1 LSB on < 0.01 % of pixels, test_cuda_matches_oracle) instead of by the fixture's hash; depth, stencil and counters
 # stay bit-exact.
-TRANSCENDENTAL_CASES = {"c5_ssm_640x360", "c5_ssm_400x240x4"}
+TRANSCENDENTAL_CASES = {"c5_ssm_640x360", "c5_ssm_400x240x4", "c5_heightfield_shadowed_480x272"}
 
 # cases small enough for the CPU suite to run against the reference / oracle in seconds
 CPU_CASES = [k for k in CASES if "1920x1080" not in k]

@@ -20,9 +20,10 @@ ap.add_argument("--width", type=int, default=7680)
 ap.add_argument("--height", type=int, default=4320)
 ap.add_argument("--samples", type=int, default=1)
 ap.add_argument("--frames", type=int, default=6)
+ap.add_argument("--shadowed", action="store_true", help="colour pass = the StandardShadowMap sample's shaders, sampling pass 1's depth")
 a = ap.parse_args()
 t0 = time.time()
-sc = S.HeightFieldTwoPass(a.width, a.height, a.samples, nx=a.nx, nz=a.nz)
+sc = S.HeightFieldTwoPass(a.width, a.height, a.samples, nx=a.nx, nz=a.nz, shadowed=a.shadowed)
 print(f"mesh: {sc.mesh.prim_count} triangles, {len(sc.mesh.streams[0])} vertices, built in {time.time() - t0:.1f} s", flush=True)
 be = pkg.load(0)
 sc.setup(be)
@@ -37,7 +38,7 @@ be.event_record(1)
 ms = be.event_elapsed_ms(0, 1) / a.frames
 st = be.query_get()
 tris = 2 * sc.mesh.prim_count  # two passes
-print(f"{a.width}x{a.height}x{a.samples}: {ms:.3f} ms/frame ({1e3 / ms:.1f} frames/s), {tris / ms / 1e6:.2f} G triangles/s in, "
+print(f"{a.width}x{a.height}x{a.samples}{' shadowed (SSM colour pass)' if a.shadowed else ''}: {ms:.3f} ms/frame ({1e3 / ms:.1f} frames/s), {tris / ms / 1e6:.2f} G triangles/s in, "
       f"cprimitives/frame {st['cprimitives'] // a.frames}, ps_invocations/frame {st['ps_invocations'] // a.frames}", flush=True)
 be.profile_enable(True)
 be.query_begin()
