@@ -555,8 +555,14 @@ __device__ __forceinline__ uint32_t shade_sample_owner(const RasterParams& c, co
   return pack_color(c.color0.fmt, color);
 }
 
-constexpr uint32_t SHADE_GROUP = 8;   // items a warp of k_shade takes at a time; all their (pixel, owner) pairs share one pool
-constexpr int SHADE_POOL = 256;       // pool entries per warp (an item adds at most 32 * S = 128)
+#ifndef SLV_SHADE_GROUP
+#define SLV_SHADE_GROUP 4
+#endif
+constexpr uint32_t SHADE_GROUP = SLV_SHADE_GROUP;   // items a warp of k_shade takes at a time; all their (pixel, owner) pairs share one pool
+#ifndef SLV_SHADE_POOL
+#define SLV_SHADE_POOL 256
+#endif
+constexpr int SHADE_POOL = SLV_SHADE_POOL;       // pool entries per warp (an item adds at most 32 * S = 128)
 
 __device__ __forceinline__ uint32_t fetch_group(uint32_t* counter, uint32_t lane, uint32_t grp) {
   uint32_t v = 0;

@@ -298,7 +298,11 @@ __device__ __forceinline__ bool setup_position(const GeomParams& p, const float4
   bool any_owned = false;
   if ((tr.sx + 1 == tr.ex) && (tr.sy + 1 == tr.ey)) {
     if (tile_owned(tr.sx, tr.sy, p.shard_rank, p.shard_n)) {
-      atomicAdd(&p.tile_count[tr.sy * p.tiles_x + tr.sx], 1u);
+      // warp-aggregated count: neighbouring primitives of a fine mesh fall into the same tile, and one atomic per distinct
+      // tile among the lanes that are converged here replaces up to 32 same-address atomics (the 10 M-triangle stress config)
+      const uint32_t t = tr.sy * p.tiles_x + tr.sx;
+      const uint32_t peers = __match_any_sync(__activemask(), t);
+      if ((threadIdx.x & 31u) == (uint32_t)__ffs(peers) - 1u) atomicAdd(&p.tile_count[t], (uint32_t)__popc(peers));
       any_owned = true;
     }
   } else {
@@ -633,8 +637,15 @@ __global__ void __launch_bounds__(256) k_bin_fill(BinParams p) {
   int sx = xr & 0xFFFF, ex = xr >> 16, sy = yr & 0xFFFF, ey = yr >> 16;
   if ((sx + 1 == ex) && (sy + 1 == ey)) {
     if (tile_owned(sx, sy, p.shard_rank, p.shard_n)) {
+      // warp-aggregated cursor bump: one atomic per distinct tile among the converged lanes, consecutive entries for the group
       uint32_t t = sy * p.tiles_x + sx;
-      uint32_t at = p.tile_offset[t] + atomicAdd(&p.tile_cursor[t], 1u);
+      const uint32_t lane = threadIdx.x & 31u;
+      const uint32_t peers = __match_any_sync(__activemask(), t);
+      const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(&p.tile_cursor[t], (uint32_t)__popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      uint32_t at = p.tile_offset[t] + base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
       if (at < p.list_capacity) p.list[at] = slot << 1;
       else *p.overflow_flag = 1;
     }
@@ -751,7 +762,18 @@ __global__ void __launch_bounds__(1024) k_sort_lists_large(const uint32_t* tile_
     if (beg >= end) continue;
     const uint32_t n = end - beg;
     uint32_t* a = list + beg;
-    if (n <= (uint32_t)SORT_LARGE_SMEM) {
+    uint32_t N = 2;
+    while (N < n) N <<= 1;
+    if (N <= (uint32_t)SORT_LARGE_SMEM) {
+      // up to 32768 entries: the padded network of k_sort_lists (passes with partner distance <= 32 are warp-local, about a
+      // third of the CTA barriers of the generic one) - these lists sit on the critical path of the front half
+      for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) s_dyn[i] = i < n ? a[i] : 0xFFFFFFFFu;
+      __syncthreads();
+      bitonic_sort_padded<1024>(s_dyn, N, threadIdx.x, 0);
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) a[i] = s_dyn[i];
+      __syncthreads();
+    } else if (n <= (uint32_t)SORT_LARGE_SMEM) {
       for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_dyn[i] = a[i];
       __syncthreads();
       bitonic_sort_block(s_dyn, n);

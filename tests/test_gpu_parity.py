@@ -70,6 +70,21 @@ def test_empty_and_degenerate_draws(cuda, oracle):
     assert not cases.compare_frames(a.run(cuda), b.run(oracle))
 
 
+@pytest.mark.parametrize("n,w,h,samples", [(9000, 128, 64, 1), (20000, 64, 64, 4), (34000, 64, 64, 1), (64000, 64, 64, 2)])
+def test_very_long_tile_lists(cuda, oracle, n, w, h, samples):
+    """Thousands to tens of thousands of triangles in ONE 64x64 tile: the per-tile list goes through every size class of the
+    order-restoring sort (k_sort_lists: <= 4096 entries; k_sort_lists_large: the padded shared-memory network up to 32768,
+    the generic shared-memory one up to 49152, in place in global memory beyond), and k_region_bin / k_cover walk chains of
+    that length.  Any ordering mistake shows up in depth, colour and the early-Z dependent counters."""
+    a = S.TriangleSoup(samples=samples, n=n, w=w, h=h, seed=31, bs=A.BS_REPLACE, index_dtype=np.uint32, size=0.6)
+    b = S.TriangleSoup(samples=samples, n=n, w=w, h=h, seed=31, bs=A.BS_REPLACE, index_dtype=np.uint32, size=0.6)
+    a.setup(cuda)
+    b.setup(oracle)
+    ra, rb = a.run(cuda), b.run(oracle)
+    assert rb.stats["cprimitives"] > n
+    assert not cases.compare_frames(ra, rb, color_tol=COLOR_TOL_LSB)
+
+
 def test_render_is_deterministic_and_idempotent_clear(cuda):
     sc = S.SponzaLike(1280, 720, 4, tex_size=256)
     sc.setup(cuda)
