@@ -115,6 +115,7 @@ struct slv_device_t {
     uint32_t* work_counter = nullptr;  // [0] k_raster / k_cover queue head, [1] k_shade queue head, [2] region-list cursor, [3] long lists
     uint32_t *region_list = nullptr, *region_offset = nullptr, *region_count = nullptr;  // deferred path: per-region lists
     uint32_t* region_mask = nullptr;  // one word per tile-list entry
+    uint32_t* region_tile_cnt = nullptr;  // [tile * 16 + region] survivor counters (k_region_decide -> k_region_bin, self-cleaning)
     uint8_t* item_flag = nullptr;
     uint2* block_desc = nullptr;  // (first entry, entries) of each (region, warp block) sub-list
     uint32_t* list = nullptr;
@@ -256,6 +257,7 @@ slv_result ensure_scratch(slv_device dev, size_t tris_needed_total, uint32_t n_t
         CU(cudaFree(S.tile_count)); CU(cudaFree(S.tile_offset)); CU(cudaFree(S.tile_cursor));
         CU(cudaFree(S.active_tiles)); CU(cudaFree(S.large_tiles));
         CU(cudaFree(S.region_offset)); CU(cudaFree(S.region_count)); CU(cudaFree(S.item_flag)); CU(cudaFree(S.block_desc));
+        CU(cudaFree(S.region_tile_cnt));
       }
       CU(cudaMalloc(&S.tile_count, cap * sizeof(uint32_t)));
       CU(cudaMalloc(&S.tile_offset, cap * sizeof(uint32_t)));
@@ -268,6 +270,8 @@ slv_result ensure_scratch(slv_device dev, size_t tris_needed_total, uint32_t n_t
       CU(cudaMalloc(&S.block_desc, (size_t)cap * 128 * sizeof(uint2)));
       CU(cudaMemsetAsync(S.tile_count, 0, cap * sizeof(uint32_t), dev->stream));
       CU(cudaMemsetAsync(S.tile_cursor, 0, cap * sizeof(uint32_t), dev->stream));
+      CU(cudaMalloc(&S.region_tile_cnt, (size_t)cap * 16 * sizeof(uint32_t)));
+      CU(cudaMemsetAsync(S.region_tile_cnt, 0, (size_t)cap * 16 * sizeof(uint32_t), dev->stream));
     }
     CU(cudaStreamSynchronize(dev->stream));
     dev->tiles_cap = cap;
@@ -579,6 +583,7 @@ slv_result flush_batch(slv_device dev) {
     db.region_list = S.region_list;
     db.region_cap = dev->region_cap;
     db.region_mask = S.region_mask;
+    db.region_tile_cnt = S.region_tile_cnt;
     db.region_offset = S.region_offset;
     db.region_count = S.region_count;
     db.cursor = S.work_counter + 2;
@@ -600,8 +605,9 @@ slv_result flush_batch(slv_device dev) {
       db.resolve_dst = dev->resolve_dst;
       dev->resolve_done = true;
     }
+    k_region_decide<<<dev->sm_count * 8, 256, 0, fs>>>(first, db);
     k_region_bin<<<owned_tiles, RBIN_THREADS, 0, fs>>>(first, db);
-    dev->n_launches += 1;
+    dev->n_launches += 2;
     if (dev->profile) e_rbin = mark(dev);
   }
   // ---- back half, on the main stream
@@ -827,7 +833,7 @@ void slv_device_destroy(slv_device dev) {
   for (auto& S : dev->sc) {
     cudaFree(S.tris); cudaFree(S.valid_slots); cudaFree(S.valid_count);
     cudaFree(S.tile_count); cudaFree(S.tile_offset); cudaFree(S.tile_cursor); cudaFree(S.active_tiles); cudaFree(S.large_tiles);
-    cudaFree(S.work_counter); cudaFree(S.region_list); cudaFree(S.region_mask); cudaFree(S.region_offset); cudaFree(S.region_count);
+    cudaFree(S.work_counter); cudaFree(S.region_list); cudaFree(S.region_mask); cudaFree(S.region_tile_cnt); cudaFree(S.region_offset); cudaFree(S.region_count);
     cudaFree(S.item_flag); cudaFree(S.block_desc); cudaFree(S.list); cudaFree(S.d_batch); cudaFree(S.d_geom);
     cudaFreeHost(S.h_batch); cudaFreeHost(S.h_geom);
     cudaEventDestroy(S.ev_front_done); cudaEventDestroy(S.ev_back_done);

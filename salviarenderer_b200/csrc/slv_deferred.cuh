@@ -62,6 +62,7 @@ struct DeferredBufs {
                               // (slot << 4) | status of the warp's two 4x4 blocks, in API order
   uint2* block_desc;          // [item = (active tile index * 16 + region) * 8 + warp block]: (first entry, entries)
   uint32_t* region_mask;      // scratch, one word per tile-list entry: regions survived | regions fully inside << 16
+  uint32_t* region_tile_cnt;  // [tile id * 16 + region]: survivors counted by k_region_decide, consumed AND re-zeroed by k_region_bin
   uint32_t region_cap;
   uint32_t* region_offset;    // [active tile index * 16 + region]
   uint32_t* region_count;
@@ -98,30 +99,38 @@ __device__ __forceinline__ uint32_t region_block_bits(const TriEntry& te, float 
 }
 
 #ifndef SLV_JIT_PS  // k_region_bin is the library's; a JIT unit only instantiates shade_quad_main
-// Phase 1: one thread per tile-list entry evaluates the reference's level-16 decision (subdivide_tile at the 16-px
-// level, rasterizer.cpp:441-602, 698-772) for all 16 regions of the tile and stores survive | accept << 16.
-// Phase 2: warp r compacts, IN ORDER, the entries surviving in region r into the region's list (two streaming passes
-// over the masks: count, then fill; allocation = one atomicAdd per tile).
-__global__ void __launch_bounds__(RBIN_THREADS, 2) k_region_bin(RasterParams c, DeferredBufs d) {
-  __shared__ uint32_t s_cnt[16], s_base[16];
-  const uint32_t b = blockIdx.x;
-  if (b >= c.active_tiles[0]) return;
-  const uint32_t tile = c.active_tiles[1 + b];
-  const uint32_t lane = threadIdx.x & 31, r = threadIdx.x >> 5;
-  const uint32_t tile_x = tile % c.tiles_x, tile_y = tile / c.tiles_x;
-  const float vpx = (float)(tile_x * TILE), vpy = (float)(tile_y * TILE);
-  const uint32_t beg = c.tile_offset[tile];
-  uint32_t end = c.tile_offset[tile + 1];
-  if (end > c.list_capacity) end = c.list_capacity;
-  // regions that start outside the target: "Sub tile is out of screen" (rasterizer.cpp:721-724)
-  uint32_t on_screen = 0;
+// Level-16 and level-4 decisions of EVERY tile-list entry of the batch, one thread per entry over a flat grid (the lists are
+// one dense array): the arithmetic-heavy part of region binning no longer runs one CTA per tile, where the longest list was
+// the kernel's critical path and the warps of a CTA idled at the barrier behind the one with the most partially covered
+// regions.  Stores survive | accept << 16 and the block bits of up to RMASK_STRIDE - 1 partial regions per entry, and counts
+// the survivors per (tile, region).
+__global__ void __launch_bounds__(256, 4) k_region_decide(RasterParams c, DeferredBufs d) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t n_tiles = c.tiles_x * c.tiles_y;
+  uint32_t total = c.tile_offset[n_tiles];
+  if (total > c.list_capacity) total = c.list_capacity;
+  for (uint32_t base_i = blockIdx.x * blockDim.x; base_i < total; base_i += gridDim.x * blockDim.x) {
+    const uint32_t i = base_i + threadIdx.x;
+    const bool valid = i < total;
+    // the entry's tile: last t with tile_offset[t] <= i (offsets are non-decreasing; empty tiles share an offset)
+    uint32_t tile = 0xFFFFFFFFu;
+    if (valid) {
+      uint32_t lo = 0, hi = n_tiles;  // invariant: tile_offset[lo] <= i < tile_offset[hi]
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(c.tile_offset + mid) <= i) lo = mid; else hi = mid;
+      }
+      tile = lo;
+    }
+    const uint32_t tile_x = valid ? tile % c.tiles_x : 0u, tile_y = valid ? tile / c.tiles_x : 0u;
+    const float vpx = (float)(tile_x * TILE), vpy = (float)(tile_y * TILE);
+    // regions that start outside the target: "Sub tile is out of screen" (rasterizer.cpp:721-724)
+    uint32_t on_screen = 0;
 #pragma unroll
-  for (int k = 0; k < 16; ++k)
-    if (!((float)(tile_x * TILE + (k & 3) * REGION) >= (float)c.target_w || (float)(tile_y * TILE + (k >> 2) * REGION) >= (float)c.target_h))
-      on_screen |= 1u << k;
-
-  for (uint32_t i = beg + threadIdx.x; i < end; i += RBIN_THREADS) {
-    const uint32_t e = __ldg(c.list + i);
+    for (int k = 0; k < 16; ++k)
+      if (!((float)(tile_x * TILE + (k & 3) * REGION) >= (float)c.target_w || (float)(tile_y * TILE + (k >> 2) * REGION) >= (float)c.target_h))
+        on_screen |= 1u << k;
+    const uint32_t e = valid ? __ldg(c.list + i) : 1u;
     uint32_t survive = 0xFFFFu, accept = 0xFFFFu;  // e & 1: the whole 64x64 tile is inside (rasterizer.cpp:736-743)
     if (!(e & 1)) {
       const float4* rec = c.tris + (size_t)(e >> 1) * c.tri_stride;
@@ -157,9 +166,20 @@ __global__ void __launch_bounds__(RBIN_THREADS, 2) k_region_bin(RasterParams c, 
         accept |= (!rej && acc) ? (1u << reg) : 0u;
       }
     }
-    survive &= on_screen;
+    survive &= valid ? on_screen : 0u;
     accept &= survive;
-    d.region_mask[(size_t)i * RMASK_STRIDE] = survive | (accept << 16);
+    if (valid) d.region_mask[(size_t)i * RMASK_STRIDE] = survive | (accept << 16);
+    // per-(tile, region) survivor counts: one atomic per region and distinct tile among the warp's 32 entries (a warp's
+    // entries are consecutive list positions, i.e. nearly always one tile)
+    {
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, tile);
+      const bool leader = lane == (uint32_t)__ffs(peers) - 1u;
+#pragma unroll
+      for (int reg = 0; reg < 16; ++reg) {
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, (survive >> reg) & 1u) & peers;
+        if (leader && valid && bal) atomicAdd(&d.region_tile_cnt[tile * 16u + reg], (uint32_t)__popc(bal));
+      }
+    }
     // level-4 decisions (subdivide_tile at the 4-px level) of the first RMASK_STRIDE - 1 partially covered regions,
     // 2 bits per 4x4 block: evaluated here, with one thread per entry, so that the ordered compaction below is cheap
     uint32_t partial = survive & ~accept;
@@ -178,16 +198,28 @@ __global__ void __launch_bounds__(RBIN_THREADS, 2) k_region_bin(RasterParams c, 
       }
     }
   }
-  __syncthreads();
+}
 
-  uint32_t cnt = 0;
-  for (uint32_t i = beg; i < end; i += 32) {
-    const uint32_t ei = i + lane;
-    const uint32_t m = ei < end ? d.region_mask[(size_t)ei * RMASK_STRIDE] : 0u;
-    cnt += __popc(__ballot_sync(0xFFFFFFFFu, (m >> r) & 1u));
+// One CTA per non-empty tile, one warp per 16x16 region: warp r appends, IN ORDER, the entries that survive in region r
+// (decisions and counts from k_region_decide; the reference's level-16 / level-4 subdivide_tile, rasterizer.cpp:441-602,
+// 698-772) to the sub-lists of the region's eight 8x4 warp blocks.  Allocation = one atomicAdd per tile.
+__global__ void __launch_bounds__(RBIN_THREADS, 2) k_region_bin(RasterParams c, DeferredBufs d) {
+  __shared__ uint32_t s_cnt[16], s_base[16];
+  const uint32_t b = blockIdx.x;
+  if (b >= c.active_tiles[0]) return;
+  const uint32_t tile = c.active_tiles[1 + b];
+  const uint32_t lane = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const uint32_t tile_x = tile % c.tiles_x, tile_y = tile / c.tiles_x;
+  const float vpx = (float)(tile_x * TILE), vpy = (float)(tile_y * TILE);
+  const uint32_t beg = c.tile_offset[tile];
+  uint32_t end = c.tile_offset[tile + 1];
+  if (end > c.list_capacity) end = c.list_capacity;
+  if (threadIdx.x < 16) {  // survivors per region, counted by k_region_decide; re-zeroed here for the next batch of this scratch set
+    s_cnt[threadIdx.x] = d.region_tile_cnt[tile * 16u + threadIdx.x];
+    d.region_tile_cnt[tile * 16u + threadIdx.x] = 0;
   }
-  if (lane == 0) s_cnt[r] = cnt;
   __syncthreads();
+  const uint32_t cnt = s_cnt[r];
   if (threadIdx.x == 0) {
     uint32_t total = 0;
     for (int k = 0; k < 16; ++k) total += s_cnt[k];
@@ -218,36 +250,50 @@ __global__ void __launch_bounds__(RBIN_THREADS, 2) k_region_bin(RasterParams c, 
   if (ok && cnt) {
     const uint32_t rbase = s_base[r];
     const uint32_t below = (1u << lane) - 1;
-    for (uint32_t i = beg; i < end; i += 32) {
-      const uint32_t ei = i + lane;
-      const uint32_t m = ei < end ? d.region_mask[(size_t)ei * RMASK_STRIDE] : 0u;
-      uint32_t st_bits = 0, slot = 0;
-      if ((m >> r) & 1u) {
-        slot = __ldg(c.list + ei) >> 1;
-        if ((m >> (16 + r)) & 1u) {
-          st_bits = 0xAAAAAAAAu;  // region fully inside: every block full
-        } else {
-          const uint32_t partial = (m & 0xFFFFu) & ~(m >> 16);
-          const uint32_t k = __popc(partial & ((1u << r) - 1));  // rank of this region among the entry's partial ones
-          if (k < (uint32_t)RMASK_STRIDE - 1) {
-            st_bits = d.region_mask[(size_t)ei * RMASK_STRIDE + 1 + k];
-          } else {  // an entry with more partially covered regions than phase 1 stores: evaluate here
-            const float4* rec = c.tris + (size_t)slot * c.tri_stride;
-            const float4 e0 = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2), bb = __ldg(rec + 3);
-            TriEntry te;
-            te.A[0] = e0.x; te.B[0] = e0.y; te.C[0] = e0.z;
-            te.A[1] = e1.x; te.B[1] = e1.y; te.C[1] = e1.z;
-            te.A[2] = e2.x; te.B[2] = e2.y; te.C[2] = e2.z;
-            st_bits = region_block_bits(te, bb.x - vpx, bb.y - vpx, bb.z - vpy, bb.w - vpy, tile_x, tile_y, (int)r);
+    constexpr int U = 4;  // chunks of 32 entries per iteration: the loads of all U are in flight together (a long list is a
+                          // chain of dependent L2 round trips otherwise - the critical path of the front half on heavy tiles)
+    for (uint32_t i = beg; i < end; i += 32 * U) {
+      uint32_t m[U], slot[U], st_bits[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t ei = i + u * 32 + lane;
+        m[u] = ei < end ? d.region_mask[(size_t)ei * RMASK_STRIDE] : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t ei = i + u * 32 + lane;
+        st_bits[u] = 0; slot[u] = 0;
+        if ((m[u] >> r) & 1u) {
+          slot[u] = __ldg(c.list + ei) >> 1;
+          if ((m[u] >> (16 + r)) & 1u) {
+            st_bits[u] = 0xAAAAAAAAu;  // region fully inside: every block full
+          } else {
+            const uint32_t partial = (m[u] & 0xFFFFu) & ~(m[u] >> 16);
+            const uint32_t k = __popc(partial & ((1u << r) - 1));  // rank of this region among the entry's partial ones
+            if (k < (uint32_t)RMASK_STRIDE - 1) st_bits[u] = d.region_mask[(size_t)ei * RMASK_STRIDE + 1 + k];
+            else st_bits[u] = 0xFFFFFFFFu;  // marker: more partially covered regions than phase 1 stores, evaluated below
           }
         }
       }
 #pragma unroll
-      for (int w = 0; w < 8; ++w) {  // warp block w owns blocks (by = w >> 1, bx = (w & 1) * 2 + {0, 1})
-        const uint32_t four = (st_bits >> (2 * ((w >> 1) * 4 + (w & 1) * 2))) & 0xFu;
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, four != 0);
-        if (four) d.region_list[rbase + (uint32_t)w * cnt + pos[w] + __popc(bal & below)] = (slot << 4) | four;
-        pos[w] += __popc(bal);
+      for (int u = 0; u < U; ++u) {
+        if (i + u * 32 >= end) break;  // warp-uniform
+        if (st_bits[u] == 0xFFFFFFFFu) {
+          const float4* rec = c.tris + (size_t)slot[u] * c.tri_stride;
+          const float4 e0 = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2), bb = __ldg(rec + 3);
+          TriEntry te;
+          te.A[0] = e0.x; te.B[0] = e0.y; te.C[0] = e0.z;
+          te.A[1] = e1.x; te.B[1] = e1.y; te.C[1] = e1.z;
+          te.A[2] = e2.x; te.B[2] = e2.y; te.C[2] = e2.z;
+          st_bits[u] = region_block_bits(te, bb.x - vpx, bb.y - vpx, bb.z - vpy, bb.w - vpy, tile_x, tile_y, (int)r);
+        }
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {  // warp block w owns blocks (by = w >> 1, bx = (w & 1) * 2 + {0, 1})
+          const uint32_t four = (st_bits[u] >> (2 * ((w >> 1) * 4 + (w & 1) * 2))) & 0xFu;
+          const uint32_t bal = __ballot_sync(0xFFFFFFFFu, four != 0);
+          if (four) d.region_list[rbase + (uint32_t)w * cnt + pos[w] + __popc(bal & below)] = (slot[u] << 4) | four;
+          pos[w] += __popc(bal);
+        }
       }
     }
   }
