@@ -112,7 +112,7 @@ struct slv_device_t {
     uint32_t* valid_slots = nullptr;  // one entry per slot of the tris arena
     uint32_t* valid_count = nullptr;
     uint32_t *tile_count = nullptr, *tile_offset = nullptr, *tile_cursor = nullptr, *active_tiles = nullptr, *large_tiles = nullptr;
-    uint32_t* work_counter = nullptr;  // [0] k_raster / k_cover queue head, [1] k_shade queue head, [2] region-list cursor, [3] long lists
+    uint32_t* work_counter = nullptr;  // [0] k_raster / k_cover queue head, [1] k_shade queue head, [2] region-list cursor, [3] long lists, [4] block-bits pool cursor
     uint32_t *region_list = nullptr, *region_offset = nullptr, *region_count = nullptr;  // deferred path: per-region lists
     uint32_t* region_mask = nullptr;  // one word per tile-list entry
     uint32_t* region_tile_cnt = nullptr;  // [tile * 16 + region] survivor counters (k_region_decide -> k_region_bin, self-cleaning)
@@ -584,6 +584,9 @@ slv_result flush_batch(slv_device dev) {
     db.region_cap = dev->region_cap;
     db.region_mask = S.region_mask;
     db.region_tile_cnt = S.region_tile_cnt;
+    db.bits_pool = S.region_mask + 2 * (size_t)dev->list_cap;
+    db.bits_cap = (RMASK_STRIDE - 2) * dev->list_cap;
+    db.pool_cursor = S.work_counter + 4;
     db.region_offset = S.region_offset;
     db.region_count = S.region_count;
     db.cursor = S.work_counter + 2;
@@ -768,7 +771,8 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   CU(cudaMalloc(&dev->peer_flags, SLV_PEER_FLAGS * sizeof(uint32_t)));
   CU(cudaMemset(dev->peer_flags, 0, SLV_PEER_FLAGS * sizeof(uint32_t)));
   for (auto& S : dev->sc) {
-    CU(cudaMalloc(&S.work_counter, 4 * sizeof(uint32_t)));
+    CU(cudaMalloc(&S.work_counter, 8 * sizeof(uint32_t)));
+    CU(cudaMemset(S.work_counter, 0, 8 * sizeof(uint32_t)));
     CU(cudaMalloc(&S.valid_count, sizeof(uint32_t)));
     CU(cudaMemset(S.valid_count, 0, sizeof(uint32_t)));  // k_sort_lists_large re-zeroes it at the end of every binning chain
     CU(cudaMalloc(&S.d_batch, MAX_BATCH * sizeof(RasterParams)));

@@ -62,6 +62,9 @@ struct DeferredBufs {
                               // (slot << 4) | status of the warp's two 4x4 blocks, in API order
   uint2* block_desc;          // [item = (active tile index * 16 + region) * 8 + warp block]: (first entry, entries)
   uint32_t* region_mask;      // scratch, one word per tile-list entry: regions survived | regions fully inside << 16
+  uint32_t* bits_pool;        // level-4 block bits (2 bits per 4x4 block) of every partially covered (entry, region) pair, allocated
+  uint32_t bits_cap;          // per entry by k_region_decide from pool_cursor (reset by k_scan_tiles)
+  uint32_t* pool_cursor;
   uint32_t* region_tile_cnt;  // [tile id * 16 + region]: survivors counted by k_region_decide, consumed AND re-zeroed by k_region_bin
   uint32_t region_cap;
   uint32_t* region_offset;    // [active tile index * 16 + region]
@@ -83,7 +86,8 @@ struct DeferredBufs {
 #endif
 
 constexpr int RBIN_THREADS = 512;  // 16 warps == the 16 regions of a tile
-constexpr int RMASK_STRIDE = 5;    // scratch words per tile-list entry: region masks + block bits of up to 4 partial regions
+constexpr int RMASK_STRIDE = 6;    // scratch words per tile-list entry: 2 (region masks, offset of the entry's block bits) + a pool of
+                                   // 4 per entry on average for the block bits of its partially covered regions
 
 // level-4 decision of the 16 blocks of region `reg` of tile (tile_x, tile_y): 2 bits per block, 0 rejected, 1 partial, 2 full
 __device__ __forceinline__ uint32_t region_block_bits(const TriEntry& te, float x_min, float x_max, float y_min, float y_max,
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(256, 4) k_region_decide(RasterParams c, Deferr
     }
     survive &= valid ? on_screen : 0u;
     accept &= survive;
-    if (valid) d.region_mask[(size_t)i * RMASK_STRIDE] = survive | (accept << 16);
+    if (valid) d.region_mask[(size_t)i * 2] = survive | (accept << 16);
     // per-(tile, region) survivor counts: one atomic per region and distinct tile among the warp's 32 entries (a warp's
     // entries are consecutive list positions, i.e. nearly always one tile)
     {
@@ -180,10 +184,24 @@ __global__ void __launch_bounds__(256, 4) k_region_decide(RasterParams c, Deferr
         if (leader && valid && bal) atomicAdd(&d.region_tile_cnt[tile * 16u + reg], (uint32_t)__popc(bal));
       }
     }
-    // level-4 decisions (subdivide_tile at the 4-px level) of the first RMASK_STRIDE - 1 partially covered regions,
-    // 2 bits per 4x4 block: evaluated here, with one thread per entry, so that the ordered compaction below is cheap
+    // level-4 decisions (subdivide_tile at the 4-px level) of EVERY partially covered region of the entry, 2 bits per 4x4
+    // block, into a pool slice allocated with one atomic per warp: the ordered fill of k_region_bin then only copies bits
     uint32_t partial = survive & ~accept;
-    if (partial) {
+    const uint32_t np = (uint32_t)__popc(partial);
+    uint32_t incl = np;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    const uint32_t warp_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    uint32_t wbase = 0;
+    if (lane == 31 && warp_total) wbase = atomicAdd(d.pool_cursor, warp_total);
+    wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
+    const uint32_t off = wbase + incl - np;
+    const bool fits = (uint64_t)off + np <= (uint64_t)d.bits_cap;  // else: k_region_bin evaluates the entry's blocks itself
+    if (valid) d.region_mask[(size_t)i * 2 + 1] = (np && fits) ? off : 0xFFFFFFFFu;
+    if (np && fits) {
       const float4* rec = c.tris + (size_t)(e >> 1) * c.tri_stride;
       const float4 e0 = __ldg(rec), e1 = __ldg(rec + 1), e2 = __ldg(rec + 2), bb = __ldg(rec + 3);
       TriEntry te;
@@ -191,10 +209,10 @@ __global__ void __launch_bounds__(256, 4) k_region_decide(RasterParams c, Deferr
       te.A[1] = e1.x; te.B[1] = e1.y; te.C[1] = e1.z;
       te.A[2] = e2.x; te.B[2] = e2.y; te.C[2] = e2.z;
       const float x_min = bb.x - vpx, x_max = bb.y - vpx, y_min = bb.z - vpy, y_max = bb.w - vpy;
-      for (int k = 1; k < RMASK_STRIDE && partial; ++k) {
+      for (uint32_t k = 0; partial; ++k) {
         const int reg = __ffs(partial) - 1;
         partial &= partial - 1;
-        d.region_mask[(size_t)i * RMASK_STRIDE + k] = region_block_bits(te, x_min, x_max, y_min, y_max, tile_x, tile_y, reg);
+        d.bits_pool[off + k] = region_block_bits(te, x_min, x_max, y_min, y_max, tile_x, tile_y, reg);
       }
     }
   }
@@ -257,7 +275,7 @@ __global__ void __launch_bounds__(RBIN_THREADS, 2) k_region_bin(RasterParams c, 
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const uint32_t ei = i + u * 32 + lane;
-        m[u] = ei < end ? d.region_mask[(size_t)ei * RMASK_STRIDE] : 0u;
+        m[u] = ei < end ? d.region_mask[(size_t)ei * 2] : 0u;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -270,8 +288,8 @@ __global__ void __launch_bounds__(RBIN_THREADS, 2) k_region_bin(RasterParams c, 
           } else {
             const uint32_t partial = (m[u] & 0xFFFFu) & ~(m[u] >> 16);
             const uint32_t k = __popc(partial & ((1u << r) - 1));  // rank of this region among the entry's partial ones
-            if (k < (uint32_t)RMASK_STRIDE - 1) st_bits[u] = d.region_mask[(size_t)ei * RMASK_STRIDE + 1 + k];
-            else st_bits[u] = 0xFFFFFFFFu;  // marker: more partially covered regions than phase 1 stores, evaluated below
+            const uint32_t off = d.region_mask[(size_t)ei * 2 + 1];
+            st_bits[u] = off != 0xFFFFFFFFu ? d.bits_pool[off + k] : 0xFFFFFFFFu;  // marker: the pool was full, evaluated below
           }
         }
       }

@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint3
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { s_carry = 0; s_active = 0; s_large = 0; work_counter[0] = 0; work_counter[1] = 0; work_counter[2] = 0; work_counter[3] = 0; }
+  if (tid == 0) { s_carry = 0; s_active = 0; s_large = 0; work_counter[0] = 0; work_counter[1] = 0; work_counter[2] = 0; work_counter[3] = 0; work_counter[4] = 0; }
   __syncthreads();
   // active-tile compaction, longest lists first (classes >= 2048, >= 512, >= 128, rest): the raster work queue hands
   // items out in this order, so the few very long in-order chains start early instead of forming the kernel's tail
