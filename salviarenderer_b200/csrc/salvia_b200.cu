@@ -146,6 +146,7 @@ struct slv_device_t {
   bool jit_immediate = false;        // SLV_JIT_IMMEDIATE=1: SASL pixel shaders always take k_raster
   bool front_grids = true;           // SLV_FRONT_GRIDS=0: full-size k_sort_lists / k_region_bin / k_sort_lists_large grids
   int sort_large_grid = 0;           // SLV_SORT_LARGE_GRID: CTAs of k_sort_lists_large (0 = by tile count)
+  long long bits_pool_cap = -1;      // SLV_BITS_POOL_CAP: caps the block-bits pool (tests force k_region_bin's fallback evaluation)
   int cover_grid = 0, shade_grid = 0, sm_count = 0;
   int raster_grid = 0;  // persistent raster CTAs (SM count x resident CTAs per SM)
   // ---- draw batching: geometry + binning run at slv_draw time, the raster pass of all queued draws of a
@@ -586,6 +587,7 @@ slv_result flush_batch(slv_device dev) {
     db.region_tile_cnt = S.region_tile_cnt;
     db.bits_pool = S.region_mask + 2 * (size_t)dev->list_cap;
     db.bits_cap = (RMASK_STRIDE - 2) * dev->list_cap;
+    if (dev->bits_pool_cap >= 0) db.bits_cap = std::min<uint32_t>(db.bits_cap, (uint32_t)dev->bits_pool_cap);
     db.pool_cursor = S.work_counter + 4;
     db.region_offset = S.region_offset;
     db.region_count = S.region_count;
@@ -812,6 +814,7 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   const char* fg = getenv("SLV_FRONT_GRIDS");
   dev->front_grids = !(fg && fg[0] == '0');
   if (const char* sg = getenv("SLV_SORT_LARGE_GRID")) dev->sort_large_grid = atoi(sg);
+  if (const char* bp = getenv("SLV_BITS_POOL_CAP")) dev->bits_pool_cap = atoll(bp);
   const char* ji = getenv("SLV_JIT_IMMEDIATE");
   dev->jit_immediate = ji && ji[0] == '1';
   for (auto& ev : dev->user_ev) CU(cudaEventCreate(&ev));

@@ -227,6 +227,28 @@ def test_deferred_equals_immediate(cuda, cuda_immediate, name):
         assert ra.stats["ps_invocations"] > 0 or "depthfunc0" in name
 
 
+@pytest.mark.parametrize("cap", [0, 1000])
+def test_block_bits_pool_overflow_falls_back(cuda, built, cap):
+    """k_region_decide stores the level-4 block bits of every partially covered (entry, region) pair in a pool; entries that do
+    not fit are evaluated by k_region_bin itself.  A device with the pool capped (SLV_BITS_POOL_CAP: nothing fits / only the
+    first thousand words fit) must render the same frames as the normal one."""
+    import salviarenderer_b200 as pkg
+    os.environ["SLV_BITS_POOL_CAP"] = str(cap)
+    try:
+        small = pkg.load(0)
+    finally:
+        del os.environ["SLV_BITS_POOL_CAP"]
+    for mk, frames in ((lambda: S.SponzaLike(960, 540, 4, tex_size=64), (0, 5)), (_soup(samples=4, n=1500, size=0.3, w=1000, h=600, seed=5), (0,))):
+        a, b = mk(), mk()
+        a.setup(cuda)
+        b.setup(small)
+        for f in frames:
+            ra, rb = a.run(cuda, f), b.run(small, f)
+            assert not cases.compare_frames(ra, rb)
+            assert ra.stats["ps_invocations"] > 0
+    small.close()
+
+
 def test_deferred_full_size_sponza_equals_immediate(cuda, cuda_immediate):
     a, b = S.SponzaLike(3840, 2160, 4, tex_size=256), S.SponzaLike(3840, 2160, 4, tex_size=256)
     a.setup(cuda)
