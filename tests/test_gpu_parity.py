@@ -281,3 +281,15 @@ def test_heightfield_two_pass_large(cuda):
     assert not is_clear[covered].any() or is_clear[covered].mean() < 1e-3   # lit terrain is never exactly the clear colour
     assert is_clear[~covered].all()
     assert (a.count[..., 0] < 1.0).mean() > 0.2                             # the shadow map was written by the depth-only pass
+
+
+def test_full_size_shadow_map_1080p_msaa4(cuda, oracle):
+    """The StandardShadowMap sample (BASELINE configs[4]) at 1920x1080, 4x MSAA + resolve, against the oracle: the shadow map
+    (pass 1 depth), depth, stencil and counters bit-exact, colour within the north_star tolerance (measured: identical)."""
+    a, b = S.StandardShadowMap(1920, 1080, 4), S.StandardShadowMap(1920, 1080, 4)
+    a.setup(cuda)
+    b.setup(oracle)
+    for f in (0, 4):
+        ra, rb = a.run(cuda, f), b.run(oracle, f)
+        assert not cases.compare_frames(ra, rb, color_tol=COLOR_TOL_LSB)
+        assert ra.stats["ps_invocations"] > 1_000_000
