@@ -634,6 +634,117 @@ __device__ __forceinline__ uint32_t fetch_group(uint32_t* counter, uint32_t lane
   return v;
 }
 
+// ---- pieces shared by k_shade and shade_quad_main (the pixel- and the quad-granular form) -----------------------------------
+// One item (8x4 warp block) of a shading group: owners of the lane's pixel, the per-pixel flags and the colour row the
+// shader results are merged into.  false: the item needs no visit (warp-uniform).
+template <int S>
+__device__ __forceinline__ bool shade_item_setup(const RasterParams& c, const DeferredBufs& d, uint32_t item, uint32_t k, uint32_t grp,
+                                                 uint32_t n_items, uint32_t lane, int wlx, int wly, uint32_t* s_org,
+                                                 uint8_t (*s_touched)[32], uint32_t (*s_color)[32][S], uint32_t (&own)[S], uint32_t& rem) {
+  const uint32_t fullmask = (1u << S) - 1;
+  const bool flagged = k < grp && item < n_items && d.item_flag[item];
+  // lazy colour clear / fused resolve: every item of the active tiles is visited, not only those with new owners
+  const bool live = flagged || ((d.lazy_color || d.resolve_dst.data) && k < grp && item < n_items);
+  if (lane == 0) s_org[k] = 0xFFFFFFFFu;
+  if (!live) return false;
+  const uint32_t b = item >> 7, sub = (item >> 3) & 15, w = item & 7;
+  const uint32_t tile = c.active_tiles[1 + b];
+  const uint32_t tile_x = tile % c.tiles_x, tile_y = tile / c.tiles_x;
+  const int gx0 = tile_x * TILE + (sub & 3) * REGION + (w & 1) * 8, gy0 = tile_y * TILE + (sub >> 2) * REGION + (w >> 1) * 4;
+  const int x = gx0 + wlx, y = gy0 + wly;
+  const bool in_target = (uint32_t)x < c.target_w && (uint32_t)y < c.target_h;
+  if (lane == 0) s_org[k] = (uint32_t)gx0 | ((uint32_t)gy0 << 16);
+
+#pragma unroll
+  for (int s = 0; s < S; ++s) own[s] = VIS_NONE;
+  if (in_target && flagged) {  // unflagged items hold stale owners from an earlier batch
+    const uint32_t* vp = d.vis + ((size_t)y * d.vis_pitch + x) * S;
+    if (S == 4) {
+      const uint4 v = *reinterpret_cast<const uint4*>(vp);
+      own[0] = v.x; own[1 % S] = v.y; own[2 % S] = v.z; own[3 % S] = v.w;
+    } else if (S == 2) {
+      const uint2 v = *reinterpret_cast<const uint2*>(vp);
+      own[0] = v.x; own[1 % S] = v.y;
+    } else {
+      own[0] = *vp;
+    }
+  }
+  rem = 0;
+#pragma unroll
+  for (int s = 0; s < S; ++s) rem |= (own[s] != VIS_NONE) ? (1u << s) : 0u;
+  const uint32_t touched = rem;
+  // bit 7: the pixel is written even when no sample was touched (lazy colour clear, pixels inside the target)
+  // bit 6: the pixel lies inside the target (fused resolve)
+  s_touched[k][lane] = (uint8_t)(touched | ((d.lazy_color && in_target) ? 0x80u : 0u) | (in_target ? 0x40u : 0u));
+  if (d.lazy_color) {
+    if (touched != fullmask) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) s_color[k][lane][s] = d.clear_color;
+    }
+  } else if (touched != fullmask && in_target && (touched || d.resolve_dst.data)) {
+    // some samples keep their colour: fetch it for the 128-bit store (and for the resolve of untouched pixels)
+    const uint32_t* cptr = reinterpret_cast<const uint32_t*>(c.color0.data + ((size_t)y * c.color0.w + x) * S * 4);
+#pragma unroll
+    for (int s = 0; s < S; ++s) s_color[k][lane][s] = cptr[s];
+  }
+  return true;
+}
+
+// The end of a group: one 128-bit colour store per touched pixel, and the fused MSAA resolve.
+template <int S>
+__device__ __forceinline__ void shade_group_store(const RasterParams& c, const DeferredBufs& d, uint32_t lane, int wlx, int wly, uint32_t below,
+                                                  const uint32_t* s_org, const uint8_t (*s_touched)[32], const uint32_t (*s_color)[32][S],
+                                                  uint2* s_pool) {
+  uint32_t n_slow = 0;
+#pragma unroll 1
+  for (uint32_t kk = 0; kk < SHADE_GROUP; ++kk) {
+    const uint32_t org = s_org[kk];
+    if (org == 0xFFFFFFFFu) continue;
+    const uint32_t fl = s_touched[kk][lane];
+    const int x = (int)(org & 0xFFFF) + wlx, y = (int)(org >> 16) + wly;
+    if (fl & 0x8Fu) {
+      uint32_t* cptr = reinterpret_cast<uint32_t*>(c.color0.data + ((size_t)y * c.color0.w + x) * S * 4);
+      if (S == 4) *reinterpret_cast<uint4*>(cptr) = make_uint4(s_color[kk][lane][0], s_color[kk][lane][1 % S], s_color[kk][lane][2 % S], s_color[kk][lane][3 % S]);
+      else if (S == 2) *reinterpret_cast<uint2*>(cptr) = make_uint2(s_color[kk][lane][0], s_color[kk][lane][1 % S]);
+      else *cptr = s_color[kk][lane][0];
+    }
+    // fused resolve.  Pixels whose S samples are equal (the great majority) resolve to that very value: for unorm8 c,
+    // ((v+v)+v)+v with v = c/255 is off 4v by < 3 ulp, so * (1/S) * 255 lies within 1e-4 of c and rounds back to c.
+    // The others (triangle edges) are pooled over the group's items and resolved densely below.
+    bool slow = false;
+    if (d.resolve_dst.data && (fl & 0x40u)) {
+      bool same = d.resolve_dst.fmt == c.color0.fmt;
+#pragma unroll
+      for (int s = 1; s < S; ++s) same = same && s_color[kk][lane][s] == s_color[kk][lane][0];
+      if (same) *reinterpret_cast<uint32_t*>(d.resolve_dst.data + ((size_t)y * d.resolve_dst.w + x) * 4) = s_color[kk][lane][0];
+      slow = !same;
+    }
+    if (d.resolve_dst.data) {
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, slow);
+      if (slow) s_pool[n_slow + __popc(bal & below)] = make_uint2(lane | (kk << 5), 0u);
+      n_slow += __popc(bal);
+    }
+  }
+  if (n_slow) {  // sum of to_rgba32f(sample) in sample order, * (1 / S), convert (RNE)  (surface.cpp:123-140)
+    __syncwarp();
+    for (uint32_t j = lane; j < n_slow; j += 32) {
+      const uint32_t pl = s_pool[j].x & 31, k2 = s_pool[j].x >> 5;
+      const uint32_t org = s_org[k2];
+      const uint32_t pq = pl >> 2, pp = pl & 3;
+      const int x = (int)(org & 0xFFFF) + (int)((pq & 3) * 2 + (pp & 1)), y = (int)(org >> 16) + (int)((pq >> 2) * 2 + (pp >> 1));
+      float4 clr = make_float4(0, 0, 0, 0);
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const float4 t = unpack_color(c.color0.fmt, s_color[k2][pl][s]);
+        clr.x += t.x; clr.y += t.y; clr.z += t.z; clr.w += t.w;
+      }
+      const float inv = 1 / (float)S;
+      clr.x *= inv; clr.y *= inv; clr.z *= inv; clr.w *= inv;
+      store_texel_rgba32f(d.resolve_dst.fmt, d.resolve_dst.data + ((size_t)y * d.resolve_dst.w + x) * d.resolve_dst.bpp, clr);
+    }
+  }
+}
+
 template <int S, int PS>
 __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
     k_shade(RasterParams c, const RasterParams* __restrict__ batch, uint32_t n_draws, DeferredBufs d) {
@@ -650,7 +761,6 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
   uint8_t (*s_touched)[32] = s_touched_all[wid];
   const int q = lane >> 2, pi = lane & 3;
   const int wlx = (q & 3) * 2 + (pi & 1), wly = (q >> 2) * 2 + (pi >> 1);  // same pixel <-> lane map as k_cover
-  const uint32_t fullmask = (1u << S) - 1;
   const uint32_t below = (1u << lane) - 1;
 
   uint32_t n_exec = 0;
@@ -670,53 +780,8 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
       // ---- fill: analyse items while the pool has room for a whole item ----
 #pragma unroll 1
       for (; k < SHADE_GROUP && pool_n + 32 * S <= (uint32_t)SHADE_POOL; ++k) {
-        const uint32_t item = base_item + k;
-        const bool flagged = k < grp && item < n_items && d.item_flag[item];
-        // lazy colour clear / fused resolve: every item of the active tiles is visited, not only those with new owners
-        const bool live = flagged || ((d.lazy_color || d.resolve_dst.data) && k < grp && item < n_items);
-        if (lane == 0) s_org[k] = 0xFFFFFFFFu;
-        if (!live) continue;
-        const uint32_t b = item >> 7, sub = (item >> 3) & 15, w = item & 7;
-        const uint32_t tile = c.active_tiles[1 + b];
-        const uint32_t tile_x = tile % c.tiles_x, tile_y = tile / c.tiles_x;
-        const int gx0 = tile_x * TILE + (sub & 3) * REGION + (w & 1) * 8, gy0 = tile_y * TILE + (sub >> 2) * REGION + (w >> 1) * 4;
-        const int x = gx0 + wlx, y = gy0 + wly;
-        const bool in_target = (uint32_t)x < c.target_w && (uint32_t)y < c.target_h;
-        if (lane == 0) s_org[k] = (uint32_t)gx0 | ((uint32_t)gy0 << 16);
-
-        uint32_t own[S];
-#pragma unroll
-        for (int s = 0; s < S; ++s) own[s] = VIS_NONE;
-        if (in_target && flagged) {  // unflagged items hold stale owners from an earlier batch
-          const uint32_t* vp = d.vis + ((size_t)y * d.vis_pitch + x) * S;
-          if (S == 4) {
-            const uint4 v = *reinterpret_cast<const uint4*>(vp);
-            own[0] = v.x; own[1 % S] = v.y; own[2 % S] = v.z; own[3 % S] = v.w;
-          } else if (S == 2) {
-            const uint2 v = *reinterpret_cast<const uint2*>(vp);
-            own[0] = v.x; own[1 % S] = v.y;
-          } else {
-            own[0] = *vp;
-          }
-        }
-        uint32_t rem = 0;
-#pragma unroll
-        for (int s = 0; s < S; ++s) rem |= (own[s] != VIS_NONE) ? (1u << s) : 0u;
-        const uint32_t touched = rem;
-        // bit 7: the pixel is written even when no sample was touched (lazy colour clear, pixels inside the target)
-        // bit 6: the pixel lies inside the target (fused resolve)
-        s_touched[k][lane] = (uint8_t)(touched | ((d.lazy_color && in_target) ? 0x80u : 0u) | (in_target ? 0x40u : 0u));
-        if (d.lazy_color) {
-          if (touched != fullmask) {
-#pragma unroll
-            for (int s = 0; s < S; ++s) s_color[k][lane][s] = d.clear_color;
-          }
-        } else if (touched != fullmask && in_target && (touched || d.resolve_dst.data)) {
-          // some samples keep their colour: fetch it for the 128-bit store (and for the resolve of untouched pixels)
-          const uint32_t* cptr = reinterpret_cast<const uint32_t*>(c.color0.data + ((size_t)y * c.color0.w + x) * S * 4);
-#pragma unroll
-          for (int s = 0; s < S; ++s) s_color[k][lane][s] = cptr[s];
-        }
+        uint32_t own[S], rem;
+        if (!shade_item_setup<S>(c, d, base_item + k, k, grp, n_items, lane, wlx, wly, s_org, s_touched, s_color, own, rem)) continue;
         // the pixel's distinct owners -> the pool, one ballot-compacted round per owner rank (order irrelevant:
         // every (pixel, sample) has exactly one writer); round 0 = everybody's first owner, dense for covered blocks
 #pragma unroll
@@ -755,54 +820,7 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_SHADE_CTAS_PER_SM)
       if (k >= SHADE_GROUP) break;
     }
     // ---- store the group's items, one 128-bit store per touched pixel at 4x ----
-    uint32_t n_slow = 0;
-#pragma unroll 1
-    for (uint32_t kk = 0; kk < SHADE_GROUP; ++kk) {
-      const uint32_t org = s_org[kk];
-      if (org == 0xFFFFFFFFu) continue;
-      const uint32_t fl = s_touched[kk][lane];
-      const int x = (int)(org & 0xFFFF) + wlx, y = (int)(org >> 16) + wly;
-      if (fl & 0x8Fu) {
-        uint32_t* cptr = reinterpret_cast<uint32_t*>(c.color0.data + ((size_t)y * c.color0.w + x) * S * 4);
-        if (S == 4) *reinterpret_cast<uint4*>(cptr) = make_uint4(s_color[kk][lane][0], s_color[kk][lane][1 % S], s_color[kk][lane][2 % S], s_color[kk][lane][3 % S]);
-        else if (S == 2) *reinterpret_cast<uint2*>(cptr) = make_uint2(s_color[kk][lane][0], s_color[kk][lane][1 % S]);
-        else *cptr = s_color[kk][lane][0];
-      }
-      // fused resolve.  Pixels whose S samples are equal (the great majority) resolve to that very value: for unorm8 c,
-      // ((v+v)+v)+v with v = c/255 is off 4v by < 3 ulp, so * (1/S) * 255 lies within 1e-4 of c and rounds back to c.
-      // The others (triangle edges) are pooled over the group's items and resolved densely below.
-      bool slow = false;
-      if (d.resolve_dst.data && (fl & 0x40u)) {
-        bool same = d.resolve_dst.fmt == c.color0.fmt;
-#pragma unroll
-        for (int s = 1; s < S; ++s) same = same && s_color[kk][lane][s] == s_color[kk][lane][0];
-        if (same) *reinterpret_cast<uint32_t*>(d.resolve_dst.data + ((size_t)y * d.resolve_dst.w + x) * 4) = s_color[kk][lane][0];
-        slow = !same;
-      }
-      if (d.resolve_dst.data) {
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, slow);
-        if (slow) s_pool[n_slow + __popc(bal & below)] = make_uint2(lane | (kk << 5), 0u);
-        n_slow += __popc(bal);
-      }
-    }
-    if (n_slow) {  // sum of to_rgba32f(sample) in sample order, * (1 / S), convert (RNE)  (surface.cpp:123-140)
-      __syncwarp();
-      for (uint32_t j = lane; j < n_slow; j += 32) {
-        const uint32_t pl = s_pool[j].x & 31, k2 = s_pool[j].x >> 5;
-        const uint32_t org = s_org[k2];
-        const uint32_t pq = pl >> 2, pp = pl & 3;
-        const int x = (int)(org & 0xFFFF) + (int)((pq & 3) * 2 + (pp & 1)), y = (int)(org >> 16) + (int)((pq >> 2) * 2 + (pp >> 1));
-        float4 clr = make_float4(0, 0, 0, 0);
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          const float4 t = unpack_color(c.color0.fmt, s_color[k2][pl][s]);
-          clr.x += t.x; clr.y += t.y; clr.z += t.z; clr.w += t.w;
-        }
-        const float inv = 1 / (float)S;
-        clr.x *= inv; clr.y *= inv; clr.z *= inv; clr.w *= inv;
-        store_texel_rgba32f(d.resolve_dst.fmt, d.resolve_dst.data + ((size_t)y * d.resolve_dst.w + x) * d.resolve_dst.bpp, clr);
-      }
-    }
+    shade_group_store<S>(c, d, lane, wlx, wly, below, s_org, s_touched, s_color, s_pool);
     __syncwarp();
   }
 #pragma unroll
@@ -856,7 +874,6 @@ __device__ __forceinline__ void shade_quad_main(const RasterParams& c, const Ras
   uint8_t (*s_touched)[32] = s_touched_all[wid];
   const uint32_t q = lane >> 2, pi = lane & 3;
   const int wlx = (q & 3) * 2 + (pi & 1), wly = (q >> 2) * 2 + (pi >> 1);  // same pixel <-> lane map as k_cover
-  const uint32_t fullmask = (1u << S) - 1;
   const uint32_t below = (1u << lane) - 1;
 
   uint32_t n_exec = 0;
@@ -874,49 +891,8 @@ __device__ __forceinline__ void shade_quad_main(const RasterParams& c, const Ras
       // ---- fill: an item adds at most 8 quads x min(4 S, 16) owners = 32 S pairs ----
 #pragma unroll 1
       for (; k < SHADE_GROUP && pool_n + 32 * S <= (uint32_t)SHADE_POOL; ++k) {
-        const uint32_t item = base_item + k;
-        const bool flagged = k < grp && item < n_items && d.item_flag[item];
-        const bool live = flagged || ((d.lazy_color || d.resolve_dst.data) && k < grp && item < n_items);
-        if (lane == 0) s_org[k] = 0xFFFFFFFFu;
-        if (!live) continue;
-        const uint32_t b = item >> 7, sub = (item >> 3) & 15, w = item & 7;
-        const uint32_t tile = c.active_tiles[1 + b];
-        const uint32_t tile_x = tile % c.tiles_x, tile_y = tile / c.tiles_x;
-        const int gx0 = tile_x * TILE + (sub & 3) * REGION + (w & 1) * 8, gy0 = tile_y * TILE + (sub >> 2) * REGION + (w >> 1) * 4;
-        const int x = gx0 + wlx, y = gy0 + wly;
-        const bool in_target = (uint32_t)x < c.target_w && (uint32_t)y < c.target_h;
-        if (lane == 0) s_org[k] = (uint32_t)gx0 | ((uint32_t)gy0 << 16);
-
-        uint32_t own[S];
-#pragma unroll
-        for (int s = 0; s < S; ++s) own[s] = VIS_NONE;
-        if (in_target && flagged) {
-          const uint32_t* vp = d.vis + ((size_t)y * d.vis_pitch + x) * S;
-          if (S == 4) {
-            const uint4 v = *reinterpret_cast<const uint4*>(vp);
-            own[0] = v.x; own[1 % S] = v.y; own[2 % S] = v.z; own[3 % S] = v.w;
-          } else if (S == 2) {
-            const uint2 v = *reinterpret_cast<const uint2*>(vp);
-            own[0] = v.x; own[1 % S] = v.y;
-          } else {
-            own[0] = *vp;
-          }
-        }
-        uint32_t rem = 0;
-#pragma unroll
-        for (int s = 0; s < S; ++s) rem |= (own[s] != VIS_NONE) ? (1u << s) : 0u;
-        const uint32_t touched = rem;
-        s_touched[k][lane] = (uint8_t)(touched | ((d.lazy_color && in_target) ? 0x80u : 0u) | (in_target ? 0x40u : 0u));
-        if (d.lazy_color) {
-          if (touched != fullmask) {
-#pragma unroll
-            for (int s = 0; s < S; ++s) s_color[k][lane][s] = d.clear_color;
-          }
-        } else if (touched != fullmask && in_target && (touched || d.resolve_dst.data)) {
-          const uint32_t* cptr = reinterpret_cast<const uint32_t*>(c.color0.data + ((size_t)y * c.color0.w + x) * S * 4);
-#pragma unroll
-          for (int s = 0; s < S; ++s) s_color[k][lane][s] = cptr[s];
-        }
+        uint32_t own[S], rem;
+        if (!shade_item_setup<S>(c, d, base_item + k, k, grp, n_items, lane, wlx, wly, s_org, s_touched, s_color, own, rem)) continue;
         // the quad's distinct owners -> the pool.  Per round every quad with samples left elects the owner of its lowest
         // such lane's lowest remaining sample; all four lanes hand in the samples they hold of that owner.
         for (;;) {
@@ -965,52 +941,7 @@ __device__ __forceinline__ void shade_quad_main(const RasterParams& c, const Ras
       pool_n = 0;
       if (k >= SHADE_GROUP) break;
     }
-    // ---- store the group's items (identical to k_shade) ----
-    uint32_t n_slow = 0;
-#pragma unroll 1
-    for (uint32_t kk = 0; kk < SHADE_GROUP; ++kk) {
-      const uint32_t org = s_org[kk];
-      if (org == 0xFFFFFFFFu) continue;
-      const uint32_t fl = s_touched[kk][lane];
-      const int x = (int)(org & 0xFFFF) + wlx, y = (int)(org >> 16) + wly;
-      if (fl & 0x8Fu) {
-        uint32_t* cptr = reinterpret_cast<uint32_t*>(c.color0.data + ((size_t)y * c.color0.w + x) * S * 4);
-        if (S == 4) *reinterpret_cast<uint4*>(cptr) = make_uint4(s_color[kk][lane][0], s_color[kk][lane][1 % S], s_color[kk][lane][2 % S], s_color[kk][lane][3 % S]);
-        else if (S == 2) *reinterpret_cast<uint2*>(cptr) = make_uint2(s_color[kk][lane][0], s_color[kk][lane][1 % S]);
-        else *cptr = s_color[kk][lane][0];
-      }
-      bool slow = false;
-      if (d.resolve_dst.data && (fl & 0x40u)) {
-        bool same = d.resolve_dst.fmt == c.color0.fmt;
-#pragma unroll
-        for (int s = 1; s < S; ++s) same = same && s_color[kk][lane][s] == s_color[kk][lane][0];
-        if (same) *reinterpret_cast<uint32_t*>(d.resolve_dst.data + ((size_t)y * d.resolve_dst.w + x) * 4) = s_color[kk][lane][0];
-        slow = !same;
-      }
-      if (d.resolve_dst.data) {
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, slow);
-        if (slow) s_pool[n_slow + __popc(bal & below)] = make_uint2(lane | (kk << 5), 0u);
-        n_slow += __popc(bal);
-      }
-    }
-    if (n_slow) {  // surface.cpp:123-140
-      __syncwarp();
-      for (uint32_t j = lane; j < n_slow; j += 32) {
-        const uint32_t pl = s_pool[j].x & 31, k2 = s_pool[j].x >> 5;
-        const uint32_t org = s_org[k2];
-        const uint32_t pq = pl >> 2, pp = pl & 3;
-        const int x = (int)(org & 0xFFFF) + (int)((pq & 3) * 2 + (pp & 1)), y = (int)(org >> 16) + (int)((pq >> 2) * 2 + (pp >> 1));
-        float4 clr = make_float4(0, 0, 0, 0);
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          const float4 t = unpack_color(c.color0.fmt, s_color[k2][pl][s]);
-          clr.x += t.x; clr.y += t.y; clr.z += t.z; clr.w += t.w;
-        }
-        const float inv = 1 / (float)S;
-        clr.x *= inv; clr.y *= inv; clr.z *= inv; clr.w *= inv;
-        store_texel_rgba32f(d.resolve_dst.fmt, d.resolve_dst.data + ((size_t)y * d.resolve_dst.w + x) * d.resolve_dst.bpp, clr);
-      }
-    }
+    shade_group_store<S>(c, d, lane, wlx, wly, below, s_org, s_touched, s_color, s_pool);
     __syncwarp();
   }
 #pragma unroll
