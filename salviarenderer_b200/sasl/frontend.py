@@ -313,6 +313,28 @@ class Parser:
             self.expect(")")
             self.expect(";")
             return Node("dowhile", (body, c), line)
+        if self.accept("switch"):
+            self.expect("(")
+            sel = self.expr()
+            self.expect(")")
+            self.expect("{")
+            groups = []  # [(labels, statements)]: labels = case expressions, None for `default`
+            while not self.accept("}"):
+                labels = []
+                while self.t.text in ("case", "default"):
+                    if self.accept("default"):
+                        labels.append(None)
+                    else:
+                        self.expect("case")
+                        labels.append(self.expr())
+                    self.expect(":")
+                if not labels:
+                    raise CompileError(f"line {self.t.line}: statement before the first case label of a switch")
+                stmts = []
+                while self.t.text not in ("case", "default", "}"):
+                    stmts.append(self.statement())
+                groups.append((tuple(labels), tuple(stmts)))
+            return Node("switch", (sel, tuple(groups)), line)
         if self.accept("break"):
             self.expect(";")
             return Node("break", (), line)
@@ -492,15 +514,18 @@ class ShaderUnit:
 
 
 SWZ = {"x": 0, "y": 1, "z": 2, "w": 3, "r": 0, "g": 1, "b": 2, "a": 3}
-# transcendental functions go through sasl_rt.h's sasl_m_* wrappers: the host C library's float function on the CPU, the
-# double-precision device function rounded ONCE to float on the GPU (= the correctly rounded result, which is what glibc's
-# float functions return but for rare last-bit cases; CUDA's own float versions are 1-2 ulp off)
+# Math intrinsics go through sasl_rt.h's sasl_m_* wrappers, which mirror the host functions the reference links its JIT-ed code
+# to (sasl/src/drivers/compiler_impl.cpp:340-404): exp / log10 / sin ... pow / fmod are the C library's float functions (on the
+# GPU: the double-precision device function rounded ONCE to float = the correctly rounded result, which is what glibc's float
+# functions return but for rare last-bit cases; CUDA's own float versions are 1-2 ulp off); exp2 is ldexpf(1, (int)x); log and
+# log2 are eflib's fast_log / fast_log2 polynomial; floor / ceil / round / trunc are eflib's fast_floor / fast_ceil / fast_round
+# / trunc (magic-number rounding); ldexp(x, e) is ldexpf(x, (int)e).  Pure float arithmetic, bit-identical on host and device.
 UNARY_MATH = {"sqrt": "sqrtf", "exp": "sasl_m_exp", "exp2": "sasl_m_exp2", "log": "sasl_m_log", "log2": "sasl_m_log2",
               "log10": "sasl_m_log10", "sin": "sasl_m_sin", "cos": "sasl_m_cos", "tan": "sasl_m_tan", "asin": "sasl_m_asin",
               "acos": "sasl_m_acos", "atan": "sasl_m_atan", "sinh": "sasl_m_sinh", "cosh": "sasl_m_cosh", "tanh": "sasl_m_tanh",
-              "floor": "floorf", "ceil": "ceilf", "trunc": "truncf", "round": "rintf"}
+              "floor": "sasl_m_floor", "ceil": "sasl_m_ceil", "trunc": "sasl_m_trunc", "round": "sasl_m_round"}
 INTRINSICS = sorted(list(UNARY_MATH) + ["abs", "rsqrt", "frac", "saturate", "sign", "radians", "degrees", "min", "max", "pow",
-                                         "fmod", "step", "atan2", "ldexp", "clamp", "lerp", "smoothstep", "mad", "dot", "cross",
+                                         "fmod", "step", "atan2", "ldexp", "clamp", "lerp", "smoothstep", "mad", "dot", "cross", "dst",
                                          "length", "distance", "normalize", "reflect", "mul", "transpose", "any", "all",
                                          "ddx", "ddy", "tex2D", "tex2Dlod", "tex2Dbias", "tex2Dproj", "tex2Dgrad", "asfloat",
                                          "asint", "asuint", "countbits"])
@@ -864,7 +889,10 @@ class Gen:
         return self.map1(a, n, lambda c: f"fabsf({c})")
 
     def i_rsqrt(self, a, n): return self.map1(a, n, lambda c: f"(1.0f / sqrtf({c}))")
-    def i_frac(self, a, n): return self.map1(a, n, lambda c: f"({c} - floorf({c}))")
+    def i_frac(self, a, n):  # the reference's definition: |v| - floor(|v|) (sasl/src/codegen/cg_impl.cpp:1139-1150)
+        return self.map1(a, n, lambda c: f"(fabsf({c}) - sasl_m_floor(fabsf({c})))")
+
+    def i_ldexp(self, a, n): return self.mapn(a, n, lambda x, y: f"sasl_m_ldexp({x}, {y})", 2)
     def i_saturate(self, a, n): return self.map1(a, n, lambda c: f"sasl_clamp({c}, 0.0f, 1.0f)")
     def i_sign(self, a, n): return self.map1(a, n, lambda c: f"(({c} > 0.0f) ? 1.0f : (({c} < 0.0f) ? -1.0f : 0.0f))")
     def i_radians(self, a, n): return self.map1(a, n, lambda c: f"({c} * 0.017453292519943295f)")
@@ -905,6 +933,12 @@ class Gen:
         (ax, ay, az), (bx, by, bz) = x.comps, y.comps
         return Value(vec("float", 3), [self.temp("float", f"({ay} * {bz}) - ({az} * {by})"), self.temp("float", f"({az} * {bx}) - ({ax} * {bz})"),
                                        self.temp("float", f"({ax} * {by}) - ({ay} * {bx})")])
+
+    def i_dst(self, a, n):  # distance vector: (1, a.y * b.y, a.z, b.w)
+        if len(a) != 2:
+            self.err(n, "dst(float4, float4)")
+        x, y = (self.convert(self.to_base(v, "float", n), vec("float", 4), n) for v in a)
+        return Value(vec("float", 4), [self.temp("float", "1.0f"), self.temp("float", f"{x.comps[1]} * {y.comps[1]}"), x.comps[2], y.comps[3]])
 
     def i_length(self, a, n):
         v = self.to_base(a[0], "float", n)
@@ -1139,14 +1173,84 @@ class Gen:
         self.emit("}")
         self.loop_ids = self.loop_ids[:-1]
 
+    def case_value(self, e, n):
+        """Case labels are integer literals (optionally negated)."""
+        neg = False
+        while e.op == "un" and e.args[0] in ("-", "+"):
+            neg ^= e.args[0] == "-"
+            e = e.args[1]
+        t = e.args[0] if e.op == "num" else ""
+        if t.lower().startswith("0x") and re.fullmatch(r"0[xX][0-9a-fA-F]+[uU]?", t):
+            v = int(t.rstrip("uU"), 16)
+        elif re.fullmatch(r"\d+[uUlL]?", t):
+            v = int(t.rstrip("uUlL"))
+        else:
+            self.err(n, "case labels must be integer literals")
+        return -v if neg else v
+
+    def s_switch(self, n):
+        """switch with C fall-through semantics, lowered to guarded blocks inside one `do { } while (0)`: a group runs when
+        an earlier group fell through into it or the selector equals one of its labels (`default`: none of the switch's
+        labels); `break` leaves the do-while, `continue` (inside a loop) leaves it with the loop's continue flag raised."""
+        sel_e, groups = n.args
+        sel = self.convert(self.expr(sel_e), INT, n)
+        self.ntemp += 1
+        sid = self.ntemp
+        labels = [[None if l is None else self.case_value(l, n) for l in ls] for ls, _ in groups]
+        all_vals = [v for ls in labels for v in ls if v is not None]
+        if len(set(all_vals)) != len(all_vals):
+            self.err(n, "duplicate case label")
+        if sum(1 for ls in labels for v in ls if v is None) > 1:
+            self.err(n, "more than one default label")
+        self.emit("{")
+        self.indent += 1
+        self.emit(f"const int sel{sid} = {sel.comps[0]};")
+        self.emit(f"bool fall{sid} = false;")
+        if getattr(self, "loop_ids", []):
+            self.emit(f"bool cnt{sid} = false;")
+        self.emit("do {")
+        self.indent += 1
+        self.divergent += 1
+        self.switch_ids = getattr(self, "switch_ids", []) + [(sid, len(getattr(self, "loop_ids", [])))]
+        for ls, (_, stmts) in zip(labels, groups):
+            conds = [f"sel{sid} == {v}" for v in ls if v is not None]
+            if None in ls:
+                conds.append("(" + " && ".join([f"sel{sid} != {v}" for v in all_vals] or ["true"]) + ")")
+            self.emit(f"if (fall{sid} || {' || '.join(conds)}) {{")
+            self.indent += 1
+            self.emit(f"fall{sid} = true;")
+            self.s_block(Node("block", stmts, n.line))
+            self.indent -= 1
+            self.emit("}")
+        self.switch_ids = self.switch_ids[:-1]
+        self.divergent -= 1
+        self.indent -= 1
+        self.emit("} while (0);")
+        if getattr(self, "loop_ids", []):
+            self.emit(f"if (cnt{sid}) break;")  # `continue` inside the switch: leave the loop body's do { } while (0)
+        self.indent -= 1
+        self.emit("}")
+
+    def in_switch(self):
+        """The innermost breakable construct is a switch (opened after the innermost loop)."""
+        sw = getattr(self, "switch_ids", [])
+        return bool(sw) and sw[-1][1] == len(getattr(self, "loop_ids", []))
+
     def s_break(self, n):
+        if self.in_switch():
+            self.emit("break;")  # leaves the switch's do { } while (0)
+            return
         if not getattr(self, "loop_ids", []):
-            self.err(n, "break outside a loop")
+            self.err(n, "break outside a loop or switch")
         self.emit(f"brk{self.loop_ids[-1]} = true; break;")
 
     def s_continue(self, n):
         if not getattr(self, "loop_ids", []):
             self.err(n, "continue outside a loop")
+        if self.in_switch():
+            for sid, depth in self.switch_ids:  # every switch opened inside the innermost loop hands the request outwards
+                if depth == len(self.loop_ids):
+                    self.emit(f"cnt{sid} = true;")
         self.emit("break;")  # leaves the do { } while (0) around the body; the loop's step still runs
 
     def s_return(self, n):

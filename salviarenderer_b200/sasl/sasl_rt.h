@@ -41,18 +41,52 @@ SASL_FN unsigned sasl_countbits(unsigned v) {
 #endif
 }
 
-// libm (see frontend.py UNARY_MATH)
+// math intrinsics (see frontend.py UNARY_MATH): what the reference binds its JIT-ed code to, sasl/src/drivers/compiler_impl.cpp:340-404
 #if defined(__CUDACC__)
 #define SASL_M1(name) SASL_FN float sasl_m_##name(float x) { return (float)name((double)x); }
 #define SASL_M2(name) SASL_FN float sasl_m_##name(float x, float y) { return (float)name((double)x, (double)y); }
+#define SASL_FADD(a, b) __fadd_rn(a, b)
+#define SASL_FSUB(a, b) __fsub_rn(a, b)
 #else
 #define SASL_M1(name) SASL_FN float sasl_m_##name(float x) { return std::name(x); }
 #define SASL_M2(name) SASL_FN float sasl_m_##name(float x, float y) { return std::name(x, y); }
+SASL_FN float sasl_host_add(float a, float b) { volatile float r = a + b; return r; }
+SASL_FN float sasl_host_sub(float a, float b) { volatile float r = a - b; return r; }
+#define SASL_FADD(a, b) sasl_host_add(a, b)
+#define SASL_FSUB(a, b) sasl_host_sub(a, b)
 #endif
-SASL_M1(exp) SASL_M1(exp2) SASL_M1(log) SASL_M1(log2) SASL_M1(log10) SASL_M1(sin) SASL_M1(cos) SASL_M1(tan) SASL_M1(asin)
+SASL_M1(exp) SASL_M1(log10) SASL_M1(sin) SASL_M1(cos) SASL_M1(tan) SASL_M1(asin)
 SASL_M1(acos) SASL_M1(atan) SASL_M1(sinh) SASL_M1(cosh) SASL_M1(tanh) SASL_M2(pow) SASL_M2(atan2)
 #undef SASL_M1
 #undef SASL_M2
+// eflib::fast_log2 / fast_log (eflib/include/eflib/math/math.h:89-109): exponent + a quadratic in the mantissa
+SASL_FN float sasl_m_log2(float val) {
+  int x;
+  memcpy(&x, &val, 4);
+  const int log_2 = ((x >> 23) & 255) - 128;
+  x &= ~(255 << 23);
+  x += 127 << 23;
+  float f;
+  memcpy(&f, &x, 4);
+  f = ((-1.0f / 3) * f + 2) * f - 2.0f / 3;
+  return f + (float)log_2;
+}
+SASL_FN float sasl_m_log(float val) { return sasl_m_log2(val) * 0.69314718f; }
+// eflib::fast_round / fast_ceil / fast_floor / trunc (math.h:56-60, 111-134): round to nearest even through the 2^23 bias
+SASL_FN float sasl_m_round(float val) {
+  int n;
+  memcpy(&n, &val, 4);
+  const int bi = ((23 + 127) << 23) + (int)((unsigned)n & 0x80000000u);
+  float bias;
+  memcpy(&bias, &bi, 4);
+  return SASL_FSUB(SASL_FADD(val, bias), bias);
+}
+SASL_FN float sasl_m_ceil(float val) { const float f = sasl_m_round(val); return (f < val) ? f + 1 : f; }
+SASL_FN float sasl_m_floor(float val) { const float f = sasl_m_round(val); return (f > val) ? f - 1 : f; }
+SASL_FN float sasl_m_trunc(float val) { return val > 0.0f ? sasl_m_floor(val) : sasl_m_ceil(val); }
+// sasl.exp2.f32 = ldexpf(1, (int)v), sasl.ldexp.f32 = ldexpf(x, (int)e): the exponent is truncated to an integer
+SASL_FN float sasl_m_exp2(float v) { return ldexpf(1.0f, (int)v); }
+SASL_FN float sasl_m_ldexp(float x, float e) { return ldexpf(x, (int)e); }
 
 #if defined(__CUDACC__)
 typedef slv::SamplerRef SaslSampler;

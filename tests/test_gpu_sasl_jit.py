@@ -295,20 +295,34 @@ float4 ps_main(PSIn in): COLOR {
 
 
 @pytest.mark.parametrize("w,h,samples", [(640, 360, 1), (400, 240, 4)])
-def test_sasl_two_sampler_shadow_map_shader_equals_builtin(cuda, w, h, samples):
+def test_sasl_two_sampler_shadow_map_shader(cuda, cuda_jit_immediate, w, h, samples):
     """The colour pass of samples/StandardShadowMap written in SASL — TWO samplers (diffuse texture through tex2D, the shadow
-    map through nine tex2Dlod taps), exp / log / pow — against the built-in SLV_PS_SSM_DRAW, which is pinned to the reference
-    (cases c5_ssm_*).  Both run on the visibility-first path; cpp derivative convention so that tex2D's LOD equals the
-    built-in's cpp tex2d."""
+    map through nine tex2Dlod taps), exp / log / pow.  (1) The visibility-first path (quad-granular k_shade) and the immediate
+    k_raster path of the same module give identical frames.  (2) Against the built-in SLV_PS_SSM_DRAW (pinned to the reference,
+    cases c5_ssm_*): geometry, depth, the shadow map and the counters are identical; the colour differs only through SASL's
+    `log`, which is eflib's fast_log polynomial in the reference (sasl/src/drivers/compiler_impl.cpp:389, |error| < 0.01) where
+    the cpp shader calls logf — a fraction of a percent of the occlusion term, i.e. a few LSB in penumbra pixels only."""
     sh = jit.compile(PS_SSM_DRAW, "ps", derivatives="cpp")
     assert sh.reflection.samplers == ["texSamp", "smSamp"]
-    mod = jit.load(cuda, sh)
+
+    def sasl_scene(be):
+        mod = jit.load(be, sh)
+        sc = S.StandardShadowMap(w, h, samples, tex_size=64, textured_plane=True, ps_binding=lambda amb, dif, spe, shin, ts, ss: A.shader_binding(
+            A.program_jit(mod), sh.unit.pack_uniforms({"ambient": amb, "diffuse": dif, "specular": spe, "shininess": float(shin)}), [ts, ss]))
+        sc.setup(be)
+        return sc
+
+    got, imm = sasl_scene(cuda), sasl_scene(cuda_jit_immediate)
     ref = S.StandardShadowMap(w, h, samples, tex_size=64, textured_plane=True)
     ref.setup(cuda)
-    got = S.StandardShadowMap(w, h, samples, tex_size=64, textured_plane=True, ps_binding=lambda amb, dif, spe, shin, ts, ss: A.shader_binding(
-        A.program_jit(mod), sh.unit.pack_uniforms({"ambient": amb, "diffuse": dif, "specular": spe, "shininess": float(shin)}), [ts, ss]))
-    got.setup(cuda)
     for f in (1, 6):
-        a, b = ref.run(cuda, f), got.run(cuda, f)
-        assert cases.compare_frames(a, b) == [], f"frame {f}"
+        a, b, c = ref.run(cuda, f), got.run(cuda, f), imm.run(cuda_jit_immediate, f)
+        assert cases.compare_frames(b, c) == [], f"frame {f}: visibility-first vs immediate"
         assert a.stats["ps_invocations"] > 1000
+        for k in cases.GATED_COUNTERS:
+            assert a.stats[k] == b.stats[k], k
+        assert np.array_equal(a.depth.view(np.uint32), b.depth.view(np.uint32)) and np.array_equal(a.count.view(np.uint32), b.count.view(np.uint32))
+        d = np.abs(a.color.astype(np.int32) - b.color.astype(np.int32))
+        assert d.max() <= 6, f"frame {f}: SASL vs built-in colour differs by up to {d.max()} LSB"
+        assert (d > 0).any(-1).mean() < 0.25, f"frame {f}: {(d > 0).any(-1).mean():.1%} of the samples differ"
+        assert (d == 0).all(-1).mean() > 0.5

@@ -294,3 +294,118 @@ def test_reference_sasl_units_outside_subset_fail_cleanly(name):
     stage = "vs" if ext == "svs" else ("ps" if ext == "sps" else "lib")
     with pytest.raises(CompileError):
         compile_shader(_ref_unit(name), stage)
+
+
+# ---- the math intrinsics mirror the host functions the reference binds its JIT-ed code to, and `switch` --------------------
+PS_MATH = """
+float4 k;
+int    sel;
+struct PSIn { float4 a: TEXCOORD0; float4 b: TEXCOORD1; };
+int pick(int n, int base) {
+    int ret = 0;
+    switch (n) {
+    case 1: return base;
+    case 2: return base * base;
+    case 3:
+    case 4: ret = base + 100;
+    case 7: ret = ret + 1; break;
+    case -2: ret = -5; break;
+    default: return 0;
+    }
+    return ret;
+}
+float4 fn(PSIn in): COLOR {
+    float4 r;
+    r.x = log(in.a.x) + log2(in.a.y) * 0.5f + exp2(in.a.z);
+    r.y = floor(in.b.x) + ceil(in.b.y) * 2.0f + round(in.b.z) * 4.0f + trunc(in.b.w) * 8.0f;
+    r.z = frac(in.b.x) + ldexp(in.a.w, in.b.y);
+    float4 d = dst(in.a, in.b);
+    int acc = 0;
+    for (int i = 0; i < 6; ++i) {
+        switch (i) {
+        case 1: continue;
+        case 4: acc = acc + 1000; break;
+        default: acc = acc + pick(sel + i, 3);
+        }
+        acc = acc + 1;
+    }
+    r.w = d.y + d.z + d.w + d.x + (float)acc;
+    return r;
+}
+"""
+
+
+def _np_fast_log2(v):
+    x = np.array(v, np.float32).view(np.int32).astype(np.int64)
+    log_2 = ((x >> 23) & 255) - 128
+    x = (x & ~(255 << 23)) + (127 << 23)
+    f = np.array(x, np.int32).view(np.float32)
+    f = f32(f32(f32(f32(f32(-1.0) / f32(3)) * f) + f32(2)) * f) - f32(f32(2.0) / f32(3))
+    return f32(f32(f) + f32(log_2))
+
+
+def _np_fast_round(v):
+    v = f32(v)
+    bias = f32(-8388608.0) if np.signbit(v) else f32(8388608.0)
+    return f32(f32(v + bias) - bias)
+
+
+def _np_floor(v):
+    f = _np_fast_round(v)
+    return f32(f - f32(1)) if f > v else f
+
+
+def _np_ceil(v):
+    f = _np_fast_round(v)
+    return f32(f + f32(1)) if f < v else f
+
+
+def _py_pick(n, base):
+    ret = 0
+    if n == 1:
+        return base
+    if n == 2:
+        return base * base
+    if n in (3, 4):
+        return base + 100 + 1
+    if n == 7:
+        return 1
+    if n == -2:
+        return -5
+    return 0
+
+
+def test_math_intrinsics_mirror_the_reference_and_switch():
+    """log / log2 = eflib fast_log / fast_log2, exp2 = ldexpf(1, (int)x), floor / ceil / round / trunc = eflib's magic-number
+    versions, frac = |v| - floor(|v|), ldexp truncates its exponent (sasl/src/drivers/compiler_impl.cpp:340-404,
+    sasl/src/codegen/cg_impl.cpp:1139-1150); switch with fall-through, negative labels, default, and break / continue inside a
+    loop (sasl/test/repo/branches.ss)."""
+    unit = compile_shader(PS_MATH, "ps")
+    hs = HostShader(unit)
+    rng = np.random.default_rng(5)
+    for kcase in range(60):
+        a = rng.uniform(0.05, 9.0, 4).astype(f32)
+        b = (rng.uniform(-6.0, 6.0, 4)).astype(f32)
+        if kcase % 7 == 0:
+            b[2] = f32(np.floor(b[2])) + f32(0.5)      # ties: round half to even
+        sel = int(rng.integers(-4, 6))
+        got, keep = hs.ps([a, b], unit.pack_uniforms({"k": (0, 0, 0, 0), "sel": sel}))
+        assert keep
+        exp2 = f32(np.ldexp(np.float32(1.0), int(a[2])))
+        rx = f32(f32(f32(_np_fast_log2(a[0]) * f32(0.69314718)) + f32(_np_fast_log2(a[1]) * f32(0.5))) + exp2)
+        tr = _np_floor(b[3]) if b[3] > 0 else _np_ceil(b[3])
+        ry = f32(f32(f32(_np_floor(b[0]) + f32(_np_ceil(b[1]) * f32(2))) + f32(_np_fast_round(b[2]) * f32(4))) + f32(tr * f32(8)))
+        ab = f32(abs(b[0]))
+        rz = f32(f32(ab - _np_floor(ab)) + f32(np.ldexp(a[3], int(b[1]))))
+        acc = 0
+        for i in range(6):
+            if i == 1:
+                continue
+            if i == 4:
+                acc += 1000
+            else:
+                acc += _py_pick(sel + i, 3)
+            acc += 1
+        rw = f32(f32(f32(f32(f32(a[1] * b[1]) + a[2]) + b[3]) + f32(1.0)) + f32(acc))
+        want = np.array([rx, ry, rz, rw], f32)
+        assert np.array_equal(got, want), (kcase, got, want, a, b, sel)
