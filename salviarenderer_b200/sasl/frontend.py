@@ -528,7 +528,8 @@ INTRINSICS = sorted(list(UNARY_MATH) + ["abs", "rsqrt", "frac", "saturate", "sig
                                          "fmod", "step", "atan2", "ldexp", "clamp", "lerp", "smoothstep", "mad", "dot", "cross", "dst",
                                          "length", "distance", "normalize", "reflect", "mul", "transpose", "any", "all",
                                          "ddx", "ddy", "tex2D", "tex2Dlod", "tex2Dbias", "tex2Dproj", "tex2Dgrad", "asfloat",
-                                         "asint", "asuint", "countbits"])
+                                         "asint", "asuint", "countbits", "count_bits", "firstbithigh", "firstbitlow", "reversebits",
+                                         "isinf", "isfinite", "isnan", "rcp", "refract", "lit", "faceforward"])
 
 
 class Gen:
@@ -1010,6 +1011,71 @@ class Gen:
     def i_countbits(self, a, n):
         v = self.to_base(a[0], "uint", n)
         return Value(v.type, [self.temp("uint", f"sasl_countbits({c})") for c in v.comps])
+
+    i_count_bits = i_countbits  # both spellings are registered upstream (semantic_analyser.cpp:1981-1982)
+
+    def bits1(self, a, n, fn):  # sasl.firstbithigh / firstbitlow / reversebits .u32; the result keeps the argument's int / uint base
+        if len(a) != 1 or a[0].type.base not in ("int", "uint"):
+            self.err(n, "expects one int or uint argument")
+        v = a[0]
+        return Value(v.type, [self.temp(v.type.base, f"({'int' if v.type.base == 'int' else 'unsigned'}){fn}((unsigned){c})") for c in v.comps])
+
+    def i_firstbithigh(self, a, n): return self.bits1(a, n, "sasl_firstbithigh")
+    def i_firstbitlow(self, a, n): return self.bits1(a, n, "sasl_firstbitlow")
+    def i_reversebits(self, a, n): return self.bits1(a, n, "sasl_reversebits")
+
+    def fclass(self, a, n, fmt):
+        if len(a) != 1:
+            self.err(n, "expects 1 argument")
+        v = self.to_base(a[0], "float", n)
+        return Value(Type(v.type.kind, "bool", v.type.rows, v.type.cols), [self.temp("bool", fmt(c)) for c in v.comps])
+
+    # cgs.cpp:1828-1842: isinf = |v| == inf, isfinite = !isinf && v == v, isnan = unordered(v, v)
+    def i_isinf(self, a, n): return self.fclass(a, n, lambda c: f"(fabsf({c}) == sasl_asfloat(0x7F800000u))")
+    def i_isfinite(self, a, n): return self.fclass(a, n, lambda c: f"(!(fabsf({c}) == sasl_asfloat(0x7F800000u)) && ({c} == {c}))")
+    def i_isnan(self, a, n): return self.fclass(a, n, lambda c: f"({c} != {c})")
+
+    def i_rcp(self, a, n): return self.map1(a, n, lambda c: f"(1.0f / {c})")
+
+    def i_refract(self, a, n):  # cg_impl.cpp:1229-1269, in the reference's order of operations
+        if len(a) != 3:
+            self.err(n, "refract(i, n, eta)")
+        i, nn, _ = self.unify(self.to_base(a[0], "float", n), self.to_base(a[1], "float", n), n)
+        eta = self.convert(self.to_base(a[2], "float", n), FLOAT, n).comps[0]
+        eta2 = self.temp("float", f"{eta} * {eta}")
+        ndi = self.dot_comps(nn.comps, i.comps)
+        eta_i = [self.temp("float", f"{eta} * {c}") for c in i.comps]
+        k = self.temp("float", f"{ndi} * {ndi}")
+        k = self.temp("float", f"1.0f - {k}")
+        k = self.temp("float", f"{eta2} * {k}")
+        k = self.temp("float", f"1.0f - {k}")
+        flag = self.temp("bool", f"{k} < 0.0f")
+        k = self.temp("float", f"{flag} ? 0.0f : {k}")
+        r = self.temp("float", f"{eta} * {ndi}")
+        r = self.temp("float", f"{r} + sqrtf({k})")
+        out = []
+        for ei, c in zip(eta_i, nn.comps):
+            t = self.temp("float", f"{r} * {c}")
+            t = self.temp("float", f"{ei} - {t}")
+            out.append(self.temp("float", f"{flag} ? 0.0f : {t}"))
+        return Value(i.type, out)
+
+    def i_faceforward(self, a, n):  # cg_impl.cpp:1300-1319: dot(i, ng) < 0 ? n : 0 - n
+        if len(a) != 3:
+            self.err(n, "faceforward(n, i, ng)")
+        nn, i, _ = self.unify(self.to_base(a[0], "float", n), self.to_base(a[1], "float", n), n)
+        ng = self.convert(self.to_base(a[2], "float", n), i.type, n)
+        d = self.dot_comps(i.comps, ng.comps)
+        flag = self.temp("bool", f"{d} < 0.0f")
+        return Value(nn.type, [self.temp("float", f"{flag} ? {c} : (0.0f - {c})") for c in nn.comps])
+
+    def i_lit(self, a, n):  # cg_impl.cpp:1320-1352: (1, max(n.l, 0), n.l < 0 || n.h < 0 ? 0 : n.h * m, 1)
+        if len(a) != 3:
+            self.err(n, "lit(n_dot_l, n_dot_h, m)")
+        l, h, m = (self.convert(self.to_base(v, "float", n), FLOAT, n).comps[0] for v in a)
+        diffuse = self.temp("float", f"({l} < 0.0f) ? 0.0f : {l}")
+        spec = self.temp("float", f"(({l} < 0.0f) || ({h} < 0.0f)) ? 0.0f : ({h} * {m})")
+        return Value(vec("float", 4), [self.temp("float", "1.0f"), diffuse, spec, self.temp("float", "1.0f")])
 
     # ---- screen-space derivatives and texture sampling (pixel shaders)
     def need_quad(self, n, what):

@@ -41,6 +41,30 @@ SASL_FN unsigned sasl_countbits(unsigned v) {
 #endif
 }
 
+// sasl.firstbithigh.u32 = 31 - bsr(v), sasl.firstbitlow.u32 = bsf(v), sasl.reversebits.u32 (compiler_impl.cpp:414-432);
+// bsr / bsf of 0 are undefined upstream: all ones here
+SASL_FN unsigned sasl_firstbithigh(unsigned v) {
+#if defined(__CUDACC__)
+  return v ? (unsigned)__clz((int)v) : 0xFFFFFFFFu;
+#else
+  return v ? (unsigned)__builtin_clz(v) : 0xFFFFFFFFu;
+#endif
+}
+SASL_FN unsigned sasl_firstbitlow(unsigned v) {
+#if defined(__CUDACC__)
+  return v ? (unsigned)(__ffs((int)v) - 1) : 0xFFFFFFFFu;
+#else
+  return v ? (unsigned)__builtin_ctz(v) : 0xFFFFFFFFu;
+#endif
+}
+SASL_FN unsigned sasl_reversebits(unsigned v) {
+  v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+  v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+  v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+  v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+  return (v >> 16) | (v << 16);
+}
+
 // math intrinsics (see frontend.py UNARY_MATH): what the reference binds its JIT-ed code to, sasl/src/drivers/compiler_impl.cpp:340-404
 #if defined(__CUDACC__)
 #define SASL_M1(name) SASL_FN float sasl_m_##name(float x) { return (float)name((double)x); }

@@ -253,9 +253,9 @@ def test_texture_shader_reflection():
 # subset must go through the front end AND the generated code must compile (host C++).  Read in place, never copied;
 # skipped where /root/reference does not exist (the GPU box).
 REFERENCE_UNITS_OK = [
-    "arithmetic.sps", "arithmetic.ss", "array_and_index.ss", "assigns.ss", "bit_ops.ss", "branches.sps", "casts.ss", "comments.ss",
+    "arithmetic.sps", "arithmetic.ss", "array_and_index.ss", "assigns.ss", "bit_ops.ss", "branches.sps", "branches.ss", "casts.ss", "comments.ss",
     "constructors.ss", "ddx_ddy.sps", "decl.ss", "deps.ss", "do_while.sps", "empty.ss", "for_loop.sps", "host_intrinsic_detection.ss",
-    "initializer.ss", "intrinsics.sps", "intrinsics.svs", "local_var.ss", "null.ss", "swizzle.ss", "swizzle_and_wm.sps", "tex.sps",
+    "initializer.ss", "intrinsics.sps", "intrinsics.ss", "intrinsics.svs", "local_var.ss", "null.ss", "swizzle.ss", "swizzle_and_wm.sps", "tex.sps",
     "unary_operators.ss", "vec_and_mat.sps", "vec_and_mat.svs", "while.sps",
 ]
 REFERENCE_UNITS_REJECTED = {  # outside the subset (or erroneous on purpose upstream): must fail with CompileError, not crash
@@ -409,3 +409,66 @@ def test_math_intrinsics_mirror_the_reference_and_switch():
         rw = f32(f32(f32(f32(f32(a[1] * b[1]) + a[2]) + b[3]) + f32(1.0)) + f32(acc))
         want = np.array([rx, ry, rz, rw], f32)
         assert np.array_equal(got, want), (kcase, got, want, a, b, sel)
+
+
+PS_MORE = """
+int4 bits;
+struct PSIn { float4 a: TEXCOORD0; float4 b: TEXCOORD1; float4 c: TEXCOORD2; };
+float4 fn(PSIn in): COLOR {
+    float3 r = refract(in.a.xyz, in.b.xyz, in.a.w);
+    float3 ff = faceforward(in.a.xyz, in.b.xyz, in.c.xyz);
+    float4 l = lit(in.c.x, in.c.y, in.c.z);
+    uint2 hb = firstbithigh(uint2(asuint(bits.x), asuint(bits.y)));
+    int lb = firstbitlow(bits.z);
+    uint rb = reversebits(asuint(bits.w));
+    bool3 cls = bool3(isnan(in.c.w), isinf(in.b.w), isfinite(in.b.w));
+    float4 o;
+    o.x = r.x + r.y * 2.0f + r.z * 4.0f;
+    o.y = ff.x + ff.y * 2.0f + ff.z * 4.0f + rcp(in.c.z);
+    o.z = l.x + l.y * 2.0f + l.z * 4.0f + l.w * 8.0f;
+    o.w = (float)hb.x + (float)hb.y * 64.0f + (float)lb * 4096.0f + (float)(rb >> 24) * 0.001f + (cls.x ? 1.0f : 0.0f) * 0.25f
+          + (cls.y ? 1.0f : 0.0f) * 0.5f + (cls.z ? 1.0f : 0.0f) * 0.125f;
+    return o;
+}
+"""
+
+
+def test_more_intrinsics_follow_the_reference_code_generator():
+    """refract / faceforward / lit in the reference's order of operations (sasl/src/codegen/cg_impl.cpp:1229-1352), the bit
+    intrinsics of compiler_impl.cpp:414-432 and the float classification of cgs.cpp:1828-1842."""
+    unit = compile_shader(PS_MORE, "ps")
+    hs = HostShader(unit)
+    rng = np.random.default_rng(9)
+    for kcase in range(50):
+        a, b, c = (rng.standard_normal(4).astype(f32) for _ in range(3))
+        a[3] = f32(rng.uniform(0.3, 1.6))
+        if kcase % 5 == 0:
+            c[3] = f32(np.nan)
+        if kcase % 4 == 0:
+            b[3] = f32(np.inf)
+        bits = [int(v) for v in rng.integers(1, 2 ** 31 - 1, 4)]
+        got, keep = hs.ps([a, b, c], unit.pack_uniforms({"bits": bits}))
+        eta = a[3]
+        ndi = f32(f32(f32(b[0] * a[0]) + f32(b[1] * a[1])) + f32(b[2] * a[2]))
+        k = f32(f32(1) - f32(f32(eta * eta) * f32(f32(1) - f32(ndi * ndi))))
+        flag = k < 0
+        k = f32(0) if flag else k
+        rr = f32(f32(eta * ndi) + np.sqrt(k, dtype=f32))
+        r = [f32(0) if flag else f32(f32(eta * a[i]) - f32(rr * b[i])) for i in range(3)]
+        idn = f32(f32(f32(b[0] * c[0]) + f32(b[1] * c[1])) + f32(b[2] * c[2]))
+        ff = [a[i] if idn < 0 else f32(f32(0) - a[i]) for i in range(3)]
+        l = [f32(1), f32(0) if c[0] < 0 else c[0], f32(0) if (c[0] < 0 or c[1] < 0) else f32(c[1] * c[2]), f32(1)]
+        ox = f32(f32(r[0] + f32(r[1] * f32(2))) + f32(r[2] * f32(4)))
+        oy = f32(f32(f32(ff[0] + f32(ff[1] * f32(2))) + f32(ff[2] * f32(4))) + f32(f32(1) / c[2]))
+        oz = f32(f32(f32(l[0] + f32(l[1] * f32(2))) + f32(l[2] * f32(4))) + f32(l[3] * f32(8)))
+        clz = lambda v: 32 - int(v).bit_length()
+        ctz = lambda v: (int(v) & -int(v)).bit_length() - 1
+        rev = int(format(bits[3], "032b")[::-1], 2)
+        ow = f32(f32(clz(bits[0])) + f32(f32(clz(bits[1])) * f32(64)))
+        ow = f32(ow + f32(f32(ctz(bits[2])) * f32(4096)))
+        ow = f32(ow + f32(f32(rev >> 24) * f32(0.001)))
+        ow = f32(ow + f32(f32(1.0 if np.isnan(c[3]) else 0.0) * f32(0.25)))
+        ow = f32(ow + f32(f32(1.0 if np.isinf(b[3]) else 0.0) * f32(0.5)))
+        ow = f32(ow + f32(f32(1.0 if np.isfinite(b[3]) else 0.0) * f32(0.125)))
+        want = np.array([ox, oy, oz, ow], f32)
+        assert np.array_equal(got, want, equal_nan=True), (kcase, got, want)
