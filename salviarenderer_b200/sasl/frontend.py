@@ -257,6 +257,8 @@ class Parser:
                 while True:
                     arr = 0
                     if self.accept("["):
+                        if self.t.kind != "num" or not re.fullmatch(r"\d+", self.t.text):
+                            raise CompileError(f"line {self.t.line}: the size of an array must be an integer literal")
                         arr = int(self.t.text)
                         self.i += 1
                         self.expect("]")
@@ -761,8 +763,14 @@ class Gen:
     def e_bin(self, n):
         op = n.args[0]
         if op in ("&&", "||"):  # no side effects in operands of the supported subset: evaluate both
-            a = self.convert(self.expr(n.args[1]), BOOL, n)
-            b = self.convert(self.expr(n.args[2]), BOOL, n)
+            a, b = self.expr(n.args[1]), self.expr(n.args[2])
+            if a.type.kind in ("vector", "matrix") or b.type.kind in ("vector", "matrix"):  # component-wise on vectors / matrices
+                shape = a.type if a.type.kind in ("vector", "matrix") else b.type
+                bt = Type(shape.kind, "bool", shape.rows, shape.cols)
+                a, b = self.convert(a, bt, n), self.convert(b, bt, n)
+                return Value(bt, [self.temp("bool", f"{x} {op} {y}") for x, y in zip(a.comps, b.comps)])
+            a = self.convert(a, BOOL, n)
+            b = self.convert(b, BOOL, n)
             return Value(BOOL, [self.temp("bool", f"{a.comps[0]} {op} {b.comps[0]}")])
         a, b = self.expr(n.args[1]), self.expr(n.args[2])
         if op in ("==", "!=", "<", ">", "<=", ">="):

@@ -253,13 +253,13 @@ def test_texture_shader_reflection():
 # subset must go through the front end AND the generated code must compile (host C++).  Read in place, never copied;
 # skipped where /root/reference does not exist (the GPU box).
 REFERENCE_UNITS_OK = [
-    "arithmetic.sps", "arithmetic.ss", "array_and_index.ss", "assigns.ss", "bit_ops.ss", "branches.sps", "branches.ss", "casts.ss", "comments.ss",
+    "arithmetic.sps", "arithmetic.ss", "array_and_index.ss", "assigns.ss", "bit_ops.ss", "bool.ss", "branches.sps", "branches.ss", "casts.ss", "comments.ss",
     "constructors.ss", "ddx_ddy.sps", "decl.ss", "deps.ss", "do_while.sps", "empty.ss", "for_loop.sps", "host_intrinsic_detection.ss",
     "initializer.ss", "intrinsics.sps", "intrinsics.ss", "intrinsics.svs", "local_var.ss", "null.ss", "swizzle.ss", "swizzle_and_wm.sps", "tex.sps",
     "unary_operators.ss", "vec_and_mat.sps", "vec_and_mat.svs", "while.sps",
 ]
 REFERENCE_UNITS_REJECTED = {  # outside the subset (or erroneous on purpose upstream): must fail with CompileError, not crash
-    "incomplete.ss", "semantic_errors.ss", "preprocessors.ss", "include_main.ss", "function.ss", "scalar.sps",
+    "incomplete.ss", "semantic_errors.ss", "preprocessors.ss", "include_main.ss", "function.ss", "scalar.sps", "array.svs",
 }
 
 
@@ -472,3 +472,22 @@ def test_more_intrinsics_follow_the_reference_code_generator():
         ow = f32(ow + f32(f32(1.0 if np.isfinite(b[3]) else 0.0) * f32(0.125)))
         want = np.array([ox, oy, oz, ow], f32)
         assert np.array_equal(got, want, equal_nan=True), (kcase, got, want)
+
+
+def test_componentwise_logical_operators_on_vectors():
+    """`||` / `&&` on bool vectors work per component (sasl/test/repo/bool.ss: `i > j || i > k && i <= j + k` on int3 / float3x4)."""
+    src = """
+    struct PSIn { float4 a: TEXCOORD0; float4 b: TEXCOORD1; float4 c: TEXCOORD2; };
+    float4 fn(PSIn in): COLOR {
+        bool4 r = in.a > in.b || in.a > in.c && in.a <= in.b + in.c;
+        return float4(r.x ? 1.0f : 0.0f, r.y ? 1.0f : 0.0f, r.z ? 1.0f : 0.0f, r.w ? 1.0f : 0.0f);
+    }
+    """
+    unit = compile_shader(src, "ps")
+    hs = HostShader(unit)
+    rng = np.random.default_rng(3)
+    for _ in range(40):
+        a, b, c = (rng.integers(-3, 4, 4).astype(f32) for _ in range(3))
+        got, _keep = hs.ps([a, b, c])
+        want = ((a > b) | ((a > c) & (a <= (b + c).astype(f32)))).astype(f32)
+        assert np.array_equal(got, want), (a, b, c, got, want)
