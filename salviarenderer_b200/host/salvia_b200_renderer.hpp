@@ -314,6 +314,22 @@ public:
     std::memcpy(dst, &u, sizeof(u)); return sizeof(u);
   }
 };
+class vs_terrain_vtf : public cpp_vertex_shader {  // the SASL vertex shader of samples/VertexTextureFetch/VertexTextureFetch.cpp:38-61
+public:
+  mat44 wvp; float terrain_offset[2] = {0, 0}, terrain_scale[2] = {1, 1}; sampler_ptr sampler_;
+  vs_terrain_vtf() {
+    declare_constant("wvpMatrix", wvp); declare_constant("terrainOffset", terrain_offset); declare_constant("terrainScale", terrain_scale);
+    declare_sampler("terrainSamp", sampler_);
+    bind_semantic("POSITION", 0, 0); bind_semantic("TEXCOORD", 0, 1);
+  }
+  uint32_t device_program() const override { return SLV_VS_TERRAIN_VTF; }
+  uint32_t num_output_attributes() const override { return 1; }
+  size_t pack_uniforms(uint8_t* dst, size_t) const override {
+    slv_vs_terrain_vtf_uniforms u{}; std::memcpy(u.wvp, wvp.m, 64); std::memcpy(u.offset, terrain_offset, 8); std::memcpy(u.scale, terrain_scale, 8);
+    std::memcpy(dst, &u, sizeof(u)); return sizeof(u);
+  }
+  void samplers(slv_handle (&out)[SLV_MAX_SAMPLERS]) const override { out[0] = sampler_ ? sampler_->handle() : 0; }
+};
 class vs_ssm_draw : public cpp_vertex_shader {  // resources/ssm/Draw.savs (StandardShadowMap.cpp:192, colour pass)
 public:
   mat44 camera_wvp, light_wvp; vec4 light_pos, camera_pos;
@@ -331,6 +347,7 @@ public:
   }
 };
 class ps_lights3 : public cpp_pixel_shader { public: uint32_t device_program() const override { return SLV_PS_LIGHTS3; } };  // ColorizedTriangle.cpp:55-92
+class ps_height_color : public cpp_pixel_shader { public: uint32_t device_program() const override { return SLV_PS_HEIGHT_COLOR; } };  // VertexTextureFetch.cpp:70-113
 class ps_attr0_color : public cpp_pixel_shader { public: uint32_t device_program() const override { return SLV_PS_ATTR0_COLOR; } };
 class ps_sponza : public cpp_pixel_shader {  // samples/Sponza/Sponza.cpp:99-146
 public:
@@ -383,11 +400,14 @@ public:
     std::memcpy(block_.data() + it->second.first, v, size);
     return result::ok;
   }
+  void declare_sampler_name(std::string const& name) { declare_sampler(name, sampler_); }  // the shader's `sampler` global (slot 0)
+  void samplers(slv_handle (&out)[SLV_MAX_SAMPLERS]) const override { out[0] = sampler_ ? sampler_->handle() : 0; }
   uint32_t device_program() const override { return SLV_PROGRAM_JIT(module_); }
   uint32_t num_output_attributes() const override { return n_attrs_; }
   size_t pack_uniforms(uint8_t* dst, size_t cap) const override { size_t n = block_.size() < cap ? block_.size() : cap; std::memcpy(dst, block_.data(), n); return n; }
 private:
   slv_handle module_; uint32_t n_attrs_; std::vector<uint8_t> block_; std::map<std::string, std::pair<size_t, size_t>> layout_;
+  sampler_ptr sampler_;
 };
 
 // ---- input layout: input_element_descs resolved against the vertex shader's register map (stream_assembler.cpp:52-86) ----
@@ -508,7 +528,7 @@ public:
   result set_ps_variable(std::string const& name, void const* data, size_t sz) { return ps_ ? ps_->set_constant_raw(name, data, sz) : result::failed; }
   template <typename T> result set_ps_variable(std::string const& name, T const* data) { return set_ps_variable(name, static_cast<void const*>(data), sizeof(T)); }
   result set_ps_sampler(std::string const& name, sampler_ptr const& samp) { return ps_ ? ps_->set_sampler(name, samp) : result::failed; }
-  result set_vs_sampler(std::string const&, sampler_ptr const&) { return result::failed; }  // vertex texture fetch: scope row f-4
+  result set_vs_sampler(std::string const& name, sampler_ptr const& samp) { return vs_ ? vs_->set_sampler(name, samp) : result::failed; }  // vertex texture fetch (renderer.h:80)
   result set_rasterizer_state(raster_state_ptr const& rs) { rs_state_ = rs; return result::ok; }
   result set_blend_shader(cpp_blend_shader_ptr const& hbs) { bs_ = hbs; return result::ok; }
   result set_pixel_shader(cpp_pixel_shader_ptr const& hps) { ps_ = hps; return result::ok; }

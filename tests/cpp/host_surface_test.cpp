@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "salvia_b200_renderer.hpp"
 
@@ -196,6 +197,75 @@ int main(int argc, char** argv) {
     CHECK(r->unmap());
     std::printf("ssm color %016" PRIx64 " shadow map %016" PRIx64 " lit %zu shadowed %zu\n", h1, h2, lit, dark);
     if (lit == 0 || dark == 0) return 6;
+  }
+
+  // ---- vertex texture fetch through the surface (VertexTextureFetch.cpp:128-252): set_vs_sampler by name, the height map
+  // written through map / unmap, the sample's colour-ramp pixel shader
+  {
+    const uint32_t G = 12, TS = 16;
+    texture_ptr height = r->create_tex2d(TS, TS, 1, pixel_format_color_rg32f);
+    {
+      CHECK(r->map(m, height->subresource(0), map_write));
+      float* t = static_cast<float*>(m.data);
+      for (uint32_t y = 0; y < TS; ++y)
+        for (uint32_t x = 0; x < TS; ++x) { t[(y * TS + x) * 2] = (float)((x * 7 + y * 3) % 16) / 15.0f; t[(y * TS + x) * 2 + 1] = 0.0f; }
+      CHECK(r->unmap());
+    }
+    sampler_desc hd{};
+    hd.min_filter = hd.mag_filter = hd.mip_filter = filter_linear;
+    hd.mip_qual = mip_mi_quality;
+    hd.addr_mode_u = hd.addr_mode_v = hd.addr_mode_w = address_mirror;
+    hd.min_lod = -1e20f; hd.max_lod = 1e20f;
+    sampler_ptr hs = r->create_sampler(hd, height);
+    if (!hs) return 7;
+    std::vector<float> gp, guv;
+    std::vector<uint16_t> gi;
+    for (uint32_t i = 0; i <= G; ++i)
+      for (uint32_t j = 0; j <= G; ++j) {
+        gp.insert(gp.end(), {-3.0f + 0.5f * (float)i, -1.0f, -3.0f + 0.5f * (float)j, 1.0f});
+        guv.insert(guv.end(), {(float)i / (float)G, (float)j / (float)G, 0.0f, 0.0f});
+      }
+    for (uint32_t i = 0; i < G; ++i)
+      for (uint32_t j = 0; j < G; ++j) {
+        const uint16_t q0 = (uint16_t)(i * (G + 1) + j), q2 = (uint16_t)(q0 + G + 2);
+        gi.insert(gi.end(), {q0, (uint16_t)(q0 + 1), q2, q2, (uint16_t)(q2 - 1), q0});
+      }
+    buffer_ptr gb0 = r->create_buffer(gp.size() * 4), gb1 = r->create_buffer(guv.size() * 4), gib = r->create_buffer(gi.size() * 2);
+    CHECK(gb0->transfer(0, gp.data(), 16, gp.size() / 4));
+    CHECK(gb1->transfer(0, guv.data(), 16, guv.size() / 4));
+    CHECK(gib->transfer(0, gi.data(), 2, gi.size()));
+    texture_ptr color2 = r->create_tex2d(W, H, 1, pixel_format_color_rgba8), ds2 = r->create_tex2d(W, H, 1, pixel_format_color_rg32f);
+    surface_ptr c2 = color2->subresource(0), d2 = ds2->subresource(0);
+    auto vs_vtf = std::make_shared<vs_terrain_vtf>();
+    input_element_desc d2e[] = {{"POSITION", 0, format_r32g32b32a32_float, 0, 0}, {"TEXCOORD", 0, format_r32g32b32a32_float, 1, 0}};
+    CHECK(r->set_render_targets(1, &c2, d2));
+    CHECK(r->clear_color(c2, color_rgba32f{0.2f, 0.2f, 0.5f, 1.0f}));
+    CHECK(r->clear_depth_stencil(d2, clear_depth | clear_stencil, 1.0f, 0));
+    CHECK(r->set_input_layout(r->create_input_layout(d2e, 2, vs_vtf)));
+    CHECK(r->set_vertex_shader(vs_vtf));
+    CHECK(r->set_pixel_shader(std::make_shared<ps_height_color>()));
+    buffer_ptr gbufs[2] = {gb0, gb1};
+    size_t gst[2] = {16, 16}, gof[2] = {0, 0};
+    CHECK(r->set_vertex_buffers(0, 2, gbufs, gst, gof));
+    CHECK(r->set_index_buffer(gib, format_r16_uint));
+    CHECK(r->set_vs_variable("wvpMatrix", &wvp));
+    const float off2[2] = {0.125f, 0.25f}, scale2[2] = {1.5f, 1.25f};
+    CHECK(r->set_vs_variable("terrainOffset", &off2));
+    CHECK(r->set_vs_variable("terrainScale", &scale2));
+    if (r->set_vs_sampler("noSuchSampler", hs) != result::failed) return 7;
+    CHECK(r->set_vs_sampler("terrainSamp", hs));
+    CHECK(r->draw_index(0, G * G * 2, 0));
+    CHECK(r->flush());
+    CHECK(r->map(m, c2, map_read));
+    const uint64_t h3 = fnv(m.data, c2->bytes());
+    size_t covered = 0;  // pixels the displaced terrain reaches (the clear colour is (51, 51, 128, 255))
+    for (size_t i = 0; i < W * H; ++i) covered += static_cast<const uint8_t*>(m.data)[4 * i + 2] != 128 ? 1 : 0;
+    CHECK(r->unmap());
+    if (covered < W * H / 50) return 8;
+    CHECK(r->map(m, d2, map_read));
+    const uint64_t h4 = fnv(m.data, d2->bytes());
+    CHECK(r->unmap());
+    std::printf("vtf color %016" PRIx64 " depth %016" PRIx64 " covered %zu\n", h3, h4, covered);
   }
   return 0;
 }
