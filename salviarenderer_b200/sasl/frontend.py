@@ -1338,8 +1338,59 @@ class Gen:
         self.emit("return;")
 
     # ---- functions
-    def gen_function(self, f: Func):
-        self.cur_fn_derivs = False
+    def called_functions(self, f: Func) -> set:
+        """Names of the user functions f's body calls."""
+        names = {g.name for g in self.funcs}
+        out = set()
+
+        def walk(x):
+            if isinstance(x, Node):
+                if x.op == "call" and x.args[0] in names:
+                    out.add(x.args[0])
+                for a in x.args:
+                    walk(a)
+            elif isinstance(x, (tuple, list)):
+                for a in x:
+                    walk(a)
+            elif isinstance(x, VarDecl):
+                walk(x.init)
+
+        walk(f.body)
+        return out
+
+    def generation_order(self):
+        """Callees before callers (a function may be used before its definition), restricted to what the entry reaches
+        (every function for a library unit); functions on a call cycle are returned as `recursive`: they get a prototype
+        ahead of all bodies and are not force-inlined."""
+        by_name = {f.name: f for f in self.funcs}
+        callees = {f.name: self.called_functions(f) for f in self.funcs}
+        order, state, stack, recursive = [], {}, [], set()
+
+        def dfs(f):
+            state[f.name] = 1
+            stack.append(f.name)
+            for c in sorted(callees[f.name]):
+                if state.get(c, 0) == 0:
+                    dfs(by_name[c])
+                elif state[c] == 1:
+                    recursive.update(stack[stack.index(c):])
+            stack.pop()
+            state[f.name] = 2
+            order.append(f)
+
+        for f in ([self.entry] if self.entry is not None else self.funcs):
+            if state.get(f.name, 0) == 0:
+                dfs(by_name[f.name])
+        return order, recursive
+
+    def fn_head(self, f: Func, bases_params):
+        ctx = (["const SaslUniforms& U", "const slv::RasterParams& p", "const Ctx& px"] if self.stage == "ps"
+               else ["const SaslUniforms& U", "const SaslSampler& S0"])
+        kw = "SASL_FN_REC" if f.name in getattr(self, "recursive", ()) else "SASL_FN"
+        return ("template <class Ctx>\n" if self.stage == "ps" else "") + f"{kw} void sasl_fn_{f.name}({', '.join(ctx + bases_params)})"
+
+    def fn_signature(self, f: Func):
+        """The flattened C++ parameter list of f: (parameter declarations, scope of the parameters, names of the results)."""
         bases_params = []
         scope = {}
         for prm in f.params:
@@ -1359,10 +1410,15 @@ class Gen:
             for k, b in enumerate(self.flat_types(f.ret)):
                 ret_names.append(f"ret_{k}")
                 bases_params.append(f"{C_BASE[b]}& ret_{k}")
+        return bases_params, scope, ret_names
+
+    def gen_function(self, f: Func):
+        self.cur_fn_derivs = False
+        if f.name in getattr(self, "recursive", ()):
+            self.fn_table[f.name] = f  # visible to its own body (and to the other members of its cycle)
+        bases_params, scope, ret_names = self.fn_signature(f)
         self.cur_ret = Value(f.ret, ret_names, True) if ret_names else None
-        ctx = (["const SaslUniforms& U", "const slv::RasterParams& p", "const Ctx& px"] if self.stage == "ps"
-               else ["const SaslUniforms& U", "const SaslSampler& S0"])
-        head = ("template <class Ctx>\n" if self.stage == "ps" else "") + f"SASL_FN void sasl_fn_{f.name}({', '.join(ctx + bases_params)}) {{"
+        head = self.fn_head(f, bases_params) + " {"
         start = len(self.lines)
         self.indent = 1
         self.scopes = [scope]
@@ -1374,6 +1430,8 @@ class Gen:
         self.lines.append("}")
         self.lines.append("")
         if self.cur_fn_derivs:
+            if f.name in getattr(self, "recursive", ()):
+                raise CompileError(f"line {f.line}: {f.name}: screen-space derivatives in a recursive function")
             self.fns_with_derivatives.add(f.name)
         self.fn_table[f.name] = f
 
@@ -1403,10 +1461,15 @@ class Gen:
             off += 4 * n
         self.refl.uniform_bytes = (off + 15) & ~15
         header = ["struct SaslUniforms {"] + (fields or ["  int unused_;"]) + ["};", ""]
-        for f in self.funcs:
+        order, self.recursive = self.generation_order()
+        for f in order:  # prototypes of the functions on call cycles, ahead of every body
+            if f.name in self.recursive:
+                self.fn_table[f.name] = f
+                self.lines.append(self.fn_head(f, self.fn_signature(f)[0]) + ";")
+        if self.recursive:
+            self.lines.append("")
+        for f in order:
             self.gen_function(f)
-            if f is self.entry:
-                break
         wrapper = [] if self.stage == "lib" else (self.gen_vs_wrapper() if self.stage == "vs" else self.gen_ps_wrapper())
         code = "\n".join(header + self.lines + wrapper) + "\n"
         return ShaderUnit(self.stage, code, self.refl, self.src)

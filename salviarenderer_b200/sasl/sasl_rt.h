@@ -7,11 +7,13 @@
 
 #if defined(__CUDACC__)
 #define SASL_FN __device__ __forceinline__
+#define SASL_FN_REC __device__ __noinline__  /* functions on a call cycle (recursion) */
 #else
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 #define SASL_FN static inline
+#define SASL_FN_REC static
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 namespace slv { struct RasterParams { unsigned char ps_uniforms[256]; }; }

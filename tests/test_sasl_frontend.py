@@ -254,12 +254,12 @@ def test_texture_shader_reflection():
 # skipped where /root/reference does not exist (the GPU box).
 REFERENCE_UNITS_OK = [
     "arithmetic.sps", "arithmetic.ss", "array_and_index.ss", "assigns.ss", "bit_ops.ss", "bool.ss", "branches.sps", "branches.ss", "casts.ss", "comments.ss",
-    "constructors.ss", "ddx_ddy.sps", "decl.ss", "deps.ss", "do_while.sps", "empty.ss", "for_loop.sps", "host_intrinsic_detection.ss",
+    "constructors.ss", "ddx_ddy.sps", "decl.ss", "deps.ss", "do_while.sps", "empty.ss", "for_loop.sps", "function.ss", "host_intrinsic_detection.ss",
     "initializer.ss", "intrinsics.sps", "intrinsics.ss", "intrinsics.svs", "local_var.ss", "null.ss", "swizzle.ss", "swizzle_and_wm.sps", "tex.sps",
     "unary_operators.ss", "vec_and_mat.sps", "vec_and_mat.svs", "while.sps",
 ]
 REFERENCE_UNITS_REJECTED = {  # outside the subset (or erroneous on purpose upstream): must fail with CompileError, not crash
-    "incomplete.ss", "semantic_errors.ss", "preprocessors.ss", "include_main.ss", "function.ss", "scalar.sps", "array.svs",
+    "incomplete.ss", "semantic_errors.ss", "preprocessors.ss", "include_main.ss", "scalar.sps", "array.svs",
 }
 
 
@@ -491,3 +491,28 @@ def test_componentwise_logical_operators_on_vectors():
         got, _keep = hs.ps([a, b, c])
         want = ((a > b) | ((a > c) & (a <= (b + c).astype(f32)))).astype(f32)
         assert np.array_equal(got, want), (a, b, c, got, want)
+
+
+def test_forward_calls_and_recursion():
+    """A function may be called before its definition, and may call itself (sasl/test/repo/function.ss: fib): generation
+    follows the call graph, functions on a cycle get a prototype and are not force-inlined."""
+    src = """
+    int n;
+    struct PSIn { float4 a: TEXCOORD0; };
+    float4 fn(PSIn in): COLOR {
+        return float4((float)fib(n), later(in.a.x), (float)even(n), 1.0f);
+    }
+    float later(float x) { return x * 2.0f + 1.0f; }
+    int fib(int i) {
+        if (i < 2) { return i; }
+        return fib(i - 1) + fib(i - 2);
+    }
+    int even(int i) { if (i == 0) { return 1; } return odd(i - 1); }
+    int odd(int i) { if (i == 0) { return 0; } return even(i - 1); }
+    """
+    unit = compile_shader(src, "ps", "fn")
+    hs = HostShader(unit)
+    fib = lambda i: i if i < 2 else fib(i - 1) + fib(i - 2)
+    for n in (0, 1, 2, 7, 12):
+        got, _ = hs.ps([[0.25 * n, 0, 0, 0]], unit.pack_uniforms({"n": n}))
+        assert np.array_equal(got, np.array([fib(n), f32(f32(0.25 * n) * f32(2)) + f32(1), 1 - n % 2, 1], f32)), (n, got)
