@@ -1,6 +1,6 @@
 """Developer tool: renders the parity scenes on two backends and prints per-buffer mismatch counts.
 
-    python tools/parity_report.py [--a cuda|oracle|ref] [--b ref|oracle] [--only soup,c1,c2,probe]
+    python tests/report_parity.py [--a cuda|oracle|ref] [--b ref|oracle] [--only soup,c1,c2,probe]
 """
 import argparse
 import faulthandler

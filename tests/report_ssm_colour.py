@@ -1,4 +1,4 @@
-"""Developer tool: how close the CUDA colour of the StandardShadowMap cases (expf / logf / pow in the pixel shader) is to the
+"""Test infrastructure (report, not a test): how close the CUDA colour of the StandardShadowMap cases (expf / logf / pow in the pixel shader) is to the
 CPU oracle's — number of differing samples and the largest difference in LSB.  Test infrastructure (uses oracle/)."""
 import os
 import sys
