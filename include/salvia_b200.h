@@ -105,7 +105,7 @@ enum {
   /* diffuse texture × clamp(N·L) (Sponza.cpp:99-141).  uniforms: u32 has_sampler                   */
   SLV_PS_SPONZA = 4,
   /* color0 = sample_2d_grad(sampler0, attr[reg].xy, ddx, ddy, 0); a = alpha — the SASL tex2D path,
-   * required for anisotropic filtering.  uniforms: u32 reg; f32 alpha       */
+   * required for anisotropic filtering.  uniforms: u32 reg; f32 alpha; u32 sasl_derivatives */
   SLV_PS_TEX_GRAD_ALPHA = 5,
   SLV_PS_DISCARD_ALL = 6,   /* returns false for every pixel (early-Z quirk probe, App. B #3)       */
   SLV_PS_HEIGHT_COLOR = 7,  /* colour ramp over attr0.x (VertexTextureFetch.cpp:70-113)          no uniforms */
@@ -115,6 +115,13 @@ enum {
    * colour = tex · (ambient + (diffuse · clamp(L·N) + specular · pow(clamp(−reflect(L, N)·E), shininess)) · occlusion), a = 1.
    * exp / log evaluate in float (expf / logf), pow in double (pow(float, int) promotes).  uniforms: slv_ps_ssm_draw_uniforms */
   SLV_PS_SSM_DRAW = 8,
+  /* SLV_PS_SPONZA with the diffuse texture fetched the way a SASL pixel shader's tex2D fetches it: sample_2d_grad with the
+   * quad's derivatives of attr0.xy (sasl/src/codegen/cg_impl.cpp:902-909 -> sampler_api.cpp:13-18) - the only path on which the
+   * reference filters anisotropically.  sasl_derivatives = 1: the SASL convention, ddx per quad ROW and
+   * ddy per quad COLUMN (cgs_simd.cpp:275-313); 0: the cpp_pixel_shader one, q1 - q0 / q2 - q0 for the whole quad
+   * (cpp_pixel_shader.cpp:13-19).  The twin of the SASL Sponza pixel shader bench.py compiles at run time.
+   * uniforms: slv_ps_sponza_grad_uniforms */
+  SLV_PS_SPONZA_GRAD = 9,
   SLV_PS_JIT = 255          /* a SASL pixel shader compiled at run time; select it with SLV_PROGRAM_JIT(module) */
 };
 enum {
@@ -130,8 +137,11 @@ typedef struct slv_vs_plane_xz_uniforms { float wvp[16]; } slv_vs_plane_xz_unifo
 typedef struct slv_vs_lights3_uniforms { float wvp[16]; float light_pos[3][4]; } slv_vs_lights3_uniforms;
 typedef struct slv_vs_sponza_uniforms { float wvp[16]; float light_pos[4]; float eye_pos[4]; } slv_vs_sponza_uniforms;
 typedef struct slv_vs_terrain_vtf_uniforms { float wvp[16]; float offset[2]; float scale[2]; } slv_vs_terrain_vtf_uniforms;
-typedef struct slv_ps_tex_alpha_uniforms { uint32_t reg; float alpha; } slv_ps_tex_alpha_uniforms;
+/* sasl_derivatives (SLV_PS_TEX_GRAD_ALPHA only): 1 = ddx per quad row / ddy per quad column, the SASL convention
+ * (sasl/src/codegen/cgs_simd.cpp:275-313); 0 = q1 - q0 / q2 - q0 for the whole quad (cpp_pixel_shader.cpp:13-19) */
+typedef struct slv_ps_tex_alpha_uniforms { uint32_t reg; float alpha; uint32_t sasl_derivatives; } slv_ps_tex_alpha_uniforms;
 typedef struct slv_ps_sponza_uniforms { uint32_t has_sampler; } slv_ps_sponza_uniforms;
+typedef struct slv_ps_sponza_grad_uniforms { uint32_t has_sampler; uint32_t sasl_derivatives; } slv_ps_sponza_grad_uniforms;
 typedef struct slv_vs_ssm_draw_uniforms { float camera_wvp[16]; float light_wvp[16]; float light_pos[4]; float camera_pos[4]; } slv_vs_ssm_draw_uniforms;
 typedef struct slv_ps_ssm_draw_uniforms {
   float ambient[4], diffuse[4], specular[4];

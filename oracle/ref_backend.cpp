@@ -275,15 +275,28 @@ struct ps_tex_alpha : cpp_pixel_shader {
 // The SASL tex2D path: tex2D(s,uv) == tex2Dgrad(s, uv, ddx(uv), ddy(uv)) -> sampler::sample_2d_grad
 // (sasl/src/codegen/cg_impl.cpp:902-909, salvia/src/resource/sampler_api.cpp:13-18), with the cpp
 // quad-derivative convention (cpp_pixel_shader.cpp:13-19).
+// sasl_derivatives: ddx per quad row / ddy per quad column (cgs_simd.cpp:275-313).  cpp_pixel_shader keeps the quad private,
+// but execute() (cpp_pixel_shader.cpp:63-75) calls shader_prog for pixels 0..3 of `quad` in order with in == quad[i], and every
+// worker owns its clone - so the call count modulo 4 is the pixel's index and &in - i the quad.
 struct ps_tex_grad_alpha : cpp_pixel_shader {
   sampler_ptr sampler_;
   uint32_t reg;
   float alpha;
+  bool sasl_derivatives;
+  unsigned calls = 0;
   ps_tex_grad_alpha(sampler_ptr const& s, slv_ps_tex_alpha_uniforms const& u)
-    : sampler_(s), reg(u.reg), alpha(u.alpha) {}
+    : sampler_(s), reg(u.reg), alpha(u.alpha), sasl_derivatives(u.sasl_derivatives != 0) {}
   bool shader_prog(const vs_output& in, ps_output& out) override {
-    color_rgba32f color =
-        sampler_->sample_2d_grad(in.attribute(reg).xy(), ddx(reg).xy(), ddy(reg).xy(), 0.0f);
+    unsigned const i = calls++ & 3u;
+    color_rgba32f color;
+    if (sasl_derivatives) {
+      vs_output const* quad = &in - i;
+      vec4 dx = quad[i | 1u].attribute(reg) - quad[i & ~1u].attribute(reg);
+      vec4 dy = quad[i | 2u].attribute(reg) - quad[i & ~2u].attribute(reg);
+      color = sampler_->sample_2d_grad(in.attribute(reg).xy(), dx.xy(), dy.xy(), 0.0f);
+    } else {
+      color = sampler_->sample_2d_grad(in.attribute(reg).xy(), ddx(reg).xy(), ddy(reg).xy(), 0.0f);
+    }
     color.a = alpha;
     out.color[0] = color.get_vec4();
     return true;
@@ -299,6 +312,36 @@ struct ps_sponza : cpp_pixel_shader {
     vec4 diff_color = vec4(1.0f, 1.0f, 1.0f, 1.0f);
     if (sampler_) {
       diff_color = tex2d(*sampler_, 0).get_vec4();
+    }
+    vec3 norm(eflib::normalize3(in.attribute(1).xyz()));
+    vec3 light_dir(eflib::normalize3(in.attribute(2).xyz()));
+    float illum_diffuse = eflib::clamp(eflib::dot_prod3(light_dir, norm), 0.0f, 1.0f);
+    out.color[0] = diff_color * illum_diffuse;
+    out.color[0][3] = 1.0f;
+    return true;
+  }
+  SLV_CLONE()
+};
+
+// sponza_ps with the diffuse texture fetched the way a SASL pixel shader's tex2D fetches it (the reference's own
+// sampler::sample_2d_grad; sasl/src/codegen/cg_impl.cpp:902-909).  cpp_pixel_shader keeps the quad private, but execute()
+// (cpp_pixel_shader.cpp:63-75) calls shader_prog for pixels 0..3 of `quad` in order with in == quad[i], and every worker owns
+// its clone - so the call count modulo 4 is the pixel's index and &in - i the quad.  sasl_derivatives: per quad row / column
+// (cgs_simd.cpp:275-313) instead of q1 - q0 / q2 - q0.
+struct ps_sponza_grad : cpp_pixel_shader {
+  sampler_ptr sampler_;
+  bool sasl_derivatives;
+  unsigned calls = 0;
+  ps_sponza_grad(sampler_ptr const& s, bool sasl) : sampler_(s), sasl_derivatives(sasl) {}
+  bool shader_prog(const vs_output& in, ps_output& out) override {
+    unsigned const i = calls++ & 3u;
+    vs_output const* quad = &in - i;
+    vec4 diff_color = vec4(1.0f, 1.0f, 1.0f, 1.0f);
+    if (sampler_) {
+      unsigned const pi = sasl_derivatives ? i : 0u;
+      vec4 dx = quad[pi | 1u].attribute(0) - quad[pi & ~1u].attribute(0);
+      vec4 dy = quad[pi | 2u].attribute(0) - quad[pi & ~2u].attribute(0);
+      diff_color = sampler_->sample_2d_grad(in.attribute(0).xy(), dx.xy(), dy.xy(), 0.0f).get_vec4();
     }
     vec3 norm(eflib::normalize3(in.attribute(1).xyz()));
     vec3 light_dir(eflib::normalize3(in.attribute(2).xyz()));
@@ -606,6 +649,10 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   case SLV_PS_SPONZA: {
     auto u = (slv_ps_sponza_uniforms const*)d->ps.uniforms;
     ps.reset(new ps_sponza(u->has_sampler ? sampler_of(dev, d->ps.samplers[0]) : sampler_ptr()));
+  } break;
+  case SLV_PS_SPONZA_GRAD: {
+    auto u = (slv_ps_sponza_grad_uniforms const*)d->ps.uniforms;
+    ps.reset(new ps_sponza_grad(u->has_sampler ? sampler_of(dev, d->ps.samplers[0]) : sampler_ptr(), u->sasl_derivatives != 0));
   } break;
   case SLV_PS_DISCARD_ALL: ps.reset(new ps_discard_all()); break;
   case SLV_PS_HEIGHT_COLOR: ps.reset(new ps_height_color()); break;

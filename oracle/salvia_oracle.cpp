@@ -992,6 +992,17 @@ V4 ps_tex2d(DrawCtx& c, PsQuad& q, int pix, int samp, uint32_t reg) {
   return sample_impl(t, d, a[0], a[1], q.lod[reg], nullptr);
 }
 
+// tex2D of a SASL pixel shader: sample_2d_grad with the quad's derivatives (cg_impl.cpp:902-909 -> sampler_api.cpp:13-18).
+// sasl: ddx per quad row, ddy per quad column (cgs_simd.cpp:275-313); else q1 - q0, q2 - q0 (cpp_pixel_shader.cpp:13-19)
+V4 ps_tex2d_grad(DrawCtx& c, PsQuad& q, int pix, uint32_t reg, bool sasl) {
+  int const pi = sasl ? pix : 0;
+  V4 const& xl = q.px[pi & ~1].r[1 + reg]; V4 const& xh = q.px[pi | 1].r[1 + reg];
+  V4 const& yl = q.px[pi & ~2].r[1 + reg]; V4 const& yh = q.px[pi | 2].r[1 + reg];
+  V4 const& a = q.px[pix].r[1 + reg];
+  return sample_2d_grad(*c.sampler_tex[0], c.samplers[0]->d, a[0], a[1], xh[0] - xl[0], xh[1] - xl[1], yh[0] - yl[0],
+                        yh[1] - yl[1], 0.0f);
+}
+
 bool run_ps(DrawCtx& c, PsQuad& q, int pix, V4& color) {
   auto const& ps = c.d->ps;
   VsOut const& in = q.px[pix];
@@ -1043,12 +1054,7 @@ bool run_ps(DrawCtx& c, PsQuad& q, int pix, V4& color) {
   }
   case SLV_PS_TEX_GRAD_ALPHA: {
     auto u = (slv_ps_tex_alpha_uniforms const*)ps.uniforms;
-    V4 const& a0 = q.px[0].r[1 + u->reg];
-    V4 const& a1 = q.px[1].r[1 + u->reg];
-    V4 const& a2 = q.px[2].r[1 + u->reg];
-    V4 const& a = in.r[1 + u->reg];
-    color = sample_2d_grad(*c.sampler_tex[0], c.samplers[0]->d, a[0], a[1], a1[0] - a0[0], a1[1] - a0[1],
-                           a2[0] - a0[0], a2[1] - a0[1], 0.0f);
+    color = ps_tex2d_grad(c, q, pix, u->reg, u->sasl_derivatives != 0);
     color[3] = u->alpha;
     return true;
   }
@@ -1087,6 +1093,18 @@ bool run_ps(DrawCtx& c, PsQuad& q, int pix, V4& color) {
     float sp = (float)std::pow((double)illum_specular, (double)u->shininess);  // pow(float, int): both promoted to double
     for (int k = 0; k < 3; ++k)
       color[k] = tex[k] * (u->ambient[k] + (u->diffuse[k] * illum_diffuse + u->specular[k] * sp) * occlusion);
+    color[3] = 1.0f;
+    return true;
+  }
+  case SLV_PS_SPONZA_GRAD: {  // Sponza.cpp:117-136 with the diffuse fetch of a SASL tex2D: sample_2d_grad (cg_impl.cpp:902-909)
+    auto u = (slv_ps_sponza_grad_uniforms const*)ps.uniforms;
+    V4 diff = mk4(1, 1, 1, 1);
+    if (u->has_sampler) diff = ps_tex2d_grad(c, q, pix, 0, u->sasl_derivatives != 0);
+    float n[3], l[3];
+    normalize3(n, in.r[2].v);
+    normalize3(l, in.r[3].v);
+    float illum = clampf(dot3(l, n), 0.0f, 1.0f);
+    for (int k = 0; k < 4; ++k) color[k] = diff[k] * illum;
     color[3] = 1.0f;
     return true;
   }

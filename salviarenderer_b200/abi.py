@@ -31,6 +31,7 @@ AM_LINEAR, AM_CENTROID, AM_NOINTERPOLATION, AM_NOPERSPECTIVE = 1, 2, 4, 8
 
 VS_MVP_PASSTHROUGH, VS_PLANE_XZ, VS_LIGHTS3, VS_SPONZA, VS_TERRAIN_VTF, VS_SSM_DRAW = 1, 2, 3, 4, 5, 6
 PS_ATTR0_COLOR, PS_LIGHTS3, PS_TEX_ALPHA, PS_SPONZA, PS_TEX_GRAD_ALPHA, PS_DISCARD_ALL, PS_HEIGHT_COLOR, PS_SSM_DRAW = 1, 2, 3, 4, 5, 6, 7, 8
+PS_SPONZA_GRAD = 9
 BS_REPLACE, BS_LERP_SRC_ALPHA, BS_REPLACE_AND_COUNT = 1, 2, 3
 
 MAX_VS_INPUT_ATTRS = 8

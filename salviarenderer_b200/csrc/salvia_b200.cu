@@ -331,6 +331,7 @@ bool launch_raster_s(const RasterParams& rp, const RasterParams* batch, uint32_t
   case SLV_PS_DISCARD_ALL: k_raster<S, SLV_PS_DISCARD_ALL><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, n); return true;
   case SLV_PS_HEIGHT_COLOR: k_raster<S, SLV_PS_HEIGHT_COLOR><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, n); return true;
   case SLV_PS_SSM_DRAW: k_raster<S, SLV_PS_SSM_DRAW><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, n); return true;
+  case SLV_PS_SPONZA_GRAD: k_raster<S, SLV_PS_SPONZA_GRAD><<<blocks, RASTER_THREADS, 0, st>>>(rp, batch, n); return true;
   }
   return false;
 }
@@ -346,6 +347,7 @@ bool launch_shade_s(const RasterParams& rp, const RasterParams* batch, uint32_t 
   case SLV_PS_TEX_GRAD_ALPHA: k_shade<S, SLV_PS_TEX_GRAD_ALPHA><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, n_draws, db); return true;
   case SLV_PS_HEIGHT_COLOR: k_shade<S, SLV_PS_HEIGHT_COLOR><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, n_draws, db); return true;
   case SLV_PS_SSM_DRAW: k_shade<S, SLV_PS_SSM_DRAW><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, n_draws, db); return true;
+  case SLV_PS_SPONZA_GRAD: k_shade<S, SLV_PS_SPONZA_GRAD><<<blocks, DEF_THREADS, 0, st>>>(rp, batch, n_draws, db); return true;
   }
   return false;
 }
@@ -1275,7 +1277,7 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   memcpy(rp.ps_uniforms, d->ps.uniforms, sizeof(rp.ps_uniforms));
   bool needs_sampler = (rp.ps_program == SLV_PS_JIT && d->ps.samplers[0] != 0) ||
                        rp.ps_program == SLV_PS_TEX_ALPHA || rp.ps_program == SLV_PS_TEX_GRAD_ALPHA ||
-                       (rp.ps_program == SLV_PS_SPONZA &&
+                       ((rp.ps_program == SLV_PS_SPONZA || rp.ps_program == SLV_PS_SPONZA_GRAD) &&
                         reinterpret_cast<const slv_ps_sponza_uniforms*>(d->ps.uniforms)->has_sampler);
   bool needs_sampler1 = rp.ps_program == SLV_PS_JIT && d->ps.samplers[1] != 0;  // a SASL pixel shader's second sampler
   if (rp.ps_program == SLV_PS_SSM_DRAW) {
@@ -1289,7 +1291,7 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   if (rp.ps_program == SLV_PS_TEX_ALPHA || rp.ps_program == SLV_PS_TEX_GRAD_ALPHA) {
     if (reinterpret_cast<const slv_ps_tex_alpha_uniforms*>(d->ps.uniforms)->reg >= n_attrs) return SLV_INVALID_PARAMETER;
   }
-  if ((rp.ps_program == SLV_PS_LIGHTS3 || rp.ps_program == SLV_PS_SPONZA) && n_attrs < 4) return SLV_INVALID_PARAMETER;
+  if ((rp.ps_program == SLV_PS_LIGHTS3 || rp.ps_program == SLV_PS_SPONZA || rp.ps_program == SLV_PS_SPONZA_GRAD) && n_attrs < 4) return SLV_INVALID_PARAMETER;
   if ((rp.ps_program == SLV_PS_ATTR0_COLOR || rp.ps_program == SLV_PS_DISCARD_ALL || rp.ps_program == SLV_PS_HEIGHT_COLOR) && n_attrs < 1) return SLV_INVALID_PARAMETER;
   rp.tri_stride = tri_stride;
   rp.tiles_x = gp.tiles_x;

@@ -571,6 +571,7 @@ struct DeferredCtx {  // what a pixel shader may read when a lane shades its pix
   const uint32_t* mods;
   float dx, dy;            // quad origin relative to v0 (shader.cpp:277-281)
   float iw00, iw01, iw10;  // 1 / pos.w of pixels 0, 1, 2 of the quad
+  float w11;               // pos.w of pixel 3 (its reciprocal is only taken by the lanes / programs that need it)
   float inv_w;             // of this pixel
   bool odd_x, odd_y;
   __device__ __forceinline__ float4 attr(int i) const {
@@ -595,6 +596,24 @@ struct DeferredCtx {  // what a pixel shader may read when a lane shades its pix
     }
     u0 = x00; v0 = y00; u1 = x01; v1 = y01; u2 = x10; v2 = y10;
   }
+  // ... at all four pixels (pixel 3 = (a00 + ddx) + ddy, the order in which interp_attr steps an odd / odd pixel)
+  __device__ __forceinline__ void quad_xy4(int i, float4 a, float (&u)[4], float (&v)[4]) const {
+    quad_xy(i, a, u[0], v[0], u[1], v[1], u[2], v[2]);
+    const uint32_t mod = mods[i];
+    const float4 a0 = __ldg(rec + REC_V0 + 3 * (1 + i));
+    float x11 = a0.x, y11 = a0.y;
+    if (!(mod & SLV_AM_NOINTERPOLATION)) {
+      const float4 gx = __ldg(rec + REC_DDX + 3 * (1 + i)), gy = __ldg(rec + REC_DDY + 3 * (1 + i));
+      x11 = ((a0.x + (gx.x * dx + gy.x * dy)) + gx.x) + gy.x;
+      y11 = ((a0.y + (gx.y * dx + gy.y * dy)) + gx.y) + gy.y;
+    }
+    if (!(mod & SLV_AM_NOPERSPECTIVE)) {
+      const float iw11 = 1.0f / w11;
+      x11 *= iw11; y11 *= iw11;
+    }
+    u[3] = x11; v[3] = y11;
+  }
+  __device__ __forceinline__ int quad_index() const { return (odd_x ? 1 : 0) | (odd_y ? 2 : 0); }
 };
 
 template <int PS>
@@ -613,6 +632,7 @@ __device__ __forceinline__ uint32_t shade_sample_owner(const RasterParams& c, co
   const float w00 = v0p.w + (gxp.w * px.dx + gyp.w * px.dy);
   const float w01 = w00 + gxp.w, w10 = w00 + gyp.w, w11 = w01 + gyp.w;
   px.iw00 = 1.0f / w00; px.iw01 = 1.0f / w01; px.iw10 = 1.0f / w10;
+  px.w11 = w11;
   px.inv_w = px.odd_y ? (px.odd_x ? 1.0f / w11 : px.iw10) : (px.odd_x ? px.iw01 : px.iw00);
   float4 color;
   run_ps<PS>(p, px, color);

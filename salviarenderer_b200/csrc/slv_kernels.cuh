@@ -915,6 +915,15 @@ struct PixelCtx {  // what a pixel shader may read (immediate path: the four lan
     u1 = __shfl_sync(0xFFFFFFFFu, a.x, quad_base + 1); v1 = __shfl_sync(0xFFFFFFFFu, a.y, quad_base + 1);
     u2 = __shfl_sync(0xFFFFFFFFu, a.x, quad_base + 2); v2 = __shfl_sync(0xFFFFFFFFu, a.y, quad_base + 2);
   }
+  // ... at all four pixels of the quad
+  __device__ __forceinline__ void quad_xy4(int, float4 a, float (&u)[4], float (&v)[4]) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      u[i] = __shfl_sync(0xFFFFFFFFu, a.x, quad_base + i);
+      v[i] = __shfl_sync(0xFFFFFFFFu, a.y, quad_base + i);
+    }
+  }
+  __device__ __forceinline__ int quad_index() const { return (int)((threadIdx.x & 31u) - quad_base); }
 };
 
 // cpp_pixel_shader::tex2d (cpp_pixel_shader.cpp:13-31): ddx = q1 - q0, ddy = q2 - q0 for the whole quad,
@@ -925,6 +934,21 @@ __device__ __forceinline__ float4 ps_tex2d(const SamplerRef& sm, const Ctx& px, 
   px.quad_xy(reg, a, u0, v0, u1, v1, u2, v2);
   float lod = calc_lod_2d(sm, u1 - u0, v1 - v0, u2 - u0, v2 - v0);
   return sample_impl(sm, a.x, a.y, lod, nullptr);
+}
+
+// tex2D of a SASL pixel shader: sample_2d_grad with the derivatives of attribute `reg`.xy over the quad
+// (sasl/src/codegen/cg_impl.cpp:902-909 -> sampler_api.cpp:13-18).  sasl: ddx = right - left pixel of the pixel's own quad
+// ROW, ddy = lower - upper pixel of its COLUMN (cgs_simd.cpp:275-313); else the cpp_pixel_shader convention, q1 - q0 and
+// q2 - q0 for all four pixels (cpp_pixel_shader.cpp:13-19).
+template <class Ctx>
+__device__ __forceinline__ float4 ps_tex2d_grad(const SamplerRef& sm, const Ctx& px, int reg, float4 a, bool sasl) {
+  float qu[4], qv[4];
+  px.quad_xy4(reg, a, qu, qv);
+  const int pi = sasl ? px.quad_index() : 0;
+  const bool row1 = pi & 2, col1 = pi & 1;
+  const float ulx = row1 ? qu[2] : qu[0], vlx = row1 ? qv[2] : qv[0], uhx = row1 ? qu[3] : qu[1], vhx = row1 ? qv[3] : qv[1];
+  const float uly = col1 ? qu[1] : qu[0], vly = col1 ? qv[1] : qv[0], uhy = col1 ? qu[3] : qu[2], vhy = col1 ? qv[3] : qv[2];
+  return sample_2d_grad(sm, a.x, a.y, uhx - ulx, vhx - vlx, uhy - uly, vhy - vly, 0.0f);
 }
 
 template <int PS, class Ctx>
@@ -999,9 +1023,7 @@ __device__ __forceinline__ bool run_ps(const RasterParams& p, const Ctx& px, flo
   if (PS == SLV_PS_TEX_GRAD_ALPHA) {  // SASL tex2D == sample_2d_grad with the quad derivatives
     auto u = reinterpret_cast<const slv_ps_tex_alpha_uniforms*>(p.ps_uniforms);
     float4 a = px.attr((int)u->reg);
-    float u0, v0, u1, v1, u2, v2;
-    px.quad_xy((int)u->reg, a, u0, v0, u1, v1, u2, v2);
-    color = sample_2d_grad(p.sampler0, a.x, a.y, u1 - u0, v1 - v0, u2 - u0, v2 - v0, 0.0f);
+    color = ps_tex2d_grad(p.sampler0, px, (int)u->reg, a, u->sasl_derivatives != 0);
     color.w = u->alpha;
     return true;
   }
@@ -1010,6 +1032,22 @@ __device__ __forceinline__ bool run_ps(const RasterParams& p, const Ctx& px, flo
     float4 diff = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
     float4 uv = px.attr(0);
     if (u->has_sampler) diff = ps_tex2d(p.sampler0, px, 0, uv);
+    float4 n = px.attr(1), l = px.attr(2);
+    float nl = length3(n.x, n.y, n.z);
+    if (eq_eps(nl, 0.0f)) nl = 1.0f;
+    float ninv = 1.0f / nl;
+    float ll = length3(l.x, l.y, l.z);
+    if (eq_eps(ll, 0.0f)) ll = 1.0f;
+    float linv = 1.0f / ll;
+    float illum = clampf(dot3(l.x * linv, l.y * linv, l.z * linv, n.x * ninv, n.y * ninv, n.z * ninv), 0.0f, 1.0f);
+    color = make_float4(diff.x * illum, diff.y * illum, diff.z * illum, 1.0f);
+    return true;
+  }
+  if (PS == SLV_PS_SPONZA_GRAD) {  // Sponza.cpp:117-136 with the SASL tex2D fetch (sample_2d_grad, quad derivatives)
+    auto u = reinterpret_cast<const slv_ps_sponza_grad_uniforms*>(p.ps_uniforms);
+    float4 diff = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    float4 uv = px.attr(0);
+    if (u->has_sampler) diff = ps_tex2d_grad(p.sampler0, px, 0, uv, u->sasl_derivatives != 0);
     float4 n = px.attr(1), l = px.attr(2);
     float nl = length3(n.x, n.y, n.z);
     if (eq_eps(nl, 0.0f)) nl = 1.0f;

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import struct
 from dataclasses import dataclass, field
 
@@ -200,12 +201,16 @@ def pack_vs_sponza(wvp, light, eye):
     return np.asarray(wvp, f32).tobytes() + np.asarray(light, f32).tobytes() + np.asarray(eye, f32).tobytes()
 
 
-def pack_ps_tex_alpha(reg, alpha):
-    return struct.pack("<If", reg, alpha)
+def pack_ps_tex_alpha(reg, alpha, sasl_derivatives=False):
+    return struct.pack("<IfI", reg, alpha, int(sasl_derivatives))
 
 
 def pack_ps_sponza(has_sampler):
     return struct.pack("<I", int(has_sampler))
+
+
+def pack_ps_sponza_grad(has_sampler, sasl_derivatives=True):
+    return struct.pack("<II", int(has_sampler), int(sasl_derivatives))
 
 
 def pack_vs_ssm_draw(camera_wvp, light_wvp, light_pos, camera_pos):
@@ -332,8 +337,19 @@ class ColorizedTriangle:
 
 
 # ---- textures ----------------------------------------------------------------------------------------------
+ASSET_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "assets")
+
+
+def asset_texture(name: str) -> np.ndarray:
+    """rgba8 texels of one of the reference's own image assets (tests/golden/assets/, copied from /root/reference/resources by
+    tests/golden/fetch_assets.py), loaded the way load_texture does (tex_io.cpp:28-95: bottom-up rows, RGB gets alpha 0)."""
+    from .assets import load_texture_rgba8
+    return load_texture_rgba8(os.path.join(ASSET_DIR, name))
+
+
 def chessboard_texture(n=32, cell=4) -> np.ndarray:
-    """Procedural stand-in for resources/texture_and_blending/chessboard.png (32x32 RGBA)."""
+    """Procedural stand-in for resources/texture_and_blending/chessboard.png (32x32 RGBA); the scenes use the real file
+    (asset_texture) and fall back to this only when the fixture directory is missing."""
     y, x = np.mgrid[0:n, 0:n]
     on = ((x // cell + y // cell) & 1).astype(np.uint8)
     img = np.empty((n, n, 4), dtype=np.uint8)
@@ -377,12 +393,54 @@ def brick_texture(size=1024, seed=1) -> np.ndarray:
     return img
 
 
-def make_texture(be: A.Backend, img: np.ndarray, fmt=A.PF_RGBA8, mips=True) -> A.Texture:
+def mip_chain_rgba8(img: np.ndarray) -> list:
+    """texture_2d::gen_mipmap(filter_linear) for rgba8 texels, restated in numpy (surface.cpp:53-92, texture.h:26-35): level
+    sizes (w + 1) / 2, texel = ((c0 + c1) + c2) + c3) * 0.25 over to_rgba32f texels, RNE back to unorm8.  The reference reads
+    texels 2x + 1 / 2y + 1 without a bounds check: for an odd parent width the read wraps into the next
+    row (linear addressing, mirrored here), for an odd parent height the last row reads PAST THE ALLOCATION - undefined upstream
+    (heap garbage), defined as zeros here, in the product (k_mipgen) and in the oracle."""
+    levels = [np.ascontiguousarray(img, dtype=np.uint8)]
+    m = max(img.shape[0], img.shape[1])
+    limit = 0
+    while m > 0:
+        m >>= 1
+        limit += 1
+    inv255 = f32(1.0) / f32(255.0)
+    for _ in range(limit - 1):
+        src = levels[-1]
+        h, w = src.shape[:2]
+        mh, mw = (h + 1) // 2, (w + 1) // 2
+        flat = np.concatenate([src.reshape(-1, 4).astype(f32) * inv255, np.zeros((2 * w + 4, 4), f32)])
+        yy, xx = np.mgrid[0:mh, 0:mw]
+
+        def rd(dx, dy):
+            return flat[(2 * yy + dy) * w + 2 * xx + dx]
+
+        o = (((rd(0, 0) + rd(1, 0)) + rd(0, 1)) + rd(1, 1)) * f32(0.25)
+        o = np.clip(o * f32(255.0), f32(0.0), f32(255.0))
+        levels.append(np.rint(o).astype(np.uint8))
+    return levels
+
+
+def make_texture(be: A.Backend, img: np.ndarray, fmt=A.PF_RGBA8, mips=True, defined_mips=False) -> A.Texture:
+    """`defined_mips`: for textures whose chain has odd-sized parents (not a power of two), the levels from the first
+    undefined one on are overwritten with mip_chain_rgba8's - a no-op for the product and the oracle (their gen_mipmap IS that
+    chain, tests/test_sampler_npot.py), and what makes the unmodified reference sample defined texels instead of whatever its
+    out-of-bounds reads returned in this process."""
     h, w = img.shape[:2]
     t = be.create_texture(w, h, 1, fmt)
     be.upload_texture(t, img)
     if mips:
         be.gen_mipmap(t, A.FILTER_LINEAR)
+        if defined_mips and fmt == A.PF_RGBA8:
+            chain = mip_chain_rgba8(img)
+            assert be.level_count(t) == len(chain)
+            # the first undefined level is the child of the first parent with an odd height (whole last row reads past the
+            # allocation) or an odd width (its bottom-right texel does)
+            first = next((l + 1 for l, c in enumerate(chain[:-1]) if (c.shape[0] & 1) or (c.shape[1] & 1)), None)
+            if first is not None:
+                for l in range(first, len(chain)):
+                    be.upload_texture(t, chain[l], level=l)
     return t
 
 
@@ -406,7 +464,8 @@ class TextureAndBlending:
         self.box = box
         self.plane.elements = [(0, _V4, 0, 0, 1.0)]
         self.n_frames = 5
-        self.chess = chessboard_texture()
+        # the sample's own chessboard.png (32x32 RGBA); Dirt.jpg is a Git-LFS pointer upstream -> seeded noise
+        self.chess = asset_texture("chessboard.png") if os.path.exists(os.path.join(ASSET_DIR, "chessboard.png")) else chessboard_texture()
         self.noise = noise_texture()
 
     def setup(self, be: A.Backend):
@@ -448,6 +507,87 @@ class TextureAndBlending:
             d.ps = self.ps_binding(1, 0.5, self.box_samp) if self.ps_binding else \
                 A.shader_binding(self.ps_program, pack_ps_tex_alpha(1, 0.5), [self.box_samp])
             d.bs = A.shader_binding(A.BS_LERP_SRC_ALPHA)
+            be.draw(d)
+        if t.resolved is not None:
+            be.resolve(t.color, t.resolved)
+
+    def run(self, be: A.Backend, frame: int) -> FrameResult:
+        be.query_begin()
+        self.render(be, frame)
+        stats = be.query_get()
+        return read_frame(be, self.t, stats)
+
+
+# ===========================================================================================================
+# C3b: AnisotropicFilter
+# ===========================================================================================================
+class AnisotropicFilter:
+    """samples/AnisotropicFilter/AnisotropicFilter.cpp:44-49,186-339 (BASELINE configs[2]): a tunnel of 96 cylinder segments,
+    each one draw of create_planar((-hw, 0, -10), (hw, 0, 0), (0, 0, 1), 2, 50) = 200 triangles rotated about z by i * 3.75 degrees
+    at radius 5, camera at (0, 0, -10) looking down the axis; vs_plane (uv = pos.xz), the SASL pixel shader
+    `tex2D(samp, tex); color.w = 1` (sample_2d_grad with the SASL per-row / per-column derivatives: SLV_PS_TEX_GRAD_ALPHA with
+    sasl_derivatives), replace blend, cull back; texture = the sample's own font/font_enu.png (400x400 RGB -> rgba8 with
+    alpha 0, NOT a power of two: mip chain 400, 200, 100, 50, 25, 13, 7, 4, 2 with the odd-size steps of SURVEY App. B #9,
+    wrap addressing through the float modulo).  Frame f uses filter row f % 7 of :222-230 (three trilinear qualities,
+    then 2x / 4x / 8x / 16x anisotropic).  The sample renders 1 sample per pixel into rgba8; BASELINE configs[2] asks for
+    4x MSAA + resolve."""
+
+    FILTER_ROWS = [(A.FILTER_LINEAR, A.MIP_LO, 0), (A.FILTER_LINEAR, A.MIP_MI, 0), (A.FILTER_LINEAR, A.MIP_HI, 0),
+                   (A.FILTER_ANISOTROPIC, A.MIP_MI, 2), (A.FILTER_ANISOTROPIC, A.MIP_MI, 4),
+                   (A.FILTER_ANISOTROPIC, A.MIP_MI, 8), (A.FILTER_ANISOTROPIC, A.MIP_MI, 16)]
+    RADIUS, SEGMENTS = 5.0, 96
+
+    def __init__(self, w=1920, h=1080, samples=4, sasl_derivatives=True, segments=None):
+        self.w, self.h, self.samples, self.sasl_derivatives = w, h, samples, sasl_derivatives
+        self.segments = self.SEGMENTS if segments is None else segments
+        self.seg_angle = f32(360.0) / f32(self.SEGMENTS)
+        hw = f32(math.tan(math.radians(float(self.seg_angle) / 2.0))) * f32(self.RADIUS)
+        self.plane = create_planar((-hw, 0.0, -10.0), (hw, 0.0, 0.0), (0.0, 0.0, 1.0), 2, 50, True)
+        self.plane.elements = [(0, _V4, 0, 0, 1.0)]
+        self.n_frames = len(self.FILTER_ROWS)
+        self.ps_binding = None  # optional override (run-time compiled SASL shader): sampler -> ShaderBinding
+        self.texels = asset_texture("font_enu.png")
+        self._draw_cache = {}
+
+    def setup(self, be: A.Backend):
+        self._draw_cache = {}
+        self.t = create_targets(be, self.w, self.h, self.samples, A.PF_RGBA8)
+        self.plane.upload(be)
+        self.tex = make_texture(be, self.texels, defined_mips=True)
+        self.samplers = [be.create_sampler(A.sampler_desc(A.FILTER_LINEAR, A.FILTER_LINEAR, mip, mip_qual=q, addr_u=A.ADDR_WRAP,
+                                                          addr_v=A.ADDR_WRAP, max_anisotropy=an), self.tex)
+                         for mip, q, an in self.FILTER_ROWS]
+
+    def frame_draws(self, be: A.Backend, frame: int):
+        key = (id(be), frame)
+        if key in self._draw_cache:
+            return self._draw_cache[key]
+        samp = self.samplers[frame % len(self.FILTER_ROWS)]
+        view = mat_lookat((0.0, 0.0, -10.0), (0.0, 0.0, 0.0), (0, 1, 0))
+        proj = mat_perspective_fov(math.pi / 2, f32(self.w) / f32(self.h), 0.1, 100.0)
+        vp = mat_mul(view, proj)
+        draws = []
+        for i in range(self.segments):
+            ang = math.radians(float(f32(i) * self.seg_angle))
+            s_, c_ = f32(math.sin(ang)), f32(math.cos(ang))
+            rot = np.eye(4, dtype=f32)  # mat_rotZ (eflib/src/math.cpp:405-416)
+            rot[0, 0], rot[1, 0], rot[0, 1], rot[1, 1] = c_, -s_, s_, c_
+            wvp = mat_mul(mat_mul(mat_translate(0.0, -self.RADIUS, 0.0), rot), vp)
+            d = base_desc(self.t, self.w, self.h, cull=A.CULL_BACK)
+            self.plane.fill_desc(be, d)
+            d.vs = A.shader_binding(A.VS_PLANE_XZ, pack_vs_plane_xz(wvp))
+            d.ps = self.ps_binding(samp) if self.ps_binding else \
+                A.shader_binding(A.PS_TEX_GRAD_ALPHA, pack_ps_tex_alpha(0, 1.0, self.sasl_derivatives), [samp])
+            d.bs = A.shader_binding(A.BS_REPLACE)
+            draws.append(d)
+        self._draw_cache[key] = draws
+        return draws
+
+    def render(self, be: A.Backend, frame: int):
+        t = self.t
+        be.clear_color(t.color, (0.2, 0.2, 0.5, 1.0))
+        be.clear_depth_stencil(t.ds, A.CLEAR_DEPTH | A.CLEAR_STENCIL, 1.0, 0)
+        for d in self.frame_draws(be, frame):
             be.draw(d)
         if t.resolved is not None:
             be.resolve(t.color, t.resolved)
@@ -719,7 +859,14 @@ class TriangleSoup:
 
     def __init__(self, w=256, h=192, samples=1, n=300, seed=7, cull=A.CULL_NONE, ds=None, stencil_ref=0,
                  bs=A.BS_REPLACE_AND_COUNT, index_dtype=np.uint16, modifiers=None, strip=False, size=1.0,
-                 color_fmt=A.PF_RGBA8, ps=A.PS_ATTR0_COLOR):
+                 color_fmt=A.PF_RGBA8, ps=A.PS_ATTR0_COLOR, base_vertex=0, indexed=True, split=1):
+        """`base_vertex`: the index buffer holds (index - base_vertex) and draw_index adds it back (index_fetcher.cpp:26-115;
+        negative values wrap through uint32 exactly as upstream).  `indexed=False`: renderer::draw - the vertex buffers are
+        expanded in index order and drawn without an index buffer.  `split`: the primitives are drawn in that many draws with
+        start != 0.  Upstream quirk, mirrored by every backend and pinned by the non-indexed cases: renderer::draw's `startpos`
+        only offsets the INDEX buffer (index_fetcher.cpp:23,85), so a non-indexed draw ignores it and always begins at vertex 0
+        - a split non-indexed soup draws its first range `split` times."""
+        self.base_vertex, self.indexed, self.split = base_vertex, indexed, split
         self.w, self.h, self.samples, self.n = w, h, samples, n
         self.cull, self.ds, self.stencil_ref, self.bs, self.modifiers = cull, ds, stencil_ref, bs, modifiers
         self.color_fmt, self.ps = color_fmt, ps
@@ -744,6 +891,18 @@ class TriangleSoup:
         else:
             idx = rng.permutation(nv).astype(index_dtype)
             self.mesh = Mesh([pos, col], [(0, _V4, 0, 0, 1.0), (1, _V4, 1, 0, 0.0)], idx, n)
+        if not indexed:  # non-indexed draw(): vertex k of the stream IS vertex k of the primitive stream
+            order = self.mesh.indices.astype(np.int64)
+            self.mesh.streams = [np.ascontiguousarray(st[order]) for st in self.mesh.streams]
+            self.mesh.indices = None
+        elif base_vertex:
+            # shift the vertex data by base_vertex slots (padding in front when positive) and keep the stored indices: the
+            # fetch adds base_vertex back.  A negative base needs indices >= -base_vertex, so they are stored shifted up.
+            if base_vertex > 0:
+                pad = [np.zeros((base_vertex, st.shape[1]), f32) for st in self.mesh.streams]
+                self.mesh.streams = [np.concatenate([p_, st]) for p_, st in zip(pad, self.mesh.streams)]
+            else:
+                self.mesh.indices = (self.mesh.indices.astype(np.int64) - base_vertex).astype(index_dtype)
         self.n_frames = 1
 
     def setup(self, be: A.Backend):
@@ -757,16 +916,22 @@ class TriangleSoup:
         if t.count is not None:
             be.clear_color(t.count, (0, 0, 0, 0))
         be.clear_depth_stencil(t.ds, A.CLEAR_DEPTH | A.CLEAR_STENCIL, 0.6, 3)
-        d = base_desc(t, self.w, self.h, cull=self.cull, ds=self.ds)
-        d.stencil_ref = self.stencil_ref
-        self.mesh.fill_desc(be, d)
-        if self.modifiers:
-            for i, m in enumerate(self.modifiers):
-                d.vs_attr_modifiers[i] = m
-        d.vs = A.shader_binding(A.VS_MVP_PASSTHROUGH, pack_vs_mvp_passthrough(mat_identity(), [1]))
-        d.ps = A.shader_binding(self.ps)
-        d.bs = A.shader_binding(self.bs)
-        be.draw(d)
+        per = (self.mesh.prim_count + self.split - 1) // self.split
+        strip = self.mesh.topology == A.TOPO_TRIANGLE_STRIP
+        for first in range(0, max(self.mesh.prim_count, 1), max(per, 1)):
+            d = base_desc(t, self.w, self.h, cull=self.cull, ds=self.ds)
+            d.stencil_ref = self.stencil_ref
+            # start = first index (draw_index) / first vertex (draw) of the range: 3 per list primitive, 1 per strip primitive
+            # (an odd strip start would flip the winding parity, so strips are only split at even primitives)
+            self.mesh.fill_desc(be, d, start=first if strip else first * 3, prim_count=min(per, self.mesh.prim_count - first),
+                                base_vertex=self.base_vertex)
+            if self.modifiers:
+                for i, m in enumerate(self.modifiers):
+                    d.vs_attr_modifiers[i] = m
+            d.vs = A.shader_binding(A.VS_MVP_PASSTHROUGH, pack_vs_mvp_passthrough(mat_identity(), [1]))
+            d.ps = A.shader_binding(self.ps)
+            d.bs = A.shader_binding(self.bs)
+            be.draw(d)
         if t.resolved is not None:
             be.resolve(t.color, t.resolved)
 
@@ -883,8 +1048,9 @@ class SponzaLike:
     N_MATERIALS = 24
 
     def __init__(self, w=3840, h=2160, samples=4, tex_size=1024, max_aniso=0, color_fmt=A.PF_BGRA8, ps_program=A.PS_SPONZA,
-                 textured=True):
+                 textured=True, sasl_derivatives=True):
         self.w, self.h, self.samples, self.tex_size, self.max_aniso = w, h, samples, tex_size, max_aniso
+        self.sasl_derivatives = sasl_derivatives  # PS_SPONZA_GRAD: the derivative convention of the tex2D fetch
         self.color_fmt, self.ps_program, self.textured = color_fmt, ps_program, textured
         self.n_frames = 8
         self._draw_cache = {}
@@ -994,6 +1160,8 @@ class SponzaLike:
             d.vs = vs
             if self.ps_program == A.PS_SPONZA:
                 d.ps = A.shader_binding(A.PS_SPONZA, pack_ps_sponza(self.textured), [self.samplers[m]])
+            elif self.ps_program == A.PS_SPONZA_GRAD:
+                d.ps = A.shader_binding(A.PS_SPONZA_GRAD, pack_ps_sponza_grad(self.textured, self.sasl_derivatives), [self.samplers[m]])
             else:
                 d.ps = A.shader_binding(self.ps_program)
             d.bs = bs

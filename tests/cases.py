@@ -28,6 +28,13 @@ CASES = {
     "c3b_aniso16_640x360x4": (lambda: S.TextureAndBlending(640, 360, samples=4, ps_program=A.PS_TEX_GRAD_ALPHA,
                                                            mip_filter=A.FILTER_ANISOTROPIC, max_aniso=16), (0, 2)),
     "c3b_pointmip_320x180": (lambda: S.TextureAndBlending(320, 180, mip_filter=A.FILTER_POINT), (1,)),
+    # configs[2] (AnisotropicFilter), the sample's own scene: 96 segments x 200 triangles, the real 400x400 font_enu.png (not a
+    # power of two), the SASL tex2D path with per-row / per-column derivatives; frame = filter row (3 trilinear qualities, AF 2-16x)
+    "c3b_anisotropic_filter_640x360x4": (lambda: S.AnisotropicFilter(640, 360, 4), (0, 1, 2, 3, 4, 5, 6)),
+    "c3b_anisotropic_filter_480x272x1": (lambda: S.AnisotropicFilter(480, 272, 1), (2, 6)),
+    "c3b_anisotropic_filter_1920x1080x4": (lambda: S.AnisotropicFilter(1920, 1080, 4), (6,)),
+    # the SASL Sponza pixel shader's twin (tex2D = sample_2d_grad, SASL derivative convention), 16x anisotropic
+    "c4_sponza_like_sasl_aniso16_480x272x4": (lambda: S.SponzaLike(480, 272, 4, tex_size=128, max_aniso=16, ps_program=A.PS_SPONZA_GRAD), (1, 6)),
     # configs[3]: Sponza-like atrium, reduced size (full 4K 4x is covered by property tests on the GPU)
     "c4_sponza_like_480x272x4": (lambda: S.SponzaLike(480, 272, 4, tex_size=128), (0, 5)),
     "c4_sponza_like_960x540x1": (lambda: S.SponzaLike(960, 540, 1, tex_size=256), (3,)),
@@ -46,6 +53,11 @@ CASES = {
     "soup_blend_s4": (lambda: S.TriangleSoup(samples=4, bs=A.BS_LERP_SRC_ALPHA), (0,)),
     "soup_blend_bgra8": (lambda: S.TriangleSoup(samples=1, bs=A.BS_LERP_SRC_ALPHA, color_fmt=A.PF_BGRA8), (0,)),
     "soup_blend_rgba32f": (lambda: S.TriangleSoup(samples=1, bs=A.BS_LERP_SRC_ALPHA, color_fmt=A.PF_RGBA32F), (0,)),
+    # index_fetcher.cpp:26-115: base_vertex != 0 (positive and negative), start != 0, and renderer::draw (no index buffer)
+    "soup_base_vertex_pos_s2": (lambda: S.TriangleSoup(samples=2, base_vertex=37, split=3, seed=21), (0,)),
+    "soup_base_vertex_neg_u32": (lambda: S.TriangleSoup(samples=1, base_vertex=-19, index_dtype=np.uint32, seed=22), (0,)),
+    "soup_nonindexed_s4": (lambda: S.TriangleSoup(samples=4, indexed=False, split=4, seed=23), (0,)),
+    "soup_nonindexed_strip_s1": (lambda: S.TriangleSoup(samples=1, indexed=False, strip=True, n=400, split=2, seed=24), (0,)),
     # early-Z writes depth before a PS discard
     "soup_discard_all_s4": (lambda: S.TriangleSoup(samples=4, ps=A.PS_DISCARD_ALL), (0,)),
 }

@@ -146,6 +146,40 @@ def test_full_size_sponza_4k_msaa4_properties(cuda, oracle):
     assert not cases.compare_frames(r, r2)
 
 
+@pytest.mark.timeout(1200)
+@pytest.mark.parametrize("variant", ["trilinear_builtin", "sasl_twin_aniso16"])
+def test_full_size_sponza_4k_msaa4_equals_reference(cuda, reference, variant):
+    """THE BENCHMARKED CONFIGURATION (BASELINE.json configs[3] as bench.py times it: 3840x2160, 4x MSAA + resolve, 24 x 1024^2
+    textures) against the UNMODIFIED reference renderer (oracle/_ref, which travels to the GPU box as a prebuilt library), buffer
+    by buffer: colour, depth bits, stencil, resolved colour, the six gated counters.  Size-dependent code (16-bit packed tile
+    ranges, pixel origins, float edge functions beyond x = 2048, list lengths) is exercised here and nowhere else.
+    `trilinear_builtin`: SLV_VS_SPONZA + SLV_PS_SPONZA, trilinear (samples/Sponza's cpp shaders).
+    `sasl_twin_aniso16`: 16x anisotropic samplers through the SASL tex2D path (sample_2d_grad, per-row / per-column derivatives),
+    the twin of the SASL shaders bench.py compiles (SLV_PS_SPONZA_GRAD) - the north_star target configuration."""
+    kw = dict(tex_size=1024) if variant == "trilinear_builtin" else dict(tex_size=1024, max_aniso=16, ps_program=A.PS_SPONZA_GRAD)
+    a, b = S.SponzaLike(3840, 2160, 4, **kw), S.SponzaLike(3840, 2160, 4, **kw)
+    a.setup(cuda)
+    b.setup(reference)
+    for f in ((0, 5) if variant == "trilinear_builtin" else (3,)):
+        ra, rb = a.run(cuda, f), b.run(reference, f)
+        msgs = cases.compare_frames(ra, rb, color_tol=COLOR_TOL_LSB)
+        assert not msgs, f"{variant} frame {f}: {msgs}"
+        assert ra.stats["ia_primitives"] == 262249 and ra.stats["ps_invocations"] > 10_000_000
+
+
+@pytest.mark.timeout(900)
+def test_full_size_anisotropic_filter_1080p_msaa4_equals_reference(cuda, reference):
+    """BASELINE.json configs[2], the AnisotropicFilter sample's own scene at 1920x1080, 4x MSAA + resolve, with the sample's own
+    400x400 font_enu.png: every filter row (three trilinear qualities, 2x / 4x / 8x / 16x anisotropic) against the unmodified
+    reference."""
+    a, b = S.AnisotropicFilter(1920, 1080, 4), S.AnisotropicFilter(1920, 1080, 4)
+    a.setup(cuda)
+    b.setup(reference)
+    for f in range(7):
+        msgs = cases.compare_frames(a.run(cuda, f), b.run(reference, f), color_tol=COLOR_TOL_LSB)
+        assert not msgs, f"filter row {f}: {msgs}"
+
+
 def test_full_size_texture_and_blending_1080p(cuda, oracle):
     """BASELINE.json configs[1] at full size against the oracle, buffer by buffer."""
     a, b = S.TextureAndBlending(1920, 1080), S.TextureAndBlending(1920, 1080)
