@@ -183,7 +183,13 @@ struct slv_device_t {
   std::vector<Span> spans;
   uint32_t tiles_cap = 0;
   uint32_t list_cap = 0;
-  uint32_t* overflow_flag = nullptr;
+  uint32_t* overflow_flag = nullptr;  // device: [0] flag (1 = an arena overflowed, 2 = a peer timed out), [1] list entries needed, [2] region words needed
+  // Arena sizing.  The tile-list and region-list arenas are sized from the triangle count (a heuristic: a triangle can reach every
+  // tile), with generous minima; kernels that run out of room drop the entry, raise the flag and record what they WOULD have
+  // needed.  The next flush point reports SLV_OUT_OF_MEMORY for that frame - once, not sticky - and the arenas are grown to the
+  // recorded need before the next batch, so re-issuing the frame succeeds.  SLV_ARENA_MIN (entries) shrinks the minima (tests).
+  uint64_t list_need_hint = 0, region_need_hint = 0;
+  uint64_t arena_min_list = 1ull << 22, arena_min_region = 1ull << 26;
   unsigned long long* d_stats = nullptr;
   slv_pipeline_statistics host_stats{};  // counters that are pure functions of the draw arguments
   uint32_t shard_rank = 0, shard_n = 1;
@@ -421,14 +427,15 @@ slv_result flush_batch(slv_device dev) {
   const uint32_t n_tiles = first.tiles_x * first.tiles_y;
   const uint32_t n_slots = (uint32_t)dev->slots_queued;
   // list arena: heuristic bound, checked on the device (overflow flag -> SLV_OUT_OF_MEMORY at the next flush point)
-  const uint64_t list_need = std::min<uint64_t>(std::max<uint64_t>(4ull * n_slots, 1u << 22), 1ull << 31);
-  if (list_need > dev->list_cap) {
+  const uint64_t list_need = std::min<uint64_t>(std::max<uint64_t>(std::max<uint64_t>(4ull * n_slots, dev->arena_min_list), dev->list_need_hint), 1ull << 31);
+  const uint64_t region_need = std::min<uint64_t>(std::max<uint64_t>(std::max<uint64_t>(2ull * list_need, dev->arena_min_region), dev->region_need_hint), 0xFFFFFFF0ull);
+  if (list_need > dev->list_cap || region_need > dev->region_cap) {
     slv_result rcs = sync_all(dev);
     if (rcs != SLV_OK) return rcs;
     // (region, warp block) sub-lists of the deferred path, allocated on the device inside the region arena: 8 sub-lists of
     // capacity n per region with n surviving entries; a tile-list entry survives in 1..16 regions (about 1.5 on the
-    // Sponza-like scene, i.e. ~12 words per tile-list entry; overflow raises the sticky out-of-memory error)
-    const uint64_t rcap = std::min<uint64_t>(std::max<uint64_t>(2ull * list_need, 1ull << 24), 0xFFFFFFF0ull);
+    // Sponza-like scene, i.e. ~12 words per tile-list entry; a fully covered tile costs 128: see list_need_hint above)
+    const uint64_t rcap = region_need;
     for (auto& T : dev->sc) {
       if (T.list) CU(cudaFree(T.list));
       CU(cudaMalloc(&T.list, (size_t)list_need * sizeof(uint32_t)));
@@ -525,7 +532,7 @@ slv_result flush_batch(slv_device dev) {
   }
   if (dev->profile) dev->spans.push_back({eg0, mark(dev), 0});
   size_t e0 = dev->profile ? mark(dev) : 0;
-  k_scan_tiles<<<1, 1024, 0, fs>>>(S.tile_count, S.tile_offset, S.tile_cursor, n_tiles, S.active_tiles, S.work_counter, S.large_tiles);
+  k_scan_tiles<<<1, 1024, 0, fs>>>(S.tile_count, S.tile_offset, S.tile_cursor, n_tiles, S.active_tiles, S.work_counter, S.large_tiles, dev->overflow_flag);
   k_bin_fill<<<(n_slots + 255) / 256, 256, 0, fs>>>(bp);
   size_t e1 = dev->profile ? mark(dev) : 0;
   // k_sort_lists and k_region_bin index the COMPACTED list of non-empty tiles, which holds at most the tiles this rank owns: a
@@ -725,14 +732,22 @@ slv_result check_overflow(slv_device dev) {
   uint32_t flag = 0;
   CU(cudaMemcpyAsync(&flag, dev->overflow_flag, sizeof(flag), cudaMemcpyDeviceToHost, dev->stream));
   CU(cudaStreamSynchronize(dev->stream));
+  if (flag == 1 && dev->pipeline) CU(cudaStreamSynchronize(dev->front_stream));  // the recorded needs are final
   if (flag == 2) {
     fprintf(stderr, "[salvia_b200] slv_flags_wait timed out: a peer rank never raised its flag\n");
     dev->failed = true;
     return SLV_FAILED;
   }
   if (flag) {
-    fprintf(stderr, "[salvia_b200] per-tile triangle lists overflowed the %u-entry arena\n", dev->list_cap);
-    dev->failed = true;
+    // not sticky: the frame that overflowed is incomplete (reported once), the arenas grow before the next batch
+    uint32_t need[3] = {0, 0, 0};
+    CU(cudaMemcpyAsync(need, dev->overflow_flag, sizeof(need), cudaMemcpyDeviceToHost, dev->stream));
+    CU(cudaMemsetAsync(dev->overflow_flag, 0, 3 * sizeof(uint32_t), dev->stream));
+    CU(cudaStreamSynchronize(dev->stream));
+    dev->list_need_hint = std::max<uint64_t>(dev->list_need_hint, (uint64_t)need[1] + need[1] / 2);
+    dev->region_need_hint = std::max<uint64_t>(dev->region_need_hint, (uint64_t)need[2] + need[2] / 2);
+    fprintf(stderr, "[salvia_b200] a batch overflowed its work-list arenas (%u tile-list entries of %u, %u region-list words of %u): that "
+            "frame is incomplete (SLV_OUT_OF_MEMORY); the arenas grow before the next batch\n", need[1], dev->list_cap, need[2], dev->region_cap);
     return SLV_OUT_OF_MEMORY;
   }
   return dev->failed ? SLV_FAILED : SLV_OK;
@@ -771,7 +786,7 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   CU(cudaStreamCreateWithFlags(&dev->copy_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&dev->ev_copy, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&dev->ev_upload, cudaEventDisableTiming));
-  CU(cudaMalloc(&dev->overflow_flag, sizeof(uint32_t)));
+  CU(cudaMalloc(&dev->overflow_flag, 4 * sizeof(uint32_t)));
   CU(cudaMalloc(&dev->peer_flags, SLV_PEER_FLAGS * sizeof(uint32_t)));
   CU(cudaMemset(dev->peer_flags, 0, SLV_PEER_FLAGS * sizeof(uint32_t)));
   for (auto& S : dev->sc) {
@@ -806,7 +821,8 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
     dev->shade_grid = prop.multiProcessorCount * SLV_SHADE_CTAS_PER_SM;
     if (const char* bc = getenv("SLV_BACK_CTAS")) dev->back_ctas = atoi(bc);
   }
-  CU(cudaMemsetAsync(dev->overflow_flag, 0, sizeof(uint32_t), dev->stream));
+  CU(cudaMemsetAsync(dev->overflow_flag, 0, 4 * sizeof(uint32_t), dev->stream));
+  if (const char* am = getenv("SLV_ARENA_MIN")) { dev->arena_min_list = std::max<uint64_t>(1024, (uint64_t)atoll(am)); dev->arena_min_region = dev->arena_min_list * 4; }
   CU(cudaMalloc(&dev->d_stats, 20 * sizeof(unsigned long long)));
   CU(cudaMemsetAsync(dev->d_stats, 0, 20 * sizeof(unsigned long long), dev->stream));
   const char* prof = getenv("SLV_PROFILE");
@@ -1120,6 +1136,9 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   const slv_viewport& vp = d->viewport;
   if (vp.x < 0 || vp.y < 0 || vp.w >= SLV_MAX_RENDER_TARGET_SIZE || vp.h >= SLV_MAX_RENDER_TARGET_SIZE) return SLV_FAILED;
   if (d->n_color_targets >= SLV_MAX_RENDER_TARGETS) return SLV_FAILED;
+  // the device programs write colour target 0 (and the coverage probe target 1): further targets would be accepted and never written
+  for (uint32_t i = 2; i < d->n_color_targets; ++i)
+    if (d->color_targets[i]) return SLV_INVALID_PARAMETER;
   if (d->n_streams > 8 || d->n_elements > SLV_MAX_VS_INPUT_ATTRS) return SLV_INVALID_PARAMETER;
   // SASL shaders compiled at run time: SLV_PROGRAM_JIT(module) names a loaded shader module
   slv_handle vs_module = 0, ps_module = 0;
@@ -1220,11 +1239,15 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
 
   // counters that are pure functions of the arguments (default_vertex_cache.cpp:354-364,
   // geom_setup_engine.cpp:103, rasterizer.cpp:1137)
-  dev->host_stats.ia_vertices += 3ull * d->prim_count;
-  dev->host_stats.ia_primitives += d->prim_count;
-  dev->host_stats.vs_invocations += 3ull * d->prim_count;  // no post-transform cache: VS recomputed per corner
-  dev->host_stats.cinvocations += d->prim_count;
-  if (d->prim_count == 0 || n_tiles == 0) return SLV_OK;
+  // ... applied once the draw has passed every validation below (a rejected draw must not move the statistics)
+  auto count_draw = [&]() {
+    dev->host_stats.ia_vertices += 3ull * d->prim_count;
+    dev->host_stats.ia_primitives += d->prim_count;
+    dev->host_stats.vs_invocations += 3ull * d->prim_count;  // no post-transform cache: VS recomputed per corner
+    dev->host_stats.cinvocations += d->prim_count;
+  };
+  if (d->bs.program < SLV_BS_REPLACE || d->bs.program > SLV_BS_REPLACE_AND_COUNT) return SLV_INVALID_PARAMETER;
+  if (d->prim_count == 0 || n_tiles == 0) { count_draw(); return SLV_OK; }
 
   const uint32_t R = 1 + n_attrs;
   const uint32_t tri_stride = TRI_HEADER + 3 * MAX_REGS;  // uniform across the batch: slot -> record address
@@ -1353,6 +1376,7 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   }
 
   // ---- queue the draw: geometry, binning and the raster pass all run at the next flush point
+  count_draw();
   dev->pending.push_back(rp);
   dev->pending_geom.push_back(gp);
   dev->pending_vs_module.push_back(vs_module);
@@ -1431,7 +1455,17 @@ slv_result slv_resolve(slv_device dev, slv_handle src, slv_handle dst) {
   if (rd->resolve_peer && dev->shard_n > 1) t2.data = rd->resolve_peer;  // owned tiles go straight to the root's surface
   { slv_result rcw = wait_readback(dev, rd); if (rcw != SLV_OK) return rcw; }
   // the pending batch renders to `src`: its k_shade can write the resolved texels itself (fused resolve)
-  if (dev->fuse_resolve && !dev->pending.empty() && dev->pending[0].color0.data == s.data && rd != rs) {
+  // ... unless a queued draw READS the destination (samples it - temporal feedback - or has it bound as a second target or as
+  // depth/stencil): the reference finishes every draw before it resolves, k_shade would overwrite texels other warps still read
+  bool dst_in_use = false;
+  for (size_t i = 0; i < dev->pending.size(); ++i) {
+    const RasterParams& q = dev->pending[i];
+    const GeomParams& g = dev->pending_geom[i];
+    const uint8_t* used[] = {q.sampler0.tex.n_levels ? q.sampler0.tex.level[0].data : nullptr, q.sampler1.tex.n_levels ? q.sampler1.tex.level[0].data : nullptr,
+                             g.sampler0.tex.n_levels ? g.sampler0.tex.level[0].data : nullptr, q.color1.data, q.ds.data};
+    for (const uint8_t* u : used) dst_in_use = dst_in_use || (u && (u == t.data || u == t2.data));
+  }
+  if (dev->fuse_resolve && !dev->pending.empty() && dev->pending[0].color0.data == s.data && rd != rs && !dst_in_use) {
     { slv_result rcm__ = materialize_clear(dev, rd); if (rcm__ != SLV_OK) return rcm__; }
     dev->resolve_requested = true;
     dev->resolve_dst = t2;
@@ -1714,7 +1748,8 @@ slv_result slv_flags_wait(slv_device dev, const void* flags, uint32_t first, uin
   if (!dev || first + count > SLV_PEER_FLAGS) return SLV_INVALID_PARAMETER;
   if (count == 0) return SLV_OK;
   CU(cudaSetDevice(dev->ordinal));
-  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  // the queued batch is NOT flushed: its front half touches no render target and its back half is enqueued on the main stream
+  // behind this wait anyway - so a following slv_resolve can still be fused into the batch's k_shade
   k_flags_wait<<<1, 32, 0, dev->stream>>>(flags ? (const uint32_t*)flags : dev->peer_flags, first, count, value, dev->overflow_flag);
   ++dev->n_launches;
   CU(cudaGetLastError());

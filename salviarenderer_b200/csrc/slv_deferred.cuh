@@ -70,7 +70,7 @@ struct DeferredBufs {
   uint32_t* region_offset;    // [active tile index * 16 + region]
   uint32_t* region_count;
   uint32_t* cursor;           // region_list allocation cursor (reset by k_scan_tiles)
-  uint32_t* overflow_flag;
+  uint32_t* overflow_flag;    // [0] flag, [1] tile-list entries needed, [2] region-arena words needed (maxima since the last check)
   uint8_t* item_flag;         // [item] 1 when k_cover recorded an owner in the warp block
   uint32_t* vis;              // owner slot per sample, layout ((y * vis_pitch + x) * S + s); nullptr = depth-only batch
   uint32_t vis_pitch;
@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(RBIN_THREADS, 2) k_region_bin(RasterParams c, 
     uint32_t base = total ? atomicAdd(d.cursor, total * 8u) : 0u;
     const bool fits = (uint64_t)base + (uint64_t)total * 8u <= (uint64_t)d.region_cap;
     if (!fits) *d.overflow_flag = 1;
+    if (total) atomicMax(d.overflow_flag + 2, (uint32_t)min((uint64_t)base + (uint64_t)total * 8u, (uint64_t)0xFFFFFFF0u));  // words needed
     for (int k = 0; k < 16; ++k) {
       s_base[k] = base;
       d.region_offset[b * 16 + k] = base;

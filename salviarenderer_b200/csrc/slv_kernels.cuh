@@ -561,7 +561,7 @@ constexpr int SORT_LARGE_SMEM = 49152;  // list length k_sort_lists_large sorts 
 // non-empty tiles into active_tiles[1..] (count in [0]) and resets the raster work-queue head.
 __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint32_t* tile_offset, uint32_t* tile_cursor,
                                                      uint32_t n_tiles, uint32_t* active_tiles, uint32_t* work_counter,
-                                                     uint32_t* large_tiles) {
+                                                     uint32_t* large_tiles, uint32_t* arena_need) {
   __shared__ uint32_t s_active, s_large;
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
@@ -622,7 +622,10 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint3
     if (tid == 1023) s_carry = excl + v;
     __syncthreads();
   }
-  if (tid == 0) { tile_offset[n_tiles] = s_carry; active_tiles[0] = s_active; large_tiles[0] = s_large; }
+  if (tid == 0) {
+    tile_offset[n_tiles] = s_carry; active_tiles[0] = s_active; large_tiles[0] = s_large;
+    atomicMax(arena_need + 1, s_carry);  // tile-list entries this batch needs (the host sizes the arena from it after an overflow)
+  }
 }
 
 __global__ void __launch_bounds__(256) k_bin_fill(BinParams p) {

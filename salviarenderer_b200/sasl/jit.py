@@ -39,9 +39,27 @@ def _nvcc():
 
 
 def cache_dir():
-    d = os.environ.get("SLV_JIT_CACHE") or os.path.join(tempfile.gettempdir(), "salvia_b200_jit")
-    os.makedirs(d, exist_ok=True)
+    """Per-user cache of compiled cubins ($SLV_JIT_CACHE, else $XDG_CACHE_HOME/salvia_b200_jit, else ~/.cache/salvia_b200_jit),
+    mode 0700.  A cubin is code that runs in this process's GPU context, so a directory somebody else owns or can write to is
+    never trusted: compilation then goes to a fresh private directory and nothing is cached."""
+    d = os.environ.get("SLV_JIT_CACHE") or os.path.join(
+        os.environ.get("XDG_CACHE_HOME") or os.path.join(os.path.expanduser("~"), ".cache"), "salvia_b200_jit")
+    try:
+        os.makedirs(d, mode=0o700, exist_ok=True)
+        st = os.stat(d)
+        if st.st_uid != os.getuid() or (st.st_mode & 0o022):
+            raise PermissionError(d)
+    except OSError:
+        d = tempfile.mkdtemp(prefix="salvia_b200_jit_")  # 0700, ours
     return d
+
+
+def _trusted(path: str) -> bool:
+    try:
+        st = os.stat(path)
+    except OSError:
+        return False
+    return st.st_uid == os.getuid() and not (st.st_mode & 0o022)
 
 
 def compile(source: str, stage: str, entry: str | None = None, derivatives: str = "sasl", keep_dir: str | None = None) -> CompiledShader:  # noqa: A001
@@ -55,19 +73,25 @@ def compile(source: str, stage: str, entry: str | None = None, derivatives: str 
                      (CSRC, "slv_common.cuh"),
                      (HERE, "sasl_rt.h"), (INCLUDE, "salvia_b200.h")))
     key = hashlib.sha256(unit.code.encode() + b"\0" + " ".join(defs + NVCC_FLAGS).encode() + b"\0" + deps).hexdigest()[:24]
-    path = os.path.join(cache_dir(), key + ".cubin")
-    if not os.path.exists(path):
+    cdir = cache_dir()
+    path = os.path.join(cdir, key + ".cubin")
+    if not _trusted(path):
         work = keep_dir or tempfile.mkdtemp(prefix="slvjit_")
         try:
-            gen = os.path.join(work, "generated.cuh")
+            gen = os.path.join(work, f"generated_{key}.cuh")
             with open(gen, "w") as f:
                 f.write(unit.code)
-            tmp = os.path.join(work, "out.cubin")
+            # unique name inside the cache directory, then an atomic rename: concurrent compiles of one shader (the ranks of a
+            # multi-GPU run) never see a partial file
+            fd, tmp = tempfile.mkstemp(prefix=key + ".", suffix=".tmp", dir=cdir)
+            os.close(fd)
             cmd = [_nvcc(), *NVCC_FLAGS, *defs, f'-DSLV_JIT_GENERATED="{gen}"', "-I" + INCLUDE, "-I" + CSRC, "-I" + HERE,
                    "-o", tmp, os.path.join(CSRC, "slv_jit_unit.cu")]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
+                os.unlink(tmp)
                 raise frontend.CompileError("device compilation of the generated code failed:\n" + r.stderr[-4000:])
+            os.chmod(tmp, 0o600)
             os.replace(tmp, path)
         finally:
             if keep_dir is None:

@@ -942,6 +942,53 @@ class TriangleSoup:
         return read_frame(be, self.t, stats)
 
 
+class OverlayQuads:
+    """Robustness scene (no reference twin): `n` full-target quads (2 triangles each), front to back and back to front
+    interleaved, each with its own colour: every triangle trivially accepts nearly every 64x64 tile it touches, the worst case
+    for the per-tile / per-region work lists (a fully covered tile costs a list entry in each of its 16 regions)."""
+
+    def __init__(self, w=3840, h=2160, samples=1, n=100, seed=3, draws=4):
+        self.w, self.h, self.samples, self.n, self.draws = w, h, samples, n, draws
+        rng = np.random.default_rng(seed)
+        pos, col, idx = [], [], []
+        for k in range(n):
+            z = f32(0.05 + 0.9 * (((k * 37) % n) / n))      # a permutation of depths: some quads win, most lose early-Z
+            x0, x1 = (-1.0, 1.0) if k % 3 else (-1.0 + 0.3 * rng.random(), 1.0 - 0.3 * rng.random())
+            c = rng.uniform(0, 1, size=4).astype(f32)
+            b = len(pos)
+            pos += [(x0, -1.0, z, 1.0), (x1, -1.0, z, 1.0), (x1, 1.0, z, 1.0), (x0, 1.0, z, 1.0)]
+            col += [c, c * f32(0.5), c, c * f32(0.25)]
+            idx += [b, b + 1, b + 2, b + 2, b + 3, b]
+        self.mesh = Mesh([np.array(pos, f32), np.array(col, f32)], [(0, _V4, 0, 0, 1.0), (1, _V4, 1, 0, 0.0)],
+                         np.array(idx, np.uint32), 2 * n)
+        self.n_frames = 1
+
+    def setup(self, be: A.Backend):
+        self.t = create_targets(be, self.w, self.h, self.samples, A.PF_RGBA8)
+        self.mesh.upload(be)
+
+    def render(self, be: A.Backend, frame: int = 0):
+        t = self.t
+        be.clear_color(t.color, (0.1, 0.2, 0.3, 1.0))
+        be.clear_depth_stencil(t.ds, A.CLEAR_DEPTH | A.CLEAR_STENCIL, 1.0, 0)
+        per = (self.mesh.prim_count + self.draws - 1) // self.draws
+        for first in range(0, self.mesh.prim_count, per):
+            d = base_desc(t, self.w, self.h, cull=A.CULL_NONE)
+            self.mesh.fill_desc(be, d, start=first * 3, prim_count=min(per, self.mesh.prim_count - first))
+            d.vs = A.shader_binding(A.VS_MVP_PASSTHROUGH, pack_vs_mvp_passthrough(mat_identity(), [1]))
+            d.ps = A.shader_binding(A.PS_ATTR0_COLOR)
+            d.bs = A.shader_binding(A.BS_REPLACE)
+            be.draw(d)
+        if t.resolved is not None:
+            be.resolve(t.color, t.resolved)
+
+    def run(self, be: A.Backend, frame: int = 0) -> FrameResult:
+        be.query_begin()
+        self.render(be, frame)
+        stats = be.query_get()
+        return read_frame(be, self.t, stats)
+
+
 # ===========================================================================================================
 # C4: Sponza-like atrium (procedural stand-in for resources/sponza_lq/sponza.obj, a Git-LFS pointer upstream)
 # ===========================================================================================================

@@ -247,6 +247,23 @@ def test_sasl_pixel_shader_visibility_first_equals_builtin_twin(cuda):
         assert ra.stats["ps_invocations"] > 1000
 
 
+@pytest.mark.parametrize("w,h,samples,aniso,frames", [(800, 448, 4, 16, (1, 6)), (960, 540, 1, 0, (3,))])
+def test_sasl_sponza_pair_equals_builtin_twins(cuda, w, h, samples, aniso, frames):
+    """bench.py's headline shaders - the SASL Sponza vertex + pixel shader (tex2D with the SASL per-row / per-column
+    derivatives) - against their built-in twins SLV_VS_SPONZA + SLV_PS_SPONZA_GRAD, which tests/test_gpu_parity.py pins to the
+    unmodified reference at full size: quad-granular k_shade of the JIT module against the pixel-granular built-in one."""
+    import bench
+    got = S.SponzaLike(w, h, samples, tex_size=128, max_aniso=aniso)
+    bench.install_sasl_shaders(got, cuda, A)
+    got.setup(cuda)
+    ref = S.SponzaLike(w, h, samples, tex_size=128, max_aniso=aniso, ps_program=A.PS_SPONZA_GRAD, sasl_derivatives=True)
+    ref.setup(cuda)
+    for f in frames:
+        ra, rb = ref.run(cuda, f), got.run(cuda, f)
+        assert cases.compare_frames(ra, rb) == [], f"frame {f}"
+        assert ra.stats["ps_invocations"] > 1000
+
+
 # ---- two samplers in one SASL pixel shader: the StandardShadowMap colour pass ---------------------------------------------
 PS_SSM_DRAW = """
 sampler texSamp;

@@ -21,9 +21,18 @@ ap.add_argument("--height", type=int, default=2160)
 ap.add_argument("--samples", type=int, default=4)
 ap.add_argument("--tex-size", type=int, default=1024)
 ap.add_argument("--aniso", type=int, default=0)
+ap.add_argument("--shaders", default="builtin", choices=["builtin", "sasl", "twins"],
+                help="builtin: SLV_VS_SPONZA + SLV_PS_SPONZA; sasl: bench.py's SASL pair compiled at run time; twins: SLV_PS_SPONZA_GRAD")
 a = ap.parse_args()
 be = pkg.load(0)
-sc = S.SponzaLike(a.width, a.height, a.samples, tex_size=a.tex_size, max_aniso=a.aniso)
+from salviarenderer_b200 import abi as A  # noqa: E402
+if a.shaders == "twins":
+    sc = S.SponzaLike(a.width, a.height, a.samples, tex_size=a.tex_size, max_aniso=a.aniso, ps_program=A.PS_SPONZA_GRAD)
+else:
+    sc = S.SponzaLike(a.width, a.height, a.samples, tex_size=a.tex_size, max_aniso=a.aniso)
+if a.shaders == "sasl":
+    import bench  # noqa: E402
+    bench.install_sasl_shaders(sc, be, A)
 sc.setup(be)
 for f in range(4):
     sc.render(be, f)
