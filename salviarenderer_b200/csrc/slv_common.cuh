@@ -192,6 +192,40 @@ __device__ __forceinline__ float f4_get(const float4& v, int i) {
   return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
 }
 
+// ---- packed IEEE fp32 pairs (Blackwell FADD2 / FMUL2: two results per lane per issue slot) ------------------------------------
+// Each half is the correctly rounded fp32 result, so a packed op equals the two scalar ops bit for bit.  Explicit .rn in the
+// PTX; all the same ptxas (12.9) contracts a mul.rn.f32x2 feeding an add.rn.f32x2 into one FFMA2 - even with --fmad=false -
+// which would round once instead of twice.  So a SUM THAT CONSUMES A PACKED PRODUCT IS ALWAYS WRITTEN WITH SCALAR ADDS
+// (add2_after_mul); packed adds are only used on operands that are not products.  The SASS of the library is checked for
+// FFMA2 by tests/test_abi.py.
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc; }"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 add2_after_mul(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 lo2(float4 v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(float4 v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float4 cat4(float2 a, float2 b) { return make_float4(a.x, a.y, b.x, b.y); }
+__device__ __forceinline__ float2 sub2_after_mul(float2 a, float2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+// a + (b - a) * t on a pair whose inputs may themselves be packed products (the two taps of a trilinear fetch end in
+// * (1 / 255)): difference and sum in scalar ops, only the product packed
+__device__ __forceinline__ float2 lerp2_of_products(float2 a, float2 b, float2 t) { return add2_after_mul(a, mul2(sub2_after_mul(b, a), t)); }
+
 // float -> unorm8: mul 255, max 0, min 255, cvtps2dq (round-to-nearest-even)  (colors.h:182-192)
 __device__ __forceinline__ uint32_t unorm8_rne(float x) {
   float m = x * 255.0f;

@@ -876,23 +876,22 @@ struct SamplePattern<4> {  // rasterizer.cpp:1095-1100
 __device__ __forceinline__ float4 interp_attr(const float4* rec, int R, int reg, uint32_t mod, float dx, float dy, bool odd_x,
                                               bool odd_y, bool centroid_path, float pdx, float pdy, float inv_w) {
   float4 a0 = __ldg(rec + REC_V0 + 3 * reg);
-  float4 r;
-  if (mod & SLV_AM_NOINTERPOLATION) {
-    r = a0;
-  } else {
-    float4 gx = __ldg(rec + REC_DDX + 3 * reg), gy = __ldg(rec + REC_DDY + 3 * reg);
-    if (centroid_path) {
-      r = make_float4(a0.x + (gx.x * pdx + gy.x * pdy), a0.y + (gx.y * pdx + gy.y * pdy),
-                      a0.z + (gx.z * pdx + gy.z * pdy), a0.w + (gx.w * pdx + gy.w * pdy));
-    } else {
-      r = make_float4(a0.x + (gx.x * dx + gy.x * dy), a0.y + (gx.y * dx + gy.y * dy), a0.z + (gx.z * dx + gy.z * dy),
-                      a0.w + (gx.w * dx + gy.w * dy));
-      if (odd_x) { r.x += gx.x; r.y += gx.y; r.z += gx.z; r.w += gx.w; }
-      if (odd_y) { r.x += gy.x; r.y += gy.y; r.z += gy.z; r.w += gy.w; }
+  float2 rl = lo2(a0), rh = hi2(a0);  // two channels per instruction (FMUL2 / FADD2); every half is the scalar result
+  if (!(mod & SLV_AM_NOINTERPOLATION)) {
+    const float4 gx = __ldg(rec + REC_DDX + 3 * reg), gy = __ldg(rec + REC_DDY + 3 * reg);
+    const float sx = centroid_path ? pdx : dx, sy = centroid_path ? pdy : dy;
+    // a0 + (gx * s + gy * t): the sum of the two products in scalar adds (see add2_after_mul), the rest packed
+    const float2 pl = mul2(lo2(gx), splat2(sx)), ph = mul2(hi2(gx), splat2(sx));
+    const float2 ql = mul2(lo2(gy), splat2(sy)), qh = mul2(hi2(gy), splat2(sy));
+    rl = add2(rl, add2_after_mul(pl, ql));
+    rh = add2(rh, add2_after_mul(ph, qh));
+    if (!centroid_path) {
+      if (odd_x) { rl = add2(rl, lo2(gx)); rh = add2(rh, hi2(gx)); }
+      if (odd_y) { rl = add2(rl, lo2(gy)); rh = add2(rh, hi2(gy)); }
     }
   }
-  if (!(mod & SLV_AM_NOPERSPECTIVE)) { r.x *= inv_w; r.y *= inv_w; r.z *= inv_w; r.w *= inv_w; }
-  return r;
+  if (!(mod & SLV_AM_NOPERSPECTIVE)) { rl = mul2(rl, splat2(inv_w)); rh = mul2(rh, splat2(inv_w)); }
+  return cat4(rl, rh);
 }
 
 // expf / logf of the host C library, on the device: evaluated in double and rounded once to float, i.e. the correctly

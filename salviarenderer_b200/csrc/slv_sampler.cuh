@@ -149,6 +149,26 @@ __device__ __forceinline__ const uint8_t* texel_ptr(const SurfaceRef& s, int x, 
 
 __device__ __forceinline__ float lerp1(float a, float b, float t) { return a + (b - a) * t; }
 
+// Two channels (lo, lo + 1) of an rgba8 texel as floats BIASED by 2^23: the byte goes into the mantissa of 0x4B000000
+// (= 8388608.0f), one PRMT per channel on the ALU pipe instead of an I2F.U8 on the quarter-rate XU pipe.  8388608 + b is exact.
+__device__ __forceinline__ float2 biased_pair(uint32_t t, int lo) {
+  return make_float2(__uint_as_float(__byte_perm(t, 0x4B000000u, 0x7440 | lo)), __uint_as_float(__byte_perm(t, 0x4B000000u, 0x7440 | (lo + 1))));
+}
+// lerp(lerp(c0, c1, tx), lerp(c2, c3, tx), ty) * (1 / 255) per channel with c = (float)byte (colors.h:341-488), two channels per
+// instruction.  c1 - c0 is taken on the biased values: both are integers below 2^24, so the difference is the same exact float.
+__device__ __forceinline__ float4 bilinear_rgba8(uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, float tx, float ty) {
+  const float2 bias = splat2(8388608.0f), txx = splat2(tx), tyy = splat2(ty), k = splat2(1.0f / 255);
+  float2 o[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float2 m0 = biased_pair(t0, 2 * h), m1 = biased_pair(t1, 2 * h), m2 = biased_pair(t2, 2 * h), m3 = biased_pair(t3, 2 * h);
+    const float2 c0 = sub2(m0, bias), c2 = sub2(m2, bias);
+    const float2 c01 = add2_after_mul(c0, mul2(sub2(m1, m0), txx)), c23 = add2_after_mul(c2, mul2(sub2(m3, m2), txx));
+    o[h] = mul2(add2_after_mul(c01, mul2(sub2(c23, c01), tyy)), k);
+  }
+  return cat4(o[0], o[1]);
+}
+
 // surface::get_texel(x0,y0,x1,y1,tx,ty): bilinear in the NATIVE format (colors.h:341-488)
 __device__ inline float4 bilinear(const SurfaceRef& s, int x0, int y0, int x1, int y1, float tx, float ty, bool in_range) {
   if (s.fmt == SLV_PF_RGBA8) {
@@ -161,15 +181,7 @@ __device__ inline float4 bilinear(const SurfaceRef& s, int x0, int y0, int x1, i
     const uint32_t r0 = (uint32_t)y0 * s.w, r1 = (uint32_t)y1 * s.w;
     uint32_t t0 = __ldg(base + (r0 + (uint32_t)x0)), t1 = __ldg(base + (r0 + (uint32_t)x1));
     uint32_t t2 = __ldg(base + (r1 + (uint32_t)x0)), t3 = __ldg(base + (r1 + (uint32_t)x1));
-    float o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float c0 = (float)((t0 >> (8 * j)) & 0xFF), c1 = (float)((t1 >> (8 * j)) & 0xFF);
-      float c2 = (float)((t2 >> (8 * j)) & 0xFF), c3 = (float)((t3 >> (8 * j)) & 0xFF);
-      float c01 = lerp1(c0, c1, tx), c23 = lerp1(c2, c3, tx);
-      o[j] = lerp1(c01, c23, ty) * (1.0f / 255);
-    }
-    return make_float4(o[0], o[1], o[2], o[3]);
+    return bilinear_rgba8(t0, t1, t2, t3, tx, ty);
   }
   const uint8_t* p0 = texel_ptr(s, x0, y0);
   const uint8_t* p1 = texel_ptr(s, x1, y0);
@@ -273,15 +285,7 @@ __device__ __forceinline__ float4 sample_wrap_rgba8_linear(const SurfaceRef& s, 
   const uint32_t* base = reinterpret_cast<const uint32_t*>(s.data);
   const uint32_t t0 = __ldg(base + (r0 + x0)), t1 = __ldg(base + (r0 + x1));
   const uint32_t t2 = __ldg(base + (r1 + x0)), t3 = __ldg(base + (r1 + x1));
-  float o[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float c0 = (float)((t0 >> (8 * j)) & 0xFF), c1 = (float)((t1 >> (8 * j)) & 0xFF);
-    const float c2 = (float)((t2 >> (8 * j)) & 0xFF), c3 = (float)((t3 >> (8 * j)) & 0xFF);
-    const float c01 = lerp1(c0, c1, tx), c23 = lerp1(c2, c3, tx);
-    o[j] = lerp1(c01, c23, ty) * (1.0f / 255);
-  }
-  return make_float4(o[0], o[1], o[2], o[3]);
+  return bilinear_rgba8(t0, t1, t2, t3, tx, ty);
 }
 
 struct AfInfo { float lod, probe_count, weight_D, du, dv; };
@@ -399,7 +403,7 @@ __device__ inline float4 sample_impl(const SamplerRef& sm, float cx, float cy, f
     c0 = sample_wrap_rgba8_linear(t.level[lv0], sx, sy);
     if (n == 1) return c0;
     c1 = sample_wrap_rgba8_linear(t.level[lv1], sx, sy);
-    return make_float4(lerp1(c0.x, c1.x, frac), lerp1(c0.y, c1.y, frac), lerp1(c0.z, c1.z, frac), lerp1(c0.w, c1.w, frac));
+    return cat4(lerp2_of_products(lo2(c0), lo2(c1), splat2(frac)), lerp2_of_products(hi2(c0), hi2(c1), splat2(frac)));
   }
 #pragma unroll 1
   for (int k = 0; k < n; ++k) {
@@ -408,7 +412,7 @@ __device__ inline float4 sample_impl(const SamplerRef& sm, float cx, float cy, f
     if (aniso) {
       const int wi = (int)((float)(tap_i * tap_i) * weight_D);
       const float w = c_ewa_wts[min(max(wi, 0), 255)];
-      c0.x += v.x * w; c0.y += v.y * w; c0.z += v.z * w; c0.w += v.w * w;
+      c0 = cat4(add2_after_mul(lo2(c0), mul2(lo2(v), splat2(w))), add2_after_mul(hi2(c0), mul2(hi2(v), splat2(w))));
       w_sum += w;
       sx += du;
       sy += dv;
@@ -421,10 +425,10 @@ __device__ inline float4 sample_impl(const SamplerRef& sm, float cx, float cy, f
   }
   if (aniso) {
     const float inv = 1 / w_sum;
-    return make_float4(c0.x * inv, c0.y * inv, c0.z * inv, c0.w * inv);
+    return cat4(mul2(lo2(c0), splat2(inv)), mul2(hi2(c0), splat2(inv)));
   }
   if (n == 1) return c0;
-  return make_float4(lerp1(c0.x, c1.x, frac), lerp1(c0.y, c1.y, frac), lerp1(c0.z, c1.z, frac), lerp1(c0.w, c1.w, frac));
+  return cat4(lerp2_of_products(lo2(c0), lo2(c1), splat2(frac)), lerp2_of_products(hi2(c0), hi2(c1), splat2(frac)));
 }
 
 // sampler::calc_lod_2d (sampler.cpp:831-848)

@@ -74,3 +74,17 @@ def test_package_does_not_reference_oracle():
                 for needle in ("libsalvia_oracle", "libsalvia_ref", "oracle/", "salvia_oracle"):
                     hits = [ln for ln in txt.splitlines() if needle in ln and not ln.strip().startswith(("#", "//", "*", '"""')) and "test infrastructure" not in ln and "unmodified reference" not in ln and "CPU restatement" not in ln]
                     assert not hits, f"{f} references {needle}: {hits[:2]}"
+
+
+def test_no_fused_packed_multiply_add_in_the_product():
+    """The kernels use Blackwell's packed fp32 pairs (FADD2 / FMUL2).  ptxas 12.9 contracts a packed multiply that feeds a packed
+    add into one FFMA2 - rounding once instead of twice - whatever --fmad says, so the sources keep every such sum in scalar adds
+    (slv_common.cuh: add2_after_mul).  This pins it: the library's SASS holds packed adds and multiplies and no FFMA2."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", PRODUCT_LIB], capture_output=True, text=True).stdout
+    assert sass.count("FADD2") > 100 and sass.count("FMUL2") > 100
+    assert sass.count("FFMA2") == 0

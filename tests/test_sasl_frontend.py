@@ -516,3 +516,22 @@ def test_forward_calls_and_recursion():
     for n in (0, 1, 2, 7, 12):
         got, _ = hs.ps([[0.25 * n, 0, 0, 0]], unit.pack_uniforms({"n": n}))
         assert np.array_equal(got, np.array([fib(n), f32(f32(0.25 * n) * f32(2)) + f32(1), 1 - n % 2, 1], f32)), (n, got)
+
+
+def test_jit_cubins_hold_no_fused_packed_multiply_add():
+    """The run-time compiled kernels include the library's own headers (packed fp32 pairs): no FFMA2 may appear (tests/test_abi.py)."""
+    import shutil
+    import subprocess
+    import tempfile
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not (os.path.exists(cuobjdump) and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"))):
+        pytest.skip("CUDA toolkit not available")
+    import bench
+    from salviarenderer_b200.sasl import jit
+    for src, stage in ((bench.SASL_PS_SPONZA, "ps"), (bench.SASL_VS_SPONZA, "vs")):
+        sh = jit.compile(src, stage)
+        with tempfile.NamedTemporaryFile(suffix=".cubin") as f:
+            f.write(sh.cubin)
+            f.flush()
+            sass = subprocess.run([cuobjdump, "-sass", f.name], capture_output=True, text=True).stdout
+        assert sass.count("FADD2") > 10 and sass.count("FFMA2") == 0, stage

@@ -66,9 +66,20 @@ def source_page(rep, kernel_id):
     return hdr, agg
 
 
+# buckets of the per-line view: (file, first line, last line, name), loaded from --buckets <json> when given
+def bucket_of(buckets, fname, line):
+    for f, lo, hi, name in buckets:
+        if f == fname and lo <= line <= hi:
+            return name
+    return fname
+
+
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[sys.argv.index("--top") + 1]) if "--top" in sys.argv else 25
+    import json
+    buckets = json.load(open(sys.argv[sys.argv.index("--buckets") + 1])) if "--buckets" in sys.argv else []
+    dump = sys.argv[sys.argv.index("--dump-lines") + 1] if "--dump-lines" in sys.argv else None
     kernels = raw_page(rep)
     print(f"# {rep}: {len(kernels)} profiled launch(es)\n")
     for i, k in enumerate(kernels):
@@ -101,6 +112,21 @@ def main():
                 except ValueError:
                     pass
         print("  stall reasons (all samples): " + ", ".join(f"{n[6:]} {100.0 * s / ts:.1f}%" for n, s in sorted(zip(names, sums), key=lambda t: -t[1])[:9]))
+        if buckets:
+            agg_b = {}
+            for a in agg:
+                b = bucket_of(buckets, a[2], a[3])
+                x = agg_b.setdefault(b, [0, 0])
+                x[0] += a[0]
+                x[1] += a[1]
+            print("  by function (instructions executed / stall samples):")
+            for b, (ni, ns) in sorted(agg_b.items(), key=lambda t: -t[1][0]):
+                print(f"    {100.0 * ni / tot:5.1f}% inst {100.0 * ns / ts:5.1f}% stall  {b}")
+        if dump:
+            with open(f"{dump}_{short.split('<')[0]}.csv", "w") as fh:
+                fh.write("file,line,inst,stall_samples\n")
+                for a in sorted(agg, key=lambda t: (t[2] or "", t[3])):
+                    fh.write(f"{a[2]},{a[3]},{a[0]},{a[1]}\n")
         print(f"  top {top} source lines by instructions executed:")
         for a in sorted(agg, key=lambda t: -t[0])[:top]:
             print(f"    {100.0 * a[0] / tot:5.1f}% inst {100.0 * a[1] / ts:5.1f}% stall  {a[2]}:{a[3]:<5d} {a[4]}")
