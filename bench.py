@@ -428,7 +428,32 @@ def main():
     out_bytes = args.width * args.height * 4
     h2d = vb_host.numel() * 4 + ib_host.numel() * 4
     d2h = out_bytes if rank == 0 else 0
-    if sc.t.resolved is not None:
+    hf = None
+    if sc.t.resolved is not None and n > 1:
+        # N > 1: no frame is gathered on one GPU.  Every rank resolves its tiles locally and exports them straight into ONE pinned
+        # host frame shared by the ranks (POSIX shared memory, slv_texture_export_tiles_async) over its OWN host link: the device ->
+        # host traffic of a frame is spread over N links.  Two host frames / local targets alternate; the timed region ends after
+        # every rank's last export has landed (slv_readback_wait on each rank, then the barrier of `timed`).
+        hf = sortfirst.HostFrame(be, out_bytes, rank, n, nbuf=2)
+        local_targets = [be.create_texture(args.width, args.height, 1, resolved.fmt) for _ in range(2)]
+        d2h = sum(be.packed_tiles_bytes(resolved, r, n) for r in range(n))  # all ranks together: the whole frame
+        kctr = [0]
+
+        def frame_e2e(i):
+            be.upload_from_ptr(vb_h, vb_host.data_ptr(), vb_host.numel() * 4)
+            be.upload_from_ptr(ib_h, ib_host.data_ptr(), ib_host.numel() * 4)
+            k = kctr[0]
+            kctr[0] += 1
+            sc.t.resolved = local_targets[k % 2]
+            sc.render(be, i % sc.n_frames)
+            hf.export(local_targets[k % 2], k)
+
+        finish_e2e = be.readback_wait
+        e2e_how = ("every rank: slv_buffer_upload of the vertex+index buffers from pinned host memory, the frame's draws on its own tiles, "
+                   "MSAA resolve into a local surface, slv_texture_export_tiles_async of the tiles it owns into ONE pinned host frame shared "
+                   "by the ranks (POSIX shared memory) over its own PCIe link, every step; two host frames alternate; d2h_bytes_per_step is "
+                   "the sum over the ranks (= one whole frame); the timed region ends after every rank's last export has landed")
+    elif sc.t.resolved is not None:
         # the assembled frame goes back through slv_texture_readback_async into one of two pinned buffers while the next frame
         # renders into the other frame buffer (what an application pipelining frames does); every step's upload and readback is
         # inside the timed region, which ends only after the last copy has landed
@@ -444,7 +469,7 @@ def main():
 
         finish_e2e = be.readback_wait
         e2e_how = ("slv_buffer_upload of the vertex+index buffers from pinned host memory, the full frame, and "
-                   "slv_texture_readback_async of the resolved 4K frame into pinned host memory (rank 0), every step; two frame buffers "
+                   "slv_texture_readback_async of the resolved 4K frame into pinned host memory, every step; two frame buffers "
                    "/ host buffers alternate so that the readback of frame k overlaps the rendering of frame k+1; the timed region ends "
                    "after the last readback has landed (slv_readback_wait)")
     else:
@@ -466,6 +491,8 @@ def main():
     if finish_e2e:
         finish_e2e()
     e2e_ms = timed(frame_e2e, args.steps, finish_e2e) / args.steps
+    if hf is not None:
+        sc.t.resolved = resolved
 
     # ---- roofline: per-stage CUDA events on the launching stream, algorithmic bytes from exact counters ----
     be.profile_enable(True)
@@ -598,6 +625,8 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if n > 1:
+        if hf is not None:
+            hf.close()
         fg.close()
         dist.destroy_process_group()
 

@@ -279,6 +279,16 @@ slv_result slv_readback_wait(slv_device dev);
 /* device-side: orders everything submitted after this call behind the pending asynchronous readback of `tex` (no host wait).
  * The sort-first root uses it before it tells the other ranks that a frame buffer may be overwritten. */
 slv_result slv_readback_fence(slv_device dev, slv_handle tex);
+/* Sort-first frame assembly on the HOST (multi-GPU end to end): every rank writes the 64x64 tiles it owns (slv_set_tile_shard) of
+ * its single-sampled resolved surface `tex` straight into ONE host frame of the texture's linear layout, shared by the ranks
+ * (e.g. POSIX shared memory mapped by every process), over ITS OWN host link - so the device -> host traffic of a frame spreads
+ * over N links instead of crossing rank 0's.  `host_frame` must have been registered with slv_host_register by this process
+ * (page-locked + mapped: the kernel stores whole 256-byte tile rows over PCIe).  Asynchronous like slv_texture_readback_async:
+ * enqueued on the copy stream behind everything submitted so far, complete after slv_readback_wait / slv_flush; the next writer
+ * of `tex` waits for it on the device.  The CPU checkers copy synchronously. */
+slv_result slv_host_register(slv_device dev, void* ptr, size_t bytes);
+slv_result slv_host_unregister(slv_device dev, void* ptr);
+slv_result slv_texture_export_tiles_async(slv_device dev, slv_handle tex, void* host_frame, size_t bytes);
 /* renderer::create_sampler (renderer.h:50) */
 slv_result slv_sampler_create(slv_device dev, const slv_sampler_desc* desc, slv_handle tex, slv_handle* out);
 /* SASL shaders compiled at run time.  The reference's compile(code, profile) + set_vertex_shader_code /

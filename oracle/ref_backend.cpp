@@ -868,6 +868,12 @@ slv_result slv_texture_readback_async(slv_device dev, slv_handle tex, uint32_t l
 }
 slv_result slv_readback_wait(slv_device) { return SLV_OK; }
 slv_result slv_readback_fence(slv_device, slv_handle) { return SLV_OK; }
+slv_result slv_host_register(slv_device, void*, size_t) { return SLV_OK; }
+slv_result slv_host_unregister(slv_device, void*) { return SLV_OK; }
+// single process, unsharded: the whole (single-sampled) frame
+slv_result slv_texture_export_tiles_async(slv_device dev, slv_handle tex, void* host_frame, size_t bytes) {
+  return slv_texture_readback(dev, tex, 0, host_frame, bytes);
+}
 // peer-memory frame assembly is a property of the CUDA product (NVLink); the CPU checkers do not implement it
 slv_result slv_peer_export_texture(slv_device, slv_handle, uint32_t, uint8_t*) { return SLV_FAILED; }
 slv_result slv_peer_export_flags(slv_device, uint8_t*) { return SLV_FAILED; }

@@ -1773,6 +1773,26 @@ slv_result slv_texture_readback_async(slv_device dev, slv_handle tex, uint32_t l
   return slv_texture_readback(dev, tex, level, dst, bytes);
 }
 slv_result slv_readback_wait(slv_device) { return SLV_OK; }
+slv_result slv_host_register(slv_device, void*, size_t) { return SLV_OK; }
+slv_result slv_host_unregister(slv_device, void*) { return SLV_OK; }
+// the owned tiles of a single-sampled surface into a host frame of the same linear layout (synchronous here)
+slv_result slv_texture_export_tiles_async(slv_device dev, slv_handle tex, void* host_frame, size_t bytes) {
+  auto r = dev->get(tex, Resource::TEXTURE);
+  if (!r || !host_frame) return SLV_INVALID_PARAMETER;
+  Surface const& s = r->tex.levels[0];
+  if (s.samples != 1 || bytes != s.data.size()) return SLV_INVALID_PARAMETER;
+  uint32_t const tiles_x = (s.w + 63) / 64, tiles_y = (s.h + 63) / 64;
+  for (uint32_t ty = 0; ty < tiles_y; ++ty)
+    for (uint32_t tx = 0; tx < tiles_x; ++tx) {
+      if (dev->shard_n > 1 && (tx + 3 * ty) % dev->shard_n != dev->shard_rank) continue;
+      uint32_t const w = std::min(64u, s.w - tx * 64), h = std::min(64u, s.h - ty * 64);
+      for (uint32_t y = 0; y < h; ++y) {
+        size_t const off = ((size_t)(ty * 64 + y) * s.w + tx * 64) * s.bpp;
+        memcpy((uint8_t*)host_frame + off, s.data.data() + off, (size_t)w * s.bpp);
+      }
+    }
+  return SLV_OK;
+}
 slv_result slv_readback_fence(slv_device, slv_handle) { return SLV_OK; }
 // peer-memory frame assembly is a property of the CUDA product (NVLink); the CPU checkers do not implement it
 slv_result slv_peer_export_texture(slv_device, slv_handle, uint32_t, uint8_t*) { return SLV_FAILED; }

@@ -137,7 +137,7 @@ ENTRY_POINTS = [
     "slv_texture_device_ptr", "slv_pack_tiles", "slv_unpack_tiles", "slv_set_stream", "slv_profile_get_stages",
     "slv_peer_export_texture", "slv_peer_export_flags", "slv_peer_open", "slv_peer_close", "slv_resolve_target_peer",
     "slv_peer_signal", "slv_flags_wait", "slv_shader_module_load", "slv_texture_readback_async", "slv_readback_wait",
-    "slv_readback_fence",
+    "slv_readback_fence", "slv_host_register", "slv_host_unregister", "slv_texture_export_tiles_async",
 ]
 
 
@@ -252,6 +252,9 @@ class Backend:
         L.slv_texture_readback_async.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]
         L.slv_readback_wait.argtypes = [C.c_void_p]
         L.slv_readback_fence.argtypes = [C.c_void_p, C.c_uint32]
+        L.slv_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.slv_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
+        L.slv_texture_export_tiles_async.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]
         L.slv_shader_module_load.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_uint32)]
         L.slv_peer_export_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.slv_peer_export_flags.argtypes = [C.c_void_p, C.c_void_p]
@@ -470,6 +473,16 @@ class Backend:
     def read_texture_into_async(self, tex: Texture, host_ptr: int, nbytes: int, level: int = 0):
         """Enqueues the copy on the library's copy stream; the bytes are valid after readback_wait() / flush()."""
         _chk(self.lib.slv_texture_readback_async(self.dev, tex.handle, level, C.c_void_p(host_ptr), nbytes), "slv_texture_readback_async")
+
+    def host_register(self, host_ptr: int, nbytes: int):
+        _chk(self.lib.slv_host_register(self.dev, C.c_void_p(host_ptr), nbytes), "slv_host_register")
+
+    def host_unregister(self, host_ptr: int):
+        _chk(self.lib.slv_host_unregister(self.dev, C.c_void_p(host_ptr)), "slv_host_unregister")
+
+    def export_tiles_async(self, tex: Texture, host_ptr: int, nbytes: int):
+        """This rank's owned tiles of the resolved surface -> the shared host frame (see sortfirst.HostFrame)."""
+        _chk(self.lib.slv_texture_export_tiles_async(self.dev, tex.handle, C.c_void_p(host_ptr), nbytes), "slv_texture_export_tiles_async")
 
     def readback_fence(self, tex: Texture):
         _chk(self.lib.slv_readback_fence(self.dev, tex.handle), "slv_readback_fence")

@@ -1028,6 +1028,42 @@ slv_result slv_texture_readback_async(slv_device dev, slv_handle h, uint32_t lev
   return SLV_OK;
 }
 
+slv_result slv_host_register(slv_device dev, void* ptr, size_t bytes) {
+  if (!dev || !ptr || !bytes) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  CU(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+  return SLV_OK;
+}
+
+slv_result slv_host_unregister(slv_device dev, void* ptr) {
+  if (!dev || !ptr) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  CU(cudaStreamSynchronize(dev->copy_stream));
+  CU(cudaHostUnregister(ptr));
+  return SLV_OK;
+}
+
+slv_result slv_texture_export_tiles_async(slv_device dev, slv_handle h, void* host_frame, size_t bytes) {
+  auto r = dev ? dev->get(h, Resource::TEXTURE) : nullptr;
+  if (!r || !host_frame || r->tex.level[0].samples != 1 || bytes != r->tex.level[0].bytes) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  { slv_result rcm__ = materialize_clear(dev, r); if (rcm__ != SLV_OK) return rcm__; }
+  void* dptr = nullptr;
+  CU(cudaHostGetDevicePointer(&dptr, host_frame, 0));  // fails unless the range was registered (slv_host_register)
+  const SurfaceRef& s = r->tex.level[0];
+  const uint32_t tiles_x = (s.w + TILE - 1) / TILE, tiles_y = (s.h + TILE - 1) / TILE;
+  if (!r->rb_event) CU(cudaEventCreateWithFlags(&r->rb_event, cudaEventDisableTiming));
+  CU(cudaEventRecord(dev->ev_copy, dev->stream));            // the texture's producers are ahead of this point
+  CU(cudaStreamWaitEvent(dev->copy_stream, dev->ev_copy, 0));
+  k_export_tiles<<<tiles_x * tiles_y, 256, 0, dev->copy_stream>>>(s, tiles_x, dev->shard_rank, dev->shard_n, (uint8_t*)dptr);
+  ++dev->n_launches;
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(r->rb_event, dev->copy_stream));
+  r->rb_pending = true;                                      // the next writer of the texture waits for the export
+  return SLV_OK;
+}
+
 slv_result slv_readback_fence(slv_device dev, slv_handle h) {
   auto r = dev ? dev->get(h, Resource::TEXTURE) : nullptr;
   if (!r) return SLV_INVALID_PARAMETER;

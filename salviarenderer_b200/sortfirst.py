@@ -27,6 +27,62 @@ import torch.distributed as dist
 from . import abi
 
 
+class HostFrame:
+    """End-to-end sort-first assembly on the HOST: `nbuf` frames in POSIX shared memory, mapped by every rank's process and
+    page-locked for its GPU (slv_host_register).  Rank r writes the tiles it owns of frame k into frames[k % nbuf] over its own
+    PCIe link (slv_texture_export_tiles_async); the application reads the assembled frame through `view(k)` on any rank once
+    every rank's export has landed (readback_wait on each rank + a barrier, or the ranks' own completion protocol).
+
+    The owned tiles never travel between GPUs on this path - each rank exports what it rendered - so the device -> host
+    bandwidth of a frame is N host links instead of rank 0's one."""
+
+    def __init__(self, be: abi.Backend, nbytes: int, rank: int, nranks: int, nbuf: int = 2):
+        import mmap
+        import tempfile
+        self.be, self.nbytes, self.rank, self.n, self.nbuf = be, nbytes, rank, nranks, nbuf
+        page = mmap.PAGESIZE
+        self.stride = (nbytes + page - 1) // page * page
+        total = self.stride * nbuf
+        name = [None]
+        if rank == 0:
+            shm_dir = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+            fd, path = tempfile.mkstemp(prefix="slv_hostframe_", dir=shm_dir)
+            os.ftruncate(fd, total)
+            name = [path]
+        else:
+            fd = -1
+        if nranks > 1:
+            dist.broadcast_object_list(name, src=0)
+        self.path = name[0]
+        if rank != 0:
+            fd = os.open(self.path, os.O_RDWR)
+        self.map = mmap.mmap(fd, total)
+        os.close(fd)
+        import ctypes
+        self.base = ctypes.addressof(ctypes.c_char.from_buffer(self.map))
+        be.host_register(self.base, total)
+        if nranks > 1:
+            dist.barrier()
+        if rank == 0:
+            os.unlink(self.path)  # every rank holds its own mapping now
+
+    def ptr(self, k: int) -> int:
+        return self.base + (k % self.nbuf) * self.stride
+
+    def view(self, k: int):
+        import numpy as np
+        off = (k % self.nbuf) * self.stride
+        return np.frombuffer(self.map, dtype=np.uint8, count=self.nbytes, offset=off)
+
+    def export(self, tex: abi.Texture, k: int):
+        self.be.export_tiles_async(tex, self.ptr(k), self.nbytes)
+
+    def close(self):
+        self.be.readback_wait()
+        self.be.host_unregister(self.base)
+        # the mmap object is released with the last numpy view of it
+
+
 def tile_owner(tx: int, ty: int, nranks: int) -> int:
     """The rank that owns tile (tx, ty) — must equal `tile_owned` in csrc/slv_kernels.cuh."""
     return (tx + 3 * ty) % nranks

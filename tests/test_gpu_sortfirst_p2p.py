@@ -87,3 +87,55 @@ def test_world2_assembled_frames_equal_unsharded(cuda, tmp_path, transport, nbuf
         sc.render(cuda, f)
         want = cuda.read_texture(sc.t.resolved)
         assert np.array_equal(got[i].reshape(want.shape), want), f"frame {f} ({transport}, {nbuf} buffers)"
+
+
+def _worker_hostframe(rank, world, port, out_path):
+    """End-to-end assembly on the host: every rank exports the tiles it owns into one shared pinned host frame."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import salviarenderer_b200 as pkg
+    from salviarenderer_b200 import scenes, sortfirst
+    ordinal = rank % torch.cuda.device_count()
+    be = pkg.load(ordinal)
+    torch.cuda.set_device(ordinal)
+    be.set_tile_shard(rank, world)
+    sc = scenes.SponzaLike(W, H, S, tex_size=64)
+    sc.setup(be)
+    local = [sc.t.resolved, be.create_texture(W, H, 1, sc.t.resolved.fmt)]
+    hf = sortfirst.HostFrame(be, W * H * 4, rank, world, nbuf=2)
+    frames = []
+    for i, f in enumerate(FRAMES):
+        sc.t.resolved = local[i % 2]
+        sc.render(be, f)
+        hf.export(local[i % 2], i)
+        if i % 2 == 1 or i == len(FRAMES) - 1:  # every second frame: wait for both buffers, as an application consuming them would
+            be.readback_wait()
+            dist.barrier()  # every rank's tiles of the frames in flight have landed
+            if rank == 0:
+                for j in range(max(0, i - 1 if i % 2 == 1 else i), i + 1):
+                    frames.append(hf.view(j).reshape(H, W, 1, 4).copy())
+            dist.barrier()  # nobody overwrites a buffer before rank 0 has read it
+    if rank == 0:
+        np.save(out_path, np.stack(frames))
+    hf.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_world2_host_frame_export_equals_unsharded(cuda, tmp_path):
+    """Multi-GPU end to end: the tiles each rank exports over its own host link (slv_texture_export_tiles_async into POSIX shared
+    memory registered by both processes) assemble, on the host, the frames an unsharded render produces."""
+    from salviarenderer_b200 import scenes
+    out = str(tmp_path / "frames.npy")
+    mp.spawn(_worker_hostframe, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    sc = scenes.SponzaLike(W, H, S, tex_size=64)
+    sc.setup(cuda)
+    cuda.set_tile_shard(0, 1)
+    assert len(got) == len(FRAMES)
+    for i, f in enumerate(FRAMES):
+        sc.render(cuda, f)
+        want = cuda.read_texture(sc.t.resolved)
+        assert np.array_equal(got[i].reshape(want.shape), want), f"frame {f}"

@@ -86,3 +86,42 @@ def test_frame_gather_rejects_bad_arguments(oracle):
     sizes = [oracle.packed_tiles_bytes(t1, r, 3) for r in range(3)]
     assert sum(sizes) == 4 * 64 * 64 * 4  # 2x2 tiles of 64x64 rgba8, every tile owned by exactly one rank
     oracle.set_tile_shard(0, 1)
+
+
+def _worker_hostframe(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from salviarenderer_b200 import abi, scenes, sortfirst
+    be = abi.Backend(ORACLE_LIB)
+    be.set_tile_shard(rank, world)
+    sc = scenes.SponzaLike(320, 192, 4, tex_size=64)
+    sc.setup(be)
+    hf = sortfirst.HostFrame(be, 320 * 192 * 4, rank, world, nbuf=2)
+    for k, f in enumerate((1, 4, 6)):
+        sc.render(be, f)
+        hf.export(sc.t.resolved, k)
+        be.readback_wait()
+        dist.barrier()
+        if rank == 0:
+            np.save(out_path + f".{k}.npy", hf.view(k).reshape(192, 320, 1, 4).copy())
+        dist.barrier()
+    hf.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_world2_host_frame_assembly_equals_single_rank(oracle, tmp_path):
+    """The end-to-end transport of bench.py at N > 1 (sortfirst.HostFrame): every rank exports the tiles it owns into one host
+    frame in POSIX shared memory; three frames through the two alternating buffers equal the unsharded render."""
+    from salviarenderer_b200 import scenes
+    out = str(tmp_path / "hostframe")
+    mp.spawn(_worker_hostframe, args=(2, _free_port(), out), nprocs=2, join=True)
+    sc = scenes.SponzaLike(320, 192, 4, tex_size=64)
+    sc.setup(oracle)
+    oracle.set_tile_shard(0, 1)
+    for k, f in enumerate((1, 4, 6)):
+        sc.render(oracle, f)
+        oracle.flush()
+        assert np.array_equal(np.load(out + f".{k}.npy"), oracle.read_texture(sc.t.resolved)), f"frame {f}"
