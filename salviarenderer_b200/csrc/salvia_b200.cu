@@ -105,8 +105,8 @@ struct slv_device_t {
   cudaStream_t own_stream = nullptr;  // created with the device; `stream` may point at a caller-owned one
   std::vector<Resource> res;
   // scratch written by the front half of a batch (geometry, binning, region lists) and read by its back half (coverage,
-  // shading).  Two sets: the front half of batch k+1 runs on `front_stream` while the back half of batch k is still
-  // running on `stream` (frame pipelining); a set is reused for batch k+2 once ev_back_done of batch k has fired.
+  // shading).  N_SETS sets: the front halves of batches k+1 .. run on the two front streams while the back half of batch k is
+  // still running on `stream` (frame pipelining); a set is reused N_SETS batches later, once its ev_back_done has fired.
   struct Scratch {
     float4* tris = nullptr;           // triangle records (grown on demand, never shrunk)
     uint32_t* valid_slots = nullptr;  // one entry per slot of the tris arena
@@ -126,18 +126,24 @@ struct slv_device_t {
     cudaEvent_t ev_front_done = nullptr, ev_back_done = nullptr;
     bool in_flight = false;           // ev_back_done has been recorded and not yet waited for
   };
-  Scratch sc[2];
+  static constexpr int N_SETS = 4;    // batches in flight: the back half of batch k, the front halves of k+1 .. k+3
+  Scratch sc[N_SETS];
   int cur = 0;                        // the set the queued draws point at
+  int last_flushed = -1;              // the set of the most recently flushed batch (-1: none since the last full sync)
   Scratch& S() { return sc[cur]; }
   size_t tris_cap = 0;  // float4 units (both sets)
   uint32_t region_cap = 0;
-  cudaStream_t front_stream = nullptr;  // front halves run here when pipelining
-  cudaEvent_t ev_sync = nullptr;        // scratch event: orders front_stream after buffer uploads on `stream`
+  // front halves run on these when pipelining, alternating per batch: a front half is a chain of short, latency-bound kernels
+  // (scan, sort of the longest list, ordered region fill) that leaves most of the GPU idle, so TWO of them are kept in flight -
+  // what a sort-first rank needs once its back half is an N-th of the frame and the front chain is the longer of the two
+  cudaStream_t front_streams[2] = {nullptr, nullptr};
+  cudaStream_t front_stream_of(int set) const { return front_streams[set & 1]; }
+  cudaEvent_t ev_sync = nullptr;        // scratch event: orders the front streams after buffer uploads on `stream`
   bool buffers_dirty = false;           // a vertex / index buffer was written on `stream` since the last front half
   bool pipeline = true;                 // SLV_PIPELINE=0: everything on `stream`
   cudaStream_t copy_stream = nullptr;   // asynchronous readbacks (overlap the next frame's rendering)
   cudaEvent_t ev_copy = nullptr;        // orders the copy stream after the producer of the texture on `stream`
-  cudaEvent_t ev_upload = nullptr;      // last buffer upload enqueued on front_stream
+  cudaEvent_t ev_upload = nullptr;      // last buffer upload enqueued on a front stream
   bool upload_on_front = false;         // ... and not yet ordered before work on `stream`
   uint32_t* peer_flags = nullptr;       // SLV_PEER_FLAGS words other ranks raise over NVLink (slv_peer_signal / slv_flags_wait)
   uint32_t* vis = nullptr;           // visibility buffer of the deferred path: owner slot per sample
@@ -227,10 +233,11 @@ slv_result materialize_clear(slv_device dev, Resource* r);
 slv_result wait_readback(slv_device dev, Resource* r);
 
 slv_result sync_all(slv_device dev) {  // both streams idle
-  CU(cudaStreamSynchronize(dev->front_stream));
+  for (auto fsx : dev->front_streams) CU(cudaStreamSynchronize(fsx));
   CU(cudaStreamSynchronize(dev->stream));
   CU(cudaStreamSynchronize(dev->copy_stream));
   for (auto& S : dev->sc) S.in_flight = false;
+  dev->last_flushed = -1;
   for (auto& r : dev->res) r.rb_pending = false;
   dev->upload_on_front = false;
   return SLV_OK;
@@ -414,14 +421,14 @@ Resource* texture_of_data(slv_device dev, const uint8_t* data) {
 
 // Batch flush: geometry and binning (scan, fill, sort, region lists) over the triangles of every queued draw - the FRONT
 // half, which touches no render target - then the raster pass of all of them, in submission order - the BACK half.
-// When pipelining, the front half is enqueued on front_stream, so it overlaps the back half / clears / resolve of the
+// When pipelining, the front half is enqueued on a front stream, so it overlaps the back half / clears / resolve of the
 // previous batch still running on the main stream; the back half waits for it with an event.
 slv_result flush_batch(slv_device dev) {
   if (dev->pending.empty()) return SLV_OK;
   cudaStream_t st = dev->stream;
   slv_device_t::Scratch& S = dev->S();
   const bool piped = dev->pipeline && !dev->profile;
-  cudaStream_t fs = piped ? dev->front_stream : st;
+  cudaStream_t fs = piped ? dev->front_stream_of(dev->cur) : st;
   RasterParams& first = dev->pending[0];
   const uint32_t n = (uint32_t)dev->pending.size();
   const uint32_t n_tiles = first.tiles_x * first.tiles_y;
@@ -453,9 +460,9 @@ slv_result flush_batch(slv_device dev) {
   }
   if (piped) {
     // the front half reads vertex / index buffers: order it after the uploads enqueued on the main stream
-    if (dev->buffers_dirty) {
+    if (dev->buffers_dirty) {  // both front streams: the batch after this one reads the same buffers on the other stream
       CU(cudaEventRecord(dev->ev_sync, st));
-      CU(cudaStreamWaitEvent(fs, dev->ev_sync, 0));
+      for (auto fsx : dev->front_streams) CU(cudaStreamWaitEvent(fsx, dev->ev_sync, 0));
     }
     // this scratch set was last read by the back half of the batch before the previous one
     if (S.in_flight) {
@@ -700,7 +707,8 @@ slv_result flush_batch(slv_device dev) {
   if (piped) {
     CU(cudaEventRecord(S.ev_back_done, st));
     S.in_flight = true;
-    dev->cur ^= 1;  // the next batch is built in the other set
+    dev->last_flushed = dev->cur;
+    dev->cur = (dev->cur + 1) % slv_device_t::N_SETS;  // the next batch is built in the next set
   }
   dev->n_launches += 5;
   if (dev->profile) {
@@ -732,7 +740,8 @@ slv_result check_overflow(slv_device dev) {
   uint32_t flag = 0;
   CU(cudaMemcpyAsync(&flag, dev->overflow_flag, sizeof(flag), cudaMemcpyDeviceToHost, dev->stream));
   CU(cudaStreamSynchronize(dev->stream));
-  if (flag == 1 && dev->pipeline) CU(cudaStreamSynchronize(dev->front_stream));  // the recorded needs are final
+  if (flag == 1 && dev->pipeline)
+    for (auto fsx : dev->front_streams) CU(cudaStreamSynchronize(fsx));  // the recorded needs are final
   if (flag == 2) {
     fprintf(stderr, "[salvia_b200] slv_flags_wait timed out: a peer rank never raised its flag\n");
     dev->failed = true;
@@ -780,7 +789,7 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   {  // the front half of the NEXT frame is on the critical path: its CTAs go first whenever SM resources free up
     int least = 0, greatest = 0;
     CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-    CU(cudaStreamCreateWithPriority(&dev->front_stream, cudaStreamNonBlocking, greatest));
+    for (auto& fsx : dev->front_streams) CU(cudaStreamCreateWithPriority(&fsx, cudaStreamNonBlocking, greatest));
   }
   CU(cudaEventCreateWithFlags(&dev->ev_sync, cudaEventDisableTiming));
   CU(cudaStreamCreateWithFlags(&dev->copy_stream, cudaStreamNonBlocking));
@@ -845,7 +854,7 @@ void slv_device_destroy(slv_device dev) {
   if (!dev) return;
   cudaSetDevice(dev->ordinal);
   flush_batch(dev);
-  cudaStreamSynchronize(dev->front_stream);
+  for (auto fsx : dev->front_streams) cudaStreamSynchronize(fsx);
   cudaStreamSynchronize(dev->stream);
   cudaStreamSynchronize(dev->copy_stream);
   for (auto& r : dev->res) {
@@ -873,7 +882,7 @@ void slv_device_destroy(slv_device dev) {
   cudaEventDestroy(dev->ev_copy);
   cudaEventDestroy(dev->ev_upload);
   cudaStreamDestroy(dev->copy_stream);
-  cudaStreamDestroy(dev->front_stream);
+  for (auto fsx : dev->front_streams) cudaStreamDestroy(fsx);
 
   for (auto& t : dev->slot_tables) cudaFree(t.d_slot);
   cudaStreamDestroy(dev->own_stream);
@@ -900,13 +909,17 @@ slv_result slv_buffer_upload(slv_device dev, slv_handle h, size_t off, const voi
   if (dev->pipeline && !dev->profile) {
     // vertex / index data is only read by the front half: upload on its stream, so the copy (and the next frame's geometry
     // after it) does not queue behind the previous frame's raster work on the main stream
-    CU(cudaMemcpyAsync(r->dptr + off, src, bytes, cudaMemcpyHostToDevice, dev->front_stream));
-    CU(cudaEventRecord(dev->ev_upload, dev->front_stream));
+    // ... the stream of the NEXT batch's front half (its reader); the previous batch's front half, on the other front stream,
+    // may still be reading the old contents
+    cudaStream_t fs = dev->front_stream_of(dev->cur);
+    if (dev->last_flushed >= 0 && dev->sc[dev->last_flushed].in_flight) CU(cudaStreamWaitEvent(fs, dev->sc[dev->last_flushed].ev_front_done, 0));
+    CU(cudaMemcpyAsync(r->dptr + off, src, bytes, cudaMemcpyHostToDevice, fs));
+    CU(cudaEventRecord(dev->ev_upload, fs));
     dev->upload_on_front = true;
     return SLV_OK;
   }
   CU(cudaMemcpyAsync(r->dptr + off, src, bytes, cudaMemcpyHostToDevice, dev->stream));
-  dev->buffers_dirty = true;  // the next front half (front_stream) must order after this copy
+  dev->buffers_dirty = true;  // the next front halves (front streams) must order after this copy
   return SLV_OK;
 }
 
@@ -1587,7 +1600,7 @@ slv_result slv_debug_read(slv_device dev, uint32_t which, void* dst, size_t byte
   if (!dev || !dst) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
-  const slv_device_t::Scratch& L = dev->sc[(dev->pipeline && !dev->profile) ? (dev->cur ^ 1) : dev->cur];  // the last flushed batch's set
+  const slv_device_t::Scratch& L = dev->sc[(dev->pipeline && !dev->profile && dev->last_flushed >= 0) ? dev->last_flushed : dev->cur];  // the last flushed batch's set
   const void* src = which == 0 ? (const void*)L.active_tiles : which == 1 ? (const void*)L.tile_offset : (const void*)L.block_desc;
   const size_t cap = which == 0 ? ((size_t)dev->tiles_cap + 1) * 4 : which == 1 ? (size_t)dev->tiles_cap * 4 : (size_t)dev->tiles_cap * 128 * 8;
   if (!src || bytes > cap) return SLV_INVALID_PARAMETER;
