@@ -390,6 +390,15 @@ slv_result slv_peer_close(slv_device dev, void* dptr);
 slv_result slv_resolve_target_peer(slv_device dev, slv_handle dst, void* peer_surface);
 slv_result slv_peer_signal(slv_device dev, void* peer_flags, uint32_t index, uint32_t value);
 slv_result slv_flags_wait(slv_device dev, const void* flags, uint32_t first, uint32_t count, uint32_t value);
+/* The ROOT's side of the same protocol without stalling its render stream.  slv_assembly_wait: the wait for the other ranks'
+ * tiles of the frame being assembled in `tex` is enqueued on the copy stream (behind this device's own work on `tex`); what
+ * consumes the assembled frame orders after it - slv_texture_readback_async / slv_texture_export_tiles_async by stream order, a
+ * draw that samples `tex`, a synchronous readback and the next WRITER of `tex` through the texture's event - while the next
+ * frame's kernels, which touch another buffer, start at once.  slv_peer_signal_after_consumers: raises the flag once the
+ * copy-stream work enqueued so far ON `tex` (its assembly wait, its readback) is done - on a stream of its own, so the release of
+ * one frame buffer never waits for the assembly of another. */
+slv_result slv_assembly_wait(slv_device dev, slv_handle tex, const void* flags, uint32_t first, uint32_t count, uint32_t value);
+slv_result slv_peer_signal_after_consumers(slv_device dev, slv_handle tex, void* peer_flags, uint32_t index, uint32_t value);
 
 /* sampler probe used by the sampler parity tests: evaluates sampler::sample_2d_grad
  * (sampler.cpp:854-873) [use_lod = 0] or sample_2d_lod (:850-852) [use_lod = 1] for n coordinates.

@@ -868,6 +868,8 @@ slv_result slv_texture_readback_async(slv_device dev, slv_handle tex, uint32_t l
 }
 slv_result slv_readback_wait(slv_device) { return SLV_OK; }
 slv_result slv_readback_fence(slv_device, slv_handle) { return SLV_OK; }
+slv_result slv_assembly_wait(slv_device, slv_handle, const void*, uint32_t, uint32_t, uint32_t) { return SLV_FAILED; }
+slv_result slv_peer_signal_after_consumers(slv_device, slv_handle, void*, uint32_t, uint32_t) { return SLV_FAILED; }
 slv_result slv_host_register(slv_device, void*, size_t) { return SLV_OK; }
 slv_result slv_host_unregister(slv_device, void*) { return SLV_OK; }
 // single process, unsharded: the whole (single-sampled) frame

@@ -138,6 +138,7 @@ ENTRY_POINTS = [
     "slv_peer_export_texture", "slv_peer_export_flags", "slv_peer_open", "slv_peer_close", "slv_resolve_target_peer",
     "slv_peer_signal", "slv_flags_wait", "slv_shader_module_load", "slv_texture_readback_async", "slv_readback_wait",
     "slv_readback_fence", "slv_host_register", "slv_host_unregister", "slv_texture_export_tiles_async",
+    "slv_assembly_wait", "slv_peer_signal_after_consumers",
 ]
 
 
@@ -252,6 +253,8 @@ class Backend:
         L.slv_texture_readback_async.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]
         L.slv_readback_wait.argtypes = [C.c_void_p]
         L.slv_readback_fence.argtypes = [C.c_void_p, C.c_uint32]
+        L.slv_assembly_wait.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.slv_peer_signal_after_consumers.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
         L.slv_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.slv_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
         L.slv_texture_export_tiles_async.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]
@@ -446,6 +449,13 @@ class Backend:
 
     def resolve_target_peer(self, dst: Texture, peer_surface: int | None):
         _chk(self.lib.slv_resolve_target_peer(self.dev, dst.handle, C.c_void_p(peer_surface or 0)), "slv_resolve_target_peer")
+
+    def assembly_wait(self, tex: Texture, flags: int | None, first: int, count: int, value: int):
+        _chk(self.lib.slv_assembly_wait(self.dev, tex.handle, C.c_void_p(flags or 0), first, count, value & 0xFFFFFFFF), "slv_assembly_wait")
+
+    def peer_signal_after_consumers(self, tex: Texture, peer_flags: int | None, index: int, value: int):
+        _chk(self.lib.slv_peer_signal_after_consumers(self.dev, tex.handle, C.c_void_p(peer_flags or 0), index, value & 0xFFFFFFFF),
+             "slv_peer_signal_after_consumers")
 
     def peer_signal(self, peer_flags: int | None, index: int, value: int):
         _chk(self.lib.slv_peer_signal(self.dev, C.c_void_p(peer_flags or 0), index, value & 0xFFFFFFFF), "slv_peer_signal")

@@ -46,6 +46,8 @@ struct Resource {
   // writer of the texture waits for it on the device
   cudaEvent_t rb_event = nullptr;
   bool rb_pending = false;
+  // ... or a sort-first assembly wait (slv_assembly_wait) on the copy stream: READERS on the main stream wait for it as well
+  bool asm_pending = false;
   // shader modules (SASL shaders compiled at run time, salviarenderer_b200/sasl): the pipeline kernels with the shader inlined
   CUmodule module = nullptr;
   uint32_t module_stage = 0;        // SLV_STAGE_VS / SLV_STAGE_PS
@@ -142,6 +144,7 @@ struct slv_device_t {
   bool buffers_dirty = false;           // a vertex / index buffer was written on `stream` since the last front half
   bool pipeline = true;                 // SLV_PIPELINE=0: everything on `stream`
   cudaStream_t copy_stream = nullptr;   // asynchronous readbacks (overlap the next frame's rendering)
+  cudaStream_t signal_stream = nullptr; // sort-first root: frame-buffer releases (slv_peer_signal_after_consumers), created on first use
   cudaEvent_t ev_copy = nullptr;        // orders the copy stream after the producer of the texture on `stream`
   cudaEvent_t ev_upload = nullptr;      // last buffer upload enqueued on a front stream
   bool upload_on_front = false;         // ... and not yet ordered before work on `stream`
@@ -231,11 +234,13 @@ constexpr uint32_t MAX_BATCH = MAX_BATCH_DRAWS;  // draws whose geometry / raste
 slv_result flush_batch(slv_device dev);
 slv_result materialize_clear(slv_device dev, Resource* r);
 slv_result wait_readback(slv_device dev, Resource* r);
+slv_result wait_assembly(slv_device dev, Resource* r);
 
 slv_result sync_all(slv_device dev) {  // both streams idle
   for (auto fsx : dev->front_streams) CU(cudaStreamSynchronize(fsx));
   CU(cudaStreamSynchronize(dev->stream));
   CU(cudaStreamSynchronize(dev->copy_stream));
+  if (dev->signal_stream) CU(cudaStreamSynchronize(dev->signal_stream));
   for (auto& S : dev->sc) S.in_flight = false;
   dev->last_flushed = -1;
   for (auto& r : dev->res) r.rb_pending = false;
@@ -393,7 +398,13 @@ slv_result wait_readback(slv_device dev, Resource* r) {
   if (r && r->rb_pending) {
     CU(cudaStreamWaitEvent(dev->stream, r->rb_event, 0));
     r->rb_pending = false;
+    r->asm_pending = false;
   }
+  return SLV_OK;
+}
+// a texture about to be READ on the main stream: order the read after a pending sort-first assembly of it
+slv_result wait_assembly(slv_device dev, Resource* r) {
+  if (r && r->asm_pending) return wait_readback(dev, r);
   return SLV_OK;
 }
 
@@ -882,6 +893,7 @@ void slv_device_destroy(slv_device dev) {
   cudaEventDestroy(dev->ev_copy);
   cudaEventDestroy(dev->ev_upload);
   cudaStreamDestroy(dev->copy_stream);
+  if (dev->signal_stream) { cudaStreamSynchronize(dev->signal_stream); cudaStreamDestroy(dev->signal_stream); }
   for (auto fsx : dev->front_streams) cudaStreamDestroy(fsx);
 
   for (auto& t : dev->slot_tables) cudaFree(t.d_slot);
@@ -1021,6 +1033,7 @@ slv_result slv_texture_readback(slv_device dev, slv_handle h, uint32_t level, vo
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   { slv_result rcm__ = materialize_clear(dev, r); if (rcm__ != SLV_OK) return rcm__; }
+  { slv_result rca__ = wait_assembly(dev, r); if (rca__ != SLV_OK) return rca__; }
   CU(cudaMemcpyAsync(dst, r->tex.level[level].data, bytes, cudaMemcpyDeviceToHost, dev->stream));
   CU(cudaStreamSynchronize(dev->stream));
   return check_overflow(dev);
@@ -1401,8 +1414,16 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   }
 
   // lazy clears: a texture this draw SAMPLES, and the second colour target, must hold their cleared contents for real
-  if (needs_sampler) { slv_result rcm__ = materialize_clear(dev, texture_of_data(dev, rp.sampler0.tex.level[0].data)); if (rcm__ != SLV_OK) return rcm__; }
-  if (needs_sampler1) { slv_result rcm__ = materialize_clear(dev, texture_of_data(dev, rp.sampler1.tex.level[0].data)); if (rcm__ != SLV_OK) return rcm__; }
+  if (needs_sampler) {
+    Resource* rt = texture_of_data(dev, rp.sampler0.tex.level[0].data);
+    { slv_result rcm__ = materialize_clear(dev, rt); if (rcm__ != SLV_OK) return rcm__; }
+    { slv_result rca__ = wait_assembly(dev, rt); if (rca__ != SLV_OK) return rca__; }
+  }
+  if (needs_sampler1) {
+    Resource* rt = texture_of_data(dev, rp.sampler1.tex.level[0].data);
+    { slv_result rcm__ = materialize_clear(dev, rt); if (rcm__ != SLV_OK) return rcm__; }
+    { slv_result rca__ = wait_assembly(dev, rt); if (rca__ != SLV_OK) return rca__; }
+  }
   if (rp.color1.data) { slv_result rcm__ = materialize_clear(dev, texture_of_data(dev, rp.color1.data)); if (rcm__ != SLV_OK) return rcm__; }
   dev->batch_color = d->n_color_targets ? d->color_targets[0] : 0;
   dev->batch_ds = d->ds_target;
@@ -1800,6 +1821,37 @@ slv_result slv_flags_wait(slv_device dev, const void* flags, uint32_t first, uin
   // the queued batch is NOT flushed: its front half touches no render target and its back half is enqueued on the main stream
   // behind this wait anyway - so a following slv_resolve can still be fused into the batch's k_shade
   k_flags_wait<<<1, 32, 0, dev->stream>>>(flags ? (const uint32_t*)flags : dev->peer_flags, first, count, value, dev->overflow_flag);
+  ++dev->n_launches;
+  CU(cudaGetLastError());
+  return SLV_OK;
+}
+
+slv_result slv_assembly_wait(slv_device dev, slv_handle tex, const void* flags, uint32_t first, uint32_t count, uint32_t value) {
+  auto r = dev ? dev->get(tex, Resource::TEXTURE) : nullptr;
+  if (!r || first + count > SLV_PEER_FLAGS) return SLV_INVALID_PARAMETER;
+  if (count == 0) return SLV_OK;
+  CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }  // this device's own tiles of the frame are enqueued
+  if (!r->rb_event) CU(cudaEventCreateWithFlags(&r->rb_event, cudaEventDisableTiming));
+  CU(cudaEventRecord(dev->ev_copy, dev->stream));
+  CU(cudaStreamWaitEvent(dev->copy_stream, dev->ev_copy, 0));
+  k_flags_wait<<<1, 32, 0, dev->copy_stream>>>(flags ? (const uint32_t*)flags : dev->peer_flags, first, count, value, dev->overflow_flag);
+  ++dev->n_launches;
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(r->rb_event, dev->copy_stream));
+  r->rb_pending = true;   // the next writer of the texture waits for the assembly (and whatever consumes it on the copy stream)
+  r->asm_pending = true;  // ... and so do readers on the main stream
+  return SLV_OK;
+}
+
+slv_result slv_peer_signal_after_consumers(slv_device dev, slv_handle tex, void* peer_flags, uint32_t index, uint32_t value) {
+  auto r = dev ? dev->get(tex, Resource::TEXTURE) : nullptr;
+  if (!r || index >= SLV_PEER_FLAGS) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  if (!dev->signal_stream) CU(cudaStreamCreateWithFlags(&dev->signal_stream, cudaStreamNonBlocking));
+  if (r->rb_event && r->rb_pending) CU(cudaStreamWaitEvent(dev->signal_stream, r->rb_event, 0));
+  uint32_t* base = peer_flags ? (uint32_t*)peer_flags : dev->peer_flags;
+  k_peer_signal<<<1, 1, 0, dev->signal_stream>>>(base + index, value);
   ++dev->n_launches;
   CU(cudaGetLastError());
   return SLV_OK;

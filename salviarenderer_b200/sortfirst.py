@@ -8,9 +8,10 @@ the RESOLVED colour surface have to reach rank 0.  Two transports:
   other rank opens them and redirects `slv_resolve` into rank 0's memory, so the MSAA resolve and the exchange are ONE
   kernel storing over NVLink / NVSwitch — no staging buffer, no pack / unpack kernels, no collective.  Per frame the
   ranks' streams are ordered on the device by flags in rank 0's memory (`slv_peer_signal` / `slv_flags_wait`):
-  rank r raises flags[r] = k+1 after its resolve of frame k; rank 0's stream waits for all of them, and raises
-  flags[0] = k once everything it enqueued that reads frame k-1.. is behind it, which the other ranks poll before they
-  overwrite the surface with frame k.  No host synchronisation anywhere.
+  rank r raises flags[r] = k+1 after its resolve of frame k; rank 0 waits for all of them ON ITS COPY STREAM
+  (`slv_assembly_wait`: consumers of the assembled frame order behind it, rank 0's render stream goes straight on to the next
+  frame in the other buffer), and raises flags[0] = k - nbuf + 1 there once the consumers of that buffer's previous frame are
+  done, which the other ranks poll before they overwrite it with frame k.  No host synchronisation anywhere.
 * ``gather`` (fallback, and what the CPU checkers use under gloo): `slv_pack_tiles` -> `torch.distributed.gather`
   (NCCL on the GPUs) -> `slv_unpack_tiles` on rank 0.
 
@@ -192,8 +193,10 @@ class FrameGather:
         k = self.frame
         if self.rank == 0:
             if k >= self.nbuf:
-                self.be.readback_fence(self.surfaces[k % self.nbuf])
-                self.be.peer_signal(None, 0, k - self.nbuf + 1)
+                # behind the assembly wait and every copy-stream consumer (readback) of this buffer's previous frame - and of nothing
+                # else; rank 0's render stream is never stalled by the protocol (its own next write of the buffer waits for the
+                # texture's event)
+                self.be.peer_signal_after_consumers(self.surfaces[k % self.nbuf], None, 0, k - self.nbuf + 1)
         elif self.nbuf > 1:
             self.be.resolve_target_peer(self.surface, self.root_surfaces[k % self.nbuf])
 
@@ -209,7 +212,7 @@ class FrameGather:
             return
         if self.transport == "p2p":
             if self.rank == 0:
-                self.be.flags_wait(None, 1, self.n - 1, self.frame + 1)
+                self.be.assembly_wait(self.target(), None, 1, self.n - 1, self.frame + 1)
             else:
                 self.be.peer_signal(self.root_flags, self.rank, self.frame + 1)
             self.frame += 1
