@@ -437,11 +437,14 @@ def main():
         hf = sortfirst.HostFrame(be, out_bytes, rank, n, nbuf=2)
         local_targets = [be.create_texture(args.width, args.height, 1, resolved.fmt) for _ in range(2)]
         d2h = sum(be.packed_tiles_bytes(resolved, r, n) for r in range(n))  # all ranks together: the whole frame
+        # the replicated geometry: every rank uploads an N-th of it from pinned host memory, an NCCL all-gather over NVLink
+        # assembles the vertex + index buffers on every GPU (sortfirst.ShardedUpload) - each input byte crosses a host link once
+        su = sortfirst.ShardedUpload(be, [vb_h, ib_h], [vb_np, ib_np], rank, n)
+        h2d = su.h2d_bytes_per_rank * n
         kctr = [0]
 
         def frame_e2e(i):
-            be.upload_from_ptr(vb_h, vb_host.data_ptr(), vb_host.numel() * 4)
-            be.upload_from_ptr(ib_h, ib_host.data_ptr(), ib_host.numel() * 4)
+            su.upload()
             k = kctr[0]
             kctr[0] += 1
             sc.t.resolved = local_targets[k % 2]
@@ -449,7 +452,8 @@ def main():
             hf.export(local_targets[k % 2], k)
 
         finish_e2e = be.readback_wait
-        e2e_how = ("every rank: slv_buffer_upload of the vertex+index buffers from pinned host memory, the frame's draws on its own tiles, "
+        e2e_how = ("every rank: an N-th of the vertex+index data from pinned host memory to its GPU + an NCCL all-gather over NVLink into the "
+                   "library's buffers (h2d_bytes_per_step is the sum over the ranks = the whole geometry once), the frame's draws on its own tiles, "
                    "MSAA resolve into a local surface, slv_texture_export_tiles_async of the tiles it owns into ONE pinned host frame shared "
                    "by the ranks (POSIX shared memory) over its own PCIe link, every step; two host frames alternate; d2h_bytes_per_step is "
                    "the sum over the ranks (= one whole frame); the timed region ends after every rank's last export has landed")

@@ -868,6 +868,16 @@ slv_result slv_texture_readback_async(slv_device dev, slv_handle tex, uint32_t l
 }
 slv_result slv_readback_wait(slv_device) { return SLV_OK; }
 slv_result slv_readback_fence(slv_device, slv_handle) { return SLV_OK; }
+slv_result slv_buffer_device_ptr(slv_device dev, slv_handle h, void** out, size_t* bytes) {
+  auto e = dev->get(h);
+  if (!e || !e->buf || !out) return SLV_INVALID_PARAMETER;
+  dev->r->flush();
+  *out = e->buf->raw_data(0);
+  if (bytes) *bytes = e->buf->size();
+  return SLV_OK;
+}
+slv_result slv_external_write_begin(slv_device dev, void*) { dev->r->flush(); return SLV_OK; }
+slv_result slv_external_write_end(slv_device, void*) { return SLV_OK; }
 slv_result slv_assembly_wait(slv_device, slv_handle, const void*, uint32_t, uint32_t, uint32_t) { return SLV_FAILED; }
 slv_result slv_peer_signal_after_consumers(slv_device, slv_handle, void*, uint32_t, uint32_t) { return SLV_FAILED; }
 slv_result slv_host_register(slv_device, void*, size_t) { return SLV_OK; }

@@ -1773,6 +1773,15 @@ slv_result slv_texture_readback_async(slv_device dev, slv_handle tex, uint32_t l
   return slv_texture_readback(dev, tex, level, dst, bytes);
 }
 slv_result slv_readback_wait(slv_device) { return SLV_OK; }
+slv_result slv_buffer_device_ptr(slv_device dev, slv_handle h, void** out, size_t* bytes) {
+  auto r = dev->get(h, Resource::BUFFER);
+  if (!r || !out) return SLV_INVALID_PARAMETER;
+  *out = r->buf.data();
+  if (bytes) *bytes = r->buf.size();
+  return SLV_OK;
+}
+slv_result slv_external_write_begin(slv_device, void*) { return SLV_OK; }
+slv_result slv_external_write_end(slv_device, void*) { return SLV_OK; }
 slv_result slv_assembly_wait(slv_device, slv_handle, const void*, uint32_t, uint32_t, uint32_t) { return SLV_FAILED; }
 slv_result slv_peer_signal_after_consumers(slv_device, slv_handle, void*, uint32_t, uint32_t) { return SLV_FAILED; }
 slv_result slv_host_register(slv_device, void*, size_t) { return SLV_OK; }

@@ -139,6 +139,7 @@ ENTRY_POINTS = [
     "slv_peer_signal", "slv_flags_wait", "slv_shader_module_load", "slv_texture_readback_async", "slv_readback_wait",
     "slv_readback_fence", "slv_host_register", "slv_host_unregister", "slv_texture_export_tiles_async",
     "slv_assembly_wait", "slv_peer_signal_after_consumers",
+    "slv_buffer_device_ptr", "slv_external_write_begin", "slv_external_write_end",
 ]
 
 
@@ -255,6 +256,9 @@ class Backend:
         L.slv_readback_fence.argtypes = [C.c_void_p, C.c_uint32]
         L.slv_assembly_wait.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
         L.slv_peer_signal_after_consumers.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.slv_buffer_device_ptr.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.slv_external_write_begin.argtypes = [C.c_void_p, C.c_void_p]
+        L.slv_external_write_end.argtypes = [C.c_void_p, C.c_void_p]
         L.slv_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.slv_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
         L.slv_texture_export_tiles_async.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]
@@ -483,6 +487,18 @@ class Backend:
     def read_texture_into_async(self, tex: Texture, host_ptr: int, nbytes: int, level: int = 0):
         """Enqueues the copy on the library's copy stream; the bytes are valid after readback_wait() / flush()."""
         _chk(self.lib.slv_texture_readback_async(self.dev, tex.handle, level, C.c_void_p(host_ptr), nbytes), "slv_texture_readback_async")
+
+    def buffer_device_ptr(self, buf: int):
+        """(pointer, bytes) of a buffer's allocation (device memory for the product, host memory for the CPU checkers)."""
+        p, n = C.c_void_p(), C.c_size_t()
+        _chk(self.lib.slv_buffer_device_ptr(self.dev, buf, C.byref(p), C.byref(n)), "slv_buffer_device_ptr")
+        return p.value, n.value
+
+    def external_write_begin(self, cuda_stream: int):
+        _chk(self.lib.slv_external_write_begin(self.dev, C.c_void_p(cuda_stream)), "slv_external_write_begin")
+
+    def external_write_end(self, cuda_stream: int):
+        _chk(self.lib.slv_external_write_end(self.dev, C.c_void_p(cuda_stream)), "slv_external_write_end")
 
     def host_register(self, host_ptr: int, nbytes: int):
         _chk(self.lib.slv_host_register(self.dev, C.c_void_p(host_ptr), nbytes), "slv_host_register")

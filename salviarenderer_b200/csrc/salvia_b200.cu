@@ -935,6 +935,44 @@ slv_result slv_buffer_upload(slv_device dev, slv_handle h, size_t off, const voi
   return SLV_OK;
 }
 
+slv_result slv_buffer_device_ptr(slv_device dev, slv_handle h, void** out, size_t* bytes) {
+  auto r = dev ? dev->get(h, Resource::BUFFER) : nullptr;
+  if (!r || !out) return SLV_INVALID_PARAMETER;
+  *out = r->dptr;
+  if (bytes) *bytes = r->bytes;
+  return SLV_OK;
+}
+
+slv_result slv_external_write_begin(slv_device dev, void* cuda_stream) {
+  if (!dev || !cuda_stream) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  cudaStream_t ext = (cudaStream_t)cuda_stream;
+  if (dev->pipeline && !dev->profile) {
+    // buffers are read by the front halves only: the last flushed one (earlier ones precede it on the same two streams)
+    for (int k = 0; k < 2; ++k) {
+      const int set = dev->last_flushed - k;
+      if (dev->last_flushed >= 0 && set >= -1) {
+        const slv_device_t::Scratch& T = dev->sc[(set + slv_device_t::N_SETS) % slv_device_t::N_SETS];
+        if (T.in_flight) CU(cudaStreamWaitEvent(ext, T.ev_front_done, 0));
+      }
+    }
+  } else {
+    CU(cudaEventRecord(dev->ev_sync, dev->stream));
+    CU(cudaStreamWaitEvent(ext, dev->ev_sync, 0));
+  }
+  return SLV_OK;
+}
+
+slv_result slv_external_write_end(slv_device dev, void* cuda_stream) {
+  if (!dev || !cuda_stream) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  CU(cudaEventRecord(dev->ev_sync, (cudaStream_t)cuda_stream));
+  for (auto fsx : dev->front_streams) CU(cudaStreamWaitEvent(fsx, dev->ev_sync, 0));
+  CU(cudaStreamWaitEvent(dev->stream, dev->ev_sync, 0));
+  return SLV_OK;
+}
+
 slv_result slv_buffer_readback(slv_device dev, slv_handle h, size_t off, void* dst, size_t bytes) {
   auto r = dev ? dev->get(h, Resource::BUFFER) : nullptr;
   if (!r || off + bytes > r->bytes) return SLV_INVALID_PARAMETER;

@@ -84,6 +84,52 @@ class HostFrame:
         # the mmap object is released with the last numpy view of it
 
 
+class _DevicePtr:
+    """Hands a raw device pointer to torch (zero-copy, __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+class ShardedUpload:
+    """Per-frame upload of replicated geometry on N ranks with every byte crossing a host link ONCE: rank r copies the r-th slice
+    of the (concatenated) vertex + index data from pinned host memory to its GPU, an all-gather over NVLink (NCCL) assembles the
+    whole on every GPU, and two device-to-device copies drop it into the library's buffers.  Everything runs on a side stream:
+    slv_external_write_begin / _end order it after the previous frame's geometry pass (the buffers' reader) and before the next
+    one, so the upload of frame k+1 overlaps the back half of frame k."""
+
+    def __init__(self, be: abi.Backend, buffers, host_arrays, rank: int, nranks: int):
+        import numpy as np
+        self.be, self.rank, self.n = be, rank, nranks
+        self.side = torch.cuda.Stream()
+        raw = [np.ascontiguousarray(a).view(np.uint8).reshape(-1) for a in host_arrays]
+        self.sizes = [r.size for r in raw]
+        total = sum(self.sizes)
+        self.chunk = (total + nranks * 16 - 1) // (nranks * 16) * 16
+        padded = np.zeros(self.chunk * nranks, np.uint8)
+        padded[:total] = np.concatenate(raw)
+        self.host_slice = torch.from_numpy(padded[rank * self.chunk:(rank + 1) * self.chunk].copy()).pin_memory()
+        self.stage = torch.empty(self.chunk, dtype=torch.uint8, device="cuda")
+        self.gathered = torch.empty(self.chunk * nranks, dtype=torch.uint8, device="cuda")
+        self.views = []
+        off = 0
+        for h, nbytes in zip(buffers, self.sizes):
+            ptr, cap = be.buffer_device_ptr(h)
+            assert cap >= nbytes
+            self.views.append((torch.as_tensor(_DevicePtr(ptr, nbytes), device="cuda"), off, nbytes))
+            off += nbytes
+        self.h2d_bytes_per_rank = self.chunk
+
+    def upload(self):
+        self.be.external_write_begin(self.side.cuda_stream)
+        with torch.cuda.stream(self.side):
+            self.stage.copy_(self.host_slice, non_blocking=True)
+            dist.all_gather_into_tensor(self.gathered, self.stage)
+            for view, off, nbytes in self.views:
+                view.copy_(self.gathered[off:off + nbytes], non_blocking=True)
+        self.be.external_write_end(self.side.cuda_stream)
+
+
 def tile_owner(tx: int, ty: int, nranks: int) -> int:
     """The rank that owns tile (tx, ty) — must equal `tile_owned` in csrc/slv_kernels.cuh."""
     return (tx + 3 * ty) % nranks
