@@ -439,12 +439,18 @@ def main():
         d2h = sum(be.packed_tiles_bytes(resolved, r, n) for r in range(n))  # all ranks together: the whole frame
         # the replicated geometry: every rank uploads an N-th of it from pinned host memory, an NCCL all-gather over NVLink
         # assembles the vertex + index buffers on every GPU (sortfirst.ShardedUpload) - each input byte crosses a host link once
-        su = sortfirst.ShardedUpload(be, [vb_h, ib_h], [vb_np, ib_np], rank, n)
+        # two buffer sets alternate, so the upload of frame k+1 does not wait for the geometry pass of frame k
+        vb2 = be.create_buffer(np.ascontiguousarray(vb_np, dtype=np.float32))
+        ib2 = be.create_buffer(np.ascontiguousarray(ib_np))
+        geo_sets = [(vb_h, ib_h), (vb2, ib2)]
+        su = sortfirst.ShardedUpload(be, [list(g) for g in geo_sets], [vb_np, ib_np], rank, n)
         h2d = su.h2d_bytes_per_rank * n
         kctr = [0]
 
         def frame_e2e(i):
-            su.upload()
+            which = su.upload()
+            for d in sc.frame_draws(be, i % sc.n_frames):  # this frame's draws read the set just uploaded
+                d.streams[0].buffer, d.index_buffer = geo_sets[which]
             k = kctr[0]
             kctr[0] += 1
             sc.t.resolved = local_targets[k % 2]
@@ -497,6 +503,9 @@ def main():
     e2e_ms = timed(frame_e2e, args.steps, finish_e2e) / args.steps
     if hf is not None:
         sc.t.resolved = resolved
+        for f in range(sc.n_frames):
+            for d in sc.frame_draws(be, f):
+                d.streams[0].buffer, d.index_buffer = geo_sets[0]
 
     # ---- roofline: per-stage CUDA events on the launching stream, algorithmic bytes from exact counters ----
     be.profile_enable(True)

@@ -283,10 +283,12 @@ slv_result slv_readback_fence(slv_device dev, slv_handle tex);
  * index data each and assembling the whole buffer with an all-gather over NVLink, so that every input byte crosses a host link
  * once instead of once per GPU.  slv_buffer_device_ptr returns the allocation.  slv_external_write_begin flushes the queued draws
  * and makes `cuda_stream` (a cudaStream_t) wait until the library's readers of buffers enqueued so far - the geometry passes of
- * the flushed batches - are done; slv_external_write_end makes the library's next geometry passes (and its render stream) wait
- * for everything enqueued on `cuda_stream` so far.  The CPU checkers return the host pointer and ignore the ordering calls. */
+ * the flushed batches - are done, except those of the `skip_latest` most recent batches (a writer that alternates between two
+ * buffer sets passes 1: the latest batch reads the other set); slv_external_write_end makes the library's next geometry passes
+ * (and its render stream) wait for everything enqueued on `cuda_stream` so far.  The CPU checkers return the host pointer and
+ * ignore the ordering calls. */
 slv_result slv_buffer_device_ptr(slv_device dev, slv_handle buf, void** out, size_t* bytes);
-slv_result slv_external_write_begin(slv_device dev, void* cuda_stream);
+slv_result slv_external_write_begin(slv_device dev, void* cuda_stream, uint32_t skip_latest);
 slv_result slv_external_write_end(slv_device dev, void* cuda_stream);
 /* Sort-first frame assembly on the HOST (multi-GPU end to end): every rank writes the 64x64 tiles it owns (slv_set_tile_shard) of
  * its single-sampled resolved surface `tex` straight into ONE host frame of the texture's linear layout, shared by the ranks

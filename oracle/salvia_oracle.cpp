@@ -1780,7 +1780,7 @@ slv_result slv_buffer_device_ptr(slv_device dev, slv_handle h, void** out, size_
   if (bytes) *bytes = r->buf.size();
   return SLV_OK;
 }
-slv_result slv_external_write_begin(slv_device, void*) { return SLV_OK; }
+slv_result slv_external_write_begin(slv_device, void*, uint32_t) { return SLV_OK; }
 slv_result slv_external_write_end(slv_device, void*) { return SLV_OK; }
 slv_result slv_assembly_wait(slv_device, slv_handle, const void*, uint32_t, uint32_t, uint32_t) { return SLV_FAILED; }
 slv_result slv_peer_signal_after_consumers(slv_device, slv_handle, void*, uint32_t, uint32_t) { return SLV_FAILED; }

@@ -257,7 +257,7 @@ class Backend:
         L.slv_assembly_wait.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
         L.slv_peer_signal_after_consumers.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
         L.slv_buffer_device_ptr.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
-        L.slv_external_write_begin.argtypes = [C.c_void_p, C.c_void_p]
+        L.slv_external_write_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.slv_external_write_end.argtypes = [C.c_void_p, C.c_void_p]
         L.slv_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.slv_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
@@ -494,8 +494,8 @@ class Backend:
         _chk(self.lib.slv_buffer_device_ptr(self.dev, buf, C.byref(p), C.byref(n)), "slv_buffer_device_ptr")
         return p.value, n.value
 
-    def external_write_begin(self, cuda_stream: int):
-        _chk(self.lib.slv_external_write_begin(self.dev, C.c_void_p(cuda_stream)), "slv_external_write_begin")
+    def external_write_begin(self, cuda_stream: int, skip_latest: int = 0):
+        _chk(self.lib.slv_external_write_begin(self.dev, C.c_void_p(cuda_stream), skip_latest), "slv_external_write_begin")
 
     def external_write_end(self, cuda_stream: int):
         _chk(self.lib.slv_external_write_end(self.dev, C.c_void_p(cuda_stream)), "slv_external_write_end")

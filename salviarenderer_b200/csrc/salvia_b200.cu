@@ -943,19 +943,16 @@ slv_result slv_buffer_device_ptr(slv_device dev, slv_handle h, void** out, size_
   return SLV_OK;
 }
 
-slv_result slv_external_write_begin(slv_device dev, void* cuda_stream) {
+slv_result slv_external_write_begin(slv_device dev, void* cuda_stream, uint32_t skip_latest) {
   if (!dev || !cuda_stream) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
   cudaStream_t ext = (cudaStream_t)cuda_stream;
   if (dev->pipeline && !dev->profile) {
     // buffers are read by the front halves only: the last flushed one (earlier ones precede it on the same two streams)
-    for (int k = 0; k < 2; ++k) {
-      const int set = dev->last_flushed - k;
-      if (dev->last_flushed >= 0 && set >= -1) {
-        const slv_device_t::Scratch& T = dev->sc[(set + slv_device_t::N_SETS) % slv_device_t::N_SETS];
-        if (T.in_flight) CU(cudaStreamWaitEvent(ext, T.ev_front_done, 0));
-      }
+    for (int k = (int)skip_latest; k < (int)skip_latest + 2 && k < slv_device_t::N_SETS - 1 && dev->last_flushed >= 0; ++k) {
+      const slv_device_t::Scratch& T = dev->sc[(dev->last_flushed - k + 2 * slv_device_t::N_SETS) % slv_device_t::N_SETS];
+      if (T.in_flight) CU(cudaStreamWaitEvent(ext, T.ev_front_done, 0));
     }
   } else {
     CU(cudaEventRecord(dev->ev_sync, dev->stream));
@@ -1120,7 +1117,10 @@ slv_result slv_texture_export_tiles_async(slv_device dev, slv_handle h, void* ho
   if (!r->rb_event) CU(cudaEventCreateWithFlags(&r->rb_event, cudaEventDisableTiming));
   CU(cudaEventRecord(dev->ev_copy, dev->stream));            // the texture's producers are ahead of this point
   CU(cudaStreamWaitEvent(dev->copy_stream, dev->ev_copy, 0));
-  k_export_tiles<<<tiles_x * tiles_y, 256, 0, dev->copy_stream>>>(s, tiles_x, dev->shard_rank, dev->shard_n, (uint8_t*)dptr);
+  {
+    static const int export_ctas = getenv("SLV_EXPORT_CTAS") ? atoi(getenv("SLV_EXPORT_CTAS")) : 32;
+    k_export_tiles<<<std::max(1, std::min<int>(export_ctas, (int)(tiles_x * tiles_y))), 256, 0, dev->copy_stream>>>(s, tiles_x, tiles_x * tiles_y, dev->shard_rank, dev->shard_n, (uint8_t*)dptr);
+  }
   ++dev->n_launches;
   CU(cudaGetLastError());
   CU(cudaEventRecord(r->rb_event, dev->copy_stream));

@@ -1809,28 +1809,32 @@ __global__ void k_pack_tiles(SurfaceRef s, uint32_t tiles_x, uint32_t tiles_y, u
 }
 
 // sort-first, end to end: the owned 64x64 tiles of a single-sampled surface -> a host frame of the same linear layout (mapped
-// pinned memory).  One CTA per tile; a tile row is 64 px * bpp contiguous bytes written with 128-bit stores by consecutive
-// lanes, i.e. full-size PCIe write transactions.
-__global__ void __launch_bounds__(256) k_export_tiles(SurfaceRef s, uint32_t tiles_x, uint32_t rank, uint32_t n, uint8_t* host) {
-  const uint32_t tile = blockIdx.x, tx = tile % tiles_x, ty = tile / tiles_x;
-  if (!tile_owned(tx, ty, rank, n)) return;
-  const uint32_t x0 = tx * TILE, y0 = ty * TILE;
-  const uint32_t w = min((uint32_t)TILE, s.w - x0), h = min((uint32_t)TILE, s.h - y0);
-  const uint32_t row_bytes = w * s.bpp;
+// pinned memory).  A tile row is 64 px * bpp contiguous bytes written with 128-bit stores by consecutive lanes, i.e. full-size
+// PCIe write transactions.  The kernel is bound by the host link (~50 GB/s), not by the SMs: a SMALL persistent grid walks the
+// tiles, so that the stores in flight saturate the link while the render kernels of the next frame keep (almost) every SM slot -
+// one CTA per tile would park a thousand CTAs behind the link's back-pressure for the whole copy.
+__global__ void __launch_bounds__(256) k_export_tiles(SurfaceRef s, uint32_t tiles_x, uint32_t n_tiles, uint32_t rank, uint32_t n, uint8_t* host) {
   const size_t pitch = (size_t)s.w * s.bpp;
-  if (((pitch | ((size_t)x0 * s.bpp) | row_bytes) & 15) == 0) {
-    const uint32_t vec_per_row = row_bytes / 16;
-    for (uint32_t i = threadIdx.x; i < h * vec_per_row; i += blockDim.x) {
-      const uint32_t r = i / vec_per_row, v = i % vec_per_row;
-      const size_t off = (size_t)(y0 + r) * pitch + (size_t)x0 * s.bpp + (size_t)v * 16;
-      *reinterpret_cast<uint4*>(host + off) = *reinterpret_cast<const uint4*>(s.data + off);
-    }
-  } else {
-    const uint32_t words_per_row = row_bytes / 4;
-    for (uint32_t i = threadIdx.x; i < h * words_per_row; i += blockDim.x) {
-      const uint32_t r = i / words_per_row, v = i % words_per_row;
-      const size_t off = (size_t)(y0 + r) * pitch + (size_t)x0 * s.bpp + (size_t)v * 4;
-      *reinterpret_cast<uint32_t*>(host + off) = *reinterpret_cast<const uint32_t*>(s.data + off);
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+    if (!tile_owned(tx, ty, rank, n)) continue;
+    const uint32_t x0 = tx * TILE, y0 = ty * TILE;
+    const uint32_t w = min((uint32_t)TILE, s.w - x0), h = min((uint32_t)TILE, s.h - y0);
+    const uint32_t row_bytes = w * s.bpp;
+    if (((pitch | ((size_t)x0 * s.bpp) | row_bytes) & 15) == 0) {
+      const uint32_t vec_per_row = row_bytes / 16;
+      for (uint32_t i = threadIdx.x; i < h * vec_per_row; i += blockDim.x) {
+        const uint32_t r = i / vec_per_row, v = i % vec_per_row;
+        const size_t off = (size_t)(y0 + r) * pitch + (size_t)x0 * s.bpp + (size_t)v * 16;
+        *reinterpret_cast<uint4*>(host + off) = *reinterpret_cast<const uint4*>(s.data + off);
+      }
+    } else {
+      const uint32_t words_per_row = row_bytes / 4;
+      for (uint32_t i = threadIdx.x; i < h * words_per_row; i += blockDim.x) {
+        const uint32_t r = i / words_per_row, v = i % words_per_row;
+        const size_t off = (size_t)(y0 + r) * pitch + (size_t)x0 * s.bpp + (size_t)v * 4;
+        *reinterpret_cast<uint32_t*>(host + off) = *reinterpret_cast<const uint32_t*>(s.data + off);
+      }
     }
   }
 }

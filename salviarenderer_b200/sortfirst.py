@@ -98,7 +98,9 @@ class ShardedUpload:
     slv_external_write_begin / _end order it after the previous frame's geometry pass (the buffers' reader) and before the next
     one, so the upload of frame k+1 overlaps the back half of frame k."""
 
-    def __init__(self, be: abi.Backend, buffers, host_arrays, rank: int, nranks: int):
+    def __init__(self, be: abi.Backend, buffer_sets, host_arrays, rank: int, nranks: int):
+        """`buffer_sets`: one list of buffer handles (matching `host_arrays`) per set; upload k writes set k % len(buffer_sets).
+        With two sets the upload of frame k+1 does not wait for the geometry pass of frame k (which reads the other set)."""
         import numpy as np
         self.be, self.rank, self.n = be, rank, nranks
         self.side = torch.cuda.Stream()
@@ -111,23 +113,30 @@ class ShardedUpload:
         self.host_slice = torch.from_numpy(padded[rank * self.chunk:(rank + 1) * self.chunk].copy()).pin_memory()
         self.stage = torch.empty(self.chunk, dtype=torch.uint8, device="cuda")
         self.gathered = torch.empty(self.chunk * nranks, dtype=torch.uint8, device="cuda")
-        self.views = []
-        off = 0
-        for h, nbytes in zip(buffers, self.sizes):
-            ptr, cap = be.buffer_device_ptr(h)
-            assert cap >= nbytes
-            self.views.append((torch.as_tensor(_DevicePtr(ptr, nbytes), device="cuda"), off, nbytes))
-            off += nbytes
+        self.sets = []
+        for buffers in buffer_sets:
+            views, off = [], 0
+            for h, nbytes in zip(buffers, self.sizes):
+                ptr, cap = be.buffer_device_ptr(h)
+                assert cap >= nbytes
+                views.append((torch.as_tensor(_DevicePtr(ptr, nbytes), device="cuda"), off, nbytes))
+                off += nbytes
+            self.sets.append(views)
         self.h2d_bytes_per_rank = self.chunk
+        self.k = 0
 
-    def upload(self):
-        self.be.external_write_begin(self.side.cuda_stream)
+    def upload(self) -> int:
+        """Enqueues the upload into the next buffer set; returns the index of that set (the frame's draws must read it)."""
+        which = self.k % len(self.sets)
+        self.k += 1
+        self.be.external_write_begin(self.side.cuda_stream, skip_latest=len(self.sets) - 1)
         with torch.cuda.stream(self.side):
             self.stage.copy_(self.host_slice, non_blocking=True)
             dist.all_gather_into_tensor(self.gathered, self.stage)
-            for view, off, nbytes in self.views:
+            for view, off, nbytes in self.sets[which]:
                 view.copy_(self.gathered[off:off + nbytes], non_blocking=True)
         self.be.external_write_end(self.side.cuda_stream)
+        return which
 
 
 def tile_owner(tx: int, ty: int, nranks: int) -> int:

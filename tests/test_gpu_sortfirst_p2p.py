@@ -162,7 +162,7 @@ def _worker_sharded_upload(rank, world, port, out_path):
     zeros = np.zeros_like(np.ascontiguousarray(sc.mesh.streams[0], dtype=np.float32))
     be.upload_from_ptr(vb_h, zeros.ctypes.data, zeros.nbytes)
     be.flush()
-    su = sortfirst.ShardedUpload(be, [vb_h, ib_h], [sc.mesh.streams[0], sc.mesh.indices], rank, world)
+    su = sortfirst.ShardedUpload(be, [[vb_h, ib_h]], [sc.mesh.streams[0], sc.mesh.indices], rank, world)
     local = [sc.t.resolved, be.create_texture(W, H, 1, sc.t.resolved.fmt)]
     hf = sortfirst.HostFrame(be, W * H * 4, rank, world, nbuf=2)
     frames = []
