@@ -540,8 +540,11 @@ __device__ __forceinline__ void geometry_main(const GeomParams* __restrict__ dra
   if ((threadIdx.x & 31) == 0 && total) atomicAdd(&p.stats[6], (unsigned long long)total);
 }
 
+#ifndef SLV_GEOM_CTAS_PER_SM
+#define SLV_GEOM_CTAS_PER_SM 4
+#endif
 template <int R>
-__global__ void __launch_bounds__(128, 4) k_geometry(const GeomParams* __restrict__ draws, GeomBatch hb) {
+__global__ void __launch_bounds__(128, SLV_GEOM_CTAS_PER_SM) k_geometry(const GeomParams* __restrict__ draws, GeomBatch hb) {
   geometry_main<R>(draws, hb);
 }
 
