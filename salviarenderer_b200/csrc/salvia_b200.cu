@@ -649,7 +649,7 @@ slv_result flush_batch(slv_device dev) {
   }
   uint32_t cover_grid = (uint32_t)dev->cover_grid, shade_grid = (uint32_t)dev->shade_grid;
   {
-    int k = dev->back_ctas > 0 ? dev->back_ctas : (dev->shard_n >= 4 ? 6 : 8);  // r02 sweep (tools/variant_sweep.py): 8 beats 7 on a whole frame
+    int k = dev->back_ctas > 0 ? dev->back_ctas : 8;  // r02 sweeps (tools/variant_sweep.py, tools/shard_sweep.py): 8 wins on a whole frame and on an eighth
     if (!(dev->pipeline && !dev->profile)) k = SLV_COVER_CTAS_PER_SM;  // nothing to overlap with on a single stream
     if (k >= 1 && k <= SLV_COVER_CTAS_PER_SM) cover_grid = (uint32_t)(dev->sm_count * k);
     if (k >= 1 && k <= SLV_SHADE_CTAS_PER_SM) shade_grid = (uint32_t)(dev->sm_count * k);

@@ -2,6 +2,7 @@
 executed (tests/sasl_host.py); expected values are restated in numpy float32 with the same operation order.  The
 shaders are written for these tests; the features are the ones sasl/test/repo/*.svs|*.sps and the samples' shaders use
 (struct semantics, swizzles and write masks, branches, loops, intrinsics, constructors, casts, functions)."""
+import os
 import numpy as np
 import pytest
 
