@@ -244,6 +244,8 @@ typedef struct slv_pipeline_profiles {   /* pipeline_profiles, nanoseconds (asyn
 } slv_pipeline_profiles;
 
 /* ---- entry points ----------------------------------------------------------------------------- */
+/* (not visible to run-time device compilation: NVRTC translation units include this header for the POD types only) */
+#ifndef __CUDACC_RTC__
 /* replaces create_software_renderer()/create_benchmark_renderer() (renderer.h:133-134).
  * `ordinal` = CUDA device index (ignored by the CPU checkers).  Product: fails with SLV_FAILED when
  * no CUDA device is usable — there is no CPU fallback. */
@@ -419,6 +421,7 @@ slv_result slv_sampler_probe(slv_device dev, slv_handle sampler, uint32_t n, con
                              const float* ddx, const float* ddy, const float* lod, uint32_t use_lod,
                              float* out_rgba);
 
+#endif /* !__CUDACC_RTC__ */
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,7 @@ struct Resource {
   uint32_t module_stage = 0;        // SLV_STAGE_VS / SLV_STAGE_PS
   uint32_t module_attrs = 0;        // VS: output attributes
   CUfunction fn_geometry = nullptr; // VS: slv_jit_k_geometry
+  CUfunction fn_vertex_shade = nullptr; // VS: slv_jit_k_vertex_shade (post-transform vertex cache; absent in older cubins)
   CUfunction fn_raster[3] = {};     // PS: slv_jit_k_raster_s1 / _s2 / _s4
   CUfunction fn_shade[3] = {};      // PS: slv_jit_k_shade_s1 / _s2 / _s4 (visibility-first path; absent in older cubins)
 };
@@ -125,6 +126,11 @@ struct slv_device_t {
     GeomParams* d_geom = nullptr;
     RasterParams* h_batch = nullptr;  // pinned staging of d_batch / d_geom: the uploads never synchronise a stream
     GeomParams* h_geom = nullptr;
+    // post-transform vertex cache of the batch (k_vertex_mark / k_vertex_shade -> k_geometry): clip-space positions, attributes
+    // and the "referenced" marks, one range per group of draws with the same vertex state; grown on demand
+    float4 *vc_pos = nullptr, *vc_attr = nullptr;
+    uint8_t* vc_flags = nullptr;
+    size_t vc_pos_cap = 0, vc_attr_cap = 0;  // vertices / float4s
     cudaEvent_t ev_front_done = nullptr, ev_back_done = nullptr;
     bool in_flight = false;           // ev_back_done has been recorded and not yet waited for
   };
@@ -151,6 +157,13 @@ struct slv_device_t {
   uint32_t* peer_flags = nullptr;       // SLV_PEER_FLAGS words other ranks raise over NVLink (slv_peer_signal / slv_flags_wait)
   uint32_t* vis = nullptr;           // visibility buffer of the deferred path: owner slot per sample
   size_t vis_cap = 0;                // in uint32 units
+  // post-transform vertex cache: indexed draws run the vertex shader once per referenced vertex instead of once
+  // per corner.  1 (default): only where it pays - vertex shaders that sample a texture (vertex texture fetch: ~3 k instructions
+  // per run, up to six runs per primitive without the cache).  For the arithmetic-only programs the per-corner recompute is
+  // FASTER on this machine: it reads the 2-3 input registers of a corner where the cache would write and re-read the 4-5 output
+  // registers (measured, profiles/r02_vertex_cache.txt: k_geometry 0.065 -> 0.081 ms on the Sponza-like scene, 5.66 -> 6.13 ms on
+  // the 10 M-triangle mesh).  SLV_VERTEX_CACHE=0 disables, =2 caches every indexed draw whatever its size and shader (tests).
+  int vertex_cache = 1;
   bool force_immediate = false;      // SLV_FORCE_IMMEDIATE=1: always use k_raster (tests compare both paths)
   bool jit_immediate = false;        // SLV_JIT_IMMEDIATE=1: SASL pixel shaders always take k_raster
   bool front_grids = true;           // SLV_FRONT_GRIDS=0: full-size k_sort_lists / k_region_bin / k_sort_lists_large grids
@@ -164,6 +177,7 @@ struct slv_device_t {
   std::vector<RasterParams> pending;
   std::vector<GeomParams> pending_geom;  // geometry parameters of the queued draws (same index as `pending`)
   std::vector<slv_handle> pending_vs_module;  // run-time vertex-shader module of each queued draw (0 = built-in program)
+  std::vector<uint64_t> pending_vs_runs;      // per-corner vertex-shader runs of each queued draw (counted at flush unless the draw is cached)
   slv_handle batch_ps_module = 0;             // run-time pixel-shader module of the batch (0 = built-in program)
   slv_handle batch_color = 0, batch_ds = 0;   // texture handles of the batch's colour target 0 and depth/stencil target
   bool lazy_clear = true;                     // SLV_LAZY_CLEAR=0: clears always execute immediately
@@ -487,6 +501,83 @@ slv_result flush_batch(slv_device dev) {
     dev->upload_on_front = false;
   }
   dev->buffers_dirty = false;
+  // ---- post-transform vertex cache: group the indexed draws by vertex state, give each group a range of the cache arenas
+  GeomBatch vc_mark{};                              // every cached draw (k_vertex_mark: CTAs over its indices)
+  std::vector<uint32_t> vc_groups;                  // representative draw of each group (k_vertex_shade: CTAs over [0, vc_cap))
+  {
+    std::vector<int> group_of(n, -1);
+    struct Group { uint32_t rep; uint64_t indices; };
+    std::vector<Group> groups;
+    auto n_indices = [](const GeomParams& g) -> uint64_t { return g.topology == SLV_TOPO_TRIANGLE_LIST ? 3ull * g.prim_count : (uint64_t)g.prim_count + 2; };
+    auto same_vertex_state = [&](uint32_t a, uint32_t b) {
+      const GeomParams &x = dev->pending_geom[a], &y = dev->pending_geom[b];
+      return dev->pending_vs_module[a] == dev->pending_vs_module[b] && x.vs_program == y.vs_program && x.n_attrs == y.n_attrs &&
+             x.n_elements == y.n_elements && x.fast_layout == y.fast_layout && x.vc_cap == y.vc_cap &&
+             memcmp(x.streams, y.streams, sizeof(x.streams)) == 0 && memcmp(x.elements, y.elements, sizeof(x.elements)) == 0 &&
+             memcmp(x.vs_uniforms, y.vs_uniforms, sizeof(x.vs_uniforms)) == 0 && memcmp(&x.sampler0, &y.sampler0, sizeof(SamplerRef)) == 0;
+    };
+    if (dev->vertex_cache > 0)
+      for (uint32_t i = 0; i < n; ++i) {
+        const GeomParams& g = dev->pending_geom[i];
+        if (!g.indices || g.vc_cap == 0) continue;
+        const slv_handle m = dev->pending_vs_module[i];
+        if (m && !dev->res[m].fn_vertex_shade) continue;
+        for (size_t k = 0; k < groups.size() && group_of[i] < 0; ++k)
+          if (same_vertex_state(groups[k].rep, i)) group_of[i] = (int)k;
+        if (group_of[i] < 0) { group_of[i] = (int)groups.size(); groups.push_back({i, 0}); }
+        groups[group_of[i]].indices += n_indices(g);
+      }
+    // a group is cached when that is cheaper than re-running the shader per corner: an expensive (texture-sampling) shader,
+    // enough index references for the two extra launches, a vertex range not much larger than what the draws can reference
+    size_t pos_need = 0, attr_need = 0;
+    std::vector<size_t> pos_off(groups.size()), attr_off(groups.size());
+    std::vector<char> cached(groups.size(), 0);
+    for (size_t k = 0; k < groups.size(); ++k) {
+      const GeomParams& g = dev->pending_geom[groups[k].rep];
+      const bool samples_texture = g.sampler0.tex.n_levels != 0;
+      const bool worth = dev->vertex_cache >= 2 || (samples_texture && groups[k].indices >= 768 && (uint64_t)g.vc_cap <= 4 * groups[k].indices + 1024);
+      if (!worth || (uint64_t)g.vc_cap * (1 + g.n_attrs) > (1ull << 27)) continue;  // <= 2 GB of cache per group
+      cached[k] = 1;
+      pos_off[k] = pos_need;
+      attr_off[k] = attr_need;
+      pos_need += g.vc_cap;
+      attr_need += (size_t)g.vc_cap * std::max(g.n_attrs, 1u);
+    }
+    if (pos_need > S.vc_pos_cap || attr_need > S.vc_attr_cap) {
+      slv_result rcs = sync_all(dev);  // the arenas of this set may still be read by a batch in flight
+      if (rcs != SLV_OK) return rcs;
+      if (pos_need > S.vc_pos_cap) {
+        const size_t cap = std::max(pos_need, S.vc_pos_cap * 2);
+        if (S.vc_pos) { CU(cudaFree(S.vc_pos)); CU(cudaFree(S.vc_flags)); }
+        CU(cudaMalloc(&S.vc_pos, cap * sizeof(float4)));
+        CU(cudaMalloc(&S.vc_flags, cap));
+        CU(cudaMemsetAsync(S.vc_flags, 0, cap, fs));
+        S.vc_pos_cap = cap;
+      }
+      if (attr_need > S.vc_attr_cap) {
+        const size_t cap = std::max(attr_need, S.vc_attr_cap * 2);
+        if (S.vc_attr) CU(cudaFree(S.vc_attr));
+        CU(cudaMalloc(&S.vc_attr, cap * sizeof(float4)));
+        S.vc_attr_cap = cap;
+      }
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+      GeomParams& g = dev->pending_geom[i];
+      const int k = group_of[i];
+      if (k < 0 || !cached[k]) {
+        g.vc_pos = nullptr; g.vc_attr = nullptr; g.vc_flags = nullptr;
+        dev->host_stats.vs_invocations += dev->pending_vs_runs[i];
+        continue;
+      }
+      g.vc_pos = S.vc_pos + pos_off[k];
+      g.vc_attr = S.vc_attr + attr_off[k];
+      g.vc_flags = S.vc_flags + pos_off[k];
+      vc_mark.draw_of[vc_mark.n] = i;
+      vc_mark.cta_prefix[vc_mark.n + 1] = vc_mark.cta_prefix[vc_mark.n] + (uint32_t)((n_indices(g) + 256 * VC_MARK_PER_THREAD - 1) / (256 * VC_MARK_PER_THREAD));
+      ++vc_mark.n;
+      if (groups[k].rep == i) vc_groups.push_back(i);
+    }
+  }
   // parameter upload: through this set's pinned staging when pipelining (no stream synchronisation; the staging is free
   // again once ev_front_done has fired, checked above), else straight from pageable memory (the driver stages it)
   const RasterParams* src_batch = dev->pending.data();
@@ -520,6 +611,38 @@ slv_result flush_batch(slv_device dev) {
     std::vector<slv_handle> mods;  // distinct vertex-shader modules of the batch (0 = the built-in programs)
     for (slv_handle m : dev->pending_vs_module)
       if (std::find(mods.begin(), mods.end(), m) == mods.end()) mods.push_back(m);
+    // post-transform vertex cache: mark the referenced vertices, then the vertex shader once per marked vertex
+    if (vc_mark.n) {
+      k_vertex_mark<<<vc_mark.cta_prefix[vc_mark.n], 256, 0, fs>>>(S.d_geom, vc_mark);
+      dev->n_launches += 1;
+      for (slv_handle m : mods)
+        for (uint32_t R = 1; R <= (uint32_t)MAX_REGS; ++R) {
+          GeomBatch hb{};
+          for (uint32_t i : vc_groups) {
+            if (1 + dev->pending_geom[i].n_attrs != R || dev->pending_vs_module[i] != m) continue;
+            hb.draw_of[hb.n] = i;
+            hb.cta_prefix[hb.n + 1] = hb.cta_prefix[hb.n] + (dev->pending_geom[i].vc_cap + 127) / 128;
+            ++hb.n;
+          }
+          if (!hb.n) continue;
+          if (m) {
+            const GeomParams* d_geom = S.d_geom;
+            void* args[] = {(void*)&d_geom, (void*)&hb};
+            if (driver_api().LaunchKernel(dev->res[m].fn_vertex_shade, hb.cta_prefix[hb.n], 1, 1, 128, 1, 1, 0, (CUstream)fs, args, nullptr) != CUDA_SUCCESS)
+              return SLV_FAILED;
+          } else {
+            switch (R) {
+            case 1: k_vertex_shade<1><<<hb.cta_prefix[hb.n], 128, 0, fs>>>(S.d_geom, hb); break;
+            case 2: k_vertex_shade<2><<<hb.cta_prefix[hb.n], 128, 0, fs>>>(S.d_geom, hb); break;
+            case 3: k_vertex_shade<3><<<hb.cta_prefix[hb.n], 128, 0, fs>>>(S.d_geom, hb); break;
+            case 4: k_vertex_shade<4><<<hb.cta_prefix[hb.n], 128, 0, fs>>>(S.d_geom, hb); break;
+            case 5: k_vertex_shade<5><<<hb.cta_prefix[hb.n], 128, 0, fs>>>(S.d_geom, hb); break;
+            default: k_vertex_shade<6><<<hb.cta_prefix[hb.n], 128, 0, fs>>>(S.d_geom, hb); break;
+            }
+          }
+          dev->n_launches += 1;
+        }
+    }
     for (slv_handle m : mods)
       for (uint32_t R = 1; R <= (uint32_t)MAX_REGS; ++R) {
         GeomBatch hb{};
@@ -739,6 +862,7 @@ slv_result flush_batch(slv_device dev) {
   }
   dev->pending.clear();
   dev->pending_geom.clear();
+  dev->pending_vs_runs.clear();
   dev->pending_vs_module.clear();
   dev->tris_used = 0;
   dev->slots_queued = 0;
@@ -855,6 +979,7 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   if (const char* bp = getenv("SLV_BITS_POOL_CAP")) dev->bits_pool_cap = atoll(bp);
   const char* ji = getenv("SLV_JIT_IMMEDIATE");
   dev->jit_immediate = ji && ji[0] == '1';
+  if (const char* vc = getenv("SLV_VERTEX_CACHE")) dev->vertex_cache = atoi(vc);
   for (auto& ev : dev->user_ev) CU(cudaEventCreate(&ev));
 
   *out = dev;
@@ -881,6 +1006,7 @@ void slv_device_destroy(slv_device dev) {
     cudaFree(S.work_counter); cudaFree(S.region_list); cudaFree(S.region_mask); cudaFree(S.region_tile_cnt); cudaFree(S.region_offset); cudaFree(S.region_count);
     cudaFree(S.item_flag); cudaFree(S.block_desc); cudaFree(S.list); cudaFree(S.d_batch); cudaFree(S.d_geom);
     cudaFreeHost(S.h_batch); cudaFreeHost(S.h_geom);
+    cudaFree(S.vc_pos); cudaFree(S.vc_attr); cudaFree(S.vc_flags);
     cudaEventDestroy(S.ev_front_done); cudaEventDestroy(S.ev_back_done);
   }
   cudaFree(dev->vis);
@@ -1178,6 +1304,7 @@ slv_result slv_shader_module_load(slv_device dev, uint32_t stage, const void* im
   bool ok = true;
   if (stage == SLV_STAGE_VS) {
     ok = api.ModuleGetFunction(&r.fn_geometry, r.module, "slv_jit_k_geometry") == CUDA_SUCCESS;
+    if (api.ModuleGetFunction(&r.fn_vertex_shade, r.module, "slv_jit_k_vertex_shade") != CUDA_SUCCESS) r.fn_vertex_shade = nullptr;
   } else {
     const char* names[3] = {"slv_jit_k_raster_s1", "slv_jit_k_raster_s2", "slv_jit_k_raster_s4"};
     for (int i = 0; i < 3; ++i) ok = ok && api.ModuleGetFunction(&r.fn_raster[i], r.module, names[i]) == CUDA_SUCCESS;
@@ -1310,6 +1437,20 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
     if (!r) return SLV_INVALID_PARAMETER;
     gp.indices = r->dptr;
     gp.index_stride = d->index_format == SLV_INDEX_R16_UINT ? 2 : 4;
+    // vertices the bound streams hold for this layout: the post-transform vertex cache covers [0, vc_cap) (a hint here; the
+    // flush decides whether the draw is cached and points vc_pos / vc_attr / vc_flags at its group's range)
+    uint64_t cap = d->n_elements ? 0xFFFFFFFFull : 0;
+    for (uint32_t i = 0; i < d->n_elements; ++i) {
+      const slv_input_element& e = d->elements[i];
+      const slv_vertex_stream& vs = d->streams[e.slot];
+      const uint64_t bytes = dev->get(vs.buffer, Resource::BUFFER)->bytes;
+      const uint64_t sz = gp.fast_layout ? 16 : (e.format == SLV_FMT_R32_FLOAT ? 4 : e.format == SLV_FMT_R32G32_FLOAT ? 8 : e.format == SLV_FMT_R32G32B32_FLOAT ? 12 : 16);
+      const uint64_t first = (uint64_t)vs.offset + e.aligned_byte_offset + sz;
+      uint64_t c = 0;
+      if (first <= bytes) c = vs.stride ? (bytes - first) / vs.stride + 1 : 0xFFFFFFFFull;
+      cap = std::min(cap, c);
+    }
+    gp.vc_cap = (uint32_t)std::min<uint64_t>(cap, 0xFFFFFFFFull);
   }
   gp.topology = d->topology;
   gp.start = d->start;
@@ -1343,7 +1484,8 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   auto count_draw = [&]() {
     dev->host_stats.ia_vertices += 3ull * d->prim_count;
     dev->host_stats.ia_primitives += d->prim_count;
-    dev->host_stats.vs_invocations += 3ull * d->prim_count;  // no post-transform cache: VS recomputed per corner
+    // vs_invocations: per corner for draws without a post-transform cache (added at the flush, which decides), else the number
+    // of vertices k_vertex_shade ran (device counter)
     dev->host_stats.cinvocations += d->prim_count;
   };
   if (d->bs.program < SLV_BS_REPLACE || d->bs.program > SLV_BS_REPLACE_AND_COUNT) return SLV_INVALID_PARAMETER;
@@ -1488,6 +1630,7 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
   dev->pending.push_back(rp);
   dev->pending_geom.push_back(gp);
   dev->pending_vs_module.push_back(vs_module);
+  dev->pending_vs_runs.push_back(3ull * d->prim_count);
   dev->batch_ps_module = ps_module;
   dev->batch_S = S;
   dev->tris_used += tris_need;
@@ -1624,10 +1767,11 @@ slv_result slv_query_get(slv_device dev, slv_pipeline_statistics* out) {
   if (!dev || !out) return SLV_INVALID_PARAMETER;
   CU(cudaSetDevice(dev->ordinal));
   { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
-  unsigned long long h[9];
+  unsigned long long h[20];
   CU(cudaMemcpyAsync(h, dev->d_stats, sizeof(h), cudaMemcpyDeviceToHost, dev->stream));
   CU(cudaStreamSynchronize(dev->stream));
   *out = dev->host_stats;
+  out->vs_invocations += h[17];  // vertices shaded into the post-transform cache
   out->cprimitives = h[6];
   out->ps_invocations = h[7];
   out->backend_input_pixels = h[8];

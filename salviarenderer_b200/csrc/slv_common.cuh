@@ -73,8 +73,24 @@ struct GeomParams {
   unsigned long long* stats;  // slv_pipeline_statistics as 9 x u64
   uint32_t* valid_slots;      // compact list of the slots that hold a triangle binned on this rank
   uint32_t* valid_count;
+  // post-transform vertex cache (default_vertex_cache.cpp:128-197): when vc_pos != nullptr, k_vertex_mark / k_vertex_shade have
+  // run the vertex shader ONCE for every vertex index < vc_cap that the draws sharing this cache reference; k_geometry gathers
+  // the clip-space position (vc_pos[v]) and the attributes (vc_attr[v * n_attrs + i]) instead of re-running the shader per
+  // corner.  Indices >= vc_cap (outside the bound buffers: undefined upstream) fall back to the per-corner run.
+  const float4* vc_pos;
+  const float4* vc_attr;
+  uint8_t* vc_flags;          // [vc_cap] "referenced" marks (set by k_vertex_mark, consumed and cleared by k_vertex_shade)
+  uint32_t vc_cap;
   SamplerRef sampler0;        // vertex texture fetch (vs.samplers[0]); tex.n_levels == 0 when the draw binds none
 };
+
+// bytes of GeomParams in front of the trailing sampler block (NVRTC has no offsetof: derived from the sizes; may include a few
+// bytes of the sampler when the struct has tail padding, which is harmless for the staging copy that uses it)
+constexpr size_t GEOM_PARAMS_HEAD_BYTES = sizeof(GeomParams) - sizeof(SamplerRef);
+#ifndef __CUDACC_RTC__
+static_assert(GEOM_PARAMS_HEAD_BYTES >= offsetof(GeomParams, sampler0) && GEOM_PARAMS_HEAD_BYTES < offsetof(GeomParams, sampler0) + 16 &&
+              GEOM_PARAMS_HEAD_BYTES % 4 == 0, "sampler0 must stay the last member of GeomParams");
+#endif
 
 // geometry of all queued draws in ONE launch: CTA b works on draw draw_of[g] where cta_prefix[g] <= b < cta_prefix[g+1]
 constexpr uint32_t MAX_BATCH_DRAWS = 64;

@@ -1,7 +1,7 @@
 // slv_jit_unit.cu — the translation unit salviarenderer_b200/sasl/jit.py compiles at run time, one per SASL shader.
 // NOT part of libsalvia_b200.so.  nvcc flags (the library's, so every float operation keeps the numerics contract):
 //   -cubin -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -prec-div=true -prec-sqrt=true -ftz=false
-//   -DSLV_JIT_VS=1 -DSLV_JIT_R=<registers>        a vertex shader   -> slv_jit_k_geometry
+//   -DSLV_JIT_VS=1 -DSLV_JIT_R=<registers>        a vertex shader   -> slv_jit_k_geometry, slv_jit_k_vertex_shade
 //   -DSLV_JIT_PS=1 [-DSLV_JIT_DERIV_CPP=1]        a pixel shader    -> slv_jit_k_raster_s1 / _s2 / _s4 (immediate path)
 //                                                                  and slv_jit_k_shade_s1 / _s2 / _s4 (visibility-first path)
 //   -DSLV_JIT_GENERATED="<path of the generated .cuh>"
@@ -20,6 +20,10 @@
 static_assert(SLV_JIT_R == SLV_JIT_VS_OUTPUT_ATTRS + 1, "register count does not match the shader's outputs");
 extern "C" __global__ void __launch_bounds__(128, 4) slv_jit_k_geometry(const slv::GeomParams* __restrict__ draws, slv::GeomBatch hb) {
   slv::geometry_main<SLV_JIT_R>(draws, hb);
+}
+// post-transform vertex cache: the shader once per referenced vertex (k_vertex_shade of the library, with this shader inlined)
+extern "C" __global__ void __launch_bounds__(128) slv_jit_k_vertex_shade(const slv::GeomParams* __restrict__ draws, slv::GeomBatch hb) {
+  slv::vertex_shade_main<SLV_JIT_R>(draws, hb);
 }
 #endif
 

@@ -364,27 +364,92 @@ __device__ __forceinline__ bool setup_triangle(const GeomParams& p, const VsOut<
   return true;
 }
 
-template <int R>
-__device__ __forceinline__ void geometry_main(const GeomParams* __restrict__ draws, const GeomBatch& hb) {
-  // every queued draw with R registers shares this launch; a CTA belongs to exactly one draw
+// the CTA's entry of a GeomBatch: CTA b works on entry g with cta_prefix[g] <= b < cta_prefix[g + 1]
+__device__ __forceinline__ uint32_t batch_entry_of_cta(const GeomBatch& hb) {
   uint32_t lo = 0, hi = hb.n;
   while (hi - lo > 1) {
     const uint32_t mid = (lo + hi) >> 1;
     if (blockIdx.x >= hb.cta_prefix[mid]) lo = mid; else hi = mid;
   }
-  // the draw's parameter block, staged once per CTA: every later field access is a shared-memory broadcast
-  __shared__ GeomParams s_params;
-  {
-    const GeomParams* gsrc = draws + hb.draw_of[lo];
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(gsrc);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&s_params);
-    // the sampler block (vertex texture fetch) is the tail of the struct: staged only for draws that bind one
-    const bool has_sampler = gsrc->sampler0.tex.n_levels != 0;
-    const uint32_t n_words = (uint32_t)((has_sampler ? sizeof(GeomParams) : offsetof(GeomParams, sampler0)) / 4);
-    for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = __ldg(src + i);
-    if (!has_sampler && threadIdx.x == 0) s_params.sampler0.tex.n_levels = 0;
-  }
+  return lo;
+}
+// the draw's parameter block, staged once per CTA: every later field access is a shared-memory broadcast
+__device__ __forceinline__ void stage_geom_params(GeomParams& s_params, const GeomParams* gsrc) {
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(gsrc);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&s_params);
+  // the sampler block (vertex texture fetch) is the tail of the struct: staged only for draws that bind one
+  const bool has_sampler = gsrc->sampler0.tex.n_levels != 0;
+  const uint32_t n_words = (uint32_t)((has_sampler ? sizeof(GeomParams) : GEOM_PARAMS_HEAD_BYTES) / 4);
+  for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = __ldg(src + i);
+  if (!has_sampler && threadIdx.x == 0) s_params.sampler0.tex.n_levels = 0;
   __syncthreads();
+}
+
+// index_fetcher.cpp:26-115: the i-th index of the draw (already offset by start), plus base_vertex
+__device__ __forceinline__ uint32_t fetch_index(const GeomParams& p, uint32_t i) {
+  uint32_t v = i;
+  if (p.indices) {
+    const uint8_t* base = p.indices + (size_t)p.start * p.index_stride;
+    v = p.index_stride == 2 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(base) + i)
+                            : __ldg(reinterpret_cast<const uint32_t*>(base) + i);
+  }
+  return v + (uint32_t)p.base_vertex;
+}
+
+// ---- post-transform vertex cache (default_vertex_cache.cpp:128-197, the precomputed flavour: the vertex shader runs once per
+// distinct index of the draw).  k_vertex_mark flags the vertices the queued draws reference, k_vertex_shade runs the shader on
+// the flagged ones and stores clip-space position + attributes, k_geometry gathers.  Draws of a batch with the same vertex
+// state (streams, layout, program, uniforms) share ONE cache: a mesh drawn per material group is transformed once.
+constexpr int VC_MARK_PER_THREAD = 4;
+__global__ void __launch_bounds__(256) k_vertex_mark(const GeomParams* __restrict__ draws, GeomBatch hb) {
+  const uint32_t g = batch_entry_of_cta(hb);
+  const GeomParams& p = draws[hb.draw_of[g]];
+  const uint32_t n_idx = p.topology == SLV_TOPO_TRIANGLE_LIST ? p.prim_count * 3 : p.prim_count + 2;
+  uint8_t* flags = p.vc_flags;
+  const uint32_t cap = p.vc_cap;
+  const uint32_t base = (blockIdx.x - hb.cta_prefix[g]) * (256 * VC_MARK_PER_THREAD) + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < VC_MARK_PER_THREAD; ++k) {
+    const uint32_t i = base + k * 256;
+    if (i < n_idx) {
+      const uint32_t v = fetch_index(p, i);
+      if (v < cap) flags[v] = 1;  // same value from every writer: no atomic needed
+    }
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void vertex_shade_main(const GeomParams* __restrict__ draws, const GeomBatch& hb) {
+  const uint32_t g = batch_entry_of_cta(hb);
+  __shared__ GeomParams s_params;
+  stage_geom_params(s_params, draws + hb.draw_of[g]);
+  const GeomParams& p = s_params;
+  const uint32_t v = (blockIdx.x - hb.cta_prefix[g]) * blockDim.x + threadIdx.x;
+  uint32_t ran = 0;
+  if (v < p.vc_cap && p.vc_flags[v]) {
+    p.vc_flags[v] = 0;  // self-cleaning: the next batch that uses this scratch set starts from zeroed marks
+    VsOut<R> o;
+    run_vs<R>(p, v, o);
+    const_cast<float4*>(p.vc_pos)[v] = o.r[0];
+    float4* a = const_cast<float4*>(p.vc_attr) + (size_t)v * (R - 1);
+#pragma unroll
+    for (int i = 1; i < R; ++i) a[i - 1] = o.r[i];
+    ran = 1;
+  }
+  const uint32_t n = __popc(__ballot_sync(0xFFFFFFFFu, ran));
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(&p.stats[17], (unsigned long long)n);  // vs_invocations of cached draws
+}
+template <int R>
+__global__ void __launch_bounds__(128) k_vertex_shade(const GeomParams* __restrict__ draws, GeomBatch hb) {
+  vertex_shade_main<R>(draws, hb);
+}
+
+template <int R>
+__device__ __forceinline__ void geometry_main(const GeomParams* __restrict__ draws, const GeomBatch& hb) {
+  // every queued draw with R registers shares this launch; a CTA belongs to exactly one draw
+  const uint32_t lo = batch_entry_of_cta(hb);
+  __shared__ GeomParams s_params;
+  stage_geom_params(s_params, draws + hb.draw_of[lo]);
   const GeomParams& p = s_params;
   uint32_t prim = (blockIdx.x - hb.cta_prefix[lo]) * blockDim.x + threadIdx.x;
   uint32_t n_out = 0, valid_mask = 0;  // valid_mask bit k: slot prim*3+k holds a triangle binned on this rank
@@ -399,24 +464,23 @@ __device__ __forceinline__ void geometry_main(const GeomParams* __restrict__ dra
     }
     uint32_t idx[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      uint32_t v = ids[i];
-      if (p.indices) {
-        const uint8_t* base = p.indices + (size_t)p.start * p.index_stride;
-        v = p.index_stride == 2 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(base) + ids[i])
-                                : __ldg(reinterpret_cast<const uint32_t*>(base) + ids[i]);
-      }
-      idx[i] = v + (uint32_t)p.base_vertex;
-    }
-    // ---- vertex fetch + vertex shader, recomputed per corner (VS is pure, so this equals the
-    //      reference's post-transform cache hit: default_vertex_cache.cpp:354-390).  Positions first: most primitives
-    //      are culled, degenerate or (sort-first) outside this rank's tiles and never need their attributes.
+    for (int i = 0; i < 3; ++i) idx[i] = fetch_index(p, ids[i]);
+    // ---- post-transform vertices: gathered from the vertex cache when the draw has one (k_vertex_shade ran the shader once per
+    //      referenced vertex), else vertex fetch + vertex shader recomputed per corner (the VS is pure, so both equal the
+    //      reference's cache hit: default_vertex_cache.cpp:354-390).  Positions first: most primitives are culled, degenerate
+    //      or (sort-first) outside this rank's tiles and never need their attributes.
+    const bool use_vc = p.vc_pos != nullptr && idx[0] < p.vc_cap && idx[1] < p.vc_cap && idx[2] < p.vc_cap;
     float4 cpos[3];
+    if (use_vc) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      VsOut<R> t;
-      run_vs<R, true>(p, idx[i], t);
-      cpos[i] = t.r[0];
+      for (int i = 0; i < 3; ++i) cpos[i] = __ldg(p.vc_pos + idx[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        VsOut<R> t;
+        run_vs<R, true>(p, idx[i], t);
+        cpos[i] = t.r[0];
+      }
     }
 
     float4* rec = p.tris + ((size_t)p.slot_base + (size_t)prim * 3) * p.tri_stride;
@@ -448,9 +512,19 @@ __device__ __forceinline__ void geometry_main(const GeomParams* __restrict__ dra
         TriPos ts;
         if (setup_position(p, spos, ts)) {
           VsOut<R> o[3];
+          if (use_vc) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const float4* a = p.vc_attr + (size_t)oi[k] * (R - 1);
+#pragma unroll
+              for (int i = 1; i < R; ++i) o[k].r[i] = __ldg(a + (i - 1));
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) run_vs<R>(p, oi[k], o[k]);
+          }
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            run_vs<R>(p, oi[k], o[k]);
             o[k].r[0] = spos[k];
             project_attrs<R>(p, o[k], spos[k].w);
           }
@@ -463,7 +537,16 @@ __device__ __forceinline__ void geometry_main(const GeomParams* __restrict__ dra
       VsOut<R> pool[2][5];
       int n[2] = {3, 0};
 #pragma unroll 1
-      for (int i = 0; i < 3; ++i) run_vs<R>(p, idx[i], pool[0][i]);
+      for (int i = 0; i < 3; ++i) {
+        if (use_vc) {
+          pool[0][i].r[0] = __ldg(p.vc_pos + idx[i]);
+          const float4* a = p.vc_attr + (size_t)idx[i] * (R - 1);
+#pragma unroll
+          for (int k = 1; k < R; ++k) pool[0][i].r[k] = __ldg(a + (k - 1));
+        } else {
+          run_vs<R>(p, idx[i], pool[0][i]);
+        }
+      }
       int src = 0, dst = 1;
       bool is_front = false, culled = false;
       for (int pl = 0; pl < 2 && !culled; ++pl) {
