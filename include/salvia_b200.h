@@ -317,6 +317,22 @@ slv_result slv_sampler_create(slv_device dev, const slv_sampler_desc* desc, slv_
 #define SLV_PROGRAM_JIT(module) (0x80000000u | (uint32_t)(module))
 slv_result slv_shader_module_load(slv_device dev, uint32_t stage, const void* image, size_t bytes, uint32_t n_vs_output_attrs,
                                   slv_handle* out);
+/* compile(code, profile) (renderer.h:136-147) IN PROCESS: `device_code` is what the SASL front end generates for one shader
+ * (salviarenderer_b200/sasl: the scalarised body of slv_jit_vs / slv_jit_ps); the library compiles it with NVRTC together with
+ * its own pipeline-kernel sources (embedded in the library at build time) for sm_100a under the library's numerics flags, so the
+ * shader is inlined into k_geometry / k_vertex_shade or k_raster / k_shade exactly like a built-in program.  No nvcc, no
+ * subprocess, no GPU needed to compile.  slv_shader_compile_cubin returns the image (malloc'ed: slv_free) - the same bytes
+ * slv_shader_module_load takes; slv_shader_compile = compile + load.  flags: SLV_COMPILE_DERIV_CPP selects the cpp-shader
+ * derivative convention (ddx = q1 - q0, ddy = q2 - q0 for the whole quad) instead of SASL's per row / per column.  `log`
+ * (optional) receives the compiler's diagnostics, NUL-terminated.  Compiled images are cached on disk by content hash in
+ * $SLV_JIT_CACHE (else $XDG_CACHE_HOME/salvia_b200_jit, else ~/.cache/salvia_b200_jit; only a directory the user owns and nobody
+ * else can write).  SLV_FAILED when libnvrtc is unavailable or the code does not compile.  CPU checkers: SLV_FAILED. */
+#define SLV_COMPILE_DERIV_CPP 1u
+slv_result slv_shader_compile_cubin(uint32_t stage, const char* device_code, uint32_t n_vs_output_attrs, uint32_t flags,
+                                    void** image, size_t* bytes, char* log, size_t log_bytes);
+slv_result slv_shader_compile(slv_device dev, uint32_t stage, const char* device_code, uint32_t n_vs_output_attrs, uint32_t flags,
+                              slv_handle* out, char* log, size_t log_bytes);
+void slv_free(void* p);
 slv_result slv_resource_release(slv_device dev, slv_handle h);
 
 /* renderer::draw / draw_index -> commit_state_and_command() (renderer_impl.cpp:337-353) */

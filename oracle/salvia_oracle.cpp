@@ -1809,6 +1809,9 @@ slv_result slv_readback_fence(slv_device, slv_handle) { return SLV_OK; }
 slv_result slv_peer_export_texture(slv_device, slv_handle, uint32_t, uint8_t*) { return SLV_FAILED; }
 slv_result slv_peer_export_flags(slv_device, uint8_t*) { return SLV_FAILED; }
 slv_result slv_shader_module_load(slv_device, uint32_t, const void*, size_t, uint32_t, slv_handle*) { return SLV_FAILED; }
+slv_result slv_shader_compile_cubin(uint32_t, const char*, uint32_t, uint32_t, void**, size_t*, char*, size_t) { return SLV_FAILED; }
+slv_result slv_shader_compile(slv_device, uint32_t, const char*, uint32_t, uint32_t, slv_handle*, char*, size_t) { return SLV_FAILED; }
+void slv_free(void* p) { free(p); }
 slv_result slv_peer_open(slv_device, const uint8_t*, void**) { return SLV_FAILED; }
 slv_result slv_peer_close(slv_device, void*) { return SLV_FAILED; }
 slv_result slv_resolve_target_peer(slv_device, slv_handle, void*) { return SLV_FAILED; }

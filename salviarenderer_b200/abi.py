@@ -136,7 +136,7 @@ ENTRY_POINTS = [
     "slv_traffic_get", "slv_kernel_launch_count", "slv_event_record", "slv_event_elapsed_ms", "slv_profile_enable",
     "slv_texture_device_ptr", "slv_pack_tiles", "slv_unpack_tiles", "slv_set_stream", "slv_profile_get_stages",
     "slv_peer_export_texture", "slv_peer_export_flags", "slv_peer_open", "slv_peer_close", "slv_resolve_target_peer",
-    "slv_peer_signal", "slv_flags_wait", "slv_shader_module_load", "slv_texture_readback_async", "slv_readback_wait",
+    "slv_peer_signal", "slv_flags_wait", "slv_shader_module_load", "slv_shader_compile_cubin", "slv_shader_compile", "slv_free", "slv_texture_readback_async", "slv_readback_wait",
     "slv_readback_fence", "slv_host_register", "slv_host_unregister", "slv_texture_export_tiles_async",
     "slv_assembly_wait", "slv_peer_signal_after_consumers",
     "slv_buffer_device_ptr", "slv_external_write_begin", "slv_external_write_end",
@@ -217,7 +217,7 @@ class Backend:
         L.slv_device_destroy.argtypes = [C.c_void_p]
         for n in ENTRY_POINTS:
             f = getattr(L, n)
-            if n not in ("slv_backend_name", "slv_abi_version", "slv_device_destroy"):
+            if n not in ("slv_backend_name", "slv_abi_version", "slv_device_destroy", "slv_free"):
                 f.restype = C.c_int32
         L.slv_buffer_create.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)]
         L.slv_buffer_upload.argtypes = [C.c_void_p, C.c_uint32, C.c_size_t, C.c_void_p, C.c_size_t]
@@ -263,6 +263,11 @@ class Backend:
         L.slv_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
         L.slv_texture_export_tiles_async.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]
         L.slv_shader_module_load.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.slv_shader_compile_cubin.argtypes = [C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                               C.c_char_p, C.c_size_t]
+        L.slv_shader_compile.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_char_p, C.c_size_t]
+        L.slv_free.argtypes = [C.c_void_p]
+        L.slv_free.restype = None
         L.slv_peer_export_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.slv_peer_export_flags.argtypes = [C.c_void_p, C.c_void_p]
         L.slv_peer_open.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
@@ -429,6 +434,16 @@ class Backend:
         h = C.c_uint32()
         _chk(self.lib.slv_shader_module_load(self.dev, 0 if stage == "vs" else 1, image, len(image), n_vs_output_attrs, C.byref(h)),
              "slv_shader_module_load")
+        return h.value
+
+    def shader_compile(self, stage: str, device_code: str, n_vs_output_attrs: int = 0, deriv_cpp: bool = False) -> int:
+        """slv_shader_compile: NVRTC in process + module load; returns the module handle."""
+        h = C.c_uint32()
+        log = C.create_string_buffer(16384)
+        rc = self.lib.slv_shader_compile(self.dev, 0 if stage == "vs" else 1, device_code.encode(), n_vs_output_attrs, 1 if deriv_cpp else 0,
+                                         C.byref(h), log, len(log))
+        if rc != 0:
+            raise SlvError(f"slv_shader_compile failed ({rc}):\n{log.value.decode(errors='replace')[-4000:]}")
         return h.value
 
     # ---- peer-memory frame assembly (CUDA IPC; product only) ----

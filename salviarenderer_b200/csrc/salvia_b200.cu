@@ -19,7 +19,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
+
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "salvia_b200.h"
 #include "slv_kernels.cuh"
@@ -1320,6 +1324,189 @@ slv_result slv_shader_module_load(slv_device dev, uint32_t stage, const void* im
   *out = (slv_handle)(dev->res.size() - 1);
   return SLV_OK;
 }
+
+// ---- run-time shader compilation in process (NVRTC) -------------------------------------------------------------------------
+namespace {
+#include "slv_embedded_sources.inc"
+
+// the NVRTC entry points, bound on first use (no link-time dependency: a machine without the toolkit still loads the library)
+struct NvrtcApi {
+  typedef void* Program;
+  int (*CreateProgram)(Program*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  int (*CompileProgram)(Program, int, const char* const*) = nullptr;
+  int (*GetProgramLogSize)(Program, size_t*) = nullptr;
+  int (*GetProgramLog)(Program, char*) = nullptr;
+  int (*GetCUBINSize)(Program, size_t*) = nullptr;
+  int (*GetCUBIN)(Program, char*) = nullptr;
+  int (*DestroyProgram)(Program*) = nullptr;
+  bool ok = false;
+};
+NvrtcApi& nvrtc_api() {
+  static NvrtcApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* env = getenv("SLV_NVRTC_LIB");
+    const char* names[] = {env, "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so"};
+    void* h = nullptr;
+    for (const char* n : names)
+      if (n && !h) h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+    if (h) {
+      api.CreateProgram = (decltype(api.CreateProgram))dlsym(h, "nvrtcCreateProgram");
+      api.CompileProgram = (decltype(api.CompileProgram))dlsym(h, "nvrtcCompileProgram");
+      api.GetProgramLogSize = (decltype(api.GetProgramLogSize))dlsym(h, "nvrtcGetProgramLogSize");
+      api.GetProgramLog = (decltype(api.GetProgramLog))dlsym(h, "nvrtcGetProgramLog");
+      api.GetCUBINSize = (decltype(api.GetCUBINSize))dlsym(h, "nvrtcGetCUBINSize");
+      api.GetCUBIN = (decltype(api.GetCUBIN))dlsym(h, "nvrtcGetCUBIN");
+      api.DestroyProgram = (decltype(api.DestroyProgram))dlsym(h, "nvrtcDestroyProgram");
+      api.ok = api.CreateProgram && api.CompileProgram && api.GetProgramLogSize && api.GetProgramLog && api.GetCUBINSize && api.GetCUBIN &&
+               api.DestroyProgram;
+    }
+  }
+  return api;
+}
+
+// the few host headers the embedded sources name: NVRTC has no system include path, its built-ins cover the rest
+const char kShimStdint[] =
+    "#pragma once\n"
+    "typedef signed char int8_t; typedef unsigned char uint8_t; typedef short int16_t; typedef unsigned short uint16_t;\n"
+    "typedef int int32_t; typedef unsigned int uint32_t; typedef long long int64_t; typedef unsigned long long uint64_t;\n"
+    "typedef unsigned long uintptr_t; typedef long intptr_t;\n";
+const char kShimEmpty[] = "#pragma once\n";
+
+uint64_t fnv1a(const void* data, size_t n, uint64_t h) {
+  const unsigned char* p = (const unsigned char*)data;
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+// cache directory of compiled images: used only when this user owns it and nobody else can write to it (an image is code that
+// runs in the process's GPU context)
+std::string jit_cache_dir() {
+  std::string d;
+  if (const char* e = getenv("SLV_JIT_CACHE")) d = e;
+  else if (const char* x = getenv("XDG_CACHE_HOME")) d = std::string(x) + "/salvia_b200_jit";
+  else if (const char* hme = getenv("HOME")) { std::string c = std::string(hme) + "/.cache"; mkdir(c.c_str(), 0700); d = c + "/salvia_b200_jit"; }
+  if (d.empty()) return d;
+  mkdir(d.c_str(), 0700);
+  struct stat st;
+  if (stat(d.c_str(), &st) != 0 || !S_ISDIR(st.st_mode) || st.st_uid != getuid() || (st.st_mode & 022)) return std::string();
+  return d;
+}
+bool trusted_file(const std::string& path, struct stat* st) {
+  return stat(path.c_str(), st) == 0 && S_ISREG(st->st_mode) && st->st_uid == getuid() && !(st->st_mode & 022);
+}
+void put_log(char* log, size_t log_bytes, const std::string& text) {
+  if (!log || !log_bytes) return;
+  const size_t n = std::min(text.size(), log_bytes - 1);
+  memcpy(log, text.data(), n);
+  log[n] = 0;
+}
+}  // namespace
+
+slv_result slv_shader_compile_cubin(uint32_t stage, const char* device_code, uint32_t n_vs_output_attrs, uint32_t flags, void** image,
+                                    size_t* bytes, char* log, size_t log_bytes) {
+  if (log && log_bytes) log[0] = 0;
+  if (!device_code || !image || !bytes || (stage != SLV_STAGE_VS && stage != SLV_STAGE_PS)) return SLV_INVALID_PARAMETER;
+  if (stage == SLV_STAGE_VS && n_vs_output_attrs > SLV_MAX_VS_OUTPUT_ATTRS) return SLV_INVALID_PARAMETER;
+  *image = nullptr;
+  *bytes = 0;
+  // ---- options: the library's own numerics flags (Makefile), the stage, the register count
+  std::vector<std::string> opts = {"-arch=sm_100a", "-std=c++17", "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false", "-lineinfo",
+                                   "-DSLV_JIT_GENERATED=\"slv_generated_shader.cuh\""};
+  if (stage == SLV_STAGE_VS) {
+    opts.push_back("-DSLV_JIT_VS=1");
+    opts.push_back("-DSLV_JIT_R=" + std::to_string(n_vs_output_attrs + 1));
+  } else {
+    opts.push_back("-DSLV_JIT_PS=1");
+    if (flags & SLV_COMPILE_DERIV_CPP) opts.push_back("-DSLV_JIT_DERIV_CPP=1");
+  }
+  // ---- disk cache, keyed by the generated code, the options and the embedded sources
+  uint64_t h1 = 14695981039346656037ull, h2 = 0x9E3779B97F4A7C15ull;
+  h1 = fnv1a(device_code, strlen(device_code), h1);
+  h2 = fnv1a(device_code, strlen(device_code), h2);
+  for (const std::string& o : opts) { h1 = fnv1a(o.data(), o.size() + 1, h1); h2 = fnv1a(o.data(), o.size() + 1, h2); }
+  for (const EmbeddedSource& e : kEmbeddedSources) { h1 = fnv1a(e.text, strlen(e.text), h1); h2 = fnv1a(e.text, strlen(e.text), h2); }
+  char key[40];
+  snprintf(key, sizeof(key), "n%016llx%08llx", (unsigned long long)h1, (unsigned long long)(h2 >> 32));
+  const std::string cdir = jit_cache_dir();
+  const std::string cpath = cdir.empty() ? std::string() : cdir + "/" + key + ".cubin";
+  struct stat st;
+  if (!cpath.empty() && trusted_file(cpath, &st) && st.st_size > 0) {
+    if (FILE* f = fopen(cpath.c_str(), "rb")) {
+      void* buf = malloc((size_t)st.st_size);
+      const bool got = buf && fread(buf, 1, (size_t)st.st_size, f) == (size_t)st.st_size;
+      fclose(f);
+      if (got) { *image = buf; *bytes = (size_t)st.st_size; return SLV_OK; }
+      free(buf);
+    }
+  }
+  NvrtcApi& api = nvrtc_api();
+  if (!api.ok) {
+    put_log(log, log_bytes, "libnvrtc.so.12 is not available (set SLV_NVRTC_LIB): run-time shader compilation needs the CUDA toolkit's NVRTC");
+    return SLV_FAILED;
+  }
+  // ---- the program: slv_jit_unit.cu + every other embedded source, the generated shader and the header shims as named headers
+  const char* main_src = nullptr;
+  std::vector<const char*> h_text, h_name;
+  for (const EmbeddedSource& e : kEmbeddedSources) {
+    if (!strcmp(e.name, "slv_jit_unit.cu")) { main_src = e.text; continue; }
+    h_text.push_back(e.text);
+    h_name.push_back(e.name);
+  }
+  const std::pair<const char*, const char*> shims[] = {{"slv_generated_shader.cuh", device_code}, {"stdint.h", kShimStdint}, {"cstdint", kShimStdint},
+                                                       {"stddef.h", kShimEmpty}, {"cuda_runtime.h", kShimEmpty}, {"cmath", kShimEmpty},
+                                                       {"cstring", kShimEmpty}};
+  for (auto& sh : shims) { h_name.push_back(sh.first); h_text.push_back(sh.second); }
+  NvrtcApi::Program prog = nullptr;
+  if (!main_src || api.CreateProgram(&prog, main_src, "slv_jit_unit.cu", (int)h_text.size(), h_text.data(), h_name.data()) != 0) return SLV_FAILED;
+  std::vector<const char*> copts;
+  for (const std::string& o : opts) copts.push_back(o.c_str());
+  const int rc = api.CompileProgram(prog, (int)copts.size(), copts.data());
+  size_t ln = 0;
+  if (api.GetProgramLogSize(prog, &ln) == 0 && ln > 1) {
+    std::string text(ln, '\0');
+    api.GetProgramLog(prog, &text[0]);
+    put_log(log, log_bytes, text);
+  }
+  slv_result res = SLV_FAILED;
+  size_t n = 0;
+  if (rc == 0 && api.GetCUBINSize(prog, &n) == 0 && n) {
+    void* buf = malloc(n);
+    if (buf && api.GetCUBIN(prog, (char*)buf) == 0) {
+      *image = buf;
+      *bytes = n;
+      res = SLV_OK;
+      if (!cpath.empty()) {  // unique temporary name, then an atomic rename: concurrent compiles never expose a partial file
+        const std::string tmp = cpath + "." + std::to_string((long long)getpid()) + ".tmp";
+        if (FILE* f = fopen(tmp.c_str(), "wb")) {
+          const bool wrote = fwrite(buf, 1, n, f) == n;
+          fclose(f);
+          chmod(tmp.c_str(), 0600);
+          if (!wrote || rename(tmp.c_str(), cpath.c_str()) != 0) unlink(tmp.c_str());
+        }
+      }
+    } else {
+      free(buf);
+    }
+  }
+  api.DestroyProgram(&prog);
+  return res;
+}
+
+slv_result slv_shader_compile(slv_device dev, uint32_t stage, const char* device_code, uint32_t n_vs_output_attrs, uint32_t flags,
+                              slv_handle* out, char* log, size_t log_bytes) {
+  if (!dev || !out) return SLV_INVALID_PARAMETER;
+  void* image = nullptr;
+  size_t bytes = 0;
+  slv_result rc = slv_shader_compile_cubin(stage, device_code, n_vs_output_attrs, flags, &image, &bytes, log, log_bytes);
+  if (rc != SLV_OK) return rc;
+  rc = slv_shader_module_load(dev, stage, image, bytes, n_vs_output_attrs, out);
+  free(image);
+  return rc;
+}
+
+void slv_free(void* p) { free(p); }
 
 slv_result slv_resource_release(slv_device dev, slv_handle h) {
   if (!dev || h == 0 || h >= dev->res.size()) return SLV_INVALID_PARAMETER;

@@ -19,11 +19,16 @@
 #pragma once
 
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <map>
 #include <memory>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <typeindex>
@@ -80,7 +85,7 @@ struct abi_table {
   SLV_HOST_FN(slv_texture_level_count) SLV_HOST_FN(slv_texture_level_size) SLV_HOST_FN(slv_texture_upload) SLV_HOST_FN(slv_texture_readback)
   SLV_HOST_FN(slv_sampler_create) SLV_HOST_FN(slv_resource_release) SLV_HOST_FN(slv_draw) SLV_HOST_FN(slv_clear_color)
   SLV_HOST_FN(slv_clear_depth_stencil) SLV_HOST_FN(slv_resolve) SLV_HOST_FN(slv_flush) SLV_HOST_FN(slv_query_begin) SLV_HOST_FN(slv_query_get)
-  SLV_HOST_FN(slv_profile_get) SLV_HOST_FN(slv_shader_module_load)
+  SLV_HOST_FN(slv_profile_get) SLV_HOST_FN(slv_shader_module_load) SLV_HOST_FN(slv_shader_compile)
 #undef SLV_HOST_FN
   explicit abi_table(const std::string& path) {
     lib = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
@@ -93,7 +98,7 @@ struct abi_table {
     SLV_HOST_BIND(slv_texture_level_count) SLV_HOST_BIND(slv_texture_level_size) SLV_HOST_BIND(slv_texture_upload) SLV_HOST_BIND(slv_texture_readback)
     SLV_HOST_BIND(slv_sampler_create) SLV_HOST_BIND(slv_resource_release) SLV_HOST_BIND(slv_draw) SLV_HOST_BIND(slv_clear_color)
     SLV_HOST_BIND(slv_clear_depth_stencil) SLV_HOST_BIND(slv_resolve) SLV_HOST_BIND(slv_flush) SLV_HOST_BIND(slv_query_begin) SLV_HOST_BIND(slv_query_get)
-    SLV_HOST_BIND(slv_profile_get) SLV_HOST_BIND(slv_shader_module_load)
+    SLV_HOST_BIND(slv_profile_get) SLV_HOST_BIND(slv_shader_module_load) SLV_HOST_BIND(slv_shader_compile)
 #undef SLV_HOST_BIND
   }
   ~abi_table() { if (lib) dlclose(lib); }
@@ -360,6 +365,16 @@ public:
   size_t pack_uniforms(uint8_t* dst, size_t) const override { slv_ps_sponza_uniforms u{sampler_ ? 1u : 0u}; std::memcpy(dst, &u, sizeof(u)); return sizeof(u); }
   void samplers(slv_handle (&out)[SLV_MAX_SAMPLERS]) const override { out[0] = sampler_ ? sampler_->handle() : 0; }
 };
+// tex2D(samp, uv) * saturate(dot(normalize(light), normalize(normal))): the cpp twin of the SASL pixel shader BASELINE configs[3]
+// runs (sample_2d_grad with per-pixel derivatives; sasl_derivatives selects the per row / per column convention)
+class ps_sponza_grad : public cpp_pixel_shader {
+public:
+  sampler_ptr sampler_; bool sasl_derivatives;
+  explicit ps_sponza_grad(bool sasl_deriv = true) : sasl_derivatives(sasl_deriv) { declare_sampler("texSamp", sampler_); }
+  uint32_t device_program() const override { return SLV_PS_SPONZA_GRAD; }
+  size_t pack_uniforms(uint8_t* dst, size_t) const override { slv_ps_sponza_grad_uniforms u{sampler_ ? 1u : 0u, sasl_derivatives ? 1u : 0u}; std::memcpy(dst, &u, sizeof(u)); return sizeof(u); }
+  void samplers(slv_handle (&out)[SLV_MAX_SAMPLERS]) const override { out[0] = sampler_ ? sampler_->handle() : 0; }
+};
 class ps_ssm_draw : public cpp_pixel_shader {  // draw_cpp_ps, samples/StandardShadowMap/StandardShadowMap.cpp:62-142 (two samplers)
 public:
   vec4 ambient, diffuse, specular; int shininess = 0; sampler_ptr texsamp_, dsamp_;
@@ -388,26 +403,149 @@ public:
 };
 class bs_replace : public cpp_blend_shader { public: uint32_t device_program() const override { return SLV_BS_REPLACE; } };          // ColorizedTriangle.cpp:94-106
 class bs_lerp_src_alpha : public cpp_blend_shader { public: uint32_t device_program() const override { return SLV_BS_LERP_SRC_ALPHA; } };  // TextureAndBlending.cpp:168-180
-// A SASL shader compiled at run time (salviarenderer_b200/sasl): module handle from slv_shader_module_load, globals set by name
-// with the (offset, size) table of the compiler's reflection.
-class jit_vertex_shader : public cpp_vertex_shader {
+// ---- SASL (renderer.h:75-86,136-147; salvia/include/salvia/shader/shader_object.h) -----------------------------------------------
+// compile(code, profile) runs the SASL front end (salviarenderer_b200/sasl, a Python package: `python3 -m
+// salviarenderer_b200.sasl.emit`, found through $SLV_SASL_PYTHON / $PYTHONPATH) and returns a shader_object holding the
+// reflection (uniform layout, sampler slots, input semantics) and the generated device code.  set_vertex_shader_code /
+// set_pixel_shader_code hand that code to slv_shader_compile (NVRTC, in process) once per renderer and bind the module.
+namespace shader {
+enum languages { lang_none, lang_general, lang_vertex_shader, lang_pixel_shader, lang_blending_shader };
+struct shader_profile { languages language = lang_none; };
+class shader_object {
 public:
-  jit_vertex_shader(slv_handle module, uint32_t n_attrs, size_t uniform_bytes) : module_(module), n_attrs_(n_attrs), block_(uniform_bytes) {}
+  struct uniform { std::string type; size_t offset = 0, size = 0; };
+  struct semantic_slot { std::string semantic; uint32_t index = 0, slot = 0; };
+  languages language = lang_none;
+  std::string device_code;
+  uint32_t n_vs_output_attrs = 0;
+  size_t uniform_bytes = 0;
+  bool uses_derivatives = false;
+  std::map<std::string, uniform> uniforms;
+  std::vector<std::string> samplers;       // slot order
+  std::vector<semantic_slot> inputs;       // VS: semantic -> input register; PS: semantic -> attribute
+  std::vector<semantic_slot> outputs;
+};
+using shader_object_ptr = std::shared_ptr<shader_object>;
+using shader_log_ptr = std::shared_ptr<std::string>;
+
+inline shader_object_ptr compile(std::string const& code, shader_profile const& profile, shader_log_ptr& logs) {
+  logs = std::make_shared<std::string>();
+  if (profile.language != lang_vertex_shader && profile.language != lang_pixel_shader) { *logs = "only vertex and pixel shaders are compiled"; return nullptr; }
+  // the front end reads the source from a file and writes the unit to stdout
+  char src_path[] = "/tmp/slv_sasl_XXXXXX";
+  int fd = mkstemp(src_path);
+  if (fd < 0) { *logs = "cannot create a temporary file"; return nullptr; }
+  FILE* sf = fdopen(fd, "w");
+  fwrite(code.data(), 1, code.size(), sf);
+  fclose(sf);
+  const char* py = getenv("SLV_SASL_PYTHON");
+  std::string cmd = std::string(py ? py : "python3") + " -m salviarenderer_b200.sasl.emit " + (profile.language == lang_vertex_shader ? "vs" : "ps") + " < " + src_path + " 2>&1";
+  FILE* pf = popen(cmd.c_str(), "r");
+  std::string out;
+  if (pf) {
+    char buf[4096];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof(buf), pf)) > 0) out.append(buf, n);
+    pclose(pf);
+  }
+  unlink(src_path);
+  if (out.compare(0, 10, "SLVSASL 1\n") != 0) { *logs = out.empty() ? "the SASL front end did not run (python3 -m salviarenderer_b200.sasl.emit)" : out; return nullptr; }
+  auto obj = std::make_shared<shader_object>();
+  obj->language = profile.language;
+  size_t pos = 10;
+  while (pos < out.size()) {
+    size_t eol = out.find('\n', pos);
+    if (eol == std::string::npos) eol = out.size();
+    std::istringstream ln(out.substr(pos, eol - pos));
+    pos = eol + 1;
+    std::string key;
+    ln >> key;
+    if (key == "n_vs_output_attrs") ln >> obj->n_vs_output_attrs;
+    else if (key == "uniform_bytes") ln >> obj->uniform_bytes;
+    else if (key == "uses_derivatives") { int v = 0; ln >> v; obj->uses_derivatives = v != 0; }
+    else if (key == "uniform") { std::string name; shader_object::uniform u; ln >> name >> u.type >> u.offset >> u.size; obj->uniforms[name] = u; }
+    else if (key == "sampler") { size_t slot; std::string name; ln >> slot >> name; if (obj->samplers.size() <= slot) obj->samplers.resize(slot + 1); obj->samplers[slot] = name; }
+    else if (key == "input" || key == "output") { shader_object::semantic_slot x; ln >> x.semantic >> x.index >> x.slot; (key == "input" ? obj->inputs : obj->outputs).push_back(x); }
+    else if (key == "code") { size_t n = 0; ln >> n; obj->device_code = out.substr(pos, n); break; }
+  }
+  if (obj->device_code.empty()) { *logs = "malformed output of the SASL front end"; return nullptr; }
+  return obj;
+}
+inline shader_object_ptr compile(std::string const& code, shader_profile const& profile) { shader_log_ptr l; return compile(code, profile, l); }
+inline shader_object_ptr compile(std::string const& code, languages lang) { shader_profile p; p.language = lang; return compile(code, p); }
+inline shader_object_ptr compile_from_file(std::string const& file_name, shader_profile const& profile, shader_log_ptr& logs) {
+  std::ifstream f(file_name);
+  if (!f) { logs = std::make_shared<std::string>("cannot open " + file_name); return nullptr; }
+  std::stringstream ss;
+  ss << f.rdbuf();
+  return compile(ss.str(), profile, logs);
+}
+inline shader_object_ptr compile_from_file(std::string const& file_name, shader_profile const& profile) { shader_log_ptr l; return compile_from_file(file_name, profile, l); }
+inline shader_object_ptr compile_from_file(std::string const& file_name, languages lang) { shader_profile p; p.language = lang; return compile_from_file(file_name, p); }
+}  // namespace shader
+
+// A SASL shader bound to a device: module handle (slv_shader_compile / slv_shader_module_load), globals set by name with the
+// (offset, size) table of the compiler's reflection - by value (set_*_variable_value) or by pointer, read at every draw
+// (set_vs_variable_pointer, renderer.h:79) - and samplers by name in the reflection's slot order.
+class jit_uniform_block {
+public:
+  explicit jit_uniform_block(size_t uniform_bytes) : block_(uniform_bytes) {}
   void declare_uniform(std::string const& name, size_t offset, size_t size) { layout_[name] = {offset, size}; }
   result set_uniform(std::string const& name, void const* v, size_t size) {
     auto it = layout_.find(name);
     if (it == layout_.end() || it->second.second != size) return result::failed;
+    pointers_.erase(name);
     std::memcpy(block_.data() + it->second.first, v, size);
     return result::ok;
   }
-  void declare_sampler_name(std::string const& name) { declare_sampler(name, sampler_); }  // the shader's `sampler` global (slot 0)
-  void samplers(slv_handle (&out)[SLV_MAX_SAMPLERS]) const override { out[0] = sampler_ ? sampler_->handle() : 0; }
+  result set_uniform_pointer(std::string const& name, void const* v, size_t size) {
+    auto it = layout_.find(name);
+    if (it == layout_.end() || it->second.second != size) return result::failed;
+    pointers_[name] = v;
+    return result::ok;
+  }
+  size_t pack(uint8_t* dst, size_t cap) const {
+    size_t n = block_.size() < cap ? block_.size() : cap;
+    std::memcpy(dst, block_.data(), n);
+    for (auto const& p : pointers_) {
+      auto const& l = layout_.at(p.first);
+      if (l.first + l.second <= n) std::memcpy(dst + l.first, p.second, l.second);
+    }
+    return n;
+  }
+  void declare_sampler_slot(std::string const& name, size_t slot) { sampler_slots_[name] = slot; if (samplers_.size() <= slot) samplers_.resize(slot + 1); }
+  result set_sampler_by_name(std::string const& name, sampler_ptr const& s) {
+    auto it = sampler_slots_.find(name);
+    if (it == sampler_slots_.end()) return result::failed;
+    samplers_[it->second] = s;
+    return result::ok;
+  }
+  void sampler_handles(slv_handle (&out)[SLV_MAX_SAMPLERS]) const {
+    for (size_t i = 0; i < samplers_.size() && i < SLV_MAX_SAMPLERS; ++i) out[i] = samplers_[i] ? samplers_[i]->handle() : 0;
+  }
+private:
+  std::vector<uint8_t> block_; std::map<std::string, std::pair<size_t, size_t>> layout_; std::map<std::string, void const*> pointers_;
+  std::map<std::string, size_t> sampler_slots_; std::vector<sampler_ptr> samplers_;
+};
+class jit_vertex_shader : public cpp_vertex_shader, public jit_uniform_block {
+public:
+  jit_vertex_shader(slv_handle module, uint32_t n_attrs, size_t uniform_bytes) : jit_uniform_block(uniform_bytes), module_(module), n_attrs_(n_attrs) {}
+  void declare_sampler_name(std::string const& name) { declare_sampler_slot(name, 0); }  // the shader's `sampler` global (slot 0)
+  void samplers(slv_handle (&out)[SLV_MAX_SAMPLERS]) const override { sampler_handles(out); }
   uint32_t device_program() const override { return SLV_PROGRAM_JIT(module_); }
   uint32_t num_output_attributes() const override { return n_attrs_; }
-  size_t pack_uniforms(uint8_t* dst, size_t cap) const override { size_t n = block_.size() < cap ? block_.size() : cap; std::memcpy(dst, block_.data(), n); return n; }
+  size_t pack_uniforms(uint8_t* dst, size_t cap) const override { return pack(dst, cap); }
 private:
-  slv_handle module_; uint32_t n_attrs_; std::vector<uint8_t> block_; std::map<std::string, std::pair<size_t, size_t>> layout_;
-  sampler_ptr sampler_;
+  slv_handle module_; uint32_t n_attrs_;
+};
+class jit_pixel_shader : public cpp_pixel_shader, public jit_uniform_block {
+public:
+  jit_pixel_shader(slv_handle module, size_t uniform_bytes) : jit_uniform_block(uniform_bytes), module_(module) {}
+  void samplers(slv_handle (&out)[SLV_MAX_SAMPLERS]) const override { sampler_handles(out); }
+  uint32_t device_program() const override { return SLV_PROGRAM_JIT(module_); }
+  size_t pack_uniforms(uint8_t* dst, size_t cap) const override { return pack(dst, cap); }
+private:
+  slv_handle module_;
 };
 
 // ---- input layout: input_element_descs resolved against the vertex shader's register map (stream_assembler.cpp:52-86) ----
@@ -460,6 +598,13 @@ public:
   async_object_ptr create_query(async_object_ids id) {
     if (id != async_object_ids::pipeline_statistics && id != async_object_ids::internal_statistics && id != async_object_ids::pipeline_profiles) return nullptr;
     return std::make_shared<async_object>(id);
+  }
+  // renderer.h:52-54: the layout is resolved against the SASL shader's input semantics (the reflection's register map)
+  input_layout_ptr create_input_layout(input_element_desc const* elem_descs, size_t elems_count, shader::shader_object_ptr const& code) {
+    if (!code) return nullptr;
+    auto probe = std::make_shared<jit_vertex_shader>(0, code->n_vs_output_attrs, 0);
+    for (auto const& in : code->inputs) probe->bind_semantic(in.semantic.c_str(), in.index, in.slot);
+    return create_input_layout(elem_descs, elems_count, cpp_vertex_shader_ptr(probe));
   }
   input_layout_ptr create_input_layout(input_element_desc const* elem_descs, size_t elems_count, cpp_vertex_shader_ptr const& vs) {
     auto l = std::make_shared<input_layout>();
@@ -517,21 +662,75 @@ public:
     return result::ok;
   }
   result set_input_layout(input_layout_ptr const& layout) { layout_ = layout; return result::ok; }
-  result set_vertex_shader(cpp_vertex_shader_ptr const& hvs) { vs_ = hvs; return result::ok; }
+  result set_vertex_shader(cpp_vertex_shader_ptr const& hvs) { vs_ = hvs; vs_code_.reset(); return result::ok; }
   result set_primitive_topology(primitive_topology primtopo) {  // renderer_impl.cpp:71-78
     if (primtopo != primitive_line_list && primtopo != primitive_line_strip && primtopo != primitive_triangle_list && primtopo != primitive_triangle_strip) return result::failed;
     topology_ = primtopo;
     return result::ok;
   }
-  result set_vs_variable_value(std::string const& name, void const* pvariable, size_t sz) { return vs_ ? vs_->set_constant_raw(name, pvariable, sz) : result::failed; }
+  result set_vs_variable_value(std::string const& name, void const* pvariable, size_t sz) {
+    if (auto j = dynamic_cast<jit_uniform_block*>(vs_.get())) return j->set_uniform(name, pvariable, sz);
+    return vs_ ? vs_->set_constant_raw(name, pvariable, sz) : result::failed;
+  }
+  // the pointed-to value is read at every draw (renderer.h:79; vx_shader_unit::set_variable_pointer)
+  result set_vs_variable_pointer(std::string const& name, void const* pvariable, size_t sz) {
+    if (auto j = dynamic_cast<jit_uniform_block*>(vs_.get())) return j->set_uniform_pointer(name, pvariable, sz);
+    return result::failed;
+  }
+  // SASL shaders (renderer.h:75,86): the generated device code is compiled in process (slv_shader_compile: NVRTC) the first
+  // time a shader_object is bound to this renderer; later binds reuse the module.  Fails on a library without run-time
+  // compilation (the CPU checkers).
+  result set_vertex_shader_code(shader::shader_object_ptr const& so) {
+    if (!so || so->language != shader::lang_vertex_shader) return result::invalid_parameter;
+    auto it = vs_code_cache_.find(so.get());
+    if (it == vs_code_cache_.end()) {
+      slv_handle module = 0;
+      slv_result rc = ctx_->abi->slv_shader_compile(ctx_->dev, SLV_STAGE_VS, so->device_code.c_str(), so->n_vs_output_attrs, 0, &module, compile_log_, sizeof(compile_log_));
+      if (rc != SLV_OK) return to_result(rc);
+      auto sh = std::make_shared<jit_vertex_shader>(module, so->n_vs_output_attrs, so->uniform_bytes);
+      for (auto const& u : so->uniforms) sh->declare_uniform(u.first, u.second.offset, u.second.size);
+      for (size_t i = 0; i < so->samplers.size(); ++i) sh->declare_sampler_slot(so->samplers[i], i);
+      for (auto const& in : so->inputs) sh->bind_semantic(in.semantic.c_str(), in.index, in.slot);
+      it = vs_code_cache_.emplace(so.get(), std::make_pair(so, sh)).first;
+    }
+    vs_ = it->second.second; vs_code_ = so;
+    return result::ok;
+  }
+  result set_pixel_shader_code(shader::shader_object_ptr const& so, bool cpp_derivatives = false) {
+    if (!so || so->language != shader::lang_pixel_shader) return result::invalid_parameter;
+    auto it = ps_code_cache_.find(so.get());
+    if (it == ps_code_cache_.end()) {
+      slv_handle module = 0;
+      slv_result rc = ctx_->abi->slv_shader_compile(ctx_->dev, SLV_STAGE_PS, so->device_code.c_str(), 0, cpp_derivatives ? SLV_COMPILE_DERIV_CPP : 0u, &module, compile_log_, sizeof(compile_log_));
+      if (rc != SLV_OK) return to_result(rc);
+      auto sh = std::make_shared<jit_pixel_shader>(module, so->uniform_bytes);
+      for (auto const& u : so->uniforms) sh->declare_uniform(u.first, u.second.offset, u.second.size);
+      for (size_t i = 0; i < so->samplers.size(); ++i) sh->declare_sampler_slot(so->samplers[i], i);
+      it = ps_code_cache_.emplace(so.get(), std::make_pair(so, sh)).first;
+    }
+    ps_ = it->second.second; ps_code_ = so;
+    return result::ok;
+  }
+  shader::shader_object_ptr get_vertex_shader_code() const { return vs_code_; }
+  shader::shader_object_ptr get_pixel_shader_code() const { return ps_code_; }
+  char const* shader_compile_log() const { return compile_log_; }
   template <typename T> result set_vs_variable(std::string const& name, T const* data) { return set_vs_variable_value(name, data, sizeof(T)); }
-  result set_ps_variable(std::string const& name, void const* data, size_t sz) { return ps_ ? ps_->set_constant_raw(name, data, sz) : result::failed; }
+  result set_ps_variable(std::string const& name, void const* data, size_t sz) {
+    if (auto j = dynamic_cast<jit_uniform_block*>(ps_.get())) return j->set_uniform(name, data, sz);
+    return ps_ ? ps_->set_constant_raw(name, data, sz) : result::failed;
+  }
   template <typename T> result set_ps_variable(std::string const& name, T const* data) { return set_ps_variable(name, static_cast<void const*>(data), sizeof(T)); }
-  result set_ps_sampler(std::string const& name, sampler_ptr const& samp) { return ps_ ? ps_->set_sampler(name, samp) : result::failed; }
-  result set_vs_sampler(std::string const& name, sampler_ptr const& samp) { return vs_ ? vs_->set_sampler(name, samp) : result::failed; }  // vertex texture fetch (renderer.h:80)
+  result set_ps_sampler(std::string const& name, sampler_ptr const& samp) {
+    if (auto j = dynamic_cast<jit_uniform_block*>(ps_.get())) return j->set_sampler_by_name(name, samp);
+    return ps_ ? ps_->set_sampler(name, samp) : result::failed;
+  }
+  result set_vs_sampler(std::string const& name, sampler_ptr const& samp) {  // vertex texture fetch (renderer.h:80)
+    if (auto j = dynamic_cast<jit_uniform_block*>(vs_.get())) return j->set_sampler_by_name(name, samp);
+    return vs_ ? vs_->set_sampler(name, samp) : result::failed;
+  }
   result set_rasterizer_state(raster_state_ptr const& rs) { rs_state_ = rs; return result::ok; }
   result set_blend_shader(cpp_blend_shader_ptr const& hbs) { bs_ = hbs; return result::ok; }
-  result set_pixel_shader(cpp_pixel_shader_ptr const& hps) { ps_ = hps; return result::ok; }
+  result set_pixel_shader(cpp_pixel_shader_ptr const& hps) { ps_ = hps; ps_code_.reset(); return result::ok; }
   result set_depth_stencil_state(depth_stencil_state_ptr const& dss, int32_t stencil_ref) { ds_state_ = dss; stencil_ref_ = stencil_ref; return result::ok; }
   result set_render_targets(size_t color_target_count, surface_ptr const* color_targets, surface_ptr const& ds_target) {
     if (color_target_count >= SLV_MAX_RENDER_TARGETS) return result::failed;  // renderer_impl.cpp:159-238
@@ -634,6 +833,10 @@ private:
   buffer_ptr index_buffer_; format index_format_ = format_r16_uint;
   input_layout_ptr layout_; primitive_topology topology_ = primitive_triangle_list;
   cpp_vertex_shader_ptr vs_; cpp_pixel_shader_ptr ps_; cpp_blend_shader_ptr bs_;
+  shader::shader_object_ptr vs_code_, ps_code_;
+  std::map<shader::shader_object const*, std::pair<shader::shader_object_ptr, std::shared_ptr<jit_vertex_shader>>> vs_code_cache_;
+  std::map<shader::shader_object const*, std::pair<shader::shader_object_ptr, std::shared_ptr<jit_pixel_shader>>> ps_code_cache_;
+  char compile_log_[8192] = {0};
   raster_state_ptr rs_state_; depth_stencil_state_ptr ds_state_; int32_t stencil_ref_ = 0;
   std::vector<surface_ptr> color_targets_; surface_ptr ds_target_; viewport vp_;
   buffer_ptr mapped_buffer_; surface_ptr mapped_surface_; map_mode mapped_mode_ = map_mode_none;

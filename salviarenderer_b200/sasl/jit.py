@@ -1,12 +1,15 @@
 """SASL shader -> sm_100a cubin -> shader module of the C ABI.
 
-compile(): frontend.compile_shader -> generated .cuh -> `nvcc -cubin` of csrc/slv_jit_unit.cu (NVVM / NVPTX -> PTX ->
-SASS for sm_100a, the pipeline kernels and the shader in one translation unit) -> cubin bytes, cached on disk by content
-hash.  load(): hands the cubin to the library (slv_shader_module_load); draws then select it with
-abi.program_jit(module).  Needs the CUDA toolkit's nvcc at run time (as the reference needs LLVM at run time).
+compile(): frontend.compile_shader -> generated device code -> slv_shader_compile_cubin of the product library: NVRTC IN
+PROCESS over the library's own embedded pipeline-kernel sources (NVVM / NVPTX -> PTX -> SASS for sm_100a, the pipeline kernels
+and the shader in one translation unit) -> cubin bytes, cached on disk by content hash.  No GPU is needed to compile.
+SLV_JIT_COMPILER=nvcc selects the former path, an `nvcc -cubin` subprocess over csrc/slv_jit_unit.cu (same flags, same code).
+load(): hands the cubin to the library (slv_shader_module_load); draws then select it with abi.program_jit(module).
+Needs the CUDA toolkit's libnvrtc (or nvcc) at run time, as the reference needs LLVM at run time.
 """
 from __future__ import annotations
 
+import ctypes
 import hashlib
 import os
 import shutil
@@ -62,9 +65,46 @@ def _trusted(path: str) -> bool:
     return st.st_uid == os.getuid() and not (st.st_mode & 0o022)
 
 
+PRODUCT_LIB = os.path.join(CSRC, "libsalvia_b200.so")
+VS_ENTRY_POINTS = ("slv_jit_k_geometry", "slv_jit_k_vertex_shade")
+PS_ENTRY_POINTS = ("slv_jit_k_raster_s1", "slv_jit_k_raster_s2", "slv_jit_k_raster_s4", "slv_jit_k_shade_s1", "slv_jit_k_shade_s2", "slv_jit_k_shade_s4")
+_lib = None
+
+
+def _product_lib():
+    global _lib
+    if _lib is None:
+        lib = ctypes.CDLL(PRODUCT_LIB)
+        lib.slv_shader_compile_cubin.restype = ctypes.c_int32
+        lib.slv_shader_compile_cubin.argtypes = [ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_void_p),
+                                                 ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t]
+        lib.slv_free.restype = None
+        lib.slv_free.argtypes = [ctypes.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def compile_in_process(unit: frontend.ShaderUnit, derivatives: str = "sasl") -> bytes:
+    """slv_shader_compile_cubin (include/salvia_b200.h): NVRTC inside the product library, its disk cache included."""
+    lib = _product_lib()
+    image, n = ctypes.c_void_p(), ctypes.c_size_t()
+    log = ctypes.create_string_buffer(1 << 16)
+    rc = lib.slv_shader_compile_cubin(0 if unit.stage == "vs" else 1, unit.code.encode(), unit.reflection.n_vs_output_attrs,
+                                      1 if (unit.stage == "ps" and derivatives == "cpp") else 0, ctypes.byref(image), ctypes.byref(n), log, len(log))
+    if rc != 0:
+        raise frontend.CompileError("device compilation of the generated code failed (slv_shader_compile_cubin):\n" + log.value.decode(errors="replace")[-4000:])
+    try:
+        return ctypes.string_at(image.value, n.value)
+    finally:
+        lib.slv_free(image)
+
+
 def compile(source: str, stage: str, entry: str | None = None, derivatives: str = "sasl", keep_dir: str | None = None) -> CompiledShader:  # noqa: A001
-    """stage 'vs' | 'ps'.  derivatives: 'sasl' (per row / per column) or 'cpp' (q1 - q0 / q2 - q0 for the whole quad)."""
+    """stage 'vs' | 'ps'.  derivatives: 'sasl' (per row / per column) or 'cpp' (q1 - q0 / q2 - q0 for the whole quad).
+    keep_dir (nvcc path only): keep the generated file there."""
     unit = frontend.compile_shader(source, stage, entry)
+    if os.environ.get("SLV_JIT_COMPILER", "nvrtc") != "nvcc" and keep_dir is None and os.path.exists(PRODUCT_LIB):
+        return CompiledShader(unit, compile_in_process(unit, derivatives), VS_ENTRY_POINTS if stage == "vs" else PS_ENTRY_POINTS)
     defs = ["-DSLV_JIT_VS=1", f"-DSLV_JIT_R={unit.reflection.n_vs_output_attrs + 1}"] if stage == "vs" else ["-DSLV_JIT_PS=1"]
     if stage == "ps" and derivatives == "cpp":
         defs.append("-DSLV_JIT_DERIV_CPP=1")
@@ -96,9 +136,7 @@ def compile(source: str, stage: str, entry: str | None = None, derivatives: str 
         finally:
             if keep_dir is None:
                 shutil.rmtree(work, ignore_errors=True)
-    names = ("slv_jit_k_geometry",) if stage == "vs" else (
-        "slv_jit_k_raster_s1", "slv_jit_k_raster_s2", "slv_jit_k_raster_s4", "slv_jit_k_shade_s1", "slv_jit_k_shade_s2", "slv_jit_k_shade_s4")
-    return CompiledShader(unit, open(path, "rb").read(), names)
+    return CompiledShader(unit, open(path, "rb").read(), VS_ENTRY_POINTS if stage == "vs" else PS_ENTRY_POINTS)
 
 
 def load(be, shader: CompiledShader) -> int:

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "salvia_b200_renderer.hpp"
@@ -266,6 +267,129 @@ int main(int argc, char** argv) {
     const uint64_t h4 = fnv(m.data, d2->bytes());
     CHECK(r->unmap());
     std::printf("vtf color %016" PRIx64 " depth %016" PRIx64 " covered %zu\n", h3, h4, covered);
+  }
+
+  // ---- SASL through the surface (renderer.h:75-86,136-147): compile() -> set_vertex_shader_code / set_pixel_shader_code,
+  // globals by name (by value and by pointer), the sampler by name, the input layout from the shader's semantics.  The CUDA
+  // product runs the SASL pair BASELINE configs[3] names (the front end + NVRTC in process); a CPU checker cannot compile SASL
+  // and runs the pair's cpp twins (vs_sponza / ps_sponza_grad) - the two must print the same line.
+  {
+    static const char* kVs =
+        "float4x4 wvpMatrix; float4 lightPos; float4 eyePos;\n"
+        "struct VSIn  { float4 pos: POSITION; float4 tex: TEXCOORD0; float4 norm: NORMAL; };\n"
+        "struct VSOut { float4 pos: sv_position; float4 tex: TEXCOORD0; float4 norm: TEXCOORD1; float4 lightDir: TEXCOORD2; float4 eyeDir: TEXCOORD3; };\n"
+        "VSOut vs_main(VSIn in) {\n"
+        "  VSOut o;\n"
+        "  o.norm = in.norm; o.pos = mul(in.pos, wvpMatrix); o.lightDir = lightPos - in.pos; o.eyeDir = eyePos - in.pos; o.tex = in.tex;\n"
+        "  return o;\n"
+        "}\n";
+    static const char* kPs =
+        "sampler texSamp;\n"
+        "struct PSIn { float4 tex: TEXCOORD0; float4 norm: TEXCOORD1; float4 lightDir: TEXCOORD2; float4 eyeDir: TEXCOORD3; };\n"
+        "float4 ps_main(PSIn in): COLOR {\n"
+        "  float4 diff = tex2D(texSamp, in.tex.xy);\n"
+        "  float illum = clamp(dot(normalize(in.lightDir.xyz), normalize(in.norm.xyz)), 0.0f, 1.0f);\n"
+        "  return float4(diff.xyz * illum, 1.0f);\n"
+        "}\n";
+    const bool use_sasl = r->backend_name() == "cuda-sm100a" && !std::getenv("SLV_HOST_TEST_NO_SASL");
+    // a bumpy grid: positions, uv (tiled 3x), normals
+    const uint32_t G = 10, TS = 32;
+    std::vector<float> gp, guv, gn;
+    std::vector<uint16_t> gi;
+    for (uint32_t i = 0; i <= G; ++i)
+      for (uint32_t j = 0; j <= G; ++j) {
+        const float hgt = 0.25f * (float)((i * 5 + j * 3) % 4);
+        gp.insert(gp.end(), {-3.0f + 0.6f * (float)i, -1.0f + hgt, -3.0f + 0.6f * (float)j, 1.0f});
+        guv.insert(guv.end(), {3.0f * (float)i / (float)G, 3.0f * (float)j / (float)G, 0.0f, 0.0f});
+        gn.insert(gn.end(), {0.1f * (float)((i + j) % 3), 1.0f, 0.1f * (float)(j % 2), 0.0f});
+      }
+    for (uint32_t i = 0; i < G; ++i)
+      for (uint32_t j = 0; j < G; ++j) {
+        const uint16_t q0 = (uint16_t)(i * (G + 1) + j), q2 = (uint16_t)(q0 + G + 2);
+        gi.insert(gi.end(), {q0, (uint16_t)(q0 + 1), q2, q2, (uint16_t)(q2 - 1), q0});
+      }
+    buffer_ptr b0 = r->create_buffer(gp.size() * 4), b1 = r->create_buffer(guv.size() * 4), b2 = r->create_buffer(gn.size() * 4), bi = r->create_buffer(gi.size() * 2);
+    CHECK(b0->transfer(0, gp.data(), 16, gp.size() / 4));
+    CHECK(b1->transfer(0, guv.data(), 16, guv.size() / 4));
+    CHECK(b2->transfer(0, gn.data(), 16, gn.size() / 4));
+    CHECK(bi->transfer(0, gi.data(), 2, gi.size()));
+    texture_ptr tex = r->create_tex2d(TS, TS, 1, pixel_format_color_rgba8);
+    {
+      CHECK(r->map(m, tex->subresource(0), map_write));
+      uint8_t* t = static_cast<uint8_t*>(m.data);
+      for (uint32_t y = 0; y < TS; ++y)
+        for (uint32_t x = 0; x < TS; ++x) {
+          uint8_t* px = t + (y * TS + x) * 4;
+          px[0] = (uint8_t)(x * 8); px[1] = (uint8_t)(y * 8); px[2] = (uint8_t)(((x ^ y) & 4) ? 230 : 40); px[3] = 255;
+        }
+      CHECK(r->unmap());
+    }
+    tex->gen_mipmap(filter_linear, true);
+    sampler_desc sd{};
+    sd.min_filter = sd.mag_filter = filter_linear;
+    sd.mip_filter = filter_anisotropic;
+    sd.max_anisotropy = 8;
+    sd.mip_qual = mip_mi_quality;
+    sd.addr_mode_u = sd.addr_mode_v = sd.addr_mode_w = address_wrap;
+    sd.min_lod = -1e20f; sd.max_lod = 1e20f;
+    sampler_ptr ts = r->create_sampler(sd, tex);
+    if (!ts) return 9;
+    texture_ptr color3 = r->create_tex2d(W, H, S, pixel_format_color_rgba8), ds3 = r->create_tex2d(W, H, S, pixel_format_color_rg32f);
+    surface_ptr c3 = color3->subresource(0), d3 = ds3->subresource(0);
+    CHECK(r->set_render_targets(1, &c3, d3));
+    CHECK(r->clear_color(c3, color_rgba32f{0.1f, 0.1f, 0.1f, 1.0f}));
+    CHECK(r->clear_depth_stencil(d3, clear_depth | clear_stencil, 1.0f, 0));
+    input_element_desc e3[] = {{"POSITION", 0, format_r32g32b32a32_float, 0, 0}, {"TEXCOORD", 0, format_r32g32b32a32_float, 1, 0},
+                               {"NORMAL", 0, format_r32g32b32a32_float, 2, 0}};
+    const vec4 light{2.0f, 4.0f, -1.0f, 1.0f}, eye{0.0f, 2.5f, -5.0f, 1.0f};
+    mat44 wvp_live = wvp;  // read through set_vs_variable_pointer at draw time
+    if (use_sasl) {
+      shader::shader_log_ptr log;
+      shader::shader_profile prof; prof.language = shader::lang_vertex_shader;
+      shader::shader_object_ptr vso = shader::compile(kVs, prof, log);
+      if (!vso) { std::fprintf(stderr, "SASL vertex shader: %s\n", log ? log->c_str() : ""); return 10; }
+      prof.language = shader::lang_pixel_shader;
+      shader::shader_object_ptr pso = shader::compile(kPs, prof, log);
+      if (!pso) { std::fprintf(stderr, "SASL pixel shader: %s\n", log ? log->c_str() : ""); return 10; }
+      if (shader::compile("float4 broken(", shader::lang_pixel_shader)) return 10;  // a compile error yields no object
+      if (r->set_vertex_shader_code(vso) != result::ok) { std::fprintf(stderr, "set_vertex_shader_code: %s\n", r->shader_compile_log()); return 11; }
+      if (r->set_pixel_shader_code(pso) != result::ok) { std::fprintf(stderr, "set_pixel_shader_code: %s\n", r->shader_compile_log()); return 11; }
+      CHECK(r->set_input_layout(r->create_input_layout(e3, 3, vso)));
+      mat44 zero{}; for (auto& row : zero.m) for (float& v : row) v = 0.0f;
+      wvp_live = zero;
+      CHECK(r->set_vs_variable_pointer("wvpMatrix", &wvp_live, sizeof(wvp_live)));
+      wvp_live = wvp;  // ... so the value at draw time counts
+      if (r->set_vs_variable_value("noSuchGlobal", &light, sizeof(light)) != result::failed) return 11;
+      if (r->set_vs_variable_value("lightPos", &light, 4) != result::failed) return 11;  // wrong size
+      if (r->get_vertex_shader_code() != vso || r->get_pixel_shader_code() != pso) return 11;
+    } else {
+      auto vs3 = std::make_shared<vs_sponza>();
+      CHECK(r->set_vertex_shader(vs3));
+      CHECK(r->set_pixel_shader(std::make_shared<ps_sponza_grad>(true)));
+      CHECK(r->set_input_layout(r->create_input_layout(e3, 3, vs3)));
+      CHECK(r->set_vs_variable("wvpMatrix", &wvp_live));
+    }
+    CHECK(r->set_vs_variable("lightPos", &light));
+    CHECK(r->set_vs_variable("eyePos", &eye));
+    if (r->set_ps_sampler("noSuchSampler", ts) != result::failed) return 11;
+    CHECK(r->set_ps_sampler("texSamp", ts));
+    buffer_ptr bufs3[3] = {b0, b1, b2};
+    size_t st3[3] = {16, 16, 16}, of3[3] = {0, 0, 0};
+    CHECK(r->set_vertex_buffers(0, 3, bufs3, st3, of3));
+    CHECK(r->set_index_buffer(bi, format_r16_uint));
+    CHECK(r->set_blend_shader(std::make_shared<bs_replace>()));
+    CHECK(r->draw_index(0, G * G * 2, 0));
+    CHECK(r->flush());
+    CHECK(r->map(m, c3, map_read));
+    const uint64_t h5 = fnv(m.data, c3->bytes());
+    size_t drawn = 0;
+    for (size_t i = 0; i < W * H * S; ++i) drawn += static_cast<const uint8_t*>(m.data)[4 * i + 3] == 255 && static_cast<const uint8_t*>(m.data)[4 * i] != 26 ? 1 : 0;
+    CHECK(r->unmap());
+    CHECK(r->map(m, d3, map_read));
+    const uint64_t h6 = fnv(m.data, d3->bytes());
+    CHECK(r->unmap());
+    if (drawn < W * H * S / 50) return 12;
+    std::printf("sasl color %016" PRIx64 " depth %016" PRIx64 " drawn %zu\n", h5, h6, drawn);
   }
   return 0;
 }

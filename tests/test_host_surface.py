@@ -3,6 +3,7 @@ ABI): tests/cpp/host_surface_test.cpp renders through it and prints buffer hashe
 against different libraries and must print the same lines: CPU checkers here, the CUDA product on the GPU box."""
 import os
 import subprocess
+import sys
 
 import pytest
 
@@ -19,7 +20,9 @@ def host_binary(built, tmp_path_factory):
 
 
 def run(exe, lib, *size):
-    out = subprocess.run([exe, lib, *map(str, size)], capture_output=True, text=True, timeout=300)
+    # the SASL section's compile() runs the front end (python -m salviarenderer_b200.sasl.emit) - on the CUDA product only
+    env = dict(os.environ, SLV_SASL_PYTHON=sys.executable, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    out = subprocess.run([exe, lib, *map(str, size)], capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
     lines = out.stdout.strip().splitlines()
     return lines[0], lines[1:]
@@ -44,3 +47,16 @@ def test_cpp_surface_product_equals_checker(host_binary, size):
     checker = REF_LIB if os.path.exists(REF_LIB) else ORACLE_LIB
     _, out_c = run(host_binary, checker, *size)
     assert out_p == out_c
+
+
+@pytest.mark.gpu
+def test_cpp_surface_sasl_equals_twins_on_the_product(host_binary):
+    """The SASL section (compile() -> set_*_shader_code, NVRTC in process) against the same section with the cpp twins, both
+    on the CUDA product: identical line."""
+    _, out_sasl = run(host_binary, PRODUCT_LIB, 320, 240, 4)
+    os.environ["SLV_HOST_TEST_NO_SASL"] = "1"
+    try:
+        _, out_twin = run(host_binary, PRODUCT_LIB, 320, 240, 4)
+    finally:
+        del os.environ["SLV_HOST_TEST_NO_SASL"]
+    assert out_sasl[-1].startswith("sasl color") and out_sasl == out_twin
