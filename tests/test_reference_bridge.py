@@ -26,7 +26,8 @@ def run(lib, *size):
     return lines
 
 
-@pytest.mark.parametrize("size", [(320, 240, 4), (200, 120, 1), (260, 132, 4)]  # multiples of 4: the reference writes past targets that are not)
+# multiples of 4: the reference writes past the end of targets that are not
+@pytest.mark.parametrize("size", [(320, 240, 4), (200, 120, 1), (260, 132, 4)])
 def test_bridge_into_the_restatement(built, size):
     assert run(ORACLE_LIB, *size)[0] == "backend oracle"
 
