@@ -367,7 +367,11 @@ def main():
     # in lockstep with rank 0's consumer, and the e2e readback of frame k overlaps frame k+1 ----
     targets = [resolved]
     if sc.t.resolved is not None:
-        targets.append(be.create_texture(args.width, args.height, 1, resolved.fmt))
+        # frame buffers on rank 0 (SLV_BENCH_NBUF, default 2; N > 1: 4 - a rank may then run up to three frames ahead of the
+        # slowest one, so per-frame load differences between the ranks average out instead of adding up in lockstep)
+        nbuf = int(os.environ.get("SLV_BENCH_NBUF", "4" if n > 1 else "2"))
+        for _ in range(max(nbuf, 2) - 1):
+            targets.append(be.create_texture(args.width, args.height, 1, resolved.fmt))
     fg = sortfirst.FrameGather(be, targets, rank, n, "cuda")
 
     def frame(i):

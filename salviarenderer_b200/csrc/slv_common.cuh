@@ -242,6 +242,32 @@ __device__ __forceinline__ float2 sub2_after_mul(float2 a, float2 b) { return ma
 // * (1 / 255)): difference and sum in scalar ops, only the product packed
 __device__ __forceinline__ float2 lerp2_of_products(float2 a, float2 b, float2 t) { return add2_after_mul(a, mul2(sub2_after_mul(b, a), t)); }
 
+// ---- cache hints for data with no reuse inside a frame (L2 evict-first): SLV_STREAM_HINTS=0 builds plain accesses ------------------
+#ifndef SLV_STREAM_HINTS
+#define SLV_STREAM_HINTS 1
+#endif
+__device__ __forceinline__ void st_stream(float4* p, float4 v) {
+#if SLV_STREAM_HINTS
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+__device__ __forceinline__ void st_stream(uint4* p, uint4 v) {
+#if SLV_STREAM_HINTS
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+#if SLV_STREAM_HINTS
+  return __ldcs(p);
+#else
+  return *p;
+#endif
+}
+
 // float -> unorm8: mul 255, max 0, min 255, cvtps2dq (round-to-nearest-even)  (colors.h:182-192)
 __device__ __forceinline__ uint32_t unorm8_rne(float x) {
   float m = x * 255.0f;

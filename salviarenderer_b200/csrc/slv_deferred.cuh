@@ -531,11 +531,13 @@ __global__ void __launch_bounds__(DEF_THREADS, SLV_COVER_CTAS_PER_SM)
         const bool any_ds = __any_sync(0xFFFFFFFFu, dirty);
         if (in_target && any_ds && c.ds.data) {
           uint8_t* ds_ptr = c.ds.data + ((size_t)y * c.ds.w + x) * S * 8;
+          // depth is not read again this frame: streaming (evict-first) stores keep it from pushing the visibility surface and
+          // the textures, which k_shade is about to read, out of the L2
           if (S == 4) {
-            *reinterpret_cast<float4*>(ds_ptr) = make_float4(z[0], __uint_as_float(st[0]), z[1 % S], __uint_as_float(st[1 % S]));
-            *reinterpret_cast<float4*>(ds_ptr + 16) = make_float4(z[2 % S], __uint_as_float(st[2 % S]), z[3 % S], __uint_as_float(st[3 % S]));
+            st_stream(reinterpret_cast<float4*>(ds_ptr), make_float4(z[0], __uint_as_float(st[0]), z[1 % S], __uint_as_float(st[1 % S])));
+            st_stream(reinterpret_cast<float4*>(ds_ptr + 16), make_float4(z[2 % S], __uint_as_float(st[2 % S]), z[3 % S], __uint_as_float(st[3 % S])));
           } else if (S == 2) {
-            *reinterpret_cast<float4*>(ds_ptr) = make_float4(z[0], __uint_as_float(st[0]), z[1 % S], __uint_as_float(st[1 % S]));
+            st_stream(reinterpret_cast<float4*>(ds_ptr), make_float4(z[0], __uint_as_float(st[0]), z[1 % S], __uint_as_float(st[1 % S])));
           } else {
             *reinterpret_cast<float2*>(ds_ptr) = make_float2(z[0], __uint_as_float(st[0]));
           }
@@ -681,7 +683,7 @@ __device__ __forceinline__ bool shade_item_setup(const RasterParams& c, const De
   if (in_target && flagged) {  // unflagged items hold stale owners from an earlier batch
     const uint32_t* vp = d.vis + ((size_t)y * d.vis_pitch + x) * S;
     if (S == 4) {
-      const uint4 v = *reinterpret_cast<const uint4*>(vp);
+      const uint4 v = ld_stream(reinterpret_cast<const uint4*>(vp));  // read exactly once
       own[0] = v.x; own[1 % S] = v.y; own[2 % S] = v.z; own[3 % S] = v.w;
     } else if (S == 2) {
       const uint2 v = *reinterpret_cast<const uint2*>(vp);
@@ -725,7 +727,7 @@ __device__ __forceinline__ void shade_group_store(const RasterParams& c, const D
     const int x = (int)(org & 0xFFFF) + wlx, y = (int)(org >> 16) + wly;
     if (fl & 0x8Fu) {
       uint32_t* cptr = reinterpret_cast<uint32_t*>(c.color0.data + ((size_t)y * c.color0.w + x) * S * 4);
-      if (S == 4) *reinterpret_cast<uint4*>(cptr) = make_uint4(s_color[kk][lane][0], s_color[kk][lane][1 % S], s_color[kk][lane][2 % S], s_color[kk][lane][3 % S]);
+      if (S == 4) st_stream(reinterpret_cast<uint4*>(cptr), make_uint4(s_color[kk][lane][0], s_color[kk][lane][1 % S], s_color[kk][lane][2 % S], s_color[kk][lane][3 % S]));
       else if (S == 2) *reinterpret_cast<uint2*>(cptr) = make_uint2(s_color[kk][lane][0], s_color[kk][lane][1 % S]);
       else *cptr = s_color[kk][lane][0];
     }

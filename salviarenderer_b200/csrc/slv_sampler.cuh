@@ -266,28 +266,38 @@ __device__ inline float4 sample_surface(const SurfaceRef& s, const slv_sampler_d
 // One bilinear tap for the commonest sampler state (SamplerRef::fast_wrap_rgba8): wrap addressing with the exact
 // integer modulo, rgba8 texels.  Operation for operation the WRAP branch of linear_coord_2d + the rgba8 branch of
 // bilinear above, minus the per-tap mode / format dispatch.
-__device__ __forceinline__ float4 sample_wrap_rgba8_linear(const SurfaceRef& s, float x, float y) {
+struct WrapTap { uint32_t i00, i01, i10, i11; float tx, ty; };  // the four texel indices and the two weights of one tap
+__device__ __forceinline__ WrapTap wrap_tap_address(const SurfaceRef& s, float x, float y) {
   const float fw = (float)(int)s.w, fh = (float)(int)s.h;
   float fx = x - trunc_f(x);
   fx = fw * fx;
   fx = fx - 0.5f;
   const float ipx = floor_fix(fx);
-  const float tx = fx - ipx;
+  WrapTap t;
+  t.tx = fx - ipx;
   float fy = y - trunc_f(y);
   fy = fh * fy;
   fy = fy - 0.5f;
   const float ipy = floor_fix(fy);
-  const float ty = fy - ipy;
+  t.ty = fy - ipy;
   const int ix = (int)ipx, iy = (int)ipy;
   const uint32_t wm = s.w - 1, hm = s.h - 1;
   const uint32_t x0 = (uint32_t)ix & wm, x1 = (uint32_t)(ix + 1) & wm;
   const uint32_t r0 = ((uint32_t)iy & hm) * s.w, r1 = ((uint32_t)(iy + 1) & hm) * s.w;
+  t.i00 = r0 + x0; t.i01 = r0 + x1; t.i10 = r1 + x0; t.i11 = r1 + x1;
+  return t;
+}
+__device__ __forceinline__ float4 sample_wrap_rgba8_linear(const SurfaceRef& s, float x, float y) {
+  const WrapTap t = wrap_tap_address(s, x, y);
   const uint32_t* base = reinterpret_cast<const uint32_t*>(s.data);
-  const uint32_t t0 = __ldg(base + (r0 + x0)), t1 = __ldg(base + (r0 + x1));
-  const uint32_t t2 = __ldg(base + (r1 + x0)), t3 = __ldg(base + (r1 + x1));
-  return bilinear_rgba8(t0, t1, t2, t3, tx, ty);
+  const uint32_t t0 = __ldg(base + t.i00), t1 = __ldg(base + t.i01);
+  const uint32_t t2 = __ldg(base + t.i10), t3 = __ldg(base + t.i11);
+  return bilinear_rgba8(t0, t1, t2, t3, t.tx, t.ty);
 }
 
+#ifndef SLV_EWA_PAIR
+#define SLV_EWA_PAIR 1
+#endif
 struct AfInfo { float lod, probe_count, weight_D, du, dv; };
 
 // sampler::calc_lod (sampler.cpp:521-603)
@@ -405,6 +415,43 @@ __device__ inline float4 sample_impl(const SamplerRef& sm, float cx, float cy, f
     c1 = sample_wrap_rgba8_linear(t.level[lv1], sx, sy);
     return cat4(lerp2_of_products(lo2(c0), lo2(c1), splat2(frac)), lerp2_of_products(hi2(c0), hi2(c1), splat2(frac)));
   }
+#if SLV_EWA_PAIR
+  // anisotropic probes of the common sampler state, TWO per trip: both probes' eight texel loads are issued before either is
+  // filtered, so their latencies overlap (the probes of one pixel are independent; the weighted sum keeps its order: probe k,
+  // then probe k + 1, exactly the operations of the one-probe loop below)
+  if (aniso && sm.fast_wrap_rgba8) {
+    const SurfaceRef& lvl = t.level[lv0];
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(lvl.data);
+    int k = 0;
+#pragma unroll 1
+    for (; k + 1 < n; k += 2) {
+      const float sx1 = sx + du, sy1 = sy + dv;
+      const WrapTap a = wrap_tap_address(lvl, sx, sy), b = wrap_tap_address(lvl, sx1, sy1);
+      const uint32_t a0 = __ldg(base + a.i00), a1 = __ldg(base + a.i01), a2 = __ldg(base + a.i10), a3 = __ldg(base + a.i11);
+      const uint32_t b0 = __ldg(base + b.i00), b1 = __ldg(base + b.i01), b2 = __ldg(base + b.i10), b3 = __ldg(base + b.i11);
+      const int wia = (int)((float)(tap_i * tap_i) * weight_D), wib = (int)((float)((tap_i + 2) * (tap_i + 2)) * weight_D);
+      const float wa = c_ewa_wts[min(max(wia, 0), 255)], wb = c_ewa_wts[min(max(wib, 0), 255)];
+      const float4 va = bilinear_rgba8(a0, a1, a2, a3, a.tx, a.ty);
+      c0 = cat4(add2_after_mul(lo2(c0), mul2(lo2(va), splat2(wa))), add2_after_mul(hi2(c0), mul2(hi2(va), splat2(wa))));
+      w_sum += wa;
+      const float4 vb = bilinear_rgba8(b0, b1, b2, b3, b.tx, b.ty);
+      c0 = cat4(add2_after_mul(lo2(c0), mul2(lo2(vb), splat2(wb))), add2_after_mul(hi2(c0), mul2(hi2(vb), splat2(wb))));
+      w_sum += wb;
+      sx = sx1 + du;
+      sy = sy1 + dv;
+      tap_i += 4;
+    }
+    if (k < n) {
+      const float4 v = sample_wrap_rgba8_linear(lvl, sx, sy);
+      const int wi = (int)((float)(tap_i * tap_i) * weight_D);
+      const float w = c_ewa_wts[min(max(wi, 0), 255)];
+      c0 = cat4(add2_after_mul(lo2(c0), mul2(lo2(v), splat2(w))), add2_after_mul(hi2(c0), mul2(hi2(v), splat2(w))));
+      w_sum += w;
+    }
+    const float inv = 1 / w_sum;
+    return cat4(mul2(lo2(c0), splat2(inv)), mul2(hi2(c0), splat2(inv)));
+  }
+#endif
 #pragma unroll 1
   for (int k = 0; k < n; ++k) {
     const SurfaceRef& lvl = t.level[k ? lv1 : lv0];

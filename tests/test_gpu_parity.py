@@ -327,3 +327,16 @@ def test_full_size_shadow_map_1080p_msaa4(cuda, oracle):
         ra, rb = a.run(cuda, f), b.run(oracle, f)
         assert not cases.compare_frames(ra, rb, color_tol=COLOR_TOL_LSB)
         assert ra.stats["ps_invocations"] > 1_000_000
+
+
+def test_full_size_configs4_equals_reference_fixture(cuda):
+    """BASELINE configs[4] at FULL size - the synthetic 10,000,000-triangle height field at 7680x4320, depth-only shadow pass +
+    colour pass - against the fingerprint of the UNMODIFIED reference's frame (tests/golden/golden_fullsize.json, generated by
+    tests/golden/make_golden_fullsize.py): colour, depth bits, stencil, the shadow map and the six gated counters, bit for bit."""
+    fix = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_fullsize.json")))["cases"]["c5_10m_tris_7680x4320"]
+    sc = S.HeightFieldTwoPass(7680, 4320, 1, nx=2500, nz=2000)
+    sc.setup(cuda)
+    for f, want in fix.items():
+        got = cases.summarize(sc.run(cuda, int(f)))
+        for k in ("stats", "depth", "stencil", "count", "color", "shape"):
+            assert got.get(k) == want.get(k), f"configs[4] full size, frame {f}: {k}: {got.get(k)} vs {want.get(k)}"
