@@ -23,23 +23,28 @@ ap.add_argument("--tex-size", type=int, default=1024)
 ap.add_argument("--aniso", type=int, default=0)
 ap.add_argument("--shaders", default="builtin", choices=["builtin", "sasl", "twins"],
                 help="builtin: SLV_VS_SPONZA + SLV_PS_SPONZA; sasl: bench.py's SASL pair compiled at run time; twins: SLV_PS_SPONZA_GRAD")
+ap.add_argument("--scene", default="sponza", help="sponza | c1 | c2 | c3a | c3b | c5 (bench.small_scene: the other BASELINE.json configs at full size)")
 a = ap.parse_args()
 be = pkg.load(0)
 from salviarenderer_b200 import abi as A  # noqa: E402
-if a.shaders == "twins":
+if a.scene != "sponza":
+    import bench  # noqa: E402
+    sc, what = bench.small_scene(a.scene, S)
+    print(what)
+elif a.shaders == "twins":
     sc = S.SponzaLike(a.width, a.height, a.samples, tex_size=a.tex_size, max_aniso=a.aniso, ps_program=A.PS_SPONZA_GRAD)
 else:
     sc = S.SponzaLike(a.width, a.height, a.samples, tex_size=a.tex_size, max_aniso=a.aniso)
-if a.shaders == "sasl":
+if a.scene == "sponza" and a.shaders == "sasl":
     import bench  # noqa: E402
     bench.install_sasl_shaders(sc, be, A)
 sc.setup(be)
 for f in range(4):
-    sc.render(be, f)
+    sc.render(be, f % sc.n_frames)
 be.flush()
 rt = torch.cuda.cudart()
 rt.cudaProfilerStart()
-sc.render(be, a.frame)
+sc.render(be, a.frame % sc.n_frames)
 be.flush()
 rt.cudaProfilerStop()
 print("profiled frame", a.frame, be.query_get())
