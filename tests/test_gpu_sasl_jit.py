@@ -343,3 +343,35 @@ def test_sasl_two_sampler_shadow_map_shader(cuda, cuda_jit_immediate, w, h, samp
         assert d.max() <= 6, f"frame {f}: SASL vs built-in colour differs by up to {d.max()} LSB"
         assert (d > 0).any(-1).mean() < 0.25, f"frame {f}: {(d > 0).any(-1).mean():.1%} of the samples differ"
         assert (d == 0).all(-1).mean() > 0.5
+
+
+def test_sasl_intrinsics_match_the_reference_known_answers(cuda):
+    """The reference's own known answers (tests/golden/sasl_kat.json: eflib values for the inputs and reference expressions of
+    sasl/test/jit_test/general.cpp:159-433, generated by oracle/sasl_kat_gen.cpp) against the RUN-TIME COMPILED pixel shader on
+    the GPU: one shader holds every call of the fixture, a draw per case writes the result into an rgba32f target.  Criterion:
+    the reference test's own BOOST_CHECK_CLOSE tolerance (1e-4 %); most components are bit-identical."""
+    import sasl_kat
+    sh = jit.compile(sasl_kat.shader_source(), "ps")
+    mod = jit.load(cuda, sh)
+    t = S.create_targets(cuda, 8, 8, 1, A.PF_RGBA32F)
+    mesh = S.create_planar((-3.0, -1.0, -3.0), (6, 0, 0), (0, 0, 6), 1, 1, True)
+    mesh.elements = [(0, S._V4, 0, 0, 1.0)]
+    mesh.upload(cuda)
+    wvp = S.mat_mul(S.mat_lookat((0.0, 2.5, 0.0001), (0, 0, 0), (0, 1, 0)), S.mat_perspective_fov(np.pi / 2, 1.0, 0.1, 100.0))
+    exact = total = 0
+    for case in sasl_kat.CASES:
+        cuda.clear_color(t.color, (-7.0, -7.0, -7.0, -7.0))
+        cuda.clear_depth_stencil(t.ds, A.CLEAR_DEPTH | A.CLEAR_STENCIL, 1.0, 0)
+        d = S.base_desc(t, 8, 8, cull=A.CULL_NONE)
+        mesh.fill_desc(cuda, d)
+        d.vs = A.shader_binding(A.VS_MVP_PASSTHROUGH, S.pack_vs_mvp_passthrough(wvp, [0]))
+        d.ps = A.shader_binding(A.program_jit(mod), sasl_kat.uniforms_for(sh.unit, case))
+        d.bs = A.shader_binding(A.BS_REPLACE)
+        cuda.draw(d)
+        px = np.frombuffer(cuda.read_texture(t.color), np.float32).reshape(8, 8, 4)
+        got = px[4, 4]
+        assert not np.array_equal(got, np.full(4, -7.0, np.float32)), "the probe pixel was not covered"
+        assert np.array_equal(px[3, 3], got)  # uniform over the plane
+        exact += sasl_kat.check(case, got)
+        total += len(case["expected"])
+    assert exact >= total * 0.8, (exact, total)

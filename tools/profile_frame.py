@@ -24,8 +24,12 @@ ap.add_argument("--aniso", type=int, default=0)
 ap.add_argument("--shaders", default="builtin", choices=["builtin", "sasl", "twins"],
                 help="builtin: SLV_VS_SPONZA + SLV_PS_SPONZA; sasl: bench.py's SASL pair compiled at run time; twins: SLV_PS_SPONZA_GRAD")
 ap.add_argument("--scene", default="sponza", help="sponza | c1 | c2 | c3a | c3b | c5 (bench.small_scene: the other BASELINE.json configs at full size)")
+ap.add_argument("--shard", default=None, help="r,n: render only the tiles sort-first rank r of n owns (what one GPU of an n-GPU run executes)")
 a = ap.parse_args()
 be = pkg.load(0)
+if a.shard:
+    r_, n_ = map(int, a.shard.split(","))
+    be.set_tile_shard(r_, n_)
 from salviarenderer_b200 import abi as A  # noqa: E402
 if a.scene != "sponza":
     import bench  # noqa: E402
