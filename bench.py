@@ -505,6 +505,7 @@ def main():
     if finish_e2e:
         finish_e2e()
     e2e_ms = timed(frame_e2e, args.steps, finish_e2e) / args.steps
+    e2e_host_us = host_s[0] / args.steps * 1e6  # host time of the enqueue loop alone (Python + torch + NCCL enqueue + ctypes)
     if hf is not None:
         sc.t.resolved = resolved
         for f in range(sc.n_frames):
@@ -630,7 +631,7 @@ def main():
             "sortfirst_transport": fg.transport,
             "clocks": clocks,
             "e2e": {"value": 1e3 / e2e_ms, "unit": "frames/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h,
+                    "d2h_bytes_per_step": d2h, "host_loop_us_per_frame": e2e_host_us,
                     "what": e2e_how},
             "gpu_launches": int(launches),
             "host_frame_loop_us_per_frame": host_loop_us,
