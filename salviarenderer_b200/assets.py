@@ -21,15 +21,19 @@ from dataclasses import dataclass, field
 import numpy as np
 
 
+def _f32(x):
+    return float(np.float32(x))
+
+
 @dataclass
-class ObjMaterial:  # obj_material, salvia/include/salvia/ext/resource/mesh/material.h
-    name: str = ""
-    ambient: tuple = (0.0, 0.0, 0.0, 0.0)
-    diffuse: tuple = (0.0, 0.0, 0.0, 0.0)
-    specular: tuple = (0.0, 0.0, 0.0, 0.0)
-    alpha: float = 0.0
-    shininess: int = 0
-    is_specular: bool = False
+class ObjMaterial:  # obj_material (material.h) with the constructor's defaults (salvia/src/ext/resource/mesh/material.cpp:4-13)
+    name: str = "default"
+    ambient: tuple = (_f32(0.2), _f32(0.2), _f32(0.2), 1.0)
+    diffuse: tuple = (0.5, 0.5, 0.5, 1.0)
+    specular: tuple = (_f32(0.7), _f32(0.7), _f32(0.7), 1.0)
+    alpha: float = 1.0
+    shininess: int = 2
+    is_specular: bool = True
     tex_name: str = ""
     tex_path: str = ""
 
@@ -61,7 +65,9 @@ def _f(tok):
 
 
 def load_mtl(path: str, materials: list):
-    """load_material (mesh_io_obj.cpp:64-138): fills the materials `usemtl` created; unknown names are skipped."""
+    """load_material (mesh_io_obj.cpp:62-136): fills the materials `usemtl` created.  Upstream quirk, mirrored (pinned against
+    the reference's own loader by tests/test_assets.py): a `newmtl` the OBJ never used does NOT deselect the current material,
+    so its statements overwrite the previously selected one."""
     if not os.path.exists(path):
         return False
     cur = None
@@ -72,7 +78,9 @@ def load_mtl(path: str, materials: list):
             continue
         cmd = tok[0]
         if cmd == "newmtl":
-            cur = next((m for m in materials if m.name == (tok[1] if len(tok) > 1 else "")), None)
+            hit = next((m for m in materials if m.name == (tok[1] if len(tok) > 1 else "")), None)
+            if hit is not None:
+                cur = hit
             continue
         if cur is None:
             continue
@@ -92,8 +100,10 @@ def load_mtl(path: str, materials: list):
 
 
 def load_obj(path: str, flip_tex_v: bool = False) -> ObjMesh:
-    """load_obj_mesh_c (mesh_io_obj.cpp:140-288).  Triangulated faces only (the reference reads exactly three corners of
-    every `f` line and ignores the rest); material 0 is the unnamed default material."""
+    """load_obj_mesh_c (mesh_io_obj.cpp:140-269).  Triangulated faces only (the reference reads exactly three corners of
+    every `f` line and ignores the rest); material 0 is the default material ("default").  Upstream quirk, mirrored: the
+    texcoord / normal indices of the de-duplication key are reset per FACE, not per corner, so a corner that omits them is keyed
+    with the indices of the face's previous corner (its data are still zero) - pinned against the reference's own loader by tests/test_assets.py."""
     positions, uvs, normals = [], [], []
     verts, indices, attrs = [], [], []
     materials = [ObjMaterial()]
@@ -117,17 +127,22 @@ def load_obj(path: str, flip_tex_v: bool = False) -> ObjMesh:
             x, y, z = (_f(t) for t in (tok[1:4] + ["0"] * 3)[:3])
             normals.append((x, y, z, 0.0))
         elif cmd == "f":
+            ti = ni = 0  # declared per face, outside the corner loop, upstream: a corner inherits the face's previous indices
             for corner in tok[1:4]:
                 parts = corner.split("/")
                 pi = int(parts[0])
-                ti = int(parts[1]) if len(parts) > 1 and parts[1] else 0
-                ni = int(parts[2]) if len(parts) > 2 and parts[2] else 0
+                has_t = len(parts) > 1 and parts[1] != ""
+                has_n = len(parts) > 2 and parts[2] != ""
+                if has_t:
+                    ti = int(parts[1])
+                if has_n:
+                    ni = int(parts[2])
                 key = (pi, ti, ni)
                 idx = seen.get(key)
                 if idx is None:
                     idx = len(verts)
                     seen[key] = idx
-                    verts.append(positions[pi - 1] + (uvs[ti - 1] if ti else zero4) + (normals[ni - 1] if ni else zero4))
+                    verts.append(positions[pi - 1] + (uvs[ti - 1] if has_t else zero4) + (normals[ni - 1] if has_n else zero4))
                 indices.append(idx)
             attrs.append(subset)
         elif cmd == "mtllib" and len(tok) > 1:
