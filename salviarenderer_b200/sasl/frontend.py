@@ -1582,10 +1582,20 @@ def _Lit(v: Value) -> Node:
     return Node("lit", (v,), 0)
 
 
-def compile_shader(source: str, stage: str, entry: str | None = None) -> ShaderUnit:
-    """stage: 'vs' or 'ps' (the reference's compile(code, profile): salvia/include/salvia/core/renderer.h:136-147)."""
+def compile_shader(source: str, stage: str, entry: str | None = None, *, defines: dict | None = None, include_dirs=(),
+                   sys_include_dirs=(), virtual_files: dict | None = None, file_name: str | None = None) -> ShaderUnit:
+    """stage: 'vs' or 'ps' (the reference's compile(code, profile): salvia/include/salvia/core/renderer.h:136-147).
+    Sources with preprocessor directives go through sasl/preprocess.py first (the reference runs Boost.Wave): `defines`
+    (name -> value or None), `include_dirs` / `sys_include_dirs` and `virtual_files` (name -> text, the reference's
+    add_virtual_file) feed it; `file_name` locates `#include "..."` relative to the source."""
     if stage not in ("vs", "ps", "lib"):
         raise ValueError("stage must be 'vs', 'ps' or 'lib' (functions only, no entry point: the reference's *.ss test units)")
+    if "#" in source or defines:
+        from .preprocess import PreprocessError, preprocess
+        try:
+            source = preprocess(source, defines, include_dirs, sys_include_dirs, virtual_files, file_name)
+        except PreprocessError as e:
+            raise CompileError(f"preprocessor: {e}") from None
     g = Gen(source, stage, entry)
     unit = g.run()
     if len(unit.reflection.samplers) > (2 if stage == "ps" else 1):  # RasterParams.sampler0 / sampler1, GeomParams.sampler0

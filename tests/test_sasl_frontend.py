@@ -260,7 +260,7 @@ REFERENCE_UNITS_OK = [
     "unary_operators.ss", "vec_and_mat.sps", "vec_and_mat.svs", "while.sps",
 ]
 REFERENCE_UNITS_REJECTED = {  # outside the subset (or erroneous on purpose upstream): must fail with CompileError, not crash
-    "incomplete.ss", "semantic_errors.ss", "preprocessors.ss", "include_main.ss", "scalar.sps", "array.svs",
+    "incomplete.ss", "semantic_errors.ss", "scalar.sps", "array.svs",
 }
 
 
@@ -536,3 +536,61 @@ def test_jit_cubins_hold_no_fused_packed_multiply_add():
             f.flush()
             sass = subprocess.run([cuobjdump, "-sass", f.name], capture_output=True, text=True).stdout
         assert sass.count("FADD2") > 10 and sass.count("FFMA2") == 0, stage
+
+
+# ---- preprocessor (the reference runs Boost.Wave in front of its parser) ---------------------------------------------------------
+def test_preprocessor_directives_and_macros():
+    from salviarenderer_b200.sasl.preprocess import PreprocessError, preprocess
+    out = preprocess("#define N 4\n#define SQ(x) ((x)*(x))\nfloat a[N]; int b = SQ(N+1);\n#if N > 3 && !defined(Q)\nint yes;\n#elif N\nint maybe;\n"
+                     "#else\nint no;\n#endif\n#undef N\nint N;\n/* a\n   block */ int c; // N stays\n")
+    lines = out.split("\n")
+    assert lines[2] == "float a[4]; int b = ((4+1)*(4+1));" and lines[4] == "int yes;" and lines[6] == "" and lines[8] == ""
+    assert lines[11] == "int N;" and "int c;" in lines[13] and len(lines) == 15  # line numbers of the source survive
+    assert preprocess("#ifdef A\nx\n#else\ny\n#endif", defines={"A": None}).split("\n")[1] == "x"
+    assert preprocess("#define A B\n#define B A\nA B").split("\n")[2] == "A B"  # self-reference stops the expansion
+    for bad in ("#if 1\nx", "#endif", "#else", "#include \"nope.ss\"", "#error stop", "#frobnicate", "#define F(a) a\nF(1, 2)"):
+        with pytest.raises(PreprocessError):
+            preprocess(bad)
+    # a shader through the front end: directives, a function-like macro, a virtual include
+    src = """#include <common.sasl>
+    #define SCALE(v) ((v) * gain)
+    #ifndef GAIN_DEFAULT
+    #  define GAIN_DEFAULT 2.0f
+    #endif
+    struct PSIn { float4 c: TEXCOORD0; };
+    float4 ps_main(PSIn in): COLOR { float gain = GAIN_DEFAULT; return SCALE(in.c) + bias(); }
+    """
+    unit = compile_shader(src, "ps", virtual_files={"common.sasl": "float4 bias() { return float4(0.5f, 0.25f, 0.0f, 1.0f); }"})
+    got, _ = HostShader(unit).ps([[1, 2, 3, 4]])
+    assert np.array_equal(got, np.array([2.5, 4.25, 6.0, 9.0], f32))
+    unit = compile_shader(src, "ps", defines={"GAIN_DEFAULT": "0.5f"}, virtual_files={"common.sasl": "float4 bias() { return float4(0.0f, 0.0f, 0.0f, 0.0f); }"})
+    got, _ = HostShader(unit).ps([[1, 2, 3, 4]])
+    assert np.array_equal(got, np.array([0.5, 1.0, 1.5, 2.0], f32))
+    with pytest.raises(CompileError):
+        compile_shader(src, "ps")  # the include cannot be found
+
+
+def test_reference_preprocessor_units():
+    """sasl/test/repo/{preprocessors,include_main,include_header,include_search_path}.ss as the reference's tests drive them
+    (sasl/test/jit_test/general.cpp:111-119: main() == 0; the driver tests add a virtual file and search paths)."""
+    import os
+    repo = "/root/reference/sasl/test/repo"
+    if not os.path.isdir(repo):
+        pytest.skip("reference tree not present")
+    unit = compile_shader(_ref_unit("preprocessors.ss"), "lib")
+    assert "main" in unit.code
+    with pytest.raises(CompileError):  # the guarded garbage becomes visible
+        compile_shader(_ref_unit("preprocessors.ss"), "lib", defines={"SASL_COMPILER_ERROR": None})
+    main = os.path.join(repo, "include_main.ss")
+    unit = compile_shader(open(main).read(), "lib", file_name=main,
+                          virtual_files={"virtual_include.ss": "float virtual_add(float a, float b) { return a + b; }"})
+    assert all(fn in unit.code for fn in ("header_add", "virtual_add", "main_add"))
+    with pytest.raises(CompileError):
+        compile_shader(open(main).read(), "lib", file_name=main)  # <virtual_include.ss> exists nowhere on disk
+    with pytest.raises(CompileError):
+        compile_shader(open(main).read(), "lib", file_name=main, defines={"FAILED_INCLUDE": None},
+                       virtual_files={"virtual_include.ss": "float virtual_add(float a, float b) { return a + b; }"})
+    sp = os.path.join(repo, "include_search_path.ss")
+    compile_shader(open(sp).read(), "lib", file_name=sp, include_dirs=[os.path.join(repo, "include")], sys_include_dirs=[os.path.join(repo, "sysincl")])
+    with pytest.raises(CompileError):
+        compile_shader(open(sp).read(), "lib", file_name=sp)
