@@ -85,7 +85,7 @@ struct abi_table {
   SLV_HOST_FN(slv_texture_level_count) SLV_HOST_FN(slv_texture_level_size) SLV_HOST_FN(slv_texture_upload) SLV_HOST_FN(slv_texture_readback)
   SLV_HOST_FN(slv_sampler_create) SLV_HOST_FN(slv_resource_release) SLV_HOST_FN(slv_draw) SLV_HOST_FN(slv_clear_color)
   SLV_HOST_FN(slv_clear_depth_stencil) SLV_HOST_FN(slv_resolve) SLV_HOST_FN(slv_flush) SLV_HOST_FN(slv_query_begin) SLV_HOST_FN(slv_query_get)
-  SLV_HOST_FN(slv_profile_get) SLV_HOST_FN(slv_shader_module_load) SLV_HOST_FN(slv_shader_compile)
+  SLV_HOST_FN(slv_profile_get) SLV_HOST_FN(slv_shader_module_load) SLV_HOST_FN(slv_shader_compile) SLV_HOST_FN(slv_buffer_device_ptr)
 #undef SLV_HOST_FN
   explicit abi_table(const std::string& path) {
     lib = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
@@ -98,7 +98,7 @@ struct abi_table {
     SLV_HOST_BIND(slv_texture_level_count) SLV_HOST_BIND(slv_texture_level_size) SLV_HOST_BIND(slv_texture_upload) SLV_HOST_BIND(slv_texture_readback)
     SLV_HOST_BIND(slv_sampler_create) SLV_HOST_BIND(slv_resource_release) SLV_HOST_BIND(slv_draw) SLV_HOST_BIND(slv_clear_color)
     SLV_HOST_BIND(slv_clear_depth_stencil) SLV_HOST_BIND(slv_resolve) SLV_HOST_BIND(slv_flush) SLV_HOST_BIND(slv_query_begin) SLV_HOST_BIND(slv_query_get)
-    SLV_HOST_BIND(slv_profile_get) SLV_HOST_BIND(slv_shader_module_load) SLV_HOST_BIND(slv_shader_compile)
+    SLV_HOST_BIND(slv_profile_get) SLV_HOST_BIND(slv_shader_module_load) SLV_HOST_BIND(slv_shader_compile) SLV_HOST_BIND(slv_buffer_device_ptr)
 #undef SLV_HOST_BIND
   }
   ~abi_table() { if (lib) dlclose(lib); }
@@ -504,6 +504,18 @@ public:
     pointers_[name] = v;
     return result::ok;
   }
+  // array uniforms (`float4x4 bones[boneCount]`): the block holds the ADDRESS of a device buffer; the data are read through the
+  // pointer given to set_*_variable_pointer at every draw (renderer::submit uploads them and patches the address in)
+  struct array_binding { size_t offset = 0; void const* src = nullptr; size_t size = 0; std::shared_ptr<buffer> buf; bool uploaded = false; };
+  void declare_array(std::string const& name, size_t offset) { arrays_[name].offset = offset; }
+  result set_array_pointer(std::string const& name, void const* v, size_t size) {
+    auto it = arrays_.find(name);
+    if (it == arrays_.end() || !v || !size) return result::failed;
+    it->second.src = v; it->second.size = size;
+    return result::ok;
+  }
+  std::map<std::string, array_binding>& arrays() { return arrays_; }
+  void patch_address(size_t offset, uint64_t address) { if (offset + 8 <= block_.size()) std::memcpy(block_.data() + offset, &address, 8); }
   size_t pack(uint8_t* dst, size_t cap) const {
     size_t n = block_.size() < cap ? block_.size() : cap;
     std::memcpy(dst, block_.data(), n);
@@ -526,6 +538,7 @@ public:
 private:
   std::vector<uint8_t> block_; std::map<std::string, std::pair<size_t, size_t>> layout_; std::map<std::string, void const*> pointers_;
   std::map<std::string, size_t> sampler_slots_; std::vector<sampler_ptr> samplers_;
+  std::map<std::string, array_binding> arrays_;
 };
 class jit_vertex_shader : public cpp_vertex_shader, public jit_uniform_block {
 public:
@@ -674,7 +687,8 @@ public:
   }
   // the pointed-to value is read at every draw (renderer.h:79; vx_shader_unit::set_variable_pointer)
   result set_vs_variable_pointer(std::string const& name, void const* pvariable, size_t sz) {
-    if (auto j = dynamic_cast<jit_uniform_block*>(vs_.get())) return j->set_uniform_pointer(name, pvariable, sz);
+    if (auto j = dynamic_cast<jit_uniform_block*>(vs_.get()))
+      return j->arrays().count(name) ? j->set_array_pointer(name, pvariable, sz) : j->set_uniform_pointer(name, pvariable, sz);
     return result::failed;
   }
   // SASL shaders (renderer.h:75,86): the generated device code is compiled in process (slv_shader_compile: NVRTC) the first
@@ -688,7 +702,10 @@ public:
       slv_result rc = ctx_->abi->slv_shader_compile(ctx_->dev, SLV_STAGE_VS, so->device_code.c_str(), so->n_vs_output_attrs, 0, &module, compile_log_, sizeof(compile_log_));
       if (rc != SLV_OK) return to_result(rc);
       auto sh = std::make_shared<jit_vertex_shader>(module, so->n_vs_output_attrs, so->uniform_bytes);
-      for (auto const& u : so->uniforms) sh->declare_uniform(u.first, u.second.offset, u.second.size);
+      for (auto const& u : so->uniforms) {
+        if (u.second.type.size() > 2 && u.second.type.compare(u.second.type.size() - 2, 2, "[]") == 0) sh->declare_array(u.first, u.second.offset);
+        else sh->declare_uniform(u.first, u.second.offset, u.second.size);
+      }
       for (size_t i = 0; i < so->samplers.size(); ++i) sh->declare_sampler_slot(so->samplers[i], i);
       for (auto const& in : so->inputs) sh->bind_semantic(in.semantic.c_str(), in.index, in.slot);
       it = vs_code_cache_.emplace(so.get(), std::make_pair(so, sh)).first;
@@ -817,6 +834,20 @@ private:
     d.index_format = indexed ? (uint32_t)index_format_ : (uint32_t)SLV_INDEX_NONE;
     d.topology = (uint32_t)topology_;
     d.start = (uint32_t)startpos; d.prim_count = (uint32_t)primcnt; d.base_vertex = basevert;
+    if (auto j = dynamic_cast<jit_uniform_block*>(vs_.get()))  // array uniforms: push the pointed-to data, patch the buffer's address in
+      for (auto& a : j->arrays()) {
+        jit_uniform_block::array_binding& ab = a.second;
+        if (!ab.src) return result::failed;  // declared by the shader, never set
+        if (!ab.buf || ab.buf->size() < ab.size) { ab.buf = create_buffer(ab.size); ab.uploaded = false; }
+        if (!ab.buf) return result::failed;
+        if (!ab.uploaded || std::memcmp(ab.buf->staging_.data(), ab.src, ab.size) != 0) {  // an upload is a flush point: only when the data changed
+          if (ab.buf->transfer(0, ab.src, ab.size, 1) != result::ok) return result::failed;
+          ab.uploaded = true;
+        }
+        void* dptr = nullptr; size_t dbytes = 0;
+        if (ctx_->abi->slv_buffer_device_ptr(ctx_->dev, ab.buf->handle_, &dptr, &dbytes) != SLV_OK) return result::failed;
+        j->patch_address(ab.offset, reinterpret_cast<uint64_t>(dptr));
+      }
     vs_->bind(d.vs); ps_->bind(d.ps); bs_->bind(d.bs);
     for (uint32_t i = 0; i < vs_->num_output_attributes() && i < SLV_MAX_VS_OUTPUT_ATTRS; ++i) d.vs_attr_modifiers[i] = vs_->output_attribute_modifiers(i);
     d.raster.cull_mode = (uint32_t)rs_state_->get_desc().cm; d.raster.front_ccw = rs_state_->get_desc().front_ccw ? 1u : 0u;

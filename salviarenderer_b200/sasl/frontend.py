@@ -130,7 +130,8 @@ class VarDecl:
     semantic: str | None
     init: Node | None
     line: int
-    array: int = 0
+    array: int = 0              # > 0: literal element count; -1: sized by another global (array_len)
+    array_len: str | None = None
 
 
 @dataclass
@@ -255,16 +256,19 @@ class Parser:
                 funcs.append(Func(name, ty, rsem, params, body, line))
             else:
                 while True:
-                    arr = 0
+                    arr, arr_len = 0, None
                     if self.accept("["):
-                        if self.t.kind != "num" or not re.fullmatch(r"\d+", self.t.text):
-                            raise CompileError(f"line {self.t.line}: the size of an array must be an integer literal")
-                        arr = int(self.t.text)
+                        if self.t.kind == "num" and re.fullmatch(r"\d+", self.t.text):
+                            arr = int(self.t.text)
+                        elif self.t.kind == "id":  # `float4x4 bones[boneCount]`: sized at run time by another global
+                            arr, arr_len = -1, self.t.text
+                        else:
+                            raise CompileError(f"line {self.t.line}: the size of an array must be an integer literal or the name of a global")
                         self.i += 1
                         self.expect("]")
                     sem = self.semantic()
                     init = self.assign_expr() if self.accept("=") else None
-                    globals_.append(VarDecl(ty, name, sem, init, line, arr))
+                    globals_.append(VarDecl(ty, name, sem, init, line, arr, arr_len))
                     if not self.accept(","):
                         break
                     name = self.ident()
@@ -479,6 +483,7 @@ class Reflection:
     uniforms: list = field(default_factory=list)    # (name, type string, byte offset, byte size)
     uniform_bytes: int = 0
     samplers: list = field(default_factory=list)    # names, in slot order
+    arrays: dict = field(default_factory=dict)      # array uniform -> (element type, element bytes, length: int or the global that holds it)
     inputs: list = field(default_factory=list)      # VS: (semantic, index, type) -> input register k; PS: -> attribute k
     outputs: list = field(default_factory=list)     # VS: non-position outputs -> attribute k; PS: colour targets
     n_vs_output_attrs: int = 0
@@ -506,6 +511,9 @@ class ShaderUnit:
         buf = bytearray(self.reflection.uniform_bytes)
         for name, v in values.items():
             _, ty, off, size = self.reflection.uniform(name)
+            if ty.endswith("[]"):  # an array uniform: the address of its buffer (device pointer / host pointer)
+                struct.pack_into("<Q", buf, off, int(v))
+                continue
             flat = list(v) if hasattr(v, "__iter__") else [v]
             flat = [x for row in flat for x in (row if hasattr(row, "__iter__") else [row])]
             if len(flat) * 4 != size:
@@ -547,6 +555,7 @@ class Gen:
         self.fn_table: dict[str, Func] = {}
         self.refl = Reflection(stage, "")
         self.uniform_vars: dict[str, Value] = {}
+        self.uniform_arrays: dict[str, Type] = {}   # array uniforms: element type (the block holds the buffer's address)
         self.sampler_slots: dict[str, int] = {}
         self.loop_depth = 0
         self.divergent = 0   # > 0 while emitting code under a data-dependent branch or loop
@@ -729,12 +738,34 @@ class Gen:
         self.err(n, f"cannot take .{name} of {ty}")
 
     def e_index(self, n):
-        base = self.expr(n.args[0])
         idx = n.args[1]
-        if idx.op != "num":
-            self.err(n, "only constant indices are supported")
-        i = int(idx.args[0].rstrip("uUlL"), 0)
+        # an element of an array uniform: loads through the address the uniform block holds
+        if n.args[0].op == "var" and n.args[0].args[0] in self.uniform_arrays and not any(n.args[0].args[0] in sc for sc in self.scopes):
+            name = n.args[0].args[0]
+            ety = self.uniform_arrays[name]
+            iv = self.convert(self.expr(idx), INT, n)
+            i = self.temp("int", iv.comps[0])
+            return Value(ety, [self.temp(ety.base, f"U.{name}[{i} * {ety.n} + {k}]") for k in range(ety.n)])
+        base = self.expr(n.args[0])
         ty = base.type
+        if idx.op != "num":
+            # a run-time index into a vector / the rows of a matrix: a chain of selects over the components (read-only)
+            iv = self.expr(idx)
+            if iv.type.kind != "scalar" or iv.type.base not in ("int", "uint"):
+                self.err(n, "an index must be an integer scalar")
+            if ty.kind not in ("vector", "matrix"):
+                self.err(n, f"cannot index {ty}")
+            i = self.temp("int", self.convert(iv, INT, n).comps[0])
+            src = self.materialize(base)
+            count, width = (ty.cols, 1) if ty.kind == "vector" else (ty.rows, ty.cols)
+            comps = []
+            for c in range(width):
+                e = src.comps[(count - 1) * width + c]
+                for r in range(count - 2, -1, -1):
+                    e = f"({i} == {r} ? {src.comps[r * width + c]} : {e})"
+                comps.append(self.temp(ty.base, e))
+            return Value(vec(ty.base, width), comps)
+        i = int(idx.args[0].rstrip("uUlL"), 0)
         if ty.kind == "vector":
             if i >= ty.n:
                 self.err(n, "index out of range")
@@ -1447,8 +1478,23 @@ class Gen:
                 self.uniform_vars[g.name] = Value(SAMPLER, [str(len(self.refl.samplers))])
                 self.refl.samplers.append(g.name)
                 continue
-            if g.type.kind == "struct" or g.array:
-                raise CompileError(f"line {g.line}: global {g.name}: struct / array uniforms are not supported")
+            if g.type.kind == "struct":
+                raise CompileError(f"line {g.line}: global {g.name}: struct uniforms are not supported")
+            if g.array:
+                # an array uniform lives in a buffer of its own (bone palettes do not fit the 256-byte block): the block holds
+                # its ADDRESS - device memory for the product (slv_buffer_device_ptr), host memory for host-compiled code
+                if g.type.kind not in ("scalar", "vector", "matrix") or g.type.base == "bool":
+                    raise CompileError(f"line {g.line}: global {g.name}: arrays of {g.type} are not supported")
+                if g.array_len is not None and not any(x.name == g.array_len and x.type.kind == "scalar" and x.type.base in ("int", "uint")
+                                                       for x in self.globals_):
+                    raise CompileError(f"line {g.line}: global {g.name}: the array size {g.array_len!r} is not an integer global")
+                off = (off + 15) & ~15
+                fields.append(f"  alignas(16) const {C_BASE[g.type.base]}* {g.name};")
+                self.uniform_arrays[g.name] = g.type
+                self.refl.uniforms.append((g.name, f"{g.type}[]", off, 8))
+                self.refl.arrays[g.name] = (str(g.type), 4 * g.type.n, g.array_len if g.array_len is not None else g.array)
+                off += 8
+                continue
             n = g.type.n
             off = (off + 15) & ~15
             cb = C_BASE["int" if g.type.base == "bool" else g.type.base]
@@ -1501,10 +1547,13 @@ class Gen:
             for name, ty, sem in members:
                 if sem is None:
                     raise CompileError(f"vertex-shader input {name} has no semantic")
-                if ty.kind not in ("scalar", "vector") or ty.base != "float":
-                    raise CompileError(f"vertex-shader input {name}: only float vectors are supported")
+                if ty.kind not in ("scalar", "vector") or ty.base == "bool":
+                    raise CompileError(f"vertex-shader input {name}: only float / int vectors are supported")
                 self.refl.inputs.append((sem[0], sem[1], str(ty)))
-                args += [f"in[{reg}].{'xyzw'[k]}" for k in range(ty.n)]
+                # integer inputs: the register holds the element's raw bits (get_vec4 of the *_sint / *_uint formats
+                # reinterprets them, stream_assembler.cpp:26-45)
+                cast = {"float": "{}", "int": "sasl_asint({})", "uint": "sasl_asuint({})"}[ty.base]
+                args += [cast.format(f"in[{reg}].{'xyzw'[k]}") for k in range(ty.n)]
                 reg += 1
         if reg > 8:
             raise CompileError("more than 8 vertex-shader inputs")

@@ -389,6 +389,47 @@ int main(int argc, char** argv) {
     const uint64_t h6 = fnv(m.data, d3->bytes());
     CHECK(r->unmap());
     if (drawn < W * H * S / 50) return 12;
+    if (use_sasl) {
+      // array uniforms through the surface (samples/AstroBoy's bone palettes: `float4x4 m[count]` filled through
+      // set_vs_variable_pointer): the same vertex shader with a per-draw offset taken from an array global.  All-zero offsets
+      // must reproduce the frame above bit for bit, non-zero offsets must not.
+      static const char* kVsArr =
+          "float4x4 wvpMatrix; float4 lightPos; float4 eyePos; int nOffsets; float4 offsets[nOffsets]; int sel;\n"
+          "struct VSIn  { float4 pos: POSITION; float4 tex: TEXCOORD0; float4 norm: NORMAL; };\n"
+          "struct VSOut { float4 pos: sv_position; float4 tex: TEXCOORD0; float4 norm: TEXCOORD1; float4 lightDir: TEXCOORD2; float4 eyeDir: TEXCOORD3; };\n"
+          "VSOut vs_main(VSIn in) {\n"
+          "  VSOut o;\n"
+          "  float4 p = in.pos + offsets[sel];\n"
+          "  o.norm = in.norm; o.pos = mul(p, wvpMatrix); o.lightDir = lightPos - p; o.eyeDir = eyePos - p; o.tex = in.tex;\n"
+          "  return o;\n"
+          "}\n";
+      shader::shader_object_ptr vsa = shader::compile(kVsArr, shader::lang_vertex_shader);
+      if (!vsa) return 13;
+      if (r->set_vertex_shader_code(vsa) != result::ok) { std::fprintf(stderr, "array VS: %s\n", r->shader_compile_log()); return 13; }
+      CHECK(r->set_input_layout(r->create_input_layout(e3, 3, vsa)));
+      vec4 offs[3] = {{9.0f, 9.0f, 9.0f, 0.0f}, {0.0f, 0.0f, 0.0f, 0.0f}, {0.5f, 0.25f, 0.0f, 0.0f}};
+      const int n_offs = 3;
+      int sel = 1;
+      CHECK(r->set_vs_variable("wvpMatrix", &wvp));
+      CHECK(r->set_vs_variable("lightPos", &light));
+      CHECK(r->set_vs_variable("eyePos", &eye));
+      CHECK(r->set_vs_variable("nOffsets", &n_offs));
+      CHECK(r->set_vs_variable_pointer("offsets", offs, sizeof(offs)));
+      if (r->set_vs_variable_pointer("noSuchArray", offs, sizeof(offs)) != result::failed) return 13;
+      uint64_t ha[2];
+      for (int pass = 0; pass < 2; ++pass) {
+        sel = pass == 0 ? 1 : 2;
+        CHECK(r->set_vs_variable("sel", &sel));
+        CHECK(r->clear_color(c3, color_rgba32f{0.1f, 0.1f, 0.1f, 1.0f}));
+        CHECK(r->clear_depth_stencil(d3, clear_depth | clear_stencil, 1.0f, 0));
+        CHECK(r->draw_index(0, G * G * 2, 0));
+        CHECK(r->flush());
+        CHECK(r->map(m, c3, map_read));
+        ha[pass] = fnv(m.data, c3->bytes());
+        CHECK(r->unmap());
+      }
+      if (ha[0] != h5 || ha[1] == h5) { std::fprintf(stderr, "array uniform: %016" PRIx64 " %016" PRIx64 " vs %016" PRIx64 "\n", ha[0], ha[1], h5); return 14; }
+    }
     std::printf("sasl color %016" PRIx64 " depth %016" PRIx64 " drawn %zu\n", h5, h6, drawn);
   }
   return 0;

@@ -375,3 +375,67 @@ def test_sasl_intrinsics_match_the_reference_known_answers(cuda):
         exact += sasl_kat.check(case, got)
         total += len(case["expected"])
     assert exact >= total * 0.8, (exact, total)
+
+
+def test_sasl_skinning_vertex_shader_array_uniforms(cuda):
+    """samples/AstroBoy's skinning vertex shader (AstroBoy.cpp:39-79): bone palettes in ARRAY uniforms sized by another global
+    (device buffers whose addresses ride in the uniform block), `int4 BLEND_INDICES` inputs, run-time indices, a data-dependent
+    `break`.  The GPU frame must equal, bit for bit, the frame of the same mesh with the shader's outputs precomputed on the
+    host (the front end's code compiled for the host, itself pinned to a float32 numpy restatement in tests/test_sasl_frontend.py)
+    and passed through SLV_VS_MVP_PASSTHROUGH with an identity matrix."""
+    from sasl_host import HostShader
+    from test_sasl_frontend import VS_SKIN, skin_test_data
+    sh = jit.compile(VS_SKIN, "vs")
+    mod = jit.load(cuda, sh)
+    n = 24
+    grid = S.create_planar((-3.0, 0.0, -3.0), (6.0 / n, 0, 0), (0, 0, 6.0 / n), n, n, True, index_dtype=np.uint32)
+    nv = len(grid.streams[0])
+    bones, invs, _, _, _, _ = skin_test_data(n_bones=6)
+    rng = np.random.default_rng(4)
+    pos = np.ascontiguousarray(grid.streams[0][:, :3], dtype=np.float32)
+    pos[:, 1] += rng.uniform(-0.3, 0.3, nv).astype(np.float32)
+    nrm = rng.uniform(0.0, 1.0, (nv, 3)).astype(np.float32)
+    idx = rng.integers(0, 6, (nv, 4)).astype(np.int32)
+    for v in range(nv):
+        idx[v, 1 + v % 4:] = -1
+    wts = rng.uniform(0.2, 0.6, (nv, 4)).astype(np.float32)
+    view = S.mat_lookat((0.5, 4.0, -4.5), (0, 0, 0), (0, 1, 0))
+    wvp = np.asarray(S.mat_mul(view, S.mat_perspective_fov(np.pi / 2, 16 / 9, 0.1, 100.0)), np.float32).reshape(4, 4)
+    eye, light = np.array([0.5, 4.0, -4.5, 1], np.float32), np.array([3, 4, -1, 1], np.float32)
+
+    def render(mesh, vs_binding):
+        t = S.create_targets(cuda, 640, 360, 4, A.PF_RGBA8)
+        cuda.query_begin()
+        cuda.clear_color(t.color, (0.1, 0.1, 0.2, 1.0))
+        cuda.clear_depth_stencil(t.ds, A.CLEAR_DEPTH | A.CLEAR_STENCIL, 1.0, 0)
+        d = S.base_desc(t, 640, 360, cull=A.CULL_NONE)
+        mesh.fill_desc(cuda, d)
+        d.vs = vs_binding
+        d.ps = A.shader_binding(A.PS_ATTR0_COLOR)
+        d.bs = A.shader_binding(A.BS_REPLACE)
+        cuda.draw(d)
+        return S.read_frame(cuda, t, cuda.query_get())
+
+    # (a) the SASL shader on the GPU: four streams (float3, float3, int4 as raw bits, float4), palettes in device buffers
+    skinned = S.Mesh([pos, nrm, idx.view(np.float32), wts],
+                     [(0, A.FMT_R32G32B32_FLOAT, 0, 0, 1.0), (1, A.FMT_R32G32B32_FLOAT, 1, 0, 0.0), (2, S._V4, 2, 0, 0.0), (3, S._V4, 3, 0, 0.0)],
+                     grid.indices, grid.prim_count)
+    hb, hi = cuda.create_buffer(np.ascontiguousarray(bones)), cuda.create_buffer(np.ascontiguousarray(invs))
+    ub = sh.unit.pack_uniforms({"wvpMatrix": wvp, "eyePos": eye, "lightPos": light, "boneCount": len(bones),
+                                "boneMatrices": cuda.buffer_device_ptr(hb)[0], "invMatrices": cuda.buffer_device_ptr(hi)[0]})
+    ra = render(skinned, A.shader_binding(A.program_jit(mod), ub))
+    # (b) the same shader evaluated on the host, its four outputs as vertex data
+    hs = HostShader(sh.unit)
+    bones_c, invs_c = np.ascontiguousarray(bones), np.ascontiguousarray(invs)
+    ub_host = sh.unit.pack_uniforms({"wvpMatrix": wvp, "eyePos": eye, "lightPos": light, "boneCount": len(bones),
+                                     "boneMatrices": bones_c.ctypes.data, "invMatrices": invs_c.ctypes.data})
+    outs = np.zeros((nv, 4, 4), np.float32)
+    for v in range(nv):
+        regs = np.zeros((4, 4), np.float32)
+        regs[0, :3], regs[1, :3], regs[2], regs[3] = pos[v], nrm[v], idx[v].view(np.float32), wts[v]
+        outs[v] = hs.vs(regs, ub_host)[:4]
+    pre = S.Mesh([np.ascontiguousarray(outs[:, k]) for k in range(4)], [(k, S._V4, k, 0, 1.0 if k == 0 else 0.0) for k in range(4)],
+                 grid.indices, grid.prim_count)
+    rb = render(pre, A.shader_binding(A.VS_MVP_PASSTHROUGH, S.pack_vs_mvp_passthrough(np.eye(4, dtype=np.float32), [1, 2, 3])))
+    assert ra.stats["ps_invocations"] > 20000 and ra.stats["cprimitives"] == rb.stats["cprimitives"]
+    assert not cases.compare_frames(ra, rb)

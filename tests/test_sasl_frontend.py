@@ -260,7 +260,7 @@ REFERENCE_UNITS_OK = [
     "unary_operators.ss", "vec_and_mat.sps", "vec_and_mat.svs", "while.sps",
 ]
 REFERENCE_UNITS_REJECTED = {  # outside the subset (or erroneous on purpose upstream): must fail with CompileError, not crash
-    "incomplete.ss", "semantic_errors.ss", "scalar.sps", "array.svs",
+    "incomplete.ss", "semantic_errors.ss", "scalar.sps",
 }
 
 
@@ -594,3 +594,99 @@ def test_reference_preprocessor_units():
     compile_shader(open(sp).read(), "lib", file_name=sp, include_dirs=[os.path.join(repo, "include")], sys_include_dirs=[os.path.join(repo, "sysincl")])
     with pytest.raises(CompileError):
         compile_shader(open(sp).read(), "lib", file_name=sp)
+
+
+# ---- array uniforms, integer inputs, run-time indices: the skinning vertex shader of samples/AstroBoy (AstroBoy.cpp:39-79) ----------
+VS_SKIN = """
+float4x4 wvpMatrix; float4 eyePos; float4 lightPos;
+int      boneCount;
+float4x4 boneMatrices[boneCount];
+float4x4 invMatrices[boneCount];
+struct VSIn  { float3 pos: POSITION; float3 norm: NORMAL; int4 indices: BLEND_INDICES; float4 weights: BLEND_WEIGHTS; };
+struct VSOut { float4 pos: sv_position; float4 norm: TEXCOORD1; float4 lightDir: TEXCOORD2; float4 eyeDir: TEXCOORD3; };
+VSOut vs_main(VSIn in) {
+    VSOut o;
+    float4 n4 = float4(in.norm, 0.0f);
+    float4 p4 = float4(in.pos, 1.0f);
+    float4 skin_pos = float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4 skin_nor = float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (int i = 0; i < 4; ++i) {
+        float4 w = in.weights[i].xxxx;
+        int boneId = in.indices[i];
+        if (boneId == -1) { break; }
+        float4 posInBoneSpace = mul(invMatrices[boneId], p4);
+        skin_pos += (mul(boneMatrices[boneId], posInBoneSpace) * w);
+        float4 norInBoneSpace = mul(invMatrices[boneId], n4);
+        skin_nor += (mul(boneMatrices[boneId], norInBoneSpace) * w);
+    }
+    o.pos = mul(skin_pos, wvpMatrix);
+    o.norm = skin_nor;
+    o.lightDir = lightPos - skin_pos;
+    o.eyeDir = eyePos - skin_pos;
+    return o;
+}
+"""
+
+
+def skin_reference(pos, norm, indices, weights, bones, invs, wvp, eye, light):
+    """float32 restatement of VS_SKIN: mul(M, v) = rows of M dot v, mul(v, M) = v times the columns, sums left to right."""
+    def mv(M, v):
+        return np.array([f32(f32(f32(f32(M[r, 0] * v[0]) + f32(M[r, 1] * v[1])) + f32(M[r, 2] * v[2])) + f32(M[r, 3] * v[3])) for r in range(4)], f32)
+
+    def vm(v, M):
+        return np.array([f32(f32(f32(f32(v[0] * M[0, c]) + f32(v[1] * M[1, c])) + f32(v[2] * M[2, c])) + f32(v[3] * M[3, c])) for c in range(4)], f32)
+
+    p4, n4 = np.array([*pos, 1.0], f32), np.array([*norm, 0.0], f32)
+    sp, sn = np.zeros(4, f32), np.zeros(4, f32)
+    for i in range(4):
+        b = int(indices[i])
+        if b == -1:
+            break
+        w = f32(weights[i])
+        sp = (sp + mv(bones[b], mv(invs[b], p4)) * w).astype(f32)
+        sn = (sn + mv(bones[b], mv(invs[b], n4)) * w).astype(f32)
+    return vm(sp, wvp), sn, (light - sp).astype(f32), (eye - sp).astype(f32)
+
+
+def skin_test_data(n_bones=5, n_verts=64, seed=9):
+    rng = np.random.default_rng(seed)
+    bones = (np.eye(4, dtype=f32)[None] + rng.uniform(-0.3, 0.3, (n_bones, 4, 4)).astype(f32)).astype(f32)
+    invs = (np.eye(4, dtype=f32)[None] + rng.uniform(-0.2, 0.2, (n_bones, 4, 4)).astype(f32)).astype(f32)
+    pos = rng.uniform(-1, 1, (n_verts, 3)).astype(f32)
+    norm = rng.uniform(-1, 1, (n_verts, 3)).astype(f32)
+    idx = rng.integers(0, n_bones, (n_verts, 4)).astype(np.int32)
+    for v in range(n_verts):  # 1 .. 4 influences; -1 terminates the list
+        k = 1 + v % 4
+        idx[v, k:] = -1
+    wts = rng.uniform(0.1, 1.0, (n_verts, 4)).astype(f32)
+    return bones, invs, pos, norm, idx, wts
+
+
+def test_skinning_vertex_shader_array_uniforms_and_integer_inputs():
+    unit = compile_shader(VS_SKIN, "vs")
+    r = unit.reflection
+    assert r.arrays == {"boneMatrices": ("float4x4", 64, "boneCount"), "invMatrices": ("float4x4", 64, "boneCount")}
+    assert [u[1] for u in r.uniforms] == ["float4x4", "float4", "float4", "int", "float4x4[]", "float4x4[]"]
+    assert r.inputs == [("POSITION", 0, "float3"), ("NORMAL", 0, "float3"), ("BLEND_INDICES", 0, "int4"), ("BLEND_WEIGHTS", 0, "float4")]
+    hs = HostShader(unit)
+    bones, invs, pos, norm, idx, wts = skin_test_data()
+    wvp = (np.eye(4, dtype=f32) + np.arange(16, dtype=f32).reshape(4, 4) * f32(0.01)).astype(f32)
+    eye, light = np.array([0, 2, -5, 1], f32), np.array([3, 4, -1, 1], f32)
+    bones_c, invs_c = np.ascontiguousarray(bones), np.ascontiguousarray(invs)
+    ub = unit.pack_uniforms({"wvpMatrix": wvp, "eyePos": eye, "lightPos": light, "boneCount": len(bones),
+                             "boneMatrices": bones_c.ctypes.data, "invMatrices": invs_c.ctypes.data})
+    for v in range(len(pos)):
+        regs = np.zeros((4, 4), f32)
+        regs[0, :3], regs[1, :3], regs[3] = pos[v], norm[v], wts[v]
+        regs[2] = idx[v].view(f32)  # the register carries the integers' bits
+        out = hs.vs(regs, ub)
+        want = skin_reference(pos[v], norm[v], idx[v], wts[v], bones, invs, wvp, eye, light)
+        for k in range(4):
+            assert np.array_equal(out[k].view(np.uint32), want[k].view(np.uint32)), (v, k, out[k], want[k])
+    with pytest.raises(CompileError):
+        compile_shader("float4 a[n];\nfloat4 f(float4 p: POSITION): SV_Position { return a[0]; }", "vs")  # size is not a global
+
+
+def test_reference_array_unit_compiles():
+    unit = compile_shader(_ref_unit("array.svs"), "vs")  # int mat_size; float4x4 mat_arr[mat_size]; int4 BLEND_INDICES input
+    assert unit.reflection.arrays == {"mat_arr": ("float4x4", 64, "mat_size")}
