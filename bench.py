@@ -547,11 +547,29 @@ def main():
     b_setup = st2["cprimitives"] / K * 3 * 16 * R
     b_depth = (8 * traffic["z_tested"] + 8 * traffic["z_written"]) / K
     b_color = (4 * traffic["c_written"] + 4 * traffic["c_read"]) / K
-    if "tex_bytes_touched" in traffic and traffic["tex_bytes_touched"]:
-        b_tex, b_tex_how = traffic["tex_bytes_touched"] / K, "distinct (texture, mip level) pairs touched, per draw, counted on the device"
-    else:
-        b_tex = 24 * sum(max(args.tex_size >> l, 1) ** 2 * 4 for l in range(args.tex_size.bit_length()))
-        b_tex_how = "full mip chains of the 24 bound textures"
+    # B_tex: the texture bytes a frame TOUCHES - every mip level of every bound texture that at least one sampler call
+    # of the frame reads, once.  Counted on the device in an untimed pass (slv_texture_level_tracking: a bit mask of sampled levels
+    # per texture), per distinct frame of the animation, union over the ranks, average over the frames.
+    b_tex_full = 24 * sum(max(args.tex_size >> l, 1) ** 2 * 4 for l in range(args.tex_size.bit_length()))
+    per_frame = []
+    for f in range(sc.n_frames):
+        be.texture_level_tracking(True)
+        frame(f)
+        be.flush()
+        masks = torch.tensor([be.texture_levels_touched(t) for t in sc.textures], device="cuda", dtype=torch.int32)
+        if n > 1:
+            dist.all_reduce(masks, op=dist.ReduceOp.BOR)
+        touched = 0
+        for t, m in zip(sc.textures, masks.tolist()):
+            for l in range(be.level_count(t)):
+                if m & (1 << l):
+                    lw, lh = be.level_size(t, l)
+                    touched += lw * lh * 4
+        per_frame.append(touched)
+    be.texture_level_tracking(False)
+    b_tex = sum(per_frame) / len(per_frame)
+    b_tex_how = (f"mip levels of the 24 bound textures that the frame's sampler calls read (device-side level masks, average over the "
+                 f"{sc.n_frames} distinct frames: {b_tex / 1e6:.1f} MB of the {b_tex_full / 1e6:.1f} MB the full chains hold)")
     b_resolve = W * H * 4 * (S + 1) if S > 1 else 0
     b_frame = b_clear + b_geom + b_setup + b_depth + b_color + b_tex + b_resolve
     peak, peak_src = peaks()

@@ -376,6 +376,12 @@ typedef struct slv_traffic_counters {
   uint64_t ps_executed;
 } slv_traffic_counters;
 slv_result slv_traffic_get(slv_device dev, slv_traffic_counters* out);
+/* B_tex of SURVEY 8d counts the texture bytes a frame TOUCHES: with tracking on, every sampler call of the draws issued
+ * afterwards records the mip level(s) it reads; slv_texture_levels_touched returns the bit mask (bit l = level l) accumulated
+ * since tracking was last switched on (switching it on again resets every mask).  Measurement aid: tracking adds one atomic per
+ * sampler call, so it is off in timed regions.  CPU checkers: SLV_OK and an empty mask. */
+slv_result slv_texture_level_tracking(slv_device dev, uint32_t on);
+slv_result slv_texture_levels_touched(slv_device dev, slv_handle tex, uint32_t* mask);
 /* number of kernels this library launched since slv_query_begin (0 for the CPU checkers) */
 slv_result slv_kernel_launch_count(slv_device dev, uint64_t* out);
 /* CUDA events on the stream the kernels are launched on: record event `slot` (0..15) now; elapsed

@@ -1808,6 +1808,8 @@ slv_result slv_readback_fence(slv_device, slv_handle) { return SLV_OK; }
 // peer-memory frame assembly is a property of the CUDA product (NVLink); the CPU checkers do not implement it
 slv_result slv_peer_export_texture(slv_device, slv_handle, uint32_t, uint8_t*) { return SLV_FAILED; }
 slv_result slv_peer_export_flags(slv_device, uint8_t*) { return SLV_FAILED; }
+slv_result slv_texture_level_tracking(slv_device, uint32_t) { return SLV_OK; }
+slv_result slv_texture_levels_touched(slv_device, slv_handle, uint32_t* mask) { if (!mask) return SLV_INVALID_PARAMETER; *mask = 0; return SLV_OK; }
 slv_result slv_shader_module_load(slv_device, uint32_t, const void*, size_t, uint32_t, slv_handle*) { return SLV_FAILED; }
 slv_result slv_shader_compile_cubin(uint32_t, const char*, uint32_t, uint32_t, void**, size_t*, char*, size_t) { return SLV_FAILED; }
 slv_result slv_shader_compile(slv_device, uint32_t, const char*, uint32_t, uint32_t, slv_handle*, char*, size_t) { return SLV_FAILED; }

@@ -136,7 +136,7 @@ ENTRY_POINTS = [
     "slv_traffic_get", "slv_kernel_launch_count", "slv_event_record", "slv_event_elapsed_ms", "slv_profile_enable",
     "slv_texture_device_ptr", "slv_pack_tiles", "slv_unpack_tiles", "slv_set_stream", "slv_profile_get_stages",
     "slv_peer_export_texture", "slv_peer_export_flags", "slv_peer_open", "slv_peer_close", "slv_resolve_target_peer",
-    "slv_peer_signal", "slv_flags_wait", "slv_shader_module_load", "slv_shader_compile_cubin", "slv_shader_compile", "slv_free", "slv_texture_readback_async", "slv_readback_wait",
+    "slv_peer_signal", "slv_flags_wait", "slv_shader_module_load", "slv_shader_compile_cubin", "slv_shader_compile", "slv_free", "slv_texture_level_tracking", "slv_texture_levels_touched", "slv_texture_readback_async", "slv_readback_wait",
     "slv_readback_fence", "slv_host_register", "slv_host_unregister", "slv_texture_export_tiles_async",
     "slv_assembly_wait", "slv_peer_signal_after_consumers",
     "slv_buffer_device_ptr", "slv_external_write_begin", "slv_external_write_end",
@@ -393,6 +393,17 @@ class Backend:
         t = TrafficCounters()
         _chk(self.lib.slv_traffic_get(self.dev, C.byref(t)), "slv_traffic_get")
         return t.as_dict()
+
+    def texture_level_tracking(self, on: bool):
+        """B_tex accounting: sampler calls of draws issued from now on record the mip levels they read (resets the masks)."""
+        self.lib.slv_texture_level_tracking.argtypes = [C.c_void_p, C.c_uint32]
+        _chk(self.lib.slv_texture_level_tracking(self.dev, 1 if on else 0), "slv_texture_level_tracking")
+
+    def texture_levels_touched(self, tex: Texture) -> int:
+        self.lib.slv_texture_levels_touched.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        m = C.c_uint32()
+        _chk(self.lib.slv_texture_levels_touched(self.dev, tex.handle, C.byref(m)), "slv_texture_levels_touched")
+        return m.value
 
     def launch_count(self) -> int:
         n = C.c_uint64()

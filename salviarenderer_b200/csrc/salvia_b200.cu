@@ -218,6 +218,8 @@ struct slv_device_t {
   uint64_t list_need_hint = 0, region_need_hint = 0;
   uint64_t arena_min_list = 1ull << 22, arena_min_region = 1ull << 26;
   unsigned long long* d_stats = nullptr;
+  uint32_t* d_level_touched = nullptr;  // slv_texture_level_tracking: one mask of sampled mip levels per texture handle
+  bool level_tracking = false;
   slv_pipeline_statistics host_stats{};  // counters that are pure functions of the draw arguments
   uint32_t shard_rank = 0, shard_n = 1;
   bool failed = false;  // sticky CUDA error
@@ -247,7 +249,8 @@ struct slv_device_t {
 
 namespace {
 
-constexpr uint32_t MAX_BATCH = MAX_BATCH_DRAWS;  // draws whose geometry / raster passes are fused into one launch each
+constexpr uint32_t MAX_BATCH = MAX_BATCH_DRAWS;
+constexpr uint32_t LEVEL_TRACK_SLOTS = 1u << 16;  // texture handles below this can be tracked  // draws whose geometry / raster passes are fused into one launch each
 
 slv_result flush_batch(slv_device dev);
 slv_result materialize_clear(slv_device dev, Resource* r);
@@ -1017,6 +1020,7 @@ void slv_device_destroy(slv_device dev) {
   cudaFree(dev->overflow_flag);
   cudaFree(dev->peer_flags);
   cudaFree(dev->d_stats);
+  cudaFree(dev->d_level_touched);
   for (auto& ev : dev->ev_pool) cudaEventDestroy(ev);
   for (auto& ev : dev->user_ev) cudaEventDestroy(ev);
   cudaEventDestroy(dev->ev_sync);
@@ -1537,6 +1541,7 @@ static bool fill_sampler(slv_device dev, slv_handle h, SamplerRef& out) {
     fast = fast && lv.w <= 1024 && lv.h <= 1024 && (lv.w & (lv.w - 1)) == 0 && (lv.h & (lv.h - 1)) == 0;
   }
   out.fast_wrap_rgba8 = fast ? 1u : 0u;
+  out.touched = (dev->level_tracking && r->sampler_tex < LEVEL_TRACK_SLOTS) ? dev->d_level_touched + r->sampler_tex : nullptr;
   return true;
 }
 
@@ -2024,6 +2029,32 @@ slv_result slv_traffic_get(slv_device dev, slv_traffic_counters* out) {
   out->z_written = h[10];
   out->c_written = h[11];
   out->c_read = h[12];
+  return SLV_OK;
+}
+
+slv_result slv_texture_level_tracking(slv_device dev, uint32_t on) {
+  if (!dev) return SLV_INVALID_PARAMETER;
+  CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }  // queued draws keep the setting they were issued under
+  if (on) {
+    { slv_result rcs = sync_all(dev); if (rcs != SLV_OK) return rcs; }
+    if (!dev->d_level_touched) CU(cudaMalloc(&dev->d_level_touched, LEVEL_TRACK_SLOTS * sizeof(uint32_t)));
+    CU(cudaMemsetAsync(dev->d_level_touched, 0, LEVEL_TRACK_SLOTS * sizeof(uint32_t), dev->stream));
+    CU(cudaStreamSynchronize(dev->stream));
+  }
+  dev->level_tracking = on != 0;
+  return SLV_OK;
+}
+
+slv_result slv_texture_levels_touched(slv_device dev, slv_handle tex, uint32_t* mask) {
+  auto r = dev ? dev->get(tex, Resource::TEXTURE) : nullptr;
+  if (!r || !mask) return SLV_INVALID_PARAMETER;
+  *mask = 0;
+  if (!dev->d_level_touched || tex >= LEVEL_TRACK_SLOTS) return SLV_OK;
+  CU(cudaSetDevice(dev->ordinal));
+  { slv_result rcf__ = flush_batch(dev); if (rcf__ != SLV_OK) return rcf__; }
+  { slv_result rcs = sync_all(dev); if (rcs != SLV_OK) return rcs; }
+  CU(cudaMemcpy(mask, dev->d_level_touched + tex, sizeof(uint32_t), cudaMemcpyDeviceToHost));
   return SLV_OK;
 }
 

@@ -39,6 +39,7 @@ struct SamplerRef {
   // 1 when min = mag = linear, u and v both wrap, texels are rgba8 and every level is a power of two <= 1024 (exact
   // integer wrap): the specialised tap sample_wrap_rgba8_linear applies (same arithmetic, no mode / format dispatch)
   uint32_t fast_wrap_rgba8;
+  uint32_t* touched;  // measurement aid (slv_texture_level_tracking): bit l is set when mip level l is sampled; nullptr = off
 };
 
 // ---- per-draw parameter block (passed by value to the kernels; < 4 KB) ------------------------------

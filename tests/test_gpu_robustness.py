@@ -110,3 +110,31 @@ def test_third_colour_target_is_rejected_and_statistics_untouched(cuda):
         cuda.draw(d)
     st = cuda.query_get()
     assert st["ia_primitives"] == 0 and st["ia_vertices"] == 0 and st["cinvocations"] == 0
+
+
+def test_texture_level_tracking(cuda):
+    """slv_texture_level_tracking / slv_texture_levels_touched (the B_tex accounting of bench.py): the mask holds exactly the
+    mip levels the frame's sampler calls read; a small target minifies 256^2 textures, so the finest level stays untouched
+    there while a large target reads it; switching tracking on again resets the masks; off = nothing recorded."""
+    small = S.SponzaLike(160, 90, 1, tex_size=256)
+    small.setup(cuda)
+    cuda.texture_level_tracking(True)
+    small.render(cuda, 3)
+    cuda.flush()
+    masks = [cuda.texture_levels_touched(t) for t in small.textures]
+    n_levels = cuda.level_count(small.textures[0])
+    assert any(masks) and all(m < (1 << n_levels) for m in masks)
+    assert all(not (m & 1) for m in masks), masks  # 256^2 texels over a 160x90 frame: level 0 is never selected
+    cuda.texture_level_tracking(True)  # reset
+    assert all(cuda.texture_levels_touched(t) == 0 for t in small.textures)
+    cuda.texture_level_tracking(False)
+    small.render(cuda, 3)
+    cuda.flush()
+    assert all(cuda.texture_levels_touched(t) == 0 for t in small.textures)
+    big = S.SponzaLike(1920, 1080, 1, tex_size=64)
+    big.setup(cuda)
+    cuda.texture_level_tracking(True)
+    big.render(cuda, 3)
+    cuda.flush()
+    assert any(cuda.texture_levels_touched(t) & 1 for t in big.textures)  # magnified somewhere: level 0 is read
+    cuda.texture_level_tracking(False)
