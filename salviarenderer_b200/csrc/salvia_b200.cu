@@ -58,6 +58,7 @@ struct Resource {
   uint32_t module_attrs = 0;        // VS: output attributes
   CUfunction fn_geometry = nullptr; // VS: slv_jit_k_geometry
   CUfunction fn_vertex_shade = nullptr; // VS: slv_jit_k_vertex_shade (post-transform vertex cache; absent in older cubins)
+  CUfunction fn_geometry_cull = nullptr; // VS: slv_jit_k_geometry_cull (two-kernel geometry; absent in older cubins)
   CUfunction fn_raster[3] = {};     // PS: slv_jit_k_raster_s1 / _s2 / _s4
   CUfunction fn_shade[3] = {};      // PS: slv_jit_k_shade_s1 / _s2 / _s4 (visibility-first path; absent in older cubins)
 };
@@ -118,6 +119,10 @@ struct slv_device_t {
     float4* tris = nullptr;           // triangle records (grown on demand, never shrunk)
     uint32_t* valid_slots = nullptr;  // one entry per slot of the tris arena
     uint32_t* valid_count = nullptr;
+    uint32_t* big_slots = nullptr;    // triangles whose tile range k_big_tiles counts with a warp (one entry per slot of the tris arena)
+    uint32_t* big_count = nullptr;
+    uint32_t* surv = nullptr;         // two-kernel geometry: ids of the primitives k_geometry_cull hands to k_geometry (one range per draw)
+    uint32_t* surv_count = nullptr;   // ... and their number per queued draw
     uint32_t *tile_count = nullptr, *tile_offset = nullptr, *tile_cursor = nullptr, *active_tiles = nullptr, *large_tiles = nullptr;
     uint32_t* work_counter = nullptr;  // [0] k_raster / k_cover queue head, [1] k_shade queue head, [2] region-list cursor, [3] long lists, [4] block-bits pool cursor
     uint32_t *region_list = nullptr, *region_offset = nullptr, *region_count = nullptr;  // deferred path: per-region lists
@@ -168,6 +173,17 @@ struct slv_device_t {
   // registers (measured, profiles/r02_vertex_cache.txt: k_geometry 0.065 -> 0.081 ms on the Sponza-like scene, 5.66 -> 6.13 ms on
   // the 10 M-triangle mesh).  SLV_VERTEX_CACHE=0 disables, =2 caches every indexed draw whatever its size and shader (tests).
   int vertex_cache = 1;
+  // Two experiments on the front half that are BUILT, parity-tested (tests/test_gpu_geometry_split.py) and OFF by default because
+  // neither paid (profiles/r02_front_half_experiments.txt):
+  // * two-kernel geometry (SLV_GEOMETRY_SPLIT=1): k_geometry_cull runs the position pass of every primitive at 64 registers / full
+  //   occupancy and hands only the primitives that need set-up on this rank to k_geometry.  k_geometry 0.050 -> 0.059 ms on an
+  //   eighth of the frame, 0.071 -> 0.085 ms on the whole frame, 5.7 -> 6.5 ms on the 10 M-triangle mesh: the pass is not
+  //   occupancy-bound.
+  // * big-triangle queue (SLV_BIG_TILES=1): triangles spanning more than BIG_TILE_RANGE tiles are counted by a warp of k_big_tiles
+  //   instead of by the thread that set them up.  No change (0.070 -> 0.068 ms; an eighth of the frame 0.2005 -> 0.2045 ms per
+  //   pipelined frame because of the extra launch): one thread's 2,040-tile loop is not the critical path either.
+  int geometry_split = 0;
+  bool big_tiles = false;
   bool force_immediate = false;      // SLV_FORCE_IMMEDIATE=1: always use k_raster (tests compare both paths)
   bool jit_immediate = false;        // SLV_JIT_IMMEDIATE=1: SASL pixel shaders always take k_raster
   bool front_grids = true;           // SLV_FRONT_GRIDS=0: full-size k_sort_lists / k_region_bin / k_sort_lists_large grids
@@ -281,8 +297,12 @@ slv_result ensure_scratch(slv_device dev, size_t tris_needed_total, uint32_t n_t
     for (auto& S : dev->sc) {
       if (S.tris) CU(cudaFree(S.tris));
       if (S.valid_slots) CU(cudaFree(S.valid_slots));
+      if (S.surv) CU(cudaFree(S.surv));
+      if (S.big_slots) CU(cudaFree(S.big_slots));
+      CU(cudaMalloc(&S.big_slots, (cap / (TRI_HEADER + 3 * MAX_REGS) + 1) * sizeof(uint32_t)));
       CU(cudaMalloc(&S.tris, cap * sizeof(float4)));
       CU(cudaMalloc(&S.valid_slots, (cap / (TRI_HEADER + 3 * MAX_REGS) + 1) * sizeof(uint32_t)));
+      CU(cudaMalloc(&S.surv, (cap / (TRI_HEADER + 3 * MAX_REGS) / 3 + 1) * sizeof(uint32_t)));
     }
     dev->tris_cap = cap;
   }
@@ -585,6 +605,17 @@ slv_result flush_batch(slv_device dev) {
       if (groups[k].rep == i) vc_groups.push_back(i);
     }
   }
+  // ---- two-kernel geometry: which draws run k_geometry_cull first
+  const bool want_split = dev->geometry_split > 0;
+  bool any_split = false;
+  for (uint32_t i = 0; i < n; ++i) {
+    GeomParams& g = dev->pending_geom[i];
+    const slv_handle m = dev->pending_vs_module[i];
+    const bool split = want_split && (!m || dev->res[m].fn_geometry_cull);
+    g.surv = split ? S.surv : nullptr;
+    g.surv_count = split ? S.surv_count : nullptr;
+    any_split = any_split || split;
+  }
   // parameter upload: through this set's pinned staging when pipelining (no stream synchronisation; the staging is free
   // again once ev_front_done has fired, checked above), else straight from pageable memory (the driver stages it)
   const RasterParams* src_batch = dev->pending.data();
@@ -660,6 +691,24 @@ slv_result flush_batch(slv_device dev) {
           ++hb.n;
         }
         if (!hb.n) continue;
+        if (any_split && dev->pending_geom[hb.draw_of[0]].surv) {  // the position pass of every primitive, survivors -> k_geometry
+          if (m) {
+            const GeomParams* d_geom = S.d_geom;
+            void* args[] = {(void*)&d_geom, (void*)&hb};
+            if (driver_api().LaunchKernel(dev->res[m].fn_geometry_cull, hb.cta_prefix[hb.n], 1, 1, 128, 1, 1, 0, (CUstream)fs, args, nullptr) != CUDA_SUCCESS)
+              return SLV_FAILED;
+          } else {
+            switch (R) {
+            case 1: k_geometry_cull<1><<<hb.cta_prefix[hb.n], 128, 0, fs>>>(S.d_geom, hb); break;
+            case 2: k_geometry_cull<2><<<hb.cta_prefix[hb.n], 128, 0, fs>>>(S.d_geom, hb); break;
+            case 3: k_geometry_cull<3><<<hb.cta_prefix[hb.n], 128, 0, fs>>>(S.d_geom, hb); break;
+            case 4: k_geometry_cull<4><<<hb.cta_prefix[hb.n], 128, 0, fs>>>(S.d_geom, hb); break;
+            case 5: k_geometry_cull<5><<<hb.cta_prefix[hb.n], 128, 0, fs>>>(S.d_geom, hb); break;
+            default: k_geometry_cull<6><<<hb.cta_prefix[hb.n], 128, 0, fs>>>(S.d_geom, hb); break;
+            }
+          }
+          dev->n_launches += 1;
+        }
         if (m) {  // SASL vertex shader: the module's own k_geometry instance
           const GeomParams* d_geom = S.d_geom;
           void* args[] = {(void*)&d_geom, (void*)&hb};
@@ -680,8 +729,12 @@ slv_result flush_batch(slv_device dev) {
   }
   if (dev->profile) dev->spans.push_back({eg0, mark(dev), 0});
   size_t e0 = dev->profile ? mark(dev) : 0;
-  k_scan_tiles<<<1, 1024, 0, fs>>>(S.tile_count, S.tile_offset, S.tile_cursor, n_tiles, S.active_tiles, S.work_counter, S.large_tiles, dev->overflow_flag);
-  k_bin_fill<<<(n_slots + 255) / 256, 256, 0, fs>>>(bp);
+  if (dev->big_tiles) {  // the tile counts of the triangles k_geometry queued: a warp per triangle
+    k_big_tiles<<<dev->sm_count, 128, 0, fs>>>(S.tris, first.tri_stride, first.tiles_x, dev->shard_rank, dev->shard_n, S.tile_count, S.big_slots, S.big_count);
+    dev->n_launches += 1;
+  }
+  k_scan_tiles<<<1, 1024, 0, fs>>>(S.tile_count, S.tile_offset, S.tile_cursor, n_tiles, S.active_tiles, S.work_counter, S.large_tiles, dev->overflow_flag, S.surv_count, S.big_count);
+  k_bin_fill<<<std::max(1u, std::min((n_slots + 255) / 256, (uint32_t)dev->sm_count * 8u)), 256, 0, fs>>>(bp);
   size_t e1 = dev->profile ? mark(dev) : 0;
   // k_sort_lists and k_region_bin index the COMPACTED list of non-empty tiles, which holds at most the tiles this rank owns: a
   // sort-first rank launches an N-th of the CTAs (each empty 1024-thread CTA still has to find room on an SM next to the
@@ -944,6 +997,10 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
     CU(cudaMalloc(&S.work_counter, 8 * sizeof(uint32_t)));
     CU(cudaMemset(S.work_counter, 0, 8 * sizeof(uint32_t)));
     CU(cudaMalloc(&S.valid_count, sizeof(uint32_t)));
+    CU(cudaMalloc(&S.surv_count, MAX_BATCH * sizeof(uint32_t)));
+    CU(cudaMalloc(&S.big_count, sizeof(uint32_t)));
+    CU(cudaMemset(S.big_count, 0, sizeof(uint32_t)));
+    CU(cudaMemset(S.surv_count, 0, MAX_BATCH * sizeof(uint32_t)));  // k_scan_tiles re-zeroes it behind every geometry pass
     CU(cudaMemset(S.valid_count, 0, sizeof(uint32_t)));  // k_sort_lists_large re-zeroes it at the end of every binning chain
     CU(cudaMalloc(&S.d_batch, MAX_BATCH * sizeof(RasterParams)));
     CU(cudaMalloc(&S.d_geom, MAX_BATCH * sizeof(GeomParams)));
@@ -987,6 +1044,8 @@ slv_result slv_device_create(int32_t ordinal, slv_device* out) {
   const char* ji = getenv("SLV_JIT_IMMEDIATE");
   dev->jit_immediate = ji && ji[0] == '1';
   if (const char* vc = getenv("SLV_VERTEX_CACHE")) dev->vertex_cache = atoi(vc);
+  if (const char* gs = getenv("SLV_GEOMETRY_SPLIT")) dev->geometry_split = atoi(gs);
+  if (const char* bt = getenv("SLV_BIG_TILES")) dev->big_tiles = atoi(bt) != 0;
   for (auto& ev : dev->user_ev) CU(cudaEventCreate(&ev));
 
   *out = dev;
@@ -1008,7 +1067,7 @@ void slv_device_destroy(slv_device dev) {
     if (r.rb_event) cudaEventDestroy(r.rb_event);
   }
   for (auto& S : dev->sc) {
-    cudaFree(S.tris); cudaFree(S.valid_slots); cudaFree(S.valid_count);
+    cudaFree(S.tris); cudaFree(S.valid_slots); cudaFree(S.valid_count); cudaFree(S.surv); cudaFree(S.surv_count); cudaFree(S.big_slots); cudaFree(S.big_count);
     cudaFree(S.tile_count); cudaFree(S.tile_offset); cudaFree(S.tile_cursor); cudaFree(S.active_tiles); cudaFree(S.large_tiles);
     cudaFree(S.work_counter); cudaFree(S.region_list); cudaFree(S.region_mask); cudaFree(S.region_tile_cnt); cudaFree(S.region_offset); cudaFree(S.region_count);
     cudaFree(S.item_flag); cudaFree(S.block_desc); cudaFree(S.list); cudaFree(S.d_batch); cudaFree(S.d_geom);
@@ -1313,6 +1372,7 @@ slv_result slv_shader_module_load(slv_device dev, uint32_t stage, const void* im
   if (stage == SLV_STAGE_VS) {
     ok = api.ModuleGetFunction(&r.fn_geometry, r.module, "slv_jit_k_geometry") == CUDA_SUCCESS;
     if (api.ModuleGetFunction(&r.fn_vertex_shade, r.module, "slv_jit_k_vertex_shade") != CUDA_SUCCESS) r.fn_vertex_shade = nullptr;
+    if (api.ModuleGetFunction(&r.fn_geometry_cull, r.module, "slv_jit_k_geometry_cull") != CUDA_SUCCESS) r.fn_geometry_cull = nullptr;
   } else {
     const char* names[3] = {"slv_jit_k_raster_s1", "slv_jit_k_raster_s2", "slv_jit_k_raster_s4"};
     for (int i = 0; i < 3; ++i) ok = ok && api.ModuleGetFunction(&r.fn_raster[i], r.module, names[i]) == CUDA_SUCCESS;
@@ -1810,6 +1870,8 @@ slv_result slv_draw(slv_device dev, const slv_draw_desc* d) {
     gp.tile_count = S.tile_count;
     gp.valid_slots = S.valid_slots;
     gp.valid_count = S.valid_count;
+    gp.big_slots = dev->big_tiles ? S.big_slots : nullptr;
+    gp.big_count = S.big_count;
     rp.tile_offset = S.tile_offset;
     rp.active_tiles = S.active_tiles;
     rp.work_counter = S.work_counter;

@@ -74,6 +74,17 @@ struct GeomParams {
   unsigned long long* stats;  // slv_pipeline_statistics as 9 x u64
   uint32_t* valid_slots;      // compact list of the slots that hold a triangle binned on this rank
   uint32_t* valid_count;
+  // triangles that span many tiles: the thread that sets one up does not walk its tile range itself (a full-screen triangle is
+  // 2,040 tile tests at 4K - one thread's loop was the critical path of the whole kernel); it appends the slot here and
+  // k_big_tiles counts the tiles with a warp per triangle
+  uint32_t* big_slots;
+  uint32_t* big_count;
+  // two-kernel geometry (k_geometry_cull -> k_geometry): when surv != nullptr, k_geometry_cull has already run the position pass
+  // for every primitive of the draw and left the ids of the ones that need set-up on this rank (clipped by the near / far plane,
+  // or un-culled and reaching a tile this rank owns) in surv[slot_base / 3 ...], their number in surv_count[draw_id]; thread i of
+  // the draw's CTAs then works on primitive surv[i] instead of primitive i
+  uint32_t* surv;
+  uint32_t* surv_count;
   // post-transform vertex cache (default_vertex_cache.cpp:128-197): when vc_pos != nullptr, k_vertex_mark / k_vertex_shade have
   // run the vertex shader ONCE for every vertex index < vc_cap that the draws sharing this cache reference; k_geometry gathers
   // the clip-space position (vc_pos[v]) and the attributes (vc_attr[v * n_attrs + i]) instead of re-running the shader per
@@ -105,6 +116,7 @@ struct GeomBatch {
 // [4] misc: x = as_uint(valid | front<<1), y = sx | ex<<16, z = sy | ey<<16 (tile range), w = draw id in the batch
 // then one (v0, ddx, ddy) triple per register r (0 = position, 1.. = attributes) at TRI_HEADER + 3r: the layout does
 // not depend on the draw's register count, so readers need no per-draw state to address it
+constexpr int BIG_TILE_RANGE = 48;  // tile ranges above this many tiles are walked by a warp (k_big_tiles, k_bin_fill)
 constexpr int TRI_HEADER = 5;
 constexpr int REC_V0 = TRI_HEADER, REC_DDX = TRI_HEADER + 1, REC_DDY = TRI_HEADER + 2;  // + 3 * reg
 

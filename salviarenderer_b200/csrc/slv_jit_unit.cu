@@ -21,6 +21,10 @@ static_assert(SLV_JIT_R == SLV_JIT_VS_OUTPUT_ATTRS + 1, "register count does not
 extern "C" __global__ void __launch_bounds__(128, 4) slv_jit_k_geometry(const slv::GeomParams* __restrict__ draws, slv::GeomBatch hb) {
   slv::geometry_main<SLV_JIT_R>(draws, hb);
 }
+// two-kernel geometry: the position pass alone (k_geometry_cull of the library, with this shader's position inlined)
+extern "C" __global__ void __launch_bounds__(128, 4) slv_jit_k_geometry_cull(const slv::GeomParams* __restrict__ draws, slv::GeomBatch hb) {
+  slv::geometry_cull_main<SLV_JIT_R>(draws, hb);
+}
 // post-transform vertex cache: the shader once per referenced vertex (k_vertex_shade of the library, with this shader inlined)
 extern "C" __global__ void __launch_bounds__(128) slv_jit_k_vertex_shade(const slv::GeomParams* __restrict__ draws, slv::GeomBatch hb) {
   slv::vertex_shade_main<SLV_JIT_R>(draws, hb);

@@ -264,8 +264,11 @@ struct TriPos {
   int r0;                         // vertex nearest the origin: the record's v0 (rasterizer.cpp:873-890)
   float e01x, e01y, e02x, e02y, inv_area;
   bool front;
+  bool big;  // the tile range is left to k_big_tiles (the caller appends the slot to p.big_slots once the record is stored)
 };
 
+// COUNT = false: the ownership / coverage test only (k_geometry_cull): no tile counter is touched, the first hit ends the search
+template <bool COUNT = true>
 __device__ __forceinline__ bool setup_position(const GeomParams& p, const float4 v[3], TriPos& s) {  // true: binned somewhere
   double d0 = (double)fabsf(v[0].x) + (double)fabsf(v[0].y);
   double d1 = (double)fabsf(v[1].x) + (double)fabsf(v[1].y);
@@ -295,21 +298,28 @@ __device__ __forceinline__ bool setup_position(const GeomParams& p, const float4
   // tile coverage count (rasterizer.cpp:809-857); under sort-first sharding only this rank's tiles count
   s.tr = tile_range(s.bbox, p.tiles_x, p.tiles_y);
   const TileRange& tr = s.tr;
+  s.big = false;
+  if (COUNT && p.big_slots && (tr.ex - tr.sx) * (tr.ey - tr.sy) > BIG_TILE_RANGE) {
+    s.big = true;  // counted by a warp of k_big_tiles; with this many tiles some are this rank's in practice (if none is, the
+    return true;   // record is stored for nothing and k_bin_fill finds no tile for it: harmless)
+  }
   bool any_owned = false;
   if ((tr.sx + 1 == tr.ex) && (tr.sy + 1 == tr.ey)) {
     if (tile_owned(tr.sx, tr.sy, p.shard_rank, p.shard_n)) {
-      // warp-aggregated count: neighbouring primitives of a fine mesh fall into the same tile, and one atomic per distinct
-      // tile among the lanes that are converged here replaces up to 32 same-address atomics (the 10 M-triangle stress config)
-      const uint32_t t = tr.sy * p.tiles_x + tr.sx;
-      const uint32_t peers = __match_any_sync(__activemask(), t);
-      if ((threadIdx.x & 31u) == (uint32_t)__ffs(peers) - 1u) atomicAdd(&p.tile_count[t], (uint32_t)__popc(peers));
+      if (COUNT) {
+        // warp-aggregated count: neighbouring primitives of a fine mesh fall into the same tile, and one atomic per distinct
+        // tile among the lanes that are converged here replaces up to 32 same-address atomics (the 10 M-triangle stress config)
+        const uint32_t t = tr.sy * p.tiles_x + tr.sx;
+        const uint32_t peers = __match_any_sync(__activemask(), t);
+        if ((threadIdx.x & 31u) == (uint32_t)__ffs(peers) - 1u) atomicAdd(&p.tile_count[t], (uint32_t)__popc(peers));
+      }
       any_owned = true;
     }
   } else {
-    for (int y = tr.sy; y < tr.ey; ++y)
-      for (int x = tr.sx; x < tr.ex; ++x)
+    for (int y = tr.sy; y < tr.ey && (COUNT || !any_owned); ++y)
+      for (int x = tr.sx; x < tr.ex && (COUNT || !any_owned); ++x)
         if (tile_owned(x, y, p.shard_rank, p.shard_n) && tile_test(s.edge, x, y)) {
-          atomicAdd(&p.tile_count[y * p.tiles_x + x], 1u);
+          if (COUNT) atomicAdd(&p.tile_count[y * p.tiles_x + x], 1u);
           any_owned = true;
         }
   }
@@ -356,11 +366,12 @@ __device__ __forceinline__ void setup_store(const GeomParams& p, const VsOut<R> 
 }
 
 template <int R>
-__device__ __forceinline__ bool setup_triangle(const GeomParams& p, const VsOut<R> v[3], float4* rec) {  // true: binned somewhere
+__device__ __forceinline__ bool setup_triangle(const GeomParams& p, const VsOut<R> v[3], float4* rec, uint32_t slot) {  // true: binned somewhere
   const float4 pos[3] = {v[0].r[0], v[1].r[0], v[2].r[0]};
   TriPos s;
   if (!setup_position(p, pos, s)) return false;
   setup_store<R>(p, v, s, rec);
+  if (s.big) p.big_slots[atomicAdd(p.big_count, 1u)] = slot;
   return true;
 }
 
@@ -452,6 +463,11 @@ __device__ __forceinline__ void geometry_main(const GeomParams* __restrict__ dra
   stage_geom_params(s_params, draws + hb.draw_of[lo]);
   const GeomParams& p = s_params;
   uint32_t prim = (blockIdx.x - hb.cta_prefix[lo]) * blockDim.x + threadIdx.x;
+  if (p.surv) {  // second kernel of the two-kernel geometry: the i-th survivor of k_geometry_cull instead of primitive i
+    const uint32_t n_surv = __ldg(p.surv_count + p.draw_id);
+    if ((blockIdx.x - hb.cta_prefix[lo]) * blockDim.x >= n_surv) return;  // whole CTA beyond the list (uniform)
+    prim = prim < n_surv ? p.surv[p.slot_base / 3 + prim] : 0xFFFFFFFFu;
+  }
   uint32_t n_out = 0, valid_mask = 0;  // valid_mask bit k: slot prim*3+k holds a triangle binned on this rank
   if (prim < p.prim_count) {
     // ---- index fetch (index_fetcher.cpp:26-115)
@@ -529,9 +545,10 @@ __device__ __forceinline__ void geometry_main(const GeomParams* __restrict__ dra
             project_attrs<R>(p, o[k], spos[k].w);
           }
           setup_store<R>(p, o, ts, rec);
+          if (ts.big) p.big_slots[atomicAdd(p.big_count, 1u)] = p.slot_base + prim * 3;
           valid_mask = 1u;
         }
-        n_out = 1;
+        n_out = p.surv ? 0 : 1;  // two-kernel geometry: k_geometry_cull has counted the primitives that need no clipping
       }
     } else {
       VsOut<R> pool[2][5];
@@ -591,7 +608,7 @@ __device__ __forceinline__ void geometry_main(const GeomParams* __restrict__ dra
           o[2] = is_front ? pool[src][t + 1] : pool[src][t];
 #pragma unroll
           for (int k = 0; k < 3; ++k) viewport_project<R>(p, o[k]);
-          if (setup_triangle<R>(p, o, rec + (size_t)(t - 1) * p.tri_stride)) valid_mask |= 1u << (t - 1);
+          if (setup_triangle<R>(p, o, rec + (size_t)(t - 1) * p.tri_stride, p.slot_base + prim * 3 + (uint32_t)(t - 1))) valid_mask |= 1u << (t - 1);
         }
         n_out = nv - 2;
       }
@@ -623,6 +640,89 @@ __device__ __forceinline__ void geometry_main(const GeomParams* __restrict__ dra
   if ((threadIdx.x & 31) == 0 && total) atomicAdd(&p.stats[6], (unsigned long long)total);
 }
 
+// ---- two-kernel geometry, first kernel: the POSITION pass alone, one thread per input primitive.  Index fetch, position (cache
+// or position-only vertex shader), frustum test, facing / cull, projection, and whether the triangle reaches a tile this rank
+// owns - the operations of geometry_main up to the point where a primitive turns out to need set-up - at a quarter of
+// geometry_main's registers, so at full occupancy.  Survivors (primitives to clip, and un-culled ones that are binned here) are
+// appended to the draw's range of p.surv; cprimitives of the primitives that need no clipping is counted here.
+template <int R>
+__device__ __forceinline__ void geometry_cull_main(const GeomParams* __restrict__ draws, const GeomBatch& hb) {
+  const uint32_t lo = batch_entry_of_cta(hb);
+  __shared__ GeomParams s_params;
+  stage_geom_params(s_params, draws + hb.draw_of[lo]);
+  const GeomParams& p = s_params;
+  const uint32_t prim = (blockIdx.x - hb.cta_prefix[lo]) * blockDim.x + threadIdx.x;
+  bool survive = false;
+  uint32_t n_out = 0;
+  if (prim < p.prim_count) {
+    uint32_t ids[3];
+    if (p.topology == SLV_TOPO_TRIANGLE_LIST) {
+      ids[0] = prim * 3; ids[1] = prim * 3 + 1; ids[2] = prim * 3 + 2;
+    } else {
+      ids[0] = prim; ids[1] = prim + 1; ids[2] = prim + 2;
+      if (prim & 1) { uint32_t t = ids[0]; ids[0] = ids[2]; ids[2] = t; }
+    }
+    uint32_t idx[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) idx[i] = fetch_index(p, ids[i]);
+    const bool use_vc = p.vc_pos != nullptr && idx[0] < p.vc_cap && idx[1] < p.vc_cap && idx[2] < p.vc_cap;
+    float4 cpos[3];
+    if (use_vc) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) cpos[i] = __ldg(p.vc_pos + idx[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        VsOut<R> t;
+        run_vs<R, true>(p, idx[i], t);
+        cpos[i] = t.r[0];
+      }
+    }
+    bool in_frustum = true;
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+      for (int v = 0; v < 3; ++v)
+        if (plane_dist(pl, cpos[v]) < 0) in_frustum = false;
+    if (!in_frustum) {
+      survive = true;  // clipped (or rejected) by geometry_main, which also counts what the clipper emits
+    } else {
+      float px[3], py[3];
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        float iw = 1.0f / cpos[v].w;
+        px[v] = cpos[v].x * iw;
+        py[v] = cpos[v].y * iw;
+      }
+      const float area = (px[2] - px[0]) * (py[1] - py[0]) - (py[2] - py[0]) * (px[1] - px[0]);
+      const bool front = area > 0.0f;
+      if (!cull_tri(p.cull_mode, p.front_ccw, front ? 1.0f : -1.0f)) {
+        float4 spos[3];
+        spos[0] = viewport_project_pos(p, cpos[0]);
+        spos[1] = viewport_project_pos(p, front ? cpos[1] : cpos[2]);
+        spos[2] = viewport_project_pos(p, front ? cpos[2] : cpos[1]);
+        TriPos ts;
+        survive = setup_position<false>(p, spos, ts);
+        n_out = 1;
+      }
+    }
+  }
+  {  // append the survivors of the warp to the draw's list: one atomic per warp
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, survive);
+    uint32_t base = 0;
+    if (lane == 0 && bal) base = atomicAdd(p.surv_count + p.draw_id, (uint32_t)__popc(bal));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (survive) p.surv[p.slot_base / 3 + base + __popc(bal & ((1u << lane) - 1u))] = prim;
+    const uint32_t total = __popc(__ballot_sync(0xFFFFFFFFu, n_out != 0));
+    if (lane == 0 && total) atomicAdd(&p.stats[6], (unsigned long long)total);
+  }
+}
+template <int R>
+__global__ void __launch_bounds__(128, 8) k_geometry_cull(const GeomParams* __restrict__ draws, GeomBatch hb) {
+  geometry_cull_main<R>(draws, hb);
+}
+
 #ifndef SLV_GEOM_CTAS_PER_SM
 #define SLV_GEOM_CTAS_PER_SM 4
 #endif
@@ -647,11 +747,13 @@ constexpr int SORT_LARGE_SMEM = 49152;  // list length k_sort_lists_large sorts 
 // non-empty tiles into active_tiles[1..] (count in [0]) and resets the raster work-queue head.
 __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint32_t* tile_offset, uint32_t* tile_cursor,
                                                      uint32_t n_tiles, uint32_t* active_tiles, uint32_t* work_counter,
-                                                     uint32_t* large_tiles, uint32_t* arena_need) {
+                                                     uint32_t* large_tiles, uint32_t* arena_need, uint32_t* surv_count, uint32_t* big_count) {
   __shared__ uint32_t s_active, s_large;
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < MAX_BATCH_DRAWS) surv_count[tid] = 0;  // two-kernel geometry: the survivor counts of the batch have been consumed
+  if (tid == 0) big_count[0] = 0;                   // ... and so has the big-triangle queue (k_big_tiles runs ahead of this kernel)
   if (tid == 0) { s_carry = 0; s_active = 0; s_large = 0; work_counter[0] = 0; work_counter[1] = 0; work_counter[2] = 0; work_counter[3] = 0; work_counter[4] = 0; }
   __syncthreads();
   // active-tile compaction, longest lists first (classes >= 2048, >= 512, >= 128, rest): the raster work queue hands
@@ -714,43 +816,105 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint3
   }
 }
 
-__global__ void __launch_bounds__(256) k_bin_fill(BinParams p) {
-  const uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x;
-  if (vi >= *p.valid_count) return;  // the grid is sized for the worst case (every slot valid)
-  const uint32_t slot = p.valid_slots[vi];
-  const float4* rec = p.tris + (size_t)slot * p.tri_stride;
-  float4 misc = __ldg(rec + 4);
-  uint32_t flags = __float_as_uint(misc.x);
-  if (!(flags & 1)) return;
-  uint32_t xr = __float_as_uint(misc.y), yr = __float_as_uint(misc.z);
-  int sx = xr & 0xFFFF, ex = xr >> 16, sy = yr & 0xFFFF, ey = yr >> 16;
-  if ((sx + 1 == ex) && (sy + 1 == ey)) {
-    if (tile_owned(sx, sy, p.shard_rank, p.shard_n)) {
-      // warp-aggregated cursor bump: one atomic per distinct tile among the converged lanes, consecutive entries for the group
-      uint32_t t = sy * p.tiles_x + sx;
-      const uint32_t lane = threadIdx.x & 31u;
-      const uint32_t peers = __match_any_sync(__activemask(), t);
-      const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
-      uint32_t base = 0;
-      if (lane == leader) base = atomicAdd(&p.tile_cursor[t], (uint32_t)__popc(peers));
-      base = __shfl_sync(peers, base, leader);
-      uint32_t at = p.tile_offset[t] + base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-      if (at < p.list_capacity) p.list[at] = slot << 1;
-      else *p.overflow_flag = 1;
+// Tile counting of the triangles k_geometry left in the big-triangle queue: a WARP per triangle, lanes stride over its tile
+// range with the reference's tile test (rasterizer.cpp:831-848) - the same counts the setting-up thread would have produced.
+__global__ void __launch_bounds__(128) k_big_tiles(const float4* __restrict__ tris, uint32_t tri_stride, uint32_t tiles_x, uint32_t shard_rank,
+                                                   uint32_t shard_n, uint32_t* tile_count, const uint32_t* __restrict__ big_slots,
+                                                   const uint32_t* __restrict__ big_count) {
+  const uint32_t lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n_big = *big_count;
+  for (uint32_t i = warp; i < n_big; i += n_warps) {
+    const float4* rec = tris + (size_t)big_slots[i] * tri_stride;
+    const float4 edge[3] = {__ldg(rec), __ldg(rec + 1), __ldg(rec + 2)};
+    const float4 misc = __ldg(rec + 4);
+    const uint32_t xr = __float_as_uint(misc.y), yr = __float_as_uint(misc.z);
+    const int sx = xr & 0xFFFF, ex = xr >> 16, sy = yr & 0xFFFF, ey = yr >> 16;
+    const int ntx = ex - sx, n = ntx * (ey - sy);
+    for (int t = (int)lane; t < n; t += 32) {
+      const int x = sx + t % ntx, y = sy + t / ntx;
+      if (tile_owned(x, y, shard_rank, shard_n) && tile_test(edge, x, y)) atomicAdd(&tile_count[y * tiles_x + x], 1u);
     }
-    return;
   }
-  float4 edge[3] = {__ldg(rec), __ldg(rec + 1), __ldg(rec + 2)};
-  for (int y = sy; y < ey; ++y)
-    for (int x = sx; x < ex; ++x) {
+}
+
+// One valid slot per lane; a triangle whose tile range is large is walked by the whole warp (lanes stride over the range) instead
+// of by the one lane that owns the slot - on the Sponza-like scene a handful of wall / floor triangles span up to the whole
+// 60 x 34 tile grid and their serial loops were the kernel's critical path.  Order inside a tile list is irrelevant here: the
+// lists are sorted afterwards.
+__device__ __forceinline__ void bin_fill_warp(const BinParams& p, uint32_t slot, bool have) {
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t xr = 0, yr = 0;
+  const float4* rec = p.tris + (size_t)(have ? slot : 0) * p.tri_stride;
+  if (have) {
+    const float4 misc = __ldg(rec + 4);
+    have = (__float_as_uint(misc.x) & 1u) != 0;
+    xr = __float_as_uint(misc.y);
+    yr = __float_as_uint(misc.z);
+  }
+  const int sx = xr & 0xFFFF, ex = xr >> 16, sy = yr & 0xFFFF, ey = yr >> 16;
+  const int n_tiles = (ex - sx) * (ey - sy);
+  const bool big = have && n_tiles > BIG_TILE_RANGE;
+  if (have && !big) {
+    if (n_tiles == 1) {
+      if (tile_owned(sx, sy, p.shard_rank, p.shard_n)) {
+        // warp-aggregated cursor bump: one atomic per distinct tile among the converged lanes, consecutive entries for the group
+        const uint32_t t = sy * p.tiles_x + sx;
+        const uint32_t peers = __match_any_sync(__activemask(), t);
+        const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&p.tile_cursor[t], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        const uint32_t at = p.tile_offset[t] + base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        if (at < p.list_capacity) p.list[at] = slot << 1;
+        else *p.overflow_flag = 1;
+      }
+    } else {
+      const float4 edge[3] = {__ldg(rec), __ldg(rec + 1), __ldg(rec + 2)};
+      for (int y = sy; y < ey; ++y)
+        for (int x = sx; x < ex; ++x) {
+          if (!tile_owned(x, y, p.shard_rank, p.shard_n)) continue;
+          const int st = tile_test(edge, x, y);
+          if (!st) continue;
+          const uint32_t t = y * p.tiles_x + x;
+          const uint32_t at = p.tile_offset[t] + atomicAdd(&p.tile_cursor[t], 1u);
+          if (at < p.list_capacity) p.list[at] = (slot << 1) | (st == 3 ? 1u : 0u);
+          else *p.overflow_flag = 1;
+        }
+    }
+  }
+  // the warp's large triangles, one after the other, 32 tiles at a time
+  uint32_t todo = __ballot_sync(0xFFFFFFFFu, big);
+  while (todo) {
+    const int l = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const uint32_t bslot = __shfl_sync(0xFFFFFFFFu, slot, l);
+    const uint32_t bxr = __shfl_sync(0xFFFFFFFFu, xr, l), byr = __shfl_sync(0xFFFFFFFFu, yr, l);
+    const int bsx = bxr & 0xFFFF, bex = bxr >> 16, bsy = byr & 0xFFFF, bey = byr >> 16;
+    const int ntx = bex - bsx, n = ntx * (bey - bsy);
+    const float4* brec = p.tris + (size_t)bslot * p.tri_stride;
+    const float4 edge[3] = {__ldg(brec), __ldg(brec + 1), __ldg(brec + 2)};
+    for (int t = (int)lane; t < n; t += 32) {
+      const int x = bsx + t % ntx, y = bsy + t / ntx;
       if (!tile_owned(x, y, p.shard_rank, p.shard_n)) continue;
-      int st = tile_test(edge, x, y);
+      const int st = tile_test(edge, x, y);
       if (!st) continue;
-      uint32_t t = y * p.tiles_x + x;
-      uint32_t at = p.tile_offset[t] + atomicAdd(&p.tile_cursor[t], 1u);
-      if (at < p.list_capacity) p.list[at] = (slot << 1) | (st == 3 ? 1u : 0u);
+      const uint32_t tt = y * p.tiles_x + x;
+      const uint32_t at = p.tile_offset[tt] + atomicAdd(&p.tile_cursor[tt], 1u);
+      if (at < p.list_capacity) p.list[at] = (bslot << 1) | (st == 3 ? 1u : 0u);
       else *p.overflow_flag = 1;
     }
+  }
+}
+// grid-stride over the compact list of valid slots (warp-uniform trip count): the list holds what this RANK bins (an N-th of
+// the frame's triangles on a sort-first rank, far fewer than the slots), so the grid is a few CTAs per SM, not a thread per slot
+__global__ void __launch_bounds__(256) k_bin_fill(BinParams p) {
+  const uint32_t n_valid = *p.valid_count;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_valid; base += gridDim.x * blockDim.x) {
+    const uint32_t vi = base + lane;
+    const bool have = vi < n_valid;
+    bin_fill_warp(p, have ? p.valid_slots[vi] : 0u, have);
+  }
 }
 
 // Bitonic network over buf[0..N) (N a power of two, entries past the list padded with 0xFFFFFFFF) by NTH threads that
