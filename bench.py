@@ -556,11 +556,13 @@ def main():
         be.texture_level_tracking(True)
         frame(f)
         be.flush()
-        masks = torch.tensor([be.texture_levels_touched(t) for t in sc.textures], device="cuda", dtype=torch.int32)
-        if n > 1:
-            dist.all_reduce(masks, op=dist.ReduceOp.BOR)
+        masks = [be.texture_levels_touched(t) for t in sc.textures]
+        if n > 1:  # union over the ranks (NCCL has no bitwise OR: one 0 / 1 entry per (texture, level), MAX)
+            bits = torch.tensor([[(m >> l) & 1 for l in range(16)] for m in masks], device="cuda", dtype=torch.int32)
+            dist.all_reduce(bits, op=dist.ReduceOp.MAX)
+            masks = [sum(int(b) << l for l, b in enumerate(row)) for row in bits.tolist()]
         touched = 0
-        for t, m in zip(sc.textures, masks.tolist()):
+        for t, m in zip(sc.textures, masks):
             for l in range(be.level_count(t)):
                 if m & (1 << l):
                     lw, lh = be.level_size(t, l)

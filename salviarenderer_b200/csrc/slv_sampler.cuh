@@ -405,7 +405,10 @@ __device__ inline float4 sample_impl(const SamplerRef& sm, float cx, float cy, f
       tap_i = -pc + 1;
     }
   }
-  if (sm.touched) atomicOr(sm.touched, (1u << lv0) | (n == 2 ? (1u << lv1) : 0u));  // B_tex accounting (off in timed regions)
+  if (sm.touched) {  // B_tex accounting (off in timed regions): set the bits once - after that every call only reads the word
+    const uint32_t bits = (1u << lv0) | (n == 2 ? (1u << lv1) : 0u);
+    if ((__ldcg(sm.touched) & bits) != bits) atomicOr(sm.touched, bits);
+  }
   float4 c0 = make_float4(0, 0, 0, 0), c1 = c0;  // aniso: c0 accumulates the weighted colour
   float w_sum = 0.0f;
   if (sm.fast_wrap_rgba8 && !aniso) {
