@@ -1,3 +1,4 @@
+# Developer tool (GPU box): the bench line and the reference arm on N GPUs of one box -> gpurun_out/r02r_bench<N>*.json.   bash tools/bench_ngpu.sh <N>
 mkdir -p gpurun_out
 N=$1
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 100 --warmup 10 > gpurun_out/r02r_bench$N.json 2> gpurun_out/r02r_bench$N.err
