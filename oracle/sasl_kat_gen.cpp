@@ -11,6 +11,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -23,17 +24,25 @@ static vec4 lit_ref(float n_dot_l, float n_dot_h, float m) {
 static vec3 faceforward_ref(vec3 n, vec3 i, vec3 ng) { return -n * eflib::sign(eflib::dot_prod3(i, ng)); }
 
 struct Arg { std::string type; std::vector<float> v; };
+// JSON has no NaN / infinity: those go out as strings ("nan", "inf", "-inf"); finite values with 9 significant digits (exact)
+static std::string num(float v) {
+  if (std::isnan(v)) return "\"nan\"";
+  if (std::isinf(v)) return v > 0 ? "\"inf\"" : "\"-inf\"";
+  char b[64];
+  std::snprintf(b, sizeof(b), "%.9g", v);
+  return b;
+}
 static bool first = true;
 static void emit(const char* name, const char* call, std::vector<Arg> const& args, std::vector<float> const& expected) {
   std::printf("%s\n  {\"name\": \"%s\", \"call\": \"%s\", \"args\": [", first ? "" : ",", name, call);
   first = false;
   for (size_t i = 0; i < args.size(); ++i) {
     std::printf("%s{\"type\": \"%s\", \"values\": [", i ? ", " : "", args[i].type.c_str());
-    for (size_t k = 0; k < args[i].v.size(); ++k) std::printf("%s%.9g", k ? ", " : "", args[i].v[k]);
+    for (size_t k = 0; k < args[i].v.size(); ++k) std::printf("%s%s", k ? ", " : "", num(args[i].v[k]).c_str());
     std::printf("]}");
   }
   std::printf("], \"expected\": [");
-  for (size_t k = 0; k < expected.size(); ++k) std::printf("%s%.9g", k ? ", " : "", expected[k]);
+  for (size_t k = 0; k < expected.size(); ++k) std::printf("%s%s", k ? ", " : "", num(expected[k]).c_str());
   std::printf("]}");
 }
 static std::vector<float> f3(vec3 const& v) { return {v[0], v[1], v[2]}; }
@@ -100,6 +109,56 @@ int main() {
     emit("rad_deg", "radians(a0.xy).xxy + degrees(a0)", {a3(v0)}, f3(ref3));
     vec4 v0q = v0.xyzy();
     emit("length_f2_f4", "float2(length(a0), length(a1))", {av2, {"float4", f4(v0q)}}, {ref4[0], ref4[1]});
+  }
+  {  // general.cpp:447-566: the math intrinsics on a float3x4 (here: its three float4 rows), against the host functions the
+     // reference binds its JIT-ed code to (libm's float functions; eflib's fast_* for floor / ceil / round / log / log2)
+    const float arr0[3][4] = {{17.7f, 66.3f, 0.92f, -88.7f}, {8.6f, -0.22f, 17.1f, -64.4f}, {199.8f, 0.1f, -0.1f, 99.73f}};
+    const float arr1[3][4] = {{9.62f, 10.33f, -18.2f, 99.7f}, {-0.3f, -76.9f, 93.3f, 0.22f}, {44.1f, 0.027f, 19.9f, -33.5f}};
+    struct Fn { const char* name; const char* call; float (*f)(float); };
+    const Fn fns[] = {
+        {"exp", "exp(a0)", [](float x) { return (float)exp((double)x); }},
+        {"exp2", "exp2(a0)", [](float x) { return (float)ldexp(1.0f, (int)x); }},
+        {"sin", "sin(a0)", [](float x) { return sinf(x); }}, {"cos", "cos(a0)", [](float x) { return cosf(x); }},
+        {"tan", "tan(a0)", [](float x) { return tanf(x); }}, {"sinh", "sinh(a0)", [](float x) { return sinhf(x); }},
+        {"cosh", "cosh(a0)", [](float x) { return coshf(x); }}, {"tanh", "tanh(a0)", [](float x) { return tanhf(x); }},
+        {"asin", "asin(a0)", [](float x) { return asinf(x); }}, {"acos", "acos(a0)", [](float x) { return acosf(x); }},
+        {"atan", "atan(a0)", [](float x) { return atanf(x); }},
+        {"ceil", "ceil(a0)", [](float x) { return fast_ceil(x); }}, {"floor", "floor(a0)", [](float x) { return fast_floor(x); }},
+        {"round", "round(a0)", [](float x) { return fast_round(x); }}, {"trunc", "trunc(a0)", [](float x) { return (float)trunc(x); }},
+        {"log", "log(a0)", [](float x) { return fast_log(x); }}, {"log2", "log2(a0)", [](float x) { return fast_log2(x); }},
+        {"log10", "log10(a0)", [](float x) { return log10f(x); }},
+        {"rsqrt", "rsqrt(a0)", [](float x) { return 1.0f / sqrtf(x); }}, {"rcp", "rcp(a0)", [](float x) { return 1.0f / x; }},
+    };
+    for (Fn const& fn : fns)
+      for (int r = 0; r < 3; ++r) {
+        std::vector<float> in(arr0[r], arr0[r] + 4), out;
+        for (float x : in) out.push_back(fn.f(x));
+        emit((std::string(fn.name) + "_row" + std::to_string(r)).c_str(), fn.call, {{"float4", in}}, out);
+      }
+    for (int r = 0; r < 3; ++r) {
+      std::vector<float> a(arr0[r], arr0[r] + 4), b(arr1[r], arr1[r] + 4), p, l;
+      for (int j = 0; j < 4; ++j) { p.push_back(powf(a[j], b[j])); l.push_back(ldexpf(a[j], (int)b[j])); }
+      emit(("pow_row" + std::to_string(r)).c_str(), "pow(a0, a1)", {{"float4", a}, {"float4", b}}, p);
+      emit(("ldexp_row" + std::to_string(r)).c_str(), "ldexp(a0, a1)", {{"float4", a}, {"float4", b}}, l);
+    }
+  }
+  {  // general.cpp:1431-1494 (ps_branches): nested if / else if chains over a scalar and a float3; inputs and reference as there
+     // (srand(0); rand() / 35.0f), the SASL function restated from the reference logic (kat_branches in tests/sasl_kat.py)
+    srand(0);
+    for (int i = 0; i < 16; ++i) {
+      float in0 = (i * 0.34f) - 1.0f;
+      float in1[3];
+      for (int j = 0; j < 3; ++j) in1[j] = rand() / 35.0f;
+      float r0 = 88.3f, r1 = 75.4f;
+      if (in0 > 0.0f) r0 = in0;
+      if (in0 > 1.0f) r1 = in1[0]; else r1 = in1[1];
+      if (in0 > 2.0f) {
+        r1 = in1[2];
+        if (in0 > 3.0f) r1 = r1 + 1.0f;
+        else if (in0 > 2.5f) r1 = r1 + 2.0f;
+      }
+      emit(("ps_branches_" + std::to_string(i)).c_str(), "kat_branches(a0, a1)", {a1(in0), {"float3", {in1[0], in1[1], in1[2]}}}, {r0, r1});
+    }
   }
   std::printf("\n ]}\n");
   return 0;

@@ -6,7 +6,7 @@ from sasl_host import HostShader
 
 
 def test_fixture_shape():
-    assert len(sasl_kat.CASES) >= 30 and len(sasl_kat.BRANCH) >= 15
+    assert len(sasl_kat.CASES) >= 110 and len(sasl_kat.BRANCH) >= 38
     assert sasl_kat.FIXTURE["generator"] == "oracle/sasl_kat_gen.cpp"
 
 
