@@ -60,3 +60,34 @@ def test_cpp_surface_sasl_equals_twins_on_the_product(host_binary):
     finally:
         del os.environ["SLV_HOST_TEST_NO_SASL"]
     assert out_sasl[-1].startswith("sasl color") and out_sasl == out_twin
+
+
+def test_cpp_compile_runs_the_front_end_and_parses_its_unit(tmp_path):
+    """shader::compile() (renderer.h:136-147 on the C++ surface) needs no device: it starts the SASL front end and parses the
+    unit it prints.  The reflection the C++ side ends up with equals what the front end reports in process; a compile error comes
+    back as a null object with the front end's message."""
+    from salviarenderer_b200.sasl import compile_shader
+    from test_sasl_frontend import VS_SKIN
+    exe = str(tmp_path / "sasl_compile_test")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    "-I" + os.path.join(ROOT, "salviarenderer_b200", "host"), os.path.join(ROOT, "tests", "cpp", "sasl_compile_test.cpp"),
+                    "-o", exe, "-ldl"], check=True)
+    env = dict(os.environ, SLV_SASL_PYTHON=sys.executable, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    ps = """sampler texSamp; float4 tint; float gain;
+    struct PSIn { float4 uv: TEXCOORD0; float4 n: TEXCOORD1; };
+    float4 ps_main(PSIn in): COLOR { return tex2D(texSamp, in.uv.xy) * tint * gain + ddx(in.n); }"""
+    for stage, src in (("vs", VS_SKIN), ("ps", ps)):
+        out = subprocess.run([exe, stage], input=src, capture_output=True, text=True, timeout=120, env=env)
+        assert out.returncode == 0, out.stdout + out.stderr
+        got = out.stdout.strip().splitlines()
+        r = compile_shader(src, stage)
+        want = [f"n_vs_output_attrs {r.reflection.n_vs_output_attrs}", f"uniform_bytes {r.reflection.uniform_bytes}",
+                f"uses_derivatives {int(r.reflection.uses_derivatives)}"]
+        want += sorted(f"uniform {n} {t.replace(' ', '')} {o} {s}" for n, t, o, s in r.reflection.uniforms)  # std::map: sorted by name
+        want += [f"sampler {i} {n}" for i, n in enumerate(r.reflection.samplers)]
+        want += [f"input {s} {i} {k}" for k, (s, i, _) in enumerate(r.reflection.inputs)]
+        want += [f"output {s} {i} {k}" for k, (s, i, _) in enumerate(r.reflection.outputs)]
+        want += [f"code_bytes {len(r.code.encode())}"]
+        assert got == want, (got, want)
+    bad = subprocess.run([exe, "ps"], input="float4 broken(", capture_output=True, text=True, timeout=120, env=env)
+    assert bad.returncode == 2 and bad.stdout.startswith("error\n") and "line 1" in bad.stdout
