@@ -630,6 +630,14 @@ def main():
     variants = None
     if n == 1 and not args.no_variants:
         variants = run_variants(args, be, timed, scenes, A)
+        try:  # frame-level roofline of each variant: the same frames, so the same algorithmic bytes but for the texture term, which
+            # is charged as the headline's (the level masks were counted on the headline's sampler state)
+            for v in variants.values():
+                if isinstance(v, dict) and v.get("ms_per_step"):
+                    v["frame_roofline"] = {"algorithmic_bytes": b_frame, "achieved_gbs": b_frame / (v["ms_per_step"] * 1e-3) / 1e9,
+                                           "frac": b_frame / (v["ms_per_step"] * 1e-3) / 1e9 / peak, "peak": peak, "unit": "GB/s"}
+        except Exception:  # noqa: BLE001 - reporting only
+            pass
     other = None
     if n == 1 and not args.no_configs:
         other = run_other_configs(args, be, scenes, A)
