@@ -1453,6 +1453,11 @@ class Gen:
         start = len(self.lines)
         self.indent = 1
         self.scopes = [scope]
+        # a global the function assigns to (sasl/test/repo/input_assigned.svs: `x += 0.5f`): the uniform block is read-only and
+        # shared, so the function works on its own copy, initialised from the uniform - the write is local to the invocation
+        for name in self.assigned_globals(f.body, set(scope)):
+            src = self.uniform_vars[name]
+            self.store(self.declare(src.type, name, f), src, f)
         self.s_block(f.body)
         body = self.lines[start:]
         del self.lines[start:]
@@ -1465,6 +1470,41 @@ class Gen:
                 raise CompileError(f"line {f.line}: {f.name}: screen-space derivatives in a recursive function")
             self.fns_with_derivatives.add(f.name)
         self.fn_table[f.name] = f
+
+    def assigned_globals(self, body, local_names) -> list:
+        """Names of uniform globals (not samplers, not arrays) that `body` stores to, in order of first store; names shadowed by
+        a parameter or by a declaration anywhere in the function are left alone (conservative)."""
+        declared, out = set(local_names), []
+
+        def root(n):
+            while isinstance(n, Node) and n.op in ("member", "index"):
+                n = n.args[0]
+            return n.args[0] if isinstance(n, Node) and n.op == "var" else None
+
+        def walk(n):
+            if isinstance(n, VarDecl):
+                declared.add(n.name)
+                if n.init is not None:
+                    walk(n.init)
+                return
+            if isinstance(n, (tuple, list)):
+                for x in n:
+                    walk(x)
+                return
+            if not isinstance(n, Node):
+                return
+            if n.op == "assign":
+                r = root(n.args[1])
+                if r is not None and r not in out:
+                    out.append(r)
+            elif n.op == "postinc":
+                r = root(n.args[0])
+                if r is not None and r not in out:
+                    out.append(r)
+            walk(n.args)
+        walk(body)
+        return [r for r in out if r not in declared and r in self.uniform_vars and r not in self.uniform_arrays
+                and self.uniform_vars[r].type.kind in ("scalar", "vector", "matrix")]
 
     # ---- translation unit
     def run(self) -> ShaderUnit:
@@ -1568,9 +1608,7 @@ class Gen:
             rets += names
             full = names + ["0.0f"] * (4 - ty.n)
             if sem[0] in ("SV_POSITION", "POSITION") and not have_pos:
-                have_pos = True
-                if ty.n != 4:
-                    raise CompileError("SV_Position must be a float4")
+                have_pos = True  # a position narrower than float4 (the reference's semantic test units) is padded with zeros
                 stores.append(f"  out[0] = make_float4({', '.join(full)});")
             else:
                 attr += 1

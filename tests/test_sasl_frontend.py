@@ -258,6 +258,7 @@ REFERENCE_UNITS_OK = [
     "constructors.ss", "ddx_ddy.sps", "decl.ss", "deps.ss", "do_while.sps", "empty.ss", "for_loop.sps", "function.ss", "host_intrinsic_detection.ss",
     "initializer.ss", "intrinsics.sps", "intrinsics.ss", "intrinsics.svs", "local_var.ss", "null.ss", "swizzle.ss", "swizzle_and_wm.sps", "tex.sps",
     "unary_operators.ss", "vec_and_mat.sps", "vec_and_mat.svs", "while.sps",
+    "input_assigned.svs", "semantic_fn.svs", "semfn_par.svs", "struct_semin.svs",
 ]
 REFERENCE_UNITS_REJECTED = {  # outside the subset (or erroneous on purpose upstream): must fail with CompileError, not crash
     "incomplete.ss", "semantic_errors.ss", "scalar.sps",
@@ -690,3 +691,31 @@ def test_skinning_vertex_shader_array_uniforms_and_integer_inputs():
 def test_reference_array_unit_compiles():
     unit = compile_shader(_ref_unit("array.svs"), "vs")  # int mat_size; float4x4 mat_arr[mat_size]; int4 BLEND_INDICES input
     assert unit.reflection.arrays == {"mat_arr": ("float4x4", 64, "mat_size")}
+
+
+def test_writes_to_globals_and_inputs_are_local_copies():
+    """sasl/test/repo/input_assigned.svs: a shader may assign to a global and to its inputs; the uniform block itself is never
+    written (the function works on a copy initialised from it), so the next invocation starts from the uniform's value again."""
+    src = """
+    float x;
+    struct VSIN  { float4 pos: SV_Position; };
+    struct VSOUT { float4 pos: SV_Position; float4 k: TEXCOORD0; };
+    VSOUT fn(VSIN in) {
+        VSOUT o;
+        x += 0.5f;
+        in.pos.x += x;
+        o.pos = in.pos;
+        o.pos.x += 0.5f;
+        o.k = float4(x, x * 2.0f, 0.0f, 0.0f);
+        return o;
+    }
+    """
+    unit = compile_shader(src, "vs")
+    hs = HostShader(unit)
+    ub = unit.pack_uniforms({"x": 1.0})
+    for _ in range(2):  # twice: the second run must not see the first run's write
+        out = hs.vs([[3.0, 4.0, 5.0, 1.0]], ub)
+        assert np.array_equal(out[0], np.array([5.0, 4.0, 5.0, 1.0], f32)) and np.array_equal(out[1], np.array([1.5, 3.0, 0, 0], f32))
+    # a scalar SV_Position (semfn_par.svs) is padded with zeros
+    unit = compile_shader("float fn(float a: SV_Position): SV_Position { return a * 2.0f; }", "vs")
+    assert np.array_equal(HostShader(unit).vs([[1.5, 9, 9, 9]])[0], np.array([3.0, 0, 0, 0], f32))
