@@ -1,0 +1,19 @@
+"""CPU suite (build container only): seeded random points of the TriangleSoup parameter space (tests/fuzz.py: target size,
+MSAA, cull, depth / two-sided stencil state, blend shader and colour format, strips, index width, base vertex, split and
+non-indexed draws, attribute modifiers), the oracle restatement against the LIVE unmodified reference, every buffer and counter.
+500 seeds were run when this was written (all equal); the suite keeps the first 120."""
+import pytest
+
+import cases
+import fuzz
+
+
+@pytest.mark.parametrize("block", range(6))
+def test_oracle_equals_live_reference_on_random_soups(oracle, reference, block):
+    for seed in range(block * 20, block * 20 + 20):
+        kw, a = fuzz.soup_from_seed(seed)
+        _, b = fuzz.soup_from_seed(seed)
+        a.setup(oracle)
+        b.setup(reference)
+        msgs = cases.compare_frames(a.run(oracle, 0), b.run(reference, 0))
+        assert not msgs, f"seed {seed}: {msgs} {kw}"
