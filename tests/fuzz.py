@@ -44,3 +44,43 @@ def soup_from_seed(seed: int):
     elif m < 0.4:
         kw["modifiers"] = [A.AM_NOINTERPOLATION]
     return kw, S.TriangleSoup(**kw)
+
+
+# ANISO_NEEDS_GRADIENTS: an anisotropic mip filter is only defined for fetches that carry derivatives (sample_2d_grad: SASL tex2D,
+# PS_TEX_GRAD_ALPHA, PS_SPONZA_GRAD).  The explicit-LOD entry a C++ pixel shader's tex2d uses passes a null anisotropic_info that
+# the minification branch dereferences (sampler.cpp:768 -> sampler.cpp:731): the reference crashes on the first minified quad
+# (SURVEY.md Appendix B #6), so the random scenes never pair such a program with an anisotropic sampler.
+def scene_from_seed(seed: int):
+    """Seeded random instances of the textured scenes: TextureAndBlending (both derivative paths, point / trilinear / anisotropic
+    mip filters), the Sponza-like atrium (built-in and SASL-twin pixel shader, trilinear / anisotropic), the AnisotropicFilter
+    sample, the shadow-map sample, vertex texture fetch - random target size (multiples of 4), sample count and frame."""
+    r = np.random.default_rng(5000 + seed)
+    w, h = int(r.integers(20, 100)) * 4, int(r.integers(14, 64)) * 4
+    s = int(r.choice([1, 2, 4]))
+    kind = int(r.integers(0, 6))
+    if kind == 0:
+        ps = int(r.choice([A.PS_TEX_ALPHA, A.PS_TEX_GRAD_ALPHA]))
+        mip = int(r.choice([A.FILTER_POINT, A.FILTER_LINEAR, A.FILTER_ANISOTROPIC]))
+        if ps == A.PS_TEX_ALPHA and mip == A.FILTER_ANISOTROPIC:
+            mip = A.FILTER_LINEAR  # see ANISO_NEEDS_GRADIENTS
+        sc = S.TextureAndBlending(w, h, s, ps_program=ps, mip_filter=mip,
+                                  max_aniso=int(r.choice([2, 4, 8, 16])) if mip == A.FILTER_ANISOTROPIC else 0)
+    elif kind == 1:
+        ps = int(r.choice([A.PS_SPONZA, A.PS_SPONZA_GRAD]))
+        aniso = int(r.choice([0, 0, 4, 16]))
+        sc = S.SponzaLike(w, h, s, tex_size=int(r.choice([32, 64, 128])), max_aniso=aniso if ps == A.PS_SPONZA_GRAD else 0,
+                          ps_program=ps)
+    elif kind == 2:
+        sc = S.AnisotropicFilter(w, h, s)
+    elif kind == 3:
+        sc = S.StandardShadowMap(w, h, int(r.choice([1, 4])), tex_size=int(r.choice([32, 64])))
+    elif kind == 4:
+        sc = S.TerrainVTF(w, h, s, block=int(r.choice([8, 16])), tex_size=int(r.choice([16, 32, 64])))
+    else:
+        sc = S.HeightFieldTwoPass(w, h, s, nx=int(r.integers(10, 60)), nz=int(r.integers(10, 50)), shadowed=bool(r.random() < 0.4) and s == 1)
+    return sc, int(r.integers(0, sc.n_frames)), f"kind {kind} {w}x{h}x{s}"
+
+
+def scene_tolerance(scene):
+    """The shadow-map pixel shaders call expf / logf / pow: colour within 1 LSB there, bit-exact elsewhere."""
+    return 1 if type(scene).__name__ == "StandardShadowMap" or getattr(scene, "shadowed", False) else 0
