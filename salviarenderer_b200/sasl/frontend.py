@@ -154,6 +154,46 @@ def norm_semantic(s: str | None):
     return (m.group(1).upper(), int(m.group(2) or m.group(3) or 0))
 
 
+# salvia/include/salvia/shader/constants.h:22-37 (enum system_values) and :54-79 (the names that map to them)
+_SYSTEM_VALUE = {"POSITION": 1, "SV_POSITION": 1, "TEXCOORD": 2, "NORMAL": 3, "BLEND_INDICES": 4, "BLEND_WEIGHTS": 5, "PSIZE": 6,
+                 "COLOR": 7, "SV_TARGET": 7, "DEPTH": 8, "SV_DEPTH": 8}
+
+
+def _semantic_key(sem):
+    sv = _SYSTEM_VALUE.get(sem[0])
+    return (sv, "", sem[1]) if sv else (9, sem[0].lower(), sem[1])  # sv_customized carries its lower-case name
+
+
+def reference_semantic_order(sems) -> list:
+    """Indices of `sems` ((NAME, index) pairs, in declaration order) in the order of the reference's semantic array.
+    The reference keeps a shader's input / output semantics in an array it inserts into at std::lower_bound
+    (reflection_impl.cpp:70-118: add_input_semantic / add_output_semantic), and every consumer walks that array: vertex-shader
+    outputs -> attribute registers (sasl/src/shims/interp_shim.cpp:57-76), pixel-shader inputs <- attributes 0, 1, 2 ...
+    (pixel_shader_unit::update, shader_unit.cpp:106-140).  semantic_value::operator< is `sv < r.sv || name < r.name || index <
+    r.index` (constants.h:94-96) - not a strict weak order (NORMAL0 < TEXCOORD1 and TEXCOORD1 < NORMAL0), so the result depends on
+    the insertion sequence; this replays the binary search of libstdc++'s lower_bound with that predicate.  A semantic equal to
+    the element found is rejected (the reference's add_*_semantic returns false: "ABI analysis error")."""
+    keys = [_semantic_key(s) for s in sems]
+
+    def less(a, b):
+        return a[0] < b[0] or a[1] < b[1] or a[2] < b[2]
+
+    order = []
+    for i, k in enumerate(keys):
+        first, n = 0, len(order)
+        while n > 0:
+            half = n >> 1
+            if less(keys[order[first + half]], k):
+                first += half + 1
+                n -= half + 1
+            else:
+                n = half
+        if first < len(order) and keys[order[first]] == k:
+            raise CompileError(f"semantic {sems[i][0]}{sems[i][1]} is bound twice")
+        order.insert(first, i)
+    return order
+
+
 class Parser:
     ASSIGN_OPS = {"=", "+=", "-=", "*=", "/=", "%=", "&=", "|=", "^=", "<<=", ">>="}
     BIN_PREC = [("||",), ("&&",), ("|",), ("^",), ("&",), ("==", "!="), ("<", ">", "<=", ">="), ("<<", ">>"), ("+", "-"), ("*", "/", "%")]
@@ -1597,7 +1637,7 @@ class Gen:
                 reg += 1
         if reg > 8:
             raise CompileError("more than 8 vertex-shader inputs")
-        rets, stores, attr, have_pos = [], [], 0, False
+        rets, stores, attr, have_pos, full = [], [], 0, False, {}
         for k, (name, ty, sem) in enumerate(outs):
             if sem is None:
                 raise CompileError(f"vertex-shader output {name} has no semantic")
@@ -1606,14 +1646,17 @@ class Gen:
             names = [f"o{k}_{c}" for c in range(ty.n)]
             L.append(f"  float {', '.join(n + ' = 0' for n in names)};")
             rets += names
-            full = names + ["0.0f"] * (4 - ty.n)
+            full[k] = names + ["0.0f"] * (4 - ty.n)
+        # attribute registers follow the reference's semantic array, not the declaration order (reference_semantic_order)
+        for k in reference_semantic_order([sem for _, _, sem in outs]):
+            name, ty, sem = outs[k]
             if sem[0] in ("SV_POSITION", "POSITION") and not have_pos:
                 have_pos = True  # a position narrower than float4 (the reference's semantic test units) is padded with zeros
-                stores.append(f"  out[0] = make_float4({', '.join(full)});")
+                stores.append(f"  out[0] = make_float4({', '.join(full[k])});")
             else:
                 attr += 1
                 self.refl.outputs.append((sem[0], sem[1], str(ty)))
-                stores.append(f"  out[{attr}] = make_float4({', '.join(full)});")
+                stores.append(f"  out[{attr}] = make_float4({', '.join(full[k])});")
         if not have_pos:
             raise CompileError("the vertex shader does not write SV_Position")
         if attr > 5:
@@ -1632,19 +1675,26 @@ class Gen:
              "template <class Ctx>",
              "SASL_FN bool slv_jit_ps(const slv::RasterParams& p, const Ctx& px, float4& color) {",
              "  const SaslUniforms& U = *reinterpret_cast<const SaslUniforms*>(p.ps_uniforms);"]
-        args, k_attr = [], 0
-        for _, prm, members in ins:
-            for name, ty, sem in members:
-                if ty.kind not in ("scalar", "vector") or ty.base != "float":
-                    raise CompileError(f"pixel-shader input {name}: only float vectors are supported")
-                if sem is not None and sem[0] in ("SV_POSITION", "POSITION"):
-                    raise CompileError("reading SV_Position in a pixel shader is not supported")
-                L.append(f"  const float4 a{k_attr} = px.attr({k_attr});")
-                args += [f"a{k_attr}.{'xyzw'[k]}" for k in range(ty.n)]
-                self.refl.inputs.append(((sem or ('TEXCOORD', k_attr))[0], (sem or ('TEXCOORD', k_attr))[1], str(ty)))
-                k_attr += 1
-        if k_attr > 5:
+        args, flat = [], [m for _, _, members in ins for m in members]
+        for name, ty, sem in flat:
+            if ty.kind not in ("scalar", "vector") or ty.base != "float":
+                raise CompileError(f"pixel-shader input {name}: only float vectors are supported")
+            if sem is not None and sem[0] in ("SV_POSITION", "POSITION"):
+                raise CompileError("reading SV_Position in a pixel shader is not supported")
+        if len(flat) > 5:
             raise CompileError("more than 5 pixel-shader inputs")
+        # input -> attribute: position k of the reference's semantic array (with a C++ vertex shader bound the reference hands
+        # attribute k to the k-th entry, shader_unit.cpp:129; reference_semantic_order); inputs without a semantic - which the
+        # reference rejects - keep the declaration order
+        sems = [sem for _, _, sem in flat]
+        order = reference_semantic_order(sems) if all(s is not None for s in sems) else list(range(len(flat)))
+        attr_of = {k: a for a, k in enumerate(order)}
+        for a, k in enumerate(order):
+            name, ty, sem = flat[k]
+            L.append(f"  const float4 a{a} = px.attr({a});")
+            self.refl.inputs.append(((sem or ('TEXCOORD', a))[0], (sem or ('TEXCOORD', a))[1], str(ty)))
+        for k, (name, ty, sem) in enumerate(flat):
+            args += [f"a{attr_of[k]}.{'xyzw'[c]}" for c in range(ty.n)]
         rets, color = [], None
         for k, (name, ty, sem) in enumerate(outs):
             if ty.kind not in ("scalar", "vector") or ty.base != "float":

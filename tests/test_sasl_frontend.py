@@ -719,3 +719,55 @@ def test_writes_to_globals_and_inputs_are_local_copies():
     # a scalar SV_Position (semfn_par.svs) is padded with zeros
     unit = compile_shader("float fn(float a: SV_Position): SV_Position { return a * 2.0f; }", "vs")
     assert np.array_equal(HostShader(unit).vs([[1.5, 9, 9, 9]])[0], np.array([3.0, 0, 0, 0], f32))
+
+
+def test_reference_semantic_order_replays_the_reference_array():
+    """reflection_impl.cpp:70-118 inserts at std::lower_bound under semantic_value::operator< (constants.h:94-96), which is not
+    a strict weak order: the resulting array - and with it the attribute a semantic lands on - depends on the insertion order."""
+    from salviarenderer_b200.sasl.frontend import reference_semantic_order as order
+    T, N, P = "TEXCOORD", "NORMAL", "SV_POSITION"
+    assert order([(P, 0), (T, 0), (T, 1), (T, 2), (T, 3)]) == [0, 1, 2, 3, 4]         # ascending: declaration order
+    assert order([(T, 1), (T, 0)]) == [1, 0]                                          # sorted by index
+    assert order([(T, 2), (P, 0), (T, 0), (T, 1)]) == [1, 2, 3, 0]
+    # NORMAL0 < TEXCOORD1 (index) and TEXCOORD1 < NORMAL0 (system value): the later one is inserted BEHIND the earlier one
+    assert order([(T, 1), (N, 0)]) == [0, 1]
+    assert order([(N, 0), (T, 1)]) == [0, 1]
+    assert order([(N, 0), (T, 0)]) == [1, 0]                                          # TEXCOORD0 < NORMAL0 only
+    assert order([("COLOR", 0), ("SV_Target".upper(), 1), (T, 0)]) == [2, 0, 1]       # COLOR and SV_Target are one system value
+    assert order([("FOG", 0), ("BINORMAL", 0), (T, 0)]) == [2, 1, 0]                  # customised semantics compare by name
+    with pytest.raises(CompileError, match="bound twice"):
+        order([(T, 0), ("POSITION", 0), (P, 0)])                                       # POSITION == SV_Position
+
+
+def test_pixel_shader_inputs_map_to_attributes_in_reference_semantic_order():
+    """With a C++ vertex shader bound the reference feeds attribute k to the k-th entry of the pixel shader's semantic array
+    (pixel_shader_unit::update, shader_unit.cpp:106-140), whatever the declaration order."""
+    src = """
+    struct I { float4 late: TEXCOORD2; float2 first: TEXCOORD0; float3 mid: TEXCOORD1; };
+    float4 main(I i): COLOR { return float4(i.first.x, i.mid.y, i.late.z, i.late.w); }
+    """
+    unit = compile_shader(src, "ps")
+    assert unit.reflection.inputs == [("TEXCOORD", 0, "float2"), ("TEXCOORD", 1, "float3"), ("TEXCOORD", 2, "float4")]
+    got, keep = HostShader(unit).ps([[1, 2, 3, 4], [5, 6, 7, 8], [9, 10, 11, 12]], b"")
+    assert keep and np.array_equal(got, np.array([1, 6, 11, 12], f32))
+    # a lone TEXCOORD1 is entry 0 of the array: it reads attribute 0 (the reference's positional mapping)
+    unit = compile_shader("float4 main(float4 uv: TEXCOORD1): COLOR { return uv; }", "ps")
+    got, _ = HostShader(unit).ps([[1, 2, 3, 4], [5, 6, 7, 8]], b"")
+    assert np.array_equal(got, np.array([1, 2, 3, 4], f32))
+
+
+def test_vertex_shader_outputs_fill_attribute_registers_in_reference_semantic_order():
+    """Attribute registers are numbered along the vertex shader's output-semantic array, position aside
+    (sasl/src/shims/interp_shim.cpp:57-76)."""
+    src = """
+    struct O { float4 b: TEXCOORD1; float4 pos: SV_Position; float4 a: TEXCOORD0; };
+    O main(float4 p: POSITION) { O o; o.pos = p; o.a = p * 2.0f; o.b = p * 3.0f; return o; }
+    """
+    unit = compile_shader(src, "vs")
+    assert [(s, i) for s, i, _ in unit.reflection.outputs] == [("TEXCOORD", 0), ("TEXCOORD", 1)]
+    out = HostShader(unit).vs([[1, 2, 3, 4]])
+    assert np.array_equal(out[0], np.array([1, 2, 3, 4], f32))
+    assert np.array_equal(out[1], np.array([2, 4, 6, 8], f32)) and np.array_equal(out[2], np.array([3, 6, 9, 12], f32))
+    with pytest.raises(CompileError, match="bound twice"):
+        compile_shader("struct O { float4 p: SV_Position; float4 a: TEXCOORD0; float4 b: TEXCOORD(0); };"
+                       " O main(float4 p: POSITION) { O o; o.p = p; o.a = p; o.b = p; return o; }", "vs")
