@@ -35,6 +35,7 @@
 #include <vector>
 
 #include "salvia_b200.h"
+#include "sasl_frontend.hpp"
 
 namespace salvia_b200 {
 
@@ -404,10 +405,12 @@ public:
 class bs_replace : public cpp_blend_shader { public: uint32_t device_program() const override { return SLV_BS_REPLACE; } };          // ColorizedTriangle.cpp:94-106
 class bs_lerp_src_alpha : public cpp_blend_shader { public: uint32_t device_program() const override { return SLV_BS_LERP_SRC_ALPHA; } };  // TextureAndBlending.cpp:168-180
 // ---- SASL (renderer.h:75-86,136-147; salvia/include/salvia/shader/shader_object.h) -----------------------------------------------
-// compile(code, profile) runs the SASL front end (salviarenderer_b200/sasl, a Python package: `python3 -m
-// salviarenderer_b200.sasl.emit`, found through $SLV_SASL_PYTHON / $PYTHONPATH) and returns a shader_object holding the
-// reflection (uniform layout, sampler slots, input semantics) and the generated device code.  set_vertex_shader_code /
+// compile(code, profile) runs the SASL front end IN PROCESS (sasl_frontend.hpp: lexer, parser, semantic analysis, reflection,
+// code generation - the counterpart of the reference's sasl library) and returns a shader_object holding the reflection
+// (uniform layout, sampler slots, input semantics) and the generated device code.  set_vertex_shader_code /
 // set_pixel_shader_code hand that code to slv_shader_compile (NVRTC, in process) once per renderer and bind the module.
+// SLV_SASL_FRONTEND=python runs the Python twin of the front end instead (`$SLV_SASL_PYTHON -m salviarenderer_b200.sasl.emit`,
+// a child process; the two emit identical units, tests/test_sasl_frontend_cpp.py).
 namespace shader {
 enum languages { lang_none, lang_general, lang_vertex_shader, lang_pixel_shader, lang_blending_shader };
 struct shader_profile { languages language = lang_none; };
@@ -431,24 +434,32 @@ using shader_log_ptr = std::shared_ptr<std::string>;
 inline shader_object_ptr compile(std::string const& code, shader_profile const& profile, shader_log_ptr& logs) {
   logs = std::make_shared<std::string>();
   if (profile.language != lang_vertex_shader && profile.language != lang_pixel_shader) { *logs = "only vertex and pixel shaders are compiled"; return nullptr; }
-  // the front end reads the source from a file and writes the unit to stdout
-  char src_path[] = "/tmp/slv_sasl_XXXXXX";
-  int fd = mkstemp(src_path);
-  if (fd < 0) { *logs = "cannot create a temporary file"; return nullptr; }
-  FILE* sf = fdopen(fd, "w");
-  fwrite(code.data(), 1, code.size(), sf);
-  fclose(sf);
-  const char* py = getenv("SLV_SASL_PYTHON");
-  std::string cmd = std::string(py ? py : "python3") + " -m salviarenderer_b200.sasl.emit " + (profile.language == lang_vertex_shader ? "vs" : "ps") + " < " + src_path + " 2>&1";
-  FILE* pf = popen(cmd.c_str(), "r");
   std::string out;
-  if (pf) {
-    char buf[4096];
-    size_t n;
-    while ((n = fread(buf, 1, sizeof(buf), pf)) > 0) out.append(buf, n);
-    pclose(pf);
+  const char* which = getenv("SLV_SASL_FRONTEND");
+  if (which && std::string(which) == "python") {
+    // the Python front end reads the source from a file and writes the unit to stdout
+    char src_path[] = "/tmp/slv_sasl_XXXXXX";
+    int fd = mkstemp(src_path);
+    if (fd < 0) { *logs = "cannot create a temporary file"; return nullptr; }
+    FILE* sf = fdopen(fd, "w");
+    fwrite(code.data(), 1, code.size(), sf);
+    fclose(sf);
+    const char* py = getenv("SLV_SASL_PYTHON");
+    std::string cmd = std::string(py ? py : "python3") + " -m salviarenderer_b200.sasl.emit " + (profile.language == lang_vertex_shader ? "vs" : "ps") + " < " + src_path + " 2>&1";
+    FILE* pf = popen(cmd.c_str(), "r");
+    if (pf) {
+      char buf[4096];
+      size_t n;
+      while ((n = fread(buf, 1, sizeof(buf), pf)) > 0) out.append(buf, n);
+      pclose(pf);
+    }
+    unlink(src_path);
+  } else {
+    sasl::unit u;
+    std::string error;
+    if (!sasl::compile(code, profile.language == lang_vertex_shader ? "vs" : "ps", u, error)) { *logs = "error\n" + error + "\n"; return nullptr; }
+    out = sasl::render(u);
   }
-  unlink(src_path);
   if (out.compare(0, 10, "SLVSASL 1\n") != 0) { *logs = out.empty() ? "the SASL front end did not run (python3 -m salviarenderer_b200.sasl.emit)" : out; return nullptr; }
   auto obj = std::make_shared<shader_object>();
   obj->language = profile.language;

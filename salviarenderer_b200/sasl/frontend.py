@@ -86,7 +86,7 @@ def parse_type_name(s: str):
 # ------------------------------------------------------------------------------------------------- lexer
 TOKEN_RE = re.compile(r"""
     (?P<ws>\s+|//[^\n]*|/\*.*?\*/)
-  | (?P<num>(?:\d+\.\d*|\.\d+|\d+)(?:[eE][+-]?\d+)?[fFhHuUlL]?|0[xX][0-9a-fA-F]+[uU]?)
+  | (?P<num>0[xX][0-9a-fA-F]+[uU]?|(?:\d+\.\d*|\.\d+|\d+)(?:[eE][+-]?\d+)?[fFhHuUlL]?)
   | (?P<id>[A-Za-z_]\w*)
   | (?P<op>\+\+|--|<<=|>>=|<<|>>|<=|>=|==|!=|&&|\|\||\+=|-=|\*=|/=|%=|&=|\|=|\^=|[-+*/%<>=!&|^~?:;,.(){}\[\]])
 """, re.S | re.X)

@@ -103,8 +103,9 @@ class Preprocessor:
         expr = re.sub(r"defined\s*\(\s*([A-Za-z_]\w*)\s*\)|defined\s+([A-Za-z_]\w*)",
                       lambda m: "1" if (m.group(1) or m.group(2)) in self.macros else "0", expr)
         expr = self.expand(expr)
-        expr = IDENT.sub("0", expr)                       # remaining identifiers are 0, as in C
+        expr = re.sub(r"(?<![\w.])[A-Za-z_]\w*", "0", expr)  # remaining identifiers are 0, as in C (not the x of 0x10 / u of 10u)
         expr = re.sub(r"(\d+)[uUlL]+", r"\1", expr)
+        expr = re.sub(r"(?<![\w.])0([0-7]+)\b", r"0o\1", expr)   # C octal literals
         expr = expr.replace("&&", " and ").replace("||", " or ")
         expr = re.sub(r"!(?!=)", " not ", expr)
         if not re.fullmatch(r"[\d\s()+\-*/%<>=!&|^~xXa-fA-Fandortn]*", expr):

@@ -1,5 +1,6 @@
 // shader::compile() of the C++ host surface (salviarenderer_b200/host/salvia_b200_renderer.hpp) without a device: the SASL front
-// end is started as a child process and its unit (reflection + generated device code) is parsed into a shader_object.  Prints
+// end runs in process (or, with SLV_SASL_FRONTEND=python, as a child process) and its unit (reflection + generated device code) is
+// parsed into a shader_object.  Prints
 // the reflection in a stable text form; the Python test compares it with what the front end reports in process.
 //   usage: sasl_compile_test vs|ps < shader.sasl
 #include <cstdio>

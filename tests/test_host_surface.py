@@ -20,7 +20,8 @@ def host_binary(built, tmp_path_factory):
 
 
 def run(exe, lib, *size):
-    # the SASL section's compile() runs the front end (python -m salviarenderer_b200.sasl.emit) - on the CUDA product only
+    # the SASL section's compile() runs the C++ front end in process - on the CUDA product only; the interpreter settings only
+    # matter when SLV_SASL_FRONTEND=python selects the Python twin
     env = dict(os.environ, SLV_SASL_PYTHON=sys.executable, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
     out = subprocess.run([exe, lib, *map(str, size)], capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
@@ -63,20 +64,23 @@ def test_cpp_surface_sasl_equals_twins_on_the_product(host_binary):
 
 
 def test_cpp_compile_runs_the_front_end_and_parses_its_unit(tmp_path):
-    """shader::compile() (renderer.h:136-147 on the C++ surface) needs no device: it starts the SASL front end and parses the
-    unit it prints.  The reflection the C++ side ends up with equals what the front end reports in process; a compile error comes
-    back as a null object with the front end's message."""
+    """shader::compile() (renderer.h:136-147 on the C++ surface) needs no device and no interpreter: it runs the C++ SASL front
+    end in process (host/sasl_frontend.hpp) - or, with SLV_SASL_FRONTEND=python, the Python twin as a child process - and
+    parses the unit.  Either way the reflection the C++ side ends up with equals what the Python front end reports; a compile
+    error comes back as a null object with the front end's message."""
     from salviarenderer_b200.sasl import compile_shader
     from test_sasl_frontend import VS_SKIN
     exe = str(tmp_path / "sasl_compile_test")
     subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
                     "-I" + os.path.join(ROOT, "salviarenderer_b200", "host"), os.path.join(ROOT, "tests", "cpp", "sasl_compile_test.cpp"),
                     "-o", exe, "-ldl"], check=True)
-    env = dict(os.environ, SLV_SASL_PYTHON=sys.executable, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    in_process = {k: v for k, v in os.environ.items() if k not in ("SLV_SASL_FRONTEND", "SLV_SASL_PYTHON", "PYTHONPATH")}
+    in_process["SLV_SASL_PYTHON"] = "/nonexistent/python"  # the default path must not need an interpreter
+    child = dict(os.environ, SLV_SASL_FRONTEND="python", SLV_SASL_PYTHON=sys.executable, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
     ps = """sampler texSamp; float4 tint; float gain;
     struct PSIn { float4 uv: TEXCOORD0; float4 n: TEXCOORD1; };
     float4 ps_main(PSIn in): COLOR { return tex2D(texSamp, in.uv.xy) * tint * gain + ddx(in.n); }"""
-    for stage, src in (("vs", VS_SKIN), ("ps", ps)):
+    for env, stage, src in [(e, st, sr) for e in (in_process, child) for st, sr in (("vs", VS_SKIN), ("ps", ps))]:
         out = subprocess.run([exe, stage], input=src, capture_output=True, text=True, timeout=120, env=env)
         assert out.returncode == 0, out.stdout + out.stderr
         got = out.stdout.strip().splitlines()
@@ -89,5 +93,9 @@ def test_cpp_compile_runs_the_front_end_and_parses_its_unit(tmp_path):
         want += [f"output {s} {i} {k}" for k, (s, i, _) in enumerate(r.reflection.outputs)]
         want += [f"code_bytes {len(r.code.encode())}"]
         assert got == want, (got, want)
-    bad = subprocess.run([exe, "ps"], input="float4 broken(", capture_output=True, text=True, timeout=120, env=env)
-    assert bad.returncode == 2 and bad.stdout.startswith("error\n") and "line 1" in bad.stdout
+    msgs = []
+    for env in (in_process, child):
+        bad = subprocess.run([exe, "ps"], input="float4 broken(", capture_output=True, text=True, timeout=120, env=env)
+        assert bad.returncode == 2 and bad.stdout.startswith("error\n") and "line 1" in bad.stdout
+        msgs.append(bad.stdout)
+    assert msgs[0] == msgs[1]
