@@ -333,6 +333,18 @@ slv_result slv_shader_compile_cubin(uint32_t stage, const char* device_code, uin
 slv_result slv_shader_compile(slv_device dev, uint32_t stage, const char* device_code, uint32_t n_vs_output_attrs, uint32_t flags,
                               slv_handle* out, char* log, size_t log_bytes);
 void slv_free(void* p);
+/* The first half of compile(code, profile) (renderer.h:136-147; the reference's sasl library, sasl/src/{parser,semantic,codegen}):
+ * the SASL front end, host only - no device, no interpreter.  `source` is SASL text, `entry` the entry function (NULL: the function
+ * whose parameters or return value carry semantics).  On success `*unit` (malloc'ed: slv_free; NUL-terminated, `*unit_bytes`
+ * without the NUL) holds the compiled unit as text: the line "SLVSASL 1", then one line each of
+ *   stage vs|ps, n_vs_output_attrs N, uniform_bytes N, uses_derivatives 0|1,
+ *   uniform NAME TYPE OFFSET SIZE   (layout of the uniform block a draw passes; TYPE "float4x4[]" = address of an array's buffer),
+ *   sampler SLOT NAME, input SEMANTIC INDEX K (VS: input register K; PS: attribute K), output SEMANTIC INDEX K (VS: attribute K),
+ * then "code NBYTES" and NBYTES of device code - what slv_shader_compile / slv_shader_compile_cubin take as `device_code`.
+ * SLV_FAILED when the source does not compile; `log` (optional) receives the diagnostic ("line N: ...").  Implemented by
+ * salviarenderer_b200/host/sasl_frontend.hpp, which C++ hosts may also include directly.  CPU checkers: SLV_FAILED. */
+slv_result slv_sasl_translate(uint32_t stage, const char* source, const char* entry, char** unit, size_t* unit_bytes, char* log,
+                              size_t log_bytes);
 slv_result slv_resource_release(slv_device dev, slv_handle h);
 
 /* renderer::draw / draw_index -> commit_state_and_command() (renderer_impl.cpp:337-353) */

@@ -1814,6 +1814,7 @@ slv_result slv_shader_module_load(slv_device, uint32_t, const void*, size_t, uin
 slv_result slv_shader_compile_cubin(uint32_t, const char*, uint32_t, uint32_t, void**, size_t*, char*, size_t) { return SLV_FAILED; }
 slv_result slv_shader_compile(slv_device, uint32_t, const char*, uint32_t, uint32_t, slv_handle*, char*, size_t) { return SLV_FAILED; }
 void slv_free(void* p) { free(p); }
+slv_result slv_sasl_translate(uint32_t, const char*, const char*, char**, size_t*, char*, size_t) { return SLV_FAILED; }
 slv_result slv_peer_open(slv_device, const uint8_t*, void**) { return SLV_FAILED; }
 slv_result slv_peer_close(slv_device, void*) { return SLV_FAILED; }
 slv_result slv_resolve_target_peer(slv_device, slv_handle, void*) { return SLV_FAILED; }

@@ -136,7 +136,7 @@ ENTRY_POINTS = [
     "slv_traffic_get", "slv_kernel_launch_count", "slv_event_record", "slv_event_elapsed_ms", "slv_profile_enable",
     "slv_texture_device_ptr", "slv_pack_tiles", "slv_unpack_tiles", "slv_set_stream", "slv_profile_get_stages",
     "slv_peer_export_texture", "slv_peer_export_flags", "slv_peer_open", "slv_peer_close", "slv_resolve_target_peer",
-    "slv_peer_signal", "slv_flags_wait", "slv_shader_module_load", "slv_shader_compile_cubin", "slv_shader_compile", "slv_free", "slv_texture_level_tracking", "slv_texture_levels_touched", "slv_texture_readback_async", "slv_readback_wait",
+    "slv_peer_signal", "slv_flags_wait", "slv_shader_module_load", "slv_shader_compile_cubin", "slv_shader_compile", "slv_free", "slv_sasl_translate", "slv_texture_level_tracking", "slv_texture_levels_touched", "slv_texture_readback_async", "slv_readback_wait",
     "slv_readback_fence", "slv_host_register", "slv_host_unregister", "slv_texture_export_tiles_async",
     "slv_assembly_wait", "slv_peer_signal_after_consumers",
     "slv_buffer_device_ptr", "slv_external_write_begin", "slv_external_write_end",

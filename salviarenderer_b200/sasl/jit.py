@@ -80,8 +80,26 @@ def _product_lib():
                                                  ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t]
         lib.slv_free.restype = None
         lib.slv_free.argtypes = [ctypes.c_void_p]
+        lib.slv_sasl_translate.restype = ctypes.c_int32
+        lib.slv_sasl_translate.argtypes = [ctypes.c_uint32, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t),
+                                           ctypes.c_char_p, ctypes.c_size_t]
         _lib = lib
     return _lib
+
+
+def translate_in_library(source: str, stage: str, entry: str | None = None) -> str:
+    """slv_sasl_translate (include/salvia_b200.h): the C++ front end inside the product library; returns the unit text
+    (`SLVSASL 1 ... code NBYTES` + device code) that sasl/emit.py renders from the Python front end - the two are identical."""
+    lib = _product_lib()
+    unit, n = ctypes.c_void_p(), ctypes.c_size_t()
+    log = ctypes.create_string_buffer(1 << 14)
+    rc = lib.slv_sasl_translate(0 if stage == "vs" else 1, source.encode(), entry.encode() if entry else None, ctypes.byref(unit), ctypes.byref(n), log, len(log))
+    if rc != 0:
+        raise frontend.CompileError(log.value.decode(errors="replace"))
+    try:
+        return ctypes.string_at(unit.value, n.value).decode()
+    finally:
+        lib.slv_free(unit)
 
 
 def compile_in_process(unit: frontend.ShaderUnit, derivatives: str = "sasl") -> bytes:

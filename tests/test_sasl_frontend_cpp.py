@@ -192,3 +192,16 @@ def test_random_programs(cli, tmp_path):
     import sasl_fuzz
     accepted = sum(same(cli, sasl_fuzz.program_from_seed(seed, sloppy=0.02 if seed % 2 else 0.0), "ps", tmp_path) for seed in range(300))
     assert 100 < accepted < 300, accepted
+
+
+def test_c_abi_translate_equals_the_python_front_end(built):
+    """slv_sasl_translate (include/salvia_b200.h): the C++ front end inside the product library, callable without a device -
+    the first half of the reference's compile(code, profile); the unit text equals the Python front end's."""
+    import bench
+    from salviarenderer_b200.sasl import jit
+    for stage, src in (("vs", bench.SASL_VS_SPONZA), ("ps", bench.SASL_PS_SPONZA)):
+        assert jit.translate_in_library(src, stage) == emit.render(frontend.compile_shader(src, stage))
+    two = "float4 a(float4 p: TEXCOORD0): COLOR { return p; } float4 b(float4 p: TEXCOORD0): COLOR { return p * 2.0f; }"
+    assert jit.translate_in_library(two, "ps", entry="a") == emit.render(frontend.compile_shader(two, "ps", "a"))
+    with pytest.raises(frontend.CompileError, match="line 1"):
+        jit.translate_in_library("float4 broken(", "ps")
