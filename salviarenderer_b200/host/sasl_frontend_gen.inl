@@ -192,7 +192,9 @@ public:
     const std::string& t = n->str;
     const bool uns = !t.empty() && (t.back() == 'u' || t.back() == 'U');
     if (lower(t).compare(0, 2, "0x") == 0) {
-      const unsigned long long v = std::strtoull(rstrip_set(t, "uU").c_str(), nullptr, 16);
+      const std::string hex = rstrip_set(t, "uU");
+      const unsigned long long v = std::strtoull(hex.c_str(), nullptr, 16);
+      if (hex.size() > 2 + 16 || v > 0xFFFFFFFFull) err(n, "integer literal " + t + " does not fit 32 bits");
       return make_value(scalar_of(uns ? Base::Uint : Base::Int), {std::to_string(v) + (uns ? "u" : "")});
     }
     if (t.size() > 1 && uns && all_digits(t.substr(0, t.size() - 1))) return make_value(scalar_of(Base::Uint), {t.substr(0, t.size() - 1) + "u"});
@@ -232,7 +234,7 @@ public:
       int r = -1, c = -1;
       if (name.size() == 4 && name[0] == '_' && name[1] == 'm' && name[2] >= '0' && name[2] <= '3' && name[3] >= '0' && name[3] <= '3') { r = name[2] - '0'; c = name[3] - '0'; }
       else if (name.size() == 3 && name[0] == '_' && name[1] >= '1' && name[1] <= '4' && name[2] >= '1' && name[2] <= '4') { r = name[1] - '1'; c = name[2] - '1'; }
-      if (r >= 0) return make_value(scalar_of(ty.base), {base.comps.at((size_t)(r * ty.cols + c))}, base.lvalue);
+      if (r >= 0 && r < ty.rows && c < ty.cols) return make_value(scalar_of(ty.base), {base.comps.at((size_t)(r * ty.cols + c))}, base.lvalue);
     }
     err(n, "cannot take ." + name + " of " + to_string(ty));
   }
@@ -272,9 +274,10 @@ public:
       return make_value(vec(ty.base, width), comps);
     }
     const std::string digits = rstrip_set(idx->str, "uUlL");
-    char* endp = nullptr;
-    const long i = std::strtol(digits.c_str(), &endp, 0);
-    if (digits.empty() || *endp) err(n, "an index must be an integer literal");
+    const bool hex = digits.size() > 2 && lower(digits).compare(0, 2, "0x") == 0 &&
+                     std::all_of(digits.begin() + 2, digits.end(), [](unsigned char c) { return std::isxdigit(c); });
+    if (!hex && !all_digits(digits)) err(n, "an index must be an integer literal");
+    const long i = std::strtol(digits.c_str(), nullptr, hex ? 16 : 10);
     if (ty.kind == Kind::Vector) {
       if (i >= ty.n()) err(n, "index out of range");
       return make_value(scalar_of(ty.base), {base.comps[(size_t)i]}, base.lvalue);
@@ -660,7 +663,7 @@ public:
       return make_value(with_base(a[0].type, base), out);
     }
     if (name == "countbits" || name == "count_bits") {  // both spellings are registered upstream (semantic_analyser.cpp:1981-1982)
-      if (a.empty()) err(n, name + " expects 1 argument");
+      if (a.empty()) err(n, "countbits expects 1 argument");
       const Value v = to_base(a[0], Base::Uint, n);
       std::vector<std::string> out;
       for (const auto& c : v.comps) out.push_back(temp(Base::Uint, "sasl_countbits(" + c + ")"));

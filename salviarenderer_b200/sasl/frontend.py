@@ -734,6 +734,8 @@ class Gen:
     def e_num(self, n):
         t = n.args[0]
         if t.lower().startswith("0x"):
+            if int(t.rstrip("uU"), 16) > 0xFFFFFFFF:
+                self.err(n, f"integer literal {t} does not fit 32 bits")
             return Value(UINT if t[-1] in "uU" else INT, [str(int(t.rstrip("uU"), 16)) + ("u" if t[-1] in "uU" else "")])
         if re.fullmatch(r"\d+[uU]", t):
             return Value(UINT, [t[:-1] + "u"])
@@ -774,7 +776,8 @@ class Gen:
         m = re.fullmatch(r"_m([0-3])([0-3])|_([1-4])([1-4])", name)
         if ty.kind == "matrix" and m:
             r, c = (int(m.group(1)), int(m.group(2))) if m.group(1) is not None else (int(m.group(3)) - 1, int(m.group(4)) - 1)
-            return Value(Type("scalar", ty.base), [base.comps[r * ty.cols + c]], base.lvalue)
+            if r < ty.rows and c < ty.cols:
+                return Value(Type("scalar", ty.base), [base.comps[r * ty.cols + c]], base.lvalue)
         self.err(n, f"cannot take .{name} of {ty}")
 
     def e_index(self, n):
@@ -805,7 +808,13 @@ class Gen:
                     e = f"({i} == {r} ? {src.comps[r * width + c]} : {e})"
                 comps.append(self.temp(ty.base, e))
             return Value(vec(ty.base, width), comps)
-        i = int(idx.args[0].rstrip("uUlL"), 0)
+        digits = idx.args[0].rstrip("uUlL")
+        if re.fullmatch(r"0[xX][0-9a-fA-F]+", digits):
+            i = int(digits, 16)
+        elif re.fullmatch(r"\d+", digits):
+            i = int(digits)
+        else:
+            self.err(n, "an index must be an integer literal")
         if ty.kind == "vector":
             if i >= ty.n:
                 self.err(n, "index out of range")
@@ -1009,6 +1018,8 @@ class Gen:
         return Value(FLOAT, [self.dot_comps(x.comps, y.comps)])
 
     def i_cross(self, a, n):
+        if len(a) != 2:
+            self.err(n, "cross expects 2 arguments")
         x, y = (self.convert(self.to_base(v, "float", n), vec("float", 3), n) for v in a)
         (ax, ay, az), (bx, by, bz) = x.comps, y.comps
         return Value(vec("float", 3), [self.temp("float", f"({ay} * {bz}) - ({az} * {by})"), self.temp("float", f"({az} * {bx}) - ({ax} * {bz})"),
@@ -1021,13 +1032,19 @@ class Gen:
         return Value(vec("float", 4), [self.temp("float", "1.0f"), self.temp("float", f"{x.comps[1]} * {y.comps[1]}"), x.comps[2], y.comps[3]])
 
     def i_length(self, a, n):
+        if not a:
+            self.err(n, "length expects 1 argument")
         v = self.to_base(a[0], "float", n)
         return Value(FLOAT, [self.temp("float", f"sqrtf({self.dot_comps(v.comps, v.comps)})")])
 
     def i_distance(self, a, n):
+        if len(a) != 2:
+            self.err(n, "distance expects 2 arguments")
         return self.i_length([self.e_bin(Node("bin", ("-", _Lit(a[0]), _Lit(a[1])), n.line))], n)
 
     def i_normalize(self, a, n):  # eflib normalize3: zero-length vectors are left alone (length := 1)
+        if not a:
+            self.err(n, "normalize expects 1 argument")
         v = self.to_base(a[0], "float", n)
         ln = self.temp("float", f"sqrtf({self.dot_comps(v.comps, v.comps)})")
         ln = self.temp("float", f"sasl_eq_eps({ln}, 0.0f) ? 1.0f : {ln}")
@@ -1035,6 +1052,8 @@ class Gen:
         return Value(v.type, [self.temp("float", f"{c} * {inv}") for c in v.comps])
 
     def i_reflect(self, a, n):  # eflib reflect3(i, n) = i - 2 * dot(i, n) * n
+        if len(a) != 2:
+            self.err(n, "reflect expects 2 arguments")
         i, nn, _ = self.unify(self.to_base(a[0], "float", n), self.to_base(a[1], "float", n), n)
         d = self.dot_comps(i.comps, nn.comps)
         s = self.temp("float", f"2.0f * {d}")
@@ -1066,16 +1085,20 @@ class Gen:
         return self.e_bin(Node("bin", ("*", _Lit(x), _Lit(y)), n.line))  # scalar * matrix
 
     def i_transpose(self, a, n):
-        m = a[0]
-        if m.type.kind != "matrix":
+        if not a or a[0].type.kind != "matrix":
             self.err(n, "transpose expects a matrix")
+        m = a[0]
         return Value(mat(m.type.base, m.type.cols, m.type.rows), [m.comps[r * m.type.cols + c] for c in range(m.type.cols) for r in range(m.type.rows)])
 
     def i_any(self, a, n):
+        if not a:
+            self.err(n, "any expects 1 argument")
         v = self.to_base(a[0], "bool", n)
         return Value(BOOL, [self.temp("bool", " || ".join(v.comps))])
 
     def i_all(self, a, n):
+        if not a:
+            self.err(n, "all expects 1 argument")
         v = self.to_base(a[0], "bool", n)
         return Value(BOOL, [self.temp("bool", " && ".join(v.comps))])
 
@@ -1084,10 +1107,14 @@ class Gen:
     def i_asuint(self, a, n): return self.bitcast(a, n, "uint", "sasl_asuint")
 
     def bitcast(self, a, n, base, fn):
+        if not a:
+            self.err(n, f"{fn[5:]} expects 1 argument")
         v = a[0]
         return Value(Type(v.type.kind, base, v.type.rows, v.type.cols), [self.temp(base, f"{fn}({c})") for c in v.comps])
 
     def i_countbits(self, a, n):
+        if not a:
+            self.err(n, "countbits expects 1 argument")
         v = self.to_base(a[0], "uint", n)
         return Value(v.type, [self.temp("uint", f"sasl_countbits({c})") for c in v.comps])
 

@@ -205,3 +205,49 @@ def test_c_abi_translate_equals_the_python_front_end(built):
     assert jit.translate_in_library(two, "ps", entry="a") == emit.render(frontend.compile_shader(two, "ps", "a"))
     with pytest.raises(frontend.CompileError, match="line 1"):
         jit.translate_in_library("float4 broken(", "ps")
+
+
+REJECTED = [
+    "float3x3 N; float4 main(float4 p: TEXCOORD0): COLOR { return p * N._m33; }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { return p[1.5]; }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { return p[010]; }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { return cross(p); }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { return length(); }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { return normalize(); }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { return transpose(); }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { return asfloat(); }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { return lit(p, p); }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { return dst(p); }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { return any(); }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { return reflect(p); }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { return distance(p); }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { return count_bits(); }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { return faceforward(p, p); }",
+    "struct S { float a; }; float4 main(float4 p: TEXCOORD0): COLOR { S s; return abs(s); }",
+    "float4 main(float4 p: TEXCOORD0: COLOR { return p; }",
+    "float4 main(float4 p: TEXCOORD(1.5)): COLOR { return p; }",
+    "float4 main(float4 p: A1B): COLOR { return p; }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { switch (1) { case 1.5: return p; } return p; }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { float x[3]; return p; }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { return p; ",
+    "float4 main(float4 p: TEXCOORD0): COLOR { return p.xyzwx; }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { float2x2 m = float2x2(1,2,3,4); return float4(m[5], 0, 0); }",
+    "",
+    "float4 main(float4 p: TEXCOORD0): COLOR { return 0xFFFFFFFFFFFFFFFFFFFF + p; }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { break; return p; }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { p = 1 = 2; return p; }",
+    "void f() { return 1; } float4 main(float4 p: TEXCOORD0): COLOR { f(); return p; }",
+    "struct G { float a; }; G g; float4 main(float4 p: TEXCOORD0): COLOR { return p; }",
+    "bool flags[4]; float4 main(float4 p: TEXCOORD0): COLOR { return p; }",
+    "float4 b[n]; float4 main(float4 p: TEXCOORD0): COLOR { return b[0]; }",
+]
+
+
+def test_rejections_carry_the_same_message(cli, tmp_path):
+    """Ill-formed sources - wrong argument counts, bad indices, semantics, literals, statements - are rejected by both front
+    ends with the SAME diagnostic (a CompileError, never a stray Python exception or a C++ crash)."""
+    for src in REJECTED:
+        a, ea = run_py(src, "ps")
+        b, eb = run_cpp(cli, src, "ps", tmp=tmp_path)
+        assert a is None and b is None, src
+        assert ea == eb, (src, ea, eb)
