@@ -160,6 +160,49 @@ int main() {
       emit(("ps_branches_" + std::to_string(i)).c_str(), "kat_branches(a0, a1)", {a1(in0), {"float3", {in1[0], in1[1], in1[2]}}}, {r0, r1});
     }
   }
-  std::printf("\n ]}\n");
+  std::printf("\n ],\n \"quad_cases\": [\n");
+  // Known answers that need a whole 2x2 quad (PACKAGE_ELEMENT_COUNT = 4 pixels, two per line: pixel = row * 2 + col).
+  auto row = [](std::vector<float> const& v) {
+    std::string s = "[";
+    for (size_t k = 0; k < v.size(); ++k) s += (k ? ", " : "") + num(v[k]);
+    return s + "]";
+  };
+  auto quad = [&](const char* name, const char* what, std::vector<float> const (&in)[4], std::vector<float> const (&out)[4], bool last) {
+    std::printf("  {\"name\": \"%s\", \"what\": \"%s\",\n   \"inputs\": [%s, %s, %s, %s],\n   \"expected\": [%s, %s, %s, %s]}%s\n", name, what, row(in[0]).c_str(),
+                row(in[1]).c_str(), row(in[2]).c_str(), row(in[3]).c_str(), row(out[0]).c_str(), row(out[1]).c_str(), row(out[2]).c_str(), row(out[3]).c_str(),
+                last ? "" : ",");
+  };
+  {  // general.cpp:1526-1602 (ddx_ddy): inputs srand(0), rand() / 67.0f in the test's order (v0, v1.xy, v2.xyz, v3.xyzw per pixel);
+     // ddx = right - left of the pixel's line for both pixels of the line, ddy = lower - upper line for both pixels of the column
+     // (get_ddx / get_ddy, general.cpp:1501-1524); out = (ddx(v0) + ddy(v0), ddx(v1).xy + ddy(v1).yx, ddx(v2).xyz + ddy(v2).yzx,
+     // ddx(v3).xwzy + ddy(v3).yzxw)
+    srand(0);
+    std::vector<float> in[4], out[4];
+    for (int i = 0; i < 4; ++i) for (int k = 0; k < 10; ++k) in[i].push_back(rand() / 67.0f);
+    float ddx[4][10], ddy[4][10];
+    for (int k = 0; k < 10; ++k) {
+      ddx[0][k] = ddx[1][k] = in[1][k] - in[0][k];
+      ddx[2][k] = ddx[3][k] = in[3][k] - in[2][k];
+      ddy[0][k] = ddy[2][k] = in[2][k] - in[0][k];
+      ddy[1][k] = ddy[3][k] = in[3][k] - in[1][k];
+    }
+    // component k of the flattened (v0, v1, v2, v3): which ddx / ddy component the reference expression adds
+    const int sx[10] = {0, 1, 2, 3, 4, 5, 6, 9, 8, 7};   // .x | .xy | .xyz | .xwzy
+    const int sy[10] = {0, 2, 1, 4, 5, 3, 7, 8, 6, 9};   // .x | .yx | .yzx | .yzxw
+    for (int i = 0; i < 4; ++i) for (int k = 0; k < 10; ++k) out[i].push_back(ddx[i][sx[k]] + ddy[i][sy[k]]);
+    quad("ddx_ddy", "general.cpp:1526-1602", in, out, false);
+  }
+  {  // general.cpp:1668-1716 (ps_for_loop): x doubled up to ten times, leaving the loop once it exceeds 5000
+    srand(0);
+    std::vector<float> in[4], out[4];
+    for (int i = 0; i < 4; ++i) {
+      float x = rand() / 1000.0f;
+      in[i].push_back(x);
+      for (int j = 0; j < 10; ++j) { x *= 2.0f; if (x > 5000.0f) break; }
+      out[i].push_back(x);
+    }
+    quad("for_loop", "general.cpp:1668-1716", in, out, true);
+  }
+  std::printf(" ]}\n");
   return 0;
 }
