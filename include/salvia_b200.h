@@ -326,7 +326,9 @@ slv_result slv_shader_module_load(slv_device dev, uint32_t stage, const void* im
  * derivative convention (ddx = q1 - q0, ddy = q2 - q0 for the whole quad) instead of SASL's per row / per column.  `log`
  * (optional) receives the compiler's diagnostics, NUL-terminated.  Compiled images are cached on disk by content hash in
  * $SLV_JIT_CACHE (else $XDG_CACHE_HOME/salvia_b200_jit, else ~/.cache/salvia_b200_jit; only a directory the user owns and nobody
- * else can write).  SLV_FAILED when libnvrtc is unavailable or the code does not compile.  CPU checkers: SLV_FAILED. */
+ * else can write).  SLV_FAILED when libnvrtc is unavailable or the code does not compile.  CPU checkers: SLV_FAILED - except
+ * slv_shader_compile of the restatement (oracle/), which builds the same code for the HOST and runs it inside its pipeline, so
+ * that tests compare SASL frames on the CPU (oracle/slv_host_shader.h; test infrastructure). */
 #define SLV_COMPILE_DERIV_CPP 1u
 slv_result slv_shader_compile_cubin(uint32_t stage, const char* device_code, uint32_t n_vs_output_attrs, uint32_t flags,
                                     void** image, size_t* bytes, char* log, size_t log_bytes);

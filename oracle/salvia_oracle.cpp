@@ -25,7 +25,11 @@
 #include <chrono>
 #include <cstring>
 #include <memory>
+#include <string>
 #include <vector>
+
+#include <dlfcn.h>
+#include <unistd.h>
 
 namespace {
 
@@ -164,11 +168,27 @@ struct Sampler {
   slv_handle tex;
 };
 
+// A SASL shader compiled for the HOST (slv_shader_compile below; runtime: oracle/slv_host_shader.h) - test infrastructure on
+// top of the restatement: the generated code the product hands to NVRTC, run inside this pipeline.
+struct HostApi {  // = SlvHostApi of slv_host_shader.h
+  void* ctx;
+  void (*sample_grad)(void*, int, float, float, float, float, float, float, float, float*);
+  void (*sample_lod)(void*, int, float, float, float, float*);
+  void (*vs_sample_lod)(void*, float, float, float, float*);
+};
+struct Module {
+  uint32_t stage = 0, n_vs_output_attrs = 0;
+  void* dl = nullptr;
+  void (*vs)(const float*, const unsigned char*, float*, const HostApi*) = nullptr;
+  void (*ps_quad)(const float*, const unsigned char*, size_t, const HostApi*, float*, int*) = nullptr;
+};
+
 struct Resource {
-  enum Kind { NONE, BUFFER, TEXTURE, SAMPLER } kind = NONE;
+  enum Kind { NONE, BUFFER, TEXTURE, SAMPLER, MODULE } kind = NONE;
   std::vector<uint8_t> buf;
   Texture tex;
   Sampler samp;
+  Module mod;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -610,6 +630,9 @@ struct DrawCtx {
   Texture const* sampler_tex[SLV_MAX_SAMPLERS];
   Sampler const* vs_sampler = nullptr;       // vertex texture fetch: vs.samplers[0]
   Texture const* vs_sampler_tex = nullptr;
+  Module const* vs_module = nullptr;         // SLV_PROGRAM_JIT(module): host-compiled SASL shaders
+  Module const* ps_module = nullptr;
+  HostApi host_api{};
   uint64_t ps_invocations = 0, backend_input_pixels = 0;
 };
 
@@ -685,6 +708,13 @@ uint32_t vs_num_attrs(slv_shader_binding const& vs) {
 void run_vs(DrawCtx& c, V4 const in[SLV_MAX_VS_INPUT_ATTRS], VsOut& out) {
   auto const& vs = c.d->vs;
   for (auto& r : out.r) r = mk4(0, 0, 0, 0);
+  if (c.vs_module) {  // a SASL vertex shader compiled for the host: input registers in, position + attributes out
+    float regs[8][4] = {}, o[6][4] = {};
+    for (int k = 0; k < 8 && k < SLV_MAX_VS_INPUT_ATTRS; ++k) for (int j = 0; j < 4; ++j) regs[k][j] = in[k][j];
+    c.vs_module->vs(&regs[0][0], vs.uniforms, &o[0][0], &c.host_api);
+    for (int k = 0; k < 6 && k < (int)(sizeof(out.r) / sizeof(out.r[0])); ++k) out.r[k] = mk4(o[k][0], o[k][1], o[k][2], o[k][3]);
+    return;
+  }
   switch (vs.program) {
   case SLV_VS_MVP_PASSTHROUGH: {
     auto u = (slv_vs_mvp_passthrough_uniforms const*)vs.uniforms;
@@ -1256,7 +1286,16 @@ void draw_quad(DrawCtx& c, TriInfo const& ti, float const* aa, uint32_t left, ui
   q.lod_flag = 0;
   V4 pso[4];
   bool keep[4];
-  for (int i = 0; i < 4; ++i) keep[i] = run_ps(c, q, i, pso[i]);
+  if (c.ps_module) {  // a SASL pixel shader compiled for the host runs the whole quad at once (derivatives need all four pixels)
+    float attrs[4][5][4] = {}, colors[4][4] = {};
+    int kept[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i)
+      for (int r = 1; r < nreg && r <= 5; ++r) for (int j = 0; j < 4; ++j) attrs[i][r - 1][j] = q.px[i].r[r][j];
+    c.ps_module->ps_quad(&attrs[0][0][0], c.d->ps.uniforms, c.d->ps.uniform_bytes, &c.host_api, &colors[0][0], kept);
+    for (int i = 0; i < 4; ++i) { pso[i] = mk4(colors[i][0], colors[i][1], colors[i][2], colors[i][3]); keep[i] = kept[i] != 0; }
+  } else {
+    for (int i = 0; i < 4; ++i) keep[i] = run_ps(c, q, i, pso[i]);
+  }
   bool any_out = false;
   uint32_t final_mask[4];
   for (int i = 0; i < 4; ++i) { final_mask[i] = keep[i] ? tested[i] : 0; any_out |= final_mask[i] != 0; }
@@ -1395,6 +1434,36 @@ slv_result do_draw(Device& dev, slv_draw_desc const& d) {
   c.d = &d;
   if (d.topology != SLV_TOPO_TRIANGLE_LIST && d.topology != SLV_TOPO_TRIANGLE_STRIP) return SLV_FAILED;
   c.n_attrs = vs_num_attrs(d.vs);
+  if (d.vs.program & 0x80000000u) {
+    auto r = dev.get(d.vs.program & 0x7FFFFFFFu, Resource::MODULE);
+    if (!r || r->mod.stage != SLV_STAGE_VS) return SLV_INVALID_PARAMETER;
+    c.vs_module = &r->mod;
+    c.n_attrs = r->mod.n_vs_output_attrs;
+  }
+  if (d.ps.program & 0x80000000u) {
+    auto r = dev.get(d.ps.program & 0x7FFFFFFFu, Resource::MODULE);
+    if (!r || r->mod.stage != SLV_STAGE_PS) return SLV_INVALID_PARAMETER;
+    c.ps_module = &r->mod;
+  }
+  c.host_api.ctx = &c;
+  c.host_api.sample_grad = [](void* ctx, int slot, float u, float v, float dudx, float dvdx, float dudy, float dvdy, float bias, float* rgba) {
+    auto& dc = *static_cast<DrawCtx*>(ctx);
+    V4 r = mk4(0, 0, 0, 0);
+    if (slot >= 0 && slot < SLV_MAX_SAMPLERS && dc.sampler_tex[slot]) r = sample_2d_grad(*dc.sampler_tex[slot], dc.samplers[slot]->d, u, v, dudx, dvdx, dudy, dvdy, bias);
+    for (int j = 0; j < 4; ++j) rgba[j] = r[j];
+  };
+  c.host_api.sample_lod = [](void* ctx, int slot, float u, float v, float lod, float* rgba) {
+    auto& dc = *static_cast<DrawCtx*>(ctx);
+    V4 r = mk4(0, 0, 0, 0);
+    if (slot >= 0 && slot < SLV_MAX_SAMPLERS && dc.sampler_tex[slot]) r = sample_impl(*dc.sampler_tex[slot], dc.samplers[slot]->d, u, v, lod, nullptr);
+    for (int j = 0; j < 4; ++j) rgba[j] = r[j];
+  };
+  c.host_api.vs_sample_lod = [](void* ctx, float u, float v, float lod, float* rgba) {
+    auto& dc = *static_cast<DrawCtx*>(ctx);
+    V4 r = mk4(0, 0, 0, 0);
+    if (dc.vs_sampler_tex) r = sample_impl(*dc.vs_sampler_tex, dc.vs_sampler->d, u, v, lod, nullptr);
+    for (int j = 0; j < 4; ++j) rgba[j] = r[j];
+  };
   if (c.n_attrs > SLV_MAX_VS_OUTPUT_ATTRS) return SLV_INVALID_PARAMETER;
   c.has_centroid = false;
   for (uint32_t i = 0; i < SLV_MAX_VS_OUTPUT_ATTRS; ++i) {
@@ -1463,7 +1532,7 @@ slv_result do_draw(Device& dev, slv_draw_desc const& d) {
     if (d.ps.uniform_bytes < sizeof(slv_ps_ssm_draw_uniforms) || vs_num_attrs(d.vs) < 5) return SLV_INVALID_PARAMETER;
     if ((u->has_tex_sampler && !c.sampler_tex[0]) || (u->has_depth_sampler && !c.sampler_tex[1])) return SLV_INVALID_PARAMETER;
   }
-  if (d.vs.program == SLV_VS_TERRAIN_VTF) {
+  if (d.vs.program == SLV_VS_TERRAIN_VTF || (c.vs_module && d.vs.samplers[0])) {
     auto r = dev.get(d.vs.samplers[0], Resource::SAMPLER);
     if (!r) return SLV_INVALID_PARAMETER;
     c.vs_sampler = &r->samp;
@@ -1697,6 +1766,7 @@ slv_result slv_sampler_create(slv_device dev, const slv_sampler_desc* d, slv_han
 }
 slv_result slv_resource_release(slv_device dev, slv_handle h) {
   if (h == 0 || h >= dev->res.size()) return SLV_INVALID_PARAMETER;
+  if (dev->res[h].kind == Resource::MODULE && dev->res[h].mod.dl) dlclose(dev->res[h].mod.dl);
   dev->res[h] = Resource();
   return SLV_OK;
 }
@@ -1812,7 +1882,54 @@ slv_result slv_texture_level_tracking(slv_device, uint32_t) { return SLV_OK; }
 slv_result slv_texture_levels_touched(slv_device, slv_handle, uint32_t* mask) { if (!mask) return SLV_INVALID_PARAMETER; *mask = 0; return SLV_OK; }
 slv_result slv_shader_module_load(slv_device, uint32_t, const void*, size_t, uint32_t, slv_handle*) { return SLV_FAILED; }
 slv_result slv_shader_compile_cubin(uint32_t, const char*, uint32_t, uint32_t, void**, size_t*, char*, size_t) { return SLV_FAILED; }
-slv_result slv_shader_compile(slv_device, uint32_t, const char*, uint32_t, uint32_t, slv_handle*, char*, size_t) { return SLV_FAILED; }
+// slv_shader_compile on the checker: the generated code is compiled for the HOST (g++ over sasl_rt.h's host build and
+// oracle/slv_host_shader.h: quads as fibers, fetches through this library's sampler) into a shared object that run_vs /
+// draw_quad call.  Test infrastructure - lets SASL scenes be compared with the cpp twins on the CPU.  The directories of the two
+// headers are found next to this library ($SLV_ORACLE_SASL_RT overrides the one of sasl_rt.h).
+slv_result slv_shader_compile(slv_device dev, uint32_t stage, const char* device_code, uint32_t n_vs_output_attrs, uint32_t flags, slv_handle* out,
+                              char* log, size_t log_bytes) {
+  if (log && log_bytes) log[0] = 0;
+  if (!dev || !device_code || !out || (stage != SLV_STAGE_VS && stage != SLV_STAGE_PS)) return SLV_INVALID_PARAMETER;
+  Dl_info info{};
+  if (!dladdr((void*)&slv_shader_compile, &info) || !info.dli_fname) return SLV_FAILED;
+  std::string here(info.dli_fname);
+  here = here.find('/') == std::string::npos ? std::string(".") : here.substr(0, here.rfind('/'));
+  const char* rt_env = getenv("SLV_ORACLE_SASL_RT");
+  const std::string rt = rt_env ? rt_env : here + "/../salviarenderer_b200/sasl";
+  char dir[] = "/tmp/slv_oracle_jit_XXXXXX";
+  if (!mkdtemp(dir)) return SLV_FAILED;
+  const std::string src = std::string(dir) + "/shader.cpp", so = std::string(dir) + "/shader.so", err = std::string(dir) + "/log.txt";
+  FILE* f = fopen(src.c_str(), "w");
+  if (!f) return SLV_FAILED;
+  fprintf(f, "#include \"sasl_rt.h\"\n#include \"slv_host_shader.h\"\n%s\n%s\n", device_code, stage == SLV_STAGE_VS ? "SLV_HOST_VS_ENTRY" : "SLV_HOST_PS_ENTRY");
+  fclose(f);
+  const std::string cmd = std::string("g++ -std=c++17 -O1 -ffp-contract=off -fPIC -shared -w") + ((flags & SLV_COMPILE_DERIV_CPP) ? " -DSLV_JIT_DERIV_CPP=1" : "") +
+                          " -I'" + rt + "' -I'" + here + "' -o '" + so + "' '" + src + "' > '" + err + "' 2>&1";
+  const int rc = system(cmd.c_str());
+  Module m;
+  m.stage = stage;
+  m.n_vs_output_attrs = n_vs_output_attrs;
+  if (rc == 0) m.dl = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
+  if (m.dl) {
+    m.vs = reinterpret_cast<decltype(m.vs)>(dlsym(m.dl, "slv_host_vs"));
+    m.ps_quad = reinterpret_cast<decltype(m.ps_quad)>(dlsym(m.dl, "slv_host_ps_quad"));
+  }
+  const bool ok = m.dl && (stage == SLV_STAGE_VS ? m.vs != nullptr : m.ps_quad != nullptr);
+  if (!ok && log && log_bytes) {
+    FILE* e = fopen(err.c_str(), "r");
+    size_t n = e ? fread(log, 1, log_bytes - 1, e) : 0;
+    log[n] = 0;
+    if (e) fclose(e);
+    if (!n) snprintf(log, log_bytes, "%s", m.dl ? "entry point missing" : (rc ? "g++ failed" : dlerror()));
+  }
+  unlink(src.c_str()); unlink(so.c_str()); unlink(err.c_str()); rmdir(dir);  // the mapped object stays valid after the unlink
+  if (!ok) { if (m.dl) dlclose(m.dl); return SLV_FAILED; }
+  dev->res.emplace_back();
+  dev->res.back().kind = Resource::MODULE;
+  dev->res.back().mod = m;
+  *out = (slv_handle)(dev->res.size() - 1);
+  return SLV_OK;
+}
 void slv_free(void* p) { free(p); }
 slv_result slv_sasl_translate(uint32_t, const char*, const char*, char**, size_t*, char*, size_t) { return SLV_FAILED; }
 slv_result slv_peer_open(slv_device, const uint8_t*, void**) { return SLV_FAILED; }

@@ -29,8 +29,9 @@ NVCC_FLAGS = ["-cubin", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-l
 @dataclass
 class CompiledShader:
     unit: frontend.ShaderUnit
-    cubin: bytes
+    cubin: bytes                 # b"" when compiled with device=False (a shader only ever loaded into a CPU checker)
     ptx_entry_points: tuple
+    derivatives: str = "sasl"
 
     @property
     def reflection(self):
@@ -117,12 +118,16 @@ def compile_in_process(unit: frontend.ShaderUnit, derivatives: str = "sasl") -> 
         lib.slv_free(image)
 
 
-def compile(source: str, stage: str, entry: str | None = None, derivatives: str = "sasl", keep_dir: str | None = None) -> CompiledShader:  # noqa: A001
+def compile(source: str, stage: str, entry: str | None = None, derivatives: str = "sasl", keep_dir: str | None = None,  # noqa: A001
+            device: bool = True) -> CompiledShader:
     """stage 'vs' | 'ps'.  derivatives: 'sasl' (per row / per column) or 'cpp' (q1 - q0 / q2 - q0 for the whole quad).
-    keep_dir (nvcc path only): keep the generated file there."""
+    keep_dir (nvcc path only): keep the generated file there.  device=False: the front end only, no sm_100a image - for a
+    shader that is only loaded into a CPU checker (tests), whose slv_shader_compile builds the generated code for the host."""
     unit = frontend.compile_shader(source, stage, entry)
+    if not device:
+        return CompiledShader(unit, b"", (), derivatives)
     if os.environ.get("SLV_JIT_COMPILER", "nvrtc") != "nvcc" and keep_dir is None and os.path.exists(PRODUCT_LIB):
-        return CompiledShader(unit, compile_in_process(unit, derivatives), VS_ENTRY_POINTS if stage == "vs" else PS_ENTRY_POINTS)
+        return CompiledShader(unit, compile_in_process(unit, derivatives), VS_ENTRY_POINTS if stage == "vs" else PS_ENTRY_POINTS, derivatives)
     defs = ["-DSLV_JIT_VS=1", f"-DSLV_JIT_R={unit.reflection.n_vs_output_attrs + 1}"] if stage == "vs" else ["-DSLV_JIT_PS=1"]
     if stage == "ps" and derivatives == "cpp":
         defs.append("-DSLV_JIT_DERIV_CPP=1")
@@ -154,9 +159,14 @@ def compile(source: str, stage: str, entry: str | None = None, derivatives: str 
         finally:
             if keep_dir is None:
                 shutil.rmtree(work, ignore_errors=True)
-    return CompiledShader(unit, open(path, "rb").read(), VS_ENTRY_POINTS if stage == "vs" else PS_ENTRY_POINTS)
+    return CompiledShader(unit, open(path, "rb").read(), VS_ENTRY_POINTS if stage == "vs" else PS_ENTRY_POINTS, derivatives)
 
 
 def load(be, shader: CompiledShader) -> int:
-    """Registers the compiled shader with the library; returns the module handle for abi.program_jit()."""
+    """Registers the compiled shader with the library; returns the module handle for abi.program_jit().  The CUDA product takes
+    the sm_100a image; a CPU checker (tests) takes the generated code through slv_shader_compile and builds it for the host."""
+    if be.name != "cuda-sm100a":
+        return be.shader_compile(shader.unit.stage, shader.unit.code, shader.reflection.n_vs_output_attrs, deriv_cpp=shader.derivatives == "cpp")
+    if not shader.cubin:
+        raise frontend.CompileError("this shader was compiled with device=False: there is no sm_100a image to load")
     return be.shader_module_load(shader.unit.stage, shader.cubin, shader.reflection.n_vs_output_attrs)

@@ -271,8 +271,9 @@ int main(int argc, char** argv) {
 
   // ---- SASL through the surface (renderer.h:75-86,136-147): compile() -> set_vertex_shader_code / set_pixel_shader_code,
   // globals by name (by value and by pointer), the sampler by name, the input layout from the shader's semantics.  The CUDA
-  // product runs the SASL pair BASELINE configs[3] names (the front end + NVRTC in process); a CPU checker cannot compile SASL
-  // and runs the pair's cpp twins (vs_sponza / ps_sponza_grad) - the two must print the same line.
+  // product runs the SASL pair BASELINE configs[3] names (the front end + NVRTC in process) and so does the restatement (its
+  // slv_shader_compile builds the generated code for the host); the unmodified reference cannot compile SASL here and runs the
+  // pair's cpp twins (vs_sponza / ps_sponza_grad) - all three must print the same line.
   {
     static const char* kVs =
         "float4x4 wvpMatrix; float4 lightPos; float4 eyePos;\n"
@@ -291,7 +292,7 @@ int main(int argc, char** argv) {
         "  float illum = clamp(dot(normalize(in.lightDir.xyz), normalize(in.norm.xyz)), 0.0f, 1.0f);\n"
         "  return float4(diff.xyz * illum, 1.0f);\n"
         "}\n";
-    const bool use_sasl = r->backend_name() == "cuda-sm100a" && !std::getenv("SLV_HOST_TEST_NO_SASL");
+    const bool use_sasl = (r->backend_name() == "cuda-sm100a" || r->backend_name() == "oracle") && !std::getenv("SLV_HOST_TEST_NO_SASL");
     // a bumpy grid: positions, uv (tiled 3x), normals
     const uint32_t G = 10, TS = 32;
     std::vector<float> gp, guv, gn;
