@@ -31,6 +31,8 @@
 #include <dlfcn.h>
 #include <unistd.h>
 
+#include "sasl_frontend.hpp"  // salviarenderer_b200/host: the product's SASL front end, for slv_sasl_translate
+
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -1931,7 +1933,28 @@ slv_result slv_shader_compile(slv_device dev, uint32_t stage, const char* device
   return SLV_OK;
 }
 void slv_free(void* p) { free(p); }
-slv_result slv_sasl_translate(uint32_t, const char*, const char*, char**, size_t*, char*, size_t) { return SLV_FAILED; }
+// the first half of compile(code, profile): the product's own SASL front end (header-only, host code) - the restatement runs
+// what it generates (slv_shader_compile above), it does not restate the translation
+slv_result slv_sasl_translate(uint32_t stage, const char* source, const char* entry, char** unit, size_t* unit_bytes, char* log, size_t log_bytes) {
+  if (log && log_bytes) log[0] = 0;
+  if (!source || !unit || (stage != SLV_STAGE_VS && stage != SLV_STAGE_PS)) return SLV_INVALID_PARAMETER;
+  *unit = nullptr;
+  if (unit_bytes) *unit_bytes = 0;
+  salvia_b200::sasl::unit u;
+  std::string error;
+  if (!salvia_b200::sasl::compile(source, stage == SLV_STAGE_VS ? "vs" : "ps", entry ? entry : "", salvia_b200::sasl::options(), u, error)) {
+    if (log && log_bytes) snprintf(log, log_bytes, "%s", error.c_str());
+    return SLV_FAILED;
+  }
+  const std::string text = salvia_b200::sasl::render(u);
+  char* o = static_cast<char*>(malloc(text.size() + 1));
+  if (!o) return SLV_OUT_OF_MEMORY;
+  memcpy(o, text.data(), text.size());
+  o[text.size()] = 0;
+  *unit = o;
+  if (unit_bytes) *unit_bytes = text.size();
+  return SLV_OK;
+}
 slv_result slv_peer_open(slv_device, const uint8_t*, void**) { return SLV_FAILED; }
 slv_result slv_peer_close(slv_device, void*) { return SLV_FAILED; }
 slv_result slv_resolve_target_peer(slv_device, slv_handle, void*) { return SLV_FAILED; }

@@ -251,3 +251,29 @@ def test_rejections_carry_the_same_message(cli, tmp_path):
         b, eb = run_cpp(cli, src, "ps", tmp=tmp_path)
         assert a is None and b is None, src
         assert ea == eb, (src, ea, eb)
+
+
+def test_front_end_copies_coexist_in_one_process(built):
+    """The product library and the CPU checker each carry a copy of the header-only front end (slv_sasl_translate) and are
+    loaded into one process by every test.  Called alternately they must give the same unit - in a child process: a regression
+    here is a crash (the checker once shared function-local statics and half a C++ runtime with the other module)."""
+    import sys
+    import textwrap
+    from conftest import ORACLE_LIB, PRODUCT_LIB
+    code = textwrap.dedent(f"""
+        import ctypes as C
+        libs = [C.CDLL({PRODUCT_LIB!r}), C.CDLL({ORACLE_LIB!r})]
+        out = []
+        for lib in libs * 3:
+            lib.slv_sasl_translate.argtypes = [C.c_uint32, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t]
+            u, n, log = C.c_void_p(), C.c_size_t(), C.create_string_buffer(4096)
+            rc = lib.slv_sasl_translate(1, b"float4 main(float4 p: TEXCOORD0): COLOR {{ return p * 2 + sin(p); }}", None, C.byref(u), C.byref(n), log, 4096)
+            assert rc == 0, log.value
+            out.append(C.string_at(u.value, n.value))
+            bad = lib.slv_sasl_translate(1, b"float4 broken(", None, C.byref(u), C.byref(n), log, 4096)
+            assert bad == 1 and b"line 1" in log.value
+        assert len(set(out)) == 1 and out[0].startswith(b"SLVSASL 1")
+        print("ok")
+    """)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stderr[-2000:])
