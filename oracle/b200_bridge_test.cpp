@@ -148,6 +148,58 @@ struct ps_sponza : cpp_pixel_shader, device_shader_info {
   void device_samplers(sampler_ptr (&out)[SLV_MAX_SAMPLERS]) const override { out[0] = sampler_; }
   BRIDGE_CLONE()
 };
+// ps_sponza with the diffuse texture fetched the way a SASL pixel shader's tex2D fetches it: sampler::sample_2d_grad with the
+// quad's per-line / per-column differences (sasl/src/codegen/cg_impl.cpp:902-909, cgs_simd.cpp:275-313) - the cpp twin of the
+// SASL pixel shader below.  cpp_pixel_shader keeps the quad private, but execute() (cpp_pixel_shader.cpp:63-75) calls
+// shader_prog for pixels 0..3 of the quad in order with in == quad[i], and every worker owns its clone: the call count modulo
+// 4 is the pixel's index.
+struct ps_sponza_grad : cpp_pixel_shader, device_shader_info {
+  sampler_ptr sampler_;
+  unsigned calls = 0;
+  ps_sponza_grad() { declare_sampler("Sampler", sampler_); }
+  bool shader_prog(const vs_output& in, ps_output& out) override {
+    unsigned const i = calls++ & 3u;
+    vs_output const* quad = &in - i;
+    vec4 diff = vec4(1.0f, 1.0f, 1.0f, 1.0f);
+    if (sampler_) {
+      vec4 dx = quad[i | 1u].attribute(0) - quad[i & ~1u].attribute(0);
+      vec4 dy = quad[i | 2u].attribute(0) - quad[i & ~2u].attribute(0);
+      diff = sampler_->sample_2d_grad(in.attribute(0).xy(), dx.xy(), dy.xy(), 0.0f).get_vec4();
+    }
+    vec3 norm(eflib::normalize3(in.attribute(1).xyz()));
+    vec3 light_dir(eflib::normalize3(in.attribute(2).xyz()));
+    float illum = eflib::clamp(eflib::dot_prod3(light_dir, norm), 0.0f, 1.0f);
+    out.color[0] = diff * illum;
+    out.color[0][3] = 1.0f;
+    return true;
+  }
+  uint32_t device_program() const override { return SLV_PS_SPONZA_GRAD; }
+  size_t pack_uniforms(uint8_t* dst, size_t) const override {
+    slv_ps_sponza_grad_uniforms u{sampler_ ? 1u : 0u, 1u};
+    std::memcpy(dst, &u, sizeof(u));
+    return sizeof(u);
+  }
+  void device_samplers(sampler_ptr (&out)[SLV_MAX_SAMPLERS]) const override { out[0] = sampler_; }
+  BRIDGE_CLONE()
+};
+// the SASL pair BASELINE configs[3] names (samples/Sponza/Sponza.cpp:39-62 and its pixel shader in SASL)
+const char* kSaslVs =
+    "float4x4 wvpMatrix; float4 lightPos; float4 eyePos;\n"
+    "struct VSIn  { float4 pos: POSITION; float4 tex: TEXCOORD0; float4 norm: NORMAL; };\n"
+    "struct VSOut { float4 pos: sv_position; float4 tex: TEXCOORD0; float4 norm: TEXCOORD1; float4 lightDir: TEXCOORD2; float4 eyeDir: TEXCOORD3; };\n"
+    "VSOut vs_main(VSIn in) {\n"
+    "  VSOut o;\n"
+    "  o.norm = in.norm; o.pos = mul(in.pos, wvpMatrix); o.lightDir = lightPos - in.pos; o.eyeDir = eyePos - in.pos; o.tex = in.tex;\n"
+    "  return o;\n"
+    "}\n";
+const char* kSaslPs =
+    "sampler texSamp;\n"
+    "struct PSIn { float4 tex: TEXCOORD0; float4 norm: TEXCOORD1; float4 lightDir: TEXCOORD2; float4 eyeDir: TEXCOORD3; };\n"
+    "float4 ps_main(PSIn in): COLOR {\n"
+    "  float4 diff = tex2D(texSamp, in.tex.xy);\n"
+    "  float illum = clamp(dot(normalize(in.lightDir.xyz), normalize(in.norm.xyz)), 0.0f, 1.0f);\n"
+    "  return float4(diff.xyz * illum, 1.0f);\n"
+    "}\n";
 struct bs_replace : cpp_blend_shader, device_shader_info {  // ColorizedTriangle.cpp:94-106
   bool shader_prog(size_t sample, pixel_accessor& inout, const ps_output& in) override {
     inout.color(0, sample, color_rgba32f(in.color[0]));
@@ -184,8 +236,9 @@ result fill_buffer(renderer& r, buffer_ptr const& b, std::vector<T> const& v) {
 
 // One scene, written against salvia::core::renderer only.  `resolve` is the one call that is not a renderer method upstream
 // (surface::resolve, surface.cpp:123-140): the caller passes how its renderer resolves.
+// `sasl`: the renderer that compiles SASL (a b200_renderer bound to a library that can), or null: pass 3 then runs the cpp twins
 template <class Resolve>
-frame_hashes run_scene(renderer& r, size_t W, size_t H, size_t S, Resolve resolve) {
+frame_hashes run_scene(renderer& r, size_t W, size_t H, size_t S, Resolve resolve, b200_renderer* sasl = nullptr) {
   frame_hashes out;
   texture_ptr color = r.create_tex2d(W, H, S, pixel_format_color_rgba8), ds = r.create_tex2d(W, H, S, pixel_format_color_rg32f);
   texture_ptr resolved = r.create_tex2d(W, H, 1, pixel_format_color_rgba8);
@@ -286,6 +339,32 @@ frame_hashes run_scene(renderer& r, size_t W, size_t H, size_t S, Resolve resolv
     dsd.depth_func = compare_function_less_equal;
     CHECK(r.set_depth_stencil_state(depth_stencil_state_ptr(new depth_stencil_state(dsd)), 0));
     CHECK(r.draw_index(G * 2 * 3 * 3, G * 2 * 5, 0));  // rows 3..7 of the grid
+
+    // pass 3: rows 8..11 with the SASL pair and a 16x anisotropic sampler - through compile() / set_vertex_shader_code /
+    // set_pixel_shader_code / set_vs_variable_value / set_ps_sampler of the REFERENCE's renderer interface (renderer.h:75-86,
+    // 136-147) where the renderer can compile SASL, else (the reference here: no LLVM) with the pair's cpp twins
+    sampler_desc sa = sd;
+    sa.mip_filter = filter_anisotropic;
+    sa.max_anisotropy = 16;
+    sampler_ptr samp16 = r.create_sampler(sa, tex);
+    if (sasl) {
+      std::string log;
+      shader_object_ptr vso = sasl->compile(kSaslVs, lang_vertex_shader, &log), pso = sasl->compile(kSaslPs, lang_pixel_shader, &log);
+      if (!vso || !pso) { std::fprintf(stderr, "SASL: %s\n", log.c_str()); return out; }
+      if (sasl->compile("float4 broken(", lang_pixel_shader, &log) || log.find("line 1") == std::string::npos) return out;
+      CHECK(r.set_vertex_shader_code(vso));
+      CHECK(r.set_pixel_shader_code(pso));
+      CHECK(r.set_input_layout(r.create_input_layout(descs, 3, vso)));
+      CHECK(r.set_vs_variable_value("wvpMatrix", &wvp, sizeof(wvp)));
+      CHECK(r.set_vs_variable_value("lightPos", &light, sizeof(light)));
+      CHECK(r.set_vs_variable_value("eyePos", &eye, sizeof(eye)));
+      CHECK(r.set_ps_sampler("texSamp", samp16));
+    } else {
+      auto ps3 = std::make_shared<ps_sponza_grad>();
+      CHECK(r.set_pixel_shader(ps3));
+      CHECK(ps3->set_sampler("Sampler", samp16));
+    }
+    CHECK(r.draw_index(G * 2 * 3 * 8, G * 2 * 4, 0));
   }
   CHECK(r.end(query));
   CHECK(r.flush());
@@ -333,7 +412,11 @@ int main(int argc, char** argv) {
     return 2;
   }
   std::printf("backend %s\n", b200->backend_name().c_str());
-  frame_hashes b = run_scene(*b200, W, H, S, [&](surface_ptr const& src, surface_ptr const& dst) { return b200->resolve(src, dst); });
+  // SASL through the binding where the bound library compiles it on this machine: the CPU checker always (it builds the
+  // generated code for the host), the CUDA product when asked (SLV_BRIDGE_SASL=1: NVRTC at run time); else the cpp twins
+  const bool use_sasl = b200->backend_name() == "oracle" || std::getenv("SLV_BRIDGE_SASL");
+  std::printf("pass 3: %s\n", use_sasl ? "SASL pair through compile() / set_*_shader_code" : "cpp twins");
+  frame_hashes b = run_scene(*b200, W, H, S, [&](surface_ptr const& src, surface_ptr const& dst) { return b200->resolve(src, dst); }, use_sasl ? b200.get() : nullptr);
   print("reference sync_renderer", a);
   print("b200_renderer -> C ABI ", b);
   if (!a.ok || !b.ok || a.drawn < W * H * S / 20) return 3;  // the scene must actually cover part of the target

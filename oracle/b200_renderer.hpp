@@ -24,14 +24,20 @@
 #include <salvia/resource/sampler.h>
 #include <salvia/resource/surface.h>
 #include <salvia/resource/texture.h>
+#include <salvia/shader/reflection.h>
+#include <salvia/shader/shader_object.h>
 
 #include <dlfcn.h>
 
+#include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <map>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
+#include <vector>
 
 #include "salvia_b200.h"
 
@@ -44,6 +50,40 @@ struct device_shader_info {
   virtual uint32_t device_program() const = 0;
   virtual size_t pack_uniforms(uint8_t* dst, size_t cap) const = 0;
   virtual void device_samplers(resource::sampler_ptr (&out)[SLV_MAX_SAMPLERS]) const { (void)out; }
+};
+
+// compile(code, profile) for this renderer (renderer.h:136-147): what b200_renderer::compile returns.
+// A shader_object of the reference's own interface (shader_object.h:20-32) - it is handed to set_vertex_shader_code /
+// set_pixel_shader_code / create_input_layout unchanged - that carries the unit slv_sasl_translate produced: the reflection the
+// binding marshals with (uniform block layout, sampler slots, input semantics -> registers) and the device code that
+// slv_shader_compile turns into a module on first use.  Its shader_reflection answers what renderer_impl itself asks
+// (pixel_shader_unit::initialize sizes its CPU-side buffers from total_size: none are needed here).
+class b200_shader_object : public shader::shader_object, private shader::shader_reflection {
+public:
+  struct uniform { std::string type; size_t offset = 0, size = 0; };
+  struct semantic_slot { std::string semantic; uint32_t index = 0, slot = 0; };
+  shader::languages language = shader::lang_none;
+  std::string device_code;
+  uint32_t n_vs_output_attrs = 0;
+  size_t uniform_bytes = 0;
+  std::map<std::string, uniform> uniforms;
+  std::vector<std::string> samplers;   // slot order
+  std::vector<semantic_slot> inputs;   // VS: semantic -> input register; PS: semantic -> attribute
+  mutable slv_handle module = 0;       // compiled for the device on first use (slv_shader_compile)
+
+  shader::shader_reflection const* get_reflection() const override { return this; }
+  void* native_function() const override { return nullptr; }
+
+private:
+  shader::languages get_language() const override { return language; }
+  std::string_view entry_name() const override { return ""; }
+  std::vector<shader::sv_layout*> layouts(shader::sv_usage) const override { return {}; }
+  size_t layouts_count(shader::sv_usage) const override { return 0; }
+  size_t total_size(shader::sv_usage) const override { return 0; }
+  shader::sv_layout* input_sv_layout(shader::semantic_value const&) const override { return nullptr; }
+  shader::sv_layout* input_sv_layout(std::string_view) const override { return nullptr; }
+  shader::sv_layout* output_sv_layout(shader::semantic_value const&) const override { return nullptr; }
+  bool has_position_output() const override { return true; }
 };
 
 class b200_renderer : public renderer_impl {
@@ -66,6 +106,42 @@ public:
     if (lib_) dlclose(lib_);
   }
   std::string backend_name() const { return slv_backend_name_(); }
+
+  // salvia::core::compile(code, profile) for this renderer: the library's SASL front end (slv_sasl_translate), the unit parsed
+  // into a shader_object.  Null + `log` when the source does not compile.
+  shader::shader_object_ptr compile(std::string const& code, shader::languages lang, std::string* log = nullptr) {
+    auto translate = reinterpret_cast<decltype(&::slv_sasl_translate)>(dlsym(lib_, "slv_sasl_translate"));
+    auto release = reinterpret_cast<decltype(&::slv_free)>(dlsym(lib_, "slv_free"));
+    if (!translate || !release || (lang != shader::lang_vertex_shader && lang != shader::lang_pixel_shader)) return nullptr;
+    char* unit = nullptr;
+    size_t bytes = 0;
+    char msg[4096] = "";
+    if (translate(lang == shader::lang_vertex_shader ? SLV_STAGE_VS : SLV_STAGE_PS, code.c_str(), nullptr, &unit, &bytes, msg, sizeof(msg)) != SLV_OK) {
+      if (log) *log = msg;
+      return nullptr;
+    }
+    const std::string text(unit, bytes);
+    release(unit);
+    auto obj = std::make_shared<b200_shader_object>();
+    obj->language = lang;
+    size_t pos = text.find('\n') + 1;  // after "SLVSASL 1"
+    while (pos < text.size()) {
+      size_t eol = text.find('\n', pos);
+      if (eol == std::string::npos) eol = text.size();
+      std::istringstream ln(text.substr(pos, eol - pos));
+      pos = eol + 1;
+      std::string key;
+      ln >> key;
+      if (key == "n_vs_output_attrs") ln >> obj->n_vs_output_attrs;
+      else if (key == "uniform_bytes") ln >> obj->uniform_bytes;
+      else if (key == "uniform") { std::string name; b200_shader_object::uniform u; ln >> name >> u.type >> u.offset >> u.size; obj->uniforms[name] = u; }
+      else if (key == "sampler") { size_t slot; std::string name; ln >> slot >> name; if (obj->samplers.size() <= slot) obj->samplers.resize(slot + 1); obj->samplers[slot] = name; }
+      else if (key == "input") { b200_shader_object::semantic_slot x; ln >> x.semantic >> x.index >> x.slot; obj->inputs.push_back(x); }
+      else if (key == "code") { size_t n = 0; ln >> n; obj->device_code = text.substr(pos, n); break; }
+    }
+    if (obj->device_code.empty()) return nullptr;
+    return obj;
+  }
 
   result flush() override { return static_cast<result>(slv_flush_(dev_)); }
 
@@ -145,10 +221,13 @@ protected:
     case command_id::draw:
     case command_id::draw_index: break;
     }
-    auto* vsi = dynamic_cast<device_shader_info*>(s.cpp_vs.get());
-    auto* psi = dynamic_cast<device_shader_info*>(s.cpp_ps.get());
+    // a SASL shader object wins over the cpp shader of its stage, as in the reference (rasterizer.cpp:236, framebuffer.cpp:348)
+    auto* vso = dynamic_cast<b200_shader_object const*>(s.vx_shader.get());
+    auto* pso = dynamic_cast<b200_shader_object const*>(s.px_shader.get());
+    auto* vsi = vso ? nullptr : dynamic_cast<device_shader_info*>(s.cpp_vs.get());
+    auto* psi = pso ? nullptr : dynamic_cast<device_shader_info*>(s.cpp_ps.get());
     auto* bsi = dynamic_cast<device_shader_info*>(s.cpp_bs.get());
-    if (!vsi || !psi || !bsi || !s.layout) return result::failed;  // a cpp shader without a device twin cannot run on the GPU
+    if (!(vso || vsi) || !(pso || psi) || !bsi || !s.layout) return result::failed;  // a cpp shader without a device twin cannot run on the GPU
     slv_draw_desc d{};
     // input assembler: stream_state + input_layout resolved against the VS register map (stream_assembler.cpp:52-86)
     for (size_t slot = 0; slot < s.str_state.buffer_descs.size() && slot < 8; ++slot) {
@@ -157,12 +236,15 @@ protected:
       d.n_streams = static_cast<uint32_t>(slot + 1);
       d.streams[slot] = slv_vertex_stream{buffer_handle(b.buf), static_cast<uint32_t>(b.stride), static_cast<uint32_t>(b.offset)};
     }
-    for (auto const& sv_reg : s.cpp_vs->get_register_map()) {
+    std::vector<std::pair<shader::semantic_value, uint32_t>> registers;  // semantic -> input register of the bound vertex shader
+    if (vso) for (auto const& in : vso->inputs) registers.emplace_back(shader::semantic_value(in.semantic, in.index), in.slot);
+    else for (auto const& sv_reg : s.cpp_vs->get_register_map()) registers.emplace_back(sv_reg.first, static_cast<uint32_t>(sv_reg.second));
+    for (auto const& sv_reg : registers) {
       resource::input_element_desc const* e = s.layout->find_desc(sv_reg.first);
       if (!e) { d.n_elements = 0; break; }  // stream_assembler.cpp:61-64: one missing element drops them all
       if (d.n_elements >= SLV_MAX_VS_INPUT_ATTRS) return result::failed;
       slv_input_element& el = d.elements[d.n_elements++];
-      el.reg = static_cast<uint32_t>(sv_reg.second);
+      el.reg = sv_reg.second;
       el.slot = e->input_slot;
       el.aligned_byte_offset = e->aligned_byte_offset;
       el.format = static_cast<uint32_t>(e->data_format);
@@ -174,9 +256,11 @@ protected:
     d.topology = static_cast<uint32_t>(s.prim_topo);
     d.start = s.start_index; d.prim_count = s.prim_count; d.base_vertex = s.base_vertex;
     // shaders: program id + POD uniform block + sampler handles
-    if (!bind(d.vs, *vsi) || !bind(d.ps, *psi) || !bind(d.bs, *bsi)) return result::failed;
-    for (uint32_t i = 0; i < s.cpp_vs->num_output_attributes() && i < SLV_MAX_VS_OUTPUT_ATTRS; ++i)
-      d.vs_attr_modifiers[i] = s.cpp_vs->output_attribute_modifiers(i);
+    if (!(vso ? bind_sasl(d.vs, *vso, s.vx_cbuffer) : bind(d.vs, *vsi)) || !(pso ? bind_sasl(d.ps, *pso, s.px_cbuffer) : bind(d.ps, *psi)) || !bind(d.bs, *bsi))
+      return result::failed;
+    if (!vso)  // SASL outputs interpolate linearly with perspective (interp_shim.cpp:66-70: im_linear)
+      for (uint32_t i = 0; i < s.cpp_vs->num_output_attributes() && i < SLV_MAX_VS_OUTPUT_ATTRS; ++i)
+        d.vs_attr_modifiers[i] = s.cpp_vs->output_attribute_modifiers(i);
     // fixed-function state
     d.raster.cull_mode = static_cast<uint32_t>(s.ras_state->get_desc().cm);
     d.raster.front_ccw = s.ras_state->get_desc().front_ccw ? 1u : 0u;
@@ -292,6 +376,34 @@ private:
     info.device_samplers(sm);
     for (int i = 0; i < SLV_MAX_SAMPLERS; ++i)
       if (sm[i] && !(b.samplers[i] = sampler_handle(sm[i]))) return false;
+    return true;
+  }
+  // A SASL stage: the module (compiled on first use), the uniform block filled by NAME from the stage's shader_cbuffer
+  // (renderer::set_vs_variable_value / set_ps_variable, renderer_impl.cpp:286-325) at the offsets of the unit's reflection, the
+  // samplers by name in the reflection's slot order (set_vs_sampler / set_ps_sampler).
+  bool bind_sasl(slv_shader_binding& b, b200_shader_object const& so, shader::shader_cbuffer const& cb) {
+    std::memset(&b, 0, sizeof(b));
+    if (!so.module) {
+      auto compile_fn = reinterpret_cast<decltype(&::slv_shader_compile)>(dlsym(lib_, "slv_shader_compile"));
+      char log[8192] = "";
+      if (!compile_fn || compile_fn(dev_, so.language == shader::lang_vertex_shader ? SLV_STAGE_VS : SLV_STAGE_PS, so.device_code.c_str(), so.n_vs_output_attrs, 0,
+                                    &so.module, log, sizeof(log)) != SLV_OK) {
+        std::fprintf(stderr, "slv_shader_compile: %s\n", log);
+        return false;
+      }
+    }
+    b.program = SLV_PROGRAM_JIT(so.module);
+    if (so.uniform_bytes > sizeof(b.uniforms)) return false;
+    b.uniform_bytes = static_cast<uint32_t>(so.uniform_bytes);
+    for (auto const& var : cb.variables()) {
+      auto u = so.uniforms.find(var.first);
+      if (u == so.uniforms.end() || u->second.type.find("[]") != std::string::npos) continue;  // not a global of this shader (arrays: not marshalled here)
+      void const* src = cb.data_pointer(var.second);
+      if (src) std::memcpy(b.uniforms + u->second.offset, src, std::min(var.second.length, u->second.size));
+    }
+    for (auto const& sm : cb.samplers())
+      for (size_t slot = 0; slot < so.samplers.size() && slot < SLV_MAX_SAMPLERS; ++slot)
+        if (so.samplers[slot] == sm.first && !(b.samplers[slot] = sampler_handle(sm.second))) return false;
     return true;
   }
   result collect_query(async_object_ptr const& q) {

@@ -2,7 +2,11 @@
 own renderer_impl (salvia/include/salvia/core/renderer_impl.h:23-112) whose commit_state_and_command() marshals render_state
 into the C ABI; oracle/b200_bridge_test.cpp drives one scene (indexed lit mesh + a textured, trilinear-filtered second pass with
 a start index, 4x MSAA + resolve, a pipeline-statistics query) through salvia::core::renderer twice - into the reference's
-sync_renderer and into b200_renderer bound to a C-ABI library - and compares every buffer and counter.
+sync_renderer and into b200_renderer bound to a C-ABI library - and compares every buffer and counter.  A third pass draws with
+a 16x anisotropic sampler and, where the bound library compiles SASL on the spot (the restatement), with the SASL Sponza pair
+through the reference interface's own SASL calls - the binding's compile() (slv_sasl_translate), set_vertex_shader_code /
+set_pixel_shader_code, set_vs_variable_value, set_ps_sampler, create_input_layout(descs, n, shader_object) - against the pair's
+cpp twins on the reference's sync_renderer; elsewhere the binding runs the twins too.
 
 CPU suite: the library is a CPU checker (the restatement, and the reference behind the ABI).  GPU suite: the CUDA product.  The
 binary needs /root/reference to BUILD (oracle/Makefile target `bridge`); it then travels to the GPU box in oracle/_ref/."""
@@ -29,7 +33,8 @@ def run(lib, *size):
 # multiples of 4: the reference writes past the end of targets that are not
 @pytest.mark.parametrize("size", [(320, 240, 4), (200, 120, 1), (260, 132, 4)])
 def test_bridge_into_the_restatement(built, size):
-    assert run(ORACLE_LIB, *size)[0] == "backend oracle"
+    lines = run(ORACLE_LIB, *size)
+    assert lines[0] == "backend oracle" and lines[1].startswith("pass 3: SASL pair")
 
 
 def test_bridge_into_the_reference_behind_the_abi(built):
