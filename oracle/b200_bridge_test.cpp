@@ -238,7 +238,7 @@ result fill_buffer(renderer& r, buffer_ptr const& b, std::vector<T> const& v) {
 // (surface::resolve, surface.cpp:123-140): the caller passes how its renderer resolves.
 // `sasl`: the renderer that compiles SASL (a b200_renderer bound to a library that can), or null: pass 3 then runs the cpp twins
 template <class Resolve>
-frame_hashes run_scene(renderer& r, size_t W, size_t H, size_t S, Resolve resolve, b200_renderer* sasl = nullptr) {
+frame_hashes run_scene(renderer& r, size_t W, size_t H, size_t S, Resolve resolve, bool pass3, b200_renderer* sasl = nullptr) {
   frame_hashes out;
   texture_ptr color = r.create_tex2d(W, H, S, pixel_format_color_rgba8), ds = r.create_tex2d(W, H, S, pixel_format_color_rg32f);
   texture_ptr resolved = r.create_tex2d(W, H, 1, pixel_format_color_rgba8);
@@ -343,6 +343,7 @@ frame_hashes run_scene(renderer& r, size_t W, size_t H, size_t S, Resolve resolv
     // pass 3: rows 8..11 with the SASL pair and a 16x anisotropic sampler - through compile() / set_vertex_shader_code /
     // set_pixel_shader_code / set_vs_variable_value / set_ps_sampler of the REFERENCE's renderer interface (renderer.h:75-86,
     // 136-147) where the renderer can compile SASL, else (the reference here: no LLVM) with the pair's cpp twins
+    if (pass3) {
     sampler_desc sa = sd;
     sa.mip_filter = filter_anisotropic;
     sa.max_anisotropy = 16;
@@ -365,6 +366,7 @@ frame_hashes run_scene(renderer& r, size_t W, size_t H, size_t S, Resolve resolv
       CHECK(ps3->set_sampler("Sampler", samp16));
     }
     CHECK(r.draw_index(G * 2 * 3 * 8, G * 2 * 4, 0));
+    }
   }
   CHECK(r.end(query));
   CHECK(r.flush());
@@ -402,7 +404,6 @@ int main(int argc, char** argv) {
   const size_t W = argc > 3 ? std::atoi(argv[2]) : 320, H = argc > 3 ? std::atoi(argv[3]) : 240, S = argc > 4 ? std::atoi(argv[4]) : 4;
   // the reference's own renderer
   renderer_ptr sync = create_benchmark_renderer();  // sync_renderer (renderer.cpp:37-39)
-  frame_hashes a = run_scene(*sync, W, H, S, [](surface_ptr const& src, surface_ptr const& dst) { src->resolve(*dst); return result::ok; });
   // the same calls through the renderer_impl subclass into the C ABI
   std::shared_ptr<b200_renderer> b200;
   try {
@@ -414,9 +415,12 @@ int main(int argc, char** argv) {
   std::printf("backend %s\n", b200->backend_name().c_str());
   // SASL through the binding where the bound library compiles it on this machine: the CPU checker always (it builds the
   // generated code for the host), the CUDA product when asked (SLV_BRIDGE_SASL=1: NVRTC at run time); else the cpp twins
+  // Pass 3 runs on the CPU checkers (and on the CUDA product when SLV_BRIDGE_PASS3 / SLV_BRIDGE_SASL ask for it).
   const bool use_sasl = b200->backend_name() == "oracle" || std::getenv("SLV_BRIDGE_SASL");
-  std::printf("pass 3: %s\n", use_sasl ? "SASL pair through compile() / set_*_shader_code" : "cpp twins");
-  frame_hashes b = run_scene(*b200, W, H, S, [&](surface_ptr const& src, surface_ptr const& dst) { return b200->resolve(src, dst); }, use_sasl ? b200.get() : nullptr);
+  const bool pass3 = use_sasl || b200->backend_name() != "cuda-sm100a" || std::getenv("SLV_BRIDGE_PASS3");
+  std::printf("pass 3: %s\n", !pass3 ? "skipped" : use_sasl ? "SASL pair through compile() / set_*_shader_code" : "cpp twins");
+  frame_hashes a = run_scene(*sync, W, H, S, [](surface_ptr const& src, surface_ptr const& dst) { src->resolve(*dst); return result::ok; }, pass3);
+  frame_hashes b = run_scene(*b200, W, H, S, [&](surface_ptr const& src, surface_ptr const& dst) { return b200->resolve(src, dst); }, pass3, use_sasl ? b200.get() : nullptr);
   print("reference sync_renderer", a);
   print("b200_renderer -> C ABI ", b);
   if (!a.ok || !b.ok || a.drawn < W * H * S / 20) return 3;  // the scene must actually cover part of the target

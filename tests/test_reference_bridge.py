@@ -6,7 +6,8 @@ sync_renderer and into b200_renderer bound to a C-ABI library - and compares eve
 a 16x anisotropic sampler and, where the bound library compiles SASL on the spot (the restatement), with the SASL Sponza pair
 through the reference interface's own SASL calls - the binding's compile() (slv_sasl_translate), set_vertex_shader_code /
 set_pixel_shader_code, set_vs_variable_value, set_ps_sampler, create_input_layout(descs, n, shader_object) - against the pair's
-cpp twins on the reference's sync_renderer; elsewhere the binding runs the twins too.
+cpp twins on the reference's sync_renderer; the reference behind the ABI runs the twins on both sides, the CUDA product skips
+the pass unless SLV_BRIDGE_PASS3 / SLV_BRIDGE_SASL ask for it (NVRTC at run time).
 
 CPU suite: the library is a CPU checker (the restatement, and the reference behind the ABI).  GPU suite: the CUDA product.  The
 binary needs /root/reference to BUILD (oracle/Makefile target `bridge`); it then travels to the GPU box in oracle/_ref/."""
