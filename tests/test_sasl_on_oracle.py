@@ -103,3 +103,34 @@ def test_compile_errors_and_release(oracle):
     mod = jit.load(oracle, sh)
     assert mod > 0
     oracle.release(mod) if hasattr(oracle, "release") else None
+
+
+# ---- the remaining tests of the GPU suite's SASL module, run on the restatement -------------------------------------------------
+@pytest.fixture
+def host_jit(monkeypatch):
+    """tests/test_gpu_sasl_jit.py's test bodies with jit.compile producing no sm_100a image (nothing here loads one)."""
+    import test_gpu_sasl_jit as G
+    real = jit.compile
+    monkeypatch.setattr(G.jit, "compile", lambda source, stage, entry=None, derivatives="sasl", **kw: real(source, stage, entry, derivatives, device=False))
+    return G
+
+
+def test_known_answers_through_the_pipeline(oracle, host_jit):
+    """The reference's known answers for the intrinsics (tests/golden/sasl_kat.json), each through a draw into an rgba32f target."""
+    host_jit.test_sasl_intrinsics_match_the_reference_known_answers(oracle)
+
+
+def test_derivative_conventions_through_the_pipeline(oracle, host_jit):
+    host_jit.test_sasl_derivative_convention(oracle)
+
+
+def test_skinning_vertex_shader_array_uniforms(oracle, host_jit):
+    """samples/AstroBoy's skinning vertex shader: array uniforms (addresses in the uniform block), int4 inputs, a data-dependent break."""
+    host_jit.test_sasl_skinning_vertex_shader_array_uniforms(oracle)
+
+
+@pytest.mark.parametrize("w,h,samples", [(320, 180, 1), (200, 120, 4)])
+def test_two_sampler_shadow_map_shader(oracle, host_jit, w, h, samples):
+    """The StandardShadowMap colour pass in SASL (two samplers, nine tex2Dlod taps, exp / log / pow) against SLV_PS_SSM_DRAW:
+    everything but the colour identical, the colour within a few LSB (SASL's log is eflib's fast_log polynomial)."""
+    host_jit.test_sasl_two_sampler_shadow_map_shader(oracle, oracle, w, h, samples)
