@@ -277,3 +277,16 @@ def test_front_end_copies_coexist_in_one_process(built):
     """)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stderr[-2000:])
+
+
+def test_front_end_in_an_executable_next_to_a_library_copy(built, tmp_path):
+    """tests/cpp/frontend_coexist_test.cpp: a C++ host that includes sasl_frontend.hpp (shader::compile in process) and loads a
+    library with its own copy - the CUDA product, the CPU checker - calls both alternately; same units, same diagnostics."""
+    from conftest import ORACLE_LIB, PRODUCT_LIB
+    exe = str(tmp_path / "frontend_coexist_test")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-I" + HOST,
+                        os.path.join(ROOT, "tests", "cpp", "frontend_coexist_test.cpp"), "-o", exe, "-ldl"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    for lib in (PRODUCT_LIB, ORACLE_LIB):
+        out = subprocess.run([exe, lib], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0 and out.stdout.strip() == "ok", (lib, out.returncode, out.stdout, out.stderr)
