@@ -9,6 +9,10 @@
 // compiled in place from /root/reference) by tests/test_oracle_vs_reference.py and against the frozen
 // fixtures under tests/golden/ (generated from the reference by tests/golden/make_golden.py).
 //
+// Beyond the restatement (test infrastructure on top of it, marked where it appears): slv_shader_compile builds the code the
+// product's SASL front end generates for the HOST and run_vs / draw_quad call it (oracle/slv_host_shader.h), so that SASL frames
+// can be compared with the samples' cpp twins without a GPU; slv_sasl_translate is the product's own front end (header-only).
+//
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this library; the
 // product (salviarenderer_b200/csrc) never links, imports or falls back to it.
 //
