@@ -1,12 +1,12 @@
 """Random textured scenes (tests/fuzz.py scene_from_seed), the CUDA product against the oracle: every buffer and counter.
 No torch, no pytest: starts in a second, stops at the time limit and reports how far it got.
-    python tools/random_scenes_gpu.py [first_seed] [last_seed] [seconds]  ->  gpurun_out/random_scenes_gpu.json"""
+    python tests/random_scenes_gpu.py [first_seed] [last_seed] [seconds]  ->  gpurun_out/random_scenes_gpu.json"""
 import json
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/ -> repository root
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import cases  # noqa: E402
 import fuzz  # noqa: E402
