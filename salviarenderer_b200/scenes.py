@@ -859,7 +859,7 @@ class TriangleSoup:
 
     def __init__(self, w=256, h=192, samples=1, n=300, seed=7, cull=A.CULL_NONE, ds=None, stencil_ref=0,
                  bs=A.BS_REPLACE_AND_COUNT, index_dtype=np.uint16, modifiers=None, strip=False, size=1.0,
-                 color_fmt=A.PF_RGBA8, ps=A.PS_ATTR0_COLOR, base_vertex=0, indexed=True, split=1):
+                 color_fmt=A.PF_RGBA8, ps=A.PS_ATTR0_COLOR, base_vertex=0, indexed=True, split=1, viewport=None):
         """`base_vertex`: the index buffer holds (index - base_vertex) and draw_index adds it back (index_fetcher.cpp:26-115;
         negative values wrap through uint32 exactly as upstream).  `indexed=False`: renderer::draw - the vertex buffers are
         expanded in index order and drawn without an index buffer.  `split`: the primitives are drawn in that many draws with
@@ -867,6 +867,7 @@ class TriangleSoup:
         only offsets the INDEX buffer (index_fetcher.cpp:23,85), so a non-indexed draw ignores it and always begins at vertex 0
         - a split non-indexed soup draws its first range `split` times."""
         self.base_vertex, self.indexed, self.split = base_vertex, indexed, split
+        self.viewport = viewport  # (x, y, w, h, minz, maxz) instead of the whole target with depth range 0..1 (viewport.h:5-12)
         self.w, self.h, self.samples, self.n = w, h, samples, n
         self.cull, self.ds, self.stencil_ref, self.bs, self.modifiers = cull, ds, stencil_ref, bs, modifiers
         self.color_fmt, self.ps = color_fmt, ps
@@ -921,6 +922,8 @@ class TriangleSoup:
         for first in range(0, max(self.mesh.prim_count, 1), max(per, 1)):
             d = base_desc(t, self.w, self.h, cull=self.cull, ds=self.ds)
             d.stencil_ref = self.stencil_ref
+            if self.viewport is not None:
+                d.viewport.x, d.viewport.y, d.viewport.w, d.viewport.h, d.viewport.minz, d.viewport.maxz = self.viewport
             # start = first index (draw_index) / first vertex (draw) of the range: 3 per list primitive, 1 per strip primitive
             # (an odd strip start would flip the winding parity, so strips are only split at even primitives)
             self.mesh.fill_desc(be, d, start=first if strip else first * 3, prim_count=min(per, self.mesh.prim_count - first),

@@ -84,3 +84,28 @@ def scene_from_seed(seed: int):
 def scene_tolerance(scene):
     """The shadow-map pixel shaders call expf / logf / pow: colour within 1 LSB there, bit-exact elsewhere."""
     return 1 if type(scene).__name__ == "StandardShadowMap" or getattr(scene, "shadowed", False) else 0
+
+
+def viewport_soup_from_seed(seed: int):
+    """soup_from_seed with a random viewport instead of the whole target (viewport.h:5-12): an integer or fractional
+    sub-rectangle, a rectangle that reaches past the target, and depth ranges other than 0..1.  Upstream sizes its tile grid from
+    the viewport's WIDTH and HEIGHT but anchors it at the target's origin (rasterizer.cpp:1106), so with x / y > 0 the right /
+    bottom part of the viewport falls outside the grid and is not drawn - mirrored, and what these scenes pin."""
+    g = np.random.default_rng(7000 + seed)
+    kw, _ = soup_from_seed(seed)
+    w, h = kw["w"], kw["h"]
+    kind = int(g.integers(0, 4))
+    if kind == 0:
+        x, y = int(g.integers(0, w // 2)), int(g.integers(0, h // 2))
+        vw, vh = int(g.integers(8, w - x + 1)), int(g.integers(8, h - y + 1))
+    elif kind == 1:
+        x, y = float(g.uniform(0, w / 2)), float(g.uniform(0, h / 2))
+        vw, vh = float(g.uniform(8, w - x)), float(g.uniform(8, h - y))
+    elif kind == 2:
+        x, y = float(g.uniform(0, w / 3)), float(g.uniform(0, h / 3))
+        vw, vh = float(g.uniform(w / 2, 1.5 * w)), float(g.uniform(h / 2, 1.5 * h))
+    else:
+        x, y, vw, vh = 0, 0, w, h
+    minz, maxz = [(0.0, 1.0), (0.2, 0.9), (0.5, 0.5), (0.0, 0.5)][int(g.integers(0, 4))]
+    kw["viewport"] = (x, y, vw, vh, minz, maxz)
+    return kw, S.TriangleSoup(**kw)
