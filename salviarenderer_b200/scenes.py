@@ -859,7 +859,8 @@ class TriangleSoup:
 
     def __init__(self, w=256, h=192, samples=1, n=300, seed=7, cull=A.CULL_NONE, ds=None, stencil_ref=0,
                  bs=A.BS_REPLACE_AND_COUNT, index_dtype=np.uint16, modifiers=None, strip=False, size=1.0,
-                 color_fmt=A.PF_RGBA8, ps=A.PS_ATTR0_COLOR, base_vertex=0, indexed=True, split=1, viewport=None):
+                 color_fmt=A.PF_RGBA8, ps=A.PS_ATTR0_COLOR, base_vertex=0, indexed=True, split=1, viewport=None, front_ccw=False,
+                 stream_pad=(0, 0)):
         """`base_vertex`: the index buffer holds (index - base_vertex) and draw_index adds it back (index_fetcher.cpp:26-115;
         negative values wrap through uint32 exactly as upstream).  `indexed=False`: renderer::draw - the vertex buffers are
         expanded in index order and drawn without an index buffer.  `split`: the primitives are drawn in that many draws with
@@ -868,6 +869,9 @@ class TriangleSoup:
         - a split non-indexed soup draws its first range `split` times."""
         self.base_vertex, self.indexed, self.split = base_vertex, indexed, split
         self.viewport = viewport  # (x, y, w, h, minz, maxz) instead of the whole target with depth range 0..1 (viewport.h:5-12)
+        # front_ccw: raster_desc::front_ccw (raster_state.cpp:10-31).  stream_pad: vertices of padding in front of each vertex
+        # stream, skipped through the stream's byte OFFSET (set_vertex_buffers' offsets, stream_assembler.cpp:88-93)
+        self.front_ccw, self.stream_pad = front_ccw, stream_pad
         self.w, self.h, self.samples, self.n = w, h, samples, n
         self.cull, self.ds, self.stencil_ref, self.bs, self.modifiers = cull, ds, stencil_ref, bs, modifiers
         self.color_fmt, self.ps = color_fmt, ps
@@ -904,6 +908,10 @@ class TriangleSoup:
                 self.mesh.streams = [np.concatenate([p_, st]) for p_, st in zip(pad, self.mesh.streams)]
             else:
                 self.mesh.indices = (self.mesh.indices.astype(np.int64) - base_vertex).astype(index_dtype)
+        if any(stream_pad):
+            rng_pad = np.random.default_rng(seed + 99)
+            self.mesh.streams = [np.concatenate([rng_pad.uniform(-5, 5, size=(k, st.shape[1])).astype(f32), st]) if k else st
+                                 for k, st in zip(stream_pad, self.mesh.streams)]
         self.n_frames = 1
 
     def setup(self, be: A.Backend):
@@ -924,10 +932,13 @@ class TriangleSoup:
             d.stencil_ref = self.stencil_ref
             if self.viewport is not None:
                 d.viewport.x, d.viewport.y, d.viewport.w, d.viewport.h, d.viewport.minz, d.viewport.maxz = self.viewport
+            d.raster.front_ccw = 1 if self.front_ccw else 0
             # start = first index (draw_index) / first vertex (draw) of the range: 3 per list primitive, 1 per strip primitive
             # (an odd strip start would flip the winding parity, so strips are only split at even primitives)
             self.mesh.fill_desc(be, d, start=first if strip else first * 3, prim_count=min(per, self.mesh.prim_count - first),
                                 base_vertex=self.base_vertex)
+            for i, k in enumerate(self.stream_pad):
+                d.streams[i].offset = k * d.streams[i].stride
             if self.modifiers:
                 for i, m in enumerate(self.modifiers):
                     d.vs_attr_modifiers[i] = m

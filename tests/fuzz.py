@@ -88,7 +88,8 @@ def scene_tolerance(scene):
 
 def viewport_soup_from_seed(seed: int):
     """soup_from_seed with a random viewport instead of the whole target (viewport.h:5-12): an integer or fractional
-    sub-rectangle, a rectangle that reaches past the target, and depth ranges other than 0..1.  Upstream sizes its tile grid from
+    sub-rectangle, a rectangle that reaches past the target, and depth ranges other than 0..1 - plus front_ccw and non-zero
+    byte offsets of the vertex streams.  Upstream sizes its tile grid from
     the viewport's WIDTH and HEIGHT but anchors it at the target's origin (rasterizer.cpp:1106), so with x / y > 0 the right /
     bottom part of the viewport falls outside the grid and is not drawn - mirrored, and what these scenes pin."""
     g = np.random.default_rng(7000 + seed)
@@ -108,4 +109,8 @@ def viewport_soup_from_seed(seed: int):
         x, y, vw, vh = 0, 0, w, h
     minz, maxz = [(0.0, 1.0), (0.2, 0.9), (0.5, 0.5), (0.0, 0.5)][int(g.integers(0, 4))]
     kw["viewport"] = (x, y, vw, vh, minz, maxz)
+    # two more pieces of state no hand-picked scene varies: the winding that counts as front, byte offsets of the vertex streams
+    kw["front_ccw"] = bool(g.random() < 0.5)
+    if g.random() < 0.5:
+        kw["stream_pad"] = (int(g.integers(0, 9)), int(g.integers(0, 9)))
     return kw, S.TriangleSoup(**kw)
