@@ -860,7 +860,7 @@ class TriangleSoup:
     def __init__(self, w=256, h=192, samples=1, n=300, seed=7, cull=A.CULL_NONE, ds=None, stencil_ref=0,
                  bs=A.BS_REPLACE_AND_COUNT, index_dtype=np.uint16, modifiers=None, strip=False, size=1.0,
                  color_fmt=A.PF_RGBA8, ps=A.PS_ATTR0_COLOR, base_vertex=0, indexed=True, split=1, viewport=None, front_ccw=False,
-                 stream_pad=(0, 0)):
+                 stream_pad=(0, 0), color_element=None):
         """`base_vertex`: the index buffer holds (index - base_vertex) and draw_index adds it back (index_fetcher.cpp:26-115;
         negative values wrap through uint32 exactly as upstream).  `indexed=False`: renderer::draw - the vertex buffers are
         expanded in index order and drawn without an index buffer.  `split`: the primitives are drawn in that many draws with
@@ -872,6 +872,9 @@ class TriangleSoup:
         # front_ccw: raster_desc::front_ccw (raster_state.cpp:10-31).  stream_pad: vertices of padding in front of each vertex
         # stream, skipped through the stream's byte OFFSET (set_vertex_buffers' offsets, stream_assembler.cpp:88-93)
         self.front_ccw, self.stream_pad = front_ccw, stream_pad
+        # color_element: (format, default_w) of the colour stream's input element instead of four floats - get_vec4 reads 1 / 2 / 3
+        # floats and fills in 0 and the element's default w (stream_assembler.cpp:26-45)
+        self.color_element = color_element
         self.w, self.h, self.samples, self.n = w, h, samples, n
         self.cull, self.ds, self.stencil_ref, self.bs, self.modifiers = cull, ds, stencil_ref, bs, modifiers
         self.color_fmt, self.ps = color_fmt, ps
@@ -908,6 +911,9 @@ class TriangleSoup:
                 self.mesh.streams = [np.concatenate([p_, st]) for p_, st in zip(pad, self.mesh.streams)]
             else:
                 self.mesh.indices = (self.mesh.indices.astype(np.int64) - base_vertex).astype(index_dtype)
+        if color_element is not None:
+            reg, _, slot, off, _ = self.mesh.elements[1]
+            self.mesh.elements[1] = (reg, color_element[0], slot, off, color_element[1])
         if any(stream_pad):
             rng_pad = np.random.default_rng(seed + 99)
             self.mesh.streams = [np.concatenate([rng_pad.uniform(-5, 5, size=(k, st.shape[1])).astype(f32), st]) if k else st

@@ -88,8 +88,8 @@ def scene_tolerance(scene):
 
 def viewport_soup_from_seed(seed: int):
     """soup_from_seed with a random viewport instead of the whole target (viewport.h:5-12): an integer or fractional
-    sub-rectangle, a rectangle that reaches past the target, and depth ranges other than 0..1 - plus front_ccw and non-zero
-    byte offsets of the vertex streams.  Upstream sizes its tile grid from
+    sub-rectangle, a rectangle that reaches past the target, and depth ranges other than 0..1 - plus front_ccw, non-zero
+    byte offsets of the vertex streams and the 1 / 2 / 3-float vertex formats.  Upstream sizes its tile grid from
     the viewport's WIDTH and HEIGHT but anchors it at the target's origin (rasterizer.cpp:1106), so with x / y > 0 the right /
     bottom part of the viewport falls outside the grid and is not drawn - mirrored, and what these scenes pin."""
     g = np.random.default_rng(7000 + seed)
@@ -113,4 +113,8 @@ def viewport_soup_from_seed(seed: int):
     kw["front_ccw"] = bool(g.random() < 0.5)
     if g.random() < 0.5:
         kw["stream_pad"] = (int(g.integers(0, 9)), int(g.integers(0, 9)))
+    # the narrow vertex formats: get_vec4 pads with 0 and the element's default w - 1 for a position semantic, 0 for any other
+    # (semantic_value::default_w, constants.h: the only two values the reference can produce)
+    if g.random() < 0.5:
+        kw["color_element"] = (int(g.choice([A.FMT_R32_FLOAT, A.FMT_R32G32_FLOAT, A.FMT_R32G32B32_FLOAT])), float(g.choice([0.0, 1.0])))
     return kw, S.TriangleSoup(**kw)
