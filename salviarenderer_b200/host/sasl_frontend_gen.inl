@@ -347,6 +347,7 @@ public:
     Value b = expr(n->kids[2]);
     if (a.type.kind == Kind::Struct) err(n, "?: on structs");
     const Type to = unify(a, b, n, false);
+    if (!c.type.numeric() || (c.type.n() != 1 && c.type.n() != to.n())) err(n, "?: condition of type " + to_string(c.type) + " with operands of type " + to_string(to));
     const bool one = c.type.n() == 1;
     c = convert(c, make_type(one ? Kind::Scalar : to.kind, Base::Bool, one ? 1 : to.rows, one ? 1 : c.type.cols), n);
     std::vector<std::string> out;

@@ -870,6 +870,8 @@ class Gen:
         if a.type.kind == "struct":
             self.err(n, "?: on structs")
         a, b, to = self.unify(a, b, n, arith=False)
+        if c.type.kind not in ("scalar", "vector", "matrix") or (c.type.n != 1 and c.type.n != to.n):
+            self.err(n, f"?: condition of type {c.type} with operands of type {to}")
         c = self.convert(c, Type("scalar" if c.type.n == 1 else to.kind, "bool", 1 if c.type.n == 1 else to.rows, c.type.cols if c.type.n > 1 else 1), n)
         cs = c.comps * to.n if c.type.n == 1 else c.comps
         return Value(to, [self.temp(to.base, f"{k} ? {x} : {y}") for k, x, y in zip(cs, a.comps, b.comps)])

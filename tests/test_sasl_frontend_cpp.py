@@ -23,7 +23,7 @@ REF = "/root/reference"
 @pytest.fixture(scope="module")
 def cli(tmp_path_factory):
     exe = str(tmp_path_factory.mktemp("sasl_cli") / "sasl_frontend_cli")
-    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I" + HOST, "-o", exe, CLI_SRC], capture_output=True, text=True)
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-D_GLIBCXX_ASSERTIONS", "-I" + HOST, "-o", exe, CLI_SRC], capture_output=True, text=True)  # out-of-range accesses abort
     assert r.returncode == 0, r.stderr[-3000:]
     return exe
 
@@ -240,6 +240,8 @@ REJECTED = [
     "struct G { float a; }; G g; float4 main(float4 p: TEXCOORD0): COLOR { return p; }",
     "bool flags[4]; float4 main(float4 p: TEXCOORD0): COLOR { return p; }",
     "float4 b[n]; float4 main(float4 p: TEXCOORD0): COLOR { return b[0]; }",
+    "float4 main(float4 p: TEXCOORD0): COLOR { return int2(1, 0) ? p : p * 2.0f; }",   # condition narrower than the operands
+    "sampler s; float4 main(float4 p: TEXCOORD0): COLOR { return s ? p : p; }",
 ]
 
 
